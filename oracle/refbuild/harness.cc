@@ -1,0 +1,220 @@
+// TEST INFRASTRUCTURE ONLY (oracle/_ref).  Drives the UNMODIFIED reference exactly the way
+// its own front end does (fte/source.cc:2197-2262 sFtCirc::newCKT, fte/simulate.cc:551-620
+// sFtCirc::run): deck lines -> IP.parseDeck -> sTASK::setOptions -> sCKT::doTask(true),
+// with output points recorded from OP.appendData.  One call = one trial, as the
+// reference's Monte-Carlo loop runs them (fte/check.cc:1649-1733, serial, deck re-parsed).
+
+#include "config.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "simulator.h"
+#include "input.h"
+#include "inpline.h"
+#include "circuit.h"
+#include "optdefs.h"
+#include "trandefs.h"
+#include "output.h"
+#include "sparse/spmatrix.h"
+
+#include "harness.h"
+
+int wrsref_verbose = 0;
+
+namespace {
+    struct Recorder {
+        int numnames = 0;
+        std::vector<double> ref;
+        std::vector<double> vals;   // [pt][numnames]
+    };
+    Recorder rec;
+
+    struct RunResult {
+        int error = 0;
+        int size = 0;
+        int accepted = 0, rejected = 0, numiter = 0, timepts = 0, traniter = 0,
+            itercut = 0, trapcut = 0;
+        double loadtime = 0, decomptime = 0, solvetime = 0, reordertime = 0, cvchktime = 0,
+            trantime = 0, tottime = 0;
+        std::vector<double> names_dummy;
+    };
+    RunResult last;
+    std::vector<char> last_names;   // '\0'-separated node names in output column order
+}
+
+extern "C" void wrsref_begin_plot(int numnames)
+{
+    rec.numnames = numnames;
+    rec.ref.clear();
+    rec.vals.clear();
+}
+
+extern "C" void wrsref_append(double ref, const double *vals, int n)
+{
+    rec.ref.push_back(ref);
+    rec.vals.insert(rec.vals.end(), vals, vals + n);
+}
+
+extern "C" {
+
+void wrsref_set_verbose(int v) { wrsref_verbose = v; }
+
+// Run one deck.  deck_text: newline-separated SPICE lines, first line = title, must
+// contain one .tran (or .op) line; ".options" lines are honoured the way
+// fte/source.cc does (collected into an sOPTIONS handed to sTASK::setOptions).
+// Returns the reference's error code from doTask (0 = OK).
+int wrsref_run_deck(const char *deck_text)
+{
+    rec = Recorder();
+    last = RunResult();
+    last_names.clear();
+
+    // Split into sLine list.
+    sLine *head = 0, *tail = 0;
+    const char *s = deck_text;
+    int lnum = 0;
+    while (*s) {
+        const char *e = strchr(s, '\n');
+        size_t len = e ? (size_t)(e - s) : strlen(s);
+        char *buf = new char[len + 1];
+        memcpy(buf, s, len);
+        buf[len] = 0;
+        // strip trailing CR/space
+        while (len && (buf[len-1] == '\r' || buf[len-1] == ' '))
+            buf[--len] = 0;
+        sLine *l = new sLine;
+        l->set_line(buf);
+        l->set_line_num(++lnum);
+        delete [] buf;
+        if (!head)
+            head = tail = l;
+        else {
+            tail->set_next(l);
+            tail = l;
+        }
+        if (!e)
+            break;
+        s = e + 1;
+    }
+    if (!head || !head->next()) {
+        sLine::destroy(head);
+        return (-1);
+    }
+
+    // .options lines -> sOPTIONS (what fte/source.cc builds as ci_defOpt).
+    sOPTIONS *opts = new sOPTIONS;
+    for (sLine *l = head->next(); l; l = l->next()) {
+        const char *t = l->line();
+        while (*t == ' ' || *t == '\t')
+            t++;
+        if (lstring::cimatch(".options", t) || lstring::cimatch(".option", t) ||
+                lstring::cimatch(".opt", t)) {
+            char *tok = IP.getTok(&t, true);
+            delete [] tok;
+            OPTinfo.parse(l, 0, 0, &t, (sTASK*)opts);
+            l->comment_out();
+        }
+    }
+
+    sFtCirc *circ = new sFtCirc;
+    sCKT *ckt = new sCKT;
+    ckt->CKTbackPtr = circ;
+    IFuid taskUid;
+    int ret = ckt->newUid(&taskUid, 0, "default", UID_TASK);
+    if (ret) {
+        delete ckt;
+        delete circ;
+        sLine::destroy(head);
+        return (ret);
+    }
+    sTASK *task = new sTASK(taskUid);
+    IP.parseDeck(ckt, head->next(), task, false);
+
+    int nerr = 0;
+    for (sLine *l = head; l; l = l->next()) {
+        if (l->error()) {
+            nerr++;
+            if (wrsref_verbose)
+                fprintf(stderr, "wrsref: line %d: %s\n  %s\n", l->line_num(), l->line(),
+                    l->error());
+        }
+    }
+    if (ckt->CKTnogo) {
+        delete ckt;
+        delete circ;
+        sLine::destroy(head);
+        return (-2);
+    }
+
+    task->setOptions(opts, false);
+    ckt->setTask(task);
+
+    int err = ckt->doTask(true);
+
+    last.error = err;
+    if (ckt->CKTmatrix)
+        last.size = ckt->CKTmatrix->spGetSize(1);
+    sSTATS *st = ckt->CKTstat;
+    if (st) {
+        last.accepted = st->STATaccepted;
+        last.rejected = st->STATrejected;
+        last.numiter = st->STATnumIter;
+        last.timepts = st->STATtimePts;
+        last.traniter = st->STATtranIter;
+        last.itercut = st->STATtranIterCut;
+        last.trapcut = st->STATtranTrapCut;
+        last.loadtime = st->STATloadTime;
+        last.decomptime = st->STATdecompTime;
+        last.solvetime = st->STATsolveTime;
+        last.reordertime = st->STATreorderTime;
+        last.cvchktime = st->STATcvChkTime;
+        last.trantime = st->STATtranTime;
+        last.tottime = st->STATtotAnalTime;
+    }
+    // Output column names.
+    {
+        const sCKTnode *node = ckt->CKTnodeTab.find(1);
+        for ( ; node; node = ckt->CKTnodeTab.nextNode(node)) {
+            const char *nm = (const char*)node->name();
+            last_names.insert(last_names.end(), nm, nm + strlen(nm) + 1);
+        }
+    }
+
+    delete ckt;
+    delete circ;
+    delete opts;
+    sLine::destroy(head);
+    return (err);
+}
+
+int wrsref_num_points(void) { return ((int)rec.ref.size()); }
+int wrsref_num_names(void) { return (rec.numnames); }
+const char *wrsref_names(int *nbytes) { *nbytes = (int)last_names.size(); return (last_names.data()); }
+
+// Copy recorded output: ref[npts], vals[npts*numnames] (row-major by point).
+void wrsref_get_points(double *ref, double *vals)
+{
+    if (ref)
+        memcpy(ref, rec.ref.data(), rec.ref.size()*sizeof(double));
+    if (vals)
+        memcpy(vals, rec.vals.data(), rec.vals.size()*sizeof(double));
+}
+
+// stats[0..7]: error, size, accepted, rejected, numIter, timePts, tranIter, iterCut, trapCut
+void wrsref_get_counters(int *c)
+{
+    c[0] = last.error; c[1] = last.size; c[2] = last.accepted; c[3] = last.rejected;
+    c[4] = last.numiter; c[5] = last.timepts; c[6] = last.traniter; c[7] = last.itercut;
+    c[8] = last.trapcut;
+}
+
+// times[0..6]: load, decomp, solve, reorder, cvchk, tran, total   (sSTATS, circuit.h:1093-1163)
+void wrsref_get_times(double *t)
+{
+    t[0] = last.loadtime; t[1] = last.decomptime; t[2] = last.solvetime;
+    t[3] = last.reordertime; t[4] = last.cvchktime; t[5] = last.trantime; t[6] = last.tottime;
+}
+
+} // extern "C"
