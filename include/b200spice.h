@@ -1,0 +1,231 @@
+/*
+ * b200spice.h -- C ABI of the B200-native batched Newton engine for WRspice's hot path
+ * (per-iteration device load + fixed-pattern sparse LU/solve + the per-trial Newton /
+ * time-step driver, batched over Monte-Carlo / sweep trials that share one sparsity pattern).
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Every entry point cites the
+ * reference interface (wrcad/xictools, paths relative to the reference root) it stands in for.
+ *
+ * Three groups:
+ *   1. deck description  (what the reference builds in sCKT::setup()/temp() from parsed cards:
+ *      wrspice/src/ckt/ckt.cc:2110-2307, devlib/<dev>/<dev>set.cc, <dev>temp.cc)
+ *   2. batched run       (replaces sCHECKprms::loop / sDCTprms::loop_mt over
+ *      TRANanalysis::tran_dcoperation: fte/check.cc:1472-1733, analysis/dctprms.cc:841-1082,
+ *      analysis/tranan.cc:321-468)
+ *   3. KLU-hook seam     (the spMatlabMatrix / klu_* contract:
+ *      xt_base/include/sparse/spmatrix.h:815-868, wrspice/src/sparse/kluif.cc:569-628)
+ *
+ * There is NO CPU fallback behind any compute entry point: without a CUDA device they
+ * return B200_E_NOGPU.
+ */
+#ifndef B200SPICE_H
+#define B200SPICE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes: numerically identical to wrspice/include/errors.h:52-100 ---- */
+#define B200_OK            0
+#define B200_E_NOMEM       1
+#define B200_E_PANIC       2
+#define B200_E_BADPARM    11
+#define B200_E_UNSUPP     13
+#define B200_E_NODECON    18
+#define B200_E_SINGULAR  101
+#define B200_E_ITERLIM   103
+#define B200_E_ORDER     104
+#define B200_E_METHOD    105
+#define B200_E_TIMESTEP  106
+#define B200_E_MATHDBZ   117   /* errors.h:117-120 E_MATH* (FPEcheck emulation) */
+#define B200_E_MATHINV   118
+#define B200_E_MATHOVF   119
+#define B200_E_NOGPU    1001   /* ours: no CUDA device / extension unusable */
+
+/* ---- device kinds ---- */
+enum { B200_DEV_RES = 0, B200_DEV_CAP = 1, B200_DEV_IND = 2, B200_DEV_MUT = 3,
+       B200_DEV_SRC = 4, B200_DEV_MOS = 5, B200_DEV_JJ = 6, B200_DEV_NKINDS = 7 };
+
+/* NaN in a double field == "not given" (the reference's xxxGiven flags). */
+
+/* .options that the hot path reads: wrspice/include/circuit.h:461-631 (defaults),
+ * 999-1069 (TSK* macros). */
+typedef struct b200_options {
+    double abstol, reltol, vntol, chgtol, trtol, gmin, gmax, pivrel, pivtol;
+    double temp, tnom;          /* Kelvin */
+    double xmu, dcmu, trapratio, delmin, minbreak, resmin;
+    double defl, defw, defad, defas;
+    int    bypass, maxord, itl1, itl2, itl4, itl_gmin, itl_src;
+    int    gminsteps, srcsteps, gminfirst;
+    int    method;              /* 0 = TRAPEZOIDAL, 1 = GEAR */
+    int    trapcheck, spice3, oldsteplim, oldlimit /* TSKfixLimit */, forcegmin;
+    int    interplev, jjaccel, nojjtp, noopiter;
+    int    steptype;            /* 0 STEP_NORMAL (interpolate to user points) */
+} b200_options;
+
+/* Resistor: devlib/res/restemp.cc:186-230 (conduct = m/(r*tcfactor), preloaded). */
+typedef struct b200_res { int pos, neg; double r, m, tc1, tc2, temp; } b200_res;
+
+/* Capacitor: devlib/cap/capset.cc, captemp.cc, capload.cc:104-205. */
+typedef struct b200_cap { int pos, neg; double c, m, ic; } b200_cap;
+
+/* Inductor / mutual: devlib/ind/indset.cc, indload.cc:84-150, mutload.cc:56-108. */
+typedef struct b200_ind { int pos, neg; double l, m, ic; } b200_ind;
+typedef struct b200_mut { int ind1, ind2; double k; } b200_mut;
+
+/* Independent source: devlib/src/srcset.cc:64-370, srcload.cc:67-262,
+ * src/inp/inptran.cc (PULSE :1099-1414, PWL :1980-2388, SIN :2496-2624). */
+enum { B200_SRC_V = 0, B200_SRC_I = 1 };
+enum { B200_FN_NONE = 0, B200_FN_PULSE = 1, B200_FN_PWL = 2, B200_FN_SIN = 3 };
+typedef struct b200_src {
+    int kind;                   /* B200_SRC_V / B200_SRC_I */
+    int pos, neg;
+    double dc;                  /* NaN if not given */
+    int fn;                     /* B200_FN_* */
+    int ncoef;                  /* number of doubles in coef */
+    const double *coef;         /* function arguments exactly as on the card */
+} b200_src;
+
+/* MOSFET level 1/2/3/6 card: devlib/mos/mosdefs.h:415-600 (model), :115-328 (instance),
+ * defaults mosset.cc:83-390, preprocessing mostemp.cc:65-389. */
+typedef struct b200_mos_model {
+    int type;                   /* +1 NMOS, -1 PMOS */
+    int level;                  /* 1,2,3,6 */
+    double vto, kp, gamma, phi, lambda, rd, rs, cbd, cbs, is, pb, cgso, cgdo, cgbo;
+    double rsh, cj, mj, cjsw, mjsw, js, tox, ld, u0, fc, nsub, tpg, nss, tnom;
+    double nfs, delta, uexp, ucrit, vmax, xj, neff, eta, theta, kappa;   /* level 2/3 */
+} b200_mos_model;
+typedef struct b200_mos {
+    int d, g, s, b;             /* external node numbers (0 = ground) */
+    int model;                  /* index into b200_deck.mos_models */
+    double l, w, ad, as, pd, ps, nrd, nrs, m, temp;
+    double icvds, icvgs, icvbs;
+    int off;
+} b200_mos;
+
+/* Josephson junction, RSJ level 1: devlib/jj/jjdefs.h, jjset.cc, jjload.cc. */
+typedef struct b200_jj_model {
+    int rtype, ictype;
+    double vg, delv, icrit, r0, rn, cap, icfact, vshunt, tsfact, tsaccel;
+    double cpic, cmu, vm, icrn, gmu;   /* NaN = not given */
+} b200_jj_model;
+typedef struct b200_jj { int pos, neg, phase_node; int model; double area, ics, icphi, icv; } b200_jj;
+
+/* One deck = one topology (shared by all trials).  Node numbers: 0 is ground, 1..nnodes-1 are
+ * the external nodes in the order the reference's parser meets them (src/inp/inpdeck.cc pass2);
+ * internal nodes and branch equations are appended by b200_batch_create in the reference's
+ * setup order.  `order` lists every device in the reference's LOAD order
+ * (ckt.cc:991-1005 mutuals first, then :1146-1161 model-type list -> models -> instances). */
+typedef struct b200_deck {
+    int nnodes;
+    b200_options opt;
+    /* .tran tstep tstop [tstart [tmax]] [uic]: analysis/tranan.cc:95-217 */
+    double tstep, tstop, tstart, tmax;
+    int uic;
+    /* .ic / .nodeset: ckt.cc:908-925, 1177-1204 */
+    int nic;      const int *ic_node;  const double *ic_val;
+    int nnodeset; const int *ns_node;  const double *ns_val;
+    /* device tables */
+    int nres;  const b200_res *res;
+    int ncap;  const b200_cap *cap;
+    int nind;  const b200_ind *ind;
+    int nmut;  const b200_mut *mut;
+    int nsrc;  const b200_src *src;
+    int nmosmod; const b200_mos_model *mos_models;
+    int nmos;  const b200_mos *mos;
+    int njjmod; const b200_jj_model *jj_models;
+    int njj;   const b200_jj *jj;
+    /* load order: order_kind[i] in B200_DEV_*, order_index[i] into that kind's table */
+    int norder; const int *order_kind; const int *order_index;
+} b200_deck;
+
+void b200_options_default(b200_options *o);        /* circuit.h:461-631 */
+
+/* ---- per-trial parameter variation (what the reference's .exec block / .param text does
+ * before each trial's re-parse: fte/check.cc:1649-1700, simulate.cc:828-837) ---- */
+enum {
+    B200_P_MOS_VTO = 1, B200_P_MOS_KP, B200_P_MOS_L, B200_P_MOS_W, B200_P_MOS_GAMMA,
+    B200_P_MOS_LAMBDA, B200_P_MOS_PHI,
+    B200_P_CAP_C = 32, B200_P_RES_R = 48, B200_P_IND_L = 56, B200_P_SRC_DC = 64,
+    B200_P_JJ_AREA = 80
+};
+
+typedef struct b200_batch b200_batch;
+
+/* Create a batch of `ntrials` trials of one deck on CUDA device `device`.
+ * Does what sCKT::setup() + spSaveForInitialization() do once per trial in the reference
+ * (ckt.cc:627-674, spspice.cc:79-100): allocates nodes/branches/states, builds the CSC
+ * pattern from every device's TSTALLOC list, computes the ordering + symbolic LU. */
+int  b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch **out);
+void b200_batch_destroy(b200_batch *b);
+
+/* values[ntrials] (host) replaces instance `index`'s parameter `param` for every trial.
+ * For B200_P_MOS_VTO/KP/GAMMA/LAMBDA/PHI the value is the instance's private model card value
+ * (the reference MC decks give each varied device its own .model). */
+int  b200_batch_set_param(b200_batch *b, int param, int index, const double *values);
+
+/* Runs DCOP (or UIC start) + transient for every trial to completion on the GPU:
+ * TRANanalysis::tran_dcoperation (tranan.cc:321-468) with sCKT::op (ckt.cc:1859-2011),
+ * NIiter (niiter.cc:160-555), sTRANint::step/accept/interpolate (tranan.cc:483-1116). */
+int  b200_batch_run_tran(b200_batch *b);
+
+/* Results (host buffers).  npoints = number of user time points (count of OP.appendData calls
+ * per trial in the reference, tranan.cc:963-1116 -> ckt.cc:680-708). */
+int  b200_batch_num_unknowns(const b200_batch *b);   /* matrix size n (nodes + branches) */
+int  b200_batch_num_points(const b200_batch *b);
+/* names: '\0'-separated, reference-style ("vdd#branch", "m1#internal#drain") */
+int  b200_batch_unknown_names(const b200_batch *b, char *buf, int buflen);
+/* counters[ntrials][B200_NCOUNTERS]: sSTATS fields, circuit.h:1093-1163 */
+enum { B200_C_STATUS = 0, B200_C_ACCEPTED, B200_C_REJECTED, B200_C_NUMITER, B200_C_TIMEPTS,
+       B200_C_TRANITER, B200_C_ITERCUT, B200_C_TRAPCUT, B200_C_NPOINTS, B200_NCOUNTERS };
+int  b200_batch_get_counters(const b200_batch *b, int *counters);
+/* waves[ntrials][npoints][n] : unknown vector at each user time point; times[npoints] */
+int  b200_batch_get_waves(const b200_batch *b, double *times, double *waves);
+/* Same, restricted to a subset of unknowns (what `.save`/`.print` would keep). */
+int  b200_batch_get_waves_sel(const b200_batch *b, int nsel, const int *sel, double *waves);
+
+/* Kernel statistics of the last run (for bench.py): number of kernel launches, Newton ticks,
+ * device-load instance evaluations, seconds spent per kernel class (CUDA events). */
+typedef struct b200_run_stats {
+    long long launches, ticks, load_instances;
+    double ms_total, ms_load, ms_solve, ms_control;
+    long long solve_launches, load_launches;
+    double algbytes_load_per_launch, algbytes_solve_per_launch;
+} b200_run_stats;
+int  b200_batch_get_stats(const b200_batch *b, b200_run_stats *st);
+
+/* ---- debug / parity hooks used by tests (device state -> host) ---- */
+/* Host-side analysis products: CSC pattern of A, and the LU ordering the batch uses. */
+int  b200_batch_pattern(const b200_batch *b, int *n, int *nnz, const int **Ap, const int **Ai);
+int  b200_batch_ordering(const b200_batch *b, const int **rowperm, const int **colperm);
+/* Single load+assemble at a forced state: the per-trial matrix values Ax[nnz][ntrials] and
+ * RHS[n+1][ntrials] after sCKT::load + loadGmin, for stamp-for-stamp comparison. */
+int  b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, int order,
+                           const double *rhsold /* [n+1][ntrials] or NULL */,
+                           double *Ax, double *rhs);
+
+/* ---- KLU-hook seam (batched): spMatlabMatrix::factor/refactor/solve semantics ----
+ * xt_base/include/sparse/spmatrix.h:853-857; kluif.cc:569-628.  Pattern is CSC, 0-based,
+ * row indices ascending per column (spbuild.cc:922-958). */
+typedef struct b200_klu b200_klu;
+/* klu_analyze + first klu_factor on trial 0's values (pivot sequence is then frozen, which
+ * is exactly klu_refactor's contract).  Ax0: host, nnz doubles. */
+int  b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0,
+                      double pivrel, double pivabs, int device, b200_klu **out);
+void b200_klu_free(b200_klu *k);
+/* Batched klu_refactor + klu_solve, HOST buffers: Ax[ntrials][nnz], B[ntrials][n] overwritten
+ * with the solutions; status[ntrials] = B200_OK / B200_E_SINGULAR.  (e2e path) */
+int  b200_klu_refactor_solve_host(b200_klu *k, int ntrials, const double *Ax, double *B,
+                                  int *status);
+/* Same with DEVICE buffers in the engine's trial-minor layout Ax[nnz][ldt], B[n][ldt]. */
+int  b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double *dAx,
+                                 double *dB, int *dstatus, void *cuda_stream);
+int  b200_klu_lu_nnz(const b200_klu *k);
+
+const char *b200_version(void);
+int  b200_cuda_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,164 @@
+"""ctypes wrappers for the two CPU checkers.  TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs -- never by
+xictools_b200/.
+
+  RefSim   oracle/_ref/libwrsref.so   the UNMODIFIED reference compiled headless
+  Oracle   oracle/libwrsoracle.so     the plain-C restatement (wrs_oracle.c)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libwrsref.so")
+ORACLE_SO = os.path.join(HERE, "libwrsoracle.so")
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+class RefSim:
+    """One process-global instance: the reference keeps global singletons."""
+    _lib = None
+
+    def __init__(self):
+        if RefSim._lib is None:
+            RefSim._lib = C.CDLL(REF_SO)
+            L = RefSim._lib
+            L.wrsref_names.restype = C.POINTER(C.c_char)
+            L.wrsref_load_order.restype = C.POINTER(C.c_char)
+        self.L = RefSim._lib
+
+    def run(self, spice_text: str) -> dict:
+        L = self.L
+        err = L.wrsref_run_deck(spice_text.encode())
+        cnt = (C.c_int * 9)()
+        L.wrsref_get_counters(cnt)
+        tm = (C.c_double * 7)()
+        L.wrsref_get_times(tm)
+        npts, nn = L.wrsref_num_points(), L.wrsref_num_names()
+        t = np.zeros(npts)
+        v = np.zeros((npts, max(nn, 1)))
+        if npts:
+            L.wrsref_get_points(t.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+        nb = C.c_int()
+        p = L.wrsref_names(C.byref(nb))
+        names = [s.decode() for s in bytes(p[:nb.value]).split(b"\0")[:-1]]
+        p = L.wrsref_load_order(C.byref(nb))
+        order = [s.decode() for s in bytes(p[:nb.value]).split(b"\0")[:-1]]
+        keys = ("error", "size", "accepted", "rejected", "numiter", "timepts", "traniter",
+                "itercut", "trapcut")
+        out = dict(zip(keys, list(cnt)))
+        out.update(err=err, times=t, vals=v, names=names, load_order=order,
+                   t_load=tm[0], t_decomp=tm[1], t_solve=tm[2], t_reorder=tm[3],
+                   t_cvchk=tm[4], t_tran=tm[5], t_total=tm[6])
+        return out
+
+
+class Oracle:
+    _lib = None
+
+    def __init__(self, deck, overrides: dict | None = None, trial: int = 0):
+        if Oracle._lib is None:
+            Oracle._lib = C.CDLL(ORACLE_SO)
+            L = Oracle._lib
+            L.wo_create.restype = C.c_void_p
+            L.wo_create.argtypes = [C.c_void_p]
+            for f in ("wo_destroy", "wo_run_tran", "wo_num_unknowns", "wo_nnz", "wo_num_points",
+                      "wo_num_accepted"):
+                getattr(L, f).argtypes = [C.c_void_p]
+            L.wo_set_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+            L.wo_set_ordering.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            L.wo_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            L.wo_unknown_names.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            L.wo_get_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            L.wo_get_counters.argtypes = [C.c_void_p, C.c_void_p]
+            L.wo_get_accepted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.wo_debug_load.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+            L.wo_lu_solve_static.argtypes = [C.c_int] + [C.c_void_p] * 6
+        self.L = Oracle._lib
+        self.deck = deck
+        cd, keep = deck.to_c()
+        self._keep = (cd, keep)
+        self.h = self.L.wo_create(C.byref(cd))
+        if overrides:
+            for (pid, idx), vals in overrides.items():
+                v = vals[trial] if hasattr(vals, "__len__") else vals
+                self.L.wo_set_param(self.h, pid, idx, float(v))
+        self.n = self.L.wo_num_unknowns(self.h)
+        self.nnz = self.L.wo_nnz(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.wo_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def names(self):
+        buf = C.create_string_buffer(1 << 20)
+        nb = self.L.wo_unknown_names(self.h, buf, len(buf))
+        generic = [s.decode() for s in buf.raw[:nb].split(b"\0")[:-1]]
+        return self.deck.unknown_names(generic)
+
+    def pattern(self):
+        ap, ai = C.POINTER(C.c_int)(), C.POINTER(C.c_int)()
+        self.L.wo_pattern(self.h, C.byref(ap), C.byref(ai))
+        Ap = np.array(ap[:self.n + 1], dtype=np.int32)
+        Ai = np.array(ai[:self.nnz], dtype=np.int32)
+        return Ap, Ai
+
+    def set_ordering(self, rowperm, colperm):
+        r = np.ascontiguousarray(rowperm, dtype=np.int32)
+        c = np.ascontiguousarray(colperm, dtype=np.int32)
+        self.L.wo_set_ordering(self.h, r.ctypes.data, c.ctypes.data)
+
+    def run(self) -> dict:
+        err = self.L.wo_run_tran(self.h)
+        cnt = np.zeros(10, dtype=np.int32)
+        self.L.wo_get_counters(self.h, cnt.ctypes.data)
+        npts = self.L.wo_num_points(self.h)
+        t = np.zeros(npts)
+        v = np.zeros((npts, self.n))
+        self.L.wo_get_points(self.h, t.ctypes.data, v.ctypes.data)
+        na = self.L.wo_num_accepted(self.h)
+        at = np.zeros(na)
+        av = np.zeros((na, self.n))
+        ai = np.zeros(na, dtype=np.int32)
+        self.L.wo_get_accepted(self.h, at.ctypes.data, av.ctypes.data, ai.ctypes.data)
+        return dict(err=err, accepted=int(cnt[1]), rejected=int(cnt[2]), numiter=int(cnt[3]),
+                    timepts=int(cnt[4]), traniter=int(cnt[5]), itercut=int(cnt[6]),
+                    trapcut=int(cnt[7]), times=t, vals=v, names=self.names(),
+                    acc_times=at, acc_vals=av, acc_iters=ai)
+
+    def debug_load(self, mode, time, delta, order, rhsold=None):
+        Ax = np.zeros(self.nnz)
+        rhs = np.zeros(self.n + 1)
+        ro = None
+        if rhsold is not None:
+            ro = np.ascontiguousarray(rhsold, dtype=np.float64)
+        err = self.L.wo_debug_load(self.h, mode, time, delta, order,
+                                   ro.ctypes.data if ro is not None else None,
+                                   Ax.ctypes.data, rhs.ctypes.data)
+        return err, Ax, rhs
+
+
+def lu_solve_static(n, Ap, Ai, Ax, rowperm, colperm, b):
+    Oracle._lib or C.CDLL(ORACLE_SO)
+    L = Oracle._lib or C.CDLL(ORACLE_SO)
+    L.wo_lu_solve_static.argtypes = [C.c_int] + [C.c_void_p] * 6
+    Ap = np.ascontiguousarray(Ap, dtype=np.int32)
+    Ai = np.ascontiguousarray(Ai, dtype=np.int32)
+    Ax = np.ascontiguousarray(Ax, dtype=np.float64)
+    r = np.ascontiguousarray(rowperm, dtype=np.int32)
+    c = np.ascontiguousarray(colperm, dtype=np.int32)
+    x = np.array(b, dtype=np.float64, copy=True)
+    err = L.wo_lu_solve_static(n, Ap.ctypes.data, Ai.ctypes.data, Ax.ctypes.data,
+                               r.ctypes.data, c.ctypes.data, x.ctypes.data)
+    return err, x

@@ -42,6 +42,7 @@ namespace {
     };
     RunResult last;
     std::vector<char> last_names;   // '\0'-separated node names in output column order
+    std::vector<char> last_order;   // '\0'-separated instance names in sCKT::load order
 }
 
 extern "C" void wrsref_begin_plot(int numnames)
@@ -60,6 +61,7 @@ extern "C" void wrsref_append(double ref, const double *vals, int n)
 extern "C" {
 
 void wrsref_set_verbose(int v) { wrsref_verbose = v; }
+void wrsref_set_trantrace(int v) { Sp.SetTranTrace(v); }
 
 // Run one deck.  deck_text: newline-separated SPICE lines, first line = title, must
 // contain one .tran (or .op) line; ".options" lines are honoured the way
@@ -70,6 +72,7 @@ int wrsref_run_deck(const char *deck_text)
     rec = Recorder();
     last = RunResult();
     last_names.clear();
+    last_order.clear();
 
     // Split into sLine list.
     sLine *head = 0, *tail = 0;
@@ -182,6 +185,31 @@ int wrsref_run_deck(const char *deck_text)
         }
     }
 
+    // Instance names in the order sCKT::load visits them (ckt.cc:996-1005, 1146-1161).
+    {
+        int muttype = -1;
+        sGENmodel *mutm = 0;
+        ckt->typelook("mutual", &mutm);
+        if (mutm) {
+            muttype = mutm->GENmodType;
+            for (sGENmodel *dm = mutm; dm; dm = dm->GENnextModel)
+                for (sGENinstance *d = dm->GENinstances; d; d = d->GENnextInstance) {
+                    const char *nm = (const char*)d->GENname;
+                    last_order.insert(last_order.end(), nm, nm + strlen(nm) + 1);
+                }
+        }
+        sCKTmodGen mgen(ckt->CKTmodels);
+        for (sGENmodel *m = mgen.next(); m; m = mgen.next()) {
+            if (m->GENmodType == muttype)
+                continue;
+            for (sGENmodel *dm = m; dm; dm = dm->GENnextModel)
+                for (sGENinstance *d = dm->GENinstances; d; d = d->GENnextInstance) {
+                    const char *nm = (const char*)d->GENname;
+                    last_order.insert(last_order.end(), nm, nm + strlen(nm) + 1);
+                }
+        }
+    }
+
     delete ckt;
     delete circ;
     delete opts;
@@ -192,6 +220,8 @@ int wrsref_run_deck(const char *deck_text)
 int wrsref_num_points(void) { return ((int)rec.ref.size()); }
 int wrsref_num_names(void) { return (rec.numnames); }
 const char *wrsref_names(int *nbytes) { *nbytes = (int)last_names.size(); return (last_names.data()); }
+
+const char *wrsref_load_order(int *nbytes) { *nbytes = (int)last_order.size(); return (last_order.data()); }
 
 // Copy recorded output: ref[npts], vals[npts*numnames] (row-major by point).
 void wrsref_get_points(double *ref, double *vals)

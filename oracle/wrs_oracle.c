@@ -1,0 +1,3155 @@
+/*
+ * wrs_oracle.c -- TEST INFRASTRUCTURE ONLY (see wrs_oracle.h).
+ *
+ * Scalar CPU restatement of the WRspice Newton/transient hot path.  Written from the
+ * reference's behaviour, function by function; every block cites the file:line it follows
+ * (relative to /root/reference/wrspice).  Expression order is kept identical to the
+ * reference wherever floating-point results depend on it (compile with -ffp-contract=off).
+ */
+#define _GNU_SOURCE
+#include <fenv.h>
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "wrs_oracle.h"
+
+/* circuit.h:2158-2192 */
+#define MODETRAN        0x1
+#define MODEDC          0x70
+#define MODEDCOP        0x10
+#define MODETRANOP      0x20
+#define MODEDCTRANCURVE 0x40
+#define INITF           0x7f00
+#define MODEINITFLOAT   0x100
+#define MODEINITJCT     0x200
+#define MODEINITFIX     0x400
+#define MODEINITSMSIG   0x800
+#define MODEINITTRAN    0x1000
+#define MODEINITPRED    0x2000
+#define MODEUIC         0x10000
+#define NISHOULDREORDER 0x1
+
+/* circuit.h:111-125 */
+#define REFTEMP     298.15
+#define CHARGE      1.602176634e-19
+#define CONSTboltz  1.380649e-23
+#define CONSTKoverQ (CONSTboltz/CHARGE)
+#define CONSTroot2  M_SQRT2
+#define EPSSIL      (11.7 * 8.854214871e-12)
+#define CM3PM3 1e6
+#define CM2PM2 1e4
+#define M2PCM2 1e-4
+
+#define OK 0
+#define E_SINGULAR B200_E_SINGULAR
+#define E_ITERLIM  B200_E_ITERLIM
+#define E_TIMESTEP B200_E_TIMESTEP
+#define E_MATHDBZ  117
+#define E_MATHINV  118
+#define E_MATHOVF  119
+#define E_MATHUNF  120
+#define E_NOCHANGE 16
+
+#define SPMAX(a,b) ((a) > (b) ? (a) : (b))
+#define SPMIN(a,b) ((a) < (b) ? (a) : (b))
+#define GIVEN(x) (!isnan(x))
+
+enum { SP_VOLTAGE = 0, SP_CURRENT = 1 };
+
+/* ------------------------------------------------------------------------- */
+/* device records                                                             */
+/* ------------------------------------------------------------------------- */
+
+/* MOS states (mosdefs.h:330-375, minus the 18 write-only "ask" mirrors) */
+enum { MS_vbd, MS_vbs, MS_vgs, MS_vds, MS_capgs, MS_qgs, MS_cqgs, MS_capgd, MS_qgd, MS_cqgd,
+       MS_capgb, MS_qgb, MS_cqgb, MS_qbd, MS_cqbd, MS_qbs, MS_cqbs, MS_NSTATES };
+
+/* matrix stamp slots in the order of mosset.cc:53-77 get_node_ptr */
+enum { M_Dd, M_Gg, M_Ss, M_Bb, M_DPdp, M_SPsp, M_Ddp, M_Gb, M_Gdp, M_Gsp, M_Ssp, M_Bg, M_Bdp,
+       M_Bsp, M_DPsp, M_DPd, M_Bd_unused, M_DPg, M_DPb, M_SPg, M_SPs, M_SPb, M_SPdp, M_NPTR };
+
+typedef struct {
+    /* card */
+    b200_mos_model mod;      /* private copy so per-trial vto/kp overrides are local */
+    b200_mos in;
+    /* model-derived (mostemp.cc:65-139) */
+    double oxideCapFactor, surfaceMobility, kp_eff, gamma_eff, phi_eff, vt0_eff;
+    /* nodes */
+    int d, g, s, b, dp, sp;
+    int ptr[M_NPTR];
+    int st;
+    /* instance-derived (mosset.cc:283-373, mostemp.cc:141-300) */
+    double mult, temp, l, w, drainArea, sourceArea, drainPerimeter, sourcePerimeter;
+    double drainSquares, sourceSquares, icVBS, icVDS, icVGS;
+    double drainConductance, sourceConductance, effectiveLength;
+    double tTransconductance, tSurfMob, tPhi, tVbi, tVto, tSatCur, tSatCurDens;
+    double tCbd, tCbs, tCj, tCjsw, tBulkPot, tDepCap;
+    double sourceVcrit, drainVcrit, tDrainSatCur, tSourceSatCur;
+    double Cbd, Cbdsw, Cbs, Cbssw, f2d, f3d, f4d, f2s, f3s, f4s;
+    double gateSourceOverlapCap, gateDrainOverlapCap, gateBulkOverlapCap, beta, oxideCap;
+    /* cached op point (mosdefs.h:125,160-173) */
+    int mode;
+    double von, vdsat, cd, cbs, cbd, gm, gds, gmbs, gbd, gbs, capbd, capbs;
+} Mos;
+
+typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; int st; double capac, ic, geq, ceq; } Cap;
+typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct; } Res;
+typedef struct {
+    int kind, pos, neg, branch;
+    int pPB, pNB, pBN, pBP;
+    int dcGiven; double dc;
+    int fn, ncoef; double *coef;
+    /* run-time tran function parameters (inptran.cc) */
+    double parms[8], cache[2];
+    double *pwl_cache; int pwl_n, pwl_index;
+    int enable_tran;
+} Src;
+
+typedef struct { int kind, index; } DevRef;
+
+/* saved op-point for sCKT::backup (ckt.cc:1323-1362, mosdefs.h:386-402) */
+typedef struct { int mode; double v[12]; } MosSave;
+
+struct wo_ckt {
+    b200_options opt;
+    double tstep, tstop, tstart, tmax; int uic;
+    int nnodes_ext;          /* external nodes incl. ground */
+    int n;                   /* unknowns (matrix size); node numbers 1..n */
+    int *ntype;              /* [n+1] */
+    double *ic_val; char *ic_given; double *ns_val; char *ns_given; int hadNodeset;
+    char **names;
+
+    int nmos, ncap, nres, nsrc;
+    Mos *mos; Cap *cap; Res *res; Src *src;
+    int nord; DevRef *ord;
+
+    /* matrix: CSC, rows ascending per column (spbuild.cc:922-958) */
+    int nnz; int *Ap, *Ai; double *Ax, *Ainit;
+    int *diag;               /* [n+1] index of (i,i) in Ax or -1 */
+    /* coordinate collection during setup */
+    int ncoo, capcoo; int *coo_r, *coo_c;
+
+    /* LU */
+    int have_order; int *rowperm, *colperm;   /* position -> original (0-based) */
+    int lu_ready;
+    int *Lp, *Li; double *Lx;   /* strictly lower, by column, in permuted positions */
+    int *Up, *Ui; double *Ux;   /* strictly upper, by column */
+    double *Udiag;
+    int *cpat_p, *cpat_i;       /* per permuted column: positions < j that are nonzero in U(:,j) */
+    int *posA;                  /* for own-pivot mode */
+    double *work;
+    double *dense;              /* own-pivot dense LU, n*n */
+    int *dpiv;
+
+    /* vectors (slot 0 = ground) */
+    double *rhs, *rhsOld, *rhsSpare, *sols[8];
+    int numStates; double *states[8];
+    double *oldSol, *oldState0; MosSave *mosSave; int haveSave;
+
+    /* sCKTPOD scalars (circuit.h:1562-1662) */
+    double time, delta, deltaOld[7], saveDelta, ag[7], pred[4];
+    double srcFact, diagGmin, devMaxDelta, vt;
+    int order, mode, niState, noncon, brk, trapCheck, trapBad;
+    double breaks[2];
+    /* breakpoint table (breakpt.cc) */
+    int numBreaks; double *brks; int numLat; double *lat_offs, *lat_per;
+    /* sTRANint (trandefs.h:93-151) */
+    double t_stop, t_step, t_start, t_check, t_delmax, t_delmin, t_fixed_step;
+    int t_firsttime, t_dumpit, t_ordcnt, t_nocut, t_spice3, t_polydegree;
+    double maxStep, minBreak;
+    /* stats */
+    int accepted, rejected, numIter, timePts, tranIter, iterCut, trapCut;
+    /* outputs */
+    int npts, cappts; double *pt_t, *pt_v;
+    int nacc, capacc; double *acc_t, *acc_v; int *acc_it;
+    int lastIters;
+    int endit;
+};
+
+/* ------------------------------------------------------------------------- */
+/* helpers                                                                    */
+/* ------------------------------------------------------------------------- */
+static void *xcalloc(size_t n, size_t s) { void *p = calloc(n ? n : 1, s); if (!p) abort(); return p; }
+
+void b200_options_default_oracle(b200_options *o)
+{
+    /* circuit.h:461-631 */
+    memset(o, 0, sizeof(*o));
+    o->abstol = 1e-12; o->reltol = 1e-3; o->vntol = 1e-6; o->chgtol = 1e-14; o->trtol = 7.0;
+    o->gmin = 1e-12; o->gmax = 1e6; o->pivrel = 1e-3; o->pivtol = 1e-13;
+    o->temp = REFTEMP; o->tnom = REFTEMP;
+    o->xmu = 0.5; o->dcmu = 0.5; o->trapratio = 10.0; o->delmin = 0.0; o->minbreak = 0.0;
+    o->resmin = 1e-3;
+    o->bypass = 1; o->maxord = 2; o->itl1 = 400; o->itl2 = 100; o->itl4 = 20;
+    o->itl_gmin = 20; o->itl_src = 20; o->gminsteps = 0; o->srcsteps = 0; o->gminfirst = 0;
+    o->method = 0; o->trapcheck = 0; o->spice3 = 0; o->oldsteplim = 0; o->oldlimit = 0;
+    o->forcegmin = 0; o->interplev = 1; o->jjaccel = 0; o->nojjtp = 0; o->noopiter = 0;
+    o->steptype = 0;
+}
+
+/* add a structural entry; returns coo index (resolved to Ax index after sorting) */
+static int coo_add(wo_ckt *c, int r, int col)
+{
+    if (r == 0 || col == 0)
+        return -1;
+    for (int i = 0; i < c->ncoo; i++)
+        if (c->coo_r[i] == r && c->coo_c[i] == col)
+            return i;
+    if (c->ncoo == c->capcoo) {
+        c->capcoo = c->capcoo ? 2*c->capcoo : 256;
+        c->coo_r = realloc(c->coo_r, c->capcoo*sizeof(int));
+        c->coo_c = realloc(c->coo_c, c->capcoo*sizeof(int));
+    }
+    c->coo_r[c->ncoo] = r; c->coo_c[c->ncoo] = col;
+    return c->ncoo++;
+}
+
+static int new_node(wo_ckt *c, int type, const char *name)
+{
+    c->n++;
+    c->ntype = realloc(c->ntype, (c->n+1)*sizeof(int));
+    c->names = realloc(c->names, (c->n+1)*sizeof(char*));
+    c->ntype[c->n] = type;
+    c->names[c->n] = strdup(name);
+    return c->n;
+}
+
+static inline void ldadd(wo_ckt *c, int p, double v) { if (p >= 0) c->Ax[p] += v; }
+static inline void rhsadd(wo_ckt *c, int node, double v) { c->rhs[node] += v; }
+
+/* ------------------------------------------------------------------------- */
+/* breakpoints: ckt/breakpt.cc:58-221                                         */
+/* ------------------------------------------------------------------------- */
+static double nextbreak(wo_ckt *c, double t, double minbrk)
+{
+    double dt0 = 0.0;
+    int i;
+    for (i = 0; i < c->numLat; i++) {
+        double dt1 = c->lat_offs[i];
+        if (t > c->lat_offs[i])
+            dt1 += c->lat_per[i]*ceil((t - c->lat_offs[i])/c->lat_per[i]);
+        if (fabs(dt1 - t) < minbrk)
+            dt1 += c->lat_per[i];
+        if (dt0 == 0.0 || dt1 < dt0)
+            dt0 = dt1;
+    }
+    for (i = 0; i < c->numBreaks; i++)
+        if (c->brks[i] > t)
+            break;
+    while (i < c->numBreaks && fabs(t - c->brks[i]) < minbrk)
+        i++;
+    if (i == c->numBreaks)
+        return dt0;
+    if (dt0 > 0.0 && dt0 < c->brks[i])
+        return c->brks[i] < dt0 ? c->brks[i] : dt0;
+    return c->brks[i];
+}
+
+static void break_clr(wo_ckt *c)
+{
+    /* breakpt.cc:57-72 clear_break (the table trim does not change nextbreak results) */
+    c->breaks[0] = nextbreak(c, c->breaks[0], c->minBreak);
+    c->breaks[1] = nextbreak(c, c->breaks[0], c->minBreak);
+}
+
+static void break_set(wo_ckt *c, double time)
+{
+    /* breakpt.cc:78-160 set_break */
+    double minbrk = c->minBreak;
+    for (int i = 0; i < c->numLat; i++) {
+        double dt0, dt1;
+        if (time < c->lat_offs[i]) {
+            dt0 = c->lat_offs[i] + c->lat_per[i];
+            dt1 = c->lat_offs[i];
+        }
+        else {
+            dt0 = c->lat_per[i]*ceil((time - c->lat_offs[i])/c->lat_per[i]) + c->lat_offs[i];
+            dt1 = c->lat_per[i]*floor((time - c->lat_offs[i])/c->lat_per[i]) + c->lat_offs[i];
+        }
+        if (fabs(time - dt0) < minbrk || fabs(time - dt1) < minbrk) {
+            if (time < c->breaks[0])
+                c->breaks[0] = nextbreak(c, c->time, minbrk);
+            c->breaks[1] = nextbreak(c, c->breaks[0], minbrk);
+            return;
+        }
+    }
+    if (!c->brks) {
+        c->brks = xcalloc(1, sizeof(double));
+        c->brks[0] = time;
+        c->numBreaks = 1;
+        return;
+    }
+    int done = 0;
+    for (int i = 0; i < c->numBreaks && !done; i++) {
+        if (c->brks[i] > time) {
+            if ((c->brks[i] - time) <= minbrk)
+                c->brks[i] = time;
+            else if (time - c->brks[i-1] <= minbrk)
+                ;
+            else {
+                c->brks = realloc(c->brks, (c->numBreaks+1)*sizeof(double));
+                memmove(c->brks + i + 1, c->brks + i, (c->numBreaks - i)*sizeof(double));
+                c->brks[i] = time;
+                c->numBreaks++;
+            }
+            done = 1;
+        }
+    }
+    if (!done) {
+        if (time - c->brks[c->numBreaks-1] <= minbrk)
+            ;
+        else {
+            c->brks = realloc(c->brks, (c->numBreaks+1)*sizeof(double));
+            c->brks[c->numBreaks++] = time;
+        }
+    }
+    if (time < c->breaks[0])
+        c->breaks[0] = nextbreak(c, c->time, minbrk);
+    c->breaks[1] = nextbreak(c, c->breaks[0], minbrk);
+}
+
+static void break_set_lattice(wo_ckt *c, double offs, double per)
+{
+    for (int i = 0; i < c->numLat; i++)
+        if (offs == c->lat_offs[i] && per == c->lat_per[i])
+            return;
+    c->lat_offs = realloc(c->lat_offs, (c->numLat+1)*sizeof(double));
+    c->lat_per = realloc(c->lat_per, (c->numLat+1)*sizeof(double));
+    c->lat_offs[c->numLat] = offs;
+    c->lat_per[c->numLat] = per;
+    c->numLat++;
+}
+
+/* ------------------------------------------------------------------------- */
+/* source functions: src/inp/inptran.cc                                       */
+/* ------------------------------------------------------------------------- */
+static void src_setup_func(wo_ckt *c, Src *s, double step, double finaltime)
+{
+    s->enable_tran = (step > 0.0 && finaltime > 0.0);
+    if (s->fn == B200_FN_PULSE) {
+        /* inptran.cc:1203-1318 */
+        double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
+        memset(p, 0, 8*sizeof(double));
+        p[0] = co[0];
+        p[1] = nc >= 2 ? co[1] : co[0];
+        p[2] = nc >= 3 ? co[2] : 0.0;
+        p[3] = nc >= 4 ? co[3] : 0.0;
+        p[4] = nc >= 5 ? co[4] : 0.0;
+        p[5] = nc >= 6 ? co[5] : 0.0;
+        p[6] = nc >= 7 ? co[6] : 0.0;
+        s->cache[0] = p[3] > 0.0 ? (p[1] - p[0])/p[3] : 0.0;
+        s->cache[1] = p[4] > 0.0 ? (p[1] - p[0])/p[4] : 0.0;
+        if (s->enable_tran) {
+            if (p[3] <= 0.0) p[3] = step;
+            if (p[4] > 0.0 && p[5] <= 0.0)
+                p[5] = 0.0;
+            else {
+                if (p[4] <= 0.0) p[4] = step;
+                if (p[5] <= 0.0) p[5] = FLT_MAX;     /* MAXFLOAT */
+            }
+            if (p[6] <= 0.0) p[6] = FLT_MAX;
+            else if (p[6] < p[3] + p[5] + p[4]) p[6] = p[3] + p[5] + p[4];
+            s->cache[0] = (p[1] - p[0])/p[3];
+            s->cache[1] = (p[0] - p[1])/p[4];
+            int nrep = nc > 7 ? nc - 7 : 0;
+            for (int r = -1; r < nrep; r++) {
+                double time = (r < 0) ? p[2] : co[7 + r];
+                if (p[6] < finaltime) {
+                    break_set_lattice(c, time, p[6]);
+                    time += p[3]; break_set_lattice(c, time, p[6]);
+                    if (p[5] != 0) { time += p[5]; break_set_lattice(c, time, p[6]); }
+                    if (p[4] != 0) { time += p[4]; break_set_lattice(c, time, p[6]); }
+                }
+                else {
+                    break_set(c, time);
+                    time += p[3]; break_set(c, time);
+                    if (p[5] != 0) { time += p[5]; break_set(c, time); }
+                    if (p[4] != 0) { time += p[4]; break_set(c, time); }
+                }
+            }
+        }
+    }
+    else if (s->fn == B200_FN_PWL) {
+        /* inptran.cc:2312-2345 (no R= repeat, no TD) */
+        s->pwl_index = 0;
+        if (s->enable_tran) {
+            int n = s->pwl_n/2;
+            for (int i = 0; i < n; i++) {
+                double t = s->coef[2*i];
+                if (t > finaltime)
+                    return;
+                break_set(c, t);
+            }
+        }
+    }
+    else if (s->fn == B200_FN_SIN) {
+        /* inptran.cc:2579-2598 */
+        double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
+        memset(p, 0, 8*sizeof(double));
+        p[0] = co[0];
+        p[1] = nc >= 2 ? co[1] : 0.0;
+        p[2] = nc >= 3 ? co[2] : 0.0;
+        p[3] = nc >= 4 ? co[3] : 0.0;
+        p[4] = nc >= 5 ? co[4] : 0.0;
+        p[5] = nc >= 6 ? co[5] : 0.0;
+        if (s->enable_tran) {
+            if (!p[2]) p[2] = 1.0/finaltime;
+            if (p[3] > 0.0) break_set(c, p[3]);
+        }
+    }
+}
+
+static double src_eval(Src *s, double t)
+{
+    if (s->fn == B200_FN_PULSE) {
+        /* inptran.cc:1322-1414 (no bit pattern, extra offsets supported) */
+        const double *p = s->parms;
+        if (!s->enable_tran)
+            return p[0];
+        double value = p[0];
+        double pw = p[3] + p[5];
+        double time = t - p[2];
+        if (p[6] > 0.0) {
+            if (time > p[6]) {
+                int pnum = (int)(time/p[6]);
+                time -= (p[6]*pnum);
+            }
+        }
+        if (time < p[3] || time >= pw + p[4]) {
+            value = p[0];
+            if (time > 0 && time < p[3])
+                value += time*s->cache[0];
+        }
+        else {
+            value = p[1];
+            if (time > pw)
+                value += (time - pw)*s->cache[1];
+        }
+        for (int i = 7; i < s->ncoef; i++) {
+            time = t - s->coef[i];
+            if (p[6] > 0.0) {
+                if (time > p[6]) {
+                    int pnum = (int)(time/p[6]);
+                    time -= (p[6]*pnum);
+                }
+            }
+            if (time < p[3] || time >= pw + p[4]) {
+                if (time > 0 && time < p[3])
+                    value += time*s->cache[0];
+            }
+            else {
+                value += (p[1] - p[0]);
+                if (time > pw)
+                    value += (time - pw)*s->cache[1];
+            }
+        }
+        return value;
+    }
+    if (s->fn == B200_FN_PWL) {
+        /* inptran.cc:2350-2388 (no repeat) */
+        const double *co = s->coef;
+        int nvals = s->pwl_n/2;
+        if (nvals == 2 && co[3] == co[1])
+            return co[1];
+        if (t >= co[2*(nvals-1)])
+            return co[2*(nvals-1)+1];
+        int i = s->pwl_index;
+        while (i + 1 < nvals) {
+            if (t <= co[2*(i+1)])
+                break;
+            i++;
+        }
+        while (t < co[2*i] && i)
+            i--;
+        s->pwl_index = i;
+        if (!i && t <= co[0])
+            return co[1];
+        return co[2*i+1] + s->pwl_cache[i]*(t - co[2*i]);
+    }
+    if (s->fn == B200_FN_SIN) {
+        /* inptran.cc:2602-2624 */
+        const double *p = s->parms;
+        if (!s->enable_tran) {
+            if (p[5] != 0.0)
+                return p[0] + p[1]*sin(M_PI*(p[5]/180));
+            return p[0];
+        }
+        double time = t - p[3];
+        if (time <= 0) {
+            if (p[5] != 0.0)
+                return p[0] + p[1]*sin(M_PI*(p[5]/180));
+            return p[0];
+        }
+        double a;
+        if (p[5] != 0.0)
+            a = p[1]*sin(2*M_PI*(p[2]*time + (p[5]/360)));
+        else
+            a = p[1]*sin(2*M_PI*p[2]*time);
+        if (p[4] != 0.0)
+            a *= exp(-time*p[4]);
+        return p[0] + a;
+    }
+    return 0.0;
+}
+
+/* PWL construction: inptran.cc:1980-2074 (no TD, no R) */
+static void src_build_pwl(Src *s)
+{
+    int num = s->ncoef;
+    double *list = malloc((num + 3)*sizeof(double));
+    memcpy(list, s->coef, num*sizeof(double));
+    int add0 = (list[0] > 0.0);
+    int add1 = (num & 1);
+    if (add0 || add1) {
+        int nnum = num + 2*add0 + add1;
+        double *nl = malloc((nnum + 1)*sizeof(double)), *d = nl;
+        if (add0) { *d++ = 0.0; *d++ = num > 1 ? list[1] : 0.0; }
+        for (int i = 0; i < num; i++) *d++ = list[i];
+        if (add1) { if (num > 1) *d = *(d-2); else *d = 0.0; }
+        free(list); list = nl; num = nnum;
+    }
+    for (int i = 2; i < num; ) {
+        if (list[i] <= list[i-2]) {
+            for (int k = i; k+2 < num; k += 2) { list[k] = list[k+2]; list[k+1] = list[k+3]; }
+            num -= 2;
+            continue;
+        }
+        i += 2;
+    }
+    free(s->coef);
+    s->coef = list;
+    s->pwl_n = num;
+    int i = num/2 - 1;
+    if (i > 0) {
+        s->pwl_cache = malloc(i*sizeof(double));
+        for (int k = 0; k < i; k++)
+            s->pwl_cache[k] = (list[2*k+3] - list[2*k+1])/(list[2*k+2] - list[2*k]);
+    }
+    else {
+        s->pwl_cache = malloc(sizeof(double));
+        s->pwl_cache[0] = 0.0;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* setup: ckt.cc:2110-2227 + per-device setup                                  */
+/* ------------------------------------------------------------------------- */
+static void mos_setup(wo_ckt *c, Mos *m, int idx)
+{
+    /* mosset.cc:83-390 */
+    b200_mos_model *md = &m->mod;
+    if (md->level != 1 && md->level != 2 && md->level != 3 && md->level != 6) md->level = 1;
+    if (!GIVEN(md->vto)) md->vto = 0;
+    /* kp default 2e-5 applies only if still not given after mostemp's u0/tox rule */
+    if (!GIVEN(md->gamma)) md->gamma = 0;
+    if (!GIVEN(md->phi)) md->phi = .6;
+    if (!GIVEN(md->cbd)) md->cbd = 0;         /* "given" tested on the deck copy below */
+    if (!GIVEN(md->cbs)) md->cbs = 0;
+    if (!GIVEN(md->is)) md->is = 1e-14;
+    if (!GIVEN(md->pb)) md->pb = .8;
+    if (!GIVEN(md->cgso)) md->cgso = 0;
+    if (!GIVEN(md->cgdo)) md->cgdo = 0;
+    if (!GIVEN(md->cgbo)) md->cgbo = 0;
+    if (!GIVEN(md->mj)) md->mj = .5;
+    if (!GIVEN(md->mjsw)) md->mjsw = (md->level == 1 || md->level == 6) ? .5 : .33;
+    if (!GIVEN(md->js)) md->js = 0;
+    if (!GIVEN(md->ld)) md->ld = 0;
+    if (!GIVEN(md->fc)) md->fc = .5;
+    if (!GIVEN(md->lambda)) md->lambda = 0;
+
+    m->mode = 1;
+    m->von = 0;
+    m->st = c->numStates;
+    c->numStates += MS_NSTATES;
+
+    const b200_mos *in = &m->in;
+    m->mult = GIVEN(in->m) ? in->m : 1.0;
+    m->temp = GIVEN(in->temp) ? in->temp : c->opt.temp;
+    m->drainPerimeter = GIVEN(in->pd) ? in->pd : 0;
+    m->drainSquares = (!GIVEN(in->nrd) || in->nrd == 0) ? 1 : in->nrd;
+    m->sourcePerimeter = GIVEN(in->ps) ? in->ps : 0;
+    m->sourceSquares = (!GIVEN(in->nrs) || in->nrs == 0) ? 1 : in->nrs;
+    m->icVBS = GIVEN(in->icvbs) ? in->icvbs : 0;
+    m->icVDS = GIVEN(in->icvds) ? in->icvds : 0;
+    m->icVGS = GIVEN(in->icvgs) ? in->icvgs : 0;
+    m->vdsat = 0;
+    /* circuit.h:1957-1991 mos_default_* */
+    m->l = GIVEN(in->l) ? in->l : (c->opt.defl > 0 ? c->opt.defl : 1e-6);
+    m->w = GIVEN(in->w) ? in->w : (c->opt.defw > 0 ? c->opt.defw : 1e-6);
+    m->drainArea = GIVEN(in->ad) ? in->ad : (c->opt.defad > 0 ? c->opt.defad : 0.0);
+    m->sourceArea = GIVEN(in->as) ? in->as : (c->opt.defas > 0 ? c->opt.defas : 0.0);
+
+    double rd = GIVEN(md->rd) ? md->rd : 0, rs = GIVEN(md->rs) ? md->rs : 0;
+    double rsh = GIVEN(md->rsh) ? md->rsh : 0;
+    if (GIVEN(md->rd))
+        m->drainConductance = (md->rd != 0) ? 1/md->rd : 0;
+    else if (GIVEN(md->rsh))
+        m->drainConductance = (md->rsh != 0) ? 1/(md->rsh*m->drainSquares) : 0;
+    else
+        m->drainConductance = 0;
+    if (GIVEN(md->rs))
+        m->sourceConductance = (md->rs != 0) ? 1/md->rs : 0;
+    else if (GIVEN(md->rsh))
+        m->sourceConductance = (md->rsh != 0) ? 1/(md->rsh*m->sourceSquares) : 0;
+    else
+        m->sourceConductance = 0;
+
+    m->effectiveLength = m->l - 2*md->ld;
+    if (m->effectiveLength < 0)
+        m->effectiveLength = 0;
+
+    char nm[64];
+    m->d = in->d; m->g = in->g; m->s = in->s; m->b = in->b;
+    if (rd != 0 || rsh != 0) {
+        snprintf(nm, sizeof(nm), "mos%d#internal#drain", idx);
+        m->dp = new_node(c, SP_VOLTAGE, nm);
+    }
+    else
+        m->dp = m->d;
+    if (rs != 0 || (m->sourceSquares != 0 && rsh != 0)) {
+        snprintf(nm, sizeof(nm), "mos%d#internal#source", idx);
+        m->sp = new_node(c, SP_VOLTAGE, nm);
+    }
+    else
+        m->sp = m->s;
+
+    /* mosset.cc:53-77 get_node_ptr */
+    int *p = m->ptr;
+    for (int i = 0; i < M_NPTR; i++) p[i] = -1;
+    p[M_Dd]   = coo_add(c, m->d,  m->d);
+    p[M_Gg]   = coo_add(c, m->g,  m->g);
+    p[M_Ss]   = coo_add(c, m->s,  m->s);
+    p[M_Bb]   = coo_add(c, m->b,  m->b);
+    p[M_DPdp] = coo_add(c, m->dp, m->dp);
+    p[M_SPsp] = coo_add(c, m->sp, m->sp);
+    p[M_Ddp]  = coo_add(c, m->d,  m->dp);
+    p[M_Gb]   = coo_add(c, m->g,  m->b);
+    p[M_Gdp]  = coo_add(c, m->g,  m->dp);
+    p[M_Gsp]  = coo_add(c, m->g,  m->sp);
+    p[M_Ssp]  = coo_add(c, m->s,  m->sp);
+    p[M_Bg]   = coo_add(c, m->b,  m->g);
+    p[M_Bdp]  = coo_add(c, m->b,  m->dp);
+    p[M_Bsp]  = coo_add(c, m->b,  m->sp);
+    p[M_DPsp] = coo_add(c, m->dp, m->sp);
+    p[M_DPd]  = coo_add(c, m->dp, m->d);
+    p[M_DPg]  = coo_add(c, m->dp, m->g);
+    p[M_DPb]  = coo_add(c, m->dp, m->b);
+    p[M_SPg]  = coo_add(c, m->sp, m->g);
+    p[M_SPs]  = coo_add(c, m->sp, m->s);
+    p[M_SPb]  = coo_add(c, m->sp, m->b);
+    p[M_SPdp] = coo_add(c, m->sp, m->dp);
+}
+
+static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
+{
+    /* mostemp.cc:65-300.  deckmod = the card as given (for xxxGiven tests). */
+    b200_mos_model *md = &m->mod;
+    double tnom = GIVEN(deckmod->tnom) ? deckmod->tnom : c->opt.tnom;
+    double fact1  = tnom/REFTEMP;
+    double vtnom  = tnom*CONSTKoverQ;
+    double egfet1 = 1.16 - (7.02e-4*tnom*tnom)/(tnom + 1108);
+    double tmp    = tnom*CONSTboltz;
+    tmp = -egfet1/(tmp+tmp) + 1.1150877/(CONSTboltz*(REFTEMP+REFTEMP));
+    double pbfact1 = -2*vtnom*(1.5*log(fact1) + CHARGE*tmp);
+
+    double tox = GIVEN(deckmod->tox) ? deckmod->tox : ((md->level == 2 || md->level == 3) ? 1e-7 : 0);
+    double kp = md->kp;      /* may be NaN = not given */
+    int skip = 0;
+    if (!GIVEN(deckmod->tox) || tox == 0) {
+        if (md->level == 1 || md->level == 6) {
+            m->oxideCapFactor = 0;
+            skip = 1;
+        }
+        else
+            tox = 1e-7;
+    }
+    if (!skip) {
+        m->oxideCapFactor = 3.9*8.854214871e-12/tox;
+        m->surfaceMobility = GIVEN(deckmod->u0) ? deckmod->u0 : 600;
+        if (!GIVEN(kp))
+            kp = m->surfaceMobility*m->oxideCapFactor*M2PCM2;
+        if (GIVEN(deckmod->nsub)) {
+            /* mos_dopsetup, mostemp.cc:303-358 */
+            double doping = deckmod->nsub*CM3PM3;
+            if (doping > 1.45e16) {
+                if (!GIVEN(deckmod->phi)) {
+                    md->phi = 2*vtnom*log(doping/1.45e16);
+                    md->phi = SPMAX(.1, md->phi);
+                }
+                double gateType = GIVEN(deckmod->tpg) ? deckmod->tpg : 1;
+                if (!GIVEN(deckmod->gamma))
+                    md->gamma = sqrt(2*EPSSIL*CHARGE*doping)/m->oxideCapFactor;
+                if (!GIVEN(deckmod->vto)) {
+                    double wkfng = 3.2;
+                    if (gateType != 0) {
+                        if (md->type > 0)
+                            wkfng = 3.25 + .5*egfet1*(1 - gateType);
+                        else
+                            wkfng = 3.25 + .5*egfet1*(1 + gateType);
+                    }
+                    double wkfngs;
+                    if (md->type > 0)
+                        wkfngs = wkfng - (3.25 + .5*(egfet1 + md->phi));
+                    else
+                        wkfngs = wkfng - (3.25 + .5*(egfet1 - md->phi));
+                    double vfb;
+                    if (!GIVEN(deckmod->nss))
+                        vfb = wkfngs;
+                    else
+                        vfb = wkfngs - deckmod->nss*CM2PM2*CHARGE/m->oxideCapFactor;
+                    if (md->type > 0)
+                        md->vto = vfb + (md->gamma*sqrt(md->phi) + md->phi);
+                    else
+                        md->vto = vfb - (md->gamma*sqrt(md->phi) + md->phi);
+                }
+            }
+        }
+    }
+    else
+        m->surfaceMobility = GIVEN(deckmod->u0) ? deckmod->u0 : 0;
+    if (!GIVEN(kp))
+        kp = 2e-5;                       /* mosset.cc:101-103 */
+    m->kp_eff = kp;
+    double cj = GIVEN(deckmod->cj) ? deckmod->cj : 0;
+    double cjsw = GIVEN(deckmod->cjsw) ? deckmod->cjsw : 0;
+
+    double fact2 = m->temp/REFTEMP;
+    double vt    = m->temp*CONSTKoverQ;
+    double ratio = m->temp/tnom;
+    double egfet = 1.16 - (7.02e-4*m->temp*m->temp)/(m->temp + 1108);
+    tmp = m->temp*CONSTboltz;
+    tmp = -egfet/(tmp+tmp) + 1.1150877/(CONSTboltz*(REFTEMP+REFTEMP));
+    double pbfact = -2*vt*(1.5*log(fact2) + CHARGE*tmp);
+
+    tmp = 1/(ratio*sqrt(ratio));
+    m->tTransconductance = kp*tmp;
+    m->tSurfMob = m->surfaceMobility*tmp;
+
+    tmp = (md->phi - pbfact1)/fact1;
+    m->tPhi = fact2*tmp + pbfact;
+
+    if (md->type > 0) {
+        m->tVbi = md->vto - md->gamma*sqrt(md->phi) + .5*(egfet1 - egfet + m->tPhi - md->phi);
+        m->tVto = m->tVbi + md->gamma*sqrt(m->tPhi);
+    }
+    else {
+        m->tVbi = md->vto + md->gamma*sqrt(md->phi) + .5*(egfet1 - egfet - (m->tPhi - md->phi));
+        m->tVto = m->tVbi - md->gamma*sqrt(m->tPhi);
+    }
+
+    tmp = exp(-egfet/vt + egfet1/vtnom);
+    m->tSatCur = md->is*tmp;
+    m->tSatCurDens = md->js*tmp;
+
+    double pbo = (md->pb - pbfact1)/fact1;
+    double gmaold = (md->pb - pbo)/pbo;
+    double capfact = 1/(1 + md->mj*(4e-4*(tnom - REFTEMP) - gmaold));
+    m->tCbd = md->cbd*capfact;
+    m->tCbs = md->cbs*capfact;
+    m->tCj  = cj*capfact;
+    capfact = 1/(1 + md->mjsw*(4e-4*(tnom - REFTEMP) - gmaold));
+    m->tCjsw = cjsw*capfact;
+    m->tBulkPot = fact2*pbo + pbfact;
+    double gmanew = (m->tBulkPot - pbo)/pbo;
+    capfact = (1 + md->mj*(4e-4*(m->temp - REFTEMP) - gmanew));
+    m->tCbd *= capfact;
+    m->tCbs *= capfact;
+    m->tCj  *= capfact;
+    capfact = (1 + md->mjsw*(4e-4*(m->temp - REFTEMP) - gmanew));
+    m->tCjsw *= capfact;
+    m->tDepCap = md->fc*m->tBulkPot;
+
+    if ((m->tSatCurDens == 0) || (m->drainArea == 0) || (m->sourceArea == 0)) {
+        m->sourceVcrit = m->drainVcrit = vt*log(vt/(CONSTroot2*m->tSatCur));
+        m->tDrainSatCur = m->tSatCur;
+        m->tSourceSatCur = m->tSatCur;
+    }
+    else {
+        m->tDrainSatCur = m->tSatCurDens*m->drainArea;
+        m->tSourceSatCur = m->tSatCurDens*m->sourceArea;
+        m->drainVcrit = vt*log(vt/(CONSTroot2*m->tDrainSatCur));
+        m->sourceVcrit = vt*log(vt/(CONSTroot2*m->tSourceSatCur));
+    }
+
+    if (GIVEN(deckmod->cbd)) m->Cbd = m->tCbd;
+    else m->Cbd = GIVEN(deckmod->cj) ? m->tCj*m->drainArea : 0;
+    m->Cbdsw = GIVEN(deckmod->cjsw) ? m->tCjsw*m->drainPerimeter : 0;
+    if (GIVEN(deckmod->cbs)) m->Cbs = m->tCbs;
+    else m->Cbs = GIVEN(deckmod->cj) ? m->tCj*m->sourceArea : 0;
+    m->Cbssw = GIVEN(deckmod->cjsw) ? m->tCjsw*m->sourcePerimeter : 0;
+
+    /* MOSdev::fd / fs, mostemp.cc:335-389 */
+    {
+        double arg = 1 - md->fc;
+        double sarg = exp((-md->mj)*log(arg));
+        double sargsw = exp((-md->mjsw)*log(arg));
+        double pot = m->tBulkPot;
+        double tmp1 = (1 - md->fc*(1 + md->mj))/arg;
+        double tmp2 = 1/(arg*pot);
+        m->f2d = (m->Cbd*sarg + m->Cbdsw*sargsw)*tmp1;
+        m->f3d = (m->Cbd*md->mj*sarg + m->Cbdsw*md->mjsw*sargsw)*tmp2;
+        m->f4d = m->Cbd*pot*(1 - arg*sarg)/(1 - md->mj)
+            + m->Cbdsw*pot*(1 - arg*sargsw)/(1 - md->mjsw)
+            - m->tDepCap*(m->f2d + .5*m->f3d*m->tDepCap);
+        m->f2s = (m->Cbs*sarg + m->Cbssw*sargsw)*tmp1;
+        m->f3s = (m->Cbs*md->mj*sarg + m->Cbssw*md->mjsw*sargsw)*tmp2;
+        m->f4s = m->Cbs*pot*(1 - arg*sarg)/(1 - md->mj)
+            + m->Cbssw*pot*(1 - arg*sargsw)/(1 - md->mjsw)
+            - m->tDepCap*(m->f2s + .5*m->f3s*m->tDepCap);
+    }
+
+    m->gateSourceOverlapCap = md->cgso*m->w;
+    m->gateDrainOverlapCap = md->cgdo*m->w;
+    m->gateBulkOverlapCap = md->cgbo*m->effectiveLength;
+    m->beta = m->tTransconductance*m->w/m->effectiveLength;
+    m->oxideCap = m->oxideCapFactor*m->effectiveLength*m->w;
+}
+
+static void build_matrix(wo_ckt *c)
+{
+    /* spbuild.cc:922-958: CSC, columns ascending, rows ascending within a column */
+    int n = c->n;
+    c->nnz = c->ncoo;
+    c->Ap = xcalloc(n + 2, sizeof(int));
+    c->Ai = xcalloc(c->nnz, sizeof(int));
+    c->Ax = xcalloc(c->nnz, sizeof(double));
+    c->Ainit = xcalloc(c->nnz, sizeof(double));
+    int *cnt = xcalloc(n + 2, sizeof(int));
+    for (int i = 0; i < c->ncoo; i++) cnt[c->coo_c[i]]++;     /* cols 1..n */
+    c->Ap[0] = 0;
+    for (int j = 1; j <= n; j++) c->Ap[j] = c->Ap[j-1] + cnt[j];
+    int *map = xcalloc(c->ncoo, sizeof(int));
+    int *fill = xcalloc(n + 2, sizeof(int));
+    /* insertion sort rows within each column */
+    for (int i = 0; i < c->ncoo; i++) {
+        int col = c->coo_c[i] - 1, r = c->coo_r[i] - 1;
+        int base = c->Ap[col], k = fill[col]++;
+        int pos = base + k;
+        while (pos > base && c->Ai[pos-1] > r) { c->Ai[pos] = c->Ai[pos-1]; pos--; }
+        c->Ai[pos] = r;
+    }
+    for (int i = 0; i < c->ncoo; i++) {
+        int col = c->coo_c[i] - 1, r = c->coo_r[i] - 1;
+        for (int p = c->Ap[col]; p < c->Ap[col+1]; p++)
+            if (c->Ai[p] == r) { map[i] = p; break; }
+    }
+#define REMAP(x) do { if ((x) >= 0) (x) = map[(x)]; } while (0)
+    for (int i = 0; i < c->nmos; i++)
+        for (int k = 0; k < M_NPTR; k++) REMAP(c->mos[i].ptr[k]);
+    for (int i = 0; i < c->ncap; i++) {
+        REMAP(c->cap[i].pPP); REMAP(c->cap[i].pNN); REMAP(c->cap[i].pPN); REMAP(c->cap[i].pNP);
+    }
+    for (int i = 0; i < c->nres; i++) {
+        REMAP(c->res[i].pPP); REMAP(c->res[i].pNN); REMAP(c->res[i].pPN); REMAP(c->res[i].pNP);
+    }
+    for (int i = 0; i < c->nsrc; i++) {
+        REMAP(c->src[i].pPB); REMAP(c->src[i].pNB); REMAP(c->src[i].pBN); REMAP(c->src[i].pBP);
+    }
+#undef REMAP
+    c->diag = xcalloc(n + 1, sizeof(int));
+    for (int j = 1; j <= n; j++) {
+        c->diag[j] = -1;
+        for (int p = c->Ap[j-1]; p < c->Ap[j]; p++)
+            if (c->Ai[p] == j-1) c->diag[j] = p;
+    }
+    free(cnt); free(map); free(fill);
+}
+
+wo_ckt *wo_create(const b200_deck *dk)
+{
+    wo_ckt *c = xcalloc(1, sizeof(*c));
+    c->opt = dk->opt;
+    c->tstep = dk->tstep; c->tstop = dk->tstop; c->tstart = dk->tstart; c->tmax = dk->tmax;
+    c->uic = dk->uic;
+    c->nnodes_ext = dk->nnodes;
+    c->n = 0;
+    c->ntype = xcalloc(1, sizeof(int));
+    c->names = xcalloc(1, sizeof(char*));
+    c->names[0] = strdup("0");
+    for (int i = 1; i < dk->nnodes; i++) {
+        char nm[32];
+        snprintf(nm, sizeof(nm), "n%d", i);
+        new_node(c, SP_VOLTAGE, nm);
+    }
+    c->nmos = dk->nmos; c->ncap = dk->ncap; c->nres = dk->nres; c->nsrc = dk->nsrc;
+    c->mos = xcalloc(c->nmos, sizeof(Mos));
+    c->cap = xcalloc(c->ncap, sizeof(Cap));
+    c->res = xcalloc(c->nres, sizeof(Res));
+    c->src = xcalloc(c->nsrc, sizeof(Src));
+    c->nord = dk->norder;
+    c->ord = xcalloc(c->nord, sizeof(DevRef));
+    for (int i = 0; i < c->nord; i++) {
+        c->ord[i].kind = dk->order_kind[i];
+        c->ord[i].index = dk->order_index[i];
+    }
+    for (int i = 0; i < c->nmos; i++) {
+        c->mos[i].in = dk->mos[i];
+        c->mos[i].mod = dk->mos_models[dk->mos[i].model];
+    }
+
+    /* setup in load order (ckt.cc:2202-2210) */
+    for (int o = 0; o < c->nord; o++) {
+        int i = c->ord[o].index;
+        char nm[64];
+        switch (c->ord[o].kind) {
+        case B200_DEV_MOS:
+            mos_setup(c, &c->mos[i], i);
+            break;
+        case B200_DEV_CAP: {
+            /* capset.cc:62-103 */
+            Cap *p = &c->cap[i]; const b200_cap *in = &dk->cap[i];
+            p->pos = in->pos; p->neg = in->neg;
+            double mm = GIVEN(in->m) ? in->m : 1.0;
+            p->capac = in->c*1.0*mm;          /* captemp.cc:98 nom*tcFactor*m */
+            p->ic = GIVEN(in->ic) ? in->ic : 0.0;
+            p->st = c->numStates; c->numStates += 2;
+            p->pPP = coo_add(c, p->pos, p->pos);
+            p->pNN = coo_add(c, p->neg, p->neg);
+            p->pPN = coo_add(c, p->pos, p->neg);
+            p->pNP = coo_add(c, p->neg, p->pos);
+            break; }
+        case B200_DEV_RES: {
+            /* resset.cc:74-77, restemp.cc:171-209 */
+            Res *p = &c->res[i]; const b200_res *in = &dk->res[i];
+            p->pos = in->pos; p->neg = in->neg;
+            p->pPP = coo_add(c, p->pos, p->pos);
+            p->pNN = coo_add(c, p->neg, p->neg);
+            p->pPN = coo_add(c, p->pos, p->neg);
+            p->pNP = coo_add(c, p->neg, p->pos);
+            double r = in->r, mm = GIVEN(in->m) ? in->m : 1.0;
+            if (fabs(r) < c->opt.resmin)
+                r = (r < 0.0) ? -c->opt.resmin : c->opt.resmin;
+            p->conduct = mm/(r*1.0);
+            break; }
+        case B200_DEV_SRC: {
+            /* srcset.cc:64-273 */
+            Src *p = &c->src[i]; const b200_src *in = &dk->src[i];
+            p->kind = in->kind; p->pos = in->pos; p->neg = in->neg;
+            p->dcGiven = GIVEN(in->dc); p->dc = p->dcGiven ? in->dc : 0.0;
+            p->fn = in->fn; p->ncoef = in->ncoef;
+            p->coef = malloc((in->ncoef + 1)*sizeof(double));
+            memcpy(p->coef, in->coef, in->ncoef*sizeof(double));
+            if (p->fn == B200_FN_PWL) src_build_pwl(p);
+            p->pPB = p->pNB = p->pBN = p->pBP = -1;
+            if (p->kind == B200_SRC_V) {
+                snprintf(nm, sizeof(nm), "src%d#branch", i);
+                p->branch = new_node(c, SP_CURRENT, nm);
+                p->pPB = coo_add(c, p->pos, p->branch);
+                p->pNB = coo_add(c, p->neg, p->branch);
+                p->pBN = coo_add(c, p->branch, p->neg);
+                p->pBP = coo_add(c, p->branch, p->pos);
+            }
+            if (p->kind == B200_SRC_I && p->fn != B200_FN_NONE)
+                c->numStates += 1;
+            break; }
+        default:
+            fprintf(stderr, "wrs_oracle: device kind %d not supported\n", c->ord[o].kind);
+            abort();
+        }
+    }
+    build_matrix(c);
+
+    /* .ic / .nodeset */
+    c->ic_val = xcalloc(c->n + 1, sizeof(double)); c->ic_given = xcalloc(c->n + 1, 1);
+    c->ns_val = xcalloc(c->n + 1, sizeof(double)); c->ns_given = xcalloc(c->n + 1, 1);
+    for (int i = 0; i < dk->nic; i++) { c->ic_val[dk->ic_node[i]] = dk->ic_val[i]; c->ic_given[dk->ic_node[i]] = 1; }
+    for (int i = 0; i < dk->nnodeset; i++) { c->ns_val[dk->ns_node[i]] = dk->ns_val[i]; c->ns_given[dk->ns_node[i]] = 1; }
+
+    int n = c->n;
+    c->rhs = xcalloc(n + 1, sizeof(double));
+    c->rhsOld = xcalloc(n + 1, sizeof(double));
+    c->rhsSpare = xcalloc(n + 1, sizeof(double));
+    for (int i = 0; i < 8; i++) c->sols[i] = xcalloc(n + 1, sizeof(double));
+    for (int i = 0; i <= c->opt.maxord + 1 && i < 8; i++)
+        c->states[i] = xcalloc(c->numStates, sizeof(double));
+    c->work = xcalloc(n + 1, sizeof(double));
+    c->srcFact = 1.0;
+    return c;
+}
+
+int wo_set_param(wo_ckt *c, int param, int index, double value)
+{
+    switch (param) {
+    case B200_P_MOS_VTO:    c->mos[index].mod.vto = value; break;
+    case B200_P_MOS_KP:     c->mos[index].mod.kp = value; break;
+    case B200_P_MOS_GAMMA:  c->mos[index].mod.gamma = value; break;
+    case B200_P_MOS_LAMBDA: c->mos[index].mod.lambda = value; break;
+    case B200_P_MOS_PHI:    c->mos[index].mod.phi = value; break;
+    case B200_P_MOS_L:      c->mos[index].in.l = value; c->mos[index].l = value;
+        c->mos[index].effectiveLength = value - 2*c->mos[index].mod.ld;
+        if (c->mos[index].effectiveLength < 0) c->mos[index].effectiveLength = 0;
+        break;
+    case B200_P_MOS_W:      c->mos[index].in.w = value; c->mos[index].w = value; break;
+    case B200_P_CAP_C:      c->cap[index].capac = value*1.0*1.0; break;
+    case B200_P_RES_R: {
+        double r = value;
+        if (fabs(r) < c->opt.resmin) r = (r < 0.0) ? -c->opt.resmin : c->opt.resmin;
+        c->res[index].conduct = 1.0/(r*1.0);
+        break; }
+    case B200_P_SRC_DC:     c->src[index].dc = value; c->src[index].dcGiven = 1; break;
+    default: return B200_E_BADPARM;
+    }
+    return OK;
+}
+
+void wo_set_ordering(wo_ckt *c, const int *rowperm, const int *colperm)
+{
+    free(c->rowperm); free(c->colperm);
+    c->rowperm = malloc(c->n*sizeof(int));
+    c->colperm = malloc(c->n*sizeof(int));
+    memcpy(c->rowperm, rowperm, c->n*sizeof(int));
+    memcpy(c->colperm, colperm, c->n*sizeof(int));
+    c->have_order = 1;
+    c->lu_ready = 0;
+}
+
+int wo_num_unknowns(const wo_ckt *c) { return c->n; }
+int wo_nnz(const wo_ckt *c) { return c->nnz; }
+void wo_pattern(const wo_ckt *c, const int **Ap, const int **Ai) { *Ap = c->Ap; *Ai = c->Ai; }
+int wo_unknown_names(const wo_ckt *c, char *buf, int buflen)
+{
+    int pos = 0;
+    for (int i = 1; i <= c->n; i++) {
+        int l = (int)strlen(c->names[i]) + 1;
+        if (buf && pos + l <= buflen) memcpy(buf + pos, c->names[i], l);
+        pos += l;
+    }
+    return pos;
+}
+
+/* ------------------------------------------------------------------------- */
+/* integration: circuit.h:1995-2029, niinteg.cc:58-152, nicomcof.cc:58-147      */
+/* ------------------------------------------------------------------------- */
+static double NIceq(wo_ckt *c, int q)
+{
+    double cq = 0;
+    if (c->opt.method == 1) {
+        switch (c->order) {
+        case 6: cq += c->ag[6]*c->states[6][q]; /* fallthrough */
+        case 5: cq += c->ag[5]*c->states[5][q]; /* fallthrough */
+        case 4: cq += c->ag[4]*c->states[4][q]; /* fallthrough */
+        case 3: cq += c->ag[3]*c->states[3][q]; /* fallthrough */
+        default:
+        case 2: cq += c->ag[2]*c->states[2][q]; /* fallthrough */
+        case 1: cq += c->ag[1]*c->states[1][q]; break;
+        }
+    }
+    else {
+        if (c->order == 1)
+            cq = c->ag[1]*c->states[1][q];
+        else
+            cq = - c->states[1][q+1]*c->ag[1] - c->ag[0]*c->states[1][q];
+    }
+    return cq;
+}
+
+static double find_ceq(wo_ckt *c, int q)
+{
+    if (c->opt.method == 0)
+        return (c->order <= 1 ? c->states[1][q]*c->ag[1] :
+            - c->states[1][q+1]*c->ag[1] - c->states[1][q]*c->ag[0]);
+    return NIceq(c, q);
+}
+
+static int NItrapCheck(wo_ckt *c, int q)
+{
+    int cc = q + 1;
+    double c0 = c->states[0][cc];
+    if (fabs(c0) < 1e-6) return 0;
+    double q0 = c->states[0][q];
+    if (fabs(q0) < 1e-16) return 0;
+    double c1 = c->states[1][cc], c2 = c->states[2][cc], q1 = c->states[1][q];
+    double dqdt = fabs(q0 - q1)/c->delta;
+    double tr = c->opt.trapratio;
+    return (fabs(c1) > tr*dqdt && fabs(c0 - c1) > tr*fabs(c0 - c2));
+}
+
+static void integrate4(wo_ckt *c, double *geq, double *ceq, double cap, int q)
+{
+    double cq = find_ceq(c, q);
+    c->states[0][q+1] = c->ag[0]*c->states[0][q] + cq;
+    *ceq = cq;
+    *geq = c->ag[0]*cap;
+    if (c->trapCheck && !c->trapBad)
+        c->trapBad = NItrapCheck(c, q);
+}
+
+static void integrate2(wo_ckt *c, int q, double cq)
+{
+    c->states[0][q+1] = c->ag[0]*c->states[0][q] + cq;
+    if (c->trapCheck && !c->trapBad)
+        c->trapBad = NItrapCheck(c, q);
+}
+
+static int NIcomCof(wo_ckt *c)
+{
+    if (c->opt.method == 0) {
+        if (c->order == 2) {
+            double t0 = 1.0/(1.0 - c->opt.xmu);
+            c->ag[0] = t0/c->delta;
+            c->ag[1] = t0*c->opt.xmu;
+            return OK;
+        }
+        if (c->order == 1) {
+            c->ag[0] = 1.0/c->delta;
+            c->ag[1] = -c->ag[0];
+            return OK;
+        }
+        return B200_E_ORDER;
+    }
+    /* GEAR: nicomcof.cc:79-147 */
+    if (c->order < 1 || c->order > 6) return B200_E_ORDER;
+    double mat[8][8];
+    for (int i = 0; i < 7; i++) c->ag[i] = 0;
+    c->ag[1] = -1.0/c->delta;
+    int i, ord = c->order;
+    for (i = 0; i <= ord; i++) mat[0][i] = 1;
+    for (i = 1; i <= ord; i++) mat[i][0] = 0;
+    double arg = 0;
+    for (i = 1; i <= ord; i++) {
+        arg += c->deltaOld[i-1];
+        double arg1 = 1;
+        for (int j = 1; j <= ord; j++) { arg1 *= arg/c->delta; mat[j][i] = arg1; }
+    }
+    for (i = 1; i <= ord; i++)
+        for (int j = i+1; j <= ord; j++) {
+            mat[j][i] /= mat[i][i];
+            for (int k = i+1; k <= ord; k++) mat[j][k] -= mat[j][i]*mat[i][k];
+        }
+    for (i = 1; i <= ord; i++)
+        for (int j = i+1; j <= ord; j++) c->ag[j] = c->ag[j] - mat[j][i]*c->ag[i];
+    c->ag[ord] /= mat[ord][ord];
+    for (i = ord-1; i >= 0; i--) {
+        for (int j = i+1; j <= ord; j++) c->ag[i] = c->ag[i] - mat[i][j]*c->ag[j];
+        c->ag[i] /= mat[i][i];
+    }
+    return OK;
+}
+
+static void predict(wo_ckt *c)
+{
+    /* ckt.cc:2020-2087 */
+    if (c->mode & MODETRAN) {
+        double d1 = c->delta;
+        c->pred[1] = -d1/c->deltaOld[1];
+        c->pred[0] = 1 - c->pred[1];
+        c->pred[2] = c->pred[3] = 0;
+    }
+    else {
+        c->pred[0] = 1.0; c->pred[1] = c->pred[2] = c->pred[3] = 0.0;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* limiters: devlib/devlib.cc:475-620                                          */
+/* ------------------------------------------------------------------------- */
+static double limvds(double vnew, double vold)
+{
+    if (vold >= 3.5) {
+        if (vnew > vold)
+            vnew = SPMIN(vnew, 3*vold + 2);
+        else {
+            if (vnew < 3.5)
+                vnew = SPMAX(vnew, 2);
+        }
+    }
+    else {
+        if (vnew > vold)
+            vnew = SPMIN(vnew, 4);
+        else
+            vnew = SPMAX(vnew, -.5);
+    }
+    return vnew;
+}
+
+static double pnjlim(double vnew, double vold, double vt, double vcrit, int *icheck)
+{
+    if (vnew > vcrit && fabs(vnew - vold) > (vt + vt)) {
+        if (vold > 0) {
+            double arg = (vnew - vold)/vt;
+            if (arg > 0)
+                vnew = vold + vt*(2.0 + log(arg - 1.8));
+            else
+                vnew = vold - vt*(2.0 + log(-arg + 2.0));
+        }
+        else
+            vnew = vt*log(vnew/vt);
+        *icheck = 1;
+    }
+    else {
+        if (vnew < 0) {
+            double arg;
+            if (vold > 0)
+                arg = -1*vold - 1;
+            else
+                arg = 2*vold - 1;
+            if (vnew < arg) {
+                vnew = arg;
+                *icheck = 1;
+            }
+            else
+                *icheck = 0;
+        }
+        else
+            *icheck = 0;
+    }
+    return vnew;
+}
+
+static double fetlim(double vnew, double vold, double vto)
+{
+    double tmp = (vold - vto);
+    if (tmp < 0.0)
+        tmp = -tmp;
+    double vtsthi = tmp + tmp + 2.0;
+    double vtstlo = tmp + 1.0;
+    double vtox = vto + 3.5;
+    double delv = vnew - vold;
+    if (vold >= vto) {
+        if (vold >= vtox) {
+            if (delv <= 0.0) {
+                if (vnew >= vtox) {
+                    if (-delv > vtstlo)
+                        vnew = vold - vtstlo;
+                }
+                else
+                    vnew = SPMAX(vnew, vto + 2);
+            }
+            else {
+                if (delv >= vtsthi)
+                    vnew = vold + vtsthi;
+            }
+        }
+        else {
+            if (delv <= 0)
+                vnew = SPMAX(vnew, vto - 0.5);
+            else
+                vnew = SPMIN(vnew, vto + 4.0);
+        }
+    }
+    else {
+        if (delv <= 0) {
+            if (-delv > vtsthi)
+                vnew = vold - vtsthi;
+        }
+        else {
+            double vtemp = vto + .5;
+            if (vnew <= vtemp) {
+                if (delv > vtstlo)
+                    vnew = vold + vtstlo;
+            }
+            else
+                vnew = vtemp;
+        }
+    }
+    return vnew;
+}
+
+/* ------------------------------------------------------------------------- */
+/* MOS load: devlib/mos/mosload.cc:107-1041, moseq.cc:76-141                    */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    double vt, vbs, vgs, vds, vbd, vgd, vgb, von, vdsat, cdrain;
+    double gcgs, ceqgs, gcgd, ceqgd, gcgb, ceqgb, capgs, capgd, capgb;
+} MosStuff;
+
+static void sargs(double arg, double bot, double side, double *sarg, double *sargsw)
+{
+    /* mosdefs.h:726-735 */
+    if (bot == side) {
+        if (bot == .5) *sarg = *sargsw = 1/sqrt(arg);
+        else *sarg = *sargsw = exp(-bot*log(arg));
+    }
+    else {
+        if (bot == .5) *sarg = 1/sqrt(arg);
+        else *sarg = exp(-bot*log(arg));
+        if (side == .5) *sargsw = 1/sqrt(arg);
+        else *sargsw = exp(-side*log(arg));
+    }
+}
+
+static void qmeyer(double vgs, double vgd, double von, double vdsat,
+    double *capgs, double *capgd, double *capgb, double phi, double cox)
+{
+    /* mosload.cc:59-102 */
+    double vgst = vgs - von;
+    if (vgst <= -phi) {
+        *capgb = cox/2; *capgs = 0; *capgd = 0;
+    }
+    else if (vgst <= -phi/2) {
+        *capgb = -vgst*cox/(2*phi); *capgs = 0; *capgd = 0;
+    }
+    else if (vgst <= 0) {
+        *capgb = -vgst*cox/(2*phi);
+        *capgs = vgst*cox/(1.5*phi) + cox/3;
+        *capgd = 0;
+    }
+    else {
+        double vds = vgs - vgd;
+        if (vdsat <= vds) {
+            *capgs = cox/3; *capgd = 0; *capgb = 0;
+        }
+        else {
+            double vddif = 2.0*vdsat - vds;
+            double vddif1 = vdsat - vds;
+            double vddif2 = vddif*vddif;
+            *capgd = cox*(1.0 - vdsat*vdsat/vddif2)/3;
+            *capgs = cox*(1.0 - vddif1*vddif1/vddif2)/3;
+            *capgb = 0;
+        }
+    }
+}
+
+static double mos_eq1(Mos *m, MosStuff *ms)
+{
+    /* moseq.cc:76-141 */
+    const b200_mos_model *md = &m->mod;
+    double vbx = ((m->mode == 1) ? ms->vbs : ms->vbd);
+    double vgx = ((m->mode == 1) ? ms->vgs : ms->vgd);
+    double sarg;
+    if (vbx <= 0)
+        sarg = sqrt(m->tPhi - vbx);
+    else {
+        sarg = sqrt(m->tPhi);
+        sarg = sarg - vbx/(sarg+sarg);
+        sarg = SPMAX(0, sarg);
+    }
+    if (md->type > 0)
+        ms->von = m->tVbi + md->gamma*sarg;
+    else
+        ms->von = -m->tVbi + md->gamma*sarg;
+    double vgst = vgx - ms->von;
+    ms->vdsat = SPMAX(vgst, 0);
+    double cdrain;
+    if (vgst <= 0) {
+        cdrain = 0; m->gm = 0; m->gds = 0; m->gmbs = 0;
+    }
+    else {
+        double vds = (m->mode > 0) ? ms->vds : -ms->vds;
+        double arg;
+        if (sarg <= 0)
+            arg = 0;
+        else
+            arg = md->gamma/(sarg+sarg);
+        double betap = m->beta*(1 + md->lambda*vds);
+        if (vgst <= vds) {
+            m->gm = betap*vgst;
+            vgst *= vgst*.5;
+            cdrain = betap*vgst;
+            m->gds = md->lambda*m->beta*vgst;
+            m->gmbs = m->gm*arg;
+        }
+        else {
+            m->gm = betap*vds;
+            cdrain = m->gm*(vgst - .5*vds);
+            m->gds = betap*(vgst - vds) + md->lambda*m->beta*vds*(vgst - .5*vds);
+            m->gmbs = m->gm*arg;
+        }
+    }
+    return cdrain;
+}
+
+static int mos_limiting(wo_ckt *c, Mos *m, MosStuff *ms)
+{
+    /* mosload.cc:346-384 */
+    double *s0 = c->states[0] + m->st;
+    if (s0[MS_vds] >= 0) {
+        ms->vgs = fetlim(ms->vgs, s0[MS_vgs], ms->von);
+        ms->vds = ms->vgs - ms->vgd;
+        ms->vds = limvds(ms->vds, s0[MS_vds]);
+        ms->vgd = ms->vgs - ms->vds;
+    }
+    else {
+        double vgdo = s0[MS_vgs] - s0[MS_vds];
+        ms->vgd = fetlim(ms->vgd, vgdo, ms->von);
+        ms->vds = ms->vgs - ms->vgd;
+        if (!c->opt.oldlimit)
+            ms->vds = -limvds(-ms->vds, -(s0[MS_vds]));
+        ms->vgs = ms->vgd + ms->vds;
+    }
+    int check;
+    if (ms->vds >= 0) {
+        ms->vbs = pnjlim(ms->vbs, s0[MS_vbs], ms->vt, m->sourceVcrit, &check);
+        ms->vbd = ms->vbs - ms->vds;
+    }
+    else {
+        ms->vbd = pnjlim(ms->vbd, s0[MS_vbd], ms->vt, m->drainVcrit, &check);
+        ms->vbs = ms->vbd + ms->vds;
+    }
+    ms->vgb = ms->vgs - ms->vbs;
+    return check;
+}
+
+static void mos_iv(wo_ckt *c, Mos *m, MosStuff *ms)
+{
+    /* mosload.cc:498-593 */
+    ms->gcgs = 0; ms->ceqgs = 0; ms->gcgd = 0; ms->ceqgd = 0; ms->gcgb = 0; ms->ceqgb = 0;
+    double gmin = c->opt.gmin;
+    if (ms->vbs <= -3*ms->vt) {
+        m->gbs = gmin;
+        m->cbs = m->gbs*ms->vbs - m->tSourceSatCur;
+    }
+    else {
+        double evbs = exp(ms->vbs/ms->vt);
+        m->gbs = m->tSourceSatCur*evbs/ms->vt + gmin;
+        m->cbs = m->tSourceSatCur*(evbs-1) + gmin*ms->vbs;
+    }
+    if (ms->vbd <= -3*ms->vt) {
+        m->gbd = gmin;
+        m->cbd = m->gbd*ms->vbd - m->tDrainSatCur;
+    }
+    else {
+        double evbd = exp(ms->vbd/ms->vt);
+        m->gbd = m->tDrainSatCur*evbd/ms->vt + gmin;
+        m->cbd = m->tDrainSatCur*(evbd-1) + gmin*ms->vbd;
+    }
+    m->mode = (ms->vds >= 0) ? 1 : -1;
+    ms->cdrain = mos_eq1(m, ms);         /* level 1 only in the oracle */
+    if (m->mod.type > 0) {
+        m->von = ms->von; m->vdsat = ms->vdsat;
+    }
+    else {
+        m->von = -ms->von; m->vdsat = -ms->vdsat;
+    }
+    if (m->mode > 0)
+        m->cd = ms->cdrain - m->cbd;
+    else
+        m->cd = -ms->cdrain - m->cbd;
+}
+
+static void mos_cap(wo_ckt *c, Mos *m, MosStuff *ms)
+{
+    /* mosload.cc:597-750 */
+    const b200_mos_model *md = &m->mod;
+    double *s0 = c->states[0] + m->st, *s1 = c->states[1] + m->st;
+    if (m->Cbs != 0 || m->Cbssw != 0) {
+        if (ms->vbs < m->tDepCap) {
+            double arg = 1 - ms->vbs/m->tBulkPot, sarg, sargsw;
+            sargs(arg, md->mj, md->mjsw, &sarg, &sargsw);
+            s0[MS_qbs] = m->tBulkPot*(m->Cbs*(1 - arg*sarg)/(1 - md->mj)
+                + m->Cbssw*(1 - arg*sargsw)/(1 - md->mjsw));
+            m->capbs = m->Cbs*sarg + m->Cbssw*sargsw;
+        }
+        else {
+            s0[MS_qbs] = m->f4s + ms->vbs*(m->f2s + .5*ms->vbs*m->f3s);
+            m->capbs = m->f2s + m->f3s*ms->vbs;
+        }
+    }
+    else {
+        s0[MS_qbs] = 0; m->capbs = 0;
+    }
+    if (m->Cbd != 0 || m->Cbdsw != 0) {
+        if (ms->vbd < m->tDepCap) {
+            double arg = 1 - ms->vbd/m->tBulkPot, sarg, sargsw;
+            sargs(arg, md->mj, md->mjsw, &sarg, &sargsw);
+            s0[MS_qbd] = m->tBulkPot*(m->Cbd*(1 - arg*sarg)/(1 - md->mj)
+                + m->Cbdsw*(1 - arg*sargsw)/(1 - md->mjsw));
+            m->capbd = m->Cbd*sarg + m->Cbdsw*sargsw;
+        }
+        else {
+            s0[MS_qbd] = m->f4d + ms->vbd*(m->f2d + .5*ms->vbd*m->f3d);
+            m->capbd = m->f2d + ms->vbd*m->f3d;
+        }
+    }
+    else {
+        s0[MS_qbd] = 0; m->capbd = 0;
+    }
+
+    double vgx, vgy, *px, *py;
+    if (m->mode > 0) {
+        vgx = ms->vgs; vgy = ms->vgd; px = &s0[MS_capgs]; py = &s0[MS_capgd];
+    }
+    else {
+        vgx = ms->vgd; vgy = ms->vgs; px = &s0[MS_capgd]; py = &s0[MS_capgs];
+    }
+    qmeyer(vgx, vgy, ms->von, ms->vdsat, px, py, &s0[MS_capgb], m->tPhi, m->oxideCap);
+
+    if (c->mode & (MODEINITTRAN|MODEINITSMSIG)) {
+        s1[MS_capgs] = s0[MS_capgs];
+        s1[MS_capgd] = s0[MS_capgd];
+        s1[MS_capgb] = s0[MS_capgb];
+        ms->capgs = s0[MS_capgs] + s0[MS_capgs] + m->gateSourceOverlapCap;
+        ms->capgd = s0[MS_capgd] + s0[MS_capgd] + m->gateDrainOverlapCap;
+        ms->capgb = s0[MS_capgb] + s0[MS_capgb] + m->gateBulkOverlapCap;
+        s0[MS_qgs] = ms->capgs*ms->vgs;
+        s0[MS_qgd] = ms->capgd*ms->vgd;
+        s0[MS_qgb] = ms->capgb*ms->vgb;
+        s1[MS_qbd] = s0[MS_qbd];
+        s1[MS_qbs] = s0[MS_qbs];
+        s1[MS_qgs] = s0[MS_qgs];
+        s1[MS_qgd] = s0[MS_qgd];
+        s1[MS_qgb] = s0[MS_qgb];
+    }
+    else {
+        ms->capgs = s0[MS_capgs] + s1[MS_capgs] + m->gateSourceOverlapCap;
+        ms->capgd = s0[MS_capgd] + s1[MS_capgd] + m->gateDrainOverlapCap;
+        ms->capgb = s0[MS_capgb] + s1[MS_capgb] + m->gateBulkOverlapCap;
+        vgx = s1[MS_vgs];
+        vgy = vgx - s1[MS_vds];
+        double vxy = vgx - s1[MS_vbs];
+        s0[MS_qgs] = (ms->vgs - vgx)*ms->capgs + s1[MS_qgs];
+        s0[MS_qgd] = (ms->vgd - vgy)*ms->capgd + s1[MS_qgd];
+        s0[MS_qgb] = (ms->vgb - vxy)*ms->capgb + s1[MS_qgb];
+    }
+}
+
+static void mos_meyer_integ(wo_ckt *c, Mos *m, MosStuff *ms)
+{
+    /* mosload.cc:477-486 and :784-793 */
+    double *s0 = c->states[0] + m->st;
+    integrate4(c, &ms->gcgs, &ms->ceqgs, ms->capgs, m->st + MS_qgs);
+    integrate4(c, &ms->gcgd, &ms->ceqgd, ms->capgd, m->st + MS_qgd);
+    integrate4(c, &ms->gcgb, &ms->ceqgb, ms->capgb, m->st + MS_qgb);
+    ms->ceqgs += c->ag[0]*s0[MS_qgs] - ms->gcgs*ms->vgs;
+    ms->ceqgd += c->ag[0]*s0[MS_qgd] - ms->gcgd*ms->vgd;
+    ms->ceqgb += c->ag[0]*s0[MS_qgb] - ms->gcgb*ms->vgb;
+}
+
+static void mos_integ(wo_ckt *c, Mos *m, MosStuff *ms)
+{
+    /* mosload.cc:754-796 */
+    double *s0 = c->states[0] + m->st;
+    double geq, ceq;
+    integrate4(c, &geq, &ceq, m->capbd, m->st + MS_qbd);
+    m->gbd += geq;
+    m->cbd += s0[MS_cqbd];
+    m->cd  -= s0[MS_cqbd];
+    integrate4(c, &geq, &ceq, m->capbs, m->st + MS_qbs);
+    m->gbs += geq;
+    m->cbs += s0[MS_cqbs];
+    if (ms->capgs == 0) s0[MS_cqgs] = 0;
+    if (ms->capgd == 0) s0[MS_cqgd] = 0;
+    if (ms->capgb == 0) s0[MS_cqgb] = 0;
+    mos_meyer_integ(c, m, ms);
+}
+
+static void mos_stamp(wo_ckt *c, Mos *m, MosStuff *ms, int tran)
+{
+    /* mosload.cc:801-924 (tran) and :928-1041 (dc) */
+    double *s0 = c->states[0] + m->st;
+    const int *p = m->ptr;
+#define MSC(xx) (m->mult*(xx))
+    s0[MS_vbs] = ms->vbs;
+    s0[MS_vbd] = ms->vbd;
+    s0[MS_vgs] = ms->vgs;
+    s0[MS_vds] = ms->vds;
+    double gbd = MSC(m->gbd), gbs = MSC(m->gbs), gds = MSC(m->gds), gm = MSC(m->gm);
+    double gmbs = MSC(m->gmbs), cbd = MSC(m->cbd), cbs = MSC(m->cbs);
+    double ceqbs = cbs - gbs*ms->vbs;
+    double ceqbd = cbd - gbd*ms->vbd;
+    double cdreq;
+    if (m->mode > 0)
+        cdreq = MSC(ms->cdrain) - gds*ms->vds - gm*ms->vgs - gmbs*ms->vbs;
+    else
+        cdreq = -(MSC(ms->cdrain) + gds*ms->vds - gm*ms->vgd - gmbs*ms->vbd);
+    double dcon = MSC(m->drainConductance), scon = MSC(m->sourceConductance);
+    if (tran) {
+        if (m->mod.type > 0) {
+            rhsadd(c, m->g, -MSC(ms->ceqgs + ms->ceqgb + ms->ceqgd));
+            rhsadd(c, m->b, -(ceqbs + ceqbd - MSC(ms->ceqgb)));
+            rhsadd(c, m->dp, ceqbd - cdreq + MSC(ms->ceqgd));
+            rhsadd(c, m->sp, cdreq + ceqbs + MSC(ms->ceqgs));
+        }
+        else {
+            rhsadd(c, m->g, MSC(ms->ceqgs + ms->ceqgb + ms->ceqgd));
+            rhsadd(c, m->b, ceqbs + ceqbd - MSC(ms->ceqgb));
+            rhsadd(c, m->dp, -(ceqbd - cdreq + MSC(ms->ceqgd)));
+            rhsadd(c, m->sp, -(cdreq + ceqbs + MSC(ms->ceqgs)));
+        }
+        double gcgd = MSC(ms->gcgd), gcgs = MSC(ms->gcgs), gcgb = MSC(ms->gcgb);
+        ldadd(c, p[M_Dd], dcon);
+        ldadd(c, p[M_Gg], gcgd + gcgs + gcgb);
+        ldadd(c, p[M_Ss], scon);
+        ldadd(c, p[M_Bb], gbd + gbs + gcgb);
+        ldadd(c, p[M_Ddp], -dcon);
+        ldadd(c, p[M_Gb], -gcgb);
+        ldadd(c, p[M_Gdp], -gcgd);
+        ldadd(c, p[M_Gsp], -gcgs);
+        ldadd(c, p[M_Ssp], -scon);
+        ldadd(c, p[M_Bg], -gcgb);
+        ldadd(c, p[M_Bdp], -gbd);
+        ldadd(c, p[M_Bsp], -gbs);
+        ldadd(c, p[M_DPd], -dcon);
+        ldadd(c, p[M_SPs], -scon);
+        if (m->mode > 0) {
+            ldadd(c, p[M_DPdp], dcon + gds + gbd + gcgd);
+            ldadd(c, p[M_SPsp], scon + gds + gbs + gm + gmbs + gcgs);
+            ldadd(c, p[M_DPg], gm - gcgd);
+            ldadd(c, p[M_DPb], -gbd + gmbs);
+            ldadd(c, p[M_DPsp], -(gds + gm + gmbs));
+            ldadd(c, p[M_SPg], -(gm + gcgs));
+            ldadd(c, p[M_SPb], -(gbs + gmbs));
+            ldadd(c, p[M_SPdp], -gds);
+        }
+        else {
+            ldadd(c, p[M_DPdp], dcon + gds + gbd + gm + gmbs + gcgd);
+            ldadd(c, p[M_SPsp], scon + gds + gbs + gcgs);
+            ldadd(c, p[M_DPg], -(gm + gcgd));
+            ldadd(c, p[M_DPb], -(gbd + gmbs));
+            ldadd(c, p[M_DPsp], -gds);
+            ldadd(c, p[M_SPg], -(-gm + gcgs));
+            ldadd(c, p[M_SPb], -(gbs - gmbs));
+            ldadd(c, p[M_SPdp], -(gds + gm + gmbs));
+        }
+    }
+    else {
+        if (m->mod.type > 0) {
+            rhsadd(c, m->b, -(ceqbs + ceqbd));
+            rhsadd(c, m->dp, ceqbd - cdreq);
+            rhsadd(c, m->sp, cdreq + ceqbs);
+        }
+        else {
+            rhsadd(c, m->b, ceqbs + ceqbd);
+            rhsadd(c, m->dp, -(ceqbd - cdreq));
+            rhsadd(c, m->sp, -(cdreq + ceqbs));
+        }
+        ldadd(c, p[M_Dd], dcon);
+        ldadd(c, p[M_Ss], scon);
+        ldadd(c, p[M_Bb], gbd + gbs);
+        ldadd(c, p[M_Ddp], -dcon);
+        ldadd(c, p[M_Ssp], -scon);
+        ldadd(c, p[M_Bdp], -gbd);
+        ldadd(c, p[M_Bsp], -gbs);
+        ldadd(c, p[M_DPd], -dcon);
+        ldadd(c, p[M_SPs], -scon);
+        if (m->mode > 0) {
+            ldadd(c, p[M_DPdp], dcon + gds + gbd);
+            ldadd(c, p[M_SPsp], scon + gds + gbs + gm + gmbs);
+            ldadd(c, p[M_DPg], gm);
+            ldadd(c, p[M_DPb], -gbd + gmbs);
+            ldadd(c, p[M_DPsp], -(gds + gm + gmbs));
+            ldadd(c, p[M_SPg], -gm);
+            ldadd(c, p[M_SPb], -(gbs + gmbs));
+            ldadd(c, p[M_SPdp], -gds);
+        }
+        else {
+            ldadd(c, p[M_DPdp], dcon + gds + gbd + gm + gmbs);
+            ldadd(c, p[M_SPsp], scon + gds + gbs);
+            ldadd(c, p[M_DPg], -gm);
+            ldadd(c, p[M_DPb], -(gbd + gmbs));
+            ldadd(c, p[M_DPsp], -gds);
+            ldadd(c, p[M_SPg], gm);
+            ldadd(c, p[M_SPb], -(gbs - gmbs));
+            ldadd(c, p[M_SPdp], -(gds + gm + gmbs));
+        }
+    }
+#undef MSC
+}
+
+static int mos_bypass(wo_ckt *c, Mos *m, MosStuff *ms)
+{
+    /* mosload.cc:388-494 */
+    double *s0 = c->states[0] + m->st, *s1 = c->states[1] + m->st;
+    const b200_options *o = &c->opt;
+    double delvbs = ms->vbs - s0[MS_vbs];
+    double delvgs = ms->vgs - s0[MS_vgs];
+    double delvds = ms->vds - s0[MS_vds];
+    double delvbd = ms->vbd - s0[MS_vbd];
+    double delvgd = ms->vgd - (s0[MS_vgs] - s0[MS_vds]);
+    double cbhat = m->cbs + m->cbd + m->gbd*delvbd + m->gbs*delvbs;
+    double A1 = fabs(cbhat);
+    double A2 = m->cbs + m->cbd;
+    A2 = fabs(A2);
+    double A3 = SPMAX(A1, A2) + o->abstol;
+    A1 = cbhat - (m->cbs + m->cbd);
+    if (fabs(A1) >= o->reltol*A3) return 0;
+    A1 = fabs(ms->vbs); A2 = fabs(s0[MS_vbs]);
+    if (fabs(delvbs) >= (o->reltol*SPMAX(A1, A2) + o->vntol)) return 0;
+    A1 = fabs(ms->vbd); A2 = fabs(s0[MS_vbd]);
+    if (fabs(delvbd) >= (o->reltol*SPMAX(A1, A2) + o->vntol)) return 0;
+    A1 = fabs(ms->vgs); A2 = fabs(s0[MS_vgs]);
+    if (fabs(delvgs) >= (o->reltol*SPMAX(A1, A2) + o->vntol)) return 0;
+    A1 = fabs(ms->vds); A2 = fabs(s0[MS_vds]);
+    if (fabs(delvds) >= (o->reltol*SPMAX(A1, A2) + o->vntol)) return 0;
+    double cdhat;
+    if (m->mode >= 0)
+        cdhat = m->cd - m->gbd*delvbd + m->gmbs*delvbs + m->gm*delvgs + m->gds*delvds;
+    else
+        cdhat = m->cd + (m->gmbs - m->gbd)*delvbd - m->gm*delvgd + m->gds*delvds;
+    A1 = cdhat - m->cd;
+    A2 = fabs(cdhat);
+    A3 = fabs(m->cd);
+    if ((fabs(A1) >= o->reltol*SPMAX(A2, A3) + o->abstol)) return 0;
+
+    ms->vbs = s0[MS_vbs];
+    ms->vgs = s0[MS_vgs];
+    ms->vds = s0[MS_vds];
+    ms->vbd = s0[MS_vbd];
+    ms->vgd = ms->vgs - ms->vds;
+    ms->vgb = ms->vgs - ms->vbs;
+    ms->cdrain = m->mode*(m->cd + m->cbd);
+    if (c->mode & MODETRAN) {
+        ms->capgs = s0[MS_capgs] + s1[MS_capgs] + m->gateSourceOverlapCap;
+        ms->capgd = s0[MS_capgd] + s1[MS_capgd] + m->gateDrainOverlapCap;
+        ms->capgb = s0[MS_capgb] + s1[MS_capgb] + m->gateBulkOverlapCap;
+        mos_meyer_integ(c, m, ms);
+        mos_stamp(c, m, ms, 1);
+    }
+    else
+        mos_stamp(c, m, ms, 0);
+    return 1;
+}
+
+static void mos_get_v(wo_ckt *c, Mos *m, MosStuff *ms, const double *v)
+{
+    if (m->mod.type > 0) {
+        ms->vbs = v[m->b] - v[m->sp];
+        ms->vgs = v[m->g] - v[m->sp];
+        ms->vds = v[m->dp] - v[m->sp];
+    }
+    else {
+        ms->vbs = v[m->sp] - v[m->b];
+        ms->vgs = v[m->sp] - v[m->g];
+        ms->vds = v[m->sp] - v[m->dp];
+    }
+}
+
+static void mos_load(wo_ckt *c, Mos *m)
+{
+    /* mosload.cc:107-342 */
+    MosStuff ms;
+    memset(&ms, 0, sizeof(ms));
+    double *s0 = c->states[0] + m->st, *s1 = c->states[1] + m->st, *s2 = c->states[2] + m->st;
+    int type = m->mod.type;
+    ms.vt = CONSTKoverQ*m->temp;
+    if (c->mode & MODEINITFLOAT) {
+        mos_get_v(c, m, &ms, c->rhsOld);
+        ms.von = (type > 0) ? m->von : -m->von;
+        ms.vbd = ms.vbs - ms.vds;
+        ms.vgd = ms.vgs - ms.vds;
+        ms.vgb = ms.vgs - ms.vbs;
+        if (c->opt.bypass && mos_bypass(c, m, &ms))
+            return;
+        mos_limiting(c, m, &ms);
+        mos_iv(c, m, &ms);
+        if (c->mode & MODETRAN) {
+            mos_cap(c, m, &ms);
+            mos_integ(c, m, &ms);
+            mos_stamp(c, m, &ms, 1);
+        }
+        else
+            mos_stamp(c, m, &ms, 0);
+        return;
+    }
+    if (c->mode & MODEINITPRED) {
+        /* device.h:171-175 DEV.pred */
+        ms.vbs = s1[MS_vbs]*c->pred[0] + s2[MS_vbs]*c->pred[1];
+        ms.vgs = s1[MS_vgs]*c->pred[0] + s2[MS_vgs]*c->pred[1];
+        ms.vds = s1[MS_vds]*c->pred[0] + s2[MS_vds]*c->pred[1];
+        ms.vbd = ms.vbs - ms.vds;
+        ms.vgd = ms.vgs - ms.vds;
+        ms.vgb = ms.vgs - ms.vbs;
+        ms.von = (type > 0) ? m->von : -m->von;
+        s0[MS_vbs] = s1[MS_vbs];
+        s0[MS_vgs] = s1[MS_vgs];
+        s0[MS_vds] = s1[MS_vds];
+        s0[MS_vbd] = s0[MS_vbs] - s0[MS_vds];
+        mos_limiting(c, m, &ms);
+        mos_iv(c, m, &ms);
+        if (c->mode & MODETRAN) {
+            mos_cap(c, m, &ms);
+            mos_integ(c, m, &ms);
+            mos_stamp(c, m, &ms, 1);
+        }
+        else
+            mos_stamp(c, m, &ms, 0);
+        return;
+    }
+    if (c->mode & MODEINITFIX) {
+        ms.von = (type > 0) ? m->von : -m->von;
+        if (m->in.off) {
+            ms.vbs = ms.vgs = ms.vds = ms.vbd = ms.vgd = ms.vgb = 0;
+        }
+        else {
+            mos_get_v(c, m, &ms, c->rhsOld);
+            ms.vbd = ms.vbs - ms.vds;
+            ms.vgd = ms.vgs - ms.vds;
+            ms.vgb = ms.vgs - ms.vbs;
+            if (mos_limiting(c, m, &ms))
+                c->noncon++;
+        }
+        mos_iv(c, m, &ms);
+        mos_stamp(c, m, &ms, 0);
+        return;
+    }
+    if (c->mode & MODEINITTRAN) {
+        ms.von = (type > 0) ? m->von : -m->von;
+        ms.vbs = s1[MS_vbs];
+        ms.vgs = s1[MS_vgs];
+        ms.vds = s1[MS_vds];
+        ms.vbd = ms.vbs - ms.vds;
+        ms.vgd = ms.vgs - ms.vds;
+        ms.vgb = ms.vgs - ms.vbs;
+        mos_iv(c, m, &ms);
+        mos_cap(c, m, &ms);
+        mos_integ(c, m, &ms);
+        mos_stamp(c, m, &ms, 1);
+        return;
+    }
+    if ((c->mode & MODEINITJCT) && (c->mode & MODETRANOP) && (c->mode & MODEUIC)) {
+        if (type > 0) {
+            ms.vds = m->icVDS; ms.vgs = m->icVGS; ms.vbs = m->icVBS;
+        }
+        else {
+            ms.vds = -m->icVDS; ms.vgs = -m->icVGS; ms.vbs = -m->icVBS;
+        }
+        s0[MS_vds] = ms.vds;
+        s0[MS_vgs] = ms.vgs;
+        s0[MS_vbs] = ms.vbs;
+        return;
+    }
+    if (c->mode & MODEINITJCT) {
+        ms.von = (type > 0) ? m->von : -m->von;
+        if (m->in.off) {
+            ms.vbs = ms.vgs = ms.vds = ms.vbd = ms.vgd = ms.vgb = 0;
+        }
+        else {
+            if (m->icVDS == 0 && m->icVGS == 0 && m->icVBS == 0) {
+                ms.vbs = -1;
+                ms.vgs = (type > 0) ? m->tVto : -m->tVto;
+                ms.vds = 0;
+            }
+            else {
+                if (type > 0) {
+                    ms.vds = m->icVDS; ms.vgs = m->icVGS; ms.vbs = m->icVBS;
+                }
+                else {
+                    ms.vds = -m->icVDS; ms.vgs = -m->icVGS; ms.vbs = -m->icVBS;
+                }
+            }
+            ms.vbd = ms.vbs - ms.vds;
+            ms.vgd = ms.vgs - ms.vds;
+            ms.vgb = ms.vgs - ms.vbs;
+        }
+        mos_iv(c, m, &ms);
+        mos_stamp(c, m, &ms, 0);
+    }
+}
+
+/* MOSdev::convTest per instance: mosconv.cc:52-141.  Returns 1 if not converged. */
+static int mos_conv(wo_ckt *c, Mos *m)
+{
+    if (m->in.off && (c->mode & MODEINITFIX))
+        return 0;
+    MosStuff ms;
+    mos_get_v(c, m, &ms, c->rhs);           /* NOTE: CKTrhs (previous iterate), as in the reference */
+    double *s0 = c->states[0] + m->st;
+    double vbd = ms.vbs - ms.vds, vgd = ms.vgs - ms.vds;
+    double delvbs = ms.vbs - s0[MS_vbs];
+    double delvbd = vbd - s0[MS_vbd];
+    double delvgs = ms.vgs - s0[MS_vgs];
+    double delvds = ms.vds - s0[MS_vds];
+    double delvgd = vgd - (s0[MS_vgs] - s0[MS_vds]);
+    double cdhat;
+    if (m->mode >= 0)
+        cdhat = m->cd - m->gbd*delvbd + m->gmbs*delvbs + m->gm*delvgs + m->gds*delvds;
+    else
+        cdhat = m->cd - (m->gbd - m->gmbs)*delvbd - m->gm*delvgd + m->gds*delvds;
+    double A1 = fabs(cdhat), A2 = fabs(m->cd), A3 = cdhat - m->cd;
+    A3 = fabs(A3);
+    double tol = c->opt.reltol*SPMAX(A1, A2) + c->opt.abstol;
+    if (A3 >= tol)
+        return 1;
+    double cbhat = m->cbs + m->cbd + m->gbd*delvbd + m->gbs*delvbs;
+    A1 = fabs(cbhat);
+    A2 = m->cbs + m->cbd;
+    A2 = fabs(A2);
+    A3 = cbhat - (m->cbs + m->cbd);
+    A3 = fabs(A3);
+    tol = c->opt.reltol*SPMAX(A1, A2) + c->opt.abstol;
+    if (A3 > tol)
+        return 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* CAP / SRC load                                                             */
+/* ------------------------------------------------------------------------- */
+static void cap_stamp(wo_ckt *c, Cap *p)
+{
+    /* capload.cc:75-97 */
+    double geq = p->geq, ceq = p->ceq;
+    if (p->pos == 0) {
+        ldadd(c, p->pNN, geq);
+        rhsadd(c, p->neg, ceq);
+        return;
+    }
+    if (p->neg == 0) {
+        ldadd(c, p->pPP, geq);
+        rhsadd(c, p->pos, -ceq);
+        return;
+    }
+    ldadd(c, p->pPP, geq);
+    ldadd(c, p->pNN, geq);
+    ldadd(c, p->pPN, -geq);
+    ldadd(c, p->pNP, -geq);
+    rhsadd(c, p->pos, -ceq);
+    rhsadd(c, p->neg, ceq);
+}
+
+static void cap_load(wo_ckt *c, Cap *p)
+{
+    /* capload.cc:104-205 (linear capacitor) */
+    if (c->mode & MODEDC)
+        return;
+    if (c->mode & MODEINITFLOAT) {
+        double qcap = p->capac*(c->rhsOld[p->pos] - c->rhsOld[p->neg]);
+        c->states[0][p->st] = qcap;
+        integrate2(c, p->st, p->ceq);
+        p->ceq = find_ceq(c, p->st);
+        cap_stamp(c, p);
+        return;
+    }
+    if (c->mode & MODEINITPRED) {
+        p->geq = c->ag[0]*p->capac;
+        p->ceq = find_ceq(c, p->st);
+        cap_stamp(c, p);
+        return;
+    }
+    if (c->mode & MODEINITTRAN) {
+        double vcap;
+        if (c->mode & MODEUIC)
+            vcap = p->ic;
+        else
+            vcap = c->rhsOld[p->pos] - c->rhsOld[p->neg];
+        c->states[1][p->st] = p->capac*vcap;
+        p->geq = c->ag[0]*p->capac;
+        p->ceq = find_ceq(c, p->st);
+        cap_stamp(c, p);
+    }
+}
+
+static void src_load(wo_ckt *c, Src *s)
+{
+    /* srcload.cc:67-105, :215-262 (independent sources, no controlling variables) */
+    int is_dc = c->mode & (MODEDCOP | MODEDCTRANCURVE);
+    int ft;  /* 1 = SRC_dc, 2 = SRC_func */
+    if (s->fn == B200_FN_NONE)
+        ft = 1;
+    else
+        ft = is_dc ? (s->dcGiven ? 1 : 2) : 2;
+    double rhs;
+    if (ft == 1)
+        rhs = c->srcFact*s->dc;
+    else {
+        rhs = src_eval(s, c->time);
+        s->dc = rhs;                         /* srcload.cc:236-237 */
+        if (c->mode & (MODEDCOP | MODETRANOP))
+            rhs *= c->srcFact;
+    }
+    if (s->kind == B200_SRC_V)
+        rhsadd(c, s->branch, rhs);
+    else {
+        rhsadd(c, s->pos, -rhs);
+        rhsadd(c, s->neg, rhs);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* sCKT::load: ckt.cc:963-1207; loadGmin: ckt.cc:1221-1263, spspice.cc:259-368  */
+/* ------------------------------------------------------------------------- */
+static void preload(wo_ckt *c)
+{
+    /* spSaveForInitialization snapshot of the preloaded constants:
+     * srcset.cc:158-170 (ldset +-1), restemp.cc:218-229 (ldadd +-g) */
+    memset(c->Ainit, 0, c->nnz*sizeof(double));
+    double *save = c->Ax;
+    c->Ax = c->Ainit;
+    for (int o = 0; o < c->nord; o++) {
+        int i = c->ord[o].index;
+        if (c->ord[o].kind == B200_DEV_SRC) {
+            Src *s = &c->src[i];
+            if (s->kind == B200_SRC_V) {
+                if (s->pos) { if (s->pPB >= 0) c->Ax[s->pPB] = 1.0; if (s->pBP >= 0) c->Ax[s->pBP] = 1.0; }
+                if (s->neg) { if (s->pNB >= 0) c->Ax[s->pNB] = -1.0; if (s->pBN >= 0) c->Ax[s->pBN] = -1.0; }
+            }
+        }
+    }
+    for (int o = 0; o < c->nord; o++) {
+        int i = c->ord[o].index;
+        if (c->ord[o].kind == B200_DEV_RES) {
+            Res *r = &c->res[i];
+            if (r->conduct != 0.0) {
+                ldadd(c, r->pPP, r->conduct);
+                ldadd(c, r->pNN, r->conduct);
+                ldadd(c, r->pPN, -r->conduct);
+                ldadd(c, r->pNP, -r->conduct);
+            }
+        }
+    }
+    c->Ax = save;
+}
+
+static int ckt_load(wo_ckt *c)
+{
+    c->devMaxDelta = 0.0;
+    memset(c->rhs, 0, (c->n + 1)*sizeof(double));
+    memcpy(c->Ax, c->Ainit, c->nnz*sizeof(double));
+    int tchk = c->trapCheck;
+    c->trapCheck = tchk && (c->mode & MODEINITFLOAT) && (c->mode & MODETRAN);
+    c->trapBad = 0;
+    for (int o = 0; o < c->nord; o++) {
+        int i = c->ord[o].index;
+        switch (c->ord[o].kind) {
+        case B200_DEV_MOS: mos_load(c, &c->mos[i]); break;
+        case B200_DEV_CAP: cap_load(c, &c->cap[i]); break;
+        case B200_DEV_SRC: src_load(c, &c->src[i]); break;
+        case B200_DEV_RES: break;          /* preloaded, LOAD_SKIP_FLAG */
+        }
+    }
+    c->trapCheck = tchk;
+    if (c->mode & MODEDC) {
+        /* ckt.cc:1177-1204 */
+        if (c->mode & (MODEINITJCT | MODEINITFIX)) {
+            for (int i = 1; i <= c->n; i++)
+                if (c->ns_given[i]) {
+                    c->rhs[i] += c->ns_val[i];
+                    ldadd(c, c->diag[i], 1.0);
+                }
+        }
+        if ((c->mode & MODETRANOP) && !(c->mode & MODEUIC)) {
+            for (int i = 1; i <= c->n; i++)
+                if (c->ic_given[i]) {
+                    c->rhs[i] += c->ic_val[i];
+                    ldadd(c, c->diag[i], 1.0);
+                }
+        }
+    }
+    return OK;
+}
+
+static int load_gmin(wo_ckt *c)
+{
+    /* ckt.cc:1221-1263 -> spspice.cc:259-300.  A voltage node with no diagonal is accepted
+     * when its column holds a +-1 (junction of branch devices); we skip it. */
+    if (c->diagGmin != 0.0) {
+        for (int i = 1; i <= c->n; i++)
+            if (c->ntype[i] == SP_VOLTAGE && c->diag[i] >= 0)
+                c->Ax[c->diag[i]] += c->diagGmin;
+        return OK;
+    }
+    int checkmin = c->opt.forcegmin;
+    for (int i = 1; i <= c->n; i++)
+        if (c->ntype[i] == SP_VOLTAGE && c->diag[i] >= 0) {
+            double *r = &c->Ax[c->diag[i]];
+            if (checkmin && (*r >= 0.0 && *r < c->opt.gmin))
+                *r = c->opt.gmin;
+            else if (*r > c->opt.gmax)
+                *r = c->opt.gmax;
+        }
+    return OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Sparse LU.  Restated klu_refactor/klu_solve contract (kluif.cc:594-628):     */
+/* left-looking column LU with a FIXED pivot sequence (static row/col order),  */
+/* no scaling; L unit-diagonal stored as x[i]/pivot; updates applied in         */
+/* ascending pivot order so every entry sees the same operation sequence as the */
+/* engine's compiled program.  PARITY UNPINNED vs SuiteSparse (source absent).  */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    int n;
+    int *Lp, *Li, *Up, *Ui;     /* patterns in permuted positions, rows ascending */
+    double *Lx, *Ux, *Ud;
+    int *rinv;                  /* original row -> position */
+} StaticLU;
+
+static StaticLU *slu_symbolic(int n, const int *Ap, const int *Ai, const int *rowperm,
+    const int *colperm)
+{
+    StaticLU *f = xcalloc(1, sizeof(*f));
+    f->n = n;
+    f->rinv = xcalloc(n, sizeof(int));
+    for (int k = 0; k < n; k++) f->rinv[rowperm[k]] = k;
+    char *mark = xcalloc(n, 1);
+    int capL = 4*n + 16, capU = 4*n + 16;
+    f->Lp = xcalloc(n + 1, sizeof(int)); f->Up = xcalloc(n + 1, sizeof(int));
+    f->Li = xcalloc(capL, sizeof(int)); f->Ui = xcalloc(capU, sizeof(int));
+    int nl = 0, nu = 0;
+    for (int j = 0; j < n; j++) {
+        int cj = colperm[j];
+        memset(mark, 0, n);
+        for (int p = Ap[cj]; p < Ap[cj+1]; p++) mark[f->rinv[Ai[p]]] = 1;
+        for (int k = 0; k < j; k++) {
+            if (!mark[k]) continue;
+            for (int p = f->Lp[k]; p < f->Lp[k+1]; p++) mark[f->Li[p]] = 1;
+        }
+        for (int k = 0; k < j; k++)
+            if (mark[k]) {
+                if (nu == capU) { capU *= 2; f->Ui = realloc(f->Ui, capU*sizeof(int)); }
+                f->Ui[nu++] = k;
+            }
+        f->Up[j+1] = nu;
+        for (int k = j + 1; k < n; k++)
+            if (mark[k]) {
+                if (nl == capL) { capL *= 2; f->Li = realloc(f->Li, capL*sizeof(int)); }
+                f->Li[nl++] = k;
+            }
+        f->Lp[j+1] = nl;
+    }
+    f->Lx = xcalloc(nl, sizeof(double));
+    f->Ux = xcalloc(nu, sizeof(double));
+    f->Ud = xcalloc(n, sizeof(double));
+    free(mark);
+    return f;
+}
+
+static void slu_free(StaticLU *f)
+{
+    if (!f) return;
+    free(f->Lp); free(f->Li); free(f->Up); free(f->Ui); free(f->Lx); free(f->Ux); free(f->Ud);
+    free(f->rinv); free(f);
+}
+
+static int slu_refactor(StaticLU *f, const int *Ap, const int *Ai, const double *Ax,
+    const int *colperm, double *x /* n work */)
+{
+    int n = f->n;
+    for (int j = 0; j < n; j++) {
+        int cj = colperm[j];
+        /* scatter (pattern of column j of L+U is a superset) */
+        for (int p = f->Up[j]; p < f->Up[j+1]; p++) x[f->Ui[p]] = 0.0;
+        x[j] = 0.0;
+        for (int p = f->Lp[j]; p < f->Lp[j+1]; p++) x[f->Li[p]] = 0.0;
+        for (int p = Ap[cj]; p < Ap[cj+1]; p++) x[f->rinv[Ai[p]]] = Ax[p];
+        /* updates in ascending k */
+        for (int p = f->Up[j]; p < f->Up[j+1]; p++) {
+            int k = f->Ui[p];
+            double xk = x[k];
+            f->Ux[p] = xk;
+            for (int q = f->Lp[k]; q < f->Lp[k+1]; q++)
+                x[f->Li[q]] -= f->Lx[q]*xk;
+        }
+        double piv = x[j];
+        f->Ud[j] = piv;
+        if (piv == 0.0 || !isfinite(piv))
+            return E_SINGULAR;
+        for (int p = f->Lp[j]; p < f->Lp[j+1]; p++)
+            f->Lx[p] = x[f->Li[p]]/piv;
+    }
+    return OK;
+}
+
+static void slu_solve(StaticLU *f, const int *rowperm, const int *colperm, double *b /* n */,
+    double *y /* n work */)
+{
+    int n = f->n;
+    for (int k = 0; k < n; k++) y[k] = b[rowperm[k]];
+    for (int j = 0; j < n; j++) {
+        double yj = y[j];
+        for (int p = f->Lp[j]; p < f->Lp[j+1]; p++)
+            y[f->Li[p]] -= f->Lx[p]*yj;
+    }
+    for (int j = n - 1; j >= 0; j--) {
+        y[j] = y[j]/f->Ud[j];
+        double yj = y[j];
+        for (int p = f->Up[j+1] - 1; p >= f->Up[j]; p--)
+            y[f->Ui[p]] -= f->Ux[p]*yj;
+    }
+    for (int j = 0; j < n; j++) b[colperm[j]] = y[j];
+}
+
+int wo_lu_solve_static(int n, const int *Ap, const int *Ai, const double *Ax,
+    const int *rowperm, const int *colperm, double *b)
+{
+    StaticLU *f = slu_symbolic(n, Ap, Ai, rowperm, colperm);
+    double *x = xcalloc(n, sizeof(double)), *y = xcalloc(n, sizeof(double));
+    int err = slu_refactor(f, Ap, Ai, Ax, colperm, x);
+    if (!err) slu_solve(f, rowperm, colperm, b, y);
+    free(x); free(y); slu_free(f);
+    return err;
+}
+
+/* Own-order mode (no engine ordering supplied): dense LU with Markowitz-style complete
+ * pivoting, the strategy of the solver the compiled reference actually runs (Sparse 1.3,
+ * xt_base/sparse/spfactor.cc:286-423: among entries passing the relative threshold
+ * |a| >= pivrel*max|column|, take the smallest (r-1)(c-1), singletons first).  This is a
+ * robustness restatement, not an op-for-op one: results agree with oracle/_ref to roundoff. */
+static int dense_factor(wo_ckt *c)
+{
+    int n = c->n;
+    if (!c->dense) {
+        c->dense = xcalloc((size_t)n*n, sizeof(double));
+        c->dpiv = xcalloc(4*(size_t)n, sizeof(int));
+    }
+    double *M = c->dense;
+    int *rp = c->dpiv, *cp = c->dpiv + n, *ract = c->dpiv + 2*n, *cact = c->dpiv + 3*n;
+    memset(M, 0, (size_t)n*n*sizeof(double));
+    for (int j = 0; j < n; j++)
+        for (int p = c->Ap[j]; p < c->Ap[j+1]; p++)
+            M[(size_t)c->Ai[p]*n + j] = c->Ax[p];
+    for (int i = 0; i < n; i++) { ract[i] = 1; cact[i] = 1; }
+    int *rc = xcalloc(n, sizeof(int)), *cc = xcalloc(n, sizeof(int));
+    for (int k = 0; k < n; k++) {
+        for (int i = 0; i < n; i++) { rc[i] = 0; cc[i] = 0; }
+        for (int i = 0; i < n; i++) {
+            if (!ract[i]) continue;
+            for (int j = 0; j < n; j++)
+                if (cact[j] && M[(size_t)i*n + j] != 0.0) { rc[i]++; cc[j]++; }
+        }
+        long best = -1; int bi = -1, bj = -1; double bmag = 0.0;
+        for (int j = 0; j < n; j++) {
+            if (!cact[j]) continue;
+            double colmax = 0.0;
+            for (int i = 0; i < n; i++)
+                if (ract[i]) { double a = fabs(M[(size_t)i*n + j]); if (a > colmax) colmax = a; }
+            if (colmax == 0.0 || !isfinite(colmax)) continue;
+            for (int i = 0; i < n; i++) {
+                if (!ract[i]) continue;
+                double a = fabs(M[(size_t)i*n + j]);
+                if (a == 0.0 || a < c->opt.pivrel*colmax || a <= c->opt.pivtol) continue;
+                long mk = (long)(rc[i]-1)*(cc[j]-1);
+                if (best < 0 || mk < best || (mk == best && a > bmag)) {
+                    best = mk; bi = i; bj = j; bmag = a;
+                }
+            }
+        }
+        if (bi < 0) { free(rc); free(cc); return E_SINGULAR; }
+        rp[k] = bi; cp[k] = bj;
+        ract[bi] = 0; cact[bj] = 0;
+        double d = M[(size_t)bi*n + bj];
+        for (int i = 0; i < n; i++) {
+            if (!ract[i]) continue;
+            double l = M[(size_t)i*n + bj];
+            if (l == 0.0) continue;
+            l /= d;
+            M[(size_t)i*n + bj] = l;
+            for (int j = 0; j < n; j++)
+                if (cact[j]) M[(size_t)i*n + j] -= l*M[(size_t)bi*n + j];
+        }
+    }
+    free(rc); free(cc);
+    return OK;
+}
+
+static void dense_solve(wo_ckt *c, double *b /* n */)
+{
+    int n = c->n; double *M = c->dense;
+    int *rp = c->dpiv, *cp = c->dpiv + n;
+    double *x = xcalloc(n, sizeof(double));
+    char *done = xcalloc(n, 1);
+    /* forward: rows eliminated after step k carry multiplier M[i][cp[k]] */
+    for (int k = 0; k < n; k++) {
+        int pr = rp[k], pc = cp[k];
+        done[pr] = 1;
+        double bk = b[pr];
+        if (bk != 0.0)
+            for (int i = 0; i < n; i++)
+                if (!done[i]) b[i] -= M[(size_t)i*n + pc]*bk;
+    }
+    /* backward */
+    for (int k = n - 1; k >= 0; k--) {
+        int pr = rp[k], pc = cp[k];
+        double s = b[pr];
+        for (int q = k + 1; q < n; q++)
+            s -= M[(size_t)pr*n + cp[q]]*x[cp[q]];
+        x[pc] = s/M[(size_t)pr*n + pc];
+    }
+    memcpy(b, x, n*sizeof(double));
+    free(x); free(done);
+}
+
+static StaticLU *g_dummy;   /* silence unused warnings on some compilers */
+
+static int ckt_factor(wo_ckt *c)
+{
+    if (c->have_order) {
+        if (!c->lu_ready) {
+            StaticLU *f = slu_symbolic(c->n, c->Ap, c->Ai, c->rowperm, c->colperm);
+            c->Lp = (int*)f;       /* stash */
+            c->lu_ready = 1;
+        }
+        return slu_refactor((StaticLU*)c->Lp, c->Ap, c->Ai, c->Ax, c->colperm, c->work);
+    }
+    (void)g_dummy;
+    return dense_factor(c);
+}
+
+static void ckt_solve_inner(wo_ckt *c);
+static void ckt_solve(wo_ckt *c)
+{
+    static int ncall;
+    const char *dn = getenv("WO_DUMP_SOLVE");
+    if (dn && ++ncall == atoi(dn)) {
+        FILE *f = fopen("/tmp/wo_dump.txt", "w");
+        fprintf(f, "%d %d\n", c->n, c->nnz);
+        for (int j = 0; j <= c->n; j++) fprintf(f, "%d\n", c->Ap[j]);
+        for (int p = 0; p < c->nnz; p++) fprintf(f, "%d %.17g\n", c->Ai[p], c->Ax[p]);
+        for (int i = 1; i <= c->n; i++) fprintf(f, "%.17g\n", c->rhs[i]);
+        ckt_solve_inner(c);
+        for (int i = 1; i <= c->n; i++) fprintf(f, "%.17g\n", c->rhs[i]);
+        fclose(f);
+        return;
+    }
+    ckt_solve_inner(c);
+}
+static void ckt_solve_inner(wo_ckt *c)
+{
+    /* spSolve(CKTrhs, CKTrhs): slot 0 is ground (spsolve.cc:173-245) */
+    if (c->have_order) {
+        double *y = xcalloc(c->n, sizeof(double));
+        slu_solve((StaticLU*)c->Lp, c->rowperm, c->colperm, c->rhs + 1, y);
+        free(y);
+    }
+    else
+        dense_solve(c, c->rhs + 1);
+}
+
+/* ------------------------------------------------------------------------- */
+/* FPE check: fpe_check.h:51-71 (FPEcheck mode)                                */
+/* ------------------------------------------------------------------------- */
+static int check_fpe(int noerrret)
+{
+    int err = OK;
+    if (!noerrret) {
+        if (fetestexcept(FE_DIVBYZERO)) err = E_MATHDBZ;
+        else if (fetestexcept(FE_OVERFLOW)) err = E_MATHOVF;
+        else if (fetestexcept(FE_INVALID)) err = E_MATHINV;
+    }
+    feclearexcept(FE_ALL_EXCEPT);
+    return err;
+}
+
+/* ------------------------------------------------------------------------- */
+/* NIconvTest: niconv.cc:58-100; sCKT::convTest: ckt.cc:466-478                 */
+/* ------------------------------------------------------------------------- */
+static int NIconvTest(wo_ckt *c)
+{
+    for (int i = 1; i <= c->n; i++) {
+        double cur = c->rhs[i], old = c->rhsOld[i];
+        double acur = fabs(cur), aold = fabs(old), dd = fabs(cur - old);
+        double rel = c->opt.reltol*SPMAX(aold, acur);
+        double tol = rel + (c->ntype[i] == SP_VOLTAGE ? c->opt.vntol : c->opt.abstol);
+        if (dd > tol) {
+            if (getenv("WO_TRACE2")) fprintf(stderr, "  nonconv node %d type %d old %.17g cur %.17g\n", i, c->ntype[i], old, cur);
+            return 1;
+        }
+    }
+    /* device convTest in model-type order; only MOS has one among the supported kinds
+     * (cap/res/src inherit the no-op). mosconv.cc:55-57: skipped if noncon > 0. */
+    if (c->noncon == 0) {
+        for (int o = 0; o < c->nord; o++)
+            if (c->ord[o].kind == B200_DEV_MOS)
+                if (mos_conv(c, &c->mos[c->ord[o].index])) { if (getenv("WO_TRACE2")) fprintf(stderr, "  nonconv mos %d\n", c->ord[o].index); c->noncon++; break; }
+    }
+    return (c->noncon != 0);
+}
+
+/* ------------------------------------------------------------------------- */
+/* NIiter: niiter.cc:160-555                                                  */
+/* ------------------------------------------------------------------------- */
+static int NIiter(wo_ckt *c, int maxIter)
+{
+    int iterno = 0, ipass = 0;
+    c->noncon = 0;
+    check_fpe(1);
+    if ((c->mode & MODEINITJCT) || (c->mode & MODEINITTRAN))
+        c->niState |= NISHOULDREORDER;
+    int error = ckt_load(c);
+    if (!error) error = check_fpe(0);
+    if (error) return error;
+
+    for (;;) {
+        check_fpe(1);
+        iterno++;
+        error = load_gmin(c);
+        if (error) break;
+        if (c->niState & NISHOULDREORDER) {
+            /* spOrderAndFactor: with a frozen pivot sequence this is a refactor */
+            error = ckt_factor(c);
+            if (error) break;
+            error = check_fpe(0);
+            if (error) break;
+            c->niState &= ~NISHOULDREORDER;
+        }
+        else {
+            error = ckt_factor(c);
+            if (error) {
+                if (error == E_SINGULAR) {
+                    c->niState |= NISHOULDREORDER;
+                    if (iterno == 1) {
+                        error = ckt_load(c);
+                        if (error) break;
+                        continue;
+                    }
+                }
+                break;
+            }
+            error = check_fpe(0);
+            if (error) break;
+        }
+        ckt_solve(c);
+        error = check_fpe(0);
+        if (error) break;
+
+        double *tmp = c->rhsOld; c->rhsOld = c->rhs; c->rhs = tmp;
+        c->rhs[0] = 0; c->rhsSpare[0] = 0; c->rhsOld[0] = 0;
+
+        if (iterno > maxIter) { error = E_ITERLIM; break; }
+
+        if (!c->opt.jjaccel || (c->mode & MODEDC)) {
+            if (c->mode & (MODEINITFIX | MODEINITFLOAT)) {
+                if (c->noncon == 0 && iterno != 1)
+                    c->noncon = NIconvTest(c);
+                else
+                    c->noncon = 1;
+            }
+        }
+        if (c->mode & MODEINITFLOAT) {
+            if ((c->mode & MODEDC) && c->hadNodeset) {
+                if (ipass) c->noncon = ipass;
+                ipass = 0;
+            }
+            if (c->noncon == 0) { error = OK; break; }
+            if ((c->mode & MODEDC) && iterno > 2 && c->opt.dcmu != 0.5) {
+                double A = c->opt.dcmu + 0.5, B = 1.0 - A;
+                for (int i = 1; i <= c->n; i++)
+                    c->rhsOld[i] = A*c->rhsOld[i] + B*c->rhs[i];
+            }
+        }
+        else if (c->mode & MODEINITPRED)
+            c->mode = (c->mode & (~INITF)) | MODEINITFLOAT;
+        else if (c->mode & MODEINITTRAN) {
+            if (iterno <= 1) c->niState |= NISHOULDREORDER;
+            c->mode = (c->mode & (~INITF)) | MODEINITFLOAT;
+        }
+        else if (c->mode & MODEINITSMSIG)
+            c->mode = (c->mode & (~INITF)) | MODEINITFLOAT;
+        else if (c->mode & MODEINITJCT) {
+            c->mode = (c->mode & (~INITF)) | MODEINITFIX;
+            c->niState |= NISHOULDREORDER;
+        }
+        else if (c->mode & MODEINITFIX) {
+            if (c->noncon == 0)
+                c->mode = (c->mode & (~INITF)) | MODEINITFLOAT;
+            ipass = 1;
+        }
+        else { error = B200_E_PANIC; break; }
+        c->noncon = 0;
+        error = ckt_load(c);
+        if (error) break;
+        error = check_fpe(0);
+        if (error) break;
+        if (c->opt.jjaccel && c->noncon == 0 && (c->mode & MODEINITFLOAT) &&
+                !(c->mode & (MODEDCOP | MODETRANOP | MODEINITTRAN))) {
+            error = OK; break;
+        }
+    }
+    c->numIter += iterno;
+    if (!(c->mode & MODEDC) && (c->mode & MODETRAN))
+        c->tranIter += iterno;
+    return error;
+}
+
+/* ------------------------------------------------------------------------- */
+/* DCOP: ckt.cc:1323-1362 (backup), 1492-1610 (dynamic_gmin), 1680-1776         */
+/* (dynamic_src), 1859-2011 (op)                                              */
+/* ------------------------------------------------------------------------- */
+enum { DEV_SAVE, DEV_RESTORE, DEV_CLEAR };
+static void mos_pack(const Mos *m, MosSave *s)
+{
+    s->mode = m->mode;
+    double v[12] = { m->von, m->vdsat, m->cd, m->cbs, m->cbd, m->gm, m->gds, m->gmbs, m->gbd,
+        m->gbs, m->capbd, m->capbs };
+    memcpy(s->v, v, sizeof(v));
+}
+static void mos_unpack(Mos *m, const MosSave *s)
+{
+    m->mode = s->mode;
+    m->von = s->v[0]; m->vdsat = s->v[1]; m->cd = s->v[2]; m->cbs = s->v[3]; m->cbd = s->v[4];
+    m->gm = s->v[5]; m->gds = s->v[6]; m->gmbs = s->v[7]; m->gbd = s->v[8]; m->gbs = s->v[9];
+    m->capbd = s->v[10]; m->capbs = s->v[11];
+}
+
+static void ckt_backup(wo_ckt *c, int bmd)
+{
+    /* device part: MOSdev::backup copies the instance struct (mos.cc:395-410,
+     * mosdefs.h:386-402): SAVE stores, RESTORE restores if a save exists, CLEAR drops it */
+    if (bmd == DEV_SAVE) {
+        if (!c->mosSave) c->mosSave = xcalloc(c->nmos, sizeof(MosSave));
+        for (int i = 0; i < c->nmos; i++) mos_pack(&c->mos[i], &c->mosSave[i]);
+        c->haveSave = 1;
+        if (!c->oldSol) c->oldSol = xcalloc(c->n + 1, sizeof(double));
+        if (!c->oldState0) c->oldState0 = xcalloc(c->numStates + 1, sizeof(double));
+        memcpy(c->oldSol, c->rhsOld, (c->n + 1)*sizeof(double));
+        memcpy(c->oldState0, c->states[0], c->numStates*sizeof(double));
+    }
+    else if (bmd == DEV_RESTORE) {
+        if (c->haveSave)
+            for (int i = 0; i < c->nmos; i++) mos_unpack(&c->mos[i], &c->mosSave[i]);
+        if (c->oldSol) memcpy(c->rhsOld, c->oldSol, (c->n + 1)*sizeof(double));
+        if (c->oldState0) memcpy(c->states[0], c->oldState0, c->numStates*sizeof(double));
+    }
+    else {
+        c->haveSave = 0;
+        free(c->oldSol); c->oldSol = 0;
+        free(c->oldState0); c->oldState0 = 0;
+    }
+}
+
+static int is_math_or_iterlim(int e)
+{
+    return e == E_ITERLIM || e == E_MATHDBZ || e == E_MATHOVF || e == E_MATHUNF || e == E_MATHINV;
+}
+
+static int dynamic_gmin(wo_ckt *c, int firstmode, int continuemode, int iterlim)
+{
+    c->mode = firstmode;
+    memset(c->states[0], 0, c->numStates*sizeof(double));
+    const double gshunt = 0.0, Factor = 10.0;
+    double factor = Factor, OldGmin = 1e-2;
+    c->diagGmin = OldGmin/factor;
+    double gtarget = SPMAX(c->opt.gmin, gshunt);
+    if (gtarget < 1e-15) gtarget = 1e-15;
+    int succeeded = 0, nonconv = OK;
+    for (;;) {
+        int iters = c->numIter;
+        c->noncon = 1;
+        nonconv = NIiter(c, c->opt.itl_gmin);
+        iters = c->numIter - iters;
+        if (nonconv) {
+            if (!is_math_or_iterlim(nonconv)) {
+                c->diagGmin = gshunt;
+                ckt_backup(c, DEV_CLEAR);
+                return nonconv;
+            }
+            if (getenv("WO_TRACE")) fprintf(stderr, "Gmin step failed, Gshunt=%g iters=%d E%d\n", c->diagGmin, iters, nonconv);
+            if (factor < 1.00005) break;
+            factor = sqrt(sqrt(factor));
+            c->diagGmin = OldGmin/factor;
+            ckt_backup(c, DEV_RESTORE);
+        }
+        else {
+            if (getenv("WO_TRACE")) fprintf(stderr, "Gmin step succeeded, Gshunt=%g iters=%d\n", c->diagGmin, iters);
+            c->mode = continuemode;
+            if (c->diagGmin <= gtarget) { succeeded = 1; break; }
+            ckt_backup(c, DEV_SAVE);
+            if (iters <= c->opt.itl_gmin/4) {
+                factor *= sqrt(factor);
+                if (factor > Factor) factor = Factor;
+            }
+            else if (iters > 3*c->opt.itl_gmin/4)
+                factor = sqrt(factor);
+            OldGmin = c->diagGmin;
+            if (c->diagGmin < factor*gtarget) {
+                factor = c->diagGmin/gtarget;
+                c->diagGmin = gtarget;
+            }
+            else
+                c->diagGmin /= factor;
+        }
+    }
+    c->diagGmin = gshunt;
+    ckt_backup(c, DEV_CLEAR);
+    if (succeeded) {
+        nonconv = NIiter(c, iterlim);
+        if (!nonconv) return 0;
+    }
+    return nonconv;
+}
+
+static int dynamic_src(wo_ckt *c, int firstmode, int continuemode, int iterlim)
+{
+    c->mode = firstmode;
+    c->srcFact = 0.001;
+    double raise = 0.001, last_raise = raise, ConvFact = 0;
+    int nonconv = dynamic_gmin(c, firstmode, continuemode, iterlim);
+    if (!nonconv) {
+        ckt_backup(c, DEV_SAVE);
+        c->srcFact = ConvFact + raise;
+        do {
+            int iters = c->numIter;
+            nonconv = NIiter(c, c->opt.itl_src);
+            iters = c->numIter - iters;
+            c->mode = continuemode;
+            if (getenv("WO_TRACE")) fprintf(stderr, "Source step %s, factor=%g iters=%d\n", nonconv ? "failed" : "succeeded", c->srcFact, iters);
+            if (nonconv) {
+                if (!is_math_or_iterlim(nonconv) && nonconv != E_SINGULAR) break;
+                if (c->srcFact - ConvFact < 1e-8) break;
+                raise = 0.1*last_raise;
+                if (raise > 0.01) raise = 0.01;
+                c->srcFact = ConvFact + raise;
+                last_raise = raise;
+                ckt_backup(c, DEV_RESTORE);
+            }
+            else {
+                ConvFact = c->srcFact;
+                ckt_backup(c, DEV_SAVE);
+                c->srcFact = ConvFact + raise;
+                last_raise = raise;
+                if (iters <= c->opt.itl_src/4) raise *= 1.5;
+                else if (iters > 3*c->opt.itl_src/4) raise *= 0.5;
+            }
+            if (c->srcFact > 1) c->srcFact = 1;
+        } while (raise >= 1e-7 && ConvFact < 1);
+    }
+    ckt_backup(c, DEV_CLEAR);
+    c->srcFact = 1;
+    if (ConvFact != 1) return nonconv;
+    return 0;
+}
+
+static int err_return(int err, int first)
+{
+    /* ckt.cc:1825-1852: true => stop trying */
+    if (err == OK) return 1;
+    if (err == E_SINGULAR) return 1;
+    if (err == E_ITERLIM) return first ? 0 : 1;
+    return 1;
+}
+
+static int ckt_op(wo_ckt *c, int firstmode, int continuemode, int iterlim)
+{
+    const b200_options *o = &c->opt;
+    if (o->gminsteps < 0 && o->srcsteps < 0) {
+        c->mode = firstmode;
+        int err = NIiter(c, iterlim);
+        if (!err) c->mode = continuemode;
+        return err;
+    }
+    if (o->gminsteps <= 0 && o->srcsteps <= 0) {
+        if (o->gminfirst) {
+            if (o->gminsteps >= 0) {
+                int err = dynamic_gmin(c, firstmode, continuemode, iterlim);
+                if (err_return(err, 1)) return err;
+            }
+            if (o->srcsteps >= 0) {
+                int err = dynamic_src(c, firstmode, continuemode, iterlim);
+                if (err_return(err, 0)) return err;
+            }
+        }
+        else {
+            if (o->srcsteps >= 0) {
+                int err = dynamic_src(c, firstmode, continuemode, iterlim);
+                if (err_return(err, 1)) return err;
+            }
+            if (o->gminsteps >= 0) {
+                int err = dynamic_gmin(c, firstmode, continuemode, iterlim);
+                if (err_return(err, 0)) return err;
+            }
+        }
+        return OK;
+    }
+    /* spice3-style fixed stepping (gminsteps/srcsteps > 0) is not restated */
+    return B200_E_UNSUPP;
+}
+
+/* ------------------------------------------------------------------------- */
+/* LTE: ckt.cc:2310-2463, mostrun.cc:52-65, captrun.cc:52-63                    */
+/* ------------------------------------------------------------------------- */
+static double true_time(double tmp, int order)
+{
+    if (order == 2) return sqrt(tmp);
+    if (order == 1) return tmp;
+    if (order == 3) return cbrt(tmp);
+    if (order == 4) return sqrt(sqrt(tmp));
+    return exp(log(tmp)/order);
+}
+
+static void terr(wo_ckt *c, int qcap, double *timeStep)
+{
+    static const double gearCoeff[] = { .5, .2222222222, .1363636364, .096, .07299270073, .05830903790 };
+    static const double trapCoeff[] = { .5, .08333333333 };
+    int ccap = qcap + 1;
+    double y0 = fabs(c->states[0][ccap]), y1 = fabs(c->states[1][ccap]);
+    double volttol = c->opt.abstol + c->opt.reltol*SPMAX(y0, y1);
+    y0 = fabs(c->states[0][qcap]); y1 = fabs(c->states[1][qcap]);
+    double chargetol = SPMAX(y0, y1);
+    if (chargetol < c->opt.chgtol) chargetol = c->opt.chgtol;
+    chargetol *= c->opt.reltol/c->delta;
+    double tol = SPMAX(volttol, chargetol);
+    double diff[8], deltmp[8];
+    for (int i = c->order + 1; i >= 0; i--) diff[i] = c->states[i][qcap];
+    for (int i = 0; i <= c->order; i++) deltmp[i] = c->deltaOld[i];
+    int j = c->order;
+    for (;;) {
+        for (int i = 0; i <= j; i++) diff[i] = (diff[i] - diff[i+1])/deltmp[i];
+        if (--j < 0) break;
+        for (int i = 0; i <= j; i++) deltmp[i] = deltmp[i+1] + c->deltaOld[i];
+    }
+    double del;
+    if (c->opt.method == 0) del = fabs(diff[0]*trapCoeff[c->order-1]);
+    else del = fabs(diff[0]*gearCoeff[c->order-1]);
+    del = c->opt.trtol*tol/SPMAX(c->opt.abstol, del);
+    if (del < *timeStep) *timeStep = del;
+}
+
+static int ckt_trunc(wo_ckt *c, double *timeStep)
+{
+    double timetemp = DBL_MAX;
+    for (int o = 0; o < c->nord; o++) {
+        int i = c->ord[o].index;
+        if (c->ord[o].kind == B200_DEV_MOS) {
+            terr(c, c->mos[i].st + MS_qgs, &timetemp);
+            terr(c, c->mos[i].st + MS_qgd, &timetemp);
+            terr(c, c->mos[i].st + MS_qgb, &timetemp);
+        }
+        else if (c->ord[o].kind == B200_DEV_CAP)
+            terr(c, c->cap[i].st, &timetemp);
+    }
+    /* srctrun.cc:45-66: SIN sources bound the step through IFsinData::time_limit
+     * (inptran.cc:2666-2680, uses dphimax = .2*pi, circuit.h:495) */
+    {
+        double time_step = HUGE_VAL;
+        for (int i = 0; i < c->nsrc; i++) {
+            Src *s = &c->src[i];
+            if (s->fn == B200_FN_SIN && c->time >= s->parms[3]) {
+                double per = (.2*M_PI)/(2*M_PI*s->parms[2]);
+                if (time_step > per) time_step = per;
+            }
+        }
+        if (time_step < HUGE_VAL) {
+            double tmp = time_step;
+            for (int i = 1; i < c->order; i++) time_step *= tmp;
+        }
+        if (timetemp > time_step) timetemp = time_step;
+    }
+    *timeStep = true_time(timetemp, c->order);
+    return OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* transient driver: analysis/tranan.cc                                       */
+/* ------------------------------------------------------------------------- */
+static void record_point(wo_ckt *c, double t, const double *v /* [n+1] */)
+{
+    if (c->npts == c->cappts) {
+        c->cappts = c->cappts ? 2*c->cappts : 256;
+        c->pt_t = realloc(c->pt_t, c->cappts*sizeof(double));
+        c->pt_v = realloc(c->pt_v, (size_t)c->cappts*c->n*sizeof(double));
+    }
+    c->pt_t[c->npts] = t;
+    memcpy(c->pt_v + (size_t)c->npts*c->n, v + 1, c->n*sizeof(double));
+    c->npts++;
+}
+
+static void record_accept(wo_ckt *c)
+{
+    if (c->nacc == c->capacc) {
+        c->capacc = c->capacc ? 2*c->capacc : 256;
+        c->acc_t = realloc(c->acc_t, c->capacc*sizeof(double));
+        c->acc_v = realloc(c->acc_v, (size_t)c->capacc*c->n*sizeof(double));
+        c->acc_it = realloc(c->acc_it, c->capacc*sizeof(int));
+    }
+    c->acc_t[c->nacc] = c->time;
+    memcpy(c->acc_v + (size_t)c->nacc*c->n, c->rhsOld + 1, c->n*sizeof(double));
+    c->acc_it[c->nacc] = c->lastIters;
+    c->nacc++;
+}
+
+static void inc_check(wo_ckt *c)
+{
+    /* tranan.cc:472-479 (single .tran segment) */
+    c->t_check += c->t_step;
+}
+
+static int tran_interpolate(wo_ckt *c)
+{
+    /* tranan.cc:963-1116 */
+    if (c->mode & MODEUIC) {
+        if (c->t_firsttime) return OK;
+        if (c->npts == 0 && c->t_start == 0.0) {
+            record_point(c, c->t_check, c->rhsOld);
+            inc_check(c);
+            return OK;
+        }
+    }
+    double delta = .5*c->t_delmin;
+    double finalmax = c->t_stop + delta, finalmin = c->t_stop - delta;
+    double time = c->time + delta;
+    int degree = c->t_polydegree;
+    if (degree > c->opt.maxord) degree = c->opt.maxord;
+    double diff[4];
+    for (; c->t_check <= time; inc_check(c)) {
+        double c2 = c->deltaOld[0];
+        double d1 = c->time - c->t_check;
+        if (degree <= 1) {
+            double d2 = d1 - c2;
+            diff[0] = d2/(-c2);
+            diff[1] = d1/(c2);
+            for (int i = 1; i <= c->n; i++)
+                c->rhs[i] = diff[0]*c->sols[0][i] + diff[1]*c->sols[1][i];
+        }
+        else if (degree == 2) {
+            double c3 = c2 + c->deltaOld[1];
+            double d2 = d1 - c2, d3 = d1 - c3;
+            diff[0] = d2*d3/((c2)*(c3));
+            diff[1] = d1*d3/((c2)*(c2-c3));
+            diff[2] = d1*d2/((c3)*(c3-c2));
+            for (int i = 1; i <= c->n; i++)
+                c->rhs[i] = diff[0]*c->sols[0][i] + diff[1]*c->sols[1][i] + diff[2]*c->sols[2][i];
+        }
+        else {
+            double c3 = c2 + c->deltaOld[1], c4 = c3 + c->deltaOld[2];
+            double d2 = d1 - c2, d3 = d1 - c3, d4 = d1 - c4;
+            diff[0] = d2*d3*d4/((-c2)*(c3)*(c4));
+            diff[1] = d1*d3*d4/((c2)*(c2-c3)*(c2-c4));
+            diff[2] = d1*d2*d4/((c3)*(c3-c2)*(c3-c4));
+            diff[3] = d1*d2*d3/((c4)*(c4-c2)*(c4-c3));
+            for (int i = 1; i <= c->n; i++)
+                c->rhs[i] = diff[0]*c->sols[0][i] + diff[1]*c->sols[1][i] +
+                    diff[2]*c->sols[2][i] + diff[3]*c->sols[3][i];
+        }
+        if (c->t_check < finalmax) {
+            record_point(c, c->t_check, c->rhs);
+            if (finalmin < c->t_check) return E_NOCHANGE;
+        }
+        else
+            return E_NOCHANGE;
+    }
+    if (c->t_check >= finalmax) return E_NOCHANGE;
+    return OK;
+}
+
+static int ckt_accept(wo_ckt *c)
+{
+    /* ckt.cc:355-383 (no device accept functions among MOS/CAP/RES/SRC) */
+    c->devMaxDelta = 0.0;
+    double *tmp = c->sols[7];
+    for (int i = 7; i > 0; i--) c->sols[i] = c->sols[i-1];
+    c->sols[0] = tmp;
+    for (int i = 0; i <= c->n; i++) c->sols[0][i] = c->rhsOld[i];
+    return OK;
+}
+
+static int tran_accept(wo_ckt *c, int *done)
+{
+    /* tranan.cc:483-554 */
+    memcpy(c->rhsSpare + 1, c->rhsOld + 1, c->n*sizeof(double));
+    ckt_accept(c);
+    if (c->time > c->breaks[0])
+        break_clr(c);
+    c->accepted++;
+    c->brk = 0;
+    record_accept(c);
+    int error = tran_interpolate(c);
+    if (error == E_NOCHANGE)
+        c->endit = 1;
+    if (c->endit) { c->endit = 0; *done = 1; }
+    return OK;
+}
+
+static void tran_setbp(wo_ckt *c)
+{
+    /* tranan.cc:558-654 (STEP_NORMAL) */
+    c->brk = 0;
+    if (c->time == 0.0 || c->breaks[0] > 0) {
+        if ((c->time == c->breaks[0]) || (c->breaks[0] - c->time <= c->t_delmin)) {
+            c->order = 1;
+            c->t_ordcnt = c->t_spice3 ? 0 : 1;
+            double ttmp = c->breaks[1] - c->breaks[0];
+            if (c->saveDelta < ttmp) ttmp = c->saveDelta;
+            if (!c->t_nocut && !c->opt.jjaccel) ttmp *= 0.1;
+            double td1 = 0.1*c->saveDelta;
+            if (ttmp < td1) ttmp = td1;
+            if (ttmp < c->delta) c->delta = ttmp;
+            ttmp = 2.0*c->t_delmin;
+            if (c->delta < ttmp) c->delta = ttmp;
+        }
+        else if (c->time + 1.01*c->delta >= c->breaks[0]) {
+            double del = c->breaks[0] - c->time;
+            if (del > c->t_delmin) {
+                c->saveDelta = c->delta;
+                c->delta = del;
+                c->brk = 1;
+            }
+        }
+    }
+}
+
+#define DELTA_FACTOR 0.125
+
+static int tran_step(wo_ckt *c)
+{
+    /* tranan.cc:658-953 */
+    double intDevMaxDelta = c->devMaxDelta;
+    for (;;) {
+        double olddelta = c->delta;
+        if (c->maxStep < c->t_delmax) c->t_delmax = c->maxStep;
+        c->time += c->delta;
+        c->deltaOld[0] = c->delta;
+        NIcomCof(c);
+        predict(c);
+        c->trapCheck = c->opt.trapcheck && c->opt.method == 0 && c->order == 2;
+        int niter = c->numIter;
+        int cverr = NIiter(c, c->opt.itl4);
+        double bound_step = c->devMaxDelta;
+        if (bound_step == 0.0 || (intDevMaxDelta > 0.0 && intDevMaxDelta < bound_step))
+            c->devMaxDelta = intDevMaxDelta;
+        c->timePts++;
+        c->lastIters = c->numIter - niter;
+        if (getenv("WO_TRACE"))
+            fprintf(stderr, "time=%12g delta=%12g iters= %d order= %2d\n", c->time, c->delta, c->lastIters, c->order);
+        c->mode = (c->mode & MODEUIC) | MODETRAN | MODEINITPRED;
+        if (c->t_firsttime) {
+            for (int i = 0; i < c->numStates; i++) {
+                c->states[2][i] = c->states[1][i];
+                if (c->opt.maxord > 1) c->states[3][i] = c->states[1][i];
+            }
+        }
+        if (cverr) {
+            if (cverr != E_ITERLIM) return cverr;
+            c->time -= c->delta;
+            c->rejected++;
+            c->iterCut++;
+            c->delta *= DELTA_FACTOR;
+            if (c->t_firsttime)
+                c->mode = (c->mode & MODEUIC) | MODETRAN | MODEINITTRAN;
+            c->order = 1;
+            c->brk = 0;
+            memcpy(c->rhsOld + 1, c->rhsSpare + 1, c->n*sizeof(double));
+        }
+        else {
+            if (c->t_firsttime) { c->t_firsttime = 0; break; }
+            if (c->opt.jjaccel) {
+                c->delta = c->devMaxDelta;
+                if (c->order < c->opt.maxord) c->order++;
+                break;
+            }
+            double newd;
+            ckt_trunc(c, &newd);
+            if (getenv("WO_TRACE")) fprintf(stderr, "LTE delta=%12g\n", newd);
+            if (c->trapBad) {
+                c->time -= c->delta;
+                c->rejected++;
+                c->trapCut++;
+                c->delta *= DELTA_FACTOR;
+                c->order = 1;
+                memcpy(c->rhsOld + 1, c->rhsSpare + 1, c->n*sizeof(double));
+                c->t_ordcnt = c->t_spice3 ? 0 : 1;
+                continue;
+            }
+            if (c->t_spice3) {
+                if (newd > 2.0*c->delta) newd = 2.0*c->delta;
+                if (c->devMaxDelta > 0.0 && c->devMaxDelta < newd) newd = c->devMaxDelta;
+                if (newd > .9*c->delta) {
+                    if (c->order == 1) {
+                        if (c->t_ordcnt) c->t_ordcnt--;
+                        else {
+                            c->order++;
+                            if (c->order > c->opt.maxord) c->order = c->opt.maxord;
+                            ckt_trunc(c, &newd);
+                            if (newd > 2.0*c->delta) newd = 2.0*c->delta;
+                            if (c->devMaxDelta > 0.0 && c->devMaxDelta < newd) newd = c->devMaxDelta;
+                            if (newd <= 1.05*c->delta) c->order = 1;
+                        }
+                    }
+                    c->delta = newd;
+                    if (c->delta > c->t_delmax) c->delta = c->t_delmax;
+                    break;
+                }
+                else {
+                    c->time -= c->delta;
+                    c->rejected++;
+                    c->delta = newd;
+                    memcpy(c->rhsOld + 1, c->rhsSpare + 1, c->n*sizeof(double));
+                }
+            }
+            else {
+                if (newd > .5*c->delta) {
+                    double twodelta = 2.0*c->delta;
+                    if (c->order < c->opt.maxord) {
+                        if (c->t_ordcnt) c->t_ordcnt--;
+                        else {
+                            c->order++;
+                            double newdtmp;
+                            ckt_trunc(c, &newdtmp);
+                            if (getenv("WO_TRACE")) fprintf(stderr, "LTE delta=%12g order= %d\n", newdtmp, c->order);
+                            if (newdtmp <= 1.05*SPMIN(newd, twodelta)) c->order--;
+                            else newd = newdtmp;
+                        }
+                    }
+                    if (newd > twodelta) newd = twodelta;
+                    if (c->devMaxDelta > 0.0 && c->devMaxDelta < newd) newd = c->devMaxDelta;
+                    if (newd > c->t_delmax) newd = c->t_delmax;
+                    c->delta = newd;
+                    break;
+                }
+                else {
+                    c->time -= c->delta;
+                    c->rejected++;
+                    if (c->devMaxDelta > 0.0 && c->devMaxDelta < newd) newd = c->devMaxDelta;
+                    if (newd > c->t_delmax) newd = c->t_delmax;
+                    c->delta = newd;
+                    c->brk = 0;
+                    memcpy(c->rhsOld + 1, c->rhsSpare + 1, c->n*sizeof(double));
+                }
+            }
+        }
+        if (c->delta <= c->t_delmin) {
+            if (olddelta > c->t_delmin) c->delta = c->t_delmin;
+            else return E_TIMESTEP;
+        }
+    }
+    return OK;
+}
+
+static int has_trunc_dev(const wo_ckt *c)
+{
+    /* tranan.cc:68-77: any model type with DV_TRUNC (mos.cc:347, cap.cc:147) */
+    return (c->nmos > 0 || c->ncap > 0);
+}
+
+int wo_run_tran(wo_ckt *c)
+{
+    const b200_options *o = &c->opt;
+    feclearexcept(FE_ALL_EXCEPT);
+    /* temperature pass (ckt.cc:2297-2307) -- after any wo_set_param */
+    for (int i = 0; i < c->nmos; i++) {
+        b200_mos_model deckmod = c->mos[i].mod;
+        mos_temp(c, &c->mos[i], &deckmod);
+    }
+    preload(c);
+
+    /* sTRANAN::init, tranan.cc:94-217 */
+    c->mode = (c->uic ? MODEUIC : 0) | MODETRAN;       /* TRANmode */
+    c->t_stop = c->tstop; c->t_step = c->tstep; c->t_start = c->tstart;
+    c->maxStep = c->tmax;
+    c->t_spice3 = o->spice3;
+    c->t_nocut = !has_trunc_dev(c);
+    if (c->maxStep == 0) {
+        c->maxStep = (c->t_stop - c->t_start)/50;
+        if (o->oldsteplim) { if (c->t_step > c->maxStep) c->maxStep = c->t_step; }
+        else { if (c->t_step < c->maxStep) c->maxStep = 1.001*c->t_step; }
+    }
+    c->t_delmax = c->maxStep;
+    c->t_polydegree = o->interplev;
+    double delmin = o->delmin;
+    if (!(delmin > 0)) {
+        if (o->oldsteplim) {
+            delmin = c->maxStep*1e-9;
+            double T1 = c->t_stop*1e-12;
+            if (delmin < T1) delmin = T1;
+        }
+        else
+            delmin = c->maxStep*1e-6;
+    }
+    c->t_delmin = delmin;
+    c->minBreak = (o->minbreak > 0) ? o->minbreak : delmin*50.0;
+
+    /* tran_dcoperation, tranan.cc:321-436 */
+    c->time = 0; c->delta = 0; c->brk = 0;
+    free(c->brks); c->brks = 0; c->numBreaks = 0; c->numLat = 0;
+    c->breaks[0] = c->breaks[1] = 0.0;
+    break_set(c, 0.0);
+    break_set(c, c->t_start);
+    break_set(c, c->t_stop);
+    for (int oi = 0; oi < c->nord; oi++)
+        if (c->ord[oi].kind == B200_DEV_SRC)
+            src_setup_func(c, &c->src[c->ord[oi].index], c->t_step, c->t_stop);
+    c->t_dumpit = 0;
+    c->t_firsttime = 1;
+    c->t_check = c->t_start;
+
+    /* ckt.cc:908-925 ic() */
+    for (int i = 0; i <= c->n; i++) c->rhs[i] = 0;
+    c->hadNodeset = 0;
+    for (int i = 1; i <= c->n; i++) {
+        if (c->ns_given[i]) { c->hadNodeset = 1; c->rhs[i] = c->ns_val[i]; }
+        if (c->ic_given[i]) c->rhs[i] = c->ic_val[i];
+    }
+    int error;
+    if (c->mode & MODEUIC) {
+        /* setic(): MOS getic (mosic.cc) fills missing device ICs from node ICs in CKTrhs */
+        for (int i = 0; i < c->nmos; i++) {
+            Mos *m = &c->mos[i];
+            if (!GIVEN(m->in.icvbs)) m->icVBS = c->rhs[m->b] - c->rhs[m->s];
+            if (!GIVEN(m->in.icvds)) m->icVDS = c->rhs[m->d] - c->rhs[m->s];
+            if (!GIVEN(m->in.icvgs)) m->icVGS = c->rhs[m->g] - c->rhs[m->s];
+        }
+        for (int i = 0; i < c->ncap; i++) {
+            /* capic.cc: if no ic given use node ICs */
+            (void)i;
+        }
+        double *tmp = c->rhs; c->rhs = c->rhsOld; c->rhsOld = tmp;
+        c->rhs[0] = 0.0; c->rhsOld[0] = 0.0;
+        c->mode = MODEUIC | MODETRANOP | MODEINITJCT;
+        error = ckt_load(c);
+    }
+    else
+        error = ckt_op(c, MODETRANOP | MODEINITJCT, MODETRANOP | MODEINITFLOAT, o->itl1);
+    if (error) { return error; }
+
+    for (int i = 1; i <= o->maxord + 1; i++)
+        memcpy(c->states[i], c->states[0], c->numStates*sizeof(double));
+    c->timePts++;
+    c->order = 1;
+    c->delta = SPMIN(c->t_delmax, c->t_step);
+    if (!c->t_nocut) c->delta *= 0.1;
+    for (int i = 0; i < 7; i++) c->deltaOld[i] = c->delta;
+    c->saveDelta = c->delta;
+    c->mode = (c->mode & MODEUIC) | MODETRAN | MODEINITTRAN;
+    c->ag[0] = c->ag[1] = 0;
+    memcpy(c->states[1], c->states[0], c->numStates*sizeof(double));
+    if (c->time >= c->t_start) c->t_dumpit = 1;
+
+    int done = 0;
+    for (;;) {
+        error = tran_accept(c, &done);
+        if (error || done) break;
+        tran_setbp(c);
+        for (int i = 5; i >= 0; i--) c->deltaOld[i+1] = c->deltaOld[i];
+        c->deltaOld[0] = c->delta;
+        double *temp = c->states[o->maxord + 1];
+        for (int i = o->maxord; i >= 0; i--) c->states[i+1] = c->states[i];
+        c->states[0] = temp;
+        error = tran_step(c);
+        if (error) break;
+    }
+    return error;
+}
+
+int wo_num_points(const wo_ckt *c) { return c->npts; }
+void wo_get_points(const wo_ckt *c, double *times, double *vals)
+{
+    if (times) memcpy(times, c->pt_t, c->npts*sizeof(double));
+    if (vals) memcpy(vals, c->pt_v, (size_t)c->npts*c->n*sizeof(double));
+}
+void wo_get_counters(const wo_ckt *c, int *k)
+{
+    k[B200_C_STATUS] = 0; k[B200_C_ACCEPTED] = c->accepted; k[B200_C_REJECTED] = c->rejected;
+    k[B200_C_NUMITER] = c->numIter; k[B200_C_TIMEPTS] = c->timePts; k[B200_C_TRANITER] = c->tranIter;
+    k[B200_C_ITERCUT] = c->iterCut; k[B200_C_TRAPCUT] = c->trapCut; k[B200_C_NPOINTS] = c->npts;
+}
+int wo_num_accepted(const wo_ckt *c) { return c->nacc; }
+void wo_get_accepted(const wo_ckt *c, double *times, double *vals, int *iters)
+{
+    if (times) memcpy(times, c->acc_t, c->nacc*sizeof(double));
+    if (vals) memcpy(vals, c->acc_v, (size_t)c->nacc*c->n*sizeof(double));
+    if (iters) memcpy(iters, c->acc_it, c->nacc*sizeof(int));
+}
+
+int wo_debug_load(wo_ckt *c, int mode, double time, double delta, int order,
+    const double *rhsold, double *Ax, double *rhs)
+{
+    for (int i = 0; i < c->nmos; i++) {
+        b200_mos_model deckmod = c->mos[i].mod;
+        mos_temp(c, &c->mos[i], &deckmod);
+    }
+    preload(c);
+    c->mode = mode; c->time = time; c->delta = delta; c->order = order;
+    for (int i = 0; i < 7; i++) c->deltaOld[i] = delta;
+    if (mode & MODETRAN) { NIcomCof(c); predict(c); }
+    if (rhsold) memcpy(c->rhsOld, rhsold, (c->n + 1)*sizeof(double));
+    int err = ckt_load(c);
+    if (!err) err = load_gmin(c);
+    if (Ax) memcpy(Ax, c->Ax, c->nnz*sizeof(double));
+    if (rhs) memcpy(rhs, c->rhs, (c->n + 1)*sizeof(double));
+    return err;
+}
+
+void wo_destroy(wo_ckt *c)
+{
+    if (!c) return;
+    /* test infrastructure: process-lifetime leaks of the small tables are acceptable,
+     * the large arrays are released */
+    free(c->Ax); free(c->Ainit); free(c->Ap); free(c->Ai); free(c->dense); free(c->dpiv);
+    free(c->rhs); free(c->rhsOld); free(c->rhsSpare);
+    for (int i = 0; i < 8; i++) { free(c->sols[i]); free(c->states[i]); }
+    free(c->pt_t); free(c->pt_v); free(c->acc_t); free(c->acc_v); free(c->acc_it);
+    free(c->mos); free(c->cap); free(c->res); free(c->src); free(c->ord);
+    free(c);
+}

@@ -1,0 +1,538 @@
+"""Host-side deck description for the batched engine.
+
+Mirrors what WRspice's front end hands to the numerical core: a flat list of device cards
+plus .model/.ic/.options/.tran, and reproduces the *orderings* the reference derives from the
+deck text, because they decide floating-point summation order in the matrix and RHS:
+
+  * node numbers: order of first appearance while parsing (src/inp/inpdeck.cc pass2,
+    ckt/symtab.cc term_insert);
+  * load order: model-TYPE list in order of first model creation (include/circuit.h:1199-1223
+    sCKTmodHead::insert appends a new type), models of one type newest-first
+    (ckt.cc:1418-1421 newModl prepends), instances of one model newest-first
+    (ckt.cc:1388-1389 newInst prepends), mutual inductors before everything
+    (ckt.cc:991-1005).
+
+`Deck.to_spice()` renders the same circuit as SPICE text for the compiled reference
+(oracle/_ref, tests only); `Deck.to_c()` builds the C-ABI `b200_deck` (include/b200spice.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+NAN = float("nan")
+
+DEV_RES, DEV_CAP, DEV_IND, DEV_MUT, DEV_SRC, DEV_MOS, DEV_JJ = range(7)
+SRC_V, SRC_I = 0, 1
+FN_NONE, FN_PULSE, FN_PWL, FN_SIN = range(4)
+
+# parameter ids (include/b200spice.h)
+P_MOS_VTO, P_MOS_KP, P_MOS_L, P_MOS_W, P_MOS_GAMMA, P_MOS_LAMBDA, P_MOS_PHI = range(1, 8)
+P_CAP_C, P_RES_R, P_IND_L, P_SRC_DC, P_JJ_AREA = 32, 48, 56, 64, 80
+
+# counters
+(C_STATUS, C_ACCEPTED, C_REJECTED, C_NUMITER, C_TIMEPTS, C_TRANITER, C_ITERCUT, C_TRAPCUT,
+ C_NPOINTS, NCOUNTERS) = range(10)
+
+
+class COptions(C.Structure):
+    _fields_ = ([(n, C.c_double) for n in (
+        "abstol", "reltol", "vntol", "chgtol", "trtol", "gmin", "gmax", "pivrel", "pivtol",
+        "temp", "tnom", "xmu", "dcmu", "trapratio", "delmin", "minbreak", "resmin",
+        "defl", "defw", "defad", "defas")] +
+        [(n, C.c_int) for n in (
+            "bypass", "maxord", "itl1", "itl2", "itl4", "itl_gmin", "itl_src",
+            "gminsteps", "srcsteps", "gminfirst", "method", "trapcheck", "spice3",
+            "oldsteplim", "oldlimit", "forcegmin", "interplev", "jjaccel", "nojjtp",
+            "noopiter", "steptype")])
+
+
+class CRes(C.Structure):
+    _fields_ = [("pos", C.c_int), ("neg", C.c_int), ("r", C.c_double), ("m", C.c_double),
+                ("tc1", C.c_double), ("tc2", C.c_double), ("temp", C.c_double)]
+
+
+class CCap(C.Structure):
+    _fields_ = [("pos", C.c_int), ("neg", C.c_int), ("c", C.c_double), ("m", C.c_double),
+                ("ic", C.c_double)]
+
+
+class CInd(C.Structure):
+    _fields_ = [("pos", C.c_int), ("neg", C.c_int), ("l", C.c_double), ("m", C.c_double),
+                ("ic", C.c_double)]
+
+
+class CMut(C.Structure):
+    _fields_ = [("ind1", C.c_int), ("ind2", C.c_int), ("k", C.c_double)]
+
+
+class CSrc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("pos", C.c_int), ("neg", C.c_int), ("dc", C.c_double),
+                ("fn", C.c_int), ("ncoef", C.c_int), ("coef", C.POINTER(C.c_double))]
+
+
+MOS_MODEL_DBL = ("vto", "kp", "gamma", "phi", "lambda_", "rd", "rs", "cbd", "cbs", "is_", "pb",
+                 "cgso", "cgdo", "cgbo", "rsh", "cj", "mj", "cjsw", "mjsw", "js", "tox", "ld",
+                 "u0", "fc", "nsub", "tpg", "nss", "tnom", "nfs", "delta", "uexp", "ucrit",
+                 "vmax", "xj", "neff", "eta", "theta", "kappa")
+
+
+class CMosModel(C.Structure):
+    _fields_ = [("type", C.c_int), ("level", C.c_int)] + [(n, C.c_double) for n in MOS_MODEL_DBL]
+
+
+class CMos(C.Structure):
+    _fields_ = ([("d", C.c_int), ("g", C.c_int), ("s", C.c_int), ("b", C.c_int),
+                 ("model", C.c_int)] +
+                [(n, C.c_double) for n in ("l", "w", "ad", "as_", "pd", "ps", "nrd", "nrs", "m",
+                                           "temp", "icvds", "icvgs", "icvbs")] +
+                [("off", C.c_int)])
+
+
+JJ_MODEL_DBL = ("vg", "delv", "icrit", "r0", "rn", "cap", "icfact", "vshunt", "tsfact",
+                "tsaccel", "cpic", "cmu", "vm", "icrn", "gmu")
+
+
+class CJJModel(C.Structure):
+    _fields_ = [("rtype", C.c_int), ("ictype", C.c_int)] + [(n, C.c_double) for n in JJ_MODEL_DBL]
+
+
+class CJJ(C.Structure):
+    _fields_ = [("pos", C.c_int), ("neg", C.c_int), ("phase_node", C.c_int), ("model", C.c_int),
+                ("area", C.c_double), ("ics", C.c_double), ("icphi", C.c_double),
+                ("icv", C.c_double)]
+
+
+class CDeck(C.Structure):
+    _fields_ = [
+        ("nnodes", C.c_int), ("opt", COptions),
+        ("tstep", C.c_double), ("tstop", C.c_double), ("tstart", C.c_double),
+        ("tmax", C.c_double), ("uic", C.c_int),
+        ("nic", C.c_int), ("ic_node", C.POINTER(C.c_int)), ("ic_val", C.POINTER(C.c_double)),
+        ("nnodeset", C.c_int), ("ns_node", C.POINTER(C.c_int)), ("ns_val", C.POINTER(C.c_double)),
+        ("nres", C.c_int), ("res", C.POINTER(CRes)),
+        ("ncap", C.c_int), ("cap", C.POINTER(CCap)),
+        ("nind", C.c_int), ("ind", C.POINTER(CInd)),
+        ("nmut", C.c_int), ("mut", C.POINTER(CMut)),
+        ("nsrc", C.c_int), ("src", C.POINTER(CSrc)),
+        ("nmosmod", C.c_int), ("mos_models", C.POINTER(CMosModel)),
+        ("nmos", C.c_int), ("mos", C.POINTER(CMos)),
+        ("njjmod", C.c_int), ("jj_models", C.POINTER(CJJModel)),
+        ("njj", C.c_int), ("jj", C.POINTER(CJJ)),
+        ("norder", C.c_int), ("order_kind", C.POINTER(C.c_int)),
+        ("order_index", C.POINTER(C.c_int)),
+    ]
+
+
+# reference defaults: wrspice/include/circuit.h:461-631
+DEFAULT_OPTIONS = dict(
+    abstol=1e-12, reltol=1e-3, vntol=1e-6, chgtol=1e-14, trtol=7.0, gmin=1e-12, gmax=1e6,
+    pivrel=1e-3, pivtol=1e-13, temp=298.15, tnom=298.15, xmu=0.5, dcmu=0.5, trapratio=10.0,
+    delmin=0.0, minbreak=0.0, resmin=1e-3, defl=0.0, defw=0.0, defad=0.0, defas=0.0,
+    bypass=1, maxord=2, itl1=400, itl2=100, itl4=20, itl_gmin=20, itl_src=20,
+    gminsteps=0, srcsteps=0, gminfirst=0, method=0, trapcheck=0, spice3=0, oldsteplim=0,
+    oldlimit=0, forcegmin=0, interplev=1, jjaccel=0, nojjtp=0, noopiter=0, steptype=0)
+
+# our option name -> WRspice .options keyword (analysis/optsetp.cc:104-...)
+_OPT_SPICE = dict(abstol="abstol", reltol="reltol", vntol="vntol", chgtol="chgtol",
+                  trtol="trtol", gmin="gmin", gmax="gmax", pivrel="pivrel", pivtol="pivtol",
+                  xmu="xmu", dcmu="dcmu", trapratio="trapratio", delmin="delmin",
+                  minbreak="minbreak", resmin="resmin", bypass="bypass", maxord="maxord",
+                  itl1="itl1", itl2="itl2", itl4="itl4", itl_gmin="itl2gmin", itl_src="itl2src",
+                  gminsteps="gminsteps", srcsteps="srcsteps", interplev="interplev")
+
+
+def _fmt(x: float) -> str:
+    return repr(float(x))
+
+
+@dataclass
+class _Elem:
+    kind: int
+    name: str
+    nodes: tuple
+    params: dict
+    model: str | None = None
+
+
+@dataclass
+class Deck:
+    title: str = "b200 deck"
+    elems: list = field(default_factory=list)
+    mos_models: dict = field(default_factory=dict)     # name -> dict(type, level, params)
+    jj_models: dict = field(default_factory=dict)
+    ics: dict = field(default_factory=dict)
+    nodesets: dict = field(default_factory=dict)
+    opts: dict = field(default_factory=lambda: dict(DEFAULT_OPTIONS))
+    tran_args: tuple | None = None
+
+    # ---- construction -------------------------------------------------------------
+    def vsource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None):
+        self.elems.append(_Elem(DEV_SRC, name.lower(), (str(p).lower(), str(n).lower()),
+                                dict(kind=SRC_V, dc=dc, pulse=pulse, pwl=pwl, sin=sin)))
+        return self
+
+    def isource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None):
+        self.elems.append(_Elem(DEV_SRC, name.lower(), (str(p).lower(), str(n).lower()),
+                                dict(kind=SRC_I, dc=dc, pulse=pulse, pwl=pwl, sin=sin)))
+        return self
+
+    def resistor(self, name, p, n, r):
+        self.elems.append(_Elem(DEV_RES, name.lower(), (str(p).lower(), str(n).lower()),
+                                dict(r=float(r))))
+        return self
+
+    def capacitor(self, name, p, n, c, ic=None):
+        self.elems.append(_Elem(DEV_CAP, name.lower(), (str(p).lower(), str(n).lower()),
+                                dict(c=float(c), ic=ic)))
+        return self
+
+    def mos_model(self, name, mtype, level=1, **params):
+        self.mos_models[name.lower()] = dict(type=+1 if mtype.lower().startswith("n") else -1,
+                                             level=level, params=dict(params))
+        return self
+
+    def mosfet(self, name, d, g, s, b, model, **params):
+        self.elems.append(_Elem(DEV_MOS, name.lower(),
+                                tuple(str(x).lower() for x in (d, g, s, b)), dict(params),
+                                model.lower()))
+        return self
+
+    def ic(self, **kv):
+        for k, v in kv.items():
+            self.ics[k.lower()] = float(v)
+        return self
+
+    def nodeset(self, **kv):
+        for k, v in kv.items():
+            self.nodesets[k.lower()] = float(v)
+        return self
+
+    def options(self, **kv):
+        for k, v in kv.items():
+            if k not in DEFAULT_OPTIONS:
+                raise KeyError(k)
+            self.opts[k] = v
+        return self
+
+    def tran(self, tstep, tstop, tstart=0.0, tmax=0.0, uic=False):
+        self.tran_args = (float(tstep), float(tstop), float(tstart), float(tmax), bool(uic))
+        return self
+
+    # ---- derived orderings ----------------------------------------------------------
+    def node_numbers(self) -> dict:
+        """name -> number, ground names map to 0 (inpdeck.cc:150-162)."""
+        nums = {"0": 0, "gnd": 0}
+        nxt = 1
+        for e in self.elems:
+            for nd in e.nodes:
+                if nd not in nums:
+                    nums[nd] = nxt
+                    nxt += 1
+        return nums
+
+    def kind_tables(self) -> dict:
+        """kind -> list of elems in deck order (the table index used by the C ABI)."""
+        tabs = {k: [] for k in range(7)}
+        for e in self.elems:
+            tabs[e.kind].append(e)
+        return tabs
+
+    def load_order(self) -> list:
+        """[(kind, index)] in the reference's sCKT::load order."""
+        tabs = self.kind_tables()
+        index_of = {id(e): i for k in tabs for i, e in enumerate(tabs[k])}
+        type_order = []            # model types in order of first model creation
+        models_of = {}             # kind -> [model key newest-first]
+        insts_of = {}              # (kind, model) -> [elem newest-first]
+        for e in self.elems:
+            mkey = (e.kind, e.model if e.model is not None else "<default>")
+            if e.kind not in models_of:
+                models_of[e.kind] = []
+                type_order.append(e.kind)
+            if mkey not in insts_of:
+                insts_of[mkey] = []
+                models_of[e.kind].insert(0, mkey)
+            insts_of[mkey].insert(0, e)
+        out = []
+        if DEV_MUT in models_of:
+            for mkey in models_of[DEV_MUT]:
+                out += [(DEV_MUT, index_of[id(e)]) for e in insts_of[mkey]]
+        for k in type_order:
+            if k == DEV_MUT:
+                continue
+            for mkey in models_of[k]:
+                out += [(k, index_of[id(e)]) for e in insts_of[mkey]]
+        return out
+
+    def load_order_names(self) -> list:
+        tabs = self.kind_tables()
+        return [tabs[k][i].name for k, i in self.load_order()]
+
+    # ---- SPICE text for the compiled reference (tests only) -------------------------
+    def to_spice(self, overrides: dict | None = None) -> str:
+        """overrides: {(param_id, table_index): value} for one Monte-Carlo trial; varied MOS
+        devices get a private .model, as the reference's MC decks do."""
+        overrides = overrides or {}
+        tabs = self.kind_tables()
+        idx = {id(e): i for k in tabs for i, e in enumerate(tabs[k])}
+        lines = [self.title]
+        extra_models = []
+        for e in self.elems:
+            i = idx[id(e)]
+            if e.kind == DEV_SRC:
+                p = e.params
+                s = f"{e.name} {e.nodes[0]} {e.nodes[1]}"
+                dc = overrides.get((P_SRC_DC, i), p["dc"])
+                if dc is not None:
+                    s += f" dc {_fmt(dc)}"
+                if p["pulse"] is not None:
+                    s += " pulse(" + " ".join(_fmt(x) for x in p["pulse"]) + ")"
+                if p["pwl"] is not None:
+                    s += " pwl(" + " ".join(_fmt(x) for x in p["pwl"]) + ")"
+                if p["sin"] is not None:
+                    s += " sin(" + " ".join(_fmt(x) for x in p["sin"]) + ")"
+                lines.append(s)
+            elif e.kind == DEV_RES:
+                r = overrides.get((P_RES_R, i), e.params["r"])
+                lines.append(f"{e.name} {e.nodes[0]} {e.nodes[1]} {_fmt(r)}")
+            elif e.kind == DEV_CAP:
+                cval = overrides.get((P_CAP_C, i), e.params["c"])
+                s = f"{e.name} {e.nodes[0]} {e.nodes[1]} {_fmt(cval)}"
+                if e.params.get("ic") is not None:
+                    s += f" ic={_fmt(e.params['ic'])}"
+                lines.append(s)
+            elif e.kind == DEV_MOS:
+                mname = e.model
+                mod_over = {pid: overrides[(pid, i)] for pid in
+                            (P_MOS_VTO, P_MOS_KP, P_MOS_GAMMA, P_MOS_LAMBDA, P_MOS_PHI)
+                            if (pid, i) in overrides}
+                if mod_over:
+                    base = self.mos_models[e.model]
+                    prm = dict(base["params"])
+                    key = {P_MOS_VTO: "vto", P_MOS_KP: "kp", P_MOS_GAMMA: "gamma",
+                           P_MOS_LAMBDA: "lambda", P_MOS_PHI: "phi"}
+                    for pid, v in mod_over.items():
+                        prm[key[pid]] = v
+                    mname = f"{e.model}_{e.name}"
+                    extra_models.append((mname, base["type"], base["level"], prm))
+                prm = dict(e.params)
+                if (P_MOS_L, i) in overrides:
+                    prm["l"] = overrides[(P_MOS_L, i)]
+                if (P_MOS_W, i) in overrides:
+                    prm["w"] = overrides[(P_MOS_W, i)]
+                s = f"{e.name} {' '.join(e.nodes)} {mname}"
+                for k, v in prm.items():
+                    if k == "off":
+                        if v:
+                            s += " off"
+                    else:
+                        s += f" {k}={_fmt(v)}"
+                lines.append(s)
+            else:
+                raise NotImplementedError(e.kind)
+        for name, m in self.mos_models.items():
+            lines.append(self._model_line(name, m["type"], m["level"], m["params"]))
+        for name, t, lev, prm in extra_models:
+            lines.append(self._model_line(name, t, lev, prm))
+        if self.ics:
+            lines.append(".ic " + " ".join(f"v({k})={_fmt(v)}" for k, v in self.ics.items()))
+        if self.nodesets:
+            lines.append(".nodeset " + " ".join(f"v({k})={_fmt(v)}"
+                                                 for k, v in self.nodesets.items()))
+        optl = [f"{_OPT_SPICE[k]}={v!r}" for k, v in self.opts.items()
+                if v != DEFAULT_OPTIONS[k] and k in _OPT_SPICE]
+        if self.opts["method"] == 1:
+            optl.append("method=gear")
+        for flag in ("trapcheck", "spice3", "oldsteplim", "forcegmin", "jjaccel", "gminfirst"):
+            if self.opts[flag]:
+                optl.append(flag)
+        for k, v in self.opts.items():
+            if v != DEFAULT_OPTIONS[k] and k not in _OPT_SPICE and k not in (
+                    "method", "trapcheck", "spice3", "oldsteplim", "forcegmin", "jjaccel",
+                    "gminfirst"):
+                raise NotImplementedError(f"option {k} has no reference .options mapping")
+        if optl:
+            lines.append(".options " + " ".join(optl))
+        ts, tp, t0, tm, uic = self.tran_args
+        s = f".tran {_fmt(ts)} {_fmt(tp)}"
+        if t0 or tm:
+            s += f" {_fmt(t0)}"
+        if tm:
+            s += f" {_fmt(tm)}"
+        if uic:
+            s += " uic"
+        lines.append(s)
+        return "\n".join(lines) + "\n"
+
+    @staticmethod
+    def _model_line(name, mtype, level, prm):
+        t = "nmos" if mtype > 0 else "pmos"
+        return (f".model {name} {t} level={level} " +
+                " ".join(f"{k}={_fmt(v)}" for k, v in prm.items()))
+
+    # ---- C ABI --------------------------------------------------------------------
+    def to_c(self):
+        """Returns (CDeck, keepalive list)."""
+        keep = []
+        nums = self.node_numbers()
+        tabs = self.kind_tables()
+        d = CDeck()
+        d.nnodes = max(nums.values()) + 1
+        for k, v in self.opts.items():
+            setattr(d.opt, k, v)
+        ts, tp, t0, tm, uic = self.tran_args
+        d.tstep, d.tstop, d.tstart, d.tmax, d.uic = ts, tp, t0, tm, int(uic)
+
+        def arr(ctype, vals):
+            a = (ctype * max(1, len(vals)))(*vals)
+            keep.append(a)
+            return a
+
+        d.nic = len(self.ics)
+        d.ic_node = arr(C.c_int, [nums[k] for k in self.ics])
+        d.ic_val = arr(C.c_double, list(self.ics.values()))
+        d.nnodeset = len(self.nodesets)
+        d.ns_node = arr(C.c_int, [nums[k] for k in self.nodesets])
+        d.ns_val = arr(C.c_double, list(self.nodesets.values()))
+
+        res = (CRes * max(1, len(tabs[DEV_RES])))()
+        for i, e in enumerate(tabs[DEV_RES]):
+            res[i] = CRes(nums[e.nodes[0]], nums[e.nodes[1]], e.params["r"], NAN, NAN, NAN, NAN)
+        keep.append(res)
+        d.nres, d.res = len(tabs[DEV_RES]), res
+
+        cap = (CCap * max(1, len(tabs[DEV_CAP])))()
+        for i, e in enumerate(tabs[DEV_CAP]):
+            ic = e.params.get("ic")
+            cap[i] = CCap(nums[e.nodes[0]], nums[e.nodes[1]], e.params["c"], NAN,
+                          NAN if ic is None else ic)
+        keep.append(cap)
+        d.ncap, d.cap = len(tabs[DEV_CAP]), cap
+
+        src = (CSrc * max(1, len(tabs[DEV_SRC])))()
+        for i, e in enumerate(tabs[DEV_SRC]):
+            p = e.params
+            fn, coef = FN_NONE, []
+            if p["pulse"] is not None:
+                fn, coef = FN_PULSE, list(p["pulse"])
+            elif p["pwl"] is not None:
+                fn, coef = FN_PWL, list(p["pwl"])
+            elif p["sin"] is not None:
+                fn, coef = FN_SIN, list(p["sin"])
+            ca = arr(C.c_double, [float(x) for x in coef])
+            src[i] = CSrc(p["kind"], nums[e.nodes[0]], nums[e.nodes[1]],
+                          NAN if p["dc"] is None else float(p["dc"]), fn, len(coef), ca)
+        keep.append(src)
+        d.nsrc, d.src = len(tabs[DEV_SRC]), src
+
+        mnames = list(self.mos_models)
+        mm = (CMosModel * max(1, len(mnames)))()
+        alias = {"lambda": "lambda_", "is": "is_"}
+        for i, nme in enumerate(mnames):
+            m = self.mos_models[nme]
+            mm[i].type, mm[i].level = m["type"], m["level"]
+            for f in MOS_MODEL_DBL:
+                setattr(mm[i], f, NAN)
+            for k, v in m["params"].items():
+                setattr(mm[i], alias.get(k, k), float(v))
+        keep.append(mm)
+        d.nmosmod, d.mos_models = len(mnames), mm
+
+        mos = (CMos * max(1, len(tabs[DEV_MOS])))()
+        for i, e in enumerate(tabs[DEV_MOS]):
+            x = mos[i]
+            x.d, x.g, x.s, x.b = (nums[n] for n in e.nodes)
+            x.model = mnames.index(e.model)
+            for f in ("l", "w", "ad", "as_", "pd", "ps", "nrd", "nrs", "m", "temp", "icvds",
+                      "icvgs", "icvbs"):
+                setattr(x, f, NAN)
+            x.off = 0
+            for k, v in e.params.items():
+                if k == "off":
+                    x.off = int(bool(v))
+                else:
+                    setattr(x, {"as": "as_"}.get(k, k), float(v))
+        keep.append(mos)
+        d.nmos, d.mos = len(tabs[DEV_MOS]), mos
+
+        d.nind = d.nmut = d.njjmod = d.njj = 0
+        order = self.load_order()
+        d.norder = len(order)
+        d.order_kind = arr(C.c_int, [k for k, _ in order])
+        d.order_index = arr(C.c_int, [i for _, i in order])
+        return d, keep
+
+    def unknown_names(self, generic: list) -> list:
+        """Map the engine's generic unknown names ('n3', 'src0#branch', 'mos2#internal#drain')
+        to the reference's ('out', 'vdd#branch', 'm2#internal#drain')."""
+        nums = self.node_numbers()
+        inv = {v: k for k, v in nums.items() if not (k == "gnd")}
+        tabs = self.kind_tables()
+        out = []
+        for g in generic:
+            if g.startswith("n") and g[1:].isdigit():
+                out.append(inv[int(g[1:])])
+            elif g.startswith("src"):
+                i, rest = g[3:].split("#", 1)
+                out.append(f"{tabs[DEV_SRC][int(i)].name}#{rest}")
+            elif g.startswith("mos"):
+                i, rest = g[3:].split("#", 1)
+                out.append(f"{tabs[DEV_MOS][int(i)].name}#{rest}")
+            elif g.startswith("ind"):
+                i, rest = g[3:].split("#", 1)
+                out.append(f"{tabs[DEV_IND][int(i)].name}#{rest}")
+            else:
+                out.append(g)
+        return out
+
+
+def ring_oscillator(nstages: int, level: int = 1, vdd: float = 3.3, cload: float = 10e-15,
+                    tstep: float = 0.05e-9, tstop: float = 5e-9, uic: bool = False) -> Deck:
+    """N-stage CMOS ring oscillator (BASELINE.json configs[0]/[1] shape): 2 MOSFETs + 1 node
+    capacitor per stage, one Vdd source; alternating-rail .ic as in
+    examples/bsim465-benchmarks ro_17.b4.  Model cards are MOS level-1 cards in the style of
+    wrspice/examples/mos6inv.cir."""
+    assert nstages % 2 == 1
+    d = Deck(title=f"ro{nstages} cmos ring oscillator")
+    d.vsource("vdd", "vdd", "0", dc=vdd)
+    for i in range(nstages):
+        a, b = f"n{i}", f"n{(i + 1) % nstages}"
+        d.mosfet(f"mp{i}", b, a, "vdd", "vdd", "pm", w=2e-6, l=1e-6)
+        d.mosfet(f"mn{i}", b, a, "0", "0", "nm", w=1e-6, l=1e-6)
+        d.capacitor(f"c{i}", b, "0", cload)
+    common = dict(gamma=0.4, phi=0.65, cgso=2e-10, cgdo=2e-10, cbd=2e-15, cbs=2e-15,
+                  tox=2e-8, **{"lambda": 0.02})
+    d.mos_model("nm", "nmos", level=level, vto=0.7, kp=1e-4, **common)
+    d.mos_model("pm", "pmos", level=level, vto=-0.7, kp=4e-5, **common)
+    d.ic(**{f"n{i}": (vdd if i % 2 == 0 else 0.0) for i in range(nstages)})
+    d.tran(tstep, tstop, uic=uic)
+    return d
+
+
+def mc_variation(deck: Deck, ntrials: int, seed: int = 1, sigma_vto: float = 0.03,
+                 sigma_l: float = 0.02):
+    """Per-trial, per-MOSFET Vth0 and L variation (BASELINE.json configs[1]); trial 0 nominal.
+    Gaussian deviates follow the reference RNG algorithm (xt_base/miscutil/random.cc:51-72:
+    Box-Muller polar method on a 31-bit uniform), restated in numpy_rng.gauss_stream.
+    Returns {(param_id, mos_index): np.ndarray[ntrials]}."""
+    import numpy as np
+    from .refrand import RefRand
+    tabs = deck.kind_tables()
+    rnd = RefRand(seed)
+    out = {}
+    nm = len(tabs[DEV_MOS])
+    vto = np.empty((nm, ntrials))
+    ln = np.empty((nm, ntrials))
+    for i, e in enumerate(tabs[DEV_MOS]):
+        vto[i, :] = deck.mos_models[e.model]["params"]["vto"]
+        ln[i, :] = e.params["l"]
+    for t in range(1, ntrials):
+        for i in range(nm):
+            vto[i, t] *= 1.0 + sigma_vto * rnd.gauss()
+            ln[i, t] *= 1.0 + sigma_l * rnd.gauss()
+    for i in range(nm):
+        out[(P_MOS_VTO, i)] = vto[i]
+        out[(P_MOS_L, i)] = ln[i]
+    return out
