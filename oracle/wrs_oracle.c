@@ -95,7 +95,7 @@ typedef struct {
     double von, vdsat, cd, cbs, cbd, gm, gds, gmbs, gbd, gbs, capbd, capbs;
 } Mos;
 
-typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; int st; double capac, ic, geq, ceq; } Cap;
+typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; int st; int icGiven; double capac, ic, geq, ceq; } Cap;
 typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct; } Res;
 typedef struct {
     int kind, pos, neg, branch;
@@ -904,7 +904,8 @@ wo_ckt *wo_create(const b200_deck *dk)
             p->pos = in->pos; p->neg = in->neg;
             double mm = GIVEN(in->m) ? in->m : 1.0;
             p->capac = in->c*1.0*mm;          /* captemp.cc:98 nom*tcFactor*m */
-            p->ic = GIVEN(in->ic) ? in->ic : 0.0;
+            p->icGiven = GIVEN(in->ic);
+            p->ic = p->icGiven ? in->ic : 0.0;
             p->st = c->numStates; c->numStates += 2;
             p->pPP = coo_add(c, p->pos, p->pos);
             p->pNN = coo_add(c, p->neg, p->neg);
@@ -3061,8 +3062,9 @@ int wo_run_tran(wo_ckt *c)
             if (!GIVEN(m->in.icvgs)) m->icVGS = c->rhs[m->g] - c->rhs[m->s];
         }
         for (int i = 0; i < c->ncap; i++) {
-            /* capic.cc: if no ic given use node ICs */
-            (void)i;
+            /* capic.cc:52-71: if no ic given use node ICs */
+            Cap *p = &c->cap[i];
+            if (!p->icGiven) p->ic = c->rhs[p->pos] - c->rhs[p->neg];
         }
         double *tmp = c->rhs; c->rhs = c->rhsOld; c->rhsOld = tmp;
         c->rhs[0] = 0.0; c->rhsOld[0] = 0.0;

@@ -1,0 +1,75 @@
+"""Decks shared by the test modules (BASELINE.json config shapes at test size)."""
+from xictools_b200.deck import Deck, ring_oscillator
+
+COMMON = dict(gamma=0.4, phi=0.65, cgso=2e-10, cgdo=2e-10, cbd=2e-15, cbs=2e-15, tox=2e-8,
+              **{"lambda": 0.02})
+
+
+def inv_chain(n=4, load_res=True, **kw):
+    """Pulse-driven CMOS inverter chain (examples/mos6inv.cir shape): exercises PULSE
+    breakpoints, step rejection and the resistor preload."""
+    d = Deck(title="inverter chain")
+    d.vsource("vdd", "vdd", "0", dc=3.3)
+    d.vsource("vin", "in", "0", dc=0.0, pulse=(0, 3.3, 0.2e-9, 0.1e-9, 0.1e-9, 1e-9, 2.5e-9))
+    prev = "in"
+    for i in range(n):
+        out = f"o{i}"
+        d.mosfet(f"mp{i}", out, prev, "vdd", "vdd", "pm", w=2e-6, l=1e-6)
+        d.mosfet(f"mn{i}", out, prev, "0", "0", "nm", w=1e-6, l=1e-6)
+        d.capacitor(f"c{i}", out, "0", 20e-15)
+        prev = out
+    if load_res:
+        d.resistor("rl", prev, "0", 1e5)
+    d.mos_model("nm", "nmos", vto=0.7, kp=1e-4, **COMMON)
+    d.mos_model("pm", "pmos", vto=-0.7, kp=4e-5, **COMMON)
+    d.tran(0.05e-9, 6e-9, **kw)
+    return d
+
+
+def rc_sin():
+    """RC low-pass driven by SIN + PWL sources (source evaluators, SIN step bound)."""
+    d = Deck(title="rc sin")
+    d.vsource("v1", "a", "0", sin=(0.0, 1.0, 1e9, 0.1e-9, 0.0))
+    d.resistor("r1", "a", "b", 1e3)
+    d.capacitor("c1", "b", "0", 1e-12)
+    d.vsource("v2", "c", "0", pwl=(0.0, 0.0, 1e-9, 1.0, 2e-9, 0.5, 3e-9, 0.5))
+    d.resistor("r2", "c", "b", 2e3)
+    d.tran(0.05e-9, 4e-9)
+    return d
+
+
+def ro_rd(n=3):
+    """Ring oscillator whose MOSFETs have series rd/rs: internal drain/source nodes."""
+    d = ring_oscillator(n)
+    for m in d.mos_models.values():
+        m["params"]["rd"] = 50.0
+        m["params"]["rs"] = 30.0
+    return d
+
+
+def variants():
+    out = {
+        "ro3": ring_oscillator(3),
+        "ro5": ring_oscillator(5),
+        "ro17": ring_oscillator(17),
+        "inv4": inv_chain(4),
+        "inv7": inv_chain(7),
+        "ro7_long": ring_oscillator(7, tstep=0.2e-9, tstop=20e-9),
+        "ro9_one_ic": _one_ic(),
+        "ro5_ord1": ring_oscillator(5).options(maxord=1),
+        "ro5_trapcheck": ring_oscillator(5).options(trapcheck=1),
+        "ro5_gear3": ring_oscillator(5).options(method=1, maxord=3),
+        "ro5_nobypass": ring_oscillator(5).options(bypass=0),
+        "ro5_reltol": ring_oscillator(5).options(reltol=1e-4),
+        "ro5_interp2": ring_oscillator(5).options(interplev=2),
+        "ro3_rd": ro_rd(3),
+        "rc_sin": rc_sin(),
+    }
+    return out
+
+
+def _one_ic():
+    d = ring_oscillator(9)
+    d.ics.clear()
+    d.ic(n0=3.3)
+    return d

@@ -1,0 +1,50 @@
+"""Pins the C oracle restatement (oracle/wrs_oracle.c) against the UNMODIFIED reference
+compiled headless (oracle/_ref): identical accepted/rejected step counts and Newton
+iteration counts, waveforms at every user time point within roundoff."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import Oracle, RefSim, have_ref
+from tests.decks import variants
+from xictools_b200.deck import ring_oscillator, mc_variation
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+
+KEYS = ("err", "accepted", "rejected", "numiter", "timepts", "itercut", "trapcut")
+# order-1 integration with ~60 rejected steps is chaotic in step size: the counts still match
+# but roundoff (different LU) is amplified exponentially along the run
+LOOSE = {"ro5_ord1": 5e-2}
+
+
+@pytest.mark.parametrize("name", sorted(variants()))
+def test_counts_and_waves_match_reference(name):
+    d = variants()[name]
+    ref = RefSim().run(d.to_spice())
+    assert ref["load_order"] == d.load_order_names()
+    o = Oracle(d).run()
+    assert {k: o[k] for k in KEYS} == {k: ref[k] for k in KEYS}
+    assert len(o["times"]) == len(ref["times"])
+    np.testing.assert_allclose(o["times"], ref["times"], rtol=0, atol=1e-18)
+    idx = [o["names"].index(nm) for nm in ref["names"]]
+    dv = np.abs(o["vals"][:, idx] - ref["vals"]).max()
+    assert dv < LOOSE.get(name, 1e-9), dv
+
+
+def test_monte_carlo_trials_match_reference():
+    d = ring_oscillator(5)
+    ov = mc_variation(d, 4, seed=3)
+    for t in range(4):
+        trial = {k: v[t] for k, v in ov.items()}
+        ref = RefSim().run(d.to_spice(trial))
+        o = Oracle(d, ov, t).run()
+        assert {k: o[k] for k in KEYS} == {k: ref[k] for k in KEYS}
+        idx = [o["names"].index(nm) for nm in ref["names"]]
+        assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < 1e-9
+
+
+def test_uic_failure_mode_matches_reference():
+    # the reference aborts this UIC start with E_MATHOVF (errors.h:119); so must the oracle
+    d = ring_oscillator(5, uic=True)
+    ref = RefSim().run(d.to_spice())
+    o = Oracle(d).run()
+    assert (o["err"], o["accepted"], o["numiter"]) == (ref["err"], ref["accepted"], ref["numiter"])

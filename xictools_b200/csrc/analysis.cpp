@@ -1,0 +1,771 @@
+// analysis.cpp -- host-side, once-per-batch work: what sCKT::setup(), spSaveForInitialization()
+// and klu_analyze do once per trial in the reference (ckt.cc:2110-2227, spspice.cc:79-100,
+// kluif.cc:569-590), done ONCE for the whole batch because every trial shares the pattern.
+//
+//  * node / branch / state allocation in the reference's setup order
+//  * every device's TSTALLOC list -> CSC pattern (spbuild.cc:922-958) and, instead of
+//    pointers into Ax, ordered GATHER lists: for each matrix entry and RHS row the
+//    contribution slots in the reference's load order (ckt.cc:1146-1161), so that assembly
+//    is an atomics-free ordered sum that reproduces the reference's summation order
+//  * preloaded constants (Ainit): srcset.cc:158-170, restemp.cc:218-229
+//  * breakpoint table: breakpt.cc, inptran.cc setup functions
+//  * static pivot order (Markowitz on the structure, restricted to value-independent safe
+//    pivots) and the compiled, level-scheduled LU / triangular-solve programs.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+
+#include "b200_internal.h"
+
+namespace {
+
+inline bool given(double x) { return !std::isnan(x); }
+
+struct Coo {
+    std::map<std::pair<int,int>, int> idx;     // (row, col) 1-based -> coo id
+    std::vector<int> r, c;
+    int add(int row, int col) {
+        if (row == 0 || col == 0) return -1;
+        auto it = idx.find({row, col});
+        if (it != idx.end()) return it->second;
+        int id = (int)r.size();
+        idx[{row, col}] = id;
+        r.push_back(row); c.push_back(col);
+        return id;
+    }
+};
+
+// ---- breakpoint table construction: ckt/breakpt.cc:58-221 (host replica) ----
+struct BreakTab {
+    std::vector<double> brks, lat_offs, lat_per;
+    double breaks[2] = {0.0, 0.0};
+    double minbrk = 0.0;
+    double nextbreak(double t) const {
+        double dt0 = 0.0;
+        for (size_t i = 0; i < lat_offs.size(); i++) {
+            double dt1 = lat_offs[i];
+            if (t > lat_offs[i])
+                dt1 += lat_per[i]*ceil((t - lat_offs[i])/lat_per[i]);
+            if (fabs(dt1 - t) < minbrk)
+                dt1 += lat_per[i];
+            if (dt0 == 0.0 || dt1 < dt0)
+                dt0 = dt1;
+        }
+        size_t i;
+        for (i = 0; i < brks.size(); i++)
+            if (brks[i] > t)
+                break;
+        while (i < brks.size() && fabs(t - brks[i]) < minbrk)
+            i++;
+        if (i == brks.size())
+            return dt0;
+        if (dt0 > 0.0 && dt0 < brks[i])
+            return dt0;
+        return brks[i];
+    }
+    void set_break(double time, double ckt_time) {
+        for (size_t i = 0; i < lat_offs.size(); i++) {
+            double dt0, dt1;
+            if (time < lat_offs[i]) {
+                dt0 = lat_offs[i] + lat_per[i];
+                dt1 = lat_offs[i];
+            }
+            else {
+                dt0 = lat_per[i]*ceil((time - lat_offs[i])/lat_per[i]) + lat_offs[i];
+                dt1 = lat_per[i]*floor((time - lat_offs[i])/lat_per[i]) + lat_offs[i];
+            }
+            if (fabs(time - dt0) < minbrk || fabs(time - dt1) < minbrk) {
+                if (time < breaks[0]) breaks[0] = nextbreak(ckt_time);
+                breaks[1] = nextbreak(breaks[0]);
+                return;
+            }
+        }
+        if (brks.empty()) { brks.push_back(time); return; }
+        bool done = false;
+        for (size_t i = 0; i < brks.size() && !done; i++) {
+            if (brks[i] > time) {
+                if ((brks[i] - time) <= minbrk)
+                    brks[i] = time;
+                else if (i > 0 && time - brks[i-1] <= minbrk)
+                    ;
+                else
+                    brks.insert(brks.begin() + i, time);
+                done = true;
+            }
+        }
+        if (!done) {
+            if (time - brks.back() <= minbrk)
+                ;
+            else
+                brks.push_back(time);
+        }
+        if (time < breaks[0]) breaks[0] = nextbreak(ckt_time);
+        breaks[1] = nextbreak(breaks[0]);
+    }
+    void set_lattice(double offs, double per) {
+        for (size_t i = 0; i < lat_offs.size(); i++)
+            if (offs == lat_offs[i] && per == lat_per[i]) return;
+        lat_offs.push_back(offs); lat_per.push_back(per);
+    }
+};
+
+// PWL list normalisation: inptran.cc:1980-2074 (no TD=, no R=)
+void build_pwl(const double *coef, int num, std::vector<double> &pts, std::vector<double> &slopes)
+{
+    std::vector<double> list(coef, coef + num);
+    bool add0 = (list[0] > 0.0), add1 = (num & 1);
+    if (add0 || add1) {
+        std::vector<double> nl;
+        if (add0) { nl.push_back(0.0); nl.push_back(num > 1 ? list[1] : 0.0); }
+        nl.insert(nl.end(), list.begin(), list.end());
+        if (add1) nl.push_back(num > 1 ? nl[nl.size() - 2] : 0.0);
+        list.swap(nl);
+    }
+    int n = (int)list.size();
+    for (int i = 2; i < n; ) {
+        if (list[i] <= list[i-2]) {
+            for (int k = i; k + 2 < n; k += 2) { list[k] = list[k+2]; list[k+1] = list[k+3]; }
+            n -= 2;
+            continue;
+        }
+        i += 2;
+    }
+    list.resize(n);
+    pts = list;
+    int ns = n/2 - 1;
+    slopes.clear();
+    if (ns > 0)
+        for (int k = 0; k < ns; k++)
+            slopes.push_back((list[2*k+3] - list[2*k+1])/(list[2*k+2] - list[2*k]));
+    else
+        slopes.push_back(0.0);
+}
+
+} // namespace
+
+int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
+{
+    const b200_options &o = dk->opt;
+    if (dk->nind || dk->nmut || dk->njj) {
+        err = "inductor / mutual / JJ devices are not built yet (SURVEY.md section 8 rows a4-a6)";
+        return B200_E_UNSUPP;
+    }
+    an.n = 0;
+    an.ntype.assign(1, 0);
+    an.names.assign(1, "0");
+    auto new_node = [&](int type, const std::string &nm) {
+        an.n++;
+        an.ntype.push_back(type);
+        an.names.push_back(nm);
+        return an.n;
+    };
+    for (int i = 1; i < dk->nnodes; i++)
+        new_node(0, "n" + std::to_string(i));
+
+    MosTopo &M = an.mos; CapTopo &Cp = an.cap; SrcTopo &S = an.src;
+    M.n = dk->nmos; Cp.n = dk->ncap; S.n = dk->nsrc; an.nres = dk->nres;
+    M.d.resize(M.n); M.g.resize(M.n); M.s.resize(M.n); M.b.resize(M.n); M.dp.resize(M.n);
+    M.sp.resize(M.n); M.type.resize(M.n); M.level.resize(M.n); M.off.resize(M.n);
+    M.state.resize(M.n); M.cslot.assign((size_t)M.n*MT_NSTAMP, -1);
+    M.rslot.assign((size_t)M.n*MRH_NRHS, -1);
+    Cp.pos.resize(Cp.n); Cp.neg.resize(Cp.n); Cp.state.resize(Cp.n);
+    Cp.cslot.assign((size_t)Cp.n*4, -1); Cp.rslot.assign((size_t)Cp.n*2, -1);
+    S.kind.resize(S.n); S.pos.resize(S.n); S.neg.resize(S.n); S.branch.assign(S.n, 0);
+    S.fn.resize(S.n); S.dcgiven.resize(S.n); S.dc.resize(S.n);
+    S.rslot.assign((size_t)S.n*2, -1); S.coef_off.resize(S.n); S.ncoef.resize(S.n);
+
+    Coo coo;
+    struct Stamp { int coo; };
+    // per device, the coo ids of its stamps (resolved to Ax indices after CSC build)
+    std::vector<int> mos_coo((size_t)M.n*MT_NSTAMP, -1), cap_coo((size_t)Cp.n*4, -1);
+    std::vector<int> res_coo((size_t)dk->nres*4, -1), src_coo((size_t)S.n*4, -1);
+    std::vector<double> res_g(dk->nres, 0.0);
+    std::vector<char> mos_has_dcon(M.n, 0), mos_has_scon(M.n, 0);
+
+    an.numStates = 0;
+    // ---- setup pass in load order (ckt.cc:2202-2210) ----
+    for (int oi = 0; oi < dk->norder; oi++) {
+        int i = dk->order_index[oi];
+        switch (dk->order_kind[oi]) {
+        case B200_DEV_MOS: {
+            const b200_mos &in = dk->mos[i];
+            if (in.model < 0 || in.model >= dk->nmosmod) { err = "bad MOS model index"; return B200_E_BADPARM; }
+            const b200_mos_model &md = dk->mos_models[in.model];
+            int level = md.level;
+            if (level != 1 && level != 2 && level != 3 && level != 6) level = 1;
+            if (level != 1) { err = "only MOS level 1 is built (levels 2/3/6: SURVEY.md section 8 a2, next)"; return B200_E_UNSUPP; }
+            M.type[i] = md.type > 0 ? 1 : -1;
+            M.level[i] = level;
+            M.off[i] = in.off;
+            M.state[i] = an.numStates;
+            an.numStates += MS_NSTATES;
+            double rd = given(md.rd) ? md.rd : 0, rs = given(md.rs) ? md.rs : 0;
+            double rsh = given(md.rsh) ? md.rsh : 0;
+            double nrs = (!given(in.nrs) || in.nrs == 0) ? 1 : in.nrs;
+            M.d[i] = in.d; M.g[i] = in.g; M.s[i] = in.s; M.b[i] = in.b;
+            // mosset.cc:375-402
+            if (rd != 0 || rsh != 0)
+                M.dp[i] = new_node(0, "mos" + std::to_string(i) + "#internal#drain");
+            else
+                M.dp[i] = in.d;
+            if (rs != 0 || (nrs != 0 && rsh != 0))
+                M.sp[i] = new_node(0, "mos" + std::to_string(i) + "#internal#source");
+            else
+                M.sp[i] = in.s;
+            mos_has_dcon[i] = (given(md.rd) && md.rd != 0) || (!given(md.rd) && given(md.rsh) && md.rsh != 0);
+            mos_has_scon[i] = (given(md.rs) && md.rs != 0) || (!given(md.rs) && given(md.rsh) && md.rsh != 0);
+            int d = M.d[i], g = M.g[i], s = M.s[i], b = M.b[i], dp = M.dp[i], sp = M.sp[i];
+            int *c = &mos_coo[(size_t)i*MT_NSTAMP];
+            // mosset.cc:53-77 (allocation order), indexed by our stamp enum (load order)
+            c[MT_Dd] = coo.add(d, d);     c[MT_Gg] = coo.add(g, g);     c[MT_Ss] = coo.add(s, s);
+            c[MT_Bb] = coo.add(b, b);     c[MT_DPdp] = coo.add(dp, dp); c[MT_SPsp] = coo.add(sp, sp);
+            c[MT_Ddp] = coo.add(d, dp);   c[MT_Gb] = coo.add(g, b);     c[MT_Gdp] = coo.add(g, dp);
+            c[MT_Gsp] = coo.add(g, sp);   c[MT_Ssp] = coo.add(s, sp);   c[MT_Bg] = coo.add(b, g);
+            c[MT_Bdp] = coo.add(b, dp);   c[MT_Bsp] = coo.add(b, sp);   c[MT_DPsp] = coo.add(dp, sp);
+            c[MT_DPd] = coo.add(dp, d);   c[MT_DPg] = coo.add(dp, g);   c[MT_DPb] = coo.add(dp, b);
+            c[MT_SPg] = coo.add(sp, g);   c[MT_SPs] = coo.add(sp, s);   c[MT_SPb] = coo.add(sp, b);
+            c[MT_SPdp] = coo.add(sp, dp);
+            break; }
+        case B200_DEV_CAP: {
+            const b200_cap &in = dk->cap[i];
+            Cp.pos[i] = in.pos; Cp.neg[i] = in.neg;
+            Cp.state[i] = an.numStates; an.numStates += 2;
+            int *c = &cap_coo[(size_t)i*4];
+            c[0] = coo.add(in.pos, in.pos); c[1] = coo.add(in.neg, in.neg);
+            c[2] = coo.add(in.pos, in.neg); c[3] = coo.add(in.neg, in.pos);
+            break; }
+        case B200_DEV_RES: {
+            const b200_res &in = dk->res[i];
+            int *c = &res_coo[(size_t)i*4];
+            c[0] = coo.add(in.pos, in.pos); c[1] = coo.add(in.neg, in.neg);
+            c[2] = coo.add(in.pos, in.neg); c[3] = coo.add(in.neg, in.pos);
+            double r = in.r, mm = given(in.m) ? in.m : 1.0;
+            if (fabs(r) < o.resmin)
+                r = (r < 0.0) ? -o.resmin : o.resmin;
+            res_g[i] = mm/(r*1.0);                       // restemp.cc:209
+            break; }
+        case B200_DEV_SRC: {
+            const b200_src &in = dk->src[i];
+            S.kind[i] = in.kind; S.pos[i] = in.pos; S.neg[i] = in.neg;
+            S.fn[i] = in.fn; S.dcgiven[i] = given(in.dc); S.dc[i] = given(in.dc) ? in.dc : 0.0;
+            if (in.kind == B200_SRC_V) {
+                S.branch[i] = new_node(1, "src" + std::to_string(i) + "#branch");
+                int *c = &src_coo[(size_t)i*4];
+                c[0] = coo.add(in.pos, S.branch[i]); c[1] = coo.add(in.neg, S.branch[i]);
+                c[2] = coo.add(S.branch[i], in.neg); c[3] = coo.add(S.branch[i], in.pos);
+            }
+            if (in.kind == B200_SRC_I && in.fn != B200_FN_NONE)
+                an.numStates += 1;
+            break; }
+        default:
+            err = "unsupported device kind in load order";
+            return B200_E_UNSUPP;
+        }
+    }
+
+    // ---- CSC pattern: columns ascending, rows ascending (spbuild.cc:922-958) ----
+    int n = an.n;
+    an.nnz = (int)coo.r.size();
+    an.Ap.assign(n + 1, 0);
+    for (int e = 0; e < an.nnz; e++) an.Ap[coo.c[e]]++;          // count per col (1-based)
+    for (int j = 1; j <= n; j++) an.Ap[j] += an.Ap[j-1];
+    {
+        std::vector<std::vector<int>> colrows(n);
+        for (int e = 0; e < an.nnz; e++) colrows[coo.c[e] - 1].push_back(coo.r[e] - 1);
+        an.Ai.clear();
+        for (int j = 0; j < n; j++) {
+            std::sort(colrows[j].begin(), colrows[j].end());
+            an.Ai.insert(an.Ai.end(), colrows[j].begin(), colrows[j].end());
+        }
+    }
+    std::vector<int> coo2ax(an.nnz);
+    for (int e = 0; e < an.nnz; e++) {
+        int j = coo.c[e] - 1, r = coo.r[e] - 1;
+        auto b = an.Ai.begin() + an.Ap[j], en = an.Ai.begin() + an.Ap[j+1];
+        coo2ax[e] = (int)(std::lower_bound(b, en, r) - an.Ai.begin());
+    }
+    an.diag.assign(n + 1, -1);
+    for (int j = 0; j < n; j++)
+        for (int p = an.Ap[j]; p < an.Ap[j+1]; p++)
+            if (an.Ai[p] == j) an.diag[j+1] = p;
+
+    // ---- contribution slots + ordered gather lists, preload ----
+    std::vector<std::vector<int>> cg(an.nnz), rg(n + 1);
+    an.ncslot = an.nrslot = 0;
+    an.Ainit.assign(an.nnz, 0.0);
+    auto add_c = [&](int cooid) -> int {
+        if (cooid < 0) return -1;
+        int k = coo2ax[cooid];
+        cg[k].push_back(an.ncslot);
+        return an.ncslot++;
+    };
+    auto add_r = [&](int node) -> int {
+        if (node == 0) return -1;
+        rg[node].push_back(an.nrslot);
+        return an.nrslot++;
+    };
+    // sources' +-1 are ldset in setup (srcset.cc:158-170) ...
+    for (int oi = 0; oi < dk->norder; oi++) {
+        int i = dk->order_index[oi];
+        if (dk->order_kind[oi] == B200_DEV_SRC && S.kind[i] == B200_SRC_V) {
+            const int *c = &src_coo[(size_t)i*4];
+            if (S.pos[i]) { if (c[0] >= 0) an.Ainit[coo2ax[c[0]]] = 1.0; if (c[3] >= 0) an.Ainit[coo2ax[c[3]]] = 1.0; }
+            if (S.neg[i]) { if (c[1] >= 0) an.Ainit[coo2ax[c[1]]] = -1.0; if (c[2] >= 0) an.Ainit[coo2ax[c[2]]] = -1.0; }
+        }
+    }
+    // ... resistor conductances are ldadd in temp() (restemp.cc:218-229), load order
+    for (int oi = 0; oi < dk->norder; oi++) {
+        int i = dk->order_index[oi];
+        if (dk->order_kind[oi] == B200_DEV_RES && res_g[i] != 0.0) {
+            const int *c = &res_coo[(size_t)i*4];
+            if (c[0] >= 0) an.Ainit[coo2ax[c[0]]] += res_g[i];
+            if (c[1] >= 0) an.Ainit[coo2ax[c[1]]] += res_g[i];
+            if (c[2] >= 0) an.Ainit[coo2ax[c[2]]] += -res_g[i];
+            if (c[3] >= 0) an.Ainit[coo2ax[c[3]]] += -res_g[i];
+        }
+    }
+    for (int oi = 0; oi < dk->norder; oi++) {
+        int i = dk->order_index[oi];
+        switch (dk->order_kind[oi]) {
+        case B200_DEV_MOS: {
+            const int *c = &mos_coo[(size_t)i*MT_NSTAMP];
+            int *cs = &M.cslot[(size_t)i*MT_NSTAMP];
+            for (int k = 0; k < MT_NSTAMP; k++) {
+                // stamps that only ever carry +-dcon / +-scon contribute exact zeros when the
+                // device has no series resistance (x + 0 == x): drop them.
+                bool dconly = (k == MT_Dd || k == MT_Ddp || k == MT_DPd);
+                bool sconly = (k == MT_Ss || k == MT_Ssp || k == MT_SPs);
+                if ((dconly && !mos_has_dcon[i]) || (sconly && !mos_has_scon[i])) continue;
+                cs[k] = add_c(c[k]);
+            }
+            int *rs = &M.rslot[(size_t)i*MRH_NRHS];
+            rs[MRH_g] = add_r(M.g[i]);   rs[MRH_b] = add_r(M.b[i]);
+            rs[MRH_dp] = add_r(M.dp[i]); rs[MRH_sp] = add_r(M.sp[i]);
+            break; }
+        case B200_DEV_CAP: {
+            const int *c = &cap_coo[(size_t)i*4];
+            int *cs = &Cp.cslot[(size_t)i*4];
+            int *rs = &Cp.rslot[(size_t)i*2];
+            // capload.cc:75-97
+            if (Cp.pos[i] == 0) { cs[1] = add_c(c[1]); rs[1] = add_r(Cp.neg[i]); }
+            else if (Cp.neg[i] == 0) { cs[0] = add_c(c[0]); rs[0] = add_r(Cp.pos[i]); }
+            else {
+                cs[0] = add_c(c[0]); cs[1] = add_c(c[1]); cs[2] = add_c(c[2]); cs[3] = add_c(c[3]);
+                rs[0] = add_r(Cp.pos[i]); rs[1] = add_r(Cp.neg[i]);
+            }
+            break; }
+        case B200_DEV_SRC: {
+            int *rs = &S.rslot[(size_t)i*2];
+            if (S.kind[i] == B200_SRC_V) rs[0] = add_r(S.branch[i]);
+            else { rs[0] = add_r(S.pos[i]); rs[1] = add_r(S.neg[i]); }
+            break; }
+        default: break;
+        }
+    }
+    an.cg_ptr.assign(an.nnz + 1, 0);
+    for (int k = 0; k < an.nnz; k++) {
+        an.cg_ptr[k+1] = an.cg_ptr[k] + (int)cg[k].size();
+        an.cg_idx.insert(an.cg_idx.end(), cg[k].begin(), cg[k].end());
+    }
+    an.rg_ptr.assign(n + 2, 0);
+    for (int r = 1; r <= n; r++) {
+        an.rg_ptr[r+1] = an.rg_ptr[r] + (int)rg[r].size();
+        an.rg_idx.insert(an.rg_idx.end(), rg[r].begin(), rg[r].end());
+    }
+
+    // ---- .ic / .nodeset ----
+    an.ic_given.assign(n + 1, 0); an.ns_given.assign(n + 1, 0);
+    an.ic_val.assign(n + 1, 0.0); an.ns_val.assign(n + 1, 0.0);
+    for (int i = 0; i < dk->nic; i++) { an.ic_given[dk->ic_node[i]] = 1; an.ic_val[dk->ic_node[i]] = dk->ic_val[i]; }
+    for (int i = 0; i < dk->nnodeset; i++) { an.ns_given[dk->ns_node[i]] = 1; an.ns_val[dk->ns_node[i]] = dk->ns_val[i]; an.hadNodeset = 1; }
+
+    // ---- sTRANAN::init, tranan.cc:94-217 ----
+    an.t_stop = dk->tstop; an.t_step = dk->tstep; an.t_start = dk->tstart;
+    if (!(an.t_step > 0) || an.t_start < 0 || an.t_stop <= an.t_start) {
+        err = "bad .tran parameters"; return B200_E_BADPARM;
+    }
+    an.maxStep = dk->tmax;
+    an.nocut = !(M.n > 0 || Cp.n > 0);            // tranan.cc:68-77 DV_TRUNC devices
+    if (an.maxStep == 0) {
+        an.maxStep = (an.t_stop - an.t_start)/50;
+        if (o.oldsteplim) { if (an.t_step > an.maxStep) an.maxStep = an.t_step; }
+        else { if (an.t_step < an.maxStep) an.maxStep = 1.001*an.t_step; }
+    }
+    double delmin = o.delmin;
+    if (!(delmin > 0)) {
+        if (o.oldsteplim) {
+            delmin = an.maxStep*1e-9;
+            double T1 = an.t_stop*1e-12;
+            if (delmin < T1) delmin = T1;
+        }
+        else
+            delmin = an.maxStep*1e-6;
+    }
+    an.delmin = delmin;
+    an.minBreak = (o.minbreak > 0) ? o.minbreak : delmin*50.0;
+    an.npoints_max = (int)floor((an.t_stop - an.t_start)/an.t_step + 0.5) + 3;
+
+    // ---- breakpoints + source run-time parameters (tranan.cc:330-340, inptran.cc) ----
+    BreakTab bt;
+    bt.minbrk = an.minBreak;
+    bt.set_break(0.0, 0.0);
+    bt.set_break(an.t_start, 0.0);
+    bt.set_break(an.t_stop, 0.0);
+    S.pool.clear();
+    double step = an.t_step, finaltime = an.t_stop;
+    for (int oi = 0; oi < dk->norder; oi++) {
+        if (dk->order_kind[oi] != B200_DEV_SRC) continue;
+        int i = dk->order_index[oi];
+        const b200_src &in = dk->src[i];
+        S.coef_off[i] = (int)S.pool.size();
+        S.ncoef[i] = in.ncoef;
+        if (in.fn == B200_FN_PULSE) {
+            // inptran.cc:1203-1318.  pool: parms[8], cache[2], then the extra offsets
+            if (in.ncoef < 1) { err = "pulse needs arguments"; return B200_E_BADPARM; }
+            double p[8] = {0,0,0,0,0,0,0,0}, cache[2];
+            const double *co = in.coef; int nc = in.ncoef;
+            p[0] = co[0];
+            p[1] = nc >= 2 ? co[1] : co[0];
+            p[2] = nc >= 3 ? co[2] : 0.0;
+            p[3] = nc >= 4 ? co[3] : 0.0;
+            p[4] = nc >= 5 ? co[4] : 0.0;
+            p[5] = nc >= 6 ? co[5] : 0.0;
+            p[6] = nc >= 7 ? co[6] : 0.0;
+            if (p[3] <= 0.0) p[3] = step;
+            if (p[4] > 0.0 && p[5] <= 0.0)
+                p[5] = 0.0;
+            else {
+                if (p[4] <= 0.0) p[4] = step;
+                if (p[5] <= 0.0) p[5] = FLT_MAX;
+            }
+            if (p[6] <= 0.0) p[6] = FLT_MAX;
+            else if (p[6] < p[3] + p[5] + p[4]) p[6] = p[3] + p[5] + p[4];
+            cache[0] = (p[1] - p[0])/p[3];
+            cache[1] = (p[0] - p[1])/p[4];
+            int nrep = nc > 7 ? nc - 7 : 0;
+            for (int r = -1; r < nrep; r++) {
+                double time = (r < 0) ? p[2] : co[7 + r];
+                if (p[6] < finaltime) {
+                    bt.set_lattice(time, p[6]);
+                    time += p[3]; bt.set_lattice(time, p[6]);
+                    if (p[5] != 0) { time += p[5]; bt.set_lattice(time, p[6]); }
+                    if (p[4] != 0) { time += p[4]; bt.set_lattice(time, p[6]); }
+                }
+                else {
+                    bt.set_break(time, 0.0);
+                    time += p[3]; bt.set_break(time, 0.0);
+                    if (p[5] != 0) { time += p[5]; bt.set_break(time, 0.0); }
+                    if (p[4] != 0) { time += p[4]; bt.set_break(time, 0.0); }
+                }
+            }
+            S.pool.insert(S.pool.end(), p, p + 8);
+            S.pool.insert(S.pool.end(), cache, cache + 2);
+            for (int r = 0; r < nrep; r++) S.pool.push_back(co[7 + r]);
+            S.ncoef[i] = nrep;                       // number of extra offsets
+        }
+        else if (in.fn == B200_FN_PWL) {
+            std::vector<double> pts, slopes;
+            if (in.ncoef < 1) { err = "pwl needs arguments"; return B200_E_BADPARM; }
+            build_pwl(in.coef, in.ncoef, pts, slopes);
+            int nv = (int)pts.size()/2;
+            for (int k = 0; k < nv; k++) {
+                double t = pts[2*k];
+                if (t > finaltime) break;
+                bt.set_break(t, 0.0);
+            }
+            S.pool.insert(S.pool.end(), pts.begin(), pts.end());
+            S.pool.insert(S.pool.end(), slopes.begin(), slopes.end());
+            S.ncoef[i] = nv;                         // number of (t,v) pairs
+        }
+        else if (in.fn == B200_FN_SIN) {
+            double p[8] = {0,0,0,0,0,0,0,0};
+            const double *co = in.coef; int nc = in.ncoef;
+            if (nc < 1) { err = "sin needs arguments"; return B200_E_BADPARM; }
+            p[0] = co[0];
+            p[1] = nc >= 2 ? co[1] : 0.0;
+            p[2] = nc >= 3 ? co[2] : 0.0;
+            p[3] = nc >= 4 ? co[3] : 0.0;
+            p[4] = nc >= 5 ? co[4] : 0.0;
+            p[5] = nc >= 6 ? co[5] : 0.0;
+            if (!p[2]) p[2] = 1.0/finaltime;
+            if (p[3] > 0.0) bt.set_break(p[3], 0.0);
+            S.pool.insert(S.pool.end(), p, p + 8);
+        }
+    }
+    an.brks = bt.brks; an.lat_offs = bt.lat_offs; an.lat_per = bt.lat_per;
+    an.break0 = bt.breaks[0]; an.break1 = bt.breaks[1];
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Static pivot order.  The reference's KLU path fixes the pivot sequence at klu_factor and
+// reuses it in every klu_refactor (kluif.cc:569-606); the batch needs ONE sequence valid for
+// all trials and all times, so it may only use pivots whose acceptability does not depend
+// on values:  (a) entries that are compile-time constants +-1 (voltage-source branch
+// couplings, srcset.cc:158-170) as long as no elimination has touched them, and
+// (b) diagonal entries of voltage nodes that receive conductance stamps.
+// Among those, Markowitz's (r-1)(c-1) rule (the criterion of the Sparse 1.3 solver the
+// shipped reference runs, xt_base/sparse/spfactor.cc:1218-1560) picks the next pivot; ties go
+// to the candidate touched least recently, which yields wide, shallow elimination levels
+// (independent pivots first) for the level-scheduled GPU program.
+// ---------------------------------------------------------------------------------------
+void b200_order_markowitz(Analysis &an)
+{
+    int n = an.n;
+    std::vector<std::set<int>> rows(n), cols(n);
+    // constant: 1 if the entry is a never-updated +-1 constant; 0 otherwise
+    std::map<std::pair<int,int>, char> constant;
+    for (int j = 0; j < n; j++)
+        for (int p = an.Ap[j]; p < an.Ap[j+1]; p++) {
+            int i = an.Ai[p];
+            rows[i].insert(j); cols[j].insert(i);
+            bool is_const = (an.cg_ptr[p+1] == an.cg_ptr[p]) &&
+                (an.Ainit[p] == 1.0 || an.Ainit[p] == -1.0);
+            constant[{i, j}] = is_const ? 1 : 0;
+        }
+    std::vector<char> ract(n, 1), cact(n, 1);
+    std::vector<char> diag_ok(n, 0);
+    for (int i = 0; i < n; i++) {
+        int p = an.diag[i+1];
+        if (p >= 0 && an.ntype[i+1] == 0 &&
+                (an.cg_ptr[p+1] > an.cg_ptr[p] || an.Ainit[p] != 0.0))
+            diag_ok[i] = 1;
+    }
+    std::vector<long> rstamp(n, 0), cstamp(n, 0);
+    an.rowperm.assign(n, -1); an.colperm.assign(n, -1);
+    for (int k = 0; k < n; k++) {
+        long best = -1, bstamp = 0; int bi = -1, bj = -1; int bclass = 0;
+        for (int pass = 0; pass < 3 && bi < 0; pass++) {
+            // pass 0: safe candidates; pass 1: any remaining diagonal; pass 2: any entry
+            for (int i = 0; i < n; i++) {
+                if (!ract[i]) continue;
+                for (int j : rows[i]) {
+                    if (!cact[j]) continue;
+                    int cls;
+                    auto it = constant.find({i, j});
+                    bool is_const = (it != constant.end() && it->second);
+                    if (pass == 0) {
+                        if (is_const) cls = 2;
+                        else if (i == j && diag_ok[i]) cls = 1;
+                        else continue;
+                    }
+                    else if (pass == 1) { if (i != j) continue; cls = 1; }
+                    else cls = 0;
+                    long mk = (long)(rows[i].size() - 1)*(long)(cols[j].size() - 1);
+                    long st = std::max(rstamp[i], cstamp[j]);
+                    bool better = false;
+                    if (best < 0 || mk < best) better = true;
+                    else if (mk == best) {
+                        if (st < bstamp) better = true;
+                        else if (st == bstamp && cls > bclass) better = true;
+                    }
+                    if (better) { best = mk; bi = i; bj = j; bstamp = st; bclass = cls; }
+                }
+            }
+        }
+        if (bi < 0) {
+            // structurally singular: finish with whatever is left (refactor will flag it)
+            for (int i = 0; i < n && bi < 0; i++) if (ract[i]) bi = i;
+            for (int j = 0; j < n && bj < 0; j++) if (cact[j]) bj = j;
+        }
+        an.rowperm[k] = bi; an.colperm[k] = bj;
+        ract[bi] = 0; cact[bj] = 0;
+        // eliminate: every active row r with an entry in column bj gets row bi's pattern
+        std::vector<int> prow;
+        for (int j : rows[bi]) if (cact[j]) prow.push_back(j);
+        std::vector<int> pcol;
+        for (int r : cols[bj]) if (ract[r]) pcol.push_back(r);
+        for (int r : pcol) {
+            for (int j : prow) {
+                rows[r].insert(j); cols[j].insert(r);
+                constant[{r, j}] = 0;               // touched by an update: no longer constant
+                cstamp[j] = k + 1;
+            }
+            rstamp[r] = k + 1;
+        }
+        // remove pivot row/col from active structure
+        for (int j : rows[bi]) cols[j].erase(bi);
+        for (int r : cols[bj]) rows[r].erase(bj);
+        rows[bi].clear(); cols[bj].clear();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Symbolic LU for the fixed order + compiled programs (see b200_internal.h).
+// ---------------------------------------------------------------------------------------
+namespace {
+
+template <class Prog>
+void pack_rounds(const std::vector<std::vector<LuOp>> &task_ops, const std::vector<int> &level,
+    int nlevels, Prog &pg, std::vector<std::vector<int>> &round_tasks)
+{
+    // tasks of each level, longest first, dealt in rounds of 32 lanes
+    std::vector<std::vector<int>> by_level(nlevels);
+    for (int t = 0; t < (int)task_ops.size(); t++) by_level[level[t]].push_back(t);
+    pg.ops.clear(); pg.rounds.clear(); pg.level_round_off.assign(1, 0);
+    round_tasks.clear();
+    for (int l = 0; l < nlevels; l++) {
+        auto &v = by_level[l];
+        std::stable_sort(v.begin(), v.end(), [&](int a, int b) {
+            return task_ops[a].size() > task_ops[b].size(); });
+        for (size_t off = 0; off < v.size(); off += 32) {
+            size_t cnt = std::min<size_t>(32, v.size() - off);
+            int nsteps = 0;
+            for (size_t q = 0; q < cnt; q++)
+                nsteps = std::max(nsteps, (int)task_ops[v[off + q]].size());
+            LuRound r;
+            r.op_off = (int)pg.ops.size();
+            r.nsteps = nsteps;
+            r.fin_off = (int)round_tasks.size()*32;
+            pg.ops.resize(pg.ops.size() + (size_t)nsteps*32, LuOp{-1, 0, 0});
+            std::vector<int> rt(32, -1);
+            for (size_t q = 0; q < cnt; q++) {
+                int t = v[off + q];
+                rt[q] = t;
+                for (size_t s = 0; s < task_ops[t].size(); s++)
+                    pg.ops[r.op_off + s*32 + q] = task_ops[t][s];
+            }
+            pg.rounds.push_back(r);
+            round_tasks.push_back(rt);
+        }
+        pg.level_round_off.push_back((int)pg.rounds.size());
+    }
+}
+
+} // namespace
+
+void b200_build_lu(Analysis &an)
+{
+    int n = an.n;
+    std::vector<int> rinv(n), cinv(n);
+    for (int k = 0; k < n; k++) { rinv[an.rowperm[k]] = k; cinv[an.colperm[k]] = k; }
+    // symbolic: column patterns in permuted positions
+    an.Lp.assign(n + 1, 0); an.Up.assign(n + 1, 0); an.Li.clear(); an.Ui.clear();
+    std::vector<char> mark(n);
+    for (int j = 0; j < n; j++) {
+        int cj = an.colperm[j];
+        std::fill(mark.begin(), mark.end(), 0);
+        for (int p = an.Ap[cj]; p < an.Ap[cj+1]; p++) mark[rinv[an.Ai[p]]] = 1;
+        for (int k = 0; k < j; k++) {
+            if (!mark[k]) continue;
+            for (int p = an.Lp[k]; p < an.Lp[k+1]; p++) mark[an.Li[p]] = 1;
+        }
+        for (int k = 0; k < j; k++) if (mark[k]) an.Ui.push_back(k);
+        an.Up[j+1] = (int)an.Ui.size();
+        for (int k = j + 1; k < n; k++) if (mark[k]) an.Li.push_back(k);
+        an.Lp[j+1] = (int)an.Li.size();
+    }
+    // value slots: per column [U entries..., diag, L entries...]
+    an.slotU.resize(an.Ui.size()); an.slotL.resize(an.Li.size()); an.slotD.resize(n);
+    int slot = 0;
+    for (int j = 0; j < n; j++) {
+        for (int p = an.Up[j]; p < an.Up[j+1]; p++) an.slotU[p] = slot++;
+        an.slotD[j] = slot++;
+        for (int p = an.Lp[j]; p < an.Lp[j+1]; p++) an.slotL[p] = slot++;
+    }
+    an.nnzLU = slot;
+    an.lu_src.assign(slot, -1);
+    an.a2lu.assign(an.nnz, -1);
+    {
+        std::vector<int> pos2slot(n, -1);
+        for (int j = 0; j < n; j++) {
+            for (int p = an.Up[j]; p < an.Up[j+1]; p++) pos2slot[an.Ui[p]] = an.slotU[p];
+            pos2slot[j] = an.slotD[j];
+            for (int p = an.Lp[j]; p < an.Lp[j+1]; p++) pos2slot[an.Li[p]] = an.slotL[p];
+            int cj = an.colperm[j];
+            for (int p = an.Ap[cj]; p < an.Ap[cj+1]; p++) {
+                int s = pos2slot[rinv[an.Ai[p]]];
+                an.a2lu[p] = s;
+                an.lu_src[s] = p;
+            }
+        }
+    }
+
+    // ---- factor program: task = column j ----
+    std::vector<std::vector<LuOp>> fops(n);
+    std::vector<int> flevel(n, 0);
+    {
+        std::vector<int> pos2slot(n, -1);
+        for (int j = 0; j < n; j++) {
+            for (int p = an.Up[j]; p < an.Up[j+1]; p++) pos2slot[an.Ui[p]] = an.slotU[p];
+            pos2slot[j] = an.slotD[j];
+            for (int p = an.Lp[j]; p < an.Lp[j+1]; p++) pos2slot[an.Li[p]] = an.slotL[p];
+            int lev = 0;
+            for (int p = an.Up[j]; p < an.Up[j+1]; p++) {
+                int k = an.Ui[p];
+                lev = std::max(lev, flevel[k] + 1);
+                for (int q = an.Lp[k]; q < an.Lp[k+1]; q++)
+                    fops[j].push_back(LuOp{pos2slot[an.Li[q]], an.slotL[q], an.slotU[p]});
+            }
+            flevel[j] = lev;
+        }
+    }
+    int nfl = 0;
+    for (int j = 0; j < n; j++) nfl = std::max(nfl, flevel[j] + 1);
+    std::vector<std::vector<int>> rt;
+    pack_rounds(fops, flevel, nfl, an.fac, rt);
+    an.fac.fin_diag.assign(rt.size()*32, -1);
+    an.fac.fin_lbeg.assign(rt.size()*32, 0);
+    an.fac.fin_lend.assign(rt.size()*32, 0);
+    for (size_t r = 0; r < rt.size(); r++)
+        for (int q = 0; q < 32; q++) {
+            int j = rt[r][q];
+            if (j < 0) continue;
+            an.fac.fin_diag[r*32 + q] = an.slotD[j];
+            // L slots of column j are contiguous right after the diagonal
+            an.fac.fin_lbeg[r*32 + q] = an.slotD[j] + 1;
+            an.fac.fin_lend[r*32 + q] = an.slotD[j] + 1 + (an.Lp[j+1] - an.Lp[j]);
+        }
+
+    // ---- forward solve: task = row i of L (ascending column order) ----
+    std::vector<std::vector<LuOp>> lops(n);
+    std::vector<int> llevel(n, 0);
+    for (int k = 0; k < n; k++)
+        for (int q = an.Lp[k]; q < an.Lp[k+1]; q++) {
+            int i = an.Li[q];
+            lops[i].push_back(LuOp{0, an.slotL[q], k});
+        }
+    for (int i = 0; i < n; i++) {
+        int lev = 0;
+        for (auto &op : lops[i]) lev = std::max(lev, llevel[op.b] + 1);
+        llevel[i] = lev;
+    }
+    int nll = 0;
+    for (int i = 0; i < n; i++) nll = std::max(nll, llevel[i] + 1);
+    pack_rounds(lops, llevel, nll, an.fwd, rt);
+    an.fwd.fin_row.assign(rt.size()*32, -1); an.fwd.fin_diag.assign(rt.size()*32, -1);
+    for (size_t r = 0; r < rt.size(); r++)
+        for (int q = 0; q < 32; q++)
+            if (rt[r][q] >= 0) an.fwd.fin_row[r*32 + q] = rt[r][q];
+
+    // ---- backward solve: task = row i of U (descending column order), then / diag ----
+    std::vector<std::vector<LuOp>> uops(n);
+    std::vector<int> ulevel(n, 0);
+    for (int j = n - 1; j >= 0; j--)
+        for (int p = an.Up[j+1] - 1; p >= an.Up[j]; p--) {
+            int i = an.Ui[p];
+            uops[i].push_back(LuOp{0, an.slotU[p], j});
+        }
+    for (int i = n - 1; i >= 0; i--) {
+        int lev = 0;
+        for (auto &op : uops[i]) lev = std::max(lev, ulevel[op.b] + 1);
+        ulevel[i] = lev;
+    }
+    int nul = 0;
+    for (int i = 0; i < n; i++) nul = std::max(nul, ulevel[i] + 1);
+    pack_rounds(uops, ulevel, nul, an.bwd, rt);
+    an.bwd.fin_row.assign(rt.size()*32, -1); an.bwd.fin_diag.assign(rt.size()*32, -1);
+    for (size_t r = 0; r < rt.size(); r++)
+        for (int q = 0; q < 32; q++)
+            if (rt[r][q] >= 0) {
+                an.bwd.fin_row[r*32 + q] = rt[r][q];
+                an.bwd.fin_diag[r*32 + q] = an.slotD[rt[r][q]];
+            }
+
+    an.yperm_in.resize(n); an.yperm_out.resize(n);
+    for (int k = 0; k < n; k++) { an.yperm_in[k] = an.rowperm[k] + 1; an.yperm_out[k] = an.colperm[k] + 1; }
+}

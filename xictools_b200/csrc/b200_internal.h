@@ -1,0 +1,159 @@
+// b200_internal.h -- shared declarations of the B200 batched Newton engine.
+//
+// Layout rule: everything that varies per trial lives in HBM as
+// [slot][trial] with trial fastest (ldt = ntrials rounded up to 32), FP64.  Topology
+// (node indices, gather lists, LU programs) is shared by all trials and read through L1/L2.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "b200spice.h"
+
+// ---- mode bits: identical to wrspice/include/circuit.h:2158-2192 ----
+#define MODETRAN        0x1
+#define MODEDC          0x70
+#define MODEDCOP        0x10
+#define MODETRANOP      0x20
+#define MODEDCTRANCURVE 0x40
+#define INITF           0x7f00
+#define MODEINITFLOAT   0x100
+#define MODEINITJCT     0x200
+#define MODEINITFIX     0x400
+#define MODEINITSMSIG   0x800
+#define MODEINITTRAN    0x1000
+#define MODEINITPRED    0x2000
+#define MODEUIC         0x10000
+
+// ---- MOS per-instance state slots (mosdefs.h:330-375 minus the write-only "ask" mirrors) ----
+enum { MS_vbd, MS_vbs, MS_vgs, MS_vds, MS_capgs, MS_qgs, MS_cqgs, MS_capgd, MS_qgd, MS_cqgd,
+       MS_capgb, MS_qgb, MS_cqgb, MS_qbd, MS_cqbd, MS_qbs, MS_cqbs, MS_NSTATES };
+
+// ---- MOS cached operating point (mosdefs.h:125,160-173) ----
+enum { MC_mode, MC_von, MC_vdsat, MC_cd, MC_cbs, MC_cbd, MC_gm, MC_gds, MC_gmbs, MC_gbd, MC_gbs,
+       MC_capbd, MC_capbs, MC_NCACHE };
+
+// ---- MOS derived parameters produced by the temperature kernel (mostemp.cc:141-300) ----
+enum { MP_tPhi, MP_tVbi, MP_tVto, MP_gamma, MP_lambda, MP_beta, MP_oxideCap,
+       MP_tSourceSatCur, MP_tDrainSatCur, MP_sourceVcrit, MP_drainVcrit,
+       MP_Cbd, MP_Cbdsw, MP_Cbs, MP_Cbssw, MP_tBulkPot, MP_tDepCap,
+       MP_f2d, MP_f3d, MP_f4d, MP_f2s, MP_f3s, MP_f4s,
+       MP_gsOvl, MP_gdOvl, MP_gbOvl, MP_dcon, MP_scon, MP_mult, MP_vt, MP_mj, MP_mjsw,
+       MP_icVDS, MP_icVGS, MP_icVBS, MP_NPARAMS };
+
+// ---- MOS raw (card) parameters that may vary per trial ----
+enum { MR_vto, MR_kp, MR_gamma, MR_phi, MR_lambda, MR_l, MR_w, MR_NRAW };
+
+// matrix stamps of one MOSFET in the reference's ldadd order (mosload.cc:887-923)
+enum { MT_Dd, MT_Gg, MT_Ss, MT_Bb, MT_Ddp, MT_Gb, MT_Gdp, MT_Gsp, MT_Ssp, MT_Bg, MT_Bdp, MT_Bsp,
+       MT_DPd, MT_SPs, MT_DPdp, MT_SPsp, MT_DPg, MT_DPb, MT_DPsp, MT_SPg, MT_SPb, MT_SPdp,
+       MT_NSTAMP };
+// rhs stamps (mosload.cc:862-875)
+enum { MRH_g, MRH_b, MRH_dp, MRH_sp, MRH_NRHS };
+
+// Strided parameter accessor: value(inst, trial) = base[inst*ld + trial*ts]
+struct ParamRef {
+    const double *base;
+    int ld;     // 1 if shared across trials (then ts = 0), else ldt
+    int ts;     // 0 or 1
+};
+
+// ---- per-device-kind topology tables (device memory mirrors are plain int arrays) ----
+struct MosTopo {
+    int n = 0;
+    std::vector<int> d, g, s, b, dp, sp;        // node numbers (0 = ground)
+    std::vector<int> type;                      // +1 / -1
+    std::vector<int> level;
+    std::vector<int> off;
+    std::vector<int> state;                     // base state slot
+    std::vector<int> cslot;                     // [n*MT_NSTAMP] contribution slot or -1
+    std::vector<int> rslot;                     // [n*MRH_NRHS] rhs contribution slot or -1
+};
+struct CapTopo {
+    int n = 0;
+    std::vector<int> pos, neg, state;
+    std::vector<int> cslot;                     // [n*4] PP NN PN NP
+    std::vector<int> rslot;                     // [n*2] pos neg
+};
+struct SrcTopo {
+    int n = 0;
+    std::vector<int> kind, pos, neg, branch, fn, dcgiven;
+    std::vector<int> rslot;                     // [n*2]: V: branch,-1 ; I: pos,neg
+    std::vector<int> coef_off, ncoef;           // into coef pool (run-time parms)
+    std::vector<double> dc;
+    std::vector<double> pool;                   // per source: parms[8] cache[2] then pwl pts/slopes
+};
+
+// LU program for lane-per-task level-scheduled execution.
+// ops are stored level by level; within a level tasks are dealt to 32 lanes round-robin
+// ("rounds" of 32 tasks); a round's ops are interleaved [step][lane] and padded to the
+// round's longest task with no-ops.
+struct LuOp { int dst, a, b; };                // LU[dst] -= LU[a]*LU[b]   (dst < 0: no-op)
+struct LuRound {
+    int op_off;        // offset (in LuOp units) of this round's [steps][32] block
+    int nsteps;
+    int fin_off;       // offset into fin arrays [32]: per-lane finalisation
+};
+struct LuProgram {
+    // factor: per task (column j): ops, then L(:,j) /= pivot
+    std::vector<LuOp> ops;
+    std::vector<LuRound> rounds;
+    std::vector<int> level_round_off;          // rounds of level l: [off[l], off[l+1])
+    // finalisation of factor tasks: lane's column: diag slot, L slots range [lbeg,lend)
+    std::vector<int> fin_diag, fin_lbeg, fin_lend;   // per (round,lane), -1 if idle lane
+};
+struct SolveProgram {
+    // lane-per-row dot products: y[row] = (y[row] - sum LU[a]*y[b]) [/ LU[diag]]
+    std::vector<LuOp> ops;                     // dst unused; a = LU slot, b = y index
+    std::vector<LuRound> rounds;
+    std::vector<int> level_round_off;
+    std::vector<int> fin_row, fin_diag;        // per (round,lane): row index, diag slot (-1: L solve)
+};
+
+struct Analysis {
+    // unknowns
+    int n = 0;                                  // matrix size; node numbers 1..n
+    std::vector<int> ntype;                     // [n+1] 0 voltage, 1 current
+    std::vector<std::string> names;             // [n+1]
+    int numStates = 0;
+    // CSC pattern of A (0-based, rows ascending per column) -- spbuild.cc:922-958
+    int nnz = 0;
+    std::vector<int> Ap, Ai;
+    std::vector<int> diag;                      // [n+1] Ax index of (i,i) or -1
+    std::vector<double> Ainit;                  // preloaded constants (shared by all trials)
+    // gather lists: contributions in reference load order
+    int ncslot = 0, nrslot = 0;
+    std::vector<int> cg_ptr, cg_idx;            // per Ax entry: cslots
+    std::vector<int> rg_ptr, rg_idx;            // per rhs row (1..n): rslots
+    // .ic / nodeset
+    std::vector<char> ic_given, ns_given;
+    std::vector<double> ic_val, ns_val;
+    int hadNodeset = 0;
+    // device tables
+    MosTopo mos; CapTopo cap; SrcTopo src;
+    int nres = 0;
+    // ordering: position -> original (0-based)
+    std::vector<int> rowperm, colperm;
+    // LU structure in permuted positions
+    int nnzLU = 0;
+    std::vector<int> Lp, Li, Up, Ui;            // strictly lower / upper by column
+    std::vector<int> slotL, slotU, slotD;       // LU value slot of each L entry / U entry / diag
+    std::vector<int> a2lu;                      // Ax index -> LU slot
+    std::vector<int> lu_src;                    // LU slot -> Ax index or -1 (fill)
+    LuProgram fac;
+    SolveProgram fwd, bwd;
+    std::vector<int> yperm_in;                  // y[k] = rhs[rowperm[k]+1]
+    std::vector<int> yperm_out;                 // x[colperm[k]+1] = y[k]
+    // breakpoints (shared by all trials: sources are not varied per trial)
+    std::vector<double> brks;
+    std::vector<double> lat_offs, lat_per;
+    // tran constants (sTRANAN::init, tranan.cc:94-217)
+    double t_stop = 0, t_step = 0, t_start = 0, maxStep = 0, delmin = 0, minBreak = 0;
+    int nocut = 0, npoints_max = 0;
+    double break0 = 0, break1 = 0;
+};
+
+int  b200_analyze(const b200_deck *deck, Analysis &an, std::string &err);
+void b200_order_markowitz(Analysis &an);
+void b200_build_lu(Analysis &an);

@@ -1,0 +1,709 @@
+// capi.cu -- C ABI (include/b200spice.h): batch construction, the tick loop, result export.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "b200_internal.h"
+#include "device_state.h"
+#include "dev_load.cuh"
+#include "dev_ctl.cuh"
+#include "kernels.h"
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "b200spice: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    return B200_E_NOGPU; } } while (0)
+
+namespace {
+inline bool given(double x) { return !std::isnan(x); }
+
+// dependency of derived MOS parameters on the raw ones that may vary per trial
+// (mostemp.cc:141-300): derived parameter k is per-trial iff it depends on a varied raw one.
+const int kDep[MR_NRAW][8] = {
+    /* vto    */ { MP_tVbi, MP_tVto, -1 },
+    /* kp     */ { MP_beta, -1 },
+    /* gamma  */ { MP_gamma, MP_tVbi, MP_tVto, -1 },
+    /* phi    */ { MP_tPhi, MP_tVbi, MP_tVto, -1 },
+    /* lambda */ { MP_lambda, -1 },
+    /* l      */ { MP_beta, MP_oxideCap, MP_gbOvl, -1 },
+    /* w      */ { MP_beta, MP_oxideCap, MP_gsOvl, MP_gdOvl, -1 },
+};
+}
+
+struct b200_batch {
+    Analysis an;
+    Consts K;
+    int device = 0;
+    int ntrials = 0, ldt = 0;
+    bool uic = false;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+
+    // host-side parameter tables
+    std::vector<MosCard> cards;
+    std::vector<double> mos_raw[MR_NRAW];                   // [nmos] shared values
+    std::map<int, std::vector<double>> mos_var[MR_NRAW];    // inst -> [ntrials]
+    std::vector<double> cap_c, cap_ic, src_dc;
+    std::map<int, std::vector<double>> cap_var, src_var;
+    bool params_dirty = true;
+
+    // device views
+    HotView hot; VecView V; MosView M; CapView Cp; SrcView S; SolveView Sv; CtlAux aux;
+    CtlShared sh;
+    TrialCtl *ctl = nullptr;
+    MosCard *d_cards = nullptr;
+    int nq = 0; int *d_qslots = nullptr;
+    int *d_count = nullptr;
+    int cur = 0;
+    double *d_raw[MR_NRAW] = {0}; int raw_ts[MR_NRAW] = {0};
+    double *d_prm[MP_NPARAMS] = {0}; int prm_ts[MP_NPARAMS] = {0};
+    double *d_capc = nullptr, *d_srcdc = nullptr; int capc_ts = 0, srcdc_ts = 0;
+    double *d_capic = nullptr;
+    int *d_counters = nullptr, *d_npts = nullptr;
+
+    bool ran = false;
+    b200_run_stats stats;
+
+    template <class T> T *dalloc(size_t n) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, (n ? n : 1)*sizeof(T)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, (n ? n : 1)*sizeof(T));
+        allocs.push_back(p);
+        return (T*)p;
+    }
+    template <class T> T *dupload(const std::vector<T> &v) {
+        T *p = dalloc<T>(v.size());
+        if (p && !v.empty()) cudaMemcpy(p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice);
+        return p;
+    }
+};
+
+extern "C" {
+
+const char *b200_version(void) { return "b200spice 0.1 (sm_100a)"; }
+
+int b200_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void b200_options_default(b200_options *o)
+{
+    // wrspice/include/circuit.h:461-631
+    memset(o, 0, sizeof(*o));
+    o->abstol = 1e-12; o->reltol = 1e-3; o->vntol = 1e-6; o->chgtol = 1e-14; o->trtol = 7.0;
+    o->gmin = 1e-12; o->gmax = 1e6; o->pivrel = 1e-3; o->pivtol = 1e-13;
+    o->temp = 298.15; o->tnom = 298.15;
+    o->xmu = 0.5; o->dcmu = 0.5; o->trapratio = 10.0; o->resmin = 1e-3;
+    o->bypass = 1; o->maxord = 2; o->itl1 = 400; o->itl2 = 100; o->itl4 = 20;
+    o->itl_gmin = 20; o->itl_src = 20; o->interplev = 1;
+}
+
+static void build_cards(b200_batch *b, const b200_deck *dk)
+{
+    const Analysis &an = b->an;
+    const b200_options &o = dk->opt;
+    int nm = dk->nmos;
+    b->cards.resize(nm);
+    for (int k = 0; k < MR_NRAW; k++) b->mos_raw[k].assign(nm, 0.0);
+    for (int i = 0; i < nm; i++) {
+        const b200_mos &in = dk->mos[i];
+        const b200_mos_model &md = dk->mos_models[in.model];
+        MosCard &c = b->cards[i];
+        memset(&c, 0, sizeof(c));
+        c.type = md.type > 0 ? 1 : -1;
+        c.level = (md.level == 2 || md.level == 3 || md.level == 6) ? md.level : 1;
+        c.g_vto = given(md.vto); c.g_kp = given(md.kp); c.g_gamma = given(md.gamma);
+        c.g_phi = given(md.phi); c.g_tox = given(md.tox); c.g_u0 = given(md.u0);
+        c.g_nsub = given(md.nsub); c.g_cbd = given(md.cbd); c.g_cbs = given(md.cbs);
+        c.g_cj = given(md.cj); c.g_cjsw = given(md.cjsw); c.g_nss = given(md.nss);
+        c.g_tpg = given(md.tpg);
+        // mosset.cc:83-200 defaults
+        c.cbd = given(md.cbd) ? md.cbd : 0; c.cbs = given(md.cbs) ? md.cbs : 0;
+        c.is = given(md.is) ? md.is : 1e-14; c.pb = given(md.pb) ? md.pb : .8;
+        c.cgso = given(md.cgso) ? md.cgso : 0; c.cgdo = given(md.cgdo) ? md.cgdo : 0;
+        c.cgbo = given(md.cgbo) ? md.cgbo : 0;
+        c.cj = given(md.cj) ? md.cj : 0; c.mj = given(md.mj) ? md.mj : .5;
+        c.cjsw = given(md.cjsw) ? md.cjsw : 0;
+        c.mjsw = given(md.mjsw) ? md.mjsw : ((c.level == 1 || c.level == 6) ? .5 : .33);
+        c.js = given(md.js) ? md.js : 0;
+        c.tox = given(md.tox) ? md.tox : ((c.level == 2 || c.level == 3) ? 1e-7 : 0);
+        c.ld = given(md.ld) ? md.ld : 0; c.u0 = given(md.u0) ? md.u0 : 0;
+        c.fc = given(md.fc) ? md.fc : .5; c.nsub = given(md.nsub) ? md.nsub : 0;
+        c.tpg = given(md.tpg) ? md.tpg : 1; c.nss = given(md.nss) ? md.nss : 0;
+        c.tnom = given(md.tnom) ? md.tnom : o.tnom;
+        // instance, mosset.cc:283-373
+        c.mult = given(in.m) ? in.m : 1.0;
+        c.temp = given(in.temp) ? in.temp : o.temp;
+        c.drainPerimeter = given(in.pd) ? in.pd : 0;
+        c.sourcePerimeter = given(in.ps) ? in.ps : 0;
+        double nrd = (!given(in.nrd) || in.nrd == 0) ? 1 : in.nrd;
+        double nrs = (!given(in.nrs) || in.nrs == 0) ? 1 : in.nrs;
+        c.drainArea = given(in.ad) ? in.ad : (o.defad > 0 ? o.defad : 0.0);
+        c.sourceArea = given(in.as) ? in.as : (o.defas > 0 ? o.defas : 0.0);
+        if (given(md.rd)) c.dcon = (md.rd != 0) ? 1/md.rd : 0;
+        else if (given(md.rsh)) c.dcon = (md.rsh != 0) ? 1/(md.rsh*nrd) : 0;
+        else c.dcon = 0;
+        if (given(md.rs)) c.scon = (md.rs != 0) ? 1/md.rs : 0;
+        else if (given(md.rsh)) c.scon = (md.rsh != 0) ? 1/(md.rsh*nrs) : 0;
+        else c.scon = 0;
+        c.icVDS = given(in.icvds) ? in.icvds : 0;
+        c.icVGS = given(in.icvgs) ? in.icvgs : 0;
+        c.icVBS = given(in.icvbs) ? in.icvbs : 0;
+        if (dk->uic) {
+            // setic() -> MOSdev::getic, mosic.cc:52-81 (node ICs are shared by all trials)
+            auto icv = [&](int node) { return node ? (an.ns_given[node] && !an.ic_given[node] ? an.ns_val[node] : an.ic_val[node]) : 0.0; };
+            if (!given(in.icvbs)) c.icVBS = icv(in.b) - icv(in.s);
+            if (!given(in.icvds)) c.icVDS = icv(in.d) - icv(in.s);
+            if (!given(in.icvgs)) c.icVGS = icv(in.g) - icv(in.s);
+        }
+        b->mos_raw[MR_vto][i] = md.vto; b->mos_raw[MR_kp][i] = md.kp;
+        b->mos_raw[MR_gamma][i] = md.gamma; b->mos_raw[MR_phi][i] = md.phi;
+        b->mos_raw[MR_lambda][i] = given(md.lambda) ? md.lambda : 0;
+        b->mos_raw[MR_l][i] = given(in.l) ? in.l : (o.defl > 0 ? o.defl : 1e-6);
+        b->mos_raw[MR_w][i] = given(in.w) ? in.w : (o.defw > 0 ? o.defw : 1e-6);
+    }
+    b->cap_c.resize(dk->ncap); b->cap_ic.resize(dk->ncap);
+    for (int i = 0; i < dk->ncap; i++) {
+        const b200_cap &in = dk->cap[i];
+        double mm = given(in.m) ? in.m : 1.0;
+        b->cap_c[i] = in.c*1.0*mm;                  // captemp.cc:98
+        double ic = given(in.ic) ? in.ic : 0.0;
+        if (dk->uic && !given(in.ic)) {
+            auto icv = [&](int node) { return node ? (an.ns_given[node] && !an.ic_given[node] ? an.ns_val[node] : an.ic_val[node]) : 0.0; };
+            ic = icv(in.pos) - icv(in.neg);         // capic.cc:52-71
+        }
+        b->cap_ic[i] = ic;
+    }
+    b->src_dc = b->an.src.dc;
+}
+
+int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch **out)
+{
+    *out = nullptr;
+    if (!deck || ntrials <= 0) return B200_E_BADPARM;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
+        fprintf(stderr, "b200spice: no CUDA device (no CPU fallback exists)\n");
+        return B200_E_NOGPU;
+    }
+    if (deck->opt.dcmu != 0.5 || deck->opt.jjaccel || deck->opt.steptype != 0 ||
+            deck->opt.gminsteps > 0 || deck->opt.srcsteps > 0) {
+        fprintf(stderr, "b200spice: option not built yet (dcmu/jjaccel/steptype/spice3 stepping)\n");
+        return B200_E_UNSUPP;
+    }
+    CK(cudaSetDevice(device));
+    b200_batch *b = new b200_batch;
+    b->device = device;
+    b->ntrials = ntrials;
+    b->ldt = (ntrials + 31) & ~31;
+    b->uic = deck->uic != 0;
+    std::string err;
+    int rc = b200_analyze(deck, b->an, err);
+    if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); delete b; return rc; }
+    b200_order_markowitz(b->an);
+    b200_build_lu(b->an);
+    build_cards(b, deck);
+    Analysis &an = b->an;
+    CK(cudaStreamCreate(&b->stream));
+
+    Consts &K = b->K;
+    memset(&K, 0, sizeof(K));
+    K.opt = deck->opt;
+    K.n = an.n; K.nnz = an.nnz; K.numStates = an.numStates; K.ldt = b->ldt; K.ntrials = ntrials;
+    K.NS = deck->opt.maxord + 2; if (K.NS > 8) K.NS = 8; if (K.NS < 4) K.NS = 4;
+    K.nnzLU = an.nnzLU; K.ncslot = an.ncslot; K.nrslot = an.nrslot;
+    K.t_stop = an.t_stop; K.t_step = an.t_step; K.t_start = an.t_start; K.maxStep = an.maxStep;
+    K.delmin = an.delmin; K.minBreak = an.minBreak; K.break0 = an.break0; K.break1 = an.break1;
+    K.nocut = an.nocut; K.uic = deck->uic; K.hadNodeset = an.hadNodeset;
+    K.npoints_max = an.npoints_max; K.method = deck->opt.method;
+    K.nbrks = (int)an.brks.size(); K.nlat = (int)an.lat_offs.size();
+
+    if (solve_smem_bytes(K) > 227*1024) {
+        fprintf(stderr, "b200spice: LU (%d values) + rhs (%d) of one trial exceed shared memory; "
+            "the supernodal large-matrix path is not built yet\n", an.nnzLU, an.n);
+        delete b; return B200_E_UNSUPP;
+    }
+
+    size_t ldt = b->ldt;
+    // ---- hot arrays ----
+    HotView &h = b->hot;
+    h.mode = b->dalloc<int>(ldt); h.order = b->dalloc<int>(ldt); h.st_base = b->dalloc<int>(ldt);
+    h.noncon = b->dalloc<int>(ldt); h.trapbad = b->dalloc<int>(ldt); h.trapcheck = b->dalloc<int>(ldt);
+    h.active = b->dalloc<int>(ldt); h.do_solve = b->dalloc<int>(ldt); h.iterno = b->dalloc<int>(ldt);
+    h.time = b->dalloc<double>(ldt); h.delta = b->dalloc<double>(ldt);
+    h.srcfact = b->dalloc<double>(ldt); h.diaggmin = b->dalloc<double>(ldt);
+    h.ag = b->dalloc<double>(7*ldt); h.pred = b->dalloc<double>(2*ldt);
+    h.deltaOld = b->dalloc<double>(7*ldt);
+    h.nodeconv = b->dalloc<int>(ldt); h.solve_err = b->dalloc<int>(ldt);
+    h.need_devconv = b->dalloc<int>(ldt); h.devconv = b->dalloc<int>(ldt);
+    h.want_lte = b->dalloc<int>(ldt); h.lte = b->dalloc<double>(2*ldt);
+    // ---- vectors ----
+    VecView &V = b->V;
+    size_t vplane = (size_t)(an.n + 1)*ldt;
+    V.X[0] = b->dalloc<double>(vplane); V.X[1] = b->dalloc<double>(vplane);
+    V.spare = b->dalloc<double>(vplane); V.sols = b->dalloc<double>(8*vplane);
+    V.oldSol = b->dalloc<double>(vplane);
+    V.states = b->dalloc<double>((size_t)K.NS*an.numStates*ldt);
+    V.oldState0 = b->dalloc<double>((size_t)an.numStates*ldt);
+    V.contrib = b->dalloc<double>((size_t)an.ncslot*ldt);
+    V.rcontrib = b->dalloc<double>((size_t)an.nrslot*ldt);
+    V.out = b->dalloc<double>((size_t)an.npoints_max*an.n*ldt);
+    if (!V.out || !V.states || !V.sols) { b200_batch_destroy(b); return B200_E_NOMEM; }
+    // ---- topology ----
+    MosView &M = b->M; MosTopo &mt = an.mos;
+    M.n = mt.n;
+    M.d = b->dupload(mt.d); M.g = b->dupload(mt.g); M.s = b->dupload(mt.s); M.b = b->dupload(mt.b);
+    M.dp = b->dupload(mt.dp); M.sp = b->dupload(mt.sp); M.type = b->dupload(mt.type);
+    M.off = b->dupload(mt.off); M.state = b->dupload(mt.state);
+    M.cslot = b->dupload(mt.cslot); M.rslot = b->dupload(mt.rslot);
+    M.cache = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);
+    M.save = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);
+    b->d_cards = b->dupload(b->cards);
+    CapView &Cp = b->Cp; CapTopo &ct = an.cap;
+    Cp.n = ct.n;
+    Cp.pos = b->dupload(ct.pos); Cp.neg = b->dupload(ct.neg); Cp.state = b->dupload(ct.state);
+    Cp.cslot = b->dupload(ct.cslot); Cp.rslot = b->dupload(ct.rslot);
+    Cp.geq = b->dalloc<double>((size_t)ct.n*ldt); Cp.ceq = b->dalloc<double>((size_t)ct.n*ldt);
+    SrcView &S = b->S; SrcTopo &st = an.src;
+    S.n = st.n;
+    S.kind = b->dupload(st.kind); S.fn = b->dupload(st.fn); S.dcgiven = b->dupload(st.dcgiven);
+    S.rslot = b->dupload(st.rslot); S.coef_off = b->dupload(st.coef_off); S.ncoef = b->dupload(st.ncoef);
+    S.pool = b->dupload(st.pool);
+    S.dcval = nullptr;
+    // ---- charges for the LTE kernel (mostrun.cc:59-61, captrun.cc:58) ----
+    {
+        std::vector<int> q;
+        for (int oi = 0; oi < deck->norder; oi++) {
+            int i = deck->order_index[oi];
+            if (deck->order_kind[oi] == B200_DEV_MOS) {
+                q.push_back(mt.state[i] + MS_qgs); q.push_back(mt.state[i] + MS_qgd);
+                q.push_back(mt.state[i] + MS_qgb);
+            }
+            else if (deck->order_kind[oi] == B200_DEV_CAP)
+                q.push_back(ct.state[i]);
+        }
+        b->nq = (int)q.size();
+        b->d_qslots = b->dupload(q);
+    }
+    // ---- solve view ----
+    SolveView &Sv = b->Sv;
+    Sv.lu_src = b->dupload(an.lu_src); Sv.Ainit = b->dupload(an.Ainit);
+    Sv.cg_ptr = b->dupload(an.cg_ptr); Sv.cg_idx = b->dupload(an.cg_idx);
+    Sv.rg_ptr = b->dupload(an.rg_ptr); Sv.rg_idx = b->dupload(an.rg_idx);
+    {
+        std::vector<int> dn(an.nnz, 0);
+        for (int i = 1; i <= an.n; i++) if (an.diag[i] >= 0) dn[an.diag[i]] = i;
+        Sv.diag_node = b->dupload(dn);
+    }
+    Sv.ntype = b->dupload(an.ntype);
+    Sv.ic_given = b->dupload(an.ic_given); Sv.ns_given = b->dupload(an.ns_given);
+    Sv.ic_val = b->dupload(an.ic_val); Sv.ns_val = b->dupload(an.ns_val);
+    Sv.yperm_in = b->dupload(an.yperm_in); Sv.yperm_out = b->dupload(an.yperm_out);
+    auto sync_flags = [](const std::vector<LuRound> &rounds, const std::vector<int> &lvl) {
+        std::vector<char> f(rounds.size(), 0);
+        for (size_t l = 0; l + 1 < lvl.size(); l++)
+            if (lvl[l] < (int)rounds.size() && lvl[l] < lvl[l+1]) f[lvl[l]] = 1;
+        return f;
+    };
+    Sv.fac_nrounds = (int)an.fac.rounds.size();
+    Sv.fwd_nrounds = (int)an.fwd.rounds.size();
+    Sv.bwd_nrounds = (int)an.bwd.rounds.size();
+    Sv.fac_rounds = b->dupload(an.fac.rounds); Sv.fwd_rounds = b->dupload(an.fwd.rounds);
+    Sv.bwd_rounds = b->dupload(an.bwd.rounds);
+    Sv.fac_ops = b->dupload(an.fac.ops); Sv.fwd_ops = b->dupload(an.fwd.ops);
+    Sv.bwd_ops = b->dupload(an.bwd.ops);
+    Sv.fac_sync = b->dupload(sync_flags(an.fac.rounds, an.fac.level_round_off));
+    Sv.fwd_sync = b->dupload(sync_flags(an.fwd.rounds, an.fwd.level_round_off));
+    Sv.bwd_sync = b->dupload(sync_flags(an.bwd.rounds, an.bwd.level_round_off));
+    Sv.fac_fin_diag = b->dupload(an.fac.fin_diag); Sv.fac_fin_lbeg = b->dupload(an.fac.fin_lbeg);
+    Sv.fac_fin_lend = b->dupload(an.fac.fin_lend);
+    Sv.fwd_fin_row = b->dupload(an.fwd.fin_row);
+    Sv.bwd_fin_row = b->dupload(an.bwd.fin_row); Sv.bwd_fin_diag = b->dupload(an.bwd.fin_diag);
+    // ---- control ----
+    b->ctl = b->dalloc<TrialCtl>(ldt);
+    CtlAux &ax = b->aux;
+    ax.vecops = b->dalloc<int>(ldt); ax.sols_base = b->dalloc<int>(ldt);
+    ax.vo_stbase = b->dalloc<int>(ldt); ax.ip_n = b->dalloc<int>(ldt);
+    ax.ip_out0 = b->dalloc<int>(ldt); ax.ip_degree = b->dalloc<int>(ldt);
+    ax.ip_d = b->dalloc<double>(5*ldt);
+    CtlShared &sh = b->sh;
+    sh.K = nullptr;
+    sh.brks = b->dupload(an.brks); sh.lat_offs = b->dupload(an.lat_offs);
+    sh.lat_per = b->dupload(an.lat_per);
+    {
+        std::vector<double> tdl, fr;
+        for (int i = 0; i < st.n; i++)
+            if (st.fn[i] == B200_FN_SIN) {
+                tdl.push_back(st.pool[st.coef_off[i] + 3]);
+                fr.push_back(st.pool[st.coef_off[i] + 2]);
+            }
+        sh.nsin = (int)tdl.size();
+        sh.sin_tdl = b->dupload(tdl); sh.sin_freq = b->dupload(fr);
+    }
+    b->d_count = b->dalloc<int>(1);
+    b->d_counters = b->dalloc<int>((size_t)ldt*B200_NCOUNTERS);
+    b->d_npts = b->dalloc<int>(ldt);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    *out = b;
+    return B200_OK;
+}
+
+void b200_batch_destroy(b200_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    for (void *p : b->allocs) cudaFree(p);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int b200_batch_set_param(b200_batch *b, int param, int index, const double *values)
+{
+    if (!b || !values) return B200_E_BADPARM;
+    std::vector<double> v(values, values + b->ntrials);
+    int raw = -1;
+    switch (param) {
+    case B200_P_MOS_VTO: raw = MR_vto; break;
+    case B200_P_MOS_KP: raw = MR_kp; break;
+    case B200_P_MOS_GAMMA: raw = MR_gamma; break;
+    case B200_P_MOS_PHI: raw = MR_phi; break;
+    case B200_P_MOS_LAMBDA: raw = MR_lambda; break;
+    case B200_P_MOS_L: raw = MR_l; break;
+    case B200_P_MOS_W: raw = MR_w; break;
+    case B200_P_CAP_C:
+        if (index < 0 || index >= b->an.cap.n) return B200_E_BADPARM;
+        b->cap_var[index] = v; b->params_dirty = true; return B200_OK;
+    case B200_P_SRC_DC:
+        if (index < 0 || index >= b->an.src.n) return B200_E_BADPARM;
+        b->src_var[index] = v; b->params_dirty = true; return B200_OK;
+    default:
+        return B200_E_UNSUPP;
+    }
+    if (index < 0 || index >= b->an.mos.n) return B200_E_BADPARM;
+    // a per-trial model value makes the card "given" for that device
+    MosCard &c = b->cards[index];
+    if (raw == MR_vto) c.g_vto = 1;
+    if (raw == MR_kp) c.g_kp = 1;
+    if (raw == MR_gamma) c.g_gamma = 1;
+    if (raw == MR_phi) c.g_phi = 1;
+    b->mos_var[raw][index] = v;
+    b->params_dirty = true;
+    return B200_OK;
+}
+
+// upload parameters and run the temperature kernel (sCKT::temp, ckt.cc:2297-2307)
+static int prepare_params(b200_batch *b)
+{
+    if (!b->params_dirty) return B200_OK;
+    size_t ldt = b->ldt;
+    int nm = b->an.mos.n;
+    auto upload_strided = [&](const std::vector<double> &shared,
+            const std::map<int, std::vector<double>> &var, double *&dptr, int &ts) -> int {
+        int n = (int)shared.size();
+        int want_ts = var.empty() ? 0 : 1;
+        if (!dptr || ts != want_ts) {
+            dptr = b->dalloc<double>(want_ts ? (size_t)n*ldt : (size_t)n);
+            if (!dptr) return B200_E_NOMEM;
+            ts = want_ts;
+        }
+        if (!ts) {
+            if (n) CK(cudaMemcpy(dptr, shared.data(), n*sizeof(double), cudaMemcpyHostToDevice));
+        }
+        else {
+            std::vector<double> row(ldt);
+            for (int i = 0; i < n; i++) {
+                auto it = var.find(i);
+                if (it == var.end()) std::fill(row.begin(), row.end(), shared[i]);
+                else {
+                    std::copy(it->second.begin(), it->second.end(), row.begin());
+                    std::fill(row.begin() + b->ntrials, row.end(), it->second[0]);
+                }
+                CK(cudaMemcpy(dptr + (size_t)i*ldt, row.data(), ldt*sizeof(double), cudaMemcpyHostToDevice));
+            }
+        }
+        return B200_OK;
+    };
+    RawParams raw;
+    int tsd[MP_NPARAMS];
+    for (int k = 0; k < MP_NPARAMS; k++) tsd[k] = 0;
+    for (int k = 0; k < MR_NRAW; k++) {
+        int rc = upload_strided(b->mos_raw[k], b->mos_var[k], b->d_raw[k], b->raw_ts[k]);
+        if (rc) return rc;
+        raw.p[k].base = b->d_raw[k];
+        raw.p[k].ts = b->raw_ts[k];
+        raw.p[k].ld = b->raw_ts[k] ? (int)ldt : 1;
+        if (b->raw_ts[k])
+            for (int q = 0; kDep[k][q] >= 0; q++) tsd[kDep[k][q]] = 1;
+    }
+    MosParamsOut po;
+    for (int k = 0; k < MP_NPARAMS; k++) {
+        if (!b->d_prm[k] || b->prm_ts[k] != tsd[k]) {
+            b->d_prm[k] = b->dalloc<double>(tsd[k] ? (size_t)nm*ldt : (size_t)nm);
+            if (!b->d_prm[k]) return B200_E_NOMEM;
+            b->prm_ts[k] = tsd[k];
+        }
+        po.base[k] = b->d_prm[k]; po.ts[k] = tsd[k];
+        b->M.prm[k].base = b->d_prm[k];
+        b->M.prm[k].ts = tsd[k];
+        b->M.prm[k].ld = tsd[k] ? (int)ldt : 1;
+    }
+    CK(cudaMemcpy(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice));
+    launch_mos_temp(b->stream, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);
+    int rc = upload_strided(b->cap_c, b->cap_var, b->d_capc, b->capc_ts);
+    if (rc) return rc;
+    b->Cp.capac.base = b->d_capc; b->Cp.capac.ts = b->capc_ts; b->Cp.capac.ld = b->capc_ts ? (int)ldt : 1;
+    if (!b->d_capic) b->d_capic = b->dalloc<double>(b->cap_ic.size());
+    if (!b->cap_ic.empty())
+        CK(cudaMemcpy(b->d_capic, b->cap_ic.data(), b->cap_ic.size()*sizeof(double), cudaMemcpyHostToDevice));
+    b->Cp.ic.base = b->d_capic; b->Cp.ic.ts = 0; b->Cp.ic.ld = 1;
+    rc = upload_strided(b->src_dc, b->src_var, b->d_srcdc, b->srcdc_ts);
+    if (rc) return rc;
+    b->S.dc.base = b->d_srcdc; b->S.dc.ts = b->srcdc_ts; b->S.dc.ld = b->srcdc_ts ? (int)ldt : 1;
+    CK(cudaStreamSynchronize(b->stream));
+    b->params_dirty = false;
+    return B200_OK;
+}
+
+static int reset_state(b200_batch *b)
+{
+    const Analysis &an = b->an;
+    size_t ldt = b->ldt;
+    size_t vplane = (size_t)(an.n + 1)*ldt;
+    cudaStream_t st = b->stream;
+    CK(cudaMemsetAsync(b->V.X[0], 0, vplane*sizeof(double), st));
+    CK(cudaMemsetAsync(b->V.X[1], 0, vplane*sizeof(double), st));
+    CK(cudaMemsetAsync(b->V.spare, 0, vplane*sizeof(double), st));
+    CK(cudaMemsetAsync(b->V.sols, 0, 8*vplane*sizeof(double), st));
+    CK(cudaMemsetAsync(b->V.states, 0, (size_t)b->K.NS*an.numStates*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->V.contrib, 0, (size_t)an.ncslot*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->V.rcontrib, 0, (size_t)an.nrslot*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->M.cache, 0, (size_t)MC_NCACHE*an.mos.n*ldt*sizeof(double), st));
+    // MOSmode = 1, MOSvon = 0 (mosset.cc:283-284)
+    launch_fill(st, b->M.cache + (size_t)MC_mode*an.mos.n*ldt, (size_t)an.mos.n*ldt, 1.0);
+    CK(cudaMemsetAsync(b->Cp.geq, 0, (size_t)an.cap.n*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->Cp.ceq, 0, (size_t)an.cap.n*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->ctl, 0, ldt*sizeof(TrialCtl), st));
+    int *hz[] = { b->hot.mode, b->hot.order, b->hot.st_base, b->hot.noncon, b->hot.trapbad,
+        b->hot.trapcheck, b->hot.active, b->hot.do_solve, b->hot.iterno, b->hot.nodeconv,
+        b->hot.solve_err, b->hot.need_devconv, b->hot.devconv, b->hot.want_lte, b->aux.vecops };
+    for (int *p : hz) CK(cudaMemsetAsync(p, 0, ldt*sizeof(int), st));
+    b->cur = 0;
+    if (b->uic) {
+        // ic() + swaprhs: CKTrhsOld starts as the .ic/.nodeset vector (ckt.cc:908-925, tranan.cc:357-362)
+        std::vector<double> row(ldt);
+        for (int i = 1; i <= an.n; i++) {
+            double v = 0.0;
+            if (an.ns_given[i]) v = an.ns_val[i];
+            if (an.ic_given[i]) v = an.ic_val[i];
+            if (v != 0.0) {
+                std::fill(row.begin(), row.end(), v);
+                CK(cudaMemcpyAsync(b->V.X[0] + (size_t)i*ldt, row.data(), ldt*sizeof(double),
+                    cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));
+            }
+        }
+    }
+    return B200_OK;
+}
+
+int b200_batch_run_tran(b200_batch *b)
+{
+    if (!b) return B200_E_BADPARM;
+    CK(cudaSetDevice(b->device));
+    int rc = prepare_params(b);
+    if (rc) return rc;
+    rc = reset_state(b);
+    if (rc) return rc;
+    cudaStream_t st = b->stream;
+    const Consts &K = b->K;
+    memset(&b->stats, 0, sizeof(b->stats));
+
+    const int WIN = 32;
+    cudaEvent_t ev[WIN][4], e_begin, e_end;
+    for (int i = 0; i < WIN; i++) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ev[i][k]));
+    CK(cudaEventCreate(&e_begin)); CK(cudaEventCreate(&e_end));
+    long long launches = 0, ticks = 0, load_launches = 0, solve_launches = 0;
+    double ms_load = 0, ms_solve = 0;
+    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->S.n ? 1 : 0);
+
+    CK(cudaEventRecord(e_begin, st));
+    // tick 0: begin + first load
+    launch_ctl(st, K, b->hot, b->ctl, b->sh, b->aux, 0);
+    launch_vec(st, K, b->V, b->aux, b->M, b->V.X[b->cur]);
+    launch_loads(st, K, b->hot, b->V, b->M, b->Cp, b->S, b->V.X[b->cur]);
+    launches += 3 + nload_kernels;
+    int active = b->ntrials;
+    const long long max_ticks = 20000000;
+    while (active > 0 && ticks < max_ticks) {
+        for (int w = 0; w < WIN; w++) {
+            CK(cudaEventRecord(ev[w][0], st));
+            rc = launch_solve(st, K, b->hot, b->V, b->Sv, b->V.X[b->cur], b->V.X[b->cur ^ 1]);
+            if (rc) return rc;
+            CK(cudaEventRecord(ev[w][1], st));
+            launch_devconv(st, K, b->hot, b->V, b->M, b->V.X[b->cur]);
+            b->cur ^= 1;
+            launch_ctl(st, K, b->hot, b->ctl, b->sh, b->aux, 1);
+            launch_trunc(st, K, b->hot, b->V, b->nq, b->d_qslots);
+            launch_ctl(st, K, b->hot, b->ctl, b->sh, b->aux, 2);
+            launch_vec(st, K, b->V, b->aux, b->M, b->V.X[b->cur]);
+            CK(cudaEventRecord(ev[w][2], st));
+            launch_loads(st, K, b->hot, b->V, b->M, b->Cp, b->S, b->V.X[b->cur]);
+            CK(cudaEventRecord(ev[w][3], st));
+            launches += 7 + nload_kernels;
+            load_launches++; solve_launches++;
+            ticks++;
+        }
+        launch_count_active(st, K.ntrials, b->hot.active, b->d_count);
+        launches++;
+        CK(cudaMemcpyAsync(&active, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int w = 0; w < WIN; w++) {
+            float a = 0, c = 0;
+            cudaEventElapsedTime(&a, ev[w][0], ev[w][1]);
+            cudaEventElapsedTime(&c, ev[w][2], ev[w][3]);
+            ms_solve += a; ms_load += c;
+        }
+    }
+    launch_export_counters(st, K.ntrials, b->ctl, b->d_counters, b->d_npts);
+    CK(cudaEventRecord(e_end, st));
+    CK(cudaStreamSynchronize(st));
+    float tot = 0;
+    cudaEventElapsedTime(&tot, e_begin, e_end);
+    for (int i = 0; i < WIN; i++) for (int k = 0; k < 4; k++) cudaEventDestroy(ev[i][k]);
+    cudaEventDestroy(e_begin); cudaEventDestroy(e_end);
+    CK(cudaGetLastError());
+    b->stats.launches = launches; b->stats.ticks = ticks;
+    b->stats.ms_total = tot; b->stats.ms_load = ms_load; b->stats.ms_solve = ms_solve;
+    b->stats.ms_control = tot - ms_load - ms_solve;
+    b->stats.load_launches = load_launches; b->stats.solve_launches = solve_launches;
+    b->ran = true;
+    return (ticks >= max_ticks) ? B200_E_PANIC : B200_OK;
+}
+
+int b200_batch_num_unknowns(const b200_batch *b) { return b ? b->an.n : 0; }
+int b200_batch_num_points(const b200_batch *b) { return b ? b->an.npoints_max : 0; }
+
+int b200_batch_unknown_names(const b200_batch *b, char *buf, int buflen)
+{
+    int pos = 0;
+    for (int i = 1; i <= b->an.n; i++) {
+        int l = (int)b->an.names[i].size() + 1;
+        if (buf && pos + l <= buflen) memcpy(buf + pos, b->an.names[i].c_str(), l);
+        pos += l;
+    }
+    return pos;
+}
+
+int b200_batch_get_counters(const b200_batch *b, int *counters)
+{
+    if (!b || !b->ran) return B200_E_BADPARM;
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpy(counters, b->d_counters, (size_t)b->ntrials*B200_NCOUNTERS*sizeof(int),
+        cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+static int get_waves(const b200_batch *b, int nsel, const int *sel, double *times, double *waves)
+{
+    if (!b || !b->ran) return B200_E_BADPARM;
+    CK(cudaSetDevice(b->device));
+    const Analysis &an = b->an;
+    int np = an.npoints_max;
+    if (times) {
+        // user time points: t_check sequence, tranan.cc:472-479
+        double tc = an.t_start;
+        for (int p = 0; p < np; p++, tc += an.t_step) times[p] = tc;
+    }
+    if (!waves) return B200_OK;
+    int nn = sel ? nsel : an.n;
+    double *dw = nullptr; int *dsel = nullptr;
+    size_t total = (size_t)b->ntrials*np*nn;
+    CK(cudaMalloc(&dw, total*sizeof(double)));
+    if (sel) {
+        CK(cudaMalloc(&dsel, nsel*sizeof(int)));
+        CK(cudaMemcpy(dsel, sel, nsel*sizeof(int), cudaMemcpyHostToDevice));
+    }
+    launch_gather_waves(b->stream, an.n, b->ldt, b->ntrials, np, b->V.out, b->d_npts, nsel, dsel, dw);
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpy(waves, dw, total*sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dw);
+    if (dsel) cudaFree(dsel);
+    return B200_OK;
+}
+
+int b200_batch_get_waves(const b200_batch *b, double *times, double *waves)
+{
+    return get_waves(b, 0, nullptr, times, waves);
+}
+
+int b200_batch_get_waves_sel(const b200_batch *b, int nsel, const int *sel, double *waves)
+{
+    if (!sel || nsel <= 0) return B200_E_BADPARM;
+    return get_waves(b, nsel, sel, nullptr, waves);
+}
+
+int b200_batch_get_stats(const b200_batch *b, b200_run_stats *st)
+{
+    if (!b || !st) return B200_E_BADPARM;
+    *st = b->stats;
+    // algorithmic bytes per launch: trial-varying FP64 data that must move
+    const Analysis &an = b->an;
+    double per_mos = 8.0*(4 /*node V*/ + 17 /*state0 w*/ + 12 /*state1 r*/ + 2*MC_NCACHE);
+    int live = 0;
+    for (int s : an.mos.cslot) if (s >= 0) live++;
+    for (int s : an.mos.rslot) if (s >= 0) live++;
+    double mosbytes = per_mos*an.mos.n + 8.0*live;
+    int nvar = 0;
+    for (int k = 0; k < MP_NPARAMS; k++) nvar += b->prm_ts[k];
+    mosbytes += 8.0*nvar*an.mos.n;
+    double capbytes = 8.0*(2 + 2 + 1 + 2)*an.cap.n;
+    for (int s : an.cap.cslot) if (s >= 0) capbytes += 8.0;
+    for (int s : an.cap.rslot) if (s >= 0) capbytes += 8.0;
+    double srcbytes = 0;
+    for (int s : an.src.rslot) if (s >= 0) srcbytes += 8.0;
+    st->algbytes_load_per_launch = (mosbytes + capbytes + srcbytes)*b->ntrials;
+    st->algbytes_solve_per_launch = 8.0*((double)an.ncslot + an.nrslot + 2.0*an.n)*b->ntrials;
+    return B200_OK;
+}
+
+int b200_batch_pattern(const b200_batch *b, int *n, int *nnz, const int **Ap, const int **Ai)
+{
+    if (!b) return B200_E_BADPARM;
+    *n = b->an.n; *nnz = b->an.nnz; *Ap = b->an.Ap.data(); *Ai = b->an.Ai.data();
+    return B200_OK;
+}
+
+int b200_batch_ordering(const b200_batch *b, const int **rowperm, const int **colperm)
+{
+    if (!b) return B200_E_BADPARM;
+    *rowperm = b->an.rowperm.data(); *colperm = b->an.colperm.data();
+    return B200_OK;
+}
+
+} // extern "C"
+
+// ---- accessors for klu_seam.cu (debug load hook) ----
+int b200_internal_prepare(b200_batch *b)
+{
+    if (cudaSetDevice(b->device) != cudaSuccess) return B200_E_NOGPU;
+    int rc = prepare_params(b);
+    if (rc) return rc;
+    return reset_state(b);
+}
+
+int b200_internal_views(b200_batch *b, Consts **K, HotView **hot, VecView **V, MosView **M,
+    CapView **Cp, SrcView **S, SolveView **Sv, cudaStream_t *st, int **cur)
+{
+    *K = &b->K; *hot = &b->hot; *V = &b->V; *M = &b->M; *Cp = &b->Cp; *S = &b->S; *Sv = &b->Sv;
+    *st = b->stream; *cur = &b->cur;
+    return 0;
+}

@@ -1,0 +1,120 @@
+// device_state.h -- device-visible views of the batch (plain pointers; passed to kernels by
+// value).  All per-trial arrays are [slot][ldt], trial fastest.
+#pragma once
+
+#include "b200_internal.h"
+
+#ifndef __CUDACC__
+#ifndef __host__
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#endif
+#endif
+
+// ---- per-trial control block (AoS; touched only by the control kernel, one thread/trial) ----
+enum { PC_IDLE = 0, PC_NIITER, PC_WAIT_LTE, PC_DONE };
+enum { RET_NONE = 0, RET_OP_DIRECT, RET_GMIN_LOOP, RET_GMIN_FINAL, RET_SRC_LOOP, RET_TRAN_STEP };
+
+// vector-op request bits (consumed by k_vec / k_statevec right after the control kernel)
+#define VO_SAVE_SPARE   0x001   // rhsSpare <- rhsOld                 (tranan.cc:501-502)
+#define VO_ACCEPT_SOLS  0x002   // sols[0] <- rhsOld after rotation   (ckt.cc:372-381)
+#define VO_RESTORE_OLD  0x004   // rhsOld <- rhsSpare                 (tranan.cc:775-776)
+#define VO_BK_SAVE      0x008   // backup(DEV_SAVE)                   (ckt.cc:1329-1338)
+#define VO_BK_RESTORE   0x010   // backup(DEV_RESTORE)                (ckt.cc:1339-1352)
+#define VO_ZERO_STATE0  0x020   // memset(CKTstate0,0)                (ckt.cc:1499)
+#define VO_HIST_INIT    0x040   // states[1..maxord+1] <- state0      (tranan.cc:408-411,431)
+#define VO_FIRSTTIME    0x080   // state2 (,state3) <- state1         (tranan.cc:736-742)
+#define VO_INTERP       0x100   // emit interpolated output points    (tranan.cc:963-1116)
+#define VO_DUMP_DIRECT  0x200   // emit rhsOld as an output point     (tranan.cc:977-981)
+
+struct TrialCtl {
+    // sCKTPOD / sTRANint scalars (circuit.h:1562-1662, trandefs.h:93-151)
+    double time, delta, deltaOld[7], saveDelta, ag[7], pred[2];
+    double srcFact, diagGmin, devMaxDelta, breaks[2];
+    double t_check, t_delmax, olddelta, intDevMaxDelta;
+    // DCOP steppers (ckt.cc:1492-1776)
+    double g_factor, g_oldgmin, g_gtarget, s_raise, s_lastraise, s_convfact;
+    // interpolation request for k_vec
+    double ip_time, ip_c2, ip_c3, ip_c4, ip_tcheck0;
+    int ip_n, ip_out0, ip_degree;
+    int mode, order, iterno, ipass, maxIter, pc, ret, status;
+    int firstmode, continuemode, iterlim;       // op() arguments
+    int op_stage;                               // which stepper of op() is running
+    int g_srcstep, g_iters_mark, g_succeeded, s_iters_mark;
+    int t_firsttime, t_ordcnt, brk, trapCheck;
+    int sols_base, st_base;
+    int accepted, rejected, numIter, timePts, tranIter, iterCut, trapCut, npts, lastIters;
+    int niter_mark;
+    int vecops;
+    int have_save;
+    int want_load;                              // a load must follow in this tick
+};
+
+// ---- "hot" per-trial scalars read by the load / solve kernels (SoA, coalesced) ----
+struct HotView {
+    int    *mode;       // [ldt] CKTmode, or 0 if the trial takes no load this tick
+    int    *order;
+    int    *st_base;
+    int    *noncon;     // set (|=1) by load kernels (incNoncon), cleared by control
+    int    *trapbad;    // set by integrate() when trapcheck fires
+    int    *trapcheck;  // CKTtrapCheck for this load
+    int    *active;     // 1 while the trial is running
+    int    *do_solve;   // 1: the load of this tick is a NIiter load, solve it next tick
+    int    *iterno;     // value before the solve of this tick
+    double *time, *delta, *srcfact, *diaggmin;
+    double *ag;         // [7][ldt]
+    double *pred;       // [2][ldt]
+    double *deltaOld;   // [7][ldt]   (LTE kernel)
+    // results of the solve kernel
+    int    *nodeconv;   // 1 = node test failed
+    int    *solve_err;  // 0 / B200_E_SINGULAR / B200_E_MATHINV
+    int    *need_devconv;
+    int    *devconv;    // 1 = device convTest failed
+    // LTE
+    int    *want_lte;   // 1: compute LTE for this trial
+    double *lte;        // [2][ldt] min over charges for order, order+1 (un-normalised)
+};
+
+struct Consts {
+    b200_options opt;
+    int n, nnz, numStates, ldt, ntrials, NS /* state ring size = maxord+2 */;
+    int nnzLU, ncslot, nrslot;
+    double t_stop, t_step, t_start, maxStep, delmin, minBreak, break0, break1;
+    int nocut, uic, hadNodeset, npoints_max, method;
+    int nbrks, nlat;
+};
+
+struct MosView {
+    int n;
+    const int *d, *g, *s, *b, *dp, *sp, *type, *off, *state, *cslot, *rslot;
+    ParamRef prm[MP_NPARAMS];
+    double *cache;      // [MC_NCACHE][n][ldt]
+    double *save;       // backup copy of cache
+};
+struct CapView {
+    int n;
+    const int *pos, *neg, *state, *cslot, *rslot;
+    ParamRef capac, ic;
+    double *geq, *ceq;  // [n][ldt]  (CAPgeq / CAPceq instance fields, capload.cc:150-151)
+};
+struct SrcView {
+    int n;
+    const int *kind, *fn, *dcgiven, *rslot, *coef_off, *ncoef;
+    ParamRef dc;
+    const double *pool;
+    double *dcval;      // [n][ldt] run-time SRCdcValue (srcload.cc:236-237)
+};
+
+struct VecView {
+    double *X[2];       // rhs / rhsOld ping-pong, [n+1][ldt]
+    double *spare;      // [n+1][ldt]
+    double *sols;       // [8][n+1][ldt]
+    double *oldSol;     // [n+1][ldt]
+    double *states;     // [NS][numStates][ldt]
+    double *oldState0;  // [numStates][ldt]
+    double *contrib;    // [ncslot][ldt]
+    double *rcontrib;   // [nrslot][ldt]
+    double *out;        // [npoints_max][n][ldt] -> transposed on fetch
+};

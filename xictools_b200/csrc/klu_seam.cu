@@ -1,0 +1,363 @@
+// klu_seam.cu -- (1) the KLU-hook seam as a batched C ABI, (2) the debug load hook.
+//
+// (1) spMatlabMatrix::factor/refactor/solve (xt_base/include/sparse/spmatrix.h:853-857) as
+//     KLUmatrix implements them (wrspice/src/sparse/kluif.cc:569-628): klu_analyze +
+//     klu_factor once, then klu_refactor + klu_solve per Newton iteration with the pivot
+//     sequence frozen.  Batched: one CSC pattern, ntrials value arrays.  The same k_solve
+//     kernel as the engine is used, with identity gather lists (A[p] = 0 + Ax[p]).
+// (2) b200_batch_debug_load: one sCKT::load + loadGmin at a forced state, matrix/RHS
+//     assembled to global memory for stamp-for-stamp comparison with the oracle.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "b200_internal.h"
+#include "device_state.h"
+#include "dev_load.cuh"
+#include "dev_ctl.cuh"
+#include "kernels.h"
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "b200spice: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    return B200_E_NOGPU; } } while (0)
+
+struct b200_klu {
+    Analysis an;
+    Consts K;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    SolveView Sv;
+    int cap_trials = 0;
+    HotView hot; VecView V;
+    double *dX0 = nullptr, *dX1 = nullptr, *dAxh = nullptr, *dBh = nullptr;
+    int *dstat = nullptr;
+
+    template <class T> T *dalloc(size_t n) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, (n ? n : 1)*sizeof(T)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, (n ? n : 1)*sizeof(T));
+        allocs.push_back(p);
+        return (T*)p;
+    }
+    template <class T> T *dupload(const std::vector<T> &v) {
+        T *p = dalloc<T>(v.size());
+        if (p && !v.empty()) cudaMemcpy(p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice);
+        return p;
+    }
+};
+
+// [rows][ntrials-major host] <-> [rows][ldt] device transposes
+__global__ void k_transpose_in(int rows, int ntrials, int ldt, const double *src /* [nt][rows] */,
+    double *dst /* [rows][ldt] */)
+{
+    __shared__ double tile[32][33];
+    int r0 = blockIdx.y*32, t0 = blockIdx.x*32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int t = t0 + k, r = r0 + threadIdx.x;
+        tile[k][threadIdx.x] = (t < ntrials && r < rows) ? src[(size_t)t*rows + r] : 0.0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int r = r0 + k, t = t0 + threadIdx.x;
+        if (r < rows && t < ldt) dst[(size_t)r*ldt + t] = (t < ntrials) ? tile[threadIdx.x][k] : 0.0;
+    }
+}
+
+__global__ void k_transpose_out(int rows, int ntrials, int ldt, const double *src /* [rows+1][ldt], row 0 = ground */,
+    double *dst /* [nt][rows] */)
+{
+    __shared__ double tile[32][33];
+    int r0 = blockIdx.y*32, t0 = blockIdx.x*32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int r = r0 + k, t = t0 + threadIdx.x;
+        tile[k][threadIdx.x] = (r < rows && t < ntrials) ? src[(size_t)(r + 1)*ldt + t] : 0.0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int t = t0 + k, r = r0 + threadIdx.x;
+        if (r < rows && t < ntrials) dst[(size_t)t*rows + r] = tile[threadIdx.x][k];
+    }
+}
+
+__global__ void k_set_int(int *p, int n, int v)
+{
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// debug assemble: Ax[p][t], rhs[row][t] exactly as k_solve builds them (before the LU)
+__global__ void k_debug_assemble(Consts K, HotView hot, VecView V, SolveView Sv, int nnz,
+    const int *a2lu_unused, double *Ax, double *rhs)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int e = blockIdx.y;
+    if (t >= K.ntrials) return;
+    int ldt = K.ldt;
+    int mode = hot.mode[t];
+    double diagGmin = hot.diaggmin[t];
+    bool ns_on = (mode & MODEDC) && (mode & (MODEINITJCT | MODEINITFIX));
+    bool ic_on = (mode & MODEDC) && (mode & MODETRANOP) && !(mode & MODEUIC);
+    if (e < nnz) {
+        int p = e;
+        double v = Sv.Ainit[p];
+        for (int q = Sv.cg_ptr[p]; q < Sv.cg_ptr[p+1]; q++)
+            v += V.contrib[(size_t)Sv.cg_idx[q]*ldt + t];
+        int dn = Sv.diag_node[p];
+        if (dn) {
+            if (ns_on && Sv.ns_given[dn]) v += 1.0;
+            if (ic_on && Sv.ic_given[dn]) v += 1.0;
+            if (Sv.ntype[dn] == 0) {
+                if (diagGmin != 0.0) v += diagGmin;
+                else if (K.opt.forcegmin && (v >= 0.0 && v < K.opt.gmin)) v = K.opt.gmin;
+                else if (v > K.opt.gmax) v = K.opt.gmax;
+            }
+        }
+        Ax[(size_t)p*ldt + t] = v;
+    }
+    else {
+        int row = e - nnz;                   // 0..n
+        double v = 0.0;
+        if (row > 0) {
+            for (int q = Sv.rg_ptr[row]; q < Sv.rg_ptr[row+1]; q++)
+                v += V.rcontrib[(size_t)Sv.rg_idx[q]*ldt + t];
+            if (ns_on && Sv.ns_given[row]) v += Sv.ns_val[row];
+            if (ic_on && Sv.ic_given[row]) v += Sv.ic_val[row];
+        }
+        rhs[(size_t)row*ldt + t] = v;
+    }
+}
+
+__global__ void k_debug_set_hot(Consts K, HotView hot, int mode, double time, double delta,
+    int order, double ag0, double ag1, double p0, double p1)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= K.ldt) return;
+    hot.mode[t] = mode; hot.order[t] = order; hot.st_base[t] = 0; hot.noncon[t] = 0;
+    hot.trapbad[t] = 0; hot.trapcheck[t] = 0; hot.time[t] = time; hot.delta[t] = delta;
+    hot.srcfact[t] = 1.0; hot.diaggmin[t] = 0.0;
+    hot.ag[t] = ag0; hot.ag[K.ldt + t] = ag1;
+    hot.pred[t] = p0; hot.pred[K.ldt + t] = p1;
+}
+
+// accessors implemented in capi.cu
+int b200_internal_prepare(b200_batch *b);
+int b200_internal_views(b200_batch *b, Consts **K, HotView **hot, VecView **V, MosView **M,
+    CapView **Cp, SrcView **S, SolveView **Sv, cudaStream_t *st, int **cur);
+
+extern "C" {
+
+int b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, int order,
+    const double *rhsold, double *Ax, double *rhs)
+{
+    if (!b) return B200_E_BADPARM;
+    int rc = b200_internal_prepare(b);
+    if (rc) return rc;
+    Consts *K; HotView *hot; VecView *V; MosView *M; CapView *Cp; SrcView *S; SolveView *Sv;
+    cudaStream_t st; int *cur;
+    b200_internal_views(b, &K, &hot, &V, &M, &Cp, &S, &Sv, &st, &cur);
+    if (K->method != 0) return B200_E_UNSUPP;
+    size_t ldt = K->ldt;
+    int n = K->n, nnz = K->nnz, nt = K->ntrials;
+    double ag0 = 0, ag1 = 0, p0 = 1.0, p1 = 0.0;
+    if (mode & MODETRAN) {
+        // NIcomCof + predict with deltaOld[*] = delta (oracle wo_debug_load does the same)
+        if (order == 2) { double t0 = 1.0/(1.0 - K->opt.xmu); ag0 = t0/delta; ag1 = t0*K->opt.xmu; }
+        else { ag0 = 1.0/delta; ag1 = -ag0; }
+        p1 = -delta/delta; p0 = 1 - p1;
+    }
+    k_debug_set_hot<<<(unsigned)((ldt + 127)/128), 128, 0, st>>>(*K, *hot, mode, time, delta, order, ag0, ag1, p0, p1);
+    double *X = V->X[0];
+    if (rhsold) {
+        std::vector<double> row(ldt);
+        for (int i = 0; i <= n; i++) {
+            std::fill(row.begin(), row.end(), 0.0);
+            memcpy(row.data(), rhsold + (size_t)i*nt, nt*sizeof(double));
+            CK(cudaMemcpyAsync(X + (size_t)i*ldt, row.data(), ldt*sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
+    }
+    else
+        CK(cudaMemsetAsync(X, 0, (size_t)(n + 1)*ldt*sizeof(double), st));
+    launch_loads(st, *K, *hot, *V, *M, *Cp, *S, X);
+    double *dAx = nullptr, *drhs = nullptr;
+    CK(cudaMalloc(&dAx, (size_t)nnz*ldt*sizeof(double)));
+    CK(cudaMalloc(&drhs, (size_t)(n + 1)*ldt*sizeof(double)));
+    dim3 g((nt + 127)/128, nnz + n + 1);
+    k_debug_assemble<<<g, 128, 0, st>>>(*K, *hot, *V, *Sv, nnz, nullptr, dAx, drhs);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    std::vector<double> hb((size_t)std::max(nnz, n + 1)*ldt);
+    CK(cudaMemcpy(hb.data(), dAx, (size_t)nnz*ldt*sizeof(double), cudaMemcpyDeviceToHost));
+    for (int p = 0; p < nnz; p++) memcpy(Ax + (size_t)p*nt, hb.data() + (size_t)p*ldt, nt*sizeof(double));
+    CK(cudaMemcpy(hb.data(), drhs, (size_t)(n + 1)*ldt*sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i <= n; i++) memcpy(rhs + (size_t)i*nt, hb.data() + (size_t)i*ldt, nt*sizeof(double));
+    cudaFree(dAx); cudaFree(drhs);
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, double pivrel,
+    double pivabs, int device, b200_klu **out)
+{
+    (void)pivrel; (void)pivabs;
+    *out = nullptr;
+    if (n <= 0 || !Ap || !Ai || !Ax0) return B200_E_BADPARM;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
+        fprintf(stderr, "b200spice: no CUDA device (no CPU fallback exists)\n");
+        return B200_E_NOGPU;
+    }
+    CK(cudaSetDevice(device));
+    b200_klu *k = new b200_klu;
+    k->device = device;
+    Analysis &an = k->an;
+    an.n = n; an.nnz = Ap[n];
+    an.Ap.assign(Ap, Ap + n + 1); an.Ai.assign(Ai, Ai + an.nnz);
+    an.ntype.assign(n + 1, 0);
+    an.diag.assign(n + 1, -1);
+    for (int j = 0; j < n; j++)
+        for (int p = Ap[j]; p < Ap[j+1]; p++) if (Ai[p] == j) an.diag[j+1] = p;
+    // ordering sees the first matrix: +-1 entries count as constants, nonzero diagonals as safe
+    an.Ainit.assign(Ax0, Ax0 + an.nnz);
+    an.cg_ptr.assign(an.nnz + 1, 0);
+    an.rg_ptr.assign(n + 2, 0);
+    b200_order_markowitz(an);
+    b200_build_lu(an);
+    // run-time gather lists are the identity: A[p] = 0 + Ax[p], b[row] = 0 + B[row-1]
+    an.Ainit.assign(an.nnz, 0.0);
+    an.cg_idx.resize(an.nnz);
+    for (int p = 0; p < an.nnz; p++) { an.cg_ptr[p] = p; an.cg_idx[p] = p; }
+    an.cg_ptr[an.nnz] = an.nnz;
+    an.rg_idx.resize(n);
+    an.rg_ptr[0] = 0; an.rg_ptr[1] = 0;
+    for (int r = 1; r <= n; r++) { an.rg_idx[r-1] = r - 1; an.rg_ptr[r+1] = r; }
+    an.ic_given.assign(n + 1, 0); an.ns_given.assign(n + 1, 0);
+    an.ic_val.assign(n + 1, 0.0); an.ns_val.assign(n + 1, 0.0);
+
+    Consts &K = k->K;
+    memset(&K, 0, sizeof(K));
+    b200_options_default(&K.opt);
+    K.opt.gmax = HUGE_VAL;
+    K.n = n; K.nnz = an.nnz; K.nnzLU = an.nnzLU; K.NS = 4;
+    if (solve_smem_bytes(K) > 227*1024) { delete k; return B200_E_UNSUPP; }
+    CK(cudaStreamCreate(&k->stream));
+    SolveView &Sv = k->Sv;
+    Sv.lu_src = k->dupload(an.lu_src); Sv.Ainit = k->dupload(an.Ainit);
+    Sv.cg_ptr = k->dupload(an.cg_ptr); Sv.cg_idx = k->dupload(an.cg_idx);
+    Sv.rg_ptr = k->dupload(an.rg_ptr); Sv.rg_idx = k->dupload(an.rg_idx);
+    std::vector<int> dn(an.nnz, 0);
+    Sv.diag_node = k->dupload(dn);
+    Sv.ntype = k->dupload(an.ntype);
+    Sv.ic_given = k->dupload(an.ic_given); Sv.ns_given = k->dupload(an.ns_given);
+    Sv.ic_val = k->dupload(an.ic_val); Sv.ns_val = k->dupload(an.ns_val);
+    Sv.yperm_in = k->dupload(an.yperm_in); Sv.yperm_out = k->dupload(an.yperm_out);
+    auto sync_flags = [](const std::vector<LuRound> &rounds, const std::vector<int> &lvl) {
+        std::vector<char> f(rounds.size(), 0);
+        for (size_t l = 0; l + 1 < lvl.size(); l++)
+            if (lvl[l] < (int)rounds.size() && lvl[l] < lvl[l+1]) f[lvl[l]] = 1;
+        return f;
+    };
+    Sv.fac_nrounds = (int)an.fac.rounds.size(); Sv.fwd_nrounds = (int)an.fwd.rounds.size();
+    Sv.bwd_nrounds = (int)an.bwd.rounds.size();
+    Sv.fac_rounds = k->dupload(an.fac.rounds); Sv.fwd_rounds = k->dupload(an.fwd.rounds);
+    Sv.bwd_rounds = k->dupload(an.bwd.rounds);
+    Sv.fac_ops = k->dupload(an.fac.ops); Sv.fwd_ops = k->dupload(an.fwd.ops); Sv.bwd_ops = k->dupload(an.bwd.ops);
+    Sv.fac_sync = k->dupload(sync_flags(an.fac.rounds, an.fac.level_round_off));
+    Sv.fwd_sync = k->dupload(sync_flags(an.fwd.rounds, an.fwd.level_round_off));
+    Sv.bwd_sync = k->dupload(sync_flags(an.bwd.rounds, an.bwd.level_round_off));
+    Sv.fac_fin_diag = k->dupload(an.fac.fin_diag); Sv.fac_fin_lbeg = k->dupload(an.fac.fin_lbeg);
+    Sv.fac_fin_lend = k->dupload(an.fac.fin_lend);
+    Sv.fwd_fin_row = k->dupload(an.fwd.fin_row);
+    Sv.bwd_fin_row = k->dupload(an.bwd.fin_row); Sv.bwd_fin_diag = k->dupload(an.bwd.fin_diag);
+    CK(cudaDeviceSynchronize());
+    *out = k;
+    return B200_OK;
+}
+
+void b200_klu_free(b200_klu *k)
+{
+    if (!k) return;
+    cudaSetDevice(k->device);
+    for (void *p : k->allocs) cudaFree(p);
+    if (k->stream) cudaStreamDestroy(k->stream);
+    delete k;
+}
+
+int b200_klu_lu_nnz(const b200_klu *k) { return k ? k->an.nnzLU : 0; }
+
+static int klu_ensure(b200_klu *k, int ntrials)
+{
+    int ldt = (ntrials + 31) & ~31;
+    if (k->cap_trials >= ldt) return B200_OK;
+    HotView &h = k->hot;
+    h.mode = k->dalloc<int>(ldt); h.do_solve = k->dalloc<int>(ldt); h.iterno = k->dalloc<int>(ldt);
+    h.noncon = k->dalloc<int>(ldt); h.diaggmin = k->dalloc<double>(ldt);
+    h.solve_err = k->dalloc<int>(ldt); h.nodeconv = k->dalloc<int>(ldt);
+    h.devconv = k->dalloc<int>(ldt); h.need_devconv = k->dalloc<int>(ldt);
+    k->dX0 = k->dalloc<double>((size_t)(k->an.n + 1)*ldt);
+    k->dX1 = k->dalloc<double>((size_t)(k->an.n + 1)*ldt);
+    if (!k->dX1) return B200_E_NOMEM;
+    k_set_int<<<(ldt + 127)/128, 128, 0, k->stream>>>(h.do_solve, ldt, 1);
+    k->cap_trials = ldt;
+    return B200_OK;
+}
+
+int b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double *dAx, double *dB,
+    int *dstatus, void *cuda_stream)
+{
+    if (!k || ntrials <= 0 || ldt < ntrials) return B200_E_BADPARM;
+    CK(cudaSetDevice(k->device));
+    int rc = klu_ensure(k, ldt);
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : k->stream;
+    Consts K = k->K;
+    K.ntrials = ntrials; K.ldt = ldt;
+    VecView V;
+    memset(&V, 0, sizeof(V));
+    V.contrib = const_cast<double*>(dAx);
+    V.rcontrib = dB;
+    // solution goes to dX1 ([n+1][ldt], row 0 = ground), then back into dB
+    rc = launch_solve(st, K, k->hot, V, k->Sv, k->dX0, k->dX1);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dB, k->dX1 + ldt, (size_t)k->an.n*ldt*sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (dstatus)
+        CK(cudaMemcpyAsync(dstatus, k->hot.solve_err, ntrials*sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return B200_OK;
+}
+
+int b200_klu_refactor_solve_host(b200_klu *k, int ntrials, const double *Ax, double *B, int *status)
+{
+    if (!k || ntrials <= 0 || !Ax || !B) return B200_E_BADPARM;
+    CK(cudaSetDevice(k->device));
+    int ldt = (ntrials + 31) & ~31;
+    int n = k->an.n, nnz = k->an.nnz;
+    cudaStream_t st = k->stream;
+    double *hAx = nullptr, *hB = nullptr, *dAx = nullptr, *dB = nullptr; int *dst = nullptr;
+    CK(cudaMalloc(&hAx, (size_t)ntrials*nnz*sizeof(double)));
+    CK(cudaMalloc(&hB, (size_t)ntrials*n*sizeof(double)));
+    CK(cudaMalloc(&dAx, (size_t)nnz*ldt*sizeof(double)));
+    CK(cudaMalloc(&dB, (size_t)n*ldt*sizeof(double)));
+    CK(cudaMalloc(&dst, ldt*sizeof(int)));
+    CK(cudaMemcpyAsync(hAx, Ax, (size_t)ntrials*nnz*sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(hB, B, (size_t)ntrials*n*sizeof(double), cudaMemcpyHostToDevice, st));
+    dim3 blk(32, 8);
+    k_transpose_in<<<dim3(ldt/32, (nnz + 31)/32), blk, 0, st>>>(nnz, ntrials, ldt, hAx, dAx);
+    k_transpose_in<<<dim3(ldt/32, (n + 31)/32), blk, 0, st>>>(n, ntrials, ldt, hB, dB);
+    int rc = b200_klu_refactor_solve_dev(k, ntrials, ldt, dAx, dB, dst, st);
+    if (!rc) {
+        // dB now holds x as [n][ldt]; transpose back (k_transpose_out skips a ground row, so
+        // hand it a pointer one row before dB)
+        k_transpose_out<<<dim3(ldt/32, (n + 31)/32), blk, 0, st>>>(n, ntrials, ldt, dB - ldt, hB);
+        CK(cudaMemcpyAsync(B, hB, (size_t)ntrials*n*sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (status) CK(cudaMemcpyAsync(status, dst, ntrials*sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+    }
+    cudaFree(hAx); cudaFree(hB); cudaFree(dAx); cudaFree(dB); cudaFree(dst);
+    return rc;
+}
+
+} // extern "C"
