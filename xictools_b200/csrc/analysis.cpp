@@ -685,21 +685,38 @@ void b200_build_lu(Analysis &an)
         }
     }
 
-    // ---- factor program: task = column j ----
+    // ---- factor program: task = column j, dot-product form ----
+    // For column j the entries are finalised top to bottom: entry (i,j) = A(i,j) minus the
+    // products L(i,k)*U(k,j) over the pivots k < i of the column, in ascending k -- the same
+    // per-entry operation order as the left-looking column sweep, with the accumulator kept
+    // in a register.
     std::vector<std::vector<LuOp>> fops(n);
     std::vector<int> flevel(n, 0);
     {
         std::vector<int> pos2slot(n, -1);
+        std::vector<std::vector<LuOp>> rowops(n);
         for (int j = 0; j < n; j++) {
             for (int p = an.Up[j]; p < an.Up[j+1]; p++) pos2slot[an.Ui[p]] = an.slotU[p];
             pos2slot[j] = an.slotD[j];
             for (int p = an.Lp[j]; p < an.Lp[j+1]; p++) pos2slot[an.Li[p]] = an.slotL[p];
             int lev = 0;
+            std::vector<int> touched;
             for (int p = an.Up[j]; p < an.Up[j+1]; p++) {
                 int k = an.Ui[p];
                 lev = std::max(lev, flevel[k] + 1);
-                for (int q = an.Lp[k]; q < an.Lp[k+1]; q++)
-                    fops[j].push_back(LuOp{pos2slot[an.Li[q]], an.slotL[q], an.slotU[p]});
+                for (int q = an.Lp[k]; q < an.Lp[k+1]; q++) {
+                    int i = an.Li[q];
+                    if (rowops[i].empty()) touched.push_back(i);
+                    rowops[i].push_back(LuOp{pos2slot[i], an.slotL[q], an.slotU[p]});
+                }
+            }
+            std::sort(touched.begin(), touched.end());
+            for (int i : touched) {
+                auto &v = rowops[i];
+                v.front().dst |= LUOP_FIRST;
+                v.back().dst |= LUOP_LAST;
+                fops[j].insert(fops[j].end(), v.begin(), v.end());
+                v.clear();
             }
             flevel[j] = lev;
         }
@@ -768,4 +785,219 @@ void b200_build_lu(Analysis &an)
 
     an.yperm_in.resize(n); an.yperm_out.resize(n);
     for (int k = 0; k < n; k++) { an.yperm_in[k] = an.rowperm[k] + 1; an.yperm_out[k] = an.colperm[k] + 1; }
+
+    // ---- phase-2 stream ----
+    an.strm.clear(); an.strm_round.clear();
+    auto emit = [&](const std::vector<LuRound> &rounds, const std::vector<LuOp> &ops,
+            const std::vector<int> &lvl, int kind, const std::vector<int> *f0,
+            const std::vector<int> *f1, const std::vector<int> *f2) {
+        std::vector<char> sync(rounds.size(), 0);
+        for (size_t l = 0; l + 1 < lvl.size(); l++)
+            if (lvl[l] < (int)rounds.size() && lvl[l] < lvl[l+1]) sync[lvl[l]] = 1;
+        for (size_t r = 0; r < rounds.size(); r++) {
+            const LuRound &rd = rounds[r];
+            int row0 = (int)(an.strm.size()/96);
+            int k2 = kind;
+            if (kind == 0 && f1 && f2)
+                for (int e = 0; e < 32; e++)
+                    if ((*f2)[rd.fin_off + e] - (*f1)[rd.fin_off + e] > 32) k2 |= 4;   // cooperative pivot division
+            an.strm_round.push_back(rd.nsteps); an.strm_round.push_back(k2);
+            an.strm_round.push_back(sync[r]); an.strm_round.push_back(row0);
+            for (int e = 0; e < 32; e++) {
+                an.strm.push_back(f0 ? (*f0)[rd.fin_off + e] : -1);
+                an.strm.push_back(f1 ? (*f1)[rd.fin_off + e] : -1);
+                an.strm.push_back(f2 ? (*f2)[rd.fin_off + e] : -1);
+            }
+            for (int st = 0; st < rd.nsteps; st++)
+                for (int e = 0; e < 32; e++) {
+                    const LuOp &op = ops[rd.op_off + st*32 + e];
+                    an.strm.push_back(op.dst); an.strm.push_back(op.a); an.strm.push_back(op.b);
+                }
+        }
+    };
+    emit(an.fac.rounds, an.fac.ops, an.fac.level_round_off, 0, &an.fac.fin_diag, &an.fac.fin_lbeg, &an.fac.fin_lend);
+    emit(an.fwd.rounds, an.fwd.ops, an.fwd.level_round_off, 1, &an.fwd.fin_row, nullptr, nullptr);
+    emit(an.bwd.rounds, an.bwd.ops, an.bwd.level_round_off, 2, &an.bwd.fin_row, &an.bwd.fin_diag, nullptr);
+    // the first fwd / bwd round must see the previous phase complete
+    {
+        size_t nf = an.fac.rounds.size(), nw = an.fwd.rounds.size();
+        if (nf < an.strm_round.size()/4) an.strm_round[nf*4 + 2] = 1;
+        if (nf + nw < an.strm_round.size()/4) an.strm_round[(nf + nw)*4 + 2] = 1;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Assembly program: the ordered gather lists flattened into per-lane streams so that every
+// lane issues long runs of independent loads (no pointer chasing through cg_ptr/cg_idx in
+// the kernel).  Lists longer than `long_threshold` are left to the staged path.
+// ---------------------------------------------------------------------------------------
+void b200_build_asm(Analysis &an, int long_threshold)
+{
+    AsmProgram &A = an.asmp;
+    int n = an.n, nlu = an.nnzLU;
+    A.long_kind.clear(); A.long_idx.clear();
+    A.fin_node.assign(nlu + n, 0);
+    struct Item { int target; int init; std::vector<int> terms; };
+    std::vector<Item> items;
+    std::vector<int> p2node(an.nnz, 0);
+    for (int i = 1; i <= n; i++) if (an.diag[i] >= 0) p2node[an.diag[i]] = i;
+    for (int s = 0; s < nlu; s++) {
+        int p = an.lu_src[s];
+        Item it; it.target = s; it.init = (p >= 0) ? p : -2;
+        if (p >= 0) {
+            int dn = p2node[p];
+            if (dn) A.fin_node[s] = dn | ASM_DIAG | (an.ntype[dn] == 0 ? ASM_VNODE : 0);
+            int cnt = an.cg_ptr[p+1] - an.cg_ptr[p];
+            if (cnt > long_threshold) { A.long_kind.push_back(0); A.long_idx.push_back(s); continue; }
+            for (int q = an.cg_ptr[p]; q < an.cg_ptr[p+1]; q++) it.terms.push_back(an.cg_idx[q]);
+        }
+        items.push_back(std::move(it));
+    }
+    for (int k = 0; k < n; k++) {
+        int row = an.yperm_in[k];
+        Item it; it.target = nlu + k; it.init = -2;
+        A.fin_node[nlu + k] = row | ASM_ROW;
+        int cnt = an.rg_ptr[row+1] - an.rg_ptr[row];
+        if (cnt > long_threshold) { A.long_kind.push_back(1); A.long_idx.push_back(k); continue; }
+        for (int q = an.rg_ptr[row]; q < an.rg_ptr[row+1]; q++) it.terms.push_back(an.rg_idx[q] | ASM_RHS);
+        items.push_back(std::move(it));
+    }
+    // with long lists present, warp 0 of the CTA runs the staged path: 24 short lanes; else 32
+    A.nlanes = A.long_kind.empty() ? 32 : 24;
+    // greedy balance: longest items first onto the least-loaded lane
+    std::vector<int> order(items.size());
+    for (size_t i = 0; i < items.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return std::max<size_t>(1, items[a].terms.size()) > std::max<size_t>(1, items[b].terms.size()); });
+    std::vector<std::vector<AsmOp>> lanes(A.nlanes);
+    for (int idx : order) {
+        int best = 0;
+        for (int l = 1; l < A.nlanes; l++) if (lanes[l].size() < lanes[best].size()) best = l;
+        Item &it = items[idx];
+        if (it.terms.empty())
+            lanes[best].push_back(AsmOp{-1, it.init, it.target, A.fin_node[it.target]});
+        else
+            for (size_t q = 0; q < it.terms.size(); q++)
+                lanes[best].push_back(AsmOp{it.terms[q], q == 0 ? it.init : -1,
+                    q + 1 == it.terms.size() ? it.target : -1,
+                    q + 1 == it.terms.size() ? A.fin_node[it.target] : 0});
+    }
+    size_t ns = 0;
+    for (auto &l : lanes) ns = std::max(ns, l.size());
+    ns = (ns + 15) & ~(size_t)15;                // kernel consumes 16 steps per batch
+    A.nsteps = (int)ns;
+    A.ops.assign(ns*A.nlanes, AsmOp{-1, -1, -1, 0});
+    for (int l = 0; l < A.nlanes; l++)
+        for (size_t q = 0; q < lanes[l].size(); q++)
+            A.ops[q*A.nlanes + l] = lanes[l][q];
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Streamed assembly: renumber every contribution slot into assembly order and build the
+// per-chunk segment schedule (see SegOp).  After this call
+//   * an.cg_idx / an.rg_idx and the device tables (mos/cap/src cslot, rslot) hold the NEW
+//     indices into one contribution array of an.NC entries,
+//   * each gather list is a run of consecutive indices.
+// A run that crosses a chunk boundary is always given to lane 0, which carries the partial
+// sum in a register, so the reference's summation order is preserved across chunks.
+// ---------------------------------------------------------------------------------------
+void b200_build_stream_asm(Analysis &an)
+{
+    int n = an.n, nlu = an.nnzLU;
+    std::vector<int> newc(an.ncslot, -1), newr(an.nrslot, -1);
+    an.const_idx.clear(); an.const_val.clear(); an.seg_ops.clear(); an.seg_chunk.clear(); an.seg_maxsteps = 0;
+    struct Run { int pos, len, target, info; };
+    std::vector<Run> runs;
+    std::vector<int> p2node(an.nnz, 0);
+    for (int i = 1; i <= n; i++) if (an.diag[i] >= 0) p2node[an.diag[i]] = i;
+    int next = 0;
+    for (int s = 0; s < nlu; s++) {
+        int p = an.lu_src[s];
+        Run r; r.pos = next; r.len = 0; r.target = s; r.info = 0;
+        if (p >= 0) {
+            int dn = p2node[p];
+            if (dn) r.info = dn | ASM_DIAG | (an.ntype[dn] == 0 ? ASM_VNODE : 0);
+            // a nonzero preloaded constant (Ainit) is the first term of the run: it lives in a
+            // contribution slot of its own that is written once at batch creation
+            // (0.0 + Ainit == Ainit exactly, so the sum is the reference's Ainit + c1 + c2 ...)
+            if (an.Ainit[p] != 0.0) { an.const_idx.push_back(next++); an.const_val.push_back(an.Ainit[p]); r.len++; }
+            for (int q = an.cg_ptr[p]; q < an.cg_ptr[p+1]; q++) { newc[an.cg_idx[q]] = next++; r.len++; }
+        }
+        runs.push_back(r);
+    }
+    for (int k = 0; k < n; k++) {
+        int row = an.yperm_in[k];
+        Run r; r.pos = next; r.len = 0; r.target = nlu + k; r.info = row | ASM_ROW;
+        for (int q = an.rg_ptr[row]; q < an.rg_ptr[row+1]; q++) { newr[an.rg_idx[q]] = next++; r.len++; }
+        runs.push_back(r);
+    }
+    an.NC = next;
+    for (auto &c : an.cg_idx) c = newc[c];
+    for (auto &c : an.rg_idx) c = newr[c];
+    auto remap = [](std::vector<int> &v, const std::vector<int> &m) { for (auto &x : v) if (x >= 0) x = m[x]; };
+    remap(an.mos.cslot, newc); remap(an.mos.rslot, newr);
+    remap(an.cap.cslot, newc); remap(an.cap.rslot, newr);
+    remap(an.src.rslot, newr);
+
+    // chunk schedule
+    int nchunks = (an.NC + SEG_CHUNK - 1)/SEG_CHUNK;
+    if (nchunks == 0) nchunks = 1;
+    std::vector<std::vector<std::vector<SegOp>>> sched(nchunks, std::vector<std::vector<SegOp>>(32));
+    // zero-length runs (fill slots, entries with only Ainit) belong to the chunk of their position
+    std::vector<std::vector<SegOp>> pieces(nchunks);        // non-crossing pieces per chunk
+    for (auto &r : runs) {
+        if (r.len == 0) {
+            int c = std::min(nchunks - 1, r.pos/SEG_CHUNK);
+            pieces[c].push_back(SegOp{r.pos, 0, r.target, r.info | SEG_START});
+            continue;
+        }
+        int c0 = r.pos/SEG_CHUNK, c1 = (r.pos + r.len - 1)/SEG_CHUNK;
+        if (c0 == c1) {
+            pieces[c0].push_back(SegOp{r.pos, r.len, r.target, r.info | SEG_START});
+            continue;
+        }
+        // crossing run: lane 0 of every chunk it touches, in order
+        for (int c = c0; c <= c1; c++) {
+            int b = std::max(r.pos, c*SEG_CHUNK), e = std::min(r.pos + r.len, (c + 1)*SEG_CHUNK);
+            SegOp op{b, e - b, (c == c1) ? r.target : -1, r.info | (c == c0 ? SEG_START : 0)};
+            if (c == c0) sched[c][0].push_back(op);                    // starts here: last op of lane 0
+            else sched[c][0].insert(sched[c][0].begin(), op);          // continues: first op of lane 0
+        }
+    }
+    for (int c = 0; c < nchunks; c++) {
+        // lane 0 already holds crossing pieces: [continuing..., (others go in between), starting]
+        std::vector<SegOp> head, tail;
+        for (auto &op : sched[c][0]) ((op.info & SEG_START) ? tail : head).push_back(op);
+        std::vector<size_t> load(32, 0);
+        std::vector<std::vector<SegOp>> mid(32);
+        for (auto &op : head) { load[0] += std::max(1, op.len); if (op.target < 0) load[0] += (size_t)1 << 40; }
+        for (auto &op : tail) load[0] += std::max(1, op.len);
+        std::vector<SegOp> &pc = pieces[c];
+        std::stable_sort(pc.begin(), pc.end(), [](const SegOp &a, const SegOp &b) { return a.len > b.len; });
+        for (auto &op : pc) {
+            int best = 0;
+            for (int l = 1; l < 32; l++) if (load[l] < load[best]) best = l;
+            mid[best].push_back(op);
+            load[best] += std::max(1, op.len);
+        }
+        sched[c][0] = head;
+        sched[c][0].insert(sched[c][0].end(), mid[0].begin(), mid[0].end());
+        sched[c][0].insert(sched[c][0].end(), tail.begin(), tail.end());
+        for (int l = 1; l < 32; l++) sched[c][l] = mid[l];
+    }
+    an.seg_ops.clear(); an.seg_chunk.clear();
+    for (int c = 0; c < nchunks; c++) {
+        size_t ns = 0;
+        for (int l = 0; l < 32; l++) ns = std::max(ns, sched[c][l].size());
+        an.seg_chunk.push_back((int)an.seg_ops.size());
+        an.seg_chunk.push_back((int)ns);
+        size_t base = an.seg_ops.size();
+        an.seg_ops.resize(base + ns*32, SegOp{0, 0, -1, 0});
+        an.seg_maxsteps = std::max(an.seg_maxsteps, (int)ns);
+        for (int l = 0; l < 32; l++)
+            for (size_t q = 0; q < sched[c][l].size(); q++)
+                an.seg_ops[base + q*32 + l] = sched[c][l][q];
+    }
 }

@@ -89,7 +89,38 @@ struct SrcTopo {
 // ops are stored level by level; within a level tasks are dealt to 32 lanes round-robin
 // ("rounds" of 32 tasks); a round's ops are interleaved [step][lane] and padded to the
 // round's longest task with no-ops.
-struct LuOp { int dst, a, b; };                // LU[dst] -= LU[a]*LU[b]   (dst < 0: no-op)
+// Dot-product form: acc -= LU[a]*X[b], where the accumulator of one target entry lives in a
+// register.  dst carries the target slot in its low 24 bits plus LUOP_FIRST (load acc from
+// the target before this op) / LUOP_LAST (store acc to the target after it); dst < 0: no-op.
+struct LuOp { int dst, a, b; };
+#define LUOP_FIRST 0x40000000
+#define LUOP_LAST  0x20000000
+#define LUOP_SLOT(d) ((d) & 0x00ffffff)
+
+// Assembly stream (one per assembly lane, interleaved [step][nlanes]): v (+)= contribution.
+//   cidx >= 0: add contrib[cidx] (bit 30 set: rhs contribution array); -1: nothing to add
+//   init >= 0: before adding, start a new sum v = Ainit[init]; -2: start with 0.0; -1: continue
+//   fin  >= 0: after adding, finalise (nodeset/ic/gmin rules) and store v to smem slot fin
+struct AsmOp { int cidx, init, fin, info; };   // info: finalisation class of smem slot `fin`
+#define ASM_RHS 0x40000000
+// Segment op of the streamed assembly: contributions are numbered in ASSEMBLY ORDER (all terms
+// of one matrix entry / rhs row are consecutive, entries in LU-slot order, then rhs rows), so a
+// target's ordered sum is a run of consecutive values in the streamed chunk.
+//   pos    first term (absolute contribution index); len terms of it lie in this chunk
+//   target smem slot that receives the finished sum, or -1 if the run continues in the next chunk
+//   info   finalisation class (ASM_DIAG/ASM_ROW/ASM_VNODE | node) | SEG_START if the run starts here
+struct SegOp { int pos, len, target, info; };
+#define SEG_START  0x08000000
+#define SEG_CHUNK 512                            // contributions per streamed chunk
+struct AsmProgram {
+    int nlanes = 0, nsteps = 0;
+    std::vector<AsmOp> ops;                      // [nsteps][nlanes]
+    std::vector<int> fin_node;                   // [nnzLU + n]: 0 plain; node | ASM_DIAG / ASM_ROW
+    std::vector<int> long_kind, long_idx;        // staged long lists (kind 0 = LU slot, 1 = rhs pos)
+};
+#define ASM_DIAG 0x40000000
+#define ASM_ROW  0x20000000
+#define ASM_VNODE 0x10000000  // diagonal of a voltage node (loadGmin applies)
 struct LuRound {
     int op_off;        // offset (in LuOp units) of this round's [steps][32] block
     int nsteps;
@@ -143,6 +174,17 @@ struct Analysis {
     std::vector<int> lu_src;                    // LU slot -> Ax index or -1 (fill)
     LuProgram fac;
     SolveProgram fwd, bwd;
+    AsmProgram asmp;
+    int NC = 0;                                 // total contributions (matrix + rhs), assembly order
+    std::vector<SegOp> seg_ops;                 // [chunk][step][32 lanes]
+    std::vector<int> seg_chunk;                 // per chunk: {op offset (in SegOp), nsteps}
+    int seg_maxsteps = 0;
+    std::vector<int> const_idx; std::vector<double> const_val;   // Ainit pseudo-terms
+    // phase-2 stream: fac, fwd, bwd rounds back to back.  Round r = 1 descriptor row (32 lanes x
+    // {x0,x1,x2}: fac diag/lbeg/lend, fwd row, bwd row/diag) followed by nsteps op rows
+    // (32 lanes x LuOp).  Streamed through shared memory by the solve kernel.
+    std::vector<int> strm;                      // rows of 96 ints
+    std::vector<int> strm_round;                // per round: {nsteps, kind, sync, row offset}
     std::vector<int> yperm_in;                  // y[k] = rhs[rowperm[k]+1]
     std::vector<int> yperm_out;                 // x[colperm[k]+1] = y[k]
     // breakpoints (shared by all trials: sources are not varied per trial)
@@ -157,3 +199,5 @@ struct Analysis {
 int  b200_analyze(const b200_deck *deck, Analysis &an, std::string &err);
 void b200_order_markowitz(Analysis &an);
 void b200_build_lu(Analysis &an);
+void b200_build_asm(Analysis &an, int long_threshold);
+void b200_build_stream_asm(Analysis &an);

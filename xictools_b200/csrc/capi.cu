@@ -4,6 +4,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -58,6 +59,7 @@ struct b200_batch {
     TrialCtl *ctl = nullptr;
     MosCard *d_cards = nullptr;
     int nq = 0; int *d_qslots = nullptr;
+    int nconst = 0; int *d_const_idx = nullptr; double *d_const_val = nullptr;   // preloaded matrix constants
     int *d_count = nullptr;
     int cur = 0;
     double *d_raw[MR_NRAW] = {0}; int raw_ts[MR_NRAW] = {0};
@@ -210,6 +212,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); delete b; return rc; }
     b200_order_markowitz(b->an);
     b200_build_lu(b->an);
+    b200_build_stream_asm(b->an);
     build_cards(b, deck);
     Analysis &an = b->an;
     CK(cudaStreamCreate(&b->stream));
@@ -219,14 +222,14 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     K.opt = deck->opt;
     K.n = an.n; K.nnz = an.nnz; K.numStates = an.numStates; K.ldt = b->ldt; K.ntrials = ntrials;
     K.NS = deck->opt.maxord + 2; if (K.NS > 8) K.NS = 8; if (K.NS < 4) K.NS = 4;
-    K.nnzLU = an.nnzLU; K.ncslot = an.ncslot; K.nrslot = an.nrslot;
+    K.nnzLU = an.nnzLU; K.ncslot = an.ncslot; K.nrslot = an.nrslot; K.NC = an.NC;
     K.t_stop = an.t_stop; K.t_step = an.t_step; K.t_start = an.t_start; K.maxStep = an.maxStep;
     K.delmin = an.delmin; K.minBreak = an.minBreak; K.break0 = an.break0; K.break1 = an.break1;
     K.nocut = an.nocut; K.uic = deck->uic; K.hadNodeset = an.hadNodeset;
     K.npoints_max = an.npoints_max; K.method = deck->opt.method;
     K.nbrks = (int)an.brks.size(); K.nlat = (int)an.lat_offs.size();
 
-    if (solve_smem_bytes(K) > 227*1024) {
+    if (solve_smem_bytes(K, an.seg_maxsteps) > 227*1024 || (int)an.seg_chunk.size()/2 > SOLVE_MAXCH) {
         fprintf(stderr, "b200spice: LU (%d values) + rhs (%d) of one trial exceed shared memory; "
             "the supernodal large-matrix path is not built yet\n", an.nnzLU, an.n);
         delete b; return B200_E_UNSUPP;
@@ -253,8 +256,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     V.oldSol = b->dalloc<double>(vplane);
     V.states = b->dalloc<double>((size_t)K.NS*an.numStates*ldt);
     V.oldState0 = b->dalloc<double>((size_t)an.numStates*ldt);
-    V.contrib = b->dalloc<double>((size_t)an.ncslot*ldt);
-    V.rcontrib = b->dalloc<double>((size_t)an.nrslot*ldt);
+    V.contrib = b->dalloc<double>((size_t)an.NC*ldt);         // [ldt/SOLVE_TB][NC][SOLVE_TB]
     V.out = b->dalloc<double>((size_t)an.npoints_max*an.n*ldt);
     if (!V.out || !V.states || !V.sols) { b200_batch_destroy(b); return B200_E_NOMEM; }
     // ---- topology ----
@@ -295,38 +297,21 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     }
     // ---- solve view ----
     SolveView &Sv = b->Sv;
-    Sv.lu_src = b->dupload(an.lu_src); Sv.Ainit = b->dupload(an.Ainit);
-    Sv.cg_ptr = b->dupload(an.cg_ptr); Sv.cg_idx = b->dupload(an.cg_idx);
-    Sv.rg_ptr = b->dupload(an.rg_ptr); Sv.rg_idx = b->dupload(an.rg_idx);
-    {
-        std::vector<int> dn(an.nnz, 0);
-        for (int i = 1; i <= an.n; i++) if (an.diag[i] >= 0) dn[an.diag[i]] = i;
-        Sv.diag_node = b->dupload(dn);
-    }
     Sv.ntype = b->dupload(an.ntype);
     Sv.ic_given = b->dupload(an.ic_given); Sv.ns_given = b->dupload(an.ns_given);
     Sv.ic_val = b->dupload(an.ic_val); Sv.ns_val = b->dupload(an.ns_val);
     Sv.yperm_in = b->dupload(an.yperm_in); Sv.yperm_out = b->dupload(an.yperm_out);
-    auto sync_flags = [](const std::vector<LuRound> &rounds, const std::vector<int> &lvl) {
-        std::vector<char> f(rounds.size(), 0);
-        for (size_t l = 0; l + 1 < lvl.size(); l++)
-            if (lvl[l] < (int)rounds.size() && lvl[l] < lvl[l+1]) f[lvl[l]] = 1;
-        return f;
-    };
-    Sv.fac_nrounds = (int)an.fac.rounds.size();
-    Sv.fwd_nrounds = (int)an.fwd.rounds.size();
-    Sv.bwd_nrounds = (int)an.bwd.rounds.size();
-    Sv.fac_rounds = b->dupload(an.fac.rounds); Sv.fwd_rounds = b->dupload(an.fwd.rounds);
-    Sv.bwd_rounds = b->dupload(an.bwd.rounds);
-    Sv.fac_ops = b->dupload(an.fac.ops); Sv.fwd_ops = b->dupload(an.fwd.ops);
-    Sv.bwd_ops = b->dupload(an.bwd.ops);
-    Sv.fac_sync = b->dupload(sync_flags(an.fac.rounds, an.fac.level_round_off));
-    Sv.fwd_sync = b->dupload(sync_flags(an.fwd.rounds, an.fwd.level_round_off));
-    Sv.bwd_sync = b->dupload(sync_flags(an.bwd.rounds, an.bwd.level_round_off));
-    Sv.fac_fin_diag = b->dupload(an.fac.fin_diag); Sv.fac_fin_lbeg = b->dupload(an.fac.fin_lbeg);
-    Sv.fac_fin_lend = b->dupload(an.fac.fin_lend);
-    Sv.fwd_fin_row = b->dupload(an.fwd.fin_row);
-    Sv.bwd_fin_row = b->dupload(an.bwd.fin_row); Sv.bwd_fin_diag = b->dupload(an.bwd.fin_diag);
+    Sv.prof = getenv("B200_SOLVE_PROF") ? b->dalloc<long long>((size_t)ldt*12 + 64) : nullptr;
+    Sv.seg_ops = b->dupload(an.seg_ops); Sv.seg_chunk = b->dupload(an.seg_chunk);
+    Sv.nchunks = (int)an.seg_chunk.size()/2; Sv.seg_maxsteps = an.seg_maxsteps;
+    b->nconst = (int)an.const_idx.size();
+    b->d_const_idx = b->dupload(an.const_idx); b->d_const_val = b->dupload(an.const_val);
+    {
+        std::vector<int> padded = an.strm;
+        padded.resize(padded.size() + 3*42*96, -1);          // cp.async prefetch runs ahead
+        Sv.strm = b->dupload(padded); Sv.strm_round = b->dupload(an.strm_round);
+        Sv.strm_nrounds = (int)an.strm_round.size()/4;
+    }
     // ---- control ----
     b->ctl = b->dalloc<TrialCtl>(ldt);
     CtlAux &ax = b->aux;
@@ -353,6 +338,24 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     b->d_npts = b->dalloc<int>(ldt);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
+    if (getenv("B200_VERBOSE")) {
+        auto steps = [](const std::vector<LuRound> &r) { long s = 0; for (auto &x : r) s += x.nsteps; return s; };
+        size_t maxg = 0;
+        for (int p = 0; p < an.nnz; p++) maxg = std::max<size_t>(maxg, an.cg_ptr[p+1] - an.cg_ptr[p]);
+        for (int r = 1; r <= an.n; r++) maxg = std::max<size_t>(maxg, an.rg_ptr[r+1] - an.rg_ptr[r]);
+        long segsteps = 0;
+        for (size_t c = 0; c < an.seg_chunk.size()/2; c++) segsteps += an.seg_chunk[2*c + 1];
+        fprintf(stderr, "b200spice: contributions NC=%d (%d constants), %zu chunks, %ld assembly steps (max %d/chunk), solve smem %d B\n",
+            an.NC, b->nconst, an.seg_chunk.size()/2, segsteps, an.seg_maxsteps, solve_smem_bytes(K, an.seg_maxsteps));
+        fprintf(stderr, "b200spice: n=%d nnz=%d nnzLU=%d states=%d cslots=%d rslots=%d longest gather=%zu\n"
+            "  factor: %zu levels %zu rounds %ld steps %zu ops | fwd: %zu levels %zu rounds %ld steps | "
+            "bwd: %zu levels %zu rounds %ld steps | smem/trial %zu B\n",
+            an.n, an.nnz, an.nnzLU, an.numStates, an.ncslot, an.nrslot, maxg,
+            an.fac.level_round_off.size() - 1, an.fac.rounds.size(), steps(an.fac.rounds), an.fac.ops.size(),
+            an.fwd.level_round_off.size() - 1, an.fwd.rounds.size(), steps(an.fwd.rounds),
+            an.bwd.level_round_off.size() - 1, an.bwd.rounds.size(), steps(an.bwd.rounds),
+            (size_t)(an.nnzLU + an.n)*8);
+    }
     *out = b;
     return B200_OK;
 }
@@ -484,8 +487,8 @@ static int reset_state(b200_batch *b)
     CK(cudaMemsetAsync(b->V.spare, 0, vplane*sizeof(double), st));
     CK(cudaMemsetAsync(b->V.sols, 0, 8*vplane*sizeof(double), st));
     CK(cudaMemsetAsync(b->V.states, 0, (size_t)b->K.NS*an.numStates*ldt*sizeof(double), st));
-    CK(cudaMemsetAsync(b->V.contrib, 0, (size_t)an.ncslot*ldt*sizeof(double), st));
-    CK(cudaMemsetAsync(b->V.rcontrib, 0, (size_t)an.nrslot*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->V.contrib, 0, (size_t)an.NC*ldt*sizeof(double), st));
+    launch_fill_const(st, b->K, b->V.contrib, b->nconst, b->d_const_idx, b->d_const_val);
     CK(cudaMemsetAsync(b->M.cache, 0, (size_t)MC_NCACHE*an.mos.n*ldt*sizeof(double), st));
     // MOSmode = 1, MOSvon = 0 (mosset.cc:283-284)
     launch_fill(st, b->M.cache + (size_t)MC_mode*an.mos.n*ldt, (size_t)an.mos.n*ldt, 1.0);
@@ -581,6 +584,19 @@ int b200_batch_run_tran(b200_batch *b)
     for (int i = 0; i < WIN; i++) for (int k = 0; k < 4; k++) cudaEventDestroy(ev[i][k]);
     cudaEventDestroy(e_begin); cudaEventDestroy(e_end);
     CK(cudaGetLastError());
+    if (b->Sv.prof) {
+        std::vector<long long> hp((size_t)b->ldt*12);
+        cudaMemcpy(hp.data(), b->Sv.prof, hp.size()*sizeof(long long), cudaMemcpyDeviceToHost);
+        double acc[6] = {0,0,0,0,0,0}; int nw = 0;
+        for (int w = 0; w < b->ntrials; w++) { for (int k = 0; k < 6; k++) acc[k] += (double)hp[(size_t)w*6 + k]; nw++; }
+        const char *nm[6] = {"asm", "wait", "factor", "fwd", "bwd", "store"};
+        fprintf(stderr, "b200spice: k_solve mean cycles per warp (last launch):");
+        for (int k = 0; k < 6; k++) fprintf(stderr, " %s=%.0f", nm[k], acc[k]/nw);
+        for (int w = 0; w < 8; w++) { fprintf(stderr, "\n   warp %d:", w); for (int k = 0; k < 6; k++) fprintf(stderr, " %lld", hp[(size_t)w*6 + k]); }
+        fprintf(stderr, "\n   phase 2 detail (warps 0..3): sync ring fac fwd bwd fin");
+        for (int w = 0; w < 4; w++) { fprintf(stderr, "\n   warp %d:", w); for (int k = 0; k < 6; k++) fprintf(stderr, " %lld", hp[(size_t)b->ldt*6 + (size_t)w*6 + k]); }
+        fprintf(stderr, "\n");
+    }
     b->stats.launches = launches; b->stats.ticks = ticks;
     b->stats.ms_total = tot; b->stats.ms_load = ms_load; b->stats.ms_solve = ms_solve;
     b->stats.ms_control = tot - ms_load - ms_solve;
@@ -671,7 +687,7 @@ int b200_batch_get_stats(const b200_batch *b, b200_run_stats *st)
     double srcbytes = 0;
     for (int s : an.src.rslot) if (s >= 0) srcbytes += 8.0;
     st->algbytes_load_per_launch = (mosbytes + capbytes + srcbytes)*b->ntrials;
-    st->algbytes_solve_per_launch = 8.0*((double)an.ncslot + an.nrslot + 2.0*an.n)*b->ntrials;
+    st->algbytes_solve_per_launch = 8.0*((double)an.NC + 2.0*an.n)*b->ntrials;
     return B200_OK;
 }
 
@@ -700,6 +716,7 @@ int b200_internal_prepare(b200_batch *b)
     return reset_state(b);
 }
 
+const Analysis *b200_internal_analysis(b200_batch *b) { return &b->an; }
 int b200_internal_views(b200_batch *b, Consts **K, HotView **hot, VecView **V, MosView **M,
     CapView **Cp, SrcView **S, SolveView **Sv, cudaStream_t *st, int **cur)
 {

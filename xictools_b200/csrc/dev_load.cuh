@@ -103,6 +103,23 @@ __device__ inline void dev_integrate4(const TrialCtx &c, double *geq, double *ce
     dev_trapcheck(c, q);
 }
 
+// Same as dev_integrate4 with state1[q], state1[q+1] already in registers: the state-1 block
+// of a device is fetched with one burst of independent loads at the top of the load function,
+// so the five charge integrations do not serialise five DRAM round trips.
+__device__ inline void dev_integrate4v(const TrialCtx &c, double *geq, double *ceq, double cap, int q,
+    double s1q, double s1c)
+{
+    double cq;
+    if (c.method == 0)
+        cq = (c.order <= 1 ? s1q*c.ag[1] : - s1c*c.ag[1] - s1q*c.ag[0]);
+    else
+        cq = dev_NIceq(c, q);
+    ST(c, 0, q+1) = c.ag[0]*ST(c, 0, q) + cq;
+    *ceq = cq;
+    *geq = c.ag[0]*cap;
+    dev_trapcheck(c, q);
+}
+
 __device__ inline void dev_integrate2(const TrialCtx &c, int q, double cq)
 {
     ST(c, 0, q+1) = c.ag[0]*ST(c, 0, q) + cq;
@@ -226,6 +243,9 @@ struct MosInst {            // registers of one (instance, trial)
     // cached op point
     int mode;
     double von, vdsat, cd, cbs, cbd, gm, gds, gmbs, gbd, gbs, capbd, capbs;
+    // state-1 block and the old state-0 values, prefetched (see dev_mos_prefetch)
+    double s1[MS_NSTATES];
+    double o_vbs, o_vgs, o_vds, o_vbd, o_capgs, o_capgd, o_capgb;
 };
 
 struct MosStuff {
@@ -332,7 +352,7 @@ __device__ inline double dev_mos_eq1(MosInst &m, MosStuff &ms)
 
 __device__ inline int dev_mos_limiting(const TrialCtx &c, MosInst &m, MosStuff &ms, int oldlimit)
 {
-    double s0vds = ST(c, 0, m.st + MS_vds), s0vgs = ST(c, 0, m.st + MS_vgs);
+    double s0vds = m.o_vds, s0vgs = m.o_vgs;
     if (s0vds >= 0) {
         ms.vgs = dev_fetlim(ms.vgs, s0vgs, ms.von);
         ms.vds = ms.vgs - ms.vgd;
@@ -349,11 +369,11 @@ __device__ inline int dev_mos_limiting(const TrialCtx &c, MosInst &m, MosStuff &
     }
     int check;
     if (ms.vds >= 0) {
-        ms.vbs = dev_pnjlim(ms.vbs, ST(c, 0, m.st + MS_vbs), ms.vt, m.sourceVcrit, &check);
+        ms.vbs = dev_pnjlim(ms.vbs, m.o_vbs, ms.vt, m.sourceVcrit, &check);
         ms.vbd = ms.vbs - ms.vds;
     }
     else {
-        ms.vbd = dev_pnjlim(ms.vbd, ST(c, 0, m.st + MS_vbd), ms.vt, m.drainVcrit, &check);
+        ms.vbd = dev_pnjlim(ms.vbd, m.o_vbd, ms.vt, m.drainVcrit, &check);
         ms.vbs = ms.vbd + ms.vds;
     }
     ms.vgb = ms.vgs - ms.vbs;
@@ -446,6 +466,7 @@ __device__ inline void dev_mos_cap(const TrialCtx &c, MosInst &m, MosStuff &ms)
         ST(c, 1, st + MS_capgs) = s0capgs;
         ST(c, 1, st + MS_capgd) = s0capgd;
         ST(c, 1, st + MS_capgb) = cgb;
+        m.s1[MS_capgs] = s0capgs; m.s1[MS_capgd] = s0capgd; m.s1[MS_capgb] = cgb;
         ms.capgs = s0capgs + s0capgs + m.gsOvl;
         ms.capgd = s0capgd + s0capgd + m.gdOvl;
         ms.capgb = cgb + cgb + m.gbOvl;
@@ -453,31 +474,34 @@ __device__ inline void dev_mos_cap(const TrialCtx &c, MosInst &m, MosStuff &ms)
         ST(c, 0, st + MS_qgs) = qgs;
         ST(c, 0, st + MS_qgd) = qgd;
         ST(c, 0, st + MS_qgb) = qgb;
-        ST(c, 1, st + MS_qbd) = ST(c, 0, st + MS_qbd);
-        ST(c, 1, st + MS_qbs) = ST(c, 0, st + MS_qbs);
+        double qbd0 = ST(c, 0, st + MS_qbd), qbs0 = ST(c, 0, st + MS_qbs);
+        ST(c, 1, st + MS_qbd) = qbd0;
+        ST(c, 1, st + MS_qbs) = qbs0;
         ST(c, 1, st + MS_qgs) = qgs;
         ST(c, 1, st + MS_qgd) = qgd;
         ST(c, 1, st + MS_qgb) = qgb;
+        m.s1[MS_qbd] = qbd0; m.s1[MS_qbs] = qbs0;
+        m.s1[MS_qgs] = qgs; m.s1[MS_qgd] = qgd; m.s1[MS_qgb] = qgb;
     }
     else {
-        ms.capgs = s0capgs + ST(c, 1, st + MS_capgs) + m.gsOvl;
-        ms.capgd = s0capgd + ST(c, 1, st + MS_capgd) + m.gdOvl;
-        ms.capgb = cgb + ST(c, 1, st + MS_capgb) + m.gbOvl;
-        vgx = ST(c, 1, st + MS_vgs);
-        vgy = vgx - ST(c, 1, st + MS_vds);
-        double vxy = vgx - ST(c, 1, st + MS_vbs);
-        ST(c, 0, st + MS_qgs) = (ms.vgs - vgx)*ms.capgs + ST(c, 1, st + MS_qgs);
-        ST(c, 0, st + MS_qgd) = (ms.vgd - vgy)*ms.capgd + ST(c, 1, st + MS_qgd);
-        ST(c, 0, st + MS_qgb) = (ms.vgb - vxy)*ms.capgb + ST(c, 1, st + MS_qgb);
+        ms.capgs = s0capgs + m.s1[MS_capgs] + m.gsOvl;
+        ms.capgd = s0capgd + m.s1[MS_capgd] + m.gdOvl;
+        ms.capgb = cgb + m.s1[MS_capgb] + m.gbOvl;
+        vgx = m.s1[MS_vgs];
+        vgy = vgx - m.s1[MS_vds];
+        double vxy = vgx - m.s1[MS_vbs];
+        ST(c, 0, st + MS_qgs) = (ms.vgs - vgx)*ms.capgs + m.s1[MS_qgs];
+        ST(c, 0, st + MS_qgd) = (ms.vgd - vgy)*ms.capgd + m.s1[MS_qgd];
+        ST(c, 0, st + MS_qgb) = (ms.vgb - vxy)*ms.capgb + m.s1[MS_qgb];
     }
 }
 
 __device__ inline void dev_mos_meyer_integ(const TrialCtx &c, MosInst &m, MosStuff &ms)
 {
     const int st = m.st;
-    dev_integrate4(c, &ms.gcgs, &ms.ceqgs, ms.capgs, st + MS_qgs);
-    dev_integrate4(c, &ms.gcgd, &ms.ceqgd, ms.capgd, st + MS_qgd);
-    dev_integrate4(c, &ms.gcgb, &ms.ceqgb, ms.capgb, st + MS_qgb);
+    dev_integrate4v(c, &ms.gcgs, &ms.ceqgs, ms.capgs, st + MS_qgs, m.s1[MS_qgs], m.s1[MS_cqgs]);
+    dev_integrate4v(c, &ms.gcgd, &ms.ceqgd, ms.capgd, st + MS_qgd, m.s1[MS_qgd], m.s1[MS_cqgd]);
+    dev_integrate4v(c, &ms.gcgb, &ms.ceqgb, ms.capgb, st + MS_qgb, m.s1[MS_qgb], m.s1[MS_cqgb]);
     ms.ceqgs += c.ag[0]*ST(c, 0, st + MS_qgs) - ms.gcgs*ms.vgs;
     ms.ceqgd += c.ag[0]*ST(c, 0, st + MS_qgd) - ms.gcgd*ms.vgd;
     ms.ceqgb += c.ag[0]*ST(c, 0, st + MS_qgb) - ms.gcgb*ms.vgb;
@@ -487,12 +511,12 @@ __device__ inline void dev_mos_integ(const TrialCtx &c, MosInst &m, MosStuff &ms
 {
     const int st = m.st;
     double geq, ceq;
-    dev_integrate4(c, &geq, &ceq, m.capbd, st + MS_qbd);
+    dev_integrate4v(c, &geq, &ceq, m.capbd, st + MS_qbd, m.s1[MS_qbd], m.s1[MS_cqbd]);
     m.gbd += geq;
     double cqbd = ST(c, 0, st + MS_cqbd);
     m.cbd += cqbd;
     m.cd  -= cqbd;
-    dev_integrate4(c, &geq, &ceq, m.capbs, st + MS_qbs);
+    dev_integrate4v(c, &geq, &ceq, m.capbs, st + MS_qbs, m.s1[MS_qbs], m.s1[MS_cqbs]);
     m.gbs += geq;
     m.cbs += ST(c, 0, st + MS_cqbs);
     if (ms.capgs == 0) ST(c, 0, st + MS_cqgs) = 0;
@@ -575,8 +599,8 @@ __device__ inline int dev_mos_bypass(const TrialCtx &c, MosInst &m, MosStuff &ms
     double reltol, double abstol, double vntol)
 {
     const int st = m.st;
-    double s0vbs = ST(c, 0, st + MS_vbs), s0vgs = ST(c, 0, st + MS_vgs);
-    double s0vds = ST(c, 0, st + MS_vds), s0vbd = ST(c, 0, st + MS_vbd);
+    double s0vbs = m.o_vbs, s0vgs = m.o_vgs;
+    double s0vds = m.o_vds, s0vbd = m.o_vbd;
     double delvbs = ms.vbs - s0vbs;
     double delvgs = ms.vgs - s0vgs;
     double delvds = ms.vds - s0vds;
@@ -615,9 +639,9 @@ __device__ inline int dev_mos_bypass(const TrialCtx &c, MosInst &m, MosStuff &ms
     ms.vgb = ms.vgs - ms.vbs;
     ms.cdrain = m.mode*(m.cd + m.cbd);
     if (c.mode & MODETRAN) {
-        ms.capgs = ST(c, 0, st + MS_capgs) + ST(c, 1, st + MS_capgs) + m.gsOvl;
-        ms.capgd = ST(c, 0, st + MS_capgd) + ST(c, 1, st + MS_capgd) + m.gdOvl;
-        ms.capgb = ST(c, 0, st + MS_capgb) + ST(c, 1, st + MS_capgb) + m.gbOvl;
+        ms.capgs = m.o_capgs + m.s1[MS_capgs] + m.gsOvl;
+        ms.capgd = m.o_capgd + m.s1[MS_capgd] + m.gdOvl;
+        ms.capgb = m.o_capgb + m.s1[MS_capgb] + m.gbOvl;
         dev_mos_meyer_integ(c, m, ms);
     }
     dev_mos_stamp(c, m, ms, o);
@@ -650,6 +674,16 @@ __device__ inline int dev_mos_load(const TrialCtx &c, MosInst &m, MosOut &o,
     ms.capgs = ms.capgd = ms.capgb = 0; ms.cdrain = 0; ms.vdsat = 0;
     const int st = m.st;
     int ret = 0;
+    // one burst of independent loads: old state-0 values (limiting / bypass) and, for the
+    // transient modes, the whole state-1 block of this device
+    m.o_vbs = ST(c, 0, st + MS_vbs); m.o_vgs = ST(c, 0, st + MS_vgs);
+    m.o_vds = ST(c, 0, st + MS_vds); m.o_vbd = ST(c, 0, st + MS_vbd);
+    if (c.mode & (MODETRAN | MODEINITPRED)) {
+        m.o_capgs = ST(c, 0, st + MS_capgs); m.o_capgd = ST(c, 0, st + MS_capgd);
+        m.o_capgb = ST(c, 0, st + MS_capgb);
+#pragma unroll
+        for (int k = 0; k < MS_NSTATES; k++) m.s1[k] = ST(c, 1, st + k);
+    }
     if (c.mode & MODEINITFLOAT) {
         dev_mos_get_v(m, ms, rhsOld, c.ldt);
         ms.von = (m.type > 0) ? m.von : -m.von;
@@ -668,7 +702,7 @@ __device__ inline int dev_mos_load(const TrialCtx &c, MosInst &m, MosOut &o,
         return 3;
     }
     if (c.mode & MODEINITPRED) {
-        double s1vbs = ST(c, 1, st + MS_vbs), s1vgs = ST(c, 1, st + MS_vgs), s1vds = ST(c, 1, st + MS_vds);
+        double s1vbs = m.s1[MS_vbs], s1vgs = m.s1[MS_vgs], s1vds = m.s1[MS_vds];
         ms.vbs = s1vbs*c.pred[0] + ST(c, 2, st + MS_vbs)*c.pred[1];
         ms.vgs = s1vgs*c.pred[0] + ST(c, 2, st + MS_vgs)*c.pred[1];
         ms.vds = s1vds*c.pred[0] + ST(c, 2, st + MS_vds)*c.pred[1];
@@ -680,6 +714,8 @@ __device__ inline int dev_mos_load(const TrialCtx &c, MosInst &m, MosOut &o,
         ST(c, 0, st + MS_vgs) = s1vgs;
         ST(c, 0, st + MS_vds) = s1vds;
         ST(c, 0, st + MS_vbd) = s1vbs - s1vds;
+        // limiting reads the state-0 voltages just written (mosload.cc:172-182)
+        m.o_vbs = s1vbs; m.o_vgs = s1vgs; m.o_vds = s1vds; m.o_vbd = s1vbs - s1vds;
         dev_mos_limiting(c, m, ms, opt.oldlimit);
         dev_mos_iv(m, ms, opt.gmin);
         if (c.mode & MODETRAN) {
@@ -708,9 +744,9 @@ __device__ inline int dev_mos_load(const TrialCtx &c, MosInst &m, MosOut &o,
     }
     if (c.mode & MODEINITTRAN) {
         ms.von = (m.type > 0) ? m.von : -m.von;
-        ms.vbs = ST(c, 1, st + MS_vbs);
-        ms.vgs = ST(c, 1, st + MS_vgs);
-        ms.vds = ST(c, 1, st + MS_vds);
+        ms.vbs = m.s1[MS_vbs];
+        ms.vgs = m.s1[MS_vgs];
+        ms.vds = m.s1[MS_vds];
         ms.vbd = ms.vbs - ms.vds;
         ms.vgd = ms.vgs - ms.vds;
         ms.vgb = ms.vgs - ms.vbs;

@@ -80,7 +80,7 @@ struct HotView {
 struct Consts {
     b200_options opt;
     int n, nnz, numStates, ldt, ntrials, NS /* state ring size = maxord+2 */;
-    int nnzLU, ncslot, nrslot;
+    int nnzLU, ncslot, nrslot, NC /* contributions per trial, assembly order */;
     double t_stop, t_step, t_start, maxStep, delmin, minBreak, break0, break1;
     int nocut, uic, hadNodeset, npoints_max, method;
     int nbrks, nlat;
@@ -114,7 +114,6 @@ struct VecView {
     double *oldSol;     // [n+1][ldt]
     double *states;     // [NS][numStates][ldt]
     double *oldState0;  // [numStates][ldt]
-    double *contrib;    // [ncslot][ldt]
-    double *rcontrib;   // [nrslot][ldt]
+    double *contrib;    // [ldt/TB][NC][TB]: trial-group tiles, contiguous per k_solve CTA
     double *out;        // [npoints_max][n][ldt] -> transposed on fetch
 };

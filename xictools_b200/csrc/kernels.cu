@@ -11,8 +11,10 @@
 //   k_vec, k_statevec, k_trunc, k_devconv: one thread per (element, trial), gated by
 //               per-trial request flags.
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <float.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "device_state.h"
 #include "dev_load.cuh"
@@ -62,7 +64,8 @@ __device__ __forceinline__ void make_ctx(TrialCtx &c, const Consts &K, const Hot
     }
 }
 
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_load_mos(Consts K, HotView hot, VecView V, MosView M, const double *rhsOld)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
@@ -118,22 +121,22 @@ k_load_mos(Consts K, HotView hot, VecView V, MosView M, const double *rhsOld)
 #pragma unroll
         for (int k = 0; k < MT_NSTAMP; k++) {
             int s = cs[k];
-            if (s >= 0) V.contrib[(size_t)s*K.ldt + t] = o.m[k];
+            if (s >= 0) V.contrib[CADDR(K, s, t)] = o.m[k];
         }
 #pragma unroll
         for (int k = 0; k < MRH_NRHS; k++) {
             int s = rs[k];
-            if (s >= 0) V.rcontrib[(size_t)s*K.ldt + t] = o.r[k];
+            if (s >= 0) V.contrib[CADDR(K, s, t)] = o.r[k];
         }
     }
     else {
         for (int k = 0; k < MT_NSTAMP; k++) {
             int s = cs[k];
-            if (s >= 0) V.contrib[(size_t)s*K.ldt + t] = 0.0;
+            if (s >= 0) V.contrib[CADDR(K, s, t)] = 0.0;
         }
         for (int k = 0; k < MRH_NRHS; k++) {
             int s = rs[k];
-            if (s >= 0) V.rcontrib[(size_t)s*K.ldt + t] = 0.0;
+            if (s >= 0) V.contrib[CADDR(K, s, t)] = 0.0;
         }
     }
 }
@@ -188,12 +191,12 @@ k_load_cap(Consts K, HotView hot, VecView V, CapView Cp, const double *rhsOld)
     }
     if (!stamp) { geq = 0.0; ceq = 0.0; }
     // load_cap(): pos-only / neg-only / both (slots exist only for the live stamps)
-    if (cs[0] >= 0) V.contrib[(size_t)cs[0]*K.ldt + t] = geq;
-    if (cs[1] >= 0) V.contrib[(size_t)cs[1]*K.ldt + t] = geq;
-    if (cs[2] >= 0) V.contrib[(size_t)cs[2]*K.ldt + t] = -geq;
-    if (cs[3] >= 0) V.contrib[(size_t)cs[3]*K.ldt + t] = -geq;
-    if (rs[0] >= 0) V.rcontrib[(size_t)rs[0]*K.ldt + t] = stamp ? -ceq : 0.0;
-    if (rs[1] >= 0) V.rcontrib[(size_t)rs[1]*K.ldt + t] = stamp ? ceq : 0.0;
+    if (cs[0] >= 0) V.contrib[CADDR(K, cs[0], t)] = geq;
+    if (cs[1] >= 0) V.contrib[CADDR(K, cs[1], t)] = geq;
+    if (cs[2] >= 0) V.contrib[CADDR(K, cs[2], t)] = -geq;
+    if (cs[3] >= 0) V.contrib[CADDR(K, cs[3], t)] = -geq;
+    if (rs[0] >= 0) V.contrib[CADDR(K, rs[0], t)] = stamp ? -ceq : 0.0;
+    if (rs[1] >= 0) V.contrib[CADDR(K, rs[1], t)] = stamp ? ceq : 0.0;
 }
 
 __global__ void __launch_bounds__(128)
@@ -219,37 +222,43 @@ k_load_src(Consts K, HotView hot, VecView V, SrcView S)
     }
     const int *rs = S.rslot + (size_t)i*2;
     if (S.kind[i] == B200_SRC_V) {
-        if (rs[0] >= 0) V.rcontrib[(size_t)rs[0]*K.ldt + t] = rhs;
+        if (rs[0] >= 0) V.contrib[CADDR(K, rs[0], t)] = rhs;
     }
     else {
-        if (rs[0] >= 0) V.rcontrib[(size_t)rs[0]*K.ldt + t] = -rhs;
-        if (rs[1] >= 0) V.rcontrib[(size_t)rs[1]*K.ldt + t] = rhs;
+        if (rs[0] >= 0) V.contrib[CADDR(K, rs[0], t)] = -rhs;
+        if (rs[1] >= 0) V.contrib[CADDR(K, rs[1], t)] = rhs;
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// MOSdev::convTest, gated per trial
+// MOSdev::convTest, gated per trial; each thread walks a chunk of instances and stops at the
+// first failure ("no reason to continue", mosconv.cc:112)
+#define DEVCONV_CHUNK 8
 __global__ void __launch_bounds__(128)
 k_devconv(Consts K, HotView hot, VecView V, MosView M, const double *rhs)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i0 = blockIdx.y*DEVCONV_CHUNK;
     if (t >= K.ntrials) return;
     if (!hot.need_devconv[t]) return;
-    if (hot.devconv[t]) return;                  // "no reason to continue" (mosconv.cc:112)
     TrialCtx c;
     make_ctx(c, K, hot, V, t, hot.mode[t]);
-    MosInst m;
-    m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i];
-    m.g = M.g[i]; m.b = M.b[i]; m.dp = M.dp[i]; m.sp = M.sp[i];
     size_t cstride = (size_t)M.n*K.ldt;
-    const double *cp = M.cache + (size_t)i*K.ldt + t;
-    m.mode = (int)cp[MC_mode*cstride];
-    m.cd = cp[MC_cd*cstride]; m.cbs = cp[MC_cbs*cstride]; m.cbd = cp[MC_cbd*cstride];
-    m.gm = cp[MC_gm*cstride]; m.gds = cp[MC_gds*cstride]; m.gmbs = cp[MC_gmbs*cstride];
-    m.gbd = cp[MC_gbd*cstride]; m.gbs = cp[MC_gbs*cstride];
-    if (dev_mos_conv(c, m, rhs + t, K.opt.reltol, K.opt.abstol))
-        hot.devconv[t] = 1;
+    int i1 = min(M.n, i0 + DEVCONV_CHUNK);
+    for (int i = i0; i < i1; i++) {
+        MosInst m;
+        m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i];
+        m.g = M.g[i]; m.b = M.b[i]; m.dp = M.dp[i]; m.sp = M.sp[i];
+        const double *cp = M.cache + (size_t)i*K.ldt + t;
+        m.mode = (int)cp[MC_mode*cstride];
+        m.cd = cp[MC_cd*cstride]; m.cbs = cp[MC_cbs*cstride]; m.cbd = cp[MC_cbd*cstride];
+        m.gm = cp[MC_gm*cstride]; m.gds = cp[MC_gds*cstride]; m.gmbs = cp[MC_gmbs*cstride];
+        m.gbd = cp[MC_gbd*cstride]; m.gbs = cp[MC_gbs*cstride];
+        if (dev_mos_conv(c, m, rhs + t, K.opt.reltol, K.opt.abstol)) {
+            hot.devconv[t] = 1;
+            return;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -289,12 +298,13 @@ __device__ inline double dev_terr(const Consts &K, const double *const *sp, int 
     return del;
 }
 
+#define TRUNC_CHUNK 16
 __global__ void __launch_bounds__(128)
 k_trunc(Consts K, HotView hot, VecView V, int nq, const int *qslots)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int q = blockIdx.y;
-    if (t >= K.ntrials || q >= nq) return;
+    int q0 = blockIdx.y*TRUNC_CHUNK;
+    if (t >= K.ntrials || q0 >= nq) return;
     int want = hot.want_lte[t];
     if (!want) return;
     int base = hot.st_base[t];
@@ -308,153 +318,345 @@ k_trunc(Consts K, HotView hot, VecView V, int nq, const int *qslots)
     for (int k = 0; k < 7; k++) dOld[k] = hot.deltaOld[(size_t)k*K.ldt + t];
     int order = hot.order[t];
     double delta = hot.delta[t];
-    double d0 = dev_terr(K, sp, K.ldt, qslots[q], order, dOld, delta);
-    atomic_min_pos(&hot.lte[t], d0);
-    if (want == 2 && order + 1 <= K.opt.maxord) {
-        double d1 = dev_terr(K, sp, K.ldt, qslots[q], order + 1, dOld, delta);
-        atomic_min_pos(&hot.lte[K.ldt + t], d1);
+    bool two = (want == 2 && order + 1 <= K.opt.maxord);
+    double m0 = DBL_MAX, m1 = DBL_MAX;
+    int qe = min(nq, q0 + TRUNC_CHUNK);
+    for (int q = q0; q < qe; q++) {
+        int slot = qslots[q];
+        double d0 = dev_terr(K, sp, K.ldt, slot, order, dOld, delta);
+        if (d0 < m0) m0 = d0;
+        if (two) {
+            double d1 = dev_terr(K, sp, K.ldt, slot, order + 1, dOld, delta);
+            if (d1 < m1) m1 = d1;
+        }
     }
+    atomic_min_pos(&hot.lte[t], m0);
+    if (two) atomic_min_pos(&hot.lte[K.ldt + t], m1);
 }
 
 // ---------------------------------------------------------------------------------------
-// assemble + loadGmin + LU refactor + solve + NIconvTest node part.  One warp per trial.
-__global__ void __launch_bounds__(SOLVE_WARPS*32)
+// assemble + loadGmin + LU refactor + solve + NIconvTest node part.
+//
+// One CTA = SOLVE_TB adjacent trials; thread = (lane e0 in 0..31, trial j).  Everything a CTA
+// reads from HBM is one contiguous block: the contributions of its trial group, stored by the
+// load kernels in ASSEMBLY ORDER as [NC][TB] tiles.
+//  1. streamed assembly.  The block is pulled through a shared-memory ring with cp.async,
+//     SEG_NBUF chunks in flight, so HBM latency is paid once, not per term.  A host-built
+//     schedule gives every lane runs of consecutive contributions = one matrix entry / rhs row
+//     each; the run is summed left to right (the reference's load order), the nodeset/ic/gmin
+//     rules are applied and the value is stored to the trial-interleaved LU/rhs image in
+//     shared memory.  Runs that cross a chunk stay on lane 0, partial sum in a register.
+//  2. LU refactor + triangular solves with the frozen pivot order: level-scheduled programs
+//     in dot-product form; the op stream is double-buffered through shared memory (cp.async)
+//     and every op is applied to all TB trials at once.
+//  3. store + NIconvTest node part.
+__device__ __forceinline__ double asm_finalize(double v, int info, const Consts &K, const SolveView &Sv,
+    bool ns_on, bool ic_on, double diagGmin)
+{
+    int node = info & 0x00ffffff;
+    if (!node) return v;
+    if (info & ASM_DIAG) {
+        // ckt.cc:1177-1204 nodeset / ic pinning, then loadGmin (ckt.cc:1221-1263, spspice.cc:259-300)
+        if (ns_on && Sv.ns_given[node]) v += 1.0;
+        if (ic_on && Sv.ic_given[node]) v += 1.0;
+        if (info & ASM_VNODE) {
+            if (diagGmin != 0.0)
+                v += diagGmin;
+            else if (K.opt.forcegmin && (v >= 0.0 && v < K.opt.gmin))
+                v = K.opt.gmin;
+            else if (v > K.opt.gmax)
+                v = K.opt.gmax;
+        }
+    }
+    else {
+        if (ns_on && Sv.ns_given[node]) v += Sv.ns_val[node];
+        if (ic_on && Sv.ic_given[node]) v += Sv.ic_val[node];
+    }
+    return v;
+}
+
+// Phase-2 op stream: rows of 96 ints (32 task lanes x 3) double-buffered through shared memory.
+#define RING_HROWS 42                                   // rows per half (42*384 B = 16128 B)
+#define RING_HALF_INTS (RING_HROWS*96)
+
+struct OpRing {
+    const int *g;          // global stream (16-B aligned, padded)
+    int *buf;              // smem, 2 halves
+    int tid, nthreads;
+    __device__ __forceinline__ void issue(int h) {
+        const int4 *src = reinterpret_cast<const int4*>(g + (size_t)h*RING_HALF_INTS);
+        int4 *dst = reinterpret_cast<int4*>(buf + (h & 1)*RING_HALF_INTS);
+        for (int i = tid; i < RING_HALF_INTS/4; i += nthreads)
+            __pipeline_memcpy_async(dst + i, src + i, 16);
+        __pipeline_commit();
+    }
+    __device__ __forceinline__ void enter(int h) {
+        __pipeline_wait_prior(0);
+        __syncthreads();
+        issue(h + 1);
+    }
+    __device__ __forceinline__ const int *row(int R) const {
+        int h = R/RING_HROWS;
+        return buf + (h & 1)*RING_HALF_INTS + (R - h*RING_HROWS)*96;
+    }
+};
+
+__global__ void __launch_bounds__(SOLVE_TB*32)
 k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, double *Xnew)
 {
+    constexpr int TB = SOLVE_TB;
+    constexpr int NT = TB*32;
     extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = blockIdx.x*SOLVE_WARPS + warp;
-    if (t >= K.ntrials) return;
-    if (!hot.do_solve[t]) return;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int t0 = blockIdx.x*TB;
     const int ldt = K.ldt, n = K.n, nlu = K.nnzLU;
-    double *LU = smem + (size_t)warp*(nlu + n);
-    double *y = LU + nlu;
-    const int mode = hot.mode[t];
-    const double diagGmin = hot.diaggmin[t];
+    const int per = nlu + n;
+    double *S = smem;                                    // [per][TB], trial-interleaved
+    double *ringmem = smem + (size_t)TB*per;             // phase 1 data+op rings / phase 2 op ring
+    __shared__ int s_flags[TB];                          // bit0 singular, bit1 nonfinite, bit2 nonconv
+    __shared__ int s_any;
+    __shared__ int s_chunk[2*SOLVE_MAXCH];
+
+    const int j = tid % TB, e0 = tid / TB;               // lane e0 (0..31) x trial j
+    const int tj = t0 + j;
+    const bool live_j = (tj < K.ntrials) && hot.do_solve[tj];
+    if (tid == 0) s_any = 0;
+    if (tid < TB) s_flags[tid] = 0;
+    __syncthreads();
+    if (live_j && e0 == 0) s_any = 1;
+    const int nch = Sv.nchunks;
+    for (int i = tid; i < 2*nch; i += NT) s_chunk[i] = Sv.seg_chunk[i];
+    __syncthreads();
+    if (!s_any) return;
+
+    const int mode = live_j ? hot.mode[tj] : 0;
+    const double diagGmin = live_j ? hot.diaggmin[tj] : 0.0;
     const bool ns_on = (mode & MODEDC) && (mode & (MODEINITJCT | MODEINITFIX));
     const bool ic_on = (mode & MODEDC) && (mode & MODETRANOP) && !(mode & MODEUIC);
+    const bool PF = Sv.prof != nullptr;
+    long long tk0 = PF ? clock64() : 0;
 
-    // ---- matrix: A[k] = Ainit[k] + sum of contributions in reference load order ----
-    for (int s = lane; s < nlu; s += 32) {
-        int p = Sv.lu_src[s];
+    // ---- phase 1: streamed assembly ----
+    {
+        const double *gC = V.contrib + (size_t)blockIdx.x*(size_t)K.NC*TB;
+        double *dring = ringmem;                                     // [SEG_NBUF][SEG_CHUNK*TB]
+        SegOp *oring = reinterpret_cast<SegOp*>(ringmem + (size_t)SEG_NBUF*SEG_CHUNK*TB);
+        const int ostride = Sv.seg_maxsteps*32;                       // SegOps per ring slot
+        auto issue = [&](int c) {
+            if (c < nch) {
+                int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK)*TB/2;    // 16-B units
+                const int4 *src = reinterpret_cast<const int4*>(gC + (size_t)c*SEG_CHUNK*TB);
+                int4 *dst = reinterpret_cast<int4*>(dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB);
+                for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 16);
+                const int4 *osrc = reinterpret_cast<const int4*>(Sv.seg_ops + s_chunk[2*c]);
+                int4 *odst = reinterpret_cast<int4*>(oring + (size_t)(c % SEG_NBUF)*ostride);
+                int ocnt = s_chunk[2*c + 1]*32;
+                for (int i = tid; i < ocnt; i += NT) __pipeline_memcpy_async(odst + i, osrc + i, 16);
+            }
+            __pipeline_commit();
+        };
+        for (int c = 0; c < SEG_NBUF - 1; c++) issue(c);
         double v = 0.0;
-        if (p >= 0) {
-            v = Sv.Ainit[p];
-            int qe = Sv.cg_ptr[p+1];
-            for (int q = Sv.cg_ptr[p]; q < qe; q++)
-                v += V.contrib[(size_t)Sv.cg_idx[q]*ldt + t];
-            int dn = Sv.diag_node[p];           // node number if p is a diagonal, else 0
-            if (dn) {
-                // ckt.cc:1177-1204 nodeset / ic pinning
-                if (ns_on && Sv.ns_given[dn]) v += 1.0;
-                if (ic_on && Sv.ic_given[dn]) v += 1.0;
-                if (Sv.ntype[dn] == 0) {
-                    // loadGmin, ckt.cc:1221-1263 / spspice.cc:259-300
-                    if (diagGmin != 0.0)
-                        v += diagGmin;
-                    else if (K.opt.forcegmin && (v >= 0.0 && v < K.opt.gmin))
-                        v = K.opt.gmin;
-                    else if (v > K.opt.gmax)
-                        v = K.opt.gmax;
+        for (int c = 0; c < nch; c++) {
+            __pipeline_wait_prior(SEG_NBUF - 2);
+            __syncthreads();
+            issue(c + SEG_NBUF - 1);
+            if (!live_j) continue;
+            const double *buf = dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB + j;
+            const SegOp *ops = oring + (size_t)(c % SEG_NBUF)*ostride + e0;
+            const int ns = s_chunk[2*c + 1];
+            const int base = c*SEG_CHUNK;
+            for (int q = 0; q < ns; q++) {
+                const int4 raw = *reinterpret_cast<const int4*>(ops + q*32);
+                const int pos = raw.x, len = raw.y, target = raw.z, info = raw.w;
+                if (info & SEG_START) v = 0.0;
+                const double *x = buf + (size_t)(pos - base)*TB;
+                int k = 0;
+                for (; k + 8 <= len; k += 8) {
+                    double xx[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) xx[u] = x[(size_t)(k + u)*TB];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v += xx[u];
+                }
+                for (; k < len; k++) v += x[(size_t)k*TB];
+                if (target >= 0)
+                    S[(size_t)target*TB + j] = asm_finalize(v, info, K, Sv, ns_on, ic_on, diagGmin);
+            }
+        }
+        __pipeline_wait_prior(0);
+    }
+    long long tk1 = PF ? clock64() : 0;
+    __syncthreads();
+    long long tk2 = PF ? clock64() : 0;
+
+    // ---- phase 2: LU refactor + triangular solves, thread = (task lane e0, trial j) ----
+    {
+        OpRing ring;
+        ring.g = Sv.strm; ring.buf = reinterpret_cast<int*>(ringmem);
+        ring.tid = tid; ring.nthreads = NT;
+        ring.issue(0);
+        double *Sj = S + j;
+        double *yj = S + (size_t)nlu*TB + j;
+        int bad = 0;
+        int cur_half = -1;
+        const int nr = Sv.strm_nrounds;
+        long long pa_sync = 0, pa_ring = 0, pa_step[3] = {0, 0, 0}, pa_fin = 0, pq = 0;
+        for (int r = 0; r < nr; r++) {
+            const int4 rdsc = *reinterpret_cast<const int4*>(Sv.strm_round + 4*r);
+            const int nsteps = rdsc.x, kind = rdsc.y & 3, coop = rdsc.y & 4, sync = rdsc.z;
+            int R = rdsc.w;
+            if (PF) pq = clock64();
+            if (sync) __syncthreads();
+            if (PF) { long long z = clock64(); pa_sync += z - pq; pq = z; }
+            if (R/RING_HROWS != cur_half) { cur_half = R/RING_HROWS; ring.enter(cur_half); }
+            if (PF) { long long z = clock64(); pa_ring += z - pq; pq = z; }
+            const int *drow = ring.row(R);
+            const int x0 = drow[e0*3], x1 = drow[e0*3 + 1], x2 = drow[e0*3 + 2];
+            R++;
+            double acc = 0.0;
+            if (kind != 0 && x0 >= 0 && live_j) acc = yj[(size_t)x0*TB];
+            int left = nsteps;
+            while (left > 0) {
+                if (PF) pq = clock64();
+                if (R/RING_HROWS != cur_half) { cur_half = R/RING_HROWS; ring.enter(cur_half); }
+                if (PF) { long long z = clock64(); pa_ring += z - pq; pq = z; }
+                int avail = (cur_half + 1)*RING_HROWS - R;
+                int cnt = min(avail, left);
+                const int *op = ring.row(R) + e0*3;
+                if (live_j) {
+                    if (kind == 0) {
+                        int q = 0;
+                        for (; q + 4 <= cnt; q += 4, op += 4*96) {
+                            int d[4], ia[4], ib[4];
+                            double av[4], bv[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) { d[u] = op[u*96]; ia[u] = op[u*96 + 1]; ib[u] = op[u*96 + 2]; }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) { av[u] = Sj[(size_t)ia[u]*TB]; bv[u] = Sj[(size_t)ib[u]*TB]; }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (d[u] >= 0) {
+                                    if (d[u] & LUOP_FIRST) acc = Sj[(size_t)LUOP_SLOT(d[u])*TB];
+                                    acc -= av[u]*bv[u];
+                                    if (d[u] & LUOP_LAST) {
+                                        int slot = LUOP_SLOT(d[u]);
+                                        Sj[(size_t)slot*TB] = acc;
+                                        // U(k,j) finished inside the batch: forward it to later ops
+#pragma unroll
+                                        for (int w = u + 1; w < 4; w++)
+                                            if (ib[w] == slot) bv[w] = acc;
+                                    }
+                                }
+                            }
+                        }
+                        for (; q < cnt; q++, op += 96) {
+                            int d = op[0];
+                            if (d >= 0) {
+                                double av = Sj[(size_t)op[1]*TB];
+                                if (d & LUOP_FIRST) acc = Sj[(size_t)LUOP_SLOT(d)*TB];
+                                acc -= av*Sj[(size_t)op[2]*TB];
+                                if (d & LUOP_LAST) Sj[(size_t)LUOP_SLOT(d)*TB] = acc;
+                            }
+                        }
+                    }
+                    else {
+                        int q = 0;
+                        for (; q + 8 <= cnt; q += 8, op += 8*96) {
+                            int d[8];
+                            double av[8], bv[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                d[u] = op[u*96];
+                                av[u] = Sj[(size_t)op[u*96 + 1]*TB];
+                                bv[u] = yj[(size_t)op[u*96 + 2]*TB];
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (d[u] >= 0) acc -= av[u]*bv[u];
+                        }
+                        for (; q < cnt; q++, op += 96)
+                            if (op[0] >= 0)
+                                acc -= Sj[(size_t)op[1]*TB]*yj[(size_t)op[2]*TB];
+                    }
+                }
+                R += cnt; left -= cnt;
+                if (PF) { long long z = clock64(); pa_step[kind] += z - pq; pq = z; }
+            }
+            if (PF) pq = clock64();
+            if (kind == 0) {
+                if (coop) {
+                    // a column of this round has a long L part: all lanes divide it together
+                    __syncthreads();
+                    if (live_j) {
+                        for (int e = 0; e < 32; e++) {
+                            int dg = drow[e*3];
+                            if (dg < 0) continue;
+                            double piv = Sj[(size_t)dg*TB];
+                            if (piv == 0.0 || !isfinite(piv)) bad = 1;
+                            for (int q = drow[e*3 + 1] + e0; q < drow[e*3 + 2]; q += 32)
+                                Sj[(size_t)q*TB] = Sj[(size_t)q*TB]/piv;
+                        }
+                    }
+                }
+                else if (live_j && x0 >= 0) {
+                    double piv = Sj[(size_t)x0*TB];
+                    if (piv == 0.0 || !isfinite(piv))
+                        bad = 1;
+                    for (int q = x1; q < x2; q++)
+                        Sj[(size_t)q*TB] = Sj[(size_t)q*TB]/piv;
                 }
             }
+            else if (live_j && x0 >= 0) {
+                if (kind == 1) yj[(size_t)x0*TB] = acc;
+                else yj[(size_t)x0*TB] = acc/Sj[(size_t)x1*TB];
+            }
+            if (PF) { long long z = clock64(); pa_fin += z - pq; }
         }
-        LU[s] = v;
+        __pipeline_wait_prior(0);
+        if (bad) atomicOr(&s_flags[j], 1);
+        if (PF && (tid & 31) == 0) {
+            long long *pp = Sv.prof + (size_t)K.ldt*6 + ((size_t)blockIdx.x*TB + warp)*6;
+            pp[0] = pa_sync; pp[1] = pa_ring; pp[2] = pa_step[0]; pp[3] = pa_step[1]; pp[4] = pa_step[2]; pp[5] = pa_fin;
+        }
     }
-    // ---- rhs (permuted) ----
-    for (int k = lane; k < n; k += 32) {
-        int row = Sv.yperm_in[k];
-        double v = 0.0;
-        int qe = Sv.rg_ptr[row+1];
-        for (int q = Sv.rg_ptr[row]; q < qe; q++)
-            v += V.rcontrib[(size_t)Sv.rg_idx[q]*ldt + t];
-        if (ns_on && Sv.ns_given[row]) v += Sv.ns_val[row];
-        if (ic_on && Sv.ic_given[row]) v += Sv.ic_val[row];
-        y[k] = v;
-    }
-    __syncwarp();
+    long long tk5 = PF ? clock64() : 0;
+    __syncthreads();
 
-    // ---- refactor: levels of independent columns, lane per column ----
-    int bad = 0;
-    for (int r = 0; r < Sv.fac_nrounds; r++) {
-        if (Sv.fac_sync[r]) __syncwarp();
-        const LuRound rd = Sv.fac_rounds[r];
-        const LuOp *ops = Sv.fac_ops + rd.op_off + lane;
-        for (int s = 0; s < rd.nsteps; s++) {
-            LuOp op = ops[s*32];
-            if (op.dst >= 0)
-                LU[op.dst] -= LU[op.a]*LU[op.b];
+    // ---- phase 3: unpermute, store, NIconvTest node part (niconv.cc:58-91) ----
+    if (live_j) {
+        const double *yj = S + (size_t)nlu*TB + j;
+        int fl = 0;
+        for (int k = e0; k < n; k += 32) {
+            int node = Sv.yperm_out[k];
+            double cur = yj[(size_t)k*TB];
+            double old = Xold[(size_t)node*ldt + tj];
+            Xnew[(size_t)node*ldt + tj] = cur;
+            if (!isfinite(cur)) fl |= 2;
+            double dd = fabs(old - cur);
+            double tol = K.opt.reltol*DMAX(fabs(old), fabs(cur)) +
+                (Sv.ntype[node] == 0 ? K.opt.vntol : K.opt.abstol);
+            if (dd > tol) fl |= 4;
         }
-        int dg = Sv.fac_fin_diag[rd.fin_off + lane];
-        if (dg >= 0) {
-            double piv = LU[dg];
-            if (piv == 0.0 || !isfinite(piv))
-                bad = 1;
-            int lb = Sv.fac_fin_lbeg[rd.fin_off + lane], le = Sv.fac_fin_lend[rd.fin_off + lane];
-            for (int q = lb; q < le; q++)
-                LU[q] = LU[q]/piv;
-        }
+        if (fl) atomicOr(&s_flags[j], fl);
     }
-    __syncwarp();
-    // ---- forward: lane per row ----
-    for (int r = 0; r < Sv.fwd_nrounds; r++) {
-        if (Sv.fwd_sync[r]) __syncwarp();
-        const LuRound rd = Sv.fwd_rounds[r];
-        int row = Sv.fwd_fin_row[rd.fin_off + lane];
-        if (row >= 0) {
-            const LuOp *ops = Sv.fwd_ops + rd.op_off + lane;
-            double acc = y[row];
-            for (int s = 0; s < rd.nsteps; s++) {
-                LuOp op = ops[s*32];
-                if (op.dst >= 0)
-                    acc -= LU[op.a]*y[op.b];
-            }
-            y[row] = acc;
-        }
+    __syncthreads();
+    if (PF && (tid & 31) == 0) {
+        long long tk6 = clock64();
+        long long *pp = Sv.prof + ((size_t)blockIdx.x*TB + warp)*6;
+        pp[0] = tk1 - tk0; pp[1] = tk2 - tk1; pp[2] = tk5 - tk2; pp[3] = 0; pp[4] = 0; pp[5] = tk6 - tk5;
     }
-    __syncwarp();
-    // ---- backward ----
-    for (int r = 0; r < Sv.bwd_nrounds; r++) {
-        if (Sv.bwd_sync[r]) __syncwarp();
-        const LuRound rd = Sv.bwd_rounds[r];
-        int row = Sv.bwd_fin_row[rd.fin_off + lane];
-        if (row >= 0) {
-            const LuOp *ops = Sv.bwd_ops + rd.op_off + lane;
-            double acc = y[row];
-            for (int s = 0; s < rd.nsteps; s++) {
-                LuOp op = ops[s*32];
-                if (op.dst >= 0)
-                    acc -= LU[op.a]*y[op.b];
-            }
-            y[row] = acc/LU[Sv.bwd_fin_diag[rd.fin_off + lane]];
-        }
-    }
-    __syncwarp();
-    // ---- unpermute, store, NIconvTest node part (niconv.cc:58-91) ----
-    int fail = 0, nonfin = 0;
-    for (int k = lane; k < n; k += 32) {
-        int node = Sv.yperm_out[k];
-        double cur = y[k];
-        double old = Xold[(size_t)node*ldt + t];
-        Xnew[(size_t)node*ldt + t] = cur;
-        if (!isfinite(cur)) nonfin = 1;
-        double dd = fabs(old - cur);
-        double tol = K.opt.reltol*DMAX(fabs(old), fabs(cur)) +
-            (Sv.ntype[node] == 0 ? K.opt.vntol : K.opt.abstol);
-        if (dd > tol) fail = 1;
-    }
-    fail = __any_sync(0xffffffffu, fail);
-    nonfin = __any_sync(0xffffffffu, nonfin);
-    bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0) {
-        Xnew[t] = 0.0;                           // ground slot
-        int err = bad ? B200_E_SINGULAR : (nonfin ? B200_E_MATHOVF : 0);
-        hot.solve_err[t] = err;
-        hot.nodeconv[t] = fail;
-        hot.devconv[t] = 0;
-        int it1 = hot.iterno[t] + 1;
-        hot.need_devconv[t] = (!err && !fail && (mode & (MODEINITFIX | MODEINITFLOAT)) &&
-            hot.noncon[t] == 0 && it1 != 1) ? 1 : 0;
+    if (tid < TB && live_j) {
+        int fl = s_flags[tid];
+        Xnew[tj] = 0.0;                                  // ground slot
+        int err = (fl & 1) ? B200_E_SINGULAR : ((fl & 2) ? B200_E_MATHOVF : 0);
+        int fail = (fl & 4) ? 1 : 0;
+        hot.solve_err[tj] = err;
+        hot.nodeconv[tj] = fail;
+        hot.devconv[tj] = 0;
+        int it1 = hot.iterno[tj] + 1;
+        hot.need_devconv[tj] = (!err && !fail && (mode & (MODEINITFIX | MODEINITFLOAT)) &&
+            hot.noncon[tj] == 0 && it1 != 1) ? 1 : 0;
     }
 }
 
@@ -612,40 +814,48 @@ k_vec(Consts K, VecView V, CtlAux aux, double *rhsOld)
     }
 }
 
+#define SV_CHUNKS 64
 __global__ void __launch_bounds__(128)
 k_statevec(Consts K, VecView V, CtlAux aux, MosView M)
 {
+    // grid = (trial blocks, SV_CHUNKS): a block with no request among its 128 trials exits at
+    // once (the common case in the transient); otherwise it walks its share of the slots.
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int e = blockIdx.y;                          // state slot, then MOS cache entries
-    if (t >= K.ntrials) return;
-    int ops = aux.vecops[t];
-    if (!(ops & (VO_ZERO_STATE0 | VO_BK_SAVE | VO_BK_RESTORE | VO_HIST_INIT | VO_FIRSTTIME))) return;
+    const int mask = VO_ZERO_STATE0 | VO_BK_SAVE | VO_BK_RESTORE | VO_HIST_INIT | VO_FIRSTTIME;
+    int ops = (t < K.ntrials) ? (aux.vecops[t] & mask) : 0;
+    if (!__syncthreads_or(ops)) return;
+    if (!ops) return;
     size_t ldt = K.ldt;
-    if (e >= K.numStates) {
-        size_t at = (size_t)(e - K.numStates)*ldt + t;
-        if (ops & VO_BK_SAVE) M.save[at] = M.cache[at];
-        if (ops & VO_BK_RESTORE) M.cache[at] = M.save[at];
-        return;
-    }
+    int total = K.numStates + MC_NCACHE*M.n;
+    int per = (total + SV_CHUNKS - 1)/SV_CHUNKS;
+    int e0 = blockIdx.y*per, e1 = min(total, e0 + per);
     int base = aux.vo_stbase[t];
     size_t plane = (size_t)K.numStates*ldt;
-    size_t at = (size_t)e*ldt + t;
     double *sp[8];
     for (int k = 0; k < K.NS; k++) {
         int phys = base + k; if (phys >= K.NS) phys -= K.NS;
         sp[k] = V.states + phys*plane;
     }
-    if (ops & VO_ZERO_STATE0) sp[0][at] = 0.0;
-    if (ops & VO_BK_SAVE) V.oldState0[at] = sp[0][at];
-    if (ops & VO_BK_RESTORE) sp[0][at] = V.oldState0[at];
-    if (ops & VO_HIST_INIT) {
-        double v = sp[0][at];
-        for (int k = 1; k <= K.opt.maxord + 1 && k < K.NS; k++) sp[k][at] = v;
-    }
-    if (ops & VO_FIRSTTIME) {
-        double v = sp[1][at];
-        sp[2][at] = v;
-        if (K.opt.maxord > 1) sp[3][at] = v;
+    for (int e = e0; e < e1; e++) {
+        if (e >= K.numStates) {
+            size_t at = (size_t)(e - K.numStates)*ldt + t;
+            if (ops & VO_BK_SAVE) M.save[at] = M.cache[at];
+            if (ops & VO_BK_RESTORE) M.cache[at] = M.save[at];
+            continue;
+        }
+        size_t at = (size_t)e*ldt + t;
+        if (ops & VO_ZERO_STATE0) sp[0][at] = 0.0;
+        if (ops & VO_BK_SAVE) V.oldState0[at] = sp[0][at];
+        if (ops & VO_BK_RESTORE) sp[0][at] = V.oldState0[at];
+        if (ops & VO_HIST_INIT) {
+            double v = sp[0][at];
+            for (int k = 1; k <= K.opt.maxord + 1 && k < K.NS; k++) sp[k][at] = v;
+        }
+        if (ops & VO_FIRSTTIME) {
+            double v = sp[1][at];
+            sp[2][at] = v;
+            if (K.opt.maxord > 1) sp[3][at] = v;
+        }
     }
 }
 
@@ -719,45 +929,71 @@ void launch_ctl(cudaStream_t st, const Consts &K, const HotView &hot, TrialCtl *
 void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const CapView &Cp, const SrcView &S, const double *rhsOld)
 {
-    if (M.n) k_load_mos<<<grid2(K.ntrials, M.n), 128, 0, st>>>(K, hot, V, M, rhsOld);
+    if (M.n) {
+        static int minb = -1;
+        if (minb < 0) { const char *e = getenv("B200_LOAD_MINB"); minb = e ? atoi(e) : 4; }
+        if (minb >= 5) k_load_mos<5><<<grid2(K.ntrials, M.n), 128, 0, st>>>(K, hot, V, M, rhsOld);
+        else if (minb == 4) k_load_mos<4><<<grid2(K.ntrials, M.n), 128, 0, st>>>(K, hot, V, M, rhsOld);
+        else k_load_mos<3><<<grid2(K.ntrials, M.n), 128, 0, st>>>(K, hot, V, M, rhsOld);
+    }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
     if (S.n) k_load_src<<<grid2(K.ntrials, S.n), 128, 0, st>>>(K, hot, V, S);
 }
 void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const double *rhs)
 {
-    if (M.n) k_devconv<<<grid2(K.ntrials, M.n), 128, 0, st>>>(K, hot, V, M, rhs);
+    if (M.n) k_devconv<<<grid2(K.ntrials, (M.n + DEVCONV_CHUNK - 1)/DEVCONV_CHUNK), 128, 0, st>>>(K, hot, V, M, rhs);
 }
 void launch_trunc(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     int nq, const int *qslots)
 {
-    if (nq) k_trunc<<<grid2(K.ntrials, nq), 128, 0, st>>>(K, hot, V, nq, qslots);
+    if (nq) k_trunc<<<grid2(K.ntrials, (nq + TRUNC_CHUNK - 1)/TRUNC_CHUNK), 128, 0, st>>>(K, hot, V, nq, qslots);
 }
-int solve_smem_bytes(const Consts &K) { return (int)((size_t)SOLVE_WARPS*(K.nnzLU + K.n)*sizeof(double)); }
+int solve_smem_bytes(const Consts &K, int seg_maxsteps)
+{
+    size_t img = (size_t)SOLVE_TB*(K.nnzLU + K.n)*sizeof(double);
+    size_t ph1 = (size_t)SEG_NBUF*SEG_CHUNK*SOLVE_TB*sizeof(double) + (size_t)SEG_NBUF*seg_maxsteps*32*sizeof(SegOp);
+    size_t ph2 = (size_t)2*RING_HALF_INTS*sizeof(int);
+    return (int)(img + (ph1 > ph2 ? ph1 : ph2));
+}
 int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const SolveView &Sv, const double *Xold, double *Xnew)
 {
-    int smem = solve_smem_bytes(K);
+    int smem = solve_smem_bytes(K, Sv.seg_maxsteps);
     static int configured = -1;
     if (configured != smem) {
         if (cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return B200_E_NOMEM;
         configured = smem;
     }
-    k_solve<<<(K.ntrials + SOLVE_WARPS - 1)/SOLVE_WARPS, SOLVE_WARPS*32, smem, st>>>(K, hot, V, Sv, Xold, Xnew);
+    k_solve<<<(K.ntrials + SOLVE_TB - 1)/SOLVE_TB, SOLVE_TB*32, smem, st>>>(K, hot, V, Sv, Xold, Xnew);
     return 0;
 }
 void launch_vec(cudaStream_t st, const Consts &K, const VecView &V, const CtlAux &aux,
     const MosView &M, double *rhsOld)
 {
     k_vec<<<grid2(K.ntrials, K.n + 1), 128, 0, st>>>(K, V, aux, rhsOld);
-    k_statevec<<<grid2(K.ntrials, K.numStates + MC_NCACHE*M.n), 128, 0, st>>>(K, V, aux, M);
+    k_statevec<<<grid2(K.ntrials, SV_CHUNKS), 128, 0, st>>>(K, V, aux, M);
 }
 void launch_count_active(cudaStream_t st, int ntrials, const int *active, int *count)
 {
     cudaMemsetAsync(count, 0, sizeof(int), st);
     k_count_active<<<(ntrials + 127)/128, 128, 0, st>>>(ntrials, active, count);
 }
+// preloaded matrix constants (resistor conductances, source +-1): pseudo-contributions written once
+__global__ void k_fill_const(Consts K, double *contrib, int nconst, const int *idx, const double *val)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= K.ldt) return;
+    for (int i = 0; i < nconst; i++) contrib[CADDR(K, idx[i], t)] = val[i];
+}
+
+void launch_fill_const(cudaStream_t st, const Consts &K, double *contrib, int nconst, const int *idx,
+    const double *val)
+{
+    if (nconst) k_fill_const<<<(K.ldt + 127)/128, 128, 0, st>>>(K, contrib, nconst, idx, val);
+}
+
 void launch_fill(cudaStream_t st, double *p, size_t n, double v)
 {
     if (n) k_fill<<<(unsigned)((n + 255)/256), 256, 0, st>>>(p, n, v);

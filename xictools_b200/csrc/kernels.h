@@ -3,7 +3,13 @@
 #include <cuda_runtime.h>
 #include "device_state.h"
 
-#define SOLVE_WARPS 4
+#define SOLVE_TB 4          // trials per CTA of k_solve (4 doubles = one 32-B sector)
+#define SOLVE_LONG 48       // gather lists longer than this go through the staged path
+#define SOLVE_STAGE 1024    // staged terms per chunk (x SOLVE_TB doubles = 32 KB, shared with the op ring)
+#define ASM_BATCH 16        // contribution loads kept in flight per thread
+#define SEG_NBUF 3           // streamed-assembly ring depth (chunks in flight)
+// contribution (s) of trial (t): tile layout, TB adjacent trials of one slot = one 32-B sector
+#define CADDR(K, s, t) (((size_t)((t)/SOLVE_TB)*(size_t)(K).NC + (size_t)(s))*SOLVE_TB + ((t) % SOLVE_TB))
 
 struct MosCard;
 struct CtlShared;
@@ -17,23 +23,17 @@ struct CtlAux {
     double *ip_d;       // [5][ldt]: time, c2, c3, c4, tcheck0
 };
 
+#define SOLVE_MAXCH 1024         // chunks of the streamed assembly (table cached in shared memory)
 struct SolveView {
-    const int *lu_src;          // [nnzLU] Ax index or -1
-    const double *Ainit;        // [nnz]
-    const int *cg_ptr, *cg_idx; // gather lists per Ax entry
-    const int *rg_ptr, *rg_idx; // gather lists per rhs row (1-based rows)
-    const int *diag_node;       // [nnz] node number if the entry is (node,node), else 0
     const int *ntype;           // [n+1]
     const char *ic_given, *ns_given;
     const double *ic_val, *ns_val;
     const int *yperm_in, *yperm_out;
-    int fac_nrounds, fwd_nrounds, bwd_nrounds;
-    const LuRound *fac_rounds, *fwd_rounds, *bwd_rounds;
-    const LuOp *fac_ops, *fwd_ops, *bwd_ops;
-    const char *fac_sync, *fwd_sync, *bwd_sync;     // 1: round starts a new level
-    const int *fac_fin_diag, *fac_fin_lbeg, *fac_fin_lend;
-    const int *fwd_fin_row, *bwd_fin_row, *bwd_fin_diag;
+    const int *strm; const int *strm_round; int strm_nrounds;   // phase-2 op stream
+    const SegOp *seg_ops; const int *seg_chunk; int nchunks, seg_maxsteps;   // streamed assembly
+    long long *prof;            // optional per-warp phase cycle counters (B200_SOLVE_PROF=1)
 };
+
 
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,
     const RawParams &raw, const MosParamsOut &out);
@@ -45,13 +45,15 @@ void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const 
     const MosView &M, const double *rhs);
 void launch_trunc(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     int nq, const int *qslots);
-int  solve_smem_bytes(const Consts &K);
+int  solve_smem_bytes(const Consts &K, int seg_maxsteps);
 int  launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const SolveView &Sv, const double *Xold, double *Xnew);
 void launch_vec(cudaStream_t st, const Consts &K, const VecView &V, const CtlAux &aux,
     const MosView &M, double *rhsOld);
 void launch_count_active(cudaStream_t st, int ntrials, const int *active, int *count);
 void launch_fill(cudaStream_t st, double *p, size_t n, double v);
+void launch_fill_const(cudaStream_t st, const Consts &K, double *contrib, int nconst, const int *idx,
+    const double *val);
 void launch_gather_waves(cudaStream_t st, int n, int ldt, int ntrials, int npts_max,
     const double *out, const int *npts, int nsel, const int *sel, double *waves);
 void launch_export_counters(cudaStream_t st, int ntrials, const TrialCtl *ctl, int *counters,

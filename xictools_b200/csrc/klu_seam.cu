@@ -34,6 +34,7 @@ struct b200_klu {
     HotView hot; VecView V;
     double *dX0 = nullptr, *dX1 = nullptr, *dAxh = nullptr, *dBh = nullptr;
     int *dstat = nullptr;
+    int *d_packmap = nullptr; double *dpack = nullptr;
 
     template <class T> T *dalloc(size_t n) {
         void *p = nullptr;
@@ -89,8 +90,11 @@ __global__ void k_set_int(int *p, int n, int v)
 }
 
 // debug assemble: Ax[p][t], rhs[row][t] exactly as k_solve builds them (before the LU)
-__global__ void k_debug_assemble(Consts K, HotView hot, VecView V, SolveView Sv, int nnz,
-    const int *a2lu_unused, double *Ax, double *rhs)
+struct DebugTables {
+    const double *Ainit; const int *cg_ptr, *cg_idx, *rg_ptr, *rg_idx, *diag_node;
+};
+__global__ void k_debug_assemble(Consts K, HotView hot, VecView V, SolveView Sv, DebugTables D, int nnz,
+    double *Ax, double *rhs)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
     int e = blockIdx.y;
@@ -102,10 +106,11 @@ __global__ void k_debug_assemble(Consts K, HotView hot, VecView V, SolveView Sv,
     bool ic_on = (mode & MODEDC) && (mode & MODETRANOP) && !(mode & MODEUIC);
     if (e < nnz) {
         int p = e;
-        double v = Sv.Ainit[p];
-        for (int q = Sv.cg_ptr[p]; q < Sv.cg_ptr[p+1]; q++)
-            v += V.contrib[(size_t)Sv.cg_idx[q]*ldt + t];
-        int dn = Sv.diag_node[p];
+        double v = 0.0;
+        if (D.Ainit[p] != 0.0) v += D.Ainit[p];
+        for (int q = D.cg_ptr[p]; q < D.cg_ptr[p+1]; q++)
+            v += V.contrib[CADDR(K, D.cg_idx[q], t)];
+        int dn = D.diag_node[p];
         if (dn) {
             if (ns_on && Sv.ns_given[dn]) v += 1.0;
             if (ic_on && Sv.ic_given[dn]) v += 1.0;
@@ -121,13 +126,22 @@ __global__ void k_debug_assemble(Consts K, HotView hot, VecView V, SolveView Sv,
         int row = e - nnz;                   // 0..n
         double v = 0.0;
         if (row > 0) {
-            for (int q = Sv.rg_ptr[row]; q < Sv.rg_ptr[row+1]; q++)
-                v += V.rcontrib[(size_t)Sv.rg_idx[q]*ldt + t];
+            for (int q = D.rg_ptr[row]; q < D.rg_ptr[row+1]; q++)
+                v += V.contrib[CADDR(K, D.rg_idx[q], t)];
             if (ns_on && Sv.ns_given[row]) v += Sv.ns_val[row];
             if (ic_on && Sv.ic_given[row]) v += Sv.ic_val[row];
         }
         rhs[(size_t)row*ldt + t] = v;
     }
+}
+
+// KLU seam: [entry][ldt] value arrays -> the solve kernel's [trial group][NC][TB] stream
+__global__ void k_pack_stream(Consts K, int nent, const int *map, const double *src, double *dst)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int e = blockIdx.y;
+    if (t >= K.ldt || e >= nent) return;
+    dst[CADDR(K, map[e], t)] = src[(size_t)e*K.ldt + t];
 }
 
 __global__ void k_debug_set_hot(Consts K, HotView hot, int mode, double time, double delta,
@@ -146,6 +160,7 @@ __global__ void k_debug_set_hot(Consts K, HotView hot, int mode, double time, do
 int b200_internal_prepare(b200_batch *b);
 int b200_internal_views(b200_batch *b, Consts **K, HotView **hot, VecView **V, MosView **M,
     CapView **Cp, SrcView **S, SolveView **Sv, cudaStream_t *st, int **cur);
+const Analysis *b200_internal_analysis(b200_batch *b);
 
 extern "C" {
 
@@ -186,9 +201,28 @@ int b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, in
     CK(cudaMalloc(&dAx, (size_t)nnz*ldt*sizeof(double)));
     CK(cudaMalloc(&drhs, (size_t)(n + 1)*ldt*sizeof(double)));
     dim3 g((nt + 127)/128, nnz + n + 1);
-    k_debug_assemble<<<g, 128, 0, st>>>(*K, *hot, *V, *Sv, nnz, nullptr, dAx, drhs);
+    const Analysis &an = *b200_internal_analysis(b);
+    std::vector<int> dn(an.nnz, 0);
+    for (int i = 1; i <= an.n; i++) if (an.diag[i] >= 0) dn[an.diag[i]] = i;
+    std::vector<void*> tmp;
+    auto up = [&](const void *h, size_t bytes) -> void* {
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+        if (bytes) cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+        tmp.push_back(p);
+        return p;
+    };
+    DebugTables D;
+    D.Ainit = (const double*)up(an.Ainit.data(), an.Ainit.size()*sizeof(double));
+    D.cg_ptr = (const int*)up(an.cg_ptr.data(), an.cg_ptr.size()*sizeof(int));
+    D.cg_idx = (const int*)up(an.cg_idx.data(), an.cg_idx.size()*sizeof(int));
+    D.rg_ptr = (const int*)up(an.rg_ptr.data(), an.rg_ptr.size()*sizeof(int));
+    D.rg_idx = (const int*)up(an.rg_idx.data(), an.rg_idx.size()*sizeof(int));
+    D.diag_node = (const int*)up(dn.data(), dn.size()*sizeof(int));
+    k_debug_assemble<<<g, 128, 0, st>>>(*K, *hot, *V, *Sv, D, nnz, dAx, drhs);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    for (void *p : tmp) cudaFree(p);
     std::vector<double> hb((size_t)std::max(nnz, n + 1)*ldt);
     CK(cudaMemcpy(hb.data(), dAx, (size_t)nnz*ldt*sizeof(double), cudaMemcpyDeviceToHost));
     for (int p = 0; p < nnz; p++) memcpy(Ax + (size_t)p*nt, hb.data() + (size_t)p*ldt, nt*sizeof(double));
@@ -237,41 +271,37 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     an.ic_given.assign(n + 1, 0); an.ns_given.assign(n + 1, 0);
     an.ic_val.assign(n + 1, 0.0); an.ns_val.assign(n + 1, 0.0);
 
+    an.ncslot = an.nnz; an.nrslot = n;
+    b200_build_stream_asm(an);                // renumbers cg_idx / rg_idx into stream order
+
     Consts &K = k->K;
     memset(&K, 0, sizeof(K));
     b200_options_default(&K.opt);
     K.opt.gmax = HUGE_VAL;
-    K.n = n; K.nnz = an.nnz; K.nnzLU = an.nnzLU; K.NS = 4;
-    if (solve_smem_bytes(K) > 227*1024) { delete k; return B200_E_UNSUPP; }
+    K.n = n; K.nnz = an.nnz; K.nnzLU = an.nnzLU; K.NS = 4; K.NC = an.NC;
+    if (solve_smem_bytes(K, an.seg_maxsteps) > 227*1024 || (int)an.seg_chunk.size()/2 > SOLVE_MAXCH) {
+        delete k; return B200_E_UNSUPP;
+    }
     CK(cudaStreamCreate(&k->stream));
     SolveView &Sv = k->Sv;
-    Sv.lu_src = k->dupload(an.lu_src); Sv.Ainit = k->dupload(an.Ainit);
-    Sv.cg_ptr = k->dupload(an.cg_ptr); Sv.cg_idx = k->dupload(an.cg_idx);
-    Sv.rg_ptr = k->dupload(an.rg_ptr); Sv.rg_idx = k->dupload(an.rg_idx);
-    std::vector<int> dn(an.nnz, 0);
-    Sv.diag_node = k->dupload(dn);
     Sv.ntype = k->dupload(an.ntype);
     Sv.ic_given = k->dupload(an.ic_given); Sv.ns_given = k->dupload(an.ns_given);
     Sv.ic_val = k->dupload(an.ic_val); Sv.ns_val = k->dupload(an.ns_val);
     Sv.yperm_in = k->dupload(an.yperm_in); Sv.yperm_out = k->dupload(an.yperm_out);
-    auto sync_flags = [](const std::vector<LuRound> &rounds, const std::vector<int> &lvl) {
-        std::vector<char> f(rounds.size(), 0);
-        for (size_t l = 0; l + 1 < lvl.size(); l++)
-            if (lvl[l] < (int)rounds.size() && lvl[l] < lvl[l+1]) f[lvl[l]] = 1;
-        return f;
-    };
-    Sv.fac_nrounds = (int)an.fac.rounds.size(); Sv.fwd_nrounds = (int)an.fwd.rounds.size();
-    Sv.bwd_nrounds = (int)an.bwd.rounds.size();
-    Sv.fac_rounds = k->dupload(an.fac.rounds); Sv.fwd_rounds = k->dupload(an.fwd.rounds);
-    Sv.bwd_rounds = k->dupload(an.bwd.rounds);
-    Sv.fac_ops = k->dupload(an.fac.ops); Sv.fwd_ops = k->dupload(an.fwd.ops); Sv.bwd_ops = k->dupload(an.bwd.ops);
-    Sv.fac_sync = k->dupload(sync_flags(an.fac.rounds, an.fac.level_round_off));
-    Sv.fwd_sync = k->dupload(sync_flags(an.fwd.rounds, an.fwd.level_round_off));
-    Sv.bwd_sync = k->dupload(sync_flags(an.bwd.rounds, an.bwd.level_round_off));
-    Sv.fac_fin_diag = k->dupload(an.fac.fin_diag); Sv.fac_fin_lbeg = k->dupload(an.fac.fin_lbeg);
-    Sv.fac_fin_lend = k->dupload(an.fac.fin_lend);
-    Sv.fwd_fin_row = k->dupload(an.fwd.fin_row);
-    Sv.bwd_fin_row = k->dupload(an.bwd.fin_row); Sv.bwd_fin_diag = k->dupload(an.bwd.fin_diag);
+    Sv.prof = nullptr;
+    Sv.seg_ops = k->dupload(an.seg_ops); Sv.seg_chunk = k->dupload(an.seg_chunk);
+    Sv.nchunks = (int)an.seg_chunk.size()/2; Sv.seg_maxsteps = an.seg_maxsteps;
+    {
+        std::vector<int> map(an.cg_idx);
+        map.insert(map.end(), an.rg_idx.begin(), an.rg_idx.end());
+        k->d_packmap = k->dupload(map);
+    }
+    {
+        std::vector<int> padded = an.strm;
+        padded.resize(padded.size() + 3*42*96, -1);          // cp.async prefetch runs ahead
+        Sv.strm = k->dupload(padded); Sv.strm_round = k->dupload(an.strm_round);
+        Sv.strm_nrounds = (int)an.strm_round.size()/4;
+    }
     CK(cudaDeviceSynchronize());
     *out = k;
     return B200_OK;
@@ -299,7 +329,8 @@ static int klu_ensure(b200_klu *k, int ntrials)
     h.devconv = k->dalloc<int>(ldt); h.need_devconv = k->dalloc<int>(ldt);
     k->dX0 = k->dalloc<double>((size_t)(k->an.n + 1)*ldt);
     k->dX1 = k->dalloc<double>((size_t)(k->an.n + 1)*ldt);
-    if (!k->dX1) return B200_E_NOMEM;
+    k->dpack = k->dalloc<double>((size_t)k->an.NC*ldt);
+    if (!k->dX1 || !k->dpack) return B200_E_NOMEM;
     k_set_int<<<(ldt + 127)/128, 128, 0, k->stream>>>(h.do_solve, ldt, 1);
     k->cap_trials = ldt;
     return B200_OK;
@@ -308,7 +339,7 @@ static int klu_ensure(b200_klu *k, int ntrials)
 int b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double *dAx, double *dB,
     int *dstatus, void *cuda_stream)
 {
-    if (!k || ntrials <= 0 || ldt < ntrials) return B200_E_BADPARM;
+    if (!k || ntrials <= 0 || ldt < ntrials || (ldt % SOLVE_TB)) return B200_E_BADPARM;
     CK(cudaSetDevice(k->device));
     int rc = klu_ensure(k, ldt);
     if (rc) return rc;
@@ -317,8 +348,10 @@ int b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double 
     K.ntrials = ntrials; K.ldt = ldt;
     VecView V;
     memset(&V, 0, sizeof(V));
-    V.contrib = const_cast<double*>(dAx);
-    V.rcontrib = dB;
+    V.contrib = k->dpack;
+    int nnz = k->an.nnz, n = k->an.n;
+    k_pack_stream<<<dim3((ldt + 127)/128, nnz), 128, 0, st>>>(K, nnz, k->d_packmap, dAx, k->dpack);
+    k_pack_stream<<<dim3((ldt + 127)/128, n), 128, 0, st>>>(K, n, k->d_packmap + nnz, dB, k->dpack);
     // solution goes to dX1 ([n+1][ldt], row 0 = ground), then back into dB
     rc = launch_solve(st, K, k->hot, V, k->Sv, k->dX0, k->dX1);
     if (rc) return rc;
