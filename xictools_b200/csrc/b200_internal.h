@@ -52,6 +52,22 @@ enum { MT_Dd, MT_Gg, MT_Ss, MT_Bb, MT_Ddp, MT_Gb, MT_Gdp, MT_Gsp, MT_Ssp, MT_Bg,
 // rhs stamps (mosload.cc:862-875)
 enum { MRH_g, MRH_b, MRH_dp, MRH_sp, MRH_NRHS };
 
+// ---- shared-memory staging of the MOS load kernel (rows of MOS_TPB doubles) ----
+#define MOS_TPB 64
+enum { SR_V_B, SR_V_SP, SR_V_G, SR_V_DP,                // node voltages (rhsOld); the predictor's
+       SR_S2_vbs = SR_V_B, SR_S2_vgs = SR_V_SP, SR_S2_vds = SR_V_G,   // state-2 voltages share the rows
+       SR_S0 = 4,                                       // state 0 block (old values in, new values out)
+       SR_S1 = SR_S0 + MS_NSTATES,                      // state 1 block
+       SR_CACHE = SR_S1 + MS_NSTATES,                   // cached operating point
+       SR_PRM = SR_CACHE + MC_NCACHE,                   // per-trial parameters
+       SR_NFIXED = SR_PRM };
+struct MosStageMap {
+    int off[MP_NPARAMS];    // per-trial: row*MOS_TPB; shared: offset of the value in the shared block
+    int ts[MP_NPARAMS];     // 1 per-trial, 0 shared
+    int nvar;               // number of per-trial parameter rows
+    int var[MP_NPARAMS];    // their parameter ids
+};
+
 // Strided parameter accessor: value(inst, trial) = base[inst*ld + trial*ts]
 struct ParamRef {
     const double *base;

@@ -459,6 +459,21 @@ static int prepare_params(b200_batch *b)
         b->M.prm[k].ts = tsd[k];
         b->M.prm[k].ld = tsd[k] ? (int)ldt : 1;
     }
+    {
+        // staging layout of k_load_mos: per-trial parameters get a row each, the others one
+        // slot of the block shared by the CTA
+        MosStageMap &sm = b->M.smap;
+        sm.nvar = 0;
+        for (int k = 0; k < MP_NPARAMS; k++)
+            if (tsd[k]) sm.var[sm.nvar++] = k;
+        int shared_base = (SR_PRM + sm.nvar)*MOS_TPB;
+        int q = 0;
+        for (int k = 0; k < MP_NPARAMS; k++) {
+            sm.ts[k] = tsd[k];
+            sm.off[k] = tsd[k] ? (SR_PRM + q++)*MOS_TPB : shared_base + k;
+        }
+        b->M.stage_doubles = shared_base + MP_NPARAMS;
+    }
     CK(cudaMemcpy(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice));
     launch_mos_temp(b->stream, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);
     int rc = upload_strided(b->cap_c, b->cap_var, b->d_capc, b->capc_ts);

@@ -37,29 +37,35 @@
 // Per-thread integration context.
 struct TrialCtx {
     int mode, order, method, trapCheck;
-    double delta, ag[7], pred[2];
+    double delta, ag[2], pred[2];   // ag[0], ag[1]: all the trapezoidal rule needs
+    const double *agp;      // &hot.ag[trial]: Gear coefficients k >= 2 at agp[k*ldt]
     double trapratio;
-    double *sp[8];          // state planes for this trial: S(k,slot) = sp[k][slot*ldt]
+    double *states;         // &states[0][0][trial]; history plane k of this trial is ring slot
+    int base, NS;           // (base + k) mod NS:  S(k,slot) = states[(phys*numStates + slot)*ldt]
+    int numStates;
     int ldt;
     int *trapbad;           // per-trial flag
 };
 
 __device__ __forceinline__ double &ST(const TrialCtx &c, int k, int slot)
 {
-    return c.sp[k][(size_t)slot*c.ldt];
+    int phys = c.base + k;
+    if (phys >= c.NS) phys -= c.NS;
+    return c.states[((size_t)phys*c.numStates + slot)*c.ldt];
 }
+#define AGK(c, k) ((c).agp[(size_t)(k)*(c).ldt])
 
 __device__ inline double dev_NIceq(const TrialCtx &c, int q)
 {
     double cq = 0;
     if (c.method == 1) {
         switch (c.order) {
-        case 6: cq += c.ag[6]*ST(c, 6, q);
-        case 5: cq += c.ag[5]*ST(c, 5, q);
-        case 4: cq += c.ag[4]*ST(c, 4, q);
-        case 3: cq += c.ag[3]*ST(c, 3, q);
+        case 6: cq += AGK(c, 6)*ST(c, 6, q);
+        case 5: cq += AGK(c, 5)*ST(c, 5, q);
+        case 4: cq += AGK(c, 4)*ST(c, 4, q);
+        case 3: cq += AGK(c, 3)*ST(c, 3, q);
         default:
-        case 2: cq += c.ag[2]*ST(c, 2, q);
+        case 2: cq += AGK(c, 2)*ST(c, 2, q);
         case 1: cq += c.ag[1]*ST(c, 1, q); break;
         }
     }
@@ -232,20 +238,75 @@ __device__ inline double dev_fetlim(double vnew, double vold, double vto)
 // ---------------------------------------------------------------------------------------
 // MOS
 // ---------------------------------------------------------------------------------------
-struct MosInst {            // registers of one (instance, trial)
-    int type, off, st;
-    int d, g, s, b, dp, sp;
-    // derived parameters
-    double tPhi, tVbi, tVto, gamma, lambda, beta, oxideCap;
-    double tSourceSatCur, tDrainSatCur, sourceVcrit, drainVcrit;
-    double Cbd, Cbdsw, Cbs, Cbssw, tBulkPot, tDepCap, f2d, f3d, f4d, f2s, f3s, f4s;
-    double gsOvl, gdOvl, gbOvl, dcon, scon, mult, vt, mj, mjsw, icVDS, icVGS, icVBS;
-    // cached op point
-    int mode;
-    double von, vdsat, cd, cbs, cbd, gm, gds, gmbs, gbd, gbs, capbd, capbs;
-    // state-1 block and the old state-0 values, prefetched (see dev_mos_prefetch)
-    double s1[MS_NSTATES];
-    double o_vbs, o_vgs, o_vds, o_vbd, o_capgs, o_capgd, o_capgb;
+// One (instance, trial) of the MOS load.  Everything that is per trial is staged by the kernel
+// into shared memory with one burst of asynchronous copies (row r of this thread at
+// col[r*MOS_TPB]), so the loads are all in flight at once and nothing has to be parked in
+// registers while the model is evaluated.  Derived parameters are either per-trial rows of the
+// same staging area or values shared by all trials (MosStageMap tells which).
+struct MosInst {
+    int type, off, st, mode;
+    int g, b, dp, sp;
+    double *col;            // staging column of this thread
+    const double *shp;      // staging area base (shared parameter block addressed from here)
+    const MosStageMap *map;
+    __device__ __forceinline__ double P(int k) const { return (map->ts[k] ? col : shp)[map->off[k]]; }
+    __device__ __forceinline__ double &R(int row) const { return col[row*MOS_TPB]; }
+    __device__ __forceinline__ double &s1(int k) const { return col[(SR_S1 + k)*MOS_TPB]; }
+    __device__ __forceinline__ double &s0(int k) const { return col[(SR_S0 + k)*MOS_TPB]; }
+    __device__ __forceinline__ double tPhi() const { return P(MP_tPhi); }
+    __device__ __forceinline__ double tVbi() const { return P(MP_tVbi); }
+    __device__ __forceinline__ double tVto() const { return P(MP_tVto); }
+    __device__ __forceinline__ double gamma() const { return P(MP_gamma); }
+    __device__ __forceinline__ double lambda() const { return P(MP_lambda); }
+    __device__ __forceinline__ double beta() const { return P(MP_beta); }
+    __device__ __forceinline__ double oxideCap() const { return P(MP_oxideCap); }
+    __device__ __forceinline__ double tSourceSatCur() const { return P(MP_tSourceSatCur); }
+    __device__ __forceinline__ double tDrainSatCur() const { return P(MP_tDrainSatCur); }
+    __device__ __forceinline__ double sourceVcrit() const { return P(MP_sourceVcrit); }
+    __device__ __forceinline__ double drainVcrit() const { return P(MP_drainVcrit); }
+    __device__ __forceinline__ double Cbd() const { return P(MP_Cbd); }
+    __device__ __forceinline__ double Cbdsw() const { return P(MP_Cbdsw); }
+    __device__ __forceinline__ double Cbs() const { return P(MP_Cbs); }
+    __device__ __forceinline__ double Cbssw() const { return P(MP_Cbssw); }
+    __device__ __forceinline__ double tBulkPot() const { return P(MP_tBulkPot); }
+    __device__ __forceinline__ double tDepCap() const { return P(MP_tDepCap); }
+    __device__ __forceinline__ double f2d() const { return P(MP_f2d); }
+    __device__ __forceinline__ double f3d() const { return P(MP_f3d); }
+    __device__ __forceinline__ double f4d() const { return P(MP_f4d); }
+    __device__ __forceinline__ double f2s() const { return P(MP_f2s); }
+    __device__ __forceinline__ double f3s() const { return P(MP_f3s); }
+    __device__ __forceinline__ double f4s() const { return P(MP_f4s); }
+    __device__ __forceinline__ double gsOvl() const { return P(MP_gsOvl); }
+    __device__ __forceinline__ double gdOvl() const { return P(MP_gdOvl); }
+    __device__ __forceinline__ double gbOvl() const { return P(MP_gbOvl); }
+    __device__ __forceinline__ double dcon() const { return P(MP_dcon); }
+    __device__ __forceinline__ double scon() const { return P(MP_scon); }
+    __device__ __forceinline__ double mult() const { return P(MP_mult); }
+    __device__ __forceinline__ double vt() const { return P(MP_vt); }
+    __device__ __forceinline__ double mj() const { return P(MP_mj); }
+    __device__ __forceinline__ double mjsw() const { return P(MP_mjsw); }
+    __device__ __forceinline__ double icVDS() const { return P(MP_icVDS); }
+    __device__ __forceinline__ double icVGS() const { return P(MP_icVGS); }
+    __device__ __forceinline__ double icVBS() const { return P(MP_icVBS); }
+    __device__ __forceinline__ double &von() const { return col[(SR_CACHE + MC_von)*MOS_TPB]; }
+    __device__ __forceinline__ double &vdsat() const { return col[(SR_CACHE + MC_vdsat)*MOS_TPB]; }
+    __device__ __forceinline__ double &cd() const { return col[(SR_CACHE + MC_cd)*MOS_TPB]; }
+    __device__ __forceinline__ double &cbs() const { return col[(SR_CACHE + MC_cbs)*MOS_TPB]; }
+    __device__ __forceinline__ double &cbd() const { return col[(SR_CACHE + MC_cbd)*MOS_TPB]; }
+    __device__ __forceinline__ double &gm() const { return col[(SR_CACHE + MC_gm)*MOS_TPB]; }
+    __device__ __forceinline__ double &gds() const { return col[(SR_CACHE + MC_gds)*MOS_TPB]; }
+    __device__ __forceinline__ double &gmbs() const { return col[(SR_CACHE + MC_gmbs)*MOS_TPB]; }
+    __device__ __forceinline__ double &gbd() const { return col[(SR_CACHE + MC_gbd)*MOS_TPB]; }
+    __device__ __forceinline__ double &gbs() const { return col[(SR_CACHE + MC_gbs)*MOS_TPB]; }
+    __device__ __forceinline__ double &capbd() const { return col[(SR_CACHE + MC_capbd)*MOS_TPB]; }
+    __device__ __forceinline__ double &capbs() const { return col[(SR_CACHE + MC_capbs)*MOS_TPB]; }
+    __device__ __forceinline__ double &o_vbs() const { return col[(SR_S0 + MS_vbs)*MOS_TPB]; }
+    __device__ __forceinline__ double &o_vgs() const { return col[(SR_S0 + MS_vgs)*MOS_TPB]; }
+    __device__ __forceinline__ double &o_vds() const { return col[(SR_S0 + MS_vds)*MOS_TPB]; }
+    __device__ __forceinline__ double &o_vbd() const { return col[(SR_S0 + MS_vbd)*MOS_TPB]; }
+    __device__ __forceinline__ double &o_capgs() const { return col[(SR_S0 + MS_capgs)*MOS_TPB]; }
+    __device__ __forceinline__ double &o_capgd() const { return col[(SR_S0 + MS_capgd)*MOS_TPB]; }
+    __device__ __forceinline__ double &o_capgb() const { return col[(SR_S0 + MS_capgb)*MOS_TPB]; }
 };
 
 struct MosStuff {
@@ -253,9 +314,12 @@ struct MosStuff {
     double gcgs, ceqgs, gcgd, ceqgd, gcgb, ceqgb, capgs, capgd, capgb;
 };
 
-struct MosOut {             // stamp values in load order
-    double m[MT_NSTAMP];
-    double r[MRH_NRHS];
+struct MosOut {             // stamps go straight to this trial's contribution tile, load order
+    double *cbase;          // &contrib[tile of the trial][0][trial % TB]
+    const int *cs, *rs;     // contribution slots of this instance (-1: ground row/column)
+    int tb;                 // trials per tile
+    __device__ __forceinline__ void M(int k, double v) const { int q = cs[k]; if (q >= 0) cbase[(size_t)q*tb] = v; }
+    __device__ __forceinline__ void Rw(int k, double v) const { int q = rs[k]; if (q >= 0) cbase[(size_t)q*tb] = v; }
 };
 
 __device__ inline void dev_sargs(double arg, double bot, double side, double *sarg, double *sargsw)
@@ -309,21 +373,21 @@ __device__ inline double dev_mos_eq1(MosInst &m, MosStuff &ms)
     double vgx = ((m.mode == 1) ? ms.vgs : ms.vgd);
     double sarg;
     if (vbx <= 0)
-        sarg = sqrt(m.tPhi - vbx);
+        sarg = sqrt(m.tPhi() - vbx);
     else {
-        sarg = sqrt(m.tPhi);
+        sarg = sqrt(m.tPhi());
         sarg = sarg - vbx/(sarg+sarg);
         sarg = DMAX(0, sarg);
     }
     if (m.type > 0)
-        ms.von = m.tVbi + m.gamma*sarg;
+        ms.von = m.tVbi() + m.gamma()*sarg;
     else
-        ms.von = -m.tVbi + m.gamma*sarg;
+        ms.von = -m.tVbi() + m.gamma()*sarg;
     double vgst = vgx - ms.von;
     ms.vdsat = DMAX(vgst, 0);
     double cdrain;
     if (vgst <= 0) {
-        cdrain = 0; m.gm = 0; m.gds = 0; m.gmbs = 0;
+        cdrain = 0; m.gm() = 0; m.gds() = 0; m.gmbs() = 0;
     }
     else {
         double vds = (m.mode > 0) ? ms.vds : -ms.vds;
@@ -331,20 +395,20 @@ __device__ inline double dev_mos_eq1(MosInst &m, MosStuff &ms)
         if (sarg <= 0)
             arg = 0;
         else
-            arg = m.gamma/(sarg+sarg);
-        double betap = m.beta*(1 + m.lambda*vds);
+            arg = m.gamma()/(sarg+sarg);
+        double betap = m.beta()*(1 + m.lambda()*vds);
         if (vgst <= vds) {
-            m.gm = betap*vgst;
+            m.gm() = betap*vgst;
             vgst *= vgst*.5;
             cdrain = betap*vgst;
-            m.gds = m.lambda*m.beta*vgst;
-            m.gmbs = m.gm*arg;
+            m.gds() = m.lambda()*m.beta()*vgst;
+            m.gmbs() = m.gm()*arg;
         }
         else {
-            m.gm = betap*vds;
-            cdrain = m.gm*(vgst - .5*vds);
-            m.gds = betap*(vgst - vds) + m.lambda*m.beta*vds*(vgst - .5*vds);
-            m.gmbs = m.gm*arg;
+            m.gm() = betap*vds;
+            cdrain = m.gm()*(vgst - .5*vds);
+            m.gds() = betap*(vgst - vds) + m.lambda()*m.beta()*vds*(vgst - .5*vds);
+            m.gmbs() = m.gm()*arg;
         }
     }
     return cdrain;
@@ -352,7 +416,7 @@ __device__ inline double dev_mos_eq1(MosInst &m, MosStuff &ms)
 
 __device__ inline int dev_mos_limiting(const TrialCtx &c, MosInst &m, MosStuff &ms, int oldlimit)
 {
-    double s0vds = m.o_vds, s0vgs = m.o_vgs;
+    double s0vds = m.o_vds(), s0vgs = m.o_vgs();
     if (s0vds >= 0) {
         ms.vgs = dev_fetlim(ms.vgs, s0vgs, ms.von);
         ms.vds = ms.vgs - ms.vgd;
@@ -369,11 +433,11 @@ __device__ inline int dev_mos_limiting(const TrialCtx &c, MosInst &m, MosStuff &
     }
     int check;
     if (ms.vds >= 0) {
-        ms.vbs = dev_pnjlim(ms.vbs, m.o_vbs, ms.vt, m.sourceVcrit, &check);
+        ms.vbs = dev_pnjlim(ms.vbs, m.o_vbs(), ms.vt, m.sourceVcrit(), &check);
         ms.vbd = ms.vbs - ms.vds;
     }
     else {
-        ms.vbd = dev_pnjlim(ms.vbd, m.o_vbd, ms.vt, m.drainVcrit, &check);
+        ms.vbd = dev_pnjlim(ms.vbd, m.o_vbd(), ms.vt, m.drainVcrit(), &check);
         ms.vbs = ms.vbd + ms.vds;
     }
     ms.vgb = ms.vgs - ms.vbs;
@@ -384,159 +448,183 @@ __device__ inline void dev_mos_iv(MosInst &m, MosStuff &ms, double gmin)
 {
     ms.gcgs = 0; ms.ceqgs = 0; ms.gcgd = 0; ms.ceqgd = 0; ms.gcgb = 0; ms.ceqgb = 0;
     if (ms.vbs <= -3*ms.vt) {
-        m.gbs = gmin;
-        m.cbs = m.gbs*ms.vbs - m.tSourceSatCur;
+        m.gbs() = gmin;
+        m.cbs() = m.gbs()*ms.vbs - m.tSourceSatCur();
     }
     else {
         double evbs = exp(ms.vbs/ms.vt);
-        m.gbs = m.tSourceSatCur*evbs/ms.vt + gmin;
-        m.cbs = m.tSourceSatCur*(evbs-1) + gmin*ms.vbs;
+        m.gbs() = m.tSourceSatCur()*evbs/ms.vt + gmin;
+        m.cbs() = m.tSourceSatCur()*(evbs-1) + gmin*ms.vbs;
     }
     if (ms.vbd <= -3*ms.vt) {
-        m.gbd = gmin;
-        m.cbd = m.gbd*ms.vbd - m.tDrainSatCur;
+        m.gbd() = gmin;
+        m.cbd() = m.gbd()*ms.vbd - m.tDrainSatCur();
     }
     else {
         double evbd = exp(ms.vbd/ms.vt);
-        m.gbd = m.tDrainSatCur*evbd/ms.vt + gmin;
-        m.cbd = m.tDrainSatCur*(evbd-1) + gmin*ms.vbd;
+        m.gbd() = m.tDrainSatCur()*evbd/ms.vt + gmin;
+        m.cbd() = m.tDrainSatCur()*(evbd-1) + gmin*ms.vbd;
     }
     m.mode = (ms.vds >= 0) ? 1 : -1;
     ms.cdrain = dev_mos_eq1(m, ms);
     if (m.type > 0) {
-        m.von = ms.von; m.vdsat = ms.vdsat;
+        m.von() = ms.von; m.vdsat() = ms.vdsat;
     }
     else {
-        m.von = -ms.von; m.vdsat = -ms.vdsat;
+        m.von() = -ms.von; m.vdsat() = -ms.vdsat;
     }
     if (m.mode > 0)
-        m.cd = ms.cdrain - m.cbd;
+        m.cd() = ms.cdrain - m.cbd();
     else
-        m.cd = -ms.cdrain - m.cbd;
+        m.cd() = -ms.cdrain - m.cbd();
 }
 
 __device__ inline void dev_mos_cap(const TrialCtx &c, MosInst &m, MosStuff &ms)
 {
     const int st = m.st;
-    if (m.Cbs != 0 || m.Cbssw != 0) {
-        if (ms.vbs < m.tDepCap) {
-            double arg = 1 - ms.vbs/m.tBulkPot, sarg, sargsw;
-            dev_sargs(arg, m.mj, m.mjsw, &sarg, &sargsw);
-            ST(c, 0, st + MS_qbs) = m.tBulkPot*(m.Cbs*(1 - arg*sarg)/(1 - m.mj)
-                + m.Cbssw*(1 - arg*sargsw)/(1 - m.mjsw));
-            m.capbs = m.Cbs*sarg + m.Cbssw*sargsw;
+    if (m.Cbs() != 0 || m.Cbssw() != 0) {
+        if (ms.vbs < m.tDepCap()) {
+            double arg = 1 - ms.vbs/m.tBulkPot(), sarg, sargsw;
+            dev_sargs(arg, m.mj(), m.mjsw(), &sarg, &sargsw);
+            m.s0(MS_qbs) = m.tBulkPot()*(m.Cbs()*(1 - arg*sarg)/(1 - m.mj())
+                + m.Cbssw()*(1 - arg*sargsw)/(1 - m.mjsw()));
+            m.capbs() = m.Cbs()*sarg + m.Cbssw()*sargsw;
         }
         else {
-            ST(c, 0, st + MS_qbs) = m.f4s + ms.vbs*(m.f2s + .5*ms.vbs*m.f3s);
-            m.capbs = m.f2s + m.f3s*ms.vbs;
+            m.s0(MS_qbs) = m.f4s() + ms.vbs*(m.f2s() + .5*ms.vbs*m.f3s());
+            m.capbs() = m.f2s() + m.f3s()*ms.vbs;
         }
     }
     else {
-        ST(c, 0, st + MS_qbs) = 0; m.capbs = 0;
+        m.s0(MS_qbs) = 0; m.capbs() = 0;
     }
-    if (m.Cbd != 0 || m.Cbdsw != 0) {
-        if (ms.vbd < m.tDepCap) {
-            double arg = 1 - ms.vbd/m.tBulkPot, sarg, sargsw;
-            dev_sargs(arg, m.mj, m.mjsw, &sarg, &sargsw);
-            ST(c, 0, st + MS_qbd) = m.tBulkPot*(m.Cbd*(1 - arg*sarg)/(1 - m.mj)
-                + m.Cbdsw*(1 - arg*sargsw)/(1 - m.mjsw));
-            m.capbd = m.Cbd*sarg + m.Cbdsw*sargsw;
+    if (m.Cbd() != 0 || m.Cbdsw() != 0) {
+        if (ms.vbd < m.tDepCap()) {
+            double arg = 1 - ms.vbd/m.tBulkPot(), sarg, sargsw;
+            dev_sargs(arg, m.mj(), m.mjsw(), &sarg, &sargsw);
+            m.s0(MS_qbd) = m.tBulkPot()*(m.Cbd()*(1 - arg*sarg)/(1 - m.mj())
+                + m.Cbdsw()*(1 - arg*sargsw)/(1 - m.mjsw()));
+            m.capbd() = m.Cbd()*sarg + m.Cbdsw()*sargsw;
         }
         else {
-            ST(c, 0, st + MS_qbd) = m.f4d + ms.vbd*(m.f2d + .5*ms.vbd*m.f3d);
-            m.capbd = m.f2d + ms.vbd*m.f3d;
+            m.s0(MS_qbd) = m.f4d() + ms.vbd*(m.f2d() + .5*ms.vbd*m.f3d());
+            m.capbd() = m.f2d() + ms.vbd*m.f3d();
         }
     }
     else {
-        ST(c, 0, st + MS_qbd) = 0; m.capbd = 0;
+        m.s0(MS_qbd) = 0; m.capbd() = 0;
     }
 
     double vgx, vgy, cgx, cgy, cgb;
     if (m.mode > 0) { vgx = ms.vgs; vgy = ms.vgd; }
     else { vgx = ms.vgd; vgy = ms.vgs; }
-    dev_qmeyer(vgx, vgy, ms.von, ms.vdsat, &cgx, &cgy, &cgb, m.tPhi, m.oxideCap);
+    dev_qmeyer(vgx, vgy, ms.von, ms.vdsat, &cgx, &cgy, &cgb, m.tPhi(), m.oxideCap());
     double s0capgs, s0capgd;
     if (m.mode > 0) { s0capgs = cgx; s0capgd = cgy; }
     else { s0capgd = cgx; s0capgs = cgy; }
-    ST(c, 0, st + MS_capgs) = s0capgs;
-    ST(c, 0, st + MS_capgd) = s0capgd;
-    ST(c, 0, st + MS_capgb) = cgb;
+    m.s0(MS_capgs) = s0capgs;
+    m.s0(MS_capgd) = s0capgd;
+    m.s0(MS_capgb) = cgb;
 
     if (c.mode & (MODEINITTRAN|MODEINITSMSIG)) {
         ST(c, 1, st + MS_capgs) = s0capgs;
         ST(c, 1, st + MS_capgd) = s0capgd;
         ST(c, 1, st + MS_capgb) = cgb;
-        m.s1[MS_capgs] = s0capgs; m.s1[MS_capgd] = s0capgd; m.s1[MS_capgb] = cgb;
-        ms.capgs = s0capgs + s0capgs + m.gsOvl;
-        ms.capgd = s0capgd + s0capgd + m.gdOvl;
-        ms.capgb = cgb + cgb + m.gbOvl;
+        m.s1(MS_capgs) = s0capgs; m.s1(MS_capgd) = s0capgd; m.s1(MS_capgb) = cgb;
+        ms.capgs = s0capgs + s0capgs + m.gsOvl();
+        ms.capgd = s0capgd + s0capgd + m.gdOvl();
+        ms.capgb = cgb + cgb + m.gbOvl();
         double qgs = ms.capgs*ms.vgs, qgd = ms.capgd*ms.vgd, qgb = ms.capgb*ms.vgb;
-        ST(c, 0, st + MS_qgs) = qgs;
-        ST(c, 0, st + MS_qgd) = qgd;
-        ST(c, 0, st + MS_qgb) = qgb;
-        double qbd0 = ST(c, 0, st + MS_qbd), qbs0 = ST(c, 0, st + MS_qbs);
+        m.s0(MS_qgs) = qgs;
+        m.s0(MS_qgd) = qgd;
+        m.s0(MS_qgb) = qgb;
+        double qbd0 = m.s0(MS_qbd), qbs0 = m.s0(MS_qbs);
         ST(c, 1, st + MS_qbd) = qbd0;
         ST(c, 1, st + MS_qbs) = qbs0;
         ST(c, 1, st + MS_qgs) = qgs;
         ST(c, 1, st + MS_qgd) = qgd;
         ST(c, 1, st + MS_qgb) = qgb;
-        m.s1[MS_qbd] = qbd0; m.s1[MS_qbs] = qbs0;
-        m.s1[MS_qgs] = qgs; m.s1[MS_qgd] = qgd; m.s1[MS_qgb] = qgb;
+        m.s1(MS_qbd) = qbd0; m.s1(MS_qbs) = qbs0;
+        m.s1(MS_qgs) = qgs; m.s1(MS_qgd) = qgd; m.s1(MS_qgb) = qgb;
     }
     else {
-        ms.capgs = s0capgs + m.s1[MS_capgs] + m.gsOvl;
-        ms.capgd = s0capgd + m.s1[MS_capgd] + m.gdOvl;
-        ms.capgb = cgb + m.s1[MS_capgb] + m.gbOvl;
-        vgx = m.s1[MS_vgs];
-        vgy = vgx - m.s1[MS_vds];
-        double vxy = vgx - m.s1[MS_vbs];
-        ST(c, 0, st + MS_qgs) = (ms.vgs - vgx)*ms.capgs + m.s1[MS_qgs];
-        ST(c, 0, st + MS_qgd) = (ms.vgd - vgy)*ms.capgd + m.s1[MS_qgd];
-        ST(c, 0, st + MS_qgb) = (ms.vgb - vxy)*ms.capgb + m.s1[MS_qgb];
+        ms.capgs = s0capgs + m.s1(MS_capgs) + m.gsOvl();
+        ms.capgd = s0capgd + m.s1(MS_capgd) + m.gdOvl();
+        ms.capgb = cgb + m.s1(MS_capgb) + m.gbOvl();
+        vgx = m.s1(MS_vgs);
+        vgy = vgx - m.s1(MS_vds);
+        double vxy = vgx - m.s1(MS_vbs);
+        m.s0(MS_qgs) = (ms.vgs - vgx)*ms.capgs + m.s1(MS_qgs);
+        m.s0(MS_qgd) = (ms.vgd - vgy)*ms.capgd + m.s1(MS_qgd);
+        m.s0(MS_qgb) = (ms.vgb - vxy)*ms.capgb + m.s1(MS_qgb);
+    }
+}
+
+// sCKT::integrate (niinteg.cc:60-152) on the staged state rows of one charge: k = MS_q*,
+// k+1 = its current.
+__device__ inline void dev_mos_integrate(const TrialCtx &c, const MosInst &m, double *geq, double *ceq,
+    double cap, int k)
+{
+    double s1q = m.s1(k), s1c = m.s1(k + 1);
+    double cq;
+    if (c.method == 0)
+        cq = (c.order <= 1 ? s1q*c.ag[1] : - s1c*c.ag[1] - s1q*c.ag[0]);
+    else
+        cq = dev_NIceq(c, m.st + k);
+    double q0 = m.s0(k);
+    double c0 = c.ag[0]*q0 + cq;
+    m.s0(k + 1) = c0;
+    *ceq = cq;
+    *geq = c.ag[0]*cap;
+    // trapezoid ringing check (niinteg.cc:117-152)
+    if (c.trapCheck && !*c.trapbad && !(fabs(c0) < 1e-6) && !(fabs(q0) < 1e-16)) {
+        double c2 = ST(c, 2, m.st + k + 1);
+        double dqdt = fabs(q0 - s1q)/c.delta;
+        if (fabs(s1c) > c.trapratio*dqdt && fabs(c0 - s1c) > c.trapratio*fabs(c0 - c2))
+            *c.trapbad = 1;
     }
 }
 
 __device__ inline void dev_mos_meyer_integ(const TrialCtx &c, MosInst &m, MosStuff &ms)
 {
     const int st = m.st;
-    dev_integrate4v(c, &ms.gcgs, &ms.ceqgs, ms.capgs, st + MS_qgs, m.s1[MS_qgs], m.s1[MS_cqgs]);
-    dev_integrate4v(c, &ms.gcgd, &ms.ceqgd, ms.capgd, st + MS_qgd, m.s1[MS_qgd], m.s1[MS_cqgd]);
-    dev_integrate4v(c, &ms.gcgb, &ms.ceqgb, ms.capgb, st + MS_qgb, m.s1[MS_qgb], m.s1[MS_cqgb]);
-    ms.ceqgs += c.ag[0]*ST(c, 0, st + MS_qgs) - ms.gcgs*ms.vgs;
-    ms.ceqgd += c.ag[0]*ST(c, 0, st + MS_qgd) - ms.gcgd*ms.vgd;
-    ms.ceqgb += c.ag[0]*ST(c, 0, st + MS_qgb) - ms.gcgb*ms.vgb;
+    dev_mos_integrate(c, m, &ms.gcgs, &ms.ceqgs, ms.capgs, MS_qgs);
+    dev_mos_integrate(c, m, &ms.gcgd, &ms.ceqgd, ms.capgd, MS_qgd);
+    dev_mos_integrate(c, m, &ms.gcgb, &ms.ceqgb, ms.capgb, MS_qgb);
+    ms.ceqgs += c.ag[0]*m.s0(MS_qgs) - ms.gcgs*ms.vgs;
+    ms.ceqgd += c.ag[0]*m.s0(MS_qgd) - ms.gcgd*ms.vgd;
+    ms.ceqgb += c.ag[0]*m.s0(MS_qgb) - ms.gcgb*ms.vgb;
 }
 
 __device__ inline void dev_mos_integ(const TrialCtx &c, MosInst &m, MosStuff &ms)
 {
     const int st = m.st;
     double geq, ceq;
-    dev_integrate4v(c, &geq, &ceq, m.capbd, st + MS_qbd, m.s1[MS_qbd], m.s1[MS_cqbd]);
-    m.gbd += geq;
-    double cqbd = ST(c, 0, st + MS_cqbd);
-    m.cbd += cqbd;
-    m.cd  -= cqbd;
-    dev_integrate4v(c, &geq, &ceq, m.capbs, st + MS_qbs, m.s1[MS_qbs], m.s1[MS_cqbs]);
-    m.gbs += geq;
-    m.cbs += ST(c, 0, st + MS_cqbs);
-    if (ms.capgs == 0) ST(c, 0, st + MS_cqgs) = 0;
-    if (ms.capgd == 0) ST(c, 0, st + MS_cqgd) = 0;
-    if (ms.capgb == 0) ST(c, 0, st + MS_cqgb) = 0;
-    dev_mos_meyer_integ(c, m, ms);
+    dev_mos_integrate(c, m, &geq, &ceq, m.capbd(), MS_qbd);
+    m.gbd() += geq;
+    double cqbd = m.s0(MS_cqbd);
+    m.cbd() += cqbd;
+    m.cd()  -= cqbd;
+    dev_mos_integrate(c, m, &geq, &ceq, m.capbs(), MS_qbs);
+    m.gbs() += geq;
+    m.cbs() += m.s0(MS_cqbs);
+    if (ms.capgs == 0) m.s0(MS_cqgs) = 0;
+    if (ms.capgd == 0) m.s0(MS_cqgd) = 0;
+    if (ms.capgb == 0) m.s0(MS_cqgb) = 0;
 }
 
 // Unified stamp (tran form); with the Meyer terms zero it reproduces load_dc exactly
 // (x+0 == x, -(x+0) == -x), see DESIGN.md section 4.
-__device__ inline void dev_mos_stamp(const TrialCtx &c, MosInst &m, MosStuff &ms, MosOut &o)
+__device__ inline void dev_mos_stamp(const TrialCtx &c, MosInst &m, MosStuff &ms, const MosOut &o)
 {
     const int st = m.st;
-#define MSC(xx) (m.mult*(xx))
-    ST(c, 0, st + MS_vbs) = ms.vbs;
-    ST(c, 0, st + MS_vbd) = ms.vbd;
-    ST(c, 0, st + MS_vgs) = ms.vgs;
-    ST(c, 0, st + MS_vds) = ms.vds;
-    double gbd = MSC(m.gbd), gbs = MSC(m.gbs), gds = MSC(m.gds), gm = MSC(m.gm);
-    double gmbs = MSC(m.gmbs), cbd = MSC(m.cbd), cbs = MSC(m.cbs);
+#define MSC(xx) (m.mult()*(xx))
+    m.s0(MS_vbs) = ms.vbs;
+    m.s0(MS_vbd) = ms.vbd;
+    m.s0(MS_vgs) = ms.vgs;
+    m.s0(MS_vds) = ms.vds;
+    double gbd = MSC(m.gbd()), gbs = MSC(m.gbs()), gds = MSC(m.gds()), gm = MSC(m.gm());
+    double gmbs = MSC(m.gmbs()), cbd = MSC(m.cbd()), cbs = MSC(m.cbs());
     double ceqbs = cbs - gbs*ms.vbs;
     double ceqbd = cbd - gbd*ms.vbd;
     double cdreq;
@@ -544,114 +632,101 @@ __device__ inline void dev_mos_stamp(const TrialCtx &c, MosInst &m, MosStuff &ms
         cdreq = MSC(ms.cdrain) - gds*ms.vds - gm*ms.vgs - gmbs*ms.vbs;
     else
         cdreq = -(MSC(ms.cdrain) + gds*ms.vds - gm*ms.vgd - gmbs*ms.vbd);
-    double dcon = MSC(m.dcon), scon = MSC(m.scon);
+    double dcon = MSC(m.dcon()), scon = MSC(m.scon());
     if (m.type > 0) {
-        o.r[MRH_g]  = -MSC(ms.ceqgs + ms.ceqgb + ms.ceqgd);
-        o.r[MRH_b]  = -(ceqbs + ceqbd - MSC(ms.ceqgb));
-        o.r[MRH_dp] = ceqbd - cdreq + MSC(ms.ceqgd);
-        o.r[MRH_sp] = cdreq + ceqbs + MSC(ms.ceqgs);
+        o.Rw(MRH_g, -MSC(ms.ceqgs + ms.ceqgb + ms.ceqgd));
+        o.Rw(MRH_b, -(ceqbs + ceqbd - MSC(ms.ceqgb)));
+        o.Rw(MRH_dp, ceqbd - cdreq + MSC(ms.ceqgd));
+        o.Rw(MRH_sp, cdreq + ceqbs + MSC(ms.ceqgs));
     }
     else {
-        o.r[MRH_g]  = MSC(ms.ceqgs + ms.ceqgb + ms.ceqgd);
-        o.r[MRH_b]  = ceqbs + ceqbd - MSC(ms.ceqgb);
-        o.r[MRH_dp] = -(ceqbd - cdreq + MSC(ms.ceqgd));
-        o.r[MRH_sp] = -(cdreq + ceqbs + MSC(ms.ceqgs));
+        o.Rw(MRH_g, MSC(ms.ceqgs + ms.ceqgb + ms.ceqgd));
+        o.Rw(MRH_b, ceqbs + ceqbd - MSC(ms.ceqgb));
+        o.Rw(MRH_dp, -(ceqbd - cdreq + MSC(ms.ceqgd)));
+        o.Rw(MRH_sp, -(cdreq + ceqbs + MSC(ms.ceqgs)));
     }
     double gcgd = MSC(ms.gcgd), gcgs = MSC(ms.gcgs), gcgb = MSC(ms.gcgb);
-    o.m[MT_Dd] = dcon;
-    o.m[MT_Gg] = gcgd + gcgs + gcgb;
-    o.m[MT_Ss] = scon;
-    o.m[MT_Bb] = gbd + gbs + gcgb;
-    o.m[MT_Ddp] = -dcon;
-    o.m[MT_Gb] = -gcgb;
-    o.m[MT_Gdp] = -gcgd;
-    o.m[MT_Gsp] = -gcgs;
-    o.m[MT_Ssp] = -scon;
-    o.m[MT_Bg] = -gcgb;
-    o.m[MT_Bdp] = -gbd;
-    o.m[MT_Bsp] = -gbs;
-    o.m[MT_DPd] = -dcon;
-    o.m[MT_SPs] = -scon;
+    o.M(MT_Dd, dcon);
+    o.M(MT_Gg, gcgd + gcgs + gcgb);
+    o.M(MT_Ss, scon);
+    o.M(MT_Bb, gbd + gbs + gcgb);
+    o.M(MT_Ddp, -dcon);
+    o.M(MT_Gb, -gcgb);
+    o.M(MT_Gdp, -gcgd);
+    o.M(MT_Gsp, -gcgs);
+    o.M(MT_Ssp, -scon);
+    o.M(MT_Bg, -gcgb);
+    o.M(MT_Bdp, -gbd);
+    o.M(MT_Bsp, -gbs);
+    o.M(MT_DPd, -dcon);
+    o.M(MT_SPs, -scon);
     if (m.mode > 0) {
-        o.m[MT_DPdp] = dcon + gds + gbd + gcgd;
-        o.m[MT_SPsp] = scon + gds + gbs + gm + gmbs + gcgs;
-        o.m[MT_DPg] = gm - gcgd;
-        o.m[MT_DPb] = -gbd + gmbs;
-        o.m[MT_DPsp] = -(gds + gm + gmbs);
-        o.m[MT_SPg] = -(gm + gcgs);
-        o.m[MT_SPb] = -(gbs + gmbs);
-        o.m[MT_SPdp] = -gds;
+        o.M(MT_DPdp, dcon + gds + gbd + gcgd);
+        o.M(MT_SPsp, scon + gds + gbs + gm + gmbs + gcgs);
+        o.M(MT_DPg, gm - gcgd);
+        o.M(MT_DPb, -gbd + gmbs);
+        o.M(MT_DPsp, -(gds + gm + gmbs));
+        o.M(MT_SPg, -(gm + gcgs));
+        o.M(MT_SPb, -(gbs + gmbs));
+        o.M(MT_SPdp, -gds);
     }
     else {
-        o.m[MT_DPdp] = dcon + gds + gbd + gm + gmbs + gcgd;
-        o.m[MT_SPsp] = scon + gds + gbs + gcgs;
-        o.m[MT_DPg] = -(gm + gcgd);
-        o.m[MT_DPb] = -(gbd + gmbs);
-        o.m[MT_DPsp] = -gds;
-        o.m[MT_SPg] = -(-gm + gcgs);
-        o.m[MT_SPb] = -(gbs - gmbs);
-        o.m[MT_SPdp] = -(gds + gm + gmbs);
+        o.M(MT_DPdp, dcon + gds + gbd + gm + gmbs + gcgd);
+        o.M(MT_SPsp, scon + gds + gbs + gcgs);
+        o.M(MT_DPg, -(gm + gcgd));
+        o.M(MT_DPb, -(gbd + gmbs));
+        o.M(MT_DPsp, -gds);
+        o.M(MT_SPg, -(-gm + gcgs));
+        o.M(MT_SPb, -(gbs - gmbs));
+        o.M(MT_SPdp, -(gds + gm + gmbs));
     }
 #undef MSC
 }
 
-__device__ inline int dev_mos_bypass(const TrialCtx &c, MosInst &m, MosStuff &ms, MosOut &o,
+// MOS bypass test (mosload.cc:381-470): true if the cached operating point may be reused.
+__device__ inline bool dev_mos_bypass_ok(const MosInst &m, const MosStuff &ms,
     double reltol, double abstol, double vntol)
 {
-    const int st = m.st;
-    double s0vbs = m.o_vbs, s0vgs = m.o_vgs;
-    double s0vds = m.o_vds, s0vbd = m.o_vbd;
+    double s0vbs = m.o_vbs(), s0vgs = m.o_vgs();
+    double s0vds = m.o_vds(), s0vbd = m.o_vbd();
     double delvbs = ms.vbs - s0vbs;
     double delvgs = ms.vgs - s0vgs;
     double delvds = ms.vds - s0vds;
     double delvbd = ms.vbd - s0vbd;
     double delvgd = ms.vgd - (s0vgs - s0vds);
-    double cbhat = m.cbs + m.cbd + m.gbd*delvbd + m.gbs*delvbs;
+    double cbs = m.cbs(), cbd = m.cbd(), gbd = m.gbd(), gbs = m.gbs();
+    double cbhat = cbs + cbd + gbd*delvbd + gbs*delvbs;
     double A1 = fabs(cbhat);
-    double A2 = m.cbs + m.cbd;
+    double A2 = cbs + cbd;
     A2 = fabs(A2);
     double A3 = DMAX(A1, A2) + abstol;
-    A1 = cbhat - (m.cbs + m.cbd);
-    if (fabs(A1) >= reltol*A3) return 0;
+    A1 = cbhat - (cbs + cbd);
+    if (fabs(A1) >= reltol*A3) return false;
     A1 = fabs(ms.vbs); A2 = fabs(s0vbs);
-    if (fabs(delvbs) >= (reltol*DMAX(A1, A2) + vntol)) return 0;
+    if (fabs(delvbs) >= (reltol*DMAX(A1, A2) + vntol)) return false;
     A1 = fabs(ms.vbd); A2 = fabs(s0vbd);
-    if (fabs(delvbd) >= (reltol*DMAX(A1, A2) + vntol)) return 0;
+    if (fabs(delvbd) >= (reltol*DMAX(A1, A2) + vntol)) return false;
     A1 = fabs(ms.vgs); A2 = fabs(s0vgs);
-    if (fabs(delvgs) >= (reltol*DMAX(A1, A2) + vntol)) return 0;
+    if (fabs(delvgs) >= (reltol*DMAX(A1, A2) + vntol)) return false;
     A1 = fabs(ms.vds); A2 = fabs(s0vds);
-    if (fabs(delvds) >= (reltol*DMAX(A1, A2) + vntol)) return 0;
+    if (fabs(delvds) >= (reltol*DMAX(A1, A2) + vntol)) return false;
+    double cd = m.cd(), gmbs = m.gmbs(), gm = m.gm(), gds = m.gds();
     double cdhat;
     if (m.mode >= 0)
-        cdhat = m.cd - m.gbd*delvbd + m.gmbs*delvbs + m.gm*delvgs + m.gds*delvds;
+        cdhat = cd - gbd*delvbd + gmbs*delvbs + gm*delvgs + gds*delvds;
     else
-        cdhat = m.cd + (m.gmbs - m.gbd)*delvbd - m.gm*delvgd + m.gds*delvds;
-    A1 = cdhat - m.cd;
+        cdhat = cd + (gmbs - gbd)*delvbd - gm*delvgd + gds*delvds;
+    A1 = cdhat - cd;
     A2 = fabs(cdhat);
-    A3 = fabs(m.cd);
-    if ((fabs(A1) >= reltol*DMAX(A2, A3) + abstol)) return 0;
-
-    ms.vbs = s0vbs;
-    ms.vgs = s0vgs;
-    ms.vds = s0vds;
-    ms.vbd = s0vbd;
-    ms.vgd = ms.vgs - ms.vds;
-    ms.vgb = ms.vgs - ms.vbs;
-    ms.cdrain = m.mode*(m.cd + m.cbd);
-    if (c.mode & MODETRAN) {
-        ms.capgs = m.o_capgs + m.s1[MS_capgs] + m.gsOvl;
-        ms.capgd = m.o_capgd + m.s1[MS_capgd] + m.gdOvl;
-        ms.capgb = m.o_capgb + m.s1[MS_capgb] + m.gbOvl;
-        dev_mos_meyer_integ(c, m, ms);
-    }
-    dev_mos_stamp(c, m, ms, o);
-    return 1;
+    A3 = fabs(cd);
+    if ((fabs(A1) >= reltol*DMAX(A2, A3) + abstol)) return false;
+    return true;
 }
 
-__device__ inline void dev_mos_get_v(const MosInst &m, MosStuff &ms, const double *v, int ldt)
+__device__ inline void dev_mos_get_v(const MosInst &m, MosStuff &ms)
 {
-    double vb = v[(size_t)m.b*ldt], vsp = v[(size_t)m.sp*ldt];
-    double vg = v[(size_t)m.g*ldt], vdp = v[(size_t)m.dp*ldt];
+    double vb = m.R(SR_V_B), vsp = m.R(SR_V_SP);
+    double vg = m.R(SR_V_G), vdp = m.R(SR_V_DP);
     if (m.type > 0) {
         ms.vbs = vb - vsp;
         ms.vgs = vg - vsp;
@@ -664,156 +739,146 @@ __device__ inline void dev_mos_get_v(const MosInst &m, MosStuff &ms, const doubl
     }
 }
 
-// Returns: bit0 = stamps valid (write contributions), bit1 = cache dirty, bit2 = incNoncon
-__device__ inline int dev_mos_load(const TrialCtx &c, MosInst &m, MosOut &o,
-    const double *rhsOld /* + trial */, const b200_options &opt)
+// MOSdev::load for one (instance, trial) (mosload.cc:100-930).  The mode branches only choose
+// the terminal voltages and which stages run; limiting -> I/V -> charges -> integration -> stamp
+// exist once, in the order the reference executes them.
+// Returns: bit0 = stamps valid (contributions written), bit1 = cache dirty, bit2 = incNoncon,
+// bit3 = bypassed, bit4 = only the .ic voltages were stored (UIC)
+__device__ inline int dev_mos_load(const TrialCtx &c, MosInst &m, const MosOut &o, const b200_options &opt)
 {
     MosStuff ms;
-    ms.vt = m.vt;
+    ms.vt = m.vt();
     ms.gcgs = ms.ceqgs = ms.gcgd = ms.ceqgd = ms.gcgb = ms.ceqgb = 0;
     ms.capgs = ms.capgd = ms.capgb = 0; ms.cdrain = 0; ms.vdsat = 0;
     const int st = m.st;
-    int ret = 0;
-    // one burst of independent loads: old state-0 values (limiting / bypass) and, for the
-    // transient modes, the whole state-1 block of this device
-    m.o_vbs = ST(c, 0, st + MS_vbs); m.o_vgs = ST(c, 0, st + MS_vgs);
-    m.o_vds = ST(c, 0, st + MS_vds); m.o_vbd = ST(c, 0, st + MS_vbd);
-    if (c.mode & (MODETRAN | MODEINITPRED)) {
-        m.o_capgs = ST(c, 0, st + MS_capgs); m.o_capgd = ST(c, 0, st + MS_capgd);
-        m.o_capgb = ST(c, 0, st + MS_capgb);
-#pragma unroll
-        for (int k = 0; k < MS_NSTATES; k++) m.s1[k] = ST(c, 1, st + k);
-    }
+    bool limit = false, limit_noncon = false, charges = false;
+    int ret = 3;
+    ms.von = (m.type > 0) ? m.von() : -m.von();
     if (c.mode & MODEINITFLOAT) {
-        dev_mos_get_v(m, ms, rhsOld, c.ldt);
-        ms.von = (m.type > 0) ? m.von : -m.von;
-        ms.vbd = ms.vbs - ms.vds;
-        ms.vgd = ms.vgs - ms.vds;
-        ms.vgb = ms.vgs - ms.vbs;
-        if (opt.bypass && dev_mos_bypass(c, m, ms, o, opt.reltol, opt.abstol, opt.vntol))
-            return 1;
-        dev_mos_limiting(c, m, ms, opt.oldlimit);
-        dev_mos_iv(m, ms, opt.gmin);
-        if (c.mode & MODETRAN) {
-            dev_mos_cap(c, m, ms);
-            dev_mos_integ(c, m, ms);
-        }
-        dev_mos_stamp(c, m, ms, o);
-        return 3;
+        dev_mos_get_v(m, ms);
+        limit = true;
+        charges = (c.mode & MODETRAN) != 0;
     }
-    if (c.mode & MODEINITPRED) {
-        double s1vbs = m.s1[MS_vbs], s1vgs = m.s1[MS_vgs], s1vds = m.s1[MS_vds];
-        ms.vbs = s1vbs*c.pred[0] + ST(c, 2, st + MS_vbs)*c.pred[1];
-        ms.vgs = s1vgs*c.pred[0] + ST(c, 2, st + MS_vgs)*c.pred[1];
-        ms.vds = s1vds*c.pred[0] + ST(c, 2, st + MS_vds)*c.pred[1];
-        ms.vbd = ms.vbs - ms.vds;
-        ms.vgd = ms.vgs - ms.vds;
-        ms.vgb = ms.vgs - ms.vbs;
-        ms.von = (m.type > 0) ? m.von : -m.von;
-        ST(c, 0, st + MS_vbs) = s1vbs;
-        ST(c, 0, st + MS_vgs) = s1vgs;
-        ST(c, 0, st + MS_vds) = s1vds;
-        ST(c, 0, st + MS_vbd) = s1vbs - s1vds;
-        // limiting reads the state-0 voltages just written (mosload.cc:172-182)
-        m.o_vbs = s1vbs; m.o_vgs = s1vgs; m.o_vds = s1vds; m.o_vbd = s1vbs - s1vds;
-        dev_mos_limiting(c, m, ms, opt.oldlimit);
-        dev_mos_iv(m, ms, opt.gmin);
-        if (c.mode & MODETRAN) {
-            dev_mos_cap(c, m, ms);
-            dev_mos_integ(c, m, ms);
-        }
-        dev_mos_stamp(c, m, ms, o);
-        return 3;
+    else if (c.mode & MODEINITPRED) {
+        double s1vbs = m.s1(MS_vbs), s1vgs = m.s1(MS_vgs), s1vds = m.s1(MS_vds);
+        ms.vbs = s1vbs*c.pred[0] + m.R(SR_S2_vbs)*c.pred[1];
+        ms.vgs = s1vgs*c.pred[0] + m.R(SR_S2_vgs)*c.pred[1];
+        ms.vds = s1vds*c.pred[0] + m.R(SR_S2_vds)*c.pred[1];
+        // limiting reads the state-0 voltages the reference has just copied from state 1
+        // (mosload.cc:172-182); the stamp stage then stores the limited values to state 0
+        m.o_vbs() = s1vbs; m.o_vgs() = s1vgs; m.o_vds() = s1vds; m.o_vbd() = s1vbs - s1vds;
+        limit = true;
+        charges = (c.mode & MODETRAN) != 0;
     }
-    if (c.mode & MODEINITFIX) {
-        ms.von = (m.type > 0) ? m.von : -m.von;
-        if (m.off) {
-            ms.vbs = ms.vgs = ms.vds = ms.vbd = ms.vgd = ms.vgb = 0;
-        }
+    else if (c.mode & MODEINITFIX) {
+        if (m.off)
+            ms.vbs = ms.vgs = ms.vds = 0;
         else {
-            dev_mos_get_v(m, ms, rhsOld, c.ldt);
-            ms.vbd = ms.vbs - ms.vds;
-            ms.vgd = ms.vgs - ms.vds;
-            ms.vgb = ms.vgs - ms.vbs;
-            if (dev_mos_limiting(c, m, ms, opt.oldlimit))
-                ret |= 4;
+            dev_mos_get_v(m, ms);
+            limit = true; limit_noncon = true;
         }
-        dev_mos_iv(m, ms, opt.gmin);
-        dev_mos_stamp(c, m, ms, o);
-        return ret | 3;
     }
-    if (c.mode & MODEINITTRAN) {
-        ms.von = (m.type > 0) ? m.von : -m.von;
-        ms.vbs = m.s1[MS_vbs];
-        ms.vgs = m.s1[MS_vgs];
-        ms.vds = m.s1[MS_vds];
-        ms.vbd = ms.vbs - ms.vds;
-        ms.vgd = ms.vgs - ms.vds;
-        ms.vgb = ms.vgs - ms.vbs;
-        dev_mos_iv(m, ms, opt.gmin);
-        dev_mos_cap(c, m, ms);
-        dev_mos_integ(c, m, ms);
-        dev_mos_stamp(c, m, ms, o);
-        return 3;
+    else if (c.mode & MODEINITTRAN) {
+        ms.vbs = m.s1(MS_vbs);
+        ms.vgs = m.s1(MS_vgs);
+        ms.vds = m.s1(MS_vds);
+        charges = true;
     }
-    if ((c.mode & MODEINITJCT) && (c.mode & MODETRANOP) && (c.mode & MODEUIC)) {
-        if (m.type > 0) {
-            ms.vds = m.icVDS; ms.vgs = m.icVGS; ms.vbs = m.icVBS;
-        }
-        else {
-            ms.vds = -m.icVDS; ms.vgs = -m.icVGS; ms.vbs = -m.icVBS;
-        }
-        ST(c, 0, st + MS_vds) = ms.vds;
-        ST(c, 0, st + MS_vgs) = ms.vgs;
-        ST(c, 0, st + MS_vbs) = ms.vbs;
-        return 0;
-    }
-    if (c.mode & MODEINITJCT) {
-        ms.von = (m.type > 0) ? m.von : -m.von;
-        if (m.off) {
-            ms.vbs = ms.vgs = ms.vds = ms.vbd = ms.vgd = ms.vgb = 0;
-        }
-        else {
-            if (m.icVDS == 0 && m.icVGS == 0 && m.icVBS == 0) {
-                ms.vbs = -1;
-                ms.vgs = (m.type > 0) ? m.tVto : -m.tVto;
-                ms.vds = 0;
+    else if (c.mode & MODEINITJCT) {
+        double icVDS = m.icVDS(), icVGS = m.icVGS(), icVBS = m.icVBS();
+        if ((c.mode & MODETRANOP) && (c.mode & MODEUIC)) {
+            if (m.type > 0) {
+                ms.vds = icVDS; ms.vgs = icVGS; ms.vbs = icVBS;
             }
             else {
-                if (m.type > 0) {
-                    ms.vds = m.icVDS; ms.vgs = m.icVGS; ms.vbs = m.icVBS;
-                }
-                else {
-                    ms.vds = -m.icVDS; ms.vgs = -m.icVGS; ms.vbs = -m.icVBS;
-                }
+                ms.vds = -icVDS; ms.vgs = -icVGS; ms.vbs = -icVBS;
             }
-            ms.vbd = ms.vbs - ms.vds;
-            ms.vgd = ms.vgs - ms.vds;
-            ms.vgb = ms.vgs - ms.vbs;
+            m.s0(MS_vds) = ms.vds;
+            m.s0(MS_vgs) = ms.vgs;
+            m.s0(MS_vbs) = ms.vbs;
+            return 16;
+        }
+        if (m.off)
+            ms.vbs = ms.vgs = ms.vds = 0;
+        else if (icVDS == 0 && icVGS == 0 && icVBS == 0) {
+            ms.vbs = -1;
+            ms.vgs = (m.type > 0) ? m.tVto() : -m.tVto();
+            ms.vds = 0;
+        }
+        else if (m.type > 0) {
+            ms.vds = icVDS; ms.vgs = icVGS; ms.vbs = icVBS;
+        }
+        else {
+            ms.vds = -icVDS; ms.vgs = -icVGS; ms.vbs = -icVBS;
+        }
+    }
+    else
+        return 0;
+    ms.vbd = ms.vbs - ms.vds;
+    ms.vgd = ms.vgs - ms.vds;
+    ms.vgb = ms.vgs - ms.vbs;
+
+    if ((c.mode & MODEINITFLOAT) && opt.bypass &&
+            dev_mos_bypass_ok(m, ms, opt.reltol, opt.abstol, opt.vntol)) {
+        ret = 1 | 8;
+        ms.vbs = m.o_vbs();
+        ms.vgs = m.o_vgs();
+        ms.vds = m.o_vds();
+        ms.vbd = m.o_vbd();
+        ms.vgd = ms.vgs - ms.vds;
+        ms.vgb = ms.vgs - ms.vbs;
+        ms.cdrain = m.mode*(m.cd() + m.cbd());
+        if (charges) {
+            ms.capgs = m.o_capgs() + m.s1(MS_capgs) + m.gsOvl();
+            ms.capgd = m.o_capgd() + m.s1(MS_capgd) + m.gdOvl();
+            ms.capgb = m.o_capgb() + m.s1(MS_capgb) + m.gbOvl();
+        }
+    }
+    else {
+        if (limit) {
+            int check = dev_mos_limiting(c, m, ms, opt.oldlimit);
+            if (limit_noncon && check) ret |= 4;
         }
         dev_mos_iv(m, ms, opt.gmin);
-        dev_mos_stamp(c, m, ms, o);
-        return 3;
+        if (charges) {
+            dev_mos_cap(c, m, ms);
+            dev_mos_integ(c, m, ms);
+        }
     }
-    return 0;
+    if (charges)
+        dev_mos_meyer_integ(c, m, ms);
+    dev_mos_stamp(c, m, ms, o);
+    return ret;
 }
 
 // MOSdev::convTest for one instance (mosconv.cc:52-141).  rhs = CKTrhs (PREVIOUS iterate).
-__device__ inline int dev_mos_conv(const TrialCtx &c, const MosInst &m, const double *rhs,
+struct MosConvIn {
+    int type, off, st, mode;
+    int g, b, dp, sp;
+    double cd, cbs, cbd, gm, gds, gmbs, gbd, gbs;
+};
+__device__ inline int dev_mos_conv(const TrialCtx &c, const MosConvIn &m, const double *rhs,
     double reltol, double abstol)
 {
     if (m.off && (c.mode & MODEINITFIX))
         return 0;
-    MosStuff ms;
-    dev_mos_get_v(m, ms, rhs, c.ldt);
+    double vb = rhs[(size_t)m.b*c.ldt], vsp = rhs[(size_t)m.sp*c.ldt];
+    double vg = rhs[(size_t)m.g*c.ldt], vdp = rhs[(size_t)m.dp*c.ldt];
+    double vbs, vgs, vds;
+    if (m.type > 0) {
+        vbs = vb - vsp; vgs = vg - vsp; vds = vdp - vsp;
+    }
+    else {
+        vbs = vsp - vb; vgs = vsp - vg; vds = vsp - vdp;
+    }
     const int st = m.st;
     double s0vbs = ST(c, 0, st + MS_vbs), s0vgs = ST(c, 0, st + MS_vgs);
     double s0vds = ST(c, 0, st + MS_vds), s0vbd = ST(c, 0, st + MS_vbd);
-    double vbd = ms.vbs - ms.vds, vgd = ms.vgs - ms.vds;
-    double delvbs = ms.vbs - s0vbs;
+    double vbd = vbs - vds, vgd = vgs - vds;
+    double delvbs = vbs - s0vbs;
     double delvbd = vbd - s0vbd;
-    double delvgs = ms.vgs - s0vgs;
-    double delvds = ms.vds - s0vds;
+    double delvgs = vgs - s0vgs;
+    double delvds = vds - s0vds;
     double delvgd = vgd - (s0vgs - s0vds);
     double cdhat;
     if (m.mode >= 0)

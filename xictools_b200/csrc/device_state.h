@@ -92,6 +92,8 @@ struct MosView {
     ParamRef prm[MP_NPARAMS];
     double *cache;      // [MC_NCACHE][n][ldt]
     double *save;       // backup copy of cache
+    MosStageMap smap;   // shared-memory staging layout of k_load_mos
+    int stage_doubles;  // staging area size
 };
 struct CapView {
     int n;

@@ -53,91 +53,129 @@ __device__ __forceinline__ void make_ctx(TrialCtx &c, const Consts &K, const Hot
     c.trapratio = K.opt.trapratio;
     c.trapbad = &hot.trapbad[t];
     c.trapCheck = hot.trapcheck[t] && (mode & MODEINITFLOAT) && (mode & MODETRAN);
-    int nag = (K.method == 0) ? 2 : 7;
-    for (int k = 0; k < nag; k++) c.ag[k] = hot.ag[(size_t)k*K.ldt + t];
+    c.ag[0] = hot.ag[t]; c.ag[1] = hot.ag[(size_t)K.ldt + t];
+    c.agp = hot.ag + t;
     c.pred[0] = hot.pred[t]; c.pred[1] = hot.pred[K.ldt + t];
-    int base = hot.st_base[t];
-    size_t plane = (size_t)K.numStates*K.ldt;
-    for (int k = 0; k < K.NS; k++) {
-        int phys = base + k; if (phys >= K.NS) phys -= K.NS;
-        c.sp[k] = V.states + phys*plane + t;
-    }
+    c.base = hot.st_base[t]; c.NS = K.NS; c.numStates = K.numStates;
+    c.states = V.states + t;
 }
 
+// MOSdev::load for every (instance, trial): CTA = one instance x MOS_TPB adjacent trials.
+// Stage 1: every per-trial input of the thread (4 node voltages, old state-0 values, the state-1
+// block, the cached operating point, per-trial parameters) is copied to the thread's column of
+// the shared-memory staging area with cp.async -- ~50 independent 8-byte copies in flight per
+// thread, nothing parked in registers.  Stage 2: the model is evaluated out of shared memory;
+// state-0 results and stamps go straight to HBM, the operating point is updated in place in
+// the staging area and written back at the end.
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB)
-k_load_mos(Consts K, HotView hot, VecView V, MosView M, const double *rhsOld)
+__global__ void __launch_bounds__(MOS_TPB, MINB)
+k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, const double *rhsOld)
 {
-    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const MosStageMap &map = M.smap;
+    extern __shared__ double stage[];
+    const int tid = threadIdx.x;
+    int t = blockIdx.x*MOS_TPB + tid;
     int i = blockIdx.y;
-    if (t >= K.ntrials) return;
-    int mode = hot.mode[t];
-    if (!mode) return;
+    // shared parameter block (values common to all trials)
+    if (tid < MP_NPARAMS && !map.ts[tid])
+        stage[map.off[tid]] = M.prm[tid].base[i];
+    int mode = (t < K.ntrials) ? hot.mode[t] : 0;
+    // trials that are finished (or past the end) stage nothing but still meet the barrier
     TrialCtx c;
-    make_ctx(c, K, hot, V, t, mode);
     MosInst m;
     m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i];
-    m.d = M.d[i]; m.g = M.g[i]; m.s = M.s[i]; m.b = M.b[i]; m.dp = M.dp[i]; m.sp = M.sp[i];
-    m.tPhi = PR(M.prm[MP_tPhi], i, t); m.tVbi = PR(M.prm[MP_tVbi], i, t);
-    m.tVto = PR(M.prm[MP_tVto], i, t); m.gamma = PR(M.prm[MP_gamma], i, t);
-    m.lambda = PR(M.prm[MP_lambda], i, t); m.beta = PR(M.prm[MP_beta], i, t);
-    m.oxideCap = PR(M.prm[MP_oxideCap], i, t);
-    m.tSourceSatCur = PR(M.prm[MP_tSourceSatCur], i, t);
-    m.tDrainSatCur = PR(M.prm[MP_tDrainSatCur], i, t);
-    m.sourceVcrit = PR(M.prm[MP_sourceVcrit], i, t); m.drainVcrit = PR(M.prm[MP_drainVcrit], i, t);
-    m.Cbd = PR(M.prm[MP_Cbd], i, t); m.Cbdsw = PR(M.prm[MP_Cbdsw], i, t);
-    m.Cbs = PR(M.prm[MP_Cbs], i, t); m.Cbssw = PR(M.prm[MP_Cbssw], i, t);
-    m.tBulkPot = PR(M.prm[MP_tBulkPot], i, t); m.tDepCap = PR(M.prm[MP_tDepCap], i, t);
-    m.f2d = PR(M.prm[MP_f2d], i, t); m.f3d = PR(M.prm[MP_f3d], i, t); m.f4d = PR(M.prm[MP_f4d], i, t);
-    m.f2s = PR(M.prm[MP_f2s], i, t); m.f3s = PR(M.prm[MP_f3s], i, t); m.f4s = PR(M.prm[MP_f4s], i, t);
-    m.gsOvl = PR(M.prm[MP_gsOvl], i, t); m.gdOvl = PR(M.prm[MP_gdOvl], i, t);
-    m.gbOvl = PR(M.prm[MP_gbOvl], i, t); m.dcon = PR(M.prm[MP_dcon], i, t);
-    m.scon = PR(M.prm[MP_scon], i, t); m.mult = PR(M.prm[MP_mult], i, t);
-    m.vt = PR(M.prm[MP_vt], i, t); m.mj = PR(M.prm[MP_mj], i, t); m.mjsw = PR(M.prm[MP_mjsw], i, t);
-    m.icVDS = PR(M.prm[MP_icVDS], i, t); m.icVGS = PR(M.prm[MP_icVGS], i, t);
-    m.icVBS = PR(M.prm[MP_icVBS], i, t);
-    size_t cstride = (size_t)M.n*K.ldt;
-    double *cp = M.cache + (size_t)i*K.ldt + t;
-    m.mode = (int)cp[MC_mode*cstride];
-    m.von = cp[MC_von*cstride]; m.vdsat = cp[MC_vdsat*cstride]; m.cd = cp[MC_cd*cstride];
-    m.cbs = cp[MC_cbs*cstride]; m.cbd = cp[MC_cbd*cstride]; m.gm = cp[MC_gm*cstride];
-    m.gds = cp[MC_gds*cstride]; m.gmbs = cp[MC_gmbs*cstride]; m.gbd = cp[MC_gbd*cstride];
-    m.gbs = cp[MC_gbs*cstride]; m.capbd = cp[MC_capbd*cstride]; m.capbs = cp[MC_capbs*cstride];
-
+    m.g = M.g[i]; m.b = M.b[i]; m.dp = M.dp[i]; m.sp = M.sp[i];
+    m.col = stage + tid; m.shp = stage; m.map = &map;
+    const int st = m.st;
+    const size_t ldt = K.ldt;
+    const size_t cstride = (size_t)M.n*ldt;
+    double *cp = M.cache + (size_t)i*ldt + t;
+    if (mode) {
+        make_ctx(c, K, hot, V, t, mode);
+        if (!(mode & MODEINITPRED)) {
+            const double *x = rhsOld + t;
+            __pipeline_memcpy_async(&m.R(SR_V_B), x + (size_t)m.b*ldt, 8);
+            __pipeline_memcpy_async(&m.R(SR_V_SP), x + (size_t)m.sp*ldt, 8);
+            __pipeline_memcpy_async(&m.R(SR_V_G), x + (size_t)m.g*ldt, 8);
+            __pipeline_memcpy_async(&m.R(SR_V_DP), x + (size_t)m.dp*ldt, 8);
+        }
+        __pipeline_memcpy_async(&m.s0(MS_vbs), &ST(c, 0, st + MS_vbs), 8);
+        __pipeline_memcpy_async(&m.s0(MS_vgs), &ST(c, 0, st + MS_vgs), 8);
+        __pipeline_memcpy_async(&m.s0(MS_vds), &ST(c, 0, st + MS_vds), 8);
+        __pipeline_memcpy_async(&m.s0(MS_vbd), &ST(c, 0, st + MS_vbd), 8);
+#pragma unroll
+        for (int k = 0; k < MC_NCACHE; k++)
+            __pipeline_memcpy_async(&m.R(SR_CACHE + k), cp + k*cstride, 8);
+        if (mode & (MODETRAN | MODEINITPRED)) {
+            // old Meyer capacitances and gate charges (bypass re-integrates them)
+            __pipeline_memcpy_async(&m.s0(MS_capgs), &ST(c, 0, st + MS_capgs), 8);
+            __pipeline_memcpy_async(&m.s0(MS_capgd), &ST(c, 0, st + MS_capgd), 8);
+            __pipeline_memcpy_async(&m.s0(MS_capgb), &ST(c, 0, st + MS_capgb), 8);
+            __pipeline_memcpy_async(&m.s0(MS_qgs), &ST(c, 0, st + MS_qgs), 8);
+            __pipeline_memcpy_async(&m.s0(MS_qgd), &ST(c, 0, st + MS_qgd), 8);
+            __pipeline_memcpy_async(&m.s0(MS_qgb), &ST(c, 0, st + MS_qgb), 8);
+#pragma unroll
+            for (int k = 0; k < MS_NSTATES; k++)
+                __pipeline_memcpy_async(&m.s1(k), &ST(c, 1, st + k), 8);
+        }
+        if (mode & MODEINITPRED) {
+            __pipeline_memcpy_async(&m.R(SR_S2_vbs), &ST(c, 2, st + MS_vbs), 8);
+            __pipeline_memcpy_async(&m.R(SR_S2_vgs), &ST(c, 2, st + MS_vgs), 8);
+            __pipeline_memcpy_async(&m.R(SR_S2_vds), &ST(c, 2, st + MS_vds), 8);
+        }
+        for (int q = 0; q < map.nvar; q++) {
+            int k = map.var[q];
+            __pipeline_memcpy_async(m.col + map.off[k], M.prm[k].base + (size_t)i*ldt + t, 8);
+        }
+        __pipeline_commit();
+    }
     MosOut o;
-    int r = dev_mos_load(c, m, o, rhsOld + t, K.opt);
+    o.cbase = V.contrib + ((size_t)(t/SOLVE_TB)*(size_t)K.NC)*SOLVE_TB + (t % SOLVE_TB);
+    o.cs = M.cslot + (size_t)i*MT_NSTAMP;
+    o.rs = M.rslot + (size_t)i*MRH_NRHS;
+    o.tb = SOLVE_TB;
+    __pipeline_wait_prior(0);
+    __syncthreads();                                     // shared parameter block visible
+    if (!mode) return;
+    m.mode = (int)m.R(SR_CACHE + MC_mode);
+
+    int r = dev_mos_load(c, m, o, K.opt);
+    // ---- results: state 0, operating point, flags ----
+    const bool charges = (mode & MODEINITTRAN) || ((mode & (MODEINITFLOAT | MODEINITPRED)) && (mode & MODETRAN));
+    if (r & 8) {
+        // bypassed: voltages and charges are unchanged, only the Meyer currents were re-integrated
+        if (charges) {
+            ST(c, 0, st + MS_cqgs) = m.s0(MS_cqgs);
+            ST(c, 0, st + MS_cqgd) = m.s0(MS_cqgd);
+            ST(c, 0, st + MS_cqgb) = m.s0(MS_cqgb);
+        }
+    }
+    else if (r & 1) {
+        if (charges) {
+#pragma unroll
+            for (int k = 0; k < MS_NSTATES; k++) ST(c, 0, st + k) = m.s0(k);
+        }
+        else {
+            ST(c, 0, st + MS_vbs) = m.s0(MS_vbs); ST(c, 0, st + MS_vbd) = m.s0(MS_vbd);
+            ST(c, 0, st + MS_vgs) = m.s0(MS_vgs); ST(c, 0, st + MS_vds) = m.s0(MS_vds);
+        }
+    }
+    else if (r & 16) {
+        ST(c, 0, st + MS_vds) = m.s0(MS_vds);
+        ST(c, 0, st + MS_vgs) = m.s0(MS_vgs);
+        ST(c, 0, st + MS_vbs) = m.s0(MS_vbs);
+    }
     if (r & 2) {
-        cp[MC_mode*cstride] = (double)m.mode;
-        cp[MC_von*cstride] = m.von; cp[MC_vdsat*cstride] = m.vdsat; cp[MC_cd*cstride] = m.cd;
-        cp[MC_cbs*cstride] = m.cbs; cp[MC_cbd*cstride] = m.cbd; cp[MC_gm*cstride] = m.gm;
-        cp[MC_gds*cstride] = m.gds; cp[MC_gmbs*cstride] = m.gmbs; cp[MC_gbd*cstride] = m.gbd;
-        cp[MC_gbs*cstride] = m.gbs; cp[MC_capbd*cstride] = m.capbd; cp[MC_capbs*cstride] = m.capbs;
+        m.R(SR_CACHE + MC_mode) = (double)m.mode;
+#pragma unroll
+        for (int k = 0; k < MC_NCACHE; k++)
+            cp[k*cstride] = m.R(SR_CACHE + k);
     }
     if (r & 4)
         hot.noncon[t] = 1;
-    const int *cs = M.cslot + (size_t)i*MT_NSTAMP;
-    const int *rs = M.rslot + (size_t)i*MRH_NRHS;
-    if (r & 1) {
-#pragma unroll
-        for (int k = 0; k < MT_NSTAMP; k++) {
-            int s = cs[k];
-            if (s >= 0) V.contrib[CADDR(K, s, t)] = o.m[k];
-        }
-#pragma unroll
-        for (int k = 0; k < MRH_NRHS; k++) {
-            int s = rs[k];
-            if (s >= 0) V.contrib[CADDR(K, s, t)] = o.r[k];
-        }
-    }
-    else {
-        for (int k = 0; k < MT_NSTAMP; k++) {
-            int s = cs[k];
-            if (s >= 0) V.contrib[CADDR(K, s, t)] = 0.0;
-        }
-        for (int k = 0; k < MRH_NRHS; k++) {
-            int s = rs[k];
-            if (s >= 0) V.contrib[CADDR(K, s, t)] = 0.0;
-        }
+    if (!(r & 1)) {
+        for (int k = 0; k < MT_NSTAMP; k++) o.M(k, 0.0);
+        for (int k = 0; k < MRH_NRHS; k++) o.Rw(k, 0.0);
     }
 }
 
@@ -246,7 +284,7 @@ k_devconv(Consts K, HotView hot, VecView V, MosView M, const double *rhs)
     size_t cstride = (size_t)M.n*K.ldt;
     int i1 = min(M.n, i0 + DEVCONV_CHUNK);
     for (int i = i0; i < i1; i++) {
-        MosInst m;
+        MosConvIn m;
         m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i];
         m.g = M.g[i]; m.b = M.b[i]; m.dp = M.dp[i]; m.sp = M.sp[i];
         const double *cp = M.cache + (size_t)i*K.ldt + t;
@@ -931,10 +969,19 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
 {
     if (M.n) {
         static int minb = -1;
-        if (minb < 0) { const char *e = getenv("B200_LOAD_MINB"); minb = e ? atoi(e) : 4; }
-        if (minb >= 5) k_load_mos<5><<<grid2(K.ntrials, M.n), 128, 0, st>>>(K, hot, V, M, rhsOld);
-        else if (minb == 4) k_load_mos<4><<<grid2(K.ntrials, M.n), 128, 0, st>>>(K, hot, V, M, rhsOld);
-        else k_load_mos<3><<<grid2(K.ntrials, M.n), 128, 0, st>>>(K, hot, V, M, rhsOld);
+        if (minb < 0) { const char *e = getenv("B200_LOAD_MINB"); minb = e ? atoi(e) : 7; }
+        size_t smem = (size_t)M.stage_doubles*sizeof(double);
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(k_load_mos<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        dim3 g((K.ntrials + MOS_TPB - 1)/MOS_TPB, M.n);
+        if (minb >= 8) k_load_mos<8><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        else if (minb == 7) k_load_mos<7><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        else k_load_mos<6><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
     }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
     if (S.n) k_load_src<<<grid2(K.ntrials, S.n), 128, 0, st>>>(K, hot, V, S);
