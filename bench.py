@@ -189,8 +189,8 @@ def bench_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from xictools_b200 import engine
-    from xictools_b200.deck import C_ACCEPTED, C_NUMITER, C_STATUS
+    from xictools_b200.deck import C_NUMITER, C_STATUS
+    from xictools_b200.montecarlo import MonteCarlo
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,11 +203,13 @@ def bench_ours(args):
 
     T = args.trials
     deck = make_deck(args.stages)
-    ov = make_variation(deck, T, seed=100 + rank)        # each rank owns its own trials (shard)
-    batch = engine.Batch(deck, T, device=local)
-    names = batch.names()
-    sel = [names.index("n0"), names.index(f"n{args.stages//2}"), names.index("vdd#branch")]
-    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in ov.items()}
+    ov = make_variation(deck, T, seed=100 + rank)        # this rank's shard of the world*T trials
+    save = ["n0", f"n{args.stages//2}", "vdd#branch"]
+    mc = MonteCarlo(deck, world*T, save=save, rank=rank, world=world, device=local,
+                    local_variation=ov)
+    batch = mc.runner.batch
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in mc.variation.items()}
+    mc.variation = {k: v.numpy() for k, v in pinned.items()}     # H2D copies start from pinned memory
 
     def barrier():
         if world > 1:
@@ -218,52 +220,44 @@ def bench_ours(args):
         batch.run_tran()
 
     def step_e2e():
-        # host buffers in, host results out: per-trial parameters H2D, counters + selected
-        # waveforms D2H, (N>1) gather to rank 0 over NCCL/NVLink
-        for (pid, idx), v in pinned.items():
-            batch.set_param(pid, idx, v.numpy())
-        batch.run_tran()
-        cnt = batch.counters()
-        _, w = batch.waves(sel)
-        if world > 1:
-            tc = torch.from_numpy(cnt).cuda()
-            gl = [torch.empty_like(tc) for _ in range(world)] if rank == 0 else None
-            dist.gather(tc, gl, dst=0)
-        return cnt, w
+        # the call a user makes: host parameter arrays in (H2D), counters + selected waveforms
+        # out (D2H), shards gathered to rank 0 over NCCL/NVLink when N > 1
+        mc.run(device=torch.device("cuda", local))
+        return mc.local[0], mc.local[2]
 
-    batch.set_params(ov)
+    batch.set_params(mc.variation)
     for _ in range(args.warmup):
         step_kernel_only()
 
-    # ---- kernel-resident timing ----
+    # ---- kernel-resident timing: CUDA events on the engine's own stream (ms_total of
+    # b200_batch_get_stats brackets every launch of the run), wall clock as a cross-check ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    ev0.record()
     launches = ticks = 0
-    ms_load = ms_solve = 0.0
+    ms_load = ms_solve = ms_dev = 0.0
     nload = nsolve = 0
     for _ in range(args.steps):
         step_kernel_only()
         st = batch.stats()
         launches += st.launches
         ticks += st.ticks
+        ms_dev += st.ms_total
         ms_load += st.ms_load
         ms_solve += st.ms_solve
         nload += st.load_launches
         nsolve += st.solve_launches
-    ev1.record()
     barrier()
-    el = time.perf_counter() - t0
+    el_wall = time.perf_counter() - t0
+    el = ms_dev*1e-3
     clocks = sampler.stop() if rank == 0 else None
     st = batch.stats()
     cnt = batch.counters()
     ok_trials = int((cnt[:, C_STATUS] == 0).sum())
 
-    # ---- end-to-end timing (host buffers) ----
+    # ---- end-to-end timing (host buffers, public API) ----
     step_e2e()
     barrier()
     t1 = time.perf_counter()
@@ -272,12 +266,12 @@ def bench_ours(args):
     barrier()
     el_e2e = time.perf_counter() - t1
 
-    tmax = torch.tensor([el, el_e2e], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([el, el_e2e, el_wall], dtype=torch.float64, device="cuda")
     agg = torch.tensor([float(ok_trials), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    el, el_e2e = float(tmax[0]), float(tmax[1])
+    el, el_e2e, el_wall = float(tmax[0]), float(tmax[1]), float(tmax[2])
 
     if rank == 0:
         peaks = {}
@@ -309,10 +303,23 @@ def bench_ours(args):
             cpu = {"value": None, "unit": "trials/s", "cores": 0, "kind": "reference",
                    "sample": f"unavailable: {e}"}
         iters = int(cnt[:, C_NUMITER].sum())
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture
+        # (profiles/traffic.json: bytes per launch at the captured trial count; every per-trial
+        # array scales linearly with the number of trials)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_load_mos"]
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"])*T/tj["trials"]
+            traffic_src = (f"{tj['source']}: {tj['trials']} trials captured, scaled by "
+                           f"{T}/{tj['trials']} trials")
+        except Exception:
+            pass
         line = {
             "metric": "Monte Carlo transient trials/sec", "value": value, "unit": "trials/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3*el/args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3*el/args.steps, "wall_ms_per_step": 1e3*el_wall/args.steps,
+            "timing": "CUDA events on the launching stream, max over ranks",
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if args.stages == NSTAGES else f"ro{args.stages}_mc",
                        "trials_per_gpu": T, "unknowns": batch.n,
@@ -327,7 +334,7 @@ def bench_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_load_mos+k_load_cap+k_load_src (one tick)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach/peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "ms_per_launch": load_ms,
                          "solve_kernel": {"achieved": ach_solve, "ms_per_launch": solve_ms,
                                           "frac": ach_solve/peak}},

@@ -1,0 +1,96 @@
+"""Golden fixtures (tests/golden/*.json) were produced by the UNMODIFIED reference compiled
+headless (tests/golden/make_golden.py).  They travel to the GPU box, /root/reference does not.
+
+CPU part: the C oracle reproduces every fixture (identical counters, waveforms to roundoff).
+GPU part: the CUDA engine, through the C ABI, reproduces every fixture (identical counters,
+waveforms within WRspice's reltol/vntol)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import Oracle
+from tests.decks import variants
+from xictools_b200.deck import (C_ACCEPTED, C_NUMITER, C_REJECTED, C_STATUS, C_TIMEPTS, C_NPOINTS,
+                                mc_variation, ring_oscillator)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KEYS = ("err", "accepted", "rejected", "numiter", "timepts", "itercut", "trapcut")
+LOOSE = {"ro5_ord1": 5e-2}       # chaotic step sequence: roundoff amplified along the run
+RELTOL, VNTOL = 1e-3, 1e-6
+
+
+def fixtures():
+    return sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(HERE, "golden", "*.json")))
+
+
+def load(name):
+    with open(os.path.join(HERE, "golden", name + ".json")) as f:
+        g = json.load(f)
+    g["times"] = np.array(g["times"])
+    g["vals"] = np.array(g["vals"])
+    return g
+
+
+def deck_for(name):
+    """(deck, overrides dict of per-trial arrays or None, trial index)"""
+    if name.startswith("ro5_mc_seed3_trial"):
+        d = ring_oscillator(5)
+        return d, mc_variation(d, 4, seed=3), int(name[-1])
+    return variants()[name], None, 0
+
+
+def test_fixture_set_is_complete():
+    assert set(variants()) <= set(fixtures())
+    assert len(fixtures()) >= len(variants()) + 4
+
+
+@pytest.mark.parametrize("name", fixtures())
+def test_oracle_reproduces_reference_fixture(name):
+    g = load(name)
+    d, ov, t = deck_for(name)
+    trial = {k: v[t] for k, v in ov.items()} if ov else None
+    assert d.to_spice(trial) == g["spice"], "fixture was generated from a different deck"
+    if not ov:      # per-device model cards of an MC trial reorder the reference's model list
+        assert d.load_order_names() == g["load_order"]
+    o = Oracle(d, ov, t).run()
+    assert {k: int(o[k]) for k in KEYS} == g["counters"]
+    np.testing.assert_allclose(o["times"], g["times"], rtol=0, atol=1e-18)
+    idx = [o["names"].index(nm) for nm in g["names"]]
+    assert np.abs(o["vals"][:, idx] - g["vals"]).max() < LOOSE.get(name, 1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", fixtures())
+def test_engine_reproduces_reference_fixture(name):
+    from xictools_b200 import engine
+    g = load(name)
+    d, ov, t = deck_for(name)
+    ntr = 4 if ov else 2
+    b = engine.Batch(d, ntr)
+    if ov:
+        b.set_params(ov)
+    b.run_tran()
+    cnt = b.counters()
+    _, w = b.waves()
+    names = b.names()
+    b.close()
+    gc = g["counters"]
+    assert int(cnt[t, C_STATUS]) == gc["err"]
+    got = tuple(int(cnt[t, k]) for k in (C_ACCEPTED, C_REJECTED, C_NUMITER, C_TIMEPTS, C_NPOINTS))
+    want = (gc["accepted"], gc["rejected"], gc["numiter"], gc["timepts"], len(g["times"]))
+    if name in LOOSE:
+        # order-1 integration with ~60 LTE rejections: the step sequence is chaotic, and the
+        # engine's pivot order differs from Sparse 1.3's, so roundoff may move one Newton
+        # iteration.  Step counts must still be identical.  (With the engine's pivot order given
+        # to the oracle the counts are identical: tests/test_engine_gpu.py::test_deck_parity.)
+        assert got[:2] == want[:2] and got[3:] == want[3:] and abs(got[2] - want[2]) <= 2, (got, want)
+    else:
+        assert got == want
+    idx = [names.index(nm) for nm in g["names"]]
+    v = w[t, :len(g["times"])][:, idx]
+    scale = 50.0 if name in LOOSE else 1.0
+    tol = scale*(RELTOL*np.maximum(np.abs(v), np.abs(g["vals"])) + VNTOL)
+    assert not (np.abs(v - g["vals"]) > tol).any(), np.abs(v - g["vals"]).max()
