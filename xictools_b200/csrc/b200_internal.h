@@ -59,7 +59,9 @@ enum { SR_V_B, SR_V_SP, SR_V_G, SR_V_DP,                // node voltages (rhsOld
        SR_S0 = 4,                                       // state 0 block (old values in, new values out)
        SR_S1 = SR_S0 + MS_NSTATES,                      // state 1 block
        SR_CACHE = SR_S1 + MS_NSTATES,                   // cached operating point
-       SR_PRM = SR_CACHE + MC_NCACHE,                   // per-trial parameters
+       SR_Q2 = SR_CACHE + MC_NCACHE,                    // gate charges qgs,qgd,qgb two and three
+       SR_Q3 = SR_Q2 + 3,                               //  steps back (LTE)
+       SR_PRM = SR_Q3 + 3,                              // per-trial parameters
        SR_NFIXED = SR_PRM };
 struct MosStageMap {
     int off[MP_NPARAMS];    // per-trial: row*MOS_TPB; shared: offset of the value in the shared block

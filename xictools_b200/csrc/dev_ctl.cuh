@@ -558,8 +558,10 @@ __device__ inline void ctl_reject_common(TrialCtl &s)
     s.vecops |= VO_RESTORE_OLD;
 }
 
+__device__ inline void ctl_lte_ret(TrialCtl &s, const Consts &K, const CtlShared &sh, const CtlIn &in);
+
 __device__ inline void ctl_tran_step_ret(TrialCtl &s, const Consts &K, const CtlShared &sh,
-    int cverr, HotView &hot, int t)
+    int cverr, const CtlIn &in)
 {
     // tranan.cc:714-742
     double bound_step = s.devMaxDelta;
@@ -589,11 +591,9 @@ __device__ inline void ctl_tran_step_ret(TrialCtl &s, const Consts &K, const Ctl
         ctl_tran_loop_top(s, K, sh);
         return;
     }
-    // LTE needed: let the trunc kernel run, continue in ctl_lte_ret
-    hot.want_lte[t] = (s.order < K.opt.maxord && !K.opt.spice3 && s.t_ordcnt == 0) ? 2 :
-        ((K.opt.spice3 && s.order == 1 && s.t_ordcnt == 0) ? 2 : 1);
-    s.pc = PC_WAIT_LTE;
-    s.want_load = 0;
+    // sCKT::trunc: the per-charge bounds were min-reduced by the load kernels of the tick whose
+    // matrix has just converged (in.lte0: this order, in.lte1: order + 1)
+    ctl_lte_ret(s, K, sh, in);
 }
 
 // device-independent part of sCKT::trunc for one order: SRC trunc (srctrun.cc:45-66) + root
@@ -726,7 +726,7 @@ __device__ inline void ctl_after_solve(TrialCtl &s, const Consts &K, const CtlSh
     case RET_GMIN_LOOP:  ctl_gmin_loop_ret(s, K, sh, r); break;
     case RET_GMIN_FINAL: ctl_gmin_done(s, K, sh, r); break;
     case RET_SRC_LOOP:   ctl_src_loop_ret(s, K, sh, r); break;
-    case RET_TRAN_STEP:  ctl_tran_step_ret(s, K, sh, r, hot, t); break;
+    case RET_TRAN_STEP:  ctl_tran_step_ret(s, K, sh, r, in); break;
     default: ctl_fail(s, B200_E_PANIC); break;
     }
 }

@@ -45,6 +45,8 @@ struct TrialCtx {
     int numStates;
     int ldt;
     int *trapbad;           // per-trial flag
+    const double *dOldp;    // &hot.deltaOld[trial]: deltaOld[k] at dOldp[k*ldt]
+    double *lte;            // &hot.lte[trial]: LTE step bounds (this order, order + 1), min-reduced
 };
 
 __device__ __forceinline__ double &ST(const TrialCtx &c, int k, int slot)
@@ -130,6 +132,74 @@ __device__ inline void dev_integrate2(const TrialCtx &c, int q, double cq)
 {
     ST(c, 0, q+1) = c.ag[0]*ST(c, 0, q) + cq;
     dev_trapcheck(c, q);
+}
+
+// sCKT::terr (ckt.cc:2326-2389) for one integrated charge, evaluated inside the load of a
+// transient Newton iteration: if this iteration turns out to be the converged one, the value is
+// what sCKT::trunc would compute from the states this load leaves behind.  q[0..3]/c[0..1] are
+// the charge / current history already at hand; deeper history (Gear > 2) is read from HBM.
+__device__ __forceinline__ void atomic_min_pos(double *addr, double v)
+{
+    // positive finite doubles order like their bit patterns
+    atomicMin((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+template <int ORDER>
+__device__ __forceinline__ double dev_terr_fixed(const TrialCtx &c, const b200_options &opt,
+    const double *q, double tol, int qslot)
+{
+    // compile-time order: the divided-difference table lives in registers
+    const double gearCoeff[] = { .5, .2222222222, .1363636364, .096, .07299270073, .05830903790 };
+    const double trapCoeff[] = { .5, .08333333333 };
+    double diff[ORDER + 2], deltmp[ORDER + 1], dOld[ORDER + 1];
+#pragma unroll
+    for (int i = 0; i <= ORDER + 1; i++) diff[i] = (i < 4) ? q[i] : ST(c, i, qslot);
+#pragma unroll
+    for (int i = 0; i <= ORDER; i++) { dOld[i] = c.dOldp[(size_t)i*c.ldt]; deltmp[i] = dOld[i]; }
+#pragma unroll
+    for (int j = ORDER; j >= 0; j--) {
+#pragma unroll
+        for (int i = 0; i <= j; i++) diff[i] = (diff[i] - diff[i+1])/deltmp[i];
+        if (j > 0) {
+#pragma unroll
+            for (int i = 0; i <= j - 1; i++) deltmp[i] = deltmp[i+1] + dOld[i];
+        }
+    }
+    double del;
+    if (c.method == 0) del = fabs(diff[0]*trapCoeff[ORDER <= 2 ? ORDER - 1 : 1]);
+    else del = fabs(diff[0]*gearCoeff[ORDER - 1]);
+    return opt.trtol*tol/DMAX(opt.abstol, del);
+}
+
+__device__ inline double dev_terr_order(const TrialCtx &c, const b200_options &opt, int order,
+    const double *q, double tol, int qslot)
+{
+    switch (order) {
+    case 1: return dev_terr_fixed<1>(c, opt, q, tol, qslot);
+    case 2: return dev_terr_fixed<2>(c, opt, q, tol, qslot);
+    case 3: return dev_terr_fixed<3>(c, opt, q, tol, qslot);
+    case 4: return dev_terr_fixed<4>(c, opt, q, tol, qslot);
+    case 5: return dev_terr_fixed<5>(c, opt, q, tol, qslot);
+    default: return dev_terr_fixed<6>(c, opt, q, tol, qslot);
+    }
+}
+
+__device__ inline void dev_lte_charge(const TrialCtx &c, const b200_options &opt, const double *q,
+    double c0, double c1, int qslot, double &m0, double &m1)
+{
+    double y0 = fabs(c0), y1 = fabs(c1);
+    double volttol = opt.abstol + opt.reltol*DMAX(y0, y1);
+    y0 = fabs(q[0]); y1 = fabs(q[1]);
+    double chargetol = DMAX(y0, y1);
+    if (chargetol < opt.chgtol) chargetol = opt.chgtol;
+    chargetol *= opt.reltol/c.delta;
+    double tol = DMAX(volttol, chargetol);
+    double d0 = dev_terr_order(c, opt, c.order, q, tol, qslot);
+    if (d0 < m0) m0 = d0;
+    if (c.order + 1 <= opt.maxord) {
+        double d1 = dev_terr_order(c, opt, c.order + 1, q, tol, qslot);
+        if (d1 < m1) m1 = d1;
+    }
 }
 
 // ---- limiters: devlib/devlib.cc:475-620 ----

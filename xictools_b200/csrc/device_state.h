@@ -14,7 +14,7 @@
 #endif
 
 // ---- per-trial control block (AoS; touched only by the control kernel, one thread/trial) ----
-enum { PC_IDLE = 0, PC_NIITER, PC_WAIT_LTE, PC_DONE };
+enum { PC_IDLE = 0, PC_NIITER, PC_DONE };
 enum { RET_NONE = 0, RET_OP_DIRECT, RET_GMIN_LOOP, RET_GMIN_FINAL, RET_SRC_LOOP, RET_TRAN_STEP };
 
 // vector-op request bits (consumed by k_vec / k_statevec right after the control kernel)
@@ -73,7 +73,6 @@ struct HotView {
     int    *need_devconv;
     int    *devconv;    // 1 = device convTest failed
     // LTE
-    int    *want_lte;   // 1: compute LTE for this trial
     double *lte;        // [2][ldt] min over charges for order, order+1 (un-normalised)
 };
 

@@ -58,6 +58,8 @@ __device__ __forceinline__ void make_ctx(TrialCtx &c, const Consts &K, const Hot
     c.pred[0] = hot.pred[t]; c.pred[1] = hot.pred[K.ldt + t];
     c.base = hot.st_base[t]; c.NS = K.NS; c.numStates = K.numStates;
     c.states = V.states + t;
+    c.dOldp = hot.deltaOld + t;
+    c.lte = hot.lte + t;
 }
 
 // MOSdev::load for every (instance, trial): CTA = one instance x MOS_TPB adjacent trials.
@@ -118,6 +120,14 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
             for (int k = 0; k < MS_NSTATES; k++)
                 __pipeline_memcpy_async(&m.s1(k), &ST(c, 1, st + k), 8);
         }
+        if ((mode & MODETRAN) && (mode & MODEINITFLOAT)) {
+            const int qs[3] = { MS_qgs, MS_qgd, MS_qgb };
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                __pipeline_memcpy_async(&m.R(SR_Q2 + k), &ST(c, 2, st + qs[k]), 8);
+                __pipeline_memcpy_async(&m.R(SR_Q3 + k), &ST(c, 3, st + qs[k]), 8);
+            }
+        }
         if (mode & MODEINITPRED) {
             __pipeline_memcpy_async(&m.R(SR_S2_vbs), &ST(c, 2, st + MS_vbs), 8);
             __pipeline_memcpy_async(&m.R(SR_S2_vgs), &ST(c, 2, st + MS_vgs), 8);
@@ -165,6 +175,18 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
         ST(c, 0, st + MS_vgs) = m.s0(MS_vgs);
         ST(c, 0, st + MS_vbs) = m.s0(MS_vbs);
     }
+    if ((mode & MODETRAN) && (mode & MODEINITFLOAT) && (r & 1)) {
+        // MOSdev::trunc (mostrun.cc:52-65): the three gate charges
+        const int qs[3] = { MS_qgs, MS_qgd, MS_qgb };
+        double m0 = DBL_MAX, m1 = DBL_MAX;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double q[4] = { m.s0(qs[k]), m.s1(qs[k]), m.R(SR_Q2 + k), m.R(SR_Q3 + k) };
+            dev_lte_charge(c, K.opt, q, m.s0(qs[k] + 1), m.s1(qs[k] + 1), st + qs[k], m0, m1);
+        }
+        atomic_min_pos(c.lte, m0);
+        if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
+    }
     if (r & 2) {
         m.R(SR_CACHE + MC_mode) = (double)m.mode;
 #pragma unroll
@@ -207,6 +229,14 @@ k_load_cap(Consts K, HotView hot, VecView V, CapView Cp, const double *rhsOld)
             *pc = ceq;
             geq = *pg;
             stamp = true;
+            if (mode & MODETRAN) {
+                // CAPdev::trunc (captrun.cc:58)
+                double q[4] = { qcap, ST(c, 1, st), ST(c, 2, st), ST(c, 3, st) };
+                double m0 = DBL_MAX, m1 = DBL_MAX;
+                dev_lte_charge(c, K.opt, q, ST(c, 0, st + 1), ST(c, 1, st + 1), st, m0, m1);
+                atomic_min_pos(c.lte, m0);
+                if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
+            }
         }
         else if (mode & MODEINITPRED) {
             geq = c.ag[0]*capac;
@@ -297,79 +327,6 @@ k_devconv(Consts K, HotView hot, VecView V, MosView M, const double *rhs)
             return;
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------
-// LTE: sCKT::terr (ckt.cc:2326-2389) for every integrated charge, min-reduced per trial.
-__device__ __forceinline__ void atomic_min_pos(double *addr, double v)
-{
-    // positive finite doubles order like their bit patterns
-    atomicMin((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
-}
-
-__device__ inline double dev_terr(const Consts &K, const double *const *sp, int ldt, int qcap,
-    int order, const double *deltaOld, double delta)
-{
-    const double gearCoeff[] = { .5, .2222222222, .1363636364, .096, .07299270073, .05830903790 };
-    const double trapCoeff[] = { .5, .08333333333 };
-    int ccap = qcap + 1;
-    double y0 = fabs(sp[0][(size_t)ccap*ldt]), y1 = fabs(sp[1][(size_t)ccap*ldt]);
-    double volttol = K.opt.abstol + K.opt.reltol*DMAX(y0, y1);
-    y0 = fabs(sp[0][(size_t)qcap*ldt]); y1 = fabs(sp[1][(size_t)qcap*ldt]);
-    double chargetol = DMAX(y0, y1);
-    if (chargetol < K.opt.chgtol) chargetol = K.opt.chgtol;
-    chargetol *= K.opt.reltol/delta;
-    double tol = DMAX(volttol, chargetol);
-    double diff[8], deltmp[8];
-    for (int i = order + 1; i >= 0; i--) diff[i] = sp[i][(size_t)qcap*ldt];
-    for (int i = 0; i <= order; i++) deltmp[i] = deltaOld[i];
-    int j = order;
-    for (;;) {
-        for (int i = 0; i <= j; i++) diff[i] = (diff[i] - diff[i+1])/deltmp[i];
-        if (--j < 0) break;
-        for (int i = 0; i <= j; i++) deltmp[i] = deltmp[i+1] + deltaOld[i];
-    }
-    double del;
-    if (K.method == 0) del = fabs(diff[0]*trapCoeff[order-1]);
-    else del = fabs(diff[0]*gearCoeff[order-1]);
-    del = K.opt.trtol*tol/DMAX(K.opt.abstol, del);
-    return del;
-}
-
-#define TRUNC_CHUNK 16
-__global__ void __launch_bounds__(128)
-k_trunc(Consts K, HotView hot, VecView V, int nq, const int *qslots)
-{
-    int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int q0 = blockIdx.y*TRUNC_CHUNK;
-    if (t >= K.ntrials || q0 >= nq) return;
-    int want = hot.want_lte[t];
-    if (!want) return;
-    int base = hot.st_base[t];
-    size_t plane = (size_t)K.numStates*K.ldt;
-    const double *sp[8];
-    for (int k = 0; k < K.NS; k++) {
-        int phys = base + k; if (phys >= K.NS) phys -= K.NS;
-        sp[k] = V.states + phys*plane + t;
-    }
-    double dOld[7];
-    for (int k = 0; k < 7; k++) dOld[k] = hot.deltaOld[(size_t)k*K.ldt + t];
-    int order = hot.order[t];
-    double delta = hot.delta[t];
-    bool two = (want == 2 && order + 1 <= K.opt.maxord);
-    double m0 = DBL_MAX, m1 = DBL_MAX;
-    int qe = min(nq, q0 + TRUNC_CHUNK);
-    for (int q = q0; q < qe; q++) {
-        int slot = qslots[q];
-        double d0 = dev_terr(K, sp, K.ldt, slot, order, dOld, delta);
-        if (d0 < m0) m0 = d0;
-        if (two) {
-            double d1 = dev_terr(K, sp, K.ldt, slot, order + 1, dOld, delta);
-            if (d1 < m1) m1 = d1;
-        }
-    }
-    atomic_min_pos(&hot.lte[t], m0);
-    if (two) atomic_min_pos(&hot.lte[K.ldt + t], m1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -708,7 +665,7 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
     TrialCtl s = ctl[t];
     // st_base in force when state-vector ops are requested = value at the start of the
     // control phase (a rotation, if any, comes after the request inside the same call)
-    if (phase != 2) aux.vo_stbase[t] = s.st_base;
+    aux.vo_stbase[t] = s.st_base;
     if (phase == 0) {
         // begin
         s.vecops = 0;
@@ -718,7 +675,7 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
     else if (phase == 1) {
         if (s.status != ST_RUNNING) {
             // finished trials: no load, no solve, and no stale vector-op requests
-            hot.mode[t] = 0; hot.do_solve[t] = 0; hot.want_lte[t] = 0; aux.vecops[t] = 0;
+            hot.mode[t] = 0; hot.do_solve[t] = 0; aux.vecops[t] = 0;
             return;
         }
         s.vecops = 0;
@@ -729,33 +686,12 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
         in.devconv = hot.devconv[t];
         in.noncon_load = hot.noncon[t];
         in.trapbad = hot.trapbad[t];
-        in.lte0 = in.lte1 = 0;
-        hot.want_lte[t] = 0;
-        ctl_after_solve(s, K, sh, in, hot, t);
-        if (s.pc == PC_WAIT_LTE) {
-            hot.lte[t] = DBL_MAX;
-            hot.lte[K.ldt + t] = DBL_MAX;
-            // k_trunc needs order/delta/deltaOld/st_base of the step just solved
-            hot.order[t] = s.order;
-            hot.delta[t] = s.delta;
-            hot.st_base[t] = s.st_base;
-            for (int k = 0; k < 7; k++) hot.deltaOld[(size_t)k*K.ldt + t] = s.deltaOld[k];
-        }
-    }
-    else {
-        if (s.status != ST_RUNNING || s.pc != PC_WAIT_LTE) return;
-        CtlIn in;
-        in.solve_err = 0; in.nodeconv = 0; in.devconv = 0; in.noncon_load = 0;
-        in.trapbad = hot.trapbad[t];
         in.lte0 = hot.lte[t];
         in.lte1 = hot.lte[K.ldt + t];
-        hot.want_lte[t] = 0;
-        int keep = s.vecops;
-        ctl_lte_ret(s, K, sh, in);
-        s.vecops |= keep;
+        ctl_after_solve(s, K, sh, in, hot, t);
     }
     // publish for the vector / load kernels of this tick
-    if (!(phase == 1 && s.pc == PC_WAIT_LTE)) {
+    {
         bool load = s.want_load && s.status == ST_RUNNING;
         hot.mode[t] = load ? s.mode : 0;
         hot.do_solve[t] = (load && s.pc == PC_NIITER) ? 1 : 0;
@@ -774,10 +710,17 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
             int nag = (K.method == 0) ? 2 : 7;
             for (int k = 0; k < nag; k++) hot.ag[(size_t)k*K.ldt + t] = s.ag[k];
             hot.pred[t] = s.pred[0]; hot.pred[K.ldt + t] = s.pred[1];
+            if (s.mode & MODETRAN) {
+                // LTE bounds are accumulated by this tick's loads (min over all charges)
+                hot.lte[t] = DBL_MAX;
+                hot.lte[K.ldt + t] = DBL_MAX;
+                for (int k = 0; k <= s.order + 1 && k < 7; k++)
+                    hot.deltaOld[(size_t)k*K.ldt + t] = s.deltaOld[k];
+            }
         }
     }
     // vector-op requests
-    if (phase != 2 || s.vecops) {
+    {
         aux.vecops[t] = s.vecops;
         aux.sols_base[t] = s.sols_base;
         if (s.vecops & (VO_INTERP | VO_DUMP_DIRECT)) {
@@ -990,11 +933,6 @@ void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const 
     const MosView &M, const double *rhs)
 {
     if (M.n) k_devconv<<<grid2(K.ntrials, (M.n + DEVCONV_CHUNK - 1)/DEVCONV_CHUNK), 128, 0, st>>>(K, hot, V, M, rhs);
-}
-void launch_trunc(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
-    int nq, const int *qslots)
-{
-    if (nq) k_trunc<<<grid2(K.ntrials, (nq + TRUNC_CHUNK - 1)/TRUNC_CHUNK), 128, 0, st>>>(K, hot, V, nq, qslots);
 }
 int solve_smem_bytes(const Consts &K, int seg_maxsteps)
 {

@@ -43,8 +43,6 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
     const MosView &M, const CapView &Cp, const SrcView &S, const double *rhsOld);
 void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const double *rhs);
-void launch_trunc(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
-    int nq, const int *qslots);
 int  solve_smem_bytes(const Consts &K, int seg_maxsteps);
 int  launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const SolveView &Sv, const double *Xold, double *Xnew);
