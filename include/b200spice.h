@@ -169,6 +169,14 @@ int  b200_batch_set_param(b200_batch *b, int param, int index, const double *val
  * NIiter (niiter.cc:160-555), sTRANint::step/accept/interpolate (tranan.cc:483-1116). */
 int  b200_batch_run_tran(b200_batch *b);
 
+/* DC operating point of every trial: DCOanalysis::anFunc (analysis/dcoan.cc:100-121) = ic() +
+ * sCKT::op(MODEDCOP|MODEINITJCT, MODEDCOP|MODEINITFLOAT, itl1) with the gmin / source stepping
+ * fall-backs (ckt.cc:1859-2011).  One output point per trial (time 0 = CKTrhsOld after op());
+ * counters as for run_tran.  With per-trial parameter arrays (b200_batch_set_param, including
+ * B200_P_SRC_DC) this is the batched form of a chained-DC / parameter sweep
+ * (sDCTprms::loop_mt, analysis/dctprms.cc:924-1011): every sweep point is a trial. */
+int  b200_batch_run_op(b200_batch *b);
+
 /* Results (host buffers).  npoints = number of user time points (count of OP.appendData calls
  * per trial in the reference, tranan.cc:963-1116 -> ckt.cc:680-708). */
 int  b200_batch_num_unknowns(const b200_batch *b);   /* matrix size n (nodes + branches) */

@@ -68,7 +68,7 @@ class Oracle:
             L = Oracle._lib
             L.wo_create.restype = C.c_void_p
             L.wo_create.argtypes = [C.c_void_p]
-            for f in ("wo_destroy", "wo_run_tran", "wo_num_unknowns", "wo_nnz", "wo_num_points",
+            for f in ("wo_destroy", "wo_run_tran", "wo_run_op", "wo_num_unknowns", "wo_nnz", "wo_num_points",
                       "wo_num_accepted"):
                 getattr(L, f).argtypes = [C.c_void_p]
             L.wo_set_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
@@ -119,8 +119,8 @@ class Oracle:
         c = np.ascontiguousarray(colperm, dtype=np.int32)
         self.L.wo_set_ordering(self.h, r.ctypes.data, c.ctypes.data)
 
-    def run(self) -> dict:
-        err = self.L.wo_run_tran(self.h)
+    def run(self, analysis: str = "tran") -> dict:
+        err = self.L.wo_run_op(self.h) if analysis == "op" else self.L.wo_run_tran(self.h)
         cnt = np.zeros(10, dtype=np.int32)
         self.L.wo_get_counters(self.h, cnt.ctypes.data)
         npts = self.L.wo_num_points(self.h)

@@ -3104,6 +3104,35 @@ int wo_run_tran(wo_ckt *c)
     return error;
 }
 
+/* DCOanalysis::anFunc, analysis/dcoan.cc:100-121: ic(); op(MODEDCOP|INITJCT, MODEDCOP|INITFLOAT,
+ * dcMaxIter); [INITSMSIG load: AC small-signal data only]; dump(0.0) = CKTrhsOld */
+int wo_run_op(wo_ckt *c)
+{
+    const b200_options *o = &c->opt;
+    feclearexcept(FE_ALL_EXCEPT);
+    for (int i = 0; i < c->nmos; i++) {
+        b200_mos_model deckmod = c->mos[i].mod;
+        mos_temp(c, &c->mos[i], &deckmod);
+    }
+    preload(c);
+    c->time = 0; c->delta = 0;
+    /* initTranFuncs(0.0, 0.0) */
+    for (int oi = 0; oi < c->nord; oi++)
+        if (c->ord[oi].kind == B200_DEV_SRC)
+            src_setup_func(c, &c->src[c->ord[oi].index], 0.0, 0.0);
+    for (int i = 0; i <= c->n; i++) c->rhs[i] = 0;
+    c->hadNodeset = 0;
+    for (int i = 1; i <= c->n; i++) {
+        if (c->ns_given[i]) { c->hadNodeset = 1; c->rhs[i] = c->ns_val[i]; }
+        if (c->ic_given[i]) c->rhs[i] = c->ic_val[i];
+    }
+    c->mode = 0;
+    int error = ckt_op(c, MODEDCOP | MODEINITJCT, MODEDCOP | MODEINITFLOAT, o->itl1);
+    if (error) return error;
+    record_point(c, 0.0, c->rhsOld);
+    return OK;
+}
+
 int wo_num_points(const wo_ckt *c) { return c->npts; }
 void wo_get_points(const wo_ckt *c, double *times, double *vals)
 {

@@ -47,6 +47,33 @@ def ro_rd(n=3):
     return d
 
 
+def inv_dc(n=3):
+    """CMOS inverter chain with a DC input source: the DC operating point / transfer-curve
+    sweep deck (BASELINE config 5 shape: every sweep point is one trial)."""
+    d = Deck(title="inverter chain dc")
+    d.vsource("vdd", "vdd", "0", dc=3.3)
+    d.vsource("vin", "in", "0", dc=1.2)
+    prev = "in"
+    for i in range(n):
+        out = f"o{i}"
+        d.mosfet(f"mp{i}", out, prev, "vdd", "vdd", "pm", w=2e-6, l=1e-6)
+        d.mosfet(f"mn{i}", out, prev, "0", "0", "nm", w=1e-6, l=1e-6)
+        d.capacitor(f"c{i}", out, "0", 20e-15)
+        prev = out
+    d.resistor("rl", prev, "0", 1e5)
+    d.mos_model("nm", "nmos", vto=0.7, kp=1e-4, **COMMON)
+    d.mos_model("pm", "pmos", vto=-0.7, kp=4e-5, **COMMON)
+    d.tran(0.05e-9, 1e-9)
+    return d
+
+
+def op_decks():
+    return {"op_inv_dc": inv_dc(3), "op_inv4": inv_chain(4), "op_ro5": ring_oscillator(5),
+            "op_ro3_rd": ro_rd(3), "op_inv_dc_direct": inv_dc(3).options(gminsteps=-1, srcsteps=-1),
+            "op_inv_dc_gminfirst": inv_dc(3).options(gminfirst=1),
+            "op_inv7_nogmin": inv_chain(7).options(gminsteps=-1)}
+
+
 def variants():
     out = {
         "ro3": ring_oscillator(3),

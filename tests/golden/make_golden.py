@@ -19,14 +19,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle.pyoracle import RefSim, have_ref          # noqa: E402
-from tests.decks import variants                       # noqa: E402
+from tests.decks import op_decks, variants             # noqa: E402
 from xictools_b200.deck import ring_oscillator, mc_variation   # noqa: E402
 
 KEYS = ("err", "accepted", "rejected", "numiter", "timepts", "itercut", "trapcut")
 
 
-def record(deck, overrides=None):
-    text = deck.to_spice(overrides)
+def record(deck, overrides=None, analysis="tran"):
+    text = deck.to_spice(overrides, analysis=analysis)
     r = RefSim().run(text)
     return {
         "spice": text,
@@ -47,6 +47,8 @@ def main():
     ov = mc_variation(d, 4, seed=3)
     for t in range(4):
         out[f"ro5_mc_seed3_trial{t}"] = record(d, {k: v[t] for k, v in ov.items()})
+    for name, d in sorted(op_decks().items()):
+        out[name] = record(d, analysis="op")
     for name, rec in out.items():
         with open(os.path.join(HERE, name + ".json"), "w") as f:
             json.dump(rec, f)

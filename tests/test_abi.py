@@ -19,7 +19,7 @@ def declared_symbols():
 
 def test_header_declares_expected_groups():
     syms = declared_symbols()
-    for s in ("b200_batch_create", "b200_batch_run_tran", "b200_batch_get_waves",
+    for s in ("b200_batch_create", "b200_batch_run_tran", "b200_batch_run_op", "b200_batch_get_waves",
               "b200_klu_analyze", "b200_klu_refactor_solve_host", "b200_batch_debug_load"):
         assert s in syms
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle.pyoracle import Oracle, lu_solve_static
-from tests.decks import variants
+from tests.decks import op_decks, variants
 from xictools_b200 import engine
 from xictools_b200.deck import (C_ACCEPTED, C_NPOINTS, C_NUMITER, C_REJECTED, C_STATUS,
                                 C_TIMEPTS, mc_variation, ring_oscillator)
@@ -158,3 +158,54 @@ def test_full_size_properties_ro101():
     assert np.abs(w[:, :npt[0], 0] - 3.3).max() < 1e-9
     assert (cnt[:, C_ACCEPTED] + cnt[:, C_REJECTED] == cnt[:, C_TIMEPTS]).all()
     b.close()
+
+
+def compare_op(deck, ntr, ov=None, trials=None, tol_scale=1.0):
+    b = engine.Batch(deck, ntr)
+    if ov:
+        b.set_params(ov)
+    b.run_op()
+    cnt = b.counters()
+    _, w = b.waves()
+    rp, cp = b.ordering()
+    names = b.names()
+    b.close()
+    for t in (range(ntr) if trials is None else trials):
+        o = Oracle(deck, ov, t)
+        o.set_ordering(rp, cp)
+        r = o.run("op")
+        assert int(cnt[t, C_STATUS]) == r["err"]
+        assert int(cnt[t, C_NUMITER]) == r["numiter"], (t, int(cnt[t, C_NUMITER]), r["numiter"])
+        assert int(cnt[t, C_NPOINTS]) == 1
+        idx = [names.index(nm) for nm in r["names"]]
+        got = w[t, :1][:, idx]
+        tol = tol_scale*(RELTOL*np.maximum(np.abs(got), np.abs(r["vals"])) + VNTOL)
+        assert not (np.abs(got - r["vals"]) > tol).any(), (t, np.abs(got - r["vals"]).max())
+
+
+@pytest.mark.parametrize("name", sorted(op_decks()))
+def test_dc_operating_point_parity(name):
+    """b200_batch_run_op == DCOanalysis (dcoan.cc): same iteration count through the gmin /
+    source stepping ladders, same operating point."""
+    compare_op(op_decks()[name], 3)
+
+
+def test_dc_sweep_every_point_is_a_trial():
+    """BASELINE config 5 shape: a DC transfer-curve sweep where each sweep point is one trial
+    of the batch (per-trial source value through B200_P_SRC_DC)."""
+    from xictools_b200.deck import DEV_SRC, P_SRC_DC
+    d = op_decks()["op_inv_dc"]
+    isrc = [e.name for e in d.kind_tables()[DEV_SRC]].index("vin")
+    npts = 133
+    vin = np.linspace(0.0, 3.3, npts)
+    ov = {(P_SRC_DC, isrc): vin}
+    compare_op(d, npts, ov, trials=list(range(0, npts, 6)) + [npts - 1])
+    # monotone transfer curve of an odd inverter chain, rail to rail
+    b = engine.Batch(d, npts)
+    b.set_params(ov)
+    b.run_op()
+    _, w = b.waves()
+    out = w[:, 0, b.names().index("o2")]
+    b.close()
+    assert out[0] > 3.0 and out[-1] < 0.1
+    assert (np.diff(out) <= 1e-9).all()

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle.pyoracle import Oracle, RefSim, have_ref
-from tests.decks import variants
+from tests.decks import op_decks, variants
 from xictools_b200.deck import ring_oscillator, mc_variation
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
@@ -48,3 +48,35 @@ def test_uic_failure_mode_matches_reference():
     ref = RefSim().run(d.to_spice())
     o = Oracle(d).run()
     assert (o["err"], o["accepted"], o["numiter"]) == (ref["err"], ref["accepted"], ref["numiter"])
+
+
+@pytest.mark.parametrize("name", sorted(op_decks()))
+def test_dc_operating_point_matches_reference(name):
+    """.op (dcoan.cc): same Newton iteration count (incl. gmin / source stepping) and the same
+    operating point."""
+    d = op_decks()[name]
+    ref = RefSim().run(d.to_spice(analysis="op"))
+    o = Oracle(d).run("op")
+    assert (o["err"], o["numiter"]) == (ref["err"], ref["numiter"])
+    assert len(o["times"]) == len(ref["times"]) == 1
+    idx = [o["names"].index(nm) for nm in ref["names"]]
+    # the ring oscillator's DC solution is its metastable point: a high-gain loop amplifies the
+    # roundoff of the different LU pivot orders to ~1e-8 (vntol is 1e-6)
+    tol = 1e-6 if name == "op_ro5" else 1e-9
+    assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < tol
+
+
+def test_dc_sweep_points_match_reference():
+    """Transfer curve of the inverter chain: each sweep point = one deck with its own vin."""
+    from xictools_b200.deck import P_SRC_DC
+    d = op_decks()["op_inv_dc"]
+    isrc = [e.name for e in d.kind_tables()[3]].index("vin") if False else None
+    from xictools_b200.deck import DEV_SRC
+    isrc = [e.name for e in d.kind_tables()[DEV_SRC]].index("vin")
+    for vin in (0.0, 0.9, 1.5, 1.65, 2.4, 3.3):
+        ov = {(P_SRC_DC, isrc): vin}
+        ref = RefSim().run(d.to_spice(ov, analysis="op"))
+        o = Oracle(d, {(P_SRC_DC, isrc): [vin]}, 0).run("op")
+        assert (o["err"], o["numiter"]) == (ref["err"], ref["numiter"]), vin
+        idx = [o["names"].index(nm) for nm in ref["names"]]
+        assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < 1e-9

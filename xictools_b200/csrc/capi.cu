@@ -515,7 +515,7 @@ static int reset_state(b200_batch *b)
         b->hot.solve_err, b->hot.need_devconv, b->hot.devconv, b->aux.vecops };
     for (int *p : hz) CK(cudaMemsetAsync(p, 0, ldt*sizeof(int), st));
     b->cur = 0;
-    if (b->uic) {
+    if (b->uic && b->K.analysis == 0) {
         // ic() + swaprhs: CKTrhsOld starts as the .ic/.nodeset vector (ckt.cc:908-925, tranan.cc:357-362)
         std::vector<double> row(ldt);
         for (int i = 1; i <= an.n; i++) {
@@ -533,10 +533,15 @@ static int reset_state(b200_batch *b)
     return B200_OK;
 }
 
-int b200_batch_run_tran(b200_batch *b)
+static int run_analysis(b200_batch *b, int analysis);
+int b200_batch_run_tran(b200_batch *b) { return run_analysis(b, 0); }
+int b200_batch_run_op(b200_batch *b) { return run_analysis(b, 1); }
+
+static int run_analysis(b200_batch *b, int analysis)
 {
     if (!b) return B200_E_BADPARM;
     CK(cudaSetDevice(b->device));
+    b->K.analysis = analysis;
     int rc = prepare_params(b);
     if (rc) return rc;
     rc = reset_state(b);

@@ -368,6 +368,16 @@ __device__ inline int ctl_op_method(const Consts &K, int stage)
 __device__ inline void ctl_op_finish(TrialCtl &s, const Consts &K, const CtlShared &sh, int err)
 {
     if (err) { ctl_fail(s, err); return; }
+    if (K.analysis == 1) {
+        // dcoan.cc:117-119: dump(0.0) = CKTrhsOld (the INITSMSIG load only feeds AC analysis)
+        s.vecops |= VO_DUMP_DIRECT;
+        s.ip_out0 = 0;
+        s.npts = 1;
+        s.status = ST_DONE;
+        s.pc = PC_DONE;
+        s.want_load = 0;
+        return;
+    }
     ctl_tran_init(s, K, sh);
 }
 
@@ -697,7 +707,9 @@ __device__ inline void ctl_begin(TrialCtl &s, const Consts &K, const CtlShared &
     s.t_delmax = K.maxStep;
     s.srcFact = 1.0;
     s.status = ST_RUNNING;
-    if (K.uic) {
+    if (K.analysis == 1)
+        ctl_op_start(s, K, sh, MODEDCOP | MODEINITJCT, MODEDCOP | MODEINITFLOAT, K.opt.itl1);
+    else if (K.uic) {
         s.mode = MODEUIC | MODETRANOP | MODEINITJCT;
         s.want_load = 1;
         s.pc = PC_UIC_LOAD;

@@ -82,6 +82,7 @@ struct Consts {
     int nnzLU, ncslot, nrslot, NC /* contributions per trial, assembly order */;
     double t_stop, t_step, t_start, maxStep, delmin, minBreak, break0, break1;
     int nocut, uic, hadNodeset, npoints_max, method;
+    int analysis;       // 0: transient (tranan.cc), 1: DC operating point only (dcoan.cc)
     int nbrks, nlat;
 };
 

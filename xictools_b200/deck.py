@@ -271,9 +271,9 @@ class Deck:
         return [tabs[k][i].name for k, i in self.load_order()]
 
     # ---- SPICE text for the compiled reference (tests only) -------------------------
-    def to_spice(self, overrides: dict | None = None) -> str:
+    def to_spice(self, overrides: dict | None = None, analysis: str = "tran") -> str:
         """overrides: {(param_id, table_index): value} for one Monte-Carlo trial; varied MOS
-        devices get a private .model, as the reference's MC decks do."""
+        devices get a private .model, as the reference's MC decks do.  analysis: "tran" or "op"."""
         overrides = overrides or {}
         tabs = self.kind_tables()
         idx = {id(e): i for k in tabs for i, e in enumerate(tabs[k])}
@@ -355,6 +355,9 @@ class Deck:
                 raise NotImplementedError(f"option {k} has no reference .options mapping")
         if optl:
             lines.append(".options " + " ".join(optl))
+        if analysis == "op":
+            lines.append(".op")
+            return "\n".join(lines) + "\n"
         ts, tp, t0, tm, uic = self.tran_args
         s = f".tran {_fmt(ts)} {_fmt(tp)}"
         if t0 or tm:

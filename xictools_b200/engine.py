@@ -52,6 +52,7 @@ def load_library(path: str | None = None):
     L.b200_batch_destroy.argtypes = [C.c_void_p]
     L.b200_batch_set_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.b200_batch_run_tran.argtypes = [C.c_void_p]
+    L.b200_batch_run_op.argtypes = [C.c_void_p]
     L.b200_batch_num_unknowns.argtypes = [C.c_void_p]
     L.b200_batch_num_points.argtypes = [C.c_void_p]
     L.b200_batch_unknown_names.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -117,6 +118,12 @@ class Batch:
         rc = self.L.b200_batch_run_tran(self.h)
         if rc:
             raise B200Error(rc, "b200_batch_run_tran")
+
+    def run_op(self):
+        """DC operating point of every trial (.op); waves() then holds one point per trial."""
+        rc = self.L.b200_batch_run_op(self.h)
+        if rc:
+            raise B200Error(rc, "b200_batch_run_op")
 
     def names(self):
         buf = C.create_string_buffer(1 << 22)
