@@ -97,6 +97,9 @@ typedef struct {
 
 typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; int st; int icGiven; double capac, ic, geq, ceq; } Cap;
 typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct; } Res;
+/* sINDinstancePOD (inddefs.h): linear inductor, no series resistance / poly / expression */
+typedef struct { int pos, neg, br; int pBB, pPB, pNB, pBN, pBP; int st; int icGiven;
+    double induct, ic, req, veq, prevFlux; } Ind;
 typedef struct {
     int kind, pos, neg, branch;
     int pPB, pNB, pBN, pBP;
@@ -122,8 +125,8 @@ struct wo_ckt {
     double *ic_val; char *ic_given; double *ns_val; char *ns_given; int hadNodeset;
     char **names;
 
-    int nmos, ncap, nres, nsrc;
-    Mos *mos; Cap *cap; Res *res; Src *src;
+    int nmos, ncap, nres, nsrc, nind;
+    Mos *mos; Cap *cap; Res *res; Src *src; Ind *ind;
     int nord; DevRef *ord;
 
     /* matrix: CSC, rows ascending per column (spbuild.cc:922-958) */
@@ -845,6 +848,9 @@ static void build_matrix(wo_ckt *c)
     for (int i = 0; i < c->nres; i++) {
         REMAP(c->res[i].pPP); REMAP(c->res[i].pNN); REMAP(c->res[i].pPN); REMAP(c->res[i].pNP);
     }
+    for (int i = 0; i < c->nind; i++) {
+        REMAP(c->ind[i].pBB); REMAP(c->ind[i].pPB); REMAP(c->ind[i].pNB); REMAP(c->ind[i].pBN); REMAP(c->ind[i].pBP);
+    }
     for (int i = 0; i < c->nsrc; i++) {
         REMAP(c->src[i].pPB); REMAP(c->src[i].pNB); REMAP(c->src[i].pBN); REMAP(c->src[i].pBP);
     }
@@ -879,6 +885,8 @@ wo_ckt *wo_create(const b200_deck *dk)
     c->cap = xcalloc(c->ncap, sizeof(Cap));
     c->res = xcalloc(c->nres, sizeof(Res));
     c->src = xcalloc(c->nsrc, sizeof(Src));
+    c->nind = dk->nind;
+    c->ind = xcalloc(c->nind, sizeof(Ind));
     c->nord = dk->norder;
     c->ord = xcalloc(c->nord, sizeof(DevRef));
     for (int i = 0; i < c->nord; i++) {
@@ -946,6 +954,23 @@ wo_ckt *wo_create(const b200_deck *dk)
             if (p->kind == B200_SRC_I && p->fn != B200_FN_NONE)
                 c->numStates += 1;
             break; }
+        case B200_DEV_IND: {
+            /* indset.cc:72-135: branch "name#branch", 2 states, TSTALLOC order :50-58 */
+            Ind *p = &c->ind[i]; const b200_ind *in = &dk->ind[i];
+            p->pos = in->pos; p->neg = in->neg;
+            double mm = GIVEN(in->m) ? in->m : 1.0;
+            p->induct = in->l/mm;
+            p->icGiven = GIVEN(in->ic);
+            p->ic = p->icGiven ? in->ic : 0.0;
+            snprintf(nm, sizeof(nm), "ind%d#branch", i);
+            p->br = new_node(c, SP_CURRENT, nm);
+            p->st = c->numStates; c->numStates += 2;
+            p->pBB = coo_add(c, p->br, p->br);
+            p->pPB = coo_add(c, p->pos, p->br);
+            p->pNB = coo_add(c, p->neg, p->br);
+            p->pBN = coo_add(c, p->br, p->neg);
+            p->pBP = coo_add(c, p->br, p->pos);
+            break; }
         default:
             fprintf(stderr, "wrs_oracle: device kind %d not supported\n", c->ord[o].kind);
             abort();
@@ -991,6 +1016,7 @@ int wo_set_param(wo_ckt *c, int param, int index, double value)
         c->res[index].conduct = 1.0/(r*1.0);
         break; }
     case B200_P_SRC_DC:     c->src[index].dc = value; c->src[index].dcGiven = 1; break;
+    case B200_P_IND_L:      c->ind[index].induct = value/1.0; break;
     default: return B200_E_BADPARM;
     }
     return OK;
@@ -1923,6 +1949,45 @@ static void cap_load(wo_ckt *c, Cap *p)
     }
 }
 
+static void ind_load(wo_ckt *c, Ind *p)
+{
+    /* indload.cc:84-263 (linear inductor; the +-1 couplings are preloaded) */
+    if (c->mode & MODEDC)
+        return;
+    if (c->mode & MODEINITFLOAT) {
+        double flux = p->induct*c->rhsOld[p->br] - p->prevFlux;
+        c->states[0][p->st] += flux;
+        p->prevFlux = c->states[0][p->st];
+        integrate2(c, p->st, p->veq);
+        rhsadd(c, p->br, p->veq);
+        ldadd(c, p->pBB, -p->req);
+        return;
+    }
+    if (c->mode & MODEINITPRED) {
+        p->req = c->ag[0]*p->induct;
+        p->veq = find_ceq(c, p->st);
+        rhsadd(c, p->br, p->veq);
+        ldadd(c, p->pBB, -p->req);
+        p->prevFlux = 0;
+        c->states[0][p->st] = 0;
+        return;
+    }
+    if (c->mode & MODEINITTRAN) {
+        double ival;
+        if (c->mode & MODEUIC)
+            ival = p->ic;
+        else
+            ival = c->rhsOld[p->br];
+        c->states[1][p->st] += p->induct*ival;
+        p->prevFlux = 0;
+        c->states[0][p->st] = 0;
+        p->req = c->ag[0]*p->induct;
+        p->veq = find_ceq(c, p->st);
+        rhsadd(c, p->br, p->veq);
+        ldadd(c, p->pBB, -p->req);
+    }
+}
+
 static void src_load(wo_ckt *c, Src *s)
 {
     /* srcload.cc:67-105, :215-262 (independent sources, no controlling variables) */
@@ -1968,6 +2033,12 @@ static void preload(wo_ckt *c)
                 if (s->neg) { if (s->pNB >= 0) c->Ax[s->pNB] = -1.0; if (s->pBN >= 0) c->Ax[s->pBN] = -1.0; }
             }
         }
+        else if (c->ord[o].kind == B200_DEV_IND) {
+            /* indset.cc:117-131 */
+            Ind *p = &c->ind[i];
+            if (p->pos) { if (p->pPB >= 0) c->Ax[p->pPB] = 1.0; if (p->pBP >= 0) c->Ax[p->pBP] = 1.0; }
+            if (p->neg) { if (p->pNB >= 0) c->Ax[p->pNB] = -1.0; if (p->pBN >= 0) c->Ax[p->pBN] = -1.0; }
+        }
     }
     for (int o = 0; o < c->nord; o++) {
         int i = c->ord[o].index;
@@ -1997,6 +2068,7 @@ static int ckt_load(wo_ckt *c)
         switch (c->ord[o].kind) {
         case B200_DEV_MOS: mos_load(c, &c->mos[i]); break;
         case B200_DEV_CAP: cap_load(c, &c->cap[i]); break;
+        case B200_DEV_IND: ind_load(c, &c->ind[i]); break;
         case B200_DEV_SRC: src_load(c, &c->src[i]); break;
         case B200_DEV_RES: break;          /* preloaded, LOAD_SKIP_FLAG */
         }
@@ -2690,6 +2762,8 @@ static int ckt_trunc(wo_ckt *c, double *timeStep)
         }
         else if (c->ord[o].kind == B200_DEV_CAP)
             terr(c, c->cap[i].st, &timetemp);
+        else if (c->ord[o].kind == B200_DEV_IND)
+            terr(c, c->ind[i].st, &timetemp);       /* indtrun.cc:58 */
     }
     /* srctrun.cc:45-66: SIN sources bound the step through IFsinData::time_limit
      * (inptran.cc:2666-2680, uses dphimax = .2*pi, circuit.h:495) */
@@ -2991,7 +3065,7 @@ static int tran_step(wo_ckt *c)
 static int has_trunc_dev(const wo_ckt *c)
 {
     /* tranan.cc:68-77: any model type with DV_TRUNC (mos.cc:347, cap.cc:147) */
-    return (c->nmos > 0 || c->ncap > 0);
+    return (c->nmos > 0 || c->ncap > 0 || c->nind > 0);      /* ind.cc:128 */
 }
 
 int wo_run_tran(wo_ckt *c)
@@ -3066,6 +3140,8 @@ int wo_run_tran(wo_ckt *c)
             Cap *p = &c->cap[i];
             if (!p->icGiven) p->ic = c->rhs[p->pos] - c->rhs[p->neg];
         }
+        for (int i = 0; i < c->nind; i++)
+            if (c->ind[i].icGiven) c->rhs[c->ind[i].br] = c->ind[i].ic;      /* indic.cc:62-63 */
         double *tmp = c->rhs; c->rhs = c->rhsOld; c->rhsOld = tmp;
         c->rhs[0] = 0.0; c->rhsOld[0] = 0.0;
         c->mode = MODEUIC | MODETRANOP | MODEINITJCT;

@@ -38,6 +38,67 @@ def rc_sin():
     return d
 
 
+def rlc_series():
+    """Series RLC driven by a pulse: inductor branch equation, flux LTE, underdamped ringing."""
+    d = Deck(title="series rlc")
+    d.vsource("v1", "a", "0", dc=0.0, pulse=(0, 1.0, 0.1e-9, 0.05e-9, 0.05e-9, 2e-9, 5e-9))
+    d.resistor("r1", "a", "b", 10.0)
+    d.inductor("l1", "b", "c", 2e-9)
+    d.capacitor("c1", "c", "0", 1e-12)
+    d.tran(0.02e-9, 4e-9)
+    return d
+
+
+def lc_ladder(n=5):
+    """LC ladder (lumped transmission line) between source and load resistors: nodes that
+    touch only inductors and capacitors, several coupled branch equations."""
+    d = Deck(title="lc ladder")
+    d.vsource("vs", "in", "0", dc=0.0, pulse=(0, 1.0, 0.2e-9, 0.1e-9, 0.1e-9, 1e-9, 4e-9))
+    d.resistor("rs", "in", "n0", 50.0)
+    for i in range(n):
+        d.inductor(f"l{i}", f"n{i}", f"n{i+1}", 2.5e-9)
+        d.capacitor(f"c{i}", f"n{i+1}", "0", 1e-12)
+    d.resistor("rl", f"n{n}", "0", 50.0)
+    d.tran(0.02e-9, 3e-9)
+    return d
+
+
+def rl_isrc():
+    """Current pulse into a parallel R-L with a series L-R branch (inductor to ground,
+    inductor in series, current source rhs)."""
+    d = Deck(title="rl isrc")
+    d.isource("i1", "0", "a", dc=0.0, pulse=(0, 1e-3, 0.1e-9, 0.1e-9, 0.1e-9, 1e-9, 3e-9))
+    d.resistor("r1", "a", "0", 100.0)
+    d.inductor("l1", "a", "0", 5e-9)
+    d.inductor("l2", "a", "b", 1e-9)
+    d.resistor("r2", "b", "0", 20.0)
+    d.capacitor("c1", "b", "0", 0.2e-12)
+    d.tran(0.02e-9, 3e-9)
+    return d
+
+
+def inv_lsupply():
+    """CMOS inverter chain fed through a supply inductance with a decoupling capacitor:
+    MOS + inductor in one matrix (DCOP shorts the inductor)."""
+    d = inv_chain(3, load_res=False)
+    for e in d.elems:
+        if e.kind == 5:         # MOSFETs: move the p-channel sources/bulks to the internal rail
+            e.nodes = tuple("vddi" if nd == "vdd" else nd for nd in e.nodes)
+    d.inductor("lvdd", "vdd", "vddi", 1e-9)
+    d.capacitor("cdec", "vddi", "0", 0.5e-12)
+    return d
+
+
+def rlc_uic():
+    """UIC start with an inductor current and a capacitor voltage as initial conditions."""
+    d = Deck(title="rlc uic")
+    d.resistor("r1", "a", "0", 30.0)
+    d.inductor("l1", "a", "b", 3e-9, ic=2e-3)
+    d.capacitor("c1", "b", "0", 1e-12, ic=0.5)
+    d.tran(0.02e-9, 2e-9, uic=True)
+    return d
+
+
 def ro_rd(n=3):
     """Ring oscillator whose MOSFETs have series rd/rs: internal drain/source nodes."""
     d = ring_oscillator(n)
@@ -71,11 +132,17 @@ def op_decks():
     return {"op_inv_dc": inv_dc(3), "op_inv4": inv_chain(4), "op_ro5": ring_oscillator(5),
             "op_ro3_rd": ro_rd(3), "op_inv_dc_direct": inv_dc(3).options(gminsteps=-1, srcsteps=-1),
             "op_inv_dc_gminfirst": inv_dc(3).options(gminfirst=1),
-            "op_inv7_nogmin": inv_chain(7).options(gminsteps=-1)}
+            "op_inv7_nogmin": inv_chain(7).options(gminsteps=-1),
+            "op_inv_lsupply": inv_lsupply()}
 
 
 def variants():
     out = {
+        "rlc_series": rlc_series(),
+        "lc_ladder": lc_ladder(5),
+        "rl_isrc": rl_isrc(),
+        "inv_lsupply": inv_lsupply(),
+        "rlc_uic": rlc_uic(),
         "ro3": ring_oscillator(3),
         "ro5": ring_oscillator(5),
         "ro17": ring_oscillator(17),

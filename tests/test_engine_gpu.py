@@ -72,6 +72,21 @@ def test_monte_carlo_ro17():
     compare(d, 64, ov, trials=[0, 1, 7, 31, 63], min_same=0.8)
 
 
+def test_monte_carlo_inductor_values():
+    """Per-trial inductances (B200_P_IND_L) on the LC ladder: every trial has its own line
+    impedance, hence its own step sequence."""
+    from xictools_b200.deck import DEV_IND, P_IND_L
+    d = variants()["lc_ladder"]
+    rng = np.random.default_rng(7)
+    ntr = 19
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_IND]):
+        v = np.full(ntr, e.params["l"])
+        v[1:] *= 1.0 + 0.1*rng.standard_normal(ntr - 1)
+        ov[(P_IND_L, i)] = v
+    compare(d, ntr, ov, min_same=0.9)
+
+
 def test_single_trial_batch():
     compare(ring_oscillator(3), 1)
 

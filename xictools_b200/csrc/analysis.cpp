@@ -150,8 +150,8 @@ void build_pwl(const double *coef, int num, std::vector<double> &pts, std::vecto
 int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
 {
     const b200_options &o = dk->opt;
-    if (dk->nind || dk->nmut || dk->njj) {
-        err = "inductor / mutual / JJ devices are not built yet (SURVEY.md section 8 rows a4-a6)";
+    if (dk->nmut || dk->njj) {
+        err = "mutual inductor / JJ devices are not built yet (SURVEY.md section 8 rows a4-a6)";
         return B200_E_UNSUPP;
     }
     an.n = 0;
@@ -166,8 +166,10 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     for (int i = 1; i < dk->nnodes; i++)
         new_node(0, "n" + std::to_string(i));
 
-    MosTopo &M = an.mos; CapTopo &Cp = an.cap; SrcTopo &S = an.src;
-    M.n = dk->nmos; Cp.n = dk->ncap; S.n = dk->nsrc; an.nres = dk->nres;
+    MosTopo &M = an.mos; CapTopo &Cp = an.cap; SrcTopo &S = an.src; IndTopo &L = an.ind;
+    M.n = dk->nmos; Cp.n = dk->ncap; S.n = dk->nsrc; an.nres = dk->nres; L.n = dk->nind;
+    L.pos.resize(L.n); L.neg.resize(L.n); L.branch.assign(L.n, 0); L.state.resize(L.n);
+    L.cslot.assign(L.n, -1); L.rslot.assign(L.n, -1); L.icgiven.assign(L.n, 0); L.ic.assign(L.n, 0.0);
     M.d.resize(M.n); M.g.resize(M.n); M.s.resize(M.n); M.b.resize(M.n); M.dp.resize(M.n);
     M.sp.resize(M.n); M.type.resize(M.n); M.level.resize(M.n); M.off.resize(M.n);
     M.state.resize(M.n); M.cslot.assign((size_t)M.n*MT_NSTAMP, -1);
@@ -183,6 +185,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     // per device, the coo ids of its stamps (resolved to Ax indices after CSC build)
     std::vector<int> mos_coo((size_t)M.n*MT_NSTAMP, -1), cap_coo((size_t)Cp.n*4, -1);
     std::vector<int> res_coo((size_t)dk->nres*4, -1), src_coo((size_t)S.n*4, -1);
+    std::vector<int> ind_coo((size_t)L.n*5, -1);
     std::vector<double> res_g(dk->nres, 0.0);
     std::vector<char> mos_has_dcon(M.n, 0), mos_has_scon(M.n, 0);
 
@@ -261,6 +264,19 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (in.kind == B200_SRC_I && in.fn != B200_FN_NONE)
                 an.numStates += 1;
             break; }
+        case B200_DEV_IND: {
+            // indset.cc:72-135: branch unknown, 2 states (flux, volt), TSTALLOC order :50-58
+            const b200_ind &in = dk->ind[i];
+            if (given(in.m) && in.m != 1.0) { err = "inductor M != 1 is not built"; return B200_E_UNSUPP; }
+            L.pos[i] = in.pos; L.neg[i] = in.neg;
+            L.icgiven[i] = given(in.ic); L.ic[i] = given(in.ic) ? in.ic : 0.0;
+            L.branch[i] = new_node(1, "ind" + std::to_string(i) + "#branch");
+            L.state[i] = an.numStates; an.numStates += 2;
+            int *c = &ind_coo[(size_t)i*5];
+            int br = L.branch[i];
+            c[0] = coo.add(br, br); c[1] = coo.add(in.pos, br); c[2] = coo.add(in.neg, br);
+            c[3] = coo.add(br, in.neg); c[4] = coo.add(br, in.pos);
+            break; }
         default:
             err = "unsupported device kind in load order";
             return B200_E_UNSUPP;
@@ -297,6 +313,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     std::vector<std::vector<int>> cg(an.nnz), rg(n + 1);
     an.ncslot = an.nrslot = 0;
     an.Ainit.assign(an.nnz, 0.0);
+    an.dc_active.assign(an.nnz, 0);
     auto add_c = [&](int cooid) -> int {
         if (cooid < 0) return -1;
         int k = coo2ax[cooid];
@@ -316,6 +333,12 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (S.pos[i]) { if (c[0] >= 0) an.Ainit[coo2ax[c[0]]] = 1.0; if (c[3] >= 0) an.Ainit[coo2ax[c[3]]] = 1.0; }
             if (S.neg[i]) { if (c[1] >= 0) an.Ainit[coo2ax[c[1]]] = -1.0; if (c[2] >= 0) an.Ainit[coo2ax[c[2]]] = -1.0; }
         }
+    }
+    // inductor couplings are preldset in setup (indset.cc:117-131)
+    for (int i = 0; i < L.n; i++) {
+        const int *c = &ind_coo[(size_t)i*5];
+        if (L.pos[i]) { if (c[1] >= 0) an.Ainit[coo2ax[c[1]]] = 1.0; if (c[4] >= 0) an.Ainit[coo2ax[c[4]]] = 1.0; }
+        if (L.neg[i]) { if (c[2] >= 0) an.Ainit[coo2ax[c[2]]] = -1.0; if (c[3] >= 0) an.Ainit[coo2ax[c[3]]] = -1.0; }
     }
     // ... resistor conductances are ldadd in temp() (restemp.cc:218-229), load order
     for (int oi = 0; oi < dk->norder; oi++) {
@@ -341,6 +364,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
                 bool sconly = (k == MT_Ss || k == MT_Ssp || k == MT_SPs);
                 if ((dconly && !mos_has_dcon[i]) || (sconly && !mos_has_scon[i])) continue;
                 cs[k] = add_c(c[k]);
+                if (c[k] >= 0) an.dc_active[coo2ax[c[k]]] = 1;
             }
             int *rs = &M.rslot[(size_t)i*MRH_NRHS];
             rs[MRH_g] = add_r(M.g[i]);   rs[MRH_b] = add_r(M.b[i]);
@@ -358,6 +382,11 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
                 rs[0] = add_r(Cp.pos[i]); rs[1] = add_r(Cp.neg[i]);
             }
             break; }
+        case B200_DEV_IND:
+            // indload.cc: rhsadd(brEq, veq) then ldadd(ibrIbr, -req)
+            L.rslot[i] = add_r(L.branch[i]);
+            L.cslot[i] = add_c(ind_coo[(size_t)i*5]);
+            break;
         case B200_DEV_SRC: {
             int *rs = &S.rslot[(size_t)i*2];
             if (S.kind[i] == B200_SRC_V) rs[0] = add_r(S.branch[i]);
@@ -366,6 +395,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
         default: break;
         }
     }
+    for (int k = 0; k < an.nnz; k++) if (an.Ainit[k] != 0.0) an.dc_active[k] = 1;
     an.cg_ptr.assign(an.nnz + 1, 0);
     for (int k = 0; k < an.nnz; k++) {
         an.cg_ptr[k+1] = an.cg_ptr[k] + (int)cg[k].size();
@@ -389,7 +419,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
         err = "bad .tran parameters"; return B200_E_BADPARM;
     }
     an.maxStep = dk->tmax;
-    an.nocut = !(M.n > 0 || Cp.n > 0);            // tranan.cc:68-77 DV_TRUNC devices
+    an.nocut = !(M.n > 0 || Cp.n > 0 || L.n > 0);  // tranan.cc:68-77 DV_TRUNC devices
     if (an.maxStep == 0) {
         an.maxStep = (an.t_stop - an.t_start)/50;
         if (o.oldsteplim) { if (an.t_step > an.maxStep) an.maxStep = an.t_step; }
@@ -519,6 +549,11 @@ void b200_order_markowitz(Analysis &an)
     std::vector<std::set<int>> rows(n), cols(n);
     // constant: 1 if the entry is a never-updated +-1 constant; 0 otherwise
     std::map<std::pair<int,int>, char> constant;
+    // dcnz: the entry is structurally nonzero in the DC modes as well (capacitor and inductor
+    // companion conductances vanish there).  The pivot order is frozen for the whole run, so a
+    // pivot must be structurally nonzero in DC (hence also in transient).
+    std::map<std::pair<int,int>, char> dcnz;
+    bool have_dc = (an.dc_active.size() == (size_t)an.nnz);
     for (int j = 0; j < n; j++)
         for (int p = an.Ap[j]; p < an.Ap[j+1]; p++) {
             int i = an.Ai[p];
@@ -526,25 +561,29 @@ void b200_order_markowitz(Analysis &an)
             bool is_const = (an.cg_ptr[p+1] == an.cg_ptr[p]) &&
                 (an.Ainit[p] == 1.0 || an.Ainit[p] == -1.0);
             constant[{i, j}] = is_const ? 1 : 0;
+            dcnz[{i, j}] = have_dc ? an.dc_active[p] : 1;
         }
     std::vector<char> ract(n, 1), cact(n, 1);
     std::vector<char> diag_ok(n, 0);
     for (int i = 0; i < n; i++) {
         int p = an.diag[i+1];
         if (p >= 0 && an.ntype[i+1] == 0 &&
-                (an.cg_ptr[p+1] > an.cg_ptr[p] || an.Ainit[p] != 0.0))
+                (an.cg_ptr[p+1] > an.cg_ptr[p] || an.Ainit[p] != 0.0) &&
+                (!have_dc || an.dc_active[p]))
             diag_ok[i] = 1;
     }
     std::vector<long> rstamp(n, 0), cstamp(n, 0);
     an.rowperm.assign(n, -1); an.colperm.assign(n, -1);
     for (int k = 0; k < n; k++) {
         long best = -1, bstamp = 0; int bi = -1, bj = -1; int bclass = 0;
-        for (int pass = 0; pass < 3 && bi < 0; pass++) {
-            // pass 0: safe candidates; pass 1: any remaining diagonal; pass 2: any entry
+        for (int pass = 0; pass < 4 && bi < 0; pass++) {
+            // pass 0: safe candidates; pass 1: any remaining diagonal; pass 2: any entry -- all
+            // structurally nonzero in DC; pass 3: any entry at all
             for (int i = 0; i < n; i++) {
                 if (!ract[i]) continue;
                 for (int j : rows[i]) {
                     if (!cact[j]) continue;
+                    if (pass < 3 && !dcnz[{i, j}]) continue;
                     int cls;
                     auto it = constant.find({i, j});
                     bool is_const = (it != constant.end() && it->second);
@@ -582,6 +621,7 @@ void b200_order_markowitz(Analysis &an)
         for (int r : pcol) {
             for (int j : prow) {
                 rows[r].insert(j); cols[j].insert(r);
+                if (r != bi && j != bj && dcnz[{r, bj}] && dcnz[{bi, j}]) dcnz[{r, j}] = 1;
                 constant[{r, j}] = 0;               // touched by an update: no longer constant
                 cstamp[j] = k + 1;
             }
@@ -940,6 +980,7 @@ void b200_build_stream_asm(Analysis &an)
     remap(an.mos.cslot, newc); remap(an.mos.rslot, newr);
     remap(an.cap.cslot, newc); remap(an.cap.rslot, newr);
     remap(an.src.rslot, newr);
+    remap(an.ind.cslot, newc); remap(an.ind.rslot, newr);
 
     // chunk schedule
     int nchunks = (an.NC + SEG_CHUNK - 1)/SEG_CHUNK;

@@ -94,6 +94,13 @@ struct CapTopo {
     std::vector<int> cslot;                     // [n*4] PP NN PN NP
     std::vector<int> rslot;                     // [n*2] pos neg
 };
+struct IndTopo {
+    int n = 0;
+    std::vector<int> pos, neg, branch, state;
+    std::vector<int> cslot;                     // [n] (br,br) contribution: -req
+    std::vector<int> rslot;                     // [n] branch row: veq
+    std::vector<int> icgiven; std::vector<double> ic;
+};
 struct SrcTopo {
     int n = 0;
     std::vector<int> kind, pos, neg, branch, fn, dcgiven;
@@ -171,6 +178,8 @@ struct Analysis {
     std::vector<int> Ap, Ai;
     std::vector<int> diag;                      // [n+1] Ax index of (i,i) or -1
     std::vector<double> Ainit;                  // preloaded constants (shared by all trials)
+    std::vector<char> dc_active;                // [nnz] entry is structurally nonzero in DC modes too
+                                                //  (capacitor / inductor companions vanish in DC)
     // gather lists: contributions in reference load order
     int ncslot = 0, nrslot = 0;
     std::vector<int> cg_ptr, cg_idx;            // per Ax entry: cslots
@@ -180,7 +189,7 @@ struct Analysis {
     std::vector<double> ic_val, ns_val;
     int hadNodeset = 0;
     // device tables
-    MosTopo mos; CapTopo cap; SrcTopo src;
+    MosTopo mos; CapTopo cap; SrcTopo src; IndTopo ind;
     int nres = 0;
     // ordering: position -> original (0-based)
     std::vector<int> rowperm, colperm;

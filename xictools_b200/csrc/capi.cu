@@ -49,8 +49,8 @@ struct b200_batch {
     std::vector<MosCard> cards;
     std::vector<double> mos_raw[MR_NRAW];                   // [nmos] shared values
     std::map<int, std::vector<double>> mos_var[MR_NRAW];    // inst -> [ntrials]
-    std::vector<double> cap_c, cap_ic, src_dc;
-    std::map<int, std::vector<double>> cap_var, src_var;
+    std::vector<double> cap_c, cap_ic, src_dc, ind_l, ind_ic;
+    std::map<int, std::vector<double>> cap_var, src_var, ind_var;
     bool params_dirty = true;
 
     // device views
@@ -66,6 +66,7 @@ struct b200_batch {
     double *d_prm[MP_NPARAMS] = {0}; int prm_ts[MP_NPARAMS] = {0};
     double *d_capc = nullptr, *d_srcdc = nullptr; int capc_ts = 0, srcdc_ts = 0;
     double *d_capic = nullptr;
+    double *d_indl = nullptr, *d_indic = nullptr; int indl_ts = 0;
     int *d_counters = nullptr, *d_npts = nullptr;
 
     bool ran = false;
@@ -184,6 +185,11 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
         }
         b->cap_ic[i] = ic;
     }
+    b->ind_l.resize(dk->nind); b->ind_ic.resize(dk->nind);
+    for (int i = 0; i < dk->nind; i++) {
+        b->ind_l[i] = dk->ind[i].l;                 // indset.cc:145 INDnomInduct/INDm (m = 1)
+        b->ind_ic[i] = given(dk->ind[i].ic) ? dk->ind[i].ic : 0.0;
+    }
     b->src_dc = b->an.src.dc;
 }
 
@@ -274,6 +280,12 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Cp.pos = b->dupload(ct.pos); Cp.neg = b->dupload(ct.neg); Cp.state = b->dupload(ct.state);
     Cp.cslot = b->dupload(ct.cslot); Cp.rslot = b->dupload(ct.rslot);
     Cp.geq = b->dalloc<double>((size_t)ct.n*ldt); Cp.ceq = b->dalloc<double>((size_t)ct.n*ldt);
+    IndView &Li = Cp.L; IndTopo &lt = an.ind;
+    Li.n = lt.n;
+    Li.branch = b->dupload(lt.branch); Li.state = b->dupload(lt.state);
+    Li.cslot = b->dupload(lt.cslot); Li.rslot = b->dupload(lt.rslot);
+    Li.req = b->dalloc<double>((size_t)lt.n*ldt); Li.veq = b->dalloc<double>((size_t)lt.n*ldt);
+    Li.prevFlux = b->dalloc<double>((size_t)lt.n*ldt);
     SrcView &S = b->S; SrcTopo &st = an.src;
     S.n = st.n;
     S.kind = b->dupload(st.kind); S.fn = b->dupload(st.fn); S.dcgiven = b->dupload(st.dcgiven);
@@ -385,6 +397,9 @@ int b200_batch_set_param(b200_batch *b, int param, int index, const double *valu
     case B200_P_CAP_C:
         if (index < 0 || index >= b->an.cap.n) return B200_E_BADPARM;
         b->cap_var[index] = v; b->params_dirty = true; return B200_OK;
+    case B200_P_IND_L:
+        if (index < 0 || index >= b->an.ind.n) return B200_E_BADPARM;
+        b->ind_var[index] = v; b->params_dirty = true; return B200_OK;
     case B200_P_SRC_DC:
         if (index < 0 || index >= b->an.src.n) return B200_E_BADPARM;
         b->src_var[index] = v; b->params_dirty = true; return B200_OK;
@@ -483,6 +498,13 @@ static int prepare_params(b200_batch *b)
     if (!b->cap_ic.empty())
         CK(cudaMemcpy(b->d_capic, b->cap_ic.data(), b->cap_ic.size()*sizeof(double), cudaMemcpyHostToDevice));
     b->Cp.ic.base = b->d_capic; b->Cp.ic.ts = 0; b->Cp.ic.ld = 1;
+    rc = upload_strided(b->ind_l, b->ind_var, b->d_indl, b->indl_ts);
+    if (rc) return rc;
+    b->Cp.L.induct.base = b->d_indl; b->Cp.L.induct.ts = b->indl_ts; b->Cp.L.induct.ld = b->indl_ts ? (int)ldt : 1;
+    if (!b->d_indic) b->d_indic = b->dalloc<double>(b->ind_ic.size());
+    if (!b->ind_ic.empty())
+        CK(cudaMemcpy(b->d_indic, b->ind_ic.data(), b->ind_ic.size()*sizeof(double), cudaMemcpyHostToDevice));
+    b->Cp.L.ic.base = b->d_indic; b->Cp.L.ic.ts = 0; b->Cp.L.ic.ld = 1;
     rc = upload_strided(b->src_dc, b->src_var, b->d_srcdc, b->srcdc_ts);
     if (rc) return rc;
     b->S.dc.base = b->d_srcdc; b->S.dc.ts = b->srcdc_ts; b->S.dc.ld = b->srcdc_ts ? (int)ldt : 1;
@@ -509,6 +531,9 @@ static int reset_state(b200_batch *b)
     launch_fill(st, b->M.cache + (size_t)MC_mode*an.mos.n*ldt, (size_t)an.mos.n*ldt, 1.0);
     CK(cudaMemsetAsync(b->Cp.geq, 0, (size_t)an.cap.n*ldt*sizeof(double), st));
     CK(cudaMemsetAsync(b->Cp.ceq, 0, (size_t)an.cap.n*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->Cp.L.req, 0, (size_t)an.ind.n*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->Cp.L.veq, 0, (size_t)an.ind.n*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(b->Cp.L.prevFlux, 0, (size_t)an.ind.n*ldt*sizeof(double), st));
     CK(cudaMemsetAsync(b->ctl, 0, ldt*sizeof(TrialCtl), st));
     int *hz[] = { b->hot.mode, b->hot.order, b->hot.st_base, b->hot.noncon, b->hot.trapbad,
         b->hot.trapcheck, b->hot.active, b->hot.do_solve, b->hot.iterno, b->hot.nodeconv,
@@ -526,6 +551,15 @@ static int reset_state(b200_batch *b)
                 std::fill(row.begin(), row.end(), v);
                 CK(cudaMemcpyAsync(b->V.X[0] + (size_t)i*ldt, row.data(), ldt*sizeof(double),
                     cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));
+            }
+        }
+        for (int k = 0; k < an.ind.n; k++) {
+            // INDdev::getic (indic.cc:62-63): a given ic is the branch current
+            if (an.ind.icgiven[k] && an.ind.ic[k] != 0.0) {
+                std::fill(row.begin(), row.end(), an.ind.ic[k]);
+                CK(cudaMemcpyAsync(b->V.X[0] + (size_t)an.ind.branch[k]*ldt, row.data(),
+                    ldt*sizeof(double), cudaMemcpyHostToDevice, st));
                 CK(cudaStreamSynchronize(st));
             }
         }
@@ -556,7 +590,7 @@ static int run_analysis(b200_batch *b, int analysis)
     CK(cudaEventCreate(&e_begin)); CK(cudaEventCreate(&e_end));
     long long launches = 0, ticks = 0, load_launches = 0, solve_launches = 0;
     double ms_load = 0, ms_solve = 0;
-    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->S.n ? 1 : 0);
+    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->S.n ? 1 : 0);
 
     CK(cudaEventRecord(e_begin, st));
     // tick 0: begin + first load
@@ -702,6 +736,7 @@ int b200_batch_get_stats(const b200_batch *b, b200_run_stats *st)
     double capbytes = 8.0*(2 + 2 + 1 + 2)*an.cap.n;
     for (int s : an.cap.cslot) if (s >= 0) capbytes += 8.0;
     for (int s : an.cap.rslot) if (s >= 0) capbytes += 8.0;
+    capbytes += 8.0*(1 + 3 + 3 + 2 + 2)*an.ind.n;   // branch current, req/veq/prevFlux, 2 states r/w, 2 stamps
     double srcbytes = 0;
     for (int s : an.src.rslot) if (s >= 0) srcbytes += 8.0;
     st->algbytes_load_per_launch = (mosbytes + capbytes + srcbytes)*b->ntrials;

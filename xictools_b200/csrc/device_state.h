@@ -95,11 +95,20 @@ struct MosView {
     MosStageMap smap;   // shared-memory staging layout of k_load_mos
     int stage_doubles;  // staging area size
 };
+// Linear inductors (indload.cc).  Carried inside CapView: the two linear reactive elements
+// travel together through the launchers.
+struct IndView {
+    int n;
+    const int *branch, *state, *cslot, *rslot;
+    ParamRef induct, ic;
+    double *req, *veq, *prevFlux;   // [n][ldt]  (INDreq / INDveq / INDprevFlux instance fields)
+};
 struct CapView {
     int n;
     const int *pos, *neg, *state, *cslot, *rslot;
     ParamRef capac, ic;
     double *geq, *ceq;  // [n][ldt]  (CAPgeq / CAPceq instance fields, capload.cc:150-151)
+    IndView L;
 };
 struct SrcView {
     int n;

@@ -268,6 +268,67 @@ k_load_cap(Consts K, HotView hot, VecView V, CapView Cp, const double *rhsOld)
 }
 
 __global__ void __launch_bounds__(128)
+k_load_ind(Consts K, HotView hot, VecView V, IndView L, const double *rhsOld)
+{
+    // indload.cc:84-263 (linear inductor; the +-1 couplings are preloaded constants)
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t >= K.ntrials) return;
+    int mode = hot.mode[t];
+    if (!mode) return;
+    int cs = L.cslot[i], rs = L.rslot[i];
+    double req = 0.0, veq = 0.0;
+    if (!(mode & MODEDC)) {
+        TrialCtx c;
+        make_ctx(c, K, hot, V, t, mode);
+        int st = L.state[i], br = L.branch[i];
+        double induct = PR(L.induct, i, t);
+        size_t at = (size_t)i*K.ldt + t;
+        if (mode & MODEINITFLOAT) {
+            double prev = L.prevFlux[at];
+            double flux = induct*rhsOld[(size_t)br*K.ldt + t] - prev;
+            double f0 = ST(c, 0, st) + flux;
+            ST(c, 0, st) = f0;
+            L.prevFlux[at] = f0;
+            veq = L.veq[at];
+            dev_integrate2(c, st, veq);
+            req = L.req[at];
+            if (mode & MODETRAN) {
+                // INDdev::trunc (indtrun.cc:58)
+                double q[4] = { f0, ST(c, 1, st), ST(c, 2, st), ST(c, 3, st) };
+                double m0 = DBL_MAX, m1 = DBL_MAX;
+                dev_lte_charge(c, K.opt, q, ST(c, 0, st + 1), ST(c, 1, st + 1), st, m0, m1);
+                atomic_min_pos(c.lte, m0);
+                if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
+            }
+        }
+        else if (mode & MODEINITPRED) {
+            req = c.ag[0]*induct;
+            veq = dev_find_ceq(c, st);
+            L.req[at] = req; L.veq[at] = veq;
+            L.prevFlux[at] = 0.0;
+            ST(c, 0, st) = 0.0;
+        }
+        else if (mode & MODEINITTRAN) {
+            double ival;
+            if (mode & MODEUIC)
+                ival = PR(L.ic, i, t);
+            else
+                ival = rhsOld[(size_t)br*K.ldt + t];
+            ST(c, 1, st) = ST(c, 1, st) + induct*ival;
+            L.prevFlux[at] = 0.0;
+            ST(c, 0, st) = 0.0;
+            req = c.ag[0]*induct;
+            veq = dev_find_ceq(c, st);
+            L.req[at] = req; L.veq[at] = veq;
+        }
+    }
+    // DC modes: nothing but the preloaded +-1 (the branch equation shorts the inductor)
+    if (rs >= 0) V.contrib[CADDR(K, rs, t)] = veq;
+    if (cs >= 0) V.contrib[CADDR(K, cs, t)] = -req;
+}
+
+__global__ void __launch_bounds__(128)
 k_load_src(Consts K, HotView hot, VecView V, SrcView S)
 {
     // srcload.cc:67-105, 215-262
@@ -927,6 +988,7 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
         else k_load_mos<6><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
     }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
+    if (Cp.L.n) k_load_ind<<<grid2(K.ntrials, Cp.L.n), 128, 0, st>>>(K, hot, V, Cp.L, rhsOld);
     if (S.n) k_load_src<<<grid2(K.ntrials, S.n), 128, 0, st>>>(K, hot, V, S);
 }
 void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,

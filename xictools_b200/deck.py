@@ -188,6 +188,11 @@ class Deck:
                                 dict(c=float(c), ic=ic)))
         return self
 
+    def inductor(self, name, p, n, l, ic=None):
+        self.elems.append(_Elem(DEV_IND, name.lower(), (str(p).lower(), str(n).lower()),
+                                dict(l=float(l), ic=ic)))
+        return self
+
     def mos_model(self, name, mtype, level=1, **params):
         self.mos_models[name.lower()] = dict(type=+1 if mtype.lower().startswith("n") else -1,
                                              level=level, params=dict(params))
@@ -300,6 +305,12 @@ class Deck:
             elif e.kind == DEV_CAP:
                 cval = overrides.get((P_CAP_C, i), e.params["c"])
                 s = f"{e.name} {e.nodes[0]} {e.nodes[1]} {_fmt(cval)}"
+                if e.params.get("ic") is not None:
+                    s += f" ic={_fmt(e.params['ic'])}"
+                lines.append(s)
+            elif e.kind == DEV_IND:
+                lval = overrides.get((P_IND_L, i), e.params["l"])
+                s = f"{e.name} {e.nodes[0]} {e.nodes[1]} {_fmt(lval)}"
                 if e.params.get("ic") is not None:
                     s += f" ic={_fmt(e.params['ic'])}"
                 lines.append(s)
@@ -460,7 +471,14 @@ class Deck:
         keep.append(mos)
         d.nmos, d.mos = len(tabs[DEV_MOS]), mos
 
-        d.nind = d.nmut = d.njjmod = d.njj = 0
+        ind = (CInd * max(1, len(tabs[DEV_IND])))()
+        for i, e in enumerate(tabs[DEV_IND]):
+            ic = e.params.get("ic")
+            ind[i] = CInd(nums[e.nodes[0]], nums[e.nodes[1]], e.params["l"], NAN,
+                          NAN if ic is None else ic)
+        keep.append(ind)
+        d.nind, d.ind = len(tabs[DEV_IND]), ind
+        d.nmut = d.njjmod = d.njj = 0
         order = self.load_order()
         d.norder = len(order)
         d.order_kind = arr(C.c_int, [k for k, _ in order])
