@@ -253,7 +253,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     h.deltaOld = b->dalloc<double>(7*ldt);
     h.nodeconv = b->dalloc<int>(ldt); h.solve_err = b->dalloc<int>(ldt);
     h.need_devconv = b->dalloc<int>(ldt); h.devconv = b->dalloc<int>(ldt);
-    h.lte = b->dalloc<double>(2*ldt);
+    h.lte = b->dalloc<double>(2*ldt); h.sync = b->dalloc<int>(ldt);
     // ---- vectors ----
     VecView &V = b->V;
     size_t vplane = (size_t)(an.n + 1)*ldt;
@@ -537,7 +537,7 @@ static int reset_state(b200_batch *b)
     CK(cudaMemsetAsync(b->ctl, 0, ldt*sizeof(TrialCtl), st));
     int *hz[] = { b->hot.mode, b->hot.order, b->hot.st_base, b->hot.noncon, b->hot.trapbad,
         b->hot.trapcheck, b->hot.active, b->hot.do_solve, b->hot.iterno, b->hot.nodeconv,
-        b->hot.solve_err, b->hot.need_devconv, b->hot.devconv, b->aux.vecops };
+        b->hot.solve_err, b->hot.need_devconv, b->hot.devconv, b->hot.sync, b->aux.vecops };
     for (int *p : hz) CK(cudaMemsetAsync(p, 0, ldt*sizeof(int), st));
     b->cur = 0;
     if (b->uic && b->K.analysis == 0) {
@@ -609,11 +609,12 @@ static int run_analysis(b200_batch *b, int analysis)
             launch_devconv(st, K, b->hot, b->V, b->M, b->V.X[b->cur]);
             b->cur ^= 1;
             launch_ctl(st, K, b->hot, b->ctl, b->sh, b->aux, 1);
+            launch_ctl(st, K, b->hot, b->ctl, b->sh, b->aux, 2);
             launch_vec(st, K, b->V, b->aux, b->M, b->V.X[b->cur]);
             CK(cudaEventRecord(ev[w][2], st));
             launch_loads(st, K, b->hot, b->V, b->M, b->Cp, b->S, b->V.X[b->cur]);
             CK(cudaEventRecord(ev[w][3], st));
-            launches += 5 + nload_kernels;
+            launches += 6 + nload_kernels;
             load_launches++; solve_launches++;
             ticks++;
         }

@@ -192,6 +192,13 @@ __device__ inline void ctl_op_method_done(TrialCtl &s, const Consts &K, const Ct
 __device__ inline void ctl_tran_init(TrialCtl &s, const Consts &K, const CtlShared &sh);
 __device__ inline void ctl_tran_loop_top(TrialCtl &s, const Consts &K, const CtlShared &sh);
 __device__ inline void ctl_step_begin(TrialCtl &s, const Consts &K);
+// A time point has been accepted.  The trial parks here until the other running trials of its
+// group of 32 adjacent trials (one warp of every per-trial kernel) have accepted theirs too,
+// then all of them run accept + the predictor load of the next step in the same tick: the lanes
+// of a warp stay in the same Newton phase (same load mode, same history ring position), which
+// is what keeps the device-load warps convergent and their state accesses coalesced.  Pure
+// scheduling: no trial's arithmetic depends on it.
+__device__ inline void ctl_sync_point(TrialCtl &s) { s.pc = PC_SYNC; s.want_load = 0; }
 
 // ---- backup(): ckt.cc:1323-1362 ----
 __device__ inline void ctl_backup_save(TrialCtl &s) { s.vecops |= VO_BK_SAVE; s.have_save = 1; }
@@ -430,7 +437,7 @@ __device__ inline void ctl_tran_init(TrialCtl &s, const Consts &K, const CtlShar
     s.saveDelta = s.delta;
     s.mode = (s.mode & MODEUIC) | MODETRAN | MODEINITTRAN;
     s.ag[0] = s.ag[1] = 0;
-    ctl_tran_loop_top(s, K, sh);
+    ctl_sync_point(s);
 }
 
 __device__ inline void ctl_check_delmin_and_step(TrialCtl &s, const Consts &K)
@@ -598,7 +605,7 @@ __device__ inline void ctl_tran_step_ret(TrialCtl &s, const Consts &K, const Ctl
     }
     if (s.t_firsttime) {
         s.t_firsttime = 0;
-        ctl_tran_loop_top(s, K, sh);
+        ctl_sync_point(s);
         return;
     }
     // sCKT::trunc: the per-charge bounds were min-reduced by the load kernels of the tick whose
@@ -658,7 +665,7 @@ __device__ inline void ctl_lte_ret(TrialCtl &s, const Consts &K, const CtlShared
             }
             s.delta = newd;
             if (s.delta > s.t_delmax) s.delta = s.t_delmax;
-            ctl_tran_loop_top(s, K, sh);
+            ctl_sync_point(s);
             return;
         }
         s.time -= s.delta;
@@ -683,7 +690,7 @@ __device__ inline void ctl_lte_ret(TrialCtl &s, const Consts &K, const CtlShared
         if (s.devMaxDelta > 0.0 && s.devMaxDelta < newd) newd = s.devMaxDelta;
         if (newd > s.t_delmax) newd = s.t_delmax;
         s.delta = newd;
-        ctl_tran_loop_top(s, K, sh);
+        ctl_sync_point(s);
         return;
     }
     s.time -= s.delta;

@@ -14,7 +14,7 @@
 #endif
 
 // ---- per-trial control block (AoS; touched only by the control kernel, one thread/trial) ----
-enum { PC_IDLE = 0, PC_NIITER, PC_DONE };
+enum { PC_IDLE = 0, PC_NIITER, PC_DONE, PC_SYNC };
 enum { RET_NONE = 0, RET_OP_DIRECT, RET_GMIN_LOOP, RET_GMIN_FINAL, RET_SRC_LOOP, RET_TRAN_STEP };
 
 // vector-op request bits (consumed by k_vec / k_statevec right after the control kernel)
@@ -28,6 +28,8 @@ enum { RET_NONE = 0, RET_OP_DIRECT, RET_GMIN_LOOP, RET_GMIN_FINAL, RET_SRC_LOOP,
 #define VO_FIRSTTIME    0x080   // state2 (,state3) <- state1         (tranan.cc:736-742)
 #define VO_INTERP       0x100   // emit interpolated output points    (tranan.cc:963-1116)
 #define VO_DUMP_DIRECT  0x200   // emit rhsOld as an output point     (tranan.cc:977-981)
+#define VO_KEEP_X       0x400   // trial parked at a sync point: carry its rhsOld over the global
+                                //  rhs/rhsOld buffer flip of this tick
 
 struct TrialCtl {
     // sCKTPOD / sTRANint scalars (circuit.h:1562-1662, trandefs.h:93-151)
@@ -73,6 +75,7 @@ struct HotView {
     int    *need_devconv;
     int    *devconv;    // 1 = device convTest failed
     // LTE
+    int    *sync;       // 1: trial is parked at a time-point boundary (or finished)
     double *lte;        // [2][ldt] min over charges for order, order+1 (un-normalised)
 };
 

@@ -724,22 +724,23 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
     if (t >= K.ntrials) return;
     sh.K = &K;
     TrialCtl s = ctl[t];
-    // st_base in force when state-vector ops are requested = value at the start of the
-    // control phase (a rotation, if any, comes after the request inside the same call)
-    aux.vo_stbase[t] = s.st_base;
     if (phase == 0) {
         // begin
+        aux.vo_stbase[t] = s.st_base;
         s.vecops = 0;
         s.want_load = 0;
         ctl_begin(s, K, sh);
     }
     else if (phase == 1) {
+        // st_base in force when state-vector ops are requested = value at the start of the
+        // control pass (a rotation, if any, comes after the request inside the same tick)
+        aux.vo_stbase[t] = s.st_base;
         if (s.status != ST_RUNNING) {
             // finished trials: no load, no solve, and no stale vector-op requests
-            hot.mode[t] = 0; hot.do_solve[t] = 0; aux.vecops[t] = 0;
+            hot.mode[t] = 0; hot.do_solve[t] = 0; aux.vecops[t] = 0; hot.sync[t] = 1;
             return;
         }
-        s.vecops = 0;
+        s.vecops = (s.pc == PC_SYNC) ? VO_KEEP_X : 0;      // parked since an earlier tick
         s.want_load = 0;
         CtlIn in;
         in.solve_err = hot.do_solve[t] ? hot.solve_err[t] : 0;
@@ -750,6 +751,18 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
         in.lte0 = hot.lte[t];
         in.lte1 = hot.lte[K.ldt + t];
         ctl_after_solve(s, K, sh, in, hot, t);
+        hot.sync[t] = (s.status != ST_RUNNING || s.pc == PC_SYNC) ? 1 : 0;
+    }
+    else {
+        // phase 2: release the groups whose running trials have all reached the time-point
+        // boundary (ctl_sync_point); everybody else was published by phase 1
+        if (s.status != ST_RUNNING || s.pc != PC_SYNC) return;
+        int g0 = t & ~31;
+        for (int k = 0; k < 32; k++) {
+            int u = g0 + k;
+            if (u < K.ntrials && !hot.sync[u]) return;
+        }
+        ctl_tran_loop_top(s, K, sh);
     }
     // publish for the vector / load kernels of this tick
     {
@@ -809,6 +822,10 @@ k_vec(Consts K, VecView V, CtlAux aux, double *rhsOld)
     size_t ldt = K.ldt;
     size_t at = (size_t)i*ldt + t;
     size_t vplane = (size_t)(K.n + 1)*ldt;
+    if (ops & VO_KEEP_X) {
+        const double *other = (rhsOld == V.X[0]) ? V.X[1] : V.X[0];
+        rhsOld[at] = other[at];
+    }
     if (ops & VO_BK_SAVE) V.oldSol[at] = rhsOld[at];
     if (ops & VO_BK_RESTORE) rhsOld[at] = V.oldSol[at];
     if (ops & VO_RESTORE_OLD) { if (i) rhsOld[at] = V.spare[at]; }
