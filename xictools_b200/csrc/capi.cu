@@ -274,6 +274,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     M.cslot = b->dupload(mt.cslot); M.rslot = b->dupload(mt.rslot);
     M.cache = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);
     M.save = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);
+    M.lte = b->dalloc<double>((size_t)2*mt.n*ldt);
     b->d_cards = b->dupload(b->cards);
     CapView &Cp = b->Cp; CapTopo &ct = an.cap;
     Cp.n = ct.n;

@@ -95,6 +95,7 @@ struct MosView {
     ParamRef prm[MP_NPARAMS];
     double *cache;      // [MC_NCACHE][n][ldt]
     double *save;       // backup copy of cache
+    double *lte;        // [2][n][ldt] LTE bounds of the device's last transient load (this order, order+1)
     MosStageMap smap;   // shared-memory staging layout of k_load_mos
     int stage_doubles;  // staging area size
 };

@@ -92,6 +92,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     const size_t ldt = K.ldt;
     const size_t cstride = (size_t)M.n*ldt;
     double *cp = M.cache + (size_t)i*ldt + t;
+    // Stage 1a: what the bypass test needs -- node voltages, old state-0 voltages, operating point.
     if (mode) {
         make_ctx(c, K, hot, V, t, mode);
         if (!(mode & MODEINITPRED)) {
@@ -108,6 +109,33 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
 #pragma unroll
         for (int k = 0; k < MC_NCACHE; k++)
             __pipeline_memcpy_async(&m.R(SR_CACHE + k), cp + k*cstride, 8);
+        __pipeline_commit();
+    }
+    // MC_mode carries the channel direction in its sign and, as magnitude 2, the note "the last
+    // load of this device was a bypass": its stamps, Meyer currents and LTE bounds are then
+    // already in HBM, bit for bit what a second bypass load would recompute from the same
+    // cached operating point, state and integration coefficients (any non-bypass load, and the
+    // predictor load that opens every time step, rewrites the operating point with magnitude 1).
+    // Only FLOAT-mode loads can repeat a bypass; the others go straight to stage 1b.
+    bool prev_bypass = false, skip = false;
+    const bool maybe = mode && (mode & MODEINITFLOAT) && K.opt.bypass;
+    if (__syncthreads_or(maybe)) {
+        __pipeline_wait_prior(0);
+        if (maybe) {
+            double raw = m.R(SR_CACHE + MC_mode);
+            prev_bypass = (fabs(raw) == 2.0);
+            if (prev_bypass && !(hot.trapcheck[t] && (mode & MODETRAN))) {
+                m.mode = (raw > 0) ? 1 : -1;
+                MosStuff ms;
+                dev_mos_get_v(m, ms);
+                ms.vbd = ms.vbs - ms.vds;
+                ms.vgd = ms.vgs - ms.vds;
+                skip = dev_mos_bypass_ok(m, ms, K.opt.reltol, K.opt.abstol, K.opt.vntol);
+            }
+        }
+    }
+    // Stage 1b: everything else the evaluation needs, unless the device repeats its bypass.
+    if (mode && !skip) {
         if (mode & (MODETRAN | MODEINITPRED)) {
             // old Meyer capacitances and gate charges (bypass re-integrates them)
             __pipeline_memcpy_async(&m.s0(MS_capgs), &ST(c, 0, st + MS_capgs), 8);
@@ -144,10 +172,22 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     o.cs = M.cslot + (size_t)i*MT_NSTAMP;
     o.rs = M.rslot + (size_t)i*MRH_NRHS;
     o.tb = SOLVE_TB;
+    double *plte = M.lte + (size_t)i*ldt + t;              // this device's LTE bounds: [2][nmos][ldt]
     __pipeline_wait_prior(0);
     __syncthreads();                                     // shared parameter block visible
     if (!mode) return;
-    m.mode = (int)m.R(SR_CACHE + MC_mode);
+    if (skip) {
+        if (mode & MODETRAN) {
+            atomic_min_pos(c.lte, plte[0]);
+            if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, plte[cstride]);
+        }
+        return;
+    }
+    {
+        double raw = m.R(SR_CACHE + MC_mode);
+        prev_bypass = (fabs(raw) == 2.0);
+        m.mode = (raw > 0) ? 1 : -1;
+    }
 
     int r = dev_mos_load(c, m, o, K.opt);
     // ---- results: state 0, operating point, flags ----
@@ -186,7 +226,12 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
         }
         atomic_min_pos(c.lte, m0);
         if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
+        plte[0] = m0; plte[cstride] = m1;
     }
+    if ((r & 8) && !prev_bypass)
+        cp[MC_mode*cstride] = 2.0*(double)m.mode;        // bypassed: see the note above
+    else if (!(r & 2) && prev_bypass && !(r & 8))
+        cp[MC_mode*cstride] = (double)m.mode;
     if (r & 2) {
         m.R(SR_CACHE + MC_mode) = (double)m.mode;
 #pragma unroll
@@ -899,7 +944,13 @@ k_statevec(Consts K, VecView V, CtlAux aux, MosView M)
         if (e >= K.numStates) {
             size_t at = (size_t)(e - K.numStates)*ldt + t;
             if (ops & VO_BK_SAVE) M.save[at] = M.cache[at];
-            if (ops & VO_BK_RESTORE) M.cache[at] = M.save[at];
+            if (ops & VO_BK_RESTORE) {
+                double v = M.save[at];
+                // MC_mode rows: drop the "last load was a bypass" note (see k_load_mos) -- the
+                // stamps in HBM belong to the abandoned attempt, not to the restored state
+                if (e - K.numStates < M.n) v = (v > 0) ? 1.0 : -1.0;
+                M.cache[at] = v;
+            }
             continue;
         }
         size_t at = (size_t)e*ldt + t;
