@@ -285,8 +285,11 @@ def bench_ours(args):
         # dominant kernel: the device-load launch (k_load_mos + cap + src of one tick)
         load_ms = ms_load/max(nload, 1)
         solve_ms = ms_solve/max(nsolve, 1)
-        ach = st.algbytes_load_per_launch/(load_ms*1e-3)/1e9 if load_ms > 0 else 0.0
-        ach_solve = st.algbytes_solve_per_launch/(solve_ms*1e-3)/1e9 if solve_ms > 0 else 0.0
+        # a trial takes part in a tick's load + solve only while it iterates (parked or finished
+        # trials move no bytes): live fraction = Newton iterations per trial / ticks
+        live = min(1.0, float(cnt[:, C_NUMITER].mean())/max(1.0, ticks/args.steps))
+        ach = live*st.algbytes_load_per_launch/(load_ms*1e-3)/1e9 if load_ms > 0 else 0.0
+        ach_solve = live*st.algbytes_solve_per_launch/(solve_ms*1e-3)/1e9 if solve_ms > 0 else 0.0
         value = world*T*args.steps/el
         e2e_val = world*T*args.steps/el_e2e
         h2d = sum(v.numel()*8 for v in pinned.values())
@@ -336,7 +339,7 @@ def bench_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_load_mos+k_load_cap+k_load_src (one tick)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach/peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "ms_per_launch": load_ms,
+                         "ms_per_launch": load_ms, "live_trial_fraction": live,
                          "solve_kernel": {"achieved": ach_solve, "ms_per_launch": solve_ms,
                                           "frac": ach_solve/peak}},
             "cpu_baseline": cpu,
