@@ -643,7 +643,7 @@ template <class Prog>
 void pack_rounds(const std::vector<std::vector<LuOp>> &task_ops, const std::vector<int> &level,
     int nlevels, Prog &pg, std::vector<std::vector<int>> &round_tasks)
 {
-    // tasks of each level, longest first, dealt in rounds of 32 lanes
+    // tasks of each level, longest first, dealt in rounds of SOLVE_LANES lanes
     std::vector<std::vector<int>> by_level(nlevels);
     for (int t = 0; t < (int)task_ops.size(); t++) by_level[level[t]].push_back(t);
     pg.ops.clear(); pg.rounds.clear(); pg.level_round_off.assign(1, 0);
@@ -652,22 +652,22 @@ void pack_rounds(const std::vector<std::vector<LuOp>> &task_ops, const std::vect
         auto &v = by_level[l];
         std::stable_sort(v.begin(), v.end(), [&](int a, int b) {
             return task_ops[a].size() > task_ops[b].size(); });
-        for (size_t off = 0; off < v.size(); off += 32) {
-            size_t cnt = std::min<size_t>(32, v.size() - off);
+        for (size_t off = 0; off < v.size(); off += SOLVE_LANES) {
+            size_t cnt = std::min<size_t>(SOLVE_LANES, v.size() - off);
             int nsteps = 0;
             for (size_t q = 0; q < cnt; q++)
                 nsteps = std::max(nsteps, (int)task_ops[v[off + q]].size());
             LuRound r;
             r.op_off = (int)pg.ops.size();
             r.nsteps = nsteps;
-            r.fin_off = (int)round_tasks.size()*32;
-            pg.ops.resize(pg.ops.size() + (size_t)nsteps*32, LuOp{-1, 0, 0});
-            std::vector<int> rt(32, -1);
+            r.fin_off = (int)round_tasks.size()*SOLVE_LANES;
+            pg.ops.resize(pg.ops.size() + (size_t)nsteps*SOLVE_LANES, LuOp{-1, 0, 0});
+            std::vector<int> rt(SOLVE_LANES, -1);
             for (size_t q = 0; q < cnt; q++) {
                 int t = v[off + q];
                 rt[q] = t;
                 for (size_t s = 0; s < task_ops[t].size(); s++)
-                    pg.ops[r.op_off + s*32 + q] = task_ops[t][s];
+                    pg.ops[r.op_off + s*SOLVE_LANES + q] = task_ops[t][s];
             }
             pg.rounds.push_back(r);
             round_tasks.push_back(rt);
@@ -765,17 +765,17 @@ void b200_build_lu(Analysis &an)
     for (int j = 0; j < n; j++) nfl = std::max(nfl, flevel[j] + 1);
     std::vector<std::vector<int>> rt;
     pack_rounds(fops, flevel, nfl, an.fac, rt);
-    an.fac.fin_diag.assign(rt.size()*32, -1);
-    an.fac.fin_lbeg.assign(rt.size()*32, 0);
-    an.fac.fin_lend.assign(rt.size()*32, 0);
+    an.fac.fin_diag.assign(rt.size()*SOLVE_LANES, -1);
+    an.fac.fin_lbeg.assign(rt.size()*SOLVE_LANES, 0);
+    an.fac.fin_lend.assign(rt.size()*SOLVE_LANES, 0);
     for (size_t r = 0; r < rt.size(); r++)
-        for (int q = 0; q < 32; q++) {
+        for (int q = 0; q < SOLVE_LANES; q++) {
             int j = rt[r][q];
             if (j < 0) continue;
-            an.fac.fin_diag[r*32 + q] = an.slotD[j];
+            an.fac.fin_diag[r*SOLVE_LANES + q] = an.slotD[j];
             // L slots of column j are contiguous right after the diagonal
-            an.fac.fin_lbeg[r*32 + q] = an.slotD[j] + 1;
-            an.fac.fin_lend[r*32 + q] = an.slotD[j] + 1 + (an.Lp[j+1] - an.Lp[j]);
+            an.fac.fin_lbeg[r*SOLVE_LANES + q] = an.slotD[j] + 1;
+            an.fac.fin_lend[r*SOLVE_LANES + q] = an.slotD[j] + 1 + (an.Lp[j+1] - an.Lp[j]);
         }
 
     // ---- forward solve: task = row i of L (ascending column order) ----
@@ -794,10 +794,10 @@ void b200_build_lu(Analysis &an)
     int nll = 0;
     for (int i = 0; i < n; i++) nll = std::max(nll, llevel[i] + 1);
     pack_rounds(lops, llevel, nll, an.fwd, rt);
-    an.fwd.fin_row.assign(rt.size()*32, -1); an.fwd.fin_diag.assign(rt.size()*32, -1);
+    an.fwd.fin_row.assign(rt.size()*SOLVE_LANES, -1); an.fwd.fin_diag.assign(rt.size()*SOLVE_LANES, -1);
     for (size_t r = 0; r < rt.size(); r++)
-        for (int q = 0; q < 32; q++)
-            if (rt[r][q] >= 0) an.fwd.fin_row[r*32 + q] = rt[r][q];
+        for (int q = 0; q < SOLVE_LANES; q++)
+            if (rt[r][q] >= 0) an.fwd.fin_row[r*SOLVE_LANES + q] = rt[r][q];
 
     // ---- backward solve: task = row i of U (descending column order), then / diag ----
     std::vector<std::vector<LuOp>> uops(n);
@@ -815,12 +815,12 @@ void b200_build_lu(Analysis &an)
     int nul = 0;
     for (int i = 0; i < n; i++) nul = std::max(nul, ulevel[i] + 1);
     pack_rounds(uops, ulevel, nul, an.bwd, rt);
-    an.bwd.fin_row.assign(rt.size()*32, -1); an.bwd.fin_diag.assign(rt.size()*32, -1);
+    an.bwd.fin_row.assign(rt.size()*SOLVE_LANES, -1); an.bwd.fin_diag.assign(rt.size()*SOLVE_LANES, -1);
     for (size_t r = 0; r < rt.size(); r++)
-        for (int q = 0; q < 32; q++)
+        for (int q = 0; q < SOLVE_LANES; q++)
             if (rt[r][q] >= 0) {
-                an.bwd.fin_row[r*32 + q] = rt[r][q];
-                an.bwd.fin_diag[r*32 + q] = an.slotD[rt[r][q]];
+                an.bwd.fin_row[r*SOLVE_LANES + q] = rt[r][q];
+                an.bwd.fin_diag[r*SOLVE_LANES + q] = an.slotD[rt[r][q]];
             }
 
     an.yperm_in.resize(n); an.yperm_out.resize(n);
@@ -836,21 +836,21 @@ void b200_build_lu(Analysis &an)
             if (lvl[l] < (int)rounds.size() && lvl[l] < lvl[l+1]) sync[lvl[l]] = 1;
         for (size_t r = 0; r < rounds.size(); r++) {
             const LuRound &rd = rounds[r];
-            int row0 = (int)(an.strm.size()/96);
+            int row0 = (int)(an.strm.size()/(3*SOLVE_LANES));
             int k2 = kind;
             if (kind == 0 && f1 && f2)
-                for (int e = 0; e < 32; e++)
+                for (int e = 0; e < SOLVE_LANES; e++)
                     if ((*f2)[rd.fin_off + e] - (*f1)[rd.fin_off + e] > 32) k2 |= 4;   // cooperative pivot division
             an.strm_round.push_back(rd.nsteps); an.strm_round.push_back(k2);
             an.strm_round.push_back(sync[r]); an.strm_round.push_back(row0);
-            for (int e = 0; e < 32; e++) {
+            for (int e = 0; e < SOLVE_LANES; e++) {
                 an.strm.push_back(f0 ? (*f0)[rd.fin_off + e] : -1);
                 an.strm.push_back(f1 ? (*f1)[rd.fin_off + e] : -1);
                 an.strm.push_back(f2 ? (*f2)[rd.fin_off + e] : -1);
             }
             for (int st = 0; st < rd.nsteps; st++)
-                for (int e = 0; e < 32; e++) {
-                    const LuOp &op = ops[rd.op_off + st*32 + e];
+                for (int e = 0; e < SOLVE_LANES; e++) {
+                    const LuOp &op = ops[rd.op_off + st*SOLVE_LANES + e];
                     an.strm.push_back(op.dst); an.strm.push_back(op.a); an.strm.push_back(op.b);
                 }
         }
@@ -871,77 +871,6 @@ void b200_build_lu(Analysis &an)
 // Assembly program: the ordered gather lists flattened into per-lane streams so that every
 // lane issues long runs of independent loads (no pointer chasing through cg_ptr/cg_idx in
 // the kernel).  Lists longer than `long_threshold` are left to the staged path.
-// ---------------------------------------------------------------------------------------
-void b200_build_asm(Analysis &an, int long_threshold)
-{
-    AsmProgram &A = an.asmp;
-    int n = an.n, nlu = an.nnzLU;
-    A.long_kind.clear(); A.long_idx.clear();
-    A.fin_node.assign(nlu + n, 0);
-    struct Item { int target; int init; std::vector<int> terms; };
-    std::vector<Item> items;
-    std::vector<int> p2node(an.nnz, 0);
-    for (int i = 1; i <= n; i++) if (an.diag[i] >= 0) p2node[an.diag[i]] = i;
-    for (int s = 0; s < nlu; s++) {
-        int p = an.lu_src[s];
-        Item it; it.target = s; it.init = (p >= 0) ? p : -2;
-        if (p >= 0) {
-            int dn = p2node[p];
-            if (dn) A.fin_node[s] = dn | ASM_DIAG | (an.ntype[dn] == 0 ? ASM_VNODE : 0);
-            int cnt = an.cg_ptr[p+1] - an.cg_ptr[p];
-            if (cnt > long_threshold) { A.long_kind.push_back(0); A.long_idx.push_back(s); continue; }
-            for (int q = an.cg_ptr[p]; q < an.cg_ptr[p+1]; q++) it.terms.push_back(an.cg_idx[q]);
-        }
-        items.push_back(std::move(it));
-    }
-    for (int k = 0; k < n; k++) {
-        int row = an.yperm_in[k];
-        Item it; it.target = nlu + k; it.init = -2;
-        A.fin_node[nlu + k] = row | ASM_ROW;
-        int cnt = an.rg_ptr[row+1] - an.rg_ptr[row];
-        if (cnt > long_threshold) { A.long_kind.push_back(1); A.long_idx.push_back(k); continue; }
-        for (int q = an.rg_ptr[row]; q < an.rg_ptr[row+1]; q++) it.terms.push_back(an.rg_idx[q] | ASM_RHS);
-        items.push_back(std::move(it));
-    }
-    // with long lists present, warp 0 of the CTA runs the staged path: 24 short lanes; else 32
-    A.nlanes = A.long_kind.empty() ? 32 : 24;
-    // greedy balance: longest items first onto the least-loaded lane
-    std::vector<int> order(items.size());
-    for (size_t i = 0; i < items.size(); i++) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return std::max<size_t>(1, items[a].terms.size()) > std::max<size_t>(1, items[b].terms.size()); });
-    std::vector<std::vector<AsmOp>> lanes(A.nlanes);
-    for (int idx : order) {
-        int best = 0;
-        for (int l = 1; l < A.nlanes; l++) if (lanes[l].size() < lanes[best].size()) best = l;
-        Item &it = items[idx];
-        if (it.terms.empty())
-            lanes[best].push_back(AsmOp{-1, it.init, it.target, A.fin_node[it.target]});
-        else
-            for (size_t q = 0; q < it.terms.size(); q++)
-                lanes[best].push_back(AsmOp{it.terms[q], q == 0 ? it.init : -1,
-                    q + 1 == it.terms.size() ? it.target : -1,
-                    q + 1 == it.terms.size() ? A.fin_node[it.target] : 0});
-    }
-    size_t ns = 0;
-    for (auto &l : lanes) ns = std::max(ns, l.size());
-    ns = (ns + 15) & ~(size_t)15;                // kernel consumes 16 steps per batch
-    A.nsteps = (int)ns;
-    A.ops.assign(ns*A.nlanes, AsmOp{-1, -1, -1, 0});
-    for (int l = 0; l < A.nlanes; l++)
-        for (size_t q = 0; q < lanes[l].size(); q++)
-            A.ops[q*A.nlanes + l] = lanes[l][q];
-}
-
-
-// ---------------------------------------------------------------------------------------
-// Streamed assembly: renumber every contribution slot into assembly order and build the
-// per-chunk segment schedule (see SegOp).  After this call
-//   * an.cg_idx / an.rg_idx and the device tables (mos/cap/src cslot, rslot) hold the NEW
-//     indices into one contribution array of an.NC entries,
-//   * each gather list is a run of consecutive indices.
-// A run that crosses a chunk boundary is always given to lane 0, which carries the partial
-// sum in a register, so the reference's summation order is preserved across chunks.
 // ---------------------------------------------------------------------------------------
 void b200_build_stream_asm(Analysis &an)
 {
@@ -985,7 +914,7 @@ void b200_build_stream_asm(Analysis &an)
     // chunk schedule
     int nchunks = (an.NC + SEG_CHUNK - 1)/SEG_CHUNK;
     if (nchunks == 0) nchunks = 1;
-    std::vector<std::vector<std::vector<SegOp>>> sched(nchunks, std::vector<std::vector<SegOp>>(32));
+    std::vector<std::vector<std::vector<SegOp>>> sched(nchunks, std::vector<std::vector<SegOp>>(SOLVE_LANES));
     // zero-length runs (fill slots, entries with only Ainit) belong to the chunk of their position
     std::vector<std::vector<SegOp>> pieces(nchunks);        // non-crossing pieces per chunk
     for (auto &r : runs) {
@@ -1011,34 +940,34 @@ void b200_build_stream_asm(Analysis &an)
         // lane 0 already holds crossing pieces: [continuing..., (others go in between), starting]
         std::vector<SegOp> head, tail;
         for (auto &op : sched[c][0]) ((op.info & SEG_START) ? tail : head).push_back(op);
-        std::vector<size_t> load(32, 0);
-        std::vector<std::vector<SegOp>> mid(32);
+        std::vector<size_t> load(SOLVE_LANES, 0);
+        std::vector<std::vector<SegOp>> mid(SOLVE_LANES);
         for (auto &op : head) { load[0] += std::max(1, op.len); if (op.target < 0) load[0] += (size_t)1 << 40; }
         for (auto &op : tail) load[0] += std::max(1, op.len);
         std::vector<SegOp> &pc = pieces[c];
         std::stable_sort(pc.begin(), pc.end(), [](const SegOp &a, const SegOp &b) { return a.len > b.len; });
         for (auto &op : pc) {
             int best = 0;
-            for (int l = 1; l < 32; l++) if (load[l] < load[best]) best = l;
+            for (int l = 1; l < SOLVE_LANES; l++) if (load[l] < load[best]) best = l;
             mid[best].push_back(op);
             load[best] += std::max(1, op.len);
         }
         sched[c][0] = head;
         sched[c][0].insert(sched[c][0].end(), mid[0].begin(), mid[0].end());
         sched[c][0].insert(sched[c][0].end(), tail.begin(), tail.end());
-        for (int l = 1; l < 32; l++) sched[c][l] = mid[l];
+        for (int l = 1; l < SOLVE_LANES; l++) sched[c][l] = mid[l];
     }
     an.seg_ops.clear(); an.seg_chunk.clear();
     for (int c = 0; c < nchunks; c++) {
         size_t ns = 0;
-        for (int l = 0; l < 32; l++) ns = std::max(ns, sched[c][l].size());
+        for (int l = 0; l < SOLVE_LANES; l++) ns = std::max(ns, sched[c][l].size());
         an.seg_chunk.push_back((int)an.seg_ops.size());
         an.seg_chunk.push_back((int)ns);
         size_t base = an.seg_ops.size();
-        an.seg_ops.resize(base + ns*32, SegOp{0, 0, -1, 0});
+        an.seg_ops.resize(base + ns*SOLVE_LANES, SegOp{0, 0, -1, 0});
         an.seg_maxsteps = std::max(an.seg_maxsteps, (int)ns);
-        for (int l = 0; l < 32; l++)
+        for (int l = 0; l < SOLVE_LANES; l++)
             for (size_t q = 0; q < sched[c][l].size(); q++)
-                an.seg_ops[base + q*32 + l] = sched[c][l][q];
+                an.seg_ops[base + q*SOLVE_LANES + l] = sched[c][l][q];
     }
 }

@@ -122,12 +122,6 @@ struct LuOp { int dst, a, b; };
 #define LUOP_LAST  0x20000000
 #define LUOP_SLOT(d) ((d) & 0x00ffffff)
 
-// Assembly stream (one per assembly lane, interleaved [step][nlanes]): v (+)= contribution.
-//   cidx >= 0: add contrib[cidx] (bit 30 set: rhs contribution array); -1: nothing to add
-//   init >= 0: before adding, start a new sum v = Ainit[init]; -2: start with 0.0; -1: continue
-//   fin  >= 0: after adding, finalise (nodeset/ic/gmin rules) and store v to smem slot fin
-struct AsmOp { int cidx, init, fin, info; };   // info: finalisation class of smem slot `fin`
-#define ASM_RHS 0x40000000
 // Segment op of the streamed assembly: contributions are numbered in ASSEMBLY ORDER (all terms
 // of one matrix entry / rhs row are consecutive, entries in LU-slot order, then rhs rows), so a
 // target's ordered sum is a run of consecutive values in the streamed chunk.
@@ -137,12 +131,7 @@ struct AsmOp { int cidx, init, fin, info; };   // info: finalisation class of sm
 struct SegOp { int pos, len, target, info; };
 #define SEG_START  0x08000000
 #define SEG_CHUNK 512                            // contributions per streamed chunk
-struct AsmProgram {
-    int nlanes = 0, nsteps = 0;
-    std::vector<AsmOp> ops;                      // [nsteps][nlanes]
-    std::vector<int> fin_node;                   // [nnzLU + n]: 0 plain; node | ASM_DIAG / ASM_ROW
-    std::vector<int> long_kind, long_idx;        // staged long lists (kind 0 = LU slot, 1 = rhs pos)
-};
+#define SOLVE_LANES 64                           // task lanes per trial in the solve kernel
 #define ASM_DIAG 0x40000000
 #define ASM_ROW  0x20000000
 #define ASM_VNODE 0x10000000  // diagonal of a voltage node (loadGmin applies)
@@ -201,7 +190,6 @@ struct Analysis {
     std::vector<int> lu_src;                    // LU slot -> Ax index or -1 (fill)
     LuProgram fac;
     SolveProgram fwd, bwd;
-    AsmProgram asmp;
     int NC = 0;                                 // total contributions (matrix + rhs), assembly order
     std::vector<SegOp> seg_ops;                 // [chunk][step][32 lanes]
     std::vector<int> seg_chunk;                 // per chunk: {op offset (in SegOp), nsteps}
@@ -226,5 +214,4 @@ struct Analysis {
 int  b200_analyze(const b200_deck *deck, Analysis &an, std::string &err);
 void b200_order_markowitz(Analysis &an);
 void b200_build_lu(Analysis &an);
-void b200_build_asm(Analysis &an, int long_threshold);
 void b200_build_stream_asm(Analysis &an);

@@ -321,7 +321,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     b->d_const_idx = b->dupload(an.const_idx); b->d_const_val = b->dupload(an.const_val);
     {
         std::vector<int> padded = an.strm;
-        padded.resize(padded.size() + 3*42*96, -1);          // cp.async prefetch runs ahead
+        padded.resize(padded.size() + 3*RING_HROWS_PAD*3*SOLVE_LANES, -1);          // cp.async prefetch runs ahead
         Sv.strm = b->dupload(padded); Sv.strm_round = b->dupload(an.strm_round);
         Sv.strm_nrounds = (int)an.strm_round.size()/4;
     }

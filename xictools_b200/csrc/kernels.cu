@@ -476,9 +476,11 @@ __device__ __forceinline__ double asm_finalize(double v, int info, const Consts 
     return v;
 }
 
-// Phase-2 op stream: rows of 96 ints (32 task lanes x 3) double-buffered through shared memory.
-#define RING_HROWS 42                                   // rows per half (42*384 B = 16128 B)
-#define RING_HALF_INTS (RING_HROWS*96)
+// Phase-2 op stream: rows of ROW_INTS ints (SOLVE_LANES task lanes x 3) double-buffered through
+// shared memory.
+#define ROW_INTS (3*SOLVE_LANES)
+#define RING_HROWS 21                                   // rows per half (21*768 B = 16128 B)
+#define RING_HALF_INTS (RING_HROWS*ROW_INTS)
 
 struct OpRing {
     const int *g;          // global stream (16-B aligned, padded)
@@ -498,15 +500,16 @@ struct OpRing {
     }
     __device__ __forceinline__ const int *row(int R) const {
         int h = R/RING_HROWS;
-        return buf + (h & 1)*RING_HALF_INTS + (R - h*RING_HROWS)*96;
+        return buf + (h & 1)*RING_HALF_INTS + (R - h*RING_HROWS)*ROW_INTS;
     }
 };
 
-__global__ void __launch_bounds__(SOLVE_TB*32)
+__global__ void __launch_bounds__(SOLVE_TB*SOLVE_LANES)
 k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, double *Xnew)
 {
     constexpr int TB = SOLVE_TB;
-    constexpr int NT = TB*32;
+    constexpr int NL = SOLVE_LANES;
+    constexpr int NT = TB*NL;
     extern __shared__ double smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int t0 = blockIdx.x*TB;
@@ -518,7 +521,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
     __shared__ int s_any;
     __shared__ int s_chunk[2*SOLVE_MAXCH];
 
-    const int j = tid % TB, e0 = tid / TB;               // lane e0 (0..31) x trial j
+    const int j = tid % TB, e0 = tid / TB;               // lane e0 (0..NL-1) x trial j
     const int tj = t0 + j;
     const bool live_j = (tj < K.ntrials) && hot.do_solve[tj];
     if (tid == 0) s_any = 0;
@@ -542,7 +545,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
         const double *gC = V.contrib + (size_t)blockIdx.x*(size_t)K.NC*TB;
         double *dring = ringmem;                                     // [SEG_NBUF][SEG_CHUNK*TB]
         SegOp *oring = reinterpret_cast<SegOp*>(ringmem + (size_t)SEG_NBUF*SEG_CHUNK*TB);
-        const int ostride = Sv.seg_maxsteps*32;                       // SegOps per ring slot
+        const int ostride = Sv.seg_maxsteps*NL;                       // SegOps per ring slot
         auto issue = [&](int c) {
             if (c < nch) {
                 int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK)*TB/2;    // 16-B units
@@ -551,7 +554,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
                 for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 16);
                 const int4 *osrc = reinterpret_cast<const int4*>(Sv.seg_ops + s_chunk[2*c]);
                 int4 *odst = reinterpret_cast<int4*>(oring + (size_t)(c % SEG_NBUF)*ostride);
-                int ocnt = s_chunk[2*c + 1]*32;
+                int ocnt = s_chunk[2*c + 1]*NL;
                 for (int i = tid; i < ocnt; i += NT) __pipeline_memcpy_async(odst + i, osrc + i, 16);
             }
             __pipeline_commit();
@@ -568,7 +571,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
             const int ns = s_chunk[2*c + 1];
             const int base = c*SEG_CHUNK;
             for (int q = 0; q < ns; q++) {
-                const int4 raw = *reinterpret_cast<const int4*>(ops + q*32);
+                const int4 raw = *reinterpret_cast<const int4*>(ops + q*NL);
                 const int pos = raw.x, len = raw.y, target = raw.z, info = raw.w;
                 if (info & SEG_START) v = 0.0;
                 const double *x = buf + (size_t)(pos - base)*TB;
@@ -628,11 +631,11 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
                 if (live_j) {
                     if (kind == 0) {
                         int q = 0;
-                        for (; q + 4 <= cnt; q += 4, op += 4*96) {
+                        for (; q + 4 <= cnt; q += 4, op += 4*ROW_INTS) {
                             int d[4], ia[4], ib[4];
                             double av[4], bv[4];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) { d[u] = op[u*96]; ia[u] = op[u*96 + 1]; ib[u] = op[u*96 + 2]; }
+                            for (int u = 0; u < 4; u++) { d[u] = op[u*ROW_INTS]; ia[u] = op[u*ROW_INTS + 1]; ib[u] = op[u*ROW_INTS + 2]; }
 #pragma unroll
                             for (int u = 0; u < 4; u++) { av[u] = Sj[(size_t)ia[u]*TB]; bv[u] = Sj[(size_t)ib[u]*TB]; }
 #pragma unroll
@@ -651,7 +654,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
                                 }
                             }
                         }
-                        for (; q < cnt; q++, op += 96) {
+                        for (; q < cnt; q++, op += ROW_INTS) {
                             int d = op[0];
                             if (d >= 0) {
                                 double av = Sj[(size_t)op[1]*TB];
@@ -663,20 +666,20 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
                     }
                     else {
                         int q = 0;
-                        for (; q + 8 <= cnt; q += 8, op += 8*96) {
+                        for (; q + 8 <= cnt; q += 8, op += 8*ROW_INTS) {
                             int d[8];
                             double av[8], bv[8];
 #pragma unroll
                             for (int u = 0; u < 8; u++) {
-                                d[u] = op[u*96];
-                                av[u] = Sj[(size_t)op[u*96 + 1]*TB];
-                                bv[u] = yj[(size_t)op[u*96 + 2]*TB];
+                                d[u] = op[u*ROW_INTS];
+                                av[u] = Sj[(size_t)op[u*ROW_INTS + 1]*TB];
+                                bv[u] = yj[(size_t)op[u*ROW_INTS + 2]*TB];
                             }
 #pragma unroll
                             for (int u = 0; u < 8; u++)
                                 if (d[u] >= 0) acc -= av[u]*bv[u];
                         }
-                        for (; q < cnt; q++, op += 96)
+                        for (; q < cnt; q++, op += ROW_INTS)
                             if (op[0] >= 0)
                                 acc -= Sj[(size_t)op[1]*TB]*yj[(size_t)op[2]*TB];
                     }
@@ -690,12 +693,12 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
                     // a column of this round has a long L part: all lanes divide it together
                     __syncthreads();
                     if (live_j) {
-                        for (int e = 0; e < 32; e++) {
+                        for (int e = 0; e < NL; e++) {
                             int dg = drow[e*3];
                             if (dg < 0) continue;
                             double piv = Sj[(size_t)dg*TB];
                             if (piv == 0.0 || !isfinite(piv)) bad = 1;
-                            for (int q = drow[e*3 + 1] + e0; q < drow[e*3 + 2]; q += 32)
+                            for (int q = drow[e*3 + 1] + e0; q < drow[e*3 + 2]; q += NL)
                                 Sj[(size_t)q*TB] = Sj[(size_t)q*TB]/piv;
                         }
                     }
@@ -716,7 +719,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
         }
         __pipeline_wait_prior(0);
         if (bad) atomicOr(&s_flags[j], 1);
-        if (PF && (tid & 31) == 0) {
+        if (PF && (tid & 31) == 0 && warp < TB) {
             long long *pp = Sv.prof + (size_t)K.ldt*6 + ((size_t)blockIdx.x*TB + warp)*6;
             pp[0] = pa_sync; pp[1] = pa_ring; pp[2] = pa_step[0]; pp[3] = pa_step[1]; pp[4] = pa_step[2]; pp[5] = pa_fin;
         }
@@ -728,7 +731,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
     if (live_j) {
         const double *yj = S + (size_t)nlu*TB + j;
         int fl = 0;
-        for (int k = e0; k < n; k += 32) {
+        for (int k = e0; k < n; k += SOLVE_LANES) {
             int node = Sv.yperm_out[k];
             double cur = yj[(size_t)k*TB];
             double old = Xold[(size_t)node*ldt + tj];
@@ -742,7 +745,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
         if (fl) atomicOr(&s_flags[j], fl);
     }
     __syncthreads();
-    if (PF && (tid & 31) == 0) {
+    if (PF && (tid & 31) == 0 && warp < TB) {
         long long tk6 = clock64();
         long long *pp = Sv.prof + ((size_t)blockIdx.x*TB + warp)*6;
         pp[0] = tk1 - tk0; pp[1] = tk2 - tk1; pp[2] = tk5 - tk2; pp[3] = 0; pp[4] = 0; pp[5] = tk6 - tk5;
@@ -1067,7 +1070,7 @@ void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const 
 int solve_smem_bytes(const Consts &K, int seg_maxsteps)
 {
     size_t img = (size_t)SOLVE_TB*(K.nnzLU + K.n)*sizeof(double);
-    size_t ph1 = (size_t)SEG_NBUF*SEG_CHUNK*SOLVE_TB*sizeof(double) + (size_t)SEG_NBUF*seg_maxsteps*32*sizeof(SegOp);
+    size_t ph1 = (size_t)SEG_NBUF*SEG_CHUNK*SOLVE_TB*sizeof(double) + (size_t)SEG_NBUF*seg_maxsteps*SOLVE_LANES*sizeof(SegOp);
     size_t ph2 = (size_t)2*RING_HALF_INTS*sizeof(int);
     return (int)(img + (ph1 > ph2 ? ph1 : ph2));
 }
@@ -1081,7 +1084,7 @@ int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const Vec
             return B200_E_NOMEM;
         configured = smem;
     }
-    k_solve<<<(K.ntrials + SOLVE_TB - 1)/SOLVE_TB, SOLVE_TB*32, smem, st>>>(K, hot, V, Sv, Xold, Xnew);
+    k_solve<<<(K.ntrials + SOLVE_TB - 1)/SOLVE_TB, SOLVE_TB*SOLVE_LANES, smem, st>>>(K, hot, V, Sv, Xold, Xnew);
     return 0;
 }
 void launch_vec(cudaStream_t st, const Consts &K, const VecView &V, const CtlAux &aux,

@@ -298,7 +298,7 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     }
     {
         std::vector<int> padded = an.strm;
-        padded.resize(padded.size() + 3*42*96, -1);          // cp.async prefetch runs ahead
+        padded.resize(padded.size() + 3*RING_HROWS_PAD*3*SOLVE_LANES, -1);          // cp.async prefetch runs ahead
         Sv.strm = k->dupload(padded); Sv.strm_round = k->dupload(an.strm_round);
         Sv.strm_nrounds = (int)an.strm_round.size()/4;
     }
