@@ -100,6 +100,8 @@ typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct; } Res;
 /* sINDinstancePOD (inddefs.h): linear inductor, no series resistance / poly / expression */
 typedef struct { int pos, neg, br; int pBB, pPB, pNB, pBN, pBP; int st; int icGiven;
     double induct, ic, req, veq, prevFlux; } Ind;
+/* sMUTinstancePOD (inddefs.h) */
+typedef struct { int ind1, ind2; int p12, p21; double coupling, factor; } Mut;
 typedef struct {
     int kind, pos, neg, branch;
     int pPB, pNB, pBN, pBP;
@@ -125,8 +127,8 @@ struct wo_ckt {
     double *ic_val; char *ic_given; double *ns_val; char *ns_given; int hadNodeset;
     char **names;
 
-    int nmos, ncap, nres, nsrc, nind;
-    Mos *mos; Cap *cap; Res *res; Src *src; Ind *ind;
+    int nmos, ncap, nres, nsrc, nind, nmut;
+    Mos *mos; Cap *cap; Res *res; Src *src; Ind *ind; Mut *mut;
     int nord; DevRef *ord;
 
     /* matrix: CSC, rows ascending per column (spbuild.cc:922-958) */
@@ -851,6 +853,7 @@ static void build_matrix(wo_ckt *c)
     for (int i = 0; i < c->nind; i++) {
         REMAP(c->ind[i].pBB); REMAP(c->ind[i].pPB); REMAP(c->ind[i].pNB); REMAP(c->ind[i].pBN); REMAP(c->ind[i].pBP);
     }
+    for (int i = 0; i < c->nmut; i++) { REMAP(c->mut[i].p12); REMAP(c->mut[i].p21); }
     for (int i = 0; i < c->nsrc; i++) {
         REMAP(c->src[i].pPB); REMAP(c->src[i].pNB); REMAP(c->src[i].pBN); REMAP(c->src[i].pBP);
     }
@@ -887,6 +890,8 @@ wo_ckt *wo_create(const b200_deck *dk)
     c->src = xcalloc(c->nsrc, sizeof(Src));
     c->nind = dk->nind;
     c->ind = xcalloc(c->nind, sizeof(Ind));
+    c->nmut = dk->nmut;
+    c->mut = xcalloc(c->nmut, sizeof(Mut));
     c->nord = dk->norder;
     c->ord = xcalloc(c->nord, sizeof(DevRef));
     for (int i = 0; i < c->nord; i++) {
@@ -971,10 +976,21 @@ wo_ckt *wo_create(const b200_deck *dk)
             p->pBN = coo_add(c, p->br, p->neg);
             p->pBP = coo_add(c, p->br, p->pos);
             break; }
+        case B200_DEV_MUT:
+            break;              /* set up after the inductors, below */
         default:
             fprintf(stderr, "wrs_oracle: device kind %d not supported\n", c->ord[o].kind);
             abort();
         }
+    }
+    /* mutual inductors: INDdev::setup does them after all inductors (indset.cc:186-238) */
+    for (int o = 0; o < c->nord; o++) {
+        if (c->ord[o].kind != B200_DEV_MUT) continue;
+        int i = c->ord[o].index;
+        Mut *p = &c->mut[i]; const b200_mut *in = &dk->mut[i];
+        p->ind1 = in->ind1; p->ind2 = in->ind2; p->coupling = in->k; p->factor = 0.0;
+        p->p12 = coo_add(c, c->ind[p->ind1].br, c->ind[p->ind2].br);
+        p->p21 = coo_add(c, c->ind[p->ind2].br, c->ind[p->ind1].br);
     }
     build_matrix(c);
 
@@ -1016,7 +1032,9 @@ int wo_set_param(wo_ckt *c, int param, int index, double value)
         c->res[index].conduct = 1.0/(r*1.0);
         break; }
     case B200_P_SRC_DC:     c->src[index].dc = value; c->src[index].dcGiven = 1; break;
-    case B200_P_IND_L:      c->ind[index].induct = value/1.0; break;
+    case B200_P_IND_L:      c->ind[index].induct = value/1.0;
+        for (int k = 0; k < c->nmut; k++) c->mut[k].factor = 0.0;   /* recomputed at the next load */
+        break;
     default: return B200_E_BADPARM;
     }
     return OK;
@@ -1949,6 +1967,43 @@ static void cap_load(wo_ckt *c, Cap *p)
     }
 }
 
+static void mut_load(wo_ckt *c, Mut *p)
+{
+    /* mutload.cc:55-140: loaded BEFORE the inductors, adds the cross flux to their states */
+    Ind *l1 = &c->ind[p->ind1], *l2 = &c->ind[p->ind2];
+    if (p->factor == 0.0)
+        p->factor = p->coupling*sqrt(l1->induct*l2->induct);
+    if (c->mode & MODEDC)
+        return;
+    if (c->mode & MODEINITFLOAT) {
+        double factor = p->factor;
+        c->states[0][l1->st] += factor*c->rhsOld[l2->br];
+        c->states[0][l2->st] += factor*c->rhsOld[l1->br];
+        factor *= c->ag[0];
+        ldadd(c, p->p12, -factor);
+        ldadd(c, p->p21, -factor);
+    }
+    else if (c->mode & MODEINITPRED) {
+        double factor = p->factor*c->ag[0];
+        ldadd(c, p->p12, -factor);
+        ldadd(c, p->p21, -factor);
+    }
+    else if (c->mode & MODEINITTRAN) {
+        double factor = p->factor;
+        if (c->mode & MODEUIC) {
+            c->states[1][l1->st] += factor*l2->ic;
+            c->states[1][l2->st] += factor*l1->ic;
+        }
+        else {
+            c->states[1][l1->st] += factor*c->rhsOld[l2->br];
+            c->states[1][l2->st] += factor*c->rhsOld[l1->br];
+        }
+        factor *= c->ag[0];
+        ldadd(c, p->p12, -factor);
+        ldadd(c, p->p21, -factor);
+    }
+}
+
 static void ind_load(wo_ckt *c, Ind *p)
 {
     /* indload.cc:84-263 (linear inductor; the +-1 couplings are preloaded) */
@@ -2069,6 +2124,7 @@ static int ckt_load(wo_ckt *c)
         case B200_DEV_MOS: mos_load(c, &c->mos[i]); break;
         case B200_DEV_CAP: cap_load(c, &c->cap[i]); break;
         case B200_DEV_IND: ind_load(c, &c->ind[i]); break;
+        case B200_DEV_MUT: mut_load(c, &c->mut[i]); break;
         case B200_DEV_SRC: src_load(c, &c->src[i]); break;
         case B200_DEV_RES: break;          /* preloaded, LOAD_SKIP_FLAG */
         }
@@ -3257,6 +3313,6 @@ void wo_destroy(wo_ckt *c)
     free(c->rhs); free(c->rhsOld); free(c->rhsSpare);
     for (int i = 0; i < 8; i++) { free(c->sols[i]); free(c->states[i]); }
     free(c->pt_t); free(c->pt_v); free(c->acc_t); free(c->acc_v); free(c->acc_it);
-    free(c->mos); free(c->cap); free(c->res); free(c->src); free(c->ord);
+    free(c->mos); free(c->cap); free(c->res); free(c->src); free(c->ord); free(c->ind); free(c->mut);
     free(c);
 }

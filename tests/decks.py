@@ -99,6 +99,27 @@ def rlc_uic():
     return d
 
 
+def transformer():
+    """Two coupled LC tanks (k = 0.6) plus a third winding coupled to both: mutual inductors,
+    several couplings onto one inductor (ordered flux accumulation)."""
+    d = Deck(title="coupled tanks")
+    d.vsource("v1", "in", "0", dc=0.0, pulse=(0, 1.0, 0.1e-9, 0.05e-9, 0.05e-9, 1e-9, 3e-9))
+    d.resistor("r1", "in", "a", 25.0)
+    d.inductor("l1", "a", "0", 4e-9)
+    d.capacitor("c1", "a", "0", 0.5e-12)
+    d.inductor("l2", "b", "0", 9e-9)
+    d.capacitor("c2", "b", "0", 0.3e-12)
+    d.resistor("r2", "b", "0", 200.0)
+    d.inductor("l3", "c", "d", 2e-9)
+    d.resistor("r3", "c", "0", 50.0)
+    d.resistor("r4", "d", "0", 50.0)
+    d.mutual("k12", "l1", "l2", 0.6)
+    d.mutual("k13", "l1", "l3", 0.3)
+    d.mutual("k23", "l2", "l3", 0.2)
+    d.tran(0.02e-9, 3e-9)
+    return d
+
+
 def ro_rd(n=3):
     """Ring oscillator whose MOSFETs have series rd/rs: internal drain/source nodes."""
     d = ring_oscillator(n)
@@ -143,6 +164,7 @@ def variants():
         "rl_isrc": rl_isrc(),
         "inv_lsupply": inv_lsupply(),
         "rlc_uic": rlc_uic(),
+        "transformer": transformer(),
         "ro3": ring_oscillator(3),
         "ro5": ring_oscillator(5),
         "ro17": ring_oscillator(17),

@@ -87,6 +87,20 @@ def test_monte_carlo_inductor_values():
     compare(d, ntr, ov, min_same=0.9)
 
 
+def test_monte_carlo_coupled_inductors():
+    """Per-trial inductances under mutual coupling: M = k*sqrt(L1*L2) follows the trial."""
+    from xictools_b200.deck import DEV_IND, P_IND_L
+    d = variants()["transformer"]
+    rng = np.random.default_rng(9)
+    ntr = 11
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_IND]):
+        v = np.full(ntr, e.params["l"])
+        v[1:] *= 1.0 + 0.1*rng.standard_normal(ntr - 1)
+        ov[(P_IND_L, i)] = v
+    compare(d, ntr, ov, min_same=0.9)
+
+
 def test_single_trial_batch():
     compare(ring_oscillator(3), 1)
 

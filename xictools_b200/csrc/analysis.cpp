@@ -150,8 +150,8 @@ void build_pwl(const double *coef, int num, std::vector<double> &pts, std::vecto
 int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
 {
     const b200_options &o = dk->opt;
-    if (dk->nmut || dk->njj) {
-        err = "mutual inductor / JJ devices are not built yet (SURVEY.md section 8 rows a4-a6)";
+    if (dk->njj) {
+        err = "JJ devices are not built yet (SURVEY.md section 8 rows a4-a5)";
         return B200_E_UNSUPP;
     }
     an.n = 0;
@@ -186,6 +186,10 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     std::vector<int> mos_coo((size_t)M.n*MT_NSTAMP, -1), cap_coo((size_t)Cp.n*4, -1);
     std::vector<int> res_coo((size_t)dk->nres*4, -1), src_coo((size_t)S.n*4, -1);
     std::vector<int> ind_coo((size_t)L.n*5, -1);
+    MutTopo &MU = an.mut;
+    MU.n = dk->nmut; MU.ind1.resize(MU.n); MU.ind2.resize(MU.n); MU.k.resize(MU.n);
+    MU.cslot.assign((size_t)MU.n*2, -1);
+    std::vector<int> mut_coo((size_t)MU.n*2, -1);
     std::vector<double> res_g(dk->nres, 0.0);
     std::vector<char> mos_has_dcon(M.n, 0), mos_has_scon(M.n, 0);
 
@@ -277,9 +281,33 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             c[0] = coo.add(br, br); c[1] = coo.add(in.pos, br); c[2] = coo.add(in.neg, br);
             c[3] = coo.add(br, in.neg); c[4] = coo.add(br, in.pos);
             break; }
+        case B200_DEV_MUT:
+            break;              // set up after the inductors, below
         default:
             err = "unsupported device kind in load order";
             return B200_E_UNSUPP;
+        }
+    }
+    // mutual inductors: INDdev::setup does them after all inductors (indset.cc:186-238)
+    L.mptr.assign(L.n + 1, 0);
+    {
+        std::vector<std::vector<std::pair<int,double>>> per(L.n);
+        for (int oi = 0; oi < dk->norder; oi++) {
+            if (dk->order_kind[oi] != B200_DEV_MUT) continue;
+            int i = dk->order_index[oi];
+            const b200_mut &in = dk->mut[i];
+            if (in.ind1 < 0 || in.ind1 >= L.n || in.ind2 < 0 || in.ind2 >= L.n) {
+                err = "mutual inductor refers to an unknown inductor"; return B200_E_BADPARM;
+            }
+            MU.ind1[i] = in.ind1; MU.ind2[i] = in.ind2; MU.k[i] = in.k;
+            mut_coo[(size_t)i*2] = coo.add(L.branch[in.ind1], L.branch[in.ind2]);
+            mut_coo[(size_t)i*2 + 1] = coo.add(L.branch[in.ind2], L.branch[in.ind1]);
+            per[in.ind1].push_back({in.ind2, in.k});
+            per[in.ind2].push_back({in.ind1, in.k});
+        }
+        for (int i = 0; i < L.n; i++) {
+            L.mptr[i+1] = L.mptr[i] + (int)per[i].size();
+            for (auto &pr : per[i]) { L.mother.push_back(pr.first); L.mk.push_back(pr.second); }
         }
     }
 
@@ -382,6 +410,11 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
                 rs[0] = add_r(Cp.pos[i]); rs[1] = add_r(Cp.neg[i]);
             }
             break; }
+        case B200_DEV_MUT:
+            // mutload.cc: ldadd(br1br2, -factor), ldadd(br2br1, -factor)
+            MU.cslot[(size_t)i*2] = add_c(mut_coo[(size_t)i*2]);
+            MU.cslot[(size_t)i*2 + 1] = add_c(mut_coo[(size_t)i*2 + 1]);
+            break;
         case B200_DEV_IND:
             // indload.cc: rhsadd(brEq, veq) then ldadd(ibrIbr, -req)
             L.rslot[i] = add_r(L.branch[i]);
@@ -910,6 +943,7 @@ void b200_build_stream_asm(Analysis &an)
     remap(an.cap.cslot, newc); remap(an.cap.rslot, newr);
     remap(an.src.rslot, newr);
     remap(an.ind.cslot, newc); remap(an.ind.rslot, newr);
+    remap(an.mut.cslot, newc);
 
     // chunk schedule
     int nchunks = (an.NC + SEG_CHUNK - 1)/SEG_CHUNK;

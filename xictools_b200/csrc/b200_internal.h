@@ -100,6 +100,16 @@ struct IndTopo {
     std::vector<int> cslot;                     // [n] (br,br) contribution: -req
     std::vector<int> rslot;                     // [n] branch row: veq
     std::vector<int> icgiven; std::vector<double> ic;
+    // couplings onto each inductor, in MUT load order (mutload.cc adds the cross flux to the
+    // inductor's state before the inductor itself loads): CSR over inductors
+    std::vector<int> mptr, mother;              // other inductor of the pair
+    std::vector<double> mk;                     // coupling coefficient
+};
+struct MutTopo {
+    int n = 0;
+    std::vector<int> ind1, ind2;
+    std::vector<double> k;
+    std::vector<int> cslot;                     // [2n]: (br1,br2), (br2,br1)
 };
 struct SrcTopo {
     int n = 0;
@@ -178,7 +188,7 @@ struct Analysis {
     std::vector<double> ic_val, ns_val;
     int hadNodeset = 0;
     // device tables
-    MosTopo mos; CapTopo cap; SrcTopo src; IndTopo ind;
+    MosTopo mos; CapTopo cap; SrcTopo src; IndTopo ind; MutTopo mut;
     int nres = 0;
     // ordering: position -> original (0-based)
     std::vector<int> rowperm, colperm;

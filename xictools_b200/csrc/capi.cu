@@ -287,6 +287,10 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Li.cslot = b->dupload(lt.cslot); Li.rslot = b->dupload(lt.rslot);
     Li.req = b->dalloc<double>((size_t)lt.n*ldt); Li.veq = b->dalloc<double>((size_t)lt.n*ldt);
     Li.prevFlux = b->dalloc<double>((size_t)lt.n*ldt);
+    Li.mptr = b->dupload(lt.mptr); Li.mother = b->dupload(lt.mother); Li.mk = b->dupload(lt.mk);
+    Li.nmut = an.mut.n;
+    Li.mut1 = b->dupload(an.mut.ind1); Li.mut2 = b->dupload(an.mut.ind2);
+    Li.mut_cslot = b->dupload(an.mut.cslot); Li.mutk = b->dupload(an.mut.k);
     SrcView &S = b->S; SrcTopo &st = an.src;
     S.n = st.n;
     S.kind = b->dupload(st.kind); S.fn = b->dupload(st.fn); S.dcgiven = b->dupload(st.dcgiven);
@@ -591,7 +595,7 @@ static int run_analysis(b200_batch *b, int analysis)
     CK(cudaEventCreate(&e_begin)); CK(cudaEventCreate(&e_end));
     long long launches = 0, ticks = 0, load_launches = 0, solve_launches = 0;
     double ms_load = 0, ms_solve = 0;
-    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->S.n ? 1 : 0);
+    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->Cp.L.nmut ? 1 : 0) + (b->S.n ? 1 : 0);
 
     CK(cudaEventRecord(e_begin, st));
     // tick 0: begin + first load

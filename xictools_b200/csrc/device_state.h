@@ -106,6 +106,9 @@ struct IndView {
     const int *branch, *state, *cslot, *rslot;
     ParamRef induct, ic;
     double *req, *veq, *prevFlux;   // [n][ldt]  (INDreq / INDveq / INDprevFlux instance fields)
+    // couplings onto each inductor in MUT load order (CSR), and the mutual stamps
+    const int *mptr, *mother; const double *mk;
+    int nmut; const int *mut1, *mut2, *mut_cslot; const double *mutk;
 };
 struct CapView {
     int n;

@@ -331,8 +331,15 @@ k_load_ind(Consts K, HotView hot, VecView V, IndView L, const double *rhsOld)
         size_t at = (size_t)i*K.ldt + t;
         if (mode & MODEINITFLOAT) {
             double prev = L.prevFlux[at];
+            double f0 = ST(c, 0, st);
+            // MUTdev::load runs first (mutload.cc:96-104): cross fluxes, in MUT load order
+            for (int q = L.mptr[i]; q < L.mptr[i+1]; q++) {
+                int o = L.mother[q];
+                double factor = L.mk[q]*sqrt(induct*PR(L.induct, o, t));
+                f0 += factor*rhsOld[(size_t)L.branch[o]*K.ldt + t];
+            }
             double flux = induct*rhsOld[(size_t)br*K.ldt + t] - prev;
-            double f0 = ST(c, 0, st) + flux;
+            f0 = f0 + flux;
             ST(c, 0, st) = f0;
             L.prevFlux[at] = f0;
             veq = L.veq[at];
@@ -360,7 +367,15 @@ k_load_ind(Consts K, HotView hot, VecView V, IndView L, const double *rhsOld)
                 ival = PR(L.ic, i, t);
             else
                 ival = rhsOld[(size_t)br*K.ldt + t];
-            ST(c, 1, st) = ST(c, 1, st) + induct*ival;
+            double f1 = ST(c, 1, st);
+            for (int q = L.mptr[i]; q < L.mptr[i+1]; q++) {
+                // mutload.cc:118-133
+                int o = L.mother[q];
+                double factor = L.mk[q]*sqrt(induct*PR(L.induct, o, t));
+                double io = (mode & MODEUIC) ? PR(L.ic, o, t) : rhsOld[(size_t)L.branch[o]*K.ldt + t];
+                f1 += factor*io;
+            }
+            ST(c, 1, st) = f1 + induct*ival;
             L.prevFlux[at] = 0.0;
             ST(c, 0, st) = 0.0;
             req = c.ag[0]*induct;
@@ -371,6 +386,26 @@ k_load_ind(Consts K, HotView hot, VecView V, IndView L, const double *rhsOld)
     // DC modes: nothing but the preloaded +-1 (the branch equation shorts the inductor)
     if (rs >= 0) V.contrib[CADDR(K, rs, t)] = veq;
     if (cs >= 0) V.contrib[CADDR(K, cs, t)] = -req;
+}
+
+__global__ void __launch_bounds__(128)
+k_load_mut(Consts K, HotView hot, VecView V, IndView L)
+{
+    // mutload.cc:55-140, matrix part (the flux part runs inside k_load_ind, in load order)
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t >= K.ntrials) return;
+    int mode = hot.mode[t];
+    if (!mode) return;
+    double v = 0.0;
+    if (!(mode & MODEDC) && (mode & (MODEINITFLOAT | MODEINITPRED | MODEINITTRAN))) {
+        double factor = L.mutk[i]*sqrt(PR(L.induct, L.mut1[i], t)*PR(L.induct, L.mut2[i], t));
+        factor *= hot.ag[t];
+        v = -factor;
+    }
+    int c0 = L.mut_cslot[2*i], c1 = L.mut_cslot[2*i + 1];
+    if (c0 >= 0) V.contrib[CADDR(K, c0, t)] = v;
+    if (c1 >= 0) V.contrib[CADDR(K, c1, t)] = v;
 }
 
 __global__ void __launch_bounds__(128)
@@ -1059,6 +1094,7 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
         else k_load_mos<6><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
     }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
+    if (Cp.L.nmut) k_load_mut<<<grid2(K.ntrials, Cp.L.nmut), 128, 0, st>>>(K, hot, V, Cp.L);
     if (Cp.L.n) k_load_ind<<<grid2(K.ntrials, Cp.L.n), 128, 0, st>>>(K, hot, V, Cp.L, rhsOld);
     if (S.n) k_load_src<<<grid2(K.ntrials, S.n), 128, 0, st>>>(K, hot, V, S);
 }

@@ -193,6 +193,12 @@ class Deck:
                                 dict(l=float(l), ic=ic)))
         return self
 
+    def mutual(self, name, l1, l2, k):
+        """Mutual inductor coupling `k` between inductors named l1 and l2 (mutprse.cc)."""
+        self.elems.append(_Elem(DEV_MUT, name.lower(), (), dict(l1=l1.lower(), l2=l2.lower(),
+                                                                  k=float(k))))
+        return self
+
     def mos_model(self, name, mtype, level=1, **params):
         self.mos_models[name.lower()] = dict(type=+1 if mtype.lower().startswith("n") else -1,
                                              level=level, params=dict(params))
@@ -314,6 +320,8 @@ class Deck:
                 if e.params.get("ic") is not None:
                     s += f" ic={_fmt(e.params['ic'])}"
                 lines.append(s)
+            elif e.kind == DEV_MUT:
+                lines.append(f"{e.name} {e.params['l1']} {e.params['l2']} {_fmt(e.params['k'])}")
             elif e.kind == DEV_MOS:
                 mname = e.model
                 mod_over = {pid: overrides[(pid, i)] for pid in
@@ -478,7 +486,13 @@ class Deck:
                           NAN if ic is None else ic)
         keep.append(ind)
         d.nind, d.ind = len(tabs[DEV_IND]), ind
-        d.nmut = d.njjmod = d.njj = 0
+        inames = [e.name for e in tabs[DEV_IND]]
+        mut = (CMut * max(1, len(tabs[DEV_MUT])))()
+        for i, e in enumerate(tabs[DEV_MUT]):
+            mut[i] = CMut(inames.index(e.params["l1"]), inames.index(e.params["l2"]), e.params["k"])
+        keep.append(mut)
+        d.nmut, d.mut = len(tabs[DEV_MUT]), mut
+        d.njjmod = d.njj = 0
         order = self.load_order()
         d.norder = len(order)
         d.order_kind = arr(C.c_int, [k for k, _ in order])
