@@ -94,6 +94,7 @@ typedef struct b200_mos_model {
     double vto, kp, gamma, phi, lambda, rd, rs, cbd, cbs, is, pb, cgso, cgdo, cgbo;
     double rsh, cj, mj, cjsw, mjsw, js, tox, ld, u0, fc, nsub, tpg, nss, tnom;
     double nfs, delta, uexp, ucrit, vmax, xj, neff, eta, theta, kappa;   /* level 2/3 */
+    double kv, nv, kc, nc, lamda0, lamda1, sigma, gamma1;                /* level 6 (moseq.cc:1091) */
 } b200_mos_model;
 typedef struct b200_mos {
     int d, g, s, b;             /* external node numbers (0 = ground) */

@@ -563,6 +563,14 @@ static void mos_setup(wo_ckt *c, Mos *m, int idx)
     if (!GIVEN(md->js)) md->js = 0;
     if (!GIVEN(md->ld)) md->ld = 0;
     if (!GIVEN(md->fc)) md->fc = .5;
+    /* level 6, mosset.cc:255-272 (the "given" tests of lambda / kc are made on the deck card) */
+    if (!GIVEN(md->kv)) md->kv = 2;
+    if (!GIVEN(md->nv)) md->nv = 0.5;
+    if (!GIVEN(md->nc)) md->nc = 1;
+    if (!GIVEN(md->lamda0)) md->lamda0 = GIVEN(md->lambda) ? md->lambda : 0;
+    if (!GIVEN(md->lamda1)) md->lamda1 = 0;
+    if (!GIVEN(md->sigma)) md->sigma = 0;
+    if (!GIVEN(md->gamma1)) md->gamma1 = 0;
     if (!GIVEN(md->lambda)) md->lambda = 0;
 
     m->mode = 1;
@@ -662,6 +670,7 @@ static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
 
     double tox = GIVEN(deckmod->tox) ? deckmod->tox : ((md->level == 2 || md->level == 3) ? 1e-7 : 0);
     double kp = md->kp;      /* may be NaN = not given */
+    double kc = md->kc;      /* level 6; default 5e-5 (mosset.cc:260-261) */
     int skip = 0;
     if (!GIVEN(deckmod->tox) || tox == 0) {
         if (md->level == 1 || md->level == 6) {
@@ -674,7 +683,11 @@ static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
     if (!skip) {
         m->oxideCapFactor = 3.9*8.854214871e-12/tox;
         m->surfaceMobility = GIVEN(deckmod->u0) ? deckmod->u0 : 600;
-        if (!GIVEN(kp))
+        if (md->level == 6) {
+            if (!GIVEN(kc))
+                kc = .5*m->surfaceMobility*m->oxideCapFactor*M2PCM2;     /* mostemp.cc:100-105 */
+        }
+        else if (!GIVEN(kp))
             kp = m->surfaceMobility*m->oxideCapFactor*M2PCM2;
         if (GIVEN(deckmod->nsub)) {
             /* mos_dopsetup, mostemp.cc:303-358 */
@@ -717,6 +730,10 @@ static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
         m->surfaceMobility = GIVEN(deckmod->u0) ? deckmod->u0 : 0;
     if (!GIVEN(kp))
         kp = 2e-5;                       /* mosset.cc:101-103 */
+    if (!GIVEN(kc))
+        kc = 5e-5;
+    if (md->level == 6)
+        kp = kc;                         /* mostemp.cc:156-159: tTransconductance = kc*tmp */
     m->kp_eff = kp;
     double cj = GIVEN(deckmod->cj) ? deckmod->cj : 0;
     double cjsw = GIVEN(deckmod->cjsw) ? deckmod->cjsw : 0;
@@ -1016,7 +1033,9 @@ int wo_set_param(wo_ckt *c, int param, int index, double value)
 {
     switch (param) {
     case B200_P_MOS_VTO:    c->mos[index].mod.vto = value; break;
-    case B200_P_MOS_KP:     c->mos[index].mod.kp = value; break;
+    case B200_P_MOS_KP:     /* level 6: the transconductance card is kc */
+        if (c->mos[index].mod.level == 6) c->mos[index].mod.kc = value; else c->mos[index].mod.kp = value;
+        break;
     case B200_P_MOS_GAMMA:  c->mos[index].mod.gamma = value; break;
     case B200_P_MOS_LAMBDA: c->mos[index].mod.lambda = value; break;
     case B200_P_MOS_PHI:    c->mos[index].mod.phi = value; break;
@@ -1397,6 +1416,57 @@ static double mos_eq1(Mos *m, MosStuff *ms)
     return cdrain;
 }
 
+static double mos_eq6(Mos *m, MosStuff *ms)
+{
+    /* moseq.cc:1091-1172: n-th power law model */
+    const b200_mos_model *md = &m->mod;
+    double lvds, lvbs, lvgs;
+    if (m->mode > 0) { lvbs = ms->vbs; lvds = ms->vds; lvgs = ms->vgs; }
+    else { lvbs = ms->vbd; lvds = -ms->vds; lvgs = ms->vgd; }
+    double sarg;
+    if (lvbs <= 0)
+        sarg = sqrt(m->tPhi - lvbs);
+    else {
+        sarg = sqrt(m->tPhi);
+        sarg = sarg - lvbs/(sarg+sarg);
+        sarg = SPMAX(0, sarg);
+    }
+    ms->von = (m->tVbi*md->type) + md->gamma*sarg - md->gamma1*lvbs - md->sigma*lvds;
+    double vgon = lvgs - ms->von;
+    double cdrain;
+    if (vgon <= 0) {
+        ms->vdsat = 0; m->gm = 0; m->gds = 0; m->gmbs = 0; cdrain = 0;
+    }
+    else {
+        double vonbm;
+        if (sarg <= 0)
+            vonbm = 0;
+        else if (lvbs <= 0)
+            vonbm = md->gamma1 + md->gamma/(sarg + sarg);
+        else
+            vonbm = md->gamma1 + .5*md->gamma/sqrt(m->tPhi);
+        sarg = log(vgon);
+        ms->vdsat = md->kv*exp(sarg*md->nv);
+        double idsat = m->beta*exp(sarg*md->nc);
+        double lambda = md->lamda0 - md->lamda1*lvbs;
+        cdrain = idsat*(1 + lambda*lvds);
+        m->gm = cdrain*md->nc/vgon;
+        m->gds = m->gm*md->sigma + idsat*lambda;
+        m->gmbs = m->gm*vonbm - idsat*md->lamda1*lvds;
+        if (ms->vdsat > lvds) {
+            double vdst = lvds/ms->vdsat;
+            double vdst2 = (2 - vdst)*vdst;
+            double vdstg = -vdst*md->nv/vgon;
+            double ivdst1 = cdrain*(2 - vdst - vdst);
+            cdrain = cdrain*vdst2;
+            m->gm = m->gm*vdst2 + ivdst1*vdstg;
+            m->gds = m->gds*vdst2 + ivdst1*(1/ms->vdsat + vdstg*md->sigma);
+            m->gmbs = m->gmbs*vdst2 + ivdst1*vdstg*vonbm;
+        }
+    }
+    return cdrain;
+}
+
 static int mos_limiting(wo_ckt *c, Mos *m, MosStuff *ms)
 {
     /* mosload.cc:346-384 */
@@ -1452,7 +1522,7 @@ static void mos_iv(wo_ckt *c, Mos *m, MosStuff *ms)
         m->cbd = m->tDrainSatCur*(evbd-1) + gmin*ms->vbd;
     }
     m->mode = (ms->vds >= 0) ? 1 : -1;
-    ms->cdrain = mos_eq1(m, ms);         /* level 1 only in the oracle */
+    ms->cdrain = (m->mod.level == 6) ? mos_eq6(m, ms) : mos_eq1(m, ms);   /* mosload.cc:570-577; levels 2/3 not restated */
     if (m->mod.type > 0) {
         m->von = ms->von; m->vdsat = ms->vdsat;
     }

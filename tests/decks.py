@@ -120,6 +120,28 @@ def transformer():
     return d
 
 
+L6 = dict(kv=0.9, nv=0.85, kc=3.8e-5, nc=1.25, phi=0.65, gamma=0.45, gamma1=0.02, sigma=0.04,
+          lambda0=0.03, lambda1=0.01, cgso=2e-10, cgdo=2e-10, cbd=2e-15, cbs=2e-15, tox=2e-8)
+
+
+def ro_level6(n=5):
+    """Ring oscillator with MOS level 6 (n-th power law, moseq.cc:1091) devices, in the style of
+    examples/mos6inv.cir."""
+    d = ring_oscillator(n)
+    d.mos_models.clear()
+    d.mos_model("nm", "nmos", level=6, vto=0.7, **L6)
+    d.mos_model("pm", "pmos", level=6, vto=-0.7, **dict(L6, kc=1.6e-5))
+    return d
+
+
+def inv_level6():
+    d = inv_chain(4)
+    d.mos_models.clear()
+    d.mos_model("nm", "nmos", level=6, vto=0.7, **L6)
+    d.mos_model("pm", "pmos", level=6, vto=-0.7, **dict(L6, kc=1.6e-5))
+    return d
+
+
 def ro_rd(n=3):
     """Ring oscillator whose MOSFETs have series rd/rs: internal drain/source nodes."""
     d = ring_oscillator(n)
@@ -154,7 +176,7 @@ def op_decks():
             "op_ro3_rd": ro_rd(3), "op_inv_dc_direct": inv_dc(3).options(gminsteps=-1, srcsteps=-1),
             "op_inv_dc_gminfirst": inv_dc(3).options(gminfirst=1),
             "op_inv7_nogmin": inv_chain(7).options(gminsteps=-1),
-            "op_inv_lsupply": inv_lsupply()}
+            "op_inv_lsupply": inv_lsupply(), "op_inv4_level6": inv_level6()}
 
 
 def variants():
@@ -165,6 +187,8 @@ def variants():
         "inv_lsupply": inv_lsupply(),
         "rlc_uic": rlc_uic(),
         "transformer": transformer(),
+        "ro5_level6": ro_level6(5),
+        "inv4_level6": inv_level6(),
         "ro3": ring_oscillator(3),
         "ro5": ring_oscillator(5),
         "ro17": ring_oscillator(17),

@@ -101,6 +101,21 @@ def test_monte_carlo_coupled_inductors():
     compare(d, ntr, ov, min_same=0.9)
 
 
+def test_monte_carlo_level6():
+    """MOS level 6 (n-th power law) ring oscillator with per-trial vto / L / kc."""
+    from xictools_b200.deck import DEV_MOS, P_MOS_KP
+    d = variants()["ro5_level6"]
+    ntr = 13
+    ov = mc_variation(d, ntr, seed=21)
+    rng = np.random.default_rng(3)
+    for i, e in enumerate(d.kind_tables()[DEV_MOS]):
+        kc = d.mos_models[e.model]["params"]["kc"]
+        v = np.full(ntr, kc)
+        v[1:] *= 1.0 + 0.05*rng.standard_normal(ntr - 1)
+        ov[(P_MOS_KP, i)] = v
+    compare(d, ntr, ov, min_same=0.9)
+
+
 def test_single_trial_batch():
     compare(ring_oscillator(3), 1)
 

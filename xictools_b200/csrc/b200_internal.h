@@ -40,7 +40,9 @@ enum { MP_tPhi, MP_tVbi, MP_tVto, MP_gamma, MP_lambda, MP_beta, MP_oxideCap,
        MP_Cbd, MP_Cbdsw, MP_Cbs, MP_Cbssw, MP_tBulkPot, MP_tDepCap,
        MP_f2d, MP_f3d, MP_f4d, MP_f2s, MP_f3s, MP_f4s,
        MP_gsOvl, MP_gdOvl, MP_gbOvl, MP_dcon, MP_scon, MP_mult, MP_vt, MP_mj, MP_mjsw,
-       MP_icVDS, MP_icVGS, MP_icVBS, MP_NPARAMS };
+       MP_icVDS, MP_icVGS, MP_icVBS,
+       MP_kv, MP_nv, MP_nc, MP_lamda0, MP_lamda1, MP_sigma, MP_gamma1,   // level 6 (moseq.cc:1091)
+       MP_NPARAMS };
 
 // ---- MOS raw (card) parameters that may vary per trial ----
 enum { MR_vto, MR_kp, MR_gamma, MR_phi, MR_lambda, MR_l, MR_w, MR_NRAW };

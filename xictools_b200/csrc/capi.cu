@@ -123,7 +123,7 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
         memset(&c, 0, sizeof(c));
         c.type = md.type > 0 ? 1 : -1;
         c.level = (md.level == 2 || md.level == 3 || md.level == 6) ? md.level : 1;
-        c.g_vto = given(md.vto); c.g_kp = given(md.kp); c.g_gamma = given(md.gamma);
+        c.g_vto = given(md.vto); c.g_kp = given(c.level == 6 ? md.kc : md.kp); c.g_gamma = given(md.gamma);
         c.g_phi = given(md.phi); c.g_tox = given(md.tox); c.g_u0 = given(md.u0);
         c.g_nsub = given(md.nsub); c.g_cbd = given(md.cbd); c.g_cbs = given(md.cbs);
         c.g_cj = given(md.cj); c.g_cjsw = given(md.cjsw); c.g_nss = given(md.nss);
@@ -142,6 +142,12 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
         c.fc = given(md.fc) ? md.fc : .5; c.nsub = given(md.nsub) ? md.nsub : 0;
         c.tpg = given(md.tpg) ? md.tpg : 1; c.nss = given(md.nss) ? md.nss : 0;
         c.tnom = given(md.tnom) ? md.tnom : o.tnom;
+        // level 6, mosset.cc:255-272
+        c.kv = given(md.kv) ? md.kv : 2; c.nv = given(md.nv) ? md.nv : 0.5;
+        c.nc = given(md.nc) ? md.nc : 1;
+        c.lamda0 = given(md.lamda0) ? md.lamda0 : (given(md.lambda) ? md.lambda : 0);
+        c.lamda1 = given(md.lamda1) ? md.lamda1 : 0; c.sigma = given(md.sigma) ? md.sigma : 0;
+        c.gamma1 = given(md.gamma1) ? md.gamma1 : 0;
         // instance, mosset.cc:283-373
         c.mult = given(in.m) ? in.m : 1.0;
         c.temp = given(in.temp) ? in.temp : o.temp;
@@ -167,7 +173,7 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
             if (!given(in.icvds)) c.icVDS = icv(in.d) - icv(in.s);
             if (!given(in.icvgs)) c.icVGS = icv(in.g) - icv(in.s);
         }
-        b->mos_raw[MR_vto][i] = md.vto; b->mos_raw[MR_kp][i] = md.kp;
+        b->mos_raw[MR_vto][i] = md.vto; b->mos_raw[MR_kp][i] = (c.level == 6) ? md.kc : md.kp;
         b->mos_raw[MR_gamma][i] = md.gamma; b->mos_raw[MR_phi][i] = md.phi;
         b->mos_raw[MR_lambda][i] = given(md.lambda) ? md.lambda : 0;
         b->mos_raw[MR_l][i] = given(in.l) ? in.l : (o.defl > 0 ? o.defl : 1e-6);
@@ -270,7 +276,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     M.n = mt.n;
     M.d = b->dupload(mt.d); M.g = b->dupload(mt.g); M.s = b->dupload(mt.s); M.b = b->dupload(mt.b);
     M.dp = b->dupload(mt.dp); M.sp = b->dupload(mt.sp); M.type = b->dupload(mt.type);
-    M.off = b->dupload(mt.off); M.state = b->dupload(mt.state);
+    M.off = b->dupload(mt.off); M.state = b->dupload(mt.state); M.level = b->dupload(mt.level);
     M.cslot = b->dupload(mt.cslot); M.rslot = b->dupload(mt.rslot);
     M.cache = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);
     M.save = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);

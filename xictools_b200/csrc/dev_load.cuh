@@ -314,13 +314,20 @@ __device__ inline double dev_fetlim(double vnew, double vold, double vto)
 // registers while the model is evaluated.  Derived parameters are either per-trial rows of the
 // same staging area or values shared by all trials (MosStageMap tells which).
 struct MosInst {
-    int type, off, st, mode;
+    int type, off, st, mode, level;
     int g, b, dp, sp;
     double *col;            // staging column of this thread
     const double *shp;      // staging area base (shared parameter block addressed from here)
     const MosStageMap *map;
     __device__ __forceinline__ double P(int k) const { return (map->ts[k] ? col : shp)[map->off[k]]; }
     __device__ __forceinline__ double &R(int row) const { return col[row*MOS_TPB]; }
+    __device__ __forceinline__ double kv() const { return P(MP_kv); }
+    __device__ __forceinline__ double nv() const { return P(MP_nv); }
+    __device__ __forceinline__ double nc() const { return P(MP_nc); }
+    __device__ __forceinline__ double lamda0() const { return P(MP_lamda0); }
+    __device__ __forceinline__ double lamda1() const { return P(MP_lamda1); }
+    __device__ __forceinline__ double sigma() const { return P(MP_sigma); }
+    __device__ __forceinline__ double gamma1() const { return P(MP_gamma1); }
     __device__ __forceinline__ double &s1(int k) const { return col[(SR_S1 + k)*MOS_TPB]; }
     __device__ __forceinline__ double &s0(int k) const { return col[(SR_S0 + k)*MOS_TPB]; }
     __device__ __forceinline__ double tPhi() const { return P(MP_tPhi); }
@@ -484,6 +491,59 @@ __device__ inline double dev_mos_eq1(MosInst &m, MosStuff &ms)
     return cdrain;
 }
 
+// moseq.cc:1091-1172: level 6, n-th power law
+__device__ inline double dev_mos_eq6(MosInst &m, MosStuff &ms)
+{
+    double lvds, lvbs, lvgs;
+    if (m.mode > 0) { lvbs = ms.vbs; lvds = ms.vds; lvgs = ms.vgs; }
+    else { lvbs = ms.vbd; lvds = -ms.vds; lvgs = ms.vgd; }
+    double tPhi = m.tPhi(), gamma = m.gamma(), gamma1 = m.gamma1(), sigma = m.sigma();
+    double sarg;
+    if (lvbs <= 0)
+        sarg = sqrt(tPhi - lvbs);
+    else {
+        sarg = sqrt(tPhi);
+        sarg = sarg - lvbs/(sarg+sarg);
+        sarg = DMAX(0, sarg);
+    }
+    ms.von = (m.tVbi()*m.type) + gamma*sarg - gamma1*lvbs - sigma*lvds;
+    double vgon = lvgs - ms.von;
+    double cdrain;
+    if (vgon <= 0) {
+        ms.vdsat = 0; m.gm() = 0; m.gds() = 0; m.gmbs() = 0; cdrain = 0;
+    }
+    else {
+        double vonbm;
+        if (sarg <= 0)
+            vonbm = 0;
+        else if (lvbs <= 0)
+            vonbm = gamma1 + gamma/(sarg + sarg);
+        else
+            vonbm = gamma1 + .5*gamma/sqrt(tPhi);
+        double nv = m.nv(), nc = m.nc(), lamda1 = m.lamda1();
+        sarg = log(vgon);
+        ms.vdsat = m.kv()*exp(sarg*nv);
+        double idsat = m.beta()*exp(sarg*nc);
+        double lambda = m.lamda0() - lamda1*lvbs;
+        cdrain = idsat*(1 + lambda*lvds);
+        double gm = cdrain*nc/vgon;
+        double gds = gm*sigma + idsat*lambda;
+        double gmbs = gm*vonbm - idsat*lamda1*lvds;
+        if (ms.vdsat > lvds) {
+            double vdst = lvds/ms.vdsat;
+            double vdst2 = (2 - vdst)*vdst;
+            double vdstg = -vdst*nv/vgon;
+            double ivdst1 = cdrain*(2 - vdst - vdst);
+            cdrain = cdrain*vdst2;
+            gm = gm*vdst2 + ivdst1*vdstg;
+            gds = gds*vdst2 + ivdst1*(1/ms.vdsat + vdstg*sigma);
+            gmbs = gmbs*vdst2 + ivdst1*vdstg*vonbm;
+        }
+        m.gm() = gm; m.gds() = gds; m.gmbs() = gmbs;
+    }
+    return cdrain;
+}
+
 __device__ inline int dev_mos_limiting(const TrialCtx &c, MosInst &m, MosStuff &ms, int oldlimit)
 {
     double s0vds = m.o_vds(), s0vgs = m.o_vgs();
@@ -536,7 +596,7 @@ __device__ inline void dev_mos_iv(MosInst &m, MosStuff &ms, double gmin)
         m.cbd() = m.tDrainSatCur()*(evbd-1) + gmin*ms.vbd;
     }
     m.mode = (ms.vds >= 0) ? 1 : -1;
-    ms.cdrain = dev_mos_eq1(m, ms);
+    ms.cdrain = (m.level == 6) ? dev_mos_eq6(m, ms) : dev_mos_eq1(m, ms);   // mosload.cc:570-577
     if (m.type > 0) {
         m.von() = ms.von; m.vdsat() = ms.vdsat;
     }
@@ -980,6 +1040,7 @@ struct MosCard {            // per instance, shared by all trials (device array)
         tpg, nss, tnom;
     double drainArea, sourceArea, drainPerimeter, sourcePerimeter, mult, temp;
     double dcon, scon, icVDS, icVGS, icVBS;
+    double kv, nv, nc, lamda0, lamda1, sigma, gamma1;    // level 6
 };
 
 // raw[] = vto kp gamma phi lambda l w (NaN = not given for vto/kp/gamma/phi)
@@ -1017,7 +1078,9 @@ __device__ inline void dev_mos_temp(const MosCard &k, const double *raw, double 
         oxideCapFactor = 3.9*8.854214871e-12/tox;
         surfaceMobility = k.g_u0 ? k.u0 : 600;
         if (!have_kp) {
-            kp = surfaceMobility*oxideCapFactor*M2PCM2;
+            // level 6: the raw "kp" slot carries kc (mostemp.cc:100-111)
+            if (k.level == 6) kp = .5*surfaceMobility*oxideCapFactor*M2PCM2;
+            else kp = surfaceMobility*oxideCapFactor*M2PCM2;
             have_kp = 1;
         }
         if (k.g_nsub) {
@@ -1059,7 +1122,7 @@ __device__ inline void dev_mos_temp(const MosCard &k, const double *raw, double 
     else
         surfaceMobility = k.g_u0 ? k.u0 : 0;
     if (!have_kp)
-        kp = 2e-5;
+        kp = (k.level == 6) ? 5e-5 : 2e-5;       // mosset.cc:101-103, 260-261
 
     double temp = k.temp;
     double fact2 = temp/REFTEMP;
@@ -1156,6 +1219,8 @@ __device__ inline void dev_mos_temp(const MosCard &k, const double *raw, double 
     out[MP_gsOvl] = k.cgso*w; out[MP_gdOvl] = k.cgdo*w; out[MP_gbOvl] = k.cgbo*effectiveLength;
     out[MP_dcon] = k.dcon; out[MP_scon] = k.scon; out[MP_mult] = k.mult; out[MP_vt] = vt;
     out[MP_mj] = k.mj; out[MP_mjsw] = k.mjsw;
+    out[MP_kv] = k.kv; out[MP_nv] = k.nv; out[MP_nc] = k.nc; out[MP_lamda0] = k.lamda0;
+    out[MP_lamda1] = k.lamda1; out[MP_sigma] = k.sigma; out[MP_gamma1] = k.gamma1;
     out[MP_icVDS] = k.icVDS; out[MP_icVGS] = k.icVGS; out[MP_icVBS] = k.icVBS;
 }
 

@@ -91,7 +91,7 @@ struct Consts {
 
 struct MosView {
     int n;
-    const int *d, *g, *s, *b, *dp, *sp, *type, *off, *state, *cslot, *rslot;
+    const int *d, *g, *s, *b, *dp, *sp, *type, *off, *state, *level, *cslot, *rslot;
     ParamRef prm[MP_NPARAMS];
     double *cache;      // [MC_NCACHE][n][ldt]
     double *save;       // backup copy of cache

@@ -85,7 +85,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     // trials that are finished (or past the end) stage nothing but still meet the barrier
     TrialCtx c;
     MosInst m;
-    m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i];
+    m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i]; m.level = M.level[i];
     m.g = M.g[i]; m.b = M.b[i]; m.dp = M.dp[i]; m.sp = M.sp[i];
     m.col = stage + tid; m.shp = stage; m.map = &map;
     const int st = m.st;

@@ -75,7 +75,8 @@ class CSrc(C.Structure):
 MOS_MODEL_DBL = ("vto", "kp", "gamma", "phi", "lambda_", "rd", "rs", "cbd", "cbs", "is_", "pb",
                  "cgso", "cgdo", "cgbo", "rsh", "cj", "mj", "cjsw", "mjsw", "js", "tox", "ld",
                  "u0", "fc", "nsub", "tpg", "nss", "tnom", "nfs", "delta", "uexp", "ucrit",
-                 "vmax", "xj", "neff", "eta", "theta", "kappa")
+                 "vmax", "xj", "neff", "eta", "theta", "kappa",
+                 "kv", "nv", "kc", "nc", "lamda0", "lamda1", "sigma", "gamma1")
 
 
 class CMosModel(C.Structure):
@@ -332,6 +333,8 @@ class Deck:
                     prm = dict(base["params"])
                     key = {P_MOS_VTO: "vto", P_MOS_KP: "kp", P_MOS_GAMMA: "gamma",
                            P_MOS_LAMBDA: "lambda", P_MOS_PHI: "phi"}
+                    if base["level"] == 6:
+                        key[P_MOS_KP] = "kc"
                     for pid, v in mod_over.items():
                         prm[key[pid]] = v
                     mname = f"{e.model}_{e.name}"
@@ -451,7 +454,7 @@ class Deck:
 
         mnames = list(self.mos_models)
         mm = (CMosModel * max(1, len(mnames)))()
-        alias = {"lambda": "lambda_", "is": "is_"}
+        alias = {"lambda": "lambda_", "is": "is_", "lambda0": "lamda0", "lambda1": "lamda1"}
         for i, nme in enumerate(mnames):
             m = self.mos_models[nme]
             mm[i].type, mm[i].level = m["type"], m["level"]
