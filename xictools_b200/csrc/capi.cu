@@ -277,6 +277,8 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     M.d = b->dupload(mt.d); M.g = b->dupload(mt.g); M.s = b->dupload(mt.s); M.b = b->dupload(mt.b);
     M.dp = b->dupload(mt.dp); M.sp = b->dupload(mt.sp); M.type = b->dupload(mt.type);
     M.off = b->dupload(mt.off); M.state = b->dupload(mt.state); M.level = b->dupload(mt.level);
+    M.has_level6 = 0;
+    for (int lv : mt.level) if (lv == 6) M.has_level6 = 1;
     M.cslot = b->dupload(mt.cslot); M.rslot = b->dupload(mt.rslot);
     M.cache = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);
     M.save = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);

@@ -90,7 +90,7 @@ struct Consts {
 };
 
 struct MosView {
-    int n;
+    int n, has_level6;
     const int *d, *g, *s, *b, *dp, *sp, *type, *off, *state, *level, *cslot, *rslot;
     ParamRef prm[MP_NPARAMS];
     double *cache;      // [MC_NCACHE][n][ldt]

@@ -69,7 +69,7 @@ __device__ __forceinline__ void make_ctx(TrialCtx &c, const Consts &K, const Hot
 // thread, nothing parked in registers.  Stage 2: the model is evaluated out of shared memory;
 // state-0 results and stamps go straight to HBM, the operating point is updated in place in
 // the staging area and written back at the end.
-template <int MINB>
+template <int MINB, bool L6>
 __global__ void __launch_bounds__(MOS_TPB, MINB)
 k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, const double *rhsOld)
 {
@@ -85,7 +85,8 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     // trials that are finished (or past the end) stage nothing but still meet the barrier
     TrialCtx c;
     MosInst m;
-    m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i]; m.level = M.level[i];
+    m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i];
+    m.level = L6 ? M.level[i] : 1;               // decks without level-6 devices get the lean kernel
     m.g = M.g[i]; m.b = M.b[i]; m.dp = M.dp[i]; m.sp = M.sp[i];
     m.col = stage + tid; m.shp = stage; m.map = &map;
     const int st = m.st;
@@ -1078,20 +1079,16 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
     const MosView &M, const CapView &Cp, const SrcView &S, const double *rhsOld)
 {
     if (M.n) {
-        static int minb = -1;
-        if (minb < 0) { const char *e = getenv("B200_LOAD_MINB"); minb = e ? atoi(e) : 7; }
         size_t smem = (size_t)M.stage_doubles*sizeof(double);
         static size_t configured = 0;
         if (smem > configured) {
-            cudaFuncSetAttribute(k_load_mos<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
         dim3 g((K.ntrials + MOS_TPB - 1)/MOS_TPB, M.n);
-        if (minb >= 8) k_load_mos<8><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-        else if (minb == 7) k_load_mos<7><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-        else k_load_mos<6><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        if (M.has_level6) k_load_mos<7, true><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        else k_load_mos<7, false><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
     }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
     if (Cp.L.nmut) k_load_mut<<<grid2(K.ntrials, Cp.L.nmut), 128, 0, st>>>(K, hot, V, Cp.L);
