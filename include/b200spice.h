@@ -213,6 +213,12 @@ int  b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, i
                            const double *rhsold /* [n+1][ntrials] or NULL */,
                            double *Ax, double *rhs);
 
+/* Test hook: the LTE divided differences divide by per-trial constants through a correctly
+ * rounded reciprocal + FMA refinement; this compares that sequence with IEEE division on n
+ * pseudo-random operand pairs with binary exponents in [emin, emax]. */
+int  b200_debug_divcheck(long long n, unsigned long long seed, int emin, int emax,
+                         long long *mismatches);
+
 /* ---- KLU-hook seam (batched): spMatlabMatrix::factor/refactor/solve semantics ----
  * xt_base/include/sparse/spmatrix.h:853-857; kluif.cc:569-628.  Pattern is CSC, 0-based,
  * row indices ascending per column (spbuild.cc:922-958). */

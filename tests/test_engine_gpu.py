@@ -253,3 +253,17 @@ def test_dc_sweep_every_point_is_a_trial():
     b.close()
     assert out[0] > 3.0 and out[-1] < 0.1
     assert (np.diff(out) <= 1e-9).all()
+
+
+def test_reciprocal_division_is_ieee_division():
+    """The LTE kernel divides by per-trial step constants via RN(1/b) and three FMA steps
+    (Markstein); it must return the bits of a/b.  200 M random pairs over the exponent ranges
+    the divided differences see (charges 1e-21..1e-9 over steps 1e-15..1e-6) and a wide range."""
+    import ctypes as C
+    lib = engine.load_library()
+    lib.b200_debug_divcheck.argtypes = [C.c_longlong, C.c_ulonglong, C.c_int, C.c_int,
+                                        C.POINTER(C.c_longlong)]
+    for seed, (emin, emax) in enumerate(((-70, 10), (-300, 300), (-20, 20), (-1, 1))):
+        bad = C.c_longlong(-1)
+        rc = lib.b200_debug_divcheck(50_000_000, 1234 + seed, emin, emax, C.byref(bad))
+        assert rc == 0 and bad.value == 0, (emin, emax, bad.value)

@@ -260,6 +260,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     h.nodeconv = b->dalloc<int>(ldt); h.solve_err = b->dalloc<int>(ldt);
     h.need_devconv = b->dalloc<int>(ldt); h.devconv = b->dalloc<int>(ldt);
     h.lte = b->dalloc<double>(2*ldt); h.sync = b->dalloc<int>(ldt);
+    h.lte_rcp = b->dalloc<double>((size_t)LR_NROWS*ldt);
     // ---- vectors ----
     VecView &V = b->V;
     size_t vplane = (size_t)(an.n + 1)*ldt;

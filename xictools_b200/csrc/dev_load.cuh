@@ -46,6 +46,7 @@ struct TrialCtx {
     int ldt;
     int *trapbad;           // per-trial flag
     const double *dOldp;    // &hot.deltaOld[trial]: deltaOld[k] at dOldp[k*ldt]
+    const double *rcp;      // &hot.lte_rcp[trial]: LR_* rows (terr divisors, reciprocals, reltol/delta)
     double *lte;            // &hot.lte[trial]: LTE step bounds (this order, order + 1), min-reduced
 };
 
@@ -144,6 +145,24 @@ __device__ __forceinline__ void atomic_min_pos(double *addr, double v)
     atomicMin((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
 }
 
+// a/b from a correctly rounded reciprocal y = RN(1/b) (Markstein): two FMA refinement steps leave a
+// faithful quotient, the third returns RN(a/b).  Bit-identical to the IEEE division the reference
+// executes for the finite, normal operands of the divided-difference table (checked against
+// true division on the device by tests/test_engine_gpu.py); 5 instructions instead of ~35.
+__device__ __forceinline__ double dev_div_rcp(double a, double b, double y)
+{
+    double q = a*y;
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
+}
+
+// The divisors of sCKT::terr's divided-difference table depend only on the step history of the
+// trial: the control kernel publishes them with their reciprocals (LR_* rows of hot.lte_rcp).
+enum { LR_d0, LR_d1, LR_d2, LR_e0, LR_e1, LR_f0, LR_NDIV,       // d_i = deltaOld[i], e0 = d1+d0, e1 = d2+d1, f0 = e1+d0
+       LR_CT = 2*LR_NDIV, LR_NROWS };                            // reltol/delta
+
 template <int ORDER>
 __device__ __forceinline__ double dev_terr_fixed(const TrialCtx &c, const b200_options &opt,
     const double *q, double tol, int qslot)
@@ -151,18 +170,34 @@ __device__ __forceinline__ double dev_terr_fixed(const TrialCtx &c, const b200_o
     // compile-time order: the divided-difference table lives in registers
     const double gearCoeff[] = { .5, .2222222222, .1363636364, .096, .07299270073, .05830903790 };
     const double trapCoeff[] = { .5, .08333333333 };
-    double diff[ORDER + 2], deltmp[ORDER + 1], dOld[ORDER + 1];
+    double diff[ORDER + 2];
 #pragma unroll
     for (int i = 0; i <= ORDER + 1; i++) diff[i] = (i < 4) ? q[i] : ST(c, i, qslot);
+    if (ORDER <= 2) {
+        // levels: j = ORDER: d0..d_ORDER; then e0 (, e1); then f0
+        const int lvl[3][3] = { { LR_d0, LR_d1, LR_d2 }, { LR_e0, LR_e1, -1 }, { LR_f0, -1, -1 } };
+        const size_t ldt = c.ldt;
 #pragma unroll
-    for (int i = 0; i <= ORDER; i++) { dOld[i] = c.dOldp[(size_t)i*c.ldt]; deltmp[i] = dOld[i]; }
+        for (int j = ORDER; j >= 0; j--) {
 #pragma unroll
-    for (int j = ORDER; j >= 0; j--) {
+            for (int i = 0; i <= j; i++) {
+                int row = lvl[ORDER - j][i];
+                diff[i] = dev_div_rcp(diff[i] - diff[i+1], c.rcp[(size_t)row*ldt], c.rcp[(size_t)(LR_NDIV + row)*ldt]);
+            }
+        }
+    }
+    else {
+        double deltmp[ORDER + 1], dOld[ORDER + 1];
 #pragma unroll
-        for (int i = 0; i <= j; i++) diff[i] = (diff[i] - diff[i+1])/deltmp[i];
-        if (j > 0) {
+        for (int i = 0; i <= ORDER; i++) { dOld[i] = c.dOldp[(size_t)i*c.ldt]; deltmp[i] = dOld[i]; }
 #pragma unroll
-            for (int i = 0; i <= j - 1; i++) deltmp[i] = deltmp[i+1] + dOld[i];
+        for (int j = ORDER; j >= 0; j--) {
+#pragma unroll
+            for (int i = 0; i <= j; i++) diff[i] = (diff[i] - diff[i+1])/deltmp[i];
+            if (j > 0) {
+#pragma unroll
+                for (int i = 0; i <= j - 1; i++) deltmp[i] = deltmp[i+1] + dOld[i];
+            }
         }
     }
     double del;
@@ -192,7 +227,7 @@ __device__ inline void dev_lte_charge(const TrialCtx &c, const b200_options &opt
     y0 = fabs(q[0]); y1 = fabs(q[1]);
     double chargetol = DMAX(y0, y1);
     if (chargetol < opt.chgtol) chargetol = opt.chgtol;
-    chargetol *= opt.reltol/c.delta;
+    chargetol *= c.rcp[(size_t)LR_CT*c.ldt];          // reltol/delta, published per trial
     double tol = DMAX(volttol, chargetol);
     double d0 = dev_terr_order(c, opt, c.order, q, tol, qslot);
     if (d0 < m0) m0 = d0;

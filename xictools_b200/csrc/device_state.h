@@ -75,6 +75,7 @@ struct HotView {
     int    *need_devconv;
     int    *devconv;    // 1 = device convTest failed
     // LTE
+    double *lte_rcp;    // [LR_NROWS][ldt] divisors of the LTE divided differences + reciprocals
     int    *sync;       // 1: trial is parked at a time-point boundary (or finished)
     double *lte;        // [2][ldt] min over charges for order, order+1 (un-normalised)
 };

@@ -59,6 +59,7 @@ __device__ __forceinline__ void make_ctx(TrialCtx &c, const Consts &K, const Hot
     c.base = hot.st_base[t]; c.NS = K.NS; c.numStates = K.numStates;
     c.states = V.states + t;
     c.dOldp = hot.deltaOld + t;
+    c.rcp = hot.lte_rcp + t;
     c.lte = hot.lte + t;
 }
 
@@ -874,6 +875,17 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
                 hot.lte[K.ldt + t] = DBL_MAX;
                 for (int k = 0; k <= s.order + 1 && k < 7; k++)
                     hot.deltaOld[(size_t)k*K.ldt + t] = s.deltaOld[k];
+                // divisors of terr's divided-difference table, in its own association order
+                double dv[LR_NDIV];
+                dv[LR_d0] = s.deltaOld[0]; dv[LR_d1] = s.deltaOld[1]; dv[LR_d2] = s.deltaOld[2];
+                dv[LR_e0] = dv[LR_d1] + dv[LR_d0];
+                dv[LR_e1] = dv[LR_d2] + dv[LR_d1];
+                dv[LR_f0] = dv[LR_e1] + dv[LR_d0];
+                for (int k = 0; k < LR_NDIV; k++) {
+                    hot.lte_rcp[(size_t)k*K.ldt + t] = dv[k];
+                    hot.lte_rcp[(size_t)(LR_NDIV + k)*K.ldt + t] = 1.0/dv[k];
+                }
+                hot.lte_rcp[(size_t)LR_CT*K.ldt + t] = K.opt.reltol/s.delta;
             }
         }
     }

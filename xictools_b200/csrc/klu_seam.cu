@@ -162,7 +162,47 @@ int b200_internal_views(b200_batch *b, Consts **K, HotView **hot, VecView **V, M
     CapView **Cp, SrcView **S, SolveView **Sv, cudaStream_t *st, int **cur);
 const Analysis *b200_internal_analysis(b200_batch *b);
 
+// dev_div_rcp (dev_load.cuh) against IEEE division on pseudo-random operands
+__global__ void k_divcheck(long long n, unsigned long long seed, int emin, int emax, unsigned long long *bad)
+{
+    long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // splitmix64
+    auto next = [](unsigned long long &x) {
+        x += 0x9e3779b97f4a7c15ull;
+        unsigned long long z = x;
+        z = (z ^ (z >> 30))*0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27))*0x94d049bb133111ebull;
+        return z ^ (z >> 31);
+    };
+    unsigned long long st = seed + 0x632be59bd9b4e019ull*(unsigned long long)i;
+    auto rnd = [&](void) {
+        unsigned long long m = next(st), e = next(st), sg = next(st);
+        double f = 1.0 + (double)(m >> 12)*(1.0/4503599627370496.0);      // [1,2), all 52 bits
+        int ex = emin + (int)(e % (unsigned long long)(emax - emin + 1));
+        double v = ldexp(f, ex);
+        return (sg & 1) ? -v : v;
+    };
+    double a = rnd(), b = fabs(rnd());
+    double y = 1.0/b;
+    double q = dev_div_rcp(a, b, y);
+    if (__double_as_longlong(q) != __double_as_longlong(a/b)) atomicAdd(bad, 1ull);
+}
+
 extern "C" {
+
+int b200_debug_divcheck(long long n, unsigned long long seed, int emin, int emax, long long *mismatches)
+{
+    unsigned long long *d = nullptr, h = 0;
+    CK(cudaMalloc(&d, sizeof(h)));
+    CK(cudaMemset(d, 0, sizeof(h)));
+    k_divcheck<<<(unsigned)((n + 255)/256), 256>>>(n, seed, emin, emax, d);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches = (long long)h;
+    return B200_OK;
+}
 
 int b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, int order,
     const double *rhsold, double *Ax, double *rhs)
