@@ -42,6 +42,9 @@ enum { MP_tPhi, MP_tVbi, MP_tVto, MP_gamma, MP_lambda, MP_beta, MP_oxideCap,
        MP_gsOvl, MP_gdOvl, MP_gbOvl, MP_dcon, MP_scon, MP_mult, MP_vt, MP_mj, MP_mjsw,
        MP_icVDS, MP_icVGS, MP_icVBS,
        MP_kv, MP_nv, MP_nc, MP_lamda0, MP_lamda1, MP_sigma, MP_gamma1,   // level 6 (moseq.cc:1091)
+       // correctly rounded reciprocals of divisors that are constant for a device: a/b is then
+       // formed by dev_div_rcp (bit-identical to the IEEE division, 5 instructions)
+       MP_rvt, MP_rBulkPot, MP_r1mj, MP_r1mjsw, MP_r2phi, MP_r15phi,
        MP_NPARAMS };
 
 // ---- MOS raw (card) parameters that may vary per trial ----

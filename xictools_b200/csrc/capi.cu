@@ -29,7 +29,7 @@ const int kDep[MR_NRAW][8] = {
     /* vto    */ { MP_tVbi, MP_tVto, -1 },
     /* kp     */ { MP_beta, -1 },
     /* gamma  */ { MP_gamma, MP_tVbi, MP_tVto, -1 },
-    /* phi    */ { MP_tPhi, MP_tVbi, MP_tVto, -1 },
+    /* phi    */ { MP_tPhi, MP_tVbi, MP_tVto, MP_r2phi, MP_r15phi, -1 },
     /* lambda */ { MP_lambda, -1 },
     /* l      */ { MP_beta, MP_oxideCap, MP_gbOvl, -1 },
     /* w      */ { MP_beta, MP_oxideCap, MP_gsOvl, MP_gdOvl, -1 },

@@ -257,18 +257,18 @@ __device__ inline double dev_limvds(double vnew, double vold)
     return vnew;
 }
 
-__device__ inline double dev_pnjlim(double vnew, double vold, double vt, double vcrit, int *icheck)
+__device__ inline double dev_pnjlim(double vnew, double vold, double vt, double rvt, double vcrit, int *icheck)
 {
     if (vnew > vcrit && fabs(vnew - vold) > (vt + vt)) {
         if (vold > 0) {
-            double arg = (vnew - vold)/vt;
+            double arg = dev_div_rcp(vnew - vold, vt, rvt);
             if (arg > 0)
                 vnew = vold + vt*(2.0 + log(arg - 1.8));
             else
                 vnew = vold - vt*(2.0 + log(-arg + 2.0));
         }
         else
-            vnew = vt*log(vnew/vt);
+            vnew = vt*log(dev_div_rcp(vnew, vt, rvt));
         *icheck = 1;
     }
     else {
@@ -356,6 +356,12 @@ struct MosInst {
     const MosStageMap *map;
     __device__ __forceinline__ double P(int k) const { return (map->ts[k] ? col : shp)[map->off[k]]; }
     __device__ __forceinline__ double &R(int row) const { return col[row*MOS_TPB]; }
+    __device__ __forceinline__ double rvt() const { return P(MP_rvt); }
+    __device__ __forceinline__ double rBulkPot() const { return P(MP_rBulkPot); }
+    __device__ __forceinline__ double r1mj() const { return P(MP_r1mj); }
+    __device__ __forceinline__ double r1mjsw() const { return P(MP_r1mjsw); }
+    __device__ __forceinline__ double r2phi() const { return P(MP_r2phi); }
+    __device__ __forceinline__ double r15phi() const { return P(MP_r15phi); }
     __device__ __forceinline__ double kv() const { return P(MP_kv); }
     __device__ __forceinline__ double nv() const { return P(MP_nv); }
     __device__ __forceinline__ double nc() const { return P(MP_nc); }
@@ -449,31 +455,32 @@ __device__ inline void dev_sargs(double arg, double bot, double side, double *sa
 }
 
 __device__ inline void dev_qmeyer(double vgs, double vgd, double von, double vdsat,
-    double *capgs, double *capgd, double *capgb, double phi, double cox)
+    double *capgs, double *capgd, double *capgb, double phi, double cox, double r2phi, double r15phi)
 {
     double vgst = vgs - von;
     if (vgst <= -phi) {
         *capgb = cox/2; *capgs = 0; *capgd = 0;
     }
     else if (vgst <= -phi/2) {
-        *capgb = -vgst*cox/(2*phi); *capgs = 0; *capgd = 0;
+        *capgb = dev_div_rcp(-vgst*cox, 2*phi, r2phi); *capgs = 0; *capgd = 0;
     }
     else if (vgst <= 0) {
-        *capgb = -vgst*cox/(2*phi);
-        *capgs = vgst*cox/(1.5*phi) + cox/3;
+        *capgb = dev_div_rcp(-vgst*cox, 2*phi, r2phi);
+        *capgs = dev_div_rcp(vgst*cox, 1.5*phi, r15phi) + dev_div_rcp(cox, 3.0, 1.0/3.0);
         *capgd = 0;
     }
     else {
         double vds = vgs - vgd;
         if (vdsat <= vds) {
-            *capgs = cox/3; *capgd = 0; *capgb = 0;
+            *capgs = dev_div_rcp(cox, 3.0, 1.0/3.0); *capgd = 0; *capgb = 0;
         }
         else {
             double vddif = 2.0*vdsat - vds;
             double vddif1 = vdsat - vds;
             double vddif2 = vddif*vddif;
-            *capgd = cox*(1.0 - vdsat*vdsat/vddif2)/3;
-            *capgs = cox*(1.0 - vddif1*vddif1/vddif2)/3;
+            double rv = 1.0/vddif2;              // two divisions by vddif2 share its reciprocal
+            *capgd = dev_div_rcp(cox*(1.0 - dev_div_rcp(vdsat*vdsat, vddif2, rv)), 3.0, 1.0/3.0);
+            *capgs = dev_div_rcp(cox*(1.0 - dev_div_rcp(vddif1*vddif1, vddif2, rv)), 3.0, 1.0/3.0);
             *capgb = 0;
         }
     }
@@ -598,11 +605,11 @@ __device__ inline int dev_mos_limiting(const TrialCtx &c, MosInst &m, MosStuff &
     }
     int check;
     if (ms.vds >= 0) {
-        ms.vbs = dev_pnjlim(ms.vbs, m.o_vbs(), ms.vt, m.sourceVcrit(), &check);
+        ms.vbs = dev_pnjlim(ms.vbs, m.o_vbs(), ms.vt, m.rvt(), m.sourceVcrit(), &check);
         ms.vbd = ms.vbs - ms.vds;
     }
     else {
-        ms.vbd = dev_pnjlim(ms.vbd, m.o_vbd(), ms.vt, m.drainVcrit(), &check);
+        ms.vbd = dev_pnjlim(ms.vbd, m.o_vbd(), ms.vt, m.rvt(), m.drainVcrit(), &check);
         ms.vbs = ms.vbd + ms.vds;
     }
     ms.vgb = ms.vgs - ms.vbs;
@@ -617,8 +624,9 @@ __device__ inline void dev_mos_iv(MosInst &m, MosStuff &ms, double gmin)
         m.cbs() = m.gbs()*ms.vbs - m.tSourceSatCur();
     }
     else {
-        double evbs = exp(ms.vbs/ms.vt);
-        m.gbs() = m.tSourceSatCur()*evbs/ms.vt + gmin;
+        double rvt = m.rvt();
+        double evbs = exp(dev_div_rcp(ms.vbs, ms.vt, rvt));
+        m.gbs() = dev_div_rcp(m.tSourceSatCur()*evbs, ms.vt, rvt) + gmin;
         m.cbs() = m.tSourceSatCur()*(evbs-1) + gmin*ms.vbs;
     }
     if (ms.vbd <= -3*ms.vt) {
@@ -626,8 +634,9 @@ __device__ inline void dev_mos_iv(MosInst &m, MosStuff &ms, double gmin)
         m.cbd() = m.gbd()*ms.vbd - m.tDrainSatCur();
     }
     else {
-        double evbd = exp(ms.vbd/ms.vt);
-        m.gbd() = m.tDrainSatCur()*evbd/ms.vt + gmin;
+        double rvt = m.rvt();
+        double evbd = exp(dev_div_rcp(ms.vbd, ms.vt, rvt));
+        m.gbd() = dev_div_rcp(m.tDrainSatCur()*evbd, ms.vt, rvt) + gmin;
         m.cbd() = m.tDrainSatCur()*(evbd-1) + gmin*ms.vbd;
     }
     m.mode = (ms.vds >= 0) ? 1 : -1;
@@ -649,10 +658,10 @@ __device__ inline void dev_mos_cap(const TrialCtx &c, MosInst &m, MosStuff &ms)
     const int st = m.st;
     if (m.Cbs() != 0 || m.Cbssw() != 0) {
         if (ms.vbs < m.tDepCap()) {
-            double arg = 1 - ms.vbs/m.tBulkPot(), sarg, sargsw;
+            double arg = 1 - dev_div_rcp(ms.vbs, m.tBulkPot(), m.rBulkPot()), sarg, sargsw;
             dev_sargs(arg, m.mj(), m.mjsw(), &sarg, &sargsw);
-            m.s0(MS_qbs) = m.tBulkPot()*(m.Cbs()*(1 - arg*sarg)/(1 - m.mj())
-                + m.Cbssw()*(1 - arg*sargsw)/(1 - m.mjsw()));
+            m.s0(MS_qbs) = m.tBulkPot()*(dev_div_rcp(m.Cbs()*(1 - arg*sarg), 1 - m.mj(), m.r1mj())
+                + dev_div_rcp(m.Cbssw()*(1 - arg*sargsw), 1 - m.mjsw(), m.r1mjsw()));
             m.capbs() = m.Cbs()*sarg + m.Cbssw()*sargsw;
         }
         else {
@@ -665,10 +674,10 @@ __device__ inline void dev_mos_cap(const TrialCtx &c, MosInst &m, MosStuff &ms)
     }
     if (m.Cbd() != 0 || m.Cbdsw() != 0) {
         if (ms.vbd < m.tDepCap()) {
-            double arg = 1 - ms.vbd/m.tBulkPot(), sarg, sargsw;
+            double arg = 1 - dev_div_rcp(ms.vbd, m.tBulkPot(), m.rBulkPot()), sarg, sargsw;
             dev_sargs(arg, m.mj(), m.mjsw(), &sarg, &sargsw);
-            m.s0(MS_qbd) = m.tBulkPot()*(m.Cbd()*(1 - arg*sarg)/(1 - m.mj())
-                + m.Cbdsw()*(1 - arg*sargsw)/(1 - m.mjsw()));
+            m.s0(MS_qbd) = m.tBulkPot()*(dev_div_rcp(m.Cbd()*(1 - arg*sarg), 1 - m.mj(), m.r1mj())
+                + dev_div_rcp(m.Cbdsw()*(1 - arg*sargsw), 1 - m.mjsw(), m.r1mjsw()));
             m.capbd() = m.Cbd()*sarg + m.Cbdsw()*sargsw;
         }
         else {
@@ -683,7 +692,7 @@ __device__ inline void dev_mos_cap(const TrialCtx &c, MosInst &m, MosStuff &ms)
     double vgx, vgy, cgx, cgy, cgb;
     if (m.mode > 0) { vgx = ms.vgs; vgy = ms.vgd; }
     else { vgx = ms.vgd; vgy = ms.vgs; }
-    dev_qmeyer(vgx, vgy, ms.von, ms.vdsat, &cgx, &cgy, &cgb, m.tPhi(), m.oxideCap());
+    dev_qmeyer(vgx, vgy, ms.von, ms.vdsat, &cgx, &cgy, &cgb, m.tPhi(), m.oxideCap(), m.r2phi(), m.r15phi());
     double s0capgs, s0capgd;
     if (m.mode > 0) { s0capgs = cgx; s0capgd = cgy; }
     else { s0capgd = cgx; s0capgs = cgy; }
@@ -1254,6 +1263,9 @@ __device__ inline void dev_mos_temp(const MosCard &k, const double *raw, double 
     out[MP_gsOvl] = k.cgso*w; out[MP_gdOvl] = k.cgdo*w; out[MP_gbOvl] = k.cgbo*effectiveLength;
     out[MP_dcon] = k.dcon; out[MP_scon] = k.scon; out[MP_mult] = k.mult; out[MP_vt] = vt;
     out[MP_mj] = k.mj; out[MP_mjsw] = k.mjsw;
+    out[MP_rvt] = 1.0/out[MP_vt]; out[MP_rBulkPot] = 1.0/out[MP_tBulkPot];
+    out[MP_r1mj] = 1.0/(1 - k.mj); out[MP_r1mjsw] = 1.0/(1 - k.mjsw);
+    out[MP_r2phi] = 1.0/(2*out[MP_tPhi]); out[MP_r15phi] = 1.0/(1.5*out[MP_tPhi]);
     out[MP_kv] = k.kv; out[MP_nv] = k.nv; out[MP_nc] = k.nc; out[MP_lamda0] = k.lamda0;
     out[MP_lamda1] = k.lamda1; out[MP_sigma] = k.sigma; out[MP_gamma1] = k.gamma1;
     out[MP_icVDS] = k.icVDS; out[MP_icVGS] = k.icVGS; out[MP_icVBS] = k.icVBS;
