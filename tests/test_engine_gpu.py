@@ -116,6 +116,16 @@ def test_monte_carlo_level6():
     compare(d, ntr, ov, min_same=0.9)
 
 
+@pytest.mark.parametrize("nstages", [1001, 2001])
+def test_large_circuits_use_narrower_tiles(nstages):
+    """2 002 / 4 002 MOSFETs: the LU image of 4 trials no longer fits shared memory, the solve
+    kernel runs 2 resp. 1 trial per CTA (Consts::tb) and the contribution tiles narrow with it."""
+    d = ring_oscillator(nstages)
+    ntr = 6
+    ov = mc_variation(d, ntr, seed=8)
+    compare(d, ntr, ov, trials=[0, 5])
+
+
 def test_single_trial_batch():
     compare(ring_oscillator(3), 1)
 

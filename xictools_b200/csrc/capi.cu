@@ -241,7 +241,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     K.npoints_max = an.npoints_max; K.method = deck->opt.method;
     K.nbrks = (int)an.brks.size(); K.nlat = (int)an.lat_offs.size();
 
-    if (solve_smem_bytes(K, an.seg_maxsteps) > 227*1024 || (int)an.seg_chunk.size()/2 > SOLVE_MAXCH) {
+    if (!solve_pick_tb(K, an.seg_maxsteps) || (int)an.seg_chunk.size()/2 > SOLVE_MAXCH) {
         fprintf(stderr, "b200spice: LU (%d values) + rhs (%d) of one trial exceed shared memory; "
             "the supernodal large-matrix path is not built yet\n", an.nnzLU, an.n);
         delete b; return B200_E_UNSUPP;
@@ -269,7 +269,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     V.oldSol = b->dalloc<double>(vplane);
     V.states = b->dalloc<double>((size_t)K.NS*an.numStates*ldt);
     V.oldState0 = b->dalloc<double>((size_t)an.numStates*ldt);
-    V.contrib = b->dalloc<double>((size_t)an.NC*ldt);         // [ldt/SOLVE_TB][NC][SOLVE_TB]
+    V.contrib = b->dalloc<double>((size_t)an.NC*ldt);         // [ldt/tb][NC][tb]
     V.out = b->dalloc<double>((size_t)an.npoints_max*an.n*ldt);
     if (!V.out || !V.states || !V.sols) { b200_batch_destroy(b); return B200_E_NOMEM; }
     // ---- topology ----

@@ -435,9 +435,9 @@ struct MosStuff {
 struct MosOut {             // stamps go straight to this trial's contribution tile, load order
     double *cbase;          // &contrib[tile of the trial][0][trial % TB]
     const int *cs, *rs;     // contribution slots of this instance (-1: ground row/column)
-    int tb;                 // trials per tile
-    __device__ __forceinline__ void M(int k, double v) const { int q = cs[k]; if (q >= 0) cbase[(size_t)q*tb] = v; }
-    __device__ __forceinline__ void Rw(int k, double v) const { int q = rs[k]; if (q >= 0) cbase[(size_t)q*tb] = v; }
+    int tbshift;            // log2(trials per tile)
+    __device__ __forceinline__ void M(int k, double v) const { int q = cs[k]; if (q >= 0) cbase[(size_t)q << tbshift] = v; }
+    __device__ __forceinline__ void Rw(int k, double v) const { int q = rs[k]; if (q >= 0) cbase[(size_t)q << tbshift] = v; }
 };
 
 __device__ inline void dev_sargs(double arg, double bot, double side, double *sarg, double *sargsw)

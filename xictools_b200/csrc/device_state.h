@@ -86,6 +86,7 @@ struct Consts {
     int nnzLU, ncslot, nrslot, NC /* contributions per trial, assembly order */;
     double t_stop, t_step, t_start, maxStep, delmin, minBreak, break0, break1;
     int nocut, uic, hadNodeset, npoints_max, method;
+    int tb, tbshift;    // trials per contribution tile = trials per CTA of the solve kernel (1, 2, 4), log2
     int analysis;       // 0: transient (tranan.cc), 1: DC operating point only (dcoan.cc)
     int nbrks, nlat;
 };

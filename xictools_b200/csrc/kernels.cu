@@ -70,7 +70,7 @@ __device__ __forceinline__ void make_ctx(TrialCtx &c, const Consts &K, const Hot
 // thread, nothing parked in registers.  Stage 2: the model is evaluated out of shared memory;
 // state-0 results and stamps go straight to HBM, the operating point is updated in place in
 // the staging area and written back at the end.
-template <int MINB, bool L6>
+template <int MINB, bool L6, int TBS>
 __global__ void __launch_bounds__(MOS_TPB, MINB)
 k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, const double *rhsOld)
 {
@@ -170,10 +170,12 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
         __pipeline_commit();
     }
     MosOut o;
-    o.cbase = V.contrib + ((size_t)(t/SOLVE_TB)*(size_t)K.NC)*SOLVE_TB + (t % SOLVE_TB);
+    // TBS >= 0: tile width known at compile time (the common 4-trial tile), else Consts::tbshift
+    const int tbs = (TBS >= 0) ? TBS : K.tbshift;
+    o.cbase = V.contrib + ((((size_t)(t >> tbs))*(size_t)K.NC) << tbs) + (t & ((1 << tbs) - 1));
     o.cs = M.cslot + (size_t)i*MT_NSTAMP;
     o.rs = M.rslot + (size_t)i*MRH_NRHS;
-    o.tb = SOLVE_TB;
+    o.tbshift = tbs;
     double *plte = M.lte + (size_t)i*ldt + t;              // this device's LTE bounds: [2][nmos][ldt]
     __pipeline_wait_prior(0);
     __syncthreads();                                     // shared parameter block visible
@@ -475,7 +477,7 @@ k_devconv(Consts K, HotView hot, VecView V, MosView M, const double *rhs)
 // ---------------------------------------------------------------------------------------
 // assemble + loadGmin + LU refactor + solve + NIconvTest node part.
 //
-// One CTA = SOLVE_TB adjacent trials; thread = (lane e0 in 0..31, trial j).  Everything a CTA
+// One CTA = TB (= Consts::tb) adjacent trials; thread = (lane e0 in 0..31, trial j).  Everything a CTA
 // reads from HBM is one contiguous block: the contributions of its trial group, stored by the
 // load kernels in ASSEMBLY ORDER as [NC][TB] tiles.
 //  1. streamed assembly.  The block is pulled through a shared-memory ring with cp.async,
@@ -541,10 +543,10 @@ struct OpRing {
     }
 };
 
-__global__ void __launch_bounds__(SOLVE_TB*SOLVE_LANES)
+template <int TB>
+__global__ void __launch_bounds__(TB*SOLVE_LANES)
 k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, double *Xnew)
 {
-    constexpr int TB = SOLVE_TB;
     constexpr int NL = SOLVE_LANES;
     constexpr int NT = TB*NL;
     extern __shared__ double smem[];
@@ -553,7 +555,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
     const int ldt = K.ldt, n = K.n, nlu = K.nnzLU;
     const int per = nlu + n;
     double *S = smem;                                    // [per][TB], trial-interleaved
-    double *ringmem = smem + (size_t)TB*per;             // phase 1 data+op rings / phase 2 op ring
+    double *ringmem = smem + (((size_t)TB*per + 1) & ~(size_t)1);   // 16-B aligned: phase 1 data+op rings / phase 2 op ring
     __shared__ int s_flags[TB];                          // bit0 singular, bit1 nonfinite, bit2 nonconv
     __shared__ int s_any;
     __shared__ int s_chunk[2*SOLVE_MAXCH];
@@ -585,10 +587,18 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
         const int ostride = Sv.seg_maxsteps*NL;                       // SegOps per ring slot
         auto issue = [&](int c) {
             if (c < nch) {
-                int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK)*TB/2;    // 16-B units
-                const int4 *src = reinterpret_cast<const int4*>(gC + (size_t)c*SEG_CHUNK*TB);
-                int4 *dst = reinterpret_cast<int4*>(dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB);
-                for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 16);
+                if (TB >= 2) {
+                    int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK)*TB/2;    // 16-B units
+                    const int4 *src = reinterpret_cast<const int4*>(gC + (size_t)c*SEG_CHUNK*TB);
+                    int4 *dst = reinterpret_cast<int4*>(dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB);
+                    for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 16);
+                }
+                else {
+                    int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK);         // one trial: 8-B units
+                    const double *src = gC + (size_t)c*SEG_CHUNK;
+                    double *dst = dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK;
+                    for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 8);
+                }
                 const int4 *osrc = reinterpret_cast<const int4*>(Sv.seg_ops + s_chunk[2*c]);
                 int4 *odst = reinterpret_cast<int4*>(oring + (size_t)(c % SEG_NBUF)*ostride);
                 int ocnt = s_chunk[2*c + 1]*NL;
@@ -1094,13 +1104,21 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
         size_t smem = (size_t)M.stage_doubles*sizeof(double);
         static size_t configured = 0;
         if (smem > configured) {
-            cudaFuncSetAttribute(k_load_mos<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<7, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<7, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<7, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<7, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
         dim3 g((K.ntrials + MOS_TPB - 1)/MOS_TPB, M.n);
-        if (M.has_level6) k_load_mos<7, true><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-        else k_load_mos<7, false><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        if (K.tbshift == 2) {
+            if (M.has_level6) k_load_mos<7, true, 2><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+            else k_load_mos<7, false, 2><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        }
+        else {
+            if (M.has_level6) k_load_mos<7, true, -1><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+            else k_load_mos<7, false, -1><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        }
     }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
     if (Cp.L.nmut) k_load_mut<<<grid2(K.ntrials, Cp.L.nmut), 128, 0, st>>>(K, hot, V, Cp.L);
@@ -1114,23 +1132,43 @@ void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const 
 }
 int solve_smem_bytes(const Consts &K, int seg_maxsteps)
 {
-    size_t img = (size_t)SOLVE_TB*(K.nnzLU + K.n)*sizeof(double);
-    size_t ph1 = (size_t)SEG_NBUF*SEG_CHUNK*SOLVE_TB*sizeof(double) + (size_t)SEG_NBUF*seg_maxsteps*SOLVE_LANES*sizeof(SegOp);
+    size_t img = ((((size_t)K.tb*(K.nnzLU + K.n)) + 1) & ~(size_t)1)*sizeof(double);
+    size_t ph1 = (size_t)SEG_NBUF*SEG_CHUNK*K.tb*sizeof(double) + (size_t)SEG_NBUF*seg_maxsteps*SOLVE_LANES*sizeof(SegOp);
     size_t ph2 = (size_t)2*RING_HALF_INTS*sizeof(int);
     return (int)(img + (ph1 > ph2 ? ph1 : ph2));
 }
-int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
+int solve_pick_tb(Consts &K, int seg_maxsteps)
+{
+    for (int tb = SOLVE_TB_MAX; tb >= 1; tb >>= 1) {
+        K.tb = tb; K.tbshift = (tb == 4) ? 2 : (tb == 2 ? 1 : 0);
+        if (solve_smem_bytes(K, seg_maxsteps) <= 227*1024) return tb;
+    }
+    K.tb = 0;
+    return 0;
+}
+template <int TB>
+static int launch_solve_t(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const SolveView &Sv, const double *Xold, double *Xnew)
 {
     int smem = solve_smem_bytes(K, Sv.seg_maxsteps);
     static int configured = -1;
-    if (configured != smem) {
-        if (cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(k_solve<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return B200_E_NOMEM;
         configured = smem;
     }
-    k_solve<<<(K.ntrials + SOLVE_TB - 1)/SOLVE_TB, SOLVE_TB*SOLVE_LANES, smem, st>>>(K, hot, V, Sv, Xold, Xnew);
+    k_solve<TB><<<(K.ntrials + TB - 1)/TB, TB*SOLVE_LANES, smem, st>>>(K, hot, V, Sv, Xold, Xnew);
     return 0;
+}
+int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
+    const SolveView &Sv, const double *Xold, double *Xnew)
+{
+    switch (K.tb) {
+    case 4: return launch_solve_t<4>(st, K, hot, V, Sv, Xold, Xnew);
+    case 2: return launch_solve_t<2>(st, K, hot, V, Sv, Xold, Xnew);
+    case 1: return launch_solve_t<1>(st, K, hot, V, Sv, Xold, Xnew);
+    default: return B200_E_UNSUPP;
+    }
 }
 void launch_vec(cudaStream_t st, const Consts &K, const VecView &V, const CtlAux &aux,
     const MosView &M, double *rhsOld)

@@ -3,13 +3,14 @@
 #include <cuda_runtime.h>
 #include "device_state.h"
 
-#define SOLVE_TB 4          // trials per CTA of k_solve (4 doubles = one 32-B sector)
+#define SOLVE_TB_MAX 4      // trials per CTA of k_solve: 4 (one 32-B sector per value), 2 or 1
+                            // (Consts::tb), the largest whose LU image fits shared memory
 #define SOLVE_LONG 48       // gather lists longer than this go through the staged path
 #define SOLVE_STAGE 1024    // staged terms per chunk (x SOLVE_TB doubles = 32 KB, shared with the op ring)
 #define ASM_BATCH 16        // contribution loads kept in flight per thread
 #define SEG_NBUF 3           // streamed-assembly ring depth (chunks in flight)
 // contribution (s) of trial (t): tile layout, TB adjacent trials of one slot = one 32-B sector
-#define CADDR(K, s, t) (((size_t)((t)/SOLVE_TB)*(size_t)(K).NC + (size_t)(s))*SOLVE_TB + ((t) % SOLVE_TB))
+#define CADDR(K, s, t) ((((size_t)((t) >> (K).tbshift)*(size_t)(K).NC + (size_t)(s)) << (K).tbshift) + ((t) & ((K).tb - 1)))
 
 struct MosCard;
 struct CtlShared;
@@ -44,7 +45,8 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
     const MosView &M, const CapView &Cp, const SrcView &S, const double *rhsOld);
 void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const double *rhs);
-int  solve_smem_bytes(const Consts &K, int seg_maxsteps);
+int  solve_smem_bytes(const Consts &K, int seg_maxsteps);   // for K.tb
+int  solve_pick_tb(Consts &K, int seg_maxsteps);               // sets K.tb; 0 if nothing fits
 int  launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const SolveView &Sv, const double *Xold, double *Xnew);
 void launch_vec(cudaStream_t st, const Consts &K, const VecView &V, const CtlAux &aux,

@@ -319,7 +319,7 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     b200_options_default(&K.opt);
     K.opt.gmax = HUGE_VAL;
     K.n = n; K.nnz = an.nnz; K.nnzLU = an.nnzLU; K.NS = 4; K.NC = an.NC;
-    if (solve_smem_bytes(K, an.seg_maxsteps) > 227*1024 || (int)an.seg_chunk.size()/2 > SOLVE_MAXCH) {
+    if (!solve_pick_tb(K, an.seg_maxsteps) || (int)an.seg_chunk.size()/2 > SOLVE_MAXCH) {
         delete k; return B200_E_UNSUPP;
     }
     CK(cudaStreamCreate(&k->stream));
@@ -379,7 +379,7 @@ static int klu_ensure(b200_klu *k, int ntrials)
 int b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double *dAx, double *dB,
     int *dstatus, void *cuda_stream)
 {
-    if (!k || ntrials <= 0 || ldt < ntrials || (ldt % SOLVE_TB)) return B200_E_BADPARM;
+    if (!k || ntrials <= 0 || ldt < ntrials || (ldt % SOLVE_TB_MAX)) return B200_E_BADPARM;
     CK(cudaSetDevice(k->device));
     int rc = klu_ensure(k, ldt);
     if (rc) return rc;
