@@ -188,6 +188,9 @@ def variants():
         "rlc_uic": rlc_uic(),
         "transformer": transformer(),
         "ro5_level6": ro_level6(5),
+        # transient iteration limit hit: non-convergence -> delta/8 cuts (tranan.cc:744-762)
+        "ro5_itl4_4": ring_oscillator(5).options(itl4=4),
+        "inv4_itl4_4": inv_chain(4).options(itl4=4),
         "inv4_level6": inv_level6(),
         "ro3": ring_oscillator(3),
         "ro5": ring_oscillator(5),

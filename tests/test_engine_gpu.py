@@ -126,6 +126,28 @@ def test_large_circuits_use_narrower_tiles(nstages):
     compare(d, ntr, ov, trials=[0, 5])
 
 
+def test_failing_trials_report_the_reference_error():
+    """A UIC start the reference aborts with E_MATHOVF (errors.h:119; pinned in
+    tests/test_oracle_vs_ref.py): every trial of the batch must stop with that code at the same
+    point (same accepted steps / iterations), and the run must terminate."""
+    d = ring_oscillator(5, uic=True)
+    ntr = 9
+    ov = mc_variation(d, ntr, seed=12)
+    b = engine.Batch(d, ntr)
+    b.set_params(ov)
+    b.run_tran()
+    cnt = b.counters()
+    rp, cp = b.ordering()
+    b.close()
+    for t in range(ntr):
+        o = Oracle(d, ov, t)
+        o.set_ordering(rp, cp)
+        r = o.run()
+        assert r["err"] == 119
+        assert (int(cnt[t, C_STATUS]), int(cnt[t, C_ACCEPTED]), int(cnt[t, C_NUMITER])) == \
+            (r["err"], r["accepted"], r["numiter"])
+
+
 def test_single_trial_batch():
     compare(ring_oscillator(3), 1)
 

@@ -221,10 +221,16 @@ class Deck:
             self.nodesets[k.lower()] = float(v)
         return self
 
+    # optsetp.cc CHECKSET: out-of-range option values are clamped (circuit.h:579-596)
+    _OPT_RANGE = {"itl1": (10, 1000), "itl4": (4, 100)}
+
     def options(self, **kv):
         for k, v in kv.items():
             if k not in DEFAULT_OPTIONS:
                 raise KeyError(k)
+            if k in self._OPT_RANGE:
+                lo, hi = self._OPT_RANGE[k]
+                v = min(max(v, lo), hi)
             self.opts[k] = v
         return self
 
