@@ -74,9 +74,11 @@ enum { M_Dd, M_Gg, M_Ss, M_Bb, M_DPdp, M_SPsp, M_Ddp, M_Gb, M_Gdp, M_Gsp, M_Ssp,
 typedef struct {
     /* card */
     b200_mos_model mod;      /* private copy so per-trial vto/kp overrides are local */
+    b200_mos_model card;     /* the card as given (NaN = not given): the xxxGiven tests of mostemp */
     b200_mos in;
     /* model-derived (mostemp.cc:65-139) */
     double oxideCapFactor, surfaceMobility, kp_eff, gamma_eff, phi_eff, vt0_eff;
+    double xd, alpha, narrowFactor;      /* level 2/3 (mostemp.cc:113-143) */
     /* nodes */
     int d, g, s, b, dp, sp;
     int ptr[M_NPTR];
@@ -563,6 +565,14 @@ static void mos_setup(wo_ckt *c, Mos *m, int idx)
     if (!GIVEN(md->js)) md->js = 0;
     if (!GIVEN(md->ld)) md->ld = 0;
     if (!GIVEN(md->fc)) md->fc = .5;
+    /* level 2/3, mosset.cc:220-253 */
+    if (!GIVEN(md->nfs)) md->nfs = 0;
+    if (!GIVEN(md->delta)) md->delta = 0;
+    if (!GIVEN(md->vmax)) md->vmax = 0;
+    if (!GIVEN(md->xj)) md->xj = 0;
+    if (!GIVEN(md->eta)) md->eta = 0;
+    if (!GIVEN(md->theta)) md->theta = 0;
+    if (!GIVEN(md->kappa)) md->kappa = .2;
     /* level 6, mosset.cc:255-272 (the "given" tests of lambda / kc are made on the deck card) */
     if (!GIVEN(md->kv)) md->kv = 2;
     if (!GIVEN(md->nv)) md->nv = 0.5;
@@ -725,9 +735,22 @@ static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
                 }
             }
         }
+        if (GIVEN(deckmod->nsub)) {
+            /* mostemp.cc:119-128 */
+            if (md->level == 2)
+                m->xd = sqrt((EPSSIL+EPSSIL)/(CHARGE*deckmod->nsub*CM3PM3));
+            else if (md->level == 3) {
+                m->alpha = (EPSSIL+EPSSIL)/(CHARGE*deckmod->nsub*CM3PM3);
+                m->xd = sqrt(m->alpha);
+            }
+        }
     }
     else
         m->surfaceMobility = GIVEN(deckmod->u0) ? deckmod->u0 : 0;
+    /* mostemp.cc:138-142 computes narrowFactor = MOSdelta*pi/2*EPSSIL/oxideCapFactor for level 3, but
+     * the card's "delta" is stored in MOSnarrowFactor (mossetm.cc:216-219) and MOSdelta keeps its
+     * default 0 (mosset.cc:230-231): the narrow-width term is always 0 in the reference. */
+    m->narrowFactor = 0.0;
     if (!GIVEN(kp))
         kp = 2e-5;                       /* mosset.cc:101-103 */
     if (!GIVEN(kc))
@@ -918,6 +941,7 @@ wo_ckt *wo_create(const b200_deck *dk)
     for (int i = 0; i < c->nmos; i++) {
         c->mos[i].in = dk->mos[i];
         c->mos[i].mod = dk->mos_models[dk->mos[i].model];
+        c->mos[i].card = c->mos[i].mod;
     }
 
     /* setup in load order (ckt.cc:2202-2210) */
@@ -1032,13 +1056,14 @@ wo_ckt *wo_create(const b200_deck *dk)
 int wo_set_param(wo_ckt *c, int param, int index, double value)
 {
     switch (param) {
-    case B200_P_MOS_VTO:    c->mos[index].mod.vto = value; break;
+    case B200_P_MOS_VTO:    c->mos[index].mod.vto = c->mos[index].card.vto = value; break;
     case B200_P_MOS_KP:     /* level 6: the transconductance card is kc */
-        if (c->mos[index].mod.level == 6) c->mos[index].mod.kc = value; else c->mos[index].mod.kp = value;
+        if (c->mos[index].mod.level == 6) c->mos[index].mod.kc = c->mos[index].card.kc = value;
+        else c->mos[index].mod.kp = c->mos[index].card.kp = value;
         break;
-    case B200_P_MOS_GAMMA:  c->mos[index].mod.gamma = value; break;
-    case B200_P_MOS_LAMBDA: c->mos[index].mod.lambda = value; break;
-    case B200_P_MOS_PHI:    c->mos[index].mod.phi = value; break;
+    case B200_P_MOS_GAMMA:  c->mos[index].mod.gamma = c->mos[index].card.gamma = value; break;
+    case B200_P_MOS_LAMBDA: c->mos[index].mod.lambda = c->mos[index].card.lambda = value; break;
+    case B200_P_MOS_PHI:    c->mos[index].mod.phi = c->mos[index].card.phi = value; break;
     case B200_P_MOS_L:      c->mos[index].in.l = value; c->mos[index].l = value;
         c->mos[index].effectiveLength = value - 2*c->mos[index].mod.ld;
         if (c->mos[index].effectiveLength < 0) c->mos[index].effectiveLength = 0;
@@ -1467,6 +1492,227 @@ static double mos_eq6(Mos *m, MosStuff *ms)
     return cdrain;
 }
 
+static double mos_eq3(Mos *m, MosStuff *ms)
+{
+    /* moseq.cc:693-1083: level 3 (semi-empirical short-channel model) */
+    const b200_mos_model *md = &m->mod;
+    double lvbs, lvds, lvgs;
+    if (m->mode > 0) { lvbs = ms->vbs; lvds = ms->vds; lvgs = ms->vgs; }
+    else { lvbs = ms->vbd; lvds = -ms->vds; lvgs = ms->vgd; }
+    const double xl = m->effectiveLength;
+    ms->vdsat = 0.0;
+    double oneoverxl = 1.0/xl;
+    double eta = md->eta*8.15e-22/(m->oxideCapFactor*xl*xl*xl);
+    double phibs, sqphbs, dsqdvb;
+    if (lvbs <= 0.0) {
+        phibs = m->tPhi - lvbs;
+        sqphbs = sqrt(phibs);
+        dsqdvb = -0.5/sqphbs;
+    }
+    else {
+        double sqphis = sqrt(m->tPhi);
+        double sqphs3 = m->tPhi*sqphis;
+        sqphbs = sqphis/(1.0 + lvbs/(m->tPhi + m->tPhi));
+        phibs = sqphbs*sqphbs;
+        dsqdvb = -phibs/(sqphs3+sqphs3);
+    }
+    double fshort, dfsdvb;
+    if (md->xj != 0.0 && m->xd != 0.0) {
+        double coeff0 = 0.0631353e0, coeff1 = 0.8013292e0, coeff2 = -0.01110777e0;
+        double wps = m->xd*sqphbs;
+        double oneoverxj = 1.0/md->xj;
+        double xjonxl = md->xj*oneoverxl;
+        double djonxj = md->ld*oneoverxj;
+        double wponxj = wps*oneoverxj;
+        double wconxj = coeff0 + coeff1*wponxj + coeff2*wponxj*wponxj;
+        double arga = wconxj + djonxj;
+        double argc = wponxj/(1.0 + wponxj);
+        double argb = sqrt(1.0 - argc*argc);
+        fshort = 1.0 - xjonxl*(arga*argb - djonxj);
+        double dwpdvb = m->xd*dsqdvb;
+        double dadvb = (coeff1 + coeff2*(wponxj+wponxj))*dwpdvb*oneoverxj;
+        double dbdvb = -argc*argc*(1.0 - argc)*dwpdvb/(argb*wps);
+        dfsdvb = -xjonxl*(dadvb*argb + arga*dbdvb);
+    }
+    else {
+        fshort = 1.0;
+        dfsdvb = 0.0;
+    }
+    double gammas = md->gamma*fshort;
+    double fbodys = 0.5*gammas/(sqphbs+sqphbs);
+    double fbody = fbodys + m->narrowFactor/m->w;
+    double onfbdy = 1.0/(1.0 + fbody);
+    double dfbdvb = -fbodys*dsqdvb/sqphbs + fbodys*dfsdvb/fshort;
+    double qbonco = gammas*sqphbs + m->narrowFactor*phibs/m->w;
+    double dqbdvb = gammas*dsqdvb + md->gamma*dfsdvb*sqphbs - m->narrowFactor/m->w;
+    double vth = qbonco + m->tVbi*md->type - eta*lvds;
+    double dvtdvd = -eta;
+    double dvtdvb = dqbdvb;
+    ms->von = vth;
+    double cdrain;
+    double xn = 1.0, dxndvb, dvodvd, dvodvb;
+    if (md->nfs != 0.0) {
+        double csonco = CHARGE*md->nfs*CM2PM2*xl*m->w/m->oxideCap;
+        double cdonco = qbonco/(phibs + phibs);
+        xn += csonco + cdonco;
+        ms->von += ms->vt*xn;
+        dxndvb = dqbdvb/(phibs + phibs) - qbonco*dsqdvb/(phibs*sqphbs);
+        dvodvd = dvtdvd;
+        dvodvb = dvtdvb + ms->vt*dxndvb;
+    }
+    else {
+        dxndvb = 0; dvodvd = 0; dvodvb = 0;
+        if (lvgs <= ms->von) {
+            cdrain = 0.0; m->gm = 0.0; m->gds = 0.0; m->gmbs = 0.0;
+            return cdrain;
+        }
+    }
+    double vgsx = SPMAX(lvgs, ms->von);
+    double onfg = 1.0 + md->theta*(vgsx - vth);
+    double fgate = 1.0/onfg;
+    double us = m->tSurfMob*M2PCM2*fgate;
+    double dfgdvg = -md->theta*fgate*fgate;
+    double dfgdvd = -dfgdvg*dvtdvd;
+    double dfgdvb = -dfgdvg*dvtdvb;
+    double dvsdvg, dvsdvd, dvsdvb, onvdsc;
+    ms->vdsat = (vgsx - vth)*onfbdy;
+    if (md->vmax <= 0.0) {
+        dvsdvg = onfbdy;
+        dvsdvd = -dvsdvg*dvtdvd;
+        dvsdvb = -dvsdvg*dvtdvb - ms->vdsat*dfbdvb*onfbdy;
+        onvdsc = 0;
+    }
+    else {
+        double vdsc = xl*md->vmax/us;
+        onvdsc = 1.0/vdsc;
+        double arga = (vgsx - vth)*onfbdy;
+        double argb = sqrt(arga*arga + vdsc*vdsc);
+        ms->vdsat = arga + vdsc - argb;
+        double dvsdga = (1.0 - arga/argb)*onfbdy;
+        dvsdvg = dvsdga - (1.0 - vdsc/argb)*vdsc*dfgdvg*onfg;
+        dvsdvd = -dvsdvg*dvtdvd;
+        dvsdvb = -dvsdvg*dvtdvb - arga*dvsdga*dfbdvb;
+    }
+    double beta = m->beta;
+    double vdsx = SPMIN(lvds, ms->vdsat);
+    if (vdsx == 0.0) {
+        beta *= fgate;
+        cdrain = 0.0;
+        m->gm = 0.0;
+        m->gds = beta*(vgsx - vth);
+        m->gmbs = 0.0;
+        if (md->nfs != 0.0 && lvgs < ms->von)
+            m->gds *= exp((lvgs - ms->von)/(ms->vt*xn));
+        return cdrain;
+    }
+    double cdo = vgsx - vth - 0.5*(1.0 + fbody)*vdsx;
+    double dcodvb = -dvtdvb - 0.5*dfbdvb*vdsx;
+    double cdnorm = cdo*vdsx;
+    m->gm = vdsx;
+    if ((m->mode*ms->vds) > ms->vdsat)
+        m->gds = -dvtdvd*vdsx;
+    else
+        m->gds = vgsx - vth - (1.0 + fbody + dvtdvd)*vdsx;
+    m->gmbs = dcodvb*vdsx;
+    double cd1 = beta*cdnorm;
+    beta *= fgate;
+    cdrain = beta*cdnorm;
+    m->gm = beta*m->gm + dfgdvg*cd1;
+    m->gds = beta*m->gds + dfgdvd*cd1;
+    m->gmbs = beta*m->gmbs + dfgdvb*cd1;
+    double fdrain, dfddvg, dfddvb, dfddvd;
+    if (md->vmax > 0.0) {
+        fdrain = 1.0/(1.0 + vdsx*onvdsc);
+        double fd2 = fdrain*fdrain;
+        double arga = fd2*vdsx*onvdsc*onfg;
+        dfddvg = -dfgdvg*arga;
+        if (m->mode*ms->vds > ms->vdsat)
+            dfddvd = -dfgdvd*arga;
+        else
+            dfddvd = -dfgdvd*arga - fd2*onvdsc;
+        dfddvb = -dfgdvb*arga;
+        m->gm = fdrain*m->gm + dfddvg*cdrain;
+        m->gds = fdrain*m->gds + dfddvd*cdrain;
+        m->gmbs = fdrain*m->gmbs + dfddvb*cdrain;
+        cdrain = fdrain*cdrain;
+        beta *= fdrain;
+    }
+    else {
+        fdrain = 0; dfddvg = 0; dfddvd = 0; dfddvb = 0;
+    }
+    double gds0 = 0;
+    if (lvds > ms->vdsat && !(md->vmax != 0.0 && m->alpha == 0)) {
+        double delxl, dldvd, ddldvg, ddldvd, ddldvb;
+        if (md->vmax == 0.0) {
+            delxl = sqrt(md->kappa*(lvds - ms->vdsat)*m->alpha);
+            dldvd = 0.5*delxl/(lvds - ms->vdsat);
+            ddldvg = 0.0;
+            ddldvd = -dldvd;
+            ddldvb = 0.0;
+        }
+        else {
+            double cdsat = cdrain;
+            double gdsat = cdsat*(1.0 - fdrain)*onvdsc;
+            gdsat = SPMAX(1.0e-12, gdsat);
+            double gdoncd = gdsat/cdsat;
+            double gdonfd = gdsat/(1.0 - fdrain);
+            double gdonfg = gdsat*onfg;
+            double dgdvg = gdoncd*m->gm - gdonfd*dfddvg + gdonfg*dfgdvg;
+            double dgdvd = gdoncd*m->gds - gdonfd*dfddvd + gdonfg*dfgdvd;
+            double dgdvb = gdoncd*m->gmbs - gdonfd*dfddvb + gdonfg*dfgdvb;
+            double emax = md->kappa*cdsat*oneoverxl/gdsat;
+            double emoncd = emax/cdsat;
+            double emongd = emax/gdsat;
+            double demdvg = emoncd*m->gm - emongd*dgdvg;
+            double demdvd = emoncd*m->gds - emongd*dgdvd;
+            double demdvb = emoncd*m->gmbs - emongd*dgdvb;
+            double arga = 0.5*emax*m->alpha;
+            double argc = md->kappa*m->alpha;
+            double argb = sqrt(arga*arga + argc*(lvds - ms->vdsat));
+            delxl = argb - arga;
+            dldvd = argc/(argb+argb);
+            double dldem = 0.5*(arga/argb - 1.0)*m->alpha;
+            ddldvg = dldem*demdvg;
+            ddldvd = dldem*demdvd - dldvd;
+            ddldvb = dldem*demdvb;
+        }
+        if (delxl > (0.5*xl)) {
+            delxl = xl - (xl*xl/(4.0*delxl));
+            double arga = 4.0*(xl - delxl)*(xl - delxl)/(xl*xl);
+            ddldvg = ddldvg*arga;
+            ddldvd = ddldvd*arga;
+            ddldvb = ddldvb*arga;
+            dldvd = dldvd*arga;
+        }
+        double dlonxl = delxl*oneoverxl;
+        double xlfact = 1.0/(1.0 - dlonxl);
+        cd1 = cdrain;
+        cdrain = cdrain*xlfact;
+        double diddl = cdrain/(xl - delxl);
+        m->gm = m->gm*xlfact + diddl*ddldvg;
+        m->gmbs = m->gmbs*xlfact + diddl*ddldvb;
+        gds0 = diddl*ddldvd;
+        m->gm = m->gm + gds0*dvsdvg;
+        m->gmbs = m->gmbs + gds0*dvsdvb;
+        m->gds = m->gds*xlfact + diddl*dldvd + gds0*dvsdvd;
+    }
+    if (lvgs < ms->von) {
+        double onxn = 1.0/xn;
+        double ondvt = onxn/ms->vt;
+        double wfact = exp((lvgs - ms->von)*ondvt);
+        cdrain = cdrain*wfact;
+        double gms = m->gm*wfact;
+        double gmw = cdrain*ondvt;
+        m->gm = gmw;
+        if (lvds > ms->vdsat)
+            m->gm = m->gm + gds0*dvsdvg*wfact;
+        m->gds = m->gds*wfact + (gms - gmw)*dvodvd;
+        m->gmbs = m->gmbs*wfact + (gms - gmw)*dvodvb - gmw*(lvgs - ms->von)*onxn*dxndvb;
+    }
+    (void)cd1;
+    return cdrain;
+}
+
 static int mos_limiting(wo_ckt *c, Mos *m, MosStuff *ms)
 {
     /* mosload.cc:346-384 */
@@ -1522,7 +1768,8 @@ static void mos_iv(wo_ckt *c, Mos *m, MosStuff *ms)
         m->cbd = m->tDrainSatCur*(evbd-1) + gmin*ms->vbd;
     }
     m->mode = (ms->vds >= 0) ? 1 : -1;
-    ms->cdrain = (m->mod.level == 6) ? mos_eq6(m, ms) : mos_eq1(m, ms);   /* mosload.cc:570-577; levels 2/3 not restated */
+    /* mosload.cc:570-577; level 2 not restated */
+    ms->cdrain = (m->mod.level == 6) ? mos_eq6(m, ms) : (m->mod.level == 3) ? mos_eq3(m, ms) : mos_eq1(m, ms);
     if (m->mod.type > 0) {
         m->von = ms->von; m->vdsat = ms->vdsat;
     }
@@ -3200,7 +3447,7 @@ int wo_run_tran(wo_ckt *c)
     feclearexcept(FE_ALL_EXCEPT);
     /* temperature pass (ckt.cc:2297-2307) -- after any wo_set_param */
     for (int i = 0; i < c->nmos; i++) {
-        b200_mos_model deckmod = c->mos[i].mod;
+        b200_mos_model deckmod = c->mos[i].card;
         mos_temp(c, &c->mos[i], &deckmod);
     }
     preload(c);
@@ -3313,7 +3560,7 @@ int wo_run_op(wo_ckt *c)
     const b200_options *o = &c->opt;
     feclearexcept(FE_ALL_EXCEPT);
     for (int i = 0; i < c->nmos; i++) {
-        b200_mos_model deckmod = c->mos[i].mod;
+        b200_mos_model deckmod = c->mos[i].card;
         mos_temp(c, &c->mos[i], &deckmod);
     }
     preload(c);
@@ -3359,7 +3606,7 @@ int wo_debug_load(wo_ckt *c, int mode, double time, double delta, int order,
     const double *rhsold, double *Ax, double *rhs)
 {
     for (int i = 0; i < c->nmos; i++) {
-        b200_mos_model deckmod = c->mos[i].mod;
+        b200_mos_model deckmod = c->mos[i].card;
         mos_temp(c, &c->mos[i], &deckmod);
     }
     preload(c);

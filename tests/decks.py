@@ -142,6 +142,31 @@ def inv_level6():
     return d
 
 
+L3 = dict(tox=2e-8, nsub=2e16, xj=2.5e-7, ld=8e-8, u0=550, vmax=1.6e5, theta=0.08, eta=0.06,
+          kappa=0.6, delta=0.9, nfs=2e11, cgso=2e-10, cgdo=2e-10, cbd=2e-15, cbs=2e-15)
+L3S = dict(tox=2e-8, nsub=2e16, u0=550, theta=0.05, eta=0.03, kappa=0.4, kp=9e-5,
+           cgso=2e-10, cgdo=2e-10, cbd=2e-15, cbs=2e-15)
+
+
+def ro_level3(n=5, card=None):
+    """Ring oscillator with MOS level 3 devices (moseq.cc:693): short-channel factor, velocity
+    saturation, weak inversion (nfs), channel-length modulation and punch-through branches."""
+    card = L3 if card is None else card
+    d = ring_oscillator(n, tstop=8e-9, tstep=0.08e-9)
+    d.mos_models.clear()
+    d.mos_model("nm", "nmos", level=3, vto=0.7, **card)
+    d.mos_model("pm", "pmos", level=3, vto=-0.7, **dict(card, u0=card["u0"]*0.4))
+    return d
+
+
+def inv_level3():
+    d = inv_chain(4)
+    d.mos_models.clear()
+    d.mos_model("nm", "nmos", level=3, vto=0.7, **L3S)
+    d.mos_model("pm", "pmos", level=3, vto=-0.7, **dict(L3S, kp=3.5e-5))
+    return d
+
+
 def ro_rd(n=3):
     """Ring oscillator whose MOSFETs have series rd/rs: internal drain/source nodes."""
     d = ring_oscillator(n)
@@ -176,7 +201,8 @@ def op_decks():
             "op_ro3_rd": ro_rd(3), "op_inv_dc_direct": inv_dc(3).options(gminsteps=-1, srcsteps=-1),
             "op_inv_dc_gminfirst": inv_dc(3).options(gminfirst=1),
             "op_inv7_nogmin": inv_chain(7).options(gminsteps=-1),
-            "op_inv_lsupply": inv_lsupply(), "op_inv4_level6": inv_level6()}
+            "op_inv_lsupply": inv_lsupply(), "op_inv4_level6": inv_level6(), "op_inv4_level3": inv_level3(),
+            "op_ro5_level3": ro_level3(5)}
 
 
 def variants():
@@ -188,6 +214,9 @@ def variants():
         "rlc_uic": rlc_uic(),
         "transformer": transformer(),
         "ro5_level6": ro_level6(5),
+        "ro5_level3": ro_level3(5),
+        "ro3_level3_simple": ro_level3(3, L3S),
+        "inv4_level3": inv_level3(),
         # transient iteration limit hit: non-convergence -> delta/8 cuts (tranan.cc:744-762)
         "ro5_itl4_4": ring_oscillator(5).options(itl4=4),
         "inv4_itl4_4": inv_chain(4).options(itl4=4),

@@ -116,6 +116,14 @@ def test_monte_carlo_level6():
     compare(d, ntr, ov, min_same=0.9)
 
 
+def test_monte_carlo_level3():
+    """MOS level 3 ring oscillator with per-trial vto and L (L enters the short-channel, DIBL
+    and velocity-saturation terms through the effective length)."""
+    d = variants()["ro5_level3"]
+    ntr = 17
+    compare(d, ntr, mc_variation(d, ntr, seed=33), min_same=0.9)
+
+
 @pytest.mark.parametrize("nstages", [1001, 2001])
 def test_large_circuits_use_narrower_tiles(nstages):
     """2 002 / 4 002 MOSFETs: the LU image of 4 trials no longer fits shared memory, the solve

@@ -41,10 +41,15 @@ enum { MP_tPhi, MP_tVbi, MP_tVto, MP_gamma, MP_lambda, MP_beta, MP_oxideCap,
        MP_f2d, MP_f3d, MP_f4d, MP_f2s, MP_f3s, MP_f4s,
        MP_gsOvl, MP_gdOvl, MP_gbOvl, MP_dcon, MP_scon, MP_mult, MP_vt, MP_mj, MP_mjsw,
        MP_icVDS, MP_icVGS, MP_icVBS,
-       MP_kv, MP_nv, MP_nc, MP_lamda0, MP_lamda1, MP_sigma, MP_gamma1,   // level 6 (moseq.cc:1091)
        // correctly rounded reciprocals of divisors that are constant for a device: a/b is then
        // formed by dev_div_rcp (bit-identical to the IEEE division, 5 instructions)
        MP_rvt, MP_rBulkPot, MP_r1mj, MP_r1mjsw, MP_r2phi, MP_r15phi,
+       MP_NBASE,                 // everything above is all a level-1 deck needs
+       // level 6 (moseq.cc:1091)
+       MP_kv = MP_NBASE, MP_nv, MP_nc, MP_lamda0, MP_lamda1, MP_sigma, MP_gamma1,
+       // level 3 (moseq.cc:693): model cards, doping-derived xd / alpha, and the geometry
+       MP_eta, MP_theta, MP_kappa, MP_vmax, MP_xj, MP_ld, MP_nfs, MP_xd, MP_alpha,
+       MP_oxideCapFactor, MP_tSurfMob, MP_xl, MP_w,
        MP_NPARAMS };
 
 // ---- MOS raw (card) parameters that may vary per trial ----

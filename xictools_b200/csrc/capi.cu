@@ -31,8 +31,8 @@ const int kDep[MR_NRAW][8] = {
     /* gamma  */ { MP_gamma, MP_tVbi, MP_tVto, -1 },
     /* phi    */ { MP_tPhi, MP_tVbi, MP_tVto, MP_r2phi, MP_r15phi, -1 },
     /* lambda */ { MP_lambda, -1 },
-    /* l      */ { MP_beta, MP_oxideCap, MP_gbOvl, -1 },
-    /* w      */ { MP_beta, MP_oxideCap, MP_gsOvl, MP_gdOvl, -1 },
+    /* l      */ { MP_beta, MP_oxideCap, MP_gbOvl, MP_xl, -1 },
+    /* w      */ { MP_beta, MP_oxideCap, MP_gsOvl, MP_gdOvl, MP_w, -1 },
 };
 }
 
@@ -142,6 +142,10 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
         c.fc = given(md.fc) ? md.fc : .5; c.nsub = given(md.nsub) ? md.nsub : 0;
         c.tpg = given(md.tpg) ? md.tpg : 1; c.nss = given(md.nss) ? md.nss : 0;
         c.tnom = given(md.tnom) ? md.tnom : o.tnom;
+        // levels 2/3, mosset.cc:220-253
+        c.nfs = given(md.nfs) ? md.nfs : 0; c.vmax = given(md.vmax) ? md.vmax : 0;
+        c.xj = given(md.xj) ? md.xj : 0; c.eta = given(md.eta) ? md.eta : 0;
+        c.theta = given(md.theta) ? md.theta : 0; c.kappa = given(md.kappa) ? md.kappa : .2;
         // level 6, mosset.cc:255-272
         c.kv = given(md.kv) ? md.kv : 2; c.nv = given(md.nv) ? md.nv : 0.5;
         c.nc = given(md.nc) ? md.nc : 1;
@@ -278,8 +282,8 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     M.d = b->dupload(mt.d); M.g = b->dupload(mt.g); M.s = b->dupload(mt.s); M.b = b->dupload(mt.b);
     M.dp = b->dupload(mt.dp); M.sp = b->dupload(mt.sp); M.type = b->dupload(mt.type);
     M.off = b->dupload(mt.off); M.state = b->dupload(mt.state); M.level = b->dupload(mt.level);
-    M.has_level6 = 0;
-    for (int lv : mt.level) if (lv == 6) M.has_level6 = 1;
+    M.has_level6 = 0;              // any device that is not level 1
+    for (int lv : mt.level) if (lv != 1) M.has_level6 = 1;
     M.cslot = b->dupload(mt.cslot); M.rslot = b->dupload(mt.rslot);
     M.cache = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);
     M.save = b->dalloc<double>((size_t)MC_NCACHE*mt.n*ldt);
@@ -493,13 +497,17 @@ static int prepare_params(b200_batch *b)
         // slot of the block shared by the CTA
         MosStageMap &sm = b->M.smap;
         sm.nvar = 0;
+        // parameters beyond MP_NBASE are read by the level-3 / level-6 equations only: a deck of
+        // level-1 devices does not stage their per-trial rows
+        bool other = b->M.has_level6 != 0;
         for (int k = 0; k < MP_NPARAMS; k++)
-            if (tsd[k]) sm.var[sm.nvar++] = k;
+            if (tsd[k] && (other || k < MP_NBASE)) sm.var[sm.nvar++] = k;
         int shared_base = (SR_PRM + sm.nvar)*MOS_TPB;
         int q = 0;
         for (int k = 0; k < MP_NPARAMS; k++) {
-            sm.ts[k] = tsd[k];
-            sm.off[k] = tsd[k] ? (SR_PRM + q++)*MOS_TPB : shared_base + k;
+            bool row = tsd[k] && (other || k < MP_NBASE);
+            sm.ts[k] = row;
+            sm.off[k] = row ? (SR_PRM + q++)*MOS_TPB : shared_base + k;
         }
         b->M.stage_doubles = shared_base + MP_NPARAMS;
     }

@@ -356,6 +356,19 @@ struct MosInst {
     const MosStageMap *map;
     __device__ __forceinline__ double P(int k) const { return (map->ts[k] ? col : shp)[map->off[k]]; }
     __device__ __forceinline__ double &R(int row) const { return col[row*MOS_TPB]; }
+    __device__ __forceinline__ double eta() const { return P(MP_eta); }
+    __device__ __forceinline__ double theta() const { return P(MP_theta); }
+    __device__ __forceinline__ double kappa() const { return P(MP_kappa); }
+    __device__ __forceinline__ double vmax() const { return P(MP_vmax); }
+    __device__ __forceinline__ double xj() const { return P(MP_xj); }
+    __device__ __forceinline__ double ld() const { return P(MP_ld); }
+    __device__ __forceinline__ double nfs() const { return P(MP_nfs); }
+    __device__ __forceinline__ double xd() const { return P(MP_xd); }
+    __device__ __forceinline__ double alpha() const { return P(MP_alpha); }
+    __device__ __forceinline__ double oxideCapFactor() const { return P(MP_oxideCapFactor); }
+    __device__ __forceinline__ double tSurfMob() const { return P(MP_tSurfMob); }
+    __device__ __forceinline__ double xl() const { return P(MP_xl); }
+    __device__ __forceinline__ double w() const { return P(MP_w); }
     __device__ __forceinline__ double rvt() const { return P(MP_rvt); }
     __device__ __forceinline__ double rBulkPot() const { return P(MP_rBulkPot); }
     __device__ __forceinline__ double r1mj() const { return P(MP_r1mj); }
@@ -533,6 +546,230 @@ __device__ inline double dev_mos_eq1(MosInst &m, MosStuff &ms)
     return cdrain;
 }
 
+// moseq.cc:693-1083: level 3 (semi-empirical short-channel model)
+__device__ inline double dev_mos_eq3(MosInst &m, MosStuff &ms)
+{
+    double gm, gds, gmbs;       // the operating-point conductances, stored on every exit
+    double lvbs, lvds, lvgs;
+    if (m.mode > 0) { lvbs = ms.vbs; lvds = ms.vds; lvgs = ms.vgs; }
+    else { lvbs = ms.vbd; lvds = -ms.vds; lvgs = ms.vgd; }
+    const double xl = m.xl(), tPhi = m.tPhi(), xd = m.xd(), alpha = m.alpha(), xj = m.xj(), gamma = m.gamma();
+    const double nfs = m.nfs(), theta = m.theta(), vmax = m.vmax(), kappa = m.kappa();
+    ms.vdsat = 0.0;
+    double oneoverxl = 1.0/xl;
+    double eta = m.eta()*8.15e-22/(m.oxideCapFactor()*xl*xl*xl);
+    double phibs, sqphbs, dsqdvb;
+    if (lvbs <= 0.0) {
+        phibs = tPhi - lvbs;
+        sqphbs = sqrt(phibs);
+        dsqdvb = -0.5/sqphbs;
+    }
+    else {
+        double sqphis = sqrt(tPhi);
+        double sqphs3 = tPhi*sqphis;
+        sqphbs = sqphis/(1.0 + lvbs/(tPhi + tPhi));
+        phibs = sqphbs*sqphbs;
+        dsqdvb = -phibs/(sqphs3+sqphs3);
+    }
+    double fshort, dfsdvb;
+    if (xj != 0.0 && xd != 0.0) {
+        double coeff0 = 0.0631353e0, coeff1 = 0.8013292e0, coeff2 = -0.01110777e0;
+        double wps = xd*sqphbs;
+        double oneoverxj = 1.0/xj;
+        double xjonxl = xj*oneoverxl;
+        double djonxj = m.ld()*oneoverxj;
+        double wponxj = wps*oneoverxj;
+        double wconxj = coeff0 + coeff1*wponxj + coeff2*wponxj*wponxj;
+        double arga = wconxj + djonxj;
+        double argc = wponxj/(1.0 + wponxj);
+        double argb = sqrt(1.0 - argc*argc);
+        fshort = 1.0 - xjonxl*(arga*argb - djonxj);
+        double dwpdvb = xd*dsqdvb;
+        double dadvb = (coeff1 + coeff2*(wponxj+wponxj))*dwpdvb*oneoverxj;
+        double dbdvb = -argc*argc*(1.0 - argc)*dwpdvb/(argb*wps);
+        dfsdvb = -xjonxl*(dadvb*argb + arga*dbdvb);
+    }
+    else {
+        fshort = 1.0;
+        dfsdvb = 0.0;
+    }
+    double gammas = gamma*fshort;
+    double fbodys = 0.5*gammas/(sqphbs+sqphbs);
+    double fbody = fbodys + 0.0/m.w();
+    double onfbdy = 1.0/(1.0 + fbody);
+    double dfbdvb = -fbodys*dsqdvb/sqphbs + fbodys*dfsdvb/fshort;
+    double qbonco = gammas*sqphbs + 0.0*phibs/m.w();
+    double dqbdvb = gammas*dsqdvb + gamma*dfsdvb*sqphbs - 0.0/m.w();
+    double vth = qbonco + m.tVbi()*m.type - eta*lvds;
+    double dvtdvd = -eta;
+    double dvtdvb = dqbdvb;
+    ms.von = vth;
+    double cdrain;
+    double xn = 1.0, dxndvb, dvodvd, dvodvb;
+    if (nfs != 0.0) {
+        double csonco = CHARGE*nfs*CM2PM2*xl*m.w()/m.oxideCap();
+        double cdonco = qbonco/(phibs + phibs);
+        xn += csonco + cdonco;
+        ms.von += ms.vt*xn;
+        dxndvb = dqbdvb/(phibs + phibs) - qbonco*dsqdvb/(phibs*sqphbs);
+        dvodvd = dvtdvd;
+        dvodvb = dvtdvb + ms.vt*dxndvb;
+    }
+    else {
+        dxndvb = 0; dvodvd = 0; dvodvb = 0;
+        if (lvgs <= ms.von) {
+            m.gm() = 0.0; m.gds() = 0.0; m.gmbs() = 0.0;
+            return 0.0;
+        }
+    }
+    double vgsx = DMAX(lvgs, ms.von);
+    double onfg = 1.0 + theta*(vgsx - vth);
+    double fgate = 1.0/onfg;
+    double us = m.tSurfMob()*M2PCM2*fgate;
+    double dfgdvg = -theta*fgate*fgate;
+    double dfgdvd = -dfgdvg*dvtdvd;
+    double dfgdvb = -dfgdvg*dvtdvb;
+    double dvsdvg, dvsdvd, dvsdvb, onvdsc;
+    ms.vdsat = (vgsx - vth)*onfbdy;
+    if (vmax <= 0.0) {
+        dvsdvg = onfbdy;
+        dvsdvd = -dvsdvg*dvtdvd;
+        dvsdvb = -dvsdvg*dvtdvb - ms.vdsat*dfbdvb*onfbdy;
+        onvdsc = 0;
+    }
+    else {
+        double vdsc = xl*vmax/us;
+        onvdsc = 1.0/vdsc;
+        double arga = (vgsx - vth)*onfbdy;
+        double argb = sqrt(arga*arga + vdsc*vdsc);
+        ms.vdsat = arga + vdsc - argb;
+        double dvsdga = (1.0 - arga/argb)*onfbdy;
+        dvsdvg = dvsdga - (1.0 - vdsc/argb)*vdsc*dfgdvg*onfg;
+        dvsdvd = -dvsdvg*dvtdvd;
+        dvsdvb = -dvsdvg*dvtdvb - arga*dvsdga*dfbdvb;
+    }
+    double beta = m.beta();
+    double vdsx = DMIN(lvds, ms.vdsat);
+    if (vdsx == 0.0) {
+        beta *= fgate;
+        cdrain = 0.0;
+        gm = 0.0;
+        gds = beta*(vgsx - vth);
+        gmbs = 0.0;
+        if (nfs != 0.0 && lvgs < ms.von)
+            gds *= exp((lvgs - ms.von)/(ms.vt*xn));
+        m.gm() = gm; m.gds() = gds; m.gmbs() = gmbs;
+        return cdrain;
+    }
+    double cdo = vgsx - vth - 0.5*(1.0 + fbody)*vdsx;
+    double dcodvb = -dvtdvb - 0.5*dfbdvb*vdsx;
+    double cdnorm = cdo*vdsx;
+    gm = vdsx;
+    if ((m.mode*ms.vds) > ms.vdsat)
+        gds = -dvtdvd*vdsx;
+    else
+        gds = vgsx - vth - (1.0 + fbody + dvtdvd)*vdsx;
+    gmbs = dcodvb*vdsx;
+    double cd1 = beta*cdnorm;
+    beta *= fgate;
+    cdrain = beta*cdnorm;
+    gm = beta*gm + dfgdvg*cd1;
+    gds = beta*gds + dfgdvd*cd1;
+    gmbs = beta*gmbs + dfgdvb*cd1;
+    double fdrain, dfddvg, dfddvb, dfddvd;
+    if (vmax > 0.0) {
+        fdrain = 1.0/(1.0 + vdsx*onvdsc);
+        double fd2 = fdrain*fdrain;
+        double arga = fd2*vdsx*onvdsc*onfg;
+        dfddvg = -dfgdvg*arga;
+        if (m.mode*ms.vds > ms.vdsat)
+            dfddvd = -dfgdvd*arga;
+        else
+            dfddvd = -dfgdvd*arga - fd2*onvdsc;
+        dfddvb = -dfgdvb*arga;
+        gm = fdrain*gm + dfddvg*cdrain;
+        gds = fdrain*gds + dfddvd*cdrain;
+        gmbs = fdrain*gmbs + dfddvb*cdrain;
+        cdrain = fdrain*cdrain;
+        beta *= fdrain;
+    }
+    else {
+        fdrain = 0; dfddvg = 0; dfddvd = 0; dfddvb = 0;
+    }
+    double gds0 = 0;
+    if (lvds > ms.vdsat && !(vmax != 0.0 && alpha == 0)) {
+        double delxl, dldvd, ddldvg, ddldvd, ddldvb;
+        if (vmax == 0.0) {
+            delxl = sqrt(kappa*(lvds - ms.vdsat)*alpha);
+            dldvd = 0.5*delxl/(lvds - ms.vdsat);
+            ddldvg = 0.0;
+            ddldvd = -dldvd;
+            ddldvb = 0.0;
+        }
+        else {
+            double cdsat = cdrain;
+            double gdsat = cdsat*(1.0 - fdrain)*onvdsc;
+            gdsat = DMAX(1.0e-12, gdsat);
+            double gdoncd = gdsat/cdsat;
+            double gdonfd = gdsat/(1.0 - fdrain);
+            double gdonfg = gdsat*onfg;
+            double dgdvg = gdoncd*gm - gdonfd*dfddvg + gdonfg*dfgdvg;
+            double dgdvd = gdoncd*gds - gdonfd*dfddvd + gdonfg*dfgdvd;
+            double dgdvb = gdoncd*gmbs - gdonfd*dfddvb + gdonfg*dfgdvb;
+            double emax = kappa*cdsat*oneoverxl/gdsat;
+            double emoncd = emax/cdsat;
+            double emongd = emax/gdsat;
+            double demdvg = emoncd*gm - emongd*dgdvg;
+            double demdvd = emoncd*gds - emongd*dgdvd;
+            double demdvb = emoncd*gmbs - emongd*dgdvb;
+            double arga = 0.5*emax*alpha;
+            double argc = kappa*alpha;
+            double argb = sqrt(arga*arga + argc*(lvds - ms.vdsat));
+            delxl = argb - arga;
+            dldvd = argc/(argb+argb);
+            double dldem = 0.5*(arga/argb - 1.0)*alpha;
+            ddldvg = dldem*demdvg;
+            ddldvd = dldem*demdvd - dldvd;
+            ddldvb = dldem*demdvb;
+        }
+        if (delxl > (0.5*xl)) {
+            delxl = xl - (xl*xl/(4.0*delxl));
+            double arga = 4.0*(xl - delxl)*(xl - delxl)/(xl*xl);
+            ddldvg = ddldvg*arga;
+            ddldvd = ddldvd*arga;
+            ddldvb = ddldvb*arga;
+            dldvd = dldvd*arga;
+        }
+        double dlonxl = delxl*oneoverxl;
+        double xlfact = 1.0/(1.0 - dlonxl);
+        cd1 = cdrain;
+        cdrain = cdrain*xlfact;
+        double diddl = cdrain/(xl - delxl);
+        gm = gm*xlfact + diddl*ddldvg;
+        gmbs = gmbs*xlfact + diddl*ddldvb;
+        gds0 = diddl*ddldvd;
+        gm = gm + gds0*dvsdvg;
+        gmbs = gmbs + gds0*dvsdvb;
+        gds = gds*xlfact + diddl*dldvd + gds0*dvsdvd;
+    }
+    if (lvgs < ms.von) {
+        double onxn = 1.0/xn;
+        double ondvt = onxn/ms.vt;
+        double wfact = exp((lvgs - ms.von)*ondvt);
+        cdrain = cdrain*wfact;
+        double gms = gm*wfact;
+        double gmw = cdrain*ondvt;
+        gm = gmw;
+        if (lvds > ms.vdsat)
+            gm = gm + gds0*dvsdvg*wfact;
+        gds = gds*wfact + (gms - gmw)*dvodvd;
+        gmbs = gmbs*wfact + (gms - gmw)*dvodvb - gmw*(lvgs - ms.von)*onxn*dxndvb;
+    }
+    (void)cd1;
+    m.gm() = gm; m.gds() = gds; m.gmbs() = gmbs;
+    return cdrain;
+}
+
 // moseq.cc:1091-1172: level 6, n-th power law
 __device__ inline double dev_mos_eq6(MosInst &m, MosStuff &ms)
 {
@@ -640,7 +877,8 @@ __device__ inline void dev_mos_iv(MosInst &m, MosStuff &ms, double gmin)
         m.cbd() = m.tDrainSatCur()*(evbd-1) + gmin*ms.vbd;
     }
     m.mode = (ms.vds >= 0) ? 1 : -1;
-    ms.cdrain = (m.level == 6) ? dev_mos_eq6(m, ms) : dev_mos_eq1(m, ms);   // mosload.cc:570-577
+    // mosload.cc:570-577
+    ms.cdrain = (m.level == 6) ? dev_mos_eq6(m, ms) : (m.level == 3) ? dev_mos_eq3(m, ms) : dev_mos_eq1(m, ms);
     if (m.type > 0) {
         m.von() = ms.von; m.vdsat() = ms.vdsat;
     }
@@ -1085,6 +1323,7 @@ struct MosCard {            // per instance, shared by all trials (device array)
     double drainArea, sourceArea, drainPerimeter, sourcePerimeter, mult, temp;
     double dcon, scon, icVDS, icVGS, icVBS;
     double kv, nv, nc, lamda0, lamda1, sigma, gamma1;    // level 6
+    double nfs, vmax, xj, eta, theta, kappa;             // level 3
 };
 
 // raw[] = vto kp gamma phi lambda l w (NaN = not given for vto/kp/gamma/phi)
@@ -1179,6 +1418,7 @@ __device__ inline void dev_mos_temp(const MosCard &k, const double *raw, double 
 
     tmp = 1/(ratio*sqrt(ratio));
     double tTransconductance = kp*tmp;
+    const double tmp_mob = tmp;          // 1/(ratio*sqrt(ratio)), mostemp.cc:155
 
     tmp = (phi - pbfact1)/fact1;
     double tPhi = fact2*tmp + pbfact;
@@ -1266,6 +1506,25 @@ __device__ inline void dev_mos_temp(const MosCard &k, const double *raw, double 
     out[MP_rvt] = 1.0/out[MP_vt]; out[MP_rBulkPot] = 1.0/out[MP_tBulkPot];
     out[MP_r1mj] = 1.0/(1 - k.mj); out[MP_r1mjsw] = 1.0/(1 - k.mjsw);
     out[MP_r2phi] = 1.0/(2*out[MP_tPhi]); out[MP_r15phi] = 1.0/(1.5*out[MP_tPhi]);
+    // level 3: mostemp.cc:119-142.  The narrow-width factor is always 0 in the reference: the
+    // card's "delta" lands in MOSnarrowFactor (mossetm.cc:216-219) and mostemp overwrites it
+    // with MOSdelta (default 0) * pi/2 * EPSSIL / oxideCapFactor.
+    {
+        double alpha = 0, xd = 0;
+        if (!skip && k.g_nsub) {
+            if (k.level == 2)
+                xd = sqrt((EPSSIL+EPSSIL)/(CHARGE*k.nsub*CM3PM3));
+            else if (k.level == 3) {
+                alpha = (EPSSIL+EPSSIL)/(CHARGE*k.nsub*CM3PM3);
+                xd = sqrt(alpha);
+            }
+        }
+        out[MP_xd] = xd; out[MP_alpha] = alpha;
+    }
+    out[MP_eta] = k.eta; out[MP_theta] = k.theta; out[MP_kappa] = k.kappa; out[MP_vmax] = k.vmax;
+    out[MP_xj] = k.xj; out[MP_ld] = k.ld; out[MP_nfs] = k.nfs;
+    out[MP_oxideCapFactor] = oxideCapFactor; out[MP_tSurfMob] = surfaceMobility*tmp_mob;
+    out[MP_xl] = effectiveLength; out[MP_w] = w;
     out[MP_kv] = k.kv; out[MP_nv] = k.nv; out[MP_nc] = k.nc; out[MP_lamda0] = k.lamda0;
     out[MP_lamda1] = k.lamda1; out[MP_sigma] = k.sigma; out[MP_gamma1] = k.gamma1;
     out[MP_icVDS] = k.icVDS; out[MP_icVGS] = k.icVGS; out[MP_icVBS] = k.icVBS;
