@@ -78,7 +78,7 @@ typedef struct {
     b200_mos in;
     /* model-derived (mostemp.cc:65-139) */
     double oxideCapFactor, surfaceMobility, kp_eff, gamma_eff, phi_eff, vt0_eff;
-    double xd, alpha, narrowFactor;      /* level 2/3 (mostemp.cc:113-143) */
+    double xd, alpha, narrowFactor, nsub;      /* level 2/3 (mostemp.cc:113-143) */
     /* nodes */
     int d, g, s, b, dp, sp;
     int ptr[M_NPTR];
@@ -565,7 +565,10 @@ static void mos_setup(wo_ckt *c, Mos *m, int idx)
     if (!GIVEN(md->js)) md->js = 0;
     if (!GIVEN(md->ld)) md->ld = 0;
     if (!GIVEN(md->fc)) md->fc = .5;
-    /* level 2/3, mosset.cc:220-253 */
+    /* level 2/3, mosset.cc:208-253 */
+    if (!GIVEN(md->uexp)) md->uexp = 0;
+    if (!GIVEN(md->neff)) md->neff = 1;
+    if (!GIVEN(md->ucrit)) md->ucrit = 1e4;
     if (!GIVEN(md->nfs)) md->nfs = 0;
     if (!GIVEN(md->delta)) md->delta = 0;
     if (!GIVEN(md->vmax)) md->vmax = 0;
@@ -750,7 +753,7 @@ static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
     /* mostemp.cc:138-142 computes narrowFactor = MOSdelta*pi/2*EPSSIL/oxideCapFactor for level 3, but
      * the card's "delta" is stored in MOSnarrowFactor (mossetm.cc:216-219) and MOSdelta keeps its
      * default 0 (mosset.cc:230-231): the narrow-width term is always 0 in the reference. */
-    m->narrowFactor = 0.0;
+    m->narrowFactor = (md->level == 2 && GIVEN(deckmod->delta)) ? deckmod->delta : 0.0;   /* level 2: mossetm.cc:216-219 */
     if (!GIVEN(kp))
         kp = 2e-5;                       /* mosset.cc:101-103 */
     if (!GIVEN(kc))
@@ -758,6 +761,7 @@ static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
     if (md->level == 6)
         kp = kc;                         /* mostemp.cc:156-159: tTransconductance = kc*tmp */
     m->kp_eff = kp;
+    m->nsub = GIVEN(deckmod->nsub) ? deckmod->nsub : 0;
     double cj = GIVEN(deckmod->cj) ? deckmod->cj : 0;
     double cjsw = GIVEN(deckmod->cjsw) ? deckmod->cjsw : 0;
 
@@ -1492,6 +1496,382 @@ static double mos_eq6(Mos *m, MosStuff *ms)
     return cdrain;
 }
 
+#define P66 .66666666666667
+#define P33 .33333333333333
+#define P1X3 1.3333333333333
+
+static void mos2_vsat(double *vsat, double *baum)
+{
+    /* moseq.cc:602-688: Baum's scattering-limited velocity saturation (quartic) */
+    double a1 = baum[0], b1 = baum[1], c1 = baum[2], d1 = baum[3];
+    double tmp = a1*c1 - 4.0*d1;
+    double tmp1 = -P33*b1*b1 + tmp;
+    double s = -2.0*b1*b1*b1/27.0 + P33*b1*tmp;
+    tmp = -d1*(a1*a1 - 4.0*b1) - c1*c1;
+    s += tmp;
+    double s2 = s*s;
+    tmp = P33*tmp1;
+    tmp *= tmp*tmp;
+    double p = .25*s2 + tmp;
+    double p0 = fabs(p);
+    double p2 = sqrt(p0);
+    double y3;
+    if (p < 0) {
+        tmp = sqrt(.25*s2 + p0);
+        tmp = exp(P33*log(tmp));
+        y3 = 2.0*tmp*cos(P33*atan(-2.0*p2/s)) + P33*b1;
+    }
+    else {
+        tmp = (-.5*s + p2);
+        tmp = exp(P33*log(fabs(tmp)));
+        tmp1 = (-.5*s - p2);
+        tmp1 = exp(P33*log(fabs(tmp1)));
+        y3 = tmp + tmp1 + P33*b1;
+    }
+    int jknt = 0;
+    double a3 = sqrt(.25*a1*a1 - b1 + y3);
+    double b3 = sqrt(.25*y3*y3 - d1);
+    double b00 = .5*y3 + b3, b01 = .5*y3 - b3;
+    double a00 = .5*a1 + a3, a01 = .5*a1 - a3;
+    double a02 = .25*a00*a00, a03 = .25*a01*a01;
+    double a04 = -.5*a00, a05 = -.5*a01;
+    double az[4] = { a02 - b00, a03 - b00, a02 - b01, a03 - b01 };
+    double bz[4] = { a04, a05, a04, a05 };
+    for (int i = 0; i < 4; i++) {
+        tmp = az[i];
+        if (tmp >= 0) {
+            tmp = sqrt(tmp);
+            double ptmp = bz[i] + tmp;
+            if (ptmp > 0) {
+                double poly4 = d1 + ptmp*(c1 + ptmp*(b1 + ptmp*(a1 + ptmp)));
+                if (fabs(poly4) <= 1.0e-6) {
+                    if (!jknt || ptmp <= tmp1) tmp1 = ptmp;
+                    jknt++;
+                }
+            }
+            ptmp = bz[i] - tmp;
+            if (ptmp > 0) {
+                double poly4 = d1 + ptmp*(c1 + ptmp*(b1 + ptmp*(a1 + ptmp)));
+                if (fabs(poly4) <= 1.0e-6) {
+                    if (!jknt || ptmp <= tmp1) tmp1 = ptmp;
+                    jknt++;
+                }
+            }
+        }
+    }
+    if (jknt > 0)
+        *vsat = tmp1*tmp1 - baum[4];
+}
+
+static double mos_eq2(Mos *m, MosStuff *ms)
+{
+    /* moseq.cc:147-597: level 2 (Grove-Frohman / Meyer analytical model) */
+    const b200_mos_model *md = &m->mod;
+    double lvbs, lvds, lvgs;
+    if (m->mode > 0) { lvbs = ms->vbs; lvds = ms->vds; lvgs = ms->vgs; }
+    else { lvbs = ms->vbd; lvds = -ms->vds; lvgs = ms->vgd; }
+    const double xl = m->effectiveLength;
+    const double nsub = m->nsub;                 /* MOSsubstrateDoping, 0 if not given */
+    double xlamda = md->lambda;
+    double phiMinVbs = m->tPhi - lvbs;
+    double oneoverl = 1.0/xl;
+    double sarg, dsrgdb, d2sdb2;
+    double sphi = sqrt(m->tPhi);
+    double sphi3 = m->tPhi*sphi;
+    if (lvbs <= 0.0) {
+        sarg = sqrt(phiMinVbs);
+        dsrgdb = -0.5/sarg;
+        d2sdb2 = 0.5*dsrgdb/phiMinVbs;
+    }
+    else {
+        sarg = sphi/(1.0 + 0.5*lvbs/m->tPhi);
+        double tmp = sarg/sphi3;
+        dsrgdb = -0.5*sarg*tmp;
+        d2sdb2 = -dsrgdb*tmp;
+    }
+    double barg, dbrgdb, d2bdb2;
+    if ((lvds - lvbs) >= 0) {
+        barg = sqrt(phiMinVbs + lvds);
+        dbrgdb = -0.5/barg;
+        d2bdb2 = 0.5*dbrgdb/(phiMinVbs + lvds);
+    }
+    else {
+        barg = sphi/(1.0 + 0.5*(lvbs - lvds)/m->tPhi);
+        double tmp = barg/sphi3;
+        dbrgdb = -0.5*barg*tmp;
+        d2bdb2 = -dbrgdb*tmp;
+    }
+    int fssandcap = (md->nfs != 0.0 && m->oxideCap != 0.0);
+    double factor = 0.125*m->narrowFactor*2.0*M_PI*EPSSIL/m->oxideCap*xl;
+    double eta = 1.0 + factor;
+    double oneovere = 1.0/eta;
+    double vbin = m->tVbi*md->type + factor*phiMinVbs;
+    double gamasd = md->gamma, gammad = md->gamma;
+    double dgddvb = 0.0, dgdvds = 0.0, dgddb2 = 0.0;
+    if ((md->gamma > 0.0) || (nsub > 0.0)) {
+        if (md->xj > 0) {
+            double tbxwd = m->xd*dbrgdb;
+            double tbxws = m->xd*dsrgdb;
+            double tmp = 2.0/md->xj;
+            double targxs = 1.0 + tmp*m->xd*sarg;
+            double targxd = 1.0 + tmp*m->xd*barg;
+            double targs = sqrt(targxs);
+            double targd = sqrt(targxd);
+            tmp = .5*md->xj*oneoverl;
+            gamasd *= (1.0 - tmp*(targs + targd - 2.0));
+            targs = oneoverl/targs;
+            targd = oneoverl/targd;
+            dgddvb = -.5*md->gamma*(tbxws*targs + tbxwd*targd);
+            dgdvds = md->gamma*0.5*tbxwd*targd;
+            tmp = -m->xd*(d2sdb2 + dsrgdb*dsrgdb*m->xd/(md->xj*targxs))*targs;
+            double tmp1 = -m->xd*(d2bdb2 + dbrgdb*dbrgdb*m->xd/(md->xj*targxd))*targd;
+            dgddb2 = -0.5*md->gamma*(tmp + tmp1);
+        }
+    }
+    ms->von = vbin + gamasd*sarg;
+    double vth = ms->von;
+    ms->vdsat = 0.0;
+    double argg;
+    double xn = 1.0;
+    if (fssandcap) {
+        double tmp = CHARGE*md->nfs*CM2PM2;
+        double tmp1 = -(gamasd*dsrgdb + dgddvb*sarg) + factor;
+        xn += tmp/m->oxideCap*m->w*xl + tmp1;
+        tmp = ms->vt*xn;
+        ms->von += tmp;
+        argg = 1.0/tmp;
+    }
+    else {
+        argg = 0;
+        if (lvgs <= vbin)
+            m->gds = 0.0;
+    }
+    double cdrain = 0;
+    if (fssandcap || (lvgs > vbin)) {
+        double vgst = lvgs - ms->von;
+        double sarg3 = sarg*sarg*sarg;
+        double sbiarg = sqrt(m->tBulkPot);
+        gammad = gamasd;
+        double dgdvbs = dgddvb;
+        double body = barg*barg*barg - sarg3;
+        double gdbdv = 2.0*gammad*(barg*barg*dbrgdb - sarg*sarg*dsrgdb);
+        double dodvbs = -factor + dgdvbs*sarg + gammad*dsrgdb;
+        double dxndvb, dxndvd, dodvds;
+        if (fssandcap) {
+            dxndvb = 2.0*dgdvbs*dsrgdb + gammad*d2sdb2 + dgddb2*sarg;
+            dodvbs = dodvbs + ms->vt*dxndvb;
+            dxndvd = dgdvds*dsrgdb;
+            dodvds = dgdvds*sarg + ms->vt*dxndvd;
+        }
+        else {
+            dxndvb = 0; dxndvd = 0; dodvds = 0;
+        }
+        double ufact, ueff, dudvgs, dudvds, dudvbs;
+        if (m->oxideCap <= 0.0) {
+            ufact = 1.0;
+            ueff = m->surfaceMobility*M2PCM2;
+            dudvgs = 0.0; dudvds = 0.0; dudvbs = 0.0;
+        }
+        else {
+            double tmp = md->ucrit*100*EPSSIL/m->oxideCapFactor;
+            if (vgst <= tmp) {
+                ufact = 1.0;
+                ueff = m->surfaceMobility*M2PCM2;
+                dudvgs = 0.0; dudvds = 0.0; dudvbs = 0.0;
+            }
+            else {
+                ufact = exp(md->uexp*log(tmp/vgst));
+                ueff = m->surfaceMobility*M2PCM2*ufact;
+                dudvgs = -ufact*md->uexp/vgst;
+                dudvds = 0.0;
+                dudvbs = md->uexp*ufact*dodvbs/vgst;
+            }
+        }
+        gammad = gamasd*oneovere;
+        dgdvbs = dgddvb;
+        double vgsx = lvgs;
+        if (fssandcap)
+            vgsx = SPMAX(lvgs, ms->von);
+        double dsdvgs, dsdvbs;
+        if (gammad > 0) {
+            double tmp = gammad*gammad;
+            double tmp1 = (vgsx - vbin)*oneovere + phiMinVbs;
+            if (tmp1 <= 0.0) {
+                ms->vdsat = 0.0;
+                dsdvgs = 0.0;
+                dsdvbs = 0.0;
+            }
+            else {
+                double arg = sqrt(1.0 + 4.0*tmp1/tmp);
+                ms->vdsat = (vgsx - vbin)*oneovere + .5*tmp*(1.0 - arg);
+                ms->vdsat = SPMAX(ms->vdsat, 0.0);
+                dsdvgs = (1.0 - 1.0/arg)*oneovere;
+                dsdvbs = (gammad*(1.0 - arg) + 2.0*tmp1/(gammad*arg))*oneovere*dgdvbs +
+                    1.0/arg + factor*dsdvgs;
+            }
+        }
+        else {
+            ms->vdsat = (vgsx - vbin)*oneovere;
+            ms->vdsat = SPMAX(ms->vdsat, 0.0);
+            dsdvgs = 1.0;
+            dsdvbs = 0.0;
+        }
+        if (md->vmax > 0) {
+            double tmp = md->vmax*xl/ueff;
+            double tmp1 = (vgsx - vbin)*oneovere + phiMinVbs;
+            double param[5];
+            param[0] = P1X3*gammad;
+            param[1] = -2.0*(tmp1 + tmp);
+            param[2] = -2.0*gammad*tmp;
+            param[3] = 2.0*tmp1*(phiMinVbs + tmp) - phiMinVbs*phiMinVbs - P1X3*gammad*sarg3;
+            param[4] = phiMinVbs;
+            mos2_vsat(&ms->vdsat, param);
+        }
+        double dldvgs = 0.0, dldvds = 0.0, dldvbs = 0.0;
+        double bsarg, bodys, gdbdvs, dbsrdb = 0;
+        if (lvds == 0.0) {
+            bsarg = 0; bodys = 0; gdbdvs = 0;
+        }
+        else {
+            gammad = gamasd;
+            if ((lvbs - ms->vdsat) <= 0) {
+                bsarg = sqrt(ms->vdsat + phiMinVbs);
+                dbsrdb = -0.5/bsarg;
+            }
+            else {
+                bsarg = sphi/(1.0 + 0.5*(lvbs - ms->vdsat)/m->tPhi);
+                dbsrdb = -0.5*bsarg*bsarg/sphi3;
+            }
+            bodys = bsarg*bsarg*bsarg - sarg3;
+            gdbdvs = 2.0*gammad*(bsarg*bsarg*dbsrdb - sarg*sarg*dsrgdb);
+            if (md->vmax <= 0) {
+                if (nsub != 0.0 && xlamda <= 0.0) {
+                    double tmp = .25*(lvds - ms->vdsat);
+                    double tmp1 = sqrt(1.0 + tmp*tmp);
+                    tmp = sqrt(tmp + tmp1);
+                    xlamda = m->xd*tmp*oneoverl/lvds;
+                    tmp = lvds*xlamda/(8.0*tmp1);
+                    dldvgs = tmp*dsdvgs;
+                    dldvds = -xlamda + tmp;
+                    dldvbs = tmp*dsdvbs;
+                }
+            }
+            else {
+                double txdv = m->xd/sqrt(md->neff);
+                double txlv = md->vmax*txdv/(2.0*ueff);
+                double tqdsat = -1.0 + gammad*dbsrdb;
+                double tmp = md->vmax*xl;
+                double tmp1 = (vgsx - vbin)*oneovere - ms->vdsat - gammad*bsarg;
+                tmp1 = 1.0/(tmp*tqdsat - ueff*tmp1);
+                dsdvgs = -(tmp - ueff*ms->vdsat)*oneovere*tmp1;
+                dsdvbs = -(-tmp*(1.0 + tqdsat - factor*oneovere) +
+                    ueff*(gdbdvs - P66*dgdvbs*bodys)*oneovere)*tmp1;
+                if (nsub != 0.0 && xlamda <= 0.0) {
+                    tmp = lvds - ms->vdsat;
+                    tmp = SPMAX(tmp, 0.0);
+                    tmp1 = sqrt(txlv*txlv + tmp);
+                    tmp = txdv*oneoverl/(2.0*tmp1);
+                    xlamda = txdv*(tmp1 - txlv)*oneoverl/lvds;
+                    dldvgs = tmp*dsdvgs;
+                    dldvds = -xlamda + tmp;
+                    dldvbs = tmp*dsdvbs;
+                }
+            }
+        }
+        double xwb = m->xd*sbiarg;
+        double clfact = 1.0 - xlamda*lvds;
+        dldvds = -xlamda - dldvds;
+        double tmp1 = xl*clfact;
+        double tmp = xlamda*lvds*xl;
+        if (nsub == 0.0) xwb = 0.25e-6;
+        if (tmp1 < xwb) {
+            tmp1 = xwb/(1.0 + (tmp - xl - xwb)/xwb);
+            clfact = tmp1*oneoverl;
+            double dfact = tmp1/xwb;
+            dfact *= dfact;
+            dldvgs *= dfact;
+            dldvds *= dfact;
+            dldvbs *= dfact;
+        }
+        clfact = 1.0/clfact;
+        double beta1 = m->beta*ufact*clfact;
+        ufact = 1.0/ufact;
+        gammad = gamasd;
+        dgdvbs = dgddvb;
+        if (lvds > 1.0e-10) {
+            if (lvgs > ms->von) {
+                if (lvds <= ms->vdsat) {
+                    cdrain = beta1*((lvgs - vbin - .5*eta*lvds)*lvds - P66*gammad*body);
+                    tmp = cdrain*(dudvgs*ufact - dldvgs*clfact);
+                    m->gm = tmp + beta1*lvds;
+                    tmp = cdrain*(dudvds*ufact - dldvds*clfact);
+                    m->gds = tmp + beta1*(lvgs - vbin - eta*lvds - gammad*barg - P66*dgdvds*body);
+                    tmp = cdrain*(dudvbs*ufact - dldvbs*clfact);
+                    m->gmbs = tmp - beta1*(gdbdv + P66*dgdvbs*body - factor*lvds);
+                }
+                else {
+                    cdrain = beta1*((lvgs - vbin - eta*.5*ms->vdsat)*ms->vdsat - P66*gammad*bodys);
+                    tmp = cdrain*(dudvgs*ufact - dldvgs*clfact);
+                    m->gm = tmp + beta1*ms->vdsat +
+                        beta1*(lvgs - vbin - eta*ms->vdsat - gammad*bsarg)*dsdvgs;
+                    m->gds = -cdrain*dldvds*clfact - P66*beta1*dgdvds*bodys;
+                    tmp = cdrain*(dudvbs*ufact - dldvbs*clfact);
+                    m->gmbs = tmp - beta1*(gdbdvs + P66*dgdvbs*bodys - factor*ms->vdsat) +
+                        beta1*(lvgs - vbin - eta*ms->vdsat - gammad*bsarg)*dsdvbs;
+                }
+            }
+            else {
+                if (ms->vdsat <= 0) {
+                    m->gds = 0.0;
+                    if (lvgs > vth)
+                        return cdrain;
+                    m->gm = 0.0;
+                    m->gmbs = 0.0;
+                    return 0.0;
+                }
+                double vdson = SPMIN(ms->vdsat, lvds);
+                if (lvds > ms->vdsat) {
+                    barg = bsarg;
+                    dbrgdb = dbsrdb;
+                    body = bodys;
+                    gdbdv = gdbdvs;
+                }
+                double cdson = beta1*((ms->von - vbin - .5*eta*vdson)*vdson - P66*gammad*body);
+                double didvds = beta1*(ms->von - vbin - eta*vdson - gammad*barg);
+                double gdson = -cdson*dldvds*clfact - P66*beta1*dgdvds*body;
+                if (lvds < ms->vdsat)
+                    gdson += didvds;
+                double gbson = -cdson*dldvbs*clfact +
+                    beta1*(dodvbs*vdson + factor*vdson - P66*dgdvbs*body - gdbdv);
+                if (lvds > ms->vdsat)
+                    gbson += didvds*dsdvbs;
+                tmp = exp(argg*(lvgs - ms->von));
+                cdrain = cdson*tmp;
+                double gmw = cdrain*argg;
+                m->gm = gmw;
+                if (lvds > ms->vdsat) m->gm = gmw + didvds*dsdvgs*tmp;
+                tmp1 = gmw*(lvgs - ms->von)/xn;
+                m->gds = gdson*tmp - m->gm*dodvds - tmp1*dxndvd;
+                m->gmbs = gbson*tmp - m->gm*dodvbs - tmp1*dxndvb;
+            }
+            return cdrain;
+        }
+        else {
+            if (lvgs <= ms->von) {
+                if (!fssandcap)
+                    m->gds = 0.0;
+                else
+                    m->gds = beta1*(ms->von - vbin - gammad*sarg)*exp(argg*(lvgs - ms->von));
+            }
+            else
+                m->gds = beta1*(lvgs - vbin - gammad*sarg);
+        }
+    }
+    m->gm = 0.0;
+    m->gmbs = 0.0;
+    return 0.0;
+}
+
 static double mos_eq3(Mos *m, MosStuff *ms)
 {
     /* moseq.cc:693-1083: level 3 (semi-empirical short-channel model) */
@@ -1768,8 +2148,9 @@ static void mos_iv(wo_ckt *c, Mos *m, MosStuff *ms)
         m->cbd = m->tDrainSatCur*(evbd-1) + gmin*ms->vbd;
     }
     m->mode = (ms->vds >= 0) ? 1 : -1;
-    /* mosload.cc:570-577; level 2 not restated */
-    ms->cdrain = (m->mod.level == 6) ? mos_eq6(m, ms) : (m->mod.level == 3) ? mos_eq3(m, ms) : mos_eq1(m, ms);
+    /* mosload.cc:570-577 */
+    ms->cdrain = (m->mod.level == 6) ? mos_eq6(m, ms) : (m->mod.level == 3) ? mos_eq3(m, ms) :
+        (m->mod.level == 2) ? mos_eq2(m, ms) : mos_eq1(m, ms);
     if (m->mod.type > 0) {
         m->von = ms->von; m->vdsat = ms->vdsat;
     }

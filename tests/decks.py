@@ -167,6 +167,31 @@ def inv_level3():
     return d
 
 
+L2 = dict(tox=2.5e-8, nsub=1.5e16, xj=3e-7, ld=1e-7, u0=580, ucrit=5e4, uexp=0.12, neff=2.5,
+          vmax=1.2e5, nfs=1.5e11, delta=1.2, cgso=2e-10, cgdo=2e-10, cbd=2e-15, cbs=2e-15)
+L2S = dict(tox=2.5e-8, kp=8e-5, gamma=0.45, phi=0.68, ucrit=4e4, uexp=0.1,
+           cgso=2e-10, cgdo=2e-10, cbd=2e-15, cbs=2e-15, **{"lambda": 0.03})
+
+
+def ro_level2(n=5, card=None):
+    """Ring oscillator with MOS level 2 devices (moseq.cc:147): short/narrow channel threshold,
+    mobility degradation, Baum velocity saturation (quartic), weak inversion, punch-through."""
+    card = L2 if card is None else card
+    d = ring_oscillator(n, tstop=8e-9, tstep=0.08e-9)
+    d.mos_models.clear()
+    d.mos_model("nm", "nmos", level=2, vto=0.7, **card)
+    d.mos_model("pm", "pmos", level=2, vto=-0.7, **dict(card, **({"u0": card["u0"]*0.4} if "u0" in card else {"kp": card["kp"]*0.4})))
+    return d
+
+
+def inv_level2():
+    d = inv_chain(4)
+    d.mos_models.clear()
+    d.mos_model("nm", "nmos", level=2, vto=0.7, **L2S)
+    d.mos_model("pm", "pmos", level=2, vto=-0.7, **dict(L2S, kp=3.2e-5))
+    return d
+
+
 def ro_rd(n=3):
     """Ring oscillator whose MOSFETs have series rd/rs: internal drain/source nodes."""
     d = ring_oscillator(n)
@@ -202,7 +227,8 @@ def op_decks():
             "op_inv_dc_gminfirst": inv_dc(3).options(gminfirst=1),
             "op_inv7_nogmin": inv_chain(7).options(gminsteps=-1),
             "op_inv_lsupply": inv_lsupply(), "op_inv4_level6": inv_level6(), "op_inv4_level3": inv_level3(),
-            "op_ro5_level3": ro_level3(5)}
+            "op_ro5_level3": ro_level3(5), "op_inv4_level2": inv_level2(),
+            "op_ro5_level2": ro_level2(5)}
 
 
 def variants():
@@ -215,6 +241,9 @@ def variants():
         "transformer": transformer(),
         "ro5_level6": ro_level6(5),
         "ro5_level3": ro_level3(5),
+        "ro5_level2": ro_level2(5),
+        "ro3_level2_simple": ro_level2(3, L2S),
+        "inv4_level2": inv_level2(),
         "ro3_level3_simple": ro_level3(3, L3S),
         "inv4_level3": inv_level3(),
         # transient iteration limit hit: non-convergence -> delta/8 cuts (tranan.cc:744-762)

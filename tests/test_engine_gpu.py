@@ -124,6 +124,14 @@ def test_monte_carlo_level3():
     compare(d, ntr, mc_variation(d, ntr, seed=33), min_same=0.9)
 
 
+def test_monte_carlo_level2():
+    """MOS level 2 ring oscillator (Baum velocity saturation, weak inversion, punch-through
+    limit) with per-trial vto and L."""
+    d = variants()["ro5_level2"]
+    ntr = 15
+    compare(d, ntr, mc_variation(d, ntr, seed=44), min_same=0.85)
+
+
 @pytest.mark.parametrize("nstages", [1001, 2001])
 def test_large_circuits_use_narrower_tiles(nstages):
     """2 002 / 4 002 MOSFETs: the LU image of 4 trials no longer fits shared memory, the solve

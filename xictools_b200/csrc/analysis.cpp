@@ -204,7 +204,6 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             const b200_mos_model &md = dk->mos_models[in.model];
             int level = md.level;
             if (level != 1 && level != 2 && level != 3 && level != 6) level = 1;
-            if (level == 2) { err = "MOS levels 1, 3 and 6 are built (level 2: SURVEY.md section 8 a2, next)"; return B200_E_UNSUPP; }
             M.type[i] = md.type > 0 ? 1 : -1;
             M.level[i] = level;
             M.off[i] = in.off;

@@ -50,6 +50,8 @@ enum { MP_tPhi, MP_tVbi, MP_tVto, MP_gamma, MP_lambda, MP_beta, MP_oxideCap,
        // level 3 (moseq.cc:693): model cards, doping-derived xd / alpha, and the geometry
        MP_eta, MP_theta, MP_kappa, MP_vmax, MP_xj, MP_ld, MP_nfs, MP_xd, MP_alpha,
        MP_oxideCapFactor, MP_tSurfMob, MP_xl, MP_w,
+       // level 2 (moseq.cc:147)
+       MP_uexp, MP_ucrit, MP_neff, MP_narrow, MP_nsub, MP_surfMob,
        MP_NPARAMS };
 
 // ---- MOS raw (card) parameters that may vary per trial ----

@@ -142,7 +142,12 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
         c.fc = given(md.fc) ? md.fc : .5; c.nsub = given(md.nsub) ? md.nsub : 0;
         c.tpg = given(md.tpg) ? md.tpg : 1; c.nss = given(md.nss) ? md.nss : 0;
         c.tnom = given(md.tnom) ? md.tnom : o.tnom;
-        // levels 2/3, mosset.cc:220-253
+        // levels 2/3, mosset.cc:208-253
+        c.uexp = given(md.uexp) ? md.uexp : 0; c.neff = given(md.neff) ? md.neff : 1;
+        c.ucrit = given(md.ucrit) ? md.ucrit : 1e4;
+        // the card's delta is the narrow-channel factor itself (mossetm.cc:216-219); level 3 then
+        // overwrites it with 0 (mostemp.cc:138-142, MOSdelta is never set)
+        c.narrow = (c.level == 2 && given(md.delta)) ? md.delta : 0;
         c.nfs = given(md.nfs) ? md.nfs : 0; c.vmax = given(md.vmax) ? md.vmax : 0;
         c.xj = given(md.xj) ? md.xj : 0; c.eta = given(md.eta) ? md.eta : 0;
         c.theta = given(md.theta) ? md.theta : 0; c.kappa = given(md.kappa) ? md.kappa : .2;
@@ -509,7 +514,7 @@ static int prepare_params(b200_batch *b)
             sm.ts[k] = row;
             sm.off[k] = row ? (SR_PRM + q++)*MOS_TPB : shared_base + k;
         }
-        b->M.stage_doubles = shared_base + MP_NPARAMS;
+        b->M.stage_doubles = shared_base + (other ? MP_NPARAMS : MP_NBASE);
     }
     CK(cudaMemcpy(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice));
     launch_mos_temp(b->stream, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);

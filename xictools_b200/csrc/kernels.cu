@@ -80,8 +80,9 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     int t = blockIdx.x*MOS_TPB + tid;
     int i = blockIdx.y;
     // shared parameter block (values common to all trials)
-    if (tid < MP_NPARAMS && !map.ts[tid])
-        stage[map.off[tid]] = M.prm[tid].base[i];
+    constexpr int NSHARED = L6 ? MP_NPARAMS : MP_NBASE;      // a level-1 deck stages the base set only
+    for (int k = tid; k < NSHARED; k += MOS_TPB)
+        if (!map.ts[k]) stage[map.off[k]] = M.prm[k].base[i];
     int mode = (t < K.ntrials) ? hot.mode[t] : 0;
     // trials that are finished (or past the end) stage nothing but still meet the barrier
     TrialCtx c;
