@@ -252,6 +252,18 @@ def test_full_size_properties_ro101():
     b.close()
 
 
+def test_bench_workload_spot_check_ro501():
+    """The bench deck itself (RO-501, per-device vto / L variation as bench.py draws it), 512
+    trials: every trial finishes with 101 output points, and 24 trials spread over the batch
+    match the oracle in step / iteration counts and waveforms."""
+    import bench
+    d = bench.make_deck(501)
+    ntr = 512
+    ov = bench.make_variation(d, ntr, seed=100)
+    same = compare(d, ntr, ov, trials=list(range(0, ntr, 23)) + [ntr - 1], min_same=0.9)
+    assert same >= 21
+
+
 def compare_op(deck, ntr, ov=None, trials=None, tol_scale=1.0):
     b = engine.Batch(deck, ntr)
     if ov:
