@@ -260,12 +260,22 @@ def bench_ours(args):
     # ---- end-to-end timing (host buffers, public API) ----
     for _ in range(max(1, min(args.warmup, 2))):     # NCCL connection set-up, first-touch of host buffers
         step_e2e()
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()
     barrier()
     t1 = time.perf_counter()
+    e2e_steps = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         cnt_e, w_e = step_e2e()
+        e2e_steps.append(time.perf_counter() - ts)
     barrier()
     el_e2e = time.perf_counter() - t1
+    clocks_e2e = sampler2.stop() if rank == 0 else None
+    if rank == 0:
+        print("bench: e2e seconds per step", ["%.3f" % x for x in e2e_steps],
+              "engine events of the last one %.3f" % (batch.stats().ms_total*1e-3), file=sys.stderr)
 
     tmax = torch.tensor([el, el_e2e, el_wall], dtype=torch.float64, device="cuda")
     agg = torch.tensor([float(ok_trials), float(launches)], dtype=torch.float64, device="cuda")
@@ -333,7 +343,7 @@ def bench_ours(args):
                        "device_load_instances_per_s":
                            (2*args.stages + args.stages + 1)*float(ticks)*T*world/el},
             "e2e": {"value": e2e_val, "unit": "trials/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+                    "d2h_bytes_per_step": d2h, "clocks": clocks_e2e},
             "gpu_launches": int(agg[1]),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_load_mos+k_load_cap+k_load_src (one tick)",
