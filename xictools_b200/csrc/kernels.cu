@@ -546,7 +546,8 @@ struct OpRing {
 
 template <int TB>
 __global__ void __launch_bounds__(TB*SOLVE_LANES)
-k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, double *Xnew)
+k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restrict__ Xold,
+    double * __restrict__ Xnew)
 {
     constexpr int NL = SOLVE_LANES;
     constexpr int NT = TB*NL;
@@ -779,6 +780,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double *Xold, doub
     if (live_j) {
         const double *yj = S + (size_t)nlu*TB + j;
         int fl = 0;
+#pragma unroll 4
         for (int k = e0; k < n; k += SOLVE_LANES) {
             int node = Sv.yperm_out[k];
             double cur = yj[(size_t)k*TB];
