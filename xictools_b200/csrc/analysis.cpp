@@ -827,9 +827,13 @@ void b200_build_lu(Analysis &an)
     for (int i = 0; i < n; i++) nll = std::max(nll, llevel[i] + 1);
     pack_rounds(lops, llevel, nll, an.fwd, rt);
     an.fwd.fin_row.assign(rt.size()*SOLVE_LANES, -1); an.fwd.fin_diag.assign(rt.size()*SOLVE_LANES, -1);
+    an.fwd.fin_cnt.assign(rt.size()*SOLVE_LANES, 0);
     for (size_t r = 0; r < rt.size(); r++)
         for (int q = 0; q < SOLVE_LANES; q++)
-            if (rt[r][q] >= 0) an.fwd.fin_row[r*SOLVE_LANES + q] = rt[r][q];
+            if (rt[r][q] >= 0) {
+                an.fwd.fin_row[r*SOLVE_LANES + q] = rt[r][q];
+                an.fwd.fin_cnt[r*SOLVE_LANES + q] = (int)lops[rt[r][q]].size();
+            }
 
     // ---- backward solve: task = row i of U (descending column order), then / diag ----
     std::vector<std::vector<LuOp>> uops(n);
@@ -848,11 +852,13 @@ void b200_build_lu(Analysis &an)
     for (int i = 0; i < n; i++) nul = std::max(nul, ulevel[i] + 1);
     pack_rounds(uops, ulevel, nul, an.bwd, rt);
     an.bwd.fin_row.assign(rt.size()*SOLVE_LANES, -1); an.bwd.fin_diag.assign(rt.size()*SOLVE_LANES, -1);
+    an.bwd.fin_cnt.assign(rt.size()*SOLVE_LANES, 0);
     for (size_t r = 0; r < rt.size(); r++)
         for (int q = 0; q < SOLVE_LANES; q++)
             if (rt[r][q] >= 0) {
                 an.bwd.fin_row[r*SOLVE_LANES + q] = rt[r][q];
                 an.bwd.fin_diag[r*SOLVE_LANES + q] = an.slotD[rt[r][q]];
+                an.bwd.fin_cnt[r*SOLVE_LANES + q] = (int)uops[rt[r][q]].size();
             }
 
     an.yperm_in.resize(n); an.yperm_out.resize(n);
@@ -888,8 +894,9 @@ void b200_build_lu(Analysis &an)
         }
     };
     emit(an.fac.rounds, an.fac.ops, an.fac.level_round_off, 0, &an.fac.fin_diag, &an.fac.fin_lbeg, &an.fac.fin_lend);
-    emit(an.fwd.rounds, an.fwd.ops, an.fwd.level_round_off, 1, &an.fwd.fin_row, nullptr, nullptr);
-    emit(an.bwd.rounds, an.bwd.ops, an.bwd.level_round_off, 2, &an.bwd.fin_row, &an.bwd.fin_diag, nullptr);
+    // solve rounds: x0 = row, x1 = diagonal slot (bwd), x2 = number of ops of the lane's row
+    emit(an.fwd.rounds, an.fwd.ops, an.fwd.level_round_off, 1, &an.fwd.fin_row, nullptr, &an.fwd.fin_cnt);
+    emit(an.bwd.rounds, an.bwd.ops, an.bwd.level_round_off, 2, &an.bwd.fin_row, &an.bwd.fin_diag, &an.bwd.fin_cnt);
     // the first fwd / bwd round must see the previous phase complete
     {
         size_t nf = an.fac.rounds.size(), nw = an.fwd.rounds.size();

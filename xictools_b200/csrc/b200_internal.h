@@ -176,6 +176,7 @@ struct SolveProgram {
     std::vector<LuRound> rounds;
     std::vector<int> level_round_off;
     std::vector<int> fin_row, fin_diag;        // per (round,lane): row index, diag slot (-1: L solve)
+    std::vector<int> fin_cnt;                  // per (round,lane): number of ops of the lane's row
 };
 
 struct Analysis {

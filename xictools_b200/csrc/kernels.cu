@@ -521,26 +521,33 @@ __device__ __forceinline__ double asm_finalize(double v, int info, const Consts 
 #define ROW_INTS (3*SOLVE_LANES)
 #define RING_HROWS 21                                   // rows per half (21*768 B = 16128 B)
 #define RING_HALF_INTS (RING_HROWS*ROW_INTS)
+#define RING_NSLOT 4                                    // slots of the op ring: 3 blocks of rows in flight
 
 struct OpRing {
     const int *g;          // global stream (16-B aligned, padded)
-    int *buf;              // smem, 2 halves
+    int *buf;              // smem, RING_NSLOT blocks of RING_HROWS rows
     int tid, nthreads;
     __device__ __forceinline__ void issue(int h) {
         const int4 *src = reinterpret_cast<const int4*>(g + (size_t)h*RING_HALF_INTS);
-        int4 *dst = reinterpret_cast<int4*>(buf + (h & 1)*RING_HALF_INTS);
+        int4 *dst = reinterpret_cast<int4*>(buf + (h % RING_NSLOT)*RING_HALF_INTS);
         for (int i = tid; i < RING_HALF_INTS/4; i += nthreads)
             __pipeline_memcpy_async(dst + i, src + i, 16);
         __pipeline_commit();
     }
+    // blocks 0 .. RING_NSLOT-2 are requested up front; entering block h waits for it (the
+    // RING_NSLOT-2 younger requests stay in flight) and, once every thread is past block h-1,
+    // reuses that slot for block h + RING_NSLOT - 1
+    __device__ __forceinline__ void start() {
+        for (int h = 0; h < RING_NSLOT - 1; h++) issue(h);
+    }
     __device__ __forceinline__ void enter(int h) {
-        __pipeline_wait_prior(0);
+        __pipeline_wait_prior(RING_NSLOT - 2);
         __syncthreads();
-        issue(h + 1);
+        issue(h + RING_NSLOT - 1);
     }
     __device__ __forceinline__ const int *row(int R) const {
         int h = R/RING_HROWS;
-        return buf + (h & 1)*RING_HALF_INTS + (R - h*RING_HROWS)*ROW_INTS;
+        return buf + (h % RING_NSLOT)*RING_HALF_INTS + (R - h*RING_HROWS)*ROW_INTS;
     }
 };
 
@@ -648,7 +655,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restric
         OpRing ring;
         ring.g = Sv.strm; ring.buf = reinterpret_cast<int*>(ringmem);
         ring.tid = tid; ring.nthreads = NT;
-        ring.issue(0);
+        ring.start();
         double *Sj = S + j;
         double *yj = S + (size_t)nlu*TB + j;
         int bad = 0;
@@ -677,7 +684,12 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restric
                 int avail = (cur_half + 1)*RING_HROWS - R;
                 int cnt = min(avail, left);
                 const int *op = ring.row(R) + e0*3;
-                if (live_j) {
+                // idle lanes of the round (x0 < 0) touch nothing; a solve lane stops after its
+                // own row's ops (x2), the rest of the round's rows are padding for it
+                int mine = cnt;
+                if (kind != 0) mine = min(cnt, x2 - (nsteps - left));
+                if (live_j && x0 >= 0 && mine > 0) {
+                    const int cnt = mine;
                     if (kind == 0) {
                         int q = 0;
                         for (; q + 4 <= cnt; q += 4, op += 4*ROW_INTS) {
@@ -1137,7 +1149,7 @@ int solve_smem_bytes(const Consts &K, int seg_maxsteps)
 {
     size_t img = ((((size_t)K.tb*(K.nnzLU + K.n)) + 1) & ~(size_t)1)*sizeof(double);
     size_t ph1 = (size_t)SEG_NBUF*SEG_CHUNK*K.tb*sizeof(double) + (size_t)SEG_NBUF*seg_maxsteps*SOLVE_LANES*sizeof(SegOp);
-    size_t ph2 = (size_t)2*RING_HALF_INTS*sizeof(int);
+    size_t ph2 = (size_t)RING_NSLOT*RING_HALF_INTS*sizeof(int);
     return (int)(img + (ph1 > ph2 ? ph1 : ph2));
 }
 int solve_pick_tb(Consts &K, int seg_maxsteps)

@@ -24,7 +24,7 @@ struct CtlAux {
     double *ip_d;       // [5][ldt]: time, c2, c3, c4, tcheck0
 };
 
-#define RING_HROWS_PAD 21        // >= RING_HROWS of k_solve: the op-stream prefetch runs ahead
+#define RING_HROWS_PAD 28        // x3 >= (RING_NSLOT-1)*RING_HROWS of k_solve: the op-stream prefetch runs ahead
 #define SOLVE_MAXCH 1024         // chunks of the streamed assembly (table cached in shared memory)
 struct SolveView {
     const int *ntype;           // [n+1]
