@@ -103,32 +103,6 @@ __device__ inline void dev_trapcheck(const TrialCtx &c, int q)
         *c.trapbad = 1;
 }
 
-__device__ inline void dev_integrate4(const TrialCtx &c, double *geq, double *ceq, double cap, int q)
-{
-    double cq = dev_find_ceq(c, q);
-    ST(c, 0, q+1) = c.ag[0]*ST(c, 0, q) + cq;
-    *ceq = cq;
-    *geq = c.ag[0]*cap;
-    dev_trapcheck(c, q);
-}
-
-// Same as dev_integrate4 with state1[q], state1[q+1] already in registers: the state-1 block
-// of a device is fetched with one burst of independent loads at the top of the load function,
-// so the five charge integrations do not serialise five DRAM round trips.
-__device__ inline void dev_integrate4v(const TrialCtx &c, double *geq, double *ceq, double cap, int q,
-    double s1q, double s1c)
-{
-    double cq;
-    if (c.method == 0)
-        cq = (c.order <= 1 ? s1q*c.ag[1] : - s1c*c.ag[1] - s1q*c.ag[0]);
-    else
-        cq = dev_NIceq(c, q);
-    ST(c, 0, q+1) = c.ag[0]*ST(c, 0, q) + cq;
-    *ceq = cq;
-    *geq = c.ag[0]*cap;
-    dev_trapcheck(c, q);
-}
-
 __device__ inline void dev_integrate2(const TrialCtx &c, int q, double cq)
 {
     ST(c, 0, q+1) = c.ag[0]*ST(c, 0, q) + cq;

@@ -5,9 +5,6 @@
 
 #define SOLVE_TB_MAX 4      // trials per CTA of k_solve: 4 (one 32-B sector per value), 2 or 1
                             // (Consts::tb), the largest whose LU image fits shared memory
-#define SOLVE_LONG 48       // gather lists longer than this go through the staged path
-#define SOLVE_STAGE 1024    // staged terms per chunk (x SOLVE_TB doubles = 32 KB, shared with the op ring)
-#define ASM_BATCH 16        // contribution loads kept in flight per thread
 #define SEG_NBUF 3           // streamed-assembly ring depth (chunks in flight)
 // contribution (s) of trial (t): tile layout, TB adjacent trials of one slot = one 32-B sector
 #define CADDR(K, s, t) ((((size_t)((t) >> (K).tbshift)*(size_t)(K).NC + (size_t)(s)) << (K).tbshift) + ((t) & ((K).tb - 1)))
