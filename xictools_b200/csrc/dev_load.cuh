@@ -137,63 +137,70 @@ __device__ __forceinline__ double dev_div_rcp(double a, double b, double y)
 enum { LR_d0, LR_d1, LR_d2, LR_e0, LR_e1, LR_f0, LR_NDIV,       // d_i = deltaOld[i], e0 = d1+d0, e1 = d2+d1, f0 = e1+d0
        LR_CT = 2*LR_NDIV, LR_NROWS };                            // reltol/delta
 
-template <int ORDER>
-__device__ __forceinline__ double dev_terr_fixed(const TrialCtx &c, const b200_options &opt,
-    const double *q, double tol, int qslot)
+// Orders 1 and 2 (everything the trapezoidal rule uses): scalars only, so the one out-of-line
+// copy of this routine serves every charge of every kernel without forcing the callers'
+// context structs into local memory.  rcp = &hot.lte_rcp[trial] (LR_* rows, stride ldt).
+static __device__ __noinline__ double dev_terr12(int order, double q0, double q1, double q2, double q3,
+    double tol, const double *rcp, int ldt, int method, double trtol, double abstol)
 {
-    // compile-time order: the divided-difference table lives in registers
-    const double gearCoeff[] = { .5, .2222222222, .1363636364, .096, .07299270073, .05830903790 };
-    const double trapCoeff[] = { .5, .08333333333 };
-    double diff[ORDER + 2];
-#pragma unroll
-    for (int i = 0; i <= ORDER + 1; i++) diff[i] = (i < 4) ? q[i] : ST(c, i, qslot);
-    if (ORDER <= 2) {
-        // levels: j = ORDER: d0..d_ORDER; then e0 (, e1); then f0
-        const int lvl[3][3] = { { LR_d0, LR_d1, LR_d2 }, { LR_e0, LR_e1, -1 }, { LR_f0, -1, -1 } };
-        const size_t ldt = c.ldt;
-#pragma unroll
-        for (int j = ORDER; j >= 0; j--) {
-#pragma unroll
-            for (int i = 0; i <= j; i++) {
-                int row = lvl[ORDER - j][i];
-                diff[i] = dev_div_rcp(diff[i] - diff[i+1], c.rcp[(size_t)row*ldt], c.rcp[(size_t)(LR_NDIV + row)*ldt]);
-            }
-        }
+    const size_t L = (size_t)ldt;
+    double d0, d1;
+    if (order == 1) {
+        d0 = dev_div_rcp(q0 - q1, rcp[LR_d0*L], rcp[(LR_NDIV + LR_d0)*L]);
+        d1 = dev_div_rcp(q1 - q2, rcp[LR_d1*L], rcp[(LR_NDIV + LR_d1)*L]);
+        d0 = dev_div_rcp(d0 - d1, rcp[LR_e0*L], rcp[(LR_NDIV + LR_e0)*L]);
     }
     else {
-        double deltmp[ORDER + 1], dOld[ORDER + 1];
-#pragma unroll
-        for (int i = 0; i <= ORDER; i++) { dOld[i] = c.dOldp[(size_t)i*c.ldt]; deltmp[i] = dOld[i]; }
-#pragma unroll
-        for (int j = ORDER; j >= 0; j--) {
-#pragma unroll
-            for (int i = 0; i <= j; i++) diff[i] = (diff[i] - diff[i+1])/deltmp[i];
-            if (j > 0) {
-#pragma unroll
-                for (int i = 0; i <= j - 1; i++) deltmp[i] = deltmp[i+1] + dOld[i];
-            }
-        }
+        double d2;
+        d0 = dev_div_rcp(q0 - q1, rcp[LR_d0*L], rcp[(LR_NDIV + LR_d0)*L]);
+        d1 = dev_div_rcp(q1 - q2, rcp[LR_d1*L], rcp[(LR_NDIV + LR_d1)*L]);
+        d2 = dev_div_rcp(q2 - q3, rcp[LR_d2*L], rcp[(LR_NDIV + LR_d2)*L]);
+        d0 = dev_div_rcp(d0 - d1, rcp[LR_e0*L], rcp[(LR_NDIV + LR_e0)*L]);
+        d1 = dev_div_rcp(d1 - d2, rcp[LR_e1*L], rcp[(LR_NDIV + LR_e1)*L]);
+        d0 = dev_div_rcp(d0 - d1, rcp[LR_f0*L], rcp[(LR_NDIV + LR_f0)*L]);
+    }
+    const double coef = (method == 0) ? (order == 1 ? .5 : .08333333333) : (order == 1 ? .5 : .2222222222);
+    double del = fabs(d0*coef);
+    return trtol*tol/DMAX(abstol, del);
+}
+
+// Gear orders 3..6: one generic routine (local arrays; not on the trapezoidal hot path)
+static __device__ __noinline__ double dev_terr_generic(const double *states, int base, int NS, int numStates,
+    int ldt, const double *dOldp, int method, double trtol, double abstol, int order,
+    double q0, double q1, double q2, double q3, double tol, int qslot)
+{
+    const double q[4] = { q0, q1, q2, q3 };
+    const double gearCoeff[] = { .5, .2222222222, .1363636364, .096, .07299270073, .05830903790 };
+    const double trapCoeff[] = { .5, .08333333333 };
+    double diff[8], deltmp[8], dOld[8];
+    for (int i = 0; i <= order + 1; i++) {
+        if (i < 4) { diff[i] = q[i]; continue; }
+        int phys = base + i;                            // ST(c, i, qslot)
+        if (phys >= NS) phys -= NS;
+        diff[i] = states[((size_t)phys*numStates + qslot)*ldt];
+    }
+    for (int i = 0; i <= order; i++) { dOld[i] = dOldp[(size_t)i*ldt]; deltmp[i] = dOld[i]; }
+    for (int j = order; j >= 0; j--) {
+        for (int i = 0; i <= j; i++) diff[i] = (diff[i] - diff[i+1])/deltmp[i];
+        if (j > 0)
+            for (int i = 0; i <= j - 1; i++) deltmp[i] = deltmp[i+1] + dOld[i];
     }
     double del;
-    if (c.method == 0) del = fabs(diff[0]*trapCoeff[ORDER <= 2 ? ORDER - 1 : 1]);
-    else del = fabs(diff[0]*gearCoeff[ORDER - 1]);
-    return opt.trtol*tol/DMAX(opt.abstol, del);
+    if (method == 0) del = fabs(diff[0]*trapCoeff[order <= 2 ? order - 1 : 1]);
+    else del = fabs(diff[0]*gearCoeff[order - 1]);
+    return trtol*tol/DMAX(abstol, del);
 }
 
-__device__ inline double dev_terr_order(const TrialCtx &c, const b200_options &opt, int order,
+__device__ __forceinline__ double dev_terr_order(const TrialCtx &c, const b200_options &opt, int order,
     const double *q, double tol, int qslot)
 {
-    switch (order) {
-    case 1: return dev_terr_fixed<1>(c, opt, q, tol, qslot);
-    case 2: return dev_terr_fixed<2>(c, opt, q, tol, qslot);
-    case 3: return dev_terr_fixed<3>(c, opt, q, tol, qslot);
-    case 4: return dev_terr_fixed<4>(c, opt, q, tol, qslot);
-    case 5: return dev_terr_fixed<5>(c, opt, q, tol, qslot);
-    default: return dev_terr_fixed<6>(c, opt, q, tol, qslot);
-    }
+    if (order <= 2)
+        return dev_terr12(order, q[0], q[1], q[2], q[3], tol, c.rcp, c.ldt, c.method, opt.trtol, opt.abstol);
+    return dev_terr_generic(c.states, c.base, c.NS, c.numStates, c.ldt, c.dOldp, c.method, opt.trtol, opt.abstol,
+        order, q[0], q[1], q[2], q[3], tol, qslot);
 }
 
-__device__ inline void dev_lte_charge(const TrialCtx &c, const b200_options &opt, const double *q,
+__device__ __forceinline__ void dev_lte_charge(const TrialCtx &c, const b200_options &opt, const double *q,
     double c0, double c1, int qslot, double &m0, double &m1)
 {
     double y0 = fabs(c0), y1 = fabs(c1);
@@ -212,7 +219,7 @@ __device__ inline void dev_lte_charge(const TrialCtx &c, const b200_options &opt
 }
 
 // ---- limiters: devlib/devlib.cc:475-620 ----
-__device__ inline double dev_limvds(double vnew, double vold)
+static __device__ __noinline__ double dev_limvds(double vnew, double vold)
 {
     if (vold >= 3.5) {
         if (vnew > vold)
@@ -231,7 +238,7 @@ __device__ inline double dev_limvds(double vnew, double vold)
     return vnew;
 }
 
-__device__ inline double dev_pnjlim(double vnew, double vold, double vt, double rvt, double vcrit, int *icheck)
+static __device__ __noinline__ double dev_pnjlim(double vnew, double vold, double vt, double rvt, double vcrit, int *icheck)
 {
     if (vnew > vcrit && fabs(vnew - vold) > (vt + vt)) {
         if (vold > 0) {
@@ -265,7 +272,7 @@ __device__ inline double dev_pnjlim(double vnew, double vold, double vt, double 
     return vnew;
 }
 
-__device__ inline double dev_fetlim(double vnew, double vold, double vto)
+static __device__ __noinline__ double dev_fetlim(double vnew, double vold, double vto)
 {
     double tmp = (vold - vto);
     if (tmp < 0.0)
@@ -433,7 +440,7 @@ struct MosOut {             // stamps go straight to this trial's contribution t
     __device__ __forceinline__ void Rw(int k, double v) const { int q = rs[k]; if (q >= 0) cbase[(size_t)q << tbshift] = v; }
 };
 
-__device__ inline void dev_sargs(double arg, double bot, double side, double *sarg, double *sargsw)
+static __device__ __noinline__ void dev_sargs(double arg, double bot, double side, double *sarg, double *sargsw)
 {
     if (bot == side) {
         if (bot == .5) *sarg = *sargsw = 1/sqrt(arg);

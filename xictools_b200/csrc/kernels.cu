@@ -222,12 +222,13 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     }
     if ((mode & MODETRAN) && (mode & MODEINITFLOAT) && (r & 1)) {
         // MOSdev::trunc (mostrun.cc:52-65): the three gate charges
-        const int qs[3] = { MS_qgs, MS_qgd, MS_qgb };
+        // qgs, qgd, qgb are MS_qgs + 3k (state layout: cap, q, cq per gate charge)
         double m0 = DBL_MAX, m1 = DBL_MAX;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 3; k++) {
-            double q[4] = { m.s0(qs[k]), m.s1(qs[k]), m.R(SR_Q2 + k), m.R(SR_Q3 + k) };
-            dev_lte_charge(c, K.opt, q, m.s0(qs[k] + 1), m.s1(qs[k] + 1), st + qs[k], m0, m1);
+            const int qk = MS_qgs + 3*k;
+            double q[4] = { m.s0(qk), m.s1(qk), m.R(SR_Q2 + k), m.R(SR_Q3 + k) };
+            dev_lte_charge(c, K.opt, q, m.s0(qk + 1), m.s1(qk + 1), st + qk, m0, m1);
         }
         atomic_min_pos(c.lte, m0);
         if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
