@@ -58,27 +58,31 @@ __device__ __forceinline__ double &ST(const TrialCtx &c, int k, int slot)
 }
 #define AGK(c, k) ((c).agp[(size_t)(k)*(c).ldt])
 
-__device__ inline double dev_NIceq(const TrialCtx &c, int q)
+// Gear history sum (niinteg.cc:84-106), out of line with scalar arguments: the trapezoidal
+// rule never runs it and the load kernels are instruction-fetch bound.
+static __device__ __noinline__ double dev_NIceq_gear(const double *states, int base, int NS, int numStates,
+    int ldt, const double *agp, double ag1, int order, int q)
 {
     double cq = 0;
-    if (c.method == 1) {
-        switch (c.order) {
-        case 6: cq += AGK(c, 6)*ST(c, 6, q);
-        case 5: cq += AGK(c, 5)*ST(c, 5, q);
-        case 4: cq += AGK(c, 4)*ST(c, 4, q);
-        case 3: cq += AGK(c, 3)*ST(c, 3, q);
-        default:
-        case 2: cq += AGK(c, 2)*ST(c, 2, q);
-        case 1: cq += c.ag[1]*ST(c, 1, q); break;
-        }
+    const int kmax = (order == 1) ? 1 : (order >= 3 && order <= 6) ? order : 2;
+    for (int k = kmax; k >= 2; k--) {
+        int phys = base + k;
+        if (phys >= NS) phys -= NS;
+        cq += agp[(size_t)k*ldt]*states[((size_t)phys*numStates + q)*ldt];
     }
-    else {
-        if (c.order == 1)
-            cq = c.ag[1]*ST(c, 1, q);
-        else
-            cq = - ST(c, 1, q+1)*c.ag[1] - c.ag[0]*ST(c, 1, q);
-    }
+    int phys = base + 1;
+    if (phys >= NS) phys -= NS;
+    cq += ag1*states[((size_t)phys*numStates + q)*ldt];
     return cq;
+}
+
+__device__ __forceinline__ double dev_NIceq(const TrialCtx &c, int q)
+{
+    if (c.method == 1)
+        return dev_NIceq_gear(c.states, c.base, c.NS, c.numStates, c.ldt, c.agp, c.ag[1], c.order, q);
+    if (c.order == 1)
+        return c.ag[1]*ST(c, 1, q);
+    return - ST(c, 1, q+1)*c.ag[1] - c.ag[0]*ST(c, 1, q);
 }
 
 __device__ inline double dev_find_ceq(const TrialCtx &c, int q)
@@ -333,6 +337,7 @@ struct MosInst {
     int type, off, st, mode, level;
     int g, b, dp, sp;
     double *col;            // staging column of this thread
+    const double *sg2;      // this device's rows of state plane 2 (row k at sg2[k*ldt])
     const double *shp;      // staging area base (shared parameter block addressed from here)
     const MosStageMap *map;
     __device__ __forceinline__ double P(int k) const { return (map->ts[k] ? col : shp)[map->off[k]]; }
@@ -1354,7 +1359,7 @@ __device__ inline void dev_mos_integrate(const TrialCtx &c, const MosInst &m, do
     *geq = c.ag[0]*cap;
     // trapezoid ringing check (niinteg.cc:117-152)
     if (c.trapCheck && !*c.trapbad && !(fabs(c0) < 1e-6) && !(fabs(q0) < 1e-16)) {
-        double c2 = ST(c, 2, m.st + k + 1);
+        double c2 = m.sg2[(k + 1)*c.ldt];
         double dqdt = fabs(q0 - s1q)/c.delta;
         if (fabs(s1c) > c.trapratio*dqdt && fabs(c0 - s1c) > c.trapratio*fabs(c0 - c2))
             *c.trapbad = 1;

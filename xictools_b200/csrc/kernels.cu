@@ -95,9 +95,15 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     const size_t ldt = K.ldt;
     const size_t cstride = (size_t)M.n*ldt;
     double *cp = M.cache + (size_t)i*ldt + t;
+    // this device's rows of state planes 0..3 (row k of a plane at +k*ldt; 17 rows fit int offsets)
+    double *sg0 = nullptr, *sg1 = nullptr, *sg2 = nullptr, *sg3 = nullptr;
+    const int ldti = K.ldt;
+#define SG(p, k) ((p) + (k)*ldti)
     // Stage 1a: what the bypass test needs -- node voltages, old state-0 voltages, operating point.
     if (mode) {
         make_ctx(c, K, hot, V, t, mode);
+        sg0 = &ST(c, 0, st); sg1 = &ST(c, 1, st); sg2 = &ST(c, 2, st); sg3 = &ST(c, 3, st);
+        m.sg2 = sg2;
         if (!(mode & MODEINITPRED)) {
             const double *x = rhsOld + t;
             __pipeline_memcpy_async(&m.R(SR_V_B), x + (size_t)m.b*ldt, 8);
@@ -105,10 +111,10 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
             __pipeline_memcpy_async(&m.R(SR_V_G), x + (size_t)m.g*ldt, 8);
             __pipeline_memcpy_async(&m.R(SR_V_DP), x + (size_t)m.dp*ldt, 8);
         }
-        __pipeline_memcpy_async(&m.s0(MS_vbs), &ST(c, 0, st + MS_vbs), 8);
-        __pipeline_memcpy_async(&m.s0(MS_vgs), &ST(c, 0, st + MS_vgs), 8);
-        __pipeline_memcpy_async(&m.s0(MS_vds), &ST(c, 0, st + MS_vds), 8);
-        __pipeline_memcpy_async(&m.s0(MS_vbd), &ST(c, 0, st + MS_vbd), 8);
+        __pipeline_memcpy_async(&m.s0(MS_vbs), SG(sg0, MS_vbs), 8);
+        __pipeline_memcpy_async(&m.s0(MS_vgs), SG(sg0, MS_vgs), 8);
+        __pipeline_memcpy_async(&m.s0(MS_vds), SG(sg0, MS_vds), 8);
+        __pipeline_memcpy_async(&m.s0(MS_vbd), SG(sg0, MS_vbd), 8);
 #pragma unroll
         for (int k = 0; k < MC_NCACHE; k++)
             __pipeline_memcpy_async(&m.R(SR_CACHE + k), cp + k*cstride, 8);
@@ -141,29 +147,30 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     if (mode && !skip) {
         if (mode & (MODETRAN | MODEINITPRED)) {
             // old Meyer capacitances and gate charges (bypass re-integrates them)
-            __pipeline_memcpy_async(&m.s0(MS_capgs), &ST(c, 0, st + MS_capgs), 8);
-            __pipeline_memcpy_async(&m.s0(MS_capgd), &ST(c, 0, st + MS_capgd), 8);
-            __pipeline_memcpy_async(&m.s0(MS_capgb), &ST(c, 0, st + MS_capgb), 8);
-            __pipeline_memcpy_async(&m.s0(MS_qgs), &ST(c, 0, st + MS_qgs), 8);
-            __pipeline_memcpy_async(&m.s0(MS_qgd), &ST(c, 0, st + MS_qgd), 8);
-            __pipeline_memcpy_async(&m.s0(MS_qgb), &ST(c, 0, st + MS_qgb), 8);
+            __pipeline_memcpy_async(&m.s0(MS_capgs), SG(sg0, MS_capgs), 8);
+            __pipeline_memcpy_async(&m.s0(MS_capgd), SG(sg0, MS_capgd), 8);
+            __pipeline_memcpy_async(&m.s0(MS_capgb), SG(sg0, MS_capgb), 8);
+            __pipeline_memcpy_async(&m.s0(MS_qgs), SG(sg0, MS_qgs), 8);
+            __pipeline_memcpy_async(&m.s0(MS_qgd), SG(sg0, MS_qgd), 8);
+            __pipeline_memcpy_async(&m.s0(MS_qgb), SG(sg0, MS_qgb), 8);
 #pragma unroll
             for (int k = 0; k < MS_NSTATES; k++)
-                __pipeline_memcpy_async(&m.s1(k), &ST(c, 1, st + k), 8);
+                __pipeline_memcpy_async(&m.s1(k), SG(sg1, k), 8);
         }
         if ((mode & MODETRAN) && (mode & MODEINITFLOAT)) {
             const int qs[3] = { MS_qgs, MS_qgd, MS_qgb };
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                __pipeline_memcpy_async(&m.R(SR_Q2 + k), &ST(c, 2, st + qs[k]), 8);
-                __pipeline_memcpy_async(&m.R(SR_Q3 + k), &ST(c, 3, st + qs[k]), 8);
+                __pipeline_memcpy_async(&m.R(SR_Q2 + k), SG(sg2, qs[k]), 8);
+                __pipeline_memcpy_async(&m.R(SR_Q3 + k), SG(sg3, qs[k]), 8);
             }
         }
         if (mode & MODEINITPRED) {
-            __pipeline_memcpy_async(&m.R(SR_S2_vbs), &ST(c, 2, st + MS_vbs), 8);
-            __pipeline_memcpy_async(&m.R(SR_S2_vgs), &ST(c, 2, st + MS_vgs), 8);
-            __pipeline_memcpy_async(&m.R(SR_S2_vds), &ST(c, 2, st + MS_vds), 8);
+            __pipeline_memcpy_async(&m.R(SR_S2_vbs), SG(sg2, MS_vbs), 8);
+            __pipeline_memcpy_async(&m.R(SR_S2_vgs), SG(sg2, MS_vgs), 8);
+            __pipeline_memcpy_async(&m.R(SR_S2_vds), SG(sg2, MS_vds), 8);
         }
+#pragma unroll 1
         for (int q = 0; q < map.nvar; q++) {
             int k = map.var[q];
             __pipeline_memcpy_async(m.col + map.off[k], M.prm[k].base + (size_t)i*ldt + t, 8);
@@ -200,25 +207,25 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     if (r & 8) {
         // bypassed: voltages and charges are unchanged, only the Meyer currents were re-integrated
         if (charges) {
-            ST(c, 0, st + MS_cqgs) = m.s0(MS_cqgs);
-            ST(c, 0, st + MS_cqgd) = m.s0(MS_cqgd);
-            ST(c, 0, st + MS_cqgb) = m.s0(MS_cqgb);
+            *SG(sg0, MS_cqgs) = m.s0(MS_cqgs);
+            *SG(sg0, MS_cqgd) = m.s0(MS_cqgd);
+            *SG(sg0, MS_cqgb) = m.s0(MS_cqgb);
         }
     }
     else if (r & 1) {
         if (charges) {
 #pragma unroll
-            for (int k = 0; k < MS_NSTATES; k++) ST(c, 0, st + k) = m.s0(k);
+            for (int k = 0; k < MS_NSTATES; k++) *SG(sg0, k) = m.s0(k);
         }
         else {
-            ST(c, 0, st + MS_vbs) = m.s0(MS_vbs); ST(c, 0, st + MS_vbd) = m.s0(MS_vbd);
-            ST(c, 0, st + MS_vgs) = m.s0(MS_vgs); ST(c, 0, st + MS_vds) = m.s0(MS_vds);
+            *SG(sg0, MS_vbs) = m.s0(MS_vbs); *SG(sg0, MS_vbd) = m.s0(MS_vbd);
+            *SG(sg0, MS_vgs) = m.s0(MS_vgs); *SG(sg0, MS_vds) = m.s0(MS_vds);
         }
     }
     else if (r & 16) {
-        ST(c, 0, st + MS_vds) = m.s0(MS_vds);
-        ST(c, 0, st + MS_vgs) = m.s0(MS_vgs);
-        ST(c, 0, st + MS_vbs) = m.s0(MS_vbs);
+        *SG(sg0, MS_vds) = m.s0(MS_vds);
+        *SG(sg0, MS_vgs) = m.s0(MS_vgs);
+        *SG(sg0, MS_vbs) = m.s0(MS_vbs);
     }
     if ((mode & MODETRAN) && (mode & MODEINITFLOAT) && (r & 1)) {
         // MOSdev::trunc (mostrun.cc:52-65): the three gate charges
@@ -250,6 +257,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
         for (int k = 0; k < MT_NSTAMP; k++) o.M(k, 0.0);
         for (int k = 0; k < MRH_NRHS; k++) o.Rw(k, 0.0);
     }
+#undef SG
 }
 
 __global__ void __launch_bounds__(128)
