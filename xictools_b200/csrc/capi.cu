@@ -212,6 +212,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
 {
     *out = nullptr;
     if (!deck || ntrials <= 0) return B200_E_BADPARM;
+    if (deck->opt.method != 0 && deck->opt.method != 1) return B200_E_BADPARM;   // TRAPEZOIDAL | GEAR
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
         fprintf(stderr, "b200spice: no CUDA device (no CPU fallback exists)\n");

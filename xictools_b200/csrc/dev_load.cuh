@@ -1350,8 +1350,8 @@ __device__ inline void dev_mos_integrate(const TrialCtx &c, const MosInst &m, do
     double cq;
     if (c.method == 0)
         cq = (c.order <= 1 ? s1q*c.ag[1] : - s1c*c.ag[1] - s1q*c.ag[0]);
-    else
-        cq = dev_NIceq(c, m.st + k);
+    else        // Gear (the only other method)
+        cq = dev_NIceq_gear(c.states, c.base, c.NS, c.numStates, c.ldt, c.agp, c.ag[1], c.order, m.st + k);
     double q0 = m.s0(k);
     double c0 = c.ag[0]*q0 + cq;
     m.s0(k + 1) = c0;

@@ -115,7 +115,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
         __pipeline_memcpy_async(&m.s0(MS_vgs), SG(sg0, MS_vgs), 8);
         __pipeline_memcpy_async(&m.s0(MS_vds), SG(sg0, MS_vds), 8);
         __pipeline_memcpy_async(&m.s0(MS_vbd), SG(sg0, MS_vbd), 8);
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < MC_NCACHE; k++)
             __pipeline_memcpy_async(&m.R(SR_CACHE + k), cp + k*cstride, 8);
         __pipeline_commit();
@@ -153,7 +153,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
             __pipeline_memcpy_async(&m.s0(MS_qgs), SG(sg0, MS_qgs), 8);
             __pipeline_memcpy_async(&m.s0(MS_qgd), SG(sg0, MS_qgd), 8);
             __pipeline_memcpy_async(&m.s0(MS_qgb), SG(sg0, MS_qgb), 8);
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < MS_NSTATES; k++)
                 __pipeline_memcpy_async(&m.s1(k), SG(sg1, k), 8);
         }
@@ -214,7 +214,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     }
     else if (r & 1) {
         if (charges) {
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < MS_NSTATES; k++) *SG(sg0, k) = m.s0(k);
         }
         else {
@@ -247,14 +247,16 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
         cp[MC_mode*cstride] = (double)m.mode;
     if (r & 2) {
         m.R(SR_CACHE + MC_mode) = (double)m.mode;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < MC_NCACHE; k++)
             cp[k*cstride] = m.R(SR_CACHE + k);
     }
     if (r & 4)
         hot.noncon[t] = 1;
     if (!(r & 1)) {
+#pragma unroll 1
         for (int k = 0; k < MT_NSTAMP; k++) o.M(k, 0.0);
+#pragma unroll 1
         for (int k = 0; k < MRH_NRHS; k++) o.Rw(k, 0.0);
     }
 #undef SG
