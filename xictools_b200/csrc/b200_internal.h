@@ -78,6 +78,9 @@ enum { SR_V_B, SR_V_SP, SR_V_G, SR_V_DP,                // node voltages (rhsOld
 struct MosStageMap {
     int off[MP_NPARAMS];    // per-trial: row*MOS_TPB; shared: offset of the value in the shared block
     int ts[MP_NPARAMS];     // 1 per-trial, 0 shared
+    // accessor form: byte address of the value in the staging area = aoff + (8*thread & amask)
+    int aoff[MP_NPARAMS];
+    unsigned amask[MP_NPARAMS];
     int nvar;               // number of per-trial parameter rows
     int var[MP_NPARAMS];    // their parameter ids
 };

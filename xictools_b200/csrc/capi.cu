@@ -514,6 +514,8 @@ static int prepare_params(b200_batch *b)
             bool row = tsd[k] && (other || k < MP_NBASE);
             sm.ts[k] = row;
             sm.off[k] = row ? (SR_PRM + q++)*MOS_TPB : shared_base + k;
+            sm.aoff[k] = sm.off[k]*(int)sizeof(double);
+            sm.amask[k] = row ? 0xffffffffu : 0u;
         }
         b->M.stage_doubles = shared_base + (other ? MP_NPARAMS : MP_NBASE);
     }

@@ -340,7 +340,9 @@ struct MosInst {
     const double *sg2;      // this device's rows of state plane 2 (row k at sg2[k*ldt])
     const double *shp;      // staging area base (shared parameter block addressed from here)
     const MosStageMap *map;
-    __device__ __forceinline__ double P(int k) const { return (map->ts[k] ? col : shp)[map->off[k]]; }
+    unsigned tid8;          // 8*thread: byte offset of this thread's staging column
+    __device__ __forceinline__ double P(int k) const
+        { return *(const double*)((const char*)shp + (map->aoff[k] + (int)(tid8 & map->amask[k]))); }
     __device__ __forceinline__ double &R(int row) const { return col[row*MOS_TPB]; }
     __device__ __forceinline__ double eta() const { return P(MP_eta); }
     __device__ __forceinline__ double theta() const { return P(MP_theta); }

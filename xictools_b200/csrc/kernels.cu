@@ -90,7 +90,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     m.type = M.type[i]; m.off = M.off[i]; m.st = M.state[i];
     m.level = L6 ? M.level[i] : 1;               // decks without level-6 devices get the lean kernel
     m.g = M.g[i]; m.b = M.b[i]; m.dp = M.dp[i]; m.sp = M.sp[i];
-    m.col = stage + tid; m.shp = stage; m.map = &map;
+    m.col = stage + tid; m.shp = stage; m.map = &map; m.tid8 = 8u*tid;
     const int st = m.st;
     const size_t ldt = K.ldt;
     const size_t cstride = (size_t)M.n*ldt;
