@@ -141,25 +141,18 @@ __device__ __forceinline__ double dev_div_rcp(double a, double b, double y)
 enum { LR_d0, LR_d1, LR_d2, LR_e0, LR_e1, LR_f0, LR_NDIV,       // d_i = deltaOld[i], e0 = d1+d0, e1 = d2+d1, f0 = e1+d0
        LR_CT = 2*LR_NDIV, LR_NROWS };                            // reltol/delta
 
-// Orders 1 and 2 (everything the trapezoidal rule uses): scalars only, so the one out-of-line
-// copy of this routine serves every charge of every kernel without forcing the callers'
-// context structs into local memory.  rcp = &hot.lte_rcp[trial] (LR_* rows, stride ldt).
-static __device__ __noinline__ double dev_terr12(int order, double q0, double q1, double q2, double q3,
+// Orders 1 and 2 (everything the trapezoidal rule uses).  rcp = &hot.lte_rcp[trial] (LR_* rows,
+// stride ldt).  The load kernels are instruction-fetch bound: callers keep ONE inlined copy of this
+// by looping (unroll 1) over charges and over the two orders instead of repeating the call.
+__device__ __forceinline__ double dev_terr12(int order, double q0, double q1, double q2, double q3,
     double tol, const double *rcp, int ldt, int method, double trtol, double abstol)
 {
     const size_t L = (size_t)ldt;
-    double d0, d1;
-    if (order == 1) {
-        d0 = dev_div_rcp(q0 - q1, rcp[LR_d0*L], rcp[(LR_NDIV + LR_d0)*L]);
-        d1 = dev_div_rcp(q1 - q2, rcp[LR_d1*L], rcp[(LR_NDIV + LR_d1)*L]);
-        d0 = dev_div_rcp(d0 - d1, rcp[LR_e0*L], rcp[(LR_NDIV + LR_e0)*L]);
-    }
-    else {
-        double d2;
-        d0 = dev_div_rcp(q0 - q1, rcp[LR_d0*L], rcp[(LR_NDIV + LR_d0)*L]);
-        d1 = dev_div_rcp(q1 - q2, rcp[LR_d1*L], rcp[(LR_NDIV + LR_d1)*L]);
-        d2 = dev_div_rcp(q2 - q3, rcp[LR_d2*L], rcp[(LR_NDIV + LR_d2)*L]);
-        d0 = dev_div_rcp(d0 - d1, rcp[LR_e0*L], rcp[(LR_NDIV + LR_e0)*L]);
+    double d0 = dev_div_rcp(q0 - q1, rcp[LR_d0*L], rcp[(LR_NDIV + LR_d0)*L]);
+    double d1 = dev_div_rcp(q1 - q2, rcp[LR_d1*L], rcp[(LR_NDIV + LR_d1)*L]);
+    d0 = dev_div_rcp(d0 - d1, rcp[LR_e0*L], rcp[(LR_NDIV + LR_e0)*L]);
+    if (order != 1) {
+        double d2 = dev_div_rcp(q2 - q3, rcp[LR_d2*L], rcp[(LR_NDIV + LR_d2)*L]);
         d1 = dev_div_rcp(d1 - d2, rcp[LR_e1*L], rcp[(LR_NDIV + LR_e1)*L]);
         d0 = dev_div_rcp(d0 - d1, rcp[LR_f0*L], rcp[(LR_NDIV + LR_f0)*L]);
     }
@@ -214,16 +207,18 @@ __device__ __forceinline__ void dev_lte_charge(const TrialCtx &c, const b200_opt
     if (chargetol < opt.chgtol) chargetol = opt.chgtol;
     chargetol *= c.rcp[(size_t)LR_CT*c.ldt];          // reltol/delta, published per trial
     double tol = DMAX(volttol, chargetol);
-    double d0 = dev_terr_order(c, opt, c.order, q, tol, qslot);
-    if (d0 < m0) m0 = d0;
-    if (c.order + 1 <= opt.maxord) {
-        double d1 = dev_terr_order(c, opt, c.order + 1, q, tol, qslot);
-        if (d1 < m1) m1 = d1;
+#pragma unroll 1
+    for (int o = 0; o < 2; o++) {
+        const int ord = c.order + o;
+        if (o && ord > opt.maxord) break;
+        double d = dev_terr_order(c, opt, ord, q, tol, qslot);
+        if (o == 0) { if (d < m0) m0 = d; }
+        else { if (d < m1) m1 = d; }
     }
 }
 
 // ---- limiters: devlib/devlib.cc:475-620 ----
-static __device__ __noinline__ double dev_limvds(double vnew, double vold)
+__device__ __forceinline__ double dev_limvds(double vnew, double vold)
 {
     if (vold >= 3.5) {
         if (vnew > vold)
@@ -242,7 +237,7 @@ static __device__ __noinline__ double dev_limvds(double vnew, double vold)
     return vnew;
 }
 
-static __device__ __noinline__ double dev_pnjlim(double vnew, double vold, double vt, double rvt, double vcrit, int *icheck)
+__device__ __forceinline__ double dev_pnjlim(double vnew, double vold, double vt, double rvt, double vcrit, int *icheck)
 {
     if (vnew > vcrit && fabs(vnew - vold) > (vt + vt)) {
         if (vold > 0) {
@@ -276,7 +271,7 @@ static __device__ __noinline__ double dev_pnjlim(double vnew, double vold, doubl
     return vnew;
 }
 
-static __device__ __noinline__ double dev_fetlim(double vnew, double vold, double vto)
+__device__ __forceinline__ double dev_fetlim(double vnew, double vold, double vto)
 {
     double tmp = (vold - vto);
     if (tmp < 0.0)
@@ -447,18 +442,20 @@ struct MosOut {             // stamps go straight to this trial's contribution t
     __device__ __forceinline__ void Rw(int k, double v) const { int q = rs[k]; if (q >= 0) cbase[(size_t)q << tbshift] = v; }
 };
 
-static __device__ __noinline__ void dev_sargs(double arg, double bot, double side, double *sarg, double *sargsw)
+__device__ __forceinline__ void dev_sargs(double arg, double bot, double side, double *sarg, double *sargsw)
 {
-    if (bot == side) {
-        if (bot == .5) *sarg = *sargsw = 1/sqrt(arg);
-        else *sarg = *sargsw = exp(-bot*log(arg));
+    // devlib.cc SARGS: the grading exponents .5 take the sqrt form; one copy of the code, the
+    // sidewall trip skipped when both exponents agree
+    double r = 0;
+#pragma unroll 1
+    for (int j = 0; j < 2; j++) {
+        const double e = j ? side : bot;
+        if (j && side == bot) break;
+        if (e == .5) r = 1/sqrt(arg);
+        else r = exp(-e*log(arg));
+        if (j == 0) *sarg = r;
     }
-    else {
-        if (bot == .5) *sarg = 1/sqrt(arg);
-        else *sarg = exp(-bot*log(arg));
-        if (side == .5) *sargsw = 1/sqrt(arg);
-        else *sargsw = exp(-side*log(arg));
-    }
+    *sargsw = r;
 }
 
 __device__ inline void dev_qmeyer(double vgs, double vgd, double von, double vdsat,
@@ -1193,31 +1190,30 @@ __device__ inline double dev_mos_eq6(MosInst &m, MosStuff &ms)
     return cdrain;
 }
 
+// mosload.cc:440-486.  Each limiter has ONE call site (operands selected by the channel direction
+// first; negation is exact) so that a single inlined copy exists.
 __device__ inline int dev_mos_limiting(const TrialCtx &c, MosInst &m, MosStuff &ms, int oldlimit)
 {
-    double s0vds = m.o_vds(), s0vgs = m.o_vgs();
-    if (s0vds >= 0) {
-        ms.vgs = dev_fetlim(ms.vgs, s0vgs, ms.von);
-        ms.vds = ms.vgs - ms.vgd;
-        ms.vds = dev_limvds(ms.vds, s0vds);
-        ms.vgd = ms.vgs - ms.vds;
+    const double s0vds = m.o_vds(), s0vgs = m.o_vgs();
+    const bool fwd = (s0vds >= 0);
+    {
+        double vg = dev_fetlim(fwd ? ms.vgs : ms.vgd, fwd ? s0vgs : s0vgs - s0vds, ms.von);
+        if (fwd) ms.vgs = vg; else ms.vgd = vg;
     }
-    else {
-        double vgdo = s0vgs - s0vds;
-        ms.vgd = dev_fetlim(ms.vgd, vgdo, ms.von);
-        ms.vds = ms.vgs - ms.vgd;
-        if (!oldlimit)
-            ms.vds = -dev_limvds(-ms.vds, -(s0vds));
-        ms.vgs = ms.vgd + ms.vds;
+    ms.vds = ms.vgs - ms.vgd;
+    if (fwd || !oldlimit) {
+        double r = dev_limvds(fwd ? ms.vds : -ms.vds, fwd ? s0vds : -s0vds);
+        ms.vds = fwd ? r : -r;
     }
+    if (fwd) ms.vgd = ms.vgs - ms.vds;
+    else ms.vgs = ms.vgd + ms.vds;
     int check;
-    if (ms.vds >= 0) {
-        ms.vbs = dev_pnjlim(ms.vbs, m.o_vbs(), ms.vt, m.rvt(), m.sourceVcrit(), &check);
-        ms.vbd = ms.vbs - ms.vds;
-    }
-    else {
-        ms.vbd = dev_pnjlim(ms.vbd, m.o_vbd(), ms.vt, m.rvt(), m.drainVcrit(), &check);
-        ms.vbs = ms.vbd + ms.vds;
+    const bool pos = (ms.vds >= 0);
+    {
+        double vb = dev_pnjlim(pos ? ms.vbs : ms.vbd, pos ? m.o_vbs() : m.o_vbd(), ms.vt, m.rvt(),
+            pos ? m.sourceVcrit() : m.drainVcrit(), &check);
+        if (pos) { ms.vbs = vb; ms.vbd = ms.vbs - ms.vds; }
+        else { ms.vbd = vb; ms.vbs = ms.vbd + ms.vds; }
     }
     ms.vgb = ms.vgs - ms.vbs;
     return check;
@@ -1226,25 +1222,24 @@ __device__ inline int dev_mos_limiting(const TrialCtx &c, MosInst &m, MosStuff &
 __device__ inline void dev_mos_iv(MosInst &m, MosStuff &ms, double gmin)
 {
     ms.gcgs = 0; ms.ceqgs = 0; ms.gcgd = 0; ms.ceqgd = 0; ms.gcgb = 0; ms.ceqgb = 0;
-    if (ms.vbs <= -3*ms.vt) {
-        m.gbs() = gmin;
-        m.cbs() = m.gbs()*ms.vbs - m.tSourceSatCur();
-    }
-    else {
-        double rvt = m.rvt();
-        double evbs = exp(dev_div_rcp(ms.vbs, ms.vt, rvt));
-        m.gbs() = dev_div_rcp(m.tSourceSatCur()*evbs, ms.vt, rvt) + gmin;
-        m.cbs() = m.tSourceSatCur()*(evbs-1) + gmin*ms.vbs;
-    }
-    if (ms.vbd <= -3*ms.vt) {
-        m.gbd() = gmin;
-        m.cbd() = m.gbd()*ms.vbd - m.tDrainSatCur();
-    }
-    else {
-        double rvt = m.rvt();
-        double evbd = exp(dev_div_rcp(ms.vbd, ms.vt, rvt));
-        m.gbd() = dev_div_rcp(m.tDrainSatCur()*evbd, ms.vt, rvt) + gmin;
-        m.cbd() = m.tDrainSatCur()*(evbd-1) + gmin*ms.vbd;
+    // bulk-source, then bulk-drain diode (mosload.cc:520-547): one copy of the code, two trips
+#pragma unroll 1
+    for (int j = 0; j < 2; j++) {
+        const double v = j ? ms.vbd : ms.vbs;
+        const double isat = m.P(j ? MP_tDrainSatCur : MP_tSourceSatCur);
+        double g, cur;
+        if (v <= -3*ms.vt) {
+            g = gmin;
+            cur = g*v - isat;
+        }
+        else {
+            double rvt = m.rvt();
+            double ev = exp(dev_div_rcp(v, ms.vt, rvt));
+            g = dev_div_rcp(isat*ev, ms.vt, rvt) + gmin;
+            cur = isat*(ev-1) + gmin*v;
+        }
+        m.R(SR_CACHE + (j ? MC_gbd : MC_gbs)) = g;
+        m.R(SR_CACHE + (j ? MC_cbd : MC_cbs)) = cur;
     }
     m.mode = (ms.vds >= 0) ? 1 : -1;
     // mosload.cc:570-577
@@ -1265,37 +1260,28 @@ __device__ inline void dev_mos_iv(MosInst &m, MosStuff &ms, double gmin)
 __device__ inline void dev_mos_cap(const TrialCtx &c, MosInst &m, MosStuff &ms)
 {
     const int st = m.st;
-    if (m.Cbs() != 0 || m.Cbssw() != 0) {
-        if (ms.vbs < m.tDepCap()) {
-            double arg = 1 - dev_div_rcp(ms.vbs, m.tBulkPot(), m.rBulkPot()), sarg, sargsw;
-            dev_sargs(arg, m.mj(), m.mjsw(), &sarg, &sargsw);
-            m.s0(MS_qbs) = m.tBulkPot()*(dev_div_rcp(m.Cbs()*(1 - arg*sarg), 1 - m.mj(), m.r1mj())
-                + dev_div_rcp(m.Cbssw()*(1 - arg*sargsw), 1 - m.mjsw(), m.r1mjsw()));
-            m.capbs() = m.Cbs()*sarg + m.Cbssw()*sargsw;
+    // bulk-source, then bulk-drain depletion charge (mosload.cc:610-690): one copy, two trips
+#pragma unroll 1
+    for (int j = 0; j < 2; j++) {
+        const double v = j ? ms.vbd : ms.vbs;
+        const double C = m.P(j ? MP_Cbd : MP_Cbs), Csw = m.P(j ? MP_Cbdsw : MP_Cbssw);
+        double qv = 0, capv = 0;
+        if (C != 0 || Csw != 0) {
+            if (v < m.tDepCap()) {
+                double arg = 1 - dev_div_rcp(v, m.tBulkPot(), m.rBulkPot()), sarg, sargsw;
+                dev_sargs(arg, m.mj(), m.mjsw(), &sarg, &sargsw);
+                qv = m.tBulkPot()*(dev_div_rcp(C*(1 - arg*sarg), 1 - m.mj(), m.r1mj())
+                    + dev_div_rcp(Csw*(1 - arg*sargsw), 1 - m.mjsw(), m.r1mjsw()));
+                capv = C*sarg + Csw*sargsw;
+            }
+            else {
+                const double f2 = m.P(j ? MP_f2d : MP_f2s), f3 = m.P(j ? MP_f3d : MP_f3s), f4 = m.P(j ? MP_f4d : MP_f4s);
+                qv = f4 + v*(f2 + .5*v*f3);
+                capv = f2 + f3*v;
+            }
         }
-        else {
-            m.s0(MS_qbs) = m.f4s() + ms.vbs*(m.f2s() + .5*ms.vbs*m.f3s());
-            m.capbs() = m.f2s() + m.f3s()*ms.vbs;
-        }
-    }
-    else {
-        m.s0(MS_qbs) = 0; m.capbs() = 0;
-    }
-    if (m.Cbd() != 0 || m.Cbdsw() != 0) {
-        if (ms.vbd < m.tDepCap()) {
-            double arg = 1 - dev_div_rcp(ms.vbd, m.tBulkPot(), m.rBulkPot()), sarg, sargsw;
-            dev_sargs(arg, m.mj(), m.mjsw(), &sarg, &sargsw);
-            m.s0(MS_qbd) = m.tBulkPot()*(dev_div_rcp(m.Cbd()*(1 - arg*sarg), 1 - m.mj(), m.r1mj())
-                + dev_div_rcp(m.Cbdsw()*(1 - arg*sargsw), 1 - m.mjsw(), m.r1mjsw()));
-            m.capbd() = m.Cbd()*sarg + m.Cbdsw()*sargsw;
-        }
-        else {
-            m.s0(MS_qbd) = m.f4d() + ms.vbd*(m.f2d() + .5*ms.vbd*m.f3d());
-            m.capbd() = m.f2d() + ms.vbd*m.f3d();
-        }
-    }
-    else {
-        m.s0(MS_qbd) = 0; m.capbd() = 0;
+        m.s0(j ? MS_qbd : MS_qbs) = qv;
+        m.R(SR_CACHE + (j ? MC_capbd : MC_capbs)) = capv;
     }
 
     double vgx, vgy, cgx, cgy, cgb;
