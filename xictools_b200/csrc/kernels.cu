@@ -1130,20 +1130,20 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
         size_t smem = (size_t)M.stage_doubles*sizeof(double);
         static size_t configured = 0;
         if (smem > configured) {
-            cudaFuncSetAttribute(k_load_mos<7, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<7, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<7, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<7, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<6, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<6, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<6, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_load_mos<6, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
         dim3 g((K.ntrials + MOS_TPB - 1)/MOS_TPB, M.n);
         if (K.tbshift == 2) {
-            if (M.has_level6) k_load_mos<7, true, 2><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-            else k_load_mos<7, false, 2><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+            if (M.has_level6) k_load_mos<6, true, 2><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+            else k_load_mos<6, false, 2><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
         }
         else {
-            if (M.has_level6) k_load_mos<7, true, -1><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-            else k_load_mos<7, false, -1><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+            if (M.has_level6) k_load_mos<6, true, -1><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+            else k_load_mos<6, false, -1><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
         }
     }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
