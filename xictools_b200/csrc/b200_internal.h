@@ -75,6 +75,7 @@ enum { SR_V_B, SR_V_SP, SR_V_G, SR_V_DP,                // node voltages (rhsOld
        SR_Q3 = SR_Q2 + 3,                               //  steps back (LTE)
        SR_PRM = SR_Q3 + 3,                              // per-trial parameters
        SR_NFIXED = SR_PRM };
+#define MOS_NSLOT (MT_NSTAMP + MRH_NRHS)    // contribution slots of one MOSFET (matrix + rhs)
 struct MosStageMap {
     int off[MP_NPARAMS];    // per-trial: row*MOS_TPB; shared: offset of the value in the shared block
     int ts[MP_NPARAMS];     // 1 per-trial, 0 shared

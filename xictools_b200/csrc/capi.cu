@@ -517,7 +517,8 @@ static int prepare_params(b200_batch *b)
             sm.aoff[k] = sm.off[k]*(int)sizeof(double);
             sm.amask[k] = row ? 0xffffffffu : 0u;
         }
-        b->M.stage_doubles = shared_base + (other ? MP_NPARAMS : MP_NBASE);
+        // + the device's contribution slots (MOS_NSLOT ints) at the end of the area
+        b->M.stage_doubles = shared_base + (other ? MP_NPARAMS : MP_NBASE) + (MOS_NSLOT + 1)/2;
     }
     CK(cudaMemcpy(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice));
     launch_mos_temp(b->stream, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);

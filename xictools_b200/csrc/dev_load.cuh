@@ -188,30 +188,54 @@ static __device__ __noinline__ double dev_terr_generic(const double *states, int
     return trtol*tol/DMAX(abstol, del);
 }
 
-__device__ __forceinline__ double dev_terr_order(const TrialCtx &c, const b200_options &opt, int order,
-    const double *q, double tol, int qslot)
+// out-of-line copy for the small kernels (capacitor, inductor), where a call is cheaper than the
+// rolled loop the MOSFET kernel uses
+static __device__ __noinline__ double dev_terr12_ool(int order, double q0, double q1, double q2, double q3,
+    double tol, const double *rcp, int ldt, int method, double trtol, double abstol)
 {
-    if (order <= 2)
-        return dev_terr12(order, q[0], q[1], q[2], q[3], tol, c.rcp, c.ldt, c.method, opt.trtol, opt.abstol);
+    return dev_terr12(order, q0, q1, q2, q3, tol, rcp, ldt, method, trtol, abstol);
+}
+
+template <bool OOL>
+__device__ __forceinline__ double dev_terr_order(const TrialCtx &c, const b200_options &opt, int order,
+    const double *q, double tol, int qslot, const double *rcp, int rld)
+{
+    if (order <= 2) {
+        if (OOL) return dev_terr12_ool(order, q[0], q[1], q[2], q[3], tol, rcp, rld, c.method, opt.trtol, opt.abstol);
+        return dev_terr12(order, q[0], q[1], q[2], q[3], tol, rcp, rld, c.method, opt.trtol, opt.abstol);
+    }
     return dev_terr_generic(c.states, c.base, c.NS, c.numStates, c.ldt, c.dOldp, c.method, opt.trtol, opt.abstol,
         order, q[0], q[1], q[2], q[3], tol, qslot);
 }
 
+// OOL false: one inlined copy of the table code, looped over the two orders (MOSFET kernel, which
+// is instruction-fetch bound); OOL true: two calls of the out-of-line copy.
+template <bool OOL>
 __device__ __forceinline__ void dev_lte_charge(const TrialCtx &c, const b200_options &opt, const double *q,
-    double c0, double c1, int qslot, double &m0, double &m1)
+    double c0, double c1, int qslot, double &m0, double &m1, const double *rcp, int rld)
 {
+    // rcp/rld: the trial's LR_* rows and their stride (hot.lte_rcp: stride ldt; a register copy: 1)
     double y0 = fabs(c0), y1 = fabs(c1);
     double volttol = opt.abstol + opt.reltol*DMAX(y0, y1);
     y0 = fabs(q[0]); y1 = fabs(q[1]);
     double chargetol = DMAX(y0, y1);
     if (chargetol < opt.chgtol) chargetol = opt.chgtol;
-    chargetol *= c.rcp[(size_t)LR_CT*c.ldt];          // reltol/delta, published per trial
+    chargetol *= rcp[(size_t)LR_CT*rld];              // reltol/delta, published per trial
     double tol = DMAX(volttol, chargetol);
+    if (OOL) {
+        double d0 = dev_terr_order<true>(c, opt, c.order, q, tol, qslot, rcp, rld);
+        if (d0 < m0) m0 = d0;
+        if (c.order + 1 <= opt.maxord) {
+            double d1 = dev_terr_order<true>(c, opt, c.order + 1, q, tol, qslot, rcp, rld);
+            if (d1 < m1) m1 = d1;
+        }
+        return;
+    }
 #pragma unroll 1
     for (int o = 0; o < 2; o++) {
         const int ord = c.order + o;
         if (o && ord > opt.maxord) break;
-        double d = dev_terr_order(c, opt, ord, q, tol, qslot);
+        double d = dev_terr_order<false>(c, opt, ord, q, tol, qslot, rcp, rld);
         if (o == 0) { if (d < m0) m0 = d; }
         else { if (d < m1) m1 = d; }
     }

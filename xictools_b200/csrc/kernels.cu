@@ -83,6 +83,10 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     constexpr int NSHARED = L6 ? MP_NPARAMS : MP_NBASE;      // a level-1 deck stages the base set only
     for (int k = tid; k < NSHARED; k += MOS_TPB)
         if (!map.ts[k]) stage[map.off[k]] = M.prm[k].base[i];
+    // this device's contribution slots (one copy per CTA: every thread stamps the same device)
+    int *sslot = (int*)(stage + M.stage_doubles) - MOS_NSLOT;
+    for (int k = tid; k < MOS_NSLOT; k += MOS_TPB)
+        sslot[k] = (k < MT_NSTAMP) ? M.cslot[(size_t)i*MT_NSTAMP + k] : M.rslot[(size_t)i*MRH_NRHS + (k - MT_NSTAMP)];
     int mode = (t < K.ntrials) ? hot.mode[t] : 0;
     // trials that are finished (or past the end) stage nothing but still meet the barrier
     TrialCtx c;
@@ -181,8 +185,8 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     // TBS >= 0: tile width known at compile time (the common 4-trial tile), else Consts::tbshift
     const int tbs = (TBS >= 0) ? TBS : K.tbshift;
     o.cbase = V.contrib + ((((size_t)(t >> tbs))*(size_t)K.NC) << tbs) + (t & ((1 << tbs) - 1));
-    o.cs = M.cslot + (size_t)i*MT_NSTAMP;
-    o.rs = M.rslot + (size_t)i*MRH_NRHS;
+    o.cs = sslot;
+    o.rs = sslot + MT_NSTAMP;
     o.tbshift = tbs;
     double *plte = M.lte + (size_t)i*ldt + t;              // this device's LTE bounds: [2][nmos][ldt]
     __pipeline_wait_prior(0);
@@ -231,11 +235,14 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
         // MOSdev::trunc (mostrun.cc:52-65): the three gate charges
         // qgs, qgd, qgb are MS_qgs + 3k (state layout: cap, q, cq per gate charge)
         double m0 = DBL_MAX, m1 = DBL_MAX;
+        double lr[LR_NROWS];                             // the trial's divisor rows, read once
+#pragma unroll
+        for (int k = 0; k < LR_NROWS; k++) lr[k] = c.rcp[(size_t)k*ldt];
 #pragma unroll 1
         for (int k = 0; k < 3; k++) {
             const int qk = MS_qgs + 3*k;
             double q[4] = { m.s0(qk), m.s1(qk), m.R(SR_Q2 + k), m.R(SR_Q3 + k) };
-            dev_lte_charge(c, K.opt, q, m.s0(qk + 1), m.s1(qk + 1), st + qk, m0, m1);
+            dev_lte_charge<false>(c, K.opt, q, m.s0(qk + 1), m.s1(qk + 1), st + qk, m0, m1, lr, 1);
         }
         atomic_min_pos(c.lte, m0);
         if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
@@ -294,7 +301,7 @@ k_load_cap(Consts K, HotView hot, VecView V, CapView Cp, const double *rhsOld)
                 // CAPdev::trunc (captrun.cc:58)
                 double q[4] = { qcap, ST(c, 1, st), ST(c, 2, st), ST(c, 3, st) };
                 double m0 = DBL_MAX, m1 = DBL_MAX;
-                dev_lte_charge(c, K.opt, q, ST(c, 0, st + 1), ST(c, 1, st + 1), st, m0, m1);
+                dev_lte_charge<true>(c, K.opt, q, ST(c, 0, st + 1), ST(c, 1, st + 1), st, m0, m1, c.rcp, c.ldt);
                 atomic_min_pos(c.lte, m0);
                 if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
             }
@@ -365,7 +372,7 @@ k_load_ind(Consts K, HotView hot, VecView V, IndView L, const double *rhsOld)
                 // INDdev::trunc (indtrun.cc:58)
                 double q[4] = { f0, ST(c, 1, st), ST(c, 2, st), ST(c, 3, st) };
                 double m0 = DBL_MAX, m1 = DBL_MAX;
-                dev_lte_charge(c, K.opt, q, ST(c, 0, st + 1), ST(c, 1, st + 1), st, m0, m1);
+                dev_lte_charge<true>(c, K.opt, q, ST(c, 0, st + 1), ST(c, 1, st + 1), st, m0, m1, c.rcp, c.ldt);
                 atomic_min_pos(c.lte, m0);
                 if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
             }
