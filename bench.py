@@ -199,6 +199,8 @@ def bench_ours(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries the one JSON line only: NCCL's own log (version banner, INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     T = args.trials
