@@ -131,6 +131,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     // predictor load that opens every time step, rewrites the operating point with magnitude 1).
     // Only FLOAT-mode loads can repeat a bypass; the others go straight to stage 1b.
     bool prev_bypass = false, skip = false;
+    double lte0 = 0, lte1 = 0;
     const bool maybe = mode && (mode & MODEINITFLOAT) && K.opt.bypass;
     if (__syncthreads_or(maybe)) {
         __pipeline_wait_prior(0);
@@ -139,6 +140,10 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
             prev_bypass = (fabs(raw) == 2.0);
             if (prev_bypass && !(hot.trapcheck[t] && (mode & MODETRAN))) {
                 m.mode = (raw > 0) ? 1 : -1;
+                if (mode & MODETRAN) {                  // cached bounds, in flight during the test
+                    lte0 = M.lte[(size_t)i*ldt + t];
+                    lte1 = M.lte[(size_t)i*ldt + t + cstride];
+                }
                 MosStuff ms;
                 dev_mos_get_v(m, ms);
                 ms.vbd = ms.vbs - ms.vds;
@@ -194,8 +199,8 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     if (!mode) return;
     if (skip) {
         if (mode & MODETRAN) {
-            atomic_min_pos(c.lte, plte[0]);
-            if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, plte[cstride]);
+            atomic_min_pos(c.lte, lte0);
+            if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, lte1);
         }
         return;
     }
@@ -290,18 +295,36 @@ k_load_cap(Consts K, HotView hot, VecView V, CapView Cp, const double *rhsOld)
         double capac = PR(Cp.capac, i, t);
         double *pg = Cp.geq + (size_t)i*K.ldt + t, *pc = Cp.ceq + (size_t)i*K.ldt + t;
         if (mode & MODEINITFLOAT) {
-            double qcap = capac*(rhsOld[(size_t)pos*K.ldt + t] - rhsOld[(size_t)neg*K.ldt + t]);
-            ST(c, 0, st) = qcap;
-            dev_integrate2(c, st, *pc);
-            ceq = dev_find_ceq(c, st);
-            *pc = ceq;
+            // every load of the iteration is issued before the first store, so they overlap
+            // (the kernel is latency bound: a dozen values per thread, all in different rows)
+            const double vp = rhsOld[(size_t)pos*K.ldt + t], vn = rhsOld[(size_t)neg*K.ldt + t];
+            const double q1 = ST(c, 1, st), c1 = ST(c, 1, st + 1);
+            const double cq_old = *pc;
             geq = *pg;
+            double q2 = 0, q3 = 0;
+            if (mode & MODETRAN) { q2 = ST(c, 2, st); q3 = ST(c, 3, st); }
+            double qcap = capac*(vp - vn);
+            ST(c, 0, st) = qcap;
+            // sCKT::integrate's current update + trapcheck (dev_integrate2) on the values at hand
+            const double c0 = c.ag[0]*qcap + cq_old;
+            ST(c, 0, st + 1) = c0;
+            if (c.trapCheck && !*c.trapbad && !(fabs(c0) < 1e-6) && !(fabs(qcap) < 1e-16)) {
+                double c2 = ST(c, 2, st + 1);
+                double dqdt = fabs(qcap - q1)/c.delta;
+                if (fabs(c1) > c.trapratio*dqdt && fabs(c0 - c1) > c.trapratio*fabs(c0 - c2))
+                    *c.trapbad = 1;
+            }
+            if (c.method == 0)
+                ceq = (c.order <= 1 ? q1*c.ag[1] : - c1*c.ag[1] - q1*c.ag[0]);
+            else
+                ceq = dev_NIceq(c, st);
+            *pc = ceq;
             stamp = true;
             if (mode & MODETRAN) {
                 // CAPdev::trunc (captrun.cc:58)
-                double q[4] = { qcap, ST(c, 1, st), ST(c, 2, st), ST(c, 3, st) };
+                double q[4] = { qcap, q1, q2, q3 };
                 double m0 = DBL_MAX, m1 = DBL_MAX;
-                dev_lte_charge<true>(c, K.opt, q, ST(c, 0, st + 1), ST(c, 1, st + 1), st, m0, m1, c.rcp, c.ldt);
+                dev_lte_charge<true>(c, K.opt, q, c0, c1, st, m0, m1, c.rcp, c.ldt);
                 atomic_min_pos(c.lte, m0);
                 if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
             }
