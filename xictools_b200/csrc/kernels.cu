@@ -532,6 +532,31 @@ k_devconv(Consts K, HotView hot, VecView V, MosView M, const double *rhs)
 //     in dot-product form; the op stream is double-buffered through shared memory (cp.async)
 //     and every op is applied to all TB trials at once.
 //  3. store + NIconvTest node part.
+// ---- 1-D bulk copies (TMA engine) global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    // dst, src 16-byte aligned, bytes a multiple of 16
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 __device__ __forceinline__ double asm_finalize(double v, int info, const Consts &K, const SolveView &Sv,
     bool ns_on, bool ic_on, double diagGmin)
 {
@@ -567,14 +592,19 @@ __device__ __forceinline__ double asm_finalize(double v, int info, const Consts 
 struct OpRing {
     const int *g;          // global stream (16-B aligned, padded)
     int *buf;              // smem, RING_NSLOT blocks of RING_HROWS rows
-    int tid, nthreads;
+    unsigned long long *bar;   // [RING_NSLOT] arrival barriers
+    int tid;
+    // one thread hands each 16 KB block to the copy engine (cp.async.bulk); the per-thread
+    // cp.async form spent a tenth of the kernel's issue slots on the copies alone
     __device__ __forceinline__ void issue(int h) {
-        const int4 *src = reinterpret_cast<const int4*>(g + (size_t)h*RING_HALF_INTS);
-        int4 *dst = reinterpret_cast<int4*>(buf + (h % RING_NSLOT)*RING_HALF_INTS);
-        for (int i = tid; i < RING_HALF_INTS/4; i += nthreads)
-            __pipeline_memcpy_async(dst + i, src + i, 16);
-        __pipeline_commit();
+        if (tid == 0) {
+            unsigned long long *b = bar + (h % RING_NSLOT);
+            mbar_expect_tx(b, RING_HALF_INTS*(unsigned)sizeof(int));
+            bulk_g2s(buf + (h % RING_NSLOT)*RING_HALF_INTS, g + (size_t)h*RING_HALF_INTS,
+                RING_HALF_INTS*(unsigned)sizeof(int), b);
+        }
     }
+    __device__ __forceinline__ void wait(int h) { mbar_wait(bar + (h % RING_NSLOT), (unsigned)(h/RING_NSLOT) & 1u); }
     // blocks 0 .. RING_NSLOT-2 are requested up front; entering block h waits for it (the
     // RING_NSLOT-2 younger requests stay in flight) and, once every thread is past block h-1,
     // reuses that slot for block h + RING_NSLOT - 1
@@ -582,9 +612,13 @@ struct OpRing {
         for (int h = 0; h < RING_NSLOT - 1; h++) issue(h);
     }
     __device__ __forceinline__ void enter(int h) {
-        __pipeline_wait_prior(RING_NSLOT - 2);
+        wait(h);
         __syncthreads();
         issue(h + RING_NSLOT - 1);
+    }
+    // the blocks requested ahead of the last one entered must land before the CTA may exit
+    __device__ __forceinline__ void drain(int last) {
+        for (int h = last + 1; h < last + RING_NSLOT; h++) wait(h);
     }
     __device__ __forceinline__ const int *row(int R) const {
         int h = R/RING_HROWS;
@@ -609,11 +643,19 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restric
     __shared__ int s_flags[TB];                          // bit0 singular, bit1 nonfinite, bit2 nonconv
     __shared__ int s_any;
     __shared__ int s_chunk[2*SOLVE_MAXCH];
+    __shared__ unsigned long long s_bar[SEG_NBUF];         // phase-1 chunk arrival (TB >= 2)
+    __shared__ unsigned long long s_rbar[RING_NSLOT];      // phase-2 op-ring block arrival
 
     const int j = tid % TB, e0 = tid / TB;               // lane e0 (0..NL-1) x trial j
     const int tj = t0 + j;
     const bool live_j = (tj < K.ntrials) && hot.do_solve[tj];
-    if (tid == 0) s_any = 0;
+    if (tid == 0) {
+        s_any = 0;
+        if (TB >= 2)
+            for (int q = 0; q < SEG_NBUF; q++) mbar_init(&s_bar[q], 1);
+        for (int q = 0; q < RING_NSLOT; q++) mbar_init(&s_rbar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (tid < TB) s_flags[tid] = 0;
     __syncthreads();
     if (live_j && e0 == 0) s_any = 1;
@@ -635,20 +677,27 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restric
         double *dring = ringmem;                                     // [SEG_NBUF][SEG_CHUNK*TB]
         SegOp *oring = reinterpret_cast<SegOp*>(ringmem + (size_t)SEG_NBUF*SEG_CHUNK*TB);
         const int ostride = Sv.seg_maxsteps*NL;                       // SegOps per ring slot
+        // TB >= 2: one thread hands the chunk (contributions + its SegOps, both contiguous and
+        // 16-byte granular) to the copy engine; TB == 1 chunks are only 8-byte granular and go
+        // through per-thread cp.async
         auto issue = [&](int c) {
+            if (TB >= 2) {
+                if (c < nch && tid == 0) {
+                    unsigned long long *bar = &s_bar[c % SEG_NBUF];
+                    const unsigned dbytes = (unsigned)(min(SEG_CHUNK, K.NC - c*SEG_CHUNK)*TB*sizeof(double));
+                    const unsigned obytes = (unsigned)(s_chunk[2*c + 1]*NL*sizeof(SegOp));
+                    mbar_expect_tx(bar, dbytes + obytes);
+                    bulk_g2s(dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB, gC + (size_t)c*SEG_CHUNK*TB, dbytes, bar);
+                    if (obytes)
+                        bulk_g2s(oring + (size_t)(c % SEG_NBUF)*ostride, Sv.seg_ops + s_chunk[2*c], obytes, bar);
+                }
+                return;
+            }
             if (c < nch) {
-                if (TB >= 2) {
-                    int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK)*TB/2;    // 16-B units
-                    const int4 *src = reinterpret_cast<const int4*>(gC + (size_t)c*SEG_CHUNK*TB);
-                    int4 *dst = reinterpret_cast<int4*>(dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB);
-                    for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 16);
-                }
-                else {
-                    int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK);         // one trial: 8-B units
-                    const double *src = gC + (size_t)c*SEG_CHUNK;
-                    double *dst = dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK;
-                    for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 8);
-                }
+                int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK);         // one trial: 8-B units
+                const double *src = gC + (size_t)c*SEG_CHUNK;
+                double *dst = dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK;
+                for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 8);
                 const int4 *osrc = reinterpret_cast<const int4*>(Sv.seg_ops + s_chunk[2*c]);
                 int4 *odst = reinterpret_cast<int4*>(oring + (size_t)(c % SEG_NBUF)*ostride);
                 int ocnt = s_chunk[2*c + 1]*NL;
@@ -659,8 +708,9 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restric
         for (int c = 0; c < SEG_NBUF - 1; c++) issue(c);
         double v = 0.0;
         for (int c = 0; c < nch; c++) {
-            __pipeline_wait_prior(SEG_NBUF - 2);
-            __syncthreads();
+            if (TB >= 2) mbar_wait(&s_bar[c % SEG_NBUF], (unsigned)(c/SEG_NBUF) & 1u);
+            else __pipeline_wait_prior(SEG_NBUF - 2);
+            __syncthreads();                             // chunk c visible; slot of chunk c-1 free
             issue(c + SEG_NBUF - 1);
             if (!live_j) continue;
             const double *buf = dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB + j;
@@ -695,7 +745,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restric
     {
         OpRing ring;
         ring.g = Sv.strm; ring.buf = reinterpret_cast<int*>(ringmem);
-        ring.tid = tid; ring.nthreads = NT;
+        ring.tid = tid; ring.bar = s_rbar;
         ring.start();
         double *Sj = S + j;
         double *yj = S + (size_t)nlu*TB + j;
@@ -819,7 +869,7 @@ k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restric
             }
             if (PF) { long long z = clock64(); pa_fin += z - pq; }
         }
-        __pipeline_wait_prior(0);
+        ring.drain(cur_half);
         if (bad) atomicOr(&s_flags[j], 1);
         if (PF && (tid & 31) == 0 && warp < TB) {
             long long *pp = Sv.prof + (size_t)K.ldt*6 + ((size_t)blockIdx.x*TB + warp)*6;
