@@ -132,7 +132,7 @@ def bench_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -199,8 +199,6 @@ def bench_ours(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries the one JSON line only: NCCL's own log (version banner, INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     T = args.trials
@@ -356,14 +354,31 @@ def bench_ours(args):
                                           "frac": ach_solve/peak}},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries the JSON line and nothing else: keep the original fd for emit() and point
+    # fd 1 at stderr, so banners that libraries write to stdout (NCCL prints its version there
+    # when NCCL_DEBUG is set in the environment) cannot precede it
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
