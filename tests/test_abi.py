@@ -44,3 +44,14 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(engine.B200Error) as e:
         engine.Batch(ring_oscillator(3), 2)
     assert e.value.code == engine.E_NOGPU
+
+
+def test_integration_method_is_validated_before_anything_runs():
+    """TSKintegrateMethod is TRAPEZOIDAL (0) or GEAR (1) in the reference (circuit.h); any other
+    value is a caller error, reported before a device is even looked for."""
+    from xictools_b200.deck import ring_oscillator
+    d = ring_oscillator(3)
+    d.options(method=2)
+    with pytest.raises(engine.B200Error) as e:
+        engine.Batch(d, 2)
+    assert e.value.code == 11          # B200_E_BADPARM
