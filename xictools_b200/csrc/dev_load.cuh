@@ -229,15 +229,16 @@ __device__ __forceinline__ void dev_lte_charge(const TrialCtx &c, const b200_opt
             double d1 = dev_terr_order<true>(c, opt, c.order + 1, q, tol, qslot, rcp, rld);
             if (d1 < m1) m1 = d1;
         }
-        return;
     }
+    else {
 #pragma unroll 1
-    for (int o = 0; o < 2; o++) {
-        const int ord = c.order + o;
-        if (o && ord > opt.maxord) break;
-        double d = dev_terr_order<false>(c, opt, ord, q, tol, qslot, rcp, rld);
-        if (o == 0) { if (d < m0) m0 = d; }
-        else { if (d < m1) m1 = d; }
+        for (int o = 0; o < 2; o++) {
+            const int ord = c.order + o;
+            if (o && ord > opt.maxord) break;
+            double d = dev_terr_order<false>(c, opt, ord, q, tol, qslot, rcp, rld);
+            if (o == 0) { if (d < m0) m0 = d; }
+            else { if (d < m1) m1 = d; }
+        }
     }
 }
 
@@ -1380,7 +1381,6 @@ __device__ inline void dev_mos_integrate(const TrialCtx &c, const MosInst &m, do
 
 __device__ inline void dev_mos_meyer_integ(const TrialCtx &c, MosInst &m, MosStuff &ms)
 {
-    const int st = m.st;
     dev_mos_integrate(c, m, &ms.gcgs, &ms.ceqgs, ms.capgs, MS_qgs);
     dev_mos_integrate(c, m, &ms.gcgd, &ms.ceqgd, ms.capgd, MS_qgd);
     dev_mos_integrate(c, m, &ms.gcgb, &ms.ceqgb, ms.capgb, MS_qgb);
@@ -1391,7 +1391,6 @@ __device__ inline void dev_mos_meyer_integ(const TrialCtx &c, MosInst &m, MosStu
 
 __device__ inline void dev_mos_integ(const TrialCtx &c, MosInst &m, MosStuff &ms)
 {
-    const int st = m.st;
     double geq, ceq;
     dev_mos_integrate(c, m, &geq, &ceq, m.capbd(), MS_qbd);
     m.gbd() += geq;
@@ -1410,7 +1409,6 @@ __device__ inline void dev_mos_integ(const TrialCtx &c, MosInst &m, MosStuff &ms
 // (x+0 == x, -(x+0) == -x), see DESIGN.md section 4.
 __device__ inline void dev_mos_stamp(const TrialCtx &c, MosInst &m, MosStuff &ms, const MosOut &o)
 {
-    const int st = m.st;
 #define MSC(xx) (m.mult()*(xx))
     m.s0(MS_vbs) = ms.vbs;
     m.s0(MS_vbd) = ms.vbd;
@@ -1543,7 +1541,6 @@ __device__ inline int dev_mos_load(const TrialCtx &c, MosInst &m, const MosOut &
     ms.vt = m.vt();
     ms.gcgs = ms.ceqgs = ms.gcgd = ms.ceqgd = ms.gcgb = ms.ceqgb = 0;
     ms.capgs = ms.capgd = ms.capgb = 0; ms.cdrain = 0; ms.vdsat = 0;
-    const int st = m.st;
     bool limit = false, limit_noncon = false, charges = false;
     int ret = 3;
     ms.von = (m.type > 0) ? m.von() : -m.von();
