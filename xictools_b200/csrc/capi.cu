@@ -408,7 +408,8 @@ void b200_batch_destroy(b200_batch *b)
 int b200_batch_set_param(b200_batch *b, int param, int index, const double *values)
 {
     if (!b || !values) return B200_E_BADPARM;
-    std::vector<double> v(values, values + b->ntrials);
+    // one copy, into the vector the batch already owns (repeated runs reuse its storage)
+    auto put = [&](std::vector<double> &dst) { dst.assign(values, values + b->ntrials); };
     int raw = -1;
     switch (param) {
     case B200_P_MOS_VTO: raw = MR_vto; break;
@@ -420,13 +421,13 @@ int b200_batch_set_param(b200_batch *b, int param, int index, const double *valu
     case B200_P_MOS_W: raw = MR_w; break;
     case B200_P_CAP_C:
         if (index < 0 || index >= b->an.cap.n) return B200_E_BADPARM;
-        b->cap_var[index] = v; b->params_dirty = true; return B200_OK;
+        put(b->cap_var[index]); b->params_dirty = true; return B200_OK;
     case B200_P_IND_L:
         if (index < 0 || index >= b->an.ind.n) return B200_E_BADPARM;
-        b->ind_var[index] = v; b->params_dirty = true; return B200_OK;
+        put(b->ind_var[index]); b->params_dirty = true; return B200_OK;
     case B200_P_SRC_DC:
         if (index < 0 || index >= b->an.src.n) return B200_E_BADPARM;
-        b->src_var[index] = v; b->params_dirty = true; return B200_OK;
+        put(b->src_var[index]); b->params_dirty = true; return B200_OK;
     default:
         return B200_E_UNSUPP;
     }
@@ -437,7 +438,7 @@ int b200_batch_set_param(b200_batch *b, int param, int index, const double *valu
     if (raw == MR_kp) c.g_kp = 1;
     if (raw == MR_gamma) c.g_gamma = 1;
     if (raw == MR_phi) c.g_phi = 1;
-    b->mos_var[raw][index] = v;
+    put(b->mos_var[raw][index]);
     b->params_dirty = true;
     return B200_OK;
 }
