@@ -156,7 +156,10 @@ typedef struct b200_batch b200_batch;
 /* Create a batch of `ntrials` trials of one deck on CUDA device `device`.
  * Does what sCKT::setup() + spSaveForInitialization() do once per trial in the reference
  * (ckt.cc:627-674, spspice.cc:79-100): allocates nodes/branches/states, builds the CSC
- * pattern from every device's TSTALLOC list, computes the ordering + symbolic LU. */
+ * pattern from every device's TSTALLOC list, computes the ordering + symbolic LU.
+ * Errors: B200_E_BADPARM (null deck, ntrials <= 0, opt.method not TRAPEZOIDAL 0 / GEAR 1),
+ * B200_E_NOGPU (no CUDA device: there is no CPU fallback), B200_E_UNSUPP (a device model or
+ * option that is not built; the caller keeps its CPU loop), B200_E_NOMEM. */
 int  b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch **out);
 void b200_batch_destroy(b200_batch *b);
 
