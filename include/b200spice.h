@@ -216,6 +216,28 @@ int  b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, i
                            const double *rhsold /* [n+1][ntrials] or NULL */,
                            double *Ax, double *rhs);
 
+/* Host-only (no CUDA call): sizes of the once-per-batch analysis products of a deck -- the
+ * pattern (spbuild.cc:922-958), the LU under the static pivot order and the level-scheduled
+ * task program of the refactor + forward + backward solve.  out[min(nout, B200_AS_NSTATS)]. */
+enum { B200_AS_N = 0, B200_AS_NNZ, B200_AS_NNZLU, B200_AS_NC, B200_AS_NSTATES,
+       B200_AS_IMG /* doubles per trial image */, B200_AS_SCRATCH /* partial-sum slots */,
+       B200_AS_TASKS, B200_AS_OPS, B200_AS_LEVELS, B200_AS_ROUNDS, B200_AS_STEPS,
+       B200_AS_PROG_BYTES, B200_AS_LONGEST_RUN,
+       B200_AS_LU_SPLIT, B200_AS_LU_CHUNK /* the split rule of long sums (b200_internal.h) */, B200_AS_NSTATS };
+int  b200_deck_analysis_stats(const b200_deck *deck, long long *out, int nout);
+/* Host-only: the CSC pattern and the static pivot order (position -> original row / column,
+ * 0-based) into caller buffers Ap[n+1], Ai[nnz], rowperm[n], colperm[n] (any may be NULL). */
+int  b200_deck_analysis_arrays(const b200_deck *deck, int *Ap, int *Ai, int *rowperm, int *colperm);
+
+/* Test hook for the host logic (no CUDA call): orders a CSC matrix the way b200_klu_analyze
+ * does, compiles the assembly runs and the task program, and executes them on ONE value set in
+ * the order the kernels do, so the schedule can be checked bit for bit against the oracle's
+ * static LU on a machine without a GPU.  x[n], rowperm[n], colperm[n] (may be NULL),
+ * stats[8] = {nnzLU, image doubles, scratch slots, tasks, products, levels, rounds, steps}.
+ * Not a solver and not on any product path. */
+int  b200_debug_program_check(int n, const int *Ap, const int *Ai, const double *Ax, const double *b,
+                              double *x, int *rowperm, int *colperm, long long *stats, int nstats);
+
 /* Test hook: the LTE divided differences divide by per-trial constants through a correctly
  * rounded reciprocal + FMA refinement; this compares that sequence with IEEE division on n
  * pseudo-random operand pairs with binary exponents in [emin, emax]. */

@@ -2931,33 +2931,84 @@ static void slu_free(StaticLU *f)
     free(f->rinv); free(f);
 }
 
+/* The engine evaluates every LU entry / solve row as ONE left-to-right sum
+ *      x0 - a[0]*b[0] - a[1]*b[1] - ...          (products in ascending pivot order)
+ * and splits a sum of more than WO_LU_SPLIT products so that no single lane carries a long
+ * dependent chain: chunks of WO_LU_CHUNK consecutive products are accumulated from 0.0, and the
+ * partial sums p_c are then subtracted as products p_c*(-1.0) under the same rule (recursively).
+ * Restated here so both sides round identically (xictools_b200/csrc/b200_internal.h LU_SPLIT,
+ * LU_CHUNK; tests/test_abi.py checks the constants agree). */
+#define WO_LU_SPLIT 32
+#define WO_LU_CHUNK 16
+static double split_eval(double x0, const double *a, const double *b, int m)
+{
+    if (m <= WO_LU_SPLIT) {
+        double acc = x0;
+        for (int q = 0; q < m; q++) acc -= a[q]*b[q];
+        return acc;
+    }
+    int nch = (m + WO_LU_CHUNK - 1)/WO_LU_CHUNK;
+    double *pa = xcalloc(nch, sizeof(double)), *pb = xcalloc(nch, sizeof(double));
+    for (int c = 0; c < nch; c++) {
+        int len = m - c*WO_LU_CHUNK; if (len > WO_LU_CHUNK) len = WO_LU_CHUNK;
+        pa[c] = split_eval(0.0, a + c*WO_LU_CHUNK, b + c*WO_LU_CHUNK, len);
+        pb[c] = -1.0;
+    }
+    double r = split_eval(x0, pa, pb, nch);
+    free(pa); free(pb);
+    return r;
+}
+void wo_lu_split_rule(int *split, int *chunk) { *split = WO_LU_SPLIT; *chunk = WO_LU_CHUNK; }
+
 static int slu_refactor(StaticLU *f, const int *Ap, const int *Ai, const double *Ax,
     const int *colperm, double *x /* n work */)
 {
     int n = f->n;
-    for (int j = 0; j < n; j++) {
+    /* per-row product lists of the current column: (L value index, U value index) */
+    int cap = 64, *tr = xcalloc(3*(size_t)cap, sizeof(int));
+    int *cnt = xcalloc(n + 1, sizeof(int)), *start = xcalloc(n + 1, sizeof(int));
+    double *va = NULL, *vb = NULL; int vcap = 0;
+    int err = OK;
+    for (int j = 0; j < n && !err; j++) {
         int cj = colperm[j];
         /* scatter (pattern of column j of L+U is a superset) */
         for (int p = f->Up[j]; p < f->Up[j+1]; p++) x[f->Ui[p]] = 0.0;
         x[j] = 0.0;
         for (int p = f->Lp[j]; p < f->Lp[j+1]; p++) x[f->Li[p]] = 0.0;
         for (int p = Ap[cj]; p < Ap[cj+1]; p++) x[f->rinv[Ai[p]]] = Ax[p];
-        /* updates in ascending k */
+        /* products in ascending pivot order k, bucketed by target row (stable) */
+        int nt = 0;
         for (int p = f->Up[j]; p < f->Up[j+1]; p++) {
             int k = f->Ui[p];
-            double xk = x[k];
-            f->Ux[p] = xk;
-            for (int q = f->Lp[k]; q < f->Lp[k+1]; q++)
-                x[f->Li[q]] -= f->Lx[q]*xk;
+            for (int q = f->Lp[k]; q < f->Lp[k+1]; q++) {
+                if (nt == cap) { cap *= 2; tr = realloc(tr, 3*(size_t)cap*sizeof(int)); }
+                tr[3*nt] = f->Li[q]; tr[3*nt+1] = q; tr[3*nt+2] = p; nt++;
+            }
         }
-        double piv = x[j];
+        if (nt > vcap) { vcap = 2*nt + 16; va = realloc(va, vcap*sizeof(double)); vb = realloc(vb, vcap*sizeof(double)); }
+        for (int i = 0; i <= n; i++) cnt[i] = 0;
+        for (int e = 0; e < nt; e++) cnt[tr[3*e]]++;
+        start[0] = 0;
+        for (int i = 0; i < n; i++) start[i+1] = start[i] + cnt[i];
+        int *ord = xcalloc(nt + 1, sizeof(int)), *fill = xcalloc(n + 1, sizeof(int));
+        for (int e = 0; e < nt; e++) { int i = tr[3*e]; ord[start[i] + fill[i]++] = e; }
+        /* rows top to bottom: U(i,j) for i < j, the pivot, then L(i,j) = value / pivot */
+#define ROW_VALUE(i, dst) do { \
+            int m_ = cnt[i]; \
+            for (int z = 0; z < m_; z++) { int e = ord[start[i] + z]; va[z] = f->Lx[tr[3*e+1]]; vb[z] = f->Ux[tr[3*e+2]]; } \
+            (dst) = split_eval(x[i], va, vb, m_); } while (0)
+        for (int p = f->Up[j]; p < f->Up[j+1]; p++) { int i = f->Ui[p]; ROW_VALUE(i, f->Ux[p]); }
+        double piv;
+        ROW_VALUE(j, piv);
         f->Ud[j] = piv;
-        if (piv == 0.0 || !isfinite(piv))
-            return E_SINGULAR;
-        for (int p = f->Lp[j]; p < f->Lp[j+1]; p++)
-            f->Lx[p] = x[f->Li[p]]/piv;
+        if (piv == 0.0 || !isfinite(piv)) err = E_SINGULAR;
+        else
+            for (int p = f->Lp[j]; p < f->Lp[j+1]; p++) { int i = f->Li[p]; double v; ROW_VALUE(i, v); f->Lx[p] = v/piv; }
+#undef ROW_VALUE
+        free(ord); free(fill);
     }
-    return OK;
+    free(tr); free(cnt); free(start); free(va); free(vb);
+    return err;
 }
 
 static void slu_solve(StaticLU *f, const int *rowperm, const int *colperm, double *b /* n */,
@@ -2965,18 +3016,36 @@ static void slu_solve(StaticLU *f, const int *rowperm, const int *colperm, doubl
 {
     int n = f->n;
     for (int k = 0; k < n; k++) y[k] = b[rowperm[k]];
-    for (int j = 0; j < n; j++) {
-        double yj = y[j];
-        for (int p = f->Lp[j]; p < f->Lp[j+1]; p++)
-            y[f->Li[p]] -= f->Lx[p]*yj;
+    /* row-wise product lists from the column structure */
+    int nl = f->Lp[n], nu = f->Up[n];
+    int m = (nl > nu ? nl : nu) + 1;
+    int *ptr = xcalloc(n + 2, sizeof(int)), *fill = xcalloc(n + 1, sizeof(int));
+    int *ev = xcalloc(m, sizeof(int)), *ej = xcalloc(m, sizeof(int));
+    double *va = xcalloc(m, sizeof(double)), *vb = xcalloc(m, sizeof(double));
+    /* forward: y(i) = b(i) - sum_k L(i,k)*y(k), ascending k */
+    for (int k = 0; k < n; k++) for (int q = f->Lp[k]; q < f->Lp[k+1]; q++) ptr[f->Li[q] + 1]++;
+    for (int i = 0; i < n; i++) ptr[i+1] += ptr[i];
+    for (int k = 0; k < n; k++)
+        for (int q = f->Lp[k]; q < f->Lp[k+1]; q++) { int i = f->Li[q]; int at = ptr[i] + fill[i]++; ev[at] = q; ej[at] = k; }
+    for (int i = 0; i < n; i++) {
+        int c = ptr[i+1] - ptr[i];
+        for (int z = 0; z < c; z++) { va[z] = f->Lx[ev[ptr[i] + z]]; vb[z] = y[ej[ptr[i] + z]]; }
+        y[i] = split_eval(y[i], va, vb, c);
     }
-    for (int j = n - 1; j >= 0; j--) {
-        y[j] = y[j]/f->Ud[j];
-        double yj = y[j];
-        for (int p = f->Up[j+1] - 1; p >= f->Up[j]; p--)
-            y[f->Ui[p]] -= f->Ux[p]*yj;
+    /* backward: x(i) = (y(i) - sum_j U(i,j)*x(j)) / U(i,i), descending j */
+    for (int i = 0; i <= n + 1; i++) ptr[i] = 0;
+    for (int i = 0; i <= n; i++) fill[i] = 0;
+    for (int j = 0; j < n; j++) for (int p = f->Up[j]; p < f->Up[j+1]; p++) ptr[f->Ui[p] + 1]++;
+    for (int i = 0; i < n; i++) ptr[i+1] += ptr[i];
+    for (int j = n - 1; j >= 0; j--)
+        for (int p = f->Up[j+1] - 1; p >= f->Up[j]; p--) { int i = f->Ui[p]; int at = ptr[i] + fill[i]++; ev[at] = p; ej[at] = j; }
+    for (int i = n - 1; i >= 0; i--) {
+        int c = ptr[i+1] - ptr[i];
+        for (int z = 0; z < c; z++) { va[z] = f->Ux[ev[ptr[i] + z]]; vb[z] = y[ej[ptr[i] + z]]; }
+        y[i] = split_eval(y[i], va, vb, c)/f->Ud[i];
     }
     for (int j = 0; j < n; j++) b[colperm[j]] = y[j];
+    free(ptr); free(fill); free(ev); free(ej); free(va); free(vb);
 }
 
 int wo_lu_solve_static(int n, const int *Ap, const int *Ai, const double *Ax,

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <set>
 
@@ -667,50 +668,19 @@ void b200_order_markowitz(Analysis &an)
 }
 
 // ---------------------------------------------------------------------------------------
-// Symbolic LU for the fixed order + compiled programs (see b200_internal.h).
+// Symbolic LU for the fixed order, the task program of k_lu and the assembly runs of
+// k_assemble (see b200_internal.h).
 // ---------------------------------------------------------------------------------------
 namespace {
 
-template <class Prog>
-void pack_rounds(const std::vector<std::vector<LuOp>> &task_ops, const std::vector<int> &level,
-    int nlevels, Prog &pg, std::vector<std::vector<int>> &round_tasks)
-{
-    // tasks of each level, longest first, dealt in rounds of SOLVE_LANES lanes
-    std::vector<std::vector<int>> by_level(nlevels);
-    for (int t = 0; t < (int)task_ops.size(); t++) by_level[level[t]].push_back(t);
-    pg.ops.clear(); pg.rounds.clear(); pg.level_round_off.assign(1, 0);
-    round_tasks.clear();
-    for (int l = 0; l < nlevels; l++) {
-        auto &v = by_level[l];
-        std::stable_sort(v.begin(), v.end(), [&](int a, int b) {
-            return task_ops[a].size() > task_ops[b].size(); });
-        for (size_t off = 0; off < v.size(); off += SOLVE_LANES) {
-            size_t cnt = std::min<size_t>(SOLVE_LANES, v.size() - off);
-            int nsteps = 0;
-            for (size_t q = 0; q < cnt; q++)
-                nsteps = std::max(nsteps, (int)task_ops[v[off + q]].size());
-            LuRound r;
-            r.op_off = (int)pg.ops.size();
-            r.nsteps = nsteps;
-            r.fin_off = (int)round_tasks.size()*SOLVE_LANES;
-            pg.ops.resize(pg.ops.size() + (size_t)nsteps*SOLVE_LANES, LuOp{-1, 0, 0});
-            std::vector<int> rt(SOLVE_LANES, -1);
-            for (size_t q = 0; q < cnt; q++) {
-                int t = v[off + q];
-                rt[q] = t;
-                for (size_t s = 0; s < task_ops[t].size(); s++)
-                    pg.ops[r.op_off + s*SOLVE_LANES + q] = task_ops[t][s];
-            }
-            pg.rounds.push_back(r);
-            round_tasks.push_back(rt);
-        }
-        pg.level_round_off.push_back((int)pg.rounds.size());
-    }
-}
+struct HTask {
+    int dst = -1, div = -1, level = 0;
+    std::vector<std::pair<int,int>> ops;        // (a slot, b slot) in subtraction order
+};
 
 } // namespace
 
-void b200_build_lu(Analysis &an)
+int b200_build_lu(Analysis &an)
 {
     int n = an.n;
     std::vector<int> rinv(n), cinv(n);
@@ -756,174 +726,130 @@ void b200_build_lu(Analysis &an)
             }
         }
     }
+    an.yperm_in.resize(n); an.yperm_out.resize(n);
+    for (int k = 0; k < n; k++) { an.yperm_in[k] = an.rowperm[k] + 1; an.yperm_out[k] = an.colperm[k] + 1; }
 
-    // ---- factor program: task = column j, dot-product form ----
-    // For column j the entries are finalised top to bottom: entry (i,j) = A(i,j) minus the
-    // products L(i,k)*U(k,j) over the pivots k < i of the column, in ascending k -- the same
-    // per-entry operation order as the left-looking column sweep, with the accumulator kept
-    // in a register.
-    std::vector<std::vector<LuOp>> fops(n);
-    std::vector<int> flevel(n, 0);
+    // ---- tasks, in an order in which every operand's producer precedes its consumers ----
+    const int nlu = an.nnzLU;
+    auto Y = [&](int k) { return nlu + k; };
+    std::vector<HTask> tasks;
+    int nscratch = 0;
+    const int scratch0 = nlu + n;
+    // emit(dst, div, ops): splits long sums (LU_SPLIT / LU_CHUNK rule), recursively
+    std::function<void(int,int,std::vector<std::pair<int,int>>&)> emit =
+        [&](int dst, int div, std::vector<std::pair<int,int>> &ops) {
+        if ((int)ops.size() <= LU_SPLIT) {
+            if (ops.empty() && div < 0) return;              // the assembled value stands
+            HTask t; t.dst = dst; t.div = div; t.ops = ops;
+            tasks.push_back(std::move(t));
+            return;
+        }
+        std::vector<std::pair<int,int>> comb;
+        for (size_t c = 0; c < ops.size(); c += LU_CHUNK) {
+            size_t e = std::min(ops.size(), c + LU_CHUNK);
+            std::vector<std::pair<int,int>> part(ops.begin() + c, ops.begin() + e);
+            int ps = scratch0 + nscratch++;
+            emit(ps, -1, part);
+            comb.push_back({ps, -2});                        // -2: the -1.0 slot, patched below
+        }
+        emit(dst, div, comb);
+    };
     {
+        // factor: entry (i,j) = A(i,j) - sum over pivots k < min(i,j), ascending, of L(i,k)*U(k,j);
+        // L entries are then divided by the pivot (division, as Sparse and KLU do)
+        std::vector<std::vector<std::pair<int,int>>> rowops(n);
         std::vector<int> pos2slot(n, -1);
-        std::vector<std::vector<LuOp>> rowops(n);
         for (int j = 0; j < n; j++) {
             for (int p = an.Up[j]; p < an.Up[j+1]; p++) pos2slot[an.Ui[p]] = an.slotU[p];
             pos2slot[j] = an.slotD[j];
             for (int p = an.Lp[j]; p < an.Lp[j+1]; p++) pos2slot[an.Li[p]] = an.slotL[p];
-            int lev = 0;
-            std::vector<int> touched;
             for (int p = an.Up[j]; p < an.Up[j+1]; p++) {
                 int k = an.Ui[p];
-                lev = std::max(lev, flevel[k] + 1);
-                for (int q = an.Lp[k]; q < an.Lp[k+1]; q++) {
-                    int i = an.Li[q];
-                    if (rowops[i].empty()) touched.push_back(i);
-                    rowops[i].push_back(LuOp{pos2slot[i], an.slotL[q], an.slotU[p]});
-                }
+                for (int q = an.Lp[k]; q < an.Lp[k+1]; q++)
+                    rowops[an.Li[q]].push_back({an.slotL[q], an.slotU[p]});
             }
-            std::sort(touched.begin(), touched.end());
-            for (int i : touched) {
-                auto &v = rowops[i];
-                v.front().dst |= LUOP_FIRST;
-                v.back().dst |= LUOP_LAST;
-                fops[j].insert(fops[j].end(), v.begin(), v.end());
-                v.clear();
-            }
-            flevel[j] = lev;
+            for (int p = an.Up[j]; p < an.Up[j+1]; p++) { int i = an.Ui[p]; emit(pos2slot[i], -1, rowops[i]); rowops[i].clear(); }
+            emit(an.slotD[j], -1, rowops[j]); rowops[j].clear();
+            for (int p = an.Lp[j]; p < an.Lp[j+1]; p++) { int i = an.Li[p]; emit(pos2slot[i], an.slotD[j], rowops[i]); rowops[i].clear(); }
         }
+        // forward solve: y(i) = b(i) - sum_k L(i,k)*y(k), ascending k
+        std::vector<std::vector<std::pair<int,int>>> rows(n);
+        for (int k = 0; k < n; k++)
+            for (int q = an.Lp[k]; q < an.Lp[k+1]; q++) rows[an.Li[q]].push_back({an.slotL[q], Y(k)});
+        for (int i = 0; i < n; i++) emit(Y(i), -1, rows[i]);
+        // backward solve: x(i) = (y(i) - sum_j U(i,j)*x(j)) / U(i,i), descending j
+        for (auto &r : rows) r.clear();
+        for (int j = n - 1; j >= 0; j--)
+            for (int p = an.Up[j+1] - 1; p >= an.Up[j]; p--) rows[an.Ui[p]].push_back({an.slotU[p], Y(j)});
+        for (int i = n - 1; i >= 0; i--) emit(Y(i), an.slotD[i], rows[i]);
     }
-    int nfl = 0;
-    for (int j = 0; j < n; j++) nfl = std::max(nfl, flevel[j] + 1);
-    std::vector<std::vector<int>> rt;
-    pack_rounds(fops, flevel, nfl, an.fac, rt);
-    an.fac.fin_diag.assign(rt.size()*SOLVE_LANES, -1);
-    an.fac.fin_lbeg.assign(rt.size()*SOLVE_LANES, 0);
-    an.fac.fin_lend.assign(rt.size()*SOLVE_LANES, 0);
-    for (size_t r = 0; r < rt.size(); r++)
-        for (int q = 0; q < SOLVE_LANES; q++) {
-            int j = rt[r][q];
-            if (j < 0) continue;
-            an.fac.fin_diag[r*SOLVE_LANES + q] = an.slotD[j];
-            // L slots of column j are contiguous right after the diagonal
-            an.fac.fin_lbeg[r*SOLVE_LANES + q] = an.slotD[j] + 1;
-            an.fac.fin_lend[r*SOLVE_LANES + q] = an.slotD[j] + 1 + (an.Lp[j+1] - an.Lp[j]);
-        }
+    an.nscratch = nscratch;
+    an.slot_neg1 = scratch0 + nscratch;
+    an.slot_zero = an.slot_neg1 + 1;
+    an.img = (an.slot_zero + 1 + 1) & ~1;                   // 16-byte granular rows (bulk copy)
+    if (an.img > 0xfff0) return B200_E_UNSUPP;
+    for (auto &t : tasks) for (auto &op : t.ops) if (op.second == -2) op.second = an.slot_neg1;
 
-    // ---- forward solve: task = row i of L (ascending column order) ----
-    std::vector<std::vector<LuOp>> lops(n);
-    std::vector<int> llevel(n, 0);
-    for (int k = 0; k < n; k++)
-        for (int q = an.Lp[k]; q < an.Lp[k+1]; q++) {
-            int i = an.Li[q];
-            lops[i].push_back(LuOp{0, an.slotL[q], k});
-        }
-    for (int i = 0; i < n; i++) {
-        int lev = 0;
-        for (auto &op : lops[i]) lev = std::max(lev, llevel[op.b] + 1);
-        llevel[i] = lev;
-    }
-    int nll = 0;
-    for (int i = 0; i < n; i++) nll = std::max(nll, llevel[i] + 1);
-    pack_rounds(lops, llevel, nll, an.fwd, rt);
-    an.fwd.fin_row.assign(rt.size()*SOLVE_LANES, -1); an.fwd.fin_diag.assign(rt.size()*SOLVE_LANES, -1);
-    an.fwd.fin_cnt.assign(rt.size()*SOLVE_LANES, 0);
-    for (size_t r = 0; r < rt.size(); r++)
-        for (int q = 0; q < SOLVE_LANES; q++)
-            if (rt[r][q] >= 0) {
-                an.fwd.fin_row[r*SOLVE_LANES + q] = rt[r][q];
-                an.fwd.fin_cnt[r*SOLVE_LANES + q] = (int)lops[rt[r][q]].size();
-            }
-
-    // ---- backward solve: task = row i of U (descending column order), then / diag ----
-    std::vector<std::vector<LuOp>> uops(n);
-    std::vector<int> ulevel(n, 0);
-    for (int j = n - 1; j >= 0; j--)
-        for (int p = an.Up[j+1] - 1; p >= an.Up[j]; p--) {
-            int i = an.Ui[p];
-            uops[i].push_back(LuOp{0, an.slotU[p], j});
-        }
-    for (int i = n - 1; i >= 0; i--) {
-        int lev = 0;
-        for (auto &op : uops[i]) lev = std::max(lev, ulevel[op.b] + 1);
-        ulevel[i] = lev;
-    }
-    int nul = 0;
-    for (int i = 0; i < n; i++) nul = std::max(nul, ulevel[i] + 1);
-    pack_rounds(uops, ulevel, nul, an.bwd, rt);
-    an.bwd.fin_row.assign(rt.size()*SOLVE_LANES, -1); an.bwd.fin_diag.assign(rt.size()*SOLVE_LANES, -1);
-    an.bwd.fin_cnt.assign(rt.size()*SOLVE_LANES, 0);
-    for (size_t r = 0; r < rt.size(); r++)
-        for (int q = 0; q < SOLVE_LANES; q++)
-            if (rt[r][q] >= 0) {
-                an.bwd.fin_row[r*SOLVE_LANES + q] = rt[r][q];
-                an.bwd.fin_diag[r*SOLVE_LANES + q] = an.slotD[rt[r][q]];
-                an.bwd.fin_cnt[r*SOLVE_LANES + q] = (int)uops[rt[r][q]].size();
-            }
-
-    an.yperm_in.resize(n); an.yperm_out.resize(n);
-    for (int k = 0; k < n; k++) { an.yperm_in[k] = an.rowperm[k] + 1; an.yperm_out[k] = an.colperm[k] + 1; }
-
-    // ---- phase-2 stream ----
-    an.strm.clear(); an.strm_round.clear();
-    auto emit = [&](const std::vector<LuRound> &rounds, const std::vector<LuOp> &ops,
-            const std::vector<int> &lvl, int kind, const std::vector<int> *f0,
-            const std::vector<int> *f1, const std::vector<int> *f2) {
-        std::vector<char> sync(rounds.size(), 0);
-        for (size_t l = 0; l + 1 < lvl.size(); l++)
-            if (lvl[l] < (int)rounds.size() && lvl[l] < lvl[l+1]) sync[lvl[l]] = 1;
-        for (size_t r = 0; r < rounds.size(); r++) {
-            const LuRound &rd = rounds[r];
-            int row0 = (int)(an.strm.size()/(3*SOLVE_LANES));
-            int k2 = kind;
-            if (kind == 0 && f1 && f2)
-                for (int e = 0; e < SOLVE_LANES; e++)
-                    if ((*f2)[rd.fin_off + e] - (*f1)[rd.fin_off + e] > 32) k2 |= 4;   // cooperative pivot division
-            an.strm_round.push_back(rd.nsteps); an.strm_round.push_back(k2);
-            an.strm_round.push_back(sync[r]); an.strm_round.push_back(row0);
-            for (int e = 0; e < SOLVE_LANES; e++) {
-                an.strm.push_back(f0 ? (*f0)[rd.fin_off + e] : -1);
-                an.strm.push_back(f1 ? (*f1)[rd.fin_off + e] : -1);
-                an.strm.push_back(f2 ? (*f2)[rd.fin_off + e] : -1);
-            }
-            for (int st = 0; st < rd.nsteps; st++)
-                for (int e = 0; e < SOLVE_LANES; e++) {
-                    const LuOp &op = ops[rd.op_off + st*SOLVE_LANES + e];
-                    an.strm.push_back(op.dst); an.strm.push_back(op.a); an.strm.push_back(op.b);
-                }
-        }
-    };
-    emit(an.fac.rounds, an.fac.ops, an.fac.level_round_off, 0, &an.fac.fin_diag, &an.fac.fin_lbeg, &an.fac.fin_lend);
-    // solve rounds: x0 = row, x1 = diagonal slot (bwd), x2 = number of ops of the lane's row
-    emit(an.fwd.rounds, an.fwd.ops, an.fwd.level_round_off, 1, &an.fwd.fin_row, nullptr, &an.fwd.fin_cnt);
-    emit(an.bwd.rounds, an.bwd.ops, an.bwd.level_round_off, 2, &an.bwd.fin_row, &an.bwd.fin_diag, &an.bwd.fin_cnt);
-    // the first fwd / bwd round must see the previous phase complete
+    // ---- levels: RAW on every operand, and WAR on a y slot the backward solve overwrites ----
     {
-        size_t nf = an.fac.rounds.size(), nw = an.fwd.rounds.size();
-        if (nf < an.strm_round.size()/4) an.strm_round[nf*4 + 2] = 1;
-        if (nf + nw < an.strm_round.size()/4) an.strm_round[(nf + nw)*4 + 2] = 1;
+        std::vector<int> wlevel(an.img, -1), rlevel(an.img, -1);
+        for (auto &t : tasks) {
+            int lv = std::max(wlevel[t.dst], rlevel[t.dst]);
+            for (auto &op : t.ops) lv = std::max(lv, std::max(wlevel[op.first], wlevel[op.second]));
+            if (t.div >= 0) lv = std::max(lv, wlevel[t.div]);
+            t.level = lv + 1;
+            for (auto &op : t.ops) {
+                rlevel[op.first] = std::max(rlevel[op.first], t.level);
+                rlevel[op.second] = std::max(rlevel[op.second], t.level);
+            }
+            if (t.div >= 0) rlevel[t.div] = std::max(rlevel[t.div], t.level);
+            wlevel[t.dst] = t.level;
+        }
     }
-}
+    int nlev = 0;
+    for (auto &t : tasks) nlev = std::max(nlev, t.level + 1);
+    an.prog_levels = nlev;
 
+    // ---- rounds ----
+    an.prog_rows.clear(); an.prog_round.clear();
+    an.prog_steps = 0; an.prog_ops = 0; an.prog_tasks = (int)tasks.size();
+    std::vector<std::vector<int>> by_level(nlev);
+    for (int t = 0; t < (int)tasks.size(); t++) by_level[tasks[t].level].push_back(t);
+    for (int l = 0; l < nlev; l++) {
+        auto &v = by_level[l];
+        std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return tasks[a].ops.size() > tasks[b].ops.size(); });
+        for (size_t off = 0; off < v.size(); off += LU_LANES) {
+            size_t cnt = std::min<size_t>(LU_LANES, v.size() - off);
+            size_t nsteps = tasks[v[off]].ops.size();
+            an.prog_round.push_back((unsigned short)(nsteps | ((off == 0 && l > 0) ? LU_RSYNC : 0)));
+            size_t row0 = an.prog_rows.size();
+            // idle lanes run the exact no-op  S[zero] = S[zero] - S[zero]*S[zero]
+            const unsigned zz = (unsigned)an.slot_zero | ((unsigned)an.slot_zero << 16);
+            an.prog_rows.resize(row0 + LU_LANES, (unsigned)an.slot_zero | (LU_NONE << 16));
+            an.prog_rows.resize(row0 + (1 + nsteps)*LU_LANES, zz);
+            for (size_t q = 0; q < cnt; q++) {
+                const HTask &t = tasks[v[off + q]];
+                an.prog_rows[row0 + q] = (unsigned)t.dst | ((t.div >= 0 ? (unsigned)t.div : LU_NONE) << 16);
+                for (size_t s = 0; s < t.ops.size(); s++)
+                    an.prog_rows[row0 + (1 + s)*LU_LANES + q] = (unsigned)t.ops[s].first | ((unsigned)t.ops[s].second << 16);
+                an.prog_ops += (long long)t.ops.size();
+            }
+            an.prog_steps += (long long)nsteps;
+        }
+    }
 
-// ---------------------------------------------------------------------------------------
-// Assembly program: the ordered gather lists flattened into per-lane streams so that every
-// lane issues long runs of independent loads (no pointer chasing through cg_ptr/cg_idx in
-// the kernel).  Lists longer than `long_threshold` are left to the staged path.
-// ---------------------------------------------------------------------------------------
-void b200_build_stream_asm(Analysis &an)
-{
-    int n = an.n, nlu = an.nnzLU;
+    // ---- assembly runs: contributions renumbered in ASSEMBLY ORDER (all terms of one image
+    // slot consecutive, in the reference's load order; slots in image order) ----
     std::vector<int> newc(an.ncslot, -1), newr(an.nrslot, -1);
-    an.const_idx.clear(); an.const_val.clear(); an.seg_ops.clear(); an.seg_chunk.clear(); an.seg_maxsteps = 0;
-    struct Run { int pos, len, target, info; };
-    std::vector<Run> runs;
+    an.const_idx.clear(); an.const_val.clear();
+    an.runs.assign(an.img, AsmRun{0, 0, 0, 0});
     std::vector<int> p2node(an.nnz, 0);
     for (int i = 1; i <= n; i++) if (an.diag[i] >= 0) p2node[an.diag[i]] = i;
     int next = 0;
     for (int s = 0; s < nlu; s++) {
         int p = an.lu_src[s];
-        Run r; r.pos = next; r.len = 0; r.target = s; r.info = 0;
+        AsmRun &r = an.runs[s];
+        r.pos = next;
         if (p >= 0) {
             int dn = p2node[p];
             if (dn) r.info = dn | ASM_DIAG | (an.ntype[dn] == 0 ? ASM_VNODE : 0);
@@ -933,14 +859,16 @@ void b200_build_stream_asm(Analysis &an)
             if (an.Ainit[p] != 0.0) { an.const_idx.push_back(next++); an.const_val.push_back(an.Ainit[p]); r.len++; }
             for (int q = an.cg_ptr[p]; q < an.cg_ptr[p+1]; q++) { newc[an.cg_idx[q]] = next++; r.len++; }
         }
-        runs.push_back(r);
     }
     for (int k = 0; k < n; k++) {
         int row = an.yperm_in[k];
-        Run r; r.pos = next; r.len = 0; r.target = nlu + k; r.info = row | ASM_ROW;
+        AsmRun &r = an.runs[nlu + k];
+        r.pos = next; r.info = row | ASM_ROW;
         for (int q = an.rg_ptr[row]; q < an.rg_ptr[row+1]; q++) { newr[an.rg_idx[q]] = next++; r.len++; }
-        runs.push_back(r);
     }
+    for (int s = scratch0; s < an.img; s++) an.runs[s].pos = next;
+    an.runs[an.slot_neg1].len = 1;
+    an.const_idx.push_back(next++); an.const_val.push_back(-1.0);
     an.NC = next;
     for (auto &c : an.cg_idx) c = newc[c];
     for (auto &c : an.rg_idx) c = newr[c];
@@ -950,64 +878,125 @@ void b200_build_stream_asm(Analysis &an)
     remap(an.src.rslot, newr);
     remap(an.ind.cslot, newc); remap(an.ind.rslot, newr);
     remap(an.mut.cslot, newc);
+    return B200_OK;
+}
 
-    // chunk schedule
-    int nchunks = (an.NC + SEG_CHUNK - 1)/SEG_CHUNK;
-    if (nchunks == 0) nchunks = 1;
-    std::vector<std::vector<std::vector<SegOp>>> sched(nchunks, std::vector<std::vector<SegOp>>(SOLVE_LANES));
-    // zero-length runs (fill slots, entries with only Ainit) belong to the chunk of their position
-    std::vector<std::vector<SegOp>> pieces(nchunks);        // non-crossing pieces per chunk
-    for (auto &r : runs) {
-        if (r.len == 0) {
-            int c = std::min(nchunks - 1, r.pos/SEG_CHUNK);
-            pieces[c].push_back(SegOp{r.pos, 0, r.target, r.info | SEG_START});
-            continue;
-        }
-        int c0 = r.pos/SEG_CHUNK, c1 = (r.pos + r.len - 1)/SEG_CHUNK;
-        if (c0 == c1) {
-            pieces[c0].push_back(SegOp{r.pos, r.len, r.target, r.info | SEG_START});
-            continue;
-        }
-        // crossing run: lane 0 of every chunk it touches, in order
-        for (int c = c0; c <= c1; c++) {
-            int b = std::max(r.pos, c*SEG_CHUNK), e = std::min(r.pos + r.len, (c + 1)*SEG_CHUNK);
-            SegOp op{b, e - b, (c == c1) ? r.target : -1, r.info | (c == c0 ? SEG_START : 0)};
-            if (c == c0) sched[c][0].push_back(op);                    // starts here: last op of lane 0
-            else sched[c][0].insert(sched[c][0].begin(), op);          // continues: first op of lane 0
-        }
+// ---------------------------------------------------------------------------------------
+// Host-only view of the once-per-batch analysis (no CUDA call): sizes of the pattern, the LU
+// and the compiled programs.  Used by the CPU tests of the host logic and by profiles/.
+// ---------------------------------------------------------------------------------------
+extern "C" int b200_deck_analysis_stats(const b200_deck *deck, long long *out, int nout)
+{
+    if (!deck || !out) return B200_E_BADPARM;
+    Analysis an;
+    std::string err;
+    int rc = b200_analyze(deck, an, err);
+    if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); return rc; }
+    b200_order_markowitz(an);
+    rc = b200_build_lu(an);
+    if (rc) return rc;
+    long long v[B200_AS_NSTATS] = {0};
+    v[B200_AS_N] = an.n; v[B200_AS_NNZ] = an.nnz; v[B200_AS_NNZLU] = an.nnzLU; v[B200_AS_NC] = an.NC;
+    v[B200_AS_NSTATES] = an.numStates;
+    v[B200_AS_IMG] = an.img; v[B200_AS_SCRATCH] = an.nscratch;
+    v[B200_AS_TASKS] = an.prog_tasks; v[B200_AS_OPS] = an.prog_ops;
+    v[B200_AS_LEVELS] = an.prog_levels; v[B200_AS_ROUNDS] = (long long)an.prog_round.size();
+    v[B200_AS_STEPS] = an.prog_steps;
+    v[B200_AS_PROG_BYTES] = (long long)(an.prog_rows.size()*sizeof(unsigned) + an.prog_round.size()*sizeof(unsigned short));
+    { int m = 0; for (auto &r : an.runs) m = std::max(m, r.len); v[B200_AS_LONGEST_RUN] = m; }
+    v[B200_AS_LU_SPLIT] = LU_SPLIT; v[B200_AS_LU_CHUNK] = LU_CHUNK;
+    for (int i = 0; i < nout && i < B200_AS_NSTATS; i++) out[i] = v[i];
+    return B200_OK;
+}
+
+// Host-only: the CSC pattern and the static pivot order of a deck (caller-sized buffers:
+// Ap[n+1], Ai[nnz], rowperm[n], colperm[n]; sizes from b200_deck_analysis_stats).
+extern "C" int b200_deck_analysis_arrays(const b200_deck *deck, int *Ap, int *Ai, int *rowperm, int *colperm)
+{
+    if (!deck) return B200_E_BADPARM;
+    Analysis an;
+    std::string err;
+    int rc = b200_analyze(deck, an, err);
+    if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); return rc; }
+    b200_order_markowitz(an);
+    if (Ap) std::copy(an.Ap.begin(), an.Ap.end(), Ap);
+    if (Ai) std::copy(an.Ai.begin(), an.Ai.end(), Ai);
+    if (rowperm) std::copy(an.rowperm.begin(), an.rowperm.end(), rowperm);
+    if (colperm) std::copy(an.colperm.begin(), an.colperm.end(), colperm);
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Test hook for the host logic (CPU tests, no CUDA call): executes the compiled assembly runs
+// and task program of a CSC matrix the way k_assemble / k_lu do -- round by round, lanes in
+// turn -- on ONE value set, so the schedule (levels, split sums, padding, slot numbering) can
+// be checked against the oracle's static LU bit for bit without a GPU.  Not a solver: nothing
+// in the product path calls it.
+// ---------------------------------------------------------------------------------------
+extern "C" int b200_debug_program_check(int n, const int *Ap, const int *Ai, const double *Ax,
+    const double *b, double *x, int *rowperm, int *colperm, long long *stats, int nstats)
+{
+    if (n <= 0 || !Ap || !Ai || !Ax || !b || !x) return B200_E_BADPARM;
+    Analysis an;
+    an.n = n; an.nnz = Ap[n];
+    an.Ap.assign(Ap, Ap + n + 1); an.Ai.assign(Ai, Ai + an.nnz);
+    an.ntype.assign(n + 1, 0);
+    an.diag.assign(n + 1, -1);
+    for (int j = 0; j < n; j++)
+        for (int p = Ap[j]; p < Ap[j+1]; p++) if (Ai[p] == j) an.diag[j+1] = p;
+    an.Ainit.assign(Ax, Ax + an.nnz);
+    an.cg_ptr.assign(an.nnz + 1, 0);
+    an.rg_ptr.assign(n + 2, 0);
+    b200_order_markowitz(an);
+    an.Ainit.assign(an.nnz, 0.0);
+    an.cg_idx.resize(an.nnz);
+    for (int p = 0; p < an.nnz; p++) { an.cg_ptr[p] = p; an.cg_idx[p] = p; }
+    an.cg_ptr[an.nnz] = an.nnz;
+    an.rg_idx.resize(n);
+    an.rg_ptr[0] = 0; an.rg_ptr[1] = 0;
+    for (int r = 1; r <= n; r++) { an.rg_idx[r-1] = r - 1; an.rg_ptr[r+1] = r; }
+    an.ncslot = an.nnz; an.nrslot = n;
+    int rc = b200_build_lu(an);
+    if (rc) return rc;
+    // contributions in assembly order
+    std::vector<double> contrib(an.NC, 0.0);
+    for (int p = 0; p < an.nnz; p++) contrib[an.cg_idx[p]] = Ax[p];
+    for (int r = 0; r < n; r++) contrib[an.rg_idx[r]] = b[r];
+    for (size_t i = 0; i < an.const_idx.size(); i++) contrib[an.const_idx[i]] = an.const_val[i];
+    std::vector<double> S(an.img, 0.0);
+    for (int s = 0; s < an.img; s++) {
+        double v = 0.0;
+        for (int k = 0; k < an.runs[s].len; k++) v += contrib[an.runs[s].pos + k];
+        S[s] = v;
     }
-    for (int c = 0; c < nchunks; c++) {
-        // lane 0 already holds crossing pieces: [continuing..., (others go in between), starting]
-        std::vector<SegOp> head, tail;
-        for (auto &op : sched[c][0]) ((op.info & SEG_START) ? tail : head).push_back(op);
-        std::vector<size_t> load(SOLVE_LANES, 0);
-        std::vector<std::vector<SegOp>> mid(SOLVE_LANES);
-        for (auto &op : head) { load[0] += std::max(1, op.len); if (op.target < 0) load[0] += (size_t)1 << 40; }
-        for (auto &op : tail) load[0] += std::max(1, op.len);
-        std::vector<SegOp> &pc = pieces[c];
-        std::stable_sort(pc.begin(), pc.end(), [](const SegOp &a, const SegOp &b) { return a.len > b.len; });
-        for (auto &op : pc) {
-            int best = 0;
-            for (int l = 1; l < SOLVE_LANES; l++) if (load[l] < load[best]) best = l;
-            mid[best].push_back(op);
-            load[best] += std::max(1, op.len);
+    int bad = 0;
+    size_t row = 0;
+    for (size_t r = 0; r < an.prog_round.size(); r++) {
+        int nsteps = an.prog_round[r] & 0x7fff;
+        for (int e = 0; e < LU_LANES; e++) {
+            unsigned h = an.prog_rows[row*LU_LANES + e];
+            unsigned dst = h & 0xffffu, div = h >> 16;
+            double acc = S[dst];
+            for (int st = 0; st < nsteps; st++) {
+                unsigned w = an.prog_rows[(row + 1 + st)*LU_LANES + e];
+                acc -= S[w & 0xffffu]*S[w >> 16];
+            }
+            if (div != LU_NONE) {
+                double piv = S[div];
+                if (piv == 0.0 || !std::isfinite(piv)) bad = 1;
+                acc = acc/piv;
+            }
+            S[dst] = acc;
         }
-        sched[c][0] = head;
-        sched[c][0].insert(sched[c][0].end(), mid[0].begin(), mid[0].end());
-        sched[c][0].insert(sched[c][0].end(), tail.begin(), tail.end());
-        for (int l = 1; l < SOLVE_LANES; l++) sched[c][l] = mid[l];
+        row += 1 + nsteps;
     }
-    an.seg_ops.clear(); an.seg_chunk.clear();
-    for (int c = 0; c < nchunks; c++) {
-        size_t ns = 0;
-        for (int l = 0; l < SOLVE_LANES; l++) ns = std::max(ns, sched[c][l].size());
-        an.seg_chunk.push_back((int)an.seg_ops.size());
-        an.seg_chunk.push_back((int)ns);
-        size_t base = an.seg_ops.size();
-        an.seg_ops.resize(base + ns*SOLVE_LANES, SegOp{0, 0, -1, 0});
-        an.seg_maxsteps = std::max(an.seg_maxsteps, (int)ns);
-        for (int l = 0; l < SOLVE_LANES; l++)
-            for (size_t q = 0; q < sched[c][l].size(); q++)
-                an.seg_ops[base + q*SOLVE_LANES + l] = sched[c][l][q];
+    for (int k = 0; k < n; k++) x[an.yperm_out[k] - 1] = S[an.nnzLU + k];
+    if (rowperm) std::copy(an.rowperm.begin(), an.rowperm.end(), rowperm);
+    if (colperm) std::copy(an.colperm.begin(), an.colperm.end(), colperm);
+    if (stats) {
+        long long v[8] = { an.nnzLU, an.img, an.nscratch, an.prog_tasks, an.prog_ops, an.prog_levels,
+            (long long)an.prog_round.size(), an.prog_steps };
+        for (int i = 0; i < nstats && i < 8; i++) stats[i] = v[i];
     }
+    return bad ? B200_E_SINGULAR : B200_OK;
 }

@@ -136,52 +136,36 @@ struct SrcTopo {
     std::vector<double> pool;                   // per source: parms[8] cache[2] then pwl pts/slopes
 };
 
-// LU program for lane-per-task level-scheduled execution.
-// ops are stored level by level; within a level tasks are dealt to 32 lanes round-robin
-// ("rounds" of 32 tasks); a round's ops are interleaved [step][lane] and padded to the
-// round's longest task with no-ops.
-// Dot-product form: acc -= LU[a]*X[b], where the accumulator of one target entry lives in a
-// register.  dst carries the target slot in its low 24 bits plus LUOP_FIRST (load acc from
-// the target before this op) / LUOP_LAST (store acc to the target after it); dst < 0: no-op.
-struct LuOp { int dst, a, b; };
-#define LUOP_FIRST 0x40000000
-#define LUOP_LAST  0x20000000
-#define LUOP_SLOT(d) ((d) & 0x00ffffff)
-
-// Segment op of the streamed assembly: contributions are numbered in ASSEMBLY ORDER (all terms
-// of one matrix entry / rhs row are consecutive, entries in LU-slot order, then rhs rows), so a
-// target's ordered sum is a run of consecutive values in the streamed chunk.
-//   pos    first term (absolute contribution index); len terms of it lie in this chunk
-//   target smem slot that receives the finished sum, or -1 if the run continues in the next chunk
-//   info   finalisation class (ASM_DIAG/ASM_ROW/ASM_VNODE | node) | SEG_START if the run starts here
-struct SegOp { int pos, len, target, info; };
-#define SEG_START  0x08000000
-#define SEG_CHUNK 512                            // contributions per streamed chunk
-#define SOLVE_LANES 64                           // task lanes per trial in the solve kernel
+// ---- solve program (k_lu) ----
+// One trial's LU refactor + forward + backward solve is ONE task graph over the trial's value
+// image S[]: a task computes one value
+//      S[dst] = ( S[dst] - sum_q S[a_q]*S[b_q] ) [ / S[div] ]
+// with the products subtracted in list order.  Factor entries (dst = the LU slot of (i,j), ops
+// over the pivots k < min(i,j) ascending, L entries divided by the pivot), rows of the forward
+// solve (dst = y slot, ascending column) and rows of the backward solve (descending column,
+// divided by the diagonal) are all tasks of this one form, level-scheduled together.
+// A sum of more than LU_SPLIT products is split (the same rule is restated by the oracle's
+// static LU so both sides round identically): chunks of LU_CHUNK consecutive products are
+// accumulated from 0.0 into scratch slots, then added to the target in chunk order (as
+// products with the constant -1.0 slot: x - p*(-1.0) == x + p exactly); applied recursively.
+#define LU_SPLIT 32
+#define LU_CHUNK 16
+#define LU_LANES 32                              // task lanes per trial: one warp runs one trial
+#define LU_NONE 0xffffu                          // "no divisor" in a header word
+// The program is a stream of ROWS of LU_LANES 32-bit words, one word per lane, grouped in
+// rounds.  A round = up to LU_LANES tasks of one level (longest first; lane e runs task e):
+//   1 header row  : dst | div << 16   (LU_NONE: no division)
+//   nsteps op rows: a | b << 16
+// Lanes without a task, and lanes whose task has run out of products, execute the exact no-op
+// S[zero] -= S[zero]*S[zero] on a slot that holds 0.0, so the interpreter has no predicates.
+// prog_round[r] = nsteps | LU_RSYNC if the round opens a new level (its operands were written
+// by earlier rounds: the warp synchronises before it reads them).
+#define LU_RSYNC 0x8000u
+// Assembly run of one image slot: S[slot] = finalize( sum of contrib[pos .. pos+len) in order )
+struct AsmRun { int pos, len, info, pad; };
 #define ASM_DIAG 0x40000000
 #define ASM_ROW  0x20000000
 #define ASM_VNODE 0x10000000  // diagonal of a voltage node (loadGmin applies)
-struct LuRound {
-    int op_off;        // offset (in LuOp units) of this round's [steps][32] block
-    int nsteps;
-    int fin_off;       // offset into fin arrays [32]: per-lane finalisation
-};
-struct LuProgram {
-    // factor: per task (column j): ops, then L(:,j) /= pivot
-    std::vector<LuOp> ops;
-    std::vector<LuRound> rounds;
-    std::vector<int> level_round_off;          // rounds of level l: [off[l], off[l+1])
-    // finalisation of factor tasks: lane's column: diag slot, L slots range [lbeg,lend)
-    std::vector<int> fin_diag, fin_lbeg, fin_lend;   // per (round,lane), -1 if idle lane
-};
-struct SolveProgram {
-    // lane-per-row dot products: y[row] = (y[row] - sum LU[a]*y[b]) [/ LU[diag]]
-    std::vector<LuOp> ops;                     // dst unused; a = LU slot, b = y index
-    std::vector<LuRound> rounds;
-    std::vector<int> level_round_off;
-    std::vector<int> fin_row, fin_diag;        // per (round,lane): row index, diag slot (-1: L solve)
-    std::vector<int> fin_cnt;                  // per (round,lane): number of ops of the lane's row
-};
 
 struct Analysis {
     // unknowns
@@ -215,18 +199,16 @@ struct Analysis {
     std::vector<int> slotL, slotU, slotD;       // LU value slot of each L entry / U entry / diag
     std::vector<int> a2lu;                      // Ax index -> LU slot
     std::vector<int> lu_src;                    // LU slot -> Ax index or -1 (fill)
-    LuProgram fac;
-    SolveProgram fwd, bwd;
-    int NC = 0;                                 // total contributions (matrix + rhs), assembly order
-    std::vector<SegOp> seg_ops;                 // [chunk][step][32 lanes]
-    std::vector<int> seg_chunk;                 // per chunk: {op offset (in SegOp), nsteps}
-    int seg_maxsteps = 0;
-    std::vector<int> const_idx; std::vector<double> const_val;   // Ainit pseudo-terms
-    // phase-2 stream: fac, fwd, bwd rounds back to back.  Round r = 1 descriptor row (32 lanes x
-    // {x0,x1,x2}: fac diag/lbeg/lend, fwd row, bwd row/diag) followed by nsteps op rows
-    // (32 lanes x LuOp).  Streamed through shared memory by the solve kernel.
-    std::vector<int> strm;                      // rows of 96 ints
-    std::vector<int> strm_round;                // per round: {nsteps, kind, sync, row offset}
+    // image layout: [0,nnzLU) LU values, [nnzLU, nnzLU+n) rhs -> y -> x (permuted positions),
+    // then nscratch partial sums, the constant -1.0 and a 0.0; img = padded total
+    int nscratch = 0, slot_neg1 = 0, slot_zero = 0, img = 0;
+    int NC = 0;                                 // total contributions (matrix + rhs + constants), assembly order
+    std::vector<AsmRun> runs;                   // [img]
+    std::vector<int> const_idx; std::vector<double> const_val;   // Ainit pseudo-terms, the -1.0
+    // task program
+    std::vector<unsigned> prog_rows;            // [nrows][LU_LANES]
+    std::vector<unsigned short> prog_round;     // per round: nsteps | LU_RSYNC
+    int prog_levels = 0, prog_tasks = 0; long long prog_steps = 0, prog_ops = 0;
     std::vector<int> yperm_in;                  // y[k] = rhs[rowperm[k]+1]
     std::vector<int> yperm_out;                 // x[colperm[k]+1] = y[k]
     // breakpoints (shared by all trials: sources are not varied per trial)
@@ -240,5 +222,6 @@ struct Analysis {
 
 int  b200_analyze(const b200_deck *deck, Analysis &an, std::string &err);
 void b200_order_markowitz(Analysis &an);
-void b200_build_lu(Analysis &an);
-void b200_build_stream_asm(Analysis &an);
+// symbolic LU for the fixed order, the task program and the assembly runs; returns 0 or
+// B200_E_UNSUPP when the image does not fit the 16-bit slot indices of the program
+int  b200_build_lu(Analysis &an);

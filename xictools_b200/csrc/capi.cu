@@ -233,8 +233,12 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     int rc = b200_analyze(deck, b->an, err);
     if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); delete b; return rc; }
     b200_order_markowitz(b->an);
-    b200_build_lu(b->an);
-    b200_build_stream_asm(b->an);
+    rc = b200_build_lu(b->an);
+    if (rc) {
+        fprintf(stderr, "b200spice: LU (%d values) + rhs (%d) of one trial exceed the 16-bit slot "
+            "indices of the solve program\n", b->an.nnzLU, b->an.n);
+        delete b; return rc;
+    }
     build_cards(b, deck);
     Analysis &an = b->an;
     CK(cudaStreamCreate(&b->stream));
@@ -250,12 +254,6 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     K.nocut = an.nocut; K.uic = deck->uic; K.hadNodeset = an.hadNodeset;
     K.npoints_max = an.npoints_max; K.method = deck->opt.method;
     K.nbrks = (int)an.brks.size(); K.nlat = (int)an.lat_offs.size();
-
-    if (!solve_pick_tb(K, an.seg_maxsteps) || (int)an.seg_chunk.size()/2 > SOLVE_MAXCH) {
-        fprintf(stderr, "b200spice: LU (%d values) + rhs (%d) of one trial exceed shared memory; "
-            "the supernodal large-matrix path is not built yet\n", an.nnzLU, an.n);
-        delete b; return B200_E_UNSUPP;
-    }
 
     size_t ldt = b->ldt;
     // ---- hot arrays ----
@@ -279,7 +277,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     V.oldSol = b->dalloc<double>(vplane);
     V.states = b->dalloc<double>((size_t)K.NS*an.numStates*ldt);
     V.oldState0 = b->dalloc<double>((size_t)an.numStates*ldt);
-    V.contrib = b->dalloc<double>((size_t)an.NC*ldt);         // [ldt/tb][NC][tb]
+    V.contrib = b->dalloc<double>((size_t)an.NC*ldt);         // [NC][ldt]
     V.out = b->dalloc<double>((size_t)an.npoints_max*an.n*ldt);
     if (!V.out || !V.states || !V.sols) { b200_batch_destroy(b); return B200_E_NOMEM; }
     // ---- topology ----
@@ -336,18 +334,24 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Sv.ntype = b->dupload(an.ntype);
     Sv.ic_given = b->dupload(an.ic_given); Sv.ns_given = b->dupload(an.ns_given);
     Sv.ic_val = b->dupload(an.ic_val); Sv.ns_val = b->dupload(an.ns_val);
-    Sv.yperm_in = b->dupload(an.yperm_in); Sv.yperm_out = b->dupload(an.yperm_out);
-    Sv.prof = getenv("B200_SOLVE_PROF") ? b->dalloc<long long>((size_t)ldt*12 + 64) : nullptr;
-    Sv.seg_ops = b->dupload(an.seg_ops); Sv.seg_chunk = b->dupload(an.seg_chunk);
-    Sv.nchunks = (int)an.seg_chunk.size()/2; Sv.seg_maxsteps = an.seg_maxsteps;
+    Sv.yperm_out = b->dupload(an.yperm_out);
+    Sv.runs = b->dupload(an.runs);
+    Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (an.n + 31) & ~31;
+    Sv.rows = b->dupload(an.prog_rows); Sv.rounds = b->dupload(an.prog_round);
+    Sv.nrows = (int)an.prog_rows.size()/LU_LANES; Sv.nrounds = (int)an.prog_round.size();
+    Sv.image = b->dalloc<double>((size_t)ldt*an.img);
+    Sv.ysol = b->dalloc<double>((size_t)ldt*Sv.npad);
+    Sv.lu_bad = b->dalloc<int>(ldt); Sv.live = b->dalloc<int>(ldt); Sv.ctr = b->dalloc<int>(2);
+    if (!Sv.image || !Sv.ysol || !Sv.live) { b200_batch_destroy(b); return B200_E_NOMEM; }
+    rc = solve_configure(Sv);
+    if (rc) {
+        if (rc == B200_E_UNSUPP)
+            fprintf(stderr, "b200spice: LU (%d values) + rhs (%d) of one trial exceed shared memory; "
+                "the supernodal large-matrix path is not built yet\n", an.nnzLU, an.n);
+        b200_batch_destroy(b); return rc;
+    }
     b->nconst = (int)an.const_idx.size();
     b->d_const_idx = b->dupload(an.const_idx); b->d_const_val = b->dupload(an.const_val);
-    {
-        std::vector<int> padded = an.strm;
-        padded.resize(padded.size() + 3*RING_HROWS_PAD*3*SOLVE_LANES, -1);          // cp.async prefetch runs ahead
-        Sv.strm = b->dupload(padded); Sv.strm_round = b->dupload(an.strm_round);
-        Sv.strm_nrounds = (int)an.strm_round.size()/4;
-    }
     // ---- control ----
     b->ctl = b->dalloc<TrialCtl>(ldt);
     CtlAux &ax = b->aux;
@@ -375,22 +379,15 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     if (getenv("B200_VERBOSE")) {
-        auto steps = [](const std::vector<LuRound> &r) { long s = 0; for (auto &x : r) s += x.nsteps; return s; };
-        size_t maxg = 0;
-        for (int p = 0; p < an.nnz; p++) maxg = std::max<size_t>(maxg, an.cg_ptr[p+1] - an.cg_ptr[p]);
-        for (int r = 1; r <= an.n; r++) maxg = std::max<size_t>(maxg, an.rg_ptr[r+1] - an.rg_ptr[r]);
-        long segsteps = 0;
-        for (size_t c = 0; c < an.seg_chunk.size()/2; c++) segsteps += an.seg_chunk[2*c + 1];
-        fprintf(stderr, "b200spice: contributions NC=%d (%d constants), %zu chunks, %ld assembly steps (max %d/chunk), solve smem %d B\n",
-            an.NC, b->nconst, an.seg_chunk.size()/2, segsteps, an.seg_maxsteps, solve_smem_bytes(K, an.seg_maxsteps));
-        fprintf(stderr, "b200spice: n=%d nnz=%d nnzLU=%d states=%d cslots=%d rslots=%d longest gather=%zu\n"
-            "  factor: %zu levels %zu rounds %ld steps %zu ops | fwd: %zu levels %zu rounds %ld steps | "
-            "bwd: %zu levels %zu rounds %ld steps | smem/trial %zu B\n",
-            an.n, an.nnz, an.nnzLU, an.numStates, an.ncslot, an.nrslot, maxg,
-            an.fac.level_round_off.size() - 1, an.fac.rounds.size(), steps(an.fac.rounds), an.fac.ops.size(),
-            an.fwd.level_round_off.size() - 1, an.fwd.rounds.size(), steps(an.fwd.rounds),
-            an.bwd.level_round_off.size() - 1, an.bwd.rounds.size(), steps(an.bwd.rounds),
-            (size_t)(an.nnzLU + an.n)*8);
+        int maxrun = 0;
+        for (auto &r : an.runs) maxrun = std::max(maxrun, r.len);
+        fprintf(stderr, "b200spice: n=%d nnz=%d nnzLU=%d states=%d | contributions NC=%d (%d constants, longest run %d)\n"
+            "  image %d doubles (%d scratch) | program: %d tasks, %lld products, %d levels, %d rounds, %lld steps, %d rows (%zu B)\n"
+            "  k_lu: %d warps/CTA x %d CTAs, %d B shared, program in %s memory\n",
+            an.n, an.nnz, an.nnzLU, an.numStates, an.NC, b->nconst, maxrun,
+            an.img, an.nscratch, an.prog_tasks, an.prog_ops, an.prog_levels, Sv.nrounds, an.prog_steps,
+            Sv.nrows, an.prog_rows.size()*sizeof(unsigned),
+            Sv.lu_warps, Sv.lu_grid, Sv.lu_smem, Sv.prog_in_smem ? "shared" : "global");
     }
     *out = b;
     return B200_OK;
@@ -520,6 +517,7 @@ static int prepare_params(b200_batch *b)
         }
         // + the device's contribution slots (MOS_NSLOT ints) at the end of the area
         b->M.stage_doubles = shared_base + (other ? MP_NPARAMS : MP_NBASE) + (MOS_NSLOT + 1)/2;
+        if (loads_configure(b->M)) return B200_E_NOMEM;
     }
     CK(cudaMemcpy(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice));
     launch_mos_temp(b->stream, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);
@@ -603,6 +601,24 @@ static int run_analysis(b200_batch *b, int analysis);
 int b200_batch_run_tran(b200_batch *b) { return run_analysis(b, 0); }
 int b200_batch_run_op(b200_batch *b) { return run_analysis(b, 1); }
 
+namespace {
+// the CUDA events of one run: destroyed on every exit path
+struct RunEvents {
+    static const int WIN = 32;
+    cudaEvent_t ev[WIN][4], begin = nullptr, end = nullptr;
+    bool ok = true;
+    RunEvents() {
+        for (int i = 0; i < WIN; i++) for (int k = 0; k < 4; k++) { ev[i][k] = nullptr; ok = ok && cudaEventCreate(&ev[i][k]) == cudaSuccess; }
+        ok = ok && cudaEventCreate(&begin) == cudaSuccess && cudaEventCreate(&end) == cudaSuccess;
+    }
+    ~RunEvents() {
+        for (int i = 0; i < WIN; i++) for (int k = 0; k < 4; k++) if (ev[i][k]) cudaEventDestroy(ev[i][k]);
+        if (begin) cudaEventDestroy(begin);
+        if (end) cudaEventDestroy(end);
+    }
+};
+}
+
 static int run_analysis(b200_batch *b, int analysis)
 {
     if (!b) return B200_E_BADPARM;
@@ -616,15 +632,14 @@ static int run_analysis(b200_batch *b, int analysis)
     const Consts &K = b->K;
     memset(&b->stats, 0, sizeof(b->stats));
 
-    const int WIN = 32;
-    cudaEvent_t ev[WIN][4], e_begin, e_end;
-    for (int i = 0; i < WIN; i++) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&ev[i][k]));
-    CK(cudaEventCreate(&e_begin)); CK(cudaEventCreate(&e_end));
+    const int WIN = RunEvents::WIN;
+    RunEvents E;
+    if (!E.ok) return B200_E_NOGPU;
     long long launches = 0, ticks = 0, load_launches = 0, solve_launches = 0;
     double ms_load = 0, ms_solve = 0;
     int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->Cp.L.nmut ? 1 : 0) + (b->S.n ? 1 : 0);
 
-    CK(cudaEventRecord(e_begin, st));
+    CK(cudaEventRecord(E.begin, st));
     // tick 0: begin + first load
     launch_ctl(st, K, b->hot, b->ctl, b->sh, b->aux, 0);
     launch_vec(st, K, b->V, b->aux, b->M, b->V.X[b->cur]);
@@ -634,19 +649,19 @@ static int run_analysis(b200_batch *b, int analysis)
     const long long max_ticks = 20000000;
     while (active > 0 && ticks < max_ticks) {
         for (int w = 0; w < WIN; w++) {
-            CK(cudaEventRecord(ev[w][0], st));
+            CK(cudaEventRecord(E.ev[w][0], st));
             rc = launch_solve(st, K, b->hot, b->V, b->Sv, b->V.X[b->cur], b->V.X[b->cur ^ 1]);
             if (rc) return rc;
-            CK(cudaEventRecord(ev[w][1], st));
+            CK(cudaEventRecord(E.ev[w][1], st));
             launch_devconv(st, K, b->hot, b->V, b->M, b->V.X[b->cur]);
             b->cur ^= 1;
             launch_ctl(st, K, b->hot, b->ctl, b->sh, b->aux, 1);
             launch_ctl(st, K, b->hot, b->ctl, b->sh, b->aux, 2);
             launch_vec(st, K, b->V, b->aux, b->M, b->V.X[b->cur]);
-            CK(cudaEventRecord(ev[w][2], st));
+            CK(cudaEventRecord(E.ev[w][2], st));
             launch_loads(st, K, b->hot, b->V, b->M, b->Cp, b->S, b->V.X[b->cur]);
-            CK(cudaEventRecord(ev[w][3], st));
-            launches += 6 + nload_kernels;
+            CK(cudaEventRecord(E.ev[w][3], st));
+            launches += 8 + nload_kernels;               // 3 solve kernels, devconv, 2 x ctl, vec, statevec
             load_launches++; solve_launches++;
             ticks++;
         }
@@ -654,34 +669,20 @@ static int run_analysis(b200_batch *b, int analysis)
         launches++;
         CK(cudaMemcpyAsync(&active, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());                          // a failed launch must not spin the loop
         for (int w = 0; w < WIN; w++) {
             float a = 0, c = 0;
-            cudaEventElapsedTime(&a, ev[w][0], ev[w][1]);
-            cudaEventElapsedTime(&c, ev[w][2], ev[w][3]);
+            cudaEventElapsedTime(&a, E.ev[w][0], E.ev[w][1]);
+            cudaEventElapsedTime(&c, E.ev[w][2], E.ev[w][3]);
             ms_solve += a; ms_load += c;
         }
     }
     launch_export_counters(st, K.ntrials, b->ctl, b->d_counters, b->d_npts);
-    CK(cudaEventRecord(e_end, st));
+    CK(cudaEventRecord(E.end, st));
     CK(cudaStreamSynchronize(st));
     float tot = 0;
-    cudaEventElapsedTime(&tot, e_begin, e_end);
-    for (int i = 0; i < WIN; i++) for (int k = 0; k < 4; k++) cudaEventDestroy(ev[i][k]);
-    cudaEventDestroy(e_begin); cudaEventDestroy(e_end);
+    cudaEventElapsedTime(&tot, E.begin, E.end);
     CK(cudaGetLastError());
-    if (b->Sv.prof) {
-        std::vector<long long> hp((size_t)b->ldt*12);
-        cudaMemcpy(hp.data(), b->Sv.prof, hp.size()*sizeof(long long), cudaMemcpyDeviceToHost);
-        double acc[6] = {0,0,0,0,0,0}; int nw = 0;
-        for (int w = 0; w < b->ntrials; w++) { for (int k = 0; k < 6; k++) acc[k] += (double)hp[(size_t)w*6 + k]; nw++; }
-        const char *nm[6] = {"asm", "wait", "factor", "fwd", "bwd", "store"};
-        fprintf(stderr, "b200spice: k_solve mean cycles per warp (last launch):");
-        for (int k = 0; k < 6; k++) fprintf(stderr, " %s=%.0f", nm[k], acc[k]/nw);
-        for (int w = 0; w < 8; w++) { fprintf(stderr, "\n   warp %d:", w); for (int k = 0; k < 6; k++) fprintf(stderr, " %lld", hp[(size_t)w*6 + k]); }
-        fprintf(stderr, "\n   phase 2 detail (warps 0..3): sync ring fac fwd bwd fin");
-        for (int w = 0; w < 4; w++) { fprintf(stderr, "\n   warp %d:", w); for (int k = 0; k < 6; k++) fprintf(stderr, " %lld", hp[(size_t)b->ldt*6 + (size_t)w*6 + k]); }
-        fprintf(stderr, "\n");
-    }
     b->stats.launches = launches; b->stats.ticks = ticks;
     b->stats.ms_total = tot; b->stats.ms_load = ms_load; b->stats.ms_solve = ms_solve;
     b->stats.ms_control = tot - ms_load - ms_solve;

@@ -459,12 +459,12 @@ struct MosStuff {
     double gcgs, ceqgs, gcgd, ceqgd, gcgb, ceqgb, capgs, capgd, capgb;
 };
 
-struct MosOut {             // stamps go straight to this trial's contribution tile, load order
-    double *cbase;          // &contrib[tile of the trial][0][trial % TB]
+struct MosOut {             // stamps go straight to this trial's column of contrib[NC][ldt]
+    double *cbase;          // &contrib[0][trial]
     const int *cs, *rs;     // contribution slots of this instance (-1: ground row/column)
-    int tbshift;            // log2(trials per tile)
-    __device__ __forceinline__ void M(int k, double v) const { int q = cs[k]; if (q >= 0) cbase[(size_t)q << tbshift] = v; }
-    __device__ __forceinline__ void Rw(int k, double v) const { int q = rs[k]; if (q >= 0) cbase[(size_t)q << tbshift] = v; }
+    unsigned ldt;
+    __device__ __forceinline__ void M(int k, double v) const { int q = cs[k]; if (q >= 0) cbase[(size_t)(unsigned)q*ldt] = v; }
+    __device__ __forceinline__ void Rw(int k, double v) const { int q = rs[k]; if (q >= 0) cbase[(size_t)(unsigned)q*ldt] = v; }
 };
 
 __device__ __forceinline__ void dev_sargs(double arg, double bot, double side, double *sarg, double *sargsw)

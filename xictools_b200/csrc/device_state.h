@@ -86,7 +86,6 @@ struct Consts {
     int nnzLU, ncslot, nrslot, NC /* contributions per trial, assembly order */;
     double t_stop, t_step, t_start, maxStep, delmin, minBreak, break0, break1;
     int nocut, uic, hadNodeset, npoints_max, method;
-    int tb, tbshift;    // trials per contribution tile = trials per CTA of the solve kernel (1, 2, 4), log2
     int analysis;       // 0: transient (tranan.cc), 1: DC operating point only (dcoan.cc)
     int nbrks, nlat;
 };
@@ -134,6 +133,6 @@ struct VecView {
     double *oldSol;     // [n+1][ldt]
     double *states;     // [NS][numStates][ldt]
     double *oldState0;  // [numStates][ldt]
-    double *contrib;    // [ldt/TB][NC][TB]: trial-group tiles, contiguous per k_solve CTA
+    double *contrib;    // [NC][ldt]: matrix + rhs contributions in assembly order
     double *out;        // [npoints_max][n][ldt] -> transposed on fetch
 };

@@ -1,15 +1,13 @@
 // kernels.cu -- CUDA kernels of the batched Newton engine (sm_100a, FP64, -fmad=false).
 //
-// Thread mappings (DESIGN.md section 5):
+// Thread mappings (DESIGN.md section 4):
 //   k_load_*    one thread per (instance, trial), trial fastest: every global access of a warp
-//               is 32 consecutive doubles of one [slot][trial] row -> one 256-B line.
-//   k_solve     one warp per trial: gather-assemble A and b into shared memory (ordered,
-//               atomics-free), level-scheduled LU refactor with the frozen pivot order,
-//               triangular solves, node convergence test.  Lanes = independent columns/rows
-//               of one elimination level.
+//               is 32 consecutive doubles of one [slot][trial] row -> one 256-B line.  Stamps go
+//               to contrib[NC][ldt] in assembly order (no atomics).
 //   k_ctl       one thread per trial: the flattened NIiter / op / tran-step state machine.
-//   k_vec, k_statevec, k_trunc, k_devconv: one thread per (element, trial), gated by
-//               per-trial request flags.
+//   k_vec, k_statevec, k_devconv: one thread per (element, trial), gated by per-trial
+//               request flags.
+//   The solve of a tick (k_assemble -> k_lu -> k_finish) lives in solve.cu.
 #include <cuda_runtime.h>
 #include <cuda_pipeline.h>
 #include <float.h>
@@ -70,7 +68,7 @@ __device__ __forceinline__ void make_ctx(TrialCtx &c, const Consts &K, const Hot
 // thread, nothing parked in registers.  Stage 2: the model is evaluated out of shared memory;
 // state-0 results and stamps go straight to HBM, the operating point is updated in place in
 // the staging area and written back at the end.
-template <int MINB, bool L6, int TBS>
+template <int MINB, bool L6>
 __global__ void __launch_bounds__(MOS_TPB, MINB)
 k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, const double *rhsOld)
 {
@@ -187,12 +185,10 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
         __pipeline_commit();
     }
     MosOut o;
-    // TBS >= 0: tile width known at compile time (the common 4-trial tile), else Consts::tbshift
-    const int tbs = (TBS >= 0) ? TBS : K.tbshift;
-    o.cbase = V.contrib + ((((size_t)(t >> tbs))*(size_t)K.NC) << tbs) + (t & ((1 << tbs) - 1));
+    o.cbase = V.contrib + t;
     o.cs = sslot;
     o.rs = sslot + MT_NSTAMP;
-    o.tbshift = tbs;
+    o.ldt = (unsigned)K.ldt;
     double *plte = M.lte + (size_t)i*ldt + t;              // this device's LTE bounds: [2][nmos][ldt]
     __pipeline_wait_prior(0);
     __syncthreads();                                     // shared parameter block visible
@@ -517,407 +513,6 @@ k_devconv(Consts K, HotView hot, VecView V, MosView M, const double *rhs)
 }
 
 // ---------------------------------------------------------------------------------------
-// assemble + loadGmin + LU refactor + solve + NIconvTest node part.
-//
-// One CTA = TB (= Consts::tb) adjacent trials; thread = (lane e0 in 0..31, trial j).  Everything a CTA
-// reads from HBM is one contiguous block: the contributions of its trial group, stored by the
-// load kernels in ASSEMBLY ORDER as [NC][TB] tiles.
-//  1. streamed assembly.  The block is pulled through a shared-memory ring with cp.async,
-//     SEG_NBUF chunks in flight, so HBM latency is paid once, not per term.  A host-built
-//     schedule gives every lane runs of consecutive contributions = one matrix entry / rhs row
-//     each; the run is summed left to right (the reference's load order), the nodeset/ic/gmin
-//     rules are applied and the value is stored to the trial-interleaved LU/rhs image in
-//     shared memory.  Runs that cross a chunk stay on lane 0, partial sum in a register.
-//  2. LU refactor + triangular solves with the frozen pivot order: level-scheduled programs
-//     in dot-product form; the op stream is double-buffered through shared memory (cp.async)
-//     and every op is applied to all TB trials at once.
-//  3. store + NIconvTest node part.
-// ---- 1-D bulk copies (TMA engine) global -> shared, completion on an mbarrier ----
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    // dst, src 16-byte aligned, bytes a multiple of 16
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    unsigned ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-
-__device__ __forceinline__ double asm_finalize(double v, int info, const Consts &K, const SolveView &Sv,
-    bool ns_on, bool ic_on, double diagGmin)
-{
-    int node = info & 0x00ffffff;
-    if (!node) return v;
-    if (info & ASM_DIAG) {
-        // ckt.cc:1177-1204 nodeset / ic pinning, then loadGmin (ckt.cc:1221-1263, spspice.cc:259-300)
-        if (ns_on && Sv.ns_given[node]) v += 1.0;
-        if (ic_on && Sv.ic_given[node]) v += 1.0;
-        if (info & ASM_VNODE) {
-            if (diagGmin != 0.0)
-                v += diagGmin;
-            else if (K.opt.forcegmin && (v >= 0.0 && v < K.opt.gmin))
-                v = K.opt.gmin;
-            else if (v > K.opt.gmax)
-                v = K.opt.gmax;
-        }
-    }
-    else {
-        if (ns_on && Sv.ns_given[node]) v += Sv.ns_val[node];
-        if (ic_on && Sv.ic_given[node]) v += Sv.ic_val[node];
-    }
-    return v;
-}
-
-// Phase-2 op stream: rows of ROW_INTS ints (SOLVE_LANES task lanes x 3) double-buffered through
-// shared memory.
-#define ROW_INTS (3*SOLVE_LANES)
-#define RING_HROWS 21                                   // rows per half (21*768 B = 16128 B)
-#define RING_HALF_INTS (RING_HROWS*ROW_INTS)
-#define RING_NSLOT 4                                    // slots of the op ring: 3 blocks of rows in flight
-
-struct OpRing {
-    const int *g;          // global stream (16-B aligned, padded)
-    int *buf;              // smem, RING_NSLOT blocks of RING_HROWS rows
-    unsigned long long *bar;   // [RING_NSLOT] arrival barriers
-    int tid;
-    // one thread hands each 16 KB block to the copy engine (cp.async.bulk); the per-thread
-    // cp.async form spent a tenth of the kernel's issue slots on the copies alone
-    __device__ __forceinline__ void issue(int h) {
-        if (tid == 0) {
-            unsigned long long *b = bar + (h % RING_NSLOT);
-            mbar_expect_tx(b, RING_HALF_INTS*(unsigned)sizeof(int));
-            bulk_g2s(buf + (h % RING_NSLOT)*RING_HALF_INTS, g + (size_t)h*RING_HALF_INTS,
-                RING_HALF_INTS*(unsigned)sizeof(int), b);
-        }
-    }
-    __device__ __forceinline__ void wait(int h) { mbar_wait(bar + (h % RING_NSLOT), (unsigned)(h/RING_NSLOT) & 1u); }
-    // blocks 0 .. RING_NSLOT-2 are requested up front; entering block h waits for it (the
-    // RING_NSLOT-2 younger requests stay in flight) and, once every thread is past block h-1,
-    // reuses that slot for block h + RING_NSLOT - 1
-    __device__ __forceinline__ void start() {
-        for (int h = 0; h < RING_NSLOT - 1; h++) issue(h);
-    }
-    __device__ __forceinline__ void enter(int h) {
-        wait(h);
-        __syncthreads();
-        issue(h + RING_NSLOT - 1);
-    }
-    // the blocks requested ahead of the last one entered must land before the CTA may exit
-    __device__ __forceinline__ void drain(int last) {
-        for (int h = last + 1; h < last + RING_NSLOT; h++) wait(h);
-    }
-    __device__ __forceinline__ const int *row(int R) const {
-        int h = R/RING_HROWS;
-        return buf + (h % RING_NSLOT)*RING_HALF_INTS + (R - h*RING_HROWS)*ROW_INTS;
-    }
-};
-
-template <int TB>
-__global__ void __launch_bounds__(TB*SOLVE_LANES)
-k_solve(Consts K, HotView hot, VecView V, SolveView Sv, const double * __restrict__ Xold,
-    double * __restrict__ Xnew)
-{
-    constexpr int NL = SOLVE_LANES;
-    constexpr int NT = TB*NL;
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int t0 = blockIdx.x*TB;
-    const int ldt = K.ldt, n = K.n, nlu = K.nnzLU;
-    const int per = nlu + n;
-    double *S = smem;                                    // [per][TB], trial-interleaved
-    double *ringmem = smem + (((size_t)TB*per + 1) & ~(size_t)1);   // 16-B aligned: phase 1 data+op rings / phase 2 op ring
-    __shared__ int s_flags[TB];                          // bit0 singular, bit1 nonfinite, bit2 nonconv
-    __shared__ int s_any;
-    __shared__ int s_chunk[2*SOLVE_MAXCH];
-    __shared__ unsigned long long s_bar[SEG_NBUF];         // phase-1 chunk arrival (TB >= 2)
-    __shared__ unsigned long long s_rbar[RING_NSLOT];      // phase-2 op-ring block arrival
-
-    const int j = tid % TB, e0 = tid / TB;               // lane e0 (0..NL-1) x trial j
-    const int tj = t0 + j;
-    const bool live_j = (tj < K.ntrials) && hot.do_solve[tj];
-    if (tid == 0) {
-        s_any = 0;
-        if (TB >= 2)
-            for (int q = 0; q < SEG_NBUF; q++) mbar_init(&s_bar[q], 1);
-        for (int q = 0; q < RING_NSLOT; q++) mbar_init(&s_rbar[q], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (tid < TB) s_flags[tid] = 0;
-    __syncthreads();
-    if (live_j && e0 == 0) s_any = 1;
-    const int nch = Sv.nchunks;
-    for (int i = tid; i < 2*nch; i += NT) s_chunk[i] = Sv.seg_chunk[i];
-    __syncthreads();
-    if (!s_any) return;
-
-    const int mode = live_j ? hot.mode[tj] : 0;
-    const double diagGmin = live_j ? hot.diaggmin[tj] : 0.0;
-    const bool ns_on = (mode & MODEDC) && (mode & (MODEINITJCT | MODEINITFIX));
-    const bool ic_on = (mode & MODEDC) && (mode & MODETRANOP) && !(mode & MODEUIC);
-    const bool PF = Sv.prof != nullptr;
-    long long tk0 = PF ? clock64() : 0;
-
-    // ---- phase 1: streamed assembly ----
-    {
-        const double *gC = V.contrib + (size_t)blockIdx.x*(size_t)K.NC*TB;
-        double *dring = ringmem;                                     // [SEG_NBUF][SEG_CHUNK*TB]
-        SegOp *oring = reinterpret_cast<SegOp*>(ringmem + (size_t)SEG_NBUF*SEG_CHUNK*TB);
-        const int ostride = Sv.seg_maxsteps*NL;                       // SegOps per ring slot
-        // TB >= 2: one thread hands the chunk (contributions + its SegOps, both contiguous and
-        // 16-byte granular) to the copy engine; TB == 1 chunks are only 8-byte granular and go
-        // through per-thread cp.async
-        auto issue = [&](int c) {
-            if (TB >= 2) {
-                if (c < nch && tid == 0) {
-                    unsigned long long *bar = &s_bar[c % SEG_NBUF];
-                    const unsigned dbytes = (unsigned)(min(SEG_CHUNK, K.NC - c*SEG_CHUNK)*TB*sizeof(double));
-                    const unsigned obytes = (unsigned)(s_chunk[2*c + 1]*NL*sizeof(SegOp));
-                    mbar_expect_tx(bar, dbytes + obytes);
-                    bulk_g2s(dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB, gC + (size_t)c*SEG_CHUNK*TB, dbytes, bar);
-                    if (obytes)
-                        bulk_g2s(oring + (size_t)(c % SEG_NBUF)*ostride, Sv.seg_ops + s_chunk[2*c], obytes, bar);
-                }
-                return;
-            }
-            if (c < nch) {
-                int cnt = min(SEG_CHUNK, K.NC - c*SEG_CHUNK);         // one trial: 8-B units
-                const double *src = gC + (size_t)c*SEG_CHUNK;
-                double *dst = dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK;
-                for (int i = tid; i < cnt; i += NT) __pipeline_memcpy_async(dst + i, src + i, 8);
-                const int4 *osrc = reinterpret_cast<const int4*>(Sv.seg_ops + s_chunk[2*c]);
-                int4 *odst = reinterpret_cast<int4*>(oring + (size_t)(c % SEG_NBUF)*ostride);
-                int ocnt = s_chunk[2*c + 1]*NL;
-                for (int i = tid; i < ocnt; i += NT) __pipeline_memcpy_async(odst + i, osrc + i, 16);
-            }
-            __pipeline_commit();
-        };
-        for (int c = 0; c < SEG_NBUF - 1; c++) issue(c);
-        double v = 0.0;
-        for (int c = 0; c < nch; c++) {
-            if (TB >= 2) mbar_wait(&s_bar[c % SEG_NBUF], (unsigned)(c/SEG_NBUF) & 1u);
-            else __pipeline_wait_prior(SEG_NBUF - 2);
-            __syncthreads();                             // chunk c visible; slot of chunk c-1 free
-            issue(c + SEG_NBUF - 1);
-            if (!live_j) continue;
-            const double *buf = dring + (size_t)(c % SEG_NBUF)*SEG_CHUNK*TB + j;
-            const SegOp *ops = oring + (size_t)(c % SEG_NBUF)*ostride + e0;
-            const int ns = s_chunk[2*c + 1];
-            const int base = c*SEG_CHUNK;
-            for (int q = 0; q < ns; q++) {
-                const int4 raw = *reinterpret_cast<const int4*>(ops + q*NL);
-                const int pos = raw.x, len = raw.y, target = raw.z, info = raw.w;
-                if (info & SEG_START) v = 0.0;
-                const double *x = buf + (size_t)(pos - base)*TB;
-                int k = 0;
-                for (; k + 8 <= len; k += 8) {
-                    double xx[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) xx[u] = x[(size_t)(k + u)*TB];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) v += xx[u];
-                }
-                for (; k < len; k++) v += x[(size_t)k*TB];
-                if (target >= 0)
-                    S[(size_t)target*TB + j] = asm_finalize(v, info, K, Sv, ns_on, ic_on, diagGmin);
-            }
-        }
-        __pipeline_wait_prior(0);
-    }
-    long long tk1 = PF ? clock64() : 0;
-    __syncthreads();
-    long long tk2 = PF ? clock64() : 0;
-
-    // ---- phase 2: LU refactor + triangular solves, thread = (task lane e0, trial j) ----
-    {
-        OpRing ring;
-        ring.g = Sv.strm; ring.buf = reinterpret_cast<int*>(ringmem);
-        ring.tid = tid; ring.bar = s_rbar;
-        ring.start();
-        double *Sj = S + j;
-        double *yj = S + (size_t)nlu*TB + j;
-        int bad = 0;
-        int cur_half = -1;
-        const int nr = Sv.strm_nrounds;
-        long long pa_sync = 0, pa_ring = 0, pa_step[3] = {0, 0, 0}, pa_fin = 0, pq = 0;
-        for (int r = 0; r < nr; r++) {
-            const int4 rdsc = *reinterpret_cast<const int4*>(Sv.strm_round + 4*r);
-            const int nsteps = rdsc.x, kind = rdsc.y & 3, coop = rdsc.y & 4, sync = rdsc.z;
-            int R = rdsc.w;
-            if (PF) pq = clock64();
-            if (sync) __syncthreads();
-            if (PF) { long long z = clock64(); pa_sync += z - pq; pq = z; }
-            if (R/RING_HROWS != cur_half) { cur_half = R/RING_HROWS; ring.enter(cur_half); }
-            if (PF) { long long z = clock64(); pa_ring += z - pq; pq = z; }
-            const int *drow = ring.row(R);
-            const int x0 = drow[e0*3], x1 = drow[e0*3 + 1], x2 = drow[e0*3 + 2];
-            R++;
-            double acc = 0.0;
-            if (kind != 0 && x0 >= 0 && live_j) acc = yj[(size_t)x0*TB];
-            int left = nsteps;
-            while (left > 0) {
-                if (PF) pq = clock64();
-                if (R/RING_HROWS != cur_half) { cur_half = R/RING_HROWS; ring.enter(cur_half); }
-                if (PF) { long long z = clock64(); pa_ring += z - pq; pq = z; }
-                int avail = (cur_half + 1)*RING_HROWS - R;
-                int cnt = min(avail, left);
-                const int *op = ring.row(R) + e0*3;
-                // idle lanes of the round (x0 < 0) touch nothing; a solve lane stops after its
-                // own row's ops (x2), the rest of the round's rows are padding for it
-                int mine = cnt;
-                if (kind != 0) mine = min(cnt, x2 - (nsteps - left));
-                if (live_j && x0 >= 0 && mine > 0) {
-                    const int cnt = mine;
-                    if (kind == 0) {
-                        int q = 0;
-                        for (; q + 4 <= cnt; q += 4, op += 4*ROW_INTS) {
-                            int d[4], ia[4], ib[4];
-                            double av[4], bv[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) { d[u] = op[u*ROW_INTS]; ia[u] = op[u*ROW_INTS + 1]; ib[u] = op[u*ROW_INTS + 2]; }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) { av[u] = Sj[(size_t)ia[u]*TB]; bv[u] = Sj[(size_t)ib[u]*TB]; }
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                if (d[u] >= 0) {
-                                    if (d[u] & LUOP_FIRST) acc = Sj[(size_t)LUOP_SLOT(d[u])*TB];
-                                    acc -= av[u]*bv[u];
-                                    if (d[u] & LUOP_LAST) {
-                                        int slot = LUOP_SLOT(d[u]);
-                                        Sj[(size_t)slot*TB] = acc;
-                                        // U(k,j) finished inside the batch: forward it to later ops
-#pragma unroll
-                                        for (int w = u + 1; w < 4; w++)
-                                            if (ib[w] == slot) bv[w] = acc;
-                                    }
-                                }
-                            }
-                        }
-                        for (; q < cnt; q++, op += ROW_INTS) {
-                            int d = op[0];
-                            if (d >= 0) {
-                                double av = Sj[(size_t)op[1]*TB];
-                                if (d & LUOP_FIRST) acc = Sj[(size_t)LUOP_SLOT(d)*TB];
-                                acc -= av*Sj[(size_t)op[2]*TB];
-                                if (d & LUOP_LAST) Sj[(size_t)LUOP_SLOT(d)*TB] = acc;
-                            }
-                        }
-                    }
-                    else {
-                        int q = 0;
-                        for (; q + 8 <= cnt; q += 8, op += 8*ROW_INTS) {
-                            int d[8];
-                            double av[8], bv[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                d[u] = op[u*ROW_INTS];
-                                av[u] = Sj[(size_t)op[u*ROW_INTS + 1]*TB];
-                                bv[u] = yj[(size_t)op[u*ROW_INTS + 2]*TB];
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if (d[u] >= 0) acc -= av[u]*bv[u];
-                        }
-                        for (; q < cnt; q++, op += ROW_INTS)
-                            if (op[0] >= 0)
-                                acc -= Sj[(size_t)op[1]*TB]*yj[(size_t)op[2]*TB];
-                    }
-                }
-                R += cnt; left -= cnt;
-                if (PF) { long long z = clock64(); pa_step[kind] += z - pq; pq = z; }
-            }
-            if (PF) pq = clock64();
-            if (kind == 0) {
-                if (coop) {
-                    // a column of this round has a long L part: all lanes divide it together
-                    __syncthreads();
-                    if (live_j) {
-                        for (int e = 0; e < NL; e++) {
-                            int dg = drow[e*3];
-                            if (dg < 0) continue;
-                            double piv = Sj[(size_t)dg*TB];
-                            if (piv == 0.0 || !isfinite(piv)) bad = 1;
-                            for (int q = drow[e*3 + 1] + e0; q < drow[e*3 + 2]; q += NL)
-                                Sj[(size_t)q*TB] = Sj[(size_t)q*TB]/piv;
-                        }
-                    }
-                }
-                else if (live_j && x0 >= 0) {
-                    double piv = Sj[(size_t)x0*TB];
-                    if (piv == 0.0 || !isfinite(piv))
-                        bad = 1;
-                    for (int q = x1; q < x2; q++)
-                        Sj[(size_t)q*TB] = Sj[(size_t)q*TB]/piv;
-                }
-            }
-            else if (live_j && x0 >= 0) {
-                if (kind == 1) yj[(size_t)x0*TB] = acc;
-                else yj[(size_t)x0*TB] = acc/Sj[(size_t)x1*TB];
-            }
-            if (PF) { long long z = clock64(); pa_fin += z - pq; }
-        }
-        ring.drain(cur_half);
-        if (bad) atomicOr(&s_flags[j], 1);
-        if (PF && (tid & 31) == 0 && warp < TB) {
-            long long *pp = Sv.prof + (size_t)K.ldt*6 + ((size_t)blockIdx.x*TB + warp)*6;
-            pp[0] = pa_sync; pp[1] = pa_ring; pp[2] = pa_step[0]; pp[3] = pa_step[1]; pp[4] = pa_step[2]; pp[5] = pa_fin;
-        }
-    }
-    long long tk5 = PF ? clock64() : 0;
-    __syncthreads();
-
-    // ---- phase 3: unpermute, store, NIconvTest node part (niconv.cc:58-91) ----
-    if (live_j) {
-        const double *yj = S + (size_t)nlu*TB + j;
-        int fl = 0;
-#pragma unroll 4
-        for (int k = e0; k < n; k += SOLVE_LANES) {
-            int node = Sv.yperm_out[k];
-            double cur = yj[(size_t)k*TB];
-            double old = Xold[(size_t)node*ldt + tj];
-            Xnew[(size_t)node*ldt + tj] = cur;
-            if (!isfinite(cur)) fl |= 2;
-            double dd = fabs(old - cur);
-            double tol = K.opt.reltol*DMAX(fabs(old), fabs(cur)) +
-                (Sv.ntype[node] == 0 ? K.opt.vntol : K.opt.abstol);
-            if (dd > tol) fl |= 4;
-        }
-        if (fl) atomicOr(&s_flags[j], fl);
-    }
-    __syncthreads();
-    if (PF && (tid & 31) == 0 && warp < TB) {
-        long long tk6 = clock64();
-        long long *pp = Sv.prof + ((size_t)blockIdx.x*TB + warp)*6;
-        pp[0] = tk1 - tk0; pp[1] = tk2 - tk1; pp[2] = tk5 - tk2; pp[3] = 0; pp[4] = 0; pp[5] = tk6 - tk5;
-    }
-    if (tid < TB && live_j) {
-        int fl = s_flags[tid];
-        Xnew[tj] = 0.0;                                  // ground slot
-        int err = (fl & 1) ? B200_E_SINGULAR : ((fl & 2) ? B200_E_MATHOVF : 0);
-        int fail = (fl & 4) ? 1 : 0;
-        hot.solve_err[tj] = err;
-        hot.nodeconv[tj] = fail;
-        hot.devconv[tj] = 0;
-        int it1 = hot.iterno[tj] + 1;
-        hot.need_devconv[tj] = (!err && !fail && (mode & (MODEINITFIX | MODEINITFLOAT)) &&
-            hot.noncon[tj] == 0 && it1 != 1) ? 1 : 0;
-    }
-}
-
-// ---------------------------------------------------------------------------------------
 // control
 __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux aux, int phase)
 {
@@ -1203,28 +798,24 @@ void launch_ctl(cudaStream_t st, const Consts &K, const HotView &hot, TrialCtl *
 {
     k_ctl<<<(K.ntrials + 127)/128, 128, 0, st>>>(K, hot, ctl, sh, aux, phase);
 }
+int loads_configure(const MosView &M)
+{
+    // per device: called from prepare_params with the batch's device current
+    if (!M.n) return 0;
+    int smem = (int)((size_t)M.stage_doubles*sizeof(double));
+    if (cudaFuncSetAttribute(k_load_mos<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_load_mos<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return B200_E_NOMEM;
+    return 0;
+}
 void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const CapView &Cp, const SrcView &S, const double *rhsOld)
 {
     if (M.n) {
         size_t smem = (size_t)M.stage_doubles*sizeof(double);
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(k_load_mos<6, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<6, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<6, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_load_mos<6, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
         dim3 g((K.ntrials + MOS_TPB - 1)/MOS_TPB, M.n);
-        if (K.tbshift == 2) {
-            if (M.has_level6) k_load_mos<6, true, 2><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-            else k_load_mos<6, false, 2><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-        }
-        else {
-            if (M.has_level6) k_load_mos<6, true, -1><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-            else k_load_mos<6, false, -1><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-        }
+        if (M.has_level6) k_load_mos<6, true><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        else k_load_mos<6, false><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
     }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
     if (Cp.L.nmut) k_load_mut<<<grid2(K.ntrials, Cp.L.nmut), 128, 0, st>>>(K, hot, V, Cp.L);
@@ -1235,46 +826,6 @@ void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const 
     const MosView &M, const double *rhs)
 {
     if (M.n) k_devconv<<<grid2(K.ntrials, (M.n + DEVCONV_CHUNK - 1)/DEVCONV_CHUNK), 128, 0, st>>>(K, hot, V, M, rhs);
-}
-int solve_smem_bytes(const Consts &K, int seg_maxsteps)
-{
-    size_t img = ((((size_t)K.tb*(K.nnzLU + K.n)) + 1) & ~(size_t)1)*sizeof(double);
-    size_t ph1 = (size_t)SEG_NBUF*SEG_CHUNK*K.tb*sizeof(double) + (size_t)SEG_NBUF*seg_maxsteps*SOLVE_LANES*sizeof(SegOp);
-    size_t ph2 = (size_t)RING_NSLOT*RING_HALF_INTS*sizeof(int);
-    return (int)(img + (ph1 > ph2 ? ph1 : ph2));
-}
-int solve_pick_tb(Consts &K, int seg_maxsteps)
-{
-    for (int tb = SOLVE_TB_MAX; tb >= 1; tb >>= 1) {
-        K.tb = tb; K.tbshift = (tb == 4) ? 2 : (tb == 2 ? 1 : 0);
-        if (solve_smem_bytes(K, seg_maxsteps) <= 227*1024) return tb;
-    }
-    K.tb = 0;
-    return 0;
-}
-template <int TB>
-static int launch_solve_t(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
-    const SolveView &Sv, const double *Xold, double *Xnew)
-{
-    int smem = solve_smem_bytes(K, Sv.seg_maxsteps);
-    static int configured = -1;
-    if (configured < smem) {
-        if (cudaFuncSetAttribute(k_solve<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return B200_E_NOMEM;
-        configured = smem;
-    }
-    k_solve<TB><<<(K.ntrials + TB - 1)/TB, TB*SOLVE_LANES, smem, st>>>(K, hot, V, Sv, Xold, Xnew);
-    return 0;
-}
-int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
-    const SolveView &Sv, const double *Xold, double *Xnew)
-{
-    switch (K.tb) {
-    case 4: return launch_solve_t<4>(st, K, hot, V, Sv, Xold, Xnew);
-    case 2: return launch_solve_t<2>(st, K, hot, V, Sv, Xold, Xnew);
-    case 1: return launch_solve_t<1>(st, K, hot, V, Sv, Xold, Xnew);
-    default: return B200_E_UNSUPP;
-    }
 }
 void launch_vec(cudaStream_t st, const Consts &K, const VecView &V, const CtlAux &aux,
     const MosView &M, double *rhsOld)

@@ -3,11 +3,9 @@
 #include <cuda_runtime.h>
 #include "device_state.h"
 
-#define SOLVE_TB_MAX 4      // trials per CTA of k_solve: 4 (one 32-B sector per value), 2 or 1
-                            // (Consts::tb), the largest whose LU image fits shared memory
-#define SEG_NBUF 3           // streamed-assembly ring depth (chunks in flight)
-// contribution (s) of trial (t): tile layout, TB adjacent trials of one slot = one 32-B sector
-#define CADDR(K, s, t) ((((size_t)((t) >> (K).tbshift)*(size_t)(K).NC + (size_t)(s)) << (K).tbshift) + ((t) & ((K).tb - 1)))
+// contribution (s) of trial (t): [NC][ldt], trial fastest -- a warp of the load kernels writes one
+// 256-B line per stamp, a warp of k_assemble reads one per term
+#define CADDR(K, s, t) ((size_t)(s)*(size_t)(K).ldt + (size_t)(t))
 
 struct MosCard;
 struct CtlShared;
@@ -21,18 +19,28 @@ struct CtlAux {
     double *ip_d;       // [5][ldt]: time, c2, c3, c4, tcheck0
 };
 
-#define RING_HROWS_PAD 28        // x3 >= (RING_NSLOT-1)*RING_HROWS of k_solve: the op-stream prefetch runs ahead
-#define SOLVE_MAXCH 1024         // chunks of the streamed assembly (table cached in shared memory)
+// ---- the solve of one tick: k_assemble -> k_lu -> k_finish (solve.cu) ----
 struct SolveView {
     const int *ntype;           // [n+1]
     const char *ic_given, *ns_given;
     const double *ic_val, *ns_val;
-    const int *yperm_in, *yperm_out;
-    const int *strm; const int *strm_round; int strm_nrounds;   // phase-2 op stream
-    const SegOp *seg_ops; const int *seg_chunk; int nchunks, seg_maxsteps;   // streamed assembly
-    long long *prof;            // optional per-warp phase cycle counters (B200_SOLVE_PROF=1)
+    const int *yperm_out;       // x[colperm[k]+1] = y[k]
+    const AsmRun *runs;         // [img] assembly run of every image slot
+    int img;                    // doubles per trial image (even: rows are 16-byte granular)
+    int nlu;                    // LU values; the rhs / y / x part of the image starts here
+    int npad;                   // row pitch of ysol (n rounded up to a multiple of 32)
+    const unsigned *rows;       // task program, [nrows][LU_LANES] (b200_internal.h)
+    const unsigned short *rounds;
+    int nrows, nrounds;
+    double *image;              // [ldt][img] assembled A | b of every trial, trial-major
+    double *ysol;               // [ldt][npad] solutions in permuted column order
+    int *lu_bad;                // [ldt] 1: a pivot was zero or not finite
+    int *live;                  // [ldt] trials that take a solve this tick (built by k_assemble)
+    int *ctr;                   // [0] number of live trials, [1] work counter of the k_lu warps
+    int lu_warps, lu_grid;      // warps (= trials in flight) per CTA, CTAs of the persistent k_lu
+    int lu_smem;                // dynamic shared memory of k_lu
+    int prog_in_smem;           // 1: every CTA stages the program rows in shared memory
 };
-
 
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,
     const RawParams &raw, const MosParamsOut &out);
@@ -42,8 +50,11 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
     const MosView &M, const CapView &Cp, const SrcView &S, const double *rhsOld);
 void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const double *rhs);
-int  solve_smem_bytes(const Consts &K, int seg_maxsteps);   // for K.tb
-int  solve_pick_tb(Consts &K, int seg_maxsteps);               // sets K.tb; 0 if nothing fits
+// per device, at batch creation / parameter upload: dynamic shared-memory opt-ins and launch shapes
+int  loads_configure(const MosView &M);
+// sizes the k_lu launch (warps per CTA, program placement) for the current device;
+// B200_E_UNSUPP if one trial image does not fit shared memory
+int  solve_configure(SolveView &Sv);
 int  launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const SolveView &Sv, const double *Xold, double *Xnew);
 void launch_vec(cudaStream_t st, const Consts &K, const VecView &V, const CtlAux &aux,

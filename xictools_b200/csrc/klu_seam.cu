@@ -33,8 +33,9 @@ struct b200_klu {
     int cap_trials = 0;
     HotView hot; VecView V;
     double *dX0 = nullptr, *dX1 = nullptr, *dAxh = nullptr, *dBh = nullptr;
-    int *dstat = nullptr;
     int *d_packmap = nullptr; double *dpack = nullptr;
+    std::vector<void*> trial_allocs;            // buffers sized by cap_trials (re-made when it grows)
+    int d_const_n = 0; int *d_const_idx = nullptr; double *d_const_val = nullptr;
 
     template <class T> T *dalloc(size_t n) {
         void *p = nullptr;
@@ -47,6 +48,12 @@ struct b200_klu {
         T *p = dalloc<T>(v.size());
         if (p && !v.empty()) cudaMemcpy(p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice);
         return p;
+    }
+    template <class T> T *talloc(size_t n) {        // uninitialised; klu_ensure clears on the solve's stream
+        void *p = nullptr;
+        if (cudaMalloc(&p, (n ? n : 1)*sizeof(T)) != cudaSuccess) return nullptr;
+        trial_allocs.push_back(p);
+        return (T*)p;
     }
 };
 
@@ -67,14 +74,14 @@ __global__ void k_transpose_in(int rows, int ntrials, int ldt, const double *src
     }
 }
 
-__global__ void k_transpose_out(int rows, int ntrials, int ldt, const double *src /* [rows+1][ldt], row 0 = ground */,
+__global__ void k_transpose_out(int rows, int ntrials, int ldt, const double *src /* [rows][ldt] */,
     double *dst /* [nt][rows] */)
 {
     __shared__ double tile[32][33];
     int r0 = blockIdx.y*32, t0 = blockIdx.x*32;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         int r = r0 + k, t = t0 + threadIdx.x;
-        tile[k][threadIdx.x] = (r < rows && t < ntrials) ? src[(size_t)(r + 1)*ldt + t] : 0.0;
+        tile[k][threadIdx.x] = (r < rows && t < ntrials) ? src[(size_t)r*ldt + t] : 0.0;
     }
     __syncthreads();
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
@@ -135,7 +142,7 @@ __global__ void k_debug_assemble(Consts K, HotView hot, VecView V, SolveView Sv,
     }
 }
 
-// KLU seam: [entry][ldt] value arrays -> the solve kernel's [trial group][NC][TB] stream
+// KLU seam: [entry][ldt] value arrays -> rows of contrib[NC][ldt] in assembly order
 __global__ void k_pack_stream(Consts K, int nent, const int *map, const double *src, double *dst)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
@@ -299,7 +306,6 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     an.cg_ptr.assign(an.nnz + 1, 0);
     an.rg_ptr.assign(n + 2, 0);
     b200_order_markowitz(an);
-    b200_build_lu(an);
     // run-time gather lists are the identity: A[p] = 0 + Ax[p], b[row] = 0 + B[row-1]
     an.Ainit.assign(an.nnz, 0.0);
     an.cg_idx.resize(an.nnz);
@@ -310,38 +316,36 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     for (int r = 1; r <= n; r++) { an.rg_idx[r-1] = r - 1; an.rg_ptr[r+1] = r; }
     an.ic_given.assign(n + 1, 0); an.ns_given.assign(n + 1, 0);
     an.ic_val.assign(n + 1, 0.0); an.ns_val.assign(n + 1, 0.0);
-
     an.ncslot = an.nnz; an.nrslot = n;
-    b200_build_stream_asm(an);                // renumbers cg_idx / rg_idx into stream order
+    int rc = b200_build_lu(an);                // renumbers cg_idx / rg_idx into assembly order
+    if (rc) { delete k; return rc; }
 
     Consts &K = k->K;
     memset(&K, 0, sizeof(K));
     b200_options_default(&K.opt);
     K.opt.gmax = HUGE_VAL;
     K.n = n; K.nnz = an.nnz; K.nnzLU = an.nnzLU; K.NS = 4; K.NC = an.NC;
-    if (!solve_pick_tb(K, an.seg_maxsteps) || (int)an.seg_chunk.size()/2 > SOLVE_MAXCH) {
-        delete k; return B200_E_UNSUPP;
-    }
     CK(cudaStreamCreate(&k->stream));
     SolveView &Sv = k->Sv;
+    memset(&Sv, 0, sizeof(Sv));
     Sv.ntype = k->dupload(an.ntype);
     Sv.ic_given = k->dupload(an.ic_given); Sv.ns_given = k->dupload(an.ns_given);
     Sv.ic_val = k->dupload(an.ic_val); Sv.ns_val = k->dupload(an.ns_val);
-    Sv.yperm_in = k->dupload(an.yperm_in); Sv.yperm_out = k->dupload(an.yperm_out);
-    Sv.prof = nullptr;
-    Sv.seg_ops = k->dupload(an.seg_ops); Sv.seg_chunk = k->dupload(an.seg_chunk);
-    Sv.nchunks = (int)an.seg_chunk.size()/2; Sv.seg_maxsteps = an.seg_maxsteps;
+    Sv.yperm_out = k->dupload(an.yperm_out);
+    Sv.runs = k->dupload(an.runs);
+    Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (n + 31) & ~31;
+    Sv.rows = k->dupload(an.prog_rows); Sv.rounds = k->dupload(an.prog_round);
+    Sv.nrows = (int)an.prog_rows.size()/LU_LANES; Sv.nrounds = (int)an.prog_round.size();
+    Sv.ctr = k->dalloc<int>(2);
+    rc = solve_configure(Sv);
+    if (rc) { b200_klu_free(k); return rc; }
     {
         std::vector<int> map(an.cg_idx);
         map.insert(map.end(), an.rg_idx.begin(), an.rg_idx.end());
         k->d_packmap = k->dupload(map);
     }
-    {
-        std::vector<int> padded = an.strm;
-        padded.resize(padded.size() + 3*RING_HROWS_PAD*3*SOLVE_LANES, -1);          // cp.async prefetch runs ahead
-        Sv.strm = k->dupload(padded); Sv.strm_round = k->dupload(an.strm_round);
-        Sv.strm_nrounds = (int)an.strm_round.size()/4;
-    }
+    k->d_const_n = (int)an.const_idx.size();
+    k->d_const_idx = k->dupload(an.const_idx); k->d_const_val = k->dupload(an.const_val);
     CK(cudaDeviceSynchronize());
     *out = k;
     return B200_OK;
@@ -352,26 +356,48 @@ void b200_klu_free(b200_klu *k)
     if (!k) return;
     cudaSetDevice(k->device);
     for (void *p : k->allocs) cudaFree(p);
+    for (void *p : k->trial_allocs) cudaFree(p);
     if (k->stream) cudaStreamDestroy(k->stream);
     delete k;
 }
 
 int b200_klu_lu_nnz(const b200_klu *k) { return k ? k->an.nnzLU : 0; }
 
-static int klu_ensure(b200_klu *k, int ntrials)
+// (re)allocates everything sized by the trial count and initialises it ON THE SOLVE'S STREAM
+static int klu_ensure(b200_klu *k, int ldt, cudaStream_t st)
 {
-    int ldt = (ntrials + 31) & ~31;
-    if (k->cap_trials >= ldt) return B200_OK;
+    if (k->cap_trials == ldt) return B200_OK;
+    if (!k->trial_allocs.empty()) {
+        CK(cudaDeviceSynchronize());            // nothing in flight may still use the old buffers
+        for (void *p : k->trial_allocs) cudaFree(p);
+        k->trial_allocs.clear();
+    }
+    k->cap_trials = 0;
     HotView &h = k->hot;
-    h.mode = k->dalloc<int>(ldt); h.do_solve = k->dalloc<int>(ldt); h.iterno = k->dalloc<int>(ldt);
-    h.noncon = k->dalloc<int>(ldt); h.diaggmin = k->dalloc<double>(ldt);
-    h.solve_err = k->dalloc<int>(ldt); h.nodeconv = k->dalloc<int>(ldt);
-    h.devconv = k->dalloc<int>(ldt); h.need_devconv = k->dalloc<int>(ldt);
-    k->dX0 = k->dalloc<double>((size_t)(k->an.n + 1)*ldt);
-    k->dX1 = k->dalloc<double>((size_t)(k->an.n + 1)*ldt);
-    k->dpack = k->dalloc<double>((size_t)k->an.NC*ldt);
-    if (!k->dX1 || !k->dpack) return B200_E_NOMEM;
-    k_set_int<<<(ldt + 127)/128, 128, 0, k->stream>>>(h.do_solve, ldt, 1);
+    memset(&h, 0, sizeof(h));
+    h.mode = k->talloc<int>(ldt); h.do_solve = k->talloc<int>(ldt); h.iterno = k->talloc<int>(ldt);
+    h.noncon = k->talloc<int>(ldt); h.diaggmin = k->talloc<double>(ldt);
+    h.solve_err = k->talloc<int>(ldt); h.nodeconv = k->talloc<int>(ldt);
+    h.devconv = k->talloc<int>(ldt); h.need_devconv = k->talloc<int>(ldt);
+    k->dX0 = k->talloc<double>((size_t)(k->an.n + 1)*ldt);
+    k->dX1 = k->talloc<double>((size_t)(k->an.n + 1)*ldt);
+    k->dpack = k->talloc<double>((size_t)k->an.NC*ldt);
+    SolveView &Sv = k->Sv;
+    Sv.image = k->talloc<double>((size_t)ldt*Sv.img);
+    Sv.ysol = k->talloc<double>((size_t)ldt*Sv.npad);
+    Sv.lu_bad = k->talloc<int>(ldt); Sv.live = k->talloc<int>(ldt);
+    if (!k->dX1 || !k->dpack || !Sv.image || !Sv.ysol || !Sv.live) return B200_E_NOMEM;
+    int *iz[] = { h.mode, h.iterno, h.noncon, h.solve_err, h.nodeconv, h.devconv, h.need_devconv, Sv.lu_bad };
+    for (int *p : iz) CK(cudaMemsetAsync(p, 0, ldt*sizeof(int), st));
+    CK(cudaMemsetAsync(h.diaggmin, 0, ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(k->dX0, 0, (size_t)(k->an.n + 1)*ldt*sizeof(double), st));
+    CK(cudaMemsetAsync(k->dpack, 0, (size_t)k->an.NC*ldt*sizeof(double), st));
+    k_set_int<<<(ldt + 127)/128, 128, 0, st>>>(h.do_solve, ldt, 1);
+    {
+        // the constant terms of the assembly (the -1.0 of the split sums)
+        Consts K = k->K; K.ldt = ldt; K.ntrials = ldt;
+        launch_fill_const(st, K, k->dpack, k->d_const_n, k->d_const_idx, k->d_const_val);
+    }
     k->cap_trials = ldt;
     return B200_OK;
 }
@@ -379,11 +405,14 @@ static int klu_ensure(b200_klu *k, int ntrials)
 int b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double *dAx, double *dB,
     int *dstatus, void *cuda_stream)
 {
-    if (!k || ntrials <= 0 || ldt < ntrials || (ldt % SOLVE_TB_MAX)) return B200_E_BADPARM;
+    if (!k || ntrials <= 0 || ldt < ntrials || (ldt % 32)) return B200_E_BADPARM;
     CK(cudaSetDevice(k->device));
-    int rc = klu_ensure(k, ldt);
-    if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : k->stream;
+    // the scratch buffers (and the constant rows written into them) are pitched for one ldt
+    if (ldt != k->cap_trials) {
+        int rc = klu_ensure(k, ldt, st);
+        if (rc) return rc;
+    }
     Consts K = k->K;
     K.ntrials = ntrials; K.ldt = ldt;
     VecView V;
@@ -393,7 +422,7 @@ int b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double 
     k_pack_stream<<<dim3((ldt + 127)/128, nnz), 128, 0, st>>>(K, nnz, k->d_packmap, dAx, k->dpack);
     k_pack_stream<<<dim3((ldt + 127)/128, n), 128, 0, st>>>(K, n, k->d_packmap + nnz, dB, k->dpack);
     // solution goes to dX1 ([n+1][ldt], row 0 = ground), then back into dB
-    rc = launch_solve(st, K, k->hot, V, k->Sv, k->dX0, k->dX1);
+    int rc = launch_solve(st, K, k->hot, V, k->Sv, k->dX0, k->dX1);
     if (rc) return rc;
     CK(cudaMemcpyAsync(dB, k->dX1 + ldt, (size_t)k->an.n*ldt*sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (dstatus)
@@ -408,29 +437,31 @@ int b200_klu_refactor_solve_host(b200_klu *k, int ntrials, const double *Ax, dou
     int ldt = (ntrials + 31) & ~31;
     int n = k->an.n, nnz = k->an.nnz;
     cudaStream_t st = k->stream;
-    double *hAx = nullptr, *hB = nullptr, *dAx = nullptr, *dB = nullptr; int *dst = nullptr;
-    CK(cudaMalloc(&hAx, (size_t)ntrials*nnz*sizeof(double)));
-    CK(cudaMalloc(&hB, (size_t)ntrials*n*sizeof(double)));
-    CK(cudaMalloc(&dAx, (size_t)nnz*ldt*sizeof(double)));
-    CK(cudaMalloc(&dB, (size_t)n*ldt*sizeof(double)));
-    CK(cudaMalloc(&dst, ldt*sizeof(int)));
+    struct Tmp {                                   // freed on every exit path
+        std::vector<void*> p;
+        ~Tmp() { for (void *q : p) cudaFree(q); }
+        void *get(size_t bytes) { void *q = nullptr; if (cudaMalloc(&q, bytes) != cudaSuccess) return nullptr; p.push_back(q); return q; }
+    } tmp;
+    double *hAx = (double*)tmp.get((size_t)ntrials*nnz*sizeof(double));
+    double *hB = (double*)tmp.get((size_t)ntrials*n*sizeof(double));
+    double *dAx = (double*)tmp.get((size_t)nnz*ldt*sizeof(double));
+    double *dB = (double*)tmp.get((size_t)n*ldt*sizeof(double));
+    int *dst = (int*)tmp.get(ldt*sizeof(int));
+    if (!hAx || !hB || !dAx || !dB || !dst) return B200_E_NOMEM;
     CK(cudaMemcpyAsync(hAx, Ax, (size_t)ntrials*nnz*sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(hB, B, (size_t)ntrials*n*sizeof(double), cudaMemcpyHostToDevice, st));
     dim3 blk(32, 8);
     k_transpose_in<<<dim3(ldt/32, (nnz + 31)/32), blk, 0, st>>>(nnz, ntrials, ldt, hAx, dAx);
     k_transpose_in<<<dim3(ldt/32, (n + 31)/32), blk, 0, st>>>(n, ntrials, ldt, hB, dB);
     int rc = b200_klu_refactor_solve_dev(k, ntrials, ldt, dAx, dB, dst, st);
-    if (!rc) {
-        // dB now holds x as [n][ldt]; transpose back (k_transpose_out skips a ground row, so
-        // hand it a pointer one row before dB)
-        k_transpose_out<<<dim3(ldt/32, (n + 31)/32), blk, 0, st>>>(n, ntrials, ldt, dB - ldt, hB);
-        CK(cudaMemcpyAsync(B, hB, (size_t)ntrials*n*sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (status) CK(cudaMemcpyAsync(status, dst, ntrials*sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
-    }
-    cudaFree(hAx); cudaFree(hB); cudaFree(dAx); cudaFree(dB); cudaFree(dst);
-    return rc;
+    if (rc) return rc;
+    // dB now holds x as [n][ldt]
+    k_transpose_out<<<dim3(ldt/32, (n + 31)/32), blk, 0, st>>>(n, ntrials, ldt, dB, hB);
+    CK(cudaMemcpyAsync(B, hB, (size_t)ntrials*n*sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, dst, ntrials*sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return B200_OK;
 }
 
 } // extern "C"

@@ -1,0 +1,334 @@
+// solve.cu -- the linear solve of one Newton tick for every trial that asked for one:
+//
+//   k_assemble  sCKT::load's accumulation + nodeset/ic pinning + loadGmin (ckt.cc:1177-1263,
+//               spspice.cc:259-300).  contrib[NC][ldt] (trial fastest, written by the load
+//               kernels in ASSEMBLY ORDER: the terms of one matrix entry / rhs row are
+//               consecutive rows, in the reference's load order) -> image[trial][img], one
+//               contiguous A | b | scratch block per trial.  lane = trial, so every read is a
+//               256-B line; the transpose goes through shared memory so every write is too.
+//               No atomics: a value is the left-to-right sum of its run.
+//   k_lu        spFactor/klu_refactor + spSolve/klu_solve with the frozen pivot order
+//               (kluif.cc:594-628).  ONE WARP PER TRIAL: the image is pulled into shared
+//               memory by a bulk copy, the 32 lanes interpret the level-scheduled task program
+//               (b200_internal.h) with __syncwarp between levels -- no CTA barrier anywhere.
+//               Persistent CTAs; warps take trials from a work counter over the live list.
+//   k_finish    unpermute (ysol[trial][k] -> X[node][trial], transposed through shared
+//               memory) + the node part of NIconvTest (niconv.cc:58-91) + per-trial flags.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "device_state.h"
+#include "dev_load.cuh"
+#include "kernels.h"
+
+// ---- 1-D bulk copy (TMA engine) global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    // dst, src 16-byte aligned, bytes a multiple of 16
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_assemble
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double asm_finalize(double v, int info, const Consts &K, const SolveView &Sv,
+    bool ns_on, bool ic_on, double diagGmin)
+{
+    int node = info & 0x00ffffff;
+    if (!node) return v;
+    if (info & ASM_DIAG) {
+        // ckt.cc:1177-1204 nodeset / ic pinning, then loadGmin (ckt.cc:1221-1263, spspice.cc:259-300)
+        if (ns_on && Sv.ns_given[node]) v += 1.0;
+        if (ic_on && Sv.ic_given[node]) v += 1.0;
+        if (info & ASM_VNODE) {
+            if (diagGmin != 0.0)
+                v += diagGmin;
+            else if (K.opt.forcegmin && (v >= 0.0 && v < K.opt.gmin))
+                v = K.opt.gmin;
+            else if (v > K.opt.gmax)
+                v = K.opt.gmax;
+        }
+    }
+    else {
+        if (ns_on && Sv.ns_given[node]) v += Sv.ns_val[node];
+        if (ic_on && Sv.ic_given[node]) v += Sv.ic_val[node];
+    }
+    return v;
+}
+
+// left-to-right sum of len rows (pitch ldt) with U loads in flight
+template <int U>
+__device__ __forceinline__ double run_sum(double v, const double * __restrict__ x, size_t ldt, int &k, int len)
+{
+    for (; k + U <= len; k += U) {
+        double xx[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) xx[u] = __ldcs(x + (size_t)(k + u)*ldt);
+#pragma unroll
+        for (int u = 0; u < U; u++) v += xx[u];
+    }
+    return v;
+}
+
+#define ASM_SLOTS 64            // image slots per CTA
+#define ASM_WARPS 8
+__global__ void __launch_bounds__(ASM_WARPS*32)
+k_assemble(Consts K, HotView hot, VecView V, SolveView Sv)
+{
+    __shared__ double tile[ASM_SLOTS][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x*32 + lane;
+    const bool live = (t < K.ntrials) && hot.do_solve[t];
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+    if (!mask) return;                                   // same 32 trials in every warp: uniform exit
+    if (blockIdx.y == 0 && warp == 0) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&Sv.ctr[0], __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (live) Sv.live[base + __popc(mask & ((1u << lane) - 1u))] = t;
+    }
+    const int mode = live ? hot.mode[t] : 0;
+    const double diagGmin = live ? hot.diaggmin[t] : 0.0;
+    const bool ns_on = (mode & MODEDC) && (mode & (MODEINITJCT | MODEINITFIX));
+    const bool ic_on = (mode & MODEDC) && (mode & MODETRANOP) && !(mode & MODEUIC);
+    const size_t ldt = (size_t)K.ldt;
+    const int s0 = blockIdx.y*ASM_SLOTS;
+    const int cnt = min(ASM_SLOTS, Sv.img - s0);
+    const double *cb = V.contrib + t;
+    for (int sl = warp; sl < cnt; sl += ASM_WARPS) {
+        const int4 run = __ldg(reinterpret_cast<const int4*>(Sv.runs + s0 + sl));
+        double v = 0.0;
+        if (live) {
+            const double *x = cb + (size_t)run.x*ldt;
+            const int len = run.y;
+            int k = 0;
+            if (len >= 64) v = run_sum<32>(v, x, ldt, k, len);
+            v = run_sum<8>(v, x, ldt, k, len);
+            for (; k < len; k++) v += __ldcs(x + (size_t)k*ldt);
+            v = asm_finalize(v, run.z, K, Sv, ns_on, ic_on, diagGmin);
+        }
+        tile[sl][lane] = v;
+    }
+    __syncthreads();
+    for (int tr = warp; tr < 32; tr += ASM_WARPS) {
+        if (!((mask >> tr) & 1u)) continue;
+        double *dst = Sv.image + (size_t)(blockIdx.x*32 + tr)*(size_t)Sv.img + s0;
+        if (lane < cnt) dst[lane] = tile[lane][tr];
+        if (lane + 32 < cnt) dst[lane + 32] = tile[lane + 32][tr];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_lu
+// ---------------------------------------------------------------------------------------
+#define LU_MAXW 8
+template <bool PSMEM>
+__global__ void __launch_bounds__(LU_MAXW*32, 1)
+k_lu(SolveView Sv, int n)
+{
+    extern __shared__ double smem[];
+    __shared__ unsigned long long s_bar[LU_MAXW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = Sv.lu_warps;
+    const int img = Sv.img;
+    double *S = smem + (size_t)warp*img;
+    unsigned short *s_round = reinterpret_cast<unsigned short*>(smem + (size_t)W*img);
+    unsigned *s_rows = reinterpret_cast<unsigned*>(s_round + ((Sv.nrounds + 7) & ~7));
+    const int nlive = Sv.ctr[0];
+    if ((int)(blockIdx.x*W) >= nlive) return;           // the CTAs before this one have a warp per live trial
+    for (int i = threadIdx.x; i < Sv.nrounds; i += blockDim.x) s_round[i] = Sv.rounds[i];
+    if (PSMEM) {
+        const uint4 *src = reinterpret_cast<const uint4*>(Sv.rows);
+        uint4 *dst = reinterpret_cast<uint4*>(s_rows);
+        for (int i = threadIdx.x; i < Sv.nrows*(LU_LANES/4); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x < W) mbar_init(&s_bar[threadIdx.x], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const unsigned *rows0 = (PSMEM ? s_rows : Sv.rows) + lane;
+    const unsigned bytes = (unsigned)img*8u;
+    unsigned phase = 0;
+    const int nrounds = Sv.nrounds;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&Sv.ctr[1], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nlive) break;
+        const int t = Sv.live[i];
+        if (lane == 0) {
+            // the previous trial's image was read and written through the generic proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_bar[warp], bytes);
+            bulk_g2s(S, Sv.image + (size_t)t*img, bytes, &s_bar[warp]);
+        }
+        mbar_wait(&s_bar[warp], phase);
+        phase ^= 1u;
+        int bad = 0;
+        const unsigned *rp = rows0;
+        for (int r = 0; r < nrounds; r++) {
+            const unsigned meta = s_round[r];
+            const int nsteps = (int)(meta & 0x7fffu);
+            if (meta & LU_RSYNC) __syncwarp();
+            const unsigned h = PSMEM ? rp[0] : __ldg(rp);
+            rp += LU_LANES;
+            const unsigned dst = h & 0xffffu, div = h >> 16;
+            double acc = S[dst];
+            for (int s = 0; s < nsteps; s += 4) {
+                unsigned w[4];
+                double a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (s + u < nsteps) w[u] = PSMEM ? rp[(s + u)*LU_LANES] : __ldg(rp + (s + u)*LU_LANES);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (s + u < nsteps) { a[u] = S[w[u] & 0xffffu]; b[u] = S[w[u] >> 16]; }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (s + u < nsteps) acc -= a[u]*b[u];
+            }
+            rp += nsteps*LU_LANES;
+            if (div != LU_NONE) {
+                const double piv = S[div];
+                if (piv == 0.0 || !isfinite(piv)) bad = 1;
+                acc = acc/piv;
+            }
+            S[dst] = acc;
+        }
+        __syncwarp();
+        double *y = Sv.ysol + (size_t)t*Sv.npad;
+        const double *Sy = S + Sv.nlu;
+        for (int k = lane; k < n; k += 32) y[k] = Sy[k];
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) Sv.lu_bad[t] = bad;
+        __syncwarp();                                    // every lane is done with S before the next copy lands
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_finish: CTA = one group of 32 adjacent trials, all n unknowns
+// ---------------------------------------------------------------------------------------
+#define FIN_WARPS 8
+__global__ void __launch_bounds__(FIN_WARPS*32)
+k_finish(Consts K, HotView hot, SolveView Sv, const double * __restrict__ Xold, double * __restrict__ Xnew)
+{
+    __shared__ double tile[2][32][33];
+    __shared__ int s_flags[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t0 = blockIdx.x*32;
+    const int t = t0 + lane;
+    const bool live = (t < K.ntrials) && hot.do_solve[t];
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+    if (!mask) return;
+    if (threadIdx.x < 32) s_flags[threadIdx.x] = 0;
+    const int n = K.n;
+    const size_t ldt = (size_t)K.ldt;
+    int fl = 0;
+    int buf = 0;
+    for (int k0 = 0; k0 < n; k0 += 32, buf ^= 1) {
+        // rows of ysol: trial tr, unknowns k0 .. k0+31 (one 256-B line)
+        for (int tr = warp; tr < 32; tr += FIN_WARPS) {
+            double v = 0.0;
+            if (((mask >> tr) & 1u) && k0 + lane < n) v = Sv.ysol[(size_t)(t0 + tr)*Sv.npad + k0 + lane];
+            tile[buf][tr][lane] = v;
+        }
+        __syncthreads();
+        for (int kk = warp; kk < 32; kk += FIN_WARPS) {
+            const int k = k0 + kk;
+            if (k >= n || !live) continue;
+            const int node = Sv.yperm_out[k];
+            const double cur = tile[buf][lane][kk];
+            const double old = Xold[(size_t)node*ldt + t];
+            Xnew[(size_t)node*ldt + t] = cur;
+            if (!isfinite(cur)) fl |= 2;
+            const double dd = fabs(old - cur);
+            const double tol = K.opt.reltol*DMAX(fabs(old), fabs(cur)) +
+                (Sv.ntype[node] == 0 ? K.opt.vntol : K.opt.abstol);
+            if (dd > tol) fl |= 4;
+        }
+        // the other buffer is refilled next; it was last read two iterations ago
+    }
+    if (fl) atomicOr(&s_flags[lane], fl);
+    __syncthreads();
+    if (warp == 0 && live) {
+        fl = s_flags[lane] | (Sv.lu_bad[t] ? 1 : 0);
+        Xnew[t] = 0.0;                                   // ground slot
+        const int err = (fl & 1) ? B200_E_SINGULAR : ((fl & 2) ? B200_E_MATHOVF : 0);
+        const int fail = (fl & 4) ? 1 : 0;
+        const int mode = hot.mode[t];
+        hot.solve_err[t] = err;
+        hot.nodeconv[t] = fail;
+        hot.devconv[t] = 0;
+        const int it1 = hot.iterno[t] + 1;
+        hot.need_devconv[t] = (!err && !fail && (mode & (MODEINITFIX | MODEINITFLOAT)) &&
+            hot.noncon[t] == 0 && it1 != 1) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// launch side
+// ---------------------------------------------------------------------------------------
+int solve_configure(SolveView &Sv)
+{
+    int dev = 0, nsm = 0, maxsm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return B200_E_NOGPU;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_lu<true>) != cudaSuccess) return B200_E_NOGPU;
+    const size_t budget = (size_t)maxsm - fa.sharedSizeBytes;
+    const size_t imgb = (size_t)Sv.img*8;
+    const size_t rnd = (size_t)((Sv.nrounds + 7) & ~7)*sizeof(unsigned short);
+    const size_t prog = (size_t)Sv.nrows*LU_LANES*sizeof(unsigned);
+    if (imgb + rnd > budget) return B200_E_UNSUPP;
+    int w_glob = (int)((budget - rnd)/imgb);
+    if (w_glob > LU_MAXW) w_glob = LU_MAXW;
+    int w_smem = (budget > rnd + prog) ? (int)((budget - rnd - prog)/imgb) : 0;
+    if (w_smem > LU_MAXW) w_smem = LU_MAXW;
+    // the program in shared memory costs trials in flight; worth it while it costs at most a third
+    const char *force = getenv("B200_LU_PROG");        // "smem" | "global": measurement override
+    bool psmem = (w_smem >= 1) && (3*w_smem >= 2*w_glob);
+    if (force && !strcmp(force, "global")) psmem = false;
+    if (force && !strcmp(force, "smem") && w_smem >= 1) psmem = true;
+    Sv.prog_in_smem = psmem ? 1 : 0;
+    Sv.lu_warps = psmem ? w_smem : w_glob;
+    Sv.lu_smem = (int)((size_t)Sv.lu_warps*imgb + rnd + (psmem ? prog : 0));
+    Sv.lu_grid = nsm;
+    cudaError_t e = psmem
+        ? cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sv.lu_smem)
+        : cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sv.lu_smem);
+    return e == cudaSuccess ? B200_OK : B200_E_NOMEM;
+}
+
+int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
+    const SolveView &Sv, const double *Xold, double *Xnew)
+{
+    if (cudaMemsetAsync(Sv.ctr, 0, 2*sizeof(int), st) != cudaSuccess) return B200_E_NOGPU;
+    const int ngroups = K.ldt/32;
+    dim3 ga(ngroups, (Sv.img + ASM_SLOTS - 1)/ASM_SLOTS);
+    k_assemble<<<ga, ASM_WARPS*32, 0, st>>>(K, hot, V, Sv);
+    if (Sv.prog_in_smem) k_lu<true><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
+    else k_lu<false><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
+    k_finish<<<ngroups, FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew);
+    return 0;
+}
