@@ -257,6 +257,13 @@ def bench_ours(args):
     cnt = batch.counters()
     ok_trials = int((cnt[:, C_STATUS] == 0).sum())
 
+    if args.kernel_only:
+        if rank == 0:
+            print(f"bench: kernel-only {world*T*args.steps/el:.1f} trials/s, {1e3*el/args.steps:.1f} ms/step, "
+                  f"load {ms_load/max(nload, 1):.3f} solve {ms_solve/max(nsolve, 1):.3f} ms/tick, "
+                  f"{ticks//args.steps} ticks", file=sys.stderr)
+        return 0
+
     # ---- end-to-end timing (host buffers, public API) ----
     for _ in range(max(1, min(args.warmup, 2))):     # NCCL connection set-up, first-touch of host buffers
         step_e2e()
@@ -386,6 +393,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trials", type=int, default=TRIALS_PER_GPU)
     ap.add_argument("--stages", type=int, default=NSTAGES)
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="profiling aid (ncu): device-resident steps only, no e2e / CPU legs, no JSON contract")
     args = ap.parse_args()
     if args.impl == "reference":
         return bench_reference(args)

@@ -870,6 +870,14 @@ int b200_build_lu(Analysis &an)
     an.runs[an.slot_neg1].len = 1;
     an.const_idx.push_back(next++); an.const_val.push_back(-1.0);
     an.NC = next;
+    {
+        int ntiles = (an.img + ASM_TILE_SLOTS - 1)/ASM_TILE_SLOTS;
+        std::vector<int> terms(ntiles, 0);
+        for (int s = 0; s < an.img; s++) terms[s/ASM_TILE_SLOTS] += an.runs[s].len;
+        an.tile_order.resize(ntiles);
+        for (int i = 0; i < ntiles; i++) an.tile_order[i] = i;
+        std::stable_sort(an.tile_order.begin(), an.tile_order.end(), [&](int a, int b) { return terms[a] > terms[b]; });
+    }
     for (auto &c : an.cg_idx) c = newc[c];
     for (auto &c : an.rg_idx) c = newr[c];
     auto remap = [](std::vector<int> &v, const std::vector<int> &m) { for (auto &x : v) if (x >= 0) x = m[x]; };

@@ -163,6 +163,7 @@ struct SrcTopo {
 #define LU_RSYNC 0x8000u
 // Assembly run of one image slot: S[slot] = finalize( sum of contrib[pos .. pos+len) in order )
 struct AsmRun { int pos, len, info, pad; };
+#define ASM_TILE_SLOTS 16                        // slots per k_assemble warp tile
 #define ASM_DIAG 0x40000000
 #define ASM_ROW  0x20000000
 #define ASM_VNODE 0x10000000  // diagonal of a voltage node (loadGmin applies)
@@ -204,6 +205,7 @@ struct Analysis {
     int nscratch = 0, slot_neg1 = 0, slot_zero = 0, img = 0;
     int NC = 0;                                 // total contributions (matrix + rhs + constants), assembly order
     std::vector<AsmRun> runs;                   // [img]
+    std::vector<int> tile_order;                // tiles of ASM_TILE_SLOTS slots, most terms first
     std::vector<int> const_idx; std::vector<double> const_val;   // Ainit pseudo-terms, the -1.0
     // task program
     std::vector<unsigned> prog_rows;            // [nrows][LU_LANES]

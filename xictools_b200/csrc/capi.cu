@@ -336,6 +336,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Sv.ic_val = b->dupload(an.ic_val); Sv.ns_val = b->dupload(an.ns_val);
     Sv.yperm_out = b->dupload(an.yperm_out);
     Sv.runs = b->dupload(an.runs);
+    Sv.tile_order = b->dupload(an.tile_order); Sv.ntiles = (int)an.tile_order.size();
     Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (an.n + 31) & ~31;
     Sv.rows = b->dupload(an.prog_rows); Sv.rounds = b->dupload(an.prog_round);
     Sv.nrows = (int)an.prog_rows.size()/LU_LANES; Sv.nrounds = (int)an.prog_round.size();

@@ -26,6 +26,8 @@ struct SolveView {
     const double *ic_val, *ns_val;
     const int *yperm_out;       // x[colperm[k]+1] = y[k]
     const AsmRun *runs;         // [img] assembly run of every image slot
+    const int *tile_order;      // [ntiles] tiles of ASM_TILE_SLOTS slots, most terms first
+    int ntiles;
     int img;                    // doubles per trial image (even: rows are 16-byte granular)
     int nlu;                    // LU values; the rhs / y / x part of the image starts here
     int npad;                   // row pitch of ysol (n rounded up to a multiple of 32)

@@ -333,6 +333,7 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     Sv.ic_val = k->dupload(an.ic_val); Sv.ns_val = k->dupload(an.ns_val);
     Sv.yperm_out = k->dupload(an.yperm_out);
     Sv.runs = k->dupload(an.runs);
+    Sv.tile_order = k->dupload(an.tile_order); Sv.ntiles = (int)an.tile_order.size();
     Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (n + 31) & ~31;
     Sv.rows = k->dupload(an.prog_rows); Sv.rounds = k->dupload(an.prog_round);
     Sv.nrows = (int)an.prog_rows.size()/LU_LANES; Sv.nrounds = (int)an.prog_round.size();

@@ -91,12 +91,16 @@ __device__ __forceinline__ double run_sum(double v, const double * __restrict__ 
     return v;
 }
 
-#define ASM_SLOTS 64            // image slots per CTA
+// One WARP = 32 adjacent trials (lane = trial) x one tile of ASM_TS consecutive image slots; the
+// warps of a CTA share nothing (no CTA barrier: a warp that owns a long run -- the supply node's
+// diagonal collects a term from every MOSFET -- must not hold seven others at a barrier).
+// Tiles are visited in the order of the host-built list, heaviest first.
+#define ASM_TS 16               // image slots per tile (one 128-B line of a trial's image row)
 #define ASM_WARPS 8
 __global__ void __launch_bounds__(ASM_WARPS*32)
 k_assemble(Consts K, HotView hot, VecView V, SolveView Sv)
 {
-    __shared__ double tile[ASM_SLOTS][33];
+    __shared__ double tiles[ASM_WARPS][ASM_TS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x*32 + lane;
     const bool live = (t < K.ntrials) && hot.do_solve[t];
@@ -108,15 +112,18 @@ k_assemble(Consts K, HotView hot, VecView V, SolveView Sv)
         base = __shfl_sync(0xffffffffu, base, 0);
         if (live) Sv.live[base + __popc(mask & ((1u << lane) - 1u))] = t;
     }
+    const int ti = blockIdx.y*ASM_WARPS + warp;
+    if (ti >= Sv.ntiles) return;
+    const int s0 = Sv.tile_order[ti]*ASM_TS;
+    const int cnt = min(ASM_TS, Sv.img - s0);
     const int mode = live ? hot.mode[t] : 0;
     const double diagGmin = live ? hot.diaggmin[t] : 0.0;
     const bool ns_on = (mode & MODEDC) && (mode & (MODEINITJCT | MODEINITFIX));
     const bool ic_on = (mode & MODEDC) && (mode & MODETRANOP) && !(mode & MODEUIC);
     const size_t ldt = (size_t)K.ldt;
-    const int s0 = blockIdx.y*ASM_SLOTS;
-    const int cnt = min(ASM_SLOTS, Sv.img - s0);
     const double *cb = V.contrib + t;
-    for (int sl = warp; sl < cnt; sl += ASM_WARPS) {
+    double (*tile)[33] = tiles[warp];
+    for (int sl = 0; sl < cnt; sl++) {
         const int4 run = __ldg(reinterpret_cast<const int4*>(Sv.runs + s0 + sl));
         double v = 0.0;
         if (live) {
@@ -130,12 +137,12 @@ k_assemble(Consts K, HotView hot, VecView V, SolveView Sv)
         }
         tile[sl][lane] = v;
     }
-    __syncthreads();
-    for (int tr = warp; tr < 32; tr += ASM_WARPS) {
-        if (!((mask >> tr) & 1u)) continue;
-        double *dst = Sv.image + (size_t)(blockIdx.x*32 + tr)*(size_t)Sv.img + s0;
-        if (lane < cnt) dst[lane] = tile[lane][tr];
-        if (lane + 32 < cnt) dst[lane + 32] = tile[lane + 32][tr];
+    __syncwarp();
+    // two trial rows per store instruction: lanes 0..15 one row, lanes 16..31 the next
+    const int half = lane >> 4, c = lane & 15;
+    for (int tr = half; tr < 32; tr += 2) {
+        if (!((mask >> tr) & 1u) || c >= cnt) continue;
+        Sv.image[(size_t)(blockIdx.x*32 + tr)*(size_t)Sv.img + s0 + c] = tile[c][tr];
     }
 }
 
@@ -314,6 +321,7 @@ int solve_configure(SolveView &Sv)
     Sv.lu_warps = psmem ? w_smem : w_glob;
     Sv.lu_smem = (int)((size_t)Sv.lu_warps*imgb + rnd + (psmem ? prog : 0));
     Sv.lu_grid = nsm;
+    if (Sv.ntiles != (Sv.img + ASM_TS - 1)/ASM_TS) return B200_E_PANIC;     // b200_internal.h ASM_TILE_SLOTS
     cudaError_t e = psmem
         ? cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sv.lu_smem)
         : cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sv.lu_smem);
@@ -325,7 +333,7 @@ int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const Vec
 {
     if (cudaMemsetAsync(Sv.ctr, 0, 2*sizeof(int), st) != cudaSuccess) return B200_E_NOGPU;
     const int ngroups = K.ldt/32;
-    dim3 ga(ngroups, (Sv.img + ASM_SLOTS - 1)/ASM_SLOTS);
+    dim3 ga(ngroups, (Sv.ntiles + ASM_WARPS - 1)/ASM_WARPS);
     k_assemble<<<ga, ASM_WARPS*32, 0, st>>>(K, hot, V, Sv);
     if (Sv.prog_in_smem) k_lu<true><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
     else k_lu<false><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
