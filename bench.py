@@ -27,31 +27,25 @@ sys.path.insert(0, ROOT)
 
 NSTAGES = 501
 TRIALS_PER_GPU = 10000
-WORKLOAD = (f"ro{NSTAGES}_mc: {NSTAGES}-stage CMOS ring oscillator (MOS level 1, "
-            f"{2*NSTAGES} MOSFETs + {NSTAGES} caps), .tran 0.05n 5n, per-trial per-device "
-            "vto (sigma 3%) and L (sigma 2%)")
+CLOAD, TSTEP, TSTOP = 0.1e-12, 0.1e-9, 10e-9          # 0.1 pF, .tran 0.1n 10n
+SEED = 1
+WORKLOAD = (f"ro{NSTAGES}_mc (SURVEY 8d M2): {NSTAGES}-stage CMOS ring oscillator (MOS level 1, "
+            f"{2*NSTAGES} MOSFETs + {NSTAGES} x 0.1 pF), .tran 0.1n 10n, per-trial per-device "
+            "vto (sigma 3%) and L (sigma 2%) from the reference's RNG stream "
+            "(sRnd::gauss, seed 1 + rank; trial 0 nominal)")
+SAVE_NODES = ["n0", f"n{NSTAGES//2}", "vdd#branch"]
+RELTOL, VNTOL, ABSTOL = 1e-3, 1e-6, 1e-12
 
 
 def make_deck(nstages=NSTAGES):
     from xictools_b200.deck import ring_oscillator
-    return ring_oscillator(nstages)
+    return ring_oscillator(nstages, cload=CLOAD, tstep=TSTEP, tstop=TSTOP)
 
 
-def make_variation(deck, ntrials, seed):
-    """Vectorised version of deck.mc_variation (same distribution; numpy normal deviates)."""
-    import numpy as np
-    from xictools_b200.deck import DEV_MOS, P_MOS_L, P_MOS_VTO
-    rng = np.random.default_rng(seed)
-    tabs = deck.kind_tables()
-    ov = {}
-    for i, e in enumerate(tabs[DEV_MOS]):
-        vto = np.full(ntrials, deck.mos_models[e.model]["params"]["vto"])
-        ln = np.full(ntrials, e.params["l"])
-        vto[1:] *= 1.0 + 0.03*rng.standard_normal(ntrials - 1)
-        ln[1:] *= 1.0 + 0.02*rng.standard_normal(ntrials - 1)
-        ov[(P_MOS_VTO, i)] = vto
-        ov[(P_MOS_L, i)] = ln
-    return ov
+def make_variation(deck, ntrials, seed=SEED):
+    """deck.mc_variation: per-trial, per-device vto / L from the reference's own deviates."""
+    from xictools_b200.deck import mc_variation
+    return mc_variation(deck, ntrials, seed=seed)
 
 
 # ------------------------------------------------------------------------------------------
@@ -59,39 +53,86 @@ def make_variation(deck, ntrials, seed):
 # trial exactly as the reference's own Monte-Carlo loop does (fte/check.cc:1649-1733)
 # ------------------------------------------------------------------------------------------
 def _ref_worker(args):
-    texts = args
+    texts, want = args
+    import numpy as np
     from oracle.pyoracle import RefSim
     sim = RefSim()
     out = []
     for txt in texts:
         r = sim.run(txt)
+        w = None
+        if want:
+            idx = [r["names"].index(nm) for nm in want]
+            w = np.ascontiguousarray(r["vals"][:, idx])
         out.append((r["err"], r["accepted"], r["rejected"], r["numiter"], r["t_load"],
-                    r["t_decomp"], r["t_solve"]))
+                    r["t_decomp"], r["t_solve"], r["timepts"], w))
     return out
 
 
-def run_reference_sample(ntrials, cores, seed=1234):
-    """Time `ntrials` trials of the workload on `cores` host processes. Returns dict."""
+def run_reference_sample(ntrials, cores, seed=SEED, ov=None, want=None, nstages=NSTAGES):
+    """Time `ntrials` trials of the workload on `cores` host processes (trial t takes the
+    values ov[..][t]; by default the bench's own variation).  Returns dict."""
     from oracle.pyoracle import have_ref
     if not have_ref():
         raise RuntimeError("oracle/_ref/libwrsref.so missing")
-    deck = make_deck()
-    ov = make_variation(deck, ntrials, seed)
+    deck = make_deck(nstages)
+    if ov is None:
+        ov = make_variation(deck, ntrials, seed)
     texts = [deck.to_spice({k: v[t] for k, v in ov.items()}) for t in range(ntrials)]
-    chunks = [texts[i::cores] for i in range(cores)]
-    chunks = [c for c in chunks if c]
+    chunks = [(texts[i::cores], want) for i in range(cores)]
+    chunks = [c for c in chunks if c[0]]
     ctx = mp.get_context("fork")
     with ctx.Pool(len(chunks)) as pool:
-        pool.map(_ref_worker, [[texts[0]]]*len(chunks))      # warm (page in the .so)
+        pool.map(_ref_worker, [([texts[0]], None)]*len(chunks))      # warm (page in the .so)
         t0 = time.perf_counter()
         res = pool.map(_ref_worker, chunks)
         el = time.perf_counter() - t0
-    flat = [x for r in res for x in r]
+    flat = [None]*ntrials
+    for i, r in enumerate(res):
+        for j, x in enumerate(r):
+            flat[i + j*cores] = x
     ok = sum(1 for x in flat if x[0] == 0)
     return dict(seconds=el, trials=ntrials, ok=ok, cores=len(chunks),
                 trials_per_s=ntrials/el,
                 t_load=sum(x[4] for x in flat), t_decomp=sum(x[5] for x in flat),
-                t_solve=sum(x[6] for x in flat), iters=sum(x[3] for x in flat))
+                t_solve=sum(x[6] for x in flat), iters=sum(x[3] for x in flat), per_trial=flat)
+
+
+def compare_with_reference(per_trial, cnt, waves):
+    """The parity record of the bench line: GPU trials 0..k-1 (counters [T][NCOUNTERS], waves
+    [T][npoints][nsave] as the public API returned them) against the reference's own run of the
+    same trials.  Counts: (error, accepted, rejected, numiter, timepts) identical per trial.
+    Waves: every saved output point within reltol*max(|a|,|b|) + vntol (abstol for the branch
+    current), reported as the worst error/tolerance ratio."""
+    import numpy as np
+    from xictools_b200.deck import (C_ACCEPTED, C_NUMITER, C_REJECTED, C_STATUS, C_TIMEPTS)
+    k = len(per_trial)
+    same = 0
+    worst = 0.0
+    wave_ok = 0
+    off = []
+    for t, r in enumerate(per_trial):
+        err, acc, rej, nit, _, _, _, tpts, w = r
+        ek = tuple(int(cnt[t, c]) for c in (C_STATUS, C_ACCEPTED, C_REJECTED, C_NUMITER, C_TIMEPTS))
+        ok = (int(err), int(acc), int(rej), int(nit), int(tpts))
+        if ek == ok:
+            same += 1
+        elif len(off) < 8:
+            off.append({"trial": t, "engine": ek, "reference": ok})
+        if w is None or err:
+            continue
+        npt = min(w.shape[0], waves.shape[1])
+        got, ref = waves[t, :npt], w[:npt]
+        tol = RELTOL*np.maximum(np.abs(got), np.abs(ref))
+        tol[:, :-1] += VNTOL
+        tol[:, -1] += ABSTOL                      # the last saved unknown is a branch current
+        ratio = float((np.abs(got - ref)/tol).max())
+        worst = max(worst, ratio)
+        wave_ok += int(ratio <= 1.0)
+    return {"vs": "oracle/_ref (unmodified reference, Sparse 1.3 pivoting)", "trials_compared": k,
+            "counts_identical": same, "waves_within_tol": wave_ok,
+            "max_wave_err_over_tol": worst, "first_offenders": off,
+            "tolerance": f"reltol {RELTOL} * max(|a|,|b|) + vntol {VNTOL} (abstol {ABSTOL} for branch currents), every output point of {SAVE_NODES}"}
 
 
 def host_cores():
@@ -112,7 +153,7 @@ def bench_reference(args):
         run_reference_sample(max(cores, 8), cores)
     t_tot, n_tot, last = 0.0, 0, None
     for k in range(args.steps):
-        last = run_reference_sample(per_step, cores, seed=1000 + k)
+        last = run_reference_sample(per_step, cores, seed=SEED + k)
         t_tot += last["seconds"]
         n_tot += last["trials"]
     value = n_tot/t_tot
@@ -203,8 +244,8 @@ def bench_ours(args):
 
     T = args.trials
     deck = make_deck(args.stages)
-    ov = make_variation(deck, T, seed=100 + rank)        # this rank's shard of the world*T trials
-    save = ["n0", f"n{args.stages//2}", "vdd#branch"]
+    ov = make_variation(deck, T, seed=SEED + rank)       # this rank's shard of the world*T trials
+    save = ["n0", f"n{args.stages//2}", "vdd#branch"]        # = SAVE_NODES at the default size
     mc = MonteCarlo(deck, world*T, save=save, rank=rank, world=world, device=local,
                     local_variation=ov)
     batch = mc.runner.batch
@@ -284,12 +325,42 @@ def bench_ours(args):
         print("bench: e2e seconds per step", ["%.3f" % x for x in e2e_steps],
               "engine events of the last one %.3f" % (batch.stats().ms_total*1e-3), file=sys.stderr)
 
+    # ---- strong scaling in the same run (N > 1): the 10 000-trial job split over the N GPUs ----
+    strong = None
+    if world > 1:
+        from xictools_b200 import engine as _eng
+        Ts = (TRIALS_PER_GPU + world - 1)//world
+        Ts = min(Ts, T)
+        bs = _eng.Batch(deck, Ts, device=local)
+        bs.set_params({key: v[:Ts] for key, v in mc.variation.items()})
+        bs.run_tran()
+        barrier()
+        ms_s = 0.0
+        for _ in range(args.steps):
+            bs.run_tran()
+            ms_s += bs.stats().ms_total
+        barrier()
+        ts_ = torch.tensor([ms_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+        bs.close()
+        v_s = world*Ts*args.steps/(float(ts_[0])*1e-3)
+        strong = {"total_trials": world*Ts, "trials_per_gpu": Ts, "value": v_s, "unit": "trials/s",
+                  "ms_per_step": float(ts_[0])/args.steps,
+                  "note": "same deck, the 10 000-trial job split over the GPUs (device-timed, max "
+                          "over ranks); efficiency = this rate / the weak-scaling rate of the same "
+                          "run; what limits it is wave quantisation of the per-trial kernels at "
+                          f"{Ts} trials (grids of {Ts}//32 warps on 148 SMs)"}
+
     tmax = torch.tensor([el, el_e2e, el_wall], dtype=torch.float64, device="cuda")
-    agg = torch.tensor([float(ok_trials), float(launches)], dtype=torch.float64, device="cuda")
+    ninst = 2*args.stages + args.stages + 1
+    agg = torch.tensor([float(ok_trials), float(launches), float(cnt[:, C_NUMITER].sum())],
+                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     el, el_e2e, el_wall = float(tmax[0]), float(tmax[1]), float(tmax[2])
+    if strong is not None:
+        strong["efficiency_vs_weak"] = strong["value"]/(world*T*args.steps/el)
 
     if rank == 0:
         peaks = {}
@@ -311,18 +382,32 @@ def bench_ours(args):
         e2e_val = world*T*args.steps/el_e2e
         h2d = sum(v.numel()*8 for v in pinned.values())
         d2h = cnt_e.nbytes + w_e.nbytes
-        # CPU baseline on this box's cores (bounded sample)
-        cpu = None
+        # CPU baseline on this box's cores (bounded sample) = the SAME trials the GPU just ran
+        # (rank 0's trials 0..k-1 with their own parameter values), so the same run also gives
+        # the parity record: counts identical per trial, waveforms within reltol/vntol
+        cpu = parity = None
         try:
             cores = host_cores()
-            s = run_reference_sample(max(cores*100, 256), cores)     # ~10-20 s of CPU work
+            k = min(T, max(cores*64, 1024))
+            ovk = {key: v[:k] for key, v in mc.variation.items()}
+            s = run_reference_sample(k, cores, ov=ovk, want=save, nstages=args.stages)
+            tsum = s["t_load"] + s["t_decomp"] + s["t_solve"]
             cpu = {"value": s["trials_per_s"], "unit": "trials/s", "cores": s["cores"],
                    "kind": "reference",
-                   "sample": f"{s['trials']} trials of the same deck in {s['seconds']:.1f} s, one "
-                             "process per core, deck re-parsed per trial (oracle/_ref, Sparse 1.3)"}
+                   "sample": f"trials 0..{k-1} of rank 0's batch (same parameter values) in "
+                             f"{s['seconds']:.1f} s, one process per core, deck re-parsed per trial "
+                             "(oracle/_ref = unmodified reference, Sparse 1.3; KLU source absent)",
+                   "split_s_per_trial": {"load": s["t_load"]/k, "decomp": s["t_decomp"]/k,
+                                         "solve": s["t_solve"]/k},
+                   "load_fraction": s["t_load"]/tsum if tsum > 0 else None}
+            parity = compare_with_reference(s["per_trial"], cnt_e, w_e)
+            one = run_reference_sample(8, 1, ov={key: v[:8] for key, v in ovk.items()},
+                                       nstages=args.stages)
+            cpu["one_core"] = {"value": one["trials_per_s"], "unit": "trials/s", "cores": 1,
+                               "sample": f"trials 0..7 in {one['seconds']:.1f} s"}
         except Exception as e:          # pragma: no cover
-            cpu = {"value": None, "unit": "trials/s", "cores": 0, "kind": "reference",
-                   "sample": f"unavailable: {e}"}
+            cpu = cpu or {"value": None, "unit": "trials/s", "cores": 0, "kind": "reference",
+                          "sample": f"unavailable: {e!r}"}
         iters = int(cnt[:, C_NUMITER].sum())
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture
         # (profiles/traffic.json: bytes per launch at the captured trial count; every per-trial
@@ -347,8 +432,9 @@ def bench_ours(args):
                        "l2": "working set ~13 GB per GPU >> 126 MB L2 (no flush needed)",
                        "ok_trials": int(agg[0]), "ticks_per_step": ticks//args.steps,
                        "newton_iters_per_trial": iters/max(T, 1),
-                       "device_load_instances_per_s":
-                           (2*args.stages + args.stages + 1)*float(ticks)*T*world/el},
+                       "device_load_instances_per_s": ninst*float(agg[2])*args.steps/el,
+                       "device_load_instances_note": "(MOS + C + V instances) x sum over trials of "
+                                                     "Newton iterations (= load calls) / device time"},
             "e2e": {"value": e2e_val, "unit": "trials/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "clocks": clocks_e2e},
             "gpu_launches": int(agg[1]),
@@ -360,7 +446,10 @@ def bench_ours(args):
                          "solve_kernel": {"achieved": ach_solve, "ms_per_launch": solve_ms,
                                           "frac": ach_solve/peak}},
             "cpu_baseline": cpu,
+            "parity": parity,
         }
+        if strong is not None:
+            line["strong"] = strong
         emit(line)
     if world > 1:
         dist.barrier()

@@ -206,6 +206,15 @@ typedef struct b200_run_stats {
 } b200_run_stats;
 int  b200_batch_get_stats(const b200_batch *b, b200_run_stats *st);
 
+/* ---- Monte-Carlo trial generation (host code of the dispatcher) ----
+ * The deviates a WRspice Monte-Carlo run draws: sRnd::random / sRnd::gauss
+ * (xt_base/include/miscutil/random.h:76-79, xt_base/miscutil/random.cc:51-72) over the BSD
+ * random(3) TYPE_3 stream of xt_base/miscutil/randval.cc:196-258, seeded like sRnd::seed(seed).
+ * out[n] receives the first n values of the stream.  Replaces the per-trial gauss() calls of a
+ * deck's .exec block in the batched dispatcher (fte/check.cc:1649-1733). */
+int  b200_mc_uniform(int seed, long long n, double *out);
+int  b200_mc_gauss(int seed, long long n, double *out);
+
 /* ---- debug / parity hooks used by tests (device state -> host) ---- */
 /* Host-side analysis products: CSC pattern of A, and the LU ordering the batch uses. */
 int  b200_batch_pattern(const b200_batch *b, int *n, int *nnz, const int **Ap, const int **Ai);

@@ -19,6 +19,7 @@
 #include "output.h"
 #include "sparse/spmatrix.h"
 
+#include "miscutil/random.h"
 #include "harness.h"
 
 int wrsref_verbose = 0;
@@ -61,6 +62,21 @@ extern "C" void wrsref_append(double ref, const double *vals, int n)
 extern "C" {
 
 void wrsref_set_verbose(int v) { wrsref_verbose = v; }
+
+// the reference's own deviates (sRnd, xt_base/miscutil/random.cc): pins the dispatcher's
+// restatement of the Monte-Carlo random stream
+void wrsref_gauss(int seed, long n, double *out)
+{
+    sRnd r;
+    r.seed(seed);
+    for (long i = 0; i < n; i++) out[i] = r.gauss();
+}
+void wrsref_uniform(int seed, long n, double *out)
+{
+    sRnd r;
+    r.seed(seed);
+    for (long i = 0; i < n; i++) out[i] = r.random();
+}
 void wrsref_set_trantrace(int v) { Sp.SetTranTrace(v); }
 
 // Run one deck.  deck_text: newline-separated SPICE lines, first line = title, must

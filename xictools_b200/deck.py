@@ -557,26 +557,22 @@ def ring_oscillator(nstages: int, level: int = 1, vdd: float = 3.3, cload: float
 
 def mc_variation(deck: Deck, ntrials: int, seed: int = 1, sigma_vto: float = 0.03,
                  sigma_l: float = 0.02):
-    """Per-trial, per-MOSFET Vth0 and L variation (BASELINE.json configs[1]); trial 0 nominal.
-    Gaussian deviates follow the reference RNG algorithm (xt_base/miscutil/random.cc:51-72:
-    Box-Muller polar method on a 31-bit uniform), restated in numpy_rng.gauss_stream.
+    """Per-trial, per-MOSFET Vth0 and L variation (BASELINE.json configs[1], SURVEY.md 8(d) M2);
+    trial 0 nominal.  The deviates are the reference's own: trial t = 1, 2, ... draws, device by
+    device in deck order, gauss() for vto and then gauss() for L from ONE sRnd stream seeded with
+    `seed` (xt_base/miscutil/random.cc:51-72 over randval.cc; restated in csrc/mcgen.cpp).
     Returns {(param_id, mos_index): np.ndarray[ntrials]}."""
     import numpy as np
-    from .refrand import RefRand
+    from .refrand import gauss_stream
     tabs = deck.kind_tables()
-    rnd = RefRand(seed)
-    out = {}
     nm = len(tabs[DEV_MOS])
-    vto = np.empty((nm, ntrials))
-    ln = np.empty((nm, ntrials))
+    g = gauss_stream(seed, max(0, ntrials - 1)*nm*2).reshape(max(0, ntrials - 1), nm, 2)
+    out = {}
     for i, e in enumerate(tabs[DEV_MOS]):
-        vto[i, :] = deck.mos_models[e.model]["params"]["vto"]
-        ln[i, :] = e.params["l"]
-    for t in range(1, ntrials):
-        for i in range(nm):
-            vto[i, t] *= 1.0 + sigma_vto * rnd.gauss()
-            ln[i, t] *= 1.0 + sigma_l * rnd.gauss()
-    for i in range(nm):
-        out[(P_MOS_VTO, i)] = vto[i]
-        out[(P_MOS_L, i)] = ln[i]
+        vto = np.full(ntrials, float(deck.mos_models[e.model]["params"]["vto"]))
+        ln = np.full(ntrials, float(e.params["l"]))
+        vto[1:] *= 1.0 + sigma_vto*g[:, i, 0]
+        ln[1:] *= 1.0 + sigma_l*g[:, i, 1]
+        out[(P_MOS_VTO, i)] = vto
+        out[(P_MOS_L, i)] = ln
     return out

@@ -1,42 +1,55 @@
-"""Gaussian deviates the way the reference draws them for Monte-Carlo trials.
+"""Deviates the way the reference draws them for Monte-Carlo trials (dispatcher, row a20).
 
-sRnd::gauss (xt_base/miscutil/random.cc:51-72): Box-Muller *polar* method on two uniforms
-u = (r & 0x7fffffff)/2^31 (include/miscutil/random.h:76-79), returning v2*fac first and
-caching v1*fac for the next call.
-
-The 31-bit uniform stream itself comes, in the reference, from a FreeBSD random(3)
-derivative (xt_base/miscutil/randval.cc).  Trial generation is SURVEY.md section 8(f) "next"
-scope, so here the uniform integers come from a seeded numpy generator; parity tests always
-feed the same generated values to both the engine and the reference.
+sRnd::gauss (xt_base/miscutil/random.cc:51-72) is the polar Box-Muller method on the 31-bit
+uniforms of sRnd::random (include/miscutil/random.h:76-79), which come from the BSD random(3)
+TYPE_3 generator of xt_base/miscutil/randval.cc.  The stream is restated in the native library
+(csrc/mcgen.cpp: b200_mc_gauss / b200_mc_uniform) and pinned bit for bit against the compiled
+reference by tests/test_refrand.py; this module is its ctypes face.
 """
 from __future__ import annotations
 
-import math
+import ctypes as C
 
 import numpy as np
 
 
-class RefRand:
-    def __init__(self, seed: int = 1):
-        self._rng = np.random.Generator(np.random.PCG64(seed))
-        self._set = False
-        self._val = 0.0
+def _lib():
+    from .engine import load_library
+    L = load_library()
+    L.b200_mc_gauss.argtypes = [C.c_int, C.c_longlong, C.c_void_p]
+    L.b200_mc_uniform.argtypes = [C.c_int, C.c_longlong, C.c_void_p]
+    return L
 
-    def random(self) -> float:
-        r = int(self._rng.integers(0, 2**32, dtype=np.uint64))
-        return (r & 0x7FFFFFFF) / (0x7FFFFFFF + 1.0)
+
+def gauss_stream(seed: int, n: int) -> np.ndarray:
+    """The first n values gauss() returns after seed(seed)."""
+    out = np.empty(int(n), dtype=np.float64)
+    rc = _lib().b200_mc_gauss(int(seed), int(n), out.ctypes.data)
+    if rc:
+        raise RuntimeError(f"b200_mc_gauss failed ({rc})")
+    return out
+
+
+def uniform_stream(seed: int, n: int) -> np.ndarray:
+    """The first n values random() returns after seed(seed)."""
+    out = np.empty(int(n), dtype=np.float64)
+    rc = _lib().b200_mc_uniform(int(seed), int(n), out.ctypes.data)
+    if rc:
+        raise RuntimeError(f"b200_mc_uniform failed ({rc})")
+    return out
+
+
+class RefRand:
+    """Sequential face of the same stream (one value per call)."""
+
+    def __init__(self, seed: int = 1, block: int = 4096):
+        self._seed, self._block = seed, block
+        self._buf = gauss_stream(seed, block)
+        self._i = 0
 
     def gauss(self) -> float:
-        if not self._set:
-            while True:
-                v1 = 2.0 * self.random() - 1.0
-                v2 = 2.0 * self.random() - 1.0
-                r = v1 * v1 + v2 * v2
-                if r < 1.0 and r > 0.0:
-                    break
-            fac = math.sqrt(-2.0 * math.log(r) / r)
-            self._val = v1 * fac
-            self._set = True
-            return v2 * fac
-        self._set = False
-        return self._val
+        if self._i >= len(self._buf):
+            self._buf = gauss_stream(self._seed, 2*len(self._buf))
+        v = float(self._buf[self._i])
+        self._i += 1
+        return v
