@@ -37,6 +37,14 @@ SAVE_NODES = ["n0", f"n{NSTAGES//2}", "vdd#branch"]
 RELTOL, VNTOL, ABSTOL = 1e-3, 1e-6, 1e-12
 
 
+def bench_config(nstages, trials_per_gpu, world):
+    """The workload description, identical in both arms (the reference arm times a bounded
+    sample of the same job)."""
+    return {"workload": WORKLOAD if nstages == NSTAGES else f"ro{nstages}_mc",
+            "trials_per_gpu": trials_per_gpu, "unknowns": nstages + 2,
+            "l2": "working set ~13 GB per GPU >> 126 MB L2 (no flush needed)"}
+
+
 def make_deck(nstages=NSTAGES):
     from xictools_b200.deck import ring_oscillator
     return ring_oscillator(nstages, cload=CLOAD, tstep=TSTEP, tstop=TSTOP)
@@ -163,8 +171,9 @@ def bench_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3*t_tot/args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "trials_per_step": per_step,
-                   "solver": "Sparse 1.3 (what the snapshot executes; KLU source absent)"},
+        "config": bench_config(NSTAGES, TRIALS_PER_GPU, args.gpus),
+        "run": {"trials_per_step": per_step,
+                "solver": "Sparse 1.3 (what the snapshot executes; KLU source absent)"},
         "cpu_baseline": {"value": value, "unit": "trials/s", "cores": last["cores"],
                          "kind": "reference",
                          "sample": f"{per_step} trials/step of the same deck, one process per core, "
@@ -427,14 +436,12 @@ def bench_ours(args):
             "timing": "CUDA events on the launching stream, max over ranks",
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.stages == NSTAGES else f"ro{args.stages}_mc",
-                       "trials_per_gpu": T, "unknowns": batch.n,
-                       "l2": "working set ~13 GB per GPU >> 126 MB L2 (no flush needed)",
-                       "ok_trials": int(agg[0]), "ticks_per_step": ticks//args.steps,
-                       "newton_iters_per_trial": iters/max(T, 1),
-                       "device_load_instances_per_s": ninst*float(agg[2])*args.steps/el,
-                       "device_load_instances_note": "(MOS + C + V instances) x sum over trials of "
-                                                     "Newton iterations (= load calls) / device time"},
+            "config": bench_config(args.stages, T, world),
+            "run": {"ok_trials": int(agg[0]), "ticks_per_step": ticks//args.steps,
+                    "newton_iters_per_trial": iters/max(T, 1),
+                    "device_load_instances_per_s": ninst*float(agg[2])*args.steps/el,
+                    "device_load_instances_note": "(MOS + C + V instances) x sum over trials of "
+                                                  "Newton iterations (= load calls) / device time"},
             "e2e": {"value": e2e_val, "unit": "trials/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "clocks": clocks_e2e},
             "gpu_launches": int(agg[1]),

@@ -257,19 +257,28 @@ int  b200_debug_divcheck(long long n, unsigned long long seed, int emin, int ema
  * xt_base/include/sparse/spmatrix.h:853-857; kluif.cc:569-628.  Pattern is CSC, 0-based,
  * row indices ascending per column (spbuild.cc:922-958). */
 typedef struct b200_klu b200_klu;
-/* klu_analyze + first klu_factor on trial 0's values (pivot sequence is then frozen, which
- * is exactly klu_refactor's contract).  Ax0: host, nnz doubles. */
+/* klu_analyze + the pivot choice of the first klu_factor on trial 0's values Ax0 (host, nnz
+ * doubles); the pivot sequence is then frozen, which is exactly klu_refactor's contract.
+ * Order: the engine's static Markowitz order (constant +-1 entries, conductance diagonals) if
+ * every pivot of it passes |pivot| >= pivabs and |pivot| >= pivrel * max|column| on Ax0
+ * (spfactor.cc RelThreshold/AbsThreshold, KLU Common.tol), else threshold Markowitz on Ax0.
+ * pivrel outside (0,1] -> 1e-3, pivabs < 0 -> 1e-13 (the task defaults).
+ * Errors: B200_E_BADPARM, B200_E_NOGPU, B200_E_SINGULAR (no acceptable pivot sequence for
+ * Ax0), B200_E_UNSUPP (LU image beyond the shared-memory program's reach), B200_E_NOMEM. */
 int  b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0,
                       double pivrel, double pivabs, int device, b200_klu **out);
 void b200_klu_free(b200_klu *k);
 /* Batched klu_refactor + klu_solve, HOST buffers: Ax[ntrials][nnz], B[ntrials][n] overwritten
- * with the solutions; status[ntrials] = B200_OK / B200_E_SINGULAR.  (e2e path) */
+ * with the solutions; status[ntrials] = B200_OK / B200_E_SINGULAR (a zero or non-finite pivot under
+ * the frozen sequence: klu_refactor's test) / B200_E_MATHOVF (non-finite solution).  (e2e path) */
 int  b200_klu_refactor_solve_host(b200_klu *k, int ntrials, const double *Ax, double *B,
                                   int *status);
 /* Same with DEVICE buffers in the engine's trial-minor layout Ax[nnz][ldt], B[n][ldt]. */
 int  b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double *dAx,
                                  double *dB, int *dstatus, void *cuda_stream);
 int  b200_klu_lu_nnz(const b200_klu *k);
+/* KLUmatrix::rowmap / colmap (kluif.cc:666-681): position -> original row / column, 0-based. */
+int  b200_klu_get_ordering(const b200_klu *k, int *rowperm, int *colperm);
 
 const char *b200_version(void);
 int  b200_cuda_device_count(void);

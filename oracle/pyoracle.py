@@ -162,3 +162,71 @@ def lu_solve_static(n, Ap, Ai, Ax, rowperm, colperm, b):
     err = L.wo_lu_solve_static(n, Ap.ctypes.data, Ai.ctypes.data, Ax.ctypes.data,
                                r.ctypes.data, c.ctypes.data, x.ctypes.data)
     return err, x
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference with its KLU plug-in hook compiled in (oracle/_ref/libwrsref_klu.so).  Run in a
+# child process: the plug-in path comes from the environment ($XT_KLU_PATH, kluif.cc:121) and
+# the reference keeps process-global state.
+# ---------------------------------------------------------------------------------------------
+REF_KLU_SO = os.path.join(HERE, "_ref", "libwrsref_klu.so")
+
+
+def have_ref_klu() -> bool:
+    return os.path.exists(REF_KLU_SO)
+
+
+_KLU_WORKER = r"""
+import ctypes as C, json, sys
+import numpy as np
+so, deck_path = sys.argv[1], sys.argv[2]
+L = C.CDLL(so)
+L.wrsref_names.restype = C.POINTER(C.c_char)
+ok = L.wrsref_find_klu()
+out = {"klu_ok": int(ok)}
+if deck_path != "-":
+    text = open(deck_path).read()
+    err = L.wrsref_run_deck(text.encode())
+    cnt = (C.c_int*9)(); L.wrsref_get_counters(cnt)
+    npts, nn = L.wrsref_num_points(), L.wrsref_num_names()
+    t = np.zeros(npts); v = np.zeros((npts, max(nn, 1)))
+    if npts:
+        L.wrsref_get_points(t.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+    nb = C.c_int(); p = L.wrsref_names(C.byref(nb))
+    names = [s.decode() for s in bytes(p[:nb.value]).split(b"\0")[:-1]]
+    keys = ("error", "size", "accepted", "rejected", "numiter", "timepts", "traniter", "itercut", "trapcut")
+    out.update(dict(zip(keys, list(cnt))))
+    out.update(err=err, times=t.tolist(), vals=v.tolist(), names=names)
+sys.stdout.write("\n@@RESULT@@" + json.dumps(out) + "\n")
+"""
+
+
+def run_ref_klu(spice_text: str | None, klu_path: str | None, timeout: float = 600.0) -> dict:
+    """Run one deck through the KLU-enabled reference build with $XT_KLU_PATH = klu_path
+    (None: unset -> the reference falls back to Sparse).  spice_text None: only report whether
+    the reference's loader accepted the plug-in."""
+    import json
+    import subprocess
+    import sys
+    import tempfile
+    env = dict(os.environ)
+    env.pop("XT_KLU_PATH", None)
+    if klu_path:
+        env["XT_KLU_PATH"] = klu_path
+    with tempfile.TemporaryDirectory() as td:
+        dp = "-"
+        if spice_text is not None:
+            dp = os.path.join(td, "deck.cir")
+            open(dp, "w").write(spice_text)
+        r = subprocess.run([sys.executable, "-c", _KLU_WORKER, REF_KLU_SO, dp], env=env,
+                           capture_output=True, text=True, timeout=timeout)
+    if "@@RESULT@@" not in r.stdout:
+        raise RuntimeError(f"KLU worker failed (rc {r.returncode}): {r.stderr[-2000:]}")
+    out = json.loads(r.stdout.split("@@RESULT@@")[1])
+    if "vals" in out:
+        out["times"] = np.array(out["times"])
+        out["vals"] = np.array(out["vals"], dtype=float).reshape(len(out["times"]), max(len(out["names"]), 1)) \
+            if len(out["times"]) else np.zeros((0, max(len(out["names"]), 1)))
+    out["stdout"] = r.stdout.split("@@RESULT@@")[0]
+    out["stderr"] = r.stderr
+    return out

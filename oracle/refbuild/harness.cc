@@ -20,6 +20,10 @@
 #include "sparse/spmatrix.h"
 
 #include "miscutil/random.h"
+#ifdef USE_KLU
+#include "klumatrix.h"
+#include "kluif.h"
+#endif
 #include "harness.h"
 
 int wrsref_verbose = 0;
@@ -78,6 +82,19 @@ void wrsref_uniform(int seed, long n, double *out)
     for (long i = 0; i < n; i++) out[i] = r.random();
 }
 void wrsref_set_trantrace(int v) { Sp.SetTranTrace(v); }
+
+// KLU plug-in: what the front end does once at start-up (KLUif::find_klu, kluif.cc:117-266,
+// looks at $XT_KLU_PATH).  Returns 1 if a plug-in was accepted (libwrsref_klu.so only).
+int wrsref_find_klu(void)
+{
+#ifdef USE_KLU
+    if (!klu_if.is_ok())
+        klu_if.find_klu();
+    return (klu_if.is_ok() ? 1 : 0);
+#else
+    return (0);
+#endif
+}
 
 // Run one deck.  deck_text: newline-separated SPICE lines, first line = title, must
 // contain one .tran (or .op) line; ".options" lines are honoured the way

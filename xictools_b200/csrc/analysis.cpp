@@ -668,6 +668,81 @@ void b200_order_markowitz(Analysis &an)
 }
 
 // ---------------------------------------------------------------------------------------
+// Numerical pivot test on ONE value set -- what klu_factor / spOrderAndFactor do for the matrix
+// they are handed (kluif.cc:569-590, Common.tol; spfactor.cc:257-423 with RelThreshold =
+// pivrel, AbsThreshold = pivtol, circuit.h:461-631): a pivot must satisfy
+//     |pivot| >= pivabs   and   |pivot| >= pivrel * max|entries left in its column|.
+// mode 0: check the order already in an.rowperm/colperm on the values Ax (elimination carried
+//         out numerically); returns the first position that fails, or -1 if all pass.
+// mode 1: re-order: Markowitz restricted to entries that pass the test (threshold pivoting;
+//         ties to the larger |pivot|/colmax), overwriting an.rowperm/colperm; returns -1, or
+//         the position at which no acceptable pivot exists (numerically singular).
+// ---------------------------------------------------------------------------------------
+int b200_order_numeric(Analysis &an, const double *Ax, double pivrel, double pivabs, int mode)
+{
+    const int n = an.n;
+    std::vector<std::map<int,double>> rows(n);          // row -> (col -> value), active part only
+    std::vector<std::set<int>> cols(n);
+    for (int j = 0; j < n; j++)
+        for (int p = an.Ap[j]; p < an.Ap[j+1]; p++) { rows[an.Ai[p]][j] = Ax[p]; cols[j].insert(an.Ai[p]); }
+    std::vector<char> ract(n, 1), cact(n, 1);
+    if (mode == 1) { an.rowperm.assign(n, -1); an.colperm.assign(n, -1); }
+    auto colmax = [&](int j) {
+        double m = 0.0;
+        for (int r : cols[j]) if (ract[r]) { double v = fabs(rows[r][j]); if (v > m) m = v; }
+        return m;
+    };
+    for (int k = 0; k < n; k++) {
+        int bi = -1, bj = -1;
+        if (mode == 0) {
+            bi = an.rowperm[k]; bj = an.colperm[k];
+            auto it = rows[bi].find(bj);
+            double pv = it == rows[bi].end() ? 0.0 : fabs(it->second);
+            double cm = colmax(bj);
+            if (!(pv >= pivabs) || !(pv >= pivrel*cm) || pv == 0.0 || !std::isfinite(pv)) return k;
+        }
+        else {
+            long best = -1; double bratio = 0.0;
+            std::vector<double> cm(n, -1.0);
+            for (int i = 0; i < n; i++) {
+                if (!ract[i]) continue;
+                for (auto &e : rows[i]) {
+                    int j = e.first;
+                    if (!cact[j]) continue;
+                    if (cm[j] < 0.0) cm[j] = colmax(j);
+                    double pv = fabs(e.second);
+                    if (pv == 0.0 || !std::isfinite(pv) || pv < pivabs || pv < pivrel*cm[j]) continue;
+                    long rc = 0, cc = 0;
+                    for (auto &q : rows[i]) if (cact[q.first]) rc++;
+                    for (int r : cols[j]) if (ract[r]) cc++;
+                    long mk = (rc - 1)*(cc - 1);
+                    double ratio = pv/cm[j];
+                    if (best < 0 || mk < best || (mk == best && ratio > bratio)) {
+                        best = mk; bi = i; bj = j; bratio = ratio;
+                    }
+                }
+            }
+            if (bi < 0) return k;
+            an.rowperm[k] = bi; an.colperm[k] = bj;
+        }
+        ract[bi] = 0; cact[bj] = 0;
+        const double pv = rows[bi][bj];
+        for (int r : cols[bj]) {
+            if (!ract[r]) continue;
+            const double l = rows[r][bj]/pv;
+            if (l == 0.0) continue;
+            for (auto &e : rows[bi]) {
+                int j = e.first;
+                if (!cact[j]) continue;
+                rows[r][j] -= l*e.second;               // creates the fill entry if absent
+                cols[j].insert(r);
+            }
+        }
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------
 // Symbolic LU for the fixed order, the task program of k_lu and the assembly runs of
 // k_assemble (see b200_internal.h).
 // ---------------------------------------------------------------------------------------

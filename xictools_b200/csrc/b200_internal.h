@@ -224,6 +224,8 @@ struct Analysis {
 
 int  b200_analyze(const b200_deck *deck, Analysis &an, std::string &err);
 void b200_order_markowitz(Analysis &an);
+// numerical pivot test / threshold re-ordering on one value set (analysis.cpp)
+int  b200_order_numeric(Analysis &an, const double *Ax, double pivrel, double pivabs, int mode);
 // symbolic LU for the fixed order, the task program and the assembly runs; returns 0 or
 // B200_E_UNSUPP when the image does not fit the 16-bit slot indices of the program
 int  b200_build_lu(Analysis &an);

@@ -8,6 +8,7 @@
 // (2) b200_batch_debug_load: one sCKT::load + loadGmin at a forced state, matrix/RHS
 //     assembled to global memory for stamp-for-stamp comparison with the oracle.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -283,8 +284,9 @@ int b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, in
 int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, double pivrel,
     double pivabs, int device, b200_klu **out)
 {
-    (void)pivrel; (void)pivabs;
     *out = nullptr;
+    if (!(pivrel > 0.0) || pivrel > 1.0) pivrel = 1e-3;     // circuit.h:461-631 defaults, clamped like the task options
+    if (!(pivabs >= 0.0)) pivabs = 1e-13;
     if (n <= 0 || !Ap || !Ai || !Ax0) return B200_E_BADPARM;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) {
@@ -306,6 +308,14 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     an.cg_ptr.assign(an.nnz + 1, 0);
     an.rg_ptr.assign(n + 2, 0);
     b200_order_markowitz(an);
+    // klu_factor semantics on the matrix handed in: the static order is kept only if every one
+    // of its pivots passes the pivrel / pivabs test on THESE values; otherwise threshold
+    // Markowitz on the values decides (what spOrderAndFactor / klu_factor would do)
+    if (b200_order_numeric(an, Ax0, pivrel, pivabs, 0) >= 0 &&
+            b200_order_numeric(an, Ax0, pivrel, pivabs, 1) >= 0) {
+        delete k;
+        return B200_E_SINGULAR;
+    }
     // run-time gather lists are the identity: A[p] = 0 + Ax[p], b[row] = 0 + B[row-1]
     an.Ainit.assign(an.nnz, 0.0);
     an.cg_idx.resize(an.nnz);
@@ -363,6 +373,14 @@ void b200_klu_free(b200_klu *k)
 }
 
 int b200_klu_lu_nnz(const b200_klu *k) { return k ? k->an.nnzLU : 0; }
+
+int b200_klu_get_ordering(const b200_klu *k, int *rowperm, int *colperm)
+{
+    if (!k) return B200_E_BADPARM;
+    if (rowperm) std::copy(k->an.rowperm.begin(), k->an.rowperm.end(), rowperm);
+    if (colperm) std::copy(k->an.colperm.begin(), k->an.colperm.end(), colperm);
+    return B200_OK;
+}
 
 // (re)allocates everything sized by the trial count and initialises it ON THE SOLVE'S STREAM
 static int klu_ensure(b200_klu *k, int ldt, cudaStream_t st)
