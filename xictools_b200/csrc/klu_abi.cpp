@@ -10,9 +10,10 @@
 //                                                                  pivot sequence kept
 //   solve(rhs) = klu_solve(Symbolic, Numeric, n, 1, rhs)           rhs overwritten by x
 // klu_analyze sees the pattern only; the batched seam orders on the first matrix's values, so
-// the ordering is made in klu_factor and Symbolic->P/Q are filled there.  klu_refactor keeps
-// the values; the device refactor + solve run as one pass when the right-hand side arrives
-// (the LU never travels back to the host).
+// the ordering is made in klu_factor and Symbolic->P/Q are filled there.  The device program
+// is one fused refactor + forward + backward pass and the LU never travels back to the host:
+// klu_refactor runs it on a zero right-hand side to report a singular pivot where the
+// reference looks for it, klu_solve runs it again with the real one.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -98,7 +99,12 @@ klu_numeric *klu_factor(int *Ap, int *Ai, double *Ax, klu_symbolic *s, klu_commo
     if (!c) return nullptr;
     c->status = KLU_OK;
     if (!s || !Ap || !Ai || !Ax) { fail(c, KLU_INVALID); return nullptr; }
-    if (trace_on()) fprintf(stderr, "b200 klu: klu_factor n=%d nnz=%d\n", s->n, Ap[s->n]);
+    if (trace_on()) {
+        fprintf(stderr, "b200 klu: klu_factor n=%d nnz=%d\n", s->n, Ap[s->n]);
+        if (s->n <= 8)
+            for (int j = 0; j < s->n; j++)
+                for (int p = Ap[j]; p < Ap[j+1]; p++) fprintf(stderr, "   A(%d,%d) = %.17g\n", Ai[p], j, Ax[p]);
+    }
     klu_numeric *N = new (std::nothrow) klu_numeric_struct;
     if (!N) { fail(c, KLU_OUT_OF_MEMORY); return nullptr; }
     N->n = s->n; N->nnz = Ap[s->n];
@@ -134,6 +140,17 @@ int klu_refactor(int *Ap, int *Ai, double *Ax, klu_symbolic *s, klu_numeric *N, 
     c->status = KLU_OK;
     if (!s || !N || !Ap || !Ax || Ap[s->n] != N->nnz) return fail(c, KLU_INVALID);
     memcpy(N->Ax.data(), Ax, (size_t)N->nnz*sizeof(double));
+    // klu_refactor reports a zero pivot under the frozen sequence HERE (NIiter re-orders on
+    // E_SINGULAR from the factor step, niiter.cc:303-331; spSolve's result is not looked at):
+    // one device pass on a zero right-hand side gives the status
+    std::vector<double> b(s->n, 0.0);
+    int st = 0;
+    if (b200_klu_refactor_solve_host(N->k, 1, N->Ax.data(), b.data(), &st)) return fail(c, KLU_INVALID);
+    if (st) {
+        if (trace_on()) fprintf(stderr, "b200 klu: klu_refactor: singular under the frozen pivot sequence\n");
+        c->status = KLU_SINGULAR; c->singular_col = 0; c->numerical_rank = 0;
+        return c->halt_if_singular ? 0 : 1;
+    }
     return 1;
 }
 
@@ -144,7 +161,18 @@ int klu_solve(klu_symbolic *s, klu_numeric *N, int ldim, int nrhs, double *B, kl
     if (!s || !N || !B || ldim < s->n || nrhs < 0) return fail(c, KLU_INVALID);
     for (int r = 0; r < nrhs; r++) {
         int st = 0;
+        std::vector<double> b0;
+        if (trace_on() && s->n <= 8) b0.assign(B + (size_t)r*ldim, B + (size_t)r*ldim + s->n);
         int rc = b200_klu_refactor_solve_host(N->k, 1, N->Ax.data(), B + (size_t)r*ldim, &st);
+        if (!b0.empty()) {
+            bool nan = false;
+            for (int i = 0; i < s->n; i++) if (!(B[(size_t)r*ldim + i] == B[(size_t)r*ldim + i])) nan = true;
+            if (nan) {
+                fprintf(stderr, "b200 klu: NaN solution, status %d\n", st);
+                for (int i = 0; i < N->nnz; i++) fprintf(stderr, "   Ax[%d] = %.17g\n", i, N->Ax[i]);
+                for (int i = 0; i < s->n; i++) fprintf(stderr, "   b[%d] = %.17g -> %.17g  P %d Q %d\n", i, b0[i], B[(size_t)r*ldim + i], s->P[i], s->Q[i]);
+            }
+        }
         if (rc) return fail(c, KLU_INVALID);
         if (st) { c->status = KLU_SINGULAR; c->singular_col = 0; c->numerical_rank = 0; }
     }
