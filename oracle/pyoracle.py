@@ -59,6 +59,50 @@ class RefSim:
         return out
 
 
+def run_harvest(spice_text: str, libpath: str, ntrials: int, params=None, op_only=False) -> dict:
+    """Reference parser + set-up circuit -> shim/harvest.cc -> C ABI -> batched run (GPU), in
+    the same call that runs the reference's own doTask on that circuit.
+    params: [(param_id, instance_name, values[ntrials])].  ntrials = 0: host-only harvest check
+    (returns the engine's analysis sizes of the harvested deck)."""
+    sim = RefSim()
+    L = sim.L
+    params = params or []
+    n = len(params)
+    ids = (C.c_int*max(n, 1))(*[p[0] for p in params])
+    names = (C.c_char_p*max(n, 1))(*[p[1].encode() for p in params])
+    arrs = [np.ascontiguousarray(p[2], dtype=np.float64) for p in params]
+    vals = (C.c_void_p*max(n, 1))(*[a.ctypes.data for a in arrs])
+    L.wrsref_run_deck_harvest.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int]
+    err = L.wrsref_run_deck_harvest(spice_text.encode(), libpath.encode(), ntrials, n, ids, names,
+                                    vals, int(op_only))
+    out = {"ref_err": err, "rc": L.wrsref_harvest_rc()}
+    cnt = (C.c_int*9)()
+    L.wrsref_get_counters(cnt)
+    out["ref"] = dict(zip(("error", "size", "accepted", "rejected", "numiter", "timepts", "traniter",
+                           "itercut", "trapcut"), list(cnt)))
+    npts, nn = L.wrsref_num_points(), L.wrsref_num_names()
+    t = np.zeros(npts)
+    v = np.zeros((npts, max(nn, 1)))
+    if npts:
+        L.wrsref_get_points(t.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+    out["ref_times"], out["ref_vals"] = t, v
+    if ntrials <= 0:
+        st = (C.c_longlong*32)()
+        L.wrsref_harvest_stats(st)
+        out["stats"] = list(st)
+        return out
+    if out["rc"] == 0:
+        N, P = L.wrsref_harvest_n(), L.wrsref_harvest_npoints()
+        counters = np.zeros((ntrials, 9), dtype=np.int32)
+        times = np.zeros(P)
+        waves = np.zeros((ntrials, P, N))
+        L.wrsref_harvest_get(counters.ctypes.data_as(C.c_void_p), times.ctypes.data_as(C.c_void_p),
+                             waves.ctypes.data_as(C.c_void_p))
+        out.update(counters=counters, times=times, waves=waves)
+    return out
+
+
 class Oracle:
     _lib = None
 

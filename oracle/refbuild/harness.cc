@@ -25,8 +25,12 @@
 #include "kluif.h"
 #endif
 #include "harness.h"
+#include "harvest.h"
 
 int wrsref_verbose = 0;
+
+// set by wrsref_run_deck_harvest: called with the live, set-up circuit after doTask
+static int (*after_task_hook)(sCKT*) = 0;
 
 namespace {
     struct Recorder {
@@ -46,6 +50,7 @@ namespace {
         std::vector<double> names_dummy;
     };
     RunResult last;
+    int last_hook_rc = 0;
     std::vector<char> last_names;   // '\0'-separated node names in output column order
     std::vector<char> last_order;   // '\0'-separated instance names in sCKT::load order
 }
@@ -209,6 +214,9 @@ int wrsref_run_deck(const char *deck_text)
         last.trantime = st->STATtranTime;
         last.tottime = st->STATtotAnalTime;
     }
+    if (after_task_hook)
+        last_hook_rc = (*after_task_hook)(ckt);
+
     // Output column names.
     {
         const sCKTnode *node = ckt->CKTnodeTab.find(1);
@@ -248,6 +256,63 @@ int wrsref_run_deck(const char *deck_text)
     delete opts;
     sLine::destroy(head);
     return (err);
+}
+
+// ---- shim/harvest.cc driven from the reference's own parser and set-up circuit ----
+// Runs the deck through doTask (the reference's own result stays readable through the
+// wrsref_get_* calls), then hands the SAME sCKT to b200_harvest_run: harvest -> C ABI ->
+// batched run on the GPU.  Results of the batch are kept until the next call.
+namespace {
+    struct HarvestArgs {
+        const char *libpath; int ntrials, nparams, op_only;
+        const int *param_id; const char *const *inst_name; const double *const *values;
+    } hargs;
+    struct HarvestOut {
+        int rc = 0, n = 0, npoints = 0;
+        std::vector<int> counters; std::vector<double> times, waves;
+        long long stats[B200_AS_NSTATS];
+    } hout;
+
+    int harvest_hook(sCKT *ckt)
+    {
+        hout = HarvestOut();
+        if (hargs.ntrials <= 0) {       // host-only: harvest + the engine's analysis sizes
+            hout.rc = b200_harvest_stats(ckt, hargs.libpath, hout.stats, B200_AS_NSTATS);
+            return (hout.rc);
+        }
+        hout.counters.assign((size_t)hargs.ntrials*B200_NCOUNTERS, 0);
+        double *t = 0, *w = 0;
+        hout.rc = b200_harvest_run(ckt, hargs.libpath, hargs.ntrials, 0, hargs.nparams, hargs.param_id,
+            hargs.inst_name, hargs.values, hout.counters.data(), &hout.n, &hout.npoints, &t, &w,
+            hargs.op_only);
+        if (!hout.rc) {
+            hout.times.assign(t, t + hout.npoints);
+            hout.waves.assign(w, w + (size_t)hargs.ntrials*hout.npoints*hout.n);
+        }
+        free(t); free(w);
+        return (hout.rc);
+    }
+}
+
+int wrsref_run_deck_harvest(const char *deck_text, const char *libpath, int ntrials, int nparams,
+    const int *param_id, const char *const *inst_name, const double *const *values, int op_only)
+{
+    hargs = { libpath, ntrials, nparams, op_only, param_id, inst_name, values };
+    after_task_hook = harvest_hook;
+    int err = wrsref_run_deck(deck_text);
+    after_task_hook = 0;
+    return (err);
+}
+
+void wrsref_harvest_stats(long long *out) { memcpy(out, hout.stats, sizeof(hout.stats)); }
+int wrsref_harvest_rc(void) { return (hout.rc); }
+int wrsref_harvest_n(void) { return (hout.n); }
+int wrsref_harvest_npoints(void) { return (hout.npoints); }
+void wrsref_harvest_get(int *counters, double *times, double *waves)
+{
+    if (counters) memcpy(counters, hout.counters.data(), hout.counters.size()*sizeof(int));
+    if (times) memcpy(times, hout.times.data(), hout.times.size()*sizeof(double));
+    if (waves) memcpy(waves, hout.waves.data(), hout.waves.size()*sizeof(double));
 }
 
 int wrsref_num_points(void) { return ((int)rec.ref.size()); }
