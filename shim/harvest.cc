@@ -21,6 +21,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <string>
@@ -112,11 +113,19 @@ static void harvest_options(const sTASK *t, b200_options &o)
     o.itl1 = t->TSKdcMaxIter; o.itl2 = t->TSKdcTrcvMaxIter; o.itl4 = t->TSKtranMaxIter;
     o.itl_gmin = t->TSKdcOpGminMaxIter; o.itl_src = t->TSKdcOpSrcMaxIter;
     o.gminsteps = t->TSKnumGminSteps; o.srcsteps = t->TSKnumSrcSteps; o.gminfirst = t->TSKgminFirst;
-    o.method = t->TSKintegrateMethod;
+    o.method = t->TSKintegrateMethod == GEAR ? 1 : 0;         // circuit.h:451-452 TRAPEZOIDAL 1, GEAR 2
     o.trapcheck = t->TSKtrapCheck; o.spice3 = t->TSKspice3; o.oldsteplim = t->TSKoldStepLim;
     o.oldlimit = t->TSKfixLimit; o.forcegmin = t->TSKforceGmin;
     o.interplev = t->TSKinterpLev; o.jjaccel = t->TSKjjaccel; o.nojjtp = t->TSKnojjtp;
     o.noopiter = t->TSKnoOpIter; o.steptype = t->TSKtranStepType;
+    if (getenv("B200_SHIM_TRACE")) {
+        const double *d = &o.abstol;
+        fprintf(stderr, "b200 shim options:");
+        for (int i = 0; i < 21; i++) fprintf(stderr, " %g", d[i]);
+        const int *k = &o.bypass;
+        for (int i = 0; i < 20; i++) fprintf(stderr, " %d", k[i]);
+        fprintf(stderr, "\n");
+    }
 }
 
 extern "C" void b200_harvest_free(b200_harvest *h) { delete h; }
@@ -153,6 +162,10 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
         D.tstep = tj->TRANspec->step(0); D.tstop = tj->TRANspec->end(0);
         D.tstart = tj->TRANspec->tstart; D.tmax = tj->TRANmaxStep;
         D.uic = (tj->TRANmode & MODEUIC) ? 1 : 0;
+        // an analysis that already ran has written its derived delmin / minbreak back into the
+        // task (tranan.cc:183-212, 662-667); "not given" is what the engine must see
+        if (!tj->TS.t_delmin_given) D.opt.delmin = 0.0;
+        if (!tj->TS.t_minbreak_given) D.opt.minbreak = 0.0;
         H->has_tran = 1;
         break;
     }
