@@ -258,8 +258,7 @@ def bench_ours(args):
     mc = MonteCarlo(deck, world*T, save=save, rank=rank, world=world, device=local,
                     local_variation=ov)
     batch = mc.runner.batch
-    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in mc.variation.items()}
-    mc.variation = {k: v.numpy() for k, v in pinned.items()}     # H2D copies start from pinned memory
+    # mc.packed: this rank's [nrows][T] parameter rows in ONE page-locked array (H2D = one DMA)
 
     def barrier():
         if world > 1:
@@ -273,9 +272,13 @@ def bench_ours(args):
         # the call a user makes: host parameter arrays in (H2D), counters + selected waveforms
         # out (D2H), shards gathered to rank 0 over NCCL/NVLink when N > 1
         mc.run(device=torch.device("cuda", local))
-        return mc.local[0], mc.local[2]
+        if world == 1:
+            return mc.local[0], mc.local[2]
+        if rank == 0:                       # rank 0's own trials are rows 0, world, 2*world, ...
+            return mc.counters[0::world], mc.waves[0::world]
+        return None, None
 
-    batch.set_params(mc.variation)
+    mc.runner.upload(mc.variation)
     for _ in range(args.warmup):
         step_kernel_only()
 
@@ -389,8 +392,8 @@ def bench_ours(args):
         ach_solve = live*st.algbytes_solve_per_launch/(solve_ms*1e-3)/1e9 if solve_ms > 0 else 0.0
         value = world*T*args.steps/el
         e2e_val = world*T*args.steps/el_e2e
-        h2d = sum(v.numel()*8 for v in pinned.values())
-        d2h = cnt_e.nbytes + w_e.nbytes
+        h2d = int(mc.packed.nbytes)
+        d2h = int(cnt_e.nbytes + w_e.nbytes)
         # CPU baseline on this box's cores (bounded sample) = the SAME trials the GPU just ran
         # (rank 0's trials 0..k-1 with their own parameter values), so the same run also gives
         # the parity record: counts identical per trial, waveforms within reltol/vntol

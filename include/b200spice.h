@@ -169,6 +169,14 @@ void b200_batch_destroy(b200_batch *b);
  * (the reference MC decks give each varied device its own .model). */
 int  b200_batch_set_param(b200_batch *b, int param, int index, const double *values);
 
+/* The same for many rows at once: values[nrows][ntrials] (host, row r = parameter param[r] of
+ * instance index[r]) goes to the device in ONE transfer on the batch's stream -- a DMA when the
+ * buffer is page-locked -- and a device kernel scatters the rows into the trial-minor tables.
+ * The buffer must stay unchanged until the next b200_batch_run_* call returns.  Replaces the
+ * rows of an earlier call; single rows (b200_batch_set_param) override it per instance. */
+int  b200_batch_set_params(b200_batch *b, int nrows, const int *param, const int *index,
+                           const double *values);
+
 /* Runs DCOP (or UIC start) + transient for every trial to completion on the GPU:
  * TRANanalysis::tran_dcoperation (tranan.cc:321-468) with sCKT::op (ckt.cc:1859-2011),
  * NIiter (niiter.cc:160-555), sTRANint::step/accept/interpolate (tranan.cc:483-1116). */
@@ -196,6 +204,12 @@ int  b200_batch_get_counters(const b200_batch *b, int *counters);
 int  b200_batch_get_waves(const b200_batch *b, double *times, double *waves);
 /* Same, restricted to a subset of unknowns (what `.save`/`.print` would keep). */
 int  b200_batch_get_waves_sel(const b200_batch *b, int nsel, const int *sel, double *waves);
+
+/* The same into DEVICE buffers of the caller, dwaves[ntrials][npoints][nsel] and (optional)
+ * dcounters[ntrials][B200_NCOUNTERS]: what the multi-GPU dispatcher hands to the final gather
+ * (NCCL over NVLink) without a host round trip. */
+int  b200_batch_get_results_dev(const b200_batch *b, int nsel, const int *sel, double *dwaves,
+                                int *dcounters);
 
 /* Kernel statistics of the last run (for bench.py): number of kernel launches, Newton ticks,
  * device-load instance evaluations, seconds spent per kernel class (CUDA events). */

@@ -334,3 +334,52 @@ def test_reciprocal_division_is_ieee_division():
         bad = C.c_longlong(-1)
         rc = lib.b200_debug_divcheck(50_000_000, 1234 + seed, emin, emax, C.byref(bad))
         assert rc == 0 and bad.value == 0, (emin, emax, bad.value)
+
+
+def test_packed_rows_equal_single_rows():
+    """b200_batch_set_params (one transfer + device scatter) against b200_batch_set_param row by
+    row: bit-identical results; a single row given afterwards overrides its packed row."""
+    d = ring_oscillator(5)
+    ntr = 37
+    ov = mc_variation(d, ntr, seed=8)
+    a = engine.Batch(d, ntr)
+    a.set_params(ov)
+    a.run_tran()
+    ca, (_, wa) = a.counters(), a.waves()
+    keys = list(ov)
+    vals = np.ascontiguousarray(np.stack([ov[k] for k in keys]))
+    b = engine.Batch(d, ntr)
+    b.set_params_packed([k[0] for k in keys], [k[1] for k in keys], vals)
+    b.run_tran()
+    cb, (_, wb) = b.counters(), b.waves()
+    assert np.array_equal(ca, cb) and np.array_equal(wa, wb)
+    # override one packed row with the nominal value for every trial -> differs from a, equals
+    # a batch that was given that row singly
+    k0 = keys[0]
+    flat = np.full(ntr, ov[k0][0])
+    b.set_param(k0[0], k0[1], flat)
+    b.run_tran()
+    ov2 = dict(ov)
+    ov2[k0] = flat
+    a.set_params(ov2)
+    a.run_tran()
+    assert np.array_equal(a.counters(), b.counters()) and np.array_equal(a.waves()[1], b.waves()[1])
+    a.close()
+    b.close()
+
+
+def test_results_into_device_buffers():
+    import torch
+    d = ring_oscillator(5)
+    ntr = 9
+    ov = mc_variation(d, ntr, seed=4)
+    b = engine.Batch(d, ntr)
+    b.set_params(ov)
+    b.run_tran()
+    sel = [0, 2, 5]
+    _, w = b.waves(sel)
+    dw = torch.zeros((ntr, b.npoints, len(sel)), dtype=torch.float64, device="cuda")
+    dc = torch.zeros((ntr, 9), dtype=torch.int32, device="cuda")
+    b.results_to_device(sel, dw.data_ptr(), dc.data_ptr())
+    assert np.array_equal(dw.cpu().numpy(), w) and np.array_equal(dc.cpu().numpy(), b.counters())
+    b.close()

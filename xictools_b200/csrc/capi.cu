@@ -52,6 +52,14 @@ struct b200_batch {
     std::vector<double> cap_c, cap_ic, src_dc, ind_l, ind_ic;
     std::map<int, std::vector<double>> cap_var, src_var, ind_var;
     bool params_dirty = true;
+    // packed per-trial rows (b200_batch_set_params): table id (0..MR_NRAW-1 MOS raw, then
+    // PT_CAP / PT_IND / PT_SRC), instance index, values on the device as [nrows][ntrials]
+    std::vector<int> pk_tbl, pk_idx;
+    double *d_pack = nullptr; size_t pack_cap = 0;
+    int *d_pk_desc = nullptr; size_t pk_desc_cap = 0;
+    // persistent output staging of get_waves
+    mutable double *d_wout = nullptr; mutable size_t wout_cap = 0;
+    mutable int *d_wsel = nullptr; mutable int wsel_cap = 0;
 
     // device views
     HotView hot; VecView V; MosView M; CapView Cp; SrcView S; SolveView Sv; CtlAux aux;
@@ -85,6 +93,51 @@ struct b200_batch {
         return p;
     }
 };
+
+enum { PT_CAP = MR_NRAW, PT_IND = MR_NRAW + 1, PT_SRC = MR_NRAW + 2, PT_NTABLES = MR_NRAW + 3 };
+
+// row i of a [n][ldt] per-trial table <- the shared value of instance i
+__global__ void k_fill_rows(double *dst, const double *shared, int n, int ldt)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t < ldt && i < n) dst[(size_t)i*ldt + t] = shared[i];
+}
+
+// packed rows [nrows][ntrials] -> row desc[2r+1] of the table whose base is bases[desc[2r]];
+// the padding trials repeat trial 0 (they run the nominal arithmetic and are never read back)
+struct TableBases { double *p[PT_NTABLES]; };
+__global__ void k_scatter_rows(TableBases tb, const int *desc, const double *vals, int ntrials, int ldt)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int r = blockIdx.y;
+    if (t >= ldt) return;
+    double *base = tb.p[desc[2*r]];
+    if (!base || desc[2*r + 1] < 0) return;
+    const double *src = vals + (size_t)r*ntrials;
+    base[(size_t)desc[2*r + 1]*ldt + t] = src[t < ntrials ? t : 0];
+}
+
+static int param_table(const b200_batch *b, int param, int index)
+{
+    int tbl = -1, n = 0;
+    switch (param) {
+    case B200_P_MOS_VTO: tbl = MR_vto; break;
+    case B200_P_MOS_KP: tbl = MR_kp; break;
+    case B200_P_MOS_GAMMA: tbl = MR_gamma; break;
+    case B200_P_MOS_PHI: tbl = MR_phi; break;
+    case B200_P_MOS_LAMBDA: tbl = MR_lambda; break;
+    case B200_P_MOS_L: tbl = MR_l; break;
+    case B200_P_MOS_W: tbl = MR_w; break;
+    case B200_P_CAP_C: tbl = PT_CAP; break;
+    case B200_P_IND_L: tbl = PT_IND; break;
+    case B200_P_SRC_DC: tbl = PT_SRC; break;
+    default: return -B200_E_UNSUPP;
+    }
+    n = tbl < MR_NRAW ? b->an.mos.n : tbl == PT_CAP ? b->an.cap.n : tbl == PT_IND ? b->an.ind.n : b->an.src.n;
+    if (index < 0 || index >= n) return -B200_E_BADPARM;
+    return tbl;
+}
 
 extern "C" {
 
@@ -399,6 +452,8 @@ void b200_batch_destroy(b200_batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     for (void *p : b->allocs) cudaFree(p);
+    if (b->d_wout) cudaFree(b->d_wout);
+    if (b->d_wsel) cudaFree(b->d_wsel);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -406,6 +461,13 @@ void b200_batch_destroy(b200_batch *b)
 int b200_batch_set_param(b200_batch *b, int param, int index, const double *values)
 {
     if (!b || !values) return B200_E_BADPARM;
+    {
+        // a row given singly replaces a packed row of the same (table, instance)
+        int t = param_table(b, param, index);
+        if (t >= 0)
+            for (size_t r = 0; r < b->pk_tbl.size(); r++)
+                if (b->pk_tbl[r] == t && b->pk_idx[r] == index) b->pk_idx[r] = -1;
+    }
     // one copy, into the vector the batch already owns (repeated runs reuse its storage)
     auto put = [&](std::vector<double> &dst) { dst.assign(values, values + b->ntrials); };
     int raw = -1;
@@ -441,35 +503,85 @@ int b200_batch_set_param(b200_batch *b, int param, int index, const double *valu
     return B200_OK;
 }
 
+int b200_batch_set_params(b200_batch *b, int nrows, const int *param, const int *index,
+    const double *values)
+{
+    if (!b || nrows < 0 || (nrows && (!param || !index || !values))) return B200_E_BADPARM;
+    CK(cudaSetDevice(b->device));
+    std::vector<int> tbl(nrows);
+    for (int r = 0; r < nrows; r++) {
+        int t = param_table(b, param[r], index[r]);
+        if (t < 0) return -t;
+        tbl[r] = t;
+    }
+    for (int r = 0; r < nrows; r++) {
+        if (tbl[r] < MR_NRAW) {
+            // a per-trial model value makes the card "given" for that device
+            MosCard &c = b->cards[index[r]];
+            if (tbl[r] == MR_vto) c.g_vto = 1;
+            if (tbl[r] == MR_kp) c.g_kp = 1;
+            if (tbl[r] == MR_gamma) c.g_gamma = 1;
+            if (tbl[r] == MR_phi) c.g_phi = 1;
+            b->mos_var[tbl[r]].erase(index[r]);
+        }
+        else if (tbl[r] == PT_CAP) b->cap_var.erase(index[r]);
+        else if (tbl[r] == PT_IND) b->ind_var.erase(index[r]);
+        else b->src_var.erase(index[r]);
+    }
+    size_t need = (size_t)nrows*b->ntrials;
+    if (need > b->pack_cap) {
+        b->d_pack = b->dalloc<double>(need);
+        if (!b->d_pack) return B200_E_NOMEM;
+        b->pack_cap = need;
+    }
+    // ONE transfer for all rows: a DMA when the caller's buffer is page-locked
+    if (need) CK(cudaMemcpyAsync(b->d_pack, values, need*sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    b->pk_tbl = tbl;
+    b->pk_idx.assign(index, index + nrows);
+    b->params_dirty = true;
+    return B200_OK;
+}
+
 // upload parameters and run the temperature kernel (sCKT::temp, ckt.cc:2297-2307)
 static int prepare_params(b200_batch *b)
 {
     if (!b->params_dirty) return B200_OK;
     size_t ldt = b->ldt;
     int nm = b->an.mos.n;
-    auto upload_strided = [&](const std::vector<double> &shared,
+    cudaStream_t st = b->stream;
+    std::vector<char> packed_in(PT_NTABLES, 0);
+    for (int t : b->pk_tbl) packed_in[t] = 1;
+    TableBases bases;
+    for (int k = 0; k < PT_NTABLES; k++) bases.p[k] = nullptr;
+    std::vector<void*> tmp_shared;
+    auto upload_strided = [&](int tbl, const std::vector<double> &shared,
             const std::map<int, std::vector<double>> &var, double *&dptr, int &ts) -> int {
         int n = (int)shared.size();
-        int want_ts = var.empty() ? 0 : 1;
+        int want_ts = (var.empty() && !packed_in[tbl]) ? 0 : 1;
         if (!dptr || ts != want_ts) {
             dptr = b->dalloc<double>(want_ts ? (size_t)n*ldt : (size_t)n);
             if (!dptr) return B200_E_NOMEM;
             ts = want_ts;
         }
         if (!ts) {
-            if (n) CK(cudaMemcpy(dptr, shared.data(), n*sizeof(double), cudaMemcpyHostToDevice));
+            if (n) CK(cudaMemcpyAsync(dptr, shared.data(), n*sizeof(double), cudaMemcpyHostToDevice, st));
         }
         else {
+            // every row starts as the instance's shared value (filled on the device), then the
+            // rows given one by one (set_param), then the packed rows (set_params)
+            double *dsh = nullptr;
+            CK(cudaMalloc(&dsh, (n ? n : 1)*sizeof(double)));
+            tmp_shared.push_back(dsh);
+            CK(cudaMemcpyAsync(dsh, shared.data(), n*sizeof(double), cudaMemcpyHostToDevice, st));
+            k_fill_rows<<<dim3((unsigned)((ldt + 255)/256), n), 256, 0, st>>>(dptr, dsh, n, (int)ldt);
             std::vector<double> row(ldt);
-            for (int i = 0; i < n; i++) {
-                auto it = var.find(i);
-                if (it == var.end()) std::fill(row.begin(), row.end(), shared[i]);
-                else {
-                    std::copy(it->second.begin(), it->second.end(), row.begin());
-                    std::fill(row.begin() + b->ntrials, row.end(), it->second[0]);
-                }
-                CK(cudaMemcpy(dptr + (size_t)i*ldt, row.data(), ldt*sizeof(double), cudaMemcpyHostToDevice));
+            for (auto &kv : var) {
+                std::copy(kv.second.begin(), kv.second.end(), row.begin());
+                std::fill(row.begin() + b->ntrials, row.end(), kv.second[0]);
+                CK(cudaMemcpyAsync(dptr + (size_t)kv.first*ldt, row.data(), ldt*sizeof(double), cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));          // `row` is reused
             }
+            bases.p[tbl] = dptr;
         }
         return B200_OK;
     };
@@ -477,7 +589,7 @@ static int prepare_params(b200_batch *b)
     int tsd[MP_NPARAMS];
     for (int k = 0; k < MP_NPARAMS; k++) tsd[k] = 0;
     for (int k = 0; k < MR_NRAW; k++) {
-        int rc = upload_strided(b->mos_raw[k], b->mos_var[k], b->d_raw[k], b->raw_ts[k]);
+        int rc = upload_strided(k, b->mos_raw[k], b->mos_var[k], b->d_raw[k], b->raw_ts[k]);
         if (rc) return rc;
         raw.p[k].base = b->d_raw[k];
         raw.p[k].ts = b->raw_ts[k];
@@ -520,26 +632,43 @@ static int prepare_params(b200_batch *b)
         b->M.stage_doubles = shared_base + (other ? MP_NPARAMS : MP_NBASE) + (MOS_NSLOT + 1)/2;
         if (loads_configure(b->M)) return B200_E_NOMEM;
     }
-    CK(cudaMemcpy(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice));
-    launch_mos_temp(b->stream, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);
-    int rc = upload_strided(b->cap_c, b->cap_var, b->d_capc, b->capc_ts);
+    int rc = upload_strided(PT_CAP, b->cap_c, b->cap_var, b->d_capc, b->capc_ts);
     if (rc) return rc;
     b->Cp.capac.base = b->d_capc; b->Cp.capac.ts = b->capc_ts; b->Cp.capac.ld = b->capc_ts ? (int)ldt : 1;
     if (!b->d_capic) b->d_capic = b->dalloc<double>(b->cap_ic.size());
     if (!b->cap_ic.empty())
         CK(cudaMemcpy(b->d_capic, b->cap_ic.data(), b->cap_ic.size()*sizeof(double), cudaMemcpyHostToDevice));
     b->Cp.ic.base = b->d_capic; b->Cp.ic.ts = 0; b->Cp.ic.ld = 1;
-    rc = upload_strided(b->ind_l, b->ind_var, b->d_indl, b->indl_ts);
+    rc = upload_strided(PT_IND, b->ind_l, b->ind_var, b->d_indl, b->indl_ts);
     if (rc) return rc;
     b->Cp.L.induct.base = b->d_indl; b->Cp.L.induct.ts = b->indl_ts; b->Cp.L.induct.ld = b->indl_ts ? (int)ldt : 1;
     if (!b->d_indic) b->d_indic = b->dalloc<double>(b->ind_ic.size());
     if (!b->ind_ic.empty())
         CK(cudaMemcpy(b->d_indic, b->ind_ic.data(), b->ind_ic.size()*sizeof(double), cudaMemcpyHostToDevice));
     b->Cp.L.ic.base = b->d_indic; b->Cp.L.ic.ts = 0; b->Cp.L.ic.ld = 1;
-    rc = upload_strided(b->src_dc, b->src_var, b->d_srcdc, b->srcdc_ts);
+    rc = upload_strided(PT_SRC, b->src_dc, b->src_var, b->d_srcdc, b->srcdc_ts);
     if (rc) return rc;
     b->S.dc.base = b->d_srcdc; b->S.dc.ts = b->srcdc_ts; b->S.dc.ld = b->srcdc_ts ? (int)ldt : 1;
-    CK(cudaStreamSynchronize(b->stream));
+    // packed rows into their tables (after the default fill, before the temperature kernel)
+    if (!b->pk_tbl.empty()) {
+        int nrows = (int)b->pk_tbl.size();
+        if ((size_t)nrows > b->pk_desc_cap) {
+            b->d_pk_desc = b->dalloc<int>(2*(size_t)nrows);
+            if (!b->d_pk_desc) return B200_E_NOMEM;
+            b->pk_desc_cap = nrows;
+        }
+        std::vector<int> desc(2*(size_t)nrows);
+        for (int r = 0; r < nrows; r++) { desc[2*r] = b->pk_tbl[r]; desc[2*r + 1] = b->pk_idx[r]; }
+        CK(cudaMemcpyAsync(b->d_pk_desc, desc.data(), desc.size()*sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));              // `desc` is a local
+        k_scatter_rows<<<dim3((unsigned)((ldt + 255)/256), nrows), 256, 0, st>>>(bases, b->d_pk_desc,
+            b->d_pack, b->ntrials, (int)ldt);
+    }
+    CK(cudaMemcpyAsync(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice, st));
+    launch_mos_temp(st, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (void *q : tmp_shared) cudaFree(q);
     b->params_dirty = false;
     return B200_OK;
 }
@@ -728,18 +857,50 @@ static int get_waves(const b200_batch *b, int nsel, const int *sel, double *time
     }
     if (!waves) return B200_OK;
     int nn = sel ? nsel : an.n;
-    double *dw = nullptr; int *dsel = nullptr;
     size_t total = (size_t)b->ntrials*np*nn;
-    CK(cudaMalloc(&dw, total*sizeof(double)));
-    if (sel) {
-        CK(cudaMalloc(&dsel, nsel*sizeof(int)));
-        CK(cudaMemcpy(dsel, sel, nsel*sizeof(int), cudaMemcpyHostToDevice));
+    if (total > b->wout_cap) {
+        if (b->d_wout) cudaFree(b->d_wout);
+        b->d_wout = nullptr; b->wout_cap = 0;
+        CK(cudaMalloc(&b->d_wout, total*sizeof(double)));
+        b->wout_cap = total;
     }
-    launch_gather_waves(b->stream, an.n, b->ldt, b->ntrials, np, b->V.out, b->d_npts, nsel, dsel, dw);
+    if (sel) {
+        if (nsel > b->wsel_cap) {
+            if (b->d_wsel) cudaFree(b->d_wsel);
+            b->d_wsel = nullptr; b->wsel_cap = 0;
+            CK(cudaMalloc(&b->d_wsel, nsel*sizeof(int)));
+            b->wsel_cap = nsel;
+        }
+        CK(cudaMemcpyAsync(b->d_wsel, sel, nsel*sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    }
+    launch_gather_waves(b->stream, an.n, b->ldt, b->ntrials, np, b->V.out, b->d_npts, nsel,
+        sel ? b->d_wsel : nullptr, b->d_wout);
+    CK(cudaMemcpyAsync(waves, b->d_wout, total*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    CK(cudaMemcpy(waves, dw, total*sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(dw);
-    if (dsel) cudaFree(dsel);
+    return B200_OK;
+}
+
+// results straight into DEVICE buffers of the caller (the multi-GPU gather hands them to NCCL
+// without a host round trip): dwaves[ntrials][npoints][nsel], dcounters[ntrials][B200_NCOUNTERS]
+int b200_batch_get_results_dev(const b200_batch *b, int nsel, const int *sel, double *dwaves,
+    int *dcounters)
+{
+    if (!b || !b->ran || !sel || nsel <= 0 || !dwaves) return B200_E_BADPARM;
+    CK(cudaSetDevice(b->device));
+    const Analysis &an = b->an;
+    if (nsel > b->wsel_cap) {
+        if (b->d_wsel) cudaFree(b->d_wsel);
+        b->d_wsel = nullptr; b->wsel_cap = 0;
+        CK(cudaMalloc(&b->d_wsel, nsel*sizeof(int)));
+        b->wsel_cap = nsel;
+    }
+    CK(cudaMemcpyAsync(b->d_wsel, sel, nsel*sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    launch_gather_waves(b->stream, an.n, b->ldt, b->ntrials, an.npoints_max, b->V.out, b->d_npts, nsel,
+        b->d_wsel, dwaves);
+    if (dcounters)
+        CK(cudaMemcpyAsync(dcounters, b->d_counters, (size_t)b->ntrials*B200_NCOUNTERS*sizeof(int),
+            cudaMemcpyDeviceToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
     return B200_OK;
 }
 

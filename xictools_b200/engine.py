@@ -51,6 +51,8 @@ def load_library(path: str | None = None):
     L.b200_batch_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.b200_batch_destroy.argtypes = [C.c_void_p]
     L.b200_batch_set_param.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.b200_batch_set_params.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200_batch_get_results_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200_batch_run_tran.argtypes = [C.c_void_p]
     L.b200_batch_run_op.argtypes = [C.c_void_p]
     L.b200_batch_num_unknowns.argtypes = [C.c_void_p]
@@ -114,6 +116,28 @@ class Batch:
         for (pid, idx), vals in overrides.items():
             self.set_param(pid, idx, vals)
 
+    def set_params_packed(self, params, indices, values):
+        """All per-trial rows in one call: values[nrows][ntrials] (C-contiguous float64; a
+        page-locked buffer is copied by DMA) with row r = parameter params[r] of instance
+        indices[r].  `values` must stay alive and unchanged until the next run returns."""
+        p = np.ascontiguousarray(params, dtype=np.int32)
+        i = np.ascontiguousarray(indices, dtype=np.int32)
+        v = values
+        if not (isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags.c_contiguous):
+            v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.shape == (len(p), self.ntrials)
+        self._packed_keep = (p, i, v)
+        rc = self.L.b200_batch_set_params(self.h, len(p), p.ctypes.data, i.ctypes.data, v.ctypes.data)
+        if rc:
+            raise B200Error(rc, "b200_batch_set_params")
+
+    def results_to_device(self, sel, dwaves_ptr: int, dcounters_ptr: int = 0):
+        """Counters and selected waveforms into device buffers of the caller (raw pointers)."""
+        s = np.ascontiguousarray(sel, dtype=np.int32)
+        rc = self.L.b200_batch_get_results_dev(self.h, len(s), s.ctypes.data, dwaves_ptr, dcounters_ptr)
+        if rc:
+            raise B200Error(rc, "b200_batch_get_results_dev")
+
     def run_tran(self):
         rc = self.L.b200_batch_run_tran(self.h)
         if rc:
@@ -131,22 +155,31 @@ class Batch:
         generic = [s.decode() for s in buf.raw[:nb].split(b"\0")[:-1]]
         return self.deck.unknown_names(generic)
 
-    def counters(self) -> np.ndarray:
-        c = np.zeros((self.ntrials, NCOUNTERS), dtype=np.int32)
+    def counters(self, out=None) -> np.ndarray:
+        c = out if out is not None else np.empty((self.ntrials, NCOUNTERS), dtype=np.int32)
         rc = self.L.b200_batch_get_counters(self.h, c.ctypes.data)
         if rc:
             raise B200Error(rc, "b200_batch_get_counters")
         return c
 
-    def waves(self, sel=None):
-        """(times[npoints], waves[ntrials][npoints][n or len(sel)])"""
+    def times(self) -> np.ndarray:
+        """The user time points (t_check sequence, tranan.cc:472-479)."""
+        t = np.zeros(self.npoints)
+        rc = self.L.b200_batch_get_waves(self.h, t.ctypes.data, None)
+        if rc:
+            raise B200Error(rc, "b200_batch_get_waves")
+        return t
+
+    def waves(self, sel=None, out=None):
+        """(times[npoints], waves[ntrials][npoints][n or len(sel)]); `out` = a caller-owned
+        result buffer of that shape (reused across runs, may be page-locked)."""
         t = np.zeros(self.npoints)
         if sel is None:
-            w = np.zeros((self.ntrials, self.npoints, self.n))
+            w = out if out is not None else np.empty((self.ntrials, self.npoints, self.n))
             rc = self.L.b200_batch_get_waves(self.h, t.ctypes.data, w.ctypes.data)
         else:
             s = np.ascontiguousarray(sel, dtype=np.int32)
-            w = np.zeros((self.ntrials, self.npoints, len(s)))
+            w = out if out is not None else np.empty((self.ntrials, self.npoints, len(s)))
             rc = self.L.b200_batch_get_waves(self.h, t.ctypes.data, None)
             rc = rc or self.L.b200_batch_get_waves_sel(self.h, len(s), s.ctypes.data, w.ctypes.data)
         if rc:

@@ -35,23 +35,64 @@ def shard_capacity(ntrials: int, world: int) -> int:
 class EngineRunner:
     """One CUDA batch on this rank's device (fails loudly without the CUDA library / a GPU)."""
 
+    accepts_packed = True
+
     def __init__(self, deck: Deck, ntrials: int, device: int = 0):
         from . import engine
         self.batch = engine.Batch(deck, ntrials, device=device)
+        self.packed = None              # (param ids, instance indices, values[nrows][ntrials])
+        self._cnt = self._w = None
 
     def names(self):
         return self.batch.names()
 
+    def upload(self, overrides):
+        if self.packed is not None:
+            self.batch.set_params_packed(*self.packed)      # one transfer + a device scatter
+        else:
+            for (pid, idx), v in overrides.items():
+                self.batch.set_param(pid, idx, v)
+
     def run(self, overrides, sel):
-        for (pid, idx), v in overrides.items():
-            self.batch.set_param(pid, idx, v)
+        self.upload(overrides)
         self.batch.run_tran()
-        cnt = self.batch.counters()
-        times, w = self.batch.waves(sel)
+        if self._cnt is None:
+            self._cnt = _host_buffer((self.batch.ntrials, NCOUNTERS), np.int32)
+        cnt = self.batch.counters(out=self._cnt)
+        shape = (self.batch.ntrials, self.batch.npoints, len(sel))
+        if self._w is None or self._w.shape != shape:
+            self._w = _host_buffer(shape, np.float64)
+        times, w = self.batch.waves(sel, out=self._w)
         return cnt, times, w
+
+    def run_device(self, overrides, sel, dwaves_ptr, dcounters_ptr):
+        """Run, leaving counters and selected waveforms in device buffers of the caller."""
+        self.upload(overrides)
+        self.batch.run_tran()
+        self.batch.results_to_device(sel, dwaves_ptr, dcounters_ptr)
+        return self.batch.times()
 
     def close(self):
         self.batch.close()
+
+
+def _host_buffer(shape, dtype):
+    """A reusable result / parameter buffer: page-locked when torch + CUDA are there (DMA both
+    ways), plain numpy otherwise."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            tdt = {np.float64: torch.float64, np.int32: torch.int32}[dtype]
+            t = torch.empty(tuple(shape), dtype=tdt, pin_memory=True)
+            a = t.numpy()
+            _KEEP.append(t)
+            return a
+    except Exception:
+        pass
+    return np.empty(shape, dtype=dtype)
+
+
+_KEEP = []
 
 
 class MonteCarlo:
@@ -62,6 +103,9 @@ class MonteCarlo:
     (default: all).  After run(), rank 0 holds
         counters [ntrials][NCOUNTERS] int32, times [npoints], waves [ntrials][npoints][nsave]
     in global trial order; other ranks hold their own shard only.
+
+    This rank's rows live in ONE [nrows][nlocal] array (`packed`; page-locked on a GPU box), of
+    which `variation[key]` are views: the CUDA runner uploads it in a single transfer.
     """
 
     def __init__(self, deck: Deck, ntrials: int, variation: dict | None = None, *, save=None,
@@ -70,26 +114,36 @@ class MonteCarlo:
         self.deck, self.ntrials = deck, int(ntrials)
         self.rank, self.world = int(rank), int(world)
         self.mine = shard_trials(self.ntrials, self.world, self.rank)
-        self.variation = {}
+        self.nlocal = len(self.mine)
+        if self.nlocal == 0:
+            raise ValueError("more ranks than trials")
+        rows = []
         for key, v in (variation or {}).items():
             v = np.ascontiguousarray(v, dtype=np.float64)
             if v.shape != (self.ntrials,):
                 raise ValueError(f"variation {key}: expected {self.ntrials} values, got {v.shape}")
-            self.variation[key] = np.ascontiguousarray(v[self.mine])
+            rows.append((key, v[self.mine]))
         # alternatively the caller hands over this rank's slice only (arrays of len(self.mine))
         for key, v in (local_variation or {}).items():
             v = np.ascontiguousarray(v, dtype=np.float64)
-            if v.shape != (len(self.mine),):
-                raise ValueError(f"local variation {key}: expected {len(self.mine)} values")
-            self.variation[key] = v
-        self.nlocal = len(self.mine)
-        if self.nlocal == 0:
-            raise ValueError("more ranks than trials")
+            if v.shape != (self.nlocal,):
+                raise ValueError(f"local variation {key}: expected {self.nlocal} values")
+            rows.append((key, v))
         self.runner = runner(deck, self.nlocal) if runner else EngineRunner(deck, self.nlocal, device)
+        packed_ok = getattr(self.runner, "accepts_packed", False)
+        self.packed = (_host_buffer if packed_ok else np.empty)((len(rows), self.nlocal), np.float64)
+        self.variation = {}
+        for r, (key, v) in enumerate(rows):
+            self.packed[r] = v
+            self.variation[key] = self.packed[r]
+        if packed_ok and rows:
+            self.runner.packed = (np.array([k[0] for k, _ in rows], dtype=np.int32),
+                                  np.array([k[1] for k, _ in rows], dtype=np.int32), self.packed)
         names = self.runner.names()
         self.save = list(save) if save is not None else list(names)
         self.sel = [names.index(s) for s in self.save]
         self.counters = self.times = self.waves = None
+        self._dev = None
 
     def run_local(self):
         cnt, times, w = self.runner.run(self.variation, self.sel)
@@ -111,23 +165,50 @@ class MonteCarlo:
         pw = torch.zeros((cap, npts, nsel), dtype=torch.float64, device=dev)
         pc[:self.nlocal] = torch.from_numpy(np.ascontiguousarray(cnt, dtype=np.int32)).to(dev)
         pw[:self.nlocal] = torch.from_numpy(np.ascontiguousarray(w)).to(dev)
-        gc = [torch.empty_like(pc) for _ in range(self.world)] if self.rank == 0 else None
-        gw = [torch.empty_like(pw) for _ in range(self.world)] if self.rank == 0 else None
-        dist.gather(pc, gc, dst=0)
-        dist.gather(pw, gw, dst=0)
-        if self.rank == 0:
-            C = np.zeros((self.ntrials, cnt.shape[1]), dtype=np.int32)
-            W = np.zeros((self.ntrials, npts, nsel))
-            for r in range(self.world):
-                own = shard_trials(self.ntrials, self.world, r)
-                C[own] = gc[r][:len(own)].cpu().numpy()
-                W[own] = gw[r][:len(own)].cpu().numpy()
-            self.counters, self.times, self.waves = C, times, W
-        else:
+        self._gather_tensors(pc, pw, times)
+        if self.rank != 0:
             self.counters, self.times, self.waves = cnt, times, w
         return self
 
+    def _gather_tensors(self, pc, pw, times):
+        """pc [cap][NCOUNTERS], pw [cap][npts][nsel] on any device: gather to rank 0 and undo the
+        interleaving there (trial i*world + r = row i of rank r) before the one copy to host."""
+        import torch
+        import torch.distributed as dist
+        gc = gw = None
+        if self.rank == 0:
+            gc = list(torch.empty((self.world,) + tuple(pc.shape), dtype=pc.dtype, device=pc.device).unbind(0))
+            gw = list(torch.empty((self.world,) + tuple(pw.shape), dtype=pw.dtype, device=pw.device).unbind(0))
+        dist.gather(pc, gc, dst=0)
+        dist.gather(pw, gw, dst=0)
+        if self.rank == 0:
+            C = torch.stack(gc, 1).reshape((-1,) + tuple(pc.shape[1:]))[:self.ntrials]
+            W = torch.stack(gw, 1).reshape((-1,) + tuple(pw.shape[1:]))[:self.ntrials]
+            if C.is_cuda:
+                if self._dev is None or self._dev[1].shape != W.shape:
+                    self._dev = (torch.empty(C.shape, dtype=C.dtype, pin_memory=True),
+                                 torch.empty(W.shape, dtype=W.dtype, pin_memory=True))
+                self._dev[0].copy_(C, non_blocking=True)
+                self._dev[1].copy_(W, non_blocking=True)
+                torch.cuda.synchronize()
+                C, W = self._dev
+            self.counters, self.times, self.waves = C.numpy(), times, W.numpy()
+
     def run(self, device=None):
+        """Run this rank's shard and gather.  With a CUDA runner and world > 1 the results go
+        from the engine's device buffers straight into the NCCL gather (no host round trip)."""
+        if self.world > 1 and device is not None and hasattr(self.runner, "run_device") \
+                and str(device).startswith("cuda"):
+            import torch
+            cap = shard_capacity(self.ntrials, self.world)
+            b = self.runner.batch
+            pc = torch.zeros((cap, NCOUNTERS), dtype=torch.int32, device=device)
+            pw = torch.zeros((cap, b.npoints, len(self.sel)), dtype=torch.float64, device=device)
+            times = self.runner.run_device(self.variation, self.sel, pw.data_ptr(), pc.data_ptr())
+            self._gather_tensors(pc, pw, times)
+            if self.rank != 0:
+                self.counters, self.times, self.waves = pc[:self.nlocal], times, pw[:self.nlocal]
+            return self
         self.run_local()
         return self.gather(device)
 
