@@ -105,13 +105,31 @@ typedef struct b200_mos {
     int off;
 } b200_mos;
 
-/* Josephson junction, RSJ level 1: devlib/jj/jjdefs.h, jjset.cc, jjload.cc. */
+/* Josephson junction, RSJ level 1: devlib/jj/jjdefs.h, jjload.cc, jjacct.cc.
+ * The MODEL carries what sJJmodel holds after the model pass of JJdev::setup
+ * (jjset.cc:196-545: defaults, range clamps, BCS gap when vg is not on the card), i.e. values a
+ * host reads off the set-up sJJmodel (shim/harvest.cc does).  The per-INSTANCE derivation
+ * (jjset.cc:609-715: ics -> area -> criti, cap, g0, gn, gs, cr1, cr2, gshunt, vless, vmore) runs
+ * on the device, per trial where ics varies.
+ * Built: rtype 0..3, ictype 0 / 1 (no control current), vshunt, the phase node; `.tran ... uic`
+ * starts only (the phase-mode DC operating point, jjload.cc:154-250, is not built).
+ * Refused (B200_E_UNSUPP): lser / lsh parasitic inductances, rtype 4, ictype 2..4, control. */
 typedef struct b200_jj_model {
-    int rtype, ictype;
-    double vg, delv, icrit, r0, rn, cap, icfact, vshunt, tsfact, tsaccel;
-    double cpic, cmu, vm, icrn, gmu;   /* NaN = not given */
+    int rtype, ictype, pi;          /* JJrtype, JJictype, JJpi */
+    double criti;                   /* JJcriti: critical current of the reference junction */
+    double vg;                      /* JJvgnom: gap voltage at tnom */
+    double delv, r0, rn, cap, icfactor, cmu, gmu;
+    double vshunt;                  /* JJvShunt: model default of the instance vshunt (0 = none) */
+    double vdpbak, tsaccl, tsfact;  /* time-step control of JJdev::accept (jjacct.cc:57,138) */
 } b200_jj_model;
-typedef struct b200_jj { int pos, neg, phase_node; int model; double area, ics, icphi, icv; } b200_jj;
+typedef struct b200_jj {
+    int pos, neg, phase_node;       /* phase_node 0 = absent */
+    int model;
+    double area, ics;               /* NaN = not given (ics wins, jjset.cc:613-631) */
+    double vshunt;                  /* NaN = the model's */
+    double vg, tcf;                 /* JJvg, JJtcf after setup (NaN = model vg, 1.0: temp_k == tnom) */
+    double icv, icphi;              /* ic=vj,phi for the UIC start (NaN = 0) */
+} b200_jj;
 
 /* One deck = one topology (shared by all trials).  Node numbers: 0 is ground, 1..nnodes-1 are
  * the external nodes in the order the reference's parser meets them (src/inp/inpdeck.cc pass2);
@@ -149,7 +167,7 @@ enum {
     B200_P_MOS_VTO = 1, B200_P_MOS_KP, B200_P_MOS_L, B200_P_MOS_W, B200_P_MOS_GAMMA,
     B200_P_MOS_LAMBDA, B200_P_MOS_PHI,
     B200_P_CAP_C = 32, B200_P_RES_R = 48, B200_P_IND_L = 56, B200_P_SRC_DC = 64,
-    B200_P_JJ_AREA = 80
+    B200_P_JJ_ICS = 80             /* instance ics: let @b1[ics] = ... of an .exec block */
 };
 
 typedef struct b200_batch b200_batch;

@@ -98,7 +98,7 @@ typedef struct {
 } Mos;
 
 typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; int st; int icGiven; double capac, ic, geq, ceq; } Cap;
-typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct; } Res;
+typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct; int usePreload; } Res;
 /* sINDinstancePOD (inddefs.h): linear inductor, no series resistance / poly / expression */
 typedef struct { int pos, neg, br; int pBB, pPB, pNB, pBN, pBP; int st; int icGiven;
     double induct, ic, req, veq, prevFlux; } Ind;
@@ -115,6 +115,19 @@ typedef struct {
     int enable_tran;
 } Src;
 
+/* sJJinstancePOD + the model values it reads (jjdefs.h).  No lser / lsh / control. */
+enum { JS_voltage, JS_dvdt, JS_phase, JS_conI, JS_phsInt, JS_crti, JS_qpi, JS_NSTATES = 11 };  /* jjdefs.h:237-250 */
+typedef struct {
+    b200_jj_model mod; b200_jj in;
+    int pos, neg, phs;
+    int pPP, pNN, pNP, pPN, pHH;             /* jjset.cc:136-139, :195 TSTALLOC order */
+    int pRPP, pRPN, pRNP, pRNN;              /* shunt resistor stamps, jjset.cc:178-181 */
+    int st;
+    double area, criti, cap, g0, gn, gs, g1, g2, cr1, cr2, gshunt, vless, vmore, vg, tcf, vshunt;
+    double initVoltage, initPhase, delVdelT;
+    int phsN, phsF; double phsT;
+} JJ;
+
 typedef struct { int kind, index; } DevRef;
 
 /* saved op-point for sCKT::backup (ckt.cc:1323-1362, mosdefs.h:386-402) */
@@ -129,8 +142,10 @@ struct wo_ckt {
     double *ic_val; char *ic_given; double *ns_val; char *ns_given; int hadNodeset;
     char **names;
 
-    int nmos, ncap, nres, nsrc, nind, nmut;
-    Mos *mos; Cap *cap; Res *res; Src *src; Ind *ind; Mut *mut;
+    int nmos, ncap, nres, nsrc, nind, nmut, njj;
+    Mos *mos; Cap *cap; Res *res; Src *src; Ind *ind; Mut *mut; JJ *jj;
+    double initDelta;        /* CKTinitDelta (circuit.h:1581), set by JJdev::getic */
+    char *phase;             /* [n+1] node carries the phase flag (jjset.cc:656-681, indset.cc:104-120), or NULL */
     int nord; DevRef *ord;
 
     /* matrix: CSC, rows ascending per column (spbuild.cc:922-958) */
@@ -857,6 +872,9 @@ static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
     m->oxideCap = m->oxideCapFactor*m->effectiveLength*m->w;
 }
 
+static void jj_setup_instance(JJ *j);
+static void wo_sincos(double x, double *s, double *co) { *s = sin(x); *co = cos(x); }
+
 static void build_matrix(wo_ckt *c)
 {
     /* spbuild.cc:922-958: CSC, columns ascending, rows ascending within a column */
@@ -898,6 +916,11 @@ static void build_matrix(wo_ckt *c)
         REMAP(c->ind[i].pBB); REMAP(c->ind[i].pPB); REMAP(c->ind[i].pNB); REMAP(c->ind[i].pBN); REMAP(c->ind[i].pBP);
     }
     for (int i = 0; i < c->nmut; i++) { REMAP(c->mut[i].p12); REMAP(c->mut[i].p21); }
+    for (int i = 0; i < c->njj; i++) {
+        JJ *j = &c->jj[i];
+        REMAP(j->pPP); REMAP(j->pNN); REMAP(j->pNP); REMAP(j->pPN); REMAP(j->pHH);
+        REMAP(j->pRPP); REMAP(j->pRPN); REMAP(j->pRNP); REMAP(j->pRNN);
+    }
     for (int i = 0; i < c->nsrc; i++) {
         REMAP(c->src[i].pPB); REMAP(c->src[i].pNB); REMAP(c->src[i].pBN); REMAP(c->src[i].pBP);
     }
@@ -936,6 +959,8 @@ wo_ckt *wo_create(const b200_deck *dk)
     c->ind = xcalloc(c->nind, sizeof(Ind));
     c->nmut = dk->nmut;
     c->mut = xcalloc(c->nmut, sizeof(Mut));
+    c->njj = dk->njj;
+    c->jj = xcalloc(c->njj, sizeof(JJ));
     c->nord = dk->norder;
     c->ord = xcalloc(c->nord, sizeof(DevRef));
     for (int i = 0; i < c->nord; i++) {
@@ -1023,6 +1048,25 @@ wo_ckt *wo_create(const b200_deck *dk)
             break; }
         case B200_DEV_MUT:
             break;              /* set up after the inductors, below */
+        case B200_DEV_JJ: {
+            /* jjset.cc:130-200 (pointers), :609-715 + :794 (instance part of JJdev::setup).
+             * The reference sets JJ models up before every other type (ckt.cc:2140-2157); with
+             * no lser / lsh they create no nodes, so only the state offsets differ. */
+            JJ *j = &c->jj[i];
+            j->in = dk->jj[i]; j->mod = dk->jj_models[dk->jj[i].model];
+            j->pos = j->in.pos; j->neg = j->in.neg; j->phs = j->in.phase_node;
+            j->pPP = coo_add(c, j->pos, j->pos);
+            j->pNN = coo_add(c, j->neg, j->neg);
+            j->pNP = coo_add(c, j->neg, j->pos);
+            j->pPN = coo_add(c, j->pos, j->neg);
+            j->pRPP = coo_add(c, j->pos, j->pos);
+            j->pRPN = coo_add(c, j->pos, j->neg);
+            j->pRNP = coo_add(c, j->neg, j->pos);
+            j->pRNN = coo_add(c, j->neg, j->neg);
+            j->pHH = j->phs > 0 ? coo_add(c, j->phs, j->phs) : -1;
+            j->st = c->numStates; c->numStates += JS_NSTATES;
+            jj_setup_instance(j);
+            break; }
         default:
             fprintf(stderr, "wrs_oracle: device kind %d not supported\n", c->ord[o].kind);
             abort();
@@ -1054,6 +1098,16 @@ wo_ckt *wo_create(const b200_deck *dk)
         c->states[i] = xcalloc(c->numStates, sizeof(double));
     c->work = xcalloc(n + 1, sizeof(double));
     c->srcFact = 1.0;
+    c->phase = 0;
+    for (int i = 0; i < c->njj; i++)
+        if (c->jj[i].mod.ictype > 0) {
+            if (!c->phase) c->phase = xcalloc(n + 1, 1);
+            c->phase[c->jj[i].pos] = 1; c->phase[c->jj[i].neg] = 1;
+        }
+    if (c->phase) {
+        for (int i = 0; i < c->nind; i++) { c->phase[c->ind[i].pos] = 1; c->phase[c->ind[i].neg] = 1; }
+        c->phase[0] = 0;
+    }
     return c;
 }
 
@@ -1080,6 +1134,7 @@ int wo_set_param(wo_ckt *c, int param, int index, double value)
         c->res[index].conduct = 1.0/(r*1.0);
         break; }
     case B200_P_SRC_DC:     c->src[index].dc = value; c->src[index].dcGiven = 1; break;
+    case B200_P_JJ_ICS:     c->jj[index].in.ics = value; break;
     case B200_P_IND_L:      c->ind[index].induct = value/1.0;
         for (int k = 0; k < c->nmut; k++) c->mut[k].factor = 0.0;   /* recomputed at the next load */
         break;
@@ -2611,6 +2666,416 @@ static int mos_conv(wo_ckt *c, Mos *m)
 /* ------------------------------------------------------------------------- */
 /* CAP / SRC load                                                             */
 /* ------------------------------------------------------------------------- */
+
+/* ------------------------------------------------------------------------- */
+/* Josephson junction, RSJ level 1: devlib/jj/{jjset,jjload,jjacct,jjic,jjtrun}.cc */
+/* ------------------------------------------------------------------------- */
+#define PHI0      2.067833848e-15            /* wrsCONSTphi0, circuit.h:123 */
+#define PHI0_2PI  (PHI0/(2*M_PI))
+
+static void jj_setup_instance(JJ *j)
+{
+    /* jjset.cc:560-612: temperature factor (carried by the deck: depends on temp_k only),
+     * vshunt default, vless / vmore */
+    const b200_jj_model *m = &j->mod;
+    j->vg = GIVEN(j->in.vg) ? j->in.vg : m->vg;
+    j->tcf = GIVEN(j->in.tcf) ? j->in.tcf : 1.0;
+    j->vshunt = GIVEN(j->in.vshunt) ? j->in.vshunt : m->vshunt;
+    if (j->vshunt < 0.0 || j->vshunt > m->vg) j->vshunt = 0.0;
+    double halfdv = 0.5*m->delv;
+    j->vless = j->vg - halfdv;
+    j->vmore = j->vg + halfdv;
+    /* :613-635 ics / area */
+    if (GIVEN(j->in.ics)) {
+        double ics = j->in.ics;
+        if (ics < m->criti/50 || ics > m->criti*50) ics = m->criti;
+        j->area = ics/m->criti;
+    }
+    else if (GIVEN(j->in.area)) j->area = j->in.area;
+    else j->area = 1;
+    j->criti = m->criti*j->tcf*j->area;
+    /* :683-705 */
+    double sqrta = sqrt(j->area);
+    j->cap = m->cap*(j->area*(1.0 - m->cmu) + sqrta*m->cmu);
+    double gfac = j->area*(1.0 - m->gmu) + sqrta*m->gmu;
+    j->g0 = gfac/m->r0;
+    j->gn = gfac/m->rn;
+    j->gs = j->criti/(m->icfactor*m->delv);
+    j->cr1 = (j->g0 - j->gs)*j->vless;
+    j->cr2 = j->criti/m->icfactor + j->vless*j->g0 - j->vmore*j->gn;
+    j->gshunt = 0.0;
+    if (j->vshunt > 1e-12) {
+        double gshunt = j->criti/j->vshunt - j->g0;
+        if (gshunt > 0.0) j->gshunt = gshunt;
+    }
+    /* :746-790 rtype 3 polynomial */
+    if (m->rtype == 3) {
+        double Gn = (j->criti/m->icfactor + j->vless*j->g0)/j->vmore;
+        double temp = j->vmore*j->vmore;
+        j->g1 = 0.5*(5.0*Gn - j->gs - 4.0*j->g0);
+        j->g2 = (Gn - j->g0 - j->g1)/(temp*temp);
+        j->g1 /= temp;
+        j->cr1 = (Gn - j->gn)*j->vmore;
+    }
+    else { j->g1 = 0; j->g2 = 0; }
+}
+
+typedef struct { double vj, phi, ci, gqt, crhs, crt, dcrt, pfac, ddv; } JJStuff;
+
+static void jj_limiting(wo_ckt *c, JJ *j, JJStuff *js)
+{
+    /* jjload.cc:593-617 */
+    double vprev = c->states[0][j->st + JS_voltage];
+    double absold = vprev < 0 ? -vprev : vprev;
+    double vtop = vprev + js->ddv;
+    double vbot = vprev - js->ddv;
+    if (absold < j->vless) {
+        vtop = SPMAX(vtop, j->vless);
+        vbot = SPMIN(vbot, -j->vless);
+    }
+    else if (vprev > j->vmore) {
+        vtop += 1.0;
+        vbot = SPMIN(vbot, j->vmore);
+    }
+    else if (vprev < -j->vmore) {
+        vtop = SPMAX(vtop, -j->vmore);
+        vbot -= 1.0;
+    }
+    if (js->vj > vtop) js->vj = vtop;
+    else if (js->vj < vbot) js->vj = vbot;
+}
+
+static void jj_iv(JJ *j, JJStuff *js)
+{
+    /* jjload.cc:620-739 (rtype 1, 2, 3; 0 and others: no quasiparticle branch) */
+    const b200_jj_model *m = &j->mod;
+    double vj = js->vj;
+    double absvj = vj < 0 ? -vj : vj;
+    if (m->rtype == 1) {
+        if (absvj < j->vless)
+            js->gqt = j->g0;
+        else if (absvj < j->vmore) {
+            js->gqt = j->gs;
+            js->crhs = (vj >= 0 ? j->cr1 : -j->cr1);
+        }
+        else {
+            js->gqt = j->gn;
+            js->crhs = (vj >= 0 ? j->cr2 : -j->cr2);
+        }
+    }
+    else if (m->rtype == 2) {
+        double dv = 0.5*m->delv;
+        double avj = absvj/dv;
+        double vgdv = j->vg/dv;
+        double gam = avj - vgdv;
+        if (gam > 30.0) gam = 30.0;
+        else if (gam < -30.0) gam = -30.0;
+        double xp = exp(gam);
+        if (vgdv > 30.0) vgdv = 30.0;
+        double xp0 = exp(-vgdv);
+        double A = 0.5*(1.0 - m->icfactor)*j->vg;
+        double As = vj < 0.0 ? -A : A;
+        double xp1 = 1 + xp - xp0;
+        double I = ( (j->g0 + j->gn*xp0*A/dv)*vj + j->gn*(vj - As)*(xp - xp0) ) / xp1;
+        double dIdv = (j->g0 + j->gn*xp0*A/dv)*(xp1 - absvj*xp)/(xp1*xp1) +
+            j->gn*(xp*(absvj - A)/(dv*xp1*xp1) + (xp - xp0)/xp1) ;
+        js->crhs = I - dIdv*vj;
+        js->gqt = dIdv;
+    }
+    else if (m->rtype == 3) {
+        if (absvj < j->vmore) {
+            double temp1 = vj*vj;
+            double temp2 = temp1*temp1;
+            js->gqt = j->g0 + 3.0*j->g1*temp1 + 5.0*j->g2*temp2;
+            temp1 *= vj;
+            temp2 *= vj;
+            js->crhs = -2.0*temp1*j->g1 - 4.0*temp2*j->g2;
+        }
+        else {
+            js->gqt = j->gn;
+            js->crhs = (vj >= 0 ? j->cr1 : -j->cr1);
+        }
+    }
+    else
+        js->gqt = 0;
+}
+
+static void jj_stamp(wo_ckt *c, JJ *j, JJStuff *js)
+{
+    /* jjstuff::jj_load, jjload.cc:790-871 (sin / cos through libm; the reference build uses
+     * the x87 fsincos instruction, jjload.cc:55,808 -- same value to the last bit or two) */
+    double gqt = js->gqt, crhs = js->crhs, crt = js->crt;
+    double *s0 = c->states[0] + j->st;
+    s0[JS_voltage] = js->vj;
+    s0[JS_phase] = js->phi;
+    s0[JS_conI] = js->ci;
+    s0[JS_crti] = js->crt;
+    if (c->mode & MODEDC) s0[JS_qpi] = 0.0;
+    else s0[JS_qpi] = crhs + gqt*js->vj;
+    double si, sctemp;
+    wo_sincos(js->phi, &si, &sctemp);
+    double gcs = js->pfac*crt*sctemp;
+    if (j->mod.pi) { si = -si; gcs = -gcs; }
+    crt *= si;
+    if (c->mode & MODEDC) {
+        crhs += crt - gcs*js->phi;
+        gqt = gcs;
+    }
+    else {
+        crhs += crt - gcs*js->vj;
+        gqt += gcs + c->ag[0]*j->cap;
+        crhs += j->delVdelT*j->cap;
+    }
+    if (j->phs > 0) {
+        int pint;
+        memcpy(&pint, &c->states[1][j->st + JS_phsInt], sizeof(int));
+        c->rhs[j->phs] = js->phi + (4*M_PI)*pint;
+    }
+    if (!j->neg) {
+        ldadd(c, j->pPP, gqt);
+        rhsadd(c, j->pos, -crhs);
+    }
+    else if (!j->pos) {
+        ldadd(c, j->pNN, gqt);
+        rhsadd(c, j->neg, crhs);
+    }
+    else {
+        ldadd(c, j->pPP, gqt);
+        ldadd(c, j->pPN, -gqt);
+        ldadd(c, j->pNP, -gqt);
+        ldadd(c, j->pNN, gqt);
+        rhsadd(c, j->pos, -crhs);
+        rhsadd(c, j->neg, crhs);
+    }
+}
+
+static void jj_shunt(wo_ckt *c, JJ *j)
+{
+    if (j->gshunt > 1e-12) {
+        ldadd(c, j->pRPP, j->gshunt);
+        ldadd(c, j->pRPN, -j->gshunt);
+        ldadd(c, j->pRNP, -j->gshunt);
+        ldadd(c, j->pRNN, j->gshunt);
+    }
+}
+
+static void jj_load(wo_ckt *c, JJ *j)
+{
+    /* JJdev::load, jjload.cc:77-590 */
+    JJStuff js;
+    memset(&js, 0, sizeof(js));
+    double *s0 = c->states[0] + j->st, *s1 = c->states[1] + j->st;
+    if (c->mode & MODEDC) {
+        /* :154-250 phase-mode DC.  Reached here only by the single MODEUIC|MODETRANOP|MODEINITJCT
+         * load that precedes a `uic` transient (tranan.cc:342-350); no solve follows it. */
+        js.ci = 0;
+        js.vj = c->rhsOld[j->pos] - c->rhsOld[j->neg];
+        if (j->mod.ictype != 0) {
+            js.phi = js.vj;
+            s0[JS_phase] = js.phi;
+            s0[JS_voltage] = 0.0;
+            js.pfac = 1.0;
+            js.gqt = 0; js.crhs = 0; js.dcrt = 0;
+            js.crt = j->criti;
+            jj_stamp(c, j, &js);
+        }
+        else {
+            js.phi = 0.0; js.crhs = 0.0; js.dcrt = 0.0; js.crt = 0.0;
+            jj_iv(j, &js);
+            jj_stamp(c, j, &js);
+            jj_shunt(c, j);
+        }
+        return;
+    }
+    js.pfac = c->delta/PHI0_2PI;
+    if (c->order > 1) js.pfac *= .5;
+
+    if (c->mode & MODEINITFLOAT) {
+        js.ci = 0;
+        js.vj = c->rhsOld[j->pos] - c->rhsOld[j->neg];
+        double absvj = fabs(js.vj);
+        double temp = s0[JS_voltage];
+        double absold = fabs(temp);
+        double maxvj = SPMAX(absvj, absold);
+        temp -= js.vj;
+        double absdvj = fabs(temp);
+        if (maxvj >= j->vless) {
+            temp = j->mod.delv*0.5;
+            if (absdvj > temp) {
+                js.ddv = temp;
+                jj_limiting(c, j, &js);
+                absvj = fabs(js.vj);
+                maxvj = SPMAX(absvj, absold);
+                temp = js.vj - s0[JS_voltage];
+                absdvj = fabs(temp);
+            }
+        }
+        /* :335-348 convergence test inside the load */
+        if (!c->noncon) {
+            double tol = c->opt.reltol*maxvj + c->opt.abstol;
+            if (absdvj > tol) c->noncon++;
+        }
+        js.phi = s1[JS_phase];
+        temp = js.vj;
+        if (c->order > 1) temp += s1[JS_voltage];
+        js.phi += js.pfac*temp;
+        js.crhs = 0; js.dcrt = 0;
+        js.crt = j->criti;
+        jj_iv(j, &js);
+        if (j->mod.ictype != 1) js.crt = 0.0;            /* jj_ic, :747-787, ictype 0 */
+        jj_stamp(c, j, &js);
+        jj_shunt(c, j);
+        integrate2(c, j->st + JS_voltage, j->delVdelT);
+        return;
+    }
+    if (c->mode & MODEINITPRED) {
+        /* :416-462 */
+        double y0 = s1[JS_dvdt]*c->pred[0] + c->states[2][j->st + JS_dvdt]*c->pred[1];
+        if (c->order != 1) y0 += s1[JS_dvdt];
+        double temp = s1[JS_voltage];
+        double rag0 = c->order == 1 ? c->delta : .5*c->delta;
+        js.vj = temp + rag0*y0;
+        js.phi = s1[JS_phase];
+        temp = js.vj;
+        if (c->order > 1) temp += s1[JS_voltage];
+        js.phi += js.pfac*temp;
+        js.ci = 0;
+        j->delVdelT = find_ceq(c, j->st + JS_voltage);
+        js.crhs = 0; js.dcrt = 0;
+        js.crt = j->criti;
+        jj_iv(j, &js);
+        if (j->mod.ictype != 1) js.crt = 0.0;
+        jj_stamp(c, j, &js);
+        jj_shunt(c, j);
+        return;
+    }
+    if (c->mode & MODEINITTRAN) {
+        /* :495-587 */
+        if (c->mode & MODEUIC) {
+            js.vj = j->initVoltage;
+            js.phi = j->initPhase;
+            js.ci = 0;
+            s1[JS_voltage] = js.vj;
+            s1[JS_phase] = js.phi;
+            s1[JS_conI] = js.ci;
+        }
+        else {
+            js.vj = 0;
+            s1[JS_voltage] = 0.0;
+            js.phi = s1[JS_phase];
+            js.ci = 0;
+            s1[JS_conI] = js.ci;
+            s0[JS_voltage] = 0.0;
+        }
+        j->delVdelT = find_ceq(c, j->st + JS_voltage);
+        js.crhs = 0; js.dcrt = 0;
+        js.crt = j->criti;
+        jj_iv(j, &js);
+        if (j->mod.ictype != 1) js.crt = 0.0;
+        jj_stamp(c, j, &js);
+        jj_shunt(c, j);
+    }
+}
+
+static void jj_accept(wo_ckt *c)
+{
+    /* JJdev::accept, jjacct.cc:49-145.  The reference loops model by model; the time-step
+     * bound only needs the largest |vj| per model (all instances of a deck's models here share
+     * vdpbak / tsaccl / tsfact per model index). */
+    for (int mi = 0; mi < c->njj; mi++) {
+        /* models in instance order: process each distinct model once */
+        int first = 1;
+        for (int k = 0; k < mi; k++) if (c->jj[k].in.model == c->jj[mi].in.model) { first = 0; break; }
+        if (!first) continue;
+        const b200_jj_model *m = &c->jj[mi].mod;
+        int didm = 0;
+        double vmax = 0;
+        double vth = m->vdpbak/m->tsaccl;
+        for (int i = 0; i < c->njj; i++) {
+            JJ *j = &c->jj[i];
+            if (j->in.model != c->jj[mi].in.model) continue;
+            double *s0 = c->states[0] + j->st;
+            double phi = s0[JS_phase];
+            int pint;
+            memcpy(&pint, &c->states[1][j->st + JS_phsInt], sizeof(int));
+            double twopi = M_PI + M_PI;
+            double fourpi = twopi + twopi;
+            if (phi >= twopi) { phi -= fourpi; pint++; }
+            else if (phi < -twopi) { phi += fourpi; pint--; }
+            s0[JS_phase] = phi;
+            { double z = 0.0; memcpy(&z, &pint, sizeof(int)); memcpy(&s0[JS_phsInt], &pint, sizeof(int)); (void)z; }
+            double phitot = phi + fourpi*pint;
+            if (j->phs > 0) c->rhsOld[j->phs] = phitot;
+            if (j->mod.ictype != 0 && j->criti > 0) {
+                if (!didm) { didm = 1; if (vmax < vth) vmax = vth; }
+                double vj = s0[JS_voltage];
+                if (vj < 0) vj = -vj;
+                if (vmax < vj) vmax = vj;
+            }
+        }
+        if (vmax > 0.0) {
+            double delmax = m->tsfact*PHI0/vmax;
+            if (c->devMaxDelta == 0.0 || delmax < c->devMaxDelta) c->devMaxDelta = delmax;
+        }
+    }
+}
+
+static void jj_getic(wo_ckt *c)
+{
+    /* JJdev::getic, jjic.cc:49-107 (vmax is NOT reset between models, as there) */
+    for (int i = 0; i < c->njj; i++) {
+        JJ *j = &c->jj[i];
+        j->initVoltage = GIVEN(j->in.icv) ? j->in.icv : c->rhs[j->pos] - c->rhs[j->neg];
+        j->initPhase = GIVEN(j->in.icphi) ? j->in.icphi : (j->phs > 0 ? c->rhs[j->phs] : 0);
+    }
+    double vmax = 0;
+    for (int mi = 0; mi < c->njj; mi++) {
+        int first = 1;
+        for (int k = 0; k < mi; k++) if (c->jj[k].in.model == c->jj[mi].in.model) { first = 0; break; }
+        if (!first) continue;
+        const b200_jj_model *m = &c->jj[mi].mod;
+        double vth = m->vdpbak/m->tsaccl;
+        if (m->ictype != 0) {
+            if (vmax < vth) vmax = vth;
+            for (int i = 0; i < c->njj; i++) {
+                JJ *j = &c->jj[i];
+                if (j->in.model != c->jj[mi].in.model) continue;
+                if (j->criti > 0) {
+                    double temp = j->initVoltage;
+                    if (temp < 0) temp = -temp;
+                    if (vmax < temp) vmax = temp;
+                }
+            }
+        }
+        if (vmax > 0) {
+            double delmax = 0.1*m->tsfact*PHI0/vmax;
+            if (c->initDelta == 0.0 || c->initDelta > delmax) c->initDelta = delmax;
+        }
+    }
+}
+
+static void res_load(wo_ckt *c, Res *r)
+{
+    /* RESdev::load, resload.cc:250-292 (linear resistor).  In the phase-mode DC load only the
+     * single `uic` MODEINITJCT load gets here and no solve follows; its stamps are restated for
+     * the phase / ground case that the built decks have (both terminals phase or ground). */
+    if (r->usePreload) return;
+    if ((c->mode & MODEDC) && c->phase) {
+        int vp = r->pos && !c->phase[r->pos], vn = r->neg && !c->phase[r->neg];
+        if (!vp && !vn) {
+            ldadd(c, r->pPP, c->opt.gmin); ldadd(c, r->pNN, c->opt.gmin);
+            ldadd(c, r->pPN, c->opt.gmin); ldadd(c, r->pNP, c->opt.gmin);
+            return;
+        }
+        if (vp && r->neg && c->phase[r->neg]) { ldadd(c, r->pPP, r->conduct); ldadd(c, r->pNP, -r->conduct); return; }
+        if (vn && r->pos && c->phase[r->pos]) { ldadd(c, r->pNN, r->conduct); ldadd(c, r->pPN, -r->conduct); return; }
+    }
+    ldadd(c, r->pPP, r->conduct);
+    ldadd(c, r->pNN, r->conduct);
+    ldadd(c, r->pPN, -r->conduct);
+    ldadd(c, r->pNP, -r->conduct);
+}
+
 static void cap_stamp(wo_ckt *c, Cap *p)
 {
     /* capload.cc:75-97 */
@@ -2792,12 +3257,18 @@ static void preload(wo_ckt *c)
             if (p->pos) { if (p->pPB >= 0) c->Ax[p->pPB] = 1.0; if (p->pBP >= 0) c->Ax[p->pBP] = 1.0; }
             if (p->neg) { if (p->pNB >= 0) c->Ax[p->pNB] = -1.0; if (p->pBN >= 0) c->Ax[p->pBN] = -1.0; }
         }
+        else if (c->ord[o].kind == B200_DEV_JJ) {
+            /* jjset.cc:815-816: the phase node's own equation, x[phs] = rhs[phs] */
+            if (c->jj[i].phs > 0 && c->jj[i].pHH >= 0) c->Ax[c->jj[i].pHH] = 1.0;
+        }
     }
     for (int o = 0; o < c->nord; o++) {
         int i = c->ord[o].index;
         if (c->ord[o].kind == B200_DEV_RES) {
             Res *r = &c->res[i];
-            if (r->conduct != 0.0) {
+            /* restemp.cc:213-223: a resistor on a phase node is loaded, not preloaded */
+            r->usePreload = !(c->phase && ((r->pos && c->phase[r->pos]) || (r->neg && c->phase[r->neg])));
+            if (r->usePreload && r->conduct != 0.0) {
                 ldadd(c, r->pPP, r->conduct);
                 ldadd(c, r->pNN, r->conduct);
                 ldadd(c, r->pPN, -r->conduct);
@@ -2824,7 +3295,8 @@ static int ckt_load(wo_ckt *c)
         case B200_DEV_IND: ind_load(c, &c->ind[i]); break;
         case B200_DEV_MUT: mut_load(c, &c->mut[i]); break;
         case B200_DEV_SRC: src_load(c, &c->src[i]); break;
-        case B200_DEV_RES: break;          /* preloaded, LOAD_SKIP_FLAG */
+        case B200_DEV_JJ: jj_load(c, &c->jj[i]); break;
+        case B200_DEV_RES: res_load(c, &c->res[i]); break;   /* preloaded ones return at once (LOAD_SKIP_FLAG) */          /* preloaded, LOAD_SKIP_FLAG */
         }
     }
     c->trapCheck = tchk;
@@ -3587,6 +4059,11 @@ static int ckt_trunc(wo_ckt *c, double *timeStep)
             terr(c, c->cap[i].st, &timetemp);
         else if (c->ord[o].kind == B200_DEV_IND)
             terr(c, c->ind[i].st, &timetemp);       /* indtrun.cc:58 */
+        else if (c->ord[o].kind == B200_DEV_JJ) {
+            /* jjtrun.cc:52-64: only junctions without a supercurrent bound the step by LTE */
+            if (c->jj[i].mod.ictype == 0 || c->jj[i].criti == 0.0)
+                terr(c, c->jj[i].st + JS_voltage, &timetemp);
+        }
     }
     /* srctrun.cc:45-66: SIN sources bound the step through IFsinData::time_limit
      * (inptran.cc:2666-2680, uses dphimax = .2*pi, circuit.h:495) */
@@ -3704,8 +4181,9 @@ static int tran_interpolate(wo_ckt *c)
 
 static int ckt_accept(wo_ckt *c)
 {
-    /* ckt.cc:355-383 (no device accept functions among MOS/CAP/RES/SRC) */
+    /* ckt.cc:355-383 (device accept: JJ only among the built models) */
     c->devMaxDelta = 0.0;
+    if (c->njj) jj_accept(c);
     double *tmp = c->sols[7];
     for (int i = 7; i > 0; i--) c->sols[i] = c->sols[i-1];
     c->sols[0] = tmp;
@@ -3888,7 +4366,7 @@ static int tran_step(wo_ckt *c)
 static int has_trunc_dev(const wo_ckt *c)
 {
     /* tranan.cc:68-77: any model type with DV_TRUNC (mos.cc:347, cap.cc:147) */
-    return (c->nmos > 0 || c->ncap > 0 || c->nind > 0);      /* ind.cc:128 */
+    return (c->nmos > 0 || c->ncap > 0 || c->nind > 0 || c->njj > 0);      /* ind.cc:128, jj.cc:269 */
 }
 
 int wo_run_tran(wo_ckt *c)
@@ -3900,6 +4378,8 @@ int wo_run_tran(wo_ckt *c)
         b200_mos_model deckmod = c->mos[i].card;
         mos_temp(c, &c->mos[i], &deckmod);
     }
+    for (int i = 0; i < c->njj; i++) jj_setup_instance(&c->jj[i]);
+    c->initDelta = 0.0;
     preload(c);
 
     /* sTRANAN::init, tranan.cc:94-217 */
@@ -3965,6 +4445,7 @@ int wo_run_tran(wo_ckt *c)
         }
         for (int i = 0; i < c->nind; i++)
             if (c->ind[i].icGiven) c->rhs[c->ind[i].br] = c->ind[i].ic;      /* indic.cc:62-63 */
+        if (c->njj) jj_getic(c);
         double *tmp = c->rhs; c->rhs = c->rhsOld; c->rhsOld = tmp;
         c->rhs[0] = 0.0; c->rhsOld[0] = 0.0;
         c->mode = MODEUIC | MODETRANOP | MODEINITJCT;
@@ -3978,8 +4459,12 @@ int wo_run_tran(wo_ckt *c)
         memcpy(c->states[i], c->states[0], c->numStates*sizeof(double));
     c->timePts++;
     c->order = 1;
-    c->delta = SPMIN(c->t_delmax, c->t_step);
-    if (!c->t_nocut) c->delta *= 0.1;
+    if (c->initDelta > 0)                              /* tranan.cc:416-422 */
+        c->delta = c->initDelta;
+    else {
+        c->delta = SPMIN(c->t_delmax, c->t_step);
+        if (!c->t_nocut) c->delta *= 0.1;
+    }
     for (int i = 0; i < 7; i++) c->deltaOld[i] = c->delta;
     c->saveDelta = c->delta;
     c->mode = (c->mode & MODEUIC) | MODETRAN | MODEINITTRAN;

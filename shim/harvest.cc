@@ -13,6 +13,7 @@
 //                         sCKT::load's order (ckt.cc:991-1005 mutuals first, :1146-1161 the rest)
 //   R / C / L / K / V / I devlib/{res,cap,ind,src}/*defs.h instance PODs, "Given" bits -> NaN
 //   MOS levels 1/2/3/6    devlib/mos/mosdefs.h:115-328 (instance), :415-600 (model)
+//   JJ level 1            devlib/jj/jjdefs.h:80-235 (instance), :270-335 (model, post-setup values)
 //   source functions      IFparseNode::tranData() (inpptree.h:262), IFtranData (inptran.h:62-95)
 //   nodes, .ic, .nodeset  sCKTnodeTab (circuit.h:1386-1430)
 //   options               sTASK TSK* (circuit.h:999-1069), .tran job sTRANAN (trandefs.h:148-190)
@@ -39,6 +40,7 @@
 #include "ind/inddefs.h"
 #include "src/srcdefs.h"
 #include "mos/mosdefs.h"
+#include "jj/jjdefs.h"
 
 #include "b200spice.h"
 #include "harvest.h"
@@ -90,10 +92,11 @@ struct b200_harvest {
     std::vector<b200_res> res; std::vector<b200_cap> cap; std::vector<b200_ind> ind;
     std::vector<b200_mut> mut; std::vector<b200_src> src;
     std::vector<b200_mos_model> mosmod; std::vector<b200_mos> mos;
+    std::vector<b200_jj_model> jjmod; std::vector<b200_jj> jj;
     std::vector<std::vector<double>> coefs;
     std::vector<int> ic_node, ns_node, okind, oindex;
     std::vector<double> ic_val, ns_val;
-    std::map<const void*, int> ind_index, mosmod_index;
+    std::map<const void*, int> ind_index, mosmod_index, jjmod_index;
     std::vector<std::string> names[B200_DEV_NKINDS];      // instance names per kind, table order
     std::string error;
     int has_tran = 0;
@@ -341,6 +344,39 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
                         order_rest.push_back({B200_DEV_MOS, (int)H->mos.size()});
                         H->mos.push_back(x); H->names[B200_DEV_MOS].push_back(iname);
                     }
+                    else if (!strcmp(dn, "JJ")) {
+                        // the model AFTER JJdev::setup's model pass (jjset.cc:196-545); the
+                        // instance's temperature factor and gap (jjset.cc:560-596)
+                        sJJmodel *m = (sJJmodel*)dm;
+                        sJJinstance *q = (sJJinstance*)gi;
+                        if (q->JJcontrol || q->JJlser > 0.0 || q->JJlsh > 0.0) { H->error = "JJ control / lser / lsh"; return B200_E_UNSUPP; }
+                        auto it = H->jjmod_index.find(m);
+                        if (it == H->jjmod_index.end()) {
+                            b200_jj_model y;
+                            memset(&y, 0, sizeof(y));
+                            y.rtype = m->JJrtype; y.ictype = m->JJictype; y.pi = m->JJpi;
+                            y.criti = m->JJcriti; y.vg = m->JJvgnom; y.delv = m->JJdelv;
+                            y.r0 = m->JJr0; y.rn = m->JJrn; y.cap = m->JJcap;
+                            y.icfactor = m->JJicFactor; y.cmu = m->JJcmu; y.gmu = m->JJgmu;
+                            y.vshunt = m->JJvShuntGiven ? m->JJvShunt : 0.0;
+                            y.vdpbak = m->JJvdpbak; y.tsaccl = m->JJtsaccl; y.tsfact = m->JJtsfact;
+                            it = H->jjmod_index.emplace(m, (int)H->jjmod.size()).first;
+                            H->jjmod.push_back(y);
+                        }
+                        b200_jj x;
+                        memset(&x, 0, sizeof(x));
+                        x.pos = ext(q->JJrealPosNode); x.neg = ext(q->JJnegNode);
+                        x.phase_node = q->JJphsNode > 0 ? ext(q->JJphsNode) : 0;
+                        x.model = it->second;
+                        x.area = opt(q->JJareaGiven && !q->JJicsGiven, q->JJarea);
+                        x.ics = opt(q->JJicsGiven, q->JJics);
+                        x.vshunt = opt(q->JJvshuntGiven, q->JJvshunt);
+                        x.vg = q->JJvg; x.tcf = q->JJtcf;
+                        x.icv = opt(q->JJinitVoltGiven, q->JJinitVoltage);
+                        x.icphi = opt(q->JJinitPhaseGiven, q->JJinitPhase);
+                        order_rest.push_back({B200_DEV_JJ, (int)H->jj.size()});
+                        H->jj.push_back(x); H->names[B200_DEV_JJ].push_back(iname);
+                    }
                     else {
                         H->error = std::string("device not built: ") + dn;
                         return B200_E_UNSUPP;
@@ -364,6 +400,8 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
     D.nsrc = (int)H->src.size(); D.src = H->src.data();
     D.nmosmod = (int)H->mosmod.size(); D.mos_models = H->mosmod.data();
     D.nmos = (int)H->mos.size(); D.mos = H->mos.data();
+    D.njjmod = (int)H->jjmod.size(); D.jj_models = H->jjmod.data();
+    D.njj = (int)H->jj.size(); D.jj = H->jj.data();
     D.norder = (int)H->okind.size(); D.order_kind = H->okind.data(); D.order_index = H->oindex.data();
     return B200_OK;
 }
@@ -385,7 +423,7 @@ extern "C" int b200_harvest_run(sCKT *ckt, const char *libpath, int ntrials, int
     rc = api.create(&H->deck, ntrials, device, &b);
     if (rc) { b200_harvest_free(H); return rc; }
     for (int i = 0; i < nparams && !rc; i++) {
-        int kind = param_id[i] >= B200_P_SRC_DC ? B200_DEV_SRC : param_id[i] >= B200_P_IND_L ? B200_DEV_IND :
+        int kind = param_id[i] >= B200_P_JJ_ICS ? B200_DEV_JJ : param_id[i] >= B200_P_SRC_DC ? B200_DEV_SRC : param_id[i] >= B200_P_IND_L ? B200_DEV_IND :
                    param_id[i] >= B200_P_RES_R ? B200_DEV_RES : param_id[i] >= B200_P_CAP_C ? B200_DEV_CAP : B200_DEV_MOS;
         int idx = b200_harvest_find(H, kind, inst_name[i]);
         rc = idx < 0 ? B200_E_BADPARM : api.set_param(b, param_id[i], idx, values[i]);

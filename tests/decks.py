@@ -266,6 +266,7 @@ def variants():
         "ro3_rd": ro_rd(3),
         "rc_sin": rc_sin(),
     }
+    out.update(jj_variants())
     return out
 
 
@@ -274,3 +275,59 @@ def _one_ic():
     d.ics.clear()
     d.ic(n0=3.3)
     return d
+
+
+# ---- Josephson-junction decks (RSJ level 1, `uic` starts; examples/JJexamples shapes) ----------
+JJ_CARD = dict(rtype=1, cct=1, vg=2.8e-3, delv=0.1e-3, icrit=1e-3, rn=1.7, rsub=17.0, cap=0.7e-12)
+
+
+def jj_single(**card):
+    """One shunted junction driven over its critical current by a current ramp: the junction
+    switches and runs (phase slips of 2 pi, step bound tsfact*Phi0/|vj| from JJdev::accept)."""
+    d = Deck(title="single jj")
+    d.isource("i1", "0", "1", pulse=(0, 1.5e-3, 5e-12, 10e-12, 10e-12, 60e-12, 200e-12))
+    d.jj("b1", "1", "0", "jj1")
+    d.resistor("r1", "1", "0", 1.0)
+    d.jj_model("jj1", **dict(JJ_CARD, **card))
+    d.tran(0.5e-12, 100e-12, uic=True)
+    return d
+
+
+def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, **card):
+    """Josephson transmission line (the `jtl` subcircuit of examples/JJexamples/nor_mc.cir
+    flattened and repeated): biased junctions coupled by inductors, an SFQ pulse launched at
+    the input propagates down the line.  Bias currents ramp up from zero (uic start)."""
+    d = Deck(title=f"jtl{n}")
+    mc = dict(JJ_CARD, **card)
+    if vshunt is not None:
+        mc["vshunt"] = vshunt
+    d.jj_model("jj1", **mc)
+    d.isource("iin", "0", "in", pulse=(0, 0.6e-3, 40e-12, 3e-12, 3e-12, 2e-12, 200e-12))
+    d.inductor("lin", "in", "a0", 2.0e-12)
+    for i in range(n):
+        a = f"a{i}"
+        kw = {"phase": f"ph{i}"} if phase_nodes else {}
+        d.jj(f"b{i}", a, "0", "jj1", ics=ics*(1.0 + 0.05*(i % 3)), **kw)
+        if vshunt is None:
+            d.resistor(f"rs{i}", a, "0", 3.0)
+        d.isource(f"ib{i}", "0", a, pulse=(0, 0.7*ics, 0.0, 20e-12, 1e-12, 1.0, 2.0))
+        if i + 1 < n:
+            d.inductor(f"l{i}", a, f"a{i+1}", 4.0e-12)
+    d.resistor("rl", f"a{n-1}", "0", 5.0)
+    d.tran(0.5e-12, 120e-12, uic=True)
+    return d
+
+
+def jj_variants():
+    return {
+        "jj_single": jj_single(),
+        "jj_single_rtype2": jj_single(rtype=2),
+        "jj_single_rtype3": jj_single(rtype=3),
+        "jj_single_cct0": jj_single(cct=0),
+        "jj_single_pi": jj_single(pijj=1),
+        "jtl6": jtl(6),
+        "jtl6_phase": jtl(6, phase_nodes=True),
+        "jtl6_vshunt": jtl(6, vshunt=0.6857e-3),
+        "jtl6_gear": jtl(6).options(method=1),
+        "jtl12": jtl(12),
+    }

@@ -336,6 +336,34 @@ def test_reciprocal_division_is_ieee_division():
         assert rc == 0 and bad.value == 0, (emin, emax, bad.value)
 
 
+def test_monte_carlo_jj_critical_currents():
+    """Josephson transmission line with per-trial critical currents (B200_P_JJ_ICS): criti, cap,
+    g0, gn, gs, cr1, cr2 are re-derived per trial on the device (jjset.cc:613-705); the step
+    bound of JJdev::accept (tsfact*Phi0/max|vj|) makes every trial's step sequence its own."""
+    from tests.decks import jtl
+    from xictools_b200.deck import DEV_JJ, P_JJ_ICS
+    d = jtl(6)
+    rng = np.random.default_rng(12)
+    ntr = 21
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_JJ]):
+        v = np.full(ntr, e.params["ics"])
+        v[1:] *= 1.0 + 0.1*rng.standard_normal(ntr - 1)
+        ov[(P_JJ_ICS, i)] = v
+    compare(d, ntr, ov)
+
+
+def test_jj_needs_uic():
+    """The phase-mode DC operating point is not built: a JJ deck without `uic` is refused."""
+    from tests.decks import jtl
+    d = jtl(3)
+    ts, tp, t0, tm, _ = d.tran_args
+    d.tran(ts, tp, t0, tm, uic=False)
+    with pytest.raises(engine.B200Error) as e:
+        engine.Batch(d, 2)
+    assert e.value.code == 13
+
+
 def test_packed_rows_equal_single_rows():
     """b200_batch_set_params (one transfer + device scatter) against b200_batch_set_param row by
     row: bit-identical results; a single row given afterwards overrides its packed row."""

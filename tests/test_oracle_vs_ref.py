@@ -42,6 +42,30 @@ def test_monte_carlo_trials_match_reference():
         assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < 1e-9
 
 
+def test_jj_monte_carlo_trials_match_reference():
+    """Per-trial critical currents (let @b1[ics] = ... of an .exec block): instance-level
+    re-derivation of criti / cap / g0 / gn / gs / cr1 / cr2 (jjset.cc:613-705)."""
+    from tests.decks import jtl
+    from xictools_b200.deck import DEV_JJ, P_JJ_ICS
+    d = jtl(6)
+    rng = np.random.default_rng(5)
+    ntr = 4
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_JJ]):
+        v = np.full(ntr, e.params["ics"])
+        v[1:] *= 1.0 + 0.1*rng.standard_normal(ntr - 1)
+        ov[(P_JJ_ICS, i)] = v
+    counts = set()
+    for t in range(ntr):
+        ref = RefSim().run(d.to_spice({k: v[t] for k, v in ov.items()}))
+        o = Oracle(d, ov, t).run()
+        assert {k: o[k] for k in KEYS} == {k: ref[k] for k in KEYS}
+        idx = [o["names"].index(nm) for nm in ref["names"]]
+        assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < 1e-9
+        counts.add(ref["numiter"])
+    assert len(counts) > 1
+
+
 def test_uic_failure_mode_matches_reference():
     # the reference aborts this UIC start with E_MATHOVF (errors.h:119); so must the oracle
     d = ring_oscillator(5, uic=True)

@@ -152,8 +152,14 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
 {
     const b200_options &o = dk->opt;
     if (dk->njj) {
-        err = "JJ devices are not built yet (SURVEY.md section 8 rows a4-a5)";
-        return B200_E_UNSUPP;
+        // what of devlib/jj is built (include/b200spice.h, b200_jj_model)
+        if (!dk->uic) { err = "JJ decks need `.tran ... uic`: the phase-mode DC operating point (jjload.cc:154-250) is not built"; return B200_E_UNSUPP; }
+        if (dk->njjmod > JJ_MAXMODELS) { err = "more JJ models than JJ_MAXMODELS"; return B200_E_UNSUPP; }
+        for (int i = 0; i < dk->njjmod; i++) {
+            const b200_jj_model &m = dk->jj_models[i];
+            if (m.rtype < 0 || m.rtype > 3) { err = "JJ rtype 4 (control current) is not built"; return B200_E_UNSUPP; }
+            if (m.ictype < 0 || m.ictype > 1) { err = "JJ ictype 2..4 (control current) is not built"; return B200_E_UNSUPP; }
+        }
     }
     an.n = 0;
     an.ntype.assign(1, 0);
@@ -191,6 +197,33 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     MU.n = dk->nmut; MU.ind1.resize(MU.n); MU.ind2.resize(MU.n); MU.k.resize(MU.n);
     MU.cslot.assign((size_t)MU.n*2, -1);
     std::vector<int> mut_coo((size_t)MU.n*2, -1);
+    JJTopo &J = an.jj;
+    J.n = dk->njj; J.nmodels = dk->njjmod;
+    J.models.assign(dk->jj_models, dk->jj_models + dk->njjmod);
+    J.pos.resize(J.n); J.neg.resize(J.n); J.phs.resize(J.n); J.model.resize(J.n); J.state.resize(J.n);
+    J.cslot.assign((size_t)J.n*JT_NSTAMP, -1); J.rslot.assign((size_t)J.n*JR_NRHS, -1);
+    J.vless.resize(J.n); J.vmore.resize(J.n); J.vg.resize(J.n); J.initV.assign(J.n, 0.0); J.initPhi.assign(J.n, 0.0);
+    J.area0.resize(J.n); J.ics0.resize(J.n); J.vshunt.resize(J.n); J.tcf.resize(J.n);
+    std::vector<int> jj_coo((size_t)J.n*9, -1);
+    // phase flags (jjset.cc:656-681, indset.cc:104-120): nodes of junctions with a supercurrent,
+    // and -- once any such junction exists -- nodes of inductors
+    std::vector<char> phase_node(dk->nnodes + 1, 0);
+    bool jjDCphase = false;
+    for (int i = 0; i < dk->njj; i++) {
+        const b200_jj &in = dk->jj[i];
+        if (in.model < 0 || in.model >= dk->njjmod) { err = "bad JJ model index"; return B200_E_BADPARM; }
+        if (dk->jj_models[in.model].ictype > 0) {
+            if (in.pos > 0) phase_node[in.pos] = 1;
+            if (in.neg > 0) phase_node[in.neg] = 1;
+            jjDCphase = true;
+        }
+    }
+    if (jjDCphase)
+        for (int i = 0; i < dk->nind; i++) {
+            if (dk->ind[i].pos > 0) phase_node[dk->ind[i].pos] = 1;
+            if (dk->ind[i].neg > 0) phase_node[dk->ind[i].neg] = 1;
+        }
+    std::vector<char> res_preload(dk->nres, 1);
     std::vector<double> res_g(dk->nres, 0.0);
     std::vector<char> mos_has_dcon(M.n, 0), mos_has_scon(M.n, 0);
 
@@ -254,6 +287,30 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (fabs(r) < o.resmin)
                 r = (r < 0.0) ? -o.resmin : o.resmin;
             res_g[i] = mm/(r*1.0);                       // restemp.cc:209
+            // restemp.cc:213-223: no preload when a terminal is a phase node
+            if (jjDCphase && ((in.pos > 0 && phase_node[in.pos]) || (in.neg > 0 && phase_node[in.neg])))
+                res_preload[i] = 0;
+            break; }
+        case B200_DEV_JJ: {
+            // jjset.cc:130-200 (TSTALLOC order), :560-612 (vshunt, vless / vmore), :794 (states)
+            const b200_jj &in = dk->jj[i];
+            const b200_jj_model &md = dk->jj_models[in.model];
+            J.pos[i] = in.pos; J.neg[i] = in.neg; J.phs[i] = in.phase_node; J.model[i] = in.model;
+            J.state[i] = an.numStates; an.numStates += JS_NSTATES;
+            J.vg[i] = given(in.vg) ? in.vg : md.vg;
+            J.tcf[i] = given(in.tcf) ? in.tcf : 1.0;
+            double vsh = given(in.vshunt) ? in.vshunt : md.vshunt;
+            if (vsh < 0.0 || vsh > md.vg) vsh = 0.0;
+            J.vshunt[i] = vsh;
+            J.vless[i] = J.vg[i] - 0.5*md.delv;
+            J.vmore[i] = J.vg[i] + 0.5*md.delv;
+            J.area0[i] = in.area; J.ics0[i] = in.ics;
+            int *c = &jj_coo[(size_t)i*9];
+            c[JT_PP] = coo.add(in.pos, in.pos); c[JT_NN] = coo.add(in.neg, in.neg);
+            c[JT_NP] = coo.add(in.neg, in.pos); c[JT_PN] = coo.add(in.pos, in.neg);
+            c[JT_RPP] = coo.add(in.pos, in.pos); c[JT_RPN] = coo.add(in.pos, in.neg);
+            c[JT_RNP] = coo.add(in.neg, in.pos); c[JT_RNN] = coo.add(in.neg, in.neg);
+            c[8] = in.phase_node > 0 ? coo.add(in.phase_node, in.phase_node) : -1;
             break; }
         case B200_DEV_SRC: {
             const b200_src &in = dk->src[i];
@@ -371,7 +428,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     // ... resistor conductances are ldadd in temp() (restemp.cc:218-229), load order
     for (int oi = 0; oi < dk->norder; oi++) {
         int i = dk->order_index[oi];
-        if (dk->order_kind[oi] == B200_DEV_RES && res_g[i] != 0.0) {
+        if (dk->order_kind[oi] == B200_DEV_RES && res_g[i] != 0.0 && res_preload[i]) {
             const int *c = &res_coo[(size_t)i*4];
             if (c[0] >= 0) an.Ainit[coo2ax[c[0]]] += res_g[i];
             if (c[1] >= 0) an.Ainit[coo2ax[c[1]]] += res_g[i];
@@ -379,9 +436,45 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (c[3] >= 0) an.Ainit[coo2ax[c[3]]] += -res_g[i];
         }
     }
+    // the phase node's own equation x[phs] = rhs[phs] is preldset (jjset.cc:815-816)
+    for (int i = 0; i < J.n; i++)
+        if (jj_coo[(size_t)i*9 + 8] >= 0) an.Ainit[coo2ax[jj_coo[(size_t)i*9 + 8]]] = 1.0;
+    an.rload_slot.clear(); an.rload_val.clear();
     for (int oi = 0; oi < dk->norder; oi++) {
         int i = dk->order_index[oi];
         switch (dk->order_kind[oi]) {
+        case B200_DEV_RES: {
+            // RESdev::load for a resistor that was not preloaded (resload.cc:288-292): four
+            // constant terms at this place of the load order
+            if (res_preload[i]) break;
+            const int *c = &res_coo[(size_t)i*4];
+            const double v[4] = { res_g[i], res_g[i], -res_g[i], -res_g[i] };
+            for (int k = 0; k < 4; k++) {
+                int sl = add_c(c[k]);
+                if (sl >= 0) { an.rload_slot.push_back(sl); an.rload_val.push_back(v[k]); an.dc_active[coo2ax[c[k]]] = 1; }
+            }
+            break; }
+        case B200_DEV_JJ: {
+            const int *c = &jj_coo[(size_t)i*9];
+            int *cs = &J.cslot[(size_t)i*JT_NSTAMP];
+            int *rs = &J.rslot[(size_t)i*JR_NRHS];
+            // jj_load (jjload.cc:826-866): the phase node's rhs is stored first
+            if (J.phs[i] > 0) rs[JR_phs] = add_r(J.phs[i]);
+            if (!J.neg[i]) { cs[JT_PP] = add_c(c[JT_PP]); rs[JR_pos] = add_r(J.pos[i]); }
+            else if (!J.pos[i]) { cs[JT_NN] = add_c(c[JT_NN]); rs[JR_neg] = add_r(J.neg[i]); }
+            else {
+                cs[JT_PP] = add_c(c[JT_PP]); cs[JT_PN] = add_c(c[JT_PN]);
+                cs[JT_NP] = add_c(c[JT_NP]); cs[JT_NN] = add_c(c[JT_NN]);
+                rs[JR_pos] = add_r(J.pos[i]); rs[JR_neg] = add_r(J.neg[i]);
+            }
+            // the shunt implied by vshunt (jjload.cc:351-356); a trial whose gshunt is not
+            // positive adds an exact 0.0
+            if (J.vshunt[i] > 1e-12) {
+                cs[JT_RPP] = add_c(c[JT_RPP]); cs[JT_RPN] = add_c(c[JT_RPN]);
+                cs[JT_RNP] = add_c(c[JT_RNP]); cs[JT_RNN] = add_c(c[JT_RNN]);
+            }
+            for (int k = 0; k < JT_NSTAMP; k++) if (cs[k] >= 0) an.dc_active[coo2ax[c[k]]] = 1;
+            break; }
         case B200_DEV_MOS: {
             const int *c = &mos_coo[(size_t)i*MT_NSTAMP];
             int *cs = &M.cslot[(size_t)i*MT_NSTAMP];
@@ -452,7 +545,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
         err = "bad .tran parameters"; return B200_E_BADPARM;
     }
     an.maxStep = dk->tmax;
-    an.nocut = !(M.n > 0 || Cp.n > 0 || L.n > 0);  // tranan.cc:68-77 DV_TRUNC devices
+    an.nocut = !(M.n > 0 || Cp.n > 0 || L.n > 0 || J.n > 0);  // tranan.cc:68-77 DV_TRUNC devices (jj.cc:269)
     if (an.maxStep == 0) {
         an.maxStep = (an.t_stop - an.t_start)/50;
         if (o.oldsteplim) { if (an.t_step > an.maxStep) an.maxStep = an.t_step; }
@@ -471,6 +564,38 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     an.delmin = delmin;
     an.minBreak = (o.minbreak > 0) ? o.minbreak : delmin*50.0;
     an.npoints_max = (int)floor((an.t_stop - an.t_start)/an.t_step + 0.5) + 3;
+
+    // ---- JJdev::getic (jjic.cc:49-107): start values of a `uic` run and the first time step.
+    // ic() has put the .ic / nodeset values into CKTrhs (ckt.cc:908-925); vmax is carried
+    // across models as there.  criti > 0 for every junction with a supercurrent (area > 0).
+    an.initDelta = 0.0;
+    if (J.n) {
+        auto rhs0 = [&](int node) { return node > 0 ? (an.ic_given[node] ? an.ic_val[node] : (an.ns_given[node] ? an.ns_val[node] : 0.0)) : 0.0; };
+        for (int i = 0; i < J.n; i++) {
+            const b200_jj &in = dk->jj[i];
+            J.initV[i] = given(in.icv) ? in.icv : rhs0(J.pos[i]) - rhs0(J.neg[i]);
+            J.initPhi[i] = given(in.icphi) ? in.icphi : (J.phs[i] > 0 ? rhs0(J.phs[i]) : 0.0);
+        }
+        const double PHI0 = 2.067833848e-15;                 // circuit.h:123
+        double vmax = 0;
+        std::vector<char> seen(J.nmodels, 0);
+        for (int a = 0; a < J.n; a++) {                      // models in first-instance order
+            int m = J.model[a];
+            if (seen[m]) continue;
+            seen[m] = 1;
+            const b200_jj_model &md = J.models[m];
+            double vth = md.vdpbak/md.tsaccl;
+            if (md.ictype != 0) {
+                if (vmax < vth) vmax = vth;
+                for (int i = 0; i < J.n; i++)
+                    if (J.model[i] == m) { double v = fabs(J.initV[i]); if (vmax < v) vmax = v; }
+            }
+            if (vmax > 0) {
+                double delmax = 0.1*md.tsfact*PHI0/vmax;
+                if (an.initDelta == 0.0 || an.initDelta > delmax) an.initDelta = delmax;
+            }
+        }
+    }
 
     // ---- breakpoints + source run-time parameters (tranan.cc:330-340, inptran.cc) ----
     BreakTab bt;
@@ -961,6 +1086,12 @@ int b200_build_lu(Analysis &an)
     remap(an.src.rslot, newr);
     remap(an.ind.cslot, newc); remap(an.ind.rslot, newr);
     remap(an.mut.cslot, newc);
+    remap(an.jj.cslot, newc); remap(an.jj.rslot, newr);
+    // resistors loaded in place: constant terms inside the runs (written once, like Ainit)
+    for (size_t k = 0; k < an.rload_slot.size(); k++) {
+        an.const_idx.push_back(newc[an.rload_slot[k]]);
+        an.const_val.push_back(an.rload_val[k]);
+    }
     return B200_OK;
 }
 

@@ -127,6 +127,26 @@ struct MutTopo {
     std::vector<double> k;
     std::vector<int> cslot;                     // [2n]: (br1,br2), (br2,br1)
 };
+// Josephson junctions, RSJ level 1 (jjdefs.h:237-250 states; no lser / lsh / control)
+enum { JS_voltage, JS_dvdt, JS_phase, JS_conI, JS_phsInt, JS_crti, JS_qpi, JS_NSTATES };
+// per-instance derived parameters (the instance part of JJdev::setup, jjset.cc:609-790)
+enum { JP_criti, JP_cap, JP_g0, JP_gn, JP_gs, JP_g1, JP_g2, JP_cr1, JP_cr2, JP_gshunt, JP_NPARAMS };
+// contribution slots of one junction in the reference's ldadd / rhsadd order (jjload.cc:826-871,
+// then the shunt resistor :351-356)
+enum { JT_PP, JT_PN, JT_NP, JT_NN, JT_RPP, JT_RPN, JT_RNP, JT_RNN, JT_NSTAMP };
+enum { JR_phs, JR_pos, JR_neg, JR_NRHS };
+#define JJ_MAXMODELS 8
+#define JJ_PHI0      2.067833848e-15          /* wrsCONSTphi0, circuit.h:123 */
+#define JJ_PHI0_2PI  (JJ_PHI0/(2*3.14159265358979323846))
+struct JJTopo {
+    int n = 0, nmodels = 0;
+    std::vector<int> pos, neg, phs, model, state;
+    std::vector<int> cslot;                     // [n*JT_NSTAMP]
+    std::vector<int> rslot;                     // [n*JR_NRHS]
+    std::vector<double> vless, vmore, vg, initV, initPhi;   // per instance, shared by all trials
+    std::vector<double> area0, ics0, vshunt, tcf;           // card values (NaN = not given)
+    std::vector<b200_jj_model> models;
+};
 struct SrcTopo {
     int n = 0;
     std::vector<int> kind, pos, neg, branch, fn, dcgiven;
@@ -190,8 +210,13 @@ struct Analysis {
     std::vector<double> ic_val, ns_val;
     int hadNodeset = 0;
     // device tables
-    MosTopo mos; CapTopo cap; SrcTopo src; IndTopo ind; MutTopo mut;
+    MosTopo mos; CapTopo cap; SrcTopo src; IndTopo ind; MutTopo mut; JJTopo jj;
     int nres = 0;
+    double initDelta = 0;                       // CKTinitDelta from JJdev::getic (jjic.cc:78-104), 0 = unset
+    // resistors that touch a phase node are loaded every iteration instead of preloaded
+    // (restemp.cc:213-248): their +-g are constant contributions at the resistor's place in the
+    // load order (contribution slot, value)
+    std::vector<int> rload_slot; std::vector<double> rload_val;
     // ordering: position -> original (0-based)
     std::vector<int> rowperm, colperm;
     // LU structure in permuted positions

@@ -50,7 +50,11 @@ struct b200_batch {
     std::vector<double> mos_raw[MR_NRAW];                   // [nmos] shared values
     std::map<int, std::vector<double>> mos_var[MR_NRAW];    // inst -> [ntrials]
     std::vector<double> cap_c, cap_ic, src_dc, ind_l, ind_ic;
-    std::map<int, std::vector<double>> cap_var, src_var, ind_var;
+    std::map<int, std::vector<double>> cap_var, src_var, ind_var, jj_var;
+    std::vector<double> jj_ics;                             // [njj] card ics (NaN = not given)
+    double *d_jjics = nullptr; int jjics_ts = 0;
+    double *d_jjprm[JP_NPARAMS] = {0}; int jjprm_ts = -1;
+    const double *d_jj_area0 = nullptr, *d_jj_vshunt = nullptr, *d_jj_tcf = nullptr;
     bool params_dirty = true;
     // packed per-trial rows (b200_batch_set_params): table id (0..MR_NRAW-1 MOS raw, then
     // PT_CAP / PT_IND / PT_SRC), instance index, values on the device as [nrows][ntrials]
@@ -94,7 +98,8 @@ struct b200_batch {
     }
 };
 
-enum { PT_CAP = MR_NRAW, PT_IND = MR_NRAW + 1, PT_SRC = MR_NRAW + 2, PT_NTABLES = MR_NRAW + 3 };
+enum { PT_CAP = MR_NRAW, PT_IND = MR_NRAW + 1, PT_SRC = MR_NRAW + 2, PT_JJ = MR_NRAW + 3,
+       PT_NTABLES = MR_NRAW + 4 };
 
 // row i of a [n][ldt] per-trial table <- the shared value of instance i
 __global__ void k_fill_rows(double *dst, const double *shared, int n, int ldt)
@@ -132,9 +137,11 @@ static int param_table(const b200_batch *b, int param, int index)
     case B200_P_CAP_C: tbl = PT_CAP; break;
     case B200_P_IND_L: tbl = PT_IND; break;
     case B200_P_SRC_DC: tbl = PT_SRC; break;
+    case B200_P_JJ_ICS: tbl = PT_JJ; break;
     default: return -B200_E_UNSUPP;
     }
-    n = tbl < MR_NRAW ? b->an.mos.n : tbl == PT_CAP ? b->an.cap.n : tbl == PT_IND ? b->an.ind.n : b->an.src.n;
+    n = tbl < MR_NRAW ? b->an.mos.n : tbl == PT_CAP ? b->an.cap.n : tbl == PT_IND ? b->an.ind.n :
+        tbl == PT_JJ ? b->an.jj.n : b->an.src.n;
     if (index < 0 || index >= n) return -B200_E_BADPARM;
     return tbl;
 }
@@ -259,6 +266,7 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
         b->ind_ic[i] = given(dk->ind[i].ic) ? dk->ind[i].ic : 0.0;
     }
     b->src_dc = b->an.src.dc;
+    b->jj_ics = b->an.jj.ics0;
 }
 
 int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch **out)
@@ -361,6 +369,30 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Li.nmut = an.mut.n;
     Li.mut1 = b->dupload(an.mut.ind1); Li.mut2 = b->dupload(an.mut.ind2);
     Li.mut_cslot = b->dupload(an.mut.cslot); Li.mutk = b->dupload(an.mut.k);
+    JJView &Jv = Cp.J; JJTopo &jt = an.jj;
+    memset(&Jv, 0, sizeof(Jv));
+    Jv.n = jt.n; Jv.nmodels = jt.nmodels;
+    if (jt.n) {
+        Jv.pos = b->dupload(jt.pos); Jv.neg = b->dupload(jt.neg); Jv.phs = b->dupload(jt.phs);
+        Jv.model = b->dupload(jt.model); Jv.state = b->dupload(jt.state);
+        Jv.cslot = b->dupload(jt.cslot); Jv.rslot = b->dupload(jt.rslot);
+        Jv.vless = b->dupload(jt.vless); Jv.vmore = b->dupload(jt.vmore); Jv.vg = b->dupload(jt.vg);
+        Jv.initV = b->dupload(jt.initV); Jv.initPhi = b->dupload(jt.initPhi);
+        Jv.dvdt = b->dalloc<double>((size_t)jt.n*ldt);
+        b->d_jj_area0 = b->dupload(jt.area0); b->d_jj_vshunt = b->dupload(jt.vshunt);
+        b->d_jj_tcf = b->dupload(jt.tcf);
+        K.njjmod = jt.nmodels;
+        for (int m = 0; m < jt.nmodels; m++) {
+            const b200_jj_model &md = jt.models[m];
+            Jv.rtype[m] = md.rtype; Jv.ictype[m] = md.ictype; Jv.pi[m] = md.pi;
+            Jv.delv[m] = md.delv; Jv.icfactor[m] = md.icfactor;
+            K.jj_limits[m] = md.ictype != 0;
+            K.jj_vth[m] = md.vdpbak/md.tsaccl;
+            K.jj_tsfact[m] = md.tsfact;
+        }
+    }
+    K.initDelta = an.initDelta;
+    h.jj_vmax = b->dalloc<double>((size_t)(jt.nmodels ? jt.nmodels : 1)*ldt);
     SrcView &S = b->S; SrcTopo &st = an.src;
     S.n = st.n;
     S.kind = b->dupload(st.kind); S.fn = b->dupload(st.fn); S.dcgiven = b->dupload(st.dcgiven);
@@ -488,6 +520,9 @@ int b200_batch_set_param(b200_batch *b, int param, int index, const double *valu
     case B200_P_SRC_DC:
         if (index < 0 || index >= b->an.src.n) return B200_E_BADPARM;
         put(b->src_var[index]); b->params_dirty = true; return B200_OK;
+    case B200_P_JJ_ICS:
+        if (index < 0 || index >= b->an.jj.n) return B200_E_BADPARM;
+        put(b->jj_var[index]); b->params_dirty = true; return B200_OK;
     default:
         return B200_E_UNSUPP;
     }
@@ -526,6 +561,7 @@ int b200_batch_set_params(b200_batch *b, int nrows, const int *param, const int 
         }
         else if (tbl[r] == PT_CAP) b->cap_var.erase(index[r]);
         else if (tbl[r] == PT_IND) b->ind_var.erase(index[r]);
+        else if (tbl[r] == PT_JJ) b->jj_var.erase(index[r]);
         else b->src_var.erase(index[r]);
     }
     size_t need = (size_t)nrows*b->ntrials;
@@ -649,6 +685,20 @@ static int prepare_params(b200_batch *b)
     rc = upload_strided(PT_SRC, b->src_dc, b->src_var, b->d_srcdc, b->srcdc_ts);
     if (rc) return rc;
     b->S.dc.base = b->d_srcdc; b->S.dc.ts = b->srcdc_ts; b->S.dc.ld = b->srcdc_ts ? (int)ldt : 1;
+    if (b->an.jj.n) {
+        rc = upload_strided(PT_JJ, b->jj_ics, b->jj_var, b->d_jjics, b->jjics_ts);
+        if (rc) return rc;
+        if (b->jjprm_ts != b->jjics_ts) {
+            for (int k = 0; k < JP_NPARAMS; k++) {
+                b->d_jjprm[k] = b->dalloc<double>(b->jjics_ts ? (size_t)b->an.jj.n*ldt : (size_t)b->an.jj.n);
+                if (!b->d_jjprm[k]) return B200_E_NOMEM;
+                b->Cp.J.prm[k].base = b->d_jjprm[k];
+                b->Cp.J.prm[k].ts = b->jjics_ts;
+                b->Cp.J.prm[k].ld = b->jjics_ts ? (int)ldt : 1;
+            }
+            b->jjprm_ts = b->jjics_ts;
+        }
+    }
     // packed rows into their tables (after the default fill, before the temperature kernel)
     if (!b->pk_tbl.empty()) {
         int nrows = (int)b->pk_tbl.size();
@@ -666,6 +716,24 @@ static int prepare_params(b200_batch *b)
     }
     CK(cudaMemcpyAsync(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice, st));
     launch_mos_temp(st, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);
+    if (b->an.jj.n) {
+        const JJTopo &jt = b->an.jj;
+        JJTempIn in;
+        memset(&in, 0, sizeof(in));
+        in.n = jt.n; in.nmodels = jt.nmodels; in.model = b->Cp.J.model;
+        in.ics.base = b->d_jjics; in.ics.ts = b->jjics_ts; in.ics.ld = b->jjics_ts ? (int)ldt : 1;
+        in.area0 = b->d_jj_area0; in.vshunt = b->d_jj_vshunt; in.tcf = b->d_jj_tcf;
+        in.vless = b->Cp.J.vless; in.vmore = b->Cp.J.vmore;
+        for (int m = 0; m < jt.nmodels; m++) {
+            const b200_jj_model &md = jt.models[m];
+            in.criti[m] = md.criti; in.cap[m] = md.cap; in.cmu[m] = md.cmu; in.gmu[m] = md.gmu;
+            in.r0[m] = md.r0; in.rn[m] = md.rn; in.icfactor[m] = md.icfactor; in.delv[m] = md.delv;
+            in.rtype[m] = md.rtype;
+        }
+        for (int k = 0; k < JP_NPARAMS; k++) in.out[k] = b->d_jjprm[k];
+        in.ts = b->jjics_ts;
+        launch_jj_temp(st, in, b->ntrials, (int)ldt);
+    }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     for (void *q : tmp_shared) cudaFree(q);
@@ -767,7 +835,7 @@ static int run_analysis(b200_batch *b, int analysis)
     if (!E.ok) return B200_E_NOGPU;
     long long launches = 0, ticks = 0, load_launches = 0, solve_launches = 0;
     double ms_load = 0, ms_solve = 0;
-    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->Cp.L.nmut ? 1 : 0) + (b->S.n ? 1 : 0);
+    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->Cp.L.nmut ? 1 : 0) + (b->S.n ? 1 : 0) + (b->Cp.J.n ? 1 : 0);
 
     CK(cudaEventRecord(E.begin, st));
     // tick 0: begin + first load
@@ -935,7 +1003,12 @@ int b200_batch_get_stats(const b200_batch *b, b200_run_stats *st)
     capbytes += 8.0*(1 + 3 + 3 + 2 + 2)*an.ind.n;   // branch current, req/veq/prevFlux, 2 states r/w, 2 stamps
     double srcbytes = 0;
     for (int s : an.src.rslot) if (s >= 0) srcbytes += 8.0;
-    st->algbytes_load_per_launch = (mosbytes + capbytes + srcbytes)*b->ntrials;
+    // JJ: 2 node V, 5 state-1/2 reads, 7 state-0 writes, delVdelT r/w, live stamps,
+    // per-trial derived parameters where ics varies
+    double jjbytes = 8.0*(2 + 5 + 7 + 2)*an.jj.n + (b->jjics_ts ? 8.0*6*an.jj.n : 0.0);
+    for (int sl : an.jj.cslot) if (sl >= 0) jjbytes += 8.0;
+    for (int sl : an.jj.rslot) if (sl >= 0) jjbytes += 8.0;
+    st->algbytes_load_per_launch = (mosbytes + capbytes + srcbytes + jjbytes)*b->ntrials;
     st->algbytes_solve_per_launch = 8.0*((double)an.NC + 2.0*an.n)*b->ntrials;
     return B200_OK;
 }

@@ -430,9 +430,13 @@ __device__ inline void ctl_tran_init(TrialCtl &s, const Consts &K, const CtlShar
     s.vecops |= VO_HIST_INIT;
     s.timePts++;
     s.order = 1;
-    s.delta = DMIN(s.t_delmax, K.t_step);
-    if (!K.nocut)
-        s.delta *= 0.1;
+    if (K.initDelta > 0)                          // CKTinitDelta, tranan.cc:416-417
+        s.delta = K.initDelta;
+    else {
+        s.delta = DMIN(s.t_delmax, K.t_step);
+        if (!K.nocut)
+            s.delta *= 0.1;
+    }
     for (int i = 0; i < 7; i++) s.deltaOld[i] = s.delta;
     s.saveDelta = s.delta;
     s.mode = (s.mode & MODEUIC) | MODETRAN | MODEINITTRAN;
@@ -476,7 +480,7 @@ __device__ inline void ctl_tran_loop_top(TrialCtl &s, const Consts &K, const Ctl
 {
     // ---- sTRANint::accept, tranan.cc:483-554 ----
     s.vecops |= VO_SAVE_SPARE;
-    s.devMaxDelta = 0.0;                          // sCKT::accept, ckt.cc:363
+    s.devMaxDelta = s.jj_dmax;                    // sCKT::accept, ckt.cc:363 + JJdev::accept
     s.sols_base = (s.sols_base + 7) & 7;          // rotate sols, ckt.cc:372-377
     s.vecops |= VO_ACCEPT_SOLS;
     if (s.time > s.breaks[0]) {

@@ -49,6 +49,7 @@ struct TrialCtl {
     int sols_base, st_base;
     int accepted, rejected, numIter, timePts, tranIter, iterCut, trapCut, npts, lastIters;
     int niter_mark;
+    double jj_dmax;                             // JJdev::accept's step bound for the accept being processed (0 = none)
     int vecops;
     int have_save;
     int want_load;                              // a load must follow in this tick
@@ -78,6 +79,9 @@ struct HotView {
     double *lte_rcp;    // [LR_NROWS][ldt] divisors of the LTE divided differences + reciprocals
     int    *sync;       // 1: trial is parked at a time-point boundary (or finished)
     double *lte;        // [2][ldt] min over charges for order, order+1 (un-normalised)
+    // Josephson junctions: max |vj| over the junctions of a model in the trial's latest load
+    // (what JJdev::accept scans state 0 for, jjacct.cc:120-133); zeroed when a load is published
+    double *jj_vmax;    // [nmodels][ldt]
 };
 
 struct Consts {
@@ -88,6 +92,10 @@ struct Consts {
     int nocut, uic, hadNodeset, npoints_max, method;
     int analysis;       // 0: transient (tranan.cc), 1: DC operating point only (dcoan.cc)
     int nbrks, nlat;
+    // Josephson junctions: CKTinitDelta (jjic.cc:78-104) and the per-model accept constants
+    double initDelta;
+    int njjmod; int jj_limits[JJ_MAXMODELS];    // model has a supercurrent (ictype != 0)
+    double jj_vth[JJ_MAXMODELS], jj_tsfact[JJ_MAXMODELS];
 };
 
 struct MosView {
@@ -111,12 +119,22 @@ struct IndView {
     const int *mptr, *mother; const double *mk;
     int nmut; const int *mut1, *mut2, *mut_cslot; const double *mutk;
 };
+struct JJView {
+    int n, nmodels;
+    const int *pos, *neg, *phs, *model, *state, *cslot, *rslot;
+    const double *vless, *vmore, *vg, *initV, *initPhi;     // [n] shared by all trials
+    ParamRef prm[JP_NPARAMS];
+    double *dvdt;       // [n][ldt] JJdelVdelT (instance field, jjload.cc:438)
+    int rtype[JJ_MAXMODELS], ictype[JJ_MAXMODELS], pi[JJ_MAXMODELS];
+    double delv[JJ_MAXMODELS], icfactor[JJ_MAXMODELS];
+};
 struct CapView {
     int n;
     const int *pos, *neg, *state, *cslot, *rslot;
     ParamRef capac, ic;
     double *geq, *ceq;  // [n][ldt]  (CAPgeq / CAPceq instance fields, capload.cc:150-151)
     IndView L;
+    JJView J;           // Josephson junctions travel with the other two-terminal reactive elements
 };
 struct SrcView {
     int n;

@@ -558,6 +558,18 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
             int u = g0 + k;
             if (u < K.ntrials && !hot.sync[u]) return;
         }
+        // JJdev::accept's bound on the next step (jjacct.cc:52-141): per model, the largest |vj|
+        // the trial's last load left in state 0, floored at vdpbak/tsaccl
+        s.jj_dmax = 0.0;
+        for (int m = 0; m < K.njjmod; m++) {
+            if (!K.jj_limits[m]) continue;
+            double vmax = hot.jj_vmax[(size_t)m*K.ldt + t];
+            if (vmax < K.jj_vth[m]) vmax = K.jj_vth[m];
+            if (vmax > 0.0) {
+                double delmax = K.jj_tsfact[m]*JJ_PHI0/vmax;
+                if (s.jj_dmax == 0.0 || delmax < s.jj_dmax) s.jj_dmax = delmax;
+            }
+        }
         ctl_tran_loop_top(s, K, sh);
     }
     // publish for the vector / load kernels of this tick
@@ -570,6 +582,7 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
             hot.order[t] = s.order;
             hot.st_base[t] = s.st_base;
             hot.noncon[t] = 0;
+            for (int m = 0; m < K.njjmod; m++) hot.jj_vmax[(size_t)m*K.ldt + t] = 0.0;
             hot.trapbad[t] = 0;
             hot.trapcheck[t] = s.trapCheck;
             hot.iterno[t] = s.iterno;
@@ -788,6 +801,323 @@ __global__ void k_export_counters(int ntrials, const TrialCtl *ctl, int *counter
 // ---------------------------------------------------------------------------------------
 static inline dim3 grid2(int ntrials, int ny, int bs = 128) { return dim3((ntrials + bs - 1)/bs, ny > 0 ? ny : 1); }
 
+
+// ---------------------------------------------------------------------------------------
+// Josephson junction, RSJ level 1.  JJdev::load + jjstuff::{jj_limiting, jj_iv, jj_load}
+// (devlib/jj/jjload.cc:77-871), the step-bound part of JJdev::accept (jjacct.cc:120-141) and
+// JJdev::trunc (jjtrun.cc:52-64).  One thread per (junction, trial).
+//
+// JJdev::accept also folds the phase into (-2pi, 2pi] with an integer count of 4pi
+// (jjacct.cc:63-80) before the state rotation.  Here the fold is applied where the folded
+// values are first read -- the predictor / first load of the next step reads state 1 -- and
+// written back to state 1; it is idempotent, so a rejected step that re-runs that load changes
+// nothing.  The phase node's value phi + 4pi*n is the same number before and after the fold
+// (up to one rounding of the sum).
+// ---------------------------------------------------------------------------------------
+
+struct JJOp { double vj, phi, gqt, crhs, crt, pfac; };
+
+__device__ __forceinline__ void jj_iv(const JJView &J, int i, int m, int t, JJOp &js)
+{
+    // jjload.cc:620-739, rtype 1 / 2 / 3 (0: no quasiparticle branch)
+    const double vj = js.vj;
+    const double absvj = vj < 0 ? -vj : vj;
+    const int rtype = J.rtype[m];
+    const double g0 = PR(J.prm[JP_g0], i, t), gn = PR(J.prm[JP_gn], i, t);
+    if (rtype == 1) {
+        if (absvj < J.vless[i])
+            js.gqt = g0;
+        else if (absvj < J.vmore[i]) {
+            js.gqt = PR(J.prm[JP_gs], i, t);
+            const double cr1 = PR(J.prm[JP_cr1], i, t);
+            js.crhs = (vj >= 0 ? cr1 : -cr1);
+        }
+        else {
+            js.gqt = gn;
+            const double cr2 = PR(J.prm[JP_cr2], i, t);
+            js.crhs = (vj >= 0 ? cr2 : -cr2);
+        }
+    }
+    else if (rtype == 2) {
+        const double dv = 0.5*J.delv[m];
+        const double avj = absvj/dv;
+        double vgdv = J.vg[i]/dv;
+        double gam = avj - vgdv;
+        if (gam > 30.0) gam = 30.0;
+        else if (gam < -30.0) gam = -30.0;
+        const double xp = exp(gam);
+        if (vgdv > 30.0) vgdv = 30.0;
+        const double xp0 = exp(-vgdv);
+        const double A = 0.5*(1.0 - J.icfactor[m])*J.vg[i];
+        const double As = vj < 0.0 ? -A : A;
+        const double xp1 = 1 + xp - xp0;
+        const double I = ( (g0 + gn*xp0*A/dv)*vj + gn*(vj - As)*(xp - xp0) ) / xp1;
+        const double dIdv = (g0 + gn*xp0*A/dv)*(xp1 - absvj*xp)/(xp1*xp1) +
+            gn*(xp*(absvj - A)/(dv*xp1*xp1) + (xp - xp0)/xp1) ;
+        js.crhs = I - dIdv*vj;
+        js.gqt = dIdv;
+    }
+    else if (rtype == 3) {
+        if (absvj < J.vmore[i]) {
+            const double g1 = PR(J.prm[JP_g1], i, t), g2 = PR(J.prm[JP_g2], i, t);
+            double temp1 = vj*vj;
+            double temp2 = temp1*temp1;
+            js.gqt = g0 + 3.0*g1*temp1 + 5.0*g2*temp2;
+            temp1 *= vj;
+            temp2 *= vj;
+            js.crhs = -2.0*temp1*g1 - 4.0*temp2*g2;
+        }
+        else {
+            js.gqt = gn;
+            const double cr1 = PR(J.prm[JP_cr1], i, t);
+            js.crhs = (vj >= 0 ? cr1 : -cr1);
+        }
+    }
+    else
+        js.gqt = 0;
+}
+
+__global__ void __launch_bounds__(128)
+k_load_jj(Consts K, HotView hot, VecView V, JJView J, const double *rhsOld)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t >= K.ntrials) return;
+    int mode = hot.mode[t];
+    if (!mode) return;
+    TrialCtx c;
+    make_ctx(c, K, hot, V, t, mode);
+    const int st = J.state[i], m = J.model[i];
+    const int pos = J.pos[i], neg = J.neg[i], phs = J.phs[i];
+    const size_t ldt = K.ldt;
+    const double criti = PR(J.prm[JP_criti], i, t);
+    const double cap = PR(J.prm[JP_cap], i, t);
+    const double gshunt = PR(J.prm[JP_gshunt], i, t);
+    double *pdv = J.dvdt + (size_t)i*ldt + t;
+    JJOp js;
+    js.gqt = 0; js.crhs = 0; js.crt = 0; js.pfac = 0; js.vj = 0; js.phi = 0;
+    bool shunt = true;
+    double pint = 0.0;                          // the 4pi count the phase node adds (state 1)
+    if (mode & MODEDC) {
+        // jjload.cc:154-250.  Only the single MODEUIC|MODETRANOP|MODEINITJCT load ahead of a `uic`
+        // transient gets here (tranan.cc:342-350); no solve follows, the states are what counts.
+        js.vj = rhsOld[(size_t)pos*ldt + t] - rhsOld[(size_t)neg*ldt + t];
+        if (J.ictype[m] != 0) {
+            js.phi = js.vj;
+            js.pfac = 1.0;
+            js.crt = criti;
+            shunt = false;
+        }
+        else
+            jj_iv(J, i, m, t, js);
+    }
+    else {
+        js.pfac = c.delta/JJ_PHI0_2PI;
+        if (c.order > 1) js.pfac *= .5;
+        // state 1 as JJdev::accept left it: phase folded into (-2pi, 2pi], 4pi count adjusted
+        double phi1 = ST(c, 1, st + JS_phase);
+        pint = ST(c, 1, st + JS_phsInt);
+        if (!(mode & MODEINITFLOAT)) {
+            const double twopi = M_PI + M_PI, fourpi = twopi + twopi;
+            bool fold = false;
+            if (phi1 >= twopi) { phi1 -= fourpi; pint += 1.0; fold = true; }
+            else if (phi1 < -twopi) { phi1 += fourpi; pint -= 1.0; fold = true; }
+            if (fold) { ST(c, 1, st + JS_phase) = phi1; ST(c, 1, st + JS_phsInt) = pint; }
+        }
+        if (mode & MODEINITFLOAT) {
+            js.vj = rhsOld[(size_t)pos*ldt + t] - rhsOld[(size_t)neg*ldt + t];
+            const double vprev = ST(c, 0, st + JS_voltage);
+            double absvj = fabs(js.vj);
+            const double absold = fabs(vprev);
+            double maxvj = DMAX(absvj, absold);
+            double temp = vprev - js.vj;
+            double absdvj = fabs(temp);
+            const double vless = J.vless[i], vmore = J.vmore[i];
+            if (maxvj >= vless) {
+                temp = J.delv[m]*0.5;
+                if (absdvj > temp) {
+                    // jj_limiting, jjload.cc:593-617
+                    double vtop = vprev + temp;
+                    double vbot = vprev - temp;
+                    if (absold < vless) {
+                        vtop = DMAX(vtop, vless);
+                        vbot = DMIN(vbot, -vless);
+                    }
+                    else if (vprev > vmore) {
+                        vtop += 1.0;
+                        vbot = DMIN(vbot, vmore);
+                    }
+                    else if (vprev < -vmore) {
+                        vtop = DMAX(vtop, -vmore);
+                        vbot -= 1.0;
+                    }
+                    if (js.vj > vtop) js.vj = vtop;
+                    else if (js.vj < vbot) js.vj = vbot;
+                    absvj = fabs(js.vj);
+                    maxvj = DMAX(absvj, absold);
+                    temp = js.vj - vprev;
+                    absdvj = fabs(temp);
+                }
+            }
+            // the convergence test inside the load (jjload.cc:335-348): noncon only ever matters
+            // as zero / nonzero, so "if nobody has flagged yet" reduces to a flag
+            if (absdvj > K.opt.reltol*maxvj + K.opt.abstol) hot.noncon[t] = 1;
+            js.phi = phi1;
+            temp = js.vj;
+            if (c.order > 1) temp += ST(c, 1, st + JS_voltage);
+            js.phi += js.pfac*temp;
+            js.crt = criti;
+        }
+        else if (mode & MODEINITPRED) {
+            double y0 = ST(c, 1, st + JS_dvdt)*c.pred[0] + ST(c, 2, st + JS_dvdt)*c.pred[1];
+            if (c.order != 1) y0 += ST(c, 1, st + JS_dvdt);
+            double temp = ST(c, 1, st + JS_voltage);
+            const double rag0 = c.order == 1 ? c.delta : .5*c.delta;
+            js.vj = temp + rag0*y0;
+            js.phi = phi1;
+            temp = js.vj;
+            if (c.order > 1) temp += ST(c, 1, st + JS_voltage);
+            js.phi += js.pfac*temp;
+            *pdv = dev_find_ceq(c, st + JS_voltage);
+            js.crt = criti;
+        }
+        else if (mode & MODEINITTRAN) {
+            if (mode & MODEUIC) {
+                js.vj = J.initV[i];
+                js.phi = J.initPhi[i];
+                ST(c, 1, st + JS_voltage) = js.vj;
+                ST(c, 1, st + JS_phase) = js.phi;
+                ST(c, 1, st + JS_conI) = 0.0;
+            }
+            else {
+                js.vj = 0;
+                ST(c, 1, st + JS_voltage) = 0.0;
+                js.phi = phi1;
+                ST(c, 1, st + JS_conI) = 0.0;
+            }
+            *pdv = dev_find_ceq(c, st + JS_voltage);
+            js.crt = criti;
+        }
+        else
+            return;
+        jj_iv(J, i, m, t, js);
+        if (J.ictype[m] != 1) js.crt = 0.0;        // jj_ic, jjload.cc:747-787 (ictype 0)
+    }
+    // ---- jjstuff::jj_load, jjload.cc:790-871 ----
+    double gqt = js.gqt, crhs = js.crhs, crt = js.crt;
+    ST(c, 0, st + JS_voltage) = js.vj;          // (the 0.0 of jjload.cc:163 is overwritten here, :800)
+    ST(c, 0, st + JS_phase) = js.phi;
+    ST(c, 0, st + JS_conI) = 0.0;
+    ST(c, 0, st + JS_crti) = js.crt;
+    ST(c, 0, st + JS_qpi) = (mode & MODEDC) ? 0.0 : crhs + gqt*js.vj;
+    if (!(mode & MODEDC)) ST(c, 0, st + JS_phsInt) = pint;
+    double si, co;
+    sincos(js.phi, &si, &co);
+    double gcs = js.pfac*crt*co;
+    if (J.pi[m]) { si = -si; gcs = -gcs; }
+    crt *= si;
+    const double delVdelT = *pdv;
+    if (mode & MODEDC) {
+        crhs += crt - gcs*js.phi;
+        gqt = gcs;
+    }
+    else {
+        crhs += crt - gcs*js.vj;
+        gqt += gcs + c.ag[0]*cap;
+        crhs += delVdelT*cap;
+    }
+    const int *cs = J.cslot + (size_t)i*JT_NSTAMP;
+    const int *rs = J.rslot + (size_t)i*JR_NRHS;
+    if (rs[JR_phs] >= 0) V.contrib[CADDR(K, rs[JR_phs], t)] = js.phi + (4*M_PI)*pint;
+    if (cs[JT_PP] >= 0) V.contrib[CADDR(K, cs[JT_PP], t)] = gqt;
+    if (cs[JT_PN] >= 0) V.contrib[CADDR(K, cs[JT_PN], t)] = -gqt;
+    if (cs[JT_NP] >= 0) V.contrib[CADDR(K, cs[JT_NP], t)] = -gqt;
+    if (cs[JT_NN] >= 0) V.contrib[CADDR(K, cs[JT_NN], t)] = gqt;
+    if (rs[JR_pos] >= 0) V.contrib[CADDR(K, rs[JR_pos], t)] = -crhs;
+    if (rs[JR_neg] >= 0) V.contrib[CADDR(K, rs[JR_neg], t)] = crhs;
+    // the shunt implied by vshunt (jjload.cc:351-356, 462-467, 537-542); not in phase-mode DC
+    const double gsh = (shunt && gshunt > 1e-12) ? gshunt : 0.0;
+    if (cs[JT_RPP] >= 0) V.contrib[CADDR(K, cs[JT_RPP], t)] = gsh;
+    if (cs[JT_RPN] >= 0) V.contrib[CADDR(K, cs[JT_RPN], t)] = -gsh;
+    if (cs[JT_RNP] >= 0) V.contrib[CADDR(K, cs[JT_RNP], t)] = -gsh;
+    if (cs[JT_RNN] >= 0) V.contrib[CADDR(K, cs[JT_RNN], t)] = gsh;
+    if ((mode & MODEINITFLOAT) && !(mode & MODEDC)) {
+        // ckt->integrate(JJvoltage, JJdelVdelT), jjload.cc:391
+        const double q0 = js.vj;
+        const double c0 = c.ag[0]*q0 + delVdelT;
+        ST(c, 0, st + JS_dvdt) = c0;
+        dev_trapcheck(c, st + JS_voltage);
+        if ((mode & MODETRAN) && J.ictype[m] == 0) {
+            // JJdev::trunc: a junction without supercurrent bounds the step by LTE (jjtrun.cc:52-64)
+            double q[4] = { q0, ST(c, 1, st + JS_voltage), ST(c, 2, st + JS_voltage), ST(c, 3, st + JS_voltage) };
+            double m0 = DBL_MAX, m1 = DBL_MAX;
+            dev_lte_charge<true>(c, K.opt, q, c0, ST(c, 1, st + JS_dvdt), st + JS_voltage, m0, m1, c.rcp, c.ldt);
+            atomic_min_pos(c.lte, m0);
+            if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
+        }
+    }
+    // what JJdev::accept will scan if this load turns out to be the last of an accepted step
+    if (J.ictype[m] != 0 && criti > 0) {
+        const double av = fabs(js.vj);
+        atomicMax((unsigned long long*)(hot.jj_vmax + (size_t)m*ldt + t), (unsigned long long)__double_as_longlong(av));
+    }
+}
+
+// The instance part of JJdev::setup (jjset.cc:613-790) per (junction, trial): ics / area ->
+// criti, cap, g0, gn, gs, the piecewise-linear offsets, the rtype 3 polynomial and the shunt.
+__global__ void k_jj_temp(JJTempIn in, int ntrials, int ldt)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t >= (in.ts ? ldt : 1)) return;
+    const int m = in.model[i];
+    const int tt = t < ntrials ? t : 0;         // padding trials repeat trial 0
+    double area;
+    const double ics = PR(in.ics, i, tt);
+    if (!isnan(ics)) {
+        double v = ics;
+        if (v < in.criti[m]/50 || v > in.criti[m]*50) v = in.criti[m];
+        area = v/in.criti[m];
+    }
+    else if (!isnan(in.area0[i])) area = in.area0[i];
+    else area = 1;
+    const double criti = in.criti[m]*in.tcf[i]*area;
+    const double sqrta = sqrt(area);
+    const double cap = in.cap[m]*(area*(1.0 - in.cmu[m]) + sqrta*in.cmu[m]);
+    const double gfac = area*(1.0 - in.gmu[m]) + sqrta*in.gmu[m];
+    const double g0 = gfac/in.r0[m];
+    const double gn = gfac/in.rn[m];
+    const double gs = criti/(in.icfactor[m]*in.delv[m]);
+    const double vless = in.vless[i], vmore = in.vmore[i];
+    double cr1 = (g0 - gs)*vless;
+    const double cr2 = criti/in.icfactor[m] + vless*g0 - vmore*gn;
+    double gshunt = 0.0;
+    if (in.vshunt[i] > 1e-12) {
+        double g = criti/in.vshunt[i] - g0;
+        if (g > 0.0) gshunt = g;
+    }
+    double g1 = 0, g2 = 0;
+    if (in.rtype[m] == 3) {
+        const double Gn = (criti/in.icfactor[m] + vless*g0)/vmore;
+        const double temp = vmore*vmore;
+        g1 = 0.5*(5.0*Gn - gs - 4.0*g0);
+        g2 = (Gn - g0 - g1)/(temp*temp);
+        g1 /= temp;
+        cr1 = (Gn - gn)*vmore;
+    }
+    const size_t at = in.ts ? (size_t)i*ldt + t : (size_t)i;
+    in.out[JP_criti][at] = criti; in.out[JP_cap][at] = cap; in.out[JP_g0][at] = g0;
+    in.out[JP_gn][at] = gn; in.out[JP_gs][at] = gs; in.out[JP_g1][at] = g1; in.out[JP_g2][at] = g2;
+    in.out[JP_cr1][at] = cr1; in.out[JP_cr2][at] = cr2; in.out[JP_gshunt][at] = gshunt;
+}
+
+void launch_jj_temp(cudaStream_t st, const JJTempIn &in, int ntrials, int ldt)
+{
+    if (!in.n) return;
+    int nt = in.ts ? ldt : 1;
+    k_jj_temp<<<dim3((nt + 127)/128, in.n), 128, 0, st>>>(in, ntrials, ldt);
+}
+
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,
     const RawParams &raw, const MosParamsOut &out)
 {
@@ -821,6 +1151,7 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
     if (Cp.L.nmut) k_load_mut<<<grid2(K.ntrials, Cp.L.nmut), 128, 0, st>>>(K, hot, V, Cp.L);
     if (Cp.L.n) k_load_ind<<<grid2(K.ntrials, Cp.L.n), 128, 0, st>>>(K, hot, V, Cp.L, rhsOld);
     if (S.n) k_load_src<<<grid2(K.ntrials, S.n), 128, 0, st>>>(K, hot, V, S);
+    if (Cp.J.n) k_load_jj<<<grid2(K.ntrials, Cp.J.n), 128, 0, st>>>(K, hot, V, Cp.J, rhsOld);
 }
 void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const double *rhs)

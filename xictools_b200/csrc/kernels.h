@@ -46,6 +46,17 @@ struct SolveView {
 
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,
     const RawParams &raw, const MosParamsOut &out);
+struct JJTempIn {
+    int n, nmodels;
+    const int *model;
+    ParamRef ics;                       // NaN = not given
+    const double *area0, *vshunt, *vless, *vmore, *tcf;
+    double criti[JJ_MAXMODELS], cap[JJ_MAXMODELS], cmu[JJ_MAXMODELS], gmu[JJ_MAXMODELS], r0[JJ_MAXMODELS],
+        rn[JJ_MAXMODELS], icfactor[JJ_MAXMODELS], delv[JJ_MAXMODELS];
+    int rtype[JJ_MAXMODELS];
+    double *out[JP_NPARAMS]; int ts;    // out[k][i*ld + t*ts]
+};
+void launch_jj_temp(cudaStream_t st, const JJTempIn &in, int ntrials, int ldt);
 void launch_ctl(cudaStream_t st, const Consts &K, const HotView &hot, TrialCtl *ctl,
     const CtlShared &sh, const CtlAux &aux, int phase);
 void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,

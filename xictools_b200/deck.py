@@ -29,7 +29,7 @@ FN_NONE, FN_PULSE, FN_PWL, FN_SIN = range(4)
 
 # parameter ids (include/b200spice.h)
 P_MOS_VTO, P_MOS_KP, P_MOS_L, P_MOS_W, P_MOS_GAMMA, P_MOS_LAMBDA, P_MOS_PHI = range(1, 8)
-P_CAP_C, P_RES_R, P_IND_L, P_SRC_DC, P_JJ_AREA = 32, 48, 56, 64, 80
+P_CAP_C, P_RES_R, P_IND_L, P_SRC_DC, P_JJ_ICS = 32, 48, 56, 64, 80
 
 # counters
 (C_STATUS, C_ACCEPTED, C_REJECTED, C_NUMITER, C_TIMEPTS, C_TRANITER, C_ITERCUT, C_TRAPCUT,
@@ -91,18 +91,58 @@ class CMos(C.Structure):
                 [("off", C.c_int)])
 
 
-JJ_MODEL_DBL = ("vg", "delv", "icrit", "r0", "rn", "cap", "icfact", "vshunt", "tsfact",
-                "tsaccel", "cpic", "cmu", "vm", "icrn", "gmu")
+JJ_MODEL_DBL = ("criti", "vg", "delv", "r0", "rn", "cap", "icfactor", "cmu", "gmu", "vshunt",
+                "vdpbak", "tsaccl", "tsfact")
 
 
 class CJJModel(C.Structure):
-    _fields_ = [("rtype", C.c_int), ("ictype", C.c_int)] + [(n, C.c_double) for n in JJ_MODEL_DBL]
+    _fields_ = [("rtype", C.c_int), ("ictype", C.c_int), ("pi", C.c_int)] + \
+               [(n, C.c_double) for n in JJ_MODEL_DBL]
 
 
 class CJJ(C.Structure):
     _fields_ = [("pos", C.c_int), ("neg", C.c_int), ("phase_node", C.c_int), ("model", C.c_int),
-                ("area", C.c_double), ("ics", C.c_double), ("icphi", C.c_double),
-                ("icv", C.c_double)]
+                ("area", C.c_double), ("ics", C.c_double), ("vshunt", C.c_double),
+                ("vg", C.c_double), ("tcf", C.c_double), ("icv", C.c_double), ("icphi", C.c_double)]
+
+
+PHI0 = 2.067833848e-15              # wrsCONSTphi0 (include/circuit.h:123-124)
+PHI0_2PI = PHI0/(2*3.14159265358979323846)
+
+
+def jj_model_setup(card: dict, dphimax: float = 0.2*3.14159265358979323846) -> dict:
+    """What sJJmodel holds after the model pass of JJdev::setup for a `.model NAME jj(...)` card
+    whose values are inside the documented ranges (jjset.cc:196-545; out-of-range values are
+    reset there with a warning and are not restated here).  `vg` must be on the card: without
+    it the reference integrates the BCS gap equation (devlib/tempr.cc:177), which only the
+    harvest path (shim/harvest.cc) carries."""
+    import math
+    c = {k.lower(): v for k, v in card.items()}
+    if "vg" not in c:
+        raise ValueError("hand-built JJ model needs vg (the BCS default comes through the harvest path)")
+    m = dict(rtype=int(c.get("rtype", 1)), ictype=int(c.get("cct", c.get("ictype", 1))),
+             pi=int(c.get("pijj", 0)))
+    m["vg"] = float(c["vg"])
+    m["delv"] = float(c.get("delv", 0.08e-3))
+    m["criti"] = float(c.get("icrit", 1e-3))
+    cpic = float(c.get("cpic", 1e-9*70.0/100.0))
+    m["cap"] = float(c["cap"]) if "cap" in c else cpic*m["criti"]
+    cpic = m["cap"]/m["criti"] if "cap" in c else cpic
+    m["icfactor"] = float(c.get("icfct", c.get("icfactor", math.pi/4)))
+    icrn = float(c.get("icrn", 1.65e-3))
+    m["rn"] = float(c["rn"]) if "rn" in c else icrn/m["criti"]
+    vm = float(c.get("vm", 16.5e-3))
+    m["r0"] = float(c["rsub"]) if "rsub" in c else vm/m["criti"]
+    if m["r0"] < m["rn"]:
+        m["rn"] = m["r0"]
+    m["cmu"] = float(c.get("cmu", 0.0))
+    m["gmu"] = float(c.get("gmu", 0.0))
+    m["vshunt"] = float(c.get("vshunt", 0.0))
+    m["tsfact"] = float(c.get("tsfactor", dphimax/(2*math.pi)))
+    m["tsaccl"] = float(c.get("tsaccel", 1.0))
+    halfvg = m["vg"]/2
+    m["vdpbak"] = min(math.sqrt(PHI0_2PI/cpic), halfvg) if m["cap"] > 0.0 else halfvg
+    return m
 
 
 class CDeck(C.Structure):
@@ -200,6 +240,18 @@ class Deck:
                                                                   k=float(k))))
         return self
 
+    def jj_model(self, name, **card):
+        """`.model NAME jj(card)`; card keys as in the reference (rtype, cct, vg, delv, icrit,
+        cap/cpic, icrn/rn, vm/rsub, icfct, cmu, gmu, vshunt, tsfactor, tsaccel, pijj)."""
+        self.jj_models[name.lower()] = dict(card)
+        return self
+
+    def jj(self, name, p, n, model, phase=None, **params):
+        """Josephson junction `Bname p n [phase] model [area= ics= vshunt= ic=vj,phi]`."""
+        nodes = (str(p).lower(), str(n).lower()) + ((str(phase).lower(),) if phase is not None else ())
+        self.elems.append(_Elem(DEV_JJ, name.lower(), nodes, dict(params), model.lower()))
+        return self
+
     def mos_model(self, name, mtype, level=1, **params):
         self.mos_models[name.lower()] = dict(type=+1 if mtype.lower().startswith("n") else -1,
                                              level=level, params=dict(params))
@@ -273,6 +325,22 @@ class Deck:
                 insts_of[mkey] = []
                 models_of[e.kind].insert(0, mkey)
             insts_of[mkey].insert(0, e)
+        # Resistors that touch a phase node (a terminal of a junction with supercurrent, or of
+        # an inductor once such a junction exists: jjset.cc:656-681, indset.cc:104-120) are not
+        # preloaded; RESdev::temperature moves each of them to the head of its model's list as
+        # it walks the list (restemp.cc:240-248), which leaves them in front, in deck order.
+        phase = self.phase_nodes()
+        if phase:
+            for mkey in models_of.get(DEV_RES, []):
+                lst = insts_of[mkey]
+                work = list(lst)
+                for k, e in enumerate(lst):
+                    if k == 0:
+                        continue
+                    if any(nd in phase for nd in e.nodes):
+                        work.remove(e)
+                        work.insert(0, e)
+                insts_of[mkey] = work
         out = []
         if DEV_MUT in models_of:
             for mkey in models_of[DEV_MUT]:
@@ -283,6 +351,18 @@ class Deck:
             for mkey in models_of[k]:
                 out += [(k, index_of[id(e)]) for e in insts_of[mkey]]
         return out
+
+    def phase_nodes(self) -> set:
+        """Names of the nodes flagged `phase` by the reference's setup (phase-mode DC support)."""
+        ph = set()
+        for e in self.elems:
+            if e.kind == DEV_JJ and int(self.jj_models[e.model].get("cct", 1)) > 0:
+                ph.update(nd for nd in e.nodes[:2] if nd not in ("0", "gnd"))
+        if ph:
+            for e in self.elems:
+                if e.kind == DEV_IND:
+                    ph.update(nd for nd in e.nodes if nd not in ("0", "gnd"))
+        return ph
 
     def load_order_names(self) -> list:
         tabs = self.kind_tables()
@@ -358,8 +438,23 @@ class Deck:
                     else:
                         s += f" {k}={_fmt(v)}"
                 lines.append(s)
+            elif e.kind == DEV_JJ:
+                prm = dict(e.params)
+                if (P_JJ_ICS, i) in overrides:
+                    prm["ics"] = overrides[(P_JJ_ICS, i)]
+                    prm.pop("area", None)
+                sline = f"{e.name} {' '.join(e.nodes)} {e.model}"
+                for k, v in prm.items():
+                    if k == "ic":
+                        sline += f" ic={_fmt(v[0])},{_fmt(v[1])}"
+                    else:
+                        sline += f" {k}={_fmt(v)}"
+                lines.append(sline)
             else:
                 raise NotImplementedError(e.kind)
+        for name, card in self.jj_models.items():
+            lines.append(f".model {name} jj(" + " ".join(f"{k}={_fmt(v) if isinstance(v, float) else v}"
+                                                          for k, v in card.items()) + ")")
         for name, m in self.mos_models.items():
             lines.append(self._model_line(name, m["type"], m["level"], m["params"]))
         for name, t, lev, prm in extra_models:
@@ -501,7 +596,28 @@ class Deck:
             mut[i] = CMut(inames.index(e.params["l1"]), inames.index(e.params["l2"]), e.params["k"])
         keep.append(mut)
         d.nmut, d.mut = len(tabs[DEV_MUT]), mut
-        d.njjmod = d.njj = 0
+        jnames = list(self.jj_models)
+        jm = (CJJModel * max(1, len(jnames)))()
+        for i, nme in enumerate(jnames):
+            for k, v in jj_model_setup(self.jj_models[nme]).items():
+                setattr(jm[i], k, v)
+        keep.append(jm)
+        d.njjmod, d.jj_models = len(jnames), jm
+        jj = (CJJ * max(1, len(tabs[DEV_JJ])))()
+        for i, e in enumerate(tabs[DEV_JJ]):
+            x = jj[i]
+            x.pos, x.neg = nums[e.nodes[0]], nums[e.nodes[1]]
+            x.phase_node = nums[e.nodes[2]] if len(e.nodes) > 2 else 0
+            x.model = jnames.index(e.model)
+            for f in ("area", "ics", "vshunt", "vg", "tcf", "icv", "icphi"):
+                setattr(x, f, NAN)
+            for k, v in e.params.items():
+                if k == "ic":
+                    x.icv, x.icphi = float(v[0]), float(v[1])
+                else:
+                    setattr(x, k, float(v))
+        keep.append(jj)
+        d.njj, d.jj = len(tabs[DEV_JJ]), jj
         order = self.load_order()
         d.norder = len(order)
         d.order_kind = arr(C.c_int, [k for k, _ in order])
