@@ -252,6 +252,11 @@ int  b200_mc_gauss(int seed, long long n, double *out);
 /* Host-side analysis products: CSC pattern of A, and the LU ordering the batch uses. */
 int  b200_batch_pattern(const b200_batch *b, int *n, int *nnz, const int **Ap, const int **Ai);
 int  b200_batch_ordering(const b200_batch *b, const int **rowperm, const int **colperm);
+/* A deck whose DC and transient matrices need different pivots (inductors: the branch diagonal
+ * is 0 in DC and -L*ag0 in a transient) keeps two sequences, as the reference re-orders at the
+ * first transient step (niiter.cc:501-509): this is the one of the transient modes (equal to
+ * the one above for a batch with a single sequence). */
+int  b200_batch_ordering_tran(const b200_batch *b, const int **rowperm, const int **colperm);
 /* Single load+assemble at a forced state: the per-trial matrix values Ax[nnz][ntrials] and
  * RHS[n+1][ntrials] after sCKT::load + loadGmin, for stamp-for-stamp comparison. */
 int  b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, int order,
@@ -270,6 +275,10 @@ int  b200_deck_analysis_stats(const b200_deck *deck, long long *out, int nout);
 /* Host-only: the CSC pattern and the static pivot order (position -> original row / column,
  * 0-based) into caller buffers Ap[n+1], Ai[nnz], rowperm[n], colperm[n] (any may be NULL). */
 int  b200_deck_analysis_arrays(const b200_deck *deck, int *Ap, int *Ai, int *rowperm, int *colperm);
+/* Host-only: the pivot order of the DC modes (which = 0) or the transient modes (which = 1);
+ * *nprograms = 2 when the two differ (the batch then keeps two solve programs). */
+int  b200_deck_analysis_order(const b200_deck *deck, int which, int *rowperm, int *colperm,
+                              int *nprograms);
 
 /* Test hook for the host logic (no CUDA call): orders a CSC matrix the way b200_klu_analyze
  * does, compiles the assembly runs and the task program, and executes them on ONE value set in

@@ -158,6 +158,19 @@ class Oracle:
         Ai = np.array(ai[:self.nnz], dtype=np.int32)
         return Ap, Ai
 
+    def set_ordering_tran(self, rowperm, colperm):
+        """The engine's pivot order of the transient modes (two-program batches)."""
+        r = np.ascontiguousarray(rowperm, dtype=np.int32)
+        c = np.ascontiguousarray(colperm, dtype=np.int32)
+        self.L.wo_set_ordering_tran.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.wo_set_ordering_tran(self.h, r.ctypes.data, c.ctypes.data)
+
+    def follow(self, batch):
+        """Use the pivot order(s) of an engine batch."""
+        self.set_ordering(*batch.ordering())
+        self.set_ordering_tran(*batch.ordering_tran())
+        return self
+
     def set_ordering(self, rowperm, colperm):
         r = np.ascontiguousarray(rowperm, dtype=np.int32)
         c = np.ascontiguousarray(colperm, dtype=np.int32)

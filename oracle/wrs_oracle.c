@@ -157,6 +157,8 @@ struct wo_ckt {
     /* LU */
     int have_order; int *rowperm, *colperm;   /* position -> original (0-based) */
     int lu_ready;
+    /* the engine keeps a second sequence for the transient modes when its DC one does not fit */
+    int have_order2; int *rowperm2, *colperm2; int lu_ready2; void *slu2;
     int *Lp, *Li; double *Lx;   /* strictly lower, by column, in permuted positions */
     int *Up, *Ui; double *Ux;   /* strictly upper, by column */
     double *Udiag;
@@ -1152,6 +1154,17 @@ void wo_set_ordering(wo_ckt *c, const int *rowperm, const int *colperm)
     memcpy(c->colperm, colperm, c->n*sizeof(int));
     c->have_order = 1;
     c->lu_ready = 0;
+}
+
+void wo_set_ordering_tran(wo_ckt *c, const int *rowperm, const int *colperm)
+{
+    free(c->rowperm2); free(c->colperm2);
+    c->rowperm2 = malloc(c->n*sizeof(int));
+    c->colperm2 = malloc(c->n*sizeof(int));
+    memcpy(c->rowperm2, rowperm, c->n*sizeof(int));
+    memcpy(c->colperm2, colperm, c->n*sizeof(int));
+    c->have_order2 = 1;
+    c->lu_ready2 = 0;
 }
 
 int wo_num_unknowns(const wo_ckt *c) { return c->n; }
@@ -3624,6 +3637,13 @@ static StaticLU *g_dummy;   /* silence unused warnings on some compilers */
 
 static int ckt_factor(wo_ckt *c)
 {
+    if (c->have_order && c->have_order2 && !(c->mode & MODEDC)) {
+        if (!c->lu_ready2) {
+            c->slu2 = slu_symbolic(c->n, c->Ap, c->Ai, c->rowperm2, c->colperm2);
+            c->lu_ready2 = 1;
+        }
+        return slu_refactor((StaticLU*)c->slu2, c->Ap, c->Ai, c->Ax, c->colperm2, c->work);
+    }
     if (c->have_order) {
         if (!c->lu_ready) {
             StaticLU *f = slu_symbolic(c->n, c->Ap, c->Ai, c->rowperm, c->colperm);
@@ -3657,7 +3677,12 @@ static void ckt_solve(wo_ckt *c)
 static void ckt_solve_inner(wo_ckt *c)
 {
     /* spSolve(CKTrhs, CKTrhs): slot 0 is ground (spsolve.cc:173-245) */
-    if (c->have_order) {
+    if (c->have_order && c->have_order2 && !(c->mode & MODEDC)) {
+        double *y = xcalloc(c->n, sizeof(double));
+        slu_solve((StaticLU*)c->slu2, c->rowperm2, c->colperm2, c->rhs + 1, y);
+        free(y);
+    }
+    else if (c->have_order) {
         double *y = xcalloc(c->n, sizeof(double));
         slu_solve((StaticLU*)c->Lp, c->rowperm, c->colperm, c->rhs + 1, y);
         free(y);

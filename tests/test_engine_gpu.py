@@ -31,12 +31,14 @@ def compare(deck, ntr, ov=None, trials=None, wave_tol_scale=1.0):
     cnt = b.counters()
     _, w = b.waves()
     rp, cp = b.ordering()
+    rp2, cp2 = b.ordering_tran()
     names = b.names()
     trials = list(range(ntr)) if trials is None else trials
     off = []
     for t in trials:
         o = Oracle(deck, ov, t)
         o.set_ordering(rp, cp)
+        o.set_ordering_tran(rp2, cp2)
         r = o.run()
         if int(cnt[t, C_STATUS]) != r["err"]:
             off.append((t, "status", int(cnt[t, C_STATUS]), r["err"]))
@@ -162,10 +164,12 @@ def test_failing_trials_report_the_reference_error():
     b.run_tran()
     cnt = b.counters()
     rp, cp = b.ordering()
+    rp2, cp2 = b.ordering_tran()
     b.close()
     for t in range(ntr):
         o = Oracle(d, ov, t)
         o.set_ordering(rp, cp)
+        o.set_ordering_tran(rp2, cp2)
         r = o.run()
         assert r["err"] == 119
         assert (int(cnt[t, C_STATUS]), int(cnt[t, C_ACCEPTED]), int(cnt[t, C_NUMITER])) == \
@@ -220,6 +224,7 @@ def test_klu_seam_bit_exact_vs_oracle_lu():
     # needed -- the engine exposes it through the batch API on the same pattern
     b = engine.Batch(d, 1)
     rp, cp = b.ordering()
+    rp2, cp2 = b.ordering_tran()
     b.close()
     worst = 0.0
     for t in range(ntr):
@@ -279,11 +284,13 @@ def compare_op(deck, ntr, ov=None, trials=None, tol_scale=1.0):
     cnt = b.counters()
     _, w = b.waves()
     rp, cp = b.ordering()
+    rp2, cp2 = b.ordering_tran()
     names = b.names()
     b.close()
     for t in (range(ntr) if trials is None else trials):
         o = Oracle(deck, ov, t)
         o.set_ordering(rp, cp)
+        o.set_ordering_tran(rp2, cp2)
         r = o.run("op")
         assert int(cnt[t, C_STATUS]) == r["err"]
         assert int(cnt[t, C_NUMITER]) == r["numiter"], (t, int(cnt[t, C_NUMITER]), r["numiter"])

@@ -17,10 +17,11 @@ b.run_tran()
 cnt = b.counters()
 _, w = b.waves()
 rp, cp = b.ordering()
+rp2, cp2 = b.ordering_tran()
 names = b.names()
 bad = []
 for t in range(nt):
-    o = Oracle(d, ov, t); o.set_ordering(rp, cp); r = o.run()
+    o = Oracle(d, ov, t); o.set_ordering(rp, cp); o.set_ordering_tran(rp2, cp2); r = o.run()
     ek = tuple(int(cnt[t, k]) for k in (C_ACCEPTED, C_REJECTED, C_NUMITER, C_TIMEPTS, C_NPOINTS))
     ok = (r["accepted"], r["rejected"], r["numiter"], r["timepts"], len(r["times"]))
     idx = [names.index(nm) for nm in r["names"]]
@@ -42,5 +43,5 @@ for t in bad[:4]:
     print("  trial", t, "alone:", tuple(int(c1[0, k]) for k in (C_ACCEPTED, C_REJECTED, C_NUMITER, C_TIMEPTS, C_NPOINTS)))
     b1.close()
     # per accepted point iteration counts of the oracle
-    o = Oracle(d, ov, t); o.set_ordering(rp, cp); r = o.run()
+    o = Oracle(d, ov, t); o.set_ordering(rp, cp); o.set_ordering_tran(rp2, cp2); r = o.run()
     print("   oracle acc_iters", r.get("acc_iters", [])[:40])

@@ -691,17 +691,28 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
 
 // ---------------------------------------------------------------------------------------
 // Static pivot order.  The reference's KLU path fixes the pivot sequence at klu_factor and
-// reuses it in every klu_refactor (kluif.cc:569-606); the batch needs ONE sequence valid for
-// all trials and all times, so it may only use pivots whose acceptability does not depend
-// on values:  (a) entries that are compile-time constants +-1 (voltage-source branch
-// couplings, srcset.cc:158-170) as long as no elimination has touched them, and
-// (b) diagonal entries of voltage nodes that receive conductance stamps.
+// reuses it in every klu_refactor (kluif.cc:569-606); NIiter asks for a new one when the matrix
+// changes character -- at the start of the DC operating point and again at the first transient
+// step (NISHOULDREORDER: niiter.cc:181, 501-509).  The batch needs sequences that are valid for
+// all trials, so it may only use pivots whose acceptability does not depend on the trial's
+// values, and it keeps up to TWO of them: one for the DC modes (capacitor and inductor
+// companions vanish there) and one for the transient modes (b200_build_programs).
+//   (a) entries that are compile-time constants +-1 (source / inductor branch couplings,
+//       srcset.cc:158-170, indset.cc:117-131) while no elimination has touched them, and only
+//       where they cannot cause growth: every other live entry of the pivot's column is such a
+//       constant too (all multipliers are +-1), or the pivot's row has no other live entry
+//       (nothing propagates).  An inductor's coupling is such a pivot in DC (its (br,br) entry
+//       is zero there) but not in a transient, where (br,br) = -L*ag0 would make multipliers of
+//       that size: a chain of inductors multiplies them up (4e12 over 12 stages).
+//   (b) diagonal entries that receive conductance stamps: voltage-node diagonals, and in the
+//       transient order the branch diagonals of inductors (-req): the transient MNA matrix
+//       [G+C*ag0, B; B^T, -L*ag0] is quasi-definite, diagonal pivots are stable in any order.
 // Among those, Markowitz's (r-1)(c-1) rule (the criterion of the Sparse 1.3 solver the
 // shipped reference runs, xt_base/sparse/spfactor.cc:1218-1560) picks the next pivot; ties go
 // to the candidate touched least recently, which yields wide, shallow elimination levels
 // (independent pivots first) for the level-scheduled GPU program.
 // ---------------------------------------------------------------------------------------
-void b200_order_markowitz(Analysis &an)
+void b200_order_markowitz(Analysis &an, bool tran_order)
 {
     int n = an.n;
     std::vector<std::set<int>> rows(n), cols(n);
@@ -711,7 +722,7 @@ void b200_order_markowitz(Analysis &an)
     // companion conductances vanish there).  The pivot order is frozen for the whole run, so a
     // pivot must be structurally nonzero in DC (hence also in transient).
     std::map<std::pair<int,int>, char> dcnz;
-    bool have_dc = (an.dc_active.size() == (size_t)an.nnz);
+    bool have_dc = !tran_order && (an.dc_active.size() == (size_t)an.nnz);
     for (int j = 0; j < n; j++)
         for (int p = an.Ap[j]; p < an.Ap[j+1]; p++) {
             int i = an.Ai[p];
@@ -725,7 +736,7 @@ void b200_order_markowitz(Analysis &an)
     std::vector<char> diag_ok(n, 0);
     for (int i = 0; i < n; i++) {
         int p = an.diag[i+1];
-        if (p >= 0 && an.ntype[i+1] == 0 &&
+        if (p >= 0 && (an.ntype[i+1] == 0 || tran_order) &&
                 (an.cg_ptr[p+1] > an.cg_ptr[p] || an.Ainit[p] != 0.0) &&
                 (!have_dc || an.dc_active[p]))
             diag_ok[i] = 1;
@@ -746,7 +757,23 @@ void b200_order_markowitz(Analysis &an)
                     auto it = constant.find({i, j});
                     bool is_const = (it != constant.end() && it->second);
                     if (pass == 0) {
-                        if (is_const) cls = 2;
+                        if (is_const) {
+                            // growth-safe only if the multipliers are +-1 or nothing propagates
+                            bool col_const = true, row_single = true;
+                            for (int r : cols[j]) {
+                                if (r == i || !ract[r]) continue;
+                                if (have_dc && !dcnz[{r, j}]) continue;
+                                auto ic = constant.find({r, j});
+                                if (ic == constant.end() || !ic->second) { col_const = false; break; }
+                            }
+                            for (int q : rows[i]) {
+                                if (q == j || !cact[q]) continue;
+                                if (have_dc && !dcnz[{i, q}]) continue;
+                                row_single = false; break;
+                            }
+                            if (!col_const && !row_single) continue;
+                            cls = 2;
+                        }
                         else if (i == j && diag_ok[i]) cls = 1;
                         else continue;
                     }
@@ -1096,6 +1123,54 @@ int b200_build_lu(Analysis &an)
 }
 
 // ---------------------------------------------------------------------------------------
+// One or two solve programs (see the comment above b200_order_markowitz).
+// ---------------------------------------------------------------------------------------
+int b200_build_programs(Analysis &an, bool uic)
+{
+    an.has_tranp = false;
+    an.primary_class = -1;
+    if (uic) {
+        // no solve ever happens in a DC mode (tranan.cc:342-350 loads once, without NIiter)
+        b200_order_markowitz(an, true);
+        return b200_build_lu(an);
+    }
+    Analysis tr = an;                            // before build_lu renumbers the gather lists
+    b200_order_markowitz(an, false);
+    b200_order_markowitz(tr, true);
+    if (tr.rowperm == an.rowperm && tr.colperm == an.colperm)
+        return b200_build_lu(an);
+    int rc = b200_build_lu(an);
+    if (rc) return rc;
+    rc = b200_build_lu(tr);
+    if (rc) return rc;
+    // the transient program's runs in the primary's contribution numbering
+    std::vector<int> krow(an.n + 1, -1);
+    for (int k = 0; k < an.n; k++) krow[an.yperm_in[k]] = k;
+    for (int s = 0; s < tr.nnzLU; s++) {
+        int p = tr.lu_src[s];
+        if (p < 0) continue;
+        const AsmRun &r1 = an.runs[an.a2lu[p]];
+        if (r1.len != tr.runs[s].len) return B200_E_PANIC;
+        tr.runs[s].pos = r1.pos;
+    }
+    for (int k = 0; k < tr.n; k++) {
+        const AsmRun &r1 = an.runs[an.nnzLU + krow[tr.yperm_in[k]]];
+        if (r1.len != tr.runs[tr.nnzLU + k].len) return B200_E_PANIC;
+        tr.runs[tr.nnzLU + k].pos = r1.pos;
+    }
+    tr.runs[tr.slot_neg1].pos = an.runs[an.slot_neg1].pos;
+    LuProgram &P = an.tranp;
+    P.rowperm = tr.rowperm; P.colperm = tr.colperm; P.yperm_out = tr.yperm_out;
+    P.tile_order = tr.tile_order; P.runs = tr.runs; P.prog_rows = tr.prog_rows;
+    P.prog_round = tr.prog_round; P.nnzLU = tr.nnzLU; P.img = tr.img;
+    P.prog_levels = tr.prog_levels; P.prog_tasks = tr.prog_tasks;
+    P.prog_steps = tr.prog_steps; P.prog_ops = tr.prog_ops;
+    an.has_tranp = true;
+    an.primary_class = 1;
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Host-only view of the once-per-batch analysis (no CUDA call): sizes of the pattern, the LU
 // and the compiled programs.  Used by the CPU tests of the host logic and by profiles/.
 // ---------------------------------------------------------------------------------------
@@ -1106,8 +1181,7 @@ extern "C" int b200_deck_analysis_stats(const b200_deck *deck, long long *out, i
     std::string err;
     int rc = b200_analyze(deck, an, err);
     if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); return rc; }
-    b200_order_markowitz(an);
-    rc = b200_build_lu(an);
+    rc = b200_build_programs(an, deck->uic != 0);
     if (rc) return rc;
     long long v[B200_AS_NSTATS] = {0};
     v[B200_AS_N] = an.n; v[B200_AS_NNZ] = an.nnz; v[B200_AS_NNZLU] = an.nnzLU; v[B200_AS_NC] = an.NC;
@@ -1125,6 +1199,26 @@ extern "C" int b200_deck_analysis_stats(const b200_deck *deck, long long *out, i
 
 // Host-only: the CSC pattern and the static pivot order of a deck (caller-sized buffers:
 // Ap[n+1], Ai[nnz], rowperm[n], colperm[n]; sizes from b200_deck_analysis_stats).
+// Host-only: the pivot order of the DC modes (which = 0) or of the transient modes (which = 1)
+// as b200_build_programs chooses them; *nprograms = 1 or 2.
+extern "C" int b200_deck_analysis_order(const b200_deck *deck, int which, int *rowperm, int *colperm,
+    int *nprograms)
+{
+    if (!deck) return B200_E_BADPARM;
+    Analysis an;
+    std::string err;
+    int rc = b200_analyze(deck, an, err);
+    if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); return rc; }
+    rc = b200_build_programs(an, deck->uic != 0);
+    if (rc) return rc;
+    const std::vector<int> &rp = (which && an.has_tranp) ? an.tranp.rowperm : an.rowperm;
+    const std::vector<int> &cp = (which && an.has_tranp) ? an.tranp.colperm : an.colperm;
+    if (rowperm) std::copy(rp.begin(), rp.end(), rowperm);
+    if (colperm) std::copy(cp.begin(), cp.end(), colperm);
+    if (nprograms) *nprograms = an.has_tranp ? 2 : 1;
+    return B200_OK;
+}
+
 extern "C" int b200_deck_analysis_arrays(const b200_deck *deck, int *Ap, int *Ai, int *rowperm, int *colperm)
 {
     if (!deck) return B200_E_BADPARM;
@@ -1132,7 +1226,7 @@ extern "C" int b200_deck_analysis_arrays(const b200_deck *deck, int *Ap, int *Ai
     std::string err;
     int rc = b200_analyze(deck, an, err);
     if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); return rc; }
-    b200_order_markowitz(an);
+    b200_order_markowitz(an, deck->uic != 0);
     if (Ap) std::copy(an.Ap.begin(), an.Ap.end(), Ap);
     if (Ai) std::copy(an.Ai.begin(), an.Ai.end(), Ai);
     if (rowperm) std::copy(an.rowperm.begin(), an.rowperm.end(), rowperm);
@@ -1161,7 +1255,13 @@ extern "C" int b200_debug_program_check(int n, const int *Ap, const int *Ai, con
     an.Ainit.assign(Ax, Ax + an.nnz);
     an.cg_ptr.assign(an.nnz + 1, 0);
     an.rg_ptr.assign(n + 2, 0);
+    // as b200_klu_analyze: entries that are exactly zero in this matrix are not live, and the
+    // static order stands only if it passes the numerical pivot test on these values
+    an.dc_active.assign(an.nnz, 0);
+    for (int p = 0; p < an.nnz; p++) an.dc_active[p] = (Ax[p] != 0.0);
     b200_order_markowitz(an);
+    if (b200_order_numeric(an, Ax, 1e-3, 1e-13, 0) >= 0 && b200_order_numeric(an, Ax, 1e-3, 1e-13, 1) >= 0)
+        return B200_E_SINGULAR;
     an.Ainit.assign(an.nnz, 0.0);
     an.cg_idx.resize(an.nnz);
     for (int p = 0; p < an.nnz; p++) { an.cg_ptr[p] = p; an.cg_idx[p] = p; }

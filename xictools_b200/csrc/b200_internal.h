@@ -188,7 +188,22 @@ struct AsmRun { int pos, len, info, pad; };
 #define ASM_ROW  0x20000000
 #define ASM_VNODE 0x10000000  // diagonal of a voltage node (loadGmin applies)
 
+// the per-order products of b200_build_lu that the solve kernels read
+struct LuProgram {
+    std::vector<int> rowperm, colperm, yperm_out, tile_order;
+    std::vector<AsmRun> runs;
+    std::vector<unsigned> prog_rows;
+    std::vector<unsigned short> prog_round;
+    int nnzLU = 0, img = 0;
+    int prog_levels = 0, prog_tasks = 0; long long prog_steps = 0, prog_ops = 0;
+};
+
 struct Analysis {
+    // which trials the primary program serves: -1 all, 1 the DC modes only (then tranp serves
+    // the transient modes)
+    int primary_class = -1;
+    bool has_tranp = false;
+    LuProgram tranp;
     // unknowns
     int n = 0;                                  // matrix size; node numbers 1..n
     std::vector<int> ntype;                     // [n+1] 0 voltage, 1 current
@@ -247,8 +262,13 @@ struct Analysis {
     double break0 = 0, break1 = 0;
 };
 
+// Orders + builds the solve program(s) of a deck: one program when the run never solves in a DC
+// mode (`uic`) or when the DC and the transient pivot orders coincide; otherwise the primary
+// program (an.*) serves the DC modes and an.tranp the transient modes.  Both read the SAME
+// contribution layout (the primary's assembly order).
+int  b200_build_programs(Analysis &an, bool uic);
 int  b200_analyze(const b200_deck *deck, Analysis &an, std::string &err);
-void b200_order_markowitz(Analysis &an);
+void b200_order_markowitz(Analysis &an, bool tran_order = false);
 // numerical pivot test / threshold re-ordering on one value set (analysis.cpp)
 int  b200_order_numeric(Analysis &an, const double *Ax, double pivrel, double pivabs, int mode);
 // symbolic LU for the fixed order, the task program and the assembly runs; returns 0 or

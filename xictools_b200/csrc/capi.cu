@@ -66,7 +66,8 @@ struct b200_batch {
     mutable int *d_wsel = nullptr; mutable int wsel_cap = 0;
 
     // device views
-    HotView hot; VecView V; MosView M; CapView Cp; SrcView S; SolveView Sv; CtlAux aux;
+    HotView hot; VecView V; MosView M; CapView Cp; SrcView S; SolveView Sv, Sv2; CtlAux aux;
+    bool two_programs = false;
     CtlShared sh;
     TrialCtl *ctl = nullptr;
     MosCard *d_cards = nullptr;
@@ -293,8 +294,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     std::string err;
     int rc = b200_analyze(deck, b->an, err);
     if (rc) { fprintf(stderr, "b200spice: %s\n", err.c_str()); delete b; return rc; }
-    b200_order_markowitz(b->an);
-    rc = b200_build_lu(b->an);
+    rc = b200_build_programs(b->an, deck->uic != 0);
     if (rc) {
         fprintf(stderr, "b200spice: LU (%d values) + rhs (%d) of one trial exceed the 16-bit slot "
             "indices of the solve program\n", b->an.nnzLU, b->an.n);
@@ -416,6 +416,8 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     }
     // ---- solve view ----
     SolveView &Sv = b->Sv;
+    memset(&Sv, 0, sizeof(Sv));
+    Sv.cls = an.primary_class;
     Sv.ntype = b->dupload(an.ntype);
     Sv.ic_given = b->dupload(an.ic_given); Sv.ns_given = b->dupload(an.ns_given);
     Sv.ic_val = b->dupload(an.ic_val); Sv.ns_val = b->dupload(an.ns_val);
@@ -425,7 +427,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (an.n + 31) & ~31;
     Sv.rows = b->dupload(an.prog_rows); Sv.rounds = b->dupload(an.prog_round);
     Sv.nrows = (int)an.prog_rows.size()/LU_LANES; Sv.nrounds = (int)an.prog_round.size();
-    Sv.image = b->dalloc<double>((size_t)ldt*an.img);
+    Sv.image = b->dalloc<double>((size_t)ldt*std::max(an.img, an.has_tranp ? an.tranp.img : 0));
     Sv.ysol = b->dalloc<double>((size_t)ldt*Sv.npad);
     Sv.lu_bad = b->dalloc<int>(ldt); Sv.live = b->dalloc<int>(ldt); Sv.ctr = b->dalloc<int>(2);
     if (!Sv.image || !Sv.ysol || !Sv.live) { b200_batch_destroy(b); return B200_E_NOMEM; }
@@ -435,6 +437,24 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
             fprintf(stderr, "b200spice: LU (%d values) + rhs (%d) of one trial exceed shared memory; "
                 "the supernodal large-matrix path is not built yet\n", an.nnzLU, an.n);
         b200_batch_destroy(b); return rc;
+    }
+    if (an.has_tranp) {
+        // the transient program: same contribution stream, image / ysol buffers shared with the
+        // DC program (a trial is in one class per tick), its own live list and counters
+        const LuProgram &P = an.tranp;
+        SolveView &S2 = b->Sv2;
+        S2 = Sv;
+        S2.cls = 0;
+        S2.yperm_out = b->dupload(P.yperm_out);
+        S2.runs = b->dupload(P.runs);
+        S2.tile_order = b->dupload(P.tile_order); S2.ntiles = (int)P.tile_order.size();
+        S2.img = P.img; S2.nlu = P.nnzLU;
+        S2.rows = b->dupload(P.prog_rows); S2.rounds = b->dupload(P.prog_round);
+        S2.nrows = (int)P.prog_rows.size()/LU_LANES; S2.nrounds = (int)P.prog_round.size();
+        S2.live = b->dalloc<int>(ldt); S2.ctr = b->dalloc<int>(2);
+        rc = solve_configure(S2);
+        if (rc) { b200_batch_destroy(b); return rc; }
+        b->two_programs = true;
     }
     b->nconst = (int)an.const_idx.size();
     b->d_const_idx = b->dupload(an.const_idx); b->d_const_val = b->dupload(an.const_val);
@@ -849,6 +869,8 @@ static int run_analysis(b200_batch *b, int analysis)
         for (int w = 0; w < WIN; w++) {
             CK(cudaEventRecord(E.ev[w][0], st));
             rc = launch_solve(st, K, b->hot, b->V, b->Sv, b->V.X[b->cur], b->V.X[b->cur ^ 1]);
+            if (!rc && b->two_programs)
+                rc = launch_solve(st, K, b->hot, b->V, b->Sv2, b->V.X[b->cur], b->V.X[b->cur ^ 1]);
             if (rc) return rc;
             CK(cudaEventRecord(E.ev[w][1], st));
             launch_devconv(st, K, b->hot, b->V, b->M, b->V.X[b->cur]);
@@ -859,7 +881,7 @@ static int run_analysis(b200_batch *b, int analysis)
             CK(cudaEventRecord(E.ev[w][2], st));
             launch_loads(st, K, b->hot, b->V, b->M, b->Cp, b->S, b->V.X[b->cur]);
             CK(cudaEventRecord(E.ev[w][3], st));
-            launches += 8 + nload_kernels;               // 3 solve kernels, devconv, 2 x ctl, vec, statevec
+            launches += 8 + nload_kernels + (b->two_programs ? 3 : 0);   // 3 solve kernels (per program), devconv, 2 x ctl, vec, statevec
             load_launches++; solve_launches++;
             ticks++;
         }
@@ -1017,6 +1039,16 @@ int b200_batch_pattern(const b200_batch *b, int *n, int *nnz, const int **Ap, co
 {
     if (!b) return B200_E_BADPARM;
     *n = b->an.n; *nnz = b->an.nnz; *Ap = b->an.Ap.data(); *Ai = b->an.Ai.data();
+    return B200_OK;
+}
+
+// the pivot order of the transient modes when the batch keeps two (else the one order)
+int b200_batch_ordering_tran(const b200_batch *b, const int **rowperm, const int **colperm)
+{
+    if (!b) return B200_E_BADPARM;
+    const Analysis &an = b->an;
+    *rowperm = an.has_tranp ? an.tranp.rowperm.data() : an.rowperm.data();
+    *colperm = an.has_tranp ? an.tranp.colperm.data() : an.colperm.data();
     return B200_OK;
 }
 

@@ -34,6 +34,7 @@ struct SolveView {
     const unsigned *rows;       // task program, [nrows][LU_LANES] (b200_internal.h)
     const unsigned short *rounds;
     int nrows, nrounds;
+    int cls;                    // which solving trials this program serves: -1 all, 1 DC modes, 0 transient
     double *image;              // [ldt][img] assembled A | b of every trial, trial-major
     double *ysol;               // [ldt][npad] solutions in permuted column order
     int *lu_bad;                // [ldt] 1: a pivot was zero or not finite

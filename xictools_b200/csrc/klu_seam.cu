@@ -307,6 +307,9 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     an.Ainit.assign(Ax0, Ax0 + an.nnz);
     an.cg_ptr.assign(an.nnz + 1, 0);
     an.rg_ptr.assign(n + 2, 0);
+    // entries that are exactly zero in this matrix are not live for the choice of pivots
+    an.dc_active.assign(an.nnz, 0);
+    for (int p = 0; p < an.nnz; p++) an.dc_active[p] = (Ax0[p] != 0.0);
     b200_order_markowitz(an);
     // klu_factor semantics on the matrix handed in: the static order is kept only if every one
     // of its pivots passes the pivrel / pivabs test on THESE values; otherwise threshold
@@ -338,6 +341,7 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     CK(cudaStreamCreate(&k->stream));
     SolveView &Sv = k->Sv;
     memset(&Sv, 0, sizeof(Sv));
+    Sv.cls = -1;
     Sv.ntype = k->dupload(an.ntype);
     Sv.ic_given = k->dupload(an.ic_given); Sv.ns_given = k->dupload(an.ns_given);
     Sv.ic_val = k->dupload(an.ic_val); Sv.ns_val = k->dupload(an.ns_val);

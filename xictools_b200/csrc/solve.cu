@@ -103,7 +103,10 @@ k_assemble(Consts K, HotView hot, VecView V, SolveView Sv)
     __shared__ double tiles[ASM_WARPS][ASM_TS][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x*32 + lane;
-    const bool live = (t < K.ntrials) && hot.do_solve[t];
+    // Sv.cls: -1 every solving trial; 1 only trials whose load was in a DC mode, 0 only the
+    // transient ones (two programs, b200_build_programs)
+    const bool live = (t < K.ntrials) && hot.do_solve[t] &&
+        (Sv.cls < 0 || ((hot.mode[t] & MODEDC) != 0) == (Sv.cls != 0));
     const unsigned mask = __ballot_sync(0xffffffffu, live);
     if (!mask) return;                                   // same 32 trials in every warp: uniform exit
     if (blockIdx.y == 0 && warp == 0) {
@@ -244,7 +247,8 @@ k_finish(Consts K, HotView hot, SolveView Sv, const double * __restrict__ Xold, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t0 = blockIdx.x*32;
     const int t = t0 + lane;
-    const bool live = (t < K.ntrials) && hot.do_solve[t];
+    const bool live = (t < K.ntrials) && hot.do_solve[t] &&
+        (Sv.cls < 0 || ((hot.mode[t] & MODEDC) != 0) == (Sv.cls != 0));
     const unsigned mask = __ballot_sync(0xffffffffu, live);
     if (!mask) return;
     if (threadIdx.x < 32) s_flags[threadIdx.x] = 0;
@@ -322,9 +326,11 @@ int solve_configure(SolveView &Sv)
     Sv.lu_smem = (int)((size_t)Sv.lu_warps*imgb + rnd + (psmem ? prog : 0));
     Sv.lu_grid = nsm;
     if (Sv.ntiles != (Sv.img + ASM_TS - 1)/ASM_TS) return B200_E_PANIC;     // b200_internal.h ASM_TILE_SLOTS
+    // opt in to the whole window: a batch may run two programs of different size through the
+    // same kernel, and the attribute is per function, not per launch
     cudaError_t e = psmem
-        ? cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sv.lu_smem)
-        : cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sv.lu_smem);
+        ? cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)
+        : cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     return e == cudaSuccess ? B200_OK : B200_E_NOMEM;
 }
 

@@ -64,6 +64,7 @@ def load_library(path: str | None = None):
     L.b200_batch_get_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.b200_batch_pattern.argtypes = [C.c_void_p] + [C.c_void_p] * 4
     L.b200_batch_ordering.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200_batch_ordering_tran.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200_batch_debug_load.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200_klu_analyze.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
@@ -201,6 +202,12 @@ class Batch:
     def ordering(self):
         r, c = C.POINTER(C.c_int)(), C.POINTER(C.c_int)()
         self.L.b200_batch_ordering(self.h, C.byref(r), C.byref(c))
+        return np.array(r[:self.n], dtype=np.int32), np.array(c[:self.n], dtype=np.int32)
+
+    def ordering_tran(self):
+        """The pivot order of the transient modes (= ordering() for a single-sequence batch)."""
+        r, c = C.POINTER(C.c_int)(), C.POINTER(C.c_int)()
+        self.L.b200_batch_ordering_tran(self.h, C.byref(r), C.byref(c))
         return np.array(r[:self.n], dtype=np.int32), np.array(c[:self.n], dtype=np.int32)
 
     def debug_load(self, mode, time, delta, order, rhsold=None):
