@@ -106,7 +106,7 @@ def run_reference_sample(ntrials, cores, seed=SEED, ov=None, want=None, nstages=
                 t_solve=sum(x[6] for x in flat), iters=sum(x[3] for x in flat), per_trial=flat)
 
 
-def compare_with_reference(per_trial, cnt, waves):
+def compare_with_reference(per_trial, cnt, waves, current_last=True, saved=None):
     """The parity record of the bench line: GPU trials 0..k-1 (counters [T][NCOUNTERS], waves
     [T][npoints][nsave] as the public API returned them) against the reference's own run of the
     same trials.  Counts: (error, accepted, rejected, numiter, timepts) identical per trial.
@@ -132,15 +132,129 @@ def compare_with_reference(per_trial, cnt, waves):
         npt = min(w.shape[0], waves.shape[1])
         got, ref = waves[t, :npt], w[:npt]
         tol = RELTOL*np.maximum(np.abs(got), np.abs(ref))
-        tol[:, :-1] += VNTOL
-        tol[:, -1] += ABSTOL                      # the last saved unknown is a branch current
+        if current_last:
+            tol[:, :-1] += VNTOL
+            tol[:, -1] += ABSTOL                  # the last saved unknown is a branch current
+        else:
+            tol += VNTOL
         ratio = float((np.abs(got - ref)/tol).max())
         worst = max(worst, ratio)
         wave_ok += int(ratio <= 1.0)
     return {"vs": "oracle/_ref (unmodified reference, Sparse 1.3 pivoting)", "trials_compared": k,
             "counts_identical": same, "waves_within_tol": wave_ok,
             "max_wave_err_over_tol": worst, "first_offenders": off,
-            "tolerance": f"reltol {RELTOL} * max(|a|,|b|) + vntol {VNTOL} (abstol {ABSTOL} for branch currents), every output point of {SAVE_NODES}"}
+            "tolerance": f"reltol {RELTOL} * max(|a|,|b|) + vntol {VNTOL} (abstol {ABSTOL} for branch currents), every output point of {saved or SAVE_NODES}"}
+
+
+def bench_rsfq(local, ntrials=2048, njj=1000):
+    """Secondary workload (BASELINE.json configs[2]): Monte-Carlo transient of a
+    Josephson transmission line tiled to ~1000 junctions (RSJ level 1, the `jtl` cell of
+    examples/JJexamples/nor_mc.cir), per-trial critical currents ics*(1+N(0,0.1)) from the
+    reference's RNG stream, `.tran 0.5p 120p uic`.  One warm-up + one timed run, then the first
+    trials are re-run through the unmodified reference for the parity record and the CPU rate."""
+    import numpy as np
+    from xictools_b200.workloads import jtl
+    from xictools_b200 import engine
+    from xictools_b200.deck import DEV_JJ, P_JJ_ICS, C_STATUS, C_NUMITER
+    from xictools_b200.refrand import gauss_stream
+    deck = jtl(njj)
+    jjs = deck.kind_tables()[DEV_JJ]
+    g = gauss_stream(SEED, (ntrials - 1)*len(jjs)).reshape(ntrials - 1, len(jjs))
+    vals = np.empty((len(jjs), ntrials))
+    for i, e in enumerate(jjs):
+        vals[i, 0] = e.params["ics"]
+        vals[i, 1:] = e.params["ics"]*(1.0 + 0.1*g[:, i])
+    b = engine.Batch(deck, ntrials, device=local)
+    b.set_params_packed([P_JJ_ICS]*len(jjs), list(range(len(jjs))), vals)
+    b.run_tran()
+    b.run_tran()
+    st = b.stats()
+    cnt = b.counters()
+    names = b.names()
+    save = [names.index("a0"), names.index(f"a{njj//2}"), names.index(f"a{njj-1}")]
+    _, w = b.waves(save)
+    ok = int((cnt[:, C_STATUS] == 0).sum())
+    out = {"workload": f"rsfq_mc: {njj}-junction Josephson transmission line (RSJ level 1, {njj} JJ + "
+                       f"{njj} L + {njj+1} R + {njj+1} I), .tran 0.5p 120p uic, per-trial ics sigma 10 %",
+           "trials": ntrials, "unknowns": b.n, "ok_trials": ok,
+           "value": ntrials/(st.ms_total*1e-3), "unit": "trials/s", "ms_per_step": st.ms_total,
+           "ticks": int(st.ticks), "newton_iters_per_trial": float(cnt[:, C_NUMITER].mean()),
+           "load_ms_per_tick": st.ms_load/max(st.load_launches, 1),
+           "solve_ms_per_tick": st.ms_solve/max(st.solve_launches, 1),
+           "roofline_load": {"achieved_GBs": st.algbytes_load_per_launch/(st.ms_load/max(st.load_launches, 1)*1e-3)/1e9
+                             * min(1.0, float(cnt[:, C_NUMITER].mean())/max(1.0, float(st.ticks)))}}
+    try:
+        cores = host_cores()
+        k = min(ntrials, max(cores, 16))
+        ov = {(P_JJ_ICS, i): vals[i, :k] for i in range(len(jjs))}
+        texts = [deck.to_spice({key: v[t] for key, v in ov.items()}) for t in range(k)]
+        chunks = [(texts[i::cores], ["a0", f"a{njj//2}", f"a{njj-1}"]) for i in range(cores)]
+        chunks = [c for c in chunks if c[0]]
+        ctx = mp.get_context("fork")
+        with ctx.Pool(len(chunks)) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker, chunks)
+            el = time.perf_counter() - t0
+        flat = [None]*k
+        for i, r in enumerate(res):
+            for j, x in enumerate(r):
+                flat[i + j*len(chunks)] = x
+        out["cpu_baseline"] = {"value": k/el, "unit": "trials/s", "cores": len(chunks), "kind": "reference",
+                               "sample": f"trials 0..{k-1} in {el:.1f} s (oracle/_ref, Sparse 1.3)"}
+        out["parity"] = compare_with_reference(flat, cnt, w, current_last=False,
+                                               saved=["a0", f"a{njj//2}", f"a{njj-1}"])
+    except Exception as e:          # pragma: no cover
+        out["parity"] = {"error": repr(e)}
+    b.close()
+    return out
+
+
+def bench_dc_sweep(local, npoints=100000):
+    """Secondary workload (BASELINE.json configs[4]): 1e5-point DC operating-point sweep of the
+    two-stage opamp (MOS level 1), every point a trial of one `.op` batch."""
+    import numpy as np
+    from xictools_b200.montecarlo import dc_sweep
+    from xictools_b200.workloads import opamp
+    from xictools_b200.deck import C_STATUS, C_NUMITER
+    deck = opamp()
+    vin = np.linspace(1.55, 1.75, npoints)
+    mc = dc_sweep(deck, "vinp", vin, save=["out", "y", "tail"], device=local)
+    mc.run()
+    t0 = time.perf_counter()
+    mc.run()
+    el = time.perf_counter() - t0
+    st = mc.runner.batch.stats()
+    cnt = mc.counters
+    out = {"workload": f"dc_sweep: two-stage CMOS opamp (9 MOSFETs level 1), {npoints} operating points "
+                       "(vinp 1.55 .. 1.75 V), gmin stepping per point",
+           "points": npoints, "ok_points": int((cnt[:, C_STATUS] == 0).sum()),
+           "value": npoints/(st.ms_total*1e-3), "unit": "points/s", "e2e_value": npoints/el,
+           "ms_device": st.ms_total, "ticks": int(st.ticks),
+           "newton_iters_per_point": float(cnt[:, C_NUMITER].mean())}
+    try:
+        from oracle.pyoracle import RefSim
+        from xictools_b200.deck import DEV_SRC, P_SRC_DC
+        isrc = [e.name for e in deck.kind_tables()[DEV_SRC]].index("vinp")
+        sim = RefSim()
+        idx = np.linspace(0, npoints - 1, 64).astype(int)
+        same = 0
+        worst = 0.0
+        t0 = time.perf_counter()
+        for p in idx:
+            r = sim.run(deck.to_spice({(P_SRC_DC, isrc): float(vin[p])}, analysis="op"))
+            same += int((r["err"], r["numiter"]) == (int(cnt[p, C_STATUS]), int(cnt[p, C_NUMITER])))
+            ref = np.array([r["vals"][0][r["names"].index(nm)] for nm in ("out", "y", "tail")])
+            got = mc.waves[p, 0]
+            worst = max(worst, float((np.abs(got - ref)/(RELTOL*np.maximum(np.abs(got), np.abs(ref)) + VNTOL)).max()))
+        el_ref = time.perf_counter() - t0
+        out["parity"] = {"vs": "oracle/_ref", "points_compared": len(idx), "iterations_identical": same,
+                         "max_err_over_tol": worst}
+        out["cpu_baseline"] = {"value": len(idx)/el_ref, "unit": "points/s", "cores": 1, "kind": "reference",
+                               "sample": f"{len(idx)} points, deck re-parsed per point"}
+    except Exception as e:          # pragma: no cover
+        out["parity"] = {"error": repr(e)}
+    mc.close()
+    return out
 
 
 def host_cores():
@@ -460,6 +574,15 @@ def bench_ours(args):
         }
         if strong is not None:
             line["strong"] = strong
+        if world == 1 and not args.no_secondary:
+            try:
+                line["secondary"] = {"rsfq_mc": bench_rsfq(local)}
+            except Exception as e:          # pragma: no cover
+                line["secondary"] = {"rsfq_mc": {"error": repr(e)}}
+            try:
+                line["secondary"]["dc_sweep"] = bench_dc_sweep(local)
+            except Exception as e:          # pragma: no cover
+                line["secondary"]["dc_sweep"] = {"error": repr(e)}
         emit(line)
     if world > 1:
         dist.barrier()
@@ -492,6 +615,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trials", type=int, default=TRIALS_PER_GPU)
     ap.add_argument("--stages", type=int, default=NSTAGES)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (RSFQ) workload")
     ap.add_argument("--kernel-only", action="store_true",
                     help="profiling aid (ncu): device-resident steps only, no e2e / CPU legs, no JSON contract")
     args = ap.parse_args()

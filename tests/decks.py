@@ -222,7 +222,9 @@ def inv_dc(n=3):
 
 
 def op_decks():
-    return {"op_inv_dc": inv_dc(3), "op_inv4": inv_chain(4), "op_ro5": ring_oscillator(5),
+    from xictools_b200.workloads import opamp
+    return {"op_opamp": opamp(), "op_opamp_unbalanced": opamp(vinp=1.68),
+            "op_inv_dc": inv_dc(3), "op_inv4": inv_chain(4), "op_ro5": ring_oscillator(5),
             "op_ro3_rd": ro_rd(3), "op_inv_dc_direct": inv_dc(3).options(gminsteps=-1, srcsteps=-1),
             "op_inv_dc_gminfirst": inv_dc(3).options(gminfirst=1),
             "op_inv7_nogmin": inv_chain(7).options(gminsteps=-1),
@@ -277,45 +279,7 @@ def _one_ic():
     return d
 
 
-# ---- Josephson-junction decks (RSJ level 1, `uic` starts; examples/JJexamples shapes) ----------
-JJ_CARD = dict(rtype=1, cct=1, vg=2.8e-3, delv=0.1e-3, icrit=1e-3, rn=1.7, rsub=17.0, cap=0.7e-12)
-
-
-def jj_single(**card):
-    """One shunted junction driven over its critical current by a current ramp: the junction
-    switches and runs (phase slips of 2 pi, step bound tsfact*Phi0/|vj| from JJdev::accept)."""
-    d = Deck(title="single jj")
-    d.isource("i1", "0", "1", pulse=(0, 1.5e-3, 5e-12, 10e-12, 10e-12, 60e-12, 200e-12))
-    d.jj("b1", "1", "0", "jj1")
-    d.resistor("r1", "1", "0", 1.0)
-    d.jj_model("jj1", **dict(JJ_CARD, **card))
-    d.tran(0.5e-12, 100e-12, uic=True)
-    return d
-
-
-def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, **card):
-    """Josephson transmission line (the `jtl` subcircuit of examples/JJexamples/nor_mc.cir
-    flattened and repeated): biased junctions coupled by inductors, an SFQ pulse launched at
-    the input propagates down the line.  Bias currents ramp up from zero (uic start)."""
-    d = Deck(title=f"jtl{n}")
-    mc = dict(JJ_CARD, **card)
-    if vshunt is not None:
-        mc["vshunt"] = vshunt
-    d.jj_model("jj1", **mc)
-    d.isource("iin", "0", "in", pulse=(0, 0.6e-3, 40e-12, 3e-12, 3e-12, 2e-12, 200e-12))
-    d.inductor("lin", "in", "a0", 2.0e-12)
-    for i in range(n):
-        a = f"a{i}"
-        kw = {"phase": f"ph{i}"} if phase_nodes else {}
-        d.jj(f"b{i}", a, "0", "jj1", ics=ics*(1.0 + 0.05*(i % 3)), **kw)
-        if vshunt is None:
-            d.resistor(f"rs{i}", a, "0", 3.0)
-        d.isource(f"ib{i}", "0", a, pulse=(0, 0.7*ics, 0.0, 20e-12, 1e-12, 1.0, 2.0))
-        if i + 1 < n:
-            d.inductor(f"l{i}", a, f"a{i+1}", 4.0e-12)
-    d.resistor("rl", f"a{n-1}", "0", 5.0)
-    d.tran(0.5e-12, 120e-12, uic=True)
-    return d
+from xictools_b200.workloads import JJ_CARD, jj_single, jtl, opamp      # noqa: E402,F401
 
 
 def jj_variants():

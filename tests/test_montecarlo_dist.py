@@ -104,3 +104,37 @@ def test_variation_length_is_checked():
     bad = {k: v[:-1] for k, v in ov.items()}
     with pytest.raises(ValueError):
         MonteCarlo(d, NTRIALS, bad, runner=OracleRunner)
+
+
+def test_dc_sweep_builds_one_trial_per_point():
+    """dc_sweep: every sweep value is a trial of a `.op` batch addressed at the source's DC row."""
+    from xictools_b200.deck import P_SRC_DC
+    from xictools_b200.montecarlo import dc_sweep
+    from xictools_b200.workloads import opamp
+
+    seen = {}
+
+    class Probe:
+        def __init__(self, deck, ntrials):
+            seen["n"] = ntrials
+
+        def names(self):
+            return ["out", "y"]
+
+        def run(self, overrides, sel):
+            seen["ov"] = overrides
+            cnt = np.zeros((seen["n"], NCOUNTERS), dtype=np.int32)
+            return cnt, np.zeros(1), np.zeros((seen["n"], 1, len(sel)))
+
+        def close(self):
+            pass
+
+    vals = np.linspace(1.5, 1.8, 7)
+    mc = dc_sweep(opamp(), "vinp", vals, save=["out"], runner=Probe)
+    mc.run()
+    assert mc.analysis == "op" and seen["n"] == 7
+    (pid, idx), row = next(iter(seen["ov"].items()))
+    assert pid == P_SRC_DC and np.array_equal(row, vals)
+    assert mc.waves.shape == (7, 1, 1)
+    with pytest.raises(ValueError):
+        dc_sweep(opamp(), "nosuch", vals, runner=Probe)

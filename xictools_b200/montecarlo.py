@@ -37,11 +37,18 @@ class EngineRunner:
 
     accepts_packed = True
 
-    def __init__(self, deck: Deck, ntrials: int, device: int = 0):
+    def __init__(self, deck: Deck, ntrials: int, device: int = 0, analysis: str = "tran"):
         from . import engine
         self.batch = engine.Batch(deck, ntrials, device=device)
         self.packed = None              # (param ids, instance indices, values[nrows][ntrials])
         self._cnt = self._w = None
+        self.analysis = analysis
+
+    def _go(self):
+        if self.analysis == "op":
+            self.batch.run_op()
+        else:
+            self.batch.run_tran()
 
     def names(self):
         return self.batch.names()
@@ -55,7 +62,7 @@ class EngineRunner:
 
     def run(self, overrides, sel):
         self.upload(overrides)
-        self.batch.run_tran()
+        self._go()
         if self._cnt is None:
             self._cnt = _host_buffer((self.batch.ntrials, NCOUNTERS), np.int32)
         cnt = self.batch.counters(out=self._cnt)
@@ -68,7 +75,7 @@ class EngineRunner:
     def run_device(self, overrides, sel, dwaves_ptr, dcounters_ptr):
         """Run, leaving counters and selected waveforms in device buffers of the caller."""
         self.upload(overrides)
-        self.batch.run_tran()
+        self._go()
         self.batch.results_to_device(sel, dwaves_ptr, dcounters_ptr)
         return self.batch.times()
 
@@ -110,8 +117,9 @@ class MonteCarlo:
 
     def __init__(self, deck: Deck, ntrials: int, variation: dict | None = None, *, save=None,
                  rank: int = 0, world: int = 1, device: int = 0, runner=None,
-                 local_variation: dict | None = None):
+                 local_variation: dict | None = None, analysis: str = "tran"):
         self.deck, self.ntrials = deck, int(ntrials)
+        self.analysis = analysis
         self.rank, self.world = int(rank), int(world)
         self.mine = shard_trials(self.ntrials, self.world, self.rank)
         self.nlocal = len(self.mine)
@@ -129,7 +137,7 @@ class MonteCarlo:
             if v.shape != (self.nlocal,):
                 raise ValueError(f"local variation {key}: expected {self.nlocal} values")
             rows.append((key, v))
-        self.runner = runner(deck, self.nlocal) if runner else EngineRunner(deck, self.nlocal, device)
+        self.runner = runner(deck, self.nlocal) if runner else EngineRunner(deck, self.nlocal, device, analysis)
         packed_ok = getattr(self.runner, "accepts_packed", False)
         self.packed = (_host_buffer if packed_ok else np.empty)((len(rows), self.nlocal), np.float64)
         self.variation = {}
@@ -214,6 +222,23 @@ class MonteCarlo:
 
     def close(self):
         self.runner.close()
+
+
+def dc_sweep(deck: Deck, source: str, values, *, save=None, rank: int = 0, world: int = 1,
+             device: int = 0, runner=None) -> MonteCarlo:
+    """Batched DC operating-point sweep (BASELINE.json configs[4]): every sweep value of the
+    source's DC level is one trial of a `.op` batch, sharded over the ranks like Monte-Carlo
+    trials -- the batched form of the chained-DC / loop analysis the reference threads one sCKT
+    per worker (sDCTprms::loop_mt, analysis/dctprms.cc:924-1011; DCOanalysis::anFunc per point,
+    dcoan.cc:100-121).  Returns the MonteCarlo object; run() gathers to rank 0, where
+    waves[point][0][k] is unknown save[k] at sweep value values[point]."""
+    from .deck import DEV_SRC, P_SRC_DC
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    srcs = [e.name for e in deck.kind_tables()[DEV_SRC]]
+    if source.lower() not in srcs:
+        raise ValueError(f"no source named {source}")
+    return MonteCarlo(deck, len(values), {(P_SRC_DC, srcs.index(source.lower())): values}, save=save,
+                      rank=rank, world=world, device=device, runner=runner, analysis="op")
 
 
 assert NCOUNTERS > 0
