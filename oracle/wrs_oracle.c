@@ -424,6 +424,35 @@ static void src_setup_func(wo_ckt *c, Src *s, double step, double finaltime)
             if (p[3] > 0.0) break_set(c, p[3]);
         }
     }
+    else if (s->fn == B200_FN_EXP) {
+        /* IFexpData::setup, inptran.cc:2985-3013 */
+        double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
+        memset(p, 0, 8*sizeof(double));
+        p[0] = co[0];
+        p[1] = nc >= 2 ? co[1] : co[0];
+        p[2] = nc >= 3 ? co[2] : 0.0;
+        p[3] = nc >= 4 ? co[3] : 0.0;
+        p[4] = nc >= 5 ? co[4] : 0.0;
+        p[5] = nc >= 6 ? co[5] : 0.0;
+        if (s->enable_tran) {
+            if (!p[5]) p[5] = step;
+            if (!p[2]) p[2] = step;
+            if (!p[3]) p[3] = step;
+            if (!p[4]) p[4] = p[2] + step;
+            if (p[2] > 0.0) break_set(c, p[2]);
+            if (p[4] > p[2]) break_set(c, p[4]);
+        }
+    }
+    else if (s->fn == B200_FN_SFFM || s->fn == B200_FN_AM) {
+        /* IFsffmData::setup inptran.cc:3194-3211, IFamData::setup :3373-3388 */
+        double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
+        memset(p, 0, 8*sizeof(double));
+        for (int k = 0; k < 5; k++) p[k] = nc > k ? co[k] : 0.0;
+        if (s->enable_tran) {
+            if (!p[2]) p[2] = 1.0/finaltime;
+            if (s->fn == B200_FN_SFFM && !p[4]) p[4] = 1.0/finaltime;
+        }
+    }
 }
 
 static double src_eval(Src *s, double t)
@@ -515,6 +544,33 @@ static double src_eval(Src *s, double t)
         if (p[4] != 0.0)
             a *= exp(-time*p[4]);
         return p[0] + a;
+    }
+    if (s->fn == B200_FN_EXP) {
+        /* inptran.cc:3016-3028 */
+        const double *p = s->parms;
+        if (!s->enable_tran) return p[0];
+        double value = p[0];
+        if (t <= p[2]) return value;
+        value += (p[1]-p[0])*(1-exp(-(t-p[2])/p[3]));
+        if (t <= p[4]) return value;
+        value += (p[0]-p[1])*(1-exp(-(t-p[4])/p[5]));
+        return value;
+    }
+    if (s->fn == B200_FN_SFFM) {
+        /* inptran.cc:3215-3222 */
+        const double *p = s->parms;
+        if (!s->enable_tran) return p[0];
+        double w1 = 2*M_PI*p[2];
+        double w2 = 2*M_PI*p[4];
+        return p[0] + p[1]*sin(w1*t + p[3]*sin(w2*t));
+    }
+    if (s->fn == B200_FN_AM) {
+        /* inptran.cc:3391-3399 */
+        const double *p = s->parms;
+        if (!s->enable_tran) return 0.0;
+        if (t <= p[4]) return 0.0;
+        double w = 2*M_PI*(t - p[4]);
+        return p[0]*(p[1] + sin(w*p[2]))*sin(w*p[3]);
     }
     return 0.0;
 }
@@ -4099,6 +4155,26 @@ static int ckt_trunc(wo_ckt *c, double *timeStep)
             if (s->fn == B200_FN_SIN && c->time >= s->parms[3]) {
                 double per = (.2*M_PI)/(2*M_PI*s->parms[2]);
                 if (time_step > per) time_step = per;
+            }
+            else if (s->fn == B200_FN_SFFM) {                       /* inptran.cc:3253-3260 */
+                double per = (.2*M_PI)/(2*M_PI*(s->parms[2] + s->parms[4]));
+                if (time_step > per) time_step = per;
+            }
+            else if (s->fn == B200_FN_AM) {                         /* inptran.cc:3435-3442 */
+                double per = (.2*M_PI)/(2*M_PI*(s->parms[3] + s->parms[2]));
+                if (time_step > per) time_step = per;
+            }
+            else if (s->fn == B200_FN_EXP) {                        /* inptran.cc:3064-3082 */
+                double t = c->time, f = (.2*M_PI)/(2*M_PI);
+                const double *p = s->parms;
+                if (t >= p[2] && t < p[2] + 5.0*p[3]) {
+                    double per = p[3]*f*exp((t - p[2])/p[3]);
+                    if (time_step > per) time_step = per;
+                }
+                if (t >= p[4] && t < p[4] + 5.0*p[5]) {
+                    double per = p[5]*f*exp((t - p[4])/p[5]);
+                    if (time_step > per) time_step = per;
+                }
             }
         }
         if (time_step < HUGE_VAL) {

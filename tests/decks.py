@@ -38,6 +38,18 @@ def rc_sin():
     return d
 
 
+def rc_fn(**fn):
+    """RC low-pass driven by one of the remaining analytic source functions (EXP / SFFM / AM:
+    inptran.cc:2985-3082, 3194-3260, 3373-3442): evaluation, EXP breakpoints and the step bound
+    each of them imposes through IFtranData::time_limit."""
+    d = Deck(title="rc " + "/".join(fn))
+    d.vsource("v1", "a", "0", **fn)
+    d.resistor("r1", "a", "b", 1e3)
+    d.capacitor("c1", "b", "0", 1e-12)
+    d.tran(0.05e-9, 5e-9)
+    return d
+
+
 def rlc_series():
     """Series RLC driven by a pulse: inductor branch equation, flux LTE, underdamped ringing."""
     d = Deck(title="series rlc")
@@ -267,6 +279,10 @@ def variants():
         "ro5_interp2": ring_oscillator(5).options(interplev=2),
         "ro3_rd": ro_rd(3),
         "rc_sin": rc_sin(),
+        "rc_exp": rc_fn(exp=(0.0, 1.0, 0.5e-9, 0.3e-9, 2.5e-9, 0.6e-9)),
+        "rc_exp_defaults": rc_fn(exp=(0.2, 1.0)),
+        "rc_sffm": rc_fn(sffm=(0.5, 0.4, 1.0e9, 2.0, 0.2e9)),
+        "rc_am": rc_fn(am=(0.8, 1.0, 0.3e9, 2.0e9, 0.4e-9)),
     }
     out.update(jj_variants())
     return out

@@ -684,6 +684,40 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (p[3] > 0.0) bt.set_break(p[3], 0.0);
             S.pool.insert(S.pool.end(), p, p + 8);
         }
+        else if (in.fn == B200_FN_EXP) {
+            // IFexpData::setup, inptran.cc:2985-3013: V1 V2 TD1 TAU1 TD2 TAU2
+            double p[8] = {0,0,0,0,0,0,0,0};
+            const double *co = in.coef; int nc = in.ncoef;
+            if (nc < 1) { err = "exp needs arguments"; return B200_E_BADPARM; }
+            p[0] = co[0];
+            p[1] = nc >= 2 ? co[1] : co[0];
+            p[2] = nc >= 3 ? co[2] : 0.0;
+            p[3] = nc >= 4 ? co[3] : 0.0;
+            p[4] = nc >= 5 ? co[4] : 0.0;
+            p[5] = nc >= 6 ? co[5] : 0.0;
+            if (!p[5]) p[5] = step;
+            if (!p[2]) p[2] = step;
+            if (!p[3]) p[3] = step;
+            if (!p[4]) p[4] = p[2] + step;
+            if (p[2] > 0.0) bt.set_break(p[2], 0.0);
+            if (p[4] > p[2]) bt.set_break(p[4], 0.0);
+            S.pool.insert(S.pool.end(), p, p + 8);
+        }
+        else if (in.fn == B200_FN_SFFM || in.fn == B200_FN_AM) {
+            // IFsffmData::setup (inptran.cc:3194-3211): VO VA FC MDI FS, FC / FS default 1/finaltime;
+            // IFamData::setup (:3373-3388): SA OC MF CF DL, MF default 1/finaltime.  No breakpoints.
+            double p[8] = {0,0,0,0,0,0,0,0};
+            const double *co = in.coef; int nc = in.ncoef;
+            if (nc < 1) { err = "sffm / am needs arguments"; return B200_E_BADPARM; }
+            for (int k = 0; k < 5; k++) p[k] = nc > k ? co[k] : 0.0;
+            if (in.fn == B200_FN_SFFM) { if (!p[2]) p[2] = 1.0/finaltime; if (!p[4]) p[4] = 1.0/finaltime; }
+            else { if (!p[2]) p[2] = 1.0/finaltime; }
+            S.pool.insert(S.pool.end(), p, p + 8);
+        }
+        else if (in.fn != B200_FN_NONE && in.fn != B200_FN_PULSE && in.fn != B200_FN_PWL) {
+            err = "source function not built (GPULSE / SPULSE / GAUSS / TABLE / INTERP)";
+            return B200_E_UNSUPP;
+        }
     }
     an.brks = bt.brks; an.lat_offs = bt.lat_offs; an.lat_per = bt.lat_per;
     an.break0 = bt.breaks[0]; an.break1 = bt.breaks[1];

@@ -470,14 +470,24 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     sh.brks = b->dupload(an.brks); sh.lat_offs = b->dupload(an.lat_offs);
     sh.lat_per = b->dupload(an.lat_per);
     {
-        std::vector<double> tdl, fr;
-        for (int i = 0; i < st.n; i++)
-            if (st.fn[i] == B200_FN_SIN) {
-                tdl.push_back(st.pool[st.coef_off[i] + 3]);
-                fr.push_back(st.pool[st.coef_off[i] + 2]);
+        // sources that bound the step through IFtranData::time_limit (srctrun.cc:45-66):
+        // SIN after its delay, SFFM / AM always (period of the sum frequency), EXP inside its
+        // two exponential edges
+        std::vector<double> tdl, fr, etd, etau;
+        for (int i = 0; i < st.n; i++) {
+            const double *pp = st.pool.data() + st.coef_off[i];
+            if (st.fn[i] == B200_FN_SIN) { tdl.push_back(pp[3]); fr.push_back(pp[2]); }
+            else if (st.fn[i] == B200_FN_SFFM) { tdl.push_back(-HUGE_VAL); fr.push_back(pp[2] + pp[4]); }
+            else if (st.fn[i] == B200_FN_AM) { tdl.push_back(-HUGE_VAL); fr.push_back(pp[3] + pp[2]); }
+            else if (st.fn[i] == B200_FN_EXP) {
+                etd.push_back(pp[2]); etau.push_back(pp[3]);
+                etd.push_back(pp[4]); etau.push_back(pp[5]);
             }
+        }
         sh.nsin = (int)tdl.size();
         sh.sin_tdl = b->dupload(tdl); sh.sin_freq = b->dupload(fr);
+        sh.nexp = (int)etd.size();
+        sh.exp_td = b->dupload(etd); sh.exp_tau = b->dupload(etau);
     }
     b->d_count = b->dalloc<int>(1);
     b->d_counters = b->dalloc<int>((size_t)ldt*B200_NCOUNTERS);

@@ -25,6 +25,8 @@ struct CtlShared {          // shared tables
     const double *brks, *lat_offs, *lat_per;
     // SIN sources bound the step (srctrun.cc:45-66, inptran.cc:2666-2680)
     int nsin; const double *sin_tdl, *sin_freq;
+    // EXP sources: IFexpData::time_limit, inptran.cc:3064-3082 (two edges per source)
+    int nexp; const double *exp_td, *exp_tau;
 };
 
 #define ST_RUNNING 0
@@ -625,6 +627,14 @@ __device__ inline double ctl_finish_trunc(const TrialCtl &s, const CtlShared &sh
     for (int i = 0; i < sh.nsin; i++) {
         if (s.time >= sh.sin_tdl[i]) {
             double per = (.2*M_PI)/(2*M_PI*sh.sin_freq[i]);
+            if (time_step > per) time_step = per;
+        }
+    }
+    for (int i = 0; i < sh.nexp; i++) {
+        const double td = sh.exp_td[i], tau = sh.exp_tau[i];
+        if (s.time >= td && s.time < td + 5.0*tau) {
+            double f = (.2*M_PI)/(2*M_PI);
+            double per = tau*f*exp((s.time - td)/tau);
             if (time_step > per) time_step = per;
         }
     }

@@ -1991,5 +1991,29 @@ __device__ inline double dev_src_eval(int fn, const double *p, int nextra, doubl
             a *= exp(-time*p[4]);
         return p[0] + a;
     }
+    if (fn == B200_FN_EXP) {
+        // IFexpData::eval_func, inptran.cc:3016-3028 (V1 V2 TD1 TAU1 TD2 TAU2)
+        double value = p[0];
+        if (t <= p[2])
+            return value;
+        value += (p[1]-p[0])*(1-exp(-(t-p[2])/p[3]));
+        if (t <= p[4])
+            return value;
+        value += (p[0]-p[1])*(1-exp(-(t-p[4])/p[5]));
+        return value;
+    }
+    if (fn == B200_FN_SFFM) {
+        // IFsffmData::eval_func, inptran.cc:3215-3222 (VO VA FC MDI FS)
+        double w1 = 2*M_PI*p[2];
+        double w2 = 2*M_PI*p[4];
+        return p[0] + p[1]*sin(w1*t + p[3]*sin(w2*t));
+    }
+    if (fn == B200_FN_AM) {
+        // IFamData::eval_func, inptran.cc:3391-3399 (SA OC MF CF DL)
+        if (t <= p[4])
+            return 0.0;
+        double w = 2*M_PI*(t - p[4]);
+        return p[0]*(p[1] + sin(w*p[2]))*sin(w*p[3]);
+    }
     return 0.0;
 }

@@ -25,7 +25,7 @@ NAN = float("nan")
 
 DEV_RES, DEV_CAP, DEV_IND, DEV_MUT, DEV_SRC, DEV_MOS, DEV_JJ = range(7)
 SRC_V, SRC_I = 0, 1
-FN_NONE, FN_PULSE, FN_PWL, FN_SIN = range(4)
+FN_NONE, FN_PULSE, FN_PWL, FN_SIN, FN_EXP, FN_SFFM, FN_AM, FN_GAUSS = range(8)
 
 # parameter ids (include/b200spice.h)
 P_MOS_VTO, P_MOS_KP, P_MOS_L, P_MOS_W, P_MOS_GAMMA, P_MOS_LAMBDA, P_MOS_PHI = range(1, 8)
@@ -209,14 +209,18 @@ class Deck:
     tran_args: tuple | None = None
 
     # ---- construction -------------------------------------------------------------
-    def vsource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None):
+    def vsource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None, exp=None, sffm=None,
+                am=None):
         self.elems.append(_Elem(DEV_SRC, name.lower(), (str(p).lower(), str(n).lower()),
-                                dict(kind=SRC_V, dc=dc, pulse=pulse, pwl=pwl, sin=sin)))
+                                dict(kind=SRC_V, dc=dc, pulse=pulse, pwl=pwl, sin=sin, exp=exp,
+                                     sffm=sffm, am=am)))
         return self
 
-    def isource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None):
+    def isource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None, exp=None, sffm=None,
+                am=None):
         self.elems.append(_Elem(DEV_SRC, name.lower(), (str(p).lower(), str(n).lower()),
-                                dict(kind=SRC_I, dc=dc, pulse=pulse, pwl=pwl, sin=sin)))
+                                dict(kind=SRC_I, dc=dc, pulse=pulse, pwl=pwl, sin=sin, exp=exp,
+                                     sffm=sffm, am=am)))
         return self
 
     def resistor(self, name, p, n, r):
@@ -391,6 +395,9 @@ class Deck:
                     s += " pwl(" + " ".join(_fmt(x) for x in p["pwl"]) + ")"
                 if p["sin"] is not None:
                     s += " sin(" + " ".join(_fmt(x) for x in p["sin"]) + ")"
+                for fn in ("exp", "sffm", "am"):
+                    if p.get(fn) is not None:
+                        s += f" {fn}(" + " ".join(_fmt(x) for x in p[fn]) + ")"
                 lines.append(s)
             elif e.kind == DEV_RES:
                 r = overrides.get((P_RES_R, i), e.params["r"])
@@ -547,6 +554,12 @@ class Deck:
                 fn, coef = FN_PWL, list(p["pwl"])
             elif p["sin"] is not None:
                 fn, coef = FN_SIN, list(p["sin"])
+            elif p.get("exp") is not None:
+                fn, coef = FN_EXP, list(p["exp"])
+            elif p.get("sffm") is not None:
+                fn, coef = FN_SFFM, list(p["sffm"])
+            elif p.get("am") is not None:
+                fn, coef = FN_AM, list(p["am"])
             ca = arr(C.c_double, [float(x) for x in coef])
             src[i] = CSrc(p["kind"], nums[e.nodes[0]], nums[e.nodes[1]],
                           NAN if p["dc"] is None else float(p["dc"]), fn, len(coef), ca)
