@@ -44,7 +44,7 @@ extern "C" {
 
 /* ---- device kinds ---- */
 enum { B200_DEV_RES = 0, B200_DEV_CAP = 1, B200_DEV_IND = 2, B200_DEV_MUT = 3,
-       B200_DEV_SRC = 4, B200_DEV_MOS = 5, B200_DEV_JJ = 6, B200_DEV_NKINDS = 7 };
+       B200_DEV_SRC = 4, B200_DEV_MOS = 5, B200_DEV_JJ = 6, B200_DEV_TJM = 7, B200_DEV_NKINDS = 8 };
 
 /* NaN in a double field == "not given" (the reference's xxxGiven flags). */
 
@@ -131,6 +131,30 @@ typedef struct b200_jj {
     double icv, icphi;              /* ic=vj,phi for the UIC start (NaN = 0) */
 } b200_jj;
 
+/* Josephson junction, microscopic tunnel-junction model (mmjco / TJM, JJ level 3):
+ * devlib/tjm/tjmdefs.h, tjmload.cc:65-553, tjmacct.cc:43-169.  The current is the Werthamer
+ * expression with the pair and quasiparticle kernels fitted by nterms complex exponentials
+ * (coefficients p, A, B); every Newton iteration advances 2*nterms complex recurrences.
+ * The coefficient set comes from the reference's set-up instance (TJMcoeffSet, tjmcoeffs.cc:
+ * built-in tables `tjm1` / `tjm2`, or fitted by the external `mmjco` program), AFTER
+ * sTJMinstance::tjm_init1 has renormalised it (tjmset.cc:869-918) -- none of it depends on the
+ * junction's area, so it is shared by all trials.  Per trial (ics): criti, cap, gqp, g0,
+ * gshunt, gcrit (tjmset.cc:600-660, tjmload.cc:467-470).
+ * Built for `uic` runs like the RSJ model: no phase-mode DC, no lser / lsh. */
+typedef struct b200_tjm_model {
+    int rtype, ictype, nterms;
+    double criti, cap, cmu, gmu, r0, rsint, vshunt, tsaccl, tsfact, vgnom;
+} b200_tjm_model;
+typedef struct b200_tjm {
+    int pos, neg, phase_node;       /* phase_node 0 = absent */
+    int model;
+    double area, ics, vshunt;       /* NaN = not given */
+    double tcf;                     /* TJMicTempFactor */
+    double vdpbak, omegaJ, kgap, kgap_rejpt, alphaN;    /* set-up instance values */
+    const double *coef;             /* 6*nterms doubles: p[n], A[n], B[n] as (re, im) pairs */
+    double icv, icphi;              /* ic=vj,phi of the UIC start (NaN = from the node ICs / 0) */
+} b200_tjm;
+
 /* One deck = one topology (shared by all trials).  Node numbers: 0 is ground, 1..nnodes-1 are
  * the external nodes in the order the reference's parser meets them (src/inp/inpdeck.cc pass2);
  * internal nodes and branch equations are appended by b200_batch_create in the reference's
@@ -157,6 +181,8 @@ typedef struct b200_deck {
     int njj;   const b200_jj *jj;
     /* load order: order_kind[i] in B200_DEV_*, order_index[i] into that kind's table */
     int norder; const int *order_kind; const int *order_index;
+    int ntjmmod; const b200_tjm_model *tjm_models;
+    int ntjm;  const b200_tjm *tjm;
 } b200_deck;
 
 void b200_options_default(b200_options *o);        /* circuit.h:461-631 */
@@ -167,7 +193,8 @@ enum {
     B200_P_MOS_VTO = 1, B200_P_MOS_KP, B200_P_MOS_L, B200_P_MOS_W, B200_P_MOS_GAMMA,
     B200_P_MOS_LAMBDA, B200_P_MOS_PHI,
     B200_P_CAP_C = 32, B200_P_RES_R = 48, B200_P_IND_L = 56, B200_P_SRC_DC = 64,
-    B200_P_JJ_ICS = 80             /* instance ics: let @b1[ics] = ... of an .exec block */
+    B200_P_JJ_ICS = 80,            /* instance ics: let @b1[ics] = ... of an .exec block */
+    B200_P_TJM_ICS = 88
 };
 
 typedef struct b200_batch b200_batch;

@@ -103,6 +103,41 @@ def run_harvest(spice_text: str, libpath: str, ntrials: int, params=None, op_onl
     return out
 
 
+def run_harvest_oracle(spice_text: str, params=None) -> dict:
+    """Reference parser + set-up circuit -> shim/harvest.cc -> the plain-C ORACLE, next to the
+    reference's own doTask on that circuit (for decks whose device tables only the reference's
+    setup can make: TJM coefficient sets).  params: [(param_id, instance_name, value)]."""
+    sim = RefSim()
+    L = sim.L
+    params = params or []
+    n = len(params)
+    ids = (C.c_int*max(n, 1))(*[p[0] for p in params])
+    names = (C.c_char_p*max(n, 1))(*[p[1].encode() for p in params])
+    vals = (C.c_double*max(n, 1))(*[float(p[2]) for p in params])
+    L.wrsref_run_deck_harvest_oracle.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    err = L.wrsref_run_deck_harvest_oracle(spice_text.encode(), ORACLE_SO.encode(), n, ids, names, vals)
+    cnt = (C.c_int*9)()
+    L.wrsref_get_counters(cnt)
+    out = {"ref_err": err, "rc": L.wrsref_oracle_rc(),
+           "ref": dict(zip(("error", "size", "accepted", "rejected", "numiter", "timepts", "traniter",
+                            "itercut", "trapcut"), list(cnt)))}
+    npts, nn = L.wrsref_num_points(), L.wrsref_num_names()
+    t = np.zeros(npts)
+    v = np.zeros((npts, max(nn, 1)))
+    if npts:
+        L.wrsref_get_points(t.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+    out["ref_times"], out["ref_vals"] = t, v
+    if out["rc"] == 0:
+        N, P = L.wrsref_oracle_n(), L.wrsref_oracle_npoints()
+        oc = np.zeros(9, dtype=np.int32)
+        ot = np.zeros(P)
+        ov = np.zeros((P, N))
+        L.wrsref_oracle_get(oc.ctypes.data_as(C.c_void_p), ot.ctypes.data_as(C.c_void_p),
+                            ov.ctypes.data_as(C.c_void_p))
+        out.update(counters=oc, times=ot, vals=ov)
+    return out
+
+
 class Oracle:
     _lib = None
 

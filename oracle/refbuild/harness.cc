@@ -214,7 +214,8 @@ int wrsref_run_deck(const char *deck_text)
         last.trantime = st->STATtranTime;
         last.tottime = st->STATtotAnalTime;
     }
-    if (after_task_hook)
+    // the hooks walk the set-up circuit: only after a task that got through its setup
+    if (after_task_hook && (err == OK || ckt->CKTstat->STATnumIter > 0))
         last_hook_rc = (*after_task_hook)(ckt);
 
     // Output column names.
@@ -305,6 +306,41 @@ int wrsref_run_deck_harvest(const char *deck_text, const char *libpath, int ntri
 }
 
 void wrsref_harvest_stats(long long *out) { memcpy(out, hout.stats, sizeof(hout.stats)); }
+// the harvested deck through the plain-C oracle (decks only the reference's setup can make)
+namespace {
+    struct OracleArgs { const char *path; int nparams; const int *param_id; const char *const *inst_name; const double *value; } oargs;
+    struct OracleOut { int rc = 0, n = 0, npts = 0; int counters[B200_NCOUNTERS]; std::vector<double> times, vals; } oout;
+    int oracle_hook(sCKT *ckt)
+    {
+        oout = OracleOut();
+        double *t = 0, *v = 0;
+        oout.rc = b200_harvest_oracle(ckt, oargs.path, oargs.nparams, oargs.param_id, oargs.inst_name,
+            oargs.value, oout.counters, &oout.n, &oout.npts, &t, &v);
+        if (!oout.rc) { oout.times.assign(t, t + oout.npts); oout.vals.assign(v, v + (size_t)oout.npts*oout.n); }
+        free(t); free(v);
+        return (oout.rc);
+    }
+}
+
+int wrsref_run_deck_harvest_oracle(const char *deck_text, const char *oraclepath, int nparams,
+    const int *param_id, const char *const *inst_name, const double *value)
+{
+    oargs = { oraclepath, nparams, param_id, inst_name, value };
+    after_task_hook = oracle_hook;
+    int err = wrsref_run_deck(deck_text);
+    after_task_hook = 0;
+    return (err);
+}
+int wrsref_oracle_rc(void) { return (oout.rc); }
+int wrsref_oracle_n(void) { return (oout.n); }
+int wrsref_oracle_npoints(void) { return (oout.npts); }
+void wrsref_oracle_get(int *counters, double *times, double *vals)
+{
+    if (counters) memcpy(counters, oout.counters, sizeof(oout.counters));
+    if (times) memcpy(times, oout.times.data(), oout.times.size()*sizeof(double));
+    if (vals) memcpy(vals, oout.vals.data(), oout.vals.size()*sizeof(double));
+}
+
 int wrsref_harvest_rc(void) { return (hout.rc); }
 int wrsref_harvest_n(void) { return (hout.n); }
 int wrsref_harvest_npoints(void) { return (hout.npoints); }

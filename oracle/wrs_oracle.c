@@ -128,6 +128,23 @@ typedef struct {
     int phsN, phsF; double phsT;
 } JJ;
 
+/* sTJMinstancePOD (tjmdefs.h:100-245): JJ level 3, the mmjco tunnel-junction model */
+enum { TS_voltage, TS_dvdt, TS_phase, TS_phsInt, TS_crti, TS_qpi, TS_NSTATES = 10 };    /* tjmdefs.h:245-257 */
+#define TJM_MAXTERMS 20
+typedef struct { double re, im; } Cx;
+typedef struct {
+    b200_tjm_model mod; b200_tjm in;
+    int pos, neg, phs;
+    int pPP, pNN, pNP, pPN, pHH, pRPP, pRPN, pRNP, pRNN;
+    int st, n;
+    double area, criti, cap, gqp, g0, gshunt, vshunt, gcrit;
+    double initVoltage, initPhase, delVdelT;
+    double sinphi_2_old, cosphi_2_old, cqp, cp;
+    Cx p[TJM_MAXTERMS], A[TJM_MAXTERMS], B[TJM_MAXTERMS];
+    Cx Fc[TJM_MAXTERMS], Fs[TJM_MAXTERMS], Fcprev[TJM_MAXTERMS], Fsprev[TJM_MAXTERMS];
+    Cx alpha0[TJM_MAXTERMS], alpha1[TJM_MAXTERMS], exp_z[TJM_MAXTERMS];
+} TJM;
+
 typedef struct { int kind, index; } DevRef;
 
 /* saved op-point for sCKT::backup (ckt.cc:1323-1362, mosdefs.h:386-402) */
@@ -142,8 +159,8 @@ struct wo_ckt {
     double *ic_val; char *ic_given; double *ns_val; char *ns_given; int hadNodeset;
     char **names;
 
-    int nmos, ncap, nres, nsrc, nind, nmut, njj;
-    Mos *mos; Cap *cap; Res *res; Src *src; Ind *ind; Mut *mut; JJ *jj;
+    int nmos, ncap, nres, nsrc, nind, nmut, njj, ntjm;
+    Mos *mos; Cap *cap; Res *res; Src *src; Ind *ind; Mut *mut; JJ *jj; TJM *tjm;
     double initDelta;        /* CKTinitDelta (circuit.h:1581), set by JJdev::getic */
     char *phase;             /* [n+1] node carries the phase flag (jjset.cc:656-681, indset.cc:104-120), or NULL */
     int nord; DevRef *ord;
@@ -931,6 +948,7 @@ static void mos_temp(wo_ckt *c, Mos *m, const b200_mos_model *deckmod)
 }
 
 static void jj_setup_instance(JJ *j);
+static void tjm_setup_instance(TJM *j);
 static void wo_sincos(double x, double *s, double *co) { *s = sin(x); *co = cos(x); }
 
 static void build_matrix(wo_ckt *c)
@@ -979,6 +997,11 @@ static void build_matrix(wo_ckt *c)
         REMAP(j->pPP); REMAP(j->pNN); REMAP(j->pNP); REMAP(j->pPN); REMAP(j->pHH);
         REMAP(j->pRPP); REMAP(j->pRPN); REMAP(j->pRNP); REMAP(j->pRNN);
     }
+    for (int i = 0; i < c->ntjm; i++) {
+        TJM *j = &c->tjm[i];
+        REMAP(j->pPP); REMAP(j->pNN); REMAP(j->pNP); REMAP(j->pPN); REMAP(j->pHH);
+        REMAP(j->pRPP); REMAP(j->pRPN); REMAP(j->pRNP); REMAP(j->pRNN);
+    }
     for (int i = 0; i < c->nsrc; i++) {
         REMAP(c->src[i].pPB); REMAP(c->src[i].pNB); REMAP(c->src[i].pBN); REMAP(c->src[i].pBP);
     }
@@ -1019,6 +1042,8 @@ wo_ckt *wo_create(const b200_deck *dk)
     c->mut = xcalloc(c->nmut, sizeof(Mut));
     c->njj = dk->njj;
     c->jj = xcalloc(c->njj, sizeof(JJ));
+    c->ntjm = dk->ntjm;
+    c->tjm = xcalloc(c->ntjm, sizeof(TJM));
     c->nord = dk->norder;
     c->ord = xcalloc(c->nord, sizeof(DevRef));
     for (int i = 0; i < c->nord; i++) {
@@ -1125,6 +1150,30 @@ wo_ckt *wo_create(const b200_deck *dk)
             j->st = c->numStates; c->numStates += JS_NSTATES;
             jj_setup_instance(j);
             break; }
+        case B200_DEV_TJM: {
+            /* tjmset.cc:130-200 pointers (same order as the RSJ model), :794 states */
+            TJM *j = &c->tjm[i];
+            j->in = dk->tjm[i]; j->mod = dk->tjm_models[dk->tjm[i].model];
+            j->n = j->mod.nterms;
+            if (j->n > TJM_MAXTERMS) { fprintf(stderr, "wrs_oracle: TJM nterms > %d\n", TJM_MAXTERMS); abort(); }
+            for (int k = 0; k < j->n; k++) {
+                j->p[k].re = j->in.coef[2*k];             j->p[k].im = j->in.coef[2*k+1];
+                j->A[k].re = j->in.coef[2*(j->n + k)];    j->A[k].im = j->in.coef[2*(j->n + k)+1];
+                j->B[k].re = j->in.coef[2*(2*j->n + k)];  j->B[k].im = j->in.coef[2*(2*j->n + k)+1];
+            }
+            j->pos = j->in.pos; j->neg = j->in.neg; j->phs = j->in.phase_node;
+            j->pPP = coo_add(c, j->pos, j->pos);
+            j->pNN = coo_add(c, j->neg, j->neg);
+            j->pNP = coo_add(c, j->neg, j->pos);
+            j->pPN = coo_add(c, j->pos, j->neg);
+            j->pRPP = coo_add(c, j->pos, j->pos);
+            j->pRPN = coo_add(c, j->pos, j->neg);
+            j->pRNP = coo_add(c, j->neg, j->pos);
+            j->pRNN = coo_add(c, j->neg, j->neg);
+            j->pHH = j->phs > 0 ? coo_add(c, j->phs, j->phs) : -1;
+            j->st = c->numStates; c->numStates += TS_NSTATES;
+            tjm_setup_instance(j);
+            break; }
         default:
             fprintf(stderr, "wrs_oracle: device kind %d not supported\n", c->ord[o].kind);
             abort();
@@ -1162,6 +1211,10 @@ wo_ckt *wo_create(const b200_deck *dk)
             if (!c->phase) c->phase = xcalloc(n + 1, 1);
             c->phase[c->jj[i].pos] = 1; c->phase[c->jj[i].neg] = 1;
         }
+    for (int i = 0; i < c->ntjm; i++) {                          /* tjmset.cc:690-708 (any ictype) */
+        if (!c->phase) c->phase = xcalloc(n + 1, 1);
+        c->phase[c->tjm[i].pos] = 1; c->phase[c->tjm[i].neg] = 1;
+    }
     if (c->phase) {
         for (int i = 0; i < c->nind; i++) { c->phase[c->ind[i].pos] = 1; c->phase[c->ind[i].neg] = 1; }
         c->phase[0] = 0;
@@ -1193,6 +1246,7 @@ int wo_set_param(wo_ckt *c, int param, int index, double value)
         break; }
     case B200_P_SRC_DC:     c->src[index].dc = value; c->src[index].dcGiven = 1; break;
     case B200_P_JJ_ICS:     c->jj[index].in.ics = value; break;
+    case B200_P_TJM_ICS:    c->tjm[index].in.ics = value; break;
     case B200_P_IND_L:      c->ind[index].induct = value/1.0;
         for (int k = 0; k < c->nmut; k++) c->mut[k].factor = 0.0;   /* recomputed at the next load */
         break;
@@ -3123,6 +3177,287 @@ static void jj_getic(wo_ckt *c)
     }
 }
 
+
+/* ------------------------------------------------------------------------- */
+/* Josephson junction, tunnel-junction model (JJ level 3): devlib/tjm/{tjmset,tjmload,tjmacct,tjmic,tjmtrun}.cc */
+/* complex arithmetic as include/ifcx.h:100-150                               */
+/* ------------------------------------------------------------------------- */
+static inline Cx cx_mul(Cx a, Cx b) { Cx r = { a.re*b.re - a.im*b.im, a.im*b.re + a.re*b.im }; return r; }
+static inline Cx cx_muld(Cx a, double d) { Cx r = { a.re*d, a.im*d }; return r; }
+static inline Cx cx_add(Cx a, Cx b) { Cx r = { a.re + b.re, a.im + b.im }; return r; }
+static inline Cx cx_div(Cx a, Cx b)
+{
+    double d = b.re*b.re + b.im*b.im;
+    Cx r = { (a.re*b.re + a.im*b.im)/d, (a.im*b.re - a.re*b.im)/d };
+    return r;
+}
+
+static void tjm_setup_instance(TJM *j)
+{
+    /* tjmset.cc:572-660, :714: what depends on the junction's area */
+    const b200_tjm_model *m = &j->mod;
+    j->vshunt = GIVEN(j->in.vshunt) ? j->in.vshunt : m->vshunt;
+    if (GIVEN(j->in.vshunt) && (j->in.vshunt < 0.0 || j->in.vshunt > m->vgnom)) j->vshunt = 0.0;
+    if (GIVEN(j->in.ics)) {
+        double ics = j->in.ics;
+        if (ics < m->criti/50 || ics > m->criti*50) ics = m->criti;
+        j->area = ics/m->criti;
+    }
+    else if (GIVEN(j->in.area)) j->area = j->in.area;
+    else j->area = 1;
+    j->criti = m->criti*j->area*j->in.tcf;
+    double sqrta = sqrt(j->area);
+    double gfac = j->area*(1.0 - m->gmu) + sqrta*m->gmu;
+    j->gqp = gfac/m->rsint;
+    j->g0 = m->r0 > 0.0 ? gfac/m->r0 : 0.0;
+    double tg0 = j->g0;
+    if (j->g0 >= j->gqp) j->g0 -= j->gqp;
+    j->gshunt = 0.0;
+    if (j->vshunt > 1e-12) {
+        double gshunt = j->criti/j->vshunt - SPMAX(tg0, j->gqp);
+        if (gshunt > 0.0) j->gshunt = gshunt;
+    }
+    j->cap = m->cap*(j->area*(1.0 - m->cmu) + sqrta*m->cmu);
+}
+
+static void tjm_init(TJM *j, double phi)
+{
+    /* sTJMinstance::tjm_init, tjmload.cc:459-487 */
+    double s2, c2;
+    wo_sincos(0.5*phi, &s2, &c2);
+    j->sinphi_2_old = s2; j->cosphi_2_old = c2;
+    if (j->mod.rtype > 0) j->gcrit = j->in.alphaN*sqrt(j->cap*j->criti/PHI0_2PI);
+    else j->gcrit = 0.0;
+    for (int i = 0; i < j->n; i++) {
+        j->Fcprev[i].re = c2; j->Fcprev[i].im = 0.0;
+        j->Fsprev[i].re = s2; j->Fsprev[i].im = 0.0;
+        j->Fc[i].re = j->Fc[i].im = j->Fs[i].re = j->Fs[i].im = 0.0;
+    }
+}
+
+static void tjm_newstep(wo_ckt *c, TJM *j)
+{
+    /* tjmload.cc:490-505 */
+    double kdt = j->in.kgap*j->in.omegaJ*c->delta;
+    for (int i = 0; i < j->n; i++) {
+        Cx z = cx_muld(j->p[i], kdt);
+        double d = exp(z.re);
+        Cx ez = { d*cos(z.im), d*sin(z.im) };
+        j->exp_z[i] = ez;
+        Cx em1 = { ez.re - 1.0, ez.im };
+        Cx zt = cx_div(em1, z);
+        j->alpha0[i].re = zt.re - ez.re; j->alpha0[i].im = zt.im - ez.im;
+        j->alpha1[i].re = 1.0 - zt.re;   j->alpha1[i].im = -zt.im;
+    }
+}
+
+static void tjm_update(TJM *j, double phi)
+{
+    /* tjmload.cc:508-553 */
+    double s2, c2;
+    wo_sincos(0.5*phi, &s2, &c2);
+    double FcSp = 0.0, FcSq = 0.0, FsSp = 0.0, FsSq = 0.0;
+    for (int i = 0; i < j->n; i++) {
+        j->Fc[i] = cx_add(cx_add(cx_mul(j->exp_z[i], j->Fcprev[i]), cx_muld(j->alpha0[i], j->cosphi_2_old)),
+            cx_muld(j->alpha1[i], c2));
+        j->Fs[i] = cx_add(cx_add(cx_mul(j->exp_z[i], j->Fsprev[i]), cx_muld(j->alpha0[i], j->sinphi_2_old)),
+            cx_muld(j->alpha1[i], s2));
+        FcSp += cx_mul(j->A[i], j->Fc[i]).re;
+        FcSq += cx_mul(j->B[i], j->Fc[i]).re;
+        FsSp += cx_mul(j->A[i], j->Fs[i]).re;
+        FsSq += cx_mul(j->B[i], j->Fs[i]).re;
+    }
+    double fct = j->criti*j->in.kgap_rejpt;
+    j->cp = j->mod.ictype > 0 ? fct*(s2*FcSp + c2*FsSp) : 0.0;
+    j->cqp = j->mod.rtype > 0 ? fct*(s2*FcSq - c2*FsSq) : 0.0;
+}
+
+static void tjm_stamp(wo_ckt *c, TJM *j, double vj, double phi, double pfac, double crt)
+{
+    /* sTJMinstance::tjm_load, tjmload.cc:412-456 */
+    double *s0 = c->states[0] + j->st;
+    s0[TS_voltage] = vj;
+    s0[TS_phase] = phi;
+    double crhs, gqt;
+    if (c->mode & MODEDC) {
+        double cr = crt*sin(phi);
+        gqt = pfac*crt*cos(phi);
+        crhs = cr - gqt*phi;
+        j->cp = crt*sin(phi);
+        s0[TS_crti] = j->cp;
+        s0[TS_qpi] = 0.0;
+    }
+    else {
+        tjm_update(j, phi);
+        crhs = j->cp + j->cqp + j->delVdelT*j->cap;
+        gqt = j->gcrit + j->g0 + c->ag[0]*j->cap;
+        s0[TS_crti] = j->cp;
+        s0[TS_qpi] = j->cqp + (j->gcrit + j->g0)*vj;
+    }
+    if (j->phs > 0) {
+        int pint;
+        memcpy(&pint, &c->states[1][j->st + TS_phsInt], sizeof(int));
+        c->rhs[j->phs] = phi + (4*M_PI)*pint;
+    }
+    if (!j->neg) { ldadd(c, j->pPP, gqt); rhsadd(c, j->pos, -crhs); }
+    else if (!j->pos) { ldadd(c, j->pNN, gqt); rhsadd(c, j->neg, crhs); }
+    else {
+        ldadd(c, j->pPP, gqt); ldadd(c, j->pPN, -gqt); ldadd(c, j->pNP, -gqt); ldadd(c, j->pNN, gqt);
+        rhsadd(c, j->pos, -crhs); rhsadd(c, j->neg, crhs);
+    }
+}
+
+static void tjm_shunt(wo_ckt *c, TJM *j)
+{
+    if (j->gshunt > 1e-12) {
+        ldadd(c, j->pRPP, j->gshunt); ldadd(c, j->pRPN, -j->gshunt);
+        ldadd(c, j->pRNP, -j->gshunt); ldadd(c, j->pRNN, j->gshunt);
+    }
+}
+
+static void tjm_load(wo_ckt *c, TJM *j)
+{
+    /* TJMdev::load, tjmload.cc:65-392 */
+    double *s0 = c->states[0] + j->st, *s1 = c->states[1] + j->st;
+    if (c->mode & MODEDC) {
+        if (c->mode & MODEUIC) return;                        /* :75-76 */
+        double vj = c->rhsOld[j->pos] - c->rhsOld[j->neg];
+        s0[TS_phase] = vj; s0[TS_voltage] = 0.0;
+        tjm_stamp(c, j, vj, vj, 1.0, j->criti);
+        return;
+    }
+    double pfac = c->delta/PHI0_2PI;
+    if (c->order > 1) pfac *= .5;
+    if (c->mode & MODEINITFLOAT) {
+        double vj = c->rhsOld[j->pos] - c->rhsOld[j->neg];
+        double absvj = fabs(vj);
+        double temp = s0[TS_voltage];
+        double absold = fabs(temp);
+        double maxvj = SPMAX(absvj, absold);
+        temp -= vj;
+        double absdvj = fabs(temp);
+        if (!c->noncon) {
+            double tol = c->opt.reltol*maxvj + c->opt.abstol;
+            if (absdvj > tol) c->noncon++;
+        }
+        double phi = s1[TS_phase];
+        temp = vj;
+        if (c->order > 1) temp += s1[TS_voltage];
+        phi += pfac*temp;
+        /* the reference integrates BEFORE tjm_load overwrites state 0's voltage with the new vj
+         * (tjmload.cc:209-210): dvdt comes from the PREVIOUS iteration's voltage */
+        integrate2(c, j->st + TS_voltage, j->delVdelT);
+        tjm_stamp(c, j, vj, phi, pfac, j->criti);
+        tjm_shunt(c, j);
+        return;
+    }
+    if (c->mode & MODEINITPRED) {
+        double y0 = s1[TS_dvdt]*c->pred[0] + c->states[2][j->st + TS_dvdt]*c->pred[1];
+        if (c->order != 1) y0 += s1[TS_dvdt];
+        double temp = s1[TS_voltage];
+        double rag0 = c->order == 1 ? c->delta : .5*c->delta;
+        double vj = temp + rag0*y0;
+        double phi = s1[TS_phase];
+        temp = vj;
+        if (c->order > 1) temp += s1[TS_voltage];
+        phi += pfac*temp;
+        j->delVdelT = find_ceq(c, j->st + TS_voltage);
+        tjm_newstep(c, j);
+        tjm_stamp(c, j, vj, phi, pfac, j->criti);
+        tjm_shunt(c, j);
+        return;
+    }
+    if (c->mode & MODEINITTRAN) {
+        double vj, phi;
+        if (c->mode & MODEUIC) {
+            vj = j->initVoltage; phi = j->initPhase;
+            s1[TS_voltage] = vj; s1[TS_phase] = phi;
+        }
+        else {
+            vj = 0; s1[TS_voltage] = 0.0; s0[TS_voltage] = 0.0; phi = 0;
+        }
+        j->delVdelT = find_ceq(c, j->st + TS_voltage);
+        tjm_init(j, phi);
+        tjm_newstep(c, j);
+        tjm_stamp(c, j, vj, phi, pfac, j->criti);
+        tjm_shunt(c, j);
+    }
+}
+
+static void tjm_accept(wo_ckt *c)
+{
+    /* TJMdev::accept + sTJMinstance::tjm_accept, tjmacct.cc:43-169.  Instances are visited in
+     * load order; the floor vth is the FIRST visited instance's (didm is set once per model). */
+    for (int mi = 0; mi < c->ntjm; mi++) {
+        int first = 1;
+        for (int k = 0; k < mi; k++) if (c->tjm[k].in.model == c->tjm[mi].in.model) { first = 0; break; }
+        if (!first) continue;
+        const b200_tjm_model *m = &c->tjm[mi].mod;
+        int didm = 0;
+        double vmax = 0;
+        for (int o = 0; o < c->nord; o++) {
+            if (c->ord[o].kind != B200_DEV_TJM) continue;
+            TJM *j = &c->tjm[c->ord[o].index];
+            if (j->in.model != c->tjm[mi].in.model) continue;
+            double vth = j->in.vdpbak/m->tsaccl;
+            double *s0 = c->states[0] + j->st;
+            double phi = s0[TS_phase];
+            int pint;
+            memcpy(&pint, &c->states[1][j->st + TS_phsInt], sizeof(int));
+            double twopi = M_PI + M_PI, fourpi = twopi + twopi;
+            if (phi >= twopi) { phi -= fourpi; pint++; }
+            else if (phi < -twopi) { phi += fourpi; pint--; }
+            s0[TS_phase] = phi;
+            memcpy(&s0[TS_phsInt], &pint, sizeof(int));
+            double phitot = phi + fourpi*pint;
+            if (j->phs > 0) c->rhsOld[j->phs] = phitot;
+            wo_sincos(0.5*phi, &j->sinphi_2_old, &j->cosphi_2_old);
+            for (int i = 0; i < j->n; i++) { j->Fcprev[i] = j->Fc[i]; j->Fsprev[i] = j->Fs[i]; }
+            if (!didm) { didm = 1; if (vmax < vth) vmax = vth; }
+            double vj = s0[TS_voltage];
+            if (vj < 0) vj = -vj;
+            if (vmax < vj) vmax = vj;
+        }
+        if (vmax > 0.0) {
+            double delmax = m->tsfact*PHI0/vmax;
+            if (c->devMaxDelta == 0.0 || delmax < c->devMaxDelta) c->devMaxDelta = delmax;
+        }
+    }
+}
+
+static void tjm_getic(wo_ckt *c)
+{
+    /* TJMdev::getic, tjmic.cc:45-95 */
+    for (int i = 0; i < c->ntjm; i++) {
+        TJM *j = &c->tjm[i];
+        j->initVoltage = GIVEN(j->in.icv) ? j->in.icv : c->rhs[j->pos] - c->rhs[j->neg];
+        j->initPhase = GIVEN(j->in.icphi) ? j->in.icphi : (j->phs > 0 ? c->rhs[j->phs] : 0);
+    }
+    double vmax = 0;
+    for (int mi = 0; mi < c->ntjm; mi++) {
+        int first = 1;
+        for (int k = 0; k < mi; k++) if (c->tjm[k].in.model == c->tjm[mi].in.model) { first = 0; break; }
+        if (!first) continue;
+        const b200_tjm_model *m = &c->tjm[mi].mod;
+        if (m->ictype != 0) {
+            for (int i = 0; i < c->ntjm; i++) {
+                TJM *j = &c->tjm[i];
+                if (j->in.model != c->tjm[mi].in.model) continue;
+                double vth = j->in.vdpbak/m->tsaccl;
+                if (vmax < vth) vmax = vth;
+                if (j->criti > 0) {
+                    double temp = fabs(j->initVoltage);
+                    if (vmax < temp) vmax = temp;
+                }
+            }
+        }
+        if (vmax > 0) {
+            double delmax = 0.1*m->tsfact*PHI0/vmax;
+            if (c->initDelta == 0.0 || c->initDelta > delmax) c->initDelta = delmax;
+        }
+    }
+}
+
 static void res_load(wo_ckt *c, Res *r)
 {
     /* RESdev::load, resload.cc:250-292 (linear resistor).  In the phase-mode DC load only the
@@ -3330,6 +3665,9 @@ static void preload(wo_ckt *c)
             /* jjset.cc:815-816: the phase node's own equation, x[phs] = rhs[phs] */
             if (c->jj[i].phs > 0 && c->jj[i].pHH >= 0) c->Ax[c->jj[i].pHH] = 1.0;
         }
+        else if (c->ord[o].kind == B200_DEV_TJM) {
+            if (c->tjm[i].phs > 0 && c->tjm[i].pHH >= 0) c->Ax[c->tjm[i].pHH] = 1.0;
+        }
     }
     for (int o = 0; o < c->nord; o++) {
         int i = c->ord[o].index;
@@ -3365,6 +3703,7 @@ static int ckt_load(wo_ckt *c)
         case B200_DEV_MUT: mut_load(c, &c->mut[i]); break;
         case B200_DEV_SRC: src_load(c, &c->src[i]); break;
         case B200_DEV_JJ: jj_load(c, &c->jj[i]); break;
+        case B200_DEV_TJM: tjm_load(c, &c->tjm[i]); break;
         case B200_DEV_RES: res_load(c, &c->res[i]); break;   /* preloaded ones return at once (LOAD_SKIP_FLAG) */          /* preloaded, LOAD_SKIP_FLAG */
         }
     }
@@ -4145,6 +4484,10 @@ static int ckt_trunc(wo_ckt *c, double *timeStep)
             if (c->jj[i].mod.ictype == 0 || c->jj[i].criti == 0.0)
                 terr(c, c->jj[i].st + JS_voltage, &timetemp);
         }
+        else if (c->ord[o].kind == B200_DEV_TJM) {
+            if (c->tjm[i].mod.ictype == 0 || c->tjm[i].criti == 0.0)       /* tjmtrun.cc:52-64 */
+                terr(c, c->tjm[i].st + TS_voltage, &timetemp);
+        }
     }
     /* srctrun.cc:45-66: SIN sources bound the step through IFsinData::time_limit
      * (inptran.cc:2666-2680, uses dphimax = .2*pi, circuit.h:495) */
@@ -4285,6 +4628,7 @@ static int ckt_accept(wo_ckt *c)
     /* ckt.cc:355-383 (device accept: JJ only among the built models) */
     c->devMaxDelta = 0.0;
     if (c->njj) jj_accept(c);
+    if (c->ntjm) tjm_accept(c);
     double *tmp = c->sols[7];
     for (int i = 7; i > 0; i--) c->sols[i] = c->sols[i-1];
     c->sols[0] = tmp;
@@ -4467,7 +4811,7 @@ static int tran_step(wo_ckt *c)
 static int has_trunc_dev(const wo_ckt *c)
 {
     /* tranan.cc:68-77: any model type with DV_TRUNC (mos.cc:347, cap.cc:147) */
-    return (c->nmos > 0 || c->ncap > 0 || c->nind > 0 || c->njj > 0);      /* ind.cc:128, jj.cc:269 */
+    return (c->nmos > 0 || c->ncap > 0 || c->nind > 0 || c->njj > 0 || c->ntjm > 0);      /* ind.cc:128, jj.cc:269, tjm.cc:280 */
 }
 
 int wo_run_tran(wo_ckt *c)
@@ -4480,6 +4824,7 @@ int wo_run_tran(wo_ckt *c)
         mos_temp(c, &c->mos[i], &deckmod);
     }
     for (int i = 0; i < c->njj; i++) jj_setup_instance(&c->jj[i]);
+    for (int i = 0; i < c->ntjm; i++) tjm_setup_instance(&c->tjm[i]);
     c->initDelta = 0.0;
     preload(c);
 
@@ -4547,6 +4892,7 @@ int wo_run_tran(wo_ckt *c)
         for (int i = 0; i < c->nind; i++)
             if (c->ind[i].icGiven) c->rhs[c->ind[i].br] = c->ind[i].ic;      /* indic.cc:62-63 */
         if (c->njj) jj_getic(c);
+        if (c->ntjm) tjm_getic(c);
         double *tmp = c->rhs; c->rhs = c->rhsOld; c->rhsOld = tmp;
         c->rhs[0] = 0.0; c->rhsOld[0] = 0.0;
         c->mode = MODEUIC | MODETRANOP | MODEINITJCT;

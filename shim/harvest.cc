@@ -41,6 +41,7 @@
 #include "src/srcdefs.h"
 #include "mos/mosdefs.h"
 #include "jj/jjdefs.h"
+#include "tjm/tjmdefs.h"
 
 #include "b200spice.h"
 #include "harvest.h"
@@ -93,10 +94,12 @@ struct b200_harvest {
     std::vector<b200_mut> mut; std::vector<b200_src> src;
     std::vector<b200_mos_model> mosmod; std::vector<b200_mos> mos;
     std::vector<b200_jj_model> jjmod; std::vector<b200_jj> jj;
+    std::vector<b200_tjm_model> tjmmod; std::vector<b200_tjm> tjm;
+    std::vector<std::vector<double>> tjmcoef;
     std::vector<std::vector<double>> coefs;
     std::vector<int> ic_node, ns_node, okind, oindex;
     std::vector<double> ic_val, ns_val;
-    std::map<const void*, int> ind_index, mosmod_index, jjmod_index;
+    std::map<const void*, int> ind_index, mosmod_index, jjmod_index, tjmmod_index;
     std::vector<std::string> names[B200_DEV_NKINDS];      // instance names per kind, table order
     std::string error;
     int has_tran = 0;
@@ -377,6 +380,46 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
                         order_rest.push_back({B200_DEV_JJ, (int)H->jj.size()});
                         H->jj.push_back(x); H->names[B200_DEV_JJ].push_back(iname);
                     }
+                    else if (!strcmp(dn, "TJM")) {
+                        // JJ level 3.  The set-up instance carries its coefficient set after
+                        // sTJMinstance::tjm_init1 (tjmset.cc:869-918) and the quantities that do
+                        // not depend on the junction's area.
+                        sTJMmodel *m = (sTJMmodel*)dm;
+                        sTJMinstance *q = (sTJMinstance*)gi;
+                        if (q->TJMlser > 0.0 || q->TJMlsh > 0.0) { H->error = "TJM lser / lsh"; return B200_E_UNSUPP; }
+                        if (!q->tjm_p) { H->error = "TJM instance without a coefficient set (setup failed)"; return B200_E_BADPARM; }
+                        auto it = H->tjmmod_index.find(m);
+                        if (it == H->tjmmod_index.end()) {
+                            b200_tjm_model y;
+                            memset(&y, 0, sizeof(y));
+                            y.rtype = m->TJMrtype; y.ictype = m->TJMictype; y.nterms = m->TJMnterms;
+                            y.criti = m->TJMcriti; y.cap = m->TJMcap; y.cmu = m->TJMcmu; y.gmu = m->TJMgmu;
+                            y.r0 = m->TJMr0; y.rsint = m->TJMrsint; y.vshunt = m->TJMvShunt;
+                            y.tsaccl = m->TJMtsaccl; y.tsfact = m->TJMtsfact; y.vgnom = m->TJMvgNom;
+                            it = H->tjmmod_index.emplace(m, (int)H->tjmmod.size()).first;
+                            H->tjmmod.push_back(y);
+                        }
+                        b200_tjm x;
+                        memset(&x, 0, sizeof(x));
+                        x.pos = ext(q->TJMrealPosNode); x.neg = ext(q->TJMnegNode);
+                        x.phase_node = q->TJMphsNode > 0 ? ext(q->TJMphsNode) : 0;
+                        x.model = it->second;
+                        x.area = opt(q->TJMareaGiven && !q->TJMicsGiven, q->TJMarea);
+                        x.ics = opt(q->TJMicsGiven, q->TJMics);
+                        x.vshunt = opt(q->TJMvshuntGiven, q->TJMvshunt);
+                        x.tcf = q->TJMicTempFactor;
+                        x.vdpbak = q->TJMvdpbak; x.omegaJ = q->TJMomegaJ;
+                        x.kgap = q->tjm_kgap; x.kgap_rejpt = q->tjm_kgap_rejpt; x.alphaN = q->tjm_alphaN;
+                        std::vector<double> cf;
+                        const IFcomplex *arr[3] = { q->tjm_p, q->tjm_A, q->tjm_B };
+                        for (int a = 0; a < 3; a++)
+                            for (int k = 0; k < m->TJMnterms; k++) { cf.push_back(arr[a][k].real); cf.push_back(arr[a][k].imag); }
+                        H->tjmcoef.push_back(cf);
+                        x.icv = opt(q->TJMinitVoltGiven, q->TJMinitVoltage);
+                        x.icphi = opt(q->TJMinitPhaseGiven, q->TJMinitPhase);
+                        order_rest.push_back({B200_DEV_TJM, (int)H->tjm.size()});
+                        H->tjm.push_back(x); H->names[B200_DEV_TJM].push_back(iname);
+                    }
                     else {
                         H->error = std::string("device not built: ") + dn;
                         return B200_E_UNSUPP;
@@ -402,6 +445,9 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
     D.nmos = (int)H->mos.size(); D.mos = H->mos.data();
     D.njjmod = (int)H->jjmod.size(); D.jj_models = H->jjmod.data();
     D.njj = (int)H->jj.size(); D.jj = H->jj.data();
+    for (size_t i = 0; i < H->tjm.size(); i++) H->tjm[i].coef = H->tjmcoef[i].data();
+    D.ntjmmod = (int)H->tjmmod.size(); D.tjm_models = H->tjmmod.data();
+    D.ntjm = (int)H->tjm.size(); D.tjm = H->tjm.data();
     D.norder = (int)H->okind.size(); D.order_kind = H->okind.data(); D.order_index = H->oindex.data();
     return B200_OK;
 }
@@ -423,7 +469,7 @@ extern "C" int b200_harvest_run(sCKT *ckt, const char *libpath, int ntrials, int
     rc = api.create(&H->deck, ntrials, device, &b);
     if (rc) { b200_harvest_free(H); return rc; }
     for (int i = 0; i < nparams && !rc; i++) {
-        int kind = param_id[i] >= B200_P_JJ_ICS ? B200_DEV_JJ : param_id[i] >= B200_P_SRC_DC ? B200_DEV_SRC : param_id[i] >= B200_P_IND_L ? B200_DEV_IND :
+        int kind = param_id[i] >= B200_P_TJM_ICS ? B200_DEV_TJM : param_id[i] >= B200_P_JJ_ICS ? B200_DEV_JJ : param_id[i] >= B200_P_SRC_DC ? B200_DEV_SRC : param_id[i] >= B200_P_IND_L ? B200_DEV_IND :
                    param_id[i] >= B200_P_RES_R ? B200_DEV_RES : param_id[i] >= B200_P_CAP_C ? B200_DEV_CAP : B200_DEV_MOS;
         int idx = b200_harvest_find(H, kind, inst_name[i]);
         rc = idx < 0 ? B200_E_BADPARM : api.set_param(b, param_id[i], idx, values[i]);
@@ -457,4 +503,44 @@ extern "C" int b200_harvest_stats(sCKT *ckt, const char *libpath, long long *out
     else rc = stats(&H->deck, out, nout);
     b200_harvest_free(H);
     return rc;
+}
+
+// Test plumbing: the same harvested deck through the plain-C oracle (oracle/libwrsoracle.so,
+// dlopen'ed) -- decks whose device tables only the reference's setup can make (TJM coefficient
+// sets) reach the oracle this way.  counters[9] as wo_get_counters; *vals malloc'ed [npts][n].
+extern "C" int b200_harvest_oracle(sCKT *ckt, const char *oraclepath, int nparams, const int *param_id,
+    const char *const *inst_name, const double *value, int *counters, int *n_out, int *npts_out,
+    double **times_out, double **vals_out)
+{
+    void *h = dlopen(oraclepath, RTLD_NOW | RTLD_LOCAL);
+    if (!h) { fprintf(stderr, "b200 shim: %s\n", dlerror()); return B200_E_PANIC; }
+    typedef struct wo_ckt wo_ckt;
+    wo_ckt *(*create)(const b200_deck*) = (wo_ckt*(*)(const b200_deck*))dlsym(h, "wo_create");
+    int (*setp)(wo_ckt*, int, int, double) = (int(*)(wo_ckt*, int, int, double))dlsym(h, "wo_set_param");
+    int (*run)(wo_ckt*) = (int(*)(wo_ckt*))dlsym(h, "wo_run_tran");
+    int (*nunk)(const wo_ckt*) = (int(*)(const wo_ckt*))dlsym(h, "wo_num_unknowns");
+    int (*npts)(const wo_ckt*) = (int(*)(const wo_ckt*))dlsym(h, "wo_num_points");
+    void (*getp)(const wo_ckt*, double*, double*) = (void(*)(const wo_ckt*, double*, double*))dlsym(h, "wo_get_points");
+    void (*getc)(const wo_ckt*, int*) = (void(*)(const wo_ckt*, int*))dlsym(h, "wo_get_counters");
+    void (*destroy)(wo_ckt*) = (void(*)(wo_ckt*))dlsym(h, "wo_destroy");
+    if (!create || !setp || !run || !nunk || !npts || !getp || !getc || !destroy) return B200_E_PANIC;
+    b200_harvest *H = nullptr;
+    int rc = b200_harvest_ckt(ckt, &H);
+    if (rc) { fprintf(stderr, "b200 shim: harvest: %s\n", b200_harvest_error(H)); b200_harvest_free(H); return rc; }
+    wo_ckt *c = create(&H->deck);
+    for (int i = 0; i < nparams; i++) {
+        int kind = param_id[i] >= B200_P_TJM_ICS ? B200_DEV_TJM : param_id[i] >= B200_P_JJ_ICS ? B200_DEV_JJ : B200_DEV_MOS;
+        int idx = b200_harvest_find(H, kind, inst_name[i]);
+        if (idx < 0 || setp(c, param_id[i], idx, value[i])) { destroy(c); b200_harvest_free(H); return B200_E_BADPARM; }
+    }
+    int err = run(c);
+    getc(c, counters);
+    counters[0] = err;
+    *n_out = nunk(c); *npts_out = npts(c);
+    *times_out = (double*)malloc(sizeof(double)*(*npts_out ? *npts_out : 1));
+    *vals_out = (double*)malloc(sizeof(double)*(size_t)(*npts_out ? *npts_out : 1)*(*n_out));
+    getp(c, *times_out, *vals_out);
+    destroy(c);
+    b200_harvest_free(H);
+    return B200_OK;
 }

@@ -26,6 +26,11 @@ int  b200_harvest_run(struct sCKT *ckt, const char *libpath, int ntrials, int de
                       int *counters, int *n_out, int *npoints_out, double **times_out,
                       double **waves_out, int op_only);
 
+/* test plumbing: the harvested deck through the plain-C oracle (oracle/libwrsoracle.so) */
+int  b200_harvest_oracle(struct sCKT *ckt, const char *oraclepath, int nparams, const int *param_id,
+                         const char *const *inst_name, const double *value, int *counters, int *n_out,
+                         int *npts_out, double **times_out, double **vals_out);
+
 /* host-only: b200_deck_analysis_stats of the harvested deck (sizes of pattern / LU / program) */
 int  b200_harvest_stats(struct sCKT *ckt, const char *libpath, long long *out, int nout);
 

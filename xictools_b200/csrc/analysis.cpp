@@ -162,6 +162,12 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (m.ictype < 0 || m.ictype > 1) { err = "JJ ictype 2..4 (control current) is not built"; return B200_E_UNSUPP; }
         }
     }
+    if (dk->ntjm) {
+        if (!dk->uic) { err = "TJM decks need `.tran ... uic` (phase-mode DC is not built)"; return B200_E_UNSUPP; }
+        if (dk->njjmod + dk->ntjmmod > JJ_MAXMODELS) { err = "more JJ + TJM models than JJ_MAXMODELS"; return B200_E_UNSUPP; }
+        for (int i = 0; i < dk->ntjmmod; i++)
+            if (dk->tjm_models[i].nterms < 1 || dk->tjm_models[i].nterms > TJM_MAXTERMS) { err = "TJM nterms out of range"; return B200_E_UNSUPP; }
+    }
     an.n = 0;
     an.ntype.assign(1, 0);
     an.names.assign(1, "0");
@@ -206,6 +212,17 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     J.vless.resize(J.n); J.vmore.resize(J.n); J.vg.resize(J.n); J.initV.assign(J.n, 0.0); J.initPhi.assign(J.n, 0.0);
     J.area0.resize(J.n); J.ics0.resize(J.n); J.vshunt.resize(J.n); J.tcf.resize(J.n);
     std::vector<int> jj_coo((size_t)J.n*9, -1);
+    TJMTopo &TJ = an.tjm;
+    TJ.n = dk->ntjm; TJ.nmodels = dk->ntjmmod; TJ.nterms = 0;
+    if (TJ.n) TJ.models.assign(dk->tjm_models, dk->tjm_models + dk->ntjmmod);
+    for (auto &md : TJ.models) TJ.nterms = std::max(TJ.nterms, md.nterms);
+    TJ.pos.resize(TJ.n); TJ.neg.resize(TJ.n); TJ.phs.resize(TJ.n); TJ.model.resize(TJ.n); TJ.state.resize(TJ.n);
+    TJ.cslot.assign((size_t)TJ.n*JT_NSTAMP, -1); TJ.rslot.assign((size_t)TJ.n*JR_NRHS, -1);
+    TJ.initV.assign(TJ.n, 0.0); TJ.initPhi.assign(TJ.n, 0.0);
+    TJ.area0.resize(TJ.n); TJ.ics0.resize(TJ.n); TJ.vshunt.resize(TJ.n); TJ.tcf.resize(TJ.n);
+    TJ.omegaJ.resize(TJ.n); TJ.kgap.resize(TJ.n); TJ.kgap_rejpt.resize(TJ.n); TJ.alphaN.resize(TJ.n); TJ.vdpbak.resize(TJ.n);
+    TJ.coef.assign((size_t)TJ.n*6*std::max(TJ.nterms, 1), 0.0);
+    std::vector<int> tjm_coo((size_t)TJ.n*9, -1);
     // phase flags (jjset.cc:656-681, indset.cc:104-120): nodes of junctions with a supercurrent,
     // and -- once any such junction exists -- nodes of inductors
     std::vector<char> phase_node(dk->nnodes + 1, 0);
@@ -218,6 +235,13 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (in.neg > 0) phase_node[in.neg] = 1;
             jjDCphase = true;
         }
+    }
+    for (int i = 0; i < dk->ntjm; i++) {                // tjmset.cc:690-708: whatever the ictype
+        const b200_tjm &in = dk->tjm[i];
+        if (in.model < 0 || in.model >= dk->ntjmmod) { err = "bad TJM model index"; return B200_E_BADPARM; }
+        if (in.pos > 0) phase_node[in.pos] = 1;
+        if (in.neg > 0) phase_node[in.neg] = 1;
+        jjDCphase = true;
     }
     if (jjDCphase)
         for (int i = 0; i < dk->nind; i++) {
@@ -291,6 +315,32 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             // restemp.cc:213-223: no preload when a terminal is a phase node
             if (jjDCphase && ((in.pos > 0 && phase_node[in.pos]) || (in.neg > 0 && phase_node[in.neg])))
                 res_preload[i] = 0;
+            break; }
+        case B200_DEV_TJM: {
+            // tjmset.cc: same pointer set as the RSJ model; what does not depend on the area comes
+            // with the instance (b200_tjm), the rest is derived per trial by k_tjm_temp
+            const b200_tjm &in = dk->tjm[i];
+            const b200_tjm_model &md = dk->tjm_models[in.model];
+            TJ.pos[i] = in.pos; TJ.neg[i] = in.neg; TJ.phs[i] = in.phase_node; TJ.model[i] = in.model;
+            TJ.state[i] = an.numStates; an.numStates += TS_NSTATES;
+            double vsh = given(in.vshunt) ? in.vshunt : md.vshunt;
+            if (given(in.vshunt) && (in.vshunt < 0.0 || in.vshunt > md.vgnom)) vsh = 0.0;
+            TJ.vshunt[i] = vsh;
+            TJ.area0[i] = in.area; TJ.ics0[i] = in.ics; TJ.tcf[i] = in.tcf;
+            TJ.omegaJ[i] = in.omegaJ; TJ.kgap[i] = in.kgap; TJ.kgap_rejpt[i] = in.kgap_rejpt;
+            TJ.alphaN[i] = in.alphaN; TJ.vdpbak[i] = in.vdpbak;
+            if (!in.coef) { err = "TJM instance without a coefficient set"; return B200_E_BADPARM; }
+            for (int a = 0; a < 3; a++)
+                for (int k = 0; k < md.nterms; k++) {
+                    TJ.coef[(((size_t)i*3 + a)*TJ.nterms + k)*2] = in.coef[2*(a*md.nterms + k)];
+                    TJ.coef[(((size_t)i*3 + a)*TJ.nterms + k)*2 + 1] = in.coef[2*(a*md.nterms + k) + 1];
+                }
+            int *c = &tjm_coo[(size_t)i*9];
+            c[JT_PP] = coo.add(in.pos, in.pos); c[JT_NN] = coo.add(in.neg, in.neg);
+            c[JT_NP] = coo.add(in.neg, in.pos); c[JT_PN] = coo.add(in.pos, in.neg);
+            c[JT_RPP] = coo.add(in.pos, in.pos); c[JT_RPN] = coo.add(in.pos, in.neg);
+            c[JT_RNP] = coo.add(in.neg, in.pos); c[JT_RNN] = coo.add(in.neg, in.neg);
+            c[8] = in.phase_node > 0 ? coo.add(in.phase_node, in.phase_node) : -1;
             break; }
         case B200_DEV_JJ: {
             // jjset.cc:130-200 (TSTALLOC order), :560-612 (vshunt, vless / vmore), :794 (states)
@@ -440,6 +490,8 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     // the phase node's own equation x[phs] = rhs[phs] is preldset (jjset.cc:815-816)
     for (int i = 0; i < J.n; i++)
         if (jj_coo[(size_t)i*9 + 8] >= 0) an.Ainit[coo2ax[jj_coo[(size_t)i*9 + 8]]] = 1.0;
+    for (int i = 0; i < TJ.n; i++)
+        if (tjm_coo[(size_t)i*9 + 8] >= 0) an.Ainit[coo2ax[tjm_coo[(size_t)i*9 + 8]]] = 1.0;
     an.rload_slot.clear(); an.rload_val.clear();
     for (int oi = 0; oi < dk->norder; oi++) {
         int i = dk->order_index[oi];
@@ -454,6 +506,25 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
                 int sl = add_c(c[k]);
                 if (sl >= 0) { an.rload_slot.push_back(sl); an.rload_val.push_back(v[k]); an.dc_active[coo2ax[c[k]]] = 1; }
             }
+            break; }
+        case B200_DEV_TJM: {
+            // tjm_load (tjmload.cc:436-456) stamps like jj_load, then the shunt (tjmload.cc:213-218)
+            const int *c = &tjm_coo[(size_t)i*9];
+            int *cs = &TJ.cslot[(size_t)i*JT_NSTAMP];
+            int *rs = &TJ.rslot[(size_t)i*JR_NRHS];
+            if (TJ.phs[i] > 0) rs[JR_phs] = add_r(TJ.phs[i]);
+            if (!TJ.neg[i]) { cs[JT_PP] = add_c(c[JT_PP]); rs[JR_pos] = add_r(TJ.pos[i]); }
+            else if (!TJ.pos[i]) { cs[JT_NN] = add_c(c[JT_NN]); rs[JR_neg] = add_r(TJ.neg[i]); }
+            else {
+                cs[JT_PP] = add_c(c[JT_PP]); cs[JT_PN] = add_c(c[JT_PN]);
+                cs[JT_NP] = add_c(c[JT_NP]); cs[JT_NN] = add_c(c[JT_NN]);
+                rs[JR_pos] = add_r(TJ.pos[i]); rs[JR_neg] = add_r(TJ.neg[i]);
+            }
+            if (TJ.vshunt[i] > 1e-12) {
+                cs[JT_RPP] = add_c(c[JT_RPP]); cs[JT_RPN] = add_c(c[JT_RPN]);
+                cs[JT_RNP] = add_c(c[JT_RNP]); cs[JT_RNN] = add_c(c[JT_RNN]);
+            }
+            for (int k = 0; k < JT_NSTAMP; k++) if (cs[k] >= 0) an.dc_active[coo2ax[c[k]]] = 1;
             break; }
         case B200_DEV_JJ: {
             const int *c = &jj_coo[(size_t)i*9];
@@ -546,7 +617,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
         err = "bad .tran parameters"; return B200_E_BADPARM;
     }
     an.maxStep = dk->tmax;
-    an.nocut = !(M.n > 0 || Cp.n > 0 || L.n > 0 || J.n > 0);  // tranan.cc:68-77 DV_TRUNC devices (jj.cc:269)
+    an.nocut = !(M.n > 0 || Cp.n > 0 || L.n > 0 || J.n > 0 || TJ.n > 0);  // tranan.cc:68-77 DV_TRUNC devices (jj.cc:269)
     if (an.maxStep == 0) {
         an.maxStep = (an.t_stop - an.t_start)/50;
         if (o.oldsteplim) { if (an.t_step > an.maxStep) an.maxStep = an.t_step; }
@@ -591,6 +662,36 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
                 for (int i = 0; i < J.n; i++)
                     if (J.model[i] == m) { double v = fabs(J.initV[i]); if (vmax < v) vmax = v; }
             }
+            if (vmax > 0) {
+                double delmax = 0.1*md.tsfact*PHI0/vmax;
+                if (an.initDelta == 0.0 || an.initDelta > delmax) an.initDelta = delmax;
+            }
+        }
+    }
+    if (TJ.n) {
+        // TJMdev::getic, tjmic.cc:45-95 (its own vmax; criti > 0 for every junction)
+        auto rhs0 = [&](int node) { return node > 0 ? (an.ic_given[node] ? an.ic_val[node] : (an.ns_given[node] ? an.ns_val[node] : 0.0)) : 0.0; };
+        for (int i = 0; i < TJ.n; i++) {
+            const b200_tjm &in = dk->tjm[i];
+            TJ.initV[i] = given(in.icv) ? in.icv : rhs0(TJ.pos[i]) - rhs0(TJ.neg[i]);
+            TJ.initPhi[i] = given(in.icphi) ? in.icphi : (TJ.phs[i] > 0 ? rhs0(TJ.phs[i]) : 0.0);
+        }
+        const double PHI0 = 2.067833848e-15;
+        double vmax = 0;
+        std::vector<char> seen(TJ.nmodels, 0);
+        for (int a = 0; a < TJ.n; a++) {
+            int m = TJ.model[a];
+            if (seen[m]) continue;
+            seen[m] = 1;
+            const b200_tjm_model &md = TJ.models[m];
+            if (md.ictype != 0)
+                for (int i = 0; i < TJ.n; i++)
+                    if (TJ.model[i] == m) {
+                        double vth = TJ.vdpbak[i]/md.tsaccl;
+                        if (vmax < vth) vmax = vth;
+                        double v = fabs(TJ.initV[i]);
+                        if (vmax < v) vmax = v;
+                    }
             if (vmax > 0) {
                 double delmax = 0.1*md.tsfact*PHI0/vmax;
                 if (an.initDelta == 0.0 || an.initDelta > delmax) an.initDelta = delmax;
@@ -1158,6 +1259,7 @@ int b200_build_lu(Analysis &an)
     remap(an.ind.cslot, newc); remap(an.ind.rslot, newr);
     remap(an.mut.cslot, newc);
     remap(an.jj.cslot, newc); remap(an.jj.rslot, newr);
+    remap(an.tjm.cslot, newc); remap(an.tjm.rslot, newr);
     // resistors loaded in place: constant terms inside the runs (written once, like Ainit)
     for (size_t k = 0; k < an.rload_slot.size(); k++) {
         an.const_idx.push_back(newc[an.rload_slot[k]]);

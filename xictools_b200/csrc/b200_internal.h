@@ -147,6 +147,22 @@ struct JJTopo {
     std::vector<double> area0, ics0, vshunt, tcf;           // card values (NaN = not given)
     std::vector<b200_jj_model> models;
 };
+// Tunnel-junction model (JJ level 3, devlib/tjm).  States tjmdefs.h:245-250.
+enum { TS_voltage, TS_dvdt, TS_phase, TS_phsInt, TS_crti, TS_qpi, TS_NSTATES };
+enum { TP_criti, TP_cap, TP_g0, TP_gshunt, TP_gcrit, TP_NPARAMS };
+#define TJM_MAXTERMS 20
+// per (junction, trial) work arrays, in units of nterms complex numbers: the recurrences of this
+// iteration and of the last accepted point, and the step coefficients of tjm_newstep
+enum { TF_Fc, TF_Fs, TF_Fcprev, TF_Fsprev, TF_alpha0, TF_alpha1, TF_expz, TF_NARR };
+struct TJMTopo {
+    int n = 0, nmodels = 0, nterms = 0;         // nterms: the largest of the models
+    std::vector<int> pos, neg, phs, model, state;
+    std::vector<int> cslot;                     // [n*JT_NSTAMP]
+    std::vector<int> rslot;                     // [n*JR_NRHS]
+    std::vector<double> initV, initPhi, area0, ics0, vshunt, tcf, omegaJ, kgap, kgap_rejpt, alphaN, vdpbak;
+    std::vector<double> coef;                   // [n][3][nterms][2]: p, A, B
+    std::vector<b200_tjm_model> models;
+};
 struct SrcTopo {
     int n = 0;
     std::vector<int> kind, pos, neg, branch, fn, dcgiven;
@@ -225,7 +241,7 @@ struct Analysis {
     std::vector<double> ic_val, ns_val;
     int hadNodeset = 0;
     // device tables
-    MosTopo mos; CapTopo cap; SrcTopo src; IndTopo ind; MutTopo mut; JJTopo jj;
+    MosTopo mos; CapTopo cap; SrcTopo src; IndTopo ind; MutTopo mut; JJTopo jj; TJMTopo tjm;
     int nres = 0;
     double initDelta = 0;                       // CKTinitDelta from JJdev::getic (jjic.cc:78-104), 0 = unset
     // resistors that touch a phase node are loaded every iteration instead of preloaded

@@ -51,7 +51,11 @@ struct b200_batch {
     std::map<int, std::vector<double>> mos_var[MR_NRAW];    // inst -> [ntrials]
     std::vector<double> cap_c, cap_ic, src_dc, ind_l, ind_ic;
     std::map<int, std::vector<double>> cap_var, src_var, ind_var, jj_var;
-    std::vector<double> jj_ics;                             // [njj] card ics (NaN = not given)
+    std::vector<double> jj_ics, tjm_ics;                    // [njj] / [ntjm] card ics (NaN = not given)
+    std::map<int, std::vector<double>> tjm_var;
+    double *d_tjmics = nullptr; int tjmics_ts = 0;
+    double *d_tjmprm[TP_NPARAMS] = {0}; int tjmprm_ts = -1;
+    const double *d_tjm_area0 = nullptr, *d_tjm_vshunt = nullptr, *d_tjm_tcf = nullptr, *d_tjm_alphaN = nullptr;
     double *d_jjics = nullptr; int jjics_ts = 0;
     double *d_jjprm[JP_NPARAMS] = {0}; int jjprm_ts = -1;
     const double *d_jj_area0 = nullptr, *d_jj_vshunt = nullptr, *d_jj_tcf = nullptr;
@@ -100,7 +104,7 @@ struct b200_batch {
 };
 
 enum { PT_CAP = MR_NRAW, PT_IND = MR_NRAW + 1, PT_SRC = MR_NRAW + 2, PT_JJ = MR_NRAW + 3,
-       PT_NTABLES = MR_NRAW + 4 };
+       PT_TJM = MR_NRAW + 4, PT_NTABLES = MR_NRAW + 5 };
 
 // row i of a [n][ldt] per-trial table <- the shared value of instance i
 __global__ void k_fill_rows(double *dst, const double *shared, int n, int ldt)
@@ -139,10 +143,11 @@ static int param_table(const b200_batch *b, int param, int index)
     case B200_P_IND_L: tbl = PT_IND; break;
     case B200_P_SRC_DC: tbl = PT_SRC; break;
     case B200_P_JJ_ICS: tbl = PT_JJ; break;
+    case B200_P_TJM_ICS: tbl = PT_TJM; break;
     default: return -B200_E_UNSUPP;
     }
     n = tbl < MR_NRAW ? b->an.mos.n : tbl == PT_CAP ? b->an.cap.n : tbl == PT_IND ? b->an.ind.n :
-        tbl == PT_JJ ? b->an.jj.n : b->an.src.n;
+        tbl == PT_JJ ? b->an.jj.n : tbl == PT_TJM ? b->an.tjm.n : b->an.src.n;
     if (index < 0 || index >= n) return -B200_E_BADPARM;
     return tbl;
 }
@@ -268,6 +273,7 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
     }
     b->src_dc = b->an.src.dc;
     b->jj_ics = b->an.jj.ics0;
+    b->tjm_ics = b->an.tjm.ics0;
 }
 
 int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch **out)
@@ -391,8 +397,39 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
             K.jj_tsfact[m] = md.tsfact;
         }
     }
+    TJMView &Tv = Cp.T; TJMTopo &tt = an.tjm;
+    memset(&Tv, 0, sizeof(Tv));
+    Tv.n = tt.n; Tv.nmodels = tt.nmodels; Tv.nterms = tt.nterms; Tv.model0 = jt.nmodels;
+    if (tt.n) {
+        Tv.pos = b->dupload(tt.pos); Tv.neg = b->dupload(tt.neg); Tv.phs = b->dupload(tt.phs);
+        Tv.model = b->dupload(tt.model); Tv.state = b->dupload(tt.state);
+        Tv.cslot = b->dupload(tt.cslot); Tv.rslot = b->dupload(tt.rslot);
+        Tv.initV = b->dupload(tt.initV); Tv.initPhi = b->dupload(tt.initPhi);
+        Tv.omegaJ = b->dupload(tt.omegaJ); Tv.kgap = b->dupload(tt.kgap); Tv.kgap_rejpt = b->dupload(tt.kgap_rejpt);
+        Tv.coef = b->dupload(tt.coef);
+        Tv.dvdt = b->dalloc<double>((size_t)tt.n*ldt);
+        Tv.sc_old = b->dalloc<double>((size_t)2*tt.n*ldt);
+        Tv.work = b->dalloc<double>((size_t)TF_NARR*tt.nterms*2*tt.n*ldt);
+        if (!Tv.work) { b200_batch_destroy(b); return B200_E_NOMEM; }
+        b->d_tjm_area0 = b->dupload(tt.area0); b->d_tjm_vshunt = b->dupload(tt.vshunt);
+        b->d_tjm_tcf = b->dupload(tt.tcf); b->d_tjm_alphaN = b->dupload(tt.alphaN);
+        std::vector<char> seen(tt.nmodels, 0);
+        for (int oi = 0; oi < deck->norder; oi++) {         // TJMdev::accept: the floor is the first
+            if (deck->order_kind[oi] != B200_DEV_TJM) continue;   // visited instance's vdpbak/tsaccl
+            int i = deck->order_index[oi], m = tt.model[i];
+            if (seen[m]) continue;
+            seen[m] = 1;
+            const b200_tjm_model &md = tt.models[m];
+            Tv.rtype[m] = md.rtype; Tv.ictype[m] = md.ictype; Tv.nt[m] = md.nterms;
+            K.jj_limits[jt.nmodels + m] = 1;
+            K.jj_vth[jt.nmodels + m] = tt.vdpbak[i]/md.tsaccl;
+            K.jj_tsfact[jt.nmodels + m] = md.tsfact;
+        }
+        K.njjmod = jt.nmodels + tt.nmodels;
+    }
     K.initDelta = an.initDelta;
-    h.jj_vmax = b->dalloc<double>((size_t)(jt.nmodels ? jt.nmodels : 1)*ldt);
+    h.jj_vmax = b->dalloc<double>((size_t)std::max(jt.nmodels + tt.nmodels, 1)*ldt);
+    h.accepted = b->dalloc<int>(ldt);
     SrcView &S = b->S; SrcTopo &st = an.src;
     S.n = st.n;
     S.kind = b->dupload(st.kind); S.fn = b->dupload(st.fn); S.dcgiven = b->dupload(st.dcgiven);
@@ -553,6 +590,9 @@ int b200_batch_set_param(b200_batch *b, int param, int index, const double *valu
     case B200_P_JJ_ICS:
         if (index < 0 || index >= b->an.jj.n) return B200_E_BADPARM;
         put(b->jj_var[index]); b->params_dirty = true; return B200_OK;
+    case B200_P_TJM_ICS:
+        if (index < 0 || index >= b->an.tjm.n) return B200_E_BADPARM;
+        put(b->tjm_var[index]); b->params_dirty = true; return B200_OK;
     default:
         return B200_E_UNSUPP;
     }
@@ -592,6 +632,7 @@ int b200_batch_set_params(b200_batch *b, int nrows, const int *param, const int 
         else if (tbl[r] == PT_CAP) b->cap_var.erase(index[r]);
         else if (tbl[r] == PT_IND) b->ind_var.erase(index[r]);
         else if (tbl[r] == PT_JJ) b->jj_var.erase(index[r]);
+        else if (tbl[r] == PT_TJM) b->tjm_var.erase(index[r]);
         else b->src_var.erase(index[r]);
     }
     size_t need = (size_t)nrows*b->ntrials;
@@ -729,6 +770,20 @@ static int prepare_params(b200_batch *b)
             b->jjprm_ts = b->jjics_ts;
         }
     }
+    if (b->an.tjm.n) {
+        rc = upload_strided(PT_TJM, b->tjm_ics, b->tjm_var, b->d_tjmics, b->tjmics_ts);
+        if (rc) return rc;
+        if (b->tjmprm_ts != b->tjmics_ts) {
+            for (int k = 0; k < TP_NPARAMS; k++) {
+                b->d_tjmprm[k] = b->dalloc<double>(b->tjmics_ts ? (size_t)b->an.tjm.n*ldt : (size_t)b->an.tjm.n);
+                if (!b->d_tjmprm[k]) return B200_E_NOMEM;
+                b->Cp.T.prm[k].base = b->d_tjmprm[k];
+                b->Cp.T.prm[k].ts = b->tjmics_ts;
+                b->Cp.T.prm[k].ld = b->tjmics_ts ? (int)ldt : 1;
+            }
+            b->tjmprm_ts = b->tjmics_ts;
+        }
+    }
     // packed rows into their tables (after the default fill, before the temperature kernel)
     if (!b->pk_tbl.empty()) {
         int nrows = (int)b->pk_tbl.size();
@@ -763,6 +818,22 @@ static int prepare_params(b200_batch *b)
         for (int k = 0; k < JP_NPARAMS; k++) in.out[k] = b->d_jjprm[k];
         in.ts = b->jjics_ts;
         launch_jj_temp(st, in, b->ntrials, (int)ldt);
+    }
+    if (b->an.tjm.n) {
+        const TJMTopo &tt = b->an.tjm;
+        TJMTempIn in;
+        memset(&in, 0, sizeof(in));
+        in.n = tt.n; in.model = b->Cp.T.model;
+        in.ics.base = b->d_tjmics; in.ics.ts = b->tjmics_ts; in.ics.ld = b->tjmics_ts ? (int)ldt : 1;
+        in.area0 = b->d_tjm_area0; in.vshunt = b->d_tjm_vshunt; in.tcf = b->d_tjm_tcf; in.alphaN = b->d_tjm_alphaN;
+        for (int m = 0; m < tt.nmodels; m++) {
+            const b200_tjm_model &md = tt.models[m];
+            in.criti[m] = md.criti; in.cap[m] = md.cap; in.cmu[m] = md.cmu; in.gmu[m] = md.gmu;
+            in.r0[m] = md.r0; in.rsint[m] = md.rsint; in.rtype[m] = md.rtype;
+        }
+        for (int k = 0; k < TP_NPARAMS; k++) in.out[k] = b->d_tjmprm[k];
+        in.ts = b->tjmics_ts;
+        launch_tjm_temp(st, in, b->ntrials, (int)ldt);
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
@@ -865,7 +936,7 @@ static int run_analysis(b200_batch *b, int analysis)
     if (!E.ok) return B200_E_NOGPU;
     long long launches = 0, ticks = 0, load_launches = 0, solve_launches = 0;
     double ms_load = 0, ms_solve = 0;
-    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->Cp.L.nmut ? 1 : 0) + (b->S.n ? 1 : 0) + (b->Cp.J.n ? 1 : 0);
+    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->Cp.L.nmut ? 1 : 0) + (b->S.n ? 1 : 0) + (b->Cp.J.n ? 1 : 0) + (b->Cp.T.n ? 1 : 0);
 
     CK(cudaEventRecord(E.begin, st));
     // tick 0: begin + first load
@@ -1040,6 +1111,11 @@ int b200_batch_get_stats(const b200_batch *b, b200_run_stats *st)
     double jjbytes = 8.0*(2 + 5 + 7 + 2)*an.jj.n + (b->jjics_ts ? 8.0*6*an.jj.n : 0.0);
     for (int sl : an.jj.cslot) if (sl >= 0) jjbytes += 8.0;
     for (int sl : an.jj.rslot) if (sl >= 0) jjbytes += 8.0;
+    // TJM: the RSJ figure plus its recurrences: 4 x nterms complex read + 2 x nterms written per
+    // iteration (the step coefficients are written once per step)
+    jjbytes += 8.0*(2 + 4 + 6 + 2 + 2)*an.tjm.n + 8.0*(2*(4 + 3) + 2*2)*an.tjm.nterms*an.tjm.n;
+    for (int sl : an.tjm.cslot) if (sl >= 0) jjbytes += 8.0;
+    for (int sl : an.tjm.rslot) if (sl >= 0) jjbytes += 8.0;
     st->algbytes_load_per_launch = (mosbytes + capbytes + srcbytes + jjbytes)*b->ntrials;
     st->algbytes_solve_per_launch = 8.0*((double)an.NC + 2.0*an.n)*b->ntrials;
     return B200_OK;

@@ -483,6 +483,7 @@ __device__ inline void ctl_tran_loop_top(TrialCtl &s, const Consts &K, const Ctl
     // ---- sTRANint::accept, tranan.cc:483-554 ----
     s.vecops |= VO_SAVE_SPARE;
     s.devMaxDelta = s.jj_dmax;                    // sCKT::accept, ckt.cc:363 + JJdev::accept
+    s.did_accept = 1;
     s.sols_base = (s.sols_base + 7) & 7;          // rotate sols, ckt.cc:372-377
     s.vecops |= VO_ACCEPT_SOLS;
     if (s.time > s.breaks[0]) {

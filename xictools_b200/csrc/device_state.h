@@ -50,6 +50,7 @@ struct TrialCtl {
     int accepted, rejected, numIter, timePts, tranIter, iterCut, trapCut, npts, lastIters;
     int niter_mark;
     double jj_dmax;                             // JJdev::accept's step bound for the accept being processed (0 = none)
+    int did_accept;                             // ctl_tran_loop_top ran in this control pass
     int vecops;
     int have_save;
     int want_load;                              // a load must follow in this tick
@@ -81,7 +82,9 @@ struct HotView {
     double *lte;        // [2][ldt] min over charges for order, order+1 (un-normalised)
     // Josephson junctions: max |vj| over the junctions of a model in the trial's latest load
     // (what JJdev::accept scans state 0 for, jjacct.cc:120-133); zeroed when a load is published
-    double *jj_vmax;    // [nmodels][ldt]
+    double *jj_vmax;    // [nmodels][ldt]   (RSJ models first, then the TJM models)
+    int    *accepted;   // 1: the load published in this tick directly follows an accepted time point
+                        //    (the device-side half of XXXdev::accept runs inside that load)
 };
 
 struct Consts {
@@ -128,6 +131,17 @@ struct JJView {
     int rtype[JJ_MAXMODELS], ictype[JJ_MAXMODELS], pi[JJ_MAXMODELS];
     double delv[JJ_MAXMODELS], icfactor[JJ_MAXMODELS];
 };
+// Tunnel-junction model (JJ level 3).  work[(a*nterms + k)*2 + c][n][ldt], a in TF_*, c = re / im
+struct TJMView {
+    int n, nmodels, nterms, model0;     // model0: index of its first model in the shared jj_vmax / Consts tables
+    const int *pos, *neg, *phs, *model, *state, *cslot, *rslot;
+    const double *initV, *initPhi, *omegaJ, *kgap, *kgap_rejpt;     // [n]
+    const double *coef;                 // [n][3][nterms][2]: p, A, B (shared by all trials)
+    ParamRef prm[TP_NPARAMS];
+    double *dvdt, *sc_old;              // [n][ldt], [2][n][ldt] (sin, cos of phi/2 at the last accepted point)
+    double *work;
+    int rtype[JJ_MAXMODELS], ictype[JJ_MAXMODELS], nt[JJ_MAXMODELS];
+};
 struct CapView {
     int n;
     const int *pos, *neg, *state, *cslot, *rslot;
@@ -135,6 +149,7 @@ struct CapView {
     double *geq, *ceq;  // [n][ldt]  (CAPgeq / CAPceq instance fields, capload.cc:150-151)
     IndView L;
     JJView J;           // Josephson junctions travel with the other two-terminal reactive elements
+    TJMView T;
 };
 struct SrcView {
     int n;

@@ -583,6 +583,8 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
             hot.st_base[t] = s.st_base;
             hot.noncon[t] = 0;
             for (int m = 0; m < K.njjmod; m++) hot.jj_vmax[(size_t)m*K.ldt + t] = 0.0;
+            hot.accepted[t] = s.did_accept;
+            s.did_accept = 0;
             hot.trapbad[t] = 0;
             hot.trapcheck[t] = s.trapCheck;
             hot.iterno[t] = s.iterno;
@@ -1118,6 +1120,232 @@ void launch_jj_temp(cudaStream_t st, const JJTempIn &in, int ntrials, int ldt)
     k_jj_temp<<<dim3((nt + 127)/128, in.n), 128, 0, st>>>(in, ntrials, ldt);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tunnel-junction model (JJ level 3, mmjco): TJMdev::load + sTJMinstance::{tjm_load, tjm_init,
+// tjm_newstep, tjm_update} (devlib/tjm/tjmload.cc:65-553) and the device half of TJMdev::accept
+// (tjmacct.cc:43-169: phase fold, F -> Fprev, sin / cos of the accepted phase) which runs inside
+// the first load after an accepted point (hot.accepted).  Complex arithmetic as include/ifcx.h.
+// One thread per (junction, trial); the 2*nterms complex recurrences live in work[..][n][ldt].
+// ---------------------------------------------------------------------------------------
+struct Cxd { double re, im; };
+__device__ __forceinline__ Cxd cx_mul(Cxd a, Cxd b) { Cxd r; r.re = a.re*b.re - a.im*b.im; r.im = a.im*b.re + a.re*b.im; return r; }
+
+__global__ void __launch_bounds__(128)
+k_load_tjm(Consts K, HotView hot, VecView V, TJMView J, const double *rhsOld)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t >= K.ntrials) return;
+    int mode = hot.mode[t];
+    if (!mode) return;
+    if (mode & MODEDC) return;                  // tjmload.cc:75-76: nothing in the `uic` start load
+    TrialCtx c;
+    make_ctx(c, K, hot, V, t, mode);
+    const int st = J.state[i], m = J.model[i];
+    const int pos = J.pos[i], neg = J.neg[i];
+    const int NT = J.nterms, nt = J.nt[m];
+    const size_t ldt = K.ldt;
+    const size_t wstride = (size_t)J.n*ldt;     // one double plane of work[]
+    double *W = J.work + (size_t)i*ldt + t;
+#define WK(a, k, cpt) W[(size_t)(((a)*NT + (k))*2 + (cpt))*wstride]
+    const double criti = PR(J.prm[TP_criti], i, t);
+    const double cap = PR(J.prm[TP_cap], i, t);
+    const double g0 = PR(J.prm[TP_g0], i, t);
+    const double gshunt = PR(J.prm[TP_gshunt], i, t);
+    const double gcrit = PR(J.prm[TP_gcrit], i, t);
+    double *pdv = J.dvdt + (size_t)i*ldt + t;
+    double *psin = J.sc_old + (size_t)i*ldt + t, *pcos = psin + wstride;
+    double pfac = c.delta/JJ_PHI0_2PI;
+    if (c.order > 1) pfac *= .5;
+    double phi1 = ST(c, 1, st + TS_phase);
+    double pint = ST(c, 1, st + TS_phsInt);
+    if (hot.accepted[t] && !(mode & MODEINITTRAN)) {
+        // TJMdev::accept for the point just accepted (its values are in state 1 now)
+        const double twopi = M_PI + M_PI, fourpi = twopi + twopi;
+        if (phi1 >= twopi) { phi1 -= fourpi; pint += 1.0; ST(c, 1, st + TS_phase) = phi1; ST(c, 1, st + TS_phsInt) = pint; }
+        else if (phi1 < -twopi) { phi1 += fourpi; pint -= 1.0; ST(c, 1, st + TS_phase) = phi1; ST(c, 1, st + TS_phsInt) = pint; }
+        double so, co;
+        sincos(0.5*phi1, &so, &co);
+        *psin = so; *pcos = co;
+        for (int k = 0; k < nt; k++) {
+            WK(TF_Fcprev, k, 0) = WK(TF_Fc, k, 0); WK(TF_Fcprev, k, 1) = WK(TF_Fc, k, 1);
+            WK(TF_Fsprev, k, 0) = WK(TF_Fs, k, 0); WK(TF_Fsprev, k, 1) = WK(TF_Fs, k, 1);
+        }
+    }
+    double vj, phi;
+    bool newstep = false;
+    if (mode & MODEINITFLOAT) {
+        vj = rhsOld[(size_t)pos*ldt + t] - rhsOld[(size_t)neg*ldt + t];
+        const double vprev = ST(c, 0, st + TS_voltage);
+        const double maxvj = DMAX(fabs(vj), fabs(vprev));
+        if (fabs(vprev - vj) > K.opt.reltol*maxvj + K.opt.abstol) hot.noncon[t] = 1;
+        phi = phi1;
+        double temp = vj;
+        if (c.order > 1) temp += ST(c, 1, st + TS_voltage);
+        phi += pfac*temp;
+        // ckt->integrate BEFORE tjm_load stores the new vj (tjmload.cc:209-210): state 0 still
+        // holds the previous iteration's voltage
+        ST(c, 0, st + TS_dvdt) = c.ag[0]*vprev + *pdv;
+        dev_trapcheck(c, st + TS_voltage);
+    }
+    else if (mode & MODEINITPRED) {
+        double y0 = ST(c, 1, st + TS_dvdt)*c.pred[0] + ST(c, 2, st + TS_dvdt)*c.pred[1];
+        if (c.order != 1) y0 += ST(c, 1, st + TS_dvdt);
+        double temp = ST(c, 1, st + TS_voltage);
+        const double rag0 = c.order == 1 ? c.delta : .5*c.delta;
+        vj = temp + rag0*y0;
+        phi = phi1;
+        temp = vj;
+        if (c.order > 1) temp += ST(c, 1, st + TS_voltage);
+        phi += pfac*temp;
+        *pdv = dev_find_ceq(c, st + TS_voltage);
+        newstep = true;
+    }
+    else if (mode & MODEINITTRAN) {
+        if (mode & MODEUIC) {
+            vj = J.initV[i]; phi = J.initPhi[i];
+            ST(c, 1, st + TS_voltage) = vj;
+            ST(c, 1, st + TS_phase) = phi;
+        }
+        else { vj = 0; ST(c, 1, st + TS_voltage) = 0.0; phi = 0; }
+        *pdv = dev_find_ceq(c, st + TS_voltage);
+        // tjm_init, tjmload.cc:469-487
+        double so, co;
+        sincos(0.5*phi, &so, &co);
+        *psin = so; *pcos = co;
+        for (int k = 0; k < nt; k++) {
+            WK(TF_Fcprev, k, 0) = co; WK(TF_Fcprev, k, 1) = 0.0;
+            WK(TF_Fsprev, k, 0) = so; WK(TF_Fsprev, k, 1) = 0.0;
+        }
+        newstep = true;
+    }
+    else
+        return;
+    const double *cf = J.coef + (size_t)i*6*NT;
+    if (newstep) {
+        // tjm_newstep, tjmload.cc:490-505
+        const double kdt = J.kgap[i]*J.omegaJ[i]*c.delta;
+        for (int k = 0; k < nt; k++) {
+            Cxd z; z.re = cf[2*k]*kdt; z.im = cf[2*k + 1]*kdt;
+            const double d = exp(z.re);
+            double sz, cz;
+            sincos(z.im, &sz, &cz);
+            Cxd ez; ez.re = d*cz; ez.im = d*sz;
+            const double dd = z.re*z.re + z.im*z.im;
+            const double er = ez.re - 1.0;
+            Cxd zt; zt.re = (er*z.re + ez.im*z.im)/dd; zt.im = (ez.im*z.re - er*z.im)/dd;
+            WK(TF_expz, k, 0) = ez.re; WK(TF_expz, k, 1) = ez.im;
+            WK(TF_alpha0, k, 0) = zt.re - ez.re; WK(TF_alpha0, k, 1) = zt.im - ez.im;
+            WK(TF_alpha1, k, 0) = 1.0 - zt.re;   WK(TF_alpha1, k, 1) = -zt.im;
+        }
+    }
+    // tjm_update, tjmload.cc:508-553
+    double s2, c2;
+    sincos(0.5*phi, &s2, &c2);
+    const double so = *psin, co = *pcos;
+    double FcSp = 0.0, FcSq = 0.0, FsSp = 0.0, FsSq = 0.0;
+    for (int k = 0; k < nt; k++) {
+        Cxd ez, a0, a1, fcp, fsp, A, B;
+        ez.re = WK(TF_expz, k, 0); ez.im = WK(TF_expz, k, 1);
+        a0.re = WK(TF_alpha0, k, 0); a0.im = WK(TF_alpha0, k, 1);
+        a1.re = WK(TF_alpha1, k, 0); a1.im = WK(TF_alpha1, k, 1);
+        fcp.re = WK(TF_Fcprev, k, 0); fcp.im = WK(TF_Fcprev, k, 1);
+        fsp.re = WK(TF_Fsprev, k, 0); fsp.im = WK(TF_Fsprev, k, 1);
+        A.re = cf[2*(NT + k)]; A.im = cf[2*(NT + k) + 1];
+        B.re = cf[2*(2*NT + k)]; B.im = cf[2*(2*NT + k) + 1];
+        Cxd fc = cx_mul(ez, fcp);
+        fc.re = (fc.re + a0.re*co) + a1.re*c2; fc.im = (fc.im + a0.im*co) + a1.im*c2;
+        Cxd fs = cx_mul(ez, fsp);
+        fs.re = (fs.re + a0.re*so) + a1.re*s2; fs.im = (fs.im + a0.im*so) + a1.im*s2;
+        WK(TF_Fc, k, 0) = fc.re; WK(TF_Fc, k, 1) = fc.im;
+        WK(TF_Fs, k, 0) = fs.re; WK(TF_Fs, k, 1) = fs.im;
+        FcSp += A.re*fc.re - A.im*fc.im;
+        FcSq += B.re*fc.re - B.im*fc.im;
+        FsSp += A.re*fs.re - A.im*fs.im;
+        FsSq += B.re*fs.re - B.im*fs.im;
+    }
+    const double fct = criti*J.kgap_rejpt[i];
+    const double cp = J.ictype[m] > 0 ? fct*(s2*FcSp + c2*FsSp) : 0.0;
+    const double cqp = J.rtype[m] > 0 ? fct*(s2*FcSq - c2*FsSq) : 0.0;
+    // tjm_load, tjmload.cc:412-456
+    ST(c, 0, st + TS_voltage) = vj;
+    ST(c, 0, st + TS_phase) = phi;
+    ST(c, 0, st + TS_phsInt) = pint;
+    const double crhs = cp + cqp + (*pdv)*cap;
+    const double gqt = gcrit + g0 + c.ag[0]*cap;
+    ST(c, 0, st + TS_crti) = cp;
+    ST(c, 0, st + TS_qpi) = cqp + (gcrit + g0)*vj;
+    const int *cs = J.cslot + (size_t)i*JT_NSTAMP;
+    const int *rs = J.rslot + (size_t)i*JR_NRHS;
+    if (rs[JR_phs] >= 0) V.contrib[CADDR(K, rs[JR_phs], t)] = phi + (4*M_PI)*pint;
+    if (cs[JT_PP] >= 0) V.contrib[CADDR(K, cs[JT_PP], t)] = gqt;
+    if (cs[JT_PN] >= 0) V.contrib[CADDR(K, cs[JT_PN], t)] = -gqt;
+    if (cs[JT_NP] >= 0) V.contrib[CADDR(K, cs[JT_NP], t)] = -gqt;
+    if (cs[JT_NN] >= 0) V.contrib[CADDR(K, cs[JT_NN], t)] = gqt;
+    if (rs[JR_pos] >= 0) V.contrib[CADDR(K, rs[JR_pos], t)] = -crhs;
+    if (rs[JR_neg] >= 0) V.contrib[CADDR(K, rs[JR_neg], t)] = crhs;
+    const double gsh = gshunt > 1e-12 ? gshunt : 0.0;
+    if (cs[JT_RPP] >= 0) V.contrib[CADDR(K, cs[JT_RPP], t)] = gsh;
+    if (cs[JT_RPN] >= 0) V.contrib[CADDR(K, cs[JT_RPN], t)] = -gsh;
+    if (cs[JT_RNP] >= 0) V.contrib[CADDR(K, cs[JT_RNP], t)] = -gsh;
+    if (cs[JT_RNN] >= 0) V.contrib[CADDR(K, cs[JT_RNN], t)] = gsh;
+    if ((mode & MODEINITFLOAT) && (mode & MODETRAN) && J.ictype[m] == 0) {
+        // TJMdev::trunc (tjmtrun.cc:52-64): the LTE of the voltage state as this load leaves it
+        double q[4] = { vj, ST(c, 1, st + TS_voltage), ST(c, 2, st + TS_voltage), ST(c, 3, st + TS_voltage) };
+        double m0 = DBL_MAX, m1 = DBL_MAX;
+        dev_lte_charge<true>(c, K.opt, q, ST(c, 0, st + TS_dvdt), ST(c, 1, st + TS_dvdt), st + TS_voltage, m0, m1, c.rcp, c.ldt);
+        atomic_min_pos(c.lte, m0);
+        if (c.order + 1 <= K.opt.maxord) atomic_min_pos(c.lte + K.ldt, m1);
+    }
+    // what TJMdev::accept scans (every junction counts, tjmacct.cc:127-135)
+    atomicMax((unsigned long long*)(hot.jj_vmax + (size_t)(J.model0 + m)*ldt + t), (unsigned long long)__double_as_longlong(fabs(vj)));
+#undef WK
+}
+
+// What of sTJMinstance depends on the junction's area (tjmset.cc:600-660, 714; tjmload.cc:476-479)
+__global__ void k_tjm_temp(TJMTempIn in, int ntrials, int ldt)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t >= (in.ts ? ldt : 1)) return;
+    const int m = in.model[i];
+    const int tt = t < ntrials ? t : 0;
+    double area;
+    const double ics = PR(in.ics, i, tt);
+    if (!isnan(ics)) {
+        double v = ics;
+        if (v < in.criti[m]/50 || v > in.criti[m]*50) v = in.criti[m];
+        area = v/in.criti[m];
+    }
+    else if (!isnan(in.area0[i])) area = in.area0[i];
+    else area = 1;
+    const double criti = in.criti[m]*area*in.tcf[i];
+    const double sqrta = sqrt(area);
+    const double gfac = area*(1.0 - in.gmu[m]) + sqrta*in.gmu[m];
+    const double gqp = gfac/in.rsint[m];
+    double g0 = in.r0[m] > 0.0 ? gfac/in.r0[m] : 0.0;
+    const double tg0 = g0;
+    if (g0 >= gqp) g0 -= gqp;
+    double gshunt = 0.0;
+    if (in.vshunt[i] > 1e-12) {
+        double g = criti/in.vshunt[i] - DMAX(tg0, gqp);
+        if (g > 0.0) gshunt = g;
+    }
+    const double cap = in.cap[m]*(area*(1.0 - in.cmu[m]) + sqrta*in.cmu[m]);
+    const double gcrit = in.rtype[m] > 0 ? in.alphaN[i]*sqrt(cap*criti/JJ_PHI0_2PI) : 0.0;
+    const size_t at = in.ts ? (size_t)i*ldt + t : (size_t)i;
+    in.out[TP_criti][at] = criti; in.out[TP_cap][at] = cap; in.out[TP_g0][at] = g0;
+    in.out[TP_gshunt][at] = gshunt; in.out[TP_gcrit][at] = gcrit;
+}
+
+void launch_tjm_temp(cudaStream_t st, const TJMTempIn &in, int ntrials, int ldt)
+{
+    if (!in.n) return;
+    int nt = in.ts ? ldt : 1;
+    k_tjm_temp<<<dim3((nt + 127)/128, in.n), 128, 0, st>>>(in, ntrials, ldt);
+}
+
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,
     const RawParams &raw, const MosParamsOut &out)
 {
@@ -1152,6 +1380,7 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
     if (Cp.L.n) k_load_ind<<<grid2(K.ntrials, Cp.L.n), 128, 0, st>>>(K, hot, V, Cp.L, rhsOld);
     if (S.n) k_load_src<<<grid2(K.ntrials, S.n), 128, 0, st>>>(K, hot, V, S);
     if (Cp.J.n) k_load_jj<<<grid2(K.ntrials, Cp.J.n), 128, 0, st>>>(K, hot, V, Cp.J, rhsOld);
+    if (Cp.T.n) k_load_tjm<<<grid2(K.ntrials, Cp.T.n), 128, 0, st>>>(K, hot, V, Cp.T, rhsOld);
 }
 void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const double *rhs)

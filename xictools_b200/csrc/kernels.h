@@ -58,6 +58,17 @@ struct JJTempIn {
     double *out[JP_NPARAMS]; int ts;    // out[k][i*ld + t*ts]
 };
 void launch_jj_temp(cudaStream_t st, const JJTempIn &in, int ntrials, int ldt);
+struct TJMTempIn {
+    int n;
+    const int *model;
+    ParamRef ics;                       // NaN = not given
+    const double *area0, *vshunt, *tcf, *alphaN;
+    double criti[JJ_MAXMODELS], cap[JJ_MAXMODELS], cmu[JJ_MAXMODELS], gmu[JJ_MAXMODELS], r0[JJ_MAXMODELS],
+        rsint[JJ_MAXMODELS];
+    int rtype[JJ_MAXMODELS];
+    double *out[TP_NPARAMS]; int ts;
+};
+void launch_tjm_temp(cudaStream_t st, const TJMTempIn &in, int ntrials, int ldt);
 void launch_ctl(cudaStream_t st, const Consts &K, const HotView &hot, TrialCtl *ctl,
     const CtlShared &sh, const CtlAux &aux, int phase);
 void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,

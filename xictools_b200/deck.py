@@ -23,13 +23,13 @@ from dataclasses import dataclass, field
 
 NAN = float("nan")
 
-DEV_RES, DEV_CAP, DEV_IND, DEV_MUT, DEV_SRC, DEV_MOS, DEV_JJ = range(7)
+DEV_RES, DEV_CAP, DEV_IND, DEV_MUT, DEV_SRC, DEV_MOS, DEV_JJ, DEV_TJM = range(8)
 SRC_V, SRC_I = 0, 1
 FN_NONE, FN_PULSE, FN_PWL, FN_SIN, FN_EXP, FN_SFFM, FN_AM, FN_GAUSS = range(8)
 
 # parameter ids (include/b200spice.h)
 P_MOS_VTO, P_MOS_KP, P_MOS_L, P_MOS_W, P_MOS_GAMMA, P_MOS_LAMBDA, P_MOS_PHI = range(1, 8)
-P_CAP_C, P_RES_R, P_IND_L, P_SRC_DC, P_JJ_ICS = 32, 48, 56, 64, 80
+P_CAP_C, P_RES_R, P_IND_L, P_SRC_DC, P_JJ_ICS, P_TJM_ICS = 32, 48, 56, 64, 80, 88
 
 # counters
 (C_STATUS, C_ACCEPTED, C_REJECTED, C_NUMITER, C_TIMEPTS, C_TRANITER, C_ITERCUT, C_TRAPCUT,
@@ -163,6 +163,9 @@ class CDeck(C.Structure):
         ("njj", C.c_int), ("jj", C.POINTER(CJJ)),
         ("norder", C.c_int), ("order_kind", C.POINTER(C.c_int)),
         ("order_index", C.POINTER(C.c_int)),
+        # TJM junctions come through the harvest path only (their coefficient sets are made by
+        # the reference's setup); a hand-built deck has none
+        ("ntjmmod", C.c_int), ("tjm_models", C.c_void_p), ("ntjm", C.c_int), ("tjm", C.c_void_p),
     ]
 
 
@@ -308,7 +311,7 @@ class Deck:
 
     def kind_tables(self) -> dict:
         """kind -> list of elems in deck order (the table index used by the C ABI)."""
-        tabs = {k: [] for k in range(7)}
+        tabs = {k: [] for k in range(8)}
         for e in self.elems:
             tabs[e.kind].append(e)
         return tabs
