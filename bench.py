@@ -146,7 +146,7 @@ def compare_with_reference(per_trial, cnt, waves, current_last=True, saved=None)
             "tolerance": f"reltol {RELTOL} * max(|a|,|b|) + vntol {VNTOL} (abstol {ABSTOL} for branch currents), every output point of {saved or SAVE_NODES}"}
 
 
-def bench_rsfq(local, ntrials=2048, njj=1000):
+def bench_rsfq(local, ntrials=2048, njj=1000, tjm=None):
     """Secondary workload (BASELINE.json configs[2]): Monte-Carlo transient of a
     Josephson transmission line tiled to ~1000 junctions (RSJ level 1, the `jtl` cell of
     examples/JJexamples/nor_mc.cir), per-trial critical currents ics*(1+N(0,0.1)) from the
@@ -155,10 +155,11 @@ def bench_rsfq(local, ntrials=2048, njj=1000):
     import numpy as np
     from xictools_b200.workloads import jtl
     from xictools_b200 import engine
-    from xictools_b200.deck import DEV_JJ, P_JJ_ICS, C_STATUS, C_NUMITER
+    from xictools_b200.deck import DEV_JJ, DEV_TJM, P_JJ_ICS, P_TJM_ICS, C_STATUS, C_NUMITER
     from xictools_b200.refrand import gauss_stream
-    deck = jtl(njj)
-    jjs = deck.kind_tables()[DEV_JJ]
+    deck = jtl(njj, tjm=tjm)
+    jjs = deck.kind_tables()[DEV_TJM if tjm else DEV_JJ]
+    P_JJ_ICS = P_TJM_ICS if tjm else P_JJ_ICS
     g = gauss_stream(SEED, (ntrials - 1)*len(jjs)).reshape(ntrials - 1, len(jjs))
     vals = np.empty((len(jjs), ntrials))
     for i, e in enumerate(jjs):
@@ -174,7 +175,8 @@ def bench_rsfq(local, ntrials=2048, njj=1000):
     save = [names.index("a0"), names.index(f"a{njj//2}"), names.index(f"a{njj-1}")]
     _, w = b.waves(save)
     ok = int((cnt[:, C_STATUS] == 0).sum())
-    out = {"workload": f"rsfq_mc: {njj}-junction Josephson transmission line (RSJ level 1, {njj} JJ + "
+    kind = f"tunnel-junction model level 3, coefficient set {tjm}" if tjm else "RSJ level 1"
+    out = {"workload": f"rsfq_mc: {njj}-junction Josephson transmission line ({kind}, {njj} JJ + "
                        f"{njj} L + {njj+1} R + {njj+1} I), .tran 0.5p 120p uic, per-trial ics sigma 10 %",
            "trials": ntrials, "unknowns": b.n, "ok_trials": ok,
            "value": ntrials/(st.ms_total*1e-3), "unit": "trials/s", "ms_per_step": st.ms_total,
@@ -579,6 +581,10 @@ def bench_ours(args):
                 line["secondary"] = {"rsfq_mc": bench_rsfq(local)}
             except Exception as e:          # pragma: no cover
                 line["secondary"] = {"rsfq_mc": {"error": repr(e)}}
+            try:
+                line["secondary"]["rsfq_tjm_mc"] = bench_rsfq(local, ntrials=1024, tjm="tjm1")
+            except Exception as e:          # pragma: no cover
+                line["secondary"]["rsfq_tjm_mc"] = {"error": repr(e)}
             try:
                 line["secondary"]["dc_sweep"] = bench_dc_sweep(local)
             except Exception as e:          # pragma: no cover

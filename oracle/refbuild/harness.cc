@@ -341,6 +341,44 @@ void wrsref_oracle_get(int *counters, double *times, double *vals)
     if (vals) memcpy(vals, oout.vals.data(), oout.vals.size()*sizeof(double));
 }
 
+// the set-up values of the first TJM instance of the last harvested circuit (fixture generation:
+// tools/make_tjm_fixture.py).  out: 13 model doubles (rtype, ictype, nterms, criti, cap, cmu, gmu,
+// r0, rsint, vshunt, tsaccl, tsfact, vgnom), 6 instance doubles (tcf, vdpbak, omegaJ, kgap,
+// kgap_rejpt, alphaN), then 6*nterms coefficient doubles.  Returns the count or -1.
+namespace {
+    std::vector<double> tjm_dump;
+    int tjm_dump_hook(sCKT *ckt)
+    {
+        tjm_dump.clear();
+        b200_harvest *H = 0;
+        int rc = b200_harvest_ckt(ckt, &H);
+        if (!rc) {
+            const b200_deck *d = b200_harvest_deck(H);
+            if (d->ntjm > 0) {
+                const b200_tjm &x = d->tjm[0];
+                const b200_tjm_model &m = d->tjm_models[x.model];
+                double mv[13] = { (double)m.rtype, (double)m.ictype, (double)m.nterms, m.criti, m.cap, m.cmu, m.gmu,
+                    m.r0, m.rsint, m.vshunt, m.tsaccl, m.tsfact, m.vgnom };
+                tjm_dump.assign(mv, mv + 13);
+                double iv[6] = { x.tcf, x.vdpbak, x.omegaJ, x.kgap, x.kgap_rejpt, x.alphaN };
+                tjm_dump.insert(tjm_dump.end(), iv, iv + 6);
+                tjm_dump.insert(tjm_dump.end(), x.coef, x.coef + 6*m.nterms);
+            }
+        }
+        b200_harvest_free(H);
+        return (rc);
+    }
+}
+int wrsref_tjm_setup_dump(const char *deck_text, double *out, int nout)
+{
+    after_task_hook = tjm_dump_hook;
+    wrsref_run_deck(deck_text);
+    after_task_hook = 0;
+    if (tjm_dump.empty()) return (-1);
+    for (int i = 0; i < nout && i < (int)tjm_dump.size(); i++) out[i] = tjm_dump[i];
+    return ((int)tjm_dump.size());
+}
+
 int wrsref_harvest_rc(void) { return (hout.rc); }
 int wrsref_harvest_n(void) { return (hout.n); }
 int wrsref_harvest_npoints(void) { return (hout.npoints); }

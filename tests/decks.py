@@ -310,4 +310,8 @@ def jj_variants():
         "jtl6_vshunt": jtl(6, vshunt=0.6857e-3),
         "jtl6_gear": jtl(6).options(method=1),
         "jtl12": jtl(12),
+        # tunnel-junction model (JJ level 3); set-up values from xictools_b200/data/tjm_setup.json
+        "jtl6_tjm": jtl(6, tjm="tjm1"),
+        "jtl6_tjm_vshunt": jtl(6, tjm="tjm1_vshunt"),
+        "jtl6_tjm2_phase": jtl(6, tjm="tjm2", phase_nodes=True),
     }

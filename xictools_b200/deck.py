@@ -106,6 +106,29 @@ class CJJ(C.Structure):
                 ("vg", C.c_double), ("tcf", C.c_double), ("icv", C.c_double), ("icphi", C.c_double)]
 
 
+class CTJMModel(C.Structure):
+    _fields_ = [("rtype", C.c_int), ("ictype", C.c_int), ("nterms", C.c_int)] + \
+               [(n, C.c_double) for n in ("criti", "cap", "cmu", "gmu", "r0", "rsint", "vshunt", "tsaccl",
+                                          "tsfact", "vgnom")]
+
+
+class CTJM(C.Structure):
+    _fields_ = [("pos", C.c_int), ("neg", C.c_int), ("phase_node", C.c_int), ("model", C.c_int),
+                ("area", C.c_double), ("ics", C.c_double), ("vshunt", C.c_double), ("tcf", C.c_double),
+                ("vdpbak", C.c_double), ("omegaJ", C.c_double), ("kgap", C.c_double),
+                ("kgap_rejpt", C.c_double), ("alphaN", C.c_double), ("coef", C.POINTER(C.c_double)),
+                ("icv", C.c_double), ("icphi", C.c_double)]
+
+
+def tjm_setup(name: str) -> dict:
+    """A level-3 (TJM) model card as the reference's setup leaves it: xictools_b200/data/
+    tjm_setup.json, generated from the compiled reference by tools/make_tjm_fixture.py."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tjm_setup.json")
+    return json.load(open(path))[name]
+
+
 PHI0 = 2.067833848e-15              # wrsCONSTphi0 (include/circuit.h:123-124)
 PHI0_2PI = PHI0/(2*3.14159265358979323846)
 
@@ -165,7 +188,8 @@ class CDeck(C.Structure):
         ("order_index", C.POINTER(C.c_int)),
         # TJM junctions come through the harvest path only (their coefficient sets are made by
         # the reference's setup); a hand-built deck has none
-        ("ntjmmod", C.c_int), ("tjm_models", C.c_void_p), ("ntjm", C.c_int), ("tjm", C.c_void_p),
+        ("ntjmmod", C.c_int), ("tjm_models", C.POINTER(CTJMModel)), ("ntjm", C.c_int),
+        ("tjm", C.POINTER(CTJM)),
     ]
 
 
@@ -206,6 +230,7 @@ class Deck:
     elems: list = field(default_factory=list)
     mos_models: dict = field(default_factory=dict)     # name -> dict(type, level, params)
     jj_models: dict = field(default_factory=dict)
+    tjm_models: dict = field(default_factory=dict)
     ics: dict = field(default_factory=dict)
     nodesets: dict = field(default_factory=dict)
     opts: dict = field(default_factory=lambda: dict(DEFAULT_OPTIONS))
@@ -251,6 +276,17 @@ class Deck:
         """`.model NAME jj(card)`; card keys as in the reference (rtype, cct, vg, delv, icrit,
         cap/cpic, icrn/rn, vm/rsub, icfct, cmu, gmu, vshunt, tsfactor, tsaccel, pijj)."""
         self.jj_models[name.lower()] = dict(card)
+        return self
+
+    def tjm_model(self, name, setup: str):
+        """`.model NAME jj(level=3 ...)` with the card and set-up values of tjm_setup(setup)."""
+        self.tjm_models[name.lower()] = tjm_setup(setup)
+        return self
+
+    def tjm(self, name, p, n, model, phase=None, **params):
+        """Tunnel-junction-model junction `Bname p n [phase] model [ics= area= vshunt=]`."""
+        nodes = (str(p).lower(), str(n).lower()) + ((str(phase).lower(),) if phase is not None else ())
+        self.elems.append(_Elem(DEV_TJM, name.lower(), nodes, dict(params), model.lower()))
         return self
 
     def jj(self, name, p, n, model, phase=None, **params):
@@ -365,6 +401,8 @@ class Deck:
         for e in self.elems:
             if e.kind == DEV_JJ and int(self.jj_models[e.model].get("cct", 1)) > 0:
                 ph.update(nd for nd in e.nodes[:2] if nd not in ("0", "gnd"))
+            if e.kind == DEV_TJM:
+                ph.update(nd for nd in e.nodes[:2] if nd not in ("0", "gnd"))
         if ph:
             for e in self.elems:
                 if e.kind == DEV_IND:
@@ -448,10 +486,11 @@ class Deck:
                     else:
                         s += f" {k}={_fmt(v)}"
                 lines.append(s)
-            elif e.kind == DEV_JJ:
+            elif e.kind in (DEV_JJ, DEV_TJM):
                 prm = dict(e.params)
-                if (P_JJ_ICS, i) in overrides:
-                    prm["ics"] = overrides[(P_JJ_ICS, i)]
+                pid = P_JJ_ICS if e.kind == DEV_JJ else P_TJM_ICS
+                if (pid, i) in overrides:
+                    prm["ics"] = overrides[(pid, i)]
                     prm.pop("area", None)
                 sline = f"{e.name} {' '.join(e.nodes)} {e.model}"
                 for k, v in prm.items():
@@ -465,6 +504,8 @@ class Deck:
         for name, card in self.jj_models.items():
             lines.append(f".model {name} jj(" + " ".join(f"{k}={_fmt(v) if isinstance(v, float) else v}"
                                                           for k, v in card.items()) + ")")
+        for name, su in self.tjm_models.items():
+            lines.append(f".model {name} {su['card']}")
         for name, m in self.mos_models.items():
             lines.append(self._model_line(name, m["type"], m["level"], m["params"]))
         for name, t, lev, prm in extra_models:
@@ -634,6 +675,32 @@ class Deck:
                     setattr(x, k, float(v))
         keep.append(jj)
         d.njj, d.jj = len(tabs[DEV_JJ]), jj
+        tnames = list(self.tjm_models)
+        tm = (CTJMModel * max(1, len(tnames)))()
+        for i, nme in enumerate(tnames):
+            for k, v in self.tjm_models[nme]["model"].items():
+                setattr(tm[i], k, v)
+        keep.append(tm)
+        d.ntjmmod, d.tjm_models = len(tnames), tm
+        tj = (CTJM * max(1, len(tabs[DEV_TJM])))()
+        for i, e in enumerate(tabs[DEV_TJM]):
+            x = tj[i]
+            su = self.tjm_models[e.model]
+            x.pos, x.neg = nums[e.nodes[0]], nums[e.nodes[1]]
+            x.phase_node = nums[e.nodes[2]] if len(e.nodes) > 2 else 0
+            x.model = tnames.index(e.model)
+            for f in ("area", "ics", "vshunt", "icv", "icphi"):
+                setattr(x, f, NAN)
+            for k, v in su["instance"].items():
+                setattr(x, k, v)
+            x.coef = arr(C.c_double, su["coef"])
+            for k, v in e.params.items():
+                if k == "ic":
+                    x.icv, x.icphi = float(v[0]), float(v[1])
+                else:
+                    setattr(x, k, float(v))
+        keep.append(tj)
+        d.ntjm, d.tjm = len(tabs[DEV_TJM]), tj
         order = self.load_order()
         d.norder = len(order)
         d.order_kind = arr(C.c_int, [k for k, _ in order])

@@ -20,22 +20,26 @@ def jj_single(**card):
     return d
 
 
-def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, **card):
+def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, tjm=None, **card):
     """Josephson transmission line (the `jtl` subcircuit of examples/JJexamples/nor_mc.cir
     flattened and repeated): biased junctions coupled by inductors, an SFQ pulse launched at
     the input propagates down the line.  Bias currents ramp up from zero (uic start)."""
     d = Deck(title=f"jtl{n}")
-    mc = dict(JJ_CARD, **card)
-    if vshunt is not None:
-        mc["vshunt"] = vshunt
-    d.jj_model("jj1", **mc)
+    if tjm:
+        # tunnel-junction model (JJ level 3): `tjm` names a set-up card of data/tjm_setup.json
+        d.tjm_model("jj1", tjm)
+    else:
+        mc = dict(JJ_CARD, **card)
+        if vshunt is not None:
+            mc["vshunt"] = vshunt
+        d.jj_model("jj1", **mc)
     d.isource("iin", "0", "in", pulse=(0, 0.6e-3, 40e-12, 3e-12, 3e-12, 2e-12, 200e-12))
     d.inductor("lin", "in", "a0", 2.0e-12)
     for i in range(n):
         a = f"a{i}"
         kw = {"phase": f"ph{i}"} if phase_nodes else {}
-        d.jj(f"b{i}", a, "0", "jj1", ics=ics*(1.0 + 0.05*(i % 3)), **kw)
-        if vshunt is None:
+        (d.tjm if tjm else d.jj)(f"b{i}", a, "0", "jj1", ics=ics*(1.0 + 0.05*(i % 3)), **kw)
+        if vshunt is None and not (tjm and "vshunt" in tjm):
             d.resistor(f"rs{i}", a, "0", 3.0)
         d.isource(f"ib{i}", "0", a, pulse=(0, 0.7*ics, 0.0, 20e-12, 1e-12, 1.0, 2.0))
         if i + 1 < n:
