@@ -97,7 +97,7 @@ typedef struct {
     double von, vdsat, cd, cbs, cbd, gm, gds, gmbs, gbd, gbs, capbd, capbs;
 } Mos;
 
-typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; int st; int icGiven; double capac, ic, geq, ceq; } Cap;
+typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; int st; int icGiven; double capac, ic, geq, ceq, m; } Cap;
 typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct; int usePreload; } Res;
 /* sINDinstancePOD (inddefs.h): linear inductor, no series resistance / poly / expression */
 typedef struct { int pos, neg, br; int pBB, pPB, pNB, pBN, pBP; int st; int icGiven;
@@ -1070,6 +1070,7 @@ wo_ckt *wo_create(const b200_deck *dk)
             p->pos = in->pos; p->neg = in->neg;
             double mm = GIVEN(in->m) ? in->m : 1.0;
             p->capac = in->c*1.0*mm;          /* captemp.cc:98 nom*tcFactor*m */
+            p->m = mm;
             p->icGiven = GIVEN(in->ic);
             p->ic = p->icGiven ? in->ic : 0.0;
             p->st = c->numStates; c->numStates += 2;
@@ -1238,7 +1239,7 @@ int wo_set_param(wo_ckt *c, int param, int index, double value)
         if (c->mos[index].effectiveLength < 0) c->mos[index].effectiveLength = 0;
         break;
     case B200_P_MOS_W:      c->mos[index].in.w = value; c->mos[index].w = value; break;
-    case B200_P_CAP_C:      c->cap[index].capac = value*1.0*1.0; break;
+    case B200_P_CAP_C:      c->cap[index].capac = value*1.0*c->cap[index].m; break;
     case B200_P_RES_R: {
         double r = value;
         if (fabs(r) < c->opt.resmin) r = (r < 0.0) ? -c->opt.resmin : c->opt.resmin;

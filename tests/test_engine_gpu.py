@@ -343,6 +343,19 @@ def test_reciprocal_division_is_ieee_division():
         assert rc == 0 and bad.value == 0, (emin, emax, bad.value)
 
 
+def test_per_trial_capacitance_keeps_the_multiplier():
+    """B200_P_CAP_C is the card value: CAPcapac = value * m per trial (captemp.cc:98); and a
+    per-trial DC level on a source that has a function makes the DC value `given`."""
+    from tests.decks import rc_fn
+    from xictools_b200.deck import DEV_CAP, P_CAP_C
+    d = rc_fn(sffm=(0.5, 0.4, 1.0e9, 2.0, 0.2e9))
+    d.elems = [e for e in d.elems if e.kind != DEV_CAP]
+    d.capacitor("c1", "b", "0", 1e-12, m=3.0)
+    ntr = 7
+    v = 1e-12*(1.0 + 0.2*np.arange(ntr))
+    compare(d, ntr, {(P_CAP_C, 0): v})
+
+
 def test_monte_carlo_jj_critical_currents():
     """Josephson transmission line with per-trial critical currents (B200_P_JJ_ICS): criti, cap,
     g0, gn, gs, cr1, cr2 are re-derived per trial on the device (jjset.cc:613-705); the step

@@ -50,6 +50,9 @@ struct b200_batch {
     std::vector<double> mos_raw[MR_NRAW];                   // [nmos] shared values
     std::map<int, std::vector<double>> mos_var[MR_NRAW];    // inst -> [ntrials]
     std::vector<double> cap_c, cap_ic, src_dc, ind_l, ind_ic;
+    std::vector<double> cap_craw, cap_m;                    // card value and multiplier (per-trial rows carry the card value)
+    bool cap_has_m = false;
+    std::vector<int> src_dcgiven; int *d_src_dcgiven = nullptr;
     std::map<int, std::vector<double>> cap_var, src_var, ind_var, jj_var;
     std::vector<double> jj_ics, tjm_ics;                    // [njj] / [ntjm] card ics (NaN = not given)
     std::map<int, std::vector<double>> tjm_var;
@@ -117,6 +120,14 @@ __global__ void k_fill_rows(double *dst, const double *shared, int n, int ldt)
 // packed rows [nrows][ntrials] -> row desc[2r+1] of the table whose base is bases[desc[2r]];
 // the padding trials repeat trial 0 (they run the nominal arithmetic and are never read back)
 struct TableBases { double *p[PT_NTABLES]; };
+// per-trial capacitance rows hold the card value: CAPcapac = nomCapac*tcFactor*m (captemp.cc:98)
+__global__ void k_scale_rows(double *dst, const double *scale, int n, int ldt)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t < ldt && i < n) dst[(size_t)i*ldt + t] = dst[(size_t)i*ldt + t]*scale[i];
+}
+
 __global__ void k_scatter_rows(TableBases tb, const int *desc, const double *vals, int ntrials, int ldt)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
@@ -255,10 +266,13 @@ static void build_cards(b200_batch *b, const b200_deck *dk)
         b->mos_raw[MR_w][i] = given(in.w) ? in.w : (o.defw > 0 ? o.defw : 1e-6);
     }
     b->cap_c.resize(dk->ncap); b->cap_ic.resize(dk->ncap);
+    b->cap_craw.resize(dk->ncap); b->cap_m.resize(dk->ncap);
     for (int i = 0; i < dk->ncap; i++) {
         const b200_cap &in = dk->cap[i];
         double mm = given(in.m) ? in.m : 1.0;
         b->cap_c[i] = in.c*1.0*mm;                  // captemp.cc:98
+        b->cap_craw[i] = in.c*1.0; b->cap_m[i] = mm;
+        if (mm != 1.0) b->cap_has_m = true;
         double ic = given(in.ic) ? in.ic : 0.0;
         if (dk->uic && !given(in.ic)) {
             auto icv = [&](int node) { return node ? (an.ns_given[node] && !an.ic_given[node] ? an.ns_val[node] : an.ic_val[node]) : 0.0; };
@@ -432,7 +446,10 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     h.accepted = b->dalloc<int>(ldt);
     SrcView &S = b->S; SrcTopo &st = an.src;
     S.n = st.n;
-    S.kind = b->dupload(st.kind); S.fn = b->dupload(st.fn); S.dcgiven = b->dupload(st.dcgiven);
+    S.kind = b->dupload(st.kind); S.fn = b->dupload(st.fn);
+    b->src_dcgiven = st.dcgiven;
+    b->d_src_dcgiven = b->dupload(st.dcgiven);
+    S.dcgiven = b->d_src_dcgiven;
     S.rslot = b->dupload(st.rslot); S.coef_off = b->dupload(st.coef_off); S.ncoef = b->dupload(st.ncoef);
     S.pool = b->dupload(st.pool);
     S.dcval = nullptr;
@@ -586,6 +603,7 @@ int b200_batch_set_param(b200_batch *b, int param, int index, const double *valu
         put(b->ind_var[index]); b->params_dirty = true; return B200_OK;
     case B200_P_SRC_DC:
         if (index < 0 || index >= b->an.src.n) return B200_E_BADPARM;
+        b->src_dcgiven[index] = 1;                  // a DC value makes it given (SRCdcGiven)
         put(b->src_var[index]); b->params_dirty = true; return B200_OK;
     case B200_P_JJ_ICS:
         if (index < 0 || index >= b->an.jj.n) return B200_E_BADPARM;
@@ -633,7 +651,7 @@ int b200_batch_set_params(b200_batch *b, int nrows, const int *param, const int 
         else if (tbl[r] == PT_IND) b->ind_var.erase(index[r]);
         else if (tbl[r] == PT_JJ) b->jj_var.erase(index[r]);
         else if (tbl[r] == PT_TJM) b->tjm_var.erase(index[r]);
-        else b->src_var.erase(index[r]);
+        else { b->src_var.erase(index[r]); b->src_dcgiven[index[r]] = 1; }    // a DC value makes it given
     }
     size_t need = (size_t)nrows*b->ntrials;
     if (need > b->pack_cap) {
@@ -739,7 +757,10 @@ static int prepare_params(b200_batch *b)
         b->M.stage_doubles = shared_base + (other ? MP_NPARAMS : MP_NBASE) + (MOS_NSLOT + 1)/2;
         if (loads_configure(b->M)) return B200_E_NOMEM;
     }
-    int rc = upload_strided(PT_CAP, b->cap_c, b->cap_var, b->d_capc, b->capc_ts);
+    // a per-trial capacitance table holds card values (the shared fill too) and is scaled by the
+    // instance multipliers after the rows have landed
+    bool cap_rows = !b->cap_var.empty() || packed_in[PT_CAP];
+    int rc = upload_strided(PT_CAP, (cap_rows && b->cap_has_m) ? b->cap_craw : b->cap_c, b->cap_var, b->d_capc, b->capc_ts);
     if (rc) return rc;
     b->Cp.capac.base = b->d_capc; b->Cp.capac.ts = b->capc_ts; b->Cp.capac.ld = b->capc_ts ? (int)ldt : 1;
     if (!b->d_capic) b->d_capic = b->dalloc<double>(b->cap_ic.size());
@@ -799,6 +820,16 @@ static int prepare_params(b200_batch *b)
         k_scatter_rows<<<dim3((unsigned)((ldt + 255)/256), nrows), 256, 0, st>>>(bases, b->d_pk_desc,
             b->d_pack, b->ntrials, (int)ldt);
     }
+    if (b->capc_ts && b->cap_has_m) {
+        double *dm = nullptr;
+        CK(cudaMalloc(&dm, b->cap_m.size()*sizeof(double)));
+        tmp_shared.push_back(dm);
+        CK(cudaMemcpyAsync(dm, b->cap_m.data(), b->cap_m.size()*sizeof(double), cudaMemcpyHostToDevice, st));
+        k_scale_rows<<<dim3((unsigned)((ldt + 255)/256), (unsigned)b->cap_m.size()), 256, 0, st>>>(b->d_capc, dm,
+            (int)b->cap_m.size(), (int)ldt);
+    }
+    if (!b->src_dcgiven.empty() && b->d_src_dcgiven)
+        CK(cudaMemcpyAsync(b->d_src_dcgiven, b->src_dcgiven.data(), b->src_dcgiven.size()*sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(b->d_cards, b->cards.data(), b->cards.size()*sizeof(MosCard), cudaMemcpyHostToDevice, st));
     launch_mos_temp(st, nm, b->ntrials, (int)ldt, b->d_cards, raw, po);
     if (b->an.jj.n) {

@@ -256,9 +256,9 @@ class Deck:
                                 dict(r=float(r))))
         return self
 
-    def capacitor(self, name, p, n, c, ic=None):
+    def capacitor(self, name, p, n, c, ic=None, m=None):
         self.elems.append(_Elem(DEV_CAP, name.lower(), (str(p).lower(), str(n).lower()),
-                                dict(c=float(c), ic=ic)))
+                                dict(c=float(c), ic=ic, m=m)))
         return self
 
     def inductor(self, name, p, n, l, ic=None):
@@ -448,6 +448,8 @@ class Deck:
                 s = f"{e.name} {e.nodes[0]} {e.nodes[1]} {_fmt(cval)}"
                 if e.params.get("ic") is not None:
                     s += f" ic={_fmt(e.params['ic'])}"
+                if e.params.get("m") is not None:
+                    s += f" m={_fmt(e.params['m'])}"
                 lines.append(s)
             elif e.kind == DEV_IND:
                 lval = overrides.get((P_IND_L, i), e.params["l"])
@@ -583,7 +585,8 @@ class Deck:
         cap = (CCap * max(1, len(tabs[DEV_CAP])))()
         for i, e in enumerate(tabs[DEV_CAP]):
             ic = e.params.get("ic")
-            cap[i] = CCap(nums[e.nodes[0]], nums[e.nodes[1]], e.params["c"], NAN,
+            mm = e.params.get("m")
+            cap[i] = CCap(nums[e.nodes[0]], nums[e.nodes[1]], e.params["c"], NAN if mm is None else float(mm),
                           NAN if ic is None else ic)
         keep.append(cap)
         d.ncap, d.cap = len(tabs[DEV_CAP]), cap
