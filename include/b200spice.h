@@ -112,7 +112,8 @@ typedef struct b200_mos {
  * (jjset.cc:609-715: ics -> area -> criti, cap, g0, gn, gs, cr1, cr2, gshunt, vless, vmore) runs
  * on the device, per trial where ics varies.
  * Built: rtype 0..3, ictype 0 / 1 (no control current), vshunt, the phase node; `.tran ... uic`
- * starts only (the phase-mode DC operating point, jjload.cc:154-250, is not built).
+ * starts and the phase-mode DC operating point (jjload.cc:154-250 with the phase terms it puts
+ * on inductors, mutuals and resistors: indload.cc:88-96, mutload.cc:75-87, resload.cc:261-283).
  * Refused (B200_E_UNSUPP): lser / lsh parasitic inductances, rtype 4, ictype 2..4, control. */
 typedef struct b200_jj_model {
     int rtype, ictype, pi;          /* JJrtype, JJictype, JJpi */
@@ -140,7 +141,7 @@ typedef struct b200_jj {
  * sTJMinstance::tjm_init1 has renormalised it (tjmset.cc:869-918) -- none of it depends on the
  * junction's area, so it is shared by all trials.  Per trial (ics): criti, cap, gqp, g0,
  * gshunt, gcrit (tjmset.cc:600-660, tjmload.cc:467-470).
- * Built for `uic` runs like the RSJ model: no phase-mode DC, no lser / lsh. */
+ * Built like the RSJ model (`uic` and phase-mode DC starts, tjmload.cc:78-120); no lser / lsh. */
 typedef struct b200_tjm_model {
     int rtype, ictype, nterms;
     double criti, cap, cmu, gmu, r0, rsint, vshunt, tsaccl, tsfact, vgnom;

@@ -58,6 +58,8 @@
 #define GIVEN(x) (!isnan(x))
 
 enum { SP_VOLTAGE = 0, SP_CURRENT = 1 };
+#define PHI0      2.067833848e-15            /* wrsCONSTphi0, circuit.h:123 */
+#define PHI0_2PI  (PHI0/(2*M_PI))
 
 /* ------------------------------------------------------------------------- */
 /* device records                                                             */
@@ -2794,8 +2796,6 @@ static int mos_conv(wo_ckt *c, Mos *m)
 /* ------------------------------------------------------------------------- */
 /* Josephson junction, RSJ level 1: devlib/jj/{jjset,jjload,jjacct,jjic,jjtrun}.cc */
 /* ------------------------------------------------------------------------- */
-#define PHI0      2.067833848e-15            /* wrsCONSTphi0, circuit.h:123 */
-#define PHI0_2PI  (PHI0/(2*M_PI))
 
 static void jj_setup_instance(JJ *j)
 {
@@ -3375,7 +3375,8 @@ static void tjm_load(wo_ckt *c, TJM *j)
             s1[TS_voltage] = vj; s1[TS_phase] = phi;
         }
         else {
-            vj = 0; s1[TS_voltage] = 0.0; s0[TS_voltage] = 0.0; phi = 0;
+            /* tjmload.cc:310-316 (NEWJJDC): the phase computed by the DC operating point carries over */
+            vj = 0; s1[TS_voltage] = 0.0; phi = s1[TS_phase]; s0[TS_voltage] = 0.0;
         }
         j->delVdelT = find_ceq(c, j->st + TS_voltage);
         tjm_init(j, phi);
@@ -3541,8 +3542,14 @@ static void mut_load(wo_ckt *c, Mut *p)
     Ind *l1 = &c->ind[p->ind1], *l2 = &c->ind[p->ind2];
     if (p->factor == 0.0)
         p->factor = p->coupling*sqrt(l1->induct*l2->induct);
-    if (c->mode & MODEDC)
+    if (c->mode & MODEDC) {
+        if (c->phase) {                                   /* mutload.cc:75-87 */
+            double res = 2*M_PI*p->factor/PHI0;
+            ldadd(c, p->p12, -res);
+            ldadd(c, p->p21, -res);
+        }
         return;
+    }
     if (c->mode & MODEINITFLOAT) {
         double factor = p->factor;
         c->states[0][l1->st] += factor*c->rhsOld[l2->br];
@@ -3575,8 +3582,14 @@ static void mut_load(wo_ckt *c, Mut *p)
 static void ind_load(wo_ckt *c, Ind *p)
 {
     /* indload.cc:84-263 (linear inductor; the +-1 couplings are preloaded) */
-    if (c->mode & MODEDC)
+    if (c->mode & MODEDC) {
+        /* :88-96 phase-mode DC (CKTjjDCphase): the inductor's "voltage" is its phase */
+        if (c->phase) {
+            double res = 2*M_PI*p->induct/PHI0;
+            ldadd(c, p->pBB, -res);
+        }
         return;
+    }
     if (c->mode & MODEINITFLOAT) {
         double flux = p->induct*c->rhsOld[p->br] - p->prevFlux;
         c->states[0][p->st] += flux;
@@ -4900,7 +4913,12 @@ int wo_run_tran(wo_ckt *c)
         error = ckt_load(c);
     }
     else
+    {
         error = ckt_op(c, MODETRANOP | MODEINITJCT, MODETRANOP | MODEINITFLOAT, o->itl1);
+        /* tranan.cc:378-389: what was computed on the phase nodes is phase; their voltage is 0 */
+        if (!error && c->phase)
+            for (int i = 1; i <= c->n; i++) if (c->phase[i]) c->rhsOld[i] = 0.0;
+    }
     if (error) { return error; }
 
     for (int i = 1; i <= o->maxord + 1; i++)

@@ -314,4 +314,10 @@ def jj_variants():
         "jtl6_tjm": jtl(6, tjm="tjm1"),
         "jtl6_tjm_vshunt": jtl(6, tjm="tjm1_vshunt"),
         "jtl6_tjm2_phase": jtl(6, tjm="tjm2", phase_nodes=True),
+        # no `uic`: the transient starts from a phase-mode DC operating point (jjload.cc:154-250)
+        "jtl6_dc": jtl(6, dc_bias=True),
+        "jtl6_dc_phase": jtl(6, dc_bias=True, phase_nodes=True),
+        "jtl6_dc_vshunt": jtl(6, dc_bias=True, vshunt=0.6857e-3),
+        "jtl12_dc": jtl(12, dc_bias=True),
+        "jtl6_dc_tjm": jtl(6, dc_bias=True, tjm="tjm1"),
     }

@@ -373,15 +373,28 @@ def test_monte_carlo_jj_critical_currents():
     compare(d, ntr, ov)
 
 
-def test_jj_needs_uic():
-    """The phase-mode DC operating point is not built: a JJ deck without `uic` is refused."""
+def test_monte_carlo_jj_from_a_dc_operating_point():
+    """No `uic`: every trial solves its own phase-mode DC operating point (jjload.cc:154-250,
+    indload.cc:88-96, resload.cc:261-283; phase nodes zeroed going into the transient,
+    tranan.cc:378-389) with its own critical currents, then runs the transient from it."""
     from tests.decks import jtl
-    d = jtl(3)
-    ts, tp, t0, tm, _ = d.tran_args
-    d.tran(ts, tp, t0, tm, uic=False)
-    with pytest.raises(engine.B200Error) as e:
-        engine.Batch(d, 2)
-    assert e.value.code == 13
+    from xictools_b200.deck import DEV_JJ, P_JJ_ICS
+    d = jtl(6, dc_bias=True)
+    rng = np.random.default_rng(13)
+    ntr = 19
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_JJ]):
+        v = np.full(ntr, e.params["ics"])
+        v[1:] *= 1.0 + 0.1*rng.standard_normal(ntr - 1)
+        ov[(P_JJ_ICS, i)] = v
+    compare(d, ntr, ov)
+
+
+def test_jj_operating_point_only():
+    """`.op` of a biased Josephson line: the phases across the junctions (dcoan.cc:100-121 on a
+    CKTjjDCphase circuit)."""
+    from tests.decks import jtl
+    compare_op(jtl(6, dc_bias=True), 3)
 
 
 def test_packed_rows_equal_single_rows():

@@ -41,6 +41,8 @@ CASES = {
     "jtl6_phase": (lambda: jtl(6, phase_nodes=True), TJM1),
     "jtl6_rtype0": (lambda: jtl(6), "jj(level=3 coeffset=tjm1 rtype=0 icrit=0.001 cap=7e-13)"),
     "jtl6_gear": (lambda: jtl(6).options(method=1), TJM1),
+    "jtl6_dc": (lambda: jtl(6, dc_bias=True), TJM1),
+    "jtl6_dc_phase_tjm2": (lambda: jtl(6, dc_bias=True, phase_nodes=True), "jj(level=3 coeffset=tjm2 nterms=10 icrit=0.001 cap=7e-13)"),
     "jtl12_vshunt": (lambda: jtl(12), "jj(level=3 coeffset=tjm1 icrit=0.001 cap=7e-13 vshunt=0.6m)"),
 }
 
@@ -119,9 +121,10 @@ def test_engine_monte_carlo_per_trial_ics():
     _check(r, ntr, ref_of_trial)
 
 
-def test_tjm_without_uic_is_refused():
-    d = jtl(3)
-    ts, tp, t0, tm, _ = d.tran_args
-    d.tran(ts, tp, t0, tm, uic=False)
+def test_tjm_without_uic_is_analysed():
+    """A TJM deck without `uic` starts from a phase-mode DC operating point (tjmload.cc:78-120):
+    the harvested deck is accepted by the engine's analysis (CPU part; the GPU run is
+    tests/test_golden.py[jtl6_dc_tjm] and test_harvest.py)."""
+    d = jtl(3, dc_bias=True)
     r = run_harvest(tjm_text(d), engine.LIB_PATH, 0)
-    assert r["rc"] == 13                    # B200_E_UNSUPP from the engine's analysis
+    assert r["rc"] == 0

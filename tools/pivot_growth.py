@@ -43,7 +43,8 @@ def growth(n, Ap, Ai, Ax, rp, cp):
         colmax = np.abs(B[k:, k]).max()
         if piv == 0:
             return np.inf, 0.0
-        worst = min(worst, abs(piv)/colmax if colmax else 1.0)
+        if np.count_nonzero(B[k, k+1:]):      # a pivot alone in its row propagates nothing: any size is safe
+            worst = min(worst, abs(piv)/colmax if colmax else 1.0)
         B[k+1:, k] /= piv
         B[k+1:, k+1:] -= np.outer(B[k+1:, k], B[k, k+1:])
         g = max(g, np.abs(B[k+1:, k+1:]).max()/amax if k + 1 < n else g)

@@ -154,7 +154,6 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     const b200_options &o = dk->opt;
     if (dk->njj) {
         // what of devlib/jj is built (include/b200spice.h, b200_jj_model)
-        if (!dk->uic) { err = "JJ decks need `.tran ... uic`: the phase-mode DC operating point (jjload.cc:154-250) is not built"; return B200_E_UNSUPP; }
         if (dk->njjmod > JJ_MAXMODELS) { err = "more JJ models than JJ_MAXMODELS"; return B200_E_UNSUPP; }
         for (int i = 0; i < dk->njjmod; i++) {
             const b200_jj_model &m = dk->jj_models[i];
@@ -163,7 +162,6 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
         }
     }
     if (dk->ntjm) {
-        if (!dk->uic) { err = "TJM decks need `.tran ... uic` (phase-mode DC is not built)"; return B200_E_UNSUPP; }
         if (dk->njjmod + dk->ntjmmod > JJ_MAXMODELS) { err = "more JJ + TJM models than JJ_MAXMODELS"; return B200_E_UNSUPP; }
         for (int i = 0; i < dk->ntjmmod; i++)
             if (dk->tjm_models[i].nterms < 1 || dk->tjm_models[i].nterms > TJM_MAXTERMS) { err = "TJM nterms out of range"; return B200_E_UNSUPP; }
@@ -249,6 +247,8 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (dk->ind[i].neg > 0) phase_node[dk->ind[i].neg] = 1;
         }
     std::vector<char> res_preload(dk->nres, 1);
+    an.jjDCphase = jjDCphase ? 1 : 0;
+    an.rph_res.clear(); an.rph_cls.clear(); an.rph_g.clear(); an.rph_cslot.clear();
     std::vector<double> res_g(dk->nres, 0.0);
     std::vector<char> mos_has_dcon(M.n, 0), mos_has_scon(M.n, 0);
 
@@ -501,10 +501,18 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             // constant terms at this place of the load order
             if (res_preload[i]) break;
             const int *c = &res_coo[(size_t)i*4];
-            const double v[4] = { res_g[i], res_g[i], -res_g[i], -res_g[i] };
+            const b200_res &in = dk->res[i];
+            // nodetype(): ground, voltage or phase (resload.cc:53-64)
+            bool vp = in.pos > 0 && !phase_node[in.pos], vn = in.neg > 0 && !phase_node[in.neg];
+            bool pp = in.pos > 0 && phase_node[in.pos], pn = in.neg > 0 && phase_node[in.neg];
+            int cls = (!vp && !vn) ? 0 : (vp && pn) ? 1 : (pp && vn) ? 2 : 3;
+            an.rph_res.push_back(i); an.rph_cls.push_back(cls); an.rph_g.push_back(res_g[i]);
             for (int k = 0; k < 4; k++) {
                 int sl = add_c(c[k]);
-                if (sl >= 0) { an.rload_slot.push_back(sl); an.rload_val.push_back(v[k]); an.dc_active[coo2ax[c[k]]] = 1; }
+                an.rph_cslot.push_back(sl);
+                // which of the four are live in the phase-mode DC modes
+                bool dc = cls == 0 || cls == 3 || (cls == 1 && (k == 0 || k == 3)) || (cls == 2 && (k == 1 || k == 2));
+                if (sl >= 0 && dc) an.dc_active[coo2ax[c[k]]] = 1;
             }
             break; }
         case B200_DEV_TJM: {
@@ -579,11 +587,14 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             // mutload.cc: ldadd(br1br2, -factor), ldadd(br2br1, -factor)
             MU.cslot[(size_t)i*2] = add_c(mut_coo[(size_t)i*2]);
             MU.cslot[(size_t)i*2 + 1] = add_c(mut_coo[(size_t)i*2 + 1]);
+            if (jjDCphase)
+                for (int k = 0; k < 2; k++) if (mut_coo[(size_t)i*2 + k] >= 0) an.dc_active[coo2ax[mut_coo[(size_t)i*2 + k]]] = 1;
             break;
         case B200_DEV_IND:
             // indload.cc: rhsadd(brEq, veq) then ldadd(ibrIbr, -req)
             L.rslot[i] = add_r(L.branch[i]);
             L.cslot[i] = add_c(ind_coo[(size_t)i*5]);
+            if (jjDCphase && ind_coo[(size_t)i*5] >= 0) an.dc_active[coo2ax[ind_coo[(size_t)i*5]]] = 1;   // -2*pi*L/Phi0 in phase-mode DC
             break;
         case B200_DEV_SRC: {
             int *rs = &S.rslot[(size_t)i*2];
@@ -604,6 +615,9 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
         an.rg_ptr[r+1] = an.rg_ptr[r] + (int)rg[r].size();
         an.rg_idx.insert(an.rg_idx.end(), rg[r].begin(), rg[r].end());
     }
+
+    an.phase_mask.assign(n + 1, 0);
+    if (jjDCphase) for (int i = 1; i < dk->nnodes && i <= n; i++) an.phase_mask[i] = phase_node[i];
 
     // ---- .ic / .nodeset ----
     an.ic_given.assign(n + 1, 0); an.ns_given.assign(n + 1, 0);
@@ -641,7 +655,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
     // ic() has put the .ic / nodeset values into CKTrhs (ckt.cc:908-925); vmax is carried
     // across models as there.  criti > 0 for every junction with a supercurrent (area > 0).
     an.initDelta = 0.0;
-    if (J.n) {
+    if (J.n && dk->uic) {
         auto rhs0 = [&](int node) { return node > 0 ? (an.ic_given[node] ? an.ic_val[node] : (an.ns_given[node] ? an.ns_val[node] : 0.0)) : 0.0; };
         for (int i = 0; i < J.n; i++) {
             const b200_jj &in = dk->jj[i];
@@ -668,7 +682,7 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             }
         }
     }
-    if (TJ.n) {
+    if (TJ.n && dk->uic) {
         // TJMdev::getic, tjmic.cc:45-95 (its own vmax; criti > 0 for every junction)
         auto rhs0 = [&](int node) { return node > 0 ? (an.ic_given[node] ? an.ic_val[node] : (an.ns_given[node] ? an.ns_val[node] : 0.0)) : 0.0; };
         for (int i = 0; i < TJ.n; i++) {
@@ -872,7 +886,7 @@ void b200_order_markowitz(Analysis &an, bool tran_order)
     std::vector<char> diag_ok(n, 0);
     for (int i = 0; i < n; i++) {
         int p = an.diag[i+1];
-        if (p >= 0 && (an.ntype[i+1] == 0 || tran_order) &&
+        if (p >= 0 && (an.ntype[i+1] == 0 || tran_order || an.jjDCphase) &&   // phase-mode DC: (br,br) = -2*pi*L/Phi0
                 (an.cg_ptr[p+1] > an.cg_ptr[p] || an.Ainit[p] != 0.0) &&
                 (!have_dc || an.dc_active[p]))
             diag_ok[i] = 1;
@@ -1260,11 +1274,7 @@ int b200_build_lu(Analysis &an)
     remap(an.mut.cslot, newc);
     remap(an.jj.cslot, newc); remap(an.jj.rslot, newr);
     remap(an.tjm.cslot, newc); remap(an.tjm.rslot, newr);
-    // resistors loaded in place: constant terms inside the runs (written once, like Ainit)
-    for (size_t k = 0; k < an.rload_slot.size(); k++) {
-        an.const_idx.push_back(newc[an.rload_slot[k]]);
-        an.const_val.push_back(an.rload_val[k]);
-    }
+    remap(an.rph_cslot, newc);
     return B200_OK;
 }
 

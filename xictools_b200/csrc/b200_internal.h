@@ -248,6 +248,9 @@ struct Analysis {
     // (restemp.cc:213-248): their +-g are constant contributions at the resistor's place in the
     // load order (contribution slot, value)
     std::vector<int> rload_slot; std::vector<double> rload_val;
+    std::vector<int> rph_res, rph_cls, rph_cslot; std::vector<double> rph_g;   // [n], [n], [4n], [n]
+    int jjDCphase = 0;                          // CKTjjDCphase (ckt.cc:2137-2176)
+    std::vector<char> phase_mask;               // [n+1] node carries the phase flag
     // ordering: position -> original (0-based)
     std::vector<int> rowperm, colperm;
     // LU structure in permuted positions

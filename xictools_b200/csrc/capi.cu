@@ -441,6 +441,12 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
         }
         K.njjmod = jt.nmodels + tt.nmodels;
     }
+    ResPhView &Rv = Cp.R;
+    memset(&Rv, 0, sizeof(Rv));
+    Rv.n = (int)an.rph_res.size();
+    if (Rv.n) { Rv.cslot = b->dupload(an.rph_cslot); Rv.cls = b->dupload(an.rph_cls); Rv.g = b->dupload(an.rph_g); }
+    K.jjDCphase = an.jjDCphase;
+    V.phase = an.jjDCphase ? b->dupload(an.phase_mask) : nullptr;
     K.initDelta = an.initDelta;
     h.jj_vmax = b->dalloc<double>((size_t)std::max(jt.nmodels + tt.nmodels, 1)*ldt);
     h.accepted = b->dalloc<int>(ldt);
@@ -967,7 +973,7 @@ static int run_analysis(b200_batch *b, int analysis)
     if (!E.ok) return B200_E_NOGPU;
     long long launches = 0, ticks = 0, load_launches = 0, solve_launches = 0;
     double ms_load = 0, ms_solve = 0;
-    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->Cp.L.nmut ? 1 : 0) + (b->S.n ? 1 : 0) + (b->Cp.J.n ? 1 : 0) + (b->Cp.T.n ? 1 : 0);
+    int nload_kernels = (b->M.n ? 1 : 0) + (b->Cp.n ? 1 : 0) + (b->Cp.L.n ? 1 : 0) + (b->Cp.L.nmut ? 1 : 0) + (b->S.n ? 1 : 0) + (b->Cp.J.n ? 1 : 0) + (b->Cp.T.n ? 1 : 0) + (b->Cp.R.n ? 1 : 0);
 
     CK(cudaEventRecord(E.begin, st));
     // tick 0: begin + first load

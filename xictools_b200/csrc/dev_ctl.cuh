@@ -387,6 +387,9 @@ __device__ inline void ctl_op_finish(TrialCtl &s, const Consts &K, const CtlShar
         s.want_load = 0;
         return;
     }
+    // tranan.cc:378-389: a phase-mode operating point leaves PHASE on the nodes of junctions and
+    // inductors; their voltage, going into the transient, is zero
+    if (K.jjDCphase) s.vecops |= VO_ZERO_PHASE;
     ctl_tran_init(s, K, sh);
 }
 

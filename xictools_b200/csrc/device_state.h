@@ -28,6 +28,7 @@ enum { RET_NONE = 0, RET_OP_DIRECT, RET_GMIN_LOOP, RET_GMIN_FINAL, RET_SRC_LOOP,
 #define VO_FIRSTTIME    0x080   // state2 (,state3) <- state1         (tranan.cc:736-742)
 #define VO_INTERP       0x100   // emit interpolated output points    (tranan.cc:963-1116)
 #define VO_DUMP_DIRECT  0x200   // emit rhsOld as an output point     (tranan.cc:977-981)
+#define VO_ZERO_PHASE   0x800   // zero the phase nodes of rhsOld after a phase-mode DCOP (tranan.cc:378-389)
 #define VO_KEEP_X       0x400   // trial parked at a sync point: carry its rhsOld over the global
                                 //  rhs/rhsOld buffer flip of this tick
 
@@ -97,6 +98,7 @@ struct Consts {
     int nbrks, nlat;
     // Josephson junctions: CKTinitDelta (jjic.cc:78-104) and the per-model accept constants
     double initDelta;
+    int jjDCphase;      // CKTjjDCphase: the DC modes compute phase on the nodes of junctions and inductors
     int njjmod; int jj_limits[JJ_MAXMODELS];    // model has a supercurrent (ictype != 0)
     double jj_vth[JJ_MAXMODELS], jj_tsfact[JJ_MAXMODELS];
 };
@@ -131,6 +133,13 @@ struct JJView {
     int rtype[JJ_MAXMODELS], ictype[JJ_MAXMODELS], pi[JJ_MAXMODELS];
     double delv[JJ_MAXMODELS], icfactor[JJ_MAXMODELS];
 };
+// resistors on phase nodes: loaded every iteration (resload.cc:250-292)
+struct ResPhView {
+    int n;
+    const int *cslot;   // [n*4] PP NN PN NP
+    const int *cls;     // 0: both terminals phase / ground, 1: volt - phase, 2: phase - volt
+    const double *g;
+};
 // Tunnel-junction model (JJ level 3).  work[(a*nterms + k)*2 + c][n][ldt], a in TF_*, c = re / im
 struct TJMView {
     int n, nmodels, nterms, model0;     // model0: index of its first model in the shared jj_vmax / Consts tables
@@ -150,6 +159,7 @@ struct CapView {
     IndView L;
     JJView J;           // Josephson junctions travel with the other two-terminal reactive elements
     TJMView T;
+    ResPhView R;        // the resistors a JJ deck loads in place
 };
 struct SrcView {
     int n;
@@ -168,4 +178,5 @@ struct VecView {
     double *oldState0;  // [numStates][ldt]
     double *contrib;    // [NC][ldt]: matrix + rhs contributions in assembly order
     double *out;        // [npoints_max][n][ldt] -> transposed on fetch
+    const char *phase;  // [n+1] node carries the phase flag, or NULL
 };

@@ -425,7 +425,11 @@ k_load_ind(Consts K, HotView hot, VecView V, IndView L, const double *rhsOld)
             L.req[at] = req; L.veq[at] = veq;
         }
     }
-    // DC modes: nothing but the preloaded +-1 (the branch equation shorts the inductor)
+    else if (K.jjDCphase) {
+        // phase-mode DC (indload.cc:88-96): the inductor's "voltage" is its phase
+        req = 2*M_PI*PR(L.induct, i, t)/JJ_PHI0;
+    }
+    // other DC modes: nothing but the preloaded +-1 (the branch equation shorts the inductor)
     if (rs >= 0) V.contrib[CADDR(K, rs, t)] = veq;
     if (cs >= 0) V.contrib[CADDR(K, cs, t)] = -req;
 }
@@ -444,6 +448,11 @@ k_load_mut(Consts K, HotView hot, VecView V, IndView L)
         double factor = L.mutk[i]*sqrt(PR(L.induct, L.mut1[i], t)*PR(L.induct, L.mut2[i], t));
         factor *= hot.ag[t];
         v = -factor;
+    }
+    else if ((mode & MODEDC) && K.jjDCphase) {
+        // mutload.cc:75-87
+        double factor = L.mutk[i]*sqrt(PR(L.induct, L.mut1[i], t)*PR(L.induct, L.mut2[i], t));
+        v = -(2*M_PI*factor/JJ_PHI0);
     }
     int c0 = L.mut_cslot[2*i], c1 = L.mut_cslot[2*i + 1];
     if (c0 >= 0) V.contrib[CADDR(K, c0, t)] = v;
@@ -648,6 +657,7 @@ k_vec(Consts K, VecView V, CtlAux aux, double *rhsOld)
         const double *other = (rhsOld == V.X[0]) ? V.X[1] : V.X[0];
         rhsOld[at] = other[at];
     }
+    if ((ops & VO_ZERO_PHASE) && V.phase && V.phase[i]) rhsOld[at] = 0.0;
     if (ops & VO_BK_SAVE) V.oldSol[at] = rhsOld[at];
     if (ops & VO_BK_RESTORE) rhsOld[at] = V.oldSol[at];
     if (ops & VO_RESTORE_OLD) { if (i) rhsOld[at] = V.spare[at]; }
@@ -803,6 +813,32 @@ __global__ void k_export_counters(int ntrials, const TrialCtl *ctl, int *counter
 // ---------------------------------------------------------------------------------------
 static inline dim3 grid2(int ntrials, int ny, int bs = 128) { return dim3((ntrials + bs - 1)/bs, ny > 0 ? ny : 1); }
 
+
+// ---------------------------------------------------------------------------------------
+// RESdev::load for the resistors a JJ deck does not preload (a terminal on a phase node,
+// restemp.cc:213-223): resload.cc:250-292.  In the phase-mode DC modes a resistor between two
+// phase / ground nodes leaves only gmin, one between a voltage node and a phase node loads the
+// voltage node's side (the phase node looks grounded from there).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_load_rph(Consts K, HotView hot, VecView V, ResPhView R)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (t >= K.ntrials) return;
+    int mode = hot.mode[t];
+    if (!mode) return;
+    const int *cs = R.cslot + (size_t)i*4;          // PP NN PN NP
+    const double g = R.g[i];
+    double v[4] = { g, g, -g, -g };
+    if ((mode & MODEDC) && K.jjDCphase) {
+        const int cls = R.cls[i];
+        if (cls == 0) { v[0] = v[1] = v[2] = v[3] = K.opt.gmin; }
+        else if (cls == 1) { v[0] = g; v[3] = -g; v[1] = 0.0; v[2] = 0.0; }       // volt - phase: PP, NP
+        else if (cls == 2) { v[1] = g; v[2] = -g; v[0] = 0.0; v[3] = 0.0; }       // phase - volt: NN, PN
+    }
+    for (int k = 0; k < 4; k++) if (cs[k] >= 0) V.contrib[CADDR(K, cs[k], t)] = v[k];
+}
 
 // ---------------------------------------------------------------------------------------
 // Josephson junction, RSJ level 1.  JJdev::load + jjstuff::{jj_limiting, jj_iv, jj_load}
@@ -1139,11 +1175,36 @@ k_load_tjm(Consts K, HotView hot, VecView V, TJMView J, const double *rhsOld)
     if (t >= K.ntrials) return;
     int mode = hot.mode[t];
     if (!mode) return;
-    if (mode & MODEDC) return;                  // tjmload.cc:75-76: nothing in the `uic` start load
+    if ((mode & MODEDC) && (mode & MODEUIC)) return;     // tjmload.cc:75-76: nothing in the `uic` start load
     TrialCtx c;
     make_ctx(c, K, hot, V, t, mode);
     const int st = J.state[i], m = J.model[i];
     const int pos = J.pos[i], neg = J.neg[i];
+    if (mode & MODEDC) {
+        // phase-mode DC, tjmload.cc:78-88 + tjm_load :419-430: I = Ic sin(phi), no shunt
+        const double crt0 = PR(J.prm[TP_criti], i, t);
+        const double ph = rhsOld[(size_t)pos*K.ldt + t] - rhsOld[(size_t)neg*K.ldt + t];
+        double si, co;
+        sincos(ph, &si, &co);
+        const double cr = crt0*si;
+        const double gq = 1.0*crt0*co;
+        const double crh = cr - gq*ph;
+        ST(c, 0, st + TS_voltage) = ph;              // tjm_load stores ts_vj (= the phase here)
+        ST(c, 0, st + TS_phase) = ph;
+        ST(c, 0, st + TS_crti) = cr;
+        ST(c, 0, st + TS_qpi) = 0.0;
+        const int *cs0 = J.cslot + (size_t)i*JT_NSTAMP;
+        const int *rs0 = J.rslot + (size_t)i*JR_NRHS;
+        if (rs0[JR_phs] >= 0) V.contrib[CADDR(K, rs0[JR_phs], t)] = ph + (4*M_PI)*ST(c, 1, st + TS_phsInt);
+        if (cs0[JT_PP] >= 0) V.contrib[CADDR(K, cs0[JT_PP], t)] = gq;
+        if (cs0[JT_PN] >= 0) V.contrib[CADDR(K, cs0[JT_PN], t)] = -gq;
+        if (cs0[JT_NP] >= 0) V.contrib[CADDR(K, cs0[JT_NP], t)] = -gq;
+        if (cs0[JT_NN] >= 0) V.contrib[CADDR(K, cs0[JT_NN], t)] = gq;
+        if (rs0[JR_pos] >= 0) V.contrib[CADDR(K, rs0[JR_pos], t)] = -crh;
+        if (rs0[JR_neg] >= 0) V.contrib[CADDR(K, rs0[JR_neg], t)] = crh;
+        for (int k = JT_RPP; k <= JT_RNN; k++) if (cs0[k] >= 0) V.contrib[CADDR(K, cs0[k], t)] = 0.0;
+        return;
+    }
     const int NT = J.nterms, nt = J.nt[m];
     const size_t ldt = K.ldt;
     const size_t wstride = (size_t)J.n*ldt;     // one double plane of work[]
@@ -1208,7 +1269,7 @@ k_load_tjm(Consts K, HotView hot, VecView V, TJMView J, const double *rhsOld)
             ST(c, 1, st + TS_voltage) = vj;
             ST(c, 1, st + TS_phase) = phi;
         }
-        else { vj = 0; ST(c, 1, st + TS_voltage) = 0.0; phi = 0; }
+        else { vj = 0; ST(c, 1, st + TS_voltage) = 0.0; phi = phi1; }     // tjmload.cc:310-316
         *pdv = dev_find_ceq(c, st + TS_voltage);
         // tjm_init, tjmload.cc:469-487
         double so, co;
@@ -1381,6 +1442,7 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
     if (S.n) k_load_src<<<grid2(K.ntrials, S.n), 128, 0, st>>>(K, hot, V, S);
     if (Cp.J.n) k_load_jj<<<grid2(K.ntrials, Cp.J.n), 128, 0, st>>>(K, hot, V, Cp.J, rhsOld);
     if (Cp.T.n) k_load_tjm<<<grid2(K.ntrials, Cp.T.n), 128, 0, st>>>(K, hot, V, Cp.T, rhsOld);
+    if (Cp.R.n) k_load_rph<<<grid2(K.ntrials, Cp.R.n), 128, 0, st>>>(K, hot, V, Cp.R);
 }
 void launch_devconv(cudaStream_t st, const Consts &K, const HotView &hot, const VecView &V,
     const MosView &M, const double *rhs)

@@ -20,7 +20,7 @@ def jj_single(**card):
     return d
 
 
-def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, tjm=None, **card):
+def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, tjm=None, dc_bias=False, **card):
     """Josephson transmission line (the `jtl` subcircuit of examples/JJexamples/nor_mc.cir
     flattened and repeated): biased junctions coupled by inductors, an SFQ pulse launched at
     the input propagates down the line.  Bias currents ramp up from zero (uic start)."""
@@ -41,11 +41,18 @@ def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, tjm=None, **card):
         (d.tjm if tjm else d.jj)(f"b{i}", a, "0", "jj1", ics=ics*(1.0 + 0.05*(i % 3)), **kw)
         if vshunt is None and not (tjm and "vshunt" in tjm):
             d.resistor(f"rs{i}", a, "0", 3.0)
-        d.isource(f"ib{i}", "0", a, pulse=(0, 0.7*ics, 0.0, 20e-12, 1e-12, 1.0, 2.0))
+        if dc_bias:
+            # biased from a 10 mV rail through resistors, as the cells of nor_mc.cir are: the run
+            # starts from the phase-mode DC operating point (no `uic`)
+            d.resistor(f"rb{i}", "vb", a, 10e-3/(0.7*ics))
+        else:
+            d.isource(f"ib{i}", "0", a, pulse=(0, 0.7*ics, 0.0, 20e-12, 1e-12, 1.0, 2.0))
         if i + 1 < n:
             d.inductor(f"l{i}", a, f"a{i+1}", 4.0e-12)
     d.resistor("rl", f"a{n-1}", "0", 5.0)
-    d.tran(0.5e-12, 120e-12, uic=True)
+    if dc_bias:
+        d.vsource("vdd", "vb", "0", dc=10e-3)
+    d.tran(0.5e-12, 120e-12, uic=not dc_bias)
     return d
 
 
