@@ -74,10 +74,13 @@ typedef struct b200_ind { int pos, neg; double l, m, ic; } b200_ind;
 typedef struct b200_mut { int ind1, ind2; double k; } b200_mut;
 
 /* Independent source: devlib/src/srcset.cc:64-370, srcload.cc:67-262,
- * src/inp/inptran.cc (PULSE :1099-1414, PWL :1980-2388, SIN :2496-2624). */
+ * src/inp/inptran.cc (PULSE :1099-1414, GPULSE :1567-1827, PWL :1980-2388, SIN :2496-2624,
+ * SPULSE :2708-2870, EXP :2902-3082, SFFM :3113-3260, AM :3292-3442).  GPULSE / PULSE bit patterns,
+ * GAUSS (a random source), TABLE and INTERP are refused. */
 enum { B200_SRC_V = 0, B200_SRC_I = 1 };
 enum { B200_FN_NONE = 0, B200_FN_PULSE = 1, B200_FN_PWL = 2, B200_FN_SIN = 3,
-       B200_FN_EXP = 4, B200_FN_SFFM = 5, B200_FN_AM = 6, B200_FN_GAUSS = 7 };
+       B200_FN_EXP = 4, B200_FN_SFFM = 5, B200_FN_AM = 6, B200_FN_GAUSS = 7,
+       B200_FN_GPULSE = 8, B200_FN_SPULSE = 9 };
 typedef struct b200_src {
     int kind;                   /* B200_SRC_V / B200_SRC_I */
     int pos, neg;

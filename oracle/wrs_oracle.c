@@ -462,6 +462,39 @@ static void src_setup_func(wo_ckt *c, Src *s, double step, double finaltime)
             if (p[4] > p[2]) break_set(c, p[4]);
         }
     }
+    else if (s->fn == B200_FN_GPULSE) {
+        /* IFgpulseData::setup, inptran.cc:1672-1730 (bit patterns not restated) */
+        double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
+        const double TWOSQRTLN2 = 2.0*sqrt(M_LN2), PHI0_SQRTPI = PHI0/sqrt(M_PI);  /* :74-75 */
+        memset(p, 0, 8*sizeof(double));
+        p[0] = co[0];
+        p[1] = nc >= 2 ? co[1] : co[0];
+        p[2] = nc >= 3 ? co[2] : 0.0;
+        p[3] = nc >= 4 ? (co[3] >= 0.0 ? co[3]/TWOSQRTLN2 : -co[3]) : 0.0;
+        p[4] = nc >= 5 ? co[4] : 0.0;
+        if (p[4] < 2*p[3]) p[4] = 0.0;
+        if (s->enable_tran) {
+            if (p[3] == 0.0) {
+                if (p[1] != p[0]) p[3] = PHI0_SQRTPI/fabs(p[1] - p[0]);
+                else p[3] = step/TWOSQRTLN2;
+            }
+            if (p[1] == p[0]) p[1] = p[0] + PHI0_SQRTPI/p[3];
+        }
+    }
+    else if (s->fn == B200_FN_SPULSE) {
+        /* IFspulseData::setup, inptran.cc:2790-2808 */
+        double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
+        memset(p, 0, 8*sizeof(double));
+        p[0] = co[0];
+        p[1] = nc >= 2 ? co[1] : co[0];
+        p[2] = nc >= 3 ? co[2] : 0.0;
+        p[3] = nc >= 4 ? co[3] : 0.0;
+        p[4] = nc >= 5 ? co[4] : 0.0;
+        if (s->enable_tran) {
+            if (!p[2]) p[2] = finaltime;
+            if (p[3] > 0.0) break_set(c, p[3]);
+        }
+    }
     else if (s->fn == B200_FN_SFFM || s->fn == B200_FN_AM) {
         /* IFsffmData::setup inptran.cc:3194-3211, IFamData::setup :3373-3388 */
         double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
@@ -582,6 +615,50 @@ static double src_eval(Src *s, double t)
         double w1 = 2*M_PI*p[2];
         double w2 = 2*M_PI*p[4];
         return p[0] + p[1]*sin(w1*t + p[3]*sin(w2*t));
+    }
+    if (s->fn == B200_FN_GPULSE) {
+        /* inptran.cc:1734-1827 */
+        const double *p = s->parms;
+        if (!s->enable_tran) return p[0];
+        double V = 0;
+        const double rchk = 5.0;
+        if (p[4] > 0.0) {
+            double per = p[4];
+            for (int cidx = 4; cidx < s->ncoef || cidx == 4; cidx++) {
+                double td = cidx == 4 ? p[2] : s->coef[cidx];
+                int ifirst, ilast;
+                if (t < td) { ifirst = 0; ilast = 0; }
+                else {
+                    double del = rchk*p[3];
+                    ifirst = (int)rint((t - td - del)/per);
+                    ilast = (int)rint((t - td + del)/per);
+                }
+                for (int i = ifirst; i <= ilast; i++) {
+                    double time = t - i*per;
+                    double a = (time - td)/p[3];
+                    V += exp(-a*a);
+                }
+            }
+        }
+        else {
+            double a = (t - p[2])/p[3];
+            if (fabs(a) < rchk) V += exp(-a*a);
+            for (int i = 5; i < s->ncoef; i++) {
+                a = (t - s->coef[i])/p[3];
+                if (fabs(a) < rchk) V += exp(-a*a);
+            }
+        }
+        return p[0] + (p[1] - p[0])*V;
+    }
+    if (s->fn == B200_FN_SPULSE) {
+        /* inptran.cc:2812-2824 */
+        const double *p = s->parms;
+        if (!s->enable_tran) return p[0];
+        double time = t - p[3];
+        if (time <= 0) return p[0];
+        if (p[4] != 0.0)
+            return p[0] + (p[1]-p[0])*( 1 - cos(2*M_PI*time/p[2])*exp(-time*p[4]) )/2;
+        return p[0] + (p[1]-p[0])*( 1 - cos(2*M_PI*time/p[2]) )/2;
     }
     if (s->fn == B200_FN_AM) {
         /* inptran.cc:3391-3399 */
@@ -4511,6 +4588,10 @@ static int ckt_trunc(wo_ckt *c, double *timeStep)
             Src *s = &c->src[i];
             if (s->fn == B200_FN_SIN && c->time >= s->parms[3]) {
                 double per = (.2*M_PI)/(2*M_PI*s->parms[2]);
+                if (time_step > per) time_step = per;
+            }
+            else if (s->fn == B200_FN_SPULSE && c->time >= s->parms[3]) {     /* inptran.cc:2861-2870 */
+                double per = (.2*M_PI)*s->parms[2]/(2*M_PI);
                 if (time_step > per) time_step = per;
             }
             else if (s->fn == B200_FN_SFFM) {                       /* inptran.cc:3253-3260 */

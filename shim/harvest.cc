@@ -260,6 +260,8 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
                             case PTF_tEXP:   x.fn = B200_FN_EXP; break;
                             case PTF_tSFFM:  x.fn = B200_FN_SFFM; break;
                             case PTF_tAM:    x.fn = B200_FN_AM; break;
+                            case PTF_tGPULSE: x.fn = B200_FN_GPULSE; break;     // (a bit pattern is private to the class: not seen)
+                            case PTF_tSPULSE: x.fn = B200_FN_SPULSE; break;
                             case PTF_tGAUSS: x.fn = B200_FN_GAUSS; break;
                             default: H->error = "source function"; return B200_E_UNSUPP;
                             }

@@ -283,6 +283,12 @@ def variants():
         "rc_exp_defaults": rc_fn(exp=(0.2, 1.0)),
         "rc_sffm": rc_fn(sffm=(0.5, 0.4, 1.0e9, 2.0, 0.2e9)),
         "rc_am": rc_fn(am=(0.8, 1.0, 0.3e9, 2.0e9, 0.4e-9)),
+        # GPULSE (inptran.cc:1567-1827): FWHM width + two more pulse delays; repeating; old-style width
+        "rc_gpulse": rc_fn(gpulse=(0.1, 1.0, 1.0e-9, 0.3e-9, 0, 2.2e-9, 3.1e-9)),
+        "rc_gpulse_rpt": rc_fn(gpulse=(0.0, 0.8, 0.6e-9, -0.12e-9, 1.1e-9)),
+        # SPULSE (inptran.cc:2708-2870): raised cosine after a delay, plain and damped
+        "rc_spulse": rc_fn(spulse=(0.1, 1.0, 1.5e-9, 0.7e-9)),
+        "rc_spulse_theta": rc_fn(spulse=(0.0, 1.0, 0.4e-9, 0.3e-9, 1.2e9)),
     }
     out.update(jj_variants())
     return out
@@ -320,4 +326,6 @@ def jj_variants():
         "jtl6_dc_vshunt": jtl(6, dc_bias=True, vshunt=0.6857e-3),
         "jtl12_dc": jtl(12, dc_bias=True),
         "jtl6_dc_tjm": jtl(6, dc_bias=True, tjm="tjm1"),
+        # driven by a single-flux-quantum GPULSE voltage source
+        "jtl6_dc_sfq": jtl(6, dc_bias=True, sfq_in=True),
     }

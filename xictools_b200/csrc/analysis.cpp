@@ -829,8 +829,45 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             else { if (!p[2]) p[2] = 1.0/finaltime; }
             S.pool.insert(S.pool.end(), p, p + 8);
         }
+        else if (in.fn == B200_FN_GPULSE) {
+            // IFgpulseData::setup, inptran.cc:1672-1730: V1 V2 TD GPW RPT [TD2 ...].  GPW >= 0 is
+            // the FWHM, < 0 the old "variance"; no width -> a single-flux-quantum pulse of the
+            // given amplitude (or, with no amplitude either, of FWHM = TSTEP).  pool: parms[8], extras
+            double p[8] = {0,0,0,0,0,0,0,0};
+            const double *co = in.coef; int nc = in.ncoef;
+            if (nc < 1) { err = "gpulse needs arguments"; return B200_E_BADPARM; }
+            const double twosqrtln2 = 2.0*sqrt(M_LN2), phi0_sqrtpi = JJ_PHI0/sqrt(M_PI);
+            p[0] = co[0];
+            p[1] = nc >= 2 ? co[1] : co[0];
+            p[2] = nc >= 3 ? co[2] : 0.0;
+            p[3] = nc >= 4 ? (co[3] >= 0.0 ? co[3]/twosqrtln2 : -co[3]) : 0.0;
+            p[4] = nc >= 5 ? co[4] : 0.0;
+            if (p[4] < 2*p[3]) p[4] = 0.0;
+            if (p[3] == 0.0) {
+                if (p[1] != p[0]) p[3] = phi0_sqrtpi/fabs(p[1] - p[0]);
+                else p[3] = step/twosqrtln2;
+            }
+            if (p[1] == p[0]) p[1] = p[0] + phi0_sqrtpi/p[3];
+            S.pool.insert(S.pool.end(), p, p + 8);
+            for (int k = 5; k < nc; k++) S.pool.push_back(co[k]);
+            S.ncoef[i] = nc > 5 ? nc - 5 : 0;        // number of extra delays
+        }
+        else if (in.fn == B200_FN_SPULSE) {
+            // IFspulseData::setup, inptran.cc:2790-2808: V1 V2 SPER SDEL THETA
+            double p[8] = {0,0,0,0,0,0,0,0};
+            const double *co = in.coef; int nc = in.ncoef;
+            if (nc < 1) { err = "spulse needs arguments"; return B200_E_BADPARM; }
+            p[0] = co[0];
+            p[1] = nc >= 2 ? co[1] : co[0];
+            p[2] = nc >= 3 ? co[2] : 0.0;
+            p[3] = nc >= 4 ? co[3] : 0.0;
+            p[4] = nc >= 5 ? co[4] : 0.0;
+            if (!p[2]) p[2] = finaltime;
+            if (p[3] > 0.0) bt.set_break(p[3], 0.0);
+            S.pool.insert(S.pool.end(), p, p + 8);
+        }
         else if (in.fn != B200_FN_NONE && in.fn != B200_FN_PULSE && in.fn != B200_FN_PWL) {
-            err = "source function not built (GPULSE / SPULSE / GAUSS / TABLE / INTERP)";
+            err = "source function not built (GAUSS / TABLE / INTERP)";
             return B200_E_UNSUPP;
         }
     }

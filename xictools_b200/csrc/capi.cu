@@ -532,20 +532,21 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     {
         // sources that bound the step through IFtranData::time_limit (srctrun.cc:45-66):
         // SIN after its delay, SFFM / AM always (period of the sum frequency), EXP inside its
-        // two exponential edges
+        // two exponential edges, SPULSE after its delay.  fr: the bound itself, dphimax / omega
         std::vector<double> tdl, fr, etd, etau;
         for (int i = 0; i < st.n; i++) {
             const double *pp = st.pool.data() + st.coef_off[i];
-            if (st.fn[i] == B200_FN_SIN) { tdl.push_back(pp[3]); fr.push_back(pp[2]); }
-            else if (st.fn[i] == B200_FN_SFFM) { tdl.push_back(-HUGE_VAL); fr.push_back(pp[2] + pp[4]); }
-            else if (st.fn[i] == B200_FN_AM) { tdl.push_back(-HUGE_VAL); fr.push_back(pp[3] + pp[2]); }
+            if (st.fn[i] == B200_FN_SIN) { tdl.push_back(pp[3]); fr.push_back((.2*M_PI)/(2*M_PI*pp[2])); }
+            else if (st.fn[i] == B200_FN_SFFM) { tdl.push_back(-HUGE_VAL); fr.push_back((.2*M_PI)/(2*M_PI*(pp[2] + pp[4]))); }
+            else if (st.fn[i] == B200_FN_AM) { tdl.push_back(-HUGE_VAL); fr.push_back((.2*M_PI)/(2*M_PI*(pp[3] + pp[2]))); }
+            else if (st.fn[i] == B200_FN_SPULSE) { tdl.push_back(pp[3]); fr.push_back((.2*M_PI)*pp[2]/(2*M_PI)); }    // inptran.cc:2861-2870
             else if (st.fn[i] == B200_FN_EXP) {
                 etd.push_back(pp[2]); etau.push_back(pp[3]);
                 etd.push_back(pp[4]); etau.push_back(pp[5]);
             }
         }
         sh.nsin = (int)tdl.size();
-        sh.sin_tdl = b->dupload(tdl); sh.sin_freq = b->dupload(fr);
+        sh.sin_tdl = b->dupload(tdl); sh.sin_per = b->dupload(fr);
         sh.nexp = (int)etd.size();
         sh.exp_td = b->dupload(etd); sh.exp_tau = b->dupload(etau);
     }

@@ -24,7 +24,7 @@ struct CtlShared {          // shared tables
     const Consts *K;
     const double *brks, *lat_offs, *lat_per;
     // SIN sources bound the step (srctrun.cc:45-66, inptran.cc:2666-2680)
-    int nsin; const double *sin_tdl, *sin_freq;
+    int nsin; const double *sin_tdl, *sin_per;
     // EXP sources: IFexpData::time_limit, inptran.cc:3064-3082 (two edges per source)
     int nexp; const double *exp_td, *exp_tau;
 };
@@ -630,7 +630,7 @@ __device__ inline double ctl_finish_trunc(const TrialCtl &s, const CtlShared &sh
     double time_step = HUGE_VAL;
     for (int i = 0; i < sh.nsin; i++) {
         if (s.time >= sh.sin_tdl[i]) {
-            double per = (.2*M_PI)/(2*M_PI*sh.sin_freq[i]);
+            double per = sh.sin_per[i];              // dphimax over the angular frequency (host-evaluated)
             if (time_step > per) time_step = per;
         }
     }

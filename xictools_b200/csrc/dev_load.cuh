@@ -2008,6 +2008,46 @@ __device__ inline double dev_src_eval(int fn, const double *p, int nextra, doubl
         double w2 = 2*M_PI*p[4];
         return p[0] + p[1]*sin(w1*t + p[3]*sin(w2*t));
     }
+    if (fn == B200_FN_GPULSE) {
+        // IFgpulseData::eval_func, inptran.cc:1734-1827 (V1 V2 TD GPW RPT, extra delays; no bit pattern)
+        double V = 0;
+        const double rchk = 5.0;
+        const double *offs = p + 8;
+        if (p[4] > 0.0) {
+            const double per = p[4];
+            for (int c = -1; c < nextra; c++) {
+                const double td = c < 0 ? p[2] : offs[c];
+                int ifirst = 0, ilast = 0;
+                if (!(t < td)) {
+                    double del = rchk*p[3];
+                    ifirst = (int)rint((t - td - del)/per);
+                    ilast = (int)rint((t - td + del)/per);
+                }
+                for (int i = ifirst; i <= ilast; i++) {
+                    double time = t - i*per;
+                    double a = (time - td)/p[3];
+                    V += exp(-a*a);
+                }
+            }
+        }
+        else {
+            for (int c = -1; c < nextra; c++) {
+                double a = (t - (c < 0 ? p[2] : offs[c]))/p[3];
+                if (fabs(a) < rchk)
+                    V += exp(-a*a);
+            }
+        }
+        return p[0] + (p[1] - p[0])*V;
+    }
+    if (fn == B200_FN_SPULSE) {
+        // IFspulseData::eval_func, inptran.cc:2812-2824 (V1 V2 SPER SDEL THETA)
+        double time = t - p[3];
+        if (time <= 0)
+            return p[0];
+        if (p[4] != 0.0)
+            return p[0] + (p[1]-p[0])*( 1 - cos(2*M_PI*time/p[2])*exp(-time*p[4]) )/2;
+        return p[0] + (p[1]-p[0])*( 1 - cos(2*M_PI*time/p[2]) )/2;
+    }
     if (fn == B200_FN_AM) {
         // IFamData::eval_func, inptran.cc:3391-3399 (SA OC MF CF DL)
         if (t <= p[4])

@@ -477,6 +477,8 @@ k_load_src(Consts K, HotView hot, VecView V, SrcView S)
         rhs = srcFact*PR(S.dc, i, t);
     else {
         rhs = dev_src_eval(fn, S.pool + S.coef_off[i], S.ncoef[i], hot.time[t]);
+        if (K.analysis == 1 && fn == B200_FN_GPULSE)
+            rhs = S.pool[S.coef_off[i]];           // `.op`: td_enable_tran is false, V1 (inptran.cc:1736-1737)
         if (mode & (MODEDCOP | MODETRANOP))
             rhs *= srcFact;
     }

@@ -25,7 +25,7 @@ NAN = float("nan")
 
 DEV_RES, DEV_CAP, DEV_IND, DEV_MUT, DEV_SRC, DEV_MOS, DEV_JJ, DEV_TJM = range(8)
 SRC_V, SRC_I = 0, 1
-FN_NONE, FN_PULSE, FN_PWL, FN_SIN, FN_EXP, FN_SFFM, FN_AM, FN_GAUSS = range(8)
+FN_NONE, FN_PULSE, FN_PWL, FN_SIN, FN_EXP, FN_SFFM, FN_AM, FN_GAUSS, FN_GPULSE, FN_SPULSE = range(10)
 
 # parameter ids (include/b200spice.h)
 P_MOS_VTO, P_MOS_KP, P_MOS_L, P_MOS_W, P_MOS_GAMMA, P_MOS_LAMBDA, P_MOS_PHI = range(1, 8)
@@ -238,17 +238,17 @@ class Deck:
 
     # ---- construction -------------------------------------------------------------
     def vsource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None, exp=None, sffm=None,
-                am=None):
+                am=None, gpulse=None, spulse=None):
         self.elems.append(_Elem(DEV_SRC, name.lower(), (str(p).lower(), str(n).lower()),
                                 dict(kind=SRC_V, dc=dc, pulse=pulse, pwl=pwl, sin=sin, exp=exp,
-                                     sffm=sffm, am=am)))
+                                     sffm=sffm, am=am, gpulse=gpulse, spulse=spulse)))
         return self
 
     def isource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None, exp=None, sffm=None,
-                am=None):
+                am=None, gpulse=None, spulse=None):
         self.elems.append(_Elem(DEV_SRC, name.lower(), (str(p).lower(), str(n).lower()),
                                 dict(kind=SRC_I, dc=dc, pulse=pulse, pwl=pwl, sin=sin, exp=exp,
-                                     sffm=sffm, am=am)))
+                                     sffm=sffm, am=am, gpulse=gpulse, spulse=spulse)))
         return self
 
     def resistor(self, name, p, n, r):
@@ -436,7 +436,7 @@ class Deck:
                     s += " pwl(" + " ".join(_fmt(x) for x in p["pwl"]) + ")"
                 if p["sin"] is not None:
                     s += " sin(" + " ".join(_fmt(x) for x in p["sin"]) + ")"
-                for fn in ("exp", "sffm", "am"):
+                for fn in ("exp", "sffm", "am", "gpulse", "spulse"):
                     if p.get(fn) is not None:
                         s += f" {fn}(" + " ".join(_fmt(x) for x in p[fn]) + ")"
                 lines.append(s)
@@ -607,6 +607,10 @@ class Deck:
                 fn, coef = FN_SFFM, list(p["sffm"])
             elif p.get("am") is not None:
                 fn, coef = FN_AM, list(p["am"])
+            elif p.get("gpulse") is not None:
+                fn, coef = FN_GPULSE, list(p["gpulse"])
+            elif p.get("spulse") is not None:
+                fn, coef = FN_SPULSE, list(p["spulse"])
             ca = arr(C.c_double, [float(x) for x in coef])
             src[i] = CSrc(p["kind"], nums[e.nodes[0]], nums[e.nodes[1]],
                           NAN if p["dc"] is None else float(p["dc"]), fn, len(coef), ca)

@@ -20,7 +20,7 @@ def jj_single(**card):
     return d
 
 
-def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, tjm=None, dc_bias=False, **card):
+def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, tjm=None, dc_bias=False, sfq_in=False, **card):
     """Josephson transmission line (the `jtl` subcircuit of examples/JJexamples/nor_mc.cir
     flattened and repeated): biased junctions coupled by inductors, an SFQ pulse launched at
     the input propagates down the line.  Bias currents ramp up from zero (uic start)."""
@@ -33,7 +33,11 @@ def jtl(n=6, phase_nodes=False, vshunt=None, ics=0.25e-3, tjm=None, dc_bias=Fals
         if vshunt is not None:
             mc["vshunt"] = vshunt
         d.jj_model("jj1", **mc)
-    d.isource("iin", "0", "in", pulse=(0, 0.6e-3, 40e-12, 3e-12, 3e-12, 2e-12, 200e-12))
+    if sfq_in:
+        # a voltage pulse holding one flux quantum (GPULSE with no amplitude: inptran.cc:1695-1712)
+        d.vsource("vin", "in", "0", gpulse=(0, 0, 40e-12, 2e-12))
+    else:
+        d.isource("iin", "0", "in", pulse=(0, 0.6e-3, 40e-12, 3e-12, 3e-12, 2e-12, 200e-12))
     d.inductor("lin", "in", "a0", 2.0e-12)
     for i in range(n):
         a = f"a{i}"
