@@ -305,7 +305,8 @@ enum { B200_AS_N = 0, B200_AS_NNZ, B200_AS_NNZLU, B200_AS_NC, B200_AS_NSTATES,
        B200_AS_IMG /* doubles per trial image */, B200_AS_SCRATCH /* partial-sum slots */,
        B200_AS_TASKS, B200_AS_OPS, B200_AS_LEVELS, B200_AS_ROUNDS, B200_AS_STEPS,
        B200_AS_PROG_BYTES, B200_AS_LONGEST_RUN,
-       B200_AS_LU_SPLIT, B200_AS_LU_CHUNK /* the split rule of long sums (b200_internal.h) */, B200_AS_NSTATS };
+       B200_AS_LU_SPLIT, B200_AS_LU_CHUNK /* the split rule of long sums (b200_internal.h) */,
+       B200_AS_WIDE /* 1: image beyond the shared-memory window, wide program (k_lu_wide) */, B200_AS_NSTATS };
 int  b200_deck_analysis_stats(const b200_deck *deck, long long *out, int nout);
 /* Host-only: the CSC pattern and the static pivot order (position -> original row / column,
  * 0-based) into caller buffers Ap[n+1], Ai[nnz], rowperm[n], colperm[n] (any may be NULL). */

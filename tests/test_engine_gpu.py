@@ -397,6 +397,30 @@ def test_jj_operating_point_only():
     compare_op(jtl(6, dc_bias=True), 3)
 
 
+@pytest.mark.parametrize("name", ["ro5", "rlc_series", "jtl6_dc", "inv_lsupply"])
+def test_wide_program_on_small_decks(name, monkeypatch):
+    """k_lu_wide (image in global memory, 32-bit slots) forced on small decks: same tasks, same
+    order, so the same strict parity as the shared-memory kernel -- one- and two-program decks."""
+    monkeypatch.setenv("B200_LU_WIDE", "1")
+    compare(variants()[name], 5)
+
+
+def test_large_line_runs_through_the_wide_program():
+    """3000 junctions, 6001 unknowns: a 36 k-double image per trial, beyond the 227 KB window.
+    Per-trial critical currents; trials 0 and 1 against the oracle (30 s each on the CPU)."""
+    from tests.decks import jtl
+    from xictools_b200.deck import DEV_JJ, P_JJ_ICS
+    d = jtl(3000)
+    ntr = 4
+    rng = np.random.default_rng(5)
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_JJ]):
+        v = np.full(ntr, e.params["ics"])
+        v[1:] *= 1.0 + 0.05*rng.standard_normal(ntr - 1)
+        ov[(P_JJ_ICS, i)] = v
+    compare(d, ntr, ov, trials=[0, 1])
+
+
 def test_packed_rows_equal_single_rows():
     """b200_batch_set_params (one transfer + device scatter) against b200_batch_set_param row by
     row: bit-identical results; a single row given afterwards overrides its packed row."""

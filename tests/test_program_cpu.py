@@ -50,8 +50,13 @@ def check_system(n, Ap, Ai, Ax, b, rtol=1e-9):
     return st
 
 
+@pytest.mark.parametrize("wide", [False, True])
 @pytest.mark.parametrize("name", ["inv4", "ro5", "lc_ladder", "rlc_series", "inv_lsupply"])
-def test_program_matches_oracle_static_lu_on_deck_matrices(name):
+def test_program_matches_oracle_static_lu_on_deck_matrices(name, wide, monkeypatch):
+    """`wide`: the 32-bit-slot encoding of the same program (images beyond one warp's
+    shared-memory window, k_lu_wide) -- forced here on small systems, bit-identical results."""
+    if wide:
+        monkeypatch.setenv("B200_LU_WIDE", "1")
     d = variants()[name]
     o = Oracle(d)
     Ap, Ai = o.pattern()
@@ -125,3 +130,20 @@ def test_ro501_program_shape():
     assert n == 503
     assert img*8 <= 32*1024                  # one trial image: seven fit an SM's shared memory
     assert levels <= 40 and steps <= 500     # nested-dissection-like order: shallow and short
+
+
+def test_large_line_compiles_to_a_wide_program():
+    """A 3000-junction line (6001 unknowns): the image (36 k doubles) exceeds the 227 KB window,
+    the analysis -- pivot order, symbolic LU, level schedule -- stays well under a second and
+    emits the wide encoding with the same shallow schedule as the small lines."""
+    import time
+    from xictools_b200.workloads import jtl
+    L = engine.load_library()
+    cd, keep = jtl(3000).to_c()
+    out = (C.c_longlong*32)()
+    t0 = time.time()
+    assert L.b200_deck_analysis_stats(C.byref(cd), out, 32) == 0
+    assert time.time() - t0 < 5.0
+    n, img, levels = out[0], out[5], out[9]
+    assert n == 6001 and img*8 > 229000 and levels < 64
+    assert out[16] == 1                     # B200_AS_WIDE

@@ -20,6 +20,8 @@
 #include <functional>
 #include <map>
 #include <set>
+#include <queue>
+#include <unordered_map>
 
 #include "b200_internal.h"
 
@@ -901,24 +903,29 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
 // ---------------------------------------------------------------------------------------
 void b200_order_markowitz(Analysis &an, bool tran_order)
 {
-    int n = an.n;
+    const int n = an.n;
+    typedef long long i64;
+    auto key = [n](int i, int j) { return (i64)i*(i64)(n + 1) + j; };
     std::vector<std::set<int>> rows(n), cols(n);
     // constant: 1 if the entry is a never-updated +-1 constant; 0 otherwise
-    std::map<std::pair<int,int>, char> constant;
+    std::unordered_map<i64, char> constant;
     // dcnz: the entry is structurally nonzero in the DC modes as well (capacitor and inductor
     // companion conductances vanish there).  The pivot order is frozen for the whole run, so a
     // pivot must be structurally nonzero in DC (hence also in transient).
-    std::map<std::pair<int,int>, char> dcnz;
-    bool have_dc = !tran_order && (an.dc_active.size() == (size_t)an.nnz);
+    std::unordered_map<i64, char> dcnz;
+    constant.reserve((size_t)an.nnz*4); dcnz.reserve((size_t)an.nnz*4);
+    const bool have_dc = !tran_order && (an.dc_active.size() == (size_t)an.nnz);
     for (int j = 0; j < n; j++)
         for (int p = an.Ap[j]; p < an.Ap[j+1]; p++) {
             int i = an.Ai[p];
             rows[i].insert(j); cols[j].insert(i);
             bool is_const = (an.cg_ptr[p+1] == an.cg_ptr[p]) &&
                 (an.Ainit[p] == 1.0 || an.Ainit[p] == -1.0);
-            constant[{i, j}] = is_const ? 1 : 0;
-            dcnz[{i, j}] = have_dc ? an.dc_active[p] : 1;
+            constant[key(i, j)] = is_const ? 1 : 0;
+            dcnz[key(i, j)] = have_dc ? an.dc_active[p] : 1;
         }
+    auto is_dcnz = [&](int i, int j) { auto it = dcnz.find(key(i, j)); return it != dcnz.end() && it->second; };
+    auto is_constant = [&](int i, int j) { auto it = constant.find(key(i, j)); return it != constant.end() && it->second; };
     std::vector<char> ract(n, 1), cact(n, 1);
     std::vector<char> diag_ok(n, 0);
     for (int i = 0; i < n; i++) {
@@ -938,52 +945,87 @@ void b200_order_markowitz(Analysis &an, bool tran_order)
     // of about one entry per pivot.
     long mk_floor = 4;
     if (const char *e = getenv("B200_MK_FLOOR")) mk_floor = atol(e);
+
+    // Per-column count of live non-constant entries and per-row count of live entries ("live":
+    // structurally nonzero in DC when the DC order is built) -- what the growth-safety rule of a
+    // +-1 constant needs; recomputed for the rows / columns a pivot step touches.
+    std::vector<int> col_nonconst(n, 0), row_live(n, 0);
+    auto recount_col = [&](int j) {
+        int c = 0;
+        for (int r : cols[j]) if ((!have_dc || is_dcnz(r, j)) && !is_constant(r, j)) c++;
+        col_nonconst[j] = c;
+    };
+    auto recount_row = [&](int i) {
+        int c = 0;
+        for (int q : rows[i]) if (!have_dc || is_dcnz(i, q)) c++;
+        row_live[i] = c;
+    };
+    for (int i = 0; i < n; i++) { recount_row(i); recount_col(i); }
+
+    // The safe candidates (first choice) live in a heap ordered exactly as the exhaustive scan
+    // would rank them: smaller Markowitz product, then older, then constants before diagonals,
+    // then row-major position.  Entries are re-pushed whenever their row or column changes and
+    // validated when popped (lazy deletion), so a pivot costs the size of what it touches, not
+    // a pass over the whole matrix -- the analysis of a 50 000-unknown deck stays in seconds.
+    struct Cand { long mk, st; int ncls, i, j; };
+    struct Worse {
+        bool operator()(const Cand &a, const Cand &b) const {
+            if (a.mk != b.mk) return a.mk > b.mk;
+            if (a.st != b.st) return a.st > b.st;
+            if (a.ncls != b.ncls) return a.ncls > b.ncls;
+            if (a.i != b.i) return a.i > b.i;
+            return a.j > b.j;
+        }
+    };
+    std::priority_queue<Cand, std::vector<Cand>, Worse> heap;
+    // rank of entry (i,j) as a safe candidate; false if it is none
+    auto safe_rank = [&](int i, int j, Cand &c) -> bool {
+        if (!ract[i] || !cact[j] || !rows[i].count(j) || !is_dcnz(i, j)) return false;
+        int cls;
+        if (is_constant(i, j)) {
+            // growth-safe only if the multipliers are +-1 or nothing propagates
+            bool col_const = col_nonconst[j] == 0;
+            bool row_single = row_live[i] - 1 == 0;
+            if (!col_const && !row_single) return false;
+            cls = 2;
+        }
+        else if (i == j && diag_ok[i]) cls = 1;
+        else return false;
+        long mk = (long)(rows[i].size() - 1)*(long)(cols[j].size() - 1);
+        if (mk < mk_floor) mk = mk_floor;
+        c.mk = mk; c.st = std::max(rstamp[i], cstamp[j]); c.ncls = -cls; c.i = i; c.j = j;
+        return true;
+    };
+    auto push_row = [&](int i) { Cand c; for (int j : rows[i]) if (safe_rank(i, j, c)) heap.push(c); };
+    auto push_col = [&](int j) { Cand c; for (int i : cols[j]) if (safe_rank(i, j, c)) heap.push(c); };
+    for (int i = 0; i < n; i++) push_row(i);
+
     for (int k = 0; k < n; k++) {
-        long best = -1, bstamp = 0; int bi = -1, bj = -1; int bclass = 0;
-        for (int pass = 0; pass < 4 && bi < 0; pass++) {
-            // pass 0: safe candidates; pass 1: any remaining diagonal; pass 2: any entry -- all
-            // structurally nonzero in DC; pass 3: any entry at all
-            for (int i = 0; i < n; i++) {
-                if (!ract[i]) continue;
-                for (int j : rows[i]) {
-                    if (!cact[j]) continue;
-                    if (pass < 3 && !dcnz[{i, j}]) continue;
-                    int cls;
-                    auto it = constant.find({i, j});
-                    bool is_const = (it != constant.end() && it->second);
-                    if (pass == 0) {
-                        if (is_const) {
-                            // growth-safe only if the multipliers are +-1 or nothing propagates
-                            bool col_const = true, row_single = true;
-                            for (int r : cols[j]) {
-                                if (r == i || !ract[r]) continue;
-                                if (have_dc && !dcnz[{r, j}]) continue;
-                                auto ic = constant.find({r, j});
-                                if (ic == constant.end() || !ic->second) { col_const = false; break; }
-                            }
-                            for (int q : rows[i]) {
-                                if (q == j || !cact[q]) continue;
-                                if (have_dc && !dcnz[{i, q}]) continue;
-                                row_single = false; break;
-                            }
-                            if (!col_const && !row_single) continue;
-                            cls = 2;
-                        }
-                        else if (i == j && diag_ok[i]) cls = 1;
-                        else continue;
+        int bi = -1, bj = -1;
+        while (!heap.empty()) {
+            Cand c = heap.top(), now;
+            heap.pop();
+            if (!safe_rank(c.i, c.j, now)) continue;
+            if (now.mk != c.mk || now.st != c.st || now.ncls != c.ncls) continue;    // stale: its current rank is in the heap
+            bi = c.i; bj = c.j;
+            break;
+        }
+        if (bi < 0) {
+            // no safe candidate.  pass 1: any remaining diagonal; pass 2: any entry -- both
+            // structurally nonzero in DC; pass 3: any entry at all (exhaustive scans: rare)
+            long best = -1, bstamp = 0;
+            for (int pass = 1; pass < 4 && bi < 0; pass++) {
+                for (int i = 0; i < n; i++) {
+                    if (!ract[i]) continue;
+                    for (int j : rows[i]) {
+                        if (!cact[j]) continue;
+                        if (pass < 3 && !is_dcnz(i, j)) continue;
+                        if (pass == 1 && i != j) continue;
+                        long mk = (long)(rows[i].size() - 1)*(long)(cols[j].size() - 1);
+                        if (mk < mk_floor) mk = mk_floor;
+                        long st = std::max(rstamp[i], cstamp[j]);
+                        if (best < 0 || mk < best || (mk == best && st < bstamp)) { best = mk; bi = i; bj = j; bstamp = st; }
                     }
-                    else if (pass == 1) { if (i != j) continue; cls = 1; }
-                    else cls = 0;
-                    long mk = (long)(rows[i].size() - 1)*(long)(cols[j].size() - 1);
-                    if (mk < mk_floor) mk = mk_floor;
-                    long st = std::max(rstamp[i], cstamp[j]);
-                    bool better = false;
-                    if (best < 0 || mk < best) better = true;
-                    else if (mk == best) {
-                        if (st < bstamp) better = true;
-                        else if (st == bstamp && cls > bclass) better = true;
-                    }
-                    if (better) { best = mk; bi = i; bj = j; bstamp = st; bclass = cls; }
                 }
             }
         }
@@ -1002,8 +1044,8 @@ void b200_order_markowitz(Analysis &an, bool tran_order)
         for (int r : pcol) {
             for (int j : prow) {
                 rows[r].insert(j); cols[j].insert(r);
-                if (r != bi && j != bj && dcnz[{r, bj}] && dcnz[{bi, j}]) dcnz[{r, j}] = 1;
-                constant[{r, j}] = 0;               // touched by an update: no longer constant
+                if (r != bi && j != bj && is_dcnz(r, bj) && is_dcnz(bi, j)) dcnz[key(r, j)] = 1;
+                constant[key(r, j)] = 0;            // touched by an update: no longer constant
                 cstamp[j] = k + 1;
             }
             rstamp[r] = k + 1;
@@ -1012,6 +1054,11 @@ void b200_order_markowitz(Analysis &an, bool tran_order)
         for (int j : rows[bi]) cols[j].erase(bi);
         for (int r : cols[bj]) rows[r].erase(bj);
         rows[bi].clear(); cols[bj].clear();
+        // what changed: rows pcol, columns prow
+        for (int r : pcol) recount_row(r);
+        for (int j : prow) recount_col(j);
+        for (int r : pcol) push_row(r);
+        for (int j : prow) push_col(j);
     }
 }
 
@@ -1210,7 +1257,6 @@ int b200_build_lu(Analysis &an)
     an.slot_neg1 = scratch0 + nscratch;
     an.slot_zero = an.slot_neg1 + 1;
     an.img = (an.slot_zero + 1 + 1) & ~1;                   // 16-byte granular rows (bulk copy)
-    if (an.img > 0xfff0) return B200_E_UNSUPP;
     for (auto &t : tasks) for (auto &op : t.ops) if (op.second == -2) op.second = an.slot_neg1;
 
     // ---- levels: RAW on every operand, and WAR on a y slot the backward solve overwrites ----
@@ -1238,6 +1284,9 @@ int b200_build_lu(Analysis &an)
     an.prog_steps = 0; an.prog_ops = 0; an.prog_tasks = (int)tasks.size();
     std::vector<std::vector<int>> by_level(nlev);
     for (int t = 0; t < (int)tasks.size(); t++) by_level[tasks[t].level].push_back(t);
+    // rows as (first, second) pairs; packed below once the encoding is known.  second = -1 in a
+    // header: no division
+    std::vector<std::pair<int,int>> prows;
     for (int l = 0; l < nlev; l++) {
         auto &v = by_level[l];
         std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return tasks[a].ops.size() > tasks[b].ops.size(); });
@@ -1245,19 +1294,43 @@ int b200_build_lu(Analysis &an)
             size_t cnt = std::min<size_t>(LU_LANES, v.size() - off);
             size_t nsteps = tasks[v[off]].ops.size();
             an.prog_round.push_back((unsigned short)(nsteps | ((off == 0 && l > 0) ? LU_RSYNC : 0)));
-            size_t row0 = an.prog_rows.size();
+            size_t row0 = prows.size();
             // idle lanes run the exact no-op  S[zero] = S[zero] - S[zero]*S[zero]
-            const unsigned zz = (unsigned)an.slot_zero | ((unsigned)an.slot_zero << 16);
-            an.prog_rows.resize(row0 + LU_LANES, (unsigned)an.slot_zero | (LU_NONE << 16));
-            an.prog_rows.resize(row0 + (1 + nsteps)*LU_LANES, zz);
+            prows.resize(row0 + LU_LANES, std::make_pair(an.slot_zero, -1));
+            prows.resize(row0 + (1 + nsteps)*LU_LANES, std::make_pair(an.slot_zero, an.slot_zero));
             for (size_t q = 0; q < cnt; q++) {
                 const HTask &t = tasks[v[off + q]];
-                an.prog_rows[row0 + q] = (unsigned)t.dst | ((t.div >= 0 ? (unsigned)t.div : LU_NONE) << 16);
+                prows[row0 + q] = std::make_pair(t.dst, t.div >= 0 ? t.div : -1);
                 for (size_t s = 0; s < t.ops.size(); s++)
-                    an.prog_rows[row0 + (1 + s)*LU_LANES + q] = (unsigned)t.ops[s].first | ((unsigned)t.ops[s].second << 16);
+                    prows[row0 + (1 + s)*LU_LANES + q] = t.ops[s];
                 an.prog_ops += (long long)t.ops.size();
             }
             an.prog_steps += (long long)nsteps;
+        }
+    }
+    // ---- encoding: narrow (16-bit slots, image staged in one warp's shared-memory window) while
+    // it fits, wide otherwise ----
+    {
+        const size_t rnd = ((an.prog_round.size() + 7) & ~(size_t)7)*sizeof(unsigned short);
+        an.wide = (an.img > 0xfff0 || (size_t)an.img*8 + rnd > LU_SMEM_BUDGET) ? 1 : 0;
+        if (getenv("B200_LU_WIDE")) an.wide = 1;             // measurement / test override
+        size_t row = 0;
+        if (an.wide) an.prog_rows.resize(prows.size()*2);
+        else an.prog_rows.resize(prows.size());
+        for (size_t r = 0; r < an.prog_round.size(); r++) {
+            const size_t nsteps = an.prog_round[r] & 0x7fff;
+            for (size_t q = 0; q < (1 + nsteps)*LU_LANES; q++) {
+                const std::pair<int,int> &w = prows[row*LU_LANES + q];
+                const bool header = q < LU_LANES;
+                if (an.wide) {
+                    an.prog_rows[(row*LU_LANES + q)*2] = (unsigned)w.first;
+                    an.prog_rows[(row*LU_LANES + q)*2 + 1] = (header && w.second < 0) ? LU_NONE_W : (unsigned)w.second;
+                }
+                else
+                    an.prog_rows[row*LU_LANES + q] = (unsigned)w.first |
+                        (((header && w.second < 0) ? LU_NONE : (unsigned)w.second) << 16);
+            }
+            row += 1 + nsteps;
         }
     }
 
@@ -1355,7 +1428,7 @@ int b200_build_programs(Analysis &an, bool uic)
     LuProgram &P = an.tranp;
     P.rowperm = tr.rowperm; P.colperm = tr.colperm; P.yperm_out = tr.yperm_out;
     P.tile_order = tr.tile_order; P.runs = tr.runs; P.prog_rows = tr.prog_rows;
-    P.prog_round = tr.prog_round; P.nnzLU = tr.nnzLU; P.img = tr.img;
+    P.prog_round = tr.prog_round; P.nnzLU = tr.nnzLU; P.img = tr.img; P.wide = tr.wide;
     P.prog_levels = tr.prog_levels; P.prog_tasks = tr.prog_tasks;
     P.prog_steps = tr.prog_steps; P.prog_ops = tr.prog_ops;
     an.has_tranp = true;
@@ -1386,6 +1459,7 @@ extern "C" int b200_deck_analysis_stats(const b200_deck *deck, long long *out, i
     v[B200_AS_PROG_BYTES] = (long long)(an.prog_rows.size()*sizeof(unsigned) + an.prog_round.size()*sizeof(unsigned short));
     { int m = 0; for (auto &r : an.runs) m = std::max(m, r.len); v[B200_AS_LONGEST_RUN] = m; }
     v[B200_AS_LU_SPLIT] = LU_SPLIT; v[B200_AS_LU_CHUNK] = LU_CHUNK;
+    v[B200_AS_WIDE] = an.wide;
     for (int i = 0; i < nout && i < B200_AS_NSTATS; i++) out[i] = v[i];
     return B200_OK;
 }
@@ -1481,14 +1555,21 @@ extern "C" int b200_debug_program_check(int n, const int *Ap, const int *Ai, con
     for (size_t r = 0; r < an.prog_round.size(); r++) {
         int nsteps = an.prog_round[r] & 0x7fff;
         for (int e = 0; e < LU_LANES; e++) {
-            unsigned h = an.prog_rows[row*LU_LANES + e];
-            unsigned dst = h & 0xffffu, div = h >> 16;
+            unsigned dst, div;
+            if (an.wide) { dst = an.prog_rows[(row*LU_LANES + e)*2]; div = an.prog_rows[(row*LU_LANES + e)*2 + 1]; }
+            else { unsigned h = an.prog_rows[row*LU_LANES + e]; dst = h & 0xffffu; div = h >> 16; }
             double acc = S[dst];
             for (int st = 0; st < nsteps; st++) {
-                unsigned w = an.prog_rows[(row + 1 + st)*LU_LANES + e];
-                acc -= S[w & 0xffffu]*S[w >> 16];
+                if (an.wide) {
+                    const unsigned *w = &an.prog_rows[((row + 1 + st)*LU_LANES + e)*2];
+                    acc -= S[w[0]]*S[w[1]];
+                }
+                else {
+                    unsigned w = an.prog_rows[(row + 1 + st)*LU_LANES + e];
+                    acc -= S[w & 0xffffu]*S[w >> 16];
+                }
             }
-            if (div != LU_NONE) {
+            if (div != (an.wide ? LU_NONE_W : LU_NONE)) {
                 double piv = S[div];
                 if (piv == 0.0 || !std::isfinite(piv)) bad = 1;
                 acc = acc/piv;

@@ -197,6 +197,12 @@ struct SrcTopo {
 // prog_round[r] = nsteps | LU_RSYNC if the round opens a new level (its operands were written
 // by earlier rounds: the warp synchronises before it reads them).
 #define LU_RSYNC 0x8000u
+// WIDE programs: an image that does not fit one warp's shared-memory window (or 16-bit slot
+// numbers) stays in global memory / L2 and its program carries 32-bit slot numbers -- two
+// words per lane and row: header {dst, div (LU_NONE_W: none)}, op {a, b}.  Same tasks, same
+// order, same arithmetic; k_lu_wide (solve.cu) interprets it.
+#define LU_NONE_W 0xffffffffu
+#define LU_SMEM_BUDGET 229000                    // bytes of the 227 KB window left to image + round table
 // Assembly run of one image slot: S[slot] = finalize( sum of contrib[pos .. pos+len) in order )
 struct AsmRun { int pos, len, info, pad; };
 #define ASM_TILE_SLOTS 16                        // slots per k_assemble warp tile
@@ -210,7 +216,7 @@ struct LuProgram {
     std::vector<AsmRun> runs;
     std::vector<unsigned> prog_rows;
     std::vector<unsigned short> prog_round;
-    int nnzLU = 0, img = 0;
+    int nnzLU = 0, img = 0, wide = 0;
     int prog_levels = 0, prog_tasks = 0; long long prog_steps = 0, prog_ops = 0;
 };
 
@@ -267,7 +273,8 @@ struct Analysis {
     std::vector<int> tile_order;                // tiles of ASM_TILE_SLOTS slots, most terms first
     std::vector<int> const_idx; std::vector<double> const_val;   // Ainit pseudo-terms, the -1.0
     // task program
-    std::vector<unsigned> prog_rows;            // [nrows][LU_LANES]
+    std::vector<unsigned> prog_rows;            // [nrows][LU_LANES] ([nrows][LU_LANES][2] if wide)
+    int wide = 0;                               // 1: 32-bit slot numbers, image in global memory (k_lu_wide)
     std::vector<unsigned short> prog_round;     // per round: nsteps | LU_RSYNC
     int prog_levels = 0, prog_tasks = 0; long long prog_steps = 0, prog_ops = 0;
     std::vector<int> yperm_in;                  // y[k] = rhs[rowperm[k]+1]

@@ -486,7 +486,8 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Sv.tile_order = b->dupload(an.tile_order); Sv.ntiles = (int)an.tile_order.size();
     Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (an.n + 31) & ~31;
     Sv.rows = b->dupload(an.prog_rows); Sv.rounds = b->dupload(an.prog_round);
-    Sv.nrows = (int)an.prog_rows.size()/LU_LANES; Sv.nrounds = (int)an.prog_round.size();
+    Sv.wide = an.wide;
+    Sv.nrows = (int)(an.prog_rows.size()/(LU_LANES*(an.wide ? 2 : 1))); Sv.nrounds = (int)an.prog_round.size();
     Sv.image = b->dalloc<double>((size_t)ldt*std::max(an.img, an.has_tranp ? an.tranp.img : 0));
     Sv.ysol = b->dalloc<double>((size_t)ldt*Sv.npad);
     Sv.lu_bad = b->dalloc<int>(ldt); Sv.live = b->dalloc<int>(ldt); Sv.ctr = b->dalloc<int>(2);
@@ -510,7 +511,8 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
         S2.tile_order = b->dupload(P.tile_order); S2.ntiles = (int)P.tile_order.size();
         S2.img = P.img; S2.nlu = P.nnzLU;
         S2.rows = b->dupload(P.prog_rows); S2.rounds = b->dupload(P.prog_round);
-        S2.nrows = (int)P.prog_rows.size()/LU_LANES; S2.nrounds = (int)P.prog_round.size();
+        S2.wide = P.wide;
+        S2.nrows = (int)(P.prog_rows.size()/(LU_LANES*(P.wide ? 2 : 1))); S2.nrounds = (int)P.prog_round.size();
         S2.live = b->dalloc<int>(ldt); S2.ctr = b->dalloc<int>(2);
         rc = solve_configure(S2);
         if (rc) { b200_batch_destroy(b); return rc; }

@@ -43,6 +43,7 @@ struct SolveView {
     int lu_warps, lu_grid;      // warps (= trials in flight) per CTA, CTAs of the persistent k_lu
     int lu_smem;                // dynamic shared memory of k_lu
     int prog_in_smem;           // 1: every CTA stages the program rows in shared memory
+    int wide;                   // 1: wide program (b200_internal.h), image stays in global memory
 };
 
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,

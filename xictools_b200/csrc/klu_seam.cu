@@ -350,7 +350,8 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     Sv.tile_order = k->dupload(an.tile_order); Sv.ntiles = (int)an.tile_order.size();
     Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (n + 31) & ~31;
     Sv.rows = k->dupload(an.prog_rows); Sv.rounds = k->dupload(an.prog_round);
-    Sv.nrows = (int)an.prog_rows.size()/LU_LANES; Sv.nrounds = (int)an.prog_round.size();
+    Sv.wide = an.wide;
+    Sv.nrows = (int)(an.prog_rows.size()/(LU_LANES*(an.wide ? 2 : 1))); Sv.nrounds = (int)an.prog_round.size();
     Sv.ctr = k->dalloc<int>(2);
     rc = solve_configure(Sv);
     if (rc) { b200_klu_free(k); return rc; }

@@ -236,6 +236,69 @@ k_lu(SolveView Sv, int n)
 }
 
 // ---------------------------------------------------------------------------------------
+// k_lu_wide: the same task program for images beyond one warp's shared-memory window (a few
+// thousand unknowns upward).  One warp = one trial, as in k_lu, but the image stays where
+// k_assemble put it -- global memory, in practice L2: 126 MB hold the images of every trial in
+// flight -- and the program rows carry 32-bit slot numbers.  A lane's writes are read by other
+// lanes only after the next level's __syncwarp (memory ordering among the warp's threads), so
+// no fence is needed.  Persistent CTAs pull live trials from the same work counter.
+// ---------------------------------------------------------------------------------------
+#define LUW_WARPS 8
+__global__ void __launch_bounds__(LUW_WARPS*32)
+k_lu_wide(SolveView Sv, int n)
+{
+    const int lane = threadIdx.x & 31;
+    const int nlive = Sv.ctr[0];
+    const int img = Sv.img;
+    const int nrounds = Sv.nrounds;
+    const uint2 *rows0 = reinterpret_cast<const uint2*>(Sv.rows) + lane;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&Sv.ctr[1], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nlive) break;
+        const int t = Sv.live[i];
+        double *S = Sv.image + (size_t)t*img;
+        int bad = 0;
+        const uint2 *rp = rows0;
+        for (int r = 0; r < nrounds; r++) {
+            const unsigned meta = __ldg(Sv.rounds + r);
+            const int nsteps = (int)(meta & 0x7fffu);
+            if (meta & LU_RSYNC) __syncwarp();
+            const uint2 h = __ldg(rp);
+            rp += LU_LANES;
+            double acc = S[h.x];
+            for (int s = 0; s < nsteps; s += 4) {
+                uint2 w[4];
+                double a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (s + u < nsteps) w[u] = __ldg(rp + (s + u)*LU_LANES);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (s + u < nsteps) { a[u] = S[w[u].x]; b[u] = S[w[u].y]; }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (s + u < nsteps) acc -= a[u]*b[u];
+            }
+            rp += nsteps*LU_LANES;
+            if (h.y != LU_NONE_W) {
+                const double piv = S[h.y];
+                if (piv == 0.0 || !isfinite(piv)) bad = 1;
+                acc = acc/piv;
+            }
+            S[h.x] = acc;
+        }
+        __syncwarp();
+        double *y = Sv.ysol + (size_t)t*Sv.npad;
+        const double *Sy = S + Sv.nlu;
+        for (int k = lane; k < n; k += 32) y[k] = Sy[k];
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) Sv.lu_bad[t] = bad;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_finish: CTA = one group of 32 adjacent trials, all n unknowns
 // ---------------------------------------------------------------------------------------
 #define FIN_WARPS 8
@@ -305,6 +368,18 @@ int solve_configure(SolveView &Sv)
     if (cudaGetDevice(&dev) != cudaSuccess) return B200_E_NOGPU;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (Sv.ntiles != (Sv.img + ASM_TS - 1)/ASM_TS) return B200_E_PANIC;     // b200_internal.h ASM_TILE_SLOTS
+    if (Sv.wide) {
+        // image in global memory: no window to size; as many warps per SM as the registers allow
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_wide, LUW_WARPS*32, 0) != cudaSuccess || per_sm < 1)
+            return B200_E_NOGPU;
+        Sv.prog_in_smem = 0;
+        Sv.lu_warps = LUW_WARPS;
+        Sv.lu_smem = 0;
+        Sv.lu_grid = nsm*per_sm;
+        return B200_OK;
+    }
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, k_lu<true>) != cudaSuccess) return B200_E_NOGPU;
     const size_t budget = (size_t)maxsm - fa.sharedSizeBytes;
@@ -325,7 +400,6 @@ int solve_configure(SolveView &Sv)
     Sv.lu_warps = psmem ? w_smem : w_glob;
     Sv.lu_smem = (int)((size_t)Sv.lu_warps*imgb + rnd + (psmem ? prog : 0));
     Sv.lu_grid = nsm;
-    if (Sv.ntiles != (Sv.img + ASM_TS - 1)/ASM_TS) return B200_E_PANIC;     // b200_internal.h ASM_TILE_SLOTS
     // opt in to the whole window: a batch may run two programs of different size through the
     // same kernel, and the attribute is per function, not per launch
     cudaError_t e = psmem
@@ -341,7 +415,8 @@ int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const Vec
     const int ngroups = K.ldt/32;
     dim3 ga(ngroups, (Sv.ntiles + ASM_WARPS - 1)/ASM_WARPS);
     k_assemble<<<ga, ASM_WARPS*32, 0, st>>>(K, hot, V, Sv);
-    if (Sv.prog_in_smem) k_lu<true><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
+    if (Sv.wide) k_lu_wide<<<Sv.lu_grid, LUW_WARPS*32, 0, st>>>(Sv, K.n);
+    else if (Sv.prog_in_smem) k_lu<true><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
     else k_lu<false><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
     k_finish<<<ngroups, FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew);
     return 0;

@@ -376,14 +376,10 @@ class Deck:
         if phase:
             for mkey in models_of.get(DEV_RES, []):
                 lst = insts_of[mkey]
-                work = list(lst)
-                for k, e in enumerate(lst):
-                    if k == 0:
-                        continue
-                    if any(nd in phase for nd in e.nodes):
-                        work.remove(e)
-                        work.insert(0, e)
-                insts_of[mkey] = work
+                moved = [k > 0 and any(nd in phase for nd in e.nodes) for k, e in enumerate(lst)]
+                # each moved element lands in front of the earlier ones: reverse visiting order
+                insts_of[mkey] = ([e for e, mv in zip(reversed(lst), reversed(moved)) if mv] +
+                                  [e for e, mv in zip(lst, moved) if not mv])
         out = []
         if DEV_MUT in models_of:
             for mkey in models_of[DEV_MUT]:
