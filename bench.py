@@ -211,6 +211,62 @@ def bench_rsfq(local, ntrials=2048, njj=1000, tjm=None):
     return out
 
 
+def bench_large_flat(local, nstages=50001, ntrials=16, nref=4):
+    """Secondary workload (BASELINE.json configs[3]): a large flat CMOS netlist -- a ring
+    oscillator of `nstages` stages, 2*nstages level-1 MOSFETs, nstages+2 unknowns -- run as a
+    single transient and as a small Monte-Carlo batch.  The LU image (400 k doubles per trial)
+    is far beyond one warp's shared-memory window: this runs the wide task program (k_lu_wide,
+    image in L2 / HBM).  The reference runs the first `nref` trials meanwhile on host cores
+    (one trial per core): identical counts, waveforms within tolerance, and its time per trial."""
+    import numpy as np
+    from xictools_b200 import engine
+    from xictools_b200.deck import ring_oscillator, C_STATUS, C_NUMITER
+    deck = ring_oscillator(nstages)
+    deck.tran(0.02e-9, 2e-9)
+    ov = make_variation(deck, ntrials)
+    want = ["n0", f"n{nstages//2}", "vdd#branch"]
+    nref = min(nref, ntrials, host_cores())
+    texts = [deck.to_spice({k: v[t] for k, v in ov.items()}) for t in range(nref)]
+    ctx = mp.get_context("fork")
+    pool = ctx.Pool(nref)
+    t_ref0 = time.perf_counter()
+    pending = [pool.apply_async(_ref_worker, (([txt], want),)) for txt in texts]
+    out = {"workload": f"large_flat: {nstages}-stage CMOS ring oscillator, {2*nstages} MOSFETs (level 1) + {nstages} C, "
+                       f".tran 0.02n 2n; single transient and a {ntrials}-trial Monte Carlo (vto / L as the headline workload)"}
+    try:
+        b1 = engine.Batch(deck, 1, device=local)
+        b1.run_tran()
+        s1 = b1.stats()
+        c1 = b1.counters()
+        out["single"] = {"seconds": s1.ms_total*1e-3, "ok": int(c1[0, C_STATUS] == 0), "newton_iters": int(c1[0, C_NUMITER]),
+                         "ms_per_newton_iter": s1.ms_total/max(1, int(c1[0, C_NUMITER])), "unknowns": b1.n}
+        b1.close()
+        b = engine.Batch(deck, ntrials, device=local)
+        b.set_params(ov)
+        b.run_tran()
+        st = b.stats()
+        cnt = b.counters()
+        names = b.names()
+        _, w = b.waves([names.index(x) for x in want])
+        out.update({"trials": ntrials, "ok_trials": int((cnt[:, C_STATUS] == 0).sum()),
+                    "value": ntrials/(st.ms_total*1e-3), "unit": "trials/s", "ms_per_step": st.ms_total,
+                    "ticks": int(st.ticks),
+                    "load_ms_per_tick": st.ms_load/max(st.load_launches, 1),
+                    "solve_ms_per_tick": st.ms_solve/max(st.solve_launches, 1),
+                    "device_load_instances_per_s": (3*nstages + 1)*float(cnt[:, C_NUMITER].sum())/(st.ms_total*1e-3)})
+        b.close()
+        flat = [r.get(timeout=900)[0] for r in pending]
+        el = time.perf_counter() - t_ref0
+        out["cpu_baseline"] = {"value": nref/el, "unit": "trials/s", "cores": nref, "kind": "reference",
+                               "sample": f"trials 0..{nref-1}, one per core, in {el:.1f} s (oracle/_ref, Sparse 1.3)"}
+        out["parity"] = compare_with_reference(flat, cnt, w, current_last=True, saved=want)
+    except Exception as e:          # pragma: no cover
+        out["error"] = repr(e)
+    finally:
+        pool.terminate()
+    return out
+
+
 def bench_dc_sweep(local, npoints=100000):
     """Secondary workload (BASELINE.json configs[4]): 1e5-point DC operating-point sweep of the
     two-stage opamp (MOS level 1), every point a trial of one `.op` batch."""
@@ -589,6 +645,10 @@ def bench_ours(args):
                 line["secondary"]["dc_sweep"] = bench_dc_sweep(local)
             except Exception as e:          # pragma: no cover
                 line["secondary"]["dc_sweep"] = {"error": repr(e)}
+            try:
+                line["secondary"]["large_flat"] = bench_large_flat(local)
+            except Exception as e:          # pragma: no cover
+                line["secondary"]["large_flat"] = {"error": repr(e)}
         emit(line)
     if world > 1:
         dist.barrier()

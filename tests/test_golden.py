@@ -27,7 +27,9 @@ RELTOL, VNTOL = 1e-3, 1e-6
 
 
 def fixtures():
-    return sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(HERE, "golden", "*.json")))
+    # (large_*.json: bench.py's large_flat workload, tests/test_large.py)
+    return sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(HERE, "golden", "*.json"))
+                  if not os.path.basename(p).startswith("large_"))
 
 
 def load(name):

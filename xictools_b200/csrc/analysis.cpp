@@ -1332,6 +1332,15 @@ int b200_build_lu(Analysis &an)
             }
             row += 1 + nsteps;
         }
+        // round -> first row, level -> first round (a CTA's warps share out the rounds of a level)
+        an.round_row.clear(); an.level_ptr.clear();
+        row = 0;
+        for (size_t r = 0; r < an.prog_round.size(); r++) {
+            if (r == 0 || (an.prog_round[r] & LU_RSYNC)) an.level_ptr.push_back((int)r);
+            an.round_row.push_back((int)row);
+            row += 1 + (an.prog_round[r] & 0x7fff);
+        }
+        an.level_ptr.push_back((int)an.prog_round.size());
     }
 
     // ---- assembly runs: contributions renumbered in ASSEMBLY ORDER (all terms of one image
@@ -1366,6 +1375,16 @@ int b200_build_lu(Analysis &an)
     an.runs[an.slot_neg1].len = 1;
     an.const_idx.push_back(next++); an.const_val.push_back(-1.0);
     an.NC = next;
+    an.long_chunks.clear();
+    for (int s = 0; s < an.img; s++) {
+        AsmRun &r = an.runs[s];
+        if (r.len <= ASM_LONG) continue;
+        const int first = (int)an.long_chunks.size();
+        for (int c = 0; c < r.len; c += ASM_LCHUNK)
+            an.long_chunks.push_back(AsmChunk{r.pos + c, std::min(ASM_LCHUNK, r.len - c)});
+        r.pos = an.NC + first;
+        r.len = (int)an.long_chunks.size() - first;
+    }
     {
         int ntiles = (an.img + ASM_TILE_SLOTS - 1)/ASM_TILE_SLOTS;
         std::vector<int> terms(ntiles, 0);
@@ -1429,6 +1448,7 @@ int b200_build_programs(Analysis &an, bool uic)
     P.rowperm = tr.rowperm; P.colperm = tr.colperm; P.yperm_out = tr.yperm_out;
     P.tile_order = tr.tile_order; P.runs = tr.runs; P.prog_rows = tr.prog_rows;
     P.prog_round = tr.prog_round; P.nnzLU = tr.nnzLU; P.img = tr.img; P.wide = tr.wide;
+    P.round_row = tr.round_row; P.level_ptr = tr.level_ptr;
     P.prog_levels = tr.prog_levels; P.prog_tasks = tr.prog_tasks;
     P.prog_steps = tr.prog_steps; P.prog_ops = tr.prog_ops;
     an.has_tranp = true;
@@ -1540,10 +1560,15 @@ extern "C" int b200_debug_program_check(int n, const int *Ap, const int *Ai, con
     int rc = b200_build_lu(an);
     if (rc) return rc;
     // contributions in assembly order
-    std::vector<double> contrib(an.NC, 0.0);
+    std::vector<double> contrib(an.NC + an.long_chunks.size(), 0.0);
     for (int p = 0; p < an.nnz; p++) contrib[an.cg_idx[p]] = Ax[p];
     for (int r = 0; r < n; r++) contrib[an.rg_idx[r]] = b[r];
     for (size_t i = 0; i < an.const_idx.size(); i++) contrib[an.const_idx[i]] = an.const_val[i];
+    for (size_t c = 0; c < an.long_chunks.size(); c++) {
+        double v = 0.0;
+        for (int k = 0; k < an.long_chunks[c].len; k++) v += contrib[an.long_chunks[c].pos + k];
+        contrib[an.NC + c] = v;
+    }
     std::vector<double> S(an.img, 0.0);
     for (int s = 0; s < an.img; s++) {
         double v = 0.0;

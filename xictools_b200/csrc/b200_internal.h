@@ -206,6 +206,14 @@ struct SrcTopo {
 // Assembly run of one image slot: S[slot] = finalize( sum of contrib[pos .. pos+len) in order )
 struct AsmRun { int pos, len, info, pad; };
 #define ASM_TILE_SLOTS 16                        // slots per k_assemble warp tile
+// A run of more than ASM_LONG terms (the supply node of a 100 000-transistor deck collects one
+// term per transistor) is summed in two steps: chunks of ASM_LCHUNK consecutive terms are
+// accumulated from 0.0 by k_assemble_long, one warp per chunk, into extra rows of the
+// contribution array [NC, NC + nlong); the slot's run then names those rows, so k_assemble adds
+// the chunk sums in order and finalizes the whole.  Decks without such runs never see it.
+#define ASM_LONG 4096
+#define ASM_LCHUNK 1024
+struct AsmChunk { int pos, len; };
 #define ASM_DIAG 0x40000000
 #define ASM_ROW  0x20000000
 #define ASM_VNODE 0x10000000  // diagonal of a voltage node (loadGmin applies)
@@ -217,6 +225,7 @@ struct LuProgram {
     std::vector<unsigned> prog_rows;
     std::vector<unsigned short> prog_round;
     int nnzLU = 0, img = 0, wide = 0;
+    std::vector<int> round_row, level_ptr;
     int prog_levels = 0, prog_tasks = 0; long long prog_steps = 0, prog_ops = 0;
 };
 
@@ -272,9 +281,12 @@ struct Analysis {
     std::vector<AsmRun> runs;                   // [img]
     std::vector<int> tile_order;                // tiles of ASM_TILE_SLOTS slots, most terms first
     std::vector<int> const_idx; std::vector<double> const_val;   // Ainit pseudo-terms, the -1.0
+    std::vector<AsmChunk> long_chunks;          // chunk c -> contribution row NC + c
     // task program
     std::vector<unsigned> prog_rows;            // [nrows][LU_LANES] ([nrows][LU_LANES][2] if wide)
     int wide = 0;                               // 1: 32-bit slot numbers, image in global memory (k_lu_wide)
+    std::vector<int> round_row;                 // wide: first program row of every round
+    std::vector<int> level_ptr;                 // wide: [nlevels+1] first round of every level
     std::vector<unsigned short> prog_round;     // per round: nsteps | LU_RSYNC
     int prog_levels = 0, prog_tasks = 0; long long prog_steps = 0, prog_ops = 0;
     std::vector<int> yperm_in;                  // y[k] = rhs[rowperm[k]+1]

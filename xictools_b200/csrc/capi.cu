@@ -113,7 +113,7 @@ enum { PT_CAP = MR_NRAW, PT_IND = MR_NRAW + 1, PT_SRC = MR_NRAW + 2, PT_JJ = MR_
 __global__ void k_fill_rows(double *dst, const double *shared, int n, int ldt)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
     if (t < ldt && i < n) dst[(size_t)i*ldt + t] = shared[i];
 }
 
@@ -124,15 +124,15 @@ struct TableBases { double *p[PT_NTABLES]; };
 __global__ void k_scale_rows(double *dst, const double *scale, int n, int ldt)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
     if (t < ldt && i < n) dst[(size_t)i*ldt + t] = dst[(size_t)i*ldt + t]*scale[i];
 }
 
-__global__ void k_scatter_rows(TableBases tb, const int *desc, const double *vals, int ntrials, int ldt)
+__global__ void k_scatter_rows(TableBases tb, const int *desc, const double *vals, int nrows, int ntrials, int ldt)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int r = blockIdx.y;
-    if (t >= ldt) return;
+    int r = GRID_ROW;
+    if (t >= ldt || r >= nrows) return;
     double *base = tb.p[desc[2*r]];
     if (!base || desc[2*r + 1] < 0) return;
     const double *src = vals + (size_t)r*ntrials;
@@ -358,7 +358,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     V.oldSol = b->dalloc<double>(vplane);
     V.states = b->dalloc<double>((size_t)K.NS*an.numStates*ldt);
     V.oldState0 = b->dalloc<double>((size_t)an.numStates*ldt);
-    V.contrib = b->dalloc<double>((size_t)an.NC*ldt);         // [NC][ldt]
+    V.contrib = b->dalloc<double>(((size_t)an.NC + an.long_chunks.size())*ldt);   // [NC (+ long-run chunk sums)][ldt]
     V.out = b->dalloc<double>((size_t)an.npoints_max*an.n*ldt);
     if (!V.out || !V.states || !V.sols) { b200_batch_destroy(b); return B200_E_NOMEM; }
     // ---- topology ----
@@ -487,10 +487,12 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (an.n + 31) & ~31;
     Sv.rows = b->dupload(an.prog_rows); Sv.rounds = b->dupload(an.prog_round);
     Sv.wide = an.wide;
+    Sv.long_chunks = b->dupload(an.long_chunks); Sv.nlong = (int)an.long_chunks.size(); Sv.NC = an.NC;
+    Sv.round_row = b->dupload(an.round_row); Sv.level_ptr = b->dupload(an.level_ptr); Sv.nlevels = (int)an.level_ptr.size() - 1;
     Sv.nrows = (int)(an.prog_rows.size()/(LU_LANES*(an.wide ? 2 : 1))); Sv.nrounds = (int)an.prog_round.size();
     Sv.image = b->dalloc<double>((size_t)ldt*std::max(an.img, an.has_tranp ? an.tranp.img : 0));
     Sv.ysol = b->dalloc<double>((size_t)ldt*Sv.npad);
-    Sv.lu_bad = b->dalloc<int>(ldt); Sv.live = b->dalloc<int>(ldt); Sv.ctr = b->dalloc<int>(2);
+    Sv.lu_bad = b->dalloc<int>(ldt); Sv.fin_flags = b->dalloc<int>(ldt); Sv.live = b->dalloc<int>(ldt); Sv.ctr = b->dalloc<int>(2);
     if (!Sv.image || !Sv.ysol || !Sv.live) { b200_batch_destroy(b); return B200_E_NOMEM; }
     rc = solve_configure(Sv);
     if (rc) {
@@ -512,6 +514,8 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
         S2.img = P.img; S2.nlu = P.nnzLU;
         S2.rows = b->dupload(P.prog_rows); S2.rounds = b->dupload(P.prog_round);
         S2.wide = P.wide;
+        S2.long_chunks = Sv.long_chunks; S2.nlong = Sv.nlong; S2.NC = Sv.NC;
+        S2.round_row = b->dupload(P.round_row); S2.level_ptr = b->dupload(P.level_ptr); S2.nlevels = (int)P.level_ptr.size() - 1;
         S2.nrows = (int)(P.prog_rows.size()/(LU_LANES*(P.wide ? 2 : 1))); S2.nrounds = (int)P.prog_round.size();
         S2.live = b->dalloc<int>(ldt); S2.ctr = b->dalloc<int>(2);
         rc = solve_configure(S2);
@@ -707,7 +711,7 @@ static int prepare_params(b200_batch *b)
             CK(cudaMalloc(&dsh, (n ? n : 1)*sizeof(double)));
             tmp_shared.push_back(dsh);
             CK(cudaMemcpyAsync(dsh, shared.data(), n*sizeof(double), cudaMemcpyHostToDevice, st));
-            k_fill_rows<<<dim3((unsigned)((ldt + 255)/256), n), 256, 0, st>>>(dptr, dsh, n, (int)ldt);
+            k_fill_rows<<<grid_rows((unsigned)((ldt + 255)/256), n), 256, 0, st>>>(dptr, dsh, n, (int)ldt);
             std::vector<double> row(ldt);
             for (auto &kv : var) {
                 std::copy(kv.second.begin(), kv.second.end(), row.begin());
@@ -826,15 +830,15 @@ static int prepare_params(b200_batch *b)
         for (int r = 0; r < nrows; r++) { desc[2*r] = b->pk_tbl[r]; desc[2*r + 1] = b->pk_idx[r]; }
         CK(cudaMemcpyAsync(b->d_pk_desc, desc.data(), desc.size()*sizeof(int), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));              // `desc` is a local
-        k_scatter_rows<<<dim3((unsigned)((ldt + 255)/256), nrows), 256, 0, st>>>(bases, b->d_pk_desc,
-            b->d_pack, b->ntrials, (int)ldt);
+        k_scatter_rows<<<grid_rows((unsigned)((ldt + 255)/256), nrows), 256, 0, st>>>(bases, b->d_pk_desc,
+            b->d_pack, nrows, b->ntrials, (int)ldt);
     }
     if (b->capc_ts && b->cap_has_m) {
         double *dm = nullptr;
         CK(cudaMalloc(&dm, b->cap_m.size()*sizeof(double)));
         tmp_shared.push_back(dm);
         CK(cudaMemcpyAsync(dm, b->cap_m.data(), b->cap_m.size()*sizeof(double), cudaMemcpyHostToDevice, st));
-        k_scale_rows<<<dim3((unsigned)((ldt + 255)/256), (unsigned)b->cap_m.size()), 256, 0, st>>>(b->d_capc, dm,
+        k_scale_rows<<<grid_rows((unsigned)((ldt + 255)/256), (int)b->cap_m.size()), 256, 0, st>>>(b->d_capc, dm,
             (int)b->cap_m.size(), (int)ldt);
     }
     if (!b->src_dcgiven.empty() && b->d_src_dcgiven)

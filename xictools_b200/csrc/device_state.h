@@ -13,6 +13,18 @@
 #endif
 #endif
 
+// Row (instance / node / entry) index of a CTA: grids are (trial blocks, rows) and a deck may hold
+// more rows than gridDim.y allows (65535), so the rows continue in z.
+#define GRID_ROW ((int)(blockIdx.y + blockIdx.z*gridDim.y))
+#define GRID_Y_MAX 65535
+#ifdef __CUDACC__
+static inline dim3 grid_rows(unsigned nx, int ny)
+{
+    if (ny < 1) ny = 1;
+    return dim3(nx, ny < GRID_Y_MAX ? ny : GRID_Y_MAX, (ny + GRID_Y_MAX - 1)/GRID_Y_MAX);
+}
+#endif
+
 // ---- per-trial control block (AoS; touched only by the control kernel, one thread/trial) ----
 enum { PC_IDLE = 0, PC_NIITER, PC_DONE, PC_SYNC };
 enum { RET_NONE = 0, RET_OP_DIRECT, RET_GMIN_LOOP, RET_GMIN_FINAL, RET_SRC_LOOP, RET_TRAN_STEP };

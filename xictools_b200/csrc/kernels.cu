@@ -8,6 +8,7 @@
 //   k_vec, k_statevec, k_devconv: one thread per (element, trial), gated by per-trial
 //               request flags.
 //   The solve of a tick (k_assemble -> k_lu -> k_finish) lives in solve.cu.
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <cuda_pipeline.h>
 #include <float.h>
@@ -21,12 +22,13 @@
 
 #define PR(ref, i, t) ((ref).base[(size_t)(i)*(ref).ld + (size_t)(t)*(ref).ts])
 
+
 // ---------------------------------------------------------------------------------------
 __global__ void k_mos_temp(int n, int ntrials, int ldt, const MosCard *cards,
     RawParams raw, MosParamsOut out)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
     if (t >= ntrials || i >= n) return;
     double r[MR_NRAW], o[MP_NPARAMS];
     for (int k = 0; k < MR_NRAW; k++) r[k] = PR(raw.p[k], i, t);
@@ -76,7 +78,8 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
     extern __shared__ double stage[];
     const int tid = threadIdx.x;
     int t = blockIdx.x*MOS_TPB + tid;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= M.n) return;
     // shared parameter block (values common to all trials)
     constexpr int NSHARED = L6 ? MP_NPARAMS : MP_NBASE;      // a level-1 deck stages the base set only
     for (int k = tid; k < NSHARED; k += MOS_TPB)
@@ -275,7 +278,8 @@ k_load_cap(Consts K, HotView hot, VecView V, CapView Cp, const double *rhsOld)
 {
     // capload.cc:75-205 (linear capacitor)
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= Cp.n) return;
     if (t >= K.ntrials) return;
     int mode = hot.mode[t];
     if (!mode) return;
@@ -359,7 +363,8 @@ k_load_ind(Consts K, HotView hot, VecView V, IndView L, const double *rhsOld)
 {
     // indload.cc:84-263 (linear inductor; the +-1 couplings are preloaded constants)
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= L.n) return;
     if (t >= K.ntrials) return;
     int mode = hot.mode[t];
     if (!mode) return;
@@ -439,7 +444,8 @@ k_load_mut(Consts K, HotView hot, VecView V, IndView L)
 {
     // mutload.cc:55-140, matrix part (the flux part runs inside k_load_ind, in load order)
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= L.nmut) return;
     if (t >= K.ntrials) return;
     int mode = hot.mode[t];
     if (!mode) return;
@@ -464,7 +470,8 @@ k_load_src(Consts K, HotView hot, VecView V, SrcView S)
 {
     // srcload.cc:67-105, 215-262
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= S.n) return;
     if (t >= K.ntrials) return;
     int mode = hot.mode[t];
     if (!mode) return;
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(128)
 k_devconv(Consts K, HotView hot, VecView V, MosView M, const double *rhs)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i0 = blockIdx.y*DEVCONV_CHUNK;
+    int i0 = GRID_ROW*DEVCONV_CHUNK;
     if (t >= K.ntrials) return;
     if (!hot.need_devconv[t]) return;
     TrialCtx c;
@@ -648,7 +655,8 @@ __global__ void __launch_bounds__(128)
 k_vec(Consts K, VecView V, CtlAux aux, double *rhsOld)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;                          // node 0..n
+    int i = GRID_ROW;                          // node 0..n
+    if (i >= K.n + 1) return;
     if (t >= K.ntrials) return;
     int ops = aux.vecops[t];
     if (!ops) return;
@@ -711,7 +719,7 @@ k_vec(Consts K, VecView V, CtlAux aux, double *rhsOld)
 __global__ void __launch_bounds__(128)
 k_statevec(Consts K, VecView V, CtlAux aux, MosView M)
 {
-    // grid = (trial blocks, SV_CHUNKS): a block with no request among its 128 trials exits at
+    // grid = (trial blocks, chunks): a block with no request among its 128 trials exits at
     // once (the common case in the transient); otherwise it walks its share of the slots.
     int t = blockIdx.x*blockDim.x + threadIdx.x;
     const int mask = VO_ZERO_STATE0 | VO_BK_SAVE | VO_BK_RESTORE | VO_HIST_INIT | VO_FIRSTTIME;
@@ -720,8 +728,9 @@ k_statevec(Consts K, VecView V, CtlAux aux, MosView M)
     if (!ops) return;
     size_t ldt = K.ldt;
     int total = K.numStates + MC_NCACHE*M.n;
-    int per = (total + SV_CHUNKS - 1)/SV_CHUNKS;
-    int e0 = blockIdx.y*per, e1 = min(total, e0 + per);
+    const int nchunks = gridDim.y*gridDim.z;
+    int per = (total + nchunks - 1)/nchunks;
+    int e0 = GRID_ROW*per, e1 = min(total, e0 + per);
     int base = aux.vo_stbase[t];
     size_t plane = (size_t)K.numStates*ldt;
     double *sp[8];
@@ -813,7 +822,10 @@ __global__ void k_export_counters(int ntrials, const TrialCtl *ctl, int *counter
 // ---------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------
-static inline dim3 grid2(int ntrials, int ny, int bs = 128) { return dim3((ntrials + bs - 1)/bs, ny > 0 ? ny : 1); }
+static inline dim3 grid2(int ntrials, int ny, int bs = 128)
+{
+    return grid_rows((ntrials + bs - 1)/bs, ny);
+}
 
 
 // ---------------------------------------------------------------------------------------
@@ -826,7 +838,8 @@ __global__ void __launch_bounds__(128)
 k_load_rph(Consts K, HotView hot, VecView V, ResPhView R)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= R.n) return;
     if (t >= K.ntrials) return;
     int mode = hot.mode[t];
     if (!mode) return;
@@ -921,7 +934,8 @@ __global__ void __launch_bounds__(128)
 k_load_jj(Consts K, HotView hot, VecView V, JJView J, const double *rhsOld)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= J.n) return;
     if (t >= K.ntrials) return;
     int mode = hot.mode[t];
     if (!mode) return;
@@ -1108,7 +1122,8 @@ k_load_jj(Consts K, HotView hot, VecView V, JJView J, const double *rhsOld)
 __global__ void k_jj_temp(JJTempIn in, int ntrials, int ldt)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= in.n) return;
     if (t >= (in.ts ? ldt : 1)) return;
     const int m = in.model[i];
     const int tt = t < ntrials ? t : 0;         // padding trials repeat trial 0
@@ -1155,7 +1170,7 @@ void launch_jj_temp(cudaStream_t st, const JJTempIn &in, int ntrials, int ldt)
 {
     if (!in.n) return;
     int nt = in.ts ? ldt : 1;
-    k_jj_temp<<<dim3((nt + 127)/128, in.n), 128, 0, st>>>(in, ntrials, ldt);
+    k_jj_temp<<<grid2(nt, in.n), 128, 0, st>>>(in, ntrials, ldt);
 }
 
 
@@ -1173,7 +1188,8 @@ __global__ void __launch_bounds__(128)
 k_load_tjm(Consts K, HotView hot, VecView V, TJMView J, const double *rhsOld)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= J.n) return;
     if (t >= K.ntrials) return;
     int mode = hot.mode[t];
     if (!mode) return;
@@ -1370,7 +1386,8 @@ k_load_tjm(Consts K, HotView hot, VecView V, TJMView J, const double *rhsOld)
 __global__ void k_tjm_temp(TJMTempIn in, int ntrials, int ldt)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
+    int i = GRID_ROW;
+    if (i >= in.n) return;
     if (t >= (in.ts ? ldt : 1)) return;
     const int m = in.model[i];
     const int tt = t < ntrials ? t : 0;
@@ -1406,7 +1423,7 @@ void launch_tjm_temp(cudaStream_t st, const TJMTempIn &in, int ntrials, int ldt)
 {
     if (!in.n) return;
     int nt = in.ts ? ldt : 1;
-    k_tjm_temp<<<dim3((nt + 127)/128, in.n), 128, 0, st>>>(in, ntrials, ldt);
+    k_tjm_temp<<<grid2(nt, in.n), 128, 0, st>>>(in, ntrials, ldt);
 }
 
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,
@@ -1434,7 +1451,7 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
 {
     if (M.n) {
         size_t smem = (size_t)M.stage_doubles*sizeof(double);
-        dim3 g((K.ntrials + MOS_TPB - 1)/MOS_TPB, M.n);
+        dim3 g = grid2(K.ntrials, M.n, MOS_TPB);
         if (M.has_level6) k_load_mos<6, true><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
         else k_load_mos<6, false><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
     }
@@ -1455,7 +1472,12 @@ void launch_vec(cudaStream_t st, const Consts &K, const VecView &V, const CtlAux
     const MosView &M, double *rhsOld)
 {
     k_vec<<<grid2(K.ntrials, K.n + 1), 128, 0, st>>>(K, V, aux, rhsOld);
-    k_statevec<<<grid2(K.ntrials, SV_CHUNKS), 128, 0, st>>>(K, V, aux, M);
+    {
+        // at most ~512 slots per thread, at least SV_CHUNKS chunks
+        const int total = K.numStates + MC_NCACHE*M.n;
+        const int chunks = std::max(SV_CHUNKS, (total + 511)/512);
+        k_statevec<<<grid2(K.ntrials, chunks), 128, 0, st>>>(K, V, aux, M);
+    }
 }
 void launch_count_active(cudaStream_t st, int ntrials, const int *active, int *count)
 {

@@ -38,12 +38,17 @@ struct SolveView {
     double *image;              // [ldt][img] assembled A | b of every trial, trial-major
     double *ysol;               // [ldt][npad] solutions in permuted column order
     int *lu_bad;                // [ldt] 1: a pivot was zero or not finite
+    int *fin_flags;             // [ldt] flags of the chunked k_finish (zero between solves)
     int *live;                  // [ldt] trials that take a solve this tick (built by k_assemble)
     int *ctr;                   // [0] number of live trials, [1] work counter of the k_lu warps
     int lu_warps, lu_grid;      // warps (= trials in flight) per CTA, CTAs of the persistent k_lu
     int lu_smem;                // dynamic shared memory of k_lu
     int prog_in_smem;           // 1: every CTA stages the program rows in shared memory
     int wide;                   // 1: wide program (b200_internal.h), image stays in global memory
+    const AsmChunk *long_chunks; int nlong; int NC;     // long assembly runs (b200_internal.h), chunk c -> row NC + c
+    const int *round_row;       // wide: first program row of every round
+    const int *level_ptr;       // wide: [nlevels+1] first round of every level
+    int nlevels;
 };
 
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,

@@ -105,8 +105,8 @@ __global__ void k_debug_assemble(Consts K, HotView hot, VecView V, SolveView Sv,
     double *Ax, double *rhs)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int e = blockIdx.y;
-    if (t >= K.ntrials) return;
+    int e = GRID_ROW;
+    if (t >= K.ntrials || e > nnz + K.n) return;
     int ldt = K.ldt;
     int mode = hot.mode[t];
     double diagGmin = hot.diaggmin[t];
@@ -147,7 +147,7 @@ __global__ void k_debug_assemble(Consts K, HotView hot, VecView V, SolveView Sv,
 __global__ void k_pack_stream(Consts K, int nent, const int *map, const double *src, double *dst)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    int e = blockIdx.y;
+    int e = GRID_ROW;
     if (t >= K.ldt || e >= nent) return;
     dst[CADDR(K, map[e], t)] = src[(size_t)e*K.ldt + t];
 }
@@ -248,7 +248,7 @@ int b200_batch_debug_load(b200_batch *b, int mode, double time, double delta, in
     double *dAx = nullptr, *drhs = nullptr;
     CK(cudaMalloc(&dAx, (size_t)nnz*ldt*sizeof(double)));
     CK(cudaMalloc(&drhs, (size_t)(n + 1)*ldt*sizeof(double)));
-    dim3 g((nt + 127)/128, nnz + n + 1);
+    dim3 g = grid_rows((nt + 127)/128, nnz + n + 1);
     const Analysis &an = *b200_internal_analysis(b);
     std::vector<int> dn(an.nnz, 0);
     for (int i = 1; i <= an.n; i++) if (an.diag[i] >= 0) dn[an.diag[i]] = i;
@@ -351,6 +351,8 @@ int b200_klu_analyze(int n, const int *Ap, const int *Ai, const double *Ax0, dou
     Sv.img = an.img; Sv.nlu = an.nnzLU; Sv.npad = (n + 31) & ~31;
     Sv.rows = k->dupload(an.prog_rows); Sv.rounds = k->dupload(an.prog_round);
     Sv.wide = an.wide;
+    Sv.long_chunks = k->dupload(an.long_chunks); Sv.nlong = (int)an.long_chunks.size(); Sv.NC = an.NC;
+    Sv.round_row = k->dupload(an.round_row); Sv.level_ptr = k->dupload(an.level_ptr); Sv.nlevels = (int)an.level_ptr.size() - 1;
     Sv.nrows = (int)(an.prog_rows.size()/(LU_LANES*(an.wide ? 2 : 1))); Sv.nrounds = (int)an.prog_round.size();
     Sv.ctr = k->dalloc<int>(2);
     rc = solve_configure(Sv);
@@ -405,13 +407,13 @@ static int klu_ensure(b200_klu *k, int ldt, cudaStream_t st)
     h.devconv = k->talloc<int>(ldt); h.need_devconv = k->talloc<int>(ldt);
     k->dX0 = k->talloc<double>((size_t)(k->an.n + 1)*ldt);
     k->dX1 = k->talloc<double>((size_t)(k->an.n + 1)*ldt);
-    k->dpack = k->talloc<double>((size_t)k->an.NC*ldt);
+    k->dpack = k->talloc<double>(((size_t)k->an.NC + k->an.long_chunks.size())*ldt);
     SolveView &Sv = k->Sv;
     Sv.image = k->talloc<double>((size_t)ldt*Sv.img);
     Sv.ysol = k->talloc<double>((size_t)ldt*Sv.npad);
-    Sv.lu_bad = k->talloc<int>(ldt); Sv.live = k->talloc<int>(ldt);
+    Sv.lu_bad = k->talloc<int>(ldt); Sv.fin_flags = k->talloc<int>(ldt); Sv.live = k->talloc<int>(ldt);
     if (!k->dX1 || !k->dpack || !Sv.image || !Sv.ysol || !Sv.live) return B200_E_NOMEM;
-    int *iz[] = { h.mode, h.iterno, h.noncon, h.solve_err, h.nodeconv, h.devconv, h.need_devconv, Sv.lu_bad };
+    int *iz[] = { h.mode, h.iterno, h.noncon, h.solve_err, h.nodeconv, h.devconv, h.need_devconv, Sv.lu_bad, Sv.fin_flags };
     for (int *p : iz) CK(cudaMemsetAsync(p, 0, ldt*sizeof(int), st));
     CK(cudaMemsetAsync(h.diaggmin, 0, ldt*sizeof(double), st));
     CK(cudaMemsetAsync(k->dX0, 0, (size_t)(k->an.n + 1)*ldt*sizeof(double), st));
@@ -443,8 +445,8 @@ int b200_klu_refactor_solve_dev(b200_klu *k, int ntrials, int ldt, const double 
     memset(&V, 0, sizeof(V));
     V.contrib = k->dpack;
     int nnz = k->an.nnz, n = k->an.n;
-    k_pack_stream<<<dim3((ldt + 127)/128, nnz), 128, 0, st>>>(K, nnz, k->d_packmap, dAx, k->dpack);
-    k_pack_stream<<<dim3((ldt + 127)/128, n), 128, 0, st>>>(K, n, k->d_packmap + nnz, dB, k->dpack);
+    k_pack_stream<<<grid_rows((ldt + 127)/128, nnz), 128, 0, st>>>(K, nnz, k->d_packmap, dAx, k->dpack);
+    k_pack_stream<<<grid_rows((ldt + 127)/128, n), 128, 0, st>>>(K, n, k->d_packmap + nnz, dB, k->dpack);
     // solution goes to dX1 ([n+1][ldt], row 0 = ground), then back into dB
     int rc = launch_solve(st, K, k->hot, V, k->Sv, k->dX0, k->dX1);
     if (rc) return rc;

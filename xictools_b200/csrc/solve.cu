@@ -149,6 +149,27 @@ k_assemble(Consts K, HotView hot, VecView V, SolveView Sv)
     }
 }
 
+// long runs, first step: one warp = 32 adjacent trials x one chunk (b200_internal.h ASM_LONG)
+__global__ void __launch_bounds__(ASM_WARPS*32)
+k_assemble_long(Consts K, HotView hot, VecView V, SolveView Sv)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x*32 + lane;
+    const int c = blockIdx.y*ASM_WARPS + warp;
+    if (c >= Sv.nlong) return;
+    const bool live = (t < K.ntrials) && hot.do_solve[t] &&
+        (Sv.cls < 0 || ((hot.mode[t] & MODEDC) != 0) == (Sv.cls != 0));
+    if (!live) return;
+    const size_t ldt = (size_t)K.ldt;
+    const AsmChunk ch = Sv.long_chunks[c];
+    const double *x = V.contrib + t + (size_t)ch.pos*ldt;
+    double v = 0.0;
+    int k = 0;
+    v = run_sum<32>(v, x, ldt, k, ch.len);
+    for (; k < ch.len; k++) v += __ldcs(x + (size_t)k*ldt);
+    V.contrib[((size_t)Sv.NC + c)*ldt + t] = v;
+}
+
 // ---------------------------------------------------------------------------------------
 // k_lu
 // ---------------------------------------------------------------------------------------
@@ -237,64 +258,72 @@ k_lu(SolveView Sv, int n)
 
 // ---------------------------------------------------------------------------------------
 // k_lu_wide: the same task program for images beyond one warp's shared-memory window (a few
-// thousand unknowns upward).  One warp = one trial, as in k_lu, but the image stays where
-// k_assemble put it -- global memory, in practice L2: 126 MB hold the images of every trial in
-// flight -- and the program rows carry 32-bit slot numbers.  A lane's writes are read by other
-// lanes only after the next level's __syncwarp (memory ordering among the warp's threads), so
-// no fence is needed.  Persistent CTAs pull live trials from the same work counter.
+// thousand unknowns upward).  The image stays where k_assemble put it -- global memory, in
+// practice L2 -- and the program rows carry 32-bit slot numbers.  A large system has wide
+// levels (50 000 unknowns: ~26 000 rounds in ~50 levels), so here one CTA works on one trial:
+// its warps share out the rounds of a level (round r of the level goes to warp r mod W) and
+// meet at a CTA barrier between levels, which also orders the global-memory writes of one
+// level before the reads of the next.  Same tasks, same operand order inside every task, so
+// the arithmetic is bit-identical to k_lu's.  Persistent CTAs pull live trials from the work
+// counter.
 // ---------------------------------------------------------------------------------------
-#define LUW_WARPS 8
-__global__ void __launch_bounds__(LUW_WARPS*32)
+#define LUW_MAXW 32
+__global__ void __launch_bounds__(LUW_MAXW*32)
 k_lu_wide(SolveView Sv, int n)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ int s_next;
+    __shared__ int s_bad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
     const int nlive = Sv.ctr[0];
     const int img = Sv.img;
-    const int nrounds = Sv.nrounds;
-    const uint2 *rows0 = reinterpret_cast<const uint2*>(Sv.rows) + lane;
+    const int nlevels = Sv.nlevels;
+    const uint2 *rows = reinterpret_cast<const uint2*>(Sv.rows);
     for (;;) {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(&Sv.ctr[1], 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        __syncthreads();                                 // everyone is done with the previous trial (and s_next)
+        if (threadIdx.x == 0) { s_next = atomicAdd(&Sv.ctr[1], 1); s_bad = 0; }
+        __syncthreads();
+        const int i = s_next;
         if (i >= nlive) break;
         const int t = Sv.live[i];
         double *S = Sv.image + (size_t)t*img;
         int bad = 0;
-        const uint2 *rp = rows0;
-        for (int r = 0; r < nrounds; r++) {
-            const unsigned meta = __ldg(Sv.rounds + r);
-            const int nsteps = (int)(meta & 0x7fffu);
-            if (meta & LU_RSYNC) __syncwarp();
-            const uint2 h = __ldg(rp);
-            rp += LU_LANES;
-            double acc = S[h.x];
-            for (int s = 0; s < nsteps; s += 4) {
-                uint2 w[4];
-                double a[4], b[4];
+        for (int lv = 0; lv < nlevels; lv++) {
+            const int r0 = __ldg(Sv.level_ptr + lv), r1 = __ldg(Sv.level_ptr + lv + 1);
+            for (int r = r0 + warp; r < r1; r += W) {
+                const int nsteps = (int)(__ldg(Sv.rounds + r) & 0x7fffu);
+                const uint2 *rp = rows + (size_t)__ldg(Sv.round_row + r)*LU_LANES + lane;
+                const uint2 h = __ldg(rp);
+                rp += LU_LANES;
+                double acc = S[h.x];
+                for (int s = 0; s < nsteps; s += 4) {
+                    uint2 w[4];
+                    double a[4], b[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (s + u < nsteps) w[u] = __ldg(rp + (s + u)*LU_LANES);
+                    for (int u = 0; u < 4; u++)
+                        if (s + u < nsteps) w[u] = __ldg(rp + (s + u)*LU_LANES);
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (s + u < nsteps) { a[u] = S[w[u].x]; b[u] = S[w[u].y]; }
+                    for (int u = 0; u < 4; u++)
+                        if (s + u < nsteps) { a[u] = S[w[u].x]; b[u] = S[w[u].y]; }
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (s + u < nsteps) acc -= a[u]*b[u];
+                    for (int u = 0; u < 4; u++)
+                        if (s + u < nsteps) acc -= a[u]*b[u];
+                }
+                if (h.y != LU_NONE_W) {
+                    const double piv = S[h.y];
+                    if (piv == 0.0 || !isfinite(piv)) bad = 1;
+                    acc = acc/piv;
+                }
+                S[h.x] = acc;
             }
-            rp += nsteps*LU_LANES;
-            if (h.y != LU_NONE_W) {
-                const double piv = S[h.y];
-                if (piv == 0.0 || !isfinite(piv)) bad = 1;
-                acc = acc/piv;
-            }
-            S[h.x] = acc;
+            __syncthreads();
         }
-        __syncwarp();
         double *y = Sv.ysol + (size_t)t*Sv.npad;
         const double *Sy = S + Sv.nlu;
-        for (int k = lane; k < n; k += 32) y[k] = Sy[k];
-        bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) Sv.lu_bad[t] = bad;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) y[k] = Sy[k];
+        if (bad) s_bad = 1;
+        __syncthreads();
+        if (threadIdx.x == 0) Sv.lu_bad[t] = s_bad;
     }
 }
 
@@ -302,6 +331,25 @@ k_lu_wide(SolveView Sv, int n)
 // k_finish: CTA = one group of 32 adjacent trials, all n unknowns
 // ---------------------------------------------------------------------------------------
 #define FIN_WARPS 8
+#define FIN_KCHUNK 1024         // unknowns per CTA of the chunked variant (large systems)
+// what a trial's solve leaves for the control kernel
+__device__ __forceinline__ void finish_trial(const HotView &hot, int t, int fl)
+{
+    const int err = (fl & 1) ? B200_E_SINGULAR : ((fl & 2) ? B200_E_MATHOVF : 0);
+    const int fail = (fl & 4) ? 1 : 0;
+    const int mode = hot.mode[t];
+    hot.solve_err[t] = err;
+    hot.nodeconv[t] = fail;
+    hot.devconv[t] = 0;
+    const int it1 = hot.iterno[t] + 1;
+    hot.need_devconv[t] = (!err && !fail && (mode & (MODEINITFIX | MODEINITFLOAT)) &&
+        hot.noncon[t] == 0 && it1 != 1) ? 1 : 0;
+}
+
+// CHUNKED = false: one CTA walks all n unknowns of its 32 trials and finishes them.
+// CHUNKED = true (n beyond a few thousand): grid.y CTAs share the unknowns, FIN_KCHUNK each, and
+// leave their flags in Sv.fin_flags; k_finish_tail closes the trials.
+template <bool CHUNKED>
 __global__ void __launch_bounds__(FIN_WARPS*32)
 k_finish(Consts K, HotView hot, SolveView Sv, const double * __restrict__ Xold, double * __restrict__ Xnew)
 {
@@ -319,7 +367,9 @@ k_finish(Consts K, HotView hot, SolveView Sv, const double * __restrict__ Xold, 
     const size_t ldt = (size_t)K.ldt;
     int fl = 0;
     int buf = 0;
-    for (int k0 = 0; k0 < n; k0 += 32, buf ^= 1) {
+    const int kbeg = CHUNKED ? blockIdx.y*FIN_KCHUNK : 0;
+    const int kend = CHUNKED ? min(n, kbeg + FIN_KCHUNK) : n;
+    for (int k0 = kbeg; k0 < kend; k0 += 32, buf ^= 1) {
         // rows of ysol: trial tr, unknowns k0 .. k0+31 (one 256-B line)
         for (int tr = warp; tr < 32; tr += FIN_WARPS) {
             double v = 0.0;
@@ -345,18 +395,26 @@ k_finish(Consts K, HotView hot, SolveView Sv, const double * __restrict__ Xold, 
     if (fl) atomicOr(&s_flags[lane], fl);
     __syncthreads();
     if (warp == 0 && live) {
-        fl = s_flags[lane] | (Sv.lu_bad[t] ? 1 : 0);
-        Xnew[t] = 0.0;                                   // ground slot
-        const int err = (fl & 1) ? B200_E_SINGULAR : ((fl & 2) ? B200_E_MATHOVF : 0);
-        const int fail = (fl & 4) ? 1 : 0;
-        const int mode = hot.mode[t];
-        hot.solve_err[t] = err;
-        hot.nodeconv[t] = fail;
-        hot.devconv[t] = 0;
-        const int it1 = hot.iterno[t] + 1;
-        hot.need_devconv[t] = (!err && !fail && (mode & (MODEINITFIX | MODEINITFLOAT)) &&
-            hot.noncon[t] == 0 && it1 != 1) ? 1 : 0;
+        if (CHUNKED) {
+            if (s_flags[lane]) atomicOr(&Sv.fin_flags[t], s_flags[lane]);
+        }
+        else {
+            fl = s_flags[lane] | (Sv.lu_bad[t] ? 1 : 0);
+            Xnew[t] = 0.0;                               // ground slot
+            finish_trial(hot, t, fl);
+        }
     }
+}
+
+__global__ void k_finish_tail(Consts K, HotView hot, SolveView Sv, double * __restrict__ Xnew)
+{
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= K.ntrials || !hot.do_solve[t]) return;
+    if (!(Sv.cls < 0 || ((hot.mode[t] & MODEDC) != 0) == (Sv.cls != 0))) return;
+    const int fl = Sv.fin_flags[t] | (Sv.lu_bad[t] ? 1 : 0);
+    Sv.fin_flags[t] = 0;
+    Xnew[t] = 0.0;                                       // ground slot
+    finish_trial(hot, t, fl);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -371,11 +429,15 @@ int solve_configure(SolveView &Sv)
     if (Sv.ntiles != (Sv.img + ASM_TS - 1)/ASM_TS) return B200_E_PANIC;     // b200_internal.h ASM_TILE_SLOTS
     if (Sv.wide) {
         // image in global memory: no window to size; as many warps per SM as the registers allow
+        // warps per trial: what an average level can keep busy
+        int w = Sv.nlevels > 0 ? (Sv.nrounds + Sv.nlevels - 1)/Sv.nlevels : 1;
+        if (const char *e = getenv("B200_LUW_WARPS")) w = atoi(e);      // measurement override
+        w = w >= 24 ? 32 : w >= 12 ? 16 : w >= 6 ? 8 : 4;
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_wide, LUW_WARPS*32, 0) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lu_wide, w*32, 0) != cudaSuccess || per_sm < 1)
             return B200_E_NOGPU;
         Sv.prog_in_smem = 0;
-        Sv.lu_warps = LUW_WARPS;
+        Sv.lu_warps = w;
         Sv.lu_smem = 0;
         Sv.lu_grid = nsm*per_sm;
         return B200_OK;
@@ -414,10 +476,17 @@ int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const Vec
     if (cudaMemsetAsync(Sv.ctr, 0, 2*sizeof(int), st) != cudaSuccess) return B200_E_NOGPU;
     const int ngroups = K.ldt/32;
     dim3 ga(ngroups, (Sv.ntiles + ASM_WARPS - 1)/ASM_WARPS);
+    if (Sv.nlong)
+        k_assemble_long<<<dim3(ngroups, (Sv.nlong + ASM_WARPS - 1)/ASM_WARPS), ASM_WARPS*32, 0, st>>>(K, hot, V, Sv);
     k_assemble<<<ga, ASM_WARPS*32, 0, st>>>(K, hot, V, Sv);
-    if (Sv.wide) k_lu_wide<<<Sv.lu_grid, LUW_WARPS*32, 0, st>>>(Sv, K.n);
+    if (Sv.wide) k_lu_wide<<<Sv.lu_grid, Sv.lu_warps*32, 0, st>>>(Sv, K.n);
     else if (Sv.prog_in_smem) k_lu<true><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
     else k_lu<false><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
-    k_finish<<<ngroups, FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew);
+    if (K.n > 4*FIN_KCHUNK) {
+        k_finish<true><<<dim3(ngroups, (K.n + FIN_KCHUNK - 1)/FIN_KCHUNK), FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew);
+        k_finish_tail<<<(K.ntrials + 127)/128, 128, 0, st>>>(K, hot, Sv, Xnew);
+    }
+    else
+        k_finish<false><<<ngroups, FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew);
     return 0;
 }
