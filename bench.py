@@ -211,35 +211,43 @@ def bench_rsfq(local, ntrials=2048, njj=1000, tjm=None):
     return out
 
 
-def bench_large_flat(local, nstages=50001, ntrials=16, nref=4):
+def bench_large_flat(local, ntrials=16, time_reference=False):
     """Secondary workload (BASELINE.json configs[3]): a large flat CMOS netlist -- a ring
-    oscillator of `nstages` stages, 2*nstages level-1 MOSFETs, nstages+2 unknowns -- run as a
-    single transient and as a small Monte-Carlo batch.  The LU image (400 k doubles per trial)
-    is far beyond one warp's shared-memory window: this runs the wide task program (k_lu_wide,
-    image in L2 / HBM).  The reference runs the first `nref` trials meanwhile on host cores
-    (one trial per core): identical counts, waveforms within tolerance, and its time per trial."""
+    oscillator of 50001 stages, 100 002 level-1 MOSFETs, 50 003 unknowns -- run as a single
+    transient and as a small Monte-Carlo batch.  The LU image (400 k doubles per trial) is far
+    beyond one warp's shared-memory window: this runs the wide task program (k_lu_wide: one CTA
+    per trial, image in L2 / HBM).  Parity: the first trials against tests/golden/
+    large_ro50001.json, which tests/golden/make_large_golden.py wrote from the unmodified
+    reference (2 - 10 minutes of CPU per trial, so it is not re-run inside the default bench;
+    `--large-ref` times trial 0 on this box's host)."""
+    import json as _json
     import numpy as np
     from xictools_b200 import engine
     from xictools_b200.deck import ring_oscillator, C_STATUS, C_NUMITER
+    with open(os.path.join(ROOT, "tests", "golden", "large_ro50001.json")) as f:
+        gold = _json.load(f)
+    nstages = gold["nstages"]
+    assert ntrials == gold["ntrials"]
+    want = gold["signals"]
     deck = ring_oscillator(nstages)
     deck.tran(0.02e-9, 2e-9)
     ov = make_variation(deck, ntrials)
-    want = ["n0", f"n{nstages//2}", "vdd#branch"]
-    nref = min(nref, ntrials, host_cores())
-    texts = [deck.to_spice({k: v[t] for k, v in ov.items()}) for t in range(nref)]
-    ctx = mp.get_context("fork")
-    pool = ctx.Pool(nref)
-    t_ref0 = time.perf_counter()
-    pending = [pool.apply_async(_ref_worker, (([txt], want),)) for txt in texts]
     out = {"workload": f"large_flat: {nstages}-stage CMOS ring oscillator, {2*nstages} MOSFETs (level 1) + {nstages} C, "
                        f".tran 0.02n 2n; single transient and a {ntrials}-trial Monte Carlo (vto / L as the headline workload)"}
+    pool = pending = None
+    if time_reference:
+        pool = mp.get_context("fork").Pool(1)
+        t_ref0 = time.perf_counter()
+        pending = pool.apply_async(_ref_worker, (([deck.to_spice({k: v[0] for k, v in ov.items()})], want),))
     try:
         b1 = engine.Batch(deck, 1, device=local)
         b1.run_tran()
         s1 = b1.stats()
         c1 = b1.counters()
         out["single"] = {"seconds": s1.ms_total*1e-3, "ok": int(c1[0, C_STATUS] == 0), "newton_iters": int(c1[0, C_NUMITER]),
-                         "ms_per_newton_iter": s1.ms_total/max(1, int(c1[0, C_NUMITER])), "unknowns": b1.n}
+                         "ms_per_newton_iter": s1.ms_total/max(1, int(c1[0, C_NUMITER])), "unknowns": b1.n,
+                         "load_ms_per_tick": s1.ms_load/max(s1.load_launches, 1),
+                         "solve_ms_per_tick": s1.ms_solve/max(s1.solve_launches, 1)}
         b1.close()
         b = engine.Batch(deck, ntrials, device=local)
         b.set_params(ov)
@@ -255,15 +263,26 @@ def bench_large_flat(local, nstages=50001, ntrials=16, nref=4):
                     "solve_ms_per_tick": st.ms_solve/max(st.solve_launches, 1),
                     "device_load_instances_per_s": (3*nstages + 1)*float(cnt[:, C_NUMITER].sum())/(st.ms_total*1e-3)})
         b.close()
-        flat = [r.get(timeout=900)[0] for r in pending]
-        el = time.perf_counter() - t_ref0
-        out["cpu_baseline"] = {"value": nref/el, "unit": "trials/s", "cores": nref, "kind": "reference",
-                               "sample": f"trials 0..{nref-1}, one per core, in {el:.1f} s (oracle/_ref, Sparse 1.3)"}
+        flat = []
+        for r in gold["trials"]:
+            c = r["counters"]
+            flat.append((c["err"], c["accepted"], c["rejected"], c["numiter"], 0, 0, 0, c["timepts"], np.array(r["vals"])))
         out["parity"] = compare_with_reference(flat, cnt, w, current_last=True, saved=want)
+        out["parity"]["vs"] = "tests/golden/large_ro50001.json (written by the unmodified reference, oracle/_ref)"
+        secs = [r["seconds"] for r in gold["trials"]]
+        out["cpu_baseline"] = {"value": len(secs)/max(secs), "unit": "trials/s", "cores": len(secs), "kind": "reference",
+                               "sample": f"RECORDED when the fixture was written (build container, one trial per core): "
+                                         f"{min(secs):.0f}-{max(secs):.0f} s per trial"}
+        if pending is not None:
+            pending.get(timeout=3000)
+            el = time.perf_counter() - t_ref0
+            out["cpu_baseline"] = {"value": 1.0/el, "unit": "trials/s", "cores": 1, "kind": "reference",
+                                   "sample": f"trial 0 on this host in {el:.1f} s (oracle/_ref, Sparse 1.3)"}
     except Exception as e:          # pragma: no cover
         out["error"] = repr(e)
     finally:
-        pool.terminate()
+        if pool is not None:
+            pool.terminate()
     return out
 
 
@@ -646,7 +665,7 @@ def bench_ours(args):
             except Exception as e:          # pragma: no cover
                 line["secondary"]["dc_sweep"] = {"error": repr(e)}
             try:
-                line["secondary"]["large_flat"] = bench_large_flat(local)
+                line["secondary"]["large_flat"] = bench_large_flat(local, time_reference=args.large_ref)
             except Exception as e:          # pragma: no cover
                 line["secondary"]["large_flat"] = {"error": repr(e)}
         emit(line)
@@ -682,6 +701,8 @@ def main():
     ap.add_argument("--trials", type=int, default=TRIALS_PER_GPU)
     ap.add_argument("--stages", type=int, default=NSTAGES)
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (RSFQ) workload")
+    ap.add_argument("--large-ref", action="store_true",
+                    help="large_flat: also time the reference's trial 0 on this host (minutes)")
     ap.add_argument("--kernel-only", action="store_true",
                     help="profiling aid (ncu): device-resident steps only, no e2e / CPU legs, no JSON contract")
     args = ap.parse_args()

@@ -50,6 +50,20 @@ def rc_fn(**fn):
     return d
 
 
+def float_cap():
+    """A node that only capacitors reach: the DC matrix is singular whatever the pivot order.
+    The reference ends with E_SINGULAR after trying dynamic gmin and source stepping
+    (niiter.cc:303-331 reorder + retry, ckt.cc:1492-1776): 25 Newton iterations, no time point."""
+    d = Deck(title="floating node")
+    d.vsource("v1", "a", "0", dc=0.0, pulse=(0, 1.0, 0.1e-9, 0.05e-9, 0.05e-9, 1e-9, 3e-9))
+    d.resistor("r1", "a", "b", 1e3)
+    d.capacitor("c1", "b", "0", 1e-12)
+    d.capacitor("c2", "b", "f", 1e-12)
+    d.capacitor("c3", "f", "0", 2e-12)
+    d.tran(0.05e-9, 3e-9)
+    return d
+
+
 def rlc_series():
     """Series RLC driven by a pulse: inductor branch equation, flux LTE, underdamped ringing."""
     d = Deck(title="series rlc")
@@ -283,6 +297,7 @@ def variants():
         "rc_exp_defaults": rc_fn(exp=(0.2, 1.0)),
         "rc_sffm": rc_fn(sffm=(0.5, 0.4, 1.0e9, 2.0, 0.2e9)),
         "rc_am": rc_fn(am=(0.8, 1.0, 0.3e9, 2.0e9, 0.4e-9)),
+        "float_cap": float_cap(),
         # GPULSE (inptran.cc:1567-1827): FWHM width + two more pulse delays; repeating; old-style width
         "rc_gpulse": rc_fn(gpulse=(0.1, 1.0, 1.0e-9, 0.3e-9, 0, 2.2e-9, 3.1e-9)),
         "rc_gpulse_rpt": rc_fn(gpulse=(0.0, 0.8, 0.6e-9, -0.12e-9, 1.1e-9)),

@@ -67,6 +67,8 @@ def test_oracle_reproduces_reference_fixture(name):
     o = Oracle(d, ov, t).run(an)
     assert {k: int(o[k]) for k in KEYS} == g["counters"]
     np.testing.assert_allclose(o["times"], g["times"], rtol=0, atol=1e-18)
+    if not len(g["times"]):
+        return                                  # a run that fails before its first output point
     idx = [o["names"].index(nm) for nm in g["names"]]
     assert np.abs(o["vals"][:, idx] - g["vals"]).max() < LOOSE.get(name, 1e-9)
 
@@ -101,6 +103,8 @@ def test_engine_reproduces_reference_fixture(name):
         assert got[:2] == want[:2] and got[3:] == want[3:] and abs(got[2] - want[2]) <= 2, (got, want)
     else:
         assert got == want
+    if not len(g["times"]):
+        return
     idx = [names.index(nm) for nm in g["names"]]
     v = w[t, :len(g["times"])][:, idx]
     scale = 50.0 if name in ("ro5_ord1", "inv_lsupply") else 1.0

@@ -203,6 +203,7 @@ struct SrcTopo {
 // order, same arithmetic; k_lu_wide (solve.cu) interprets it.
 #define LU_NONE_W 0xffffffffu
 #define LU_SMEM_BUDGET 229000                    // bytes of the 227 KB window left to image + round table
+#define LU_MIN_RESIDENT 4                        // images that must fit the window for the narrow path
 // Assembly run of one image slot: S[slot] = finalize( sum of contrib[pos .. pos+len) in order )
 struct AsmRun { int pos, len, info, pad; };
 #define ASM_TILE_SLOTS 16                        // slots per k_assemble warp tile

@@ -133,6 +133,8 @@ __device__ inline void ctl_ni_start(TrialCtl &s, int maxIter, int ret)
     s.ret = ret;
     s.pc = PC_NIITER;
     s.want_load = 1;
+    if (s.mode & (MODEINITJCT | MODEINITTRAN))
+        s.ni_reorder = 1;               // niiter.cc:181
 }
 
 // ---- NIiter after the solve: niiter.cc:353-540.  Returns NI_PENDING or the NIiter result ----
@@ -140,6 +142,21 @@ __device__ inline int ctl_ni_post_solve(TrialCtl &s, const Consts &K, const CtlI
 {
     s.iterno++;
     int error = NI_PENDING;
+    // niiter.cc:257-331.  The pivot sequence is frozen here, so "order and factor" and "factor"
+    // are the same numeric pass; what remains of NISHOULDREORDER is its effect on the iteration
+    // count: a singular matrix met by a plain factor on the first iteration is loaded and
+    // factored once more (now "reordering") before NIiter gives up.
+    const bool reordering = s.ni_reorder != 0;
+    if (in.solve_err == B200_E_SINGULAR && !reordering) {
+        s.ni_reorder = 1;
+        if (s.iterno == 1) {
+            s.want_load = 1;            // load() again from the same rhsOld, then `continue`
+            s.vecops |= VO_KEEP_X;
+            return NI_PENDING;
+        }
+    }
+    if (!in.solve_err && reordering)
+        s.ni_reorder = 0;
     if (in.solve_err)
         error = in.solve_err;
     else if (s.iterno > s.maxIter)
@@ -162,12 +179,16 @@ __device__ inline int ctl_ni_post_solve(TrialCtl &s, const Consts &K, const CtlI
         }
         else if (s.mode & MODEINITPRED)
             s.mode = (s.mode & (~INITF)) | MODEINITFLOAT;
-        else if (s.mode & MODEINITTRAN)
+        else if (s.mode & MODEINITTRAN) {
+            if (s.iterno <= 1) s.ni_reorder = 1;
             s.mode = (s.mode & (~INITF)) | MODEINITFLOAT;
+        }
         else if (s.mode & MODEINITSMSIG)
             s.mode = (s.mode & (~INITF)) | MODEINITFLOAT;
-        else if (s.mode & MODEINITJCT)
+        else if (s.mode & MODEINITJCT) {
             s.mode = (s.mode & (~INITF)) | MODEINITFIX;
+            s.ni_reorder = 1;
+        }
         else if (s.mode & MODEINITFIX) {
             if (noncon == 0)
                 s.mode = (s.mode & (~INITF)) | MODEINITFLOAT;

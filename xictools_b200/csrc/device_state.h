@@ -64,6 +64,7 @@ struct TrialCtl {
     int niter_mark;
     double jj_dmax;                             // JJdev::accept's step bound for the accept being processed (0 = none)
     int did_accept;                             // ctl_tran_loop_top ran in this control pass
+    int ni_reorder;                             // CKTniState & NISHOULDREORDER (niiter.cc:181, 303-331, 501-509)
     int vecops;
     int have_save;
     int want_load;                              // a load must follow in this tick
