@@ -271,8 +271,9 @@ def bench_large_flat(local, ntrials=16, time_reference=False):
         out["parity"]["vs"] = "tests/golden/large_ro50001.json (written by the unmodified reference, oracle/_ref)"
         secs = [r["seconds"] for r in gold["trials"]]
         out["cpu_baseline"] = {"value": len(secs)/max(secs), "unit": "trials/s", "cores": len(secs), "kind": "reference",
-                               "sample": f"RECORDED when the fixture was written (build container, one trial per core): "
-                                         f"{min(secs):.0f}-{max(secs):.0f} s per trial"}
+                               "sample": f"RECORDED when the fixture was written (build container, 4 trials side by side, one per core): "
+                                         f"{min(secs):.0f}-{max(secs):.0f} s per trial with the per-device .model cards of the Monte Carlo; "
+                                         f"the nominal circuit with one shared model card alone: {gold.get('single_nominal_seconds', 0):.0f} s"}
         if pending is not None:
             pending.get(timeout=3000)
             el = time.perf_counter() - t_ref0

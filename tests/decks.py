@@ -341,6 +341,12 @@ def jj_variants():
         "jtl6_dc_vshunt": jtl(6, dc_bias=True, vshunt=0.6857e-3),
         "jtl12_dc": jtl(12, dc_bias=True),
         "jtl6_dc_tjm": jtl(6, dc_bias=True, tjm="tjm1"),
+        # option jjaccel (niiter.cc:456,535-539, tranan.cc:590,787-792): the junctions' own test ends
+        # the iteration, no LTE
+        "jtl6_accel": jtl(6).options(jjaccel=1),
+        "jtl6_dc_accel": jtl(6, dc_bias=True).options(jjaccel=1),
+        "jtl12_vshunt_accel": jtl(12, vshunt=0.6857e-3).options(jjaccel=1),
+        "jtl6_tjm_accel": jtl(6, tjm="tjm1").options(jjaccel=1),
         # driven by a single-flux-quantum GPULSE voltage source
         "jtl6_dc_sfq": jtl(6, dc_bias=True, sfq_in=True),
     }

@@ -25,6 +25,8 @@ def test_counts_and_waves_match_reference(name):
     assert {k: o[k] for k in KEYS} == {k: ref[k] for k in KEYS}
     assert len(o["times"]) == len(ref["times"])
     np.testing.assert_allclose(o["times"], ref["times"], rtol=0, atol=1e-18)
+    if not len(ref["times"]):
+        return                              # a run that fails before its first output point
     idx = [o["names"].index(nm) for nm in ref["names"]]
     dv = np.abs(o["vals"][:, idx] - ref["vals"]).max()
     assert dv < LOOSE.get(name, 1e-9), dv

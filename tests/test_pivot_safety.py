@@ -13,7 +13,10 @@ from tools.pivot_growth import engine_order, growth, MODETRAN, MODETRANOP, INITJ
 from oracle.pyoracle import Oracle
 
 
-@pytest.mark.parametrize("name", sorted(variants()))
+SINGULAR = {"float_cap"}        # singular on purpose: no order factors it
+
+
+@pytest.mark.parametrize("name", sorted(set(variants()) - SINGULAR))
 def test_static_orders_are_growth_free(name):
     d = variants()[name]
     n, Ap, Ai, rp, cp, rp2, cp2, npr = engine_order(d)

@@ -300,9 +300,9 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
         fprintf(stderr, "b200spice: no CUDA device (no CPU fallback exists)\n");
         return B200_E_NOGPU;
     }
-    if (deck->opt.dcmu != 0.5 || deck->opt.jjaccel || deck->opt.steptype != 0 ||
+    if (deck->opt.dcmu != 0.5 || deck->opt.steptype != 0 ||
             deck->opt.gminsteps > 0 || deck->opt.srcsteps > 0) {
-        fprintf(stderr, "b200spice: option not built yet (dcmu/jjaccel/steptype/spice3 stepping)\n");
+        fprintf(stderr, "b200spice: option not built yet (dcmu/steptype/spice3 stepping)\n");
         return B200_E_UNSUPP;
     }
     CK(cudaSetDevice(device));
@@ -348,6 +348,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     h.deltaOld = b->dalloc<double>(7*ldt);
     h.nodeconv = b->dalloc<int>(ldt); h.solve_err = b->dalloc<int>(ldt);
     h.need_devconv = b->dalloc<int>(ldt); h.devconv = b->dalloc<int>(ldt);
+    h.accel_exit = b->dalloc<int>(ldt);
     h.lte = b->dalloc<double>(2*ldt); h.sync = b->dalloc<int>(ldt);
     h.lte_rcp = b->dalloc<double>((size_t)LR_NROWS*ldt);
     // ---- vectors ----
@@ -446,6 +447,7 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     Rv.n = (int)an.rph_res.size();
     if (Rv.n) { Rv.cslot = b->dupload(an.rph_cslot); Rv.cls = b->dupload(an.rph_cls); Rv.g = b->dupload(an.rph_g); }
     K.jjDCphase = an.jjDCphase;
+    K.jjaccel = (deck->opt.jjaccel && (an.jj.n + an.tjm.n) > 0) ? 1 : 0;
     V.phase = an.jjDCphase ? b->dupload(an.phase_mask) : nullptr;
     K.initDelta = an.initDelta;
     h.jj_vmax = b->dalloc<double>((size_t)std::max(jt.nmodels + tt.nmodels, 1)*ldt);
@@ -993,6 +995,7 @@ static int run_analysis(b200_batch *b, int analysis)
     while (active > 0 && ticks < max_ticks) {
         for (int w = 0; w < WIN; w++) {
             CK(cudaEventRecord(E.ev[w][0], st));
+            if (K.jjaccel) { launch_jjaccel_gate(st, K, b->hot); launches++; }
             rc = launch_solve(st, K, b->hot, b->V, b->Sv, b->V.X[b->cur], b->V.X[b->cur ^ 1]);
             if (!rc && b->two_programs)
                 rc = launch_solve(st, K, b->hot, b->V, b->Sv2, b->V.X[b->cur], b->V.X[b->cur ^ 1]);

@@ -16,7 +16,7 @@
 #include "dev_load.cuh"
 
 struct CtlIn {              // what the kernels of this tick produced for this trial
-    int solve_err, nodeconv, devconv, noncon_load, trapbad;
+    int solve_err, nodeconv, devconv, noncon_load, trapbad, accel_exit;
     double lte0, lte1;
 };
 
@@ -140,6 +140,14 @@ __device__ inline void ctl_ni_start(TrialCtl &s, int maxIter, int ret)
 // ---- NIiter after the solve: niiter.cc:353-540.  Returns NI_PENDING or the NIiter result ----
 __device__ inline int ctl_ni_post_solve(TrialCtl &s, const Consts &K, const CtlIn &in)
 {
+    if (in.accel_exit) {
+        // niiter.cc:535-539: left the loop after the load; rhsOld is the last solution
+        s.vecops |= VO_KEEP_X;
+        s.numIter += s.iterno;
+        if (!(s.mode & MODEDC) && (s.mode & MODETRAN))
+            s.tranIter += s.iterno;
+        return 0;
+    }
     s.iterno++;
     int error = NI_PENDING;
     // niiter.cc:257-331.  The pivot sequence is frozen here, so "order and factor" and "factor"
@@ -163,7 +171,8 @@ __device__ inline int ctl_ni_post_solve(TrialCtl &s, const Consts &K, const CtlI
         error = B200_E_ITERLIM;
     else {
         int noncon = in.noncon_load;
-        if (s.mode & (MODEINITFIX | MODEINITFLOAT)) {
+        // with jjaccel the transient relies on the devices' own convergence tests (niiter.cc:456)
+        if ((!K.jjaccel || (s.mode & MODEDC)) && (s.mode & (MODEINITFIX | MODEINITFLOAT))) {
             if (noncon == 0 && s.iterno != 1)
                 noncon = (in.nodeconv || in.devconv) ? 1 : 0;
             else
@@ -576,7 +585,7 @@ __device__ inline void ctl_tran_loop_top(TrialCtl &s, const Consts &K, const Ctl
             s.t_ordcnt = K.opt.spice3 ? 0 : 1;
             double ttmp = s.breaks[1] - s.breaks[0];
             if (s.saveDelta < ttmp) ttmp = s.saveDelta;
-            if (!K.nocut && !K.opt.jjaccel) ttmp *= 0.1;
+            if (!K.nocut && !K.jjaccel) ttmp *= 0.1;
             double td1 = 0.1*s.saveDelta;
             if (ttmp < td1) ttmp = td1;
             if (ttmp < s.delta) s.delta = ttmp;
@@ -636,6 +645,13 @@ __device__ inline void ctl_tran_step_ret(TrialCtl &s, const Consts &K, const Ctl
     }
     if (s.t_firsttime) {
         s.t_firsttime = 0;
+        ctl_sync_point(s);
+        return;
+    }
+    if (K.jjaccel) {
+        // tranan.cc:787-792: no LTE; the junctions' phase-change bound is the step
+        s.delta = s.devMaxDelta;
+        if (s.order < K.opt.maxord) s.order++;
         ctl_sync_point(s);
         return;
     }

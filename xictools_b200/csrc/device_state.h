@@ -97,6 +97,7 @@ struct HotView {
     // Josephson junctions: max |vj| over the junctions of a model in the trial's latest load
     // (what JJdev::accept scans state 0 for, jjacct.cc:120-133); zeroed when a load is published
     double *jj_vmax;    // [nmodels][ldt]   (RSJ models first, then the TJM models)
+    int    *accel_exit; // jjaccel: the load of the previous tick converged by the devices' own test, no solve (niiter.cc:535-539)
     int    *accepted;   // 1: the load published in this tick directly follows an accepted time point
                         //    (the device-side half of XXXdev::accept runs inside that load)
 };
@@ -111,6 +112,7 @@ struct Consts {
     int nbrks, nlat;
     // Josephson junctions: CKTinitDelta (jjic.cc:78-104) and the per-model accept constants
     double initDelta;
+    int jjaccel;        // sCKT::jjaccel(): option jjaccel and a junction in the deck (circuit.h:2119)
     int jjDCphase;      // CKTjjDCphase: the DC modes compute phase on the nodes of junctions and inductors
     int njjmod; int jj_limits[JJ_MAXMODELS];    // model has a supercurrent (ictype != 0)
     double jj_vth[JJ_MAXMODELS], jj_tsfact[JJ_MAXMODELS];

@@ -558,6 +558,8 @@ __global__ void k_ctl(Consts K, HotView hot, TrialCtl *ctl, CtlShared sh, CtlAux
         s.want_load = 0;
         CtlIn in;
         in.solve_err = hot.do_solve[t] ? hot.solve_err[t] : 0;
+        in.accel_exit = 0;
+        if (K.jjaccel) { in.accel_exit = hot.accel_exit[t]; hot.accel_exit[t] = 0; }
         in.nodeconv = hot.nodeconv[t];
         in.devconv = hot.devconv[t];
         in.noncon_load = hot.noncon[t];
@@ -764,6 +766,19 @@ k_statevec(Consts K, VecView V, CtlAux aux, MosView M)
             sp[2][at] = v;
             if (K.opt.maxord > 1) sp[3][at] = v;
         }
+    }
+}
+
+// jjaccel (niiter.cc:535-539): a transient FLOAT load in which no device flagged non-convergence
+// ends NIiter there and then -- its matrix is never solved.  Runs between the load and the solve.
+__global__ void k_jjaccel_gate(Consts K, HotView hot)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= K.ntrials || !hot.do_solve[t]) return;
+    const int mode = hot.mode[t];
+    if (hot.noncon[t] == 0 && (mode & MODEINITFLOAT) && !(mode & (MODEDCOP | MODETRANOP | MODEINITTRAN))) {
+        hot.do_solve[t] = 0;
+        hot.accel_exit[t] = 1;
     }
 }
 
@@ -1431,6 +1446,11 @@ void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard
 {
     if (n) k_mos_temp<<<grid2(ntrials, n), 128, 0, st>>>(n, ntrials, ldt, cards, raw, out);
 }
+void launch_jjaccel_gate(cudaStream_t st, const Consts &K, const HotView &hot)
+{
+    k_jjaccel_gate<<<(K.ntrials + 127)/128, 128, 0, st>>>(K, hot);
+}
+
 void launch_ctl(cudaStream_t st, const Consts &K, const HotView &hot, TrialCtl *ctl,
     const CtlShared &sh, const CtlAux &aux, int phase)
 {

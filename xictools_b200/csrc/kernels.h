@@ -51,6 +51,7 @@ struct SolveView {
     int nlevels;
 };
 
+void launch_jjaccel_gate(cudaStream_t st, const Consts &K, const HotView &hot);
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,
     const RawParams &raw, const MosParamsOut &out);
 struct JJTempIn {
