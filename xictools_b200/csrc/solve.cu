@@ -14,6 +14,7 @@
 //               Persistent CTAs; warps take trials from a work counter over the live list.
 //   k_finish    unpermute (ysol[trial][k] -> X[node][trial], transposed through shared
 //               memory) + the node part of NIconvTest (niconv.cc:58-91) + per-trial flags.
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdio.h>
@@ -331,7 +332,6 @@ k_lu_wide(SolveView Sv, int n)
 // k_finish: CTA = one group of 32 adjacent trials, all n unknowns
 // ---------------------------------------------------------------------------------------
 #define FIN_WARPS 8
-#define FIN_KCHUNK 1024         // unknowns per CTA of the chunked variant (large systems)
 // what a trial's solve leaves for the control kernel
 __device__ __forceinline__ void finish_trial(const HotView &hot, int t, int fl)
 {
@@ -347,11 +347,12 @@ __device__ __forceinline__ void finish_trial(const HotView &hot, int t, int fl)
 }
 
 // CHUNKED = false: one CTA walks all n unknowns of its 32 trials and finishes them.
-// CHUNKED = true (n beyond a few thousand): grid.y CTAs share the unknowns, FIN_KCHUNK each, and
-// leave their flags in Sv.fin_flags; k_finish_tail closes the trials.
+// CHUNKED = true (few trial groups, or many unknowns: the 32-trial groups alone would not fill
+// the GPU): grid.y CTAs share the unknowns, kchunk each, and leave their flags in Sv.fin_flags;
+// k_finish_tail closes the trials.
 template <bool CHUNKED>
 __global__ void __launch_bounds__(FIN_WARPS*32)
-k_finish(Consts K, HotView hot, SolveView Sv, const double * __restrict__ Xold, double * __restrict__ Xnew)
+k_finish(Consts K, HotView hot, SolveView Sv, const double * __restrict__ Xold, double * __restrict__ Xnew, int kchunk)
 {
     __shared__ double tile[2][32][33];
     __shared__ int s_flags[32];
@@ -367,8 +368,8 @@ k_finish(Consts K, HotView hot, SolveView Sv, const double * __restrict__ Xold, 
     const size_t ldt = (size_t)K.ldt;
     int fl = 0;
     int buf = 0;
-    const int kbeg = CHUNKED ? blockIdx.y*FIN_KCHUNK : 0;
-    const int kend = CHUNKED ? min(n, kbeg + FIN_KCHUNK) : n;
+    const int kbeg = CHUNKED ? blockIdx.y*kchunk : 0;
+    const int kend = CHUNKED ? min(n, kbeg + kchunk) : n;
     for (int k0 = kbeg; k0 < kend; k0 += 32, buf ^= 1) {
         // rows of ysol: trial tr, unknowns k0 .. k0+31 (one 256-B line)
         for (int tr = warp; tr < 32; tr += FIN_WARPS) {
@@ -427,6 +428,7 @@ int solve_configure(SolveView &Sv)
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (Sv.ntiles != (Sv.img + ASM_TS - 1)/ASM_TS) return B200_E_PANIC;     // b200_internal.h ASM_TILE_SLOTS
+    Sv.nsm = nsm;
     if (Sv.wide) {
         // image in global memory: no window to size; as many warps per SM as the registers allow
         // warps per trial: what an average level can keep busy
@@ -482,11 +484,15 @@ int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const Vec
     if (Sv.wide) k_lu_wide<<<Sv.lu_grid, Sv.lu_warps*32, 0, st>>>(Sv, K.n);
     else if (Sv.prog_in_smem) k_lu<true><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
     else k_lu<false><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
-    if (K.n > 4*FIN_KCHUNK) {
-        k_finish<true><<<dim3(ngroups, (K.n + FIN_KCHUNK - 1)/FIN_KCHUNK), FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew);
+    // share the unknowns among CTAs when the trial groups alone leave SMs idle: aim at ~4 CTAs per SM
+    int nchunk = (4*Sv.nsm + ngroups - 1)/ngroups;
+    nchunk = std::min(nchunk, (K.n + 63)/64);
+    if (nchunk > 2) {                                    // (2 would trade a half-empty GPU for an extra launch)
+        const int kchunk = (((K.n + nchunk - 1)/nchunk) + 31) & ~31;
+        k_finish<true><<<dim3(ngroups, (K.n + kchunk - 1)/kchunk), FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew, kchunk);
         k_finish_tail<<<(K.ntrials + 127)/128, 128, 0, st>>>(K, hot, Sv, Xnew);
     }
     else
-        k_finish<false><<<ngroups, FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew);
+        k_finish<false><<<ngroups, FIN_WARPS*32, 0, st>>>(K, hot, Sv, Xold, Xnew, 0);
     return 0;
 }
