@@ -1316,7 +1316,9 @@ int b200_build_lu(Analysis &an)
         // resident image, and below that it leaves the SM idle -- measured: the 1 000-junction
         // line (96 KB image, 2 resident) runs 1.7x faster through k_lu_wide, RO-501 (32 KB, 5-7
         // resident) 10 % slower.
-        an.wide = (an.img > 0xfff0 || (size_t)an.img*8*LU_MIN_RESIDENT + rnd > LU_SMEM_BUDGET) ? 1 : 0;
+        int min_resident = LU_MIN_RESIDENT;
+        if (const char *e = getenv("B200_LU_MIN_RESIDENT")) min_resident = atoi(e);   // measurement override
+        an.wide = (an.img > 0xfff0 || (size_t)an.img*8*min_resident + rnd > LU_SMEM_BUDGET) ? 1 : 0;
         if (const char *e = getenv("B200_LU_WIDE")) an.wide = (*e && *e != '0') ? 1 : (an.img > 0xfff0 || (size_t)an.img*8 + rnd > LU_SMEM_BUDGET);    // measurement / test override
         size_t row = 0;
         if (an.wide) an.prog_rows.resize(prows.size()*2);
