@@ -65,7 +65,12 @@ enum { MT_Dd, MT_Gg, MT_Ss, MT_Bb, MT_Ddp, MT_Gb, MT_Gdp, MT_Gsp, MT_Ssp, MT_Bg,
 enum { MRH_g, MRH_b, MRH_dp, MRH_sp, MRH_NRHS };
 
 // ---- shared-memory staging of the MOS load kernel (rows of MOS_TPB doubles) ----
-#define MOS_TPB 64
+#ifndef MOS_TPB
+#define MOS_TPB 64                               // trials per CTA of k_load_mos
+#endif
+#ifndef MOS_MINB
+#define MOS_MINB 6                               // its resident CTAs per SM (__launch_bounds__)
+#endif
 enum { SR_V_B, SR_V_SP, SR_V_G, SR_V_DP,                // node voltages (rhsOld); the predictor's
        SR_S2_vbs = SR_V_B, SR_S2_vgs = SR_V_SP, SR_S2_vds = SR_V_G,   // state-2 voltages share the rows
        SR_S0 = 4,                                       // state 0 block (old values in, new values out)

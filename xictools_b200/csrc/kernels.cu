@@ -1461,8 +1461,8 @@ int loads_configure(const MosView &M)
     // per device: called from prepare_params with the batch's device current
     if (!M.n) return 0;
     int smem = (int)((size_t)M.stage_doubles*sizeof(double));
-    if (cudaFuncSetAttribute(k_load_mos<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_load_mos<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_load_mos<MOS_MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_load_mos<MOS_MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return B200_E_NOMEM;
     return 0;
 }
@@ -1472,8 +1472,8 @@ void launch_loads(cudaStream_t st, const Consts &K, const HotView &hot, const Ve
     if (M.n) {
         size_t smem = (size_t)M.stage_doubles*sizeof(double);
         dim3 g = grid2(K.ntrials, M.n, MOS_TPB);
-        if (M.has_level6) k_load_mos<6, true><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
-        else k_load_mos<6, false><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        if (M.has_level6) k_load_mos<MOS_MINB, true><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
+        else k_load_mos<MOS_MINB, false><<<g, MOS_TPB, smem, st>>>(K, hot, V, M, rhsOld);
     }
     if (Cp.n) k_load_cap<<<grid2(K.ntrials, Cp.n), 128, 0, st>>>(K, hot, V, Cp, rhsOld);
     if (Cp.L.nmut) k_load_mut<<<grid2(K.ntrials, Cp.L.nmut), 128, 0, st>>>(K, hot, V, Cp.L);
