@@ -216,8 +216,9 @@ void b200_batch_destroy(b200_batch *b);
 /* values[ntrials] (host) replaces instance `index`'s parameter `param` for every trial.
  * B200_P_CAP_C is the card value (the instance multiplier m still applies, captemp.cc:98);
  * B200_P_SRC_DC makes the source's DC value "given" (it then wins over the source function in the
- * DC modes, srcload.cc:215-237); B200_P_RES_R is reserved: resistor conductances are constants of
- * the contribution stream and the call returns B200_E_UNSUPP.
+ * DC modes, srcload.cc:215-237); B200_P_RES_R is the card value of a resistor (conduct = m/r with
+ * the resmin clamp, restemp.cc:200-209): every trial re-sums its preloaded conductances on the
+ * device in the reference's accumulation order, resistors on phase nodes stamp their own value.
  * For B200_P_MOS_VTO/KP/GAMMA/LAMBDA/PHI the value is the instance's private model card value
  * (the reference MC decks give each varied device its own .model). */
 int  b200_batch_set_param(b200_batch *b, int param, int index, const double *values);

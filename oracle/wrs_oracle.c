@@ -100,7 +100,7 @@ typedef struct {
 } Mos;
 
 typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; int st; int icGiven; double capac, ic, geq, ceq, m; } Cap;
-typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct; int usePreload; } Res;
+typedef struct { int pos, neg; int pPP, pNN, pPN, pNP; double conduct, m; int usePreload; } Res;
 /* sINDinstancePOD (inddefs.h): linear inductor, no series resistance / poly / expression */
 typedef struct { int pos, neg, br; int pBB, pPB, pNB, pBN, pBP; int st; int icGiven;
     double induct, ic, req, veq, prevFlux; } Ind;
@@ -1170,6 +1170,7 @@ wo_ckt *wo_create(const b200_deck *dk)
             if (fabs(r) < c->opt.resmin)
                 r = (r < 0.0) ? -c->opt.resmin : c->opt.resmin;
             p->conduct = mm/(r*1.0);
+            p->m = mm;
             break; }
         case B200_DEV_SRC: {
             /* srcset.cc:64-273 */
@@ -1322,7 +1323,7 @@ int wo_set_param(wo_ckt *c, int param, int index, double value)
     case B200_P_RES_R: {
         double r = value;
         if (fabs(r) < c->opt.resmin) r = (r < 0.0) ? -c->opt.resmin : c->opt.resmin;
-        c->res[index].conduct = 1.0/(r*1.0);
+        c->res[index].conduct = c->res[index].m/(r*1.0);        /* restemp.cc:200-209 */
         break; }
     case B200_P_SRC_DC:     c->src[index].dc = value; c->src[index].dcGiven = 1; break;
     case B200_P_JJ_ICS:     c->jj[index].in.ics = value; break;

@@ -421,6 +421,22 @@ def test_large_line_runs_through_the_wide_program():
     compare(d, ntr, ov, trials=[0, 1])
 
 
+@pytest.mark.parametrize("name", ["rlc_series", "ro3_rd", "jtl6_dc", "jtl6", "inv_lsupply"])
+def test_monte_carlo_resistor_values(name):
+    """B200_P_RES_R: every trial re-sums its preloaded conductances on the device in the
+    reference's accumulation order (k_res_ainit) and, on phase nodes, stamps its own g."""
+    from xictools_b200.deck import DEV_RES, P_RES_R
+    d = variants()[name]
+    ntr = 9
+    rng = np.random.default_rng(22)
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_RES]):
+        v = np.full(ntr, e.params["r"])
+        v[1:] *= 1.0 + 0.1*rng.standard_normal(ntr - 1)
+        ov[(P_RES_R, i)] = v
+    compare(d, ntr, ov)
+
+
 def test_packed_rows_equal_single_rows():
     """b200_batch_set_params (one transfer + device scatter) against b200_batch_set_param row by
     row: bit-identical results; a single row given afterwards overrides its packed row."""

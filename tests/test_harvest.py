@@ -112,3 +112,27 @@ def test_monte_carlo_through_the_shim():
         s = sim.run(d.to_spice({k: v[t] for k, v in ov.items()}))
         return dict(s, vals=s["vals"])
     _check(r, ntr, ref_of_trial)
+
+
+@pytest.mark.gpu
+def test_resistor_monte_carlo_through_the_shim():
+    """Per-trial resistor values (B200_P_RES_R) addressed by the reference's instance names, on a
+    Josephson line biased through resistors (preloaded ones and ones loaded in place)."""
+    from xictools_b200.deck import DEV_RES, P_RES_R
+    d = variants()["jtl6_dc"]
+    ntr = 5
+    rng = np.random.default_rng(31)
+    res = d.kind_tables()[DEV_RES]
+    ov = {}
+    for i, e in enumerate(res):
+        v = np.full(ntr, e.params["r"])
+        v[1:] *= 1.0 + 0.1*rng.standard_normal(ntr - 1)
+        ov[(P_RES_R, i)] = v
+    params = [(pid, res[i].name, v) for (pid, i), v in ov.items()]
+    r = run_harvest(d.to_spice(), engine.LIB_PATH, ntr, params)
+    sim = RefSim()
+
+    def ref_of_trial(t):
+        s = sim.run(d.to_spice({k: v[t] for k, v in ov.items()}))
+        return dict(s, vals=s["vals"])
+    _check(r, ntr, ref_of_trial)

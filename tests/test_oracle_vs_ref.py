@@ -106,3 +106,29 @@ def test_dc_sweep_points_match_reference():
         assert (o["err"], o["numiter"]) == (ref["err"], ref["numiter"]), vin
         idx = [o["names"].index(nm) for nm in ref["names"]]
         assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < 1e-9
+
+
+def _res_variation(d, ntr, seed, sigma=0.1):
+    from xictools_b200.deck import DEV_RES, P_RES_R
+    rng = np.random.default_rng(seed)
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_RES]):
+        v = np.full(ntr, e.params["r"])
+        v[1:] *= 1.0 + sigma*rng.standard_normal(ntr - 1)
+        ov[(P_RES_R, i)] = v
+    return ov
+
+
+@pytest.mark.parametrize("name", ["rlc_series", "ro3_rd", "jtl6_dc", "jtl6"])
+def test_resistor_monte_carlo_trials_match_reference(name):
+    """Per-trial resistor values (B200_P_RES_R): preloaded conductances (restemp.cc:209-229) and,
+    on the phase nodes of a Josephson deck, resistors loaded in place (resload.cc:250-292)."""
+    d = variants()[name]
+    ntr = 3
+    ov = _res_variation(d, ntr, 21)
+    for t in range(ntr):
+        ref = RefSim().run(d.to_spice({k: v[t] for k, v in ov.items()}))
+        o = Oracle(d, ov, t).run()
+        assert {k: o[k] for k in KEYS} == {k: ref[k] for k in KEYS}
+        idx = [o["names"].index(nm) for nm in ref["names"]]
+        assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < LOOSE.get(name, 1e-9)

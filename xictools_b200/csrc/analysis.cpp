@@ -479,14 +479,28 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
         if (L.neg[i]) { if (c[2] >= 0) an.Ainit[coo2ax[c[2]]] = -1.0; if (c[3] >= 0) an.Ainit[coo2ax[c[3]]] = -1.0; }
     }
     // ... resistor conductances are ldadd in temp() (restemp.cc:218-229), load order
-    for (int oi = 0; oi < dk->norder; oi++) {
-        int i = dk->order_index[oi];
-        if (dk->order_kind[oi] == B200_DEV_RES && res_g[i] != 0.0 && res_preload[i]) {
-            const int *c = &res_coo[(size_t)i*4];
-            if (c[0] >= 0) an.Ainit[coo2ax[c[0]]] += res_g[i];
-            if (c[1] >= 0) an.Ainit[coo2ax[c[1]]] += res_g[i];
-            if (c[2] >= 0) an.Ainit[coo2ax[c[2]]] += -res_g[i];
-            if (c[3] >= 0) an.Ainit[coo2ax[c[3]]] += -res_g[i];
+    an.nres = dk->nres; an.resmin = o.resmin;
+    an.res_r.resize(dk->nres); an.res_m.resize(dk->nres);
+    for (int i = 0; i < dk->nres; i++) { an.res_r[i] = dk->res[i].r; an.res_m[i] = given(dk->res[i].m) ? dk->res[i].m : 1.0; }
+    {
+        std::vector<std::vector<std::pair<int, signed char>>> terms(an.nnz);
+        std::vector<double> base(an.Ainit);
+        for (int oi = 0; oi < dk->norder; oi++) {
+            int i = dk->order_index[oi];
+            if (dk->order_kind[oi] == B200_DEV_RES && res_g[i] != 0.0 && res_preload[i]) {
+                const int *c = &res_coo[(size_t)i*4];
+                if (c[0] >= 0) { an.Ainit[coo2ax[c[0]]] += res_g[i]; terms[coo2ax[c[0]]].push_back({i, 1}); }
+                if (c[1] >= 0) { an.Ainit[coo2ax[c[1]]] += res_g[i]; terms[coo2ax[c[1]]].push_back({i, 1}); }
+                if (c[2] >= 0) { an.Ainit[coo2ax[c[2]]] += -res_g[i]; terms[coo2ax[c[2]]].push_back({i, -1}); }
+                if (c[3] >= 0) { an.Ainit[coo2ax[c[3]]] += -res_g[i]; terms[coo2ax[c[3]]].push_back({i, -1}); }
+            }
+        }
+        an.rt_entry.clear(); an.rt_base.clear(); an.rt_ptr.assign(1, 0); an.rt_res.clear(); an.rt_sign.clear();
+        for (int p = 0; p < an.nnz; p++) {
+            if (terms[p].empty()) continue;
+            an.rt_entry.push_back(p); an.rt_base.push_back(base[p]);
+            for (auto &tm : terms[p]) { an.rt_res.push_back(tm.first); an.rt_sign.push_back(tm.second); }
+            an.rt_ptr.push_back((int)an.rt_res.size());
         }
     }
     // the phase node's own equation x[phs] = rhs[phs] is preldset (jjset.cc:815-816)
@@ -1353,6 +1367,7 @@ int b200_build_lu(Analysis &an)
     // slot consecutive, in the reference's load order; slots in image order) ----
     std::vector<int> newc(an.ncslot, -1), newr(an.nrslot, -1);
     an.const_idx.clear(); an.const_val.clear();
+    an.ainit_cslot.assign(an.nnz, -1);
     an.runs.assign(an.img, AsmRun{0, 0, 0, 0});
     std::vector<int> p2node(an.nnz, 0);
     for (int i = 1; i <= n; i++) if (an.diag[i] >= 0) p2node[an.diag[i]] = i;
@@ -1367,7 +1382,7 @@ int b200_build_lu(Analysis &an)
             // a nonzero preloaded constant (Ainit) is the first term of the run: it lives in a
             // contribution slot of its own that is written once at batch creation
             // (0.0 + Ainit == Ainit exactly, so the sum is the reference's Ainit + c1 + c2 ...)
-            if (an.Ainit[p] != 0.0) { an.const_idx.push_back(next++); an.const_val.push_back(an.Ainit[p]); r.len++; }
+            if (an.Ainit[p] != 0.0) { an.ainit_cslot[p] = next; an.const_idx.push_back(next++); an.const_val.push_back(an.Ainit[p]); r.len++; }
             for (int q = an.cg_ptr[p]; q < an.cg_ptr[p+1]; q++) { newc[an.cg_idx[q]] = next++; r.len++; }
         }
     }

@@ -288,6 +288,16 @@ struct Analysis {
     std::vector<int> tile_order;                // tiles of ASM_TILE_SLOTS slots, most terms first
     std::vector<int> const_idx; std::vector<double> const_val;   // Ainit pseudo-terms, the -1.0
     std::vector<AsmChunk> long_chunks;          // chunk c -> contribution row NC + c
+    // per-trial resistor values (B200_P_RES_R): the preloaded entries that hold resistor
+    // conductances, with their terms in accumulation (= load) order, so the per-trial constant
+    // can be re-summed exactly as the nominal one was (restemp.cc:209-229)
+    double resmin = 0.0;
+    std::vector<double> res_r, res_m;           // card value and multiplier of every resistor
+    std::vector<int> rt_entry;                  // [ne] CSC entry p
+    std::vector<double> rt_base;                // [ne] the entry's value before the resistor terms
+    std::vector<int> rt_ptr, rt_res;            // CSR: terms of entry e
+    std::vector<signed char> rt_sign;
+    std::vector<int> ainit_cslot;               // [nnz] contribution row of the entry's preloaded constant, or -1
     // task program
     std::vector<unsigned> prog_rows;            // [nrows][LU_LANES] ([nrows][LU_LANES][2] if wide)
     int wide = 0;                               // 1: 32-bit slot numbers, image in global memory (k_lu_wide)

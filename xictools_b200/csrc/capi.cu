@@ -53,7 +53,7 @@ struct b200_batch {
     std::vector<double> cap_craw, cap_m;                    // card value and multiplier (per-trial rows carry the card value)
     bool cap_has_m = false;
     std::vector<int> src_dcgiven; int *d_src_dcgiven = nullptr;
-    std::map<int, std::vector<double>> cap_var, src_var, ind_var, jj_var;
+    std::map<int, std::vector<double>> cap_var, src_var, ind_var, jj_var, res_var;
     std::vector<double> jj_ics, tjm_ics;                    // [njj] / [ntjm] card ics (NaN = not given)
     std::map<int, std::vector<double>> tjm_var;
     double *d_tjmics = nullptr; int tjmics_ts = 0;
@@ -87,6 +87,8 @@ struct b200_batch {
     double *d_capc = nullptr, *d_srcdc = nullptr; int capc_ts = 0, srcdc_ts = 0;
     double *d_capic = nullptr;
     double *d_indl = nullptr, *d_indic = nullptr; int indl_ts = 0;
+    double *d_resr = nullptr, *d_resm = nullptr, *d_rt_base = nullptr; int resr_ts = 0;
+    int *d_rt_cslot = nullptr, *d_rt_ptr = nullptr, *d_rt_res = nullptr; signed char *d_rt_sign = nullptr;
     int *d_counters = nullptr, *d_npts = nullptr;
 
     bool ran = false;
@@ -107,7 +109,7 @@ struct b200_batch {
 };
 
 enum { PT_CAP = MR_NRAW, PT_IND = MR_NRAW + 1, PT_SRC = MR_NRAW + 2, PT_JJ = MR_NRAW + 3,
-       PT_TJM = MR_NRAW + 4, PT_NTABLES = MR_NRAW + 5 };
+       PT_TJM = MR_NRAW + 4, PT_RES = MR_NRAW + 5, PT_NTABLES = MR_NRAW + 6 };
 
 // row i of a [n][ldt] per-trial table <- the shared value of instance i
 __global__ void k_fill_rows(double *dst, const double *shared, int n, int ldt)
@@ -155,10 +157,11 @@ static int param_table(const b200_batch *b, int param, int index)
     case B200_P_SRC_DC: tbl = PT_SRC; break;
     case B200_P_JJ_ICS: tbl = PT_JJ; break;
     case B200_P_TJM_ICS: tbl = PT_TJM; break;
+    case B200_P_RES_R: tbl = PT_RES; break;
     default: return -B200_E_UNSUPP;
     }
     n = tbl < MR_NRAW ? b->an.mos.n : tbl == PT_CAP ? b->an.cap.n : tbl == PT_IND ? b->an.ind.n :
-        tbl == PT_JJ ? b->an.jj.n : tbl == PT_TJM ? b->an.tjm.n : b->an.src.n;
+        tbl == PT_JJ ? b->an.jj.n : tbl == PT_TJM ? b->an.tjm.n : tbl == PT_RES ? b->an.nres : b->an.src.n;
     if (index < 0 || index >= n) return -B200_E_BADPARM;
     return tbl;
 }
@@ -445,7 +448,16 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     ResPhView &Rv = Cp.R;
     memset(&Rv, 0, sizeof(Rv));
     Rv.n = (int)an.rph_res.size();
-    if (Rv.n) { Rv.cslot = b->dupload(an.rph_cslot); Rv.cls = b->dupload(an.rph_cls); Rv.g = b->dupload(an.rph_g); }
+    if (Rv.n) { Rv.cslot = b->dupload(an.rph_cslot); Rv.cls = b->dupload(an.rph_cls); Rv.res = b->dupload(an.rph_res); }
+    b->d_resm = b->dupload(an.res_m);
+    Rv.m = b->d_resm; Rv.resmin = an.resmin;
+    {
+        // per-trial resistor values (B200_P_RES_R): which preloaded constants to re-sum
+        std::vector<int> cs(an.rt_entry.size());
+        for (size_t e = 0; e < cs.size(); e++) cs[e] = an.ainit_cslot[an.rt_entry[e]];
+        b->d_rt_cslot = b->dupload(cs); b->d_rt_base = b->dupload(an.rt_base);
+        b->d_rt_ptr = b->dupload(an.rt_ptr); b->d_rt_res = b->dupload(an.rt_res); b->d_rt_sign = b->dupload(an.rt_sign);
+    }
     K.jjDCphase = an.jjDCphase;
     K.jjaccel = (deck->opt.jjaccel && (an.jj.n + an.tjm.n) > 0) ? 1 : 0;
     V.phase = an.jjDCphase ? b->dupload(an.phase_mask) : nullptr;
@@ -626,6 +638,9 @@ int b200_batch_set_param(b200_batch *b, int param, int index, const double *valu
     case B200_P_TJM_ICS:
         if (index < 0 || index >= b->an.tjm.n) return B200_E_BADPARM;
         put(b->tjm_var[index]); b->params_dirty = true; return B200_OK;
+    case B200_P_RES_R:
+        if (index < 0 || index >= b->an.nres) return B200_E_BADPARM;
+        put(b->res_var[index]); b->params_dirty = true; return B200_OK;
     default:
         return B200_E_UNSUPP;
     }
@@ -666,6 +681,7 @@ int b200_batch_set_params(b200_batch *b, int nrows, const int *param, const int 
         else if (tbl[r] == PT_IND) b->ind_var.erase(index[r]);
         else if (tbl[r] == PT_JJ) b->jj_var.erase(index[r]);
         else if (tbl[r] == PT_TJM) b->tjm_var.erase(index[r]);
+        else if (tbl[r] == PT_RES) b->res_var.erase(index[r]);
         else { b->src_var.erase(index[r]); b->src_dcgiven[index[r]] = 1; }    // a DC value makes it given
     }
     size_t need = (size_t)nrows*b->ntrials;
@@ -789,6 +805,9 @@ static int prepare_params(b200_batch *b)
     if (!b->ind_ic.empty())
         CK(cudaMemcpy(b->d_indic, b->ind_ic.data(), b->ind_ic.size()*sizeof(double), cudaMemcpyHostToDevice));
     b->Cp.L.ic.base = b->d_indic; b->Cp.L.ic.ts = 0; b->Cp.L.ic.ld = 1;
+    rc = upload_strided(PT_RES, b->an.res_r, b->res_var, b->d_resr, b->resr_ts);
+    if (rc) return rc;
+    b->Cp.R.r.base = b->d_resr; b->Cp.R.r.ts = b->resr_ts; b->Cp.R.r.ld = b->resr_ts ? (int)ldt : 1;
     rc = upload_strided(PT_SRC, b->src_dc, b->src_var, b->d_srcdc, b->srcdc_ts);
     if (rc) return rc;
     b->S.dc.base = b->d_srcdc; b->S.dc.ts = b->srcdc_ts; b->S.dc.ld = b->srcdc_ts ? (int)ldt : 1;
@@ -901,6 +920,9 @@ static int reset_state(b200_batch *b)
     CK(cudaMemsetAsync(b->V.states, 0, (size_t)b->K.NS*an.numStates*ldt*sizeof(double), st));
     CK(cudaMemsetAsync(b->V.contrib, 0, (size_t)an.NC*ldt*sizeof(double), st));
     launch_fill_const(st, b->K, b->V.contrib, b->nconst, b->d_const_idx, b->d_const_val);
+    if (b->resr_ts)
+        launch_res_ainit(st, (int)an.rt_entry.size(), (int)ldt, b->d_rt_cslot, b->d_rt_base, b->d_rt_ptr, b->d_rt_res,
+            b->d_rt_sign, b->Cp.R.r, b->d_resm, an.resmin, b->V.contrib);
     CK(cudaMemsetAsync(b->M.cache, 0, (size_t)MC_NCACHE*an.mos.n*ldt*sizeof(double), st));
     // MOSmode = 1, MOSvon = 0 (mosset.cc:283-284)
     launch_fill(st, b->M.cache + (size_t)MC_mode*an.mos.n*ldt, (size_t)an.mos.n*ldt, 1.0);

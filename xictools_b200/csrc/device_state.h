@@ -153,7 +153,10 @@ struct ResPhView {
     int n;
     const int *cslot;   // [n*4] PP NN PN NP
     const int *cls;     // 0: both terminals phase / ground, 1: volt - phase, 2: phase - volt
-    const double *g;
+    const int *res;     // [n] index of the resistor
+    ParamRef r;         // card values of ALL resistors (per trial where B200_P_RES_R was given)
+    const double *m;    // multipliers
+    double resmin;
 };
 // Tunnel-junction model (JJ level 3).  work[(a*nterms + k)*2 + c][n][ldt], a in TF_*, c = re / im
 struct TJMView {

@@ -782,6 +782,30 @@ __global__ void k_jjaccel_gate(Consts K, HotView hot)
     }
 }
 
+// Per-trial resistor values: the preloaded constant of every entry that holds resistor
+// conductances, re-summed per trial in the order the nominal one was (restemp.cc:209-229)
+__global__ void k_res_ainit(int ne, int ldt, const int *cslot, const double *base, const int *ptr,
+    const int *res, const signed char *sign, ParamRef r, const double *m, double resmin, double *contrib)
+{
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int e = GRID_ROW;
+    if (t >= ldt || e >= ne || cslot[e] < 0) return;
+    double v = base[e];
+    for (int k = ptr[e]; k < ptr[e+1]; k++) {
+        double rv = PR(r, res[k], t);
+        if (fabs(rv) < resmin) rv = (rv < 0.0) ? -resmin : resmin;
+        const double g = m[res[k]]/(rv*1.0);
+        v += (sign[k] > 0) ? g : -g;
+    }
+    contrib[(size_t)cslot[e]*ldt + t] = v;
+}
+
+void launch_res_ainit(cudaStream_t st, int ne, int ldt, const int *cslot, const double *base, const int *ptr,
+    const int *res, const signed char *sign, ParamRef r, const double *m, double resmin, double *contrib)
+{
+    if (ne) k_res_ainit<<<grid_rows((ldt + 127)/128, ne), 128, 0, st>>>(ne, ldt, cslot, base, ptr, res, sign, r, m, resmin, contrib);
+}
+
 __global__ void k_count_active(int ntrials, const int *active, int *count)
 {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
@@ -859,7 +883,10 @@ k_load_rph(Consts K, HotView hot, VecView V, ResPhView R)
     int mode = hot.mode[t];
     if (!mode) return;
     const int *cs = R.cslot + (size_t)i*4;          // PP NN PN NP
-    const double g = R.g[i];
+    const int ri = R.res[i];
+    double rv = PR(R.r, ri, t);
+    if (fabs(rv) < R.resmin) rv = (rv < 0.0) ? -R.resmin : R.resmin;
+    const double g = R.m[ri]/(rv*1.0);              // restemp.cc:200-209
     double v[4] = { g, g, -g, -g };
     if ((mode & MODEDC) && K.jjDCphase) {
         const int cls = R.cls[i];

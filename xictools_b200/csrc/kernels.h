@@ -52,6 +52,8 @@ struct SolveView {
     int nlevels;
 };
 
+void launch_res_ainit(cudaStream_t st, int ne, int ldt, const int *cslot, const double *base, const int *ptr,
+    const int *res, const signed char *sign, ParamRef r, const double *m, double resmin, double *contrib);
 void launch_jjaccel_gate(cudaStream_t st, const Consts &K, const HotView &hot);
 void launch_mos_temp(cudaStream_t st, int n, int ntrials, int ldt, const MosCard *cards,
     const RawParams &raw, const MosParamsOut &out);
