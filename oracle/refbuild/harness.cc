@@ -71,6 +71,8 @@ extern "C" void wrsref_append(double ref, const double *vals, int n)
 extern "C" {
 
 void wrsref_set_verbose(int v) { wrsref_verbose = v; }
+// the reference's own per-NIiter trace on stderr (sCKT::CKTstepDebug, niiter.cc:541-546)
+void wrsref_set_stepdebug(int v) { sCKT::CKTstepDebug = v; }
 
 // the reference's own deviates (sRnd, xt_base/miscutil/random.cc): pins the dispatcher's
 // restatement of the Monte-Carlo random stream

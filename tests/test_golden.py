@@ -27,9 +27,9 @@ RELTOL, VNTOL = 1e-3, 1e-6
 
 
 def fixtures():
-    # (large_*.json: bench.py's large_flat workload, tests/test_large.py)
+    # (large_*.json: bench.py's large_flat workload, tests/test_large.py; nor_gate.json: tests/test_nor.py)
     return sorted(os.path.basename(p)[:-5] for p in glob.glob(os.path.join(HERE, "golden", "*.json"))
-                  if not os.path.basename(p).startswith("large_"))
+                  if not os.path.basename(p).startswith(("large_", "nor_")))
 
 
 def load(name):

@@ -1,0 +1,107 @@
+"""The RSFQ NOR gate of the reference's own Monte-Carlo example (examples/JJexamples/nor_mc.cir:
+26 junctions with phase nodes, 177 unknowns, phase-mode DC start), flattened by
+tools/flatten_spice.py; fixture tests/golden/nor_gate.json (tests/golden/make_nor_golden.py) holds
+the unmodified reference's run of six trials with the example's varied parameters (critical
+currents, bias resistors, an inductor).
+
+CPU: the flattener, and the reference's parser -> shim/harvest.cc -> engine analysis on the flat
+deck.  GPU: parser -> shim -> batched engine, every trial against the fixture: identical counts,
+signals within reltol / vntol; the per-trial rows are addressed by the reference's instance names."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import have_ref, run_harvest
+from tools.flatten_spice import flatten, parameters
+from xictools_b200 import engine
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RELTOL, VNTOL = 1e-3, 1e-6
+
+
+def _gold():
+    with open(os.path.join(HERE, "golden", "nor_gate.json")) as f:
+        return json.load(f)
+
+
+def test_flattener():
+    src = """title line
+.param per=50pS dly=20pS
+.param rb=40
+.subckt cell in out vb
+b0 5 0 9 jj1 ics=250u
+l0 in 5 2.1pH
+l1 5 out l1val
+r0 vb 5 rb
+.ends cell
+.param l1val=2p
+v0 1 0 gpulse(0 0 dly+15p 2p per)
+x0 1 2 vdd cell
+x1 2 3 vdd cell
+.control
+echo not for the harness
+.endc
+.tran 0.1p 0.5*per
+"""
+    assert parameters(src) == {"per": 50e-12, "dly": 20e-12, "rb": 40.0, "l1val": 2e-12}
+    flat = flatten(src, {"rb": 44.0}).splitlines()
+    assert flat[0] == "title line"
+    assert "b0.x0 5.x0 0 9.x0 jj1 ics=250u" in flat
+    assert "l0.x1 2 5.x1 2.1pH" in flat and "l1.x0 5.x0 2 2e-12" in flat
+    assert "r0.x1 vdd 5.x1 44.0" in flat
+    v0 = [l for l in flat if l.startswith("v0 ")][0]
+    assert v0.startswith("v0 1 0 gpulse(0 0 ") and v0.endswith(" 2p 5e-11)")
+    assert abs(float(v0.split()[5]) - 35e-12) < 1e-24
+    assert ".tran 0.1p 2.5e-11" in flat
+    assert not any("echo" in l or l.startswith((".subckt", ".param", "x")) for l in flat)
+
+
+def test_fixture_shape():
+    g = _gold()
+    assert g["ntrials"] == len(g["trials"]) == 6 and len(g["params"]) == 13
+    assert all(t["counters"]["err"] == 0 and t["counters"]["accepted"] > 2000 for t in g["trials"])
+    assert sum(1 for l in g["spice"].splitlines() if l.startswith("b")) == 26
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_harvested_nor_gate_is_analysed():
+    g = _gold()
+    r = run_harvest(g["spice"], engine.LIB_PATH, 0)
+    assert r["rc"] == 0
+    c = g["trials"][0]["counters"]
+    assert (r["ref"]["error"], r["ref"]["accepted"], r["ref"]["numiter"]) == (0, c["accepted"], c["numiter"])
+
+
+@pytest.mark.gpu
+def test_nor_gate_monte_carlo_matches_the_reference():
+    g = _gold()
+    ntr = g["ntrials"]
+    params = [(p["id"], p["instance"], np.array(p["values"])) for p in g["params"]]
+    r = run_harvest(g["spice"], engine.LIB_PATH, ntr, params)
+    assert r["rc"] == 0
+    idx = g["signal_cols"]           # columns of the reference's output order (the shim keeps it)
+    diffs = []
+    for t, ref in enumerate(g["trials"]):
+        c = ref["counters"]
+        got = r["counters"][t]
+        # Steps and time points must be identical.  Newton iterations: during the gmin stepping of
+        # this deck's operating point the reference's Sparse 1.3 meets a zero pivot under ITS frozen
+        # pivot order and spends one extra iteration re-ordering ("Matrix is singular, iterno=1 /
+        # Forced reordering" in its own CKTstepDebug trace, niiter.cc:303-331) -- an event of its
+        # pivot order, which the C oracle (own pivoting) does not have either: 86 against 87
+        # iterations in the operating point, everything after it identical.
+        assert (int(got[0]), int(got[1]), int(got[2])) == (c["err"], c["accepted"], c["rejected"]), (t, got[:4], c)
+        assert int(got[3]) - c["numiter"] in (-1, 0), (t, int(got[3]), c["numiter"])
+        diffs.append(int(got[3]) - c["numiter"])
+        w = r["waves"][t][::g["decimation"]][:, idx]
+        want = np.array(ref["vals"])
+        assert w.shape == want.shape
+        tol = RELTOL*np.maximum(np.abs(w), np.abs(want)) + VNTOL
+        assert not (np.abs(w - want) > tol).any(), (t, float((np.abs(w - want)/tol).max()))
+    print("numiter engine - reference per trial:", diffs)
+    # the trials really differ
+    w1 = r["waves"][1][::g["decimation"]][:, idx]
+    w0 = r["waves"][0][::g["decimation"]][:, idx]
+    assert np.abs(w1 - w0).max() > 1e-5

@@ -22,6 +22,7 @@
 #include <set>
 #include <queue>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "b200_internal.h"
 
@@ -927,6 +928,7 @@ void b200_order_markowitz(Analysis &an, bool tran_order)
     // companion conductances vanish there).  The pivot order is frozen for the whole run, so a
     // pivot must be structurally nonzero in DC (hence also in transient).
     std::unordered_map<i64, char> dcnz;
+    std::unordered_set<i64> orig_const;          // the +-1 couplings as the deck gives them
     constant.reserve((size_t)an.nnz*4); dcnz.reserve((size_t)an.nnz*4);
     const bool have_dc = !tran_order && (an.dc_active.size() == (size_t)an.nnz);
     for (int j = 0; j < n; j++)
@@ -936,6 +938,7 @@ void b200_order_markowitz(Analysis &an, bool tran_order)
             bool is_const = (an.cg_ptr[p+1] == an.cg_ptr[p]) &&
                 (an.Ainit[p] == 1.0 || an.Ainit[p] == -1.0);
             constant[key(i, j)] = is_const ? 1 : 0;
+            if (is_const) orig_const.insert(key(i, j));
             dcnz[key(i, j)] = have_dc ? an.dc_active[p] : 1;
         }
     auto is_dcnz = [&](int i, int j) { auto it = dcnz.find(key(i, j)); return it != dcnz.end() && it->second; };
@@ -1025,15 +1028,19 @@ void b200_order_markowitz(Analysis &an, bool tran_order)
             break;
         }
         if (bi < 0) {
-            // no safe candidate.  pass 1: any remaining diagonal; pass 2: any entry -- both
-            // structurally nonzero in DC; pass 3: any entry at all (exhaustive scans: rare)
+            // no safe candidate.  pass 0: a coupling that was +-1 in the deck (an elimination has
+            // touched it since: the current-sum row of a node only inductors reach, whose node
+            // voltage went with a branch row -- what is left of such an entry is 1 + a ratio of
+            // inductances, never a difference); pass 1: any remaining diagonal; pass 2: any entry
+            // -- all structurally nonzero in DC; pass 3: any entry at all (exhaustive scans: rare)
             long best = -1, bstamp = 0;
-            for (int pass = 1; pass < 4 && bi < 0; pass++) {
+            for (int pass = 0; pass < 4 && bi < 0; pass++) {
                 for (int i = 0; i < n; i++) {
                     if (!ract[i]) continue;
                     for (int j : rows[i]) {
                         if (!cact[j]) continue;
                         if (pass < 3 && !is_dcnz(i, j)) continue;
+                        if (pass == 0 && !orig_const.count(key(i, j))) continue;
                         if (pass == 1 && i != j) continue;
                         long mk = (long)(rows[i].size() - 1)*(long)(cols[j].size() - 1);
                         if (mk < mk_floor) mk = mk_floor;
