@@ -100,6 +100,9 @@ def run_harvest(spice_text: str, libpath: str, ntrials: int, params=None, op_onl
         L.wrsref_harvest_get(counters.ctypes.data_as(C.c_void_p), times.ctypes.data_as(C.c_void_p),
                              waves.ctypes.data_as(C.c_void_p))
         out.update(counters=counters, times=times, waves=waves)
+        ms, ticks = C.c_double(), C.c_longlong()
+        L.wrsref_harvest_last_run(C.byref(ms), C.byref(ticks))
+        out.update(ms_total=ms.value, ticks=ticks.value)
     return out
 
 

@@ -66,6 +66,7 @@ struct Api {
     void (*destroy)(b200_batch*) = nullptr;
     int (*set_param)(b200_batch*, int, int, const double*) = nullptr;
     int (*run_tran)(b200_batch*) = nullptr;
+    int (*get_stats)(const b200_batch*, b200_run_stats*) = nullptr;
     int (*run_op)(b200_batch*) = nullptr;
     int (*num_unknowns)(const b200_batch*) = nullptr;
     int (*num_points)(const b200_batch*) = nullptr;
@@ -77,7 +78,7 @@ struct Api {
 #define SYM(field, name) *(void**)&field = dlsym(h, name); if (!field) { fprintf(stderr, "b200 shim: %s missing\n", name); return false; }
         SYM(options_default, "b200_options_default") SYM(create, "b200_batch_create")
         SYM(destroy, "b200_batch_destroy") SYM(set_param, "b200_batch_set_param")
-        SYM(run_tran, "b200_batch_run_tran") SYM(run_op, "b200_batch_run_op")
+        SYM(run_tran, "b200_batch_run_tran") SYM(get_stats, "b200_batch_get_stats") SYM(run_op, "b200_batch_run_op")
         SYM(num_unknowns, "b200_batch_num_unknowns") SYM(num_points, "b200_batch_num_points")
         SYM(get_counters, "b200_batch_get_counters") SYM(get_waves, "b200_batch_get_waves")
 #undef SYM
@@ -454,6 +455,14 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
     return B200_OK;
 }
 
+// device time (CUDA events, b200_run_stats.ms_total) and ticks of the latest b200_harvest_run
+static b200_run_stats last_run_stats;
+extern "C" void b200_harvest_last_stats(double *ms_total, long long *ticks)
+{
+    if (ms_total) *ms_total = last_run_stats.ms_total;
+    if (ticks) *ticks = last_run_stats.ticks;
+}
+
 // harvest -> b200_batch_create -> set per-trial parameters -> run -> results, through the
 // dlopen'ed engine.  nparams parameter rows: (param id, instance name, values[ntrials]).
 // counters[ntrials][B200_NCOUNTERS]; *waves (malloc'ed, caller frees) [ntrials][npoints][n].
@@ -477,6 +486,8 @@ extern "C" int b200_harvest_run(sCKT *ckt, const char *libpath, int ntrials, int
         rc = idx < 0 ? B200_E_BADPARM : api.set_param(b, param_id[i], idx, values[i]);
     }
     if (!rc) rc = op_only ? api.run_op(b) : api.run_tran(b);
+    memset(&last_run_stats, 0, sizeof(last_run_stats));
+    if (!rc) api.get_stats(b, &last_run_stats);
     if (!rc) {
         int n = api.num_unknowns(b), np = api.num_points(b);
         *n_out = n; *npoints_out = np;
