@@ -273,6 +273,13 @@ typedef struct b200_run_stats {
     long long solve_launches, load_launches;
     double algbytes_load_per_launch, algbytes_solve_per_launch;
 } b200_run_stats;
+/* `.save`: keep only these unknowns (0-based indices as in b200_batch_unknown_names) at the output
+ * points -- the output buffer is [points][saved][trials], so a long transient of many trials fits
+ * (the reference keeps saved vectors only as well: the `.save` lines of a deck).  Before the first
+ * run.  b200_batch_get_waves then returns the saved columns in list order; get_waves_sel /
+ * get_results_dev still take unknown indices (B200_E_BADPARM for one that is not saved). */
+int  b200_batch_set_saves(b200_batch *b, int nsave, const int *unknown);
+int  b200_batch_num_saved(const b200_batch *b);
 int  b200_batch_get_stats(const b200_batch *b, b200_run_stats *st);
 
 /* ---- Monte-Carlo trial generation (host code of the dispatcher) ----

@@ -59,7 +59,7 @@ class RefSim:
         return out
 
 
-def run_harvest(spice_text: str, libpath: str, ntrials: int, params=None, op_only=False) -> dict:
+def run_harvest(spice_text: str, libpath: str, ntrials: int, params=None, op_only=False, saves=None) -> dict:
     """Reference parser + set-up circuit -> shim/harvest.cc -> C ABI -> batched run (GPU), in
     the same call that runs the reference's own doTask on that circuit.
     params: [(param_id, instance_name, values[ntrials])].  ntrials = 0: host-only harvest check
@@ -74,8 +74,11 @@ def run_harvest(spice_text: str, libpath: str, ntrials: int, params=None, op_onl
     vals = (C.c_void_p*max(n, 1))(*[a.ctypes.data for a in arrs])
     L.wrsref_run_deck_harvest.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_int]
+    sv = np.ascontiguousarray(saves if saves is not None else [], dtype=np.int32)
+    L.wrsref_harvest_set_saves(len(sv), sv.ctypes.data_as(C.c_void_p))       # `.save` list (columns of `waves`)
     err = L.wrsref_run_deck_harvest(spice_text.encode(), libpath.encode(), ntrials, n, ids, names,
                                     vals, int(op_only))
+    L.wrsref_harvest_set_saves(0, None)
     out = {"ref_err": err, "rc": L.wrsref_harvest_rc()}
     cnt = (C.c_int*9)()
     L.wrsref_get_counters(cnt)

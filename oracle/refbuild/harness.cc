@@ -309,6 +309,7 @@ int wrsref_run_deck_harvest(const char *deck_text, const char *libpath, int ntri
 
 void wrsref_harvest_stats(long long *out) { memcpy(out, hout.stats, sizeof(hout.stats)); }
 void wrsref_harvest_last_run(double *ms_total, long long *ticks) { b200_harvest_last_stats(ms_total, ticks); }
+void wrsref_harvest_set_saves(int n, const int *unknown) { b200_harvest_set_saves(n, unknown); }
 // the harvested deck through the plain-C oracle (decks only the reference's setup can make)
 namespace {
     struct OracleArgs { const char *path; int nparams; const int *param_id; const char *const *inst_name; const double *value; } oargs;

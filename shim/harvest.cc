@@ -67,6 +67,8 @@ struct Api {
     int (*set_param)(b200_batch*, int, int, const double*) = nullptr;
     int (*run_tran)(b200_batch*) = nullptr;
     int (*get_stats)(const b200_batch*, b200_run_stats*) = nullptr;
+    int (*set_saves)(b200_batch*, int, const int*) = nullptr;
+    int (*num_saved)(const b200_batch*) = nullptr;
     int (*run_op)(b200_batch*) = nullptr;
     int (*num_unknowns)(const b200_batch*) = nullptr;
     int (*num_points)(const b200_batch*) = nullptr;
@@ -78,7 +80,7 @@ struct Api {
 #define SYM(field, name) *(void**)&field = dlsym(h, name); if (!field) { fprintf(stderr, "b200 shim: %s missing\n", name); return false; }
         SYM(options_default, "b200_options_default") SYM(create, "b200_batch_create")
         SYM(destroy, "b200_batch_destroy") SYM(set_param, "b200_batch_set_param")
-        SYM(run_tran, "b200_batch_run_tran") SYM(get_stats, "b200_batch_get_stats") SYM(run_op, "b200_batch_run_op")
+        SYM(run_tran, "b200_batch_run_tran") SYM(get_stats, "b200_batch_get_stats") SYM(set_saves, "b200_batch_set_saves") SYM(num_saved, "b200_batch_num_saved") SYM(run_op, "b200_batch_run_op")
         SYM(num_unknowns, "b200_batch_num_unknowns") SYM(num_points, "b200_batch_num_points")
         SYM(get_counters, "b200_batch_get_counters") SYM(get_waves, "b200_batch_get_waves")
 #undef SYM
@@ -463,6 +465,15 @@ extern "C" void b200_harvest_last_stats(double *ms_total, long long *ticks)
     if (ticks) *ticks = last_run_stats.ticks;
 }
 
+// the `.save` list of the next b200_harvest_run: unknown indices in the reference's output order
+// (n = 0: everything).  The reference keeps its saves in the script front end (sFtCirc), which a
+// host passes on here.
+static std::vector<int> next_saves;
+extern "C" void b200_harvest_set_saves(int n, const int *unknown)
+{
+    next_saves.assign(unknown, unknown + (n > 0 ? n : 0));
+}
+
 // harvest -> b200_batch_create -> set per-trial parameters -> run -> results, through the
 // dlopen'ed engine.  nparams parameter rows: (param id, instance name, values[ntrials]).
 // counters[ntrials][B200_NCOUNTERS]; *waves (malloc'ed, caller frees) [ntrials][npoints][n].
@@ -485,11 +496,12 @@ extern "C" int b200_harvest_run(sCKT *ckt, const char *libpath, int ntrials, int
         int idx = b200_harvest_find(H, kind, inst_name[i]);
         rc = idx < 0 ? B200_E_BADPARM : api.set_param(b, param_id[i], idx, values[i]);
     }
+    if (!rc && !next_saves.empty()) rc = api.set_saves(b, (int)next_saves.size(), next_saves.data());
     if (!rc) rc = op_only ? api.run_op(b) : api.run_tran(b);
     memset(&last_run_stats, 0, sizeof(last_run_stats));
     if (!rc) api.get_stats(b, &last_run_stats);
     if (!rc) {
-        int n = api.num_unknowns(b), np = api.num_points(b);
+        int n = api.num_saved(b), np = api.num_points(b);     // columns returned: the saved unknowns
         *n_out = n; *npoints_out = np;
         api.get_counters(b, counters);
         *times_out = (double*)malloc(sizeof(double)*(np ? np : 1));

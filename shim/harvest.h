@@ -33,6 +33,8 @@ int  b200_harvest_oracle(struct sCKT *ckt, const char *oraclepath, int nparams, 
 
 /* host-only: b200_deck_analysis_stats of the harvested deck (sizes of pattern / LU / program) */
 int  b200_harvest_stats(struct sCKT *ckt, const char *libpath, long long *out, int nout);
+/* `.save` list of the next b200_harvest_run: unknown indices in the reference's output order (0: all) */
+void b200_harvest_set_saves(int n, const int *unknown);
 /* device time (CUDA events) and ticks of the latest b200_harvest_run */
 void b200_harvest_last_stats(double *ms_total, long long *ticks);
 

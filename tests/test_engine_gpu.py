@@ -437,6 +437,35 @@ def test_monte_carlo_resistor_values(name):
     compare(d, ntr, ov)
 
 
+def test_save_list_keeps_only_the_named_unknowns():
+    """b200_batch_set_saves (`.save`): the output buffer holds the listed unknowns only; their
+    waveforms are bit-identical to the same columns of a run that keeps everything, whichever
+    way they are fetched; an unknown that is not on the list is refused."""
+    d = ring_oscillator(5)
+    ntr = 7
+    ov = mc_variation(d, ntr, seed=4)
+    a = engine.Batch(d, ntr)
+    a.set_params(ov)
+    a.run_tran()
+    _, wa = a.waves()
+    names = a.names()
+    keep = [names.index("n3"), names.index("vdd#branch"), names.index("n0")]
+    b = engine.Batch(d, ntr)
+    b.set_params(ov)
+    b.set_saves(keep)
+    b.run_tran()
+    _, wb = b.waves()
+    assert wb.shape == (ntr, wa.shape[1], 3)
+    assert np.array_equal(wb, wa[:, :, keep])
+    _, ws = b.waves([keep[2], keep[0]])
+    assert np.array_equal(ws, wa[:, :, [keep[2], keep[0]]])
+    assert np.array_equal(a.counters(), b.counters())
+    with pytest.raises(engine.B200Error):
+        b.waves([names.index("n1")])
+    with pytest.raises(engine.B200Error):
+        b.set_saves(keep)                   # after the first run
+
+
 def test_packed_rows_equal_single_rows():
     """b200_batch_set_params (one transfer + device scatter) against b200_batch_set_param row by
     row: bit-identical results; a single row given afterwards overrides its packed row."""

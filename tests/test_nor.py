@@ -79,9 +79,11 @@ def test_nor_gate_monte_carlo_matches_the_reference():
     g = _gold()
     ntr = g["ntrials"]
     params = [(p["id"], p["instance"], np.array(p["values"])) for p in g["params"]]
-    r = run_harvest(g["spice"], engine.LIB_PATH, ntr, params)
+    # `.save` of the three signals (columns of the reference's output order; the shim keeps it)
+    r = run_harvest(g["spice"], engine.LIB_PATH, ntr, params, saves=g["signal_cols"])
     assert r["rc"] == 0
-    idx = g["signal_cols"]           # columns of the reference's output order (the shim keeps it)
+    assert r["waves"].shape[2] == 3
+    idx = [0, 1, 2]
     diffs = []
     for t, ref in enumerate(g["trials"]):
         c = ref["counters"]

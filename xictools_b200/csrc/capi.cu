@@ -54,6 +54,7 @@ struct b200_batch {
     bool cap_has_m = false;
     std::vector<int> src_dcgiven; int *d_src_dcgiven = nullptr;
     std::map<int, std::vector<double>> cap_var, src_var, ind_var, jj_var, res_var;
+    std::vector<int> save_slot;                             // unknown -> row of the output buffer (empty: all saved)
     std::vector<double> jj_ics, tjm_ics;                    // [njj] / [ntjm] card ics (NaN = not given)
     std::map<int, std::vector<double>> tjm_var;
     double *d_tjmics = nullptr; int tjmics_ts = 0;
@@ -363,8 +364,10 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
     V.states = b->dalloc<double>((size_t)K.NS*an.numStates*ldt);
     V.oldState0 = b->dalloc<double>((size_t)an.numStates*ldt);
     V.contrib = b->dalloc<double>(((size_t)an.NC + an.long_chunks.size())*ldt);   // [NC (+ long-run chunk sums)][ldt]
-    V.out = b->dalloc<double>((size_t)an.npoints_max*an.n*ldt);
-    if (!V.out || !V.states || !V.sols) { b200_batch_destroy(b); return B200_E_NOMEM; }
+    V.out = nullptr;                                     // sized at the first run: the save list may shrink it
+    V.outslot = nullptr;
+    K.nout = an.n;
+    if (!V.states || !V.sols) { b200_batch_destroy(b); return B200_E_NOMEM; }
     // ---- topology ----
     MosView &M = b->M; MosTopo &mt = an.mos;
     M.n = mt.n;
@@ -993,6 +996,10 @@ static int run_analysis(b200_batch *b, int analysis)
     b->K.analysis = analysis;
     int rc = prepare_params(b);
     if (rc) return rc;
+    if (!b->V.out) {
+        b->V.out = b->dalloc<double>((size_t)b->an.npoints_max*b->K.nout*b->ldt);
+        if (!b->V.out) return B200_E_NOMEM;
+    }
     rc = reset_state(b);
     if (rc) return rc;
     cudaStream_t st = b->stream;
@@ -1123,6 +1130,39 @@ int b200_batch_get_counters(const b200_batch *b, int *counters)
     return B200_OK;
 }
 
+// unknown indices -> rows of the output buffer (identity without a save list)
+static int out_rows(const b200_batch *b, int nsel, const int *sel, std::vector<int> &rows)
+{
+    rows.assign(sel, sel + nsel);
+    for (int &r : rows) {
+        if (r < 0 || r >= b->an.n) return B200_E_BADPARM;
+        if (!b->save_slot.empty()) {
+            r = b->save_slot[r];
+            if (r < 0) return B200_E_BADPARM;            // not on the save list
+        }
+    }
+    return B200_OK;
+}
+
+int b200_batch_set_saves(b200_batch *b, int nsave, const int *unknown)
+{
+    if (!b || nsave <= 0 || !unknown) return B200_E_BADPARM;
+    if (b->V.out) return B200_E_BADPARM;                 // before the first run: the buffer is sized by it
+    CK(cudaSetDevice(b->device));
+    std::vector<int> slot(b->an.n, -1), dev(b->an.n + 1, -1);
+    for (int k = 0; k < nsave; k++) {
+        if (unknown[k] < 0 || unknown[k] >= b->an.n || slot[unknown[k]] >= 0) return B200_E_BADPARM;
+        slot[unknown[k]] = k;
+        dev[unknown[k] + 1] = k;
+    }
+    b->save_slot = slot;
+    b->V.outslot = b->dupload(dev);
+    b->K.nout = nsave;
+    return B200_OK;
+}
+
+int b200_batch_num_saved(const b200_batch *b) { return b ? b->K.nout : 0; }
+
 static int get_waves(const b200_batch *b, int nsel, const int *sel, double *times, double *waves)
 {
     if (!b || !b->ran) return B200_E_BADPARM;
@@ -1135,8 +1175,10 @@ static int get_waves(const b200_batch *b, int nsel, const int *sel, double *time
         for (int p = 0; p < np; p++, tc += an.t_step) times[p] = tc;
     }
     if (!waves) return B200_OK;
-    int nn = sel ? nsel : an.n;
+    int nn = sel ? nsel : b->K.nout;
     size_t total = (size_t)b->ntrials*np*nn;
+    std::vector<int> rows;
+    if (sel) { int rc = out_rows(b, nsel, sel, rows); if (rc) return rc; sel = rows.data(); }
     if (total > b->wout_cap) {
         if (b->d_wout) cudaFree(b->d_wout);
         b->d_wout = nullptr; b->wout_cap = 0;
@@ -1152,7 +1194,7 @@ static int get_waves(const b200_batch *b, int nsel, const int *sel, double *time
         }
         CK(cudaMemcpyAsync(b->d_wsel, sel, nsel*sizeof(int), cudaMemcpyHostToDevice, b->stream));
     }
-    launch_gather_waves(b->stream, an.n, b->ldt, b->ntrials, np, b->V.out, b->d_npts, nsel,
+    launch_gather_waves(b->stream, b->K.nout, b->ldt, b->ntrials, np, b->V.out, b->d_npts, nsel,
         sel ? b->d_wsel : nullptr, b->d_wout);
     CK(cudaMemcpyAsync(waves, b->d_wout, total*sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
@@ -1167,6 +1209,8 @@ int b200_batch_get_results_dev(const b200_batch *b, int nsel, const int *sel, do
     if (!b || !b->ran || !sel || nsel <= 0 || !dwaves) return B200_E_BADPARM;
     CK(cudaSetDevice(b->device));
     const Analysis &an = b->an;
+    std::vector<int> rows;
+    { int rc = out_rows(b, nsel, sel, rows); if (rc) return rc; sel = rows.data(); }
     if (nsel > b->wsel_cap) {
         if (b->d_wsel) cudaFree(b->d_wsel);
         b->d_wsel = nullptr; b->wsel_cap = 0;
@@ -1174,7 +1218,8 @@ int b200_batch_get_results_dev(const b200_batch *b, int nsel, const int *sel, do
         b->wsel_cap = nsel;
     }
     CK(cudaMemcpyAsync(b->d_wsel, sel, nsel*sizeof(int), cudaMemcpyHostToDevice, b->stream));
-    launch_gather_waves(b->stream, an.n, b->ldt, b->ntrials, an.npoints_max, b->V.out, b->d_npts, nsel,
+    CK(cudaStreamSynchronize(b->stream));               // `rows` is a local
+    launch_gather_waves(b->stream, b->K.nout, b->ldt, b->ntrials, an.npoints_max, b->V.out, b->d_npts, nsel,
         b->d_wsel, dwaves);
     if (dcounters)
         CK(cudaMemcpyAsync(dcounters, b->d_counters, (size_t)b->ntrials*B200_NCOUNTERS*sizeof(int),

@@ -112,6 +112,7 @@ struct Consts {
     int nbrks, nlat;
     // Josephson junctions: CKTinitDelta (jjic.cc:78-104) and the per-model accept constants
     double initDelta;
+    int nout;           // unknowns kept per output point (n, or the `.save` list)
     int jjaccel;        // sCKT::jjaccel(): option jjaccel and a junction in the deck (circuit.h:2119)
     int jjDCphase;      // CKTjjDCphase: the DC modes compute phase on the nodes of junctions and inductors
     int njjmod; int jj_limits[JJ_MAXMODELS];    // model has a supercurrent (ictype != 0)
@@ -195,6 +196,7 @@ struct VecView {
     double *states;     // [NS][numStates][ldt]
     double *oldState0;  // [numStates][ldt]
     double *contrib;    // [NC][ldt]: matrix + rhs contributions in assembly order
-    double *out;        // [npoints_max][n][ldt] -> transposed on fetch
+    double *out;        // [npoints_max][nout][ldt] -> transposed on fetch
+    const int *outslot; // [n+1] row of unknown i in `out`, -1 = not saved; NULL = all, row i-1 (b200_batch_set_saves)
     const char *phase;  // [n+1] node carries the phase flag, or NULL
 };

@@ -677,9 +677,11 @@ k_vec(Consts K, VecView V, CtlAux aux, double *rhsOld)
     int sb = aux.sols_base[t];
     if (ops & VO_ACCEPT_SOLS) V.sols[(size_t)sb*vplane + at] = rhsOld[at];
     if (!i) return;
-    size_t oplane = (size_t)K.n*ldt;
+    const int os = V.outslot ? V.outslot[i] : i - 1;      // the `.save` list (b200_batch_set_saves)
+    if (os < 0) return;
+    size_t oplane = (size_t)K.nout*ldt;
     if (ops & VO_DUMP_DIRECT)
-        V.out[(size_t)aux.ip_out0[t]*oplane + (size_t)(i-1)*ldt + t] = rhsOld[at];
+        V.out[(size_t)aux.ip_out0[t]*oplane + (size_t)os*ldt + t] = rhsOld[at];
     if (ops & VO_INTERP) {
         int cnt = aux.ip_n[t], out0 = aux.ip_out0[t], degree = aux.ip_degree[t];
         if (ops & VO_DUMP_DIRECT) out0 += 1;
@@ -712,7 +714,7 @@ k_vec(Consts K, VecView V, CtlAux aux, double *rhsOld)
                 double f3 = d1*d2*d3/((c4)*(c4-c2)*(c4-c3));
                 v = f0*s0 + f1*s1 + f2*s2 + f3*s3;
             }
-            V.out[(size_t)(out0 + p)*oplane + (size_t)(i-1)*ldt + t] = v;
+            V.out[(size_t)(out0 + p)*oplane + (size_t)os*ldt + t] = v;
         }
     }
 }

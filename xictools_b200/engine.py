@@ -57,6 +57,8 @@ def load_library(path: str | None = None):
     L.b200_batch_run_op.argtypes = [C.c_void_p]
     L.b200_batch_num_unknowns.argtypes = [C.c_void_p]
     L.b200_batch_num_points.argtypes = [C.c_void_p]
+    L.b200_batch_set_saves.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.b200_batch_num_saved.argtypes = [C.c_void_p]
     L.b200_batch_unknown_names.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.b200_batch_get_counters.argtypes = [C.c_void_p, C.c_void_p]
     L.b200_batch_get_waves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -171,12 +173,20 @@ class Batch:
             raise B200Error(rc, "b200_batch_get_waves")
         return t
 
+    def set_saves(self, unknowns):
+        """`.save`: keep only these unknowns (indices into names()) at the output points; before
+        the first run.  waves() then returns these columns, in this order."""
+        s = np.ascontiguousarray(unknowns, dtype=np.int32)
+        rc = self.L.b200_batch_set_saves(self.h, len(s), s.ctypes.data)
+        if rc:
+            raise B200Error(rc, "b200_batch_set_saves")
+
     def waves(self, sel=None, out=None):
-        """(times[npoints], waves[ntrials][npoints][n or len(sel)]); `out` = a caller-owned
+        """(times[npoints], waves[ntrials][npoints][saved or len(sel)]); `out` = a caller-owned
         result buffer of that shape (reused across runs, may be page-locked)."""
         t = np.zeros(self.npoints)
         if sel is None:
-            w = out if out is not None else np.empty((self.ntrials, self.npoints, self.n))
+            w = out if out is not None else np.empty((self.ntrials, self.npoints, self.L.b200_batch_num_saved(self.h)))
             rc = self.L.b200_batch_get_waves(self.h, t.ctypes.data, w.ctypes.data)
         else:
             s = np.ascontiguousarray(sel, dtype=np.int32)
