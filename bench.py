@@ -359,10 +359,13 @@ def bench_nor_mc(local, ntrials=16384, nref=16):
                                "sample": f"trials 0..{k-1} in {el:.1f} s (oracle/_ref, Sparse 1.3)"}
         same = steps_same = wave_ok = 0
         worst = 0.0
+        diffs = {}
         for t, x in enumerate(flat):
             err, acc, rej, nit, w = x
             steps_same += int((int(cnt[t, 0]), int(cnt[t, 1]), int(cnt[t, 2])) == (err, acc, rej))
             same += int(int(cnt[t, 3]) == nit)
+            dk = str(int(cnt[t, 3]) - nit)
+            diffs[dk] = diffs.get(dk, 0) + 1
             got = r["waves"][t][:w.shape[0]]
             tol = RELTOL*np.maximum(np.abs(got), np.abs(w)) + VNTOL
             ratio = float((np.abs(got - w)/tol).max())
@@ -370,6 +373,7 @@ def bench_nor_mc(local, ntrials=16384, nref=16):
             wave_ok += int(ratio <= 1.0)
         out["parity"] = {"vs": "oracle/_ref (unmodified reference, Sparse 1.3 pivoting)", "trials_compared": k,
                          "steps_identical": steps_same, "newton_iterations_identical": same,
+                         "newton_iterations_engine_minus_reference": diffs,
                          "newton_iterations_note": "the reference re-orders once during the gmin stepping of this deck's operating point "
                                                    "(its own trace: 'Matrix is singular, iterno=1 / Forced reordering', niiter.cc:303-331) "
                                                    "and spends one more iteration there than the engine's static sequence: engine = reference - 1",

@@ -115,6 +115,7 @@ typedef struct {
     double parms[8], cache[2];
     double *pwl_cache; int pwl_n, pwl_index;
     int enable_tran;
+    int npat, prst, nargs; const double *pat;   /* GPULSE bit pattern */
 } Src;
 
 /* sJJinstancePOD + the model values it reads (jjdefs.h).  No lser / lsh / control. */
@@ -466,6 +467,11 @@ static void src_setup_func(wo_ckt *c, Src *s, double step, double finaltime)
         /* IFgpulseData::setup, inptran.cc:1672-1730 (bit patterns not restated) */
         double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
         const double TWOSQRTLN2 = 2.0*sqrt(M_LN2), PHI0_SQRTPI = PHI0/sqrt(M_PI);  /* :74-75 */
+        /* a bit pattern follows a NaN: length, repeat start, bits (include/b200spice.h) */
+        s->npat = 0; s->pat = 0;
+        for (int k = 0; k < s->ncoef; k++)
+            if (isnan(co[k])) { nc = k; s->npat = (int)co[k+1]; s->prst = (int)co[k+2]; s->pat = co + k + 3; break; }
+        s->nargs = nc;
         memset(p, 0, 8*sizeof(double));
         p[0] = co[0];
         p[1] = nc >= 2 ? co[1] : co[0];
@@ -624,7 +630,7 @@ static double src_eval(Src *s, double t)
         const double rchk = 5.0;
         if (p[4] > 0.0) {
             double per = p[4];
-            for (int cidx = 4; cidx < s->ncoef || cidx == 4; cidx++) {
+            for (int cidx = 4; cidx < s->nargs || cidx == 4; cidx++) {
                 double td = cidx == 4 ? p[2] : s->coef[cidx];
                 int ifirst, ilast;
                 if (t < td) { ifirst = 0; ilast = 0; }
@@ -634,6 +640,11 @@ static double src_eval(Src *s, double t)
                     ilast = (int)rint((t - td + del)/per);
                 }
                 for (int i = ifirst; i <= ilast; i++) {
+                    if (s->npat) {                  /* inptran.cc:1755-1772 */
+                        int j = i;
+                        if (i >= s->npat) j = s->prst ? s->prst + (i - s->prst)%(s->npat - s->prst) : -1;
+                        if (j < 0 || s->pat[j] == 0.0) continue;
+                    }
                     double time = t - i*per;
                     double a = (time - td)/p[3];
                     V += exp(-a*a);
@@ -643,7 +654,7 @@ static double src_eval(Src *s, double t)
         else {
             double a = (t - p[2])/p[3];
             if (fabs(a) < rchk) V += exp(-a*a);
-            for (int i = 5; i < s->ncoef; i++) {
+            for (int i = 5; i < s->nargs; i++) {
                 a = (t - s->coef[i])/p[3];
                 if (fabs(a) < rchk) V += exp(-a*a);
             }

@@ -30,9 +30,13 @@
 
 #include "circuit.h"
 #include "device.h"
+// the bit pattern of a PULSE / GPULSE source is a private member (inptran.h:236-276; inpptree.h
+// pulls that header in)
+#define private public
 #include "input.h"
 #include "inpptree.h"
 #include "inptran.h"
+#undef private
 #include "trandefs.h"
 #include "dcodefs.h"
 #include "res/resdefs.h"
@@ -271,7 +275,27 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
                             int nc = TranPeek::ncoeffs(td);
                             const double *cf = TranPeek::coeffs(td);
                             H->coefs.emplace_back(cf, cf + nc);
-                            x.ncoef = nc;
+                            if (x.fn == B200_FN_PULSE && ((IFpulseData*)td)->td_pblist) {
+                                H->error = "PULSE bit pattern"; return B200_E_UNSUPP;
+                            }
+                            if (x.fn == B200_FN_GPULSE && ((IFgpulseData*)td)->td_pblist) {
+                                // expanded as IFgpulseData::setup does (inptran.cc:1714-1727): the
+                                // reference's own pbitAry; handed on after a NaN separator as
+                                // length, repeat start, bits
+                                pbitAry ba;
+                                ba.add(((IFgpulseData*)td)->td_pblist);
+                                if (ba.count()) {
+                                    unsigned long *bits = ba.final();
+                                    std::vector<double> &cv = H->coefs.back();
+                                    cv.push_back(NAN);
+                                    cv.push_back((double)ba.count());
+                                    cv.push_back((double)ba.rep_start());
+                                    for (int q = 0; q < ba.count(); q++)
+                                        cv.push_back((bits[q/sizeof(unsigned long)] >> (q % sizeof(unsigned long))) & 1 ? 1.0 : 0.0);
+                                    delete [] bits;
+                                }
+                            }
+                            x.ncoef = (int)H->coefs.back().size();
                         }
                         else
                             H->coefs.emplace_back();

@@ -3,9 +3,9 @@ example (wrspice/examples/JJexamples/nor_mc.cir: 26 junctions with phase nodes i
 cells, 177 unknowns, biased from a DC rail -- no `uic`), flattened for the headless harness by
 tools/flatten_spice.py, with the example's own varied parameters (eight critical currents, four
 bias resistors, one inductor of cell X0) drawn per trial.  What the example needs from the
-reference's script front end is dropped: the .control/.exec blocks, `.stop ... call cb`, the PRBS
-bit patterns of the two data inputs (they become plain periodic SFQ pulse trains) and the logic
-comparison source.  Every trial is run by the UNMODIFIED reference (oracle/_ref); the fixture
+reference's script front end is dropped: the .control/.exec blocks, `.stop ... call cb` and the
+logic comparison source (a patterned PULSE); the PRBS bit patterns of the two data inputs
+(`gpulse(... bprbs6 r=-1)`) are kept.  Every trial is run by the UNMODIFIED reference (oracle/_ref); the fixture
 holds the flat deck, the per-trial values, the reference's counters and three signals at every
 tenth output point.  Run in the build container:
 
@@ -35,7 +35,6 @@ VARIED = {**{f"b{k}ics": (P_JJ_ICS, f"b{k}.x0") for k in range(8)},
 
 def source_text():
     src = open(SRC).read()
-    src = re.sub(r"\s+BD[12]\)", ")", src)
     src = "\n".join(l for l in src.splitlines() if not l.lower().startswith("vout"))
     return src.replace(".tran 0.1p 1n", f".tran 0.1p {TSTOP}")
 

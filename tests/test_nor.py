@@ -74,6 +74,24 @@ def test_harvested_nor_gate_is_analysed():
     assert (r["ref"]["error"], r["ref"]["accepted"], r["ref"]["numiter"]) == (0, c["accepted"], c["numiter"])
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_oracle_on_the_harvested_gate_with_its_prbs_inputs():
+    """The first 60 ps (the operating point, the clock pulse and the first data pulses selected by
+    the PRBS bit patterns `bprbs6 r=-1` / `bprbs6 rb=11 r=-1`) through the plain-C oracle, fed by
+    the shim with the bits the reference's own pbitAry expands: same steps, waveforms to
+    roundoff; one Newton iteration fewer, in the operating point (see the GPU test)."""
+    from oracle.pyoracle import run_harvest_oracle
+    g = _gold()
+    r = run_harvest_oracle(g["spice"].replace(".tran 0.1p 0.25n", ".tran 0.1p 0.06n"))
+    assert r["rc"] == 0
+    c = r["counters"]
+    assert (int(c[0]), int(c[1]), int(c[2])) == (0, r["ref"]["accepted"], r["ref"]["rejected"])
+    assert int(c[3]) - r["ref"]["numiter"] in (-1, 0)
+    n = len(r["ref_times"])
+    assert len(r["times"]) == n
+    assert np.abs(r["vals"] - r["ref_vals"]).max() < 1e-10
+
+
 @pytest.mark.gpu
 def test_nor_gate_monte_carlo_matches_the_reference():
     g = _gold()

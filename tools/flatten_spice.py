@@ -66,10 +66,14 @@ def _subst(tok, params):
     return repr(e) if e is not None and _num(tok) is None else tok
 
 
+_STRINGS = {}
+
+
 def _subst_line(ln, params):
     # source arguments: name(args) groups are substituted argument by argument
     def grp(m):
-        return m.group(1) + "(" + " ".join(_subst(a, params) for a in m.group(2).replace(",", " ").split()) + ")"
+        return m.group(1) + "(" + " ".join(_STRINGS.get(a.lower(), None) or _subst(a, params)
+                                           for a in m.group(2).replace(",", " ").split()) + ")"
     ln = re.sub(r"(\b[a-z]+)\(([^()]*)\)", grp, ln, flags=re.I)
     toks = ln.split()
     return " ".join([toks[0]] + [t if "(" in t or ")" in t else _subst(t, params) for t in toks[1:]])
@@ -96,6 +100,7 @@ def flatten(text, overrides=None):
             lines.append(raw.rstrip())
     title, body = lines[0], lines[1:]
     params, subs, top = {}, {}, []
+    strings = {}                # .param name="text": substituted verbatim (bit patterns of sources)
     cur = None
     skip = False
     for ln in body:
@@ -116,6 +121,8 @@ def flatten(text, overrides=None):
                 e = _eval(v, params)
                 if e is not None:
                     params[k.lower()] = e
+                elif v.startswith('"'):
+                    strings[k.lower()] = v.strip('"')
             continue
         if low.startswith(".subckt"):
             t = s.split()
@@ -129,6 +136,7 @@ def flatten(text, overrides=None):
     for k, v in (overrides or {}).items():
         params[k.lower()] = float(v)
     out = []
+    _STRINGS.clear(); _STRINGS.update(strings)
 
     def emit(elems, path, nodemap):
         for s in elems:

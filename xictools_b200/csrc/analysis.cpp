@@ -852,6 +852,15 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             // given amplitude (or, with no amplitude either, of FWHM = TSTEP).  pool: parms[8], extras
             double p[8] = {0,0,0,0,0,0,0,0};
             const double *co = in.coef; int nc = in.ncoef;
+            // a bit pattern follows a NaN: length, repeat start, bits (include/b200spice.h)
+            int npat = 0; const double *pat = nullptr;
+            for (int k = 0; k < in.ncoef; k++)
+                if (std::isnan(co[k])) {
+                    nc = k;
+                    if (k + 2 >= in.ncoef || (int)co[k+1] != in.ncoef - k - 3) { err = "gpulse pattern encoding"; return B200_E_BADPARM; }
+                    npat = (int)co[k+1]; pat = co + k + 2;      // pat[0] = repeat start, then the bits
+                    break;
+                }
             if (nc < 1) { err = "gpulse needs arguments"; return B200_E_BADPARM; }
             const double twosqrtln2 = 2.0*sqrt(M_LN2), phi0_sqrtpi = JJ_PHI0/sqrt(M_PI);
             p[0] = co[0];
@@ -865,9 +874,11 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
                 else p[3] = step/twosqrtln2;
             }
             if (p[1] == p[0]) p[1] = p[0] + phi0_sqrtpi/p[3];
+            p[5] = npat; p[6] = npat ? pat[0] : 0.0;             // pattern length and repeat start
             S.pool.insert(S.pool.end(), p, p + 8);
             for (int k = 5; k < nc; k++) S.pool.push_back(co[k]);
-            S.ncoef[i] = nc > 5 ? nc - 5 : 0;        // number of extra delays
+            for (int k = 0; k < npat; k++) S.pool.push_back(pat[1 + k]);
+            S.ncoef[i] = nc > 5 ? nc - 5 : 0;        // number of extra delays (the pattern bits follow them)
         }
         else if (in.fn == B200_FN_SPULSE) {
             // IFspulseData::setup, inptran.cc:2790-2808: V1 V2 SPER SDEL THETA

@@ -2015,6 +2015,8 @@ __device__ inline double dev_src_eval(int fn, const double *p, int nextra, doubl
         const double *offs = p + 8;
         if (p[4] > 0.0) {
             const double per = p[4];
+            const int plen = (int)p[5], prst = (int)p[6];     // bit pattern: which periods carry a pulse
+            const double *bits = offs + nextra;
             for (int c = -1; c < nextra; c++) {
                 const double td = c < 0 ? p[2] : offs[c];
                 int ifirst = 0, ilast = 0;
@@ -2024,6 +2026,12 @@ __device__ inline double dev_src_eval(int fn, const double *p, int nextra, doubl
                     ilast = (int)rint((t - td + del)/per);
                 }
                 for (int i = ifirst; i <= ilast; i++) {
+                    if (plen) {
+                        // inptran.cc:1755-1772 (a negative index reads no set bit)
+                        int j = i;
+                        if (i >= plen) j = prst ? prst + (i - prst)%(plen - prst) : -1;
+                        if (j < 0 || bits[j] == 0.0) continue;
+                    }
                     double time = t - i*per;
                     double a = (time - td)/p[3];
                     V += exp(-a*a);
