@@ -376,7 +376,7 @@ def bench_nor_mc(local, ntrials=16384, nref=16):
                          "newton_iterations_engine_minus_reference": diffs,
                          "newton_iterations_note": "the reference re-orders once during the gmin stepping of this deck's operating point "
                                                    "(its own trace: 'Matrix is singular, iterno=1 / Forced reordering', niiter.cc:303-331) "
-                                                   "and spends one more iteration there than the engine's static sequence: engine = reference - 1",
+                                                   "and spends one more iteration there than the engine's static sequence: engine = reference - 1; the reference itself, run through the KLU plug-in, takes the engine's count (tests/test_nor.py)",
                          "waves_within_tol": wave_ok, "max_wave_err_over_tol": worst}
     except Exception as e:          # pragma: no cover
         out["parity"] = {"error": repr(e)}

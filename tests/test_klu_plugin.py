@@ -107,7 +107,7 @@ def test_plugged_in_without_a_gpu_fails_loudly():
 @pytest.mark.gpu
 @pytest.mark.skipif(not (have_ref_klu() and have_ref()), reason="oracle/_ref not built")
 @pytest.mark.parametrize("name", ["ro5", "inv4", "rlc_series", "lc_ladder", "transformer", "rc_sin",
-                                  "ro5_level3", "ro5_gear3"])
+                                  "ro5_level3", "ro5_gear3", "jtl6", "jtl6_dc", "jtl6_dc_phase", "jtl6_dc_accel"])
 def test_reference_with_the_b200_plugin_matches_its_own_sparse_run(name):
     """parser -> sCKT::doTask -> NIiter -> KLUmatrix::factor/refactor/solve -> libb200spice.so
     (GPU) against the same reference with Sparse 1.3: identical step / iteration counts,

@@ -111,7 +111,8 @@ def test_nor_gate_monte_carlo_matches_the_reference():
         # pivot order and spends one extra iteration re-ordering ("Matrix is singular, iterno=1 /
         # Forced reordering" in its own CKTstepDebug trace, niiter.cc:303-331) -- an event of its
         # pivot order, which the C oracle (own pivoting) does not have either: 86 against 87
-        # iterations in the operating point, everything after it identical.
+        # iterations in the operating point, everything after it identical; the reference ITSELF
+        # takes the engine's count when it runs through the KLU plug-in (test below).
         assert (int(got[0]), int(got[1]), int(got[2])) == (c["err"], c["accepted"], c["rejected"]), (t, got[:4], c)
         assert int(got[3]) - c["numiter"] in (-1, 0), (t, int(got[3]), c["numiter"])
         diffs.append(int(got[3]) - c["numiter"])
@@ -125,3 +126,22 @@ def test_nor_gate_monte_carlo_matches_the_reference():
     w1 = r["waves"][1][::g["decimation"]][:, idx]
     w0 = r["waves"][0][::g["decimation"]][:, idx]
     assert np.abs(w1 - w0).max() > 1e-5
+
+
+@pytest.mark.gpu
+def test_reference_through_the_klu_plugin_counts_like_the_engine():
+    """Whose iteration is the one that differs?  The UNMODIFIED reference, run with
+    libb200spice.so plugged in as its KLU (its own NIiter, its own re-order logic, our LU), takes
+    the same steps and one Newton iteration fewer than its Sparse 1.3 run -- exactly the batched
+    engine's count: the extra iteration belongs to Sparse's pivot order, not to the circuit."""
+    from oracle.pyoracle import have_ref_klu, run_ref_klu
+    if not have_ref_klu():
+        pytest.skip("oracle/_ref KLU variant not built")
+    g = _gold()
+    c = g["trials"][0]["counters"]
+    r = run_ref_klu(g["spice"], engine.LIB_PATH)
+    assert r["klu_ok"] == 1 and r["err"] == 0
+    assert (r["accepted"], r["rejected"]) == (c["accepted"], c["rejected"])
+    assert r["numiter"] == c["numiter"] - 1
+    e = run_harvest(g["spice"], engine.LIB_PATH, 1, saves=g["signal_cols"])
+    assert int(e["counters"][0][3]) == r["numiter"]
