@@ -19,3 +19,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-s
 timeout 900 ncu --set full --clock-control none --import-source on --launch-skip 3000 -c 12 \
    -o $OUT/${TAG}_prof -f python bench.py --kernel-only --trials 4096 --steps 1 --warmup 1 > $OUT/${TAG}_ncu2.log 2>&1
 ls -la $OUT | grep ${TAG}
+# launch lists of the secondary workloads (wide LU path): 1000-junction line and the 100k-MOSFET deck
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 4000 -c 400 --csv \
+   --log-file $OUT/${TAG}_rsfq_launches.csv python -c "import bench; bench.bench_rsfq(0)" > $OUT/${TAG}_ncu3.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2000 -c 300 --csv \
+   --log-file $OUT/${TAG}_large_launches.csv python tools/t_large.py 50001 1 1 > $OUT/${TAG}_ncu4.log 2>&1
+python tools/launch_summary.py $OUT/${TAG}_rsfq_launches.csv > $OUT/${TAG}_rsfq_launch_summary.txt 2>&1
+python tools/launch_summary.py $OUT/${TAG}_large_launches.csv > $OUT/${TAG}_large_launch_summary.txt 2>&1
+ls -la $OUT | grep ${TAG}

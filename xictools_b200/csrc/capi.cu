@@ -1045,7 +1045,7 @@ static int run_analysis(b200_batch *b, int analysis)
     // kernels of a few microseconds each): two ticks -- one per parity of the rhs / rhsOld flip --
     // are captured once into a CUDA graph and the window replays it.  The load / solve split is
     // not timed in this mode.
-    bool use_graph = (double)K.ntrials*K.n < 2.0e6;
+    bool use_graph = (double)K.ntrials*K.n < 2.0e6 && K.n < 20000;     // (a huge system with few trials has long ticks)
     if (const char *e = getenv("B200_GRAPH")) use_graph = atoi(e) != 0;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
