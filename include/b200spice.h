@@ -75,11 +75,10 @@ typedef struct b200_mut { int ind1, ind2; double k; } b200_mut;
 
 /* Independent source: devlib/src/srcset.cc:64-370, srcload.cc:67-262,
  * src/inp/inptran.cc (PULSE :1099-1414, GPULSE :1567-1827, PWL :1980-2388, SIN :2496-2624,
- * SPULSE :2708-2870, EXP :2902-3082, SFFM :3113-3260, AM :3292-3442).  A GPULSE bit pattern
+ * SPULSE :2708-2870, EXP :2902-3082, SFFM :3113-3260, AM :3292-3442).  A PULSE / GPULSE bit pattern
  * (inptran.cc:285-520, `bprbs6 r=-1`, `b0110 rb=2 r=3` ...) follows the arguments in `coef` after a
  * NaN: length, repeat start, then the expanded bits as 0 / 1 (shim/harvest.cc expands it with the
- * reference's own pbitAry).  PULSE bit patterns, GAUSS (a random source), TABLE and INTERP are
- * refused. */
+ * reference's own pbitAry).  GAUSS (a random source), TABLE and INTERP are refused. */
 enum { B200_SRC_V = 0, B200_SRC_I = 1 };
 enum { B200_FN_NONE = 0, B200_FN_PULSE = 1, B200_FN_PWL = 2, B200_FN_SIN = 3,
        B200_FN_EXP = 4, B200_FN_SFFM = 5, B200_FN_AM = 6, B200_FN_GAUSS = 7,

@@ -115,7 +115,7 @@ typedef struct {
     double parms[8], cache[2];
     double *pwl_cache; int pwl_n, pwl_index;
     int enable_tran;
-    int npat, prst, nargs; const double *pat;   /* GPULSE bit pattern */
+    int npat, prst, nargs, pat_on; const double *pat;   /* PULSE / GPULSE bit pattern */
 } Src;
 
 /* sJJinstancePOD + the model values it reads (jjdefs.h).  No lser / lsh / control. */
@@ -376,6 +376,11 @@ static void src_setup_func(wo_ckt *c, Src *s, double step, double finaltime)
     if (s->fn == B200_FN_PULSE) {
         /* inptran.cc:1203-1318 */
         double *p = s->parms; const double *co = s->coef; int nc = s->ncoef;
+        /* a bit pattern follows a NaN: length, repeat start, bits (include/b200spice.h) */
+        s->npat = 0; s->pat = 0;
+        for (int k = 0; k < s->ncoef; k++)
+            if (isnan(co[k])) { nc = k; s->npat = (int)co[k+1]; s->prst = (int)co[k+2]; s->pat = co + k + 3; break; }
+        s->nargs = nc;
         memset(p, 0, 8*sizeof(double));
         p[0] = co[0];
         p[1] = nc >= 2 ? co[1] : co[0];
@@ -399,6 +404,7 @@ static void src_setup_func(wo_ckt *c, Src *s, double step, double finaltime)
             s->cache[0] = (p[1] - p[0])/p[3];
             s->cache[1] = (p[0] - p[1])/p[4];
             int nrep = nc > 7 ? nc - 7 : 0;
+            s->pat_on = 0;
             for (int r = -1; r < nrep; r++) {
                 double time = (r < 0) ? p[2] : co[7 + r];
                 if (p[6] < finaltime) {
@@ -414,6 +420,7 @@ static void src_setup_func(wo_ckt *c, Src *s, double step, double finaltime)
                     if (p[4] != 0) { time += p[4]; break_set(c, time); }
                 }
             }
+            s->pat_on = p[6] < finaltime;            /* :1305: the pattern array exists only then */
         }
     }
     else if (s->fn == B200_FN_PWL) {
@@ -516,43 +523,36 @@ static void src_setup_func(wo_ckt *c, Src *s, double step, double finaltime)
 static double src_eval(Src *s, double t)
 {
     if (s->fn == B200_FN_PULSE) {
-        /* inptran.cc:1322-1414 (no bit pattern, extra offsets supported) */
+        /* inptran.cc:1322-1414 */
         const double *p = s->parms;
         if (!s->enable_tran)
             return p[0];
         double value = p[0];
         double pw = p[3] + p[5];
-        double time = t - p[2];
-        if (p[6] > 0.0) {
-            if (time > p[6]) {
-                int pnum = (int)(time/p[6]);
-                time -= (p[6]*pnum);
-            }
-        }
-        if (time < p[3] || time >= pw + p[4]) {
-            value = p[0];
-            if (time > 0 && time < p[3])
-                value += time*s->cache[0];
-        }
-        else {
-            value = p[1];
-            if (time > pw)
-                value += (time - pw)*s->cache[1];
-        }
-        for (int i = 7; i < s->ncoef; i++) {
-            time = t - s->coef[i];
+        for (int i = 6; i < s->nargs || i == 6; i++) {
+            /* i = 6: the pulse itself; then the additional offsets */
+            double time = t - (i == 6 ? p[2] : s->coef[i]);
+            int skip = 0;
             if (p[6] > 0.0) {
+                int pnum = 0;
                 if (time > p[6]) {
-                    int pnum = (int)(time/p[6]);
+                    pnum = (int)(time/p[6]);
                     time -= (p[6]*pnum);
                 }
+                if (s->npat && s->pat_on) {
+                    int j = pnum;
+                    if (pnum >= s->npat) j = s->prst ? s->prst + (pnum - s->prst)%(s->npat - s->prst) : -1;
+                    skip = j < 0 || s->pat[j] == 0.0;
+                }
             }
+            if (skip) continue;
             if (time < p[3] || time >= pw + p[4]) {
+                if (i == 6) value = p[0];
                 if (time > 0 && time < p[3])
                     value += time*s->cache[0];
             }
             else {
-                value += (p[1] - p[0]);
+                if (i == 6) value = p[1]; else value += (p[1] - p[0]);
                 if (time > pw)
                     value += (time - pw)*s->cache[1];
             }

@@ -275,15 +275,14 @@ extern "C" int b200_harvest_ckt(sCKT *ckt, b200_harvest **out)
                             int nc = TranPeek::ncoeffs(td);
                             const double *cf = TranPeek::coeffs(td);
                             H->coefs.emplace_back(cf, cf + nc);
-                            if (x.fn == B200_FN_PULSE && ((IFpulseData*)td)->td_pblist) {
-                                H->error = "PULSE bit pattern"; return B200_E_UNSUPP;
-                            }
-                            if (x.fn == B200_FN_GPULSE && ((IFgpulseData*)td)->td_pblist) {
-                                // expanded as IFgpulseData::setup does (inptran.cc:1714-1727): the
-                                // reference's own pbitAry; handed on after a NaN separator as
-                                // length, repeat start, bits
+                            pbitList *pbl = x.fn == B200_FN_PULSE ? ((IFpulseData*)td)->td_pblist :
+                                            x.fn == B200_FN_GPULSE ? ((IFgpulseData*)td)->td_pblist : nullptr;
+                            if (pbl) {
+                                // expanded as IF[g]pulseData::setup does (inptran.cc:1305-1316,
+                                // 1714-1727): the reference's own pbitAry; handed on after a NaN
+                                // separator as length, repeat start, bits
                                 pbitAry ba;
-                                ba.add(((IFgpulseData*)td)->td_pblist);
+                                ba.add(pbl);
                                 if (ba.count()) {
                                     unsigned long *bits = ba.final();
                                     std::vector<double> &cv = H->coefs.back();

@@ -136,3 +136,38 @@ def test_resistor_monte_carlo_through_the_shim():
         s = sim.run(d.to_spice({k: v[t] for k, v in ov.items()}))
         return dict(s, vals=s["vals"])
     _check(r, ntr, ref_of_trial)
+
+
+PATTERN_DECKS = {
+    # PULSE / GPULSE with bit patterns (inptran.cc:285-520): a finite string that repeats from its
+    # second bit, a PRBS that runs forever, a string repeated twice and then silent
+    "pulse_bits": "v1 a 0 pulse(0 1 0.1n 0.05n 0.05n 0.15n 0.5n b1011 rb=2 r=-1)",
+    "pulse_prbs": "v1 a 0 pulse(0.2 1 0.05n 0.05n 0.05n 0.1n 0.4n bprbs7 r=-1)",
+    "gpulse_bits": "v1 a 0 gpulse(0 1 0.2n 0.06n 0.4n b110 r=2)",
+}
+
+
+def _pattern_text(src_line):
+    return f"pattern source\n{src_line}\nr1 a b 1k\nc1 b 0 0.1p\n.tran 0.02n 6n\n"
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(PATTERN_DECKS))
+def test_bit_patterns_through_the_shim_into_the_oracle(name):
+    from oracle.pyoracle import run_harvest_oracle
+    r = run_harvest_oracle(_pattern_text(PATTERN_DECKS[name]))
+    assert r["rc"] == 0 and r["ref_err"] == 0
+    c = r["counters"]
+    assert tuple(int(c[k]) for k in (C_STATUS, C_ACCEPTED, C_REJECTED, C_NUMITER)) == \
+        (0, r["ref"]["accepted"], r["ref"]["rejected"], r["ref"]["numiter"])
+    assert np.abs(r["vals"] - r["ref_vals"]).max() < 1e-9
+    assert np.ptp(r["ref_vals"][:, 0]) > 0.5          # the source really pulses
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(PATTERN_DECKS))
+def test_bit_patterns_through_the_shim_into_the_engine(name):
+    r = run_harvest(_pattern_text(PATTERN_DECKS[name]), engine.LIB_PATH, 2)
+    assert r["ref_err"] == 0
+    ref = dict(r["ref"], vals=r["ref_vals"])
+    _check(r, 2, lambda t: ref)

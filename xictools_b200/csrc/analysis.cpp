@@ -749,6 +749,15 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
             if (in.ncoef < 1) { err = "pulse needs arguments"; return B200_E_BADPARM; }
             double p[8] = {0,0,0,0,0,0,0,0}, cache[2];
             const double *co = in.coef; int nc = in.ncoef;
+            // a bit pattern follows a NaN: length, repeat start, bits (include/b200spice.h)
+            int npat = 0; const double *pat = nullptr;
+            for (int k = 0; k < in.ncoef; k++)
+                if (std::isnan(co[k])) {
+                    nc = k;
+                    if (k + 2 >= in.ncoef || (int)co[k+1] != in.ncoef - k - 3) { err = "pulse pattern encoding"; return B200_E_BADPARM; }
+                    npat = (int)co[k+1]; pat = co + k + 2;
+                    break;
+                }
             p[0] = co[0];
             p[1] = nc >= 2 ? co[1] : co[0];
             p[2] = nc >= 3 ? co[2] : 0.0;
@@ -783,9 +792,12 @@ int b200_analyze(const b200_deck *dk, Analysis &an, std::string &err)
                     if (p[4] != 0) { time += p[4]; bt.set_break(time, 0.0); }
                 }
             }
+            if (!(p[6] < finaltime)) npat = 0;       // the pattern exists only for a period inside the run (:1305)
+            p[7] = npat;                             // pattern: [repeat start, bits...] after the offsets
             S.pool.insert(S.pool.end(), p, p + 8);
             S.pool.insert(S.pool.end(), cache, cache + 2);
             for (int r = 0; r < nrep; r++) S.pool.push_back(co[7 + r]);
+            for (int k = 0; k <= npat && npat; k++) S.pool.push_back(pat[k]);
             S.ncoef[i] = nrep;                       // number of extra offsets
         }
         else if (in.fn == B200_FN_PWL) {

@@ -1918,39 +1918,35 @@ __device__ inline double dev_src_eval(int fn, const double *p, int nextra, doubl
 {
     if (fn == B200_FN_PULSE) {
         const double *cache = p + 8, *offs = p + 10;
+        const int plen = (int)p[7];                       // bit pattern: which periods carry a pulse
+        const int prst = plen ? (int)offs[nextra] : 0;
+        const double *bits = offs + nextra + 1;
         double value = p[0];
         double pw = p[3] + p[5];
-        double time = t - p[2];
-        if (p[6] > 0.0) {
-            if (time > p[6]) {
-                int pnum = (int)(time/p[6]);
-                time -= (p[6]*pnum);
-            }
-        }
-        if (time < p[3] || time >= pw + p[4]) {
-            value = p[0];
-            if (time > 0 && time < p[3])
-                value += time*cache[0];
-        }
-        else {
-            value = p[1];
-            if (time > pw)
-                value += (time - pw)*cache[1];
-        }
-        for (int i = 0; i < nextra; i++) {
-            time = t - offs[i];
+        for (int i = -1; i < nextra; i++) {
+            // the pulse itself (i = -1), then the additional offsets: pulse(0 V2-V1 TDi ...) added
+            double time = t - (i < 0 ? p[2] : offs[i]);
+            bool skip = false;
             if (p[6] > 0.0) {
+                int pnum = 0;
                 if (time > p[6]) {
-                    int pnum = (int)(time/p[6]);
+                    pnum = (int)(time/p[6]);
                     time -= (p[6]*pnum);
                 }
+                if (plen) {                               // inptran.cc:1338-1354
+                    int j = pnum;
+                    if (pnum >= plen) j = prst ? prst + (pnum - prst)%(plen - prst) : -1;
+                    skip = j < 0 || bits[j] == 0.0;
+                }
             }
+            if (skip) continue;
             if (time < p[3] || time >= pw + p[4]) {
+                if (i < 0) value = p[0];
                 if (time > 0 && time < p[3])
                     value += time*cache[0];
             }
             else {
-                value += (p[1] - p[0]);
+                if (i < 0) value = p[1]; else value += (p[1] - p[0]);
                 if (time > pw)
                     value += (time - pw)*cache[1];
             }
