@@ -256,7 +256,9 @@ def op_decks():
             "op_inv7_nogmin": inv_chain(7).options(gminsteps=-1),
             "op_inv_lsupply": inv_lsupply(), "op_inv4_level6": inv_level6(), "op_inv4_level3": inv_level3(),
             "op_ro5_level3": ro_level3(5), "op_inv4_level2": inv_level2(),
-            "op_ro5_level2": ro_level2(5)}
+            "op_ro5_level2": ro_level2(5),
+            # option dcmu: the operating point mixes in some of the last solution (niiter.cc:480-497)
+            "op_opamp_dcmu": opamp().options(dcmu=0.3), "op_inv7_dcmu": inv_chain(7).options(dcmu=0.4, gminsteps=-1)}
 
 
 def variants():
@@ -298,6 +300,7 @@ def variants():
         "rc_sffm": rc_fn(sffm=(0.5, 0.4, 1.0e9, 2.0, 0.2e9)),
         "rc_am": rc_fn(am=(0.8, 1.0, 0.3e9, 2.0e9, 0.4e-9)),
         "float_cap": float_cap(),
+        "ro5_dcmu": ring_oscillator(5).options(dcmu=0.35),
         # GPULSE (inptran.cc:1567-1827): FWHM width + two more pulse delays; repeating; old-style width
         "rc_gpulse": rc_fn(gpulse=(0.1, 1.0, 1.0e-9, 0.3e-9, 0, 2.2e-9, 3.1e-9)),
         "rc_gpulse_rpt": rc_fn(gpulse=(0.0, 0.8, 0.6e-9, -0.12e-9, 1.1e-9)),

@@ -304,9 +304,9 @@ int b200_batch_create(const b200_deck *deck, int ntrials, int device, b200_batch
         fprintf(stderr, "b200spice: no CUDA device (no CPU fallback exists)\n");
         return B200_E_NOGPU;
     }
-    if (deck->opt.dcmu != 0.5 || deck->opt.steptype != 0 ||
+    if (deck->opt.steptype != 0 ||
             deck->opt.gminsteps > 0 || deck->opt.srcsteps > 0) {
-        fprintf(stderr, "b200spice: option not built yet (dcmu/steptype/spice3 stepping)\n");
+        fprintf(stderr, "b200spice: option not built yet (steptype/spice3 stepping)\n");
         return B200_E_UNSUPP;
     }
     CK(cudaSetDevice(device));

@@ -185,6 +185,8 @@ __device__ inline int ctl_ni_post_solve(TrialCtl &s, const Consts &K, const CtlI
             }
             if (noncon == 0)
                 error = 0;
+            else if ((s.mode & MODEDC) && s.iterno > 2 && K.opt.dcmu != 0.5)
+                s.vecops |= VO_DCMU;    // niiter.cc:480-497
         }
         else if (s.mode & MODEINITPRED)
             s.mode = (s.mode & (~INITF)) | MODEINITFLOAT;

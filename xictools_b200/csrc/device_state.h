@@ -41,6 +41,7 @@ enum { RET_NONE = 0, RET_OP_DIRECT, RET_GMIN_LOOP, RET_GMIN_FINAL, RET_SRC_LOOP,
 #define VO_INTERP       0x100   // emit interpolated output points    (tranan.cc:963-1116)
 #define VO_DUMP_DIRECT  0x200   // emit rhsOld as an output point     (tranan.cc:977-981)
 #define VO_ZERO_PHASE   0x800   // zero the phase nodes of rhsOld after a phase-mode DCOP (tranan.cc:378-389)
+#define VO_DCMU         0x1000  // rhsOld <- (dcmu+.5)*rhsOld + (.5-dcmu)*rhs   (niiter.cc:480-497)
 #define VO_KEEP_X       0x400   // trial parked at a sync point: carry its rhsOld over the global
                                 //  rhs/rhsOld buffer flip of this tick
 

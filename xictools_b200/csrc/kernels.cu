@@ -669,6 +669,12 @@ k_vec(Consts K, VecView V, CtlAux aux, double *rhsOld)
         const double *other = (rhsOld == V.X[0]) ? V.X[1] : V.X[0];
         rhsOld[at] = other[at];
     }
+    if ((ops & VO_DCMU) && i) {
+        // option dcmu: mix in a little of the last solution (DC operating point damping)
+        const double *other = (rhsOld == V.X[0]) ? V.X[1] : V.X[0];
+        const double A = K.opt.dcmu + 0.5, B = 1.0 - A;
+        rhsOld[at] = A*rhsOld[at] + B*other[at];
+    }
     if ((ops & VO_ZERO_PHASE) && V.phase && V.phase[i]) rhsOld[at] = 0.0;
     if (ops & VO_BK_SAVE) V.oldSol[at] = rhsOld[at];
     if (ops & VO_BK_RESTORE) rhsOld[at] = V.oldSol[at];
