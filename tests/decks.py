@@ -322,6 +322,28 @@ def _one_ic():
 from xictools_b200.workloads import JJ_CARD, jj_single, jtl, opamp      # noqa: E402,F401
 
 
+def squid_coupled(uic=False):
+    """A two-junction SQUID loop biased through a resistor from a DC rail, flux-coupled (K) to an
+    input coil that a current pulse drives: mutual-inductor terms of the phase-mode DC operating
+    point (mutload.cc:75-87) and of the transient (flux through the coupled pair)."""
+    d = Deck(title="coupled squid")
+    d.jj_model("jj1", **JJ_CARD)
+    d.vsource("vdd", "vb", "0", dc=10e-3)
+    d.resistor("rb", "vb", "m", 10e-3/0.35e-3)
+    d.inductor("l1", "m", "a", 4.0e-12)
+    d.inductor("l2", "m", "b", 4.0e-12)
+    d.jj("b1", "a", "0", "jj1", ics=0.25e-3)
+    d.jj("b2", "b", "0", "jj1", ics=0.26e-3)
+    d.resistor("rs1", "a", "0", 3.0)
+    d.resistor("rs2", "b", "0", 3.0)
+    d.isource("iin", "0", "c", pulse=(0, 0.5e-3, 20e-12, 5e-12, 5e-12, 30e-12, 200e-12))
+    d.inductor("lin", "c", "0", 6.0e-12)
+    d.mutual("k1", "lin", "l1", 0.6)
+    d.mutual("k2", "lin", "l2", -0.4)
+    d.tran(0.5e-12, 100e-12, uic=uic)
+    return d
+
+
 def jj_variants():
     return {
         "jj_single": jj_single(),
@@ -350,6 +372,8 @@ def jj_variants():
         "jtl6_dc_accel": jtl(6, dc_bias=True).options(jjaccel=1),
         "jtl12_vshunt_accel": jtl(12, vshunt=0.6857e-3).options(jjaccel=1),
         "jtl6_tjm_accel": jtl(6, tjm="tjm1").options(jjaccel=1),
+        "squid_coupled": squid_coupled(),
+        "squid_coupled_uic": squid_coupled(uic=True),
         # driven by a single-flux-quantum GPULSE voltage source
         "jtl6_dc_sfq": jtl(6, dc_bias=True, sfq_in=True),
     }

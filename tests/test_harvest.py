@@ -21,7 +21,7 @@ RELTOL, VNTOL = 1e-3, 1e-6
 DECKS = ["ro5", "inv4", "lc_ladder", "transformer", "rc_sin", "rlc_series", "ro5_level2",
          "ro5_level3", "ro5_level6", "rlc_uic", "ro3_rd", "ro9_one_ic", "ro5_gear3", "ro17", "inv7",
          "ro5_trapcheck", "rc_exp", "rc_sffm", "rc_am", "rc_gpulse", "rc_gpulse_rpt", "rc_spulse", "rc_spulse_theta", "jtl6_dc_sfq", "jj_single", "jj_single_rtype3", "jtl6", "jtl6_phase", "jtl6_vshunt", "jtl12",
-         "jtl6_accel", "jtl6_dc_accel", "jtl6_dc", "jtl6_dc_phase", "jtl6_dc_vshunt", "jtl12_dc"]
+         "jtl6_accel", "jtl6_dc_accel", "squid_coupled", "squid_coupled_uic", "jtl6_dc", "jtl6_dc_phase", "jtl6_dc_vshunt", "jtl12_dc"]
 
 
 @pytest.mark.parametrize("name", DECKS)

@@ -25,7 +25,10 @@ def test_static_orders_are_growth_free(name):
     if not uic:
         err, Ax, _ = o.debug_load(MODETRANOP | INITJCT, 0.0, 0.0, 1)
         g, w = growth(n, Ap, Ai, Ax, rp, cp)
-        assert g <= 1e3 and w >= 1e-3, ("dc", g, w)
+        # (a pivot below the relative threshold is harmless where nothing grows: in the phase-mode
+        # DC matrix a junction's diagonal Ic*cos(phi) ~ 2.5e-4 sits in a column of +-1 couplings,
+        # and what its multipliers add to the branch rows stays below their 2*pi*L/Phi0 ~ 1e4)
+        assert g <= 1e3 and (w >= 1e-3 or g <= 2.0), ("dc", g, w)
     delta = min(ts, (tp - t0)/50*1.001)*0.1
     err, Ax, _ = o.debug_load(MODETRAN | INITTRAN | (UIC if uic else 0), delta, delta, 1)
     g, w = growth(n, Ap, Ai, Ax, rp2, cp2)
