@@ -145,3 +145,24 @@ def test_reference_through_the_klu_plugin_counts_like_the_engine():
     assert r["numiter"] == c["numiter"] - 1
     e = run_harvest(g["spice"], engine.LIB_PATH, 1, saves=g["signal_cols"])
     assert int(e["counters"][0][3]) == r["numiter"]
+
+
+@pytest.mark.gpu
+def test_nor_gate_with_the_tunnel_junction_model():
+    """The same gate with its 26 junctions as level-3 (TJM, coefficient set tjm1) devices: the
+    reference's own doTask on the circuit the shim harvests is the comparison."""
+    g = _gold()
+    text = g["spice"].replace(".tran 0.1p 0.25n", ".tran 0.1p 0.12n")
+    model = [l for l in text.splitlines() if l.lower().startswith(".model jj5ee")][0]
+    text = text.replace(model, ".model jj5ee jj(level=3 coeffset=tjm1 vshunt=0.6857mV)")
+    r = run_harvest(text, engine.LIB_PATH, 2, saves=g["signal_cols"])
+    assert r["rc"] == 0 and r["ref_err"] == 0
+    ref = r["ref"]
+    for t in range(2):
+        c = r["counters"][t]
+        assert (int(c[0]), int(c[1]), int(c[2])) == (0, ref["accepted"], ref["rejected"])
+        assert int(c[3]) - ref["numiter"] in (-1, 0)
+        want = r["ref_vals"][:, g["signal_cols"]]
+        got = r["waves"][t][:want.shape[0]]              # (the buffer holds npoints_max rows)
+        tol = RELTOL*np.maximum(np.abs(got), np.abs(want)) + VNTOL
+        assert not (np.abs(got - want) > tol).any()
