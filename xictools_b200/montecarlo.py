@@ -53,6 +53,10 @@ class EngineRunner:
     def names(self):
         return self.batch.names()
 
+    def set_saves(self, sel):
+        """`.save`: the device keeps only these unknowns at the output points."""
+        self.batch.set_saves(sel)
+
     def upload(self, overrides):
         if self.packed is not None:
             self.batch.set_params_packed(*self.packed)      # one transfer + a device scatter
@@ -150,6 +154,8 @@ class MonteCarlo:
         names = self.runner.names()
         self.save = list(save) if save is not None else list(names)
         self.sel = [names.index(s) for s in self.save]
+        if save is not None and hasattr(self.runner, "set_saves"):
+            self.runner.set_saves(self.sel)         # the output buffer holds the saved unknowns only
         self.counters = self.times = self.waves = None
         self._dev = None
 
