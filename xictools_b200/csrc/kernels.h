@@ -42,6 +42,7 @@ struct SolveView {
     int *live;                  // [ldt] trials that take a solve this tick (built by k_assemble)
     int *ctr;                   // [0] number of live trials, [1] work counter of the k_lu warps
     int nsm;                    // SMs of the device (grid sizing)
+    int lu_team;                // warps per resident image in k_lu_team (1: k_lu)
     int lu_warps, lu_grid;      // warps (= trials in flight) per CTA, CTAs of the persistent k_lu
     int lu_smem;                // dynamic shared memory of k_lu
     int prog_in_smem;           // 1: every CTA stages the program rows in shared memory

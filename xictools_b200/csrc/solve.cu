@@ -258,6 +258,107 @@ k_lu(SolveView Sv, int n)
 }
 
 // ---------------------------------------------------------------------------------------
+// k_lu_team: k_lu with P warps per resident image.  One warp per image leaves the SM's issue
+// slots idle (RO-501: 5 images fit, a row of the program is a chain of ~150 dependent cycles);
+// here the P warps of a team take the rounds of a level in turn (round r of the level -> warp
+// r mod P) and meet at a named barrier of their own between levels, so the other teams of the
+// CTA never wait.  Image by one bulk copy as in k_lu; program rows addressed through the
+// round -> row table.  Same tasks, same operand order: bit-identical results.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void team_sync(int team, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + team), "r"(nthreads) : "memory");
+}
+
+template <bool PSMEM, int P>
+__global__ void __launch_bounds__(LU_MAXW*P*32, 1)
+k_lu_team(SolveView Sv, int n)
+{
+    extern __shared__ double smem[];
+    __shared__ unsigned long long s_bar[LU_MAXW];
+    __shared__ int s_next[LU_MAXW], s_badf[LU_MAXW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int team = warp/P, h = warp%P;
+    const int W = Sv.lu_warps;                          // teams (= resident images) per CTA
+    const int img = Sv.img;
+    double *S = smem + (size_t)team*img;
+    unsigned short *s_round = reinterpret_cast<unsigned short*>(smem + (size_t)W*img);
+    unsigned *s_rows = reinterpret_cast<unsigned*>(s_round + ((Sv.nrounds + 7) & ~7));
+    const int nlive = Sv.ctr[0];
+    if ((int)(blockIdx.x*W) >= nlive) return;
+    for (int i = threadIdx.x; i < Sv.nrounds; i += blockDim.x) s_round[i] = Sv.rounds[i];
+    if (PSMEM) {
+        const uint4 *src = reinterpret_cast<const uint4*>(Sv.rows);
+        uint4 *dst = reinterpret_cast<uint4*>(s_rows);
+        for (int i = threadIdx.x; i < Sv.nrows*(LU_LANES/4); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x < W) mbar_init(&s_bar[threadIdx.x], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const unsigned *rows0 = (PSMEM ? s_rows : Sv.rows) + lane;
+    const unsigned bytes = (unsigned)img*8u;
+    unsigned phase = 0;
+    const int nlevels = Sv.nlevels;
+    for (;;) {
+        team_sync(team, P*32);                           // the team is done with the previous image
+        if (h == 0 && lane == 0) {
+            s_next[team] = atomicAdd(&Sv.ctr[1], 1);
+            s_badf[team] = 0;
+        }
+        team_sync(team, P*32);
+        const int i = s_next[team];
+        if (i >= nlive) break;
+        const int t = Sv.live[i];
+        if (h == 0 && lane == 0) {
+            // the previous trial's image was read and written through the generic proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_bar[team], bytes);
+            bulk_g2s(S, Sv.image + (size_t)t*img, bytes, &s_bar[team]);
+        }
+        mbar_wait(&s_bar[team], phase);
+        phase ^= 1u;
+        int bad = 0;
+        for (int lv = 0; lv < nlevels; lv++) {
+            const int r0 = __ldg(Sv.level_ptr + lv), r1 = __ldg(Sv.level_ptr + lv + 1);
+            for (int r = r0 + h; r < r1; r += P) {
+                const int nsteps = (int)(s_round[r] & 0x7fffu);
+                const unsigned *rp = rows0 + (size_t)__ldg(Sv.round_row + r)*LU_LANES;
+                const unsigned hd = PSMEM ? rp[0] : __ldg(rp);
+                rp += LU_LANES;
+                const unsigned dst = hd & 0xffffu, div = hd >> 16;
+                double acc = S[dst];
+                for (int s = 0; s < nsteps; s += 4) {
+                    unsigned w[4];
+                    double a[4], b[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (s + u < nsteps) w[u] = PSMEM ? rp[(s + u)*LU_LANES] : __ldg(rp + (s + u)*LU_LANES);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (s + u < nsteps) { a[u] = S[w[u] & 0xffffu]; b[u] = S[w[u] >> 16]; }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (s + u < nsteps) acc -= a[u]*b[u];
+                }
+                if (div != LU_NONE) {
+                    const double piv = S[div];
+                    if (piv == 0.0 || !isfinite(piv)) bad = 1;
+                    acc = acc/piv;
+                }
+                S[dst] = acc;
+            }
+            team_sync(team, P*32);                       // the level is complete
+        }
+        double *y = Sv.ysol + (size_t)t*Sv.npad;
+        const double *Sy = S + Sv.nlu;
+        for (int k = h*32 + lane; k < n; k += P*32) y[k] = Sy[k];
+        if (bad) s_badf[team] = 1;
+        team_sync(team, P*32);
+        if (h == 0 && lane == 0) Sv.lu_bad[t] = s_badf[team];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_lu_wide: the same task program for images beyond one warp's shared-memory window (a few
 // thousand unknowns upward).  The image stays where k_assemble put it -- global memory, in
 // practice L2 -- and the program rows carry 32-bit slot numbers.  A large system has wide
@@ -444,9 +545,10 @@ int solve_configure(SolveView &Sv)
         Sv.lu_grid = nsm*per_sm;
         return B200_OK;
     }
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, k_lu<true>) != cudaSuccess) return B200_E_NOGPU;
-    const size_t budget = (size_t)maxsm - fa.sharedSizeBytes;
+    cudaFuncAttributes fa, ft;
+    if (cudaFuncGetAttributes(&fa, k_lu<true>) != cudaSuccess ||
+        cudaFuncGetAttributes(&ft, k_lu_team<true, 4>) != cudaSuccess) return B200_E_NOGPU;
+    const size_t budget = (size_t)maxsm - std::max(fa.sharedSizeBytes, ft.sharedSizeBytes);
     const size_t imgb = (size_t)Sv.img*8;
     const size_t rnd = (size_t)((Sv.nrounds + 7) & ~7)*sizeof(unsigned short);
     const size_t prog = (size_t)Sv.nrows*LU_LANES*sizeof(unsigned);
@@ -464,11 +566,20 @@ int solve_configure(SolveView &Sv)
     Sv.lu_warps = psmem ? w_smem : w_glob;
     Sv.lu_smem = (int)((size_t)Sv.lu_warps*imgb + rnd + (psmem ? prog : 0));
     Sv.lu_grid = nsm;
+    // warps per resident image: 2 when the levels are wide enough to feed them
+    Sv.lu_team = (Sv.nlevels > 0 && Sv.nrounds >= 2*Sv.nlevels) ? 2 : 1;
+    if (const char *e = getenv("B200_LU_TEAM")) Sv.lu_team = atoi(e) == 2 ? 2 : (atoi(e) == 4 ? 4 : 1);   // measurement override
     // opt in to the whole window: a batch may run two programs of different size through the
     // same kernel, and the attribute is per function, not per launch
     cudaError_t e = psmem
         ? cudaFuncSetAttribute(k_lu<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)
         : cudaFuncSetAttribute(k_lu<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    if (e == cudaSuccess && Sv.lu_team == 2)
+        e = psmem ? cudaFuncSetAttribute(k_lu_team<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)
+                  : cudaFuncSetAttribute(k_lu_team<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    if (e == cudaSuccess && Sv.lu_team == 4)
+        e = psmem ? cudaFuncSetAttribute(k_lu_team<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)
+                  : cudaFuncSetAttribute(k_lu_team<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     return e == cudaSuccess ? B200_OK : B200_E_NOMEM;
 }
 
@@ -482,6 +593,14 @@ int launch_solve(cudaStream_t st, const Consts &K, const HotView &hot, const Vec
         k_assemble_long<<<dim3(ngroups, (Sv.nlong + ASM_WARPS - 1)/ASM_WARPS), ASM_WARPS*32, 0, st>>>(K, hot, V, Sv);
     k_assemble<<<ga, ASM_WARPS*32, 0, st>>>(K, hot, V, Sv);
     if (Sv.wide) k_lu_wide<<<Sv.lu_grid, Sv.lu_warps*32, 0, st>>>(Sv, K.n);
+    else if (Sv.lu_team == 2) {
+        if (Sv.prog_in_smem) k_lu_team<true, 2><<<Sv.lu_grid, Sv.lu_warps*64, Sv.lu_smem, st>>>(Sv, K.n);
+        else k_lu_team<false, 2><<<Sv.lu_grid, Sv.lu_warps*64, Sv.lu_smem, st>>>(Sv, K.n);
+    }
+    else if (Sv.lu_team == 4) {
+        if (Sv.prog_in_smem) k_lu_team<true, 4><<<Sv.lu_grid, Sv.lu_warps*128, Sv.lu_smem, st>>>(Sv, K.n);
+        else k_lu_team<false, 4><<<Sv.lu_grid, Sv.lu_warps*128, Sv.lu_smem, st>>>(Sv, K.n);
+    }
     else if (Sv.prog_in_smem) k_lu<true><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
     else k_lu<false><<<Sv.lu_grid, Sv.lu_warps*32, Sv.lu_smem, st>>>(Sv, K.n);
     // share the unknowns among CTAs when the trial groups alone leave SMs idle: aim at ~4 CTAs per SM
