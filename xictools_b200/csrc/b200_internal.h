@@ -70,8 +70,8 @@ enum { MRH_g, MRH_b, MRH_dp, MRH_sp, MRH_NRHS };
 #endif
 #ifndef MOS_MINB
 #define MOS_MINB 8                               // __launch_bounds__ minimum: caps the kernel at 128 registers without
-                                                 // spills (+1.4 % against 162); the staging area keeps 6 CTAs per SM
-                                                 // resident (7, with three rows read late from HBM instead, measured -1 %)
+                                                 // spills: 7 CTAs per SM instead of 6, +1.6 % (shrinking the staging
+                                                 // area by reading three rows late from HBM instead measured -1 %)
 #endif
 enum { SR_V_B, SR_V_SP, SR_V_G, SR_V_DP,                // node voltages (rhsOld); the predictor's
        SR_S2_vbs = SR_V_B, SR_S2_vgs = SR_V_SP, SR_S2_vds = SR_V_G,   // state-2 voltages share the rows
