@@ -992,7 +992,7 @@ k_load_jj(Consts K, HotView hot, VecView V, JJView J, const double *rhsOld)
     TrialCtx c;
     make_ctx(c, K, hot, V, t, mode);
     const int st = J.state[i], m = J.model[i];
-    const int pos = J.pos[i], neg = J.neg[i], phs = J.phs[i];
+    const int pos = J.pos[i], neg = J.neg[i];
     const size_t ldt = K.ldt;
     const double criti = PR(J.prm[JP_criti], i, t);
     const double cap = PR(J.prm[JP_cap], i, t);
