@@ -300,6 +300,12 @@ def variants():
         "rc_sffm": rc_fn(sffm=(0.5, 0.4, 1.0e9, 2.0, 0.2e9)),
         "rc_am": rc_fn(am=(0.8, 1.0, 0.3e9, 2.0e9, 0.4e-9)),
         "float_cap": float_cap(),
+        # PULSE / GPULSE bit patterns (inptran.cc:285-520), expanded by deck.expand_bit_pattern
+        "rc_pulse_bits": rc_fn(pulse=(0, 1, 0.1e-9, 0.05e-9, 0.05e-9, 0.15e-9, 0.5e-9), pattern="b1011 rb=2 r=-1"),
+        "rc_pulse_prbs": rc_fn(pulse=(0.2, 1, 0.05e-9, 0.05e-9, 0.05e-9, 0.1e-9, 0.4e-9), pattern="bprbs7 r=-1"),
+        "rc_pulse_two": rc_fn(pulse=(0, 1, 0.1e-9, 0.04e-9, 0.04e-9, 0.1e-9, 0.3e-9), pattern="b101 r=1 b0011 rb=3 r=2"),
+        "rc_gpulse_bits": rc_fn(gpulse=(0, 1, 0.2e-9, 0.06e-9, 0.4e-9), pattern="b110 r=2"),
+        "rc_gpulse_prbs": rc_fn(gpulse=(0, 1, 0.2e-9, 0.05e-9, 0.3e-9), pattern="bprbs6 rb=11 r=-1"),
         "ro5_dcmu": ring_oscillator(5).options(dcmu=0.35),
         # GPULSE (inptran.cc:1567-1827): FWHM width + two more pulse delays; repeating; old-style width
         "rc_gpulse": rc_fn(gpulse=(0.1, 1.0, 1.0e-9, 0.3e-9, 0, 2.2e-9, 3.1e-9)),

@@ -133,6 +133,95 @@ PHI0 = 2.067833848e-15              # wrsCONSTphi0 (include/circuit.h:123-124)
 PHI0_2PI = PHI0/(2*3.14159265358979323846)
 
 
+def expand_bit_pattern(spec: str):
+    """(bits, repeat_start) of a PULSE / GPULSE bit-pattern specification as the reference expands
+    it: pbitList::parse (inptran.cc:312-381: a sequence of `b<string>` items, each with optional
+    `r[=N]` repeat count, -1 = forever, and `rb=M` repeat-from bit, 1-based) and pbitAry::add /
+    addPRBS (:412-518; `bprbsN`, N = 6..12, the LFSR sequences listed there, rotated by rb-1)."""
+    toks = spec.replace("=", " ").split()
+    items = []
+    i = 0
+    while i < len(toks):
+        tk = toks[i]
+        i += 1
+        if tk[0] not in "bB":
+            continue                                # unknown token: ignored
+        it = dict(s=tk, rb=1, r=0)
+        while i < len(toks) and toks[i].lower() in ("r", "rb"):
+            key = toks[i].lower()
+            if i + 1 < len(toks) and toks[i+1].lstrip("-").isdigit():
+                val = int(toks[i+1])
+                i += 2
+            else:                                   # a bare `r`
+                val = 0
+                i += 1
+            if key == "rb":
+                it["rb"] = max(1, val)
+            else:
+                it["r"] = 0 if val < -1 else val
+        items.append(it)
+    bits, rst = [], 0
+
+    def prbs(n, bit):
+        n1, n3, n4 = n, 1, 1
+        if n1 <= 6:
+            n1, n2 = 6, 5
+        elif n1 == 7:
+            n2 = 6
+        elif n1 == 8:
+            n2, n3, n4 = 6, 5, 4
+        elif n1 == 9:
+            n2 = 5
+        elif n1 == 10:
+            n2 = 7
+        elif n1 == 11:
+            n2 = 9
+        else:
+            n1, n2, n3, n4 = 12, 11, 8, 6
+        mask = (1 << n1) - 1
+        start = a = 0x02
+        while True:
+            if not bit:
+                start = a
+            if n1 in (8, 12):
+                nb = ((a >> (n1-1)) + (a >> (n2-1)) + (a >> (n3-1)) + (a >> (n4-1))) & 1
+            else:
+                nb = ((a >> (n1-1)) + (a >> (n2-1))) & 1
+            a = ((a << 1) | nb) & mask
+            bit -= 1
+            if bit < 0:
+                bits.append(a & 1)
+                if a == start:
+                    break
+
+    for it in items:
+        strt = len(bits)
+        body = it["s"][1:]
+        if body[:4].lower() == "prbs":
+            n = int(body[4:] or 0)
+            prbs(n, it["rb"] - 1)
+            if it["r"] == -1:
+                rst = strt
+                if rst == 0:
+                    bits.append(bits[0] & 1)
+                    rst = 1
+                break
+            for _ in range(it["r"]):
+                prbs(n, it["rb"] - 1)
+        else:
+            zero = "0fnFN"
+            bits.extend(0 if ch in zero else 1 for ch in body)
+            if it["r"] == -1:
+                rst = strt + it["rb"] - 1
+                if rst == 0:
+                    bits.append(bits[0] & 1)
+                    rst = 1
+                break
+            for _ in range(it["r"]):
+                bits.extend(0 if ch in zero else 1 for ch in it["s"][it["rb"]:])
+    return bits, rst
+
+
 def jj_model_setup(card: dict, dphimax: float = 0.2*3.14159265358979323846) -> dict:
     """What sJJmodel holds after the model pass of JJdev::setup for a `.model NAME jj(...)` card
     whose values are inside the documented ranges (jjset.cc:196-545; out-of-range values are
@@ -238,17 +327,17 @@ class Deck:
 
     # ---- construction -------------------------------------------------------------
     def vsource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None, exp=None, sffm=None,
-                am=None, gpulse=None, spulse=None):
+                am=None, gpulse=None, spulse=None, pattern=None):
         self.elems.append(_Elem(DEV_SRC, name.lower(), (str(p).lower(), str(n).lower()),
                                 dict(kind=SRC_V, dc=dc, pulse=pulse, pwl=pwl, sin=sin, exp=exp,
-                                     sffm=sffm, am=am, gpulse=gpulse, spulse=spulse)))
+                                     sffm=sffm, am=am, gpulse=gpulse, spulse=spulse, pattern=pattern)))
         return self
 
     def isource(self, name, p, n, dc=None, pulse=None, pwl=None, sin=None, exp=None, sffm=None,
-                am=None, gpulse=None, spulse=None):
+                am=None, gpulse=None, spulse=None, pattern=None):
         self.elems.append(_Elem(DEV_SRC, name.lower(), (str(p).lower(), str(n).lower()),
                                 dict(kind=SRC_I, dc=dc, pulse=pulse, pwl=pwl, sin=sin, exp=exp,
-                                     sffm=sffm, am=am, gpulse=gpulse, spulse=spulse)))
+                                     sffm=sffm, am=am, gpulse=gpulse, spulse=spulse, pattern=pattern)))
         return self
 
     def resistor(self, name, p, n, r):
@@ -426,15 +515,16 @@ class Deck:
                 dc = overrides.get((P_SRC_DC, i), p["dc"])
                 if dc is not None:
                     s += f" dc {_fmt(dc)}"
+                pat = (" " + p["pattern"]) if p.get("pattern") else ""
                 if p["pulse"] is not None:
-                    s += " pulse(" + " ".join(_fmt(x) for x in p["pulse"]) + ")"
+                    s += " pulse(" + " ".join(_fmt(x) for x in p["pulse"]) + pat + ")"
                 if p["pwl"] is not None:
                     s += " pwl(" + " ".join(_fmt(x) for x in p["pwl"]) + ")"
                 if p["sin"] is not None:
                     s += " sin(" + " ".join(_fmt(x) for x in p["sin"]) + ")"
                 for fn in ("exp", "sffm", "am", "gpulse", "spulse"):
                     if p.get(fn) is not None:
-                        s += f" {fn}(" + " ".join(_fmt(x) for x in p[fn]) + ")"
+                        s += f" {fn}(" + " ".join(_fmt(x) for x in p[fn]) + (pat if fn == "gpulse" else "") + ")"
                 lines.append(s)
             elif e.kind == DEV_RES:
                 r = overrides.get((P_RES_R, i), e.params["r"])
@@ -607,6 +697,10 @@ class Deck:
                 fn, coef = FN_GPULSE, list(p["gpulse"])
             elif p.get("spulse") is not None:
                 fn, coef = FN_SPULSE, list(p["spulse"])
+            if p.get("pattern") and fn in (FN_PULSE, FN_GPULSE):
+                bits, rst = expand_bit_pattern(p["pattern"])
+                if bits:                            # after a NaN: length, repeat start, bits (b200spice.h)
+                    coef = coef + [NAN, float(len(bits)), float(rst)] + [float(b) for b in bits]
             ca = arr(C.c_double, [float(x) for x in coef])
             src[i] = CSrc(p["kind"], nums[e.nodes[0]], nums[e.nodes[1]],
                           NAN if p["dc"] is None else float(p["dc"]), fn, len(coef), ca)
