@@ -166,3 +166,22 @@ def test_nor_gate_with_the_tunnel_junction_model():
         got = r["waves"][t][:want.shape[0]]              # (the buffer holds npoints_max rows)
         tol = RELTOL*np.maximum(np.abs(got), np.abs(want)) + VNTOL
         assert not (np.abs(got - want) > tol).any()
+
+
+@pytest.mark.gpu
+def test_example_script_writes_the_verdict_file_and_a_rawfile(tmp_path, monkeypatch):
+    """examples/nor_mc_batch.py end to end (7 trials): report in check -m's layout, rawfile of
+    trial 0 that the reader takes back."""
+    import importlib.util
+    import sys
+    from xictools_b200.mcreport import read_report
+    from xictools_b200.rawfile import read_rawfile
+    spec = importlib.util.spec_from_file_location("nor_mc_batch", os.path.join(os.path.dirname(HERE), "examples", "nor_mc_batch.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(sys, "argv", ["nor_mc_batch.py", "7", str(tmp_path)])
+    mod.main()
+    rep = read_report(tmp_path/"nor_mc.m00")
+    assert len(rep) == 7 and rep[0][3] and len(rep[0][4]) == 13       # nominal trial passes; 13 altered values
+    plots = read_rawfile(tmp_path/"nor_mc_trial0.raw")
+    assert len(plots) == 1 and plots[0]["data"].shape[1] == 6         # time + 5 saved signals
