@@ -437,6 +437,15 @@ def test_monte_carlo_resistor_values(name):
     compare(d, ntr, ov)
 
 
+def test_monte_carlo_every_mos_parameter_kind():
+    """B200_P_MOS_VTO / KP / GAMMA / LAMBDA / PHI / L / W all per trial and per device at once:
+    k_mos_temp re-derives every dependent parameter on the device (mostemp.cc)."""
+    from tests.test_oracle_vs_ref import _mos_variation
+    d = ring_oscillator(5)
+    ntr = 11
+    compare(d, ntr, _mos_variation(d, ntr, 42))
+
+
 def test_save_list_keeps_only_the_named_unknowns():
     """b200_batch_set_saves (`.save`): the output buffer holds the listed unknowns only; their
     waveforms are bit-identical to the same columns of a run that keeps everything, whichever

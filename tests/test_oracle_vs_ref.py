@@ -132,3 +132,37 @@ def test_resistor_monte_carlo_trials_match_reference(name):
         assert {k: o[k] for k in KEYS} == {k: ref[k] for k in KEYS}
         idx = [o["names"].index(nm) for nm in ref["names"]]
         assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < LOOSE.get(name, 1e-9)
+
+
+def _mos_variation(d, ntr, seed):
+    """Every per-trial MOS parameter kind at once: W, KP, GAMMA, LAMBDA, PHI (plus the usual
+    VTO, L), as private model cards / instance values per device."""
+    from xictools_b200.deck import (DEV_MOS, P_MOS_GAMMA, P_MOS_KP, P_MOS_L, P_MOS_LAMBDA, P_MOS_PHI, P_MOS_VTO,
+                                    P_MOS_W)
+    rng = np.random.default_rng(seed)
+    ov = {}
+    for i, e in enumerate(d.kind_tables()[DEV_MOS]):
+        mp = d.mos_models[e.model]["params"]
+        nominal = {P_MOS_VTO: mp["vto"], P_MOS_KP: mp["kp"], P_MOS_GAMMA: mp.get("gamma", 0.4),
+                   P_MOS_LAMBDA: mp.get("lambda", 0.02), P_MOS_PHI: mp.get("phi", 0.65),
+                   P_MOS_L: e.params["l"], P_MOS_W: e.params["w"]}
+        for pid, v0 in nominal.items():
+            v = np.full(ntr, float(v0))
+            v[1:] *= 1.0 + 0.04*rng.standard_normal(ntr - 1)
+            ov[(pid, i)] = v
+    return ov
+
+
+def test_every_mos_parameter_kind_varied_matches_reference():
+    d = ring_oscillator(5)
+    ntr = 3
+    ov = _mos_variation(d, ntr, 41)
+    counts = set()
+    for t in range(ntr):
+        ref = RefSim().run(d.to_spice({k: v[t] for k, v in ov.items()}))
+        o = Oracle(d, ov, t).run()
+        assert {k: o[k] for k in KEYS} == {k: ref[k] for k in KEYS}
+        idx = [o["names"].index(nm) for nm in ref["names"]]
+        assert np.abs(o["vals"][:, idx] - ref["vals"]).max() < 1e-9
+        counts.add(ref["numiter"])
+    assert len(counts) > 1
