@@ -446,6 +446,44 @@ def test_monte_carlo_every_mos_parameter_kind():
     compare(d, ntr, _mos_variation(d, ntr, 42))
 
 
+def test_wide_path_trials_do_not_see_each_other():
+    """Size-independent properties on the wide LU path (1 000-junction line, 96 KB image per trial,
+    k_lu_wide: one CTA per trial): trials that carry the same values end bit-identical wherever
+    they sit in the batch, and trial 0 equals the same circuit run as a batch of one."""
+    from tests.decks import jtl
+    from xictools_b200.deck import DEV_JJ, P_JJ_ICS
+    d = jtl(1000)
+    ntr, half = 192, 96
+    rng = np.random.default_rng(77)
+    jjs = d.kind_tables()[DEV_JJ]
+    vals = np.empty((len(jjs), ntr))
+    for i, e in enumerate(jjs):
+        v = e.params["ics"]*(1.0 + 0.1*rng.standard_normal(half))
+        v[0] = e.params["ics"]
+        vals[i, :half] = v
+        vals[i, half:] = v[::-1]                     # the same trials again, in reverse order
+    b = engine.Batch(d, ntr)
+    b.set_params_packed([P_JJ_ICS]*len(jjs), list(range(len(jjs))), vals)
+    names = b.names()
+    keep = [names.index("a0"), names.index("a500"), names.index("a999")]
+    b.set_saves(keep)
+    b.run_tran()
+    cnt = b.counters()
+    _, w = b.waves()
+    b.close()
+    assert (cnt[:, C_STATUS] == 0).all()
+    assert np.array_equal(cnt[:half], cnt[half:][::-1])
+    assert np.array_equal(w[:half], w[half:][::-1])
+    assert len({int(x) for x in cnt[:half, C_NUMITER]}) > 4          # the trials really differ
+    one = engine.Batch(d, 1)
+    one.set_saves(keep)
+    one.run_tran()
+    c1 = one.counters()
+    _, w1 = one.waves()
+    one.close()
+    assert np.array_equal(c1[0], cnt[0]) and np.array_equal(w1[0], w[0])
+
+
 def test_save_list_keeps_only_the_named_unknowns():
     """b200_batch_set_saves (`.save`): the output buffer holds the listed unknowns only; their
     waveforms are bit-identical to the same columns of a run that keeps everything, whichever
