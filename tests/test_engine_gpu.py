@@ -484,6 +484,22 @@ def test_wide_path_trials_do_not_see_each_other():
     assert np.array_equal(c1[0], cnt[0]) and np.array_equal(w1[0], w[0])
 
 
+@pytest.mark.parametrize("name", ["ro5", "rlc_series", "jtl6_dc_accel"])
+def test_graph_tick_equals_the_plain_stream(name, monkeypatch):
+    """The CUDA-graph replay of two captured ticks (small systems) against plain launches: same
+    kernels in the same order, so counters and waveforms are bit-identical."""
+    d = variants()[name]
+    out = []
+    for g in ("0", "1"):
+        monkeypatch.setenv("B200_GRAPH", g)
+        b = engine.Batch(d, 9)
+        b.run_tran()
+        out.append((b.counters().copy(), b.waves()[1].copy(), b.stats().ms_load))
+        b.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][2] > 0.0 and out[1][2] == 0.0       # the load / solve split is timed on the plain stream only
+
+
 def test_save_list_keeps_only_the_named_unknowns():
     """b200_batch_set_saves (`.save`): the output buffer holds the listed unknowns only; their
     waveforms are bit-identical to the same columns of a run that keeps everything, whichever
