@@ -500,6 +500,28 @@ def test_graph_tick_equals_the_plain_stream(name, monkeypatch):
     assert out[0][2] > 0.0 and out[1][2] == 0.0       # the load / solve split is timed on the plain stream only
 
 
+def test_lu_kernels_agree_bit_for_bit(monkeypatch):
+    """k_lu (one warp per resident image), k_lu_team (two and four warps per image) and
+    k_lu_wide (one CTA per trial, image in L2) run the same tasks in the same operand order: RO-51
+    with per-trial parameters gives bit-identical counters and waveforms through all of them."""
+    d = ring_oscillator(51)
+    ntr = 40
+    ov = mc_variation(d, ntr, seed=9)
+    res = []
+    for env in ({"B200_LU_TEAM": "1"}, {"B200_LU_TEAM": "2"}, {"B200_LU_TEAM": "4"}, {"B200_LU_WIDE": "1"}):
+        for k in ("B200_LU_TEAM", "B200_LU_WIDE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        b = engine.Batch(d, ntr)
+        b.set_params(ov)
+        b.run_tran()
+        res.append((b.counters().copy(), b.waves()[1].copy()))
+        b.close()
+    for c, w in res[1:]:
+        assert np.array_equal(c, res[0][0]) and np.array_equal(w, res[0][1])
+
+
 def test_save_list_keeps_only_the_named_unknowns():
     """b200_batch_set_saves (`.save`): the output buffer holds the listed unknowns only; their
     waveforms are bit-identical to the same columns of a run that keeps everything, whichever
