@@ -273,7 +273,7 @@ k_load_mos(Consts K, HotView hot, VecView V, const __grid_constant__ MosView M, 
 #undef SG
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 k_load_cap(Consts K, HotView hot, VecView V, CapView Cp, const double *rhsOld)
 {
     // capload.cc:75-205 (linear capacitor)
